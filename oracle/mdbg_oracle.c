@@ -1,0 +1,368 @@
+/*
+ * mdbg_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE (see mdbg_oracle.h).
+ *
+ * Plain-C restatement of the reference algorithm, written from its behaviour;
+ * each function cites the reference lines it follows.  Parity status: PINNED
+ * against the reference's own sources compiled by oracle/Makefile into
+ * oracle/_ref/libmdbg_ref.so (tests/test_oracle_vs_ref.py, run where
+ * /root/reference exists) and against tests/golden/ (npz files) minted from that
+ * library (tests/golden/make_golden.py).
+ */
+#include "mdbg_oracle.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------ murmur */
+
+static inline uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+
+static inline uint64_t fmix64(uint64_t k) {
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdULL;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ULL;
+    k ^= k >> 33;
+    return k;
+}
+
+/* MurmurHash3.cpp:328-405 (the _original variant); :246-325 is the same
+ * arithmetic returning only h1. */
+void orc_murmur3_x64_128(const void* key, int len, uint32_t seed, uint64_t out[2]) {
+    const uint8_t* data = (const uint8_t*)key;
+    const int nblocks = len / 16;
+    uint64_t h1 = seed, h2 = seed;
+    const uint64_t c1 = 0x87c37b91114253d5ULL, c2 = 0x4cf5ad432745937fULL;
+
+    for (int i = 0; i < nblocks; i++) {
+        uint64_t k1, k2;
+        memcpy(&k1, data + 16 * (size_t)i, 8);
+        memcpy(&k2, data + 16 * (size_t)i + 8, 8);
+        k1 *= c1; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1;
+        h1 = rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729;
+        k2 *= c2; k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2;
+        h2 = rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5;
+    }
+
+    const uint8_t* tail = data + (size_t)nblocks * 16;
+    uint64_t k1 = 0, k2 = 0;
+    const int rem = len & 15;
+    for (int i = rem - 1; i >= 8; i--) k2 ^= (uint64_t)tail[i] << (8 * (i - 8));
+    if (rem > 8) { k2 *= c2; k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2; }
+    for (int i = (rem > 8 ? 7 : rem - 1); i >= 0; i--) k1 ^= (uint64_t)tail[i] << (8 * i);
+    if (rem > 0) { k1 *= c1; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1; }
+
+    h1 ^= (uint64_t)len; h2 ^= (uint64_t)len;
+    h1 += h2; h2 += h1;
+    h1 = fmix64(h1); h2 = fmix64(h2);
+    h1 += h2; h2 += h1;
+    out[0] = h1; out[1] = h2;
+}
+
+uint64_t orc_murmur3_x64_128_h1(const void* key, int len, uint32_t seed) {
+    uint64_t o[2];
+    orc_murmur3_x64_128(key, len, seed, o);
+    return o[0];
+}
+
+/* ------------------------------------------------------------------ bound */
+
+/* Kmer.hpp:1354-1356: u_int64_t maxHashValue = -1; bound = density * maxHashValue
+ * with density a double parameter fed from a float (ReadSelection.hpp:574). */
+double orc_minimizer_bound(float density) {
+    uint64_t max_hash = (uint64_t)-1;
+    return (double)density * (double)max_hash;
+}
+
+/* Kmer.hpp:1434 compares `u64 < double`, i.e. (double)h < bound with
+ * round-to-nearest conversion; (double)h is monotone in h, so the selected
+ * set is {h <= T}.  Binary search for T. */
+uint64_t orc_minimizer_threshold(float density, int* none) {
+    const double bound = orc_minimizer_bound(density);
+    if (none) *none = 0;
+    if (!((double)(uint64_t)0 < bound)) { if (none) *none = 1; return 0; }
+    uint64_t lo = 0, hi = (uint64_t)-1;            /* invariant: (double)lo < bound */
+    if ((double)hi < bound) return hi;
+    while (hi - lo > 1) {                            /* (double)hi >= bound */
+        uint64_t mid = lo + (hi - lo) / 2;
+        if ((double)mid < bound) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+/* -------------------------------------------------------------------- HPC */
+
+size_t orc_hpc(const char* seq, size_t len, int hpc, char* out, uint64_t* rle_pos) {
+    if (!hpc) {                                      /* Commons.hpp:4192-4199 */
+        /* the reference builds string(sequence): stops at the first NUL */
+        size_t n = 0;
+        while (n < len && seq[n] != '\0') n++;
+        memcpy(out, seq, n);
+        if (rle_pos) for (size_t i = 0; i < n; i++) rle_pos[i] = i;
+        return n;
+    }
+    /* Commons.hpp:4172-4190.  lastChar starts as '#': a leading '#' run is
+     * swallowed exactly as upstream does. */
+    size_t n = 0;
+    char last = '#';
+    uint64_t last_pos = 0;
+    for (size_t i = 0; i < len; i++) {
+        char c = seq[i];
+        if (c == last) continue;
+        if (last != '#') {
+            out[n] = last;
+            if (rle_pos) rle_pos[n] = last_pos;
+            n++;
+            last_pos = i;
+        }
+        last = c;
+    }
+    out[n] = last;
+    if (rle_pos) { rle_pos[n] = last_pos; rle_pos[n + 1] = len; }
+    n++;
+    return n;
+}
+
+/* ------------------------------------------------------------------ l-mers */
+
+/* Kmer.hpp:31 comp_NT, :462 ConvertASCII, :488-507 polynom, :509-518 revcomp,
+ * :570-589 iterate, :594-611 first/next, :427 updateChoice. */
+size_t orc_lmers(const char* seq, size_t len, int l, uint64_t* values, uint8_t* dirs) {
+    if (len < (size_t)l) return 0;
+    const size_t n = len - (size_t)l + 1;
+    const uint64_t mask = (l >= 32) ? ~0ULL : ((1ULL << (2 * l)) - 1);
+    static const uint64_t comp[4] = {2, 3, 0, 1};
+    uint64_t fwd = 0, rc = 0;
+    int bad = -1;                                    /* index of last bad char in window */
+    for (int i = 0; i < l; i++) {
+        unsigned char ch = (unsigned char)seq[i];
+        uint64_t c = (ch >> 1) & 3;
+        fwd = (fwd << 2) + c;
+        if ((ch >> 3) & 1) bad = i;
+    }
+    /* revcomp of the first window: complement each base, reverse order */
+    for (int i = 0; i < l; i++) {
+        uint64_t c = (fwd >> (2 * i)) & 3;           /* base l-1-i */
+        rc = (rc << 2) | comp[c];
+    }
+    size_t idx = 0;
+    {
+        int dir = (fwd < rc) ? 0 : 1;
+        values[idx] = (bad < 0) ? (dir ? rc : fwd) : ~0ULL;
+        dirs[idx] = (uint8_t)dir;
+        idx++;
+    }
+    for (size_t p = (size_t)l; p < len; p++) {
+        unsigned char ch = (unsigned char)seq[p];
+        uint64_t c = (ch >> 1) & 3;
+        if ((ch >> 3) & 1) bad = l - 1; else bad--;
+        fwd = ((fwd << 2) + c) & mask;
+        rc = ((rc >> 2) + (comp[c] << (2 * (l - 1)))) & mask;
+        int dir = (fwd < rc) ? 0 : 1;
+        values[idx] = (bad < 0) ? (dir ? rc : fwd) : ~0ULL;
+        dirs[idx] = (uint8_t)dir;
+        idx++;
+    }
+    return n;
+}
+
+/* ------------------------------------------------------------------ sketch */
+
+static int bl_contains(const uint32_t* bl, size_t n, uint32_t v) {
+    size_t lo = 0, hi = n;
+    while (lo < hi) {
+        size_t mid = (lo + hi) / 2;
+        if (bl[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    return lo < n && bl[lo] == v;
+}
+
+size_t orc_sketch_read(const char* seq, size_t len, int l, float density, int hpc,
+                       const uint32_t* blacklist, size_t n_blacklist,
+                       uint32_t* minimizers, uint32_t* positions, uint8_t* directions,
+                       size_t cap) {
+    char* hs = (char*)malloc(len + 1);
+    size_t hl = orc_hpc(seq, len, hpc, hs, NULL);
+    size_t n_out = 0;
+    if (hl >= (size_t)l) {
+        size_t n = hl - (size_t)l + 1;
+        uint64_t* vals = (uint64_t*)malloc(n * sizeof(uint64_t));
+        uint8_t* dirs = (uint8_t*)malloc(n);
+        orc_lmers(hs, hl, l, vals, dirs);
+        const double bound = orc_minimizer_bound(density);
+        /* Kmer.hpp:1395: for(pos=_trimBps; pos<kmers.size()-_trimBps; pos++), _trimBps=1
+         * (unsigned arithmetic: n>=1 here so n-1 cannot wrap). */
+        for (size_t pos = 1; pos + 1 < n; pos++) {
+            uint64_t v = vals[pos];
+            uint64_t h = orc_murmur3_x64_128_h1(&v, 8, 42);       /* Kmer.hpp:1421 */
+            if ((double)h < bound) {                                 /* Kmer.hpp:1434 */
+                /* Kmer.hpp:1437: unordered_set<u32>::find(u64) truncates the key */
+                if (n_blacklist > 0 && bl_contains(blacklist, n_blacklist, (uint32_t)v)) continue;
+                if (n_out < cap) {
+                    minimizers[n_out] = (uint32_t)v;                 /* Kmer.hpp:1441, u32 truncation */
+                    positions[n_out] = (uint32_t)pos;
+                    directions[n_out] = dirs[pos];
+                }
+                n_out++;
+            }
+        }
+        free(vals);
+        free(dirs);
+    }
+    free(hs);
+    return n_out;
+}
+
+size_t orc_sketch_batch(const char* bases, const uint64_t* offsets, size_t n_reads,
+                        int l, float density, int hpc,
+                        const uint32_t* blacklist, size_t n_blacklist,
+                        uint64_t* min_offsets, uint32_t* minimizers, uint32_t* positions,
+                        uint8_t* directions, size_t cap) {
+    size_t total = 0;
+    for (size_t r = 0; r < n_reads; r++) {
+        min_offsets[r] = total;
+        size_t room = total < cap ? cap - total : 0;
+        size_t w = total < cap ? total : cap;
+        total += orc_sketch_read(bases + offsets[r], (size_t)(offsets[r + 1] - offsets[r]), l, density,
+                                 hpc, blacklist, n_blacklist, minimizers + w, positions + w,
+                                 directions + w, room);
+    }
+    min_offsets[n_reads] = total;
+    return total;
+}
+
+/* -------------------------------------------------------- purge palindromes */
+
+/* KmerVec::isPalindrome, Commons.hpp:918-921: first size/2 entries equal the
+ * reversed last size/2. */
+static int is_palindrome(const uint32_t* v, size_t k) {
+    for (size_t i = 0; i < k / 2; i++)
+        if (v[i] != v[k - 1 - i]) return 0;
+    return 1;
+}
+
+size_t orc_purge_palindrome(const uint32_t* m, size_t n, size_t first_k, size_t last_k,
+                            uint32_t* out, uint8_t* keep) {
+    uint8_t* banned = (uint8_t*)calloc(n ? n : 1, 1);
+    uint32_t* win = (uint32_t*)malloc((last_k ? last_k : 1) * sizeof(uint32_t));
+    for (;;) {                                       /* Commons.hpp:1627 */
+        int has = 0;
+        for (size_t k = first_k; k < last_k && !has; k++) {
+            long i_max = (long)n - (long)k + 1;      /* Commons.hpp:1635 */
+            for (long i = 0; i < i_max && !has; i++) {
+                if (banned[i]) continue;
+                size_t cnt = 0;
+                for (size_t j = (size_t)i; j < n; j++) {   /* next k non-banned from i */
+                    if (banned[j]) continue;
+                    win[cnt++] = m[j];
+                    if (cnt == k) break;
+                }
+                if (cnt == k && is_palindrome(win, k)) {
+                    banned[i] = 1;                   /* Commons.hpp:1669: ban the first */
+                    has = 1;
+                }
+            }
+        }
+        if (!has) break;
+    }
+    size_t o = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (keep) keep[i] = !banned[i];
+        if (!banned[i]) out[o++] = m[i];
+    }
+    free(banned);
+    free(win);
+    return o;
+}
+
+/* ---------------------------------------------------------------- k-min-mers */
+
+size_t orc_kminmers(const uint32_t* m, size_t n, int k, uint32_t* vecs, uint8_t* reversed) {
+    if (n < (size_t)k) return 0;
+    size_t nw = n - (size_t)k + 1;
+    for (size_t i = 0; i < nw; i++) {
+        const uint32_t* w = m + i;
+        /* KmerVec::normalize Commons.hpp:886-916: first differing position
+         * decides; all-equal (palindromic vector) => reversed. */
+        int rev = 1;
+        for (int j = 0; j < k; j++) {
+            uint32_t a = w[j], b = w[k - 1 - j];
+            if (a == b) continue;
+            rev = (a < b) ? 0 : 1;
+            break;
+        }
+        for (int j = 0; j < k; j++) vecs[i * (size_t)k + j] = rev ? w[k - 1 - j] : w[j];
+        if (reversed) reversed[i] = (uint8_t)rev;
+    }
+    return nw;
+}
+
+void orc_hash128(const uint32_t* vec, int k, uint64_t out[2]) {
+    orc_murmur3_x64_128(vec, k * 4, 0, out);         /* Commons.hpp:956-961 */
+}
+
+/* -------------------------------------------------------------------- count */
+
+static int g_cmp_k;
+static int cmp_vec(const void* a, const void* b) {   /* KmerVec operator<, Commons.hpp:754-773 */
+    const uint32_t* x = (const uint32_t*)a;
+    const uint32_t* y = (const uint32_t*)b;
+    for (int i = 0; i < g_cmp_k; i++) {
+        if (x[i] == y[i]) continue;
+        return x[i] < y[i] ? -1 : 1;
+    }
+    return 0;
+}
+
+size_t orc_count(const uint32_t* mins, const uint64_t* offs, size_t n_reads, int k,
+                 uint32_t min_abundance, uint32_t** vecs_out, uint64_t** hashes_out,
+                 uint32_t** abundances_out, uint64_t* n_instances, uint64_t* n_distinct) {
+    /* partitionKminmers (CreateMdbg.hpp:3652-3724) only groups equal vectors;
+     * the partition count is unobservable, so one partition is used. */
+    size_t total = 0;
+    for (size_t r = 0; r < n_reads; r++) {
+        size_t n = (size_t)(offs[r + 1] - offs[r]);
+        if (n >= (size_t)k) total += n - (size_t)k + 1;
+    }
+    uint32_t* all = (uint32_t*)malloc((total ? total : 1) * (size_t)k * sizeof(uint32_t));
+    size_t w = 0;
+    for (size_t r = 0; r < n_reads; r++) {
+        size_t n = (size_t)(offs[r + 1] - offs[r]);
+        w += orc_kminmers(mins + offs[r], n, k, all + w * (size_t)k, NULL);
+    }
+    g_cmp_k = k;
+    qsort(all, total, (size_t)k * sizeof(uint32_t), cmp_vec);   /* CreateMdbg.hpp:3797 */
+
+    uint32_t* vecs = (uint32_t*)malloc((total ? total : 1) * (size_t)k * sizeof(uint32_t));
+    uint64_t* hashes = (uint64_t*)malloc((total ? total : 1) * 2 * sizeof(uint64_t));
+    uint32_t* abs_ = (uint32_t*)malloc((total ? total : 1) * sizeof(uint32_t));
+    size_t n_out = 0, distinct = 0;
+    size_t i = 0;
+    while (i < total) {                              /* run-length count, CreateMdbg.hpp:3808-3838 */
+        size_t j = i + 1;
+        while (j < total && cmp_vec(all + i * (size_t)k, all + j * (size_t)k) == 0) j++;
+        uint32_t ab = (uint32_t)(j - i);
+        distinct++;
+        /* dumpKminmer CreateMdbg.hpp:3862-3869 (first pass) */
+        if (ab > 1 && ab >= min_abundance) {
+            memcpy(vecs + n_out * (size_t)k, all + i * (size_t)k, (size_t)k * sizeof(uint32_t));
+            orc_hash128(all + i * (size_t)k, k, hashes + 2 * n_out);
+            abs_[n_out] = ab;
+            n_out++;
+        }
+        i = j;
+    }
+    free(all);
+    if (n_instances) *n_instances = total;
+    if (n_distinct) *n_distinct = distinct;
+    *vecs_out = vecs; *hashes_out = hashes; *abundances_out = abs_;
+    return n_out;
+}
+
+uint64_t orc_table_checksum(const uint64_t* hashes, const uint32_t* abundances, size_t n) {
+    uint64_t s = 0;
+    for (size_t i = 0; i < n; i++) s += (uint64_t)abundances[i] * hashes[2 * i + 1];
+    return s;
+}
+
+void orc_free(void* p) { free(p); }

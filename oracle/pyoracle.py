@@ -1,0 +1,243 @@
+"""ctypes binding of the TEST-ONLY CPU oracle (oracle/mdbg_oracle.c) and, when
+built, of the reference's own sources (oracle/_ref/libmdbg_ref.so).
+
+TEST INFRASTRUCTURE: may be imported only from tests/, bench.py's
+cpu_baseline / --impl reference legs and __graft_entry__.smoke().  Nothing in
+metamdbg_b200/ imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "libmdbg_oracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libmdbg_ref.so")
+
+_u8p = C.POINTER(C.c_uint8)
+_u32p = C.POINTER(C.c_uint32)
+_u64p = C.POINTER(C.c_uint64)
+
+
+def build(force: bool = False) -> None:
+    """Compile the C restatement (and oracle/_ref when /root/reference exists)."""
+    if force or not os.path.exists(ORACLE_SO) or \
+            os.path.getmtime(ORACLE_SO) < os.path.getmtime(os.path.join(HERE, "mdbg_oracle.c")):
+        subprocess.run(["make", "-s", "-C", HERE, os.path.join(HERE, "libmdbg_oracle.so")], check=True)
+    if os.path.exists("/root/reference/src/Commons.hpp"):
+        if force or not os.path.exists(REF_SO) or \
+                os.path.getmtime(REF_SO) < os.path.getmtime(os.path.join(HERE, "ref_shim.cpp")):
+            subprocess.run(["make", "-s", "-C", HERE, "ref"], check=True)
+
+
+def _p(a: np.ndarray, t):
+    return a.ctypes.data_as(t)
+
+
+class _Lib:
+    """Common numpy front-end over the `orc_*` / `ref_*` entry points."""
+
+    def __init__(self, path: str, prefix: str):
+        self.lib = C.CDLL(path)
+        self.prefix = prefix
+        L, p = self.lib, prefix
+        f = getattr(L, p + "murmur3_x64_128_h1"); f.restype = C.c_uint64; f.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
+        f = getattr(L, p + "murmur3_x64_128"); f.restype = None; f.argtypes = [C.c_void_p, C.c_int, C.c_uint32, _u64p]
+        f = getattr(L, p + "minimizer_bound"); f.restype = C.c_double; f.argtypes = [C.c_float]
+        f = getattr(L, p + "hpc"); f.restype = C.c_size_t; f.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]
+        f = getattr(L, p + "lmers"); f.restype = C.c_size_t; f.argtypes = [C.c_char_p, C.c_size_t, C.c_int, _u64p, _u8p]
+        f = getattr(L, p + "sketch_read"); f.restype = C.c_size_t
+        f.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_float, C.c_int, _u32p, C.c_size_t, _u32p, _u32p, _u8p, C.c_size_t]
+        f = getattr(L, p + "kminmers"); f.restype = C.c_size_t; f.argtypes = [_u32p, C.c_size_t, C.c_int, _u32p, _u8p]
+        f = getattr(L, p + "hash128"); f.restype = None; f.argtypes = [_u32p, C.c_int, _u64p]
+        getattr(L, p + "free").argtypes = [C.c_void_p]
+
+    # -- scalar helpers ----------------------------------------------------
+    def murmur_h1(self, key: bytes, seed: int) -> int:
+        return int(getattr(self.lib, self.prefix + "murmur3_x64_128_h1")(key, len(key), seed))
+
+    def murmur128(self, key: bytes, seed: int) -> tuple[int, int]:
+        out = (C.c_uint64 * 2)()
+        getattr(self.lib, self.prefix + "murmur3_x64_128")(key, len(key), seed, out)
+        return int(out[0]), int(out[1])
+
+    def bound(self, density: float) -> float:
+        return float(getattr(self.lib, self.prefix + "minimizer_bound")(density))
+
+    def hpc(self, seq: bytes, hpc: bool = True) -> tuple[bytes, np.ndarray]:
+        out = np.zeros(len(seq) + 2, dtype=np.uint8)
+        pos = np.zeros(len(seq) + 2, dtype=np.uint64)
+        n = getattr(self.lib, self.prefix + "hpc")(seq, len(seq), int(hpc), out.ctypes.data, pos.ctypes.data)
+        return out[:n].tobytes(), pos[:n + (1 if hpc else 0)].copy()
+
+    def lmers(self, seq: bytes, l: int) -> tuple[np.ndarray, np.ndarray]:
+        n = max(0, len(seq) - l + 1)
+        v = np.zeros(n + 1, dtype=np.uint64)
+        d = np.zeros(n + 1, dtype=np.uint8)
+        k = getattr(self.lib, self.prefix + "lmers")(seq, len(seq), l, _p(v, _u64p), _p(d, _u8p))
+        return v[:k].copy(), d[:k].copy()
+
+    def sketch_read(self, seq: bytes, l: int, density: float, hpc: bool, blacklist: np.ndarray | None = None):
+        cap = len(seq) + 1
+        m = np.zeros(cap, dtype=np.uint32)
+        p = np.zeros(cap, dtype=np.uint32)
+        d = np.zeros(cap, dtype=np.uint8)
+        bl = np.ascontiguousarray(np.sort(blacklist).astype(np.uint32)) if blacklist is not None and len(blacklist) else None
+        n = getattr(self.lib, self.prefix + "sketch_read")(
+            seq, len(seq), l, density, int(hpc), _p(bl, _u32p) if bl is not None else None,
+            0 if bl is None else len(bl), _p(m, _u32p), _p(p, _u32p), _p(d, _u8p), cap)
+        return m[:n].copy(), p[:n].copy(), d[:n].copy()
+
+    def sketch_batch(self, bases: np.ndarray, offsets: np.ndarray, l: int, density: float, hpc: bool,
+                     blacklist: np.ndarray | None = None):
+        """Per-read loop -> CSR (min_offsets u64[n+1], minimizers, positions, directions)."""
+        ms, ps, ds, offs = [], [], [], [0]
+        raw = bases.tobytes()
+        for r in range(len(offsets) - 1):
+            m, p, d = self.sketch_read(raw[int(offsets[r]):int(offsets[r + 1])], l, density, hpc, blacklist)
+            ms.append(m); ps.append(p); ds.append(d); offs.append(offs[-1] + len(m))
+        cat = lambda xs, t: np.concatenate(xs).astype(t) if xs else np.zeros(0, t)
+        return (np.array(offs, dtype=np.uint64), cat(ms, np.uint32), cat(ps, np.uint32), cat(ds, np.uint8))
+
+    def kminmers(self, m: np.ndarray, k: int):
+        m = np.ascontiguousarray(m, dtype=np.uint32)
+        nw = max(0, len(m) - k + 1)
+        v = np.zeros((nw + 1) * k, dtype=np.uint32)
+        rv = np.zeros(nw + 1, dtype=np.uint8)
+        n = getattr(self.lib, self.prefix + "kminmers")(_p(m, _u32p), len(m), k, _p(v, _u32p), _p(rv, _u8p))
+        return v[:n * k].reshape(n, k).copy(), rv[:n].copy()
+
+    def hash128(self, vec: np.ndarray) -> tuple[int, int]:
+        vec = np.ascontiguousarray(vec, dtype=np.uint32)
+        out = (C.c_uint64 * 2)()
+        getattr(self.lib, self.prefix + "hash128")(_p(vec, _u32p), len(vec), out)
+        return int(out[0]), int(out[1])
+
+    def _take(self, ptr, n, dtype):
+        if n == 0:
+            arr = np.zeros(0, dtype=dtype)
+        else:
+            arr = np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype, copy=True)
+        getattr(self.lib, self.prefix + "free")(C.cast(ptr, C.c_void_p))
+        return arr
+
+
+class Oracle(_Lib):
+    def __init__(self):
+        build()
+        super().__init__(ORACLE_SO, "orc_")
+        L = self.lib
+        L.orc_minimizer_threshold.restype = C.c_uint64
+        L.orc_minimizer_threshold.argtypes = [C.c_float, C.POINTER(C.c_int)]
+        L.orc_purge_palindrome.restype = C.c_size_t
+        L.orc_purge_palindrome.argtypes = [_u32p, C.c_size_t, C.c_size_t, C.c_size_t, _u32p, _u8p]
+        L.orc_count.restype = C.c_size_t
+        L.orc_count.argtypes = [_u32p, _u64p, C.c_size_t, C.c_int, C.c_uint32, C.POINTER(_u32p), C.POINTER(_u64p),
+                                C.POINTER(_u32p), _u64p, _u64p]
+        L.orc_sketch_batch.restype = C.c_size_t
+        L.orc_sketch_batch.argtypes = [C.c_void_p, _u64p, C.c_size_t, C.c_int, C.c_float, C.c_int, _u32p, C.c_size_t,
+                                       _u64p, _u32p, _u32p, _u8p, C.c_size_t]
+        L.orc_table_checksum.restype = C.c_uint64
+        L.orc_table_checksum.argtypes = [_u64p, _u32p, C.c_size_t]
+
+    def threshold(self, density: float) -> tuple[int, bool]:
+        none = C.c_int(0)
+        t = self.lib.orc_minimizer_threshold(density, C.byref(none))
+        return int(t), bool(none.value)
+
+    def sketch_batch(self, bases, offsets, l, density, hpc, blacklist=None, cap=None):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        if cap is None:
+            cap = max(1024, int(len(bases) * max(density, 0.001) * 4) + 64 * n)
+        bl = np.ascontiguousarray(np.sort(blacklist).astype(np.uint32)) if blacklist is not None and len(blacklist) else None
+        while True:
+            mo = np.zeros(n + 1, dtype=np.uint64)
+            m = np.zeros(cap, dtype=np.uint32); p = np.zeros(cap, dtype=np.uint32); d = np.zeros(cap, dtype=np.uint8)
+            tot = self.lib.orc_sketch_batch(bases.ctypes.data, _p(offsets, _u64p), n, l, density, int(hpc),
+                                            _p(bl, _u32p) if bl is not None else None, 0 if bl is None else len(bl),
+                                            _p(mo, _u64p), _p(m, _u32p), _p(p, _u32p), _p(d, _u8p), cap)
+            if tot <= cap:
+                return mo, m[:tot].copy(), p[:tot].copy(), d[:tot].copy()
+            cap = int(tot)
+
+    def purge_palindrome(self, m: np.ndarray, first_k: int, last_k: int):
+        m = np.ascontiguousarray(m, dtype=np.uint32)
+        out = np.zeros(len(m) + 1, dtype=np.uint32)
+        keep = np.zeros(len(m) + 1, dtype=np.uint8)
+        n = self.lib.orc_purge_palindrome(_p(m, _u32p), len(m), first_k, last_k, _p(out, _u32p), _p(keep, _u8p))
+        return out[:n].copy(), keep[:len(m)].copy()
+
+    def count(self, mins: np.ndarray, offs: np.ndarray, k: int, min_abundance: int = 2):
+        """-> dict(vecs [n,k] u32, hashes [n,2] u64 (h1,h2), abundances [n] u32, n_instances, n_distinct)."""
+        mins = np.ascontiguousarray(mins, dtype=np.uint32)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        v = _u32p(); h = _u64p(); a = _u32p()
+        ni = C.c_uint64(0); nd = C.c_uint64(0)
+        n = self.lib.orc_count(_p(mins, _u32p), _p(offs, _u64p), len(offs) - 1, k, min_abundance,
+                               C.byref(v), C.byref(h), C.byref(a), C.byref(ni), C.byref(nd))
+        vecs = self._take(v, n * k, np.uint32).reshape(n, k)
+        hashes = self._take(h, n * 2, np.uint64).reshape(n, 2)
+        abund = self._take(a, n, np.uint32)
+        return dict(vecs=vecs, hashes=hashes, abundances=abund, n_instances=int(ni.value), n_distinct=int(nd.value))
+
+    def checksum(self, hashes: np.ndarray, abundances: np.ndarray) -> int:
+        hashes = np.ascontiguousarray(hashes, dtype=np.uint64)
+        abundances = np.ascontiguousarray(abundances, dtype=np.uint32)
+        return int(self.lib.orc_table_checksum(_p(hashes, _u64p), _p(abundances, _u32p), len(abundances)))
+
+
+class Reference(_Lib):
+    """The reference's own code (oracle/_ref).  Raises FileNotFoundError when
+    the library has not been built (it cannot be built on the GPU box)."""
+
+    def __init__(self):
+        build()
+        if not os.path.exists(REF_SO):
+            raise FileNotFoundError(REF_SO)
+        super().__init__(REF_SO, "ref_")
+        L = self.lib
+        L.ref_purge_palindrome.restype = C.c_size_t
+        L.ref_purge_palindrome.argtypes = [_u32p, C.c_size_t, C.c_size_t, C.c_size_t, _u32p]
+        L.ref_count.restype = C.c_size_t
+        L.ref_count.argtypes = [_u32p, _u64p, C.c_size_t, C.c_int, C.c_uint32, C.c_int, C.POINTER(_u32p),
+                                C.POINTER(_u64p), C.POINTER(_u32p), _u64p, _u64p]
+        L.ref_pipeline.restype = C.c_size_t
+        L.ref_pipeline.argtypes = [C.c_void_p, _u64p, C.c_size_t, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
+                                   C.c_uint32, C.c_int, _u64p, _u64p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.ref_max_threads.restype = C.c_int
+
+    def purge_palindrome(self, m: np.ndarray, first_k: int, last_k: int):
+        m = np.ascontiguousarray(m, dtype=np.uint32)
+        out = np.zeros(len(m) + 1, dtype=np.uint32)
+        n = self.lib.ref_purge_palindrome(_p(m, _u32p), len(m), first_k, last_k, _p(out, _u32p))
+        return out[:n].copy()
+
+    def count(self, mins, offs, k, min_abundance=2, threads=1):
+        mins = np.ascontiguousarray(mins, dtype=np.uint32)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        v = _u32p(); h = _u64p(); a = _u32p()
+        ni = C.c_uint64(0); nd = C.c_uint64(0)
+        n = self.lib.ref_count(_p(mins, _u32p), _p(offs, _u64p), len(offs) - 1, k, min_abundance, threads,
+                               C.byref(v), C.byref(h), C.byref(a), C.byref(ni), C.byref(nd))
+        vecs = self._take(v, n * k, np.uint32).reshape(n, k)
+        hashes = self._take(h, n * 2, np.uint64).reshape(n, 2)
+        abund = self._take(a, n, np.uint32)
+        return dict(vecs=vecs, hashes=hashes, abundances=abund, n_instances=int(ni.value), n_distinct=int(nd.value))
+
+    def max_threads(self) -> int:
+        return int(self.lib.ref_max_threads())
+
+    def pipeline(self, bases: np.ndarray, offsets: np.ndarray, l: int, density: float, hpc: bool, k: int,
+                 purge_last_k: int = 0, min_abundance: int = 2, threads: int = 1):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        nm = C.c_uint64(0); cs = C.c_uint64(0); ts = C.c_double(0); tc = C.c_double(0)
+        n = self.lib.ref_pipeline(bases.ctypes.data, _p(offsets, _u64p), len(offsets) - 1, l, density, int(hpc), k,
+                                  purge_last_k, min_abundance, threads, C.byref(nm), C.byref(cs), C.byref(ts), C.byref(tc))
+        return dict(n_solid=int(n), n_minimizers=int(nm.value), checksum=int(cs.value),
+                    seconds_sketch=float(ts.value), seconds_count=float(tc.value))

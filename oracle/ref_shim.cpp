@@ -1,0 +1,235 @@
+/*
+ * ref_shim.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * Thin extern "C" wrapper that #includes metaMDBG's OWN sources where they
+ * lie under /root/reference (no reference code is copied into this repo) and
+ * exposes the hot-path functions so that
+ *   (1) oracle/mdbg_oracle.c can be validated against the real thing, and
+ *   (2) bench.py --impl reference / cpu_baseline can time the reference's own
+ *       CPU implementation (kind = "reference").
+ * Built by oracle/Makefile into oracle/_ref/libmdbg_ref.so (git-ignored, but
+ * shipped to the GPU box by gpurun).  Everything computational below is a
+ * call into reference code:
+ *   EncoderRLE::execute            src/Commons.hpp:4163-4203
+ *   MinimizerParser::parse         src/utils/kmer/Kmer.hpp:1373-1456
+ *   KmerModel::iterate             src/utils/kmer/Kmer.hpp:570-589
+ *   MurmurHash3_x64_128[_original] src/utils/MurmurHash3.cpp:246-405
+ *   Commons::purgePalindrome       src/Commons.hpp:1617-1723
+ *   MDBG::getKminmers_complete     src/Commons.hpp:5150-5367
+ *   KmerVec::{normalize,hash128,operator<}  src/Commons.hpp:740-1005
+ *   Commons::sortParallel          src/Commons.hpp:1537-1574
+ * The only logic written here is the run-length count + ">=2" filter of
+ * KminmerCounter::dereplicatePartition/dumpKminmer (src/graph/CreateMdbg.hpp:
+ * 3744-3883), whose file I/O is replaced by in-memory vectors (this favours
+ * the reference when it is timed).
+ */
+#include "Commons.hpp"
+
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+
+extern "C" {
+
+uint64_t ref_murmur3_x64_128_h1(const void* key, int len, uint32_t seed) {
+    return MurmurHash3_x64_128(key, len, seed);
+}
+
+void ref_murmur3_x64_128(const void* key, int len, uint32_t seed, uint64_t out[2]) {
+    MurmurHash3_x64_128_original(key, len, seed, out);
+}
+
+double ref_minimizer_bound(float density) {
+    unordered_set<MinimizerType> none;
+    MinimizerParser parser(15, density, none);
+    return parser._minimizerBound;
+}
+
+size_t ref_hpc(const char* seq, size_t len, int hpc, char* out, uint64_t* rle_pos) {
+    EncoderRLE enc;
+    string rle;
+    vector<u_int64_t> pos;
+    string s(seq, len);
+    enc.execute(s.c_str(), s.size(), rle, pos, hpc != 0);
+    memcpy(out, rle.data(), rle.size());
+    if (rle_pos) memcpy(rle_pos, pos.data(), pos.size() * sizeof(u_int64_t));
+    return rle.size();
+}
+
+size_t ref_lmers(const char* seq, size_t len, int l, uint64_t* values, uint8_t* dirs) {
+    KmerModel model(l);
+    vector<u_int64_t> kmers;
+    vector<u_int8_t> kdirs;
+    string s(seq, len);
+    if (!model.iterate(s.c_str(), s.size(), kmers, kdirs)) return 0;
+    memcpy(values, kmers.data(), kmers.size() * sizeof(u_int64_t));
+    memcpy(dirs, kdirs.data(), kdirs.size());
+    return kmers.size();
+}
+
+/* ReadSelectionFunctor::operator() lines 682-690: EncoderRLE then parse. */
+static size_t sketch_one(EncoderRLE& enc, MinimizerParser& parser, const char* seq, size_t len, int hpc,
+                         vector<MinimizerType>& mins, vector<u_int32_t>& pos, vector<u_int8_t>& dirs) {
+    string s(seq, len);
+    string rle;
+    vector<u_int64_t> rlePositions;
+    enc.execute(s.c_str(), s.size(), rle, rlePositions, hpc != 0);
+    parser.parse(rle, mins, pos, dirs);
+    return mins.size();
+}
+
+size_t ref_sketch_read(const char* seq, size_t len, int l, float density, int hpc,
+                       const uint32_t* blacklist, size_t n_blacklist,
+                       uint32_t* minimizers, uint32_t* positions, uint8_t* directions, size_t cap) {
+    unordered_set<MinimizerType> bl(blacklist, blacklist + n_blacklist);
+    MinimizerParser parser(l, density, bl);
+    EncoderRLE enc;
+    vector<MinimizerType> mins;
+    vector<u_int32_t> pos;
+    vector<u_int8_t> dirs;
+    size_t n = sketch_one(enc, parser, seq, len, hpc, mins, pos, dirs);
+    for (size_t i = 0; i < n && i < cap; i++) {
+        minimizers[i] = mins[i];
+        positions[i] = pos[i];
+        directions[i] = dirs[i];
+    }
+    return n;
+}
+
+size_t ref_purge_palindrome(const uint32_t* m, size_t n, size_t first_k, size_t last_k, uint32_t* out) {
+    vector<MinimizerType> v(m, m + n);
+    vector<MinimizerType> r = Commons::purgePalindrome(v, first_k, last_k);
+    memcpy(out, r.data(), r.size() * sizeof(MinimizerType));
+    return r.size();
+}
+
+size_t ref_kminmers(const uint32_t* m, size_t n, int k, uint32_t* vecs, uint8_t* reversed) {
+    vector<MinimizerType> mins(m, m + n);
+    vector<u_int32_t> pos(n, 0);
+    vector<u_int8_t> quals(n, 0);
+    vector<ReadKminmerComplete> kms;
+    MDBG::getKminmers_complete(k, mins, pos, kms, 0, quals);
+    for (size_t i = 0; i < kms.size(); i++) {
+        memcpy(vecs + i * (size_t)k, kms[i]._vec._kmers.data(), (size_t)k * sizeof(MinimizerType));
+        if (reversed) reversed[i] = kms[i]._isReversed ? 1 : 0;
+    }
+    return kms.size();
+}
+
+void ref_hash128(const uint32_t* vec, int k, uint64_t out[2]) {
+    KmerVec v;
+    v._kmers.assign(vec, vec + k);
+    u_int128_t h = v.hash128();
+    out[0] = (uint64_t)(h >> 64);
+    out[1] = (uint64_t)h;
+}
+
+/* First-pass count over an in-memory minimizer CSR using the reference's
+ * types: getKminmers_complete -> KmerVec -> sortParallel -> run-length count
+ * -> keep abundance >= max(2, min_abundance) -> hash128. */
+size_t ref_count(const uint32_t* mins, const uint64_t* offs, size_t n_reads, int k, uint32_t min_abundance,
+                 int n_threads, uint32_t** vecs_out, uint64_t** hashes_out, uint32_t** abundances_out,
+                 uint64_t* n_instances, uint64_t* n_distinct) {
+    vector<KmerVec> all;
+    if (n_threads < 1) n_threads = 1;
+#pragma omp parallel num_threads(n_threads)
+    {
+        vector<KmerVec> local;
+        vector<ReadKminmerComplete> kms;
+#pragma omp for schedule(dynamic, 64)
+        for (size_t r = 0; r < n_reads; r++) {
+            size_t n = offs[r + 1] - offs[r];
+            vector<MinimizerType> m(mins + offs[r], mins + offs[r] + n);
+            vector<u_int32_t> pos(n, 0);
+            vector<u_int8_t> quals(n, 0);
+            MDBG::getKminmers_complete(k, m, pos, kms, (int)r, quals);
+            for (auto& km : kms) local.push_back(km._vec);
+        }
+#pragma omp critical
+        all.insert(all.end(), local.begin(), local.end());
+    }
+    Commons::sortParallel(all, all.size(), n_threads);
+
+    vector<uint32_t> vecs;
+    vector<uint64_t> hashes;
+    vector<uint32_t> abs_;
+    uint64_t distinct = 0;
+    size_t i = 0;
+    while (i < all.size()) {
+        size_t j = i + 1;
+        while (j < all.size() && all[j] == all[i]) j++;
+        uint32_t ab = (uint32_t)(j - i);
+        distinct++;
+        if (ab > 1 && ab >= min_abundance) {
+            vecs.insert(vecs.end(), all[i]._kmers.begin(), all[i]._kmers.end());
+            u_int128_t h = all[i].hash128();
+            hashes.push_back((uint64_t)(h >> 64));
+            hashes.push_back((uint64_t)h);
+            abs_.push_back(ab);
+        }
+        i = j;
+    }
+    if (n_instances) *n_instances = all.size();
+    if (n_distinct) *n_distinct = distinct;
+    size_t n = abs_.size();
+    *vecs_out = (uint32_t*)malloc((vecs.size() + 1) * sizeof(uint32_t));
+    *hashes_out = (uint64_t*)malloc((hashes.size() + 1) * sizeof(uint64_t));
+    *abundances_out = (uint32_t*)malloc((n + 1) * sizeof(uint32_t));
+    memcpy(*vecs_out, vecs.data(), vecs.size() * sizeof(uint32_t));
+    memcpy(*hashes_out, hashes.data(), hashes.size() * sizeof(uint64_t));
+    memcpy(*abundances_out, abs_.data(), n * sizeof(uint32_t));
+    return n;
+}
+
+/* The reference's CPU hot path end to end, OpenMP over reads as
+ * ReadParserParallel does (src/Commons.hpp:5846-5911, one functor copy per
+ * thread): HPC -> sketch -> [purgePalindrome] -> k-min-mers -> sort-count.
+ * Returns the number of solid k-min-mers; *checksum = sum ab*low64(hash),
+ * *n_minimizers = total selected minimizers.  Used ONLY as the timed CPU
+ * baseline and as a cross-check. */
+size_t ref_pipeline(const char* bases, const uint64_t* offsets, size_t n_reads, int l, float density, int hpc,
+                    int k, int purge_last_k, uint32_t min_abundance, int n_threads, uint64_t* n_minimizers,
+                    uint64_t* checksum, double* seconds_sketch, double* seconds_count) {
+    if (n_threads < 1) n_threads = 1;
+    vector<vector<MinimizerType>> per_read(n_reads);
+    unordered_set<MinimizerType> bl;
+    auto t0 = high_resolution_clock::now();
+#pragma omp parallel num_threads(n_threads)
+    {
+        MinimizerParser parser(l, density, bl);
+        EncoderRLE enc;
+        vector<MinimizerType> mins;
+        vector<u_int32_t> pos;
+        vector<u_int8_t> dirs;
+#pragma omp for schedule(dynamic, 16)
+        for (size_t r = 0; r < n_reads; r++) {
+            sketch_one(enc, parser, bases + offsets[r], offsets[r + 1] - offsets[r], hpc, mins, pos, dirs);
+            if (purge_last_k > 0) per_read[r] = Commons::purgePalindrome(mins, 4, purge_last_k);
+            else per_read[r] = mins;
+        }
+    }
+    auto t1 = high_resolution_clock::now();
+    vector<uint64_t> offs(n_reads + 1, 0);
+    for (size_t r = 0; r < n_reads; r++) offs[r + 1] = offs[r] + per_read[r].size();
+    vector<uint32_t> flat(offs[n_reads] + 1);
+    for (size_t r = 0; r < n_reads; r++)
+        if (!per_read[r].empty()) memcpy(flat.data() + offs[r], per_read[r].data(), per_read[r].size() * 4);
+    uint32_t* v; uint64_t* h; uint32_t* a;
+    uint64_t ni, nd;
+    size_t n = ref_count(flat.data(), offs.data(), n_reads, k, min_abundance, n_threads, &v, &h, &a, &ni, &nd);
+    auto t2 = high_resolution_clock::now();
+    uint64_t cs = 0;
+    for (size_t i = 0; i < n; i++) cs += (uint64_t)a[i] * h[2 * i + 1];
+    free(v); free(h); free(a);
+    if (n_minimizers) *n_minimizers = offs[n_reads];
+    if (checksum) *checksum = cs;
+    if (seconds_sketch) *seconds_sketch = duration<double>(t1 - t0).count();
+    if (seconds_count) *seconds_count = duration<double>(t2 - t1).count();
+    return n;
+}
+
+int ref_max_threads() { return omp_get_max_threads(); }
+
+void ref_free(void* p) { free(p); }
+
+}  // extern "C"

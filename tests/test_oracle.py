@@ -1,0 +1,228 @@
+"""CPU tests: the C restatement (oracle/mdbg_oracle.c) against the known-answer
+values of SURVEY.md section 8c and against the reference's own sources compiled
+into oracle/_ref (tests marked `ref` skip where that library is absent)."""
+import struct
+
+import numpy as np
+import pytest
+
+from metamdbg_b200 import synth
+
+
+# ---- known-answer tests (reproduced with the compiled reference) ----
+
+def test_kat_murmur_invalid_lmer(oracle):
+    assert oracle.murmur_h1(struct.pack("<Q", 0xFFFFFFFFFFFFFFFF), 42) == 13161889351522953593
+
+
+def test_kat_hash128_1234(oracle):
+    h1, h2 = oracle.hash128(np.array([1, 2, 3, 4], dtype=np.uint32))
+    assert (h1, h2) == (0x333C24B23227B2C3, 0x869BB9D3950B32E1)
+
+
+def test_kat_bound(oracle):
+    assert oracle.bound(0.005) == pytest.approx(9.223371830696346e16, rel=0, abs=16)
+    assert oracle.bound(0.005) == float(np.float32(0.005)) * 2.0 ** 64
+
+
+def test_threshold_is_exact_boundary(oracle):
+    for d in (0.005, 0.025, 0.0005, 0.5):
+        t, none = oracle.threshold(d)
+        assert not none
+        b = oracle.bound(d)
+        assert float(np.float64(np.uint64(t))) < b
+        assert not (float(np.float64(np.uint64(t + 1))) < b)
+
+
+def test_hpc_edge_cases(oracle):
+    assert oracle.hpc(b"")[0] == b"#"                   # upstream quirk: empty read -> "#"
+    assert oracle.hpc(b"AAAA")[0] == b"A"
+    assert oracle.hpc(b"AACCCGTT")[0] == b"ACGT"
+    assert list(oracle.hpc(b"AACCCGTT")[1]) == [0, 2, 5, 6, 8]
+    assert oracle.hpc(b"aA")[0] == b"aA"                # case-sensitive byte compare
+    assert oracle.hpc(b"ANNNC")[0] == b"ANC"
+    assert oracle.hpc(b"A#C")[0] == b"AC"               # '#' is the sentinel and vanishes
+    assert oracle.hpc(b"AACC", hpc=False)[0] == b"AACC"
+
+
+def test_lmers_small(oracle):
+    # ACGTA, l=3: code A0 C1 T2 G3; ACG fwd=0b000111=7, rc(CGT)=0b011110=30 -> 7 dir0
+    v, d = oracle.lmers(b"ACGTA", 3)
+    assert len(v) == 3
+    assert v[0] == 7 and d[0] == 0
+    v, d = oracle.lmers(b"ACNTA", 3)
+    assert all(x == np.uint64(0xFFFFFFFFFFFFFFFF) for x in v)
+    assert len(oracle.lmers(b"AC", 3)[0]) == 0
+
+
+def test_sketch_trims_first_and_last(oracle):
+    rng = np.random.default_rng(5)
+    seq = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), 4000))
+    m, p, d = oracle.sketch_read(seq, 15, 0.9, False)     # d=0.9 selects ~everything valid
+    n_lmers = len(seq) - 15 + 1
+    assert p.min() >= 1 and p.max() <= n_lmers - 2
+    assert np.all(np.diff(p.astype(np.int64)) > 0)
+
+
+def test_kminmers_normalize_tie_and_order(oracle):
+    v, r = oracle.kminmers(np.array([5, 1, 1, 5, 9], dtype=np.uint32), 4)
+    assert list(v[0]) == [5, 1, 1, 5] and r[0] == 1      # palindromic window -> reversed flag
+    assert list(v[1]) == [1, 1, 5, 9] and r[1] == 0
+    v, r = oracle.kminmers(np.array([9, 2, 3, 4], dtype=np.uint32), 4)
+    assert list(v[0]) == [4, 3, 2, 9] and r[0] == 1
+    assert len(oracle.kminmers(np.array([1, 2, 3], dtype=np.uint32), 4)[0]) == 0
+
+
+def test_purge_palindrome_basic(oracle):
+    m = np.array([7, 5, 1, 1, 5, 9, 3], dtype=np.uint32)
+    out, keep = oracle.purge_palindrome(m, 4, 6)
+    # window [5,1,1,5] is a palindrome -> its first element (index 1) is banned
+    assert keep[1] == 0
+    nothing, keep2 = oracle.purge_palindrome(np.arange(20, dtype=np.uint32), 4, 10)
+    assert np.all(keep2 == 1) and len(nothing) == 20
+
+
+def test_count_matches_python_dict(oracle):
+    rng = np.random.default_rng(0)
+    reads = [rng.integers(0, 6, size=rng.integers(0, 30)).astype(np.uint32) for _ in range(200)]
+    offs = np.zeros(len(reads) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(r) for r in reads])
+    mins = np.concatenate(reads).astype(np.uint32)
+    for k in (4, 5, 7):
+        res = oracle.count(mins, offs, k, 2)
+        ref = {}
+        for r in reads:
+            for i in range(len(r) - k + 1):
+                w = tuple(int(x) for x in r[i:i + k])
+                wr = w[::-1]
+                key = w if w < wr else wr
+                ref[key] = ref.get(key, 0) + 1
+        solid = {kk: c for kk, c in ref.items() if c >= 2}
+        got = {tuple(int(x) for x in v): int(a) for v, a in zip(res["vecs"], res["abundances"])}
+        assert got == solid
+        assert res["n_distinct"] == len(ref)
+        assert res["n_instances"] == sum(ref.values())
+
+
+# ---- restatement vs the reference's own code (oracle/_ref) ----
+
+def _random_reads(seed, n, mean, with_n=False, lower=False):
+    rng = np.random.default_rng(seed)
+    alpha = b"ACGT" + (b"N" if with_n else b"") + (b"acgt" if lower else b"")
+    out = []
+    for _ in range(n):
+        ln = int(rng.integers(0, mean * 2))
+        s = rng.choice(np.frombuffer(alpha, dtype=np.uint8), ln)
+        # homopolymer runs so HPC has something to do
+        rep = rng.integers(1, 4, size=ln)
+        out.append(bytes(np.repeat(s, rep)[:ln]))
+    return out
+
+
+@pytest.mark.ref
+def test_ref_murmur_and_hash(oracle, reference):
+    rng = np.random.default_rng(1)
+    for ln in list(range(0, 90)):
+        key = bytes(rng.integers(0, 256, ln, dtype=np.uint8))
+        assert oracle.murmur128(key, 0) == reference.murmur128(key, 0)
+        assert oracle.murmur_h1(key, 42) == reference.murmur_h1(key, 42)
+    for k in range(2, 22):
+        v = rng.integers(0, 2 ** 32, k, dtype=np.uint64).astype(np.uint32)
+        assert oracle.hash128(v) == reference.hash128(v)
+    for d in (0.005, 0.025, 0.1):
+        assert oracle.bound(d) == reference.bound(d)
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("hpc", [True, False])
+def test_ref_hpc_lmers_sketch(oracle, reference, hpc):
+    for seq in _random_reads(2, 60, 600, with_n=True, lower=True) + [b"", b"A", b"ACGT" * 4, b"A" * 50]:
+        a, pa = oracle.hpc(seq, hpc)
+        b, pb = reference.hpc(seq, hpc)
+        assert a == b
+        assert np.array_equal(pa, pb)
+        for l in (3, 11, 15, 16):
+            va, da = oracle.lmers(a, l)
+            vb, db = reference.lmers(a, l)
+            assert np.array_equal(va, vb) and np.array_equal(da, db)
+        for dens in (0.005, 0.05, 0.3):
+            ra = oracle.sketch_read(seq, 15, dens, hpc)
+            rb = reference.sketch_read(seq, 15, dens, hpc)
+            for x, y in zip(ra, rb):
+                assert np.array_equal(x, y)
+
+
+@pytest.mark.ref
+def test_ref_sketch_blacklist(oracle, reference):
+    seq = _random_reads(3, 1, 4000)[0]
+    m, _, _ = oracle.sketch_read(seq, 15, 0.05, True)
+    assert len(m) > 4
+    bl = m[::3].copy()
+    ra = oracle.sketch_read(seq, 15, 0.05, True, bl)
+    rb = reference.sketch_read(seq, 15, 0.05, True, bl)
+    for x, y in zip(ra, rb):
+        assert np.array_equal(x, y)
+    assert len(ra[0]) < len(m)
+
+
+@pytest.mark.ref
+def test_ref_synthetic_reads_sketch(oracle, reference):
+    rs = synth.make_readset(40, 6000, seed=11, n_genomes=2, genome_len_range=(50_000, 80_000))
+    bases, offs = synth.fill_reads(rs)
+    raw = bases.tobytes()
+    tot = 0
+    for r in range(rs.n_reads):
+        seq = raw[int(offs[r]):int(offs[r + 1])]
+        ra = oracle.sketch_read(seq, 15, 0.005, True)
+        rb = reference.sketch_read(seq, 15, 0.005, True)
+        for x, y in zip(ra, rb):
+            assert np.array_equal(x, y)
+        tot += len(ra[0])
+    assert tot > 100
+    mo, m, p, d = oracle.sketch_batch(bases, offs, 15, 0.005, True)
+    assert int(mo[-1]) == tot
+
+
+@pytest.mark.ref
+def test_ref_kminmers_and_purge(oracle, reference):
+    rng = np.random.default_rng(4)
+    for trial in range(300):
+        n = int(rng.integers(0, 40))
+        m = rng.integers(0, 4, n).astype(np.uint32)      # tiny alphabet -> many palindromes
+        for k in (2, 4, 5, 8):
+            va, ra = oracle.kminmers(m, k)
+            vb, rb = reference.kminmers(m, k)
+            assert np.array_equal(va, vb) and np.array_equal(ra, rb)
+        last_k = int(rng.integers(5, 12))
+        pa, _ = oracle.purge_palindrome(m, 4, last_k)
+        pb = reference.purge_palindrome(m, 4, last_k)
+        assert np.array_equal(pa, pb)
+
+
+@pytest.mark.ref
+def test_ref_count(oracle, reference):
+    rng = np.random.default_rng(6)
+    reads = [rng.integers(0, 9, size=rng.integers(0, 60)).astype(np.uint32) for _ in range(400)]
+    offs = np.zeros(len(reads) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(r) for r in reads])
+    mins = np.concatenate(reads).astype(np.uint32)
+    for k in (4, 6, 21):
+        for min_ab in (0, 2, 3):
+            a = oracle.count(mins, offs, k, min_ab)
+            b = reference.count(mins, offs, k, min_ab, threads=3)
+            assert np.array_equal(a["vecs"], b["vecs"])
+            assert np.array_equal(a["hashes"], b["hashes"])
+            assert np.array_equal(a["abundances"], b["abundances"])
+            assert a["n_instances"] == b["n_instances"] and a["n_distinct"] == b["n_distinct"]
+
+
+@pytest.mark.ref
+def test_ref_pipeline_checksum(oracle, reference):
+    rs = synth.make_readset(300, 5000, seed=21, n_genomes=1, genome_len_range=(60_000, 60_001))
+    bases, offs = synth.fill_reads(rs)
+    res = reference.pipeline(bases, offs, 15, 0.005, True, 4, purge_last_k=0, min_abundance=2, threads=2)
+    mo, m, p, d = oracle.sketch_batch(bases, offs, 15, 0.005, True)
+    c = oracle.count(m, mo, 4, 2)
+    assert res["n_minimizers"] == len(m)
+    assert res["n_solid"] == len(c["abundances"]) and res["n_solid"] > 10
+    assert res["checksum"] == oracle.checksum(c["hashes"], c["abundances"])
