@@ -1,0 +1,185 @@
+/*
+ * mdbg_b200.h -- C ABI of the Blackwell-native minimizer-sketch + k-min-mer
+ * count engine (libmdbg_b200.so).
+ *
+ * This is the drop-in boundary for metaMDBG's hot path.  metaMDBG has no
+ * plugin/FFI interface of its own (stages are functor callbacks inside one
+ * binary), so every entry point below names the reference
+ * code it replaces (paths relative to the metaMDBG source tree):
+ *
+ *   mdbg_sketch_batch         <- ReadSelectionFunctor::operator() lines that
+ *                                chain EncoderRLE::execute and
+ *                                MinimizerParser::parse
+ *                                (src/readSelection/ReadSelection.hpp:682-690,
+ *                                 src/Commons.hpp:4163-4203,
+ *                                 src/utils/kmer/Kmer.hpp:1373-1456)
+ *   mdbg_purge_palindromes    <- ReadSelection::purgePalindromes /
+ *                                Commons::purgePalindrome
+ *                                (src/readSelection/ReadSelection.hpp:1374-1431,
+ *                                 src/Commons.hpp:1617-1723)
+ *   mdbg_store_append         <- the read_data_*.txt minimizer-space records
+ *                                KminmerParserParallel iterates
+ *                                (src/Commons.hpp:7367-7495)
+ *   mdbg_count_begin/add/finalize
+ *                             <- CreateMdbg::KminmerCounter::execute
+ *                                (src/graph/CreateMdbg.hpp:3591-3883) with
+ *                                MDBG::getKminmers_complete (src/Commons.hpp:5282-5361)
+ *                                and KmerVec::normalize/hash128 (src/Commons.hpp:886-969)
+ *   mdbg_count_merge          <- the `hash128 % P` partitioning of
+ *                                KminmerCounter::partitionKminmer
+ *                                (src/graph/CreateMdbg.hpp:3714-3724), as an
+ *                                owner-partitioned all-to-all between GPUs
+ *
+ * Conventions: plain C, no exceptions; every function returns an mdbg_status
+ * (0 = OK) and records a message readable with mdbg_last_error(); all buffers
+ * named "host" are caller-owned unless documented as library-owned; one
+ * context per device; calls on one context must be serialised by the caller
+ * (the host batches reads inside the reference's existing critical section);
+ * different contexts are independent.  There is NO CPU fallback: creating a
+ * context without a usable CUDA device fails with MDBG_ERR_CUDA.
+ */
+#ifndef MDBG_B200_H
+#define MDBG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mdbg_ctx mdbg_ctx;
+
+typedef enum {
+    MDBG_OK = 0,
+    MDBG_ERR_CUDA = 1,        /* a CUDA call failed (message holds the CUDA error) */
+    MDBG_ERR_ARG = 2,         /* invalid argument / unsupported parameter */
+    MDBG_ERR_STATE = 3,       /* call sequence error (e.g. count_add before count_begin) */
+    MDBG_ERR_TABLE_FULL = 4,  /* count table capacity exceeded: re-run with a larger expected_distinct */
+    MDBG_ERR_NCCL = 5,        /* NCCL unavailable or a collective failed */
+    MDBG_ERR_OOM = 6
+} mdbg_status;
+
+/* MinimizerParser(minimizerSize, density, repetitive set) -- Kmer.hpp:1351-1366;
+ * use_hpc = Params::_useHomopolymerCompression (AssemblyPipeline.hpp:301,318). */
+typedef struct {
+    uint32_t minimizer_size;      /* l, 2..16 (AssemblyPipeline.hpp:201-202 caps it at 16) */
+    float    density;             /* --density-assembly / --density-correction, as float */
+    uint32_t use_hpc;             /* 1 = homopolymer-compress before sketching (HiFi) */
+    const uint32_t* blacklist;    /* host: repetitiveMinimizers.bin values, may be NULL */
+    uint64_t n_blacklist;
+} mdbg_params;
+
+/* Result of one sketch batch.  Host pointers are library-owned pinned memory,
+ * valid until the next sketch call on the same context. */
+typedef struct {
+    uint32_t n_reads;
+    uint64_t n_minimizers;
+    const uint64_t* min_offsets;  /* [n_reads+1] CSR offsets into the three arrays below */
+    const uint32_t* minimizers;   /* canonical l-mer value truncated to u32 (Kmer.hpp:1441) */
+    const uint32_t* positions;    /* l-mer start in (HPC) sequence coordinates (Kmer.hpp:1442) */
+    const uint8_t*  directions;   /* 0 = forward strand is canonical, 1 = reverse complement */
+} mdbg_sketch_out;
+
+/* Device-resident view of the same CSR (pointers into context-owned HBM, valid
+ * until the next sketch call). */
+typedef struct {
+    uint32_t n_reads;
+    uint64_t n_minimizers;
+    const uint64_t* d_min_offsets;
+    const uint32_t* d_minimizers;
+    const uint32_t* d_positions;
+    const uint8_t*  d_directions;
+} mdbg_sketch_dev;
+
+/* Finalised count table (host, library-owned pinned memory, valid until the
+ * next finalize/destroy).  hashes holds the 16 on-disk bytes of each u128
+ * exactly as MDBG::writeKminmerAbundance emits them (Commons.hpp:4463-4471):
+ * hashes[2*i] = low 64 bits (Murmur h2), hashes[2*i+1] = high 64 bits (h1). */
+typedef struct {
+    uint32_t k;
+    uint64_t n_entries;           /* entries with abundance >= max(2, min_abundance) */
+    const uint64_t* hashes;       /* [2*n_entries] */
+    const uint32_t* abundances;   /* [n_entries] */
+    const uint32_t* kminmers;     /* [n_entries*k] normalized vectors (kminmerData_min.txt rows) */
+    uint64_t n_instances;         /* k-min-mer occurrences inserted */
+    uint64_t n_distinct;          /* distinct k-min-mers in the table (any abundance) */
+    uint64_t checksum;            /* sum abundance * low64(hash) mod 2^64 (CreateMdbg.cpp:3321) */
+} mdbg_table_out;
+
+/* ---- context ------------------------------------------------------------ */
+mdbg_status mdbg_ctx_create(int device, const mdbg_params* params, mdbg_ctx** out);
+void        mdbg_ctx_destroy(mdbg_ctx* ctx);
+const char* mdbg_last_error(mdbg_ctx* ctx);              /* ctx may be NULL: last create error */
+/* Run all work of this context on an existing CUDA stream (cudaStream_t passed
+ * as void*); NULL restores the context's own stream. */
+mdbg_status mdbg_ctx_set_stream(mdbg_ctx* ctx, void* cuda_stream);
+mdbg_status mdbg_ctx_synchronize(mdbg_ctx* ctx);
+/* Number of this library's kernels launched on the context so far. */
+uint64_t    mdbg_ctx_kernel_launches(mdbg_ctx* ctx);
+
+/* ---- sketch (rows A1-A3 of SURVEY.md section 8a) -------------------------- */
+/* Host reads: read r = bases[offsets[r] .. offsets[r+1]) (ASCII, as Read::_seq).
+ * The batch is copied to the device, sketched, the CSR is copied back into
+ * `out`, and the minimizer-space reads are appended to the context's device
+ * store when append_to_store != 0. */
+mdbg_status mdbg_sketch_batch(mdbg_ctx* ctx, const uint8_t* bases, const uint64_t* offsets,
+                              uint32_t n_reads, int append_to_store, mdbg_sketch_out* out);
+/* Same with the reads already in HBM.  d_bases must be 16-byte aligned;
+ * nothing is copied to the host.  `out` may be NULL. */
+mdbg_status mdbg_sketch_batch_device(mdbg_ctx* ctx, const uint8_t* d_bases, const uint64_t* d_offsets,
+                                     uint32_t n_reads, uint64_t n_bases, int append_to_store,
+                                     mdbg_sketch_dev* out);
+/* Copy the last batch's CSR to pinned host memory (after *_device). */
+mdbg_status mdbg_sketch_fetch(mdbg_ctx* ctx, mdbg_sketch_out* out);
+
+/* ---- minimizer-space read store (device-resident read_data_*.txt) -------- */
+mdbg_status mdbg_store_clear(mdbg_ctx* ctx);
+/* Append host minimizer-space reads (what KminmerParserParallel would read). */
+mdbg_status mdbg_store_append(mdbg_ctx* ctx, const uint32_t* minimizers, const uint64_t* min_offsets,
+                              uint32_t n_reads);
+mdbg_status mdbg_store_size(mdbg_ctx* ctx, uint64_t* n_reads, uint64_t* n_minimizers);
+/* Copy the store back (min_offsets [n_reads+1], minimizers [n_minimizers]). */
+mdbg_status mdbg_store_fetch(mdbg_ctx* ctx, uint64_t* min_offsets, uint32_t* minimizers);
+/* Commons::purgePalindrome on every stored read, in place (row A4). */
+mdbg_status mdbg_purge_palindromes(mdbg_ctx* ctx, uint32_t first_k, uint32_t last_k,
+                                   uint64_t* n_reads_changed);
+
+/* ---- k-min-mer count table (rows A5-A7) ----------------------------------- */
+/* expected_distinct = 0 sizes the table from the store (upper bound: one slot
+ * pair per k-min-mer occurrence). */
+mdbg_status mdbg_count_begin(mdbg_ctx* ctx, uint32_t k, uint64_t expected_distinct);
+/* Insert every k-min-mer of stored reads [read_lo, read_hi); (0, UINT64_MAX) = all. */
+mdbg_status mdbg_count_add_store(mdbg_ctx* ctx, uint64_t read_lo, uint64_t read_hi);
+/* Insert the k-min-mers of host minimizer-space reads (appends them to the store first). */
+mdbg_status mdbg_count_add(mdbg_ctx* ctx, const uint32_t* minimizers, const uint64_t* min_offsets,
+                           uint32_t n_reads);
+/* Keep abundance >= max(2, min_abundance) (dumpKminmer, CreateMdbg.hpp:3862-3869)
+ * and copy the table to the host.  out->hashes etc. are in unspecified order
+ * (as upstream, whose writer runs under an omp critical). */
+mdbg_status mdbg_count_finalize(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_table_out* out);
+/* Table statistics without the host copy (device-side reduction only). */
+mdbg_status mdbg_count_stats(mdbg_ctx* ctx, uint32_t min_abundance, uint64_t* n_entries,
+                             uint64_t* n_distinct, uint64_t* n_instances, uint64_t* checksum);
+
+/* ---- multi-GPU (one process per GPU) --------------------------------------- */
+/* NCCL is loaded at run time (dlopen libnccl.so.2).  Rank 0 creates an id,
+ * the host distributes its 128 bytes to every rank by its own means. */
+mdbg_status mdbg_nccl_unique_id(uint8_t id_out[128]);
+mdbg_status mdbg_comm_init(mdbg_ctx* ctx, int rank, int n_ranks, const uint8_t id[128]);
+/* Owner-partitioned all-to-all of the local table's (k-min-mer, count) pairs
+ * followed by reduce-by-key: afterwards this context's table holds exactly the
+ * keys it owns with their global abundances.  Collective over all ranks. */
+mdbg_status mdbg_count_merge(mdbg_ctx* ctx);
+
+/* ---- synthetic input (benchmark/test support, device side) ------------------ */
+/* Fill d_bases with the reads described by (vstart, strand, offsets, lengths) using
+ * the counter-based generator of metamdbg_b200/synth.py. */
+mdbg_status mdbg_synth_fill_reads(mdbg_ctx* ctx, uint8_t* d_bases, const uint64_t* d_offsets,
+                                  const uint64_t* d_vstart, const uint8_t* d_strand,
+                                  uint32_t n_reads, uint64_t read_index_base, uint64_t seed, uint32_t err_q24);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDBG_B200_H */

@@ -1,0 +1,87 @@
+"""ctypes binding of libmdbg_b200.so (include/mdbg_b200.h).
+
+The library is the product; this module only declares its C ABI.  It fails
+loudly when the shared object is missing or when no CUDA device is usable --
+there is no CPU fallback and nothing here imports oracle/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmdbg_b200.so")
+
+u8p = C.POINTER(C.c_uint8)
+u32p = C.POINTER(C.c_uint32)
+u64p = C.POINTER(C.c_uint64)
+
+
+class MdbgParams(C.Structure):
+    _fields_ = [("minimizer_size", C.c_uint32), ("density", C.c_float), ("use_hpc", C.c_uint32),
+                ("blacklist", u32p), ("n_blacklist", C.c_uint64)]
+
+
+class SketchOut(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32), ("n_minimizers", C.c_uint64), ("min_offsets", u64p),
+                ("minimizers", u32p), ("positions", u32p), ("directions", u8p)]
+
+
+class SketchDev(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32), ("n_minimizers", C.c_uint64), ("d_min_offsets", C.c_void_p),
+                ("d_minimizers", C.c_void_p), ("d_positions", C.c_void_p), ("d_directions", C.c_void_p)]
+
+
+class TableOut(C.Structure):
+    _fields_ = [("k", C.c_uint32), ("n_entries", C.c_uint64), ("hashes", u64p), ("abundances", u32p),
+                ("kminmers", u32p), ("n_instances", C.c_uint64), ("n_distinct", C.c_uint64),
+                ("checksum", C.c_uint64)]
+
+
+# every symbol include/mdbg_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "mdbg_ctx_create": (C.c_int, [C.c_int, C.POINTER(MdbgParams), C.POINTER(C.c_void_p)]),
+    "mdbg_ctx_destroy": (None, [C.c_void_p]),
+    "mdbg_last_error": (C.c_char_p, [C.c_void_p]),
+    "mdbg_ctx_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mdbg_ctx_synchronize": (C.c_int, [C.c_void_p]),
+    "mdbg_ctx_kernel_launches": (C.c_uint64, [C.c_void_p]),
+    "mdbg_sketch_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.POINTER(SketchOut)]),
+    "mdbg_sketch_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_int,
+                                           C.POINTER(SketchDev)]),
+    "mdbg_sketch_fetch": (C.c_int, [C.c_void_p, C.POINTER(SketchOut)]),
+    "mdbg_store_clear": (C.c_int, [C.c_void_p]),
+    "mdbg_store_append": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
+    "mdbg_store_size": (C.c_int, [C.c_void_p, u64p, u64p]),
+    "mdbg_store_fetch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mdbg_purge_palindromes": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, u64p]),
+    "mdbg_count_begin": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64]),
+    "mdbg_count_add_store": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64]),
+    "mdbg_count_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
+    "mdbg_count_finalize": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(TableOut)]),
+    "mdbg_count_stats": (C.c_int, [C.c_void_p, C.c_uint32, u64p, u64p, u64p, u64p]),
+    "mdbg_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "mdbg_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "mdbg_count_merge": (C.c_int, [C.c_void_p]),
+    "mdbg_synth_fill_reads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                        C.c_uint64, C.c_uint64, C.c_uint32]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen the engine; raises if it has not been built (`python -c 'import __graft_entry__ as g; g.build()'`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with metamdbg_b200/csrc/Makefile "
+                           "(__graft_entry__.build()); there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    for name, (res, args) in SYMBOLS.items():
+        f = getattr(lib, name)          # AttributeError = header/library mismatch
+        f.restype = res
+        f.argtypes = args
+    _lib = lib
+    return lib

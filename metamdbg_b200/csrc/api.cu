@@ -1,0 +1,864 @@
+// api.cu -- the C ABI of libmdbg_b200 (include/mdbg_b200.h): context, device
+// memory, stream plumbing and the host-side sequencing of the kernels.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/mdbg_b200.h"
+#include "engine.cuh"
+
+using namespace mdbg;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct SmallDev {                 // device-side scalars, one allocation
+    uint32_t cursor;
+    uint32_t full_flag;
+    unsigned long long n_overflow;
+    unsigned long long n_flagged;
+    unsigned long long n_changed;
+    unsigned long long emit_cursor;
+    TableStats stats;
+};
+
+}  // namespace
+
+struct mdbg_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string error;
+    uint64_t launches = 0;
+
+    // parameters
+    uint32_t l = 15;
+    float density = 0.005f;
+    uint32_t hpc = 1;
+    uint64_t threshold = 0;
+    uint32_t select_none = 0;
+    DevBuf d_blacklist;
+    uint32_t n_blacklist = 0;
+    uint32_t cap_shift = 5, cap_const = 32;
+
+    // small device scalars + pinned mirror
+    SmallDev* d_small = nullptr;
+    SmallDev* h_small = nullptr;   // pinned
+    uint64_t* h_scalar = nullptr;  // pinned, 8 u64
+
+    // last sketch batch
+    DevBuf d_bases, d_offsets;                  // host-API staging
+    DevBuf pad_min, pad_pos, pad_dir, n_min, scan_scratch;
+    DevBuf b_off, b_min, b_pos, b_dir;          // tight CSR of the batch
+    uint32_t b_reads = 0;
+    uint64_t b_total = 0;
+    PinBuf h_off, h_min, h_pos, h_dir;
+
+    // minimizer-space read store
+    DevBuf s_min, s_off, s_rem;
+    uint64_t s_reads = 0, s_mins = 0;
+    DevBuf p_flags, p_keep, p_cnt, p_newoff, p_newmin;
+
+    // count table
+    DevBuf table;
+    uint64_t t_capacity = 0;
+    uint32_t t_k = 0;
+    bool t_active = false;
+    DevBuf foreign_vecs;
+    uint64_t foreign_n = 0;
+    DevBuf o_hash, o_abund, o_vecs;
+    PinBuf ho_hash, ho_abund, ho_vecs;
+
+    // multi-GPU
+    void* nccl_comm = nullptr;
+    int rank = 0, n_ranks = 1;
+    DevBuf m_send_vecs, m_send_counts, m_recv_vecs, m_recv_counts, m_bucket;
+};
+
+namespace {
+
+mdbg_status fail(mdbg_ctx* c, mdbg_status st, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->error = buf; else g_create_error = buf;
+    return st;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? MDBG_ERR_OOM : MDBG_ERR_CUDA,       \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define CKS(expr)                          \
+    do {                                   \
+        mdbg_status s_ = (expr);           \
+        if (s_ != MDBG_OK) return s_;      \
+    } while (0)
+
+mdbg_status ensure(mdbg_ctx* ctx, DevBuf& b, size_t bytes, bool keep = false) {
+    if (bytes <= b.cap && b.p) return MDBG_OK;
+    size_t want = bytes + bytes / 8 + 256;
+    void* np = nullptr;
+    CK(cudaMalloc(&np, want));
+    if (keep && b.p && b.cap) {
+        CK(cudaMemcpyAsync(np, b.p, b.cap, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    if (b.p) cudaFree(b.p);
+    b.p = np;
+    b.cap = want;
+    return MDBG_OK;
+}
+
+mdbg_status ensure_pin(mdbg_ctx* ctx, PinBuf& b, size_t bytes) {
+    if (bytes <= b.cap && b.p) return MDBG_OK;
+    if (b.p) cudaFreeHost(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    CK(cudaMallocHost(&b.p, want));
+    b.cap = want;
+    return MDBG_OK;
+}
+
+void release(DevBuf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+void release(PinBuf& b) { if (b.p) cudaFreeHost(b.p); b.p = nullptr; b.cap = 0; }
+
+// Largest T with (double)T < bound (reference compares u64 < double, Kmer.hpp:1434).
+uint64_t threshold_from_density(float density, uint32_t* none) {
+    const uint64_t max_hash = (uint64_t)-1;
+    const double bound = (double)density * (double)max_hash;       // Kmer.hpp:1354-1356
+    *none = 0;
+    if (!((double)(uint64_t)0 < bound)) { *none = 1; return 0; }
+    uint64_t lo = 0, hi = (uint64_t)-1;
+    if ((double)hi < bound) return hi;
+    while (hi - lo > 1) {
+        const uint64_t mid = lo + (hi - lo) / 2;
+        if ((double)mid < bound) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+uint64_t pow2ceil(uint64_t x) {
+    uint64_t p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+mdbg_status check_launch(mdbg_ctx* ctx, const char* what, int n_kernels) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, MDBG_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    ctx->launches += (uint64_t)n_kernels;
+    return MDBG_OK;
+}
+
+// ---- sketch of a device-resident batch into the tight CSR b_* -------------------
+mdbg_status sketch_internal(mdbg_ctx* ctx, const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t n_reads,
+                            uint64_t n_bases, int append) {
+    cudaStream_t s = ctx->stream;
+    ctx->b_reads = n_reads;
+    ctx->b_total = 0;
+    CKS(ensure(ctx, ctx->b_off, ((size_t)n_reads + 1) * sizeof(uint64_t)));
+    if (n_reads == 0) {
+        CK(cudaMemsetAsync(ctx->b_off.p, 0, sizeof(uint64_t), s));
+        return MDBG_OK;
+    }
+    const uint64_t pad_cap = (n_bases >> ctx->cap_shift) + (uint64_t)n_reads * ctx->cap_const + 1;
+    CKS(ensure(ctx, ctx->pad_min, pad_cap * 4));
+    CKS(ensure(ctx, ctx->pad_pos, pad_cap * 4));
+    CKS(ensure(ctx, ctx->pad_dir, pad_cap));
+    CKS(ensure(ctx, ctx->n_min, (size_t)n_reads * 4));
+    CKS(ensure(ctx, ctx->scan_scratch, scan_scratch_elems(n_reads) * sizeof(uint64_t)));
+
+    SketchArgs a{};
+    a.bases = d_bases;
+    a.bases_end = d_bases + n_bases;
+    a.offsets = d_offsets;
+    a.n_reads = n_reads;
+    a.l = ctx->l;
+    a.hpc = ctx->hpc;
+    a.threshold = ctx->threshold;
+    a.select_none = ctx->select_none;
+    a.blacklist = ctx->d_blacklist.as<uint32_t>();
+    a.n_blacklist = ctx->n_blacklist;
+    a.exact_off = nullptr;
+    a.cap_shift = ctx->cap_shift;
+    a.cap_const = ctx->cap_const;
+    a.out_min = ctx->pad_min.as<uint32_t>();
+    a.out_pos = ctx->pad_pos.as<uint32_t>();
+    a.out_dir = ctx->pad_dir.as<uint8_t>();
+    a.n_min = ctx->n_min.as<uint32_t>();
+    a.cursor = &ctx->d_small->cursor;
+    a.n_overflow = &ctx->d_small->n_overflow;
+
+    CK(cudaMemsetAsync(&ctx->d_small->cursor, 0, sizeof(uint32_t), s));
+    CK(cudaMemsetAsync(&ctx->d_small->n_overflow, 0, sizeof(unsigned long long), s));
+    launch_sketch(a, ctx->sm_count, s);
+    CKS(check_launch(ctx, "sketch_kernel", 1));
+    launch_scan_u32_to_u64(ctx->n_min.as<uint32_t>(), ctx->b_off.as<uint64_t>(), n_reads,
+                           ctx->scan_scratch.as<uint64_t>(), s);
+    CKS(check_launch(ctx, "scan", 3));
+    CK(cudaMemcpyAsync(&ctx->h_scalar[0], ctx->b_off.as<uint64_t>() + n_reads, sizeof(uint64_t),
+                       cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&ctx->h_scalar[1], &ctx->d_small->n_overflow, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const uint64_t total = ctx->h_scalar[0];
+    const uint64_t n_over = ctx->h_scalar[1];
+    ctx->b_total = total;
+    CKS(ensure(ctx, ctx->b_min, (total + 1) * 4));
+    CKS(ensure(ctx, ctx->b_pos, (total + 1) * 4));
+    CKS(ensure(ctx, ctx->b_dir, total + 1));
+    if (n_over == 0) {
+        CompactArgs c{};
+        c.base_offsets = d_offsets;
+        c.cap_shift = ctx->cap_shift;
+        c.cap_const = ctx->cap_const;
+        c.n_min = ctx->n_min.as<uint32_t>();
+        c.tight_off = ctx->b_off.as<uint64_t>();
+        c.in_min = ctx->pad_min.as<uint32_t>();
+        c.in_pos = ctx->pad_pos.as<uint32_t>();
+        c.in_dir = ctx->pad_dir.as<uint8_t>();
+        c.out_min = ctx->b_min.as<uint32_t>();
+        c.out_pos = ctx->b_pos.as<uint32_t>();
+        c.out_dir = ctx->b_dir.as<uint8_t>();
+        c.n_reads = n_reads;
+        launch_compact(c, s);
+        CKS(check_launch(ctx, "compact_kernel", 1));
+    } else {
+        // some read produced more minimizers than its padded slot holds (low-complexity
+        // sequence): the exact counts are known now, so sketch again straight into the
+        // tight CSR.
+        a.exact_off = ctx->b_off.as<uint64_t>();
+        a.out_min = ctx->b_min.as<uint32_t>();
+        a.out_pos = ctx->b_pos.as<uint32_t>();
+        a.out_dir = ctx->b_dir.as<uint8_t>();
+        CK(cudaMemsetAsync(&ctx->d_small->cursor, 0, sizeof(uint32_t), s));
+        CK(cudaMemsetAsync(&ctx->d_small->n_overflow, 0, sizeof(unsigned long long), s));
+        launch_sketch(a, ctx->sm_count, s);
+        CKS(check_launch(ctx, "sketch_kernel(exact)", 1));
+    }
+    if (append) {
+        CKS(ensure(ctx, ctx->s_min, (ctx->s_mins + total + 1) * 4, true));
+        CKS(ensure(ctx, ctx->s_off, (ctx->s_reads + n_reads + 2) * sizeof(uint64_t), true));
+        if (ctx->s_reads == 0) CK(cudaMemsetAsync(ctx->s_off.p, 0, sizeof(uint64_t), s));
+        CK(cudaMemcpyAsync(ctx->s_min.as<uint32_t>() + ctx->s_mins, ctx->b_min.p, total * 4,
+                           cudaMemcpyDeviceToDevice, s));
+        launch_append_offsets(ctx->b_off.as<uint64_t>(), ctx->s_off.as<uint64_t>(), n_reads, ctx->s_reads,
+                              ctx->s_mins, s);
+        CKS(check_launch(ctx, "append_offsets_kernel", 1));
+        ctx->s_reads += n_reads;
+        ctx->s_mins += total;
+    }
+    return MDBG_OK;
+}
+
+// ---- NCCL through dlopen ---------------------------------------------------------
+struct Id128 { char b[128]; };
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, Id128 /* ncclUniqueId by value */, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+
+bool load_nccl(std::string& err) {
+    if (g_nccl.handle) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* n : names) {
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) { err = std::string("dlopen libnccl.so.2 failed: ") + dlerror(); return false; }
+#define SYM(field, name)                                                     \
+    *(void**)(&g_nccl.field) = dlsym(h, name);                               \
+    if (!g_nccl.field) { err = std::string("missing symbol ") + name; return false; }
+    SYM(GetUniqueId, "ncclGetUniqueId")
+    SYM(CommInitRank, "ncclCommInitRank")
+    SYM(CommDestroy, "ncclCommDestroy")
+    SYM(Send, "ncclSend")
+    SYM(Recv, "ncclRecv")
+    SYM(GroupStart, "ncclGroupStart")
+    SYM(GroupEnd, "ncclGroupEnd")
+    SYM(AllGather, "ncclAllGather")
+    SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    g_nccl.handle = h;
+    return true;
+}
+
+constexpr int NCCL_UINT8 = 1;    // ncclUint8 / ncclChar aliases: ncclInt8=0, ncclUint8=1
+constexpr int NCCL_UINT64 = 5;   // ncclUint64
+
+#define NK(call)                                                                                     \
+    do {                                                                                             \
+        int r_ = (call);                                                                             \
+        if (r_ != 0) return fail(ctx, MDBG_ERR_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r_)); \
+    } while (0)
+
+}  // namespace
+
+// =====================================================================================
+extern "C" {
+
+mdbg_status mdbg_ctx_create(int device, const mdbg_params* p, mdbg_ctx** out) {
+    mdbg_ctx* ctx = nullptr;   // for the CK macro: errors go to g_create_error
+    if (!p || !out) return fail(nullptr, MDBG_ERR_ARG, "mdbg_ctx_create: null argument");
+    if (p->minimizer_size < 2 || p->minimizer_size > 16)
+        return fail(nullptr, MDBG_ERR_ARG, "minimizer_size %u unsupported (2..16; metaMDBG caps l at 16)",
+                    p->minimizer_size);
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return fail(nullptr, MDBG_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                    cudaGetErrorString(e));
+    if (device < 0 || device >= n_dev) return fail(nullptr, MDBG_ERR_ARG, "device %d out of range (%d)", device, n_dev);
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(nullptr, MDBG_ERR_CUDA, "device %d is sm_%d%d; libmdbg_b200 is built for sm_100a only", device,
+                    prop.major, prop.minor);
+
+    mdbg_ctx* c = new mdbg_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->l = p->minimizer_size;
+    c->density = p->density;
+    c->hpc = p->use_hpc ? 1 : 0;
+    c->threshold = threshold_from_density(p->density, &c->select_none);
+    // padded output slots: 2^-shift >= 4 * density minimizers per base
+    {
+        int shift = 0;
+        double d4 = 4.0 * (double)p->density;
+        while (shift < 8 && 1.0 / (double)(1u << (shift + 1)) >= d4) shift++;
+        c->cap_shift = (uint32_t)shift;
+        c->cap_const = 32;
+    }
+    cudaError_t e2 = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    if (e2 != cudaSuccess) { delete c; return fail(nullptr, MDBG_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e2)); }
+    c->stream = c->own_stream;
+    if (cudaMalloc((void**)&c->d_small, sizeof(SmallDev)) != cudaSuccess ||
+        cudaMallocHost((void**)&c->h_small, sizeof(SmallDev)) != cudaSuccess ||
+        cudaMallocHost((void**)&c->h_scalar, 8 * sizeof(uint64_t)) != cudaSuccess) {
+        mdbg_ctx_destroy(c);
+        return fail(nullptr, MDBG_ERR_OOM, "context allocation failed");
+    }
+    cudaMemset(c->d_small, 0, sizeof(SmallDev));
+    if (p->blacklist && p->n_blacklist) {
+        std::vector<uint32_t> bl(p->blacklist, p->blacklist + p->n_blacklist);
+        std::sort(bl.begin(), bl.end());
+        bl.erase(std::unique(bl.begin(), bl.end()), bl.end());
+        mdbg_status st = ensure(c, c->d_blacklist, bl.size() * 4);
+        if (st != MDBG_OK) { g_create_error = c->error; mdbg_ctx_destroy(c); return st; }
+        cudaMemcpy(c->d_blacklist.p, bl.data(), bl.size() * 4, cudaMemcpyHostToDevice);
+        c->n_blacklist = (uint32_t)bl.size();
+    }
+    *out = c;
+    return MDBG_OK;
+}
+
+void mdbg_ctx_destroy(mdbg_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    DevBuf* devs[] = {&c->d_blacklist, &c->d_bases, &c->d_offsets, &c->pad_min, &c->pad_pos, &c->pad_dir, &c->n_min,
+                      &c->scan_scratch, &c->b_off, &c->b_min, &c->b_pos, &c->b_dir, &c->s_min, &c->s_off, &c->s_rem,
+                      &c->p_flags, &c->p_keep, &c->p_cnt, &c->p_newoff, &c->p_newmin, &c->table, &c->foreign_vecs,
+                      &c->o_hash, &c->o_abund, &c->o_vecs, &c->m_send_vecs, &c->m_send_counts, &c->m_recv_vecs,
+                      &c->m_recv_counts, &c->m_bucket};
+    for (DevBuf* b : devs) release(*b);
+    PinBuf* pins[] = {&c->h_off, &c->h_min, &c->h_pos, &c->h_dir, &c->ho_hash, &c->ho_abund, &c->ho_vecs};
+    for (PinBuf* b : pins) release(*b);
+    if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
+    if (c->d_small) cudaFree(c->d_small);
+    if (c->h_small) cudaFreeHost(c->h_small);
+    if (c->h_scalar) cudaFreeHost(c->h_scalar);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+const char* mdbg_last_error(mdbg_ctx* c) { return c ? c->error.c_str() : g_create_error.c_str(); }
+
+mdbg_status mdbg_ctx_set_stream(mdbg_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return MDBG_ERR_ARG;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return MDBG_OK;
+}
+
+mdbg_status mdbg_ctx_synchronize(mdbg_ctx* ctx) {
+    if (!ctx) return MDBG_ERR_ARG;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MDBG_OK;
+}
+
+uint64_t mdbg_ctx_kernel_launches(mdbg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- sketch -----------------------------------------------------------------------
+mdbg_status mdbg_sketch_batch_device(mdbg_ctx* ctx, const uint8_t* d_bases, const uint64_t* d_offsets,
+                                     uint32_t n_reads, uint64_t n_bases, int append_to_store, mdbg_sketch_dev* out) {
+    if (!ctx) return MDBG_ERR_ARG;
+    if (n_reads && (!d_bases || !d_offsets)) return fail(ctx, MDBG_ERR_ARG, "null device buffer");
+    if ((uintptr_t)d_bases & 15) return fail(ctx, MDBG_ERR_ARG, "d_bases must be 16-byte aligned");
+    CK(cudaSetDevice(ctx->device));
+    CKS(sketch_internal(ctx, d_bases, d_offsets, n_reads, n_bases, append_to_store));
+    if (out) {
+        out->n_reads = n_reads;
+        out->n_minimizers = ctx->b_total;
+        out->d_min_offsets = ctx->b_off.as<uint64_t>();
+        out->d_minimizers = ctx->b_min.as<uint32_t>();
+        out->d_positions = ctx->b_pos.as<uint32_t>();
+        out->d_directions = ctx->b_dir.as<uint8_t>();
+    }
+    return MDBG_OK;
+}
+
+mdbg_status mdbg_sketch_fetch(mdbg_ctx* ctx, mdbg_sketch_out* out) {
+    if (!ctx || !out) return MDBG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const uint32_t n = ctx->b_reads;
+    const uint64_t t = ctx->b_total;
+    CKS(ensure_pin(ctx, ctx->h_off, ((size_t)n + 1) * 8));
+    CKS(ensure_pin(ctx, ctx->h_min, (t + 1) * 4));
+    CKS(ensure_pin(ctx, ctx->h_pos, (t + 1) * 4));
+    CKS(ensure_pin(ctx, ctx->h_dir, t + 1));
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->h_off.p, ctx->b_off.p, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, s));
+    if (t) {
+        CK(cudaMemcpyAsync(ctx->h_min.p, ctx->b_min.p, t * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(ctx->h_pos.p, ctx->b_pos.p, t * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(ctx->h_dir.p, ctx->b_dir.p, t, cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    out->n_reads = n;
+    out->n_minimizers = t;
+    out->min_offsets = ctx->h_off.as<uint64_t>();
+    out->minimizers = ctx->h_min.as<uint32_t>();
+    out->positions = ctx->h_pos.as<uint32_t>();
+    out->directions = ctx->h_dir.as<uint8_t>();
+    return MDBG_OK;
+}
+
+mdbg_status mdbg_sketch_batch(mdbg_ctx* ctx, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads,
+                              int append_to_store, mdbg_sketch_out* out) {
+    if (!ctx) return MDBG_ERR_ARG;
+    if (n_reads && (!bases || !offsets)) return fail(ctx, MDBG_ERR_ARG, "null host buffer");
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t n_bases = n_reads ? offsets[n_reads] : 0;
+    if (n_reads && offsets[0] != 0) return fail(ctx, MDBG_ERR_ARG, "offsets[0] must be 0");
+    CKS(ensure(ctx, ctx->d_bases, n_bases + 64));
+    CKS(ensure(ctx, ctx->d_offsets, ((size_t)n_reads + 1) * 8));
+    cudaStream_t s = ctx->stream;
+    if (n_reads) {
+        CK(cudaMemcpyAsync(ctx->d_bases.p, bases, n_bases, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->d_offsets.p, offsets, ((size_t)n_reads + 1) * 8, cudaMemcpyHostToDevice, s));
+    }
+    CKS(sketch_internal(ctx, ctx->d_bases.as<uint8_t>(), ctx->d_offsets.as<uint64_t>(), n_reads, n_bases,
+                        append_to_store));
+    if (out) return mdbg_sketch_fetch(ctx, out);
+    return MDBG_OK;
+}
+
+// ---- store ------------------------------------------------------------------------
+mdbg_status mdbg_store_clear(mdbg_ctx* ctx) {
+    if (!ctx) return MDBG_ERR_ARG;
+    ctx->s_reads = 0;
+    ctx->s_mins = 0;
+    return MDBG_OK;
+}
+
+mdbg_status mdbg_store_append(mdbg_ctx* ctx, const uint32_t* minimizers, const uint64_t* min_offsets,
+                              uint32_t n_reads) {
+    if (!ctx) return MDBG_ERR_ARG;
+    if (n_reads == 0) return MDBG_OK;
+    if (!min_offsets) return fail(ctx, MDBG_ERR_ARG, "null min_offsets");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const uint64_t total = min_offsets[n_reads] - min_offsets[0];
+    CKS(ensure(ctx, ctx->s_min, (ctx->s_mins + total + 1) * 4, true));
+    CKS(ensure(ctx, ctx->s_off, (ctx->s_reads + n_reads + 2) * 8, true));
+    CKS(ensure(ctx, ctx->b_off, ((size_t)n_reads + 1) * 8));
+    if (ctx->s_reads == 0) CK(cudaMemsetAsync(ctx->s_off.p, 0, 8, s));
+    if (total)
+        CK(cudaMemcpyAsync(ctx->s_min.as<uint32_t>() + ctx->s_mins, minimizers + min_offsets[0], total * 4,
+                           cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->b_off.p, min_offsets, ((size_t)n_reads + 1) * 8, cudaMemcpyHostToDevice, s));
+    launch_append_offsets(ctx->b_off.as<uint64_t>(), ctx->s_off.as<uint64_t>(), n_reads, ctx->s_reads,
+                          ctx->s_mins - min_offsets[0], s);
+    CKS(check_launch(ctx, "append_offsets_kernel", 1));
+    CK(cudaStreamSynchronize(s));
+    ctx->b_reads = 0;
+    ctx->b_total = 0;
+    ctx->s_reads += n_reads;
+    ctx->s_mins += total;
+    return MDBG_OK;
+}
+
+mdbg_status mdbg_store_size(mdbg_ctx* ctx, uint64_t* n_reads, uint64_t* n_minimizers) {
+    if (!ctx) return MDBG_ERR_ARG;
+    if (n_reads) *n_reads = ctx->s_reads;
+    if (n_minimizers) *n_minimizers = ctx->s_mins;
+    return MDBG_OK;
+}
+
+mdbg_status mdbg_store_fetch(mdbg_ctx* ctx, uint64_t* min_offsets, uint32_t* minimizers) {
+    if (!ctx) return MDBG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    if (ctx->s_reads == 0) {
+        if (min_offsets) min_offsets[0] = 0;
+        return MDBG_OK;
+    }
+    if (min_offsets)
+        CK(cudaMemcpyAsync(min_offsets, ctx->s_off.p, (ctx->s_reads + 1) * 8, cudaMemcpyDeviceToHost, s));
+    if (minimizers && ctx->s_mins)
+        CK(cudaMemcpyAsync(minimizers, ctx->s_min.p, ctx->s_mins * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return MDBG_OK;
+}
+
+mdbg_status mdbg_purge_palindromes(mdbg_ctx* ctx, uint32_t first_k, uint32_t last_k, uint64_t* n_reads_changed) {
+    if (!ctx) return MDBG_ERR_ARG;
+    if (n_reads_changed) *n_reads_changed = 0;
+    if (ctx->s_reads == 0 || last_k <= first_k) return MDBG_OK;
+    if (first_k < 2) return fail(ctx, MDBG_ERR_ARG, "first_k must be >= 2");
+    if (ctx->s_reads > 0xFFFFFFFFull) return fail(ctx, MDBG_ERR_ARG, "store too large for purge");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    CKS(ensure(ctx, ctx->p_flags, ctx->s_reads));
+    CK(cudaMemsetAsync(&ctx->d_small->n_flagged, 0, 2 * sizeof(unsigned long long), s));   // n_flagged, n_changed
+    launch_purge_flag(ctx->s_min.as<uint32_t>(), ctx->s_off.as<uint64_t>(), ctx->s_reads, ctx->p_flags.as<uint8_t>(),
+                      &ctx->d_small->n_flagged, s);
+    CKS(check_launch(ctx, "purge_flag_kernel", 1));
+    CK(cudaMemcpyAsync(&ctx->h_scalar[0], &ctx->d_small->n_flagged, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (ctx->h_scalar[0] == 0) return MDBG_OK;
+
+    CKS(ensure(ctx, ctx->p_keep, ctx->s_mins + 1));
+    CKS(ensure(ctx, ctx->p_cnt, ctx->s_reads * 4));
+    CK(cudaMemsetAsync(ctx->p_keep.p, 1, ctx->s_mins + 1, s));
+    launch_purge_exact(ctx->s_min.as<uint32_t>(), ctx->s_off.as<uint64_t>(), ctx->s_reads, ctx->p_flags.as<uint8_t>(),
+                       first_k, last_k, ctx->p_keep.as<uint8_t>(), ctx->p_cnt.as<uint32_t>(),
+                       &ctx->d_small->n_changed, s);
+    CKS(check_launch(ctx, "purge_exact_kernel", 1));
+    CK(cudaMemcpyAsync(&ctx->h_scalar[1], &ctx->d_small->n_changed, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const uint64_t changed = ctx->h_scalar[1];
+    if (n_reads_changed) *n_reads_changed = changed;
+    if (changed == 0) return MDBG_OK;
+
+    CKS(ensure(ctx, ctx->p_newoff, (ctx->s_reads + 2) * 8));
+    CKS(ensure(ctx, ctx->scan_scratch, scan_scratch_elems((uint32_t)ctx->s_reads) * 8));
+    launch_scan_u32_to_u64(ctx->p_cnt.as<uint32_t>(), ctx->p_newoff.as<uint64_t>(), (uint32_t)ctx->s_reads,
+                           ctx->scan_scratch.as<uint64_t>(), s);
+    CKS(check_launch(ctx, "scan", 3));
+    CK(cudaMemcpyAsync(&ctx->h_scalar[2], ctx->p_newoff.as<uint64_t>() + ctx->s_reads, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const uint64_t new_total = ctx->h_scalar[2];
+    CKS(ensure(ctx, ctx->p_newmin, (new_total + 1) * 4));
+    launch_purge_compact(ctx->s_min.as<uint32_t>(), ctx->s_off.as<uint64_t>(), ctx->p_newoff.as<uint64_t>(),
+                         ctx->p_keep.as<uint8_t>(), ctx->s_reads, ctx->p_newmin.as<uint32_t>(), s);
+    CKS(check_launch(ctx, "purge_compact_kernel", 1));
+    CK(cudaStreamSynchronize(s));
+    std::swap(ctx->s_min, ctx->p_newmin);
+    std::swap(ctx->s_off, ctx->p_newoff);
+    ctx->s_mins = new_total;
+    return MDBG_OK;
+}
+
+// ---- count table --------------------------------------------------------------------
+mdbg_status mdbg_count_begin(mdbg_ctx* ctx, uint32_t k, uint64_t expected_distinct) {
+    if (!ctx) return MDBG_ERR_ARG;
+    if (k < 2 || k > 255) return fail(ctx, MDBG_ERR_ARG, "k=%u unsupported (2..255)", k);
+    CK(cudaSetDevice(ctx->device));
+    uint64_t expect = expected_distinct ? expected_distinct : ctx->s_mins;
+    if (expect < 512) expect = 512;
+    const uint64_t cap = pow2ceil(expect * 2);
+    CKS(ensure(ctx, ctx->table, cap * sizeof(Slot)));
+    CK(cudaMemsetAsync(ctx->table.p, 0, cap * sizeof(Slot), ctx->stream));
+    CK(cudaMemsetAsync(&ctx->d_small->full_flag, 0, sizeof(uint32_t), ctx->stream));
+    ctx->t_capacity = cap;
+    ctx->t_k = k;
+    ctx->t_active = true;
+    ctx->foreign_n = 0;
+    return MDBG_OK;
+}
+
+mdbg_status mdbg_count_add_store(mdbg_ctx* ctx, uint64_t read_lo, uint64_t read_hi) {
+    if (!ctx) return MDBG_ERR_ARG;
+    if (!ctx->t_active) return fail(ctx, MDBG_ERR_STATE, "mdbg_count_add_store before mdbg_count_begin");
+    if (read_hi > ctx->s_reads) read_hi = ctx->s_reads;
+    if (read_lo >= read_hi) return MDBG_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemcpyAsync(&ctx->h_scalar[0], ctx->s_off.as<uint64_t>() + read_lo, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&ctx->h_scalar[1], ctx->s_off.as<uint64_t>() + read_hi, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const uint64_t g_lo = ctx->h_scalar[0], g_hi = ctx->h_scalar[1];
+    CKS(ensure(ctx, ctx->s_rem, ctx->s_mins + 1));
+    launch_fill_rem(ctx->s_off.as<uint64_t>(), read_lo, read_hi, ctx->s_rem.as<uint8_t>(), s);
+    CKS(check_launch(ctx, "fill_rem_kernel", 1));
+    InsertArgs a{};
+    a.mins = ctx->s_min.as<uint32_t>();
+    a.rem = ctx->s_rem.as<uint8_t>();
+    a.g_lo = g_lo;
+    a.g_hi = g_hi;
+    a.k = ctx->t_k;
+    a.table = ctx->table.as<Slot>();
+    a.mask = ctx->t_capacity - 1;
+    a.full_flag = &ctx->d_small->full_flag;
+    launch_insert(a, s);
+    CKS(check_launch(ctx, "insert_kernel", g_hi > g_lo ? 1 : 0));
+    CK(cudaMemcpyAsync(&ctx->h_small->full_flag, &ctx->d_small->full_flag, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (ctx->h_small->full_flag)
+        return fail(ctx, MDBG_ERR_TABLE_FULL, "count table (capacity %llu slots) is full; raise expected_distinct",
+                    (unsigned long long)ctx->t_capacity);
+    return MDBG_OK;
+}
+
+mdbg_status mdbg_count_add(mdbg_ctx* ctx, const uint32_t* minimizers, const uint64_t* min_offsets, uint32_t n_reads) {
+    if (!ctx) return MDBG_ERR_ARG;
+    if (!ctx->t_active) return fail(ctx, MDBG_ERR_STATE, "mdbg_count_add before mdbg_count_begin");
+    const uint64_t lo = ctx->s_reads;
+    CKS(mdbg_store_append(ctx, minimizers, min_offsets, n_reads));
+    return mdbg_count_add_store(ctx, lo, ctx->s_reads);
+}
+
+static mdbg_status table_stats(mdbg_ctx* ctx, uint32_t thr, TableStats* st) {
+    cudaStream_t s = ctx->stream;
+    launch_table_stats(ctx->table.as<Slot>(), ctx->t_capacity, thr, &ctx->d_small->stats, s);
+    CKS(check_launch(ctx, "table_stats_kernel", 1));
+    CK(cudaMemcpyAsync(&ctx->h_small->stats, &ctx->d_small->stats, sizeof(TableStats), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    *st = ctx->h_small->stats;
+    return MDBG_OK;
+}
+
+// dumpKminmer (CreateMdbg.hpp:3862-3869): drop abundance <= 1, and on the first
+// pass abundance < min_abundance.
+static uint32_t count_threshold(uint32_t min_abundance) { return min_abundance > 2 ? min_abundance : 2; }
+
+mdbg_status mdbg_count_stats(mdbg_ctx* ctx, uint32_t min_abundance, uint64_t* n_entries, uint64_t* n_distinct,
+                             uint64_t* n_instances, uint64_t* checksum) {
+    if (!ctx) return MDBG_ERR_ARG;
+    if (!ctx->t_active) return fail(ctx, MDBG_ERR_STATE, "no active count table");
+    CK(cudaSetDevice(ctx->device));
+    TableStats st;
+    CKS(table_stats(ctx, count_threshold(min_abundance), &st));
+    if (n_entries) *n_entries = st.n_entries;
+    if (n_distinct) *n_distinct = st.n_distinct;
+    if (n_instances) *n_instances = st.n_instances;
+    if (checksum) *checksum = st.checksum;
+    return MDBG_OK;
+}
+
+mdbg_status mdbg_count_finalize(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_table_out* out) {
+    if (!ctx || !out) return MDBG_ERR_ARG;
+    if (!ctx->t_active) return fail(ctx, MDBG_ERR_STATE, "mdbg_count_finalize before mdbg_count_begin");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const uint32_t thr = count_threshold(min_abundance);
+    const uint32_t k = ctx->t_k;
+    TableStats st;
+    CKS(table_stats(ctx, thr, &st));
+    const uint64_t n = st.n_entries;
+    CKS(ensure(ctx, ctx->o_hash, (n + 1) * 16));
+    CKS(ensure(ctx, ctx->o_abund, (n + 1) * 4));
+    CKS(ensure(ctx, ctx->o_vecs, (n + 1) * 4 * k));
+    CKS(ensure_pin(ctx, ctx->ho_hash, (n + 1) * 16));
+    CKS(ensure_pin(ctx, ctx->ho_abund, (n + 1) * 4));
+    CKS(ensure_pin(ctx, ctx->ho_vecs, (n + 1) * 4 * k));
+    CK(cudaMemsetAsync(&ctx->d_small->emit_cursor, 0, 8, s));
+    EmitArgs e{};
+    e.table = ctx->table.as<Slot>();
+    e.capacity = ctx->t_capacity;
+    e.min_count = thr;
+    e.k = k;
+    e.mins = ctx->s_min.as<uint32_t>();
+    e.foreign_vecs = ctx->foreign_vecs.as<uint32_t>();
+    e.out_hashes = ctx->o_hash.as<uint64_t>();
+    e.out_abund = ctx->o_abund.as<uint32_t>();
+    e.out_vecs = ctx->o_vecs.as<uint32_t>();
+    e.cursor = &ctx->d_small->emit_cursor;
+    launch_table_emit(e, s);
+    CKS(check_launch(ctx, "table_emit_kernel", 1));
+    if (n) {
+        CK(cudaMemcpyAsync(ctx->ho_hash.p, ctx->o_hash.p, n * 16, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(ctx->ho_abund.p, ctx->o_abund.p, n * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(ctx->ho_vecs.p, ctx->o_vecs.p, n * 4 * k, cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    out->k = k;
+    out->n_entries = n;
+    out->hashes = ctx->ho_hash.as<uint64_t>();
+    out->abundances = ctx->ho_abund.as<uint32_t>();
+    out->kminmers = ctx->ho_vecs.as<uint32_t>();
+    out->n_instances = st.n_instances;
+    out->n_distinct = st.n_distinct;
+    out->checksum = st.checksum;
+    return MDBG_OK;
+}
+
+// ---- multi-GPU --------------------------------------------------------------------------
+mdbg_status mdbg_nccl_unique_id(uint8_t id_out[128]) {
+    mdbg_ctx* ctx = nullptr;
+    std::string err;
+    if (!load_nccl(err)) return fail(nullptr, MDBG_ERR_NCCL, "%s", err.c_str());
+    NK(g_nccl.GetUniqueId(id_out));
+    return MDBG_OK;
+}
+
+mdbg_status mdbg_comm_init(mdbg_ctx* ctx, int rank, int n_ranks, const uint8_t id[128]) {
+    if (!ctx || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return MDBG_ERR_ARG;
+    std::string err;
+    if (!load_nccl(err)) return fail(ctx, MDBG_ERR_NCCL, "%s", err.c_str());
+    CK(cudaSetDevice(ctx->device));
+    Id128 uid;
+    memcpy(uid.b, id, 128);
+    NK(g_nccl.CommInitRank(&ctx->nccl_comm, n_ranks, uid, rank));
+    ctx->rank = rank;
+    ctx->n_ranks = n_ranks;
+    return MDBG_OK;
+}
+
+mdbg_status mdbg_count_merge(mdbg_ctx* ctx) {
+    if (!ctx) return MDBG_ERR_ARG;
+    if (!ctx->t_active) return fail(ctx, MDBG_ERR_STATE, "mdbg_count_merge before mdbg_count_begin");
+    if (ctx->n_ranks == 1) return MDBG_OK;
+    if (!ctx->nccl_comm) return fail(ctx, MDBG_ERR_STATE, "mdbg_count_merge before mdbg_comm_init");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const uint32_t R = (uint32_t)ctx->n_ranks, k = ctx->t_k;
+    // layout of m_bucket (u64): [0,R) send counts | [R,2R) send bases | [2R, 2R+R*R) all ranks' send counts
+    CKS(ensure(ctx, ctx->m_bucket, (size_t)(2 * R + R * R) * 8));
+    uint64_t* d_cnt = ctx->m_bucket.as<uint64_t>();
+    uint64_t* d_base = d_cnt + R;
+    uint64_t* d_all = d_cnt + 2 * R;
+    CK(cudaMemsetAsync(d_cnt, 0, R * 8, s));
+    PackArgs p{};
+    p.table = ctx->table.as<Slot>();
+    p.capacity = ctx->t_capacity;
+    p.k = k;
+    p.n_ranks = R;
+    p.mins = ctx->s_min.as<uint32_t>();
+    p.foreign_vecs = ctx->foreign_vecs.as<uint32_t>();
+    p.bucket_count = reinterpret_cast<unsigned long long*>(d_cnt);
+    p.pass = 1;
+    launch_table_pack(p, s);
+    CKS(check_launch(ctx, "table_pack_kernel(count)", 1));
+    NK(g_nccl.AllGather(d_cnt, d_all, R, NCCL_UINT64, ctx->nccl_comm, s));
+    std::vector<uint64_t> all((size_t)R * R);
+    CK(cudaMemcpyAsync(all.data(), d_all, (size_t)R * R * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    std::vector<uint64_t> send_cnt(R), send_base(R), recv_cnt(R), recv_base(R);
+    uint64_t send_total = 0, recv_total = 0;
+    for (uint32_t d = 0; d < R; d++) {
+        send_cnt[d] = all[(size_t)ctx->rank * R + d];
+        send_base[d] = send_total;
+        send_total += send_cnt[d];
+        recv_cnt[d] = all[(size_t)d * R + ctx->rank];
+        recv_base[d] = recv_total;
+        recv_total += recv_cnt[d];
+    }
+    CKS(ensure(ctx, ctx->m_send_vecs, (send_total + 1) * 4 * k));
+    CKS(ensure(ctx, ctx->m_send_counts, (send_total + 1) * 4));
+    CKS(ensure(ctx, ctx->m_recv_vecs, (recv_total + 1) * 4 * k));
+    CKS(ensure(ctx, ctx->m_recv_counts, (recv_total + 1) * 4));
+    CK(cudaMemcpyAsync(d_base, send_base.data(), R * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(d_cnt, 0, R * 8, s));
+    p.bucket_base = d_base;
+    p.out_vecs = ctx->m_send_vecs.as<uint32_t>();
+    p.out_counts = ctx->m_send_counts.as<uint32_t>();
+    p.pass = 2;
+    launch_table_pack(p, s);
+    CKS(check_launch(ctx, "table_pack_kernel(scatter)", 1));
+    // one grouped all-to-all over NVLink: vectors and counts
+    NK(g_nccl.GroupStart());
+    for (uint32_t d = 0; d < R; d++) {
+        if (send_cnt[d]) {
+            NK(g_nccl.Send(ctx->m_send_vecs.as<uint32_t>() + send_base[d] * k, send_cnt[d] * 4 * k, NCCL_UINT8, (int)d,
+                           ctx->nccl_comm, s));
+            NK(g_nccl.Send(ctx->m_send_counts.as<uint32_t>() + send_base[d], send_cnt[d] * 4, NCCL_UINT8, (int)d,
+                           ctx->nccl_comm, s));
+        }
+        if (recv_cnt[d]) {
+            NK(g_nccl.Recv(ctx->m_recv_vecs.as<uint32_t>() + recv_base[d] * k, recv_cnt[d] * 4 * k, NCCL_UINT8, (int)d,
+                           ctx->nccl_comm, s));
+            NK(g_nccl.Recv(ctx->m_recv_counts.as<uint32_t>() + recv_base[d], recv_cnt[d] * 4, NCCL_UINT8, (int)d,
+                           ctx->nccl_comm, s));
+        }
+    }
+    NK(g_nccl.GroupEnd());
+    // rebuild the table with only the keys this rank owns
+    const uint64_t cap = pow2ceil((recv_total < 512 ? 512 : recv_total) * 2);
+    std::swap(ctx->foreign_vecs, ctx->m_recv_vecs);       // received vectors become the table's vector store
+    ctx->foreign_n = recv_total;
+    CKS(ensure(ctx, ctx->table, cap * sizeof(Slot)));
+    CK(cudaMemsetAsync(ctx->table.p, 0, cap * sizeof(Slot), s));
+    ctx->t_capacity = cap;
+    InsertVecArgs iv{};
+    iv.vecs = ctx->foreign_vecs.as<uint32_t>();
+    iv.counts = ctx->m_recv_counts.as<uint32_t>();
+    iv.n = recv_total;
+    iv.foreign_base = 0;
+    iv.k = k;
+    iv.table = ctx->table.as<Slot>();
+    iv.mask = cap - 1;
+    iv.full_flag = &ctx->d_small->full_flag;
+    launch_insert_vecs(iv, s);
+    CKS(check_launch(ctx, "insert_vecs_kernel", recv_total ? 1 : 0));
+    CK(cudaMemcpyAsync(&ctx->h_small->full_flag, &ctx->d_small->full_flag, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (ctx->h_small->full_flag) return fail(ctx, MDBG_ERR_TABLE_FULL, "merged table full");
+    return MDBG_OK;
+}
+
+// ---- synthetic reads -------------------------------------------------------------------
+mdbg_status mdbg_synth_fill_reads(mdbg_ctx* ctx, uint8_t* d_bases, const uint64_t* d_offsets, const uint64_t* d_vstart,
+                                  const uint8_t* d_strand, uint32_t n_reads, uint64_t read_index_base, uint64_t seed,
+                                  uint32_t err_q24) {
+    if (!ctx) return MDBG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    launch_synth_fill(d_bases, d_offsets, d_vstart, d_strand, n_reads, read_index_base, seed, err_q24, ctx->stream);
+    CKS(check_launch(ctx, "synth_fill_kernel", n_reads ? 1 : 0));
+    return MDBG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,150 @@
+// engine.cuh -- kernel launchers shared between the .cu files of libmdbg_b200.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mdbg {
+
+// ------------------------------------------------------------------ sketch
+struct SketchArgs {
+    const uint8_t* bases;        // concatenated ASCII reads (16-byte aligned allocation)
+    const uint8_t* bases_end;    // bases + n_bases: bytes at/after this address are never dereferenced
+    const uint64_t* offsets;     // [n_reads+1]
+    uint32_t n_reads;
+    uint32_t l;                  // minimizer size (2..16)
+    uint32_t hpc;                // homopolymer compression on/off
+    uint64_t threshold;          // select iff murmur_h1 <= threshold ...
+    uint32_t select_none;        // ... unless no hash value qualifies at all
+    const uint32_t* blacklist;   // sorted repetitive minimizers (device) or nullptr
+    uint32_t n_blacklist;
+    // output slots: either exact (tight CSR offsets) or padded closed form
+    const uint64_t* exact_off;   // [n_reads+1] or nullptr
+    uint32_t cap_shift;          // padded: slot_lo(r) = (offsets[r] >> cap_shift) + r * cap_const
+    uint32_t cap_const;
+    uint32_t* out_min;
+    uint32_t* out_pos;
+    uint8_t* out_dir;
+    uint32_t* n_min;             // [n_reads] true minimizer count per read
+    uint32_t* cursor;            // dynamic read scheduler (zeroed before launch)
+    unsigned long long* n_overflow;  // reads whose slot was too small (zeroed before launch)
+};
+
+void launch_sketch(const SketchArgs& a, int sm_count, cudaStream_t s);
+
+// counts (u32[n]) -> exclusive offsets (u64[n+1]); scratch must hold ceil(n/2048)+1 u64
+void launch_scan_u32_to_u64(const uint32_t* counts, uint64_t* offsets, uint32_t n, uint64_t* scratch, cudaStream_t s);
+size_t scan_scratch_elems(uint32_t n);
+
+struct CompactArgs {
+    const uint64_t* base_offsets;  // read byte offsets (for the padded slot formula)
+    uint32_t cap_shift, cap_const;
+    const uint32_t* n_min;
+    const uint64_t* tight_off;     // [n_reads+1]
+    const uint32_t* in_min; const uint32_t* in_pos; const uint8_t* in_dir;
+    uint32_t* out_min; uint32_t* out_pos; uint8_t* out_dir;
+    uint32_t n_reads;
+};
+void launch_compact(const CompactArgs& a, cudaStream_t s);
+
+// store_off[dst_read_base + 1 + i] = dst_min_base + batch_off[i + 1]
+void launch_append_offsets(const uint64_t* batch_off, uint64_t* store_off, uint32_t n_reads, uint64_t dst_read_base,
+                           uint64_t dst_min_base, cudaStream_t s);
+
+// ------------------------------------------------------------------ purge palindromes
+// flags[r] = 1 when read r may contain a palindromic window (cheap necessary test)
+void launch_purge_flag(const uint32_t* mins, const uint64_t* offs, uint64_t n_reads, uint8_t* flags,
+                       unsigned long long* n_flagged, cudaStream_t s);
+// exact Commons::purgePalindrome on flagged reads: keep[g] = 0 for banned minimizers, new_cnt[r] = survivors
+void launch_purge_exact(const uint32_t* mins, const uint64_t* offs, uint64_t n_reads, const uint8_t* flags,
+                        uint32_t first_k, uint32_t last_k, uint8_t* keep, uint32_t* new_cnt,
+                        unsigned long long* n_changed, cudaStream_t s);
+void launch_purge_compact(const uint32_t* mins, const uint64_t* offs, const uint64_t* new_offs, const uint8_t* keep,
+                          uint64_t n_reads, uint32_t* out_mins, cudaStream_t s);
+
+// ------------------------------------------------------------------ k-min-mer table
+struct __align__(32) Slot {
+    uint64_t lo;      // Murmur h2 = low 64 bits of KmerVec::hash128 (0,0 = empty)
+    uint64_t hi;      // Murmur h1 = high 64 bits
+    uint32_t count;   // abundance
+    uint32_t pad;
+    uint64_t ref;     // bit63: vector is the reversed window; bit62: index into foreign vecs; low bits: index
+};
+
+constexpr uint64_t REF_REV = 1ULL << 63;
+constexpr uint64_t REF_FOREIGN = 1ULL << 62;
+constexpr uint64_t REF_INDEX_MASK = (1ULL << 62) - 1;
+
+void launch_fill_rem(const uint64_t* offs, uint64_t read_lo, uint64_t read_hi, uint8_t* rem, cudaStream_t s);
+
+struct InsertArgs {
+    const uint32_t* mins;   // store minimizers
+    const uint8_t* rem;     // min(#minimizers from g to end of its read, 255)
+    uint64_t g_lo, g_hi;    // flat minimizer range
+    uint32_t k;
+    Slot* table;
+    uint64_t mask;          // capacity - 1 (power of two)
+    uint32_t* full_flag;
+};
+void launch_insert(const InsertArgs& a, cudaStream_t s);
+
+// insert pre-normalized foreign vectors with counts (multi-GPU merge, receive side)
+struct InsertVecArgs {
+    const uint32_t* vecs;   // [n*k]
+    const uint32_t* counts; // [n]
+    uint64_t n;
+    uint64_t foreign_base;  // index of vecs[0] in the context's foreign vector array
+    uint32_t k;
+    Slot* table;
+    uint64_t mask;
+    uint32_t* full_flag;
+};
+void launch_insert_vecs(const InsertVecArgs& a, cudaStream_t s);
+
+struct TableStats {
+    unsigned long long n_entries;    // count >= threshold
+    unsigned long long n_distinct;   // occupied
+    unsigned long long n_instances;  // sum of counts
+    unsigned long long checksum;     // sum count*lo over qualifying entries
+};
+void launch_table_stats(const Slot* table, uint64_t capacity, uint32_t min_count, TableStats* d_stats, cudaStream_t s);
+
+struct EmitArgs {
+    const Slot* table;
+    uint64_t capacity;
+    uint32_t min_count;
+    uint32_t k;
+    const uint32_t* mins;          // store minimizers
+    const uint32_t* foreign_vecs;  // merged-in vectors (may be nullptr)
+    uint64_t* out_hashes;          // [2n]: lo, hi
+    uint32_t* out_abund;           // [n]
+    uint32_t* out_vecs;            // [n*k]
+    unsigned long long* cursor;    // zeroed before launch
+};
+void launch_table_emit(const EmitArgs& a, cudaStream_t s);
+
+// multi-GPU pack: bucket every occupied slot by owner rank
+struct PackArgs {
+    const Slot* table;
+    uint64_t capacity;
+    uint32_t k;
+    uint32_t n_ranks;
+    const uint32_t* mins;
+    const uint32_t* foreign_vecs;
+    unsigned long long* bucket_count;   // [n_ranks] (pass 1 output / pass 2 cursors)
+    const uint64_t* bucket_base;        // [n_ranks] pass 2: start record of each bucket
+    uint32_t* out_vecs;                 // pass 2: [total*k]
+    uint32_t* out_counts;               // pass 2: [total]
+    int pass;                           // 1 = count, 2 = scatter
+};
+void launch_table_pack(const PackArgs& a, cudaStream_t s);
+
+__host__ __device__ inline uint32_t owner_of(uint64_t hi, uint32_t n_ranks) {
+    return (uint32_t)(((hi >> 32) * (uint64_t)n_ranks) >> 32);
+}
+
+// ------------------------------------------------------------------ synthetic reads
+void launch_synth_fill(uint8_t* bases, const uint64_t* offsets, const uint64_t* vstart, const uint8_t* strand,
+                       uint32_t n_reads, uint64_t read_index_base, uint64_t seed, uint32_t err_q24, cudaStream_t s);
+
+}  // namespace mdbg

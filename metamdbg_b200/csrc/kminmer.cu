@@ -1,0 +1,245 @@
+// kminmer.cu -- K3/K4/K5: k-min-mer extraction, orientation normalisation,
+// 128-bit Murmur hashing and the GPU-resident open-addressing count table.
+//
+// Replaces (reference, paths relative to the metaMDBG tree):
+//   MDBG::getKminmers_complete     src/Commons.hpp:5282-5361 (active #else branch)
+//   KmerVec::normalize / hash128   src/Commons.hpp:886-916, 941-969
+//   KminmerCounter::partitionKminmer / dereplicatePartition / dumpKminmer
+//                                  src/graph/CreateMdbg.hpp:3714-3883
+// The reference sorts every occurrence on disk and run-length counts; here each
+// occurrence is one 128-bit compare-and-swap probe into a 32-byte-slot table
+// plus one 32-bit reduction, so the table is the only state.
+#include "common.cuh"
+#include "engine.cuh"
+
+namespace mdbg {
+
+// ------------------------------------------------------------------ 128-bit slot primitives
+
+__device__ __forceinline__ void load_key(const Slot* s, uint64_t& lo, uint64_t& hi) {
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(s) : "memory");
+}
+
+// atom.cas.b128 (sm_90+): claims an empty slot with the full 128-bit key in one
+// transaction, so a key is never visible half-written to another CAS.
+__device__ __forceinline__ void cas_key(Slot* s, uint64_t new_lo, uint64_t new_hi, uint64_t& old_lo, uint64_t& old_hi) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b128 cmp, swp, old;\n\t"
+        "mov.b128 cmp, {%3, %3};\n\t"
+        "mov.b128 swp, {%4, %5};\n\t"
+        "atom.relaxed.gpu.global.cas.b128 old, [%2], cmp, swp;\n\t"
+        "mov.b128 {%0, %1}, old;\n\t"
+        "}"
+        : "=l"(old_lo), "=l"(old_hi)
+        : "l"(s), "l"(0ULL), "l"(new_lo), "l"(new_hi)
+        : "memory");
+}
+
+// Insert-or-add.  Returns false when the probe limit is hit (table full).
+__device__ __forceinline__ bool table_add(Slot* table, uint64_t mask, uint64_t lo, uint64_t hi, uint32_t add,
+                                          uint64_t ref) {
+    uint64_t idx = lo & mask;
+    const uint64_t max_probe = (mask + 1 < 4096) ? mask + 1 : 4096;
+    for (uint64_t probe = 0; probe < max_probe; probe++) {
+        Slot* s = table + idx;
+        uint64_t clo, chi;
+        load_key(s, clo, chi);
+        // A plain 16-byte load may in principle observe a half-written key, so a
+        // hit is only trusted when both halves are non-zero; anything with a zero
+        // half is re-examined by the atomic CAS.
+        if (clo == lo && chi == hi && lo != 0 && hi != 0) {
+            atomicAdd(&s->count, add);
+            return true;
+        }
+        if (clo == 0 || chi == 0) {
+            uint64_t olo, ohi;
+            cas_key(s, lo, hi, olo, ohi);
+            if (olo == 0 && ohi == 0) {                  // claimed
+                s->ref = ref;
+                atomicAdd(&s->count, add);
+                return true;
+            }
+            if (olo == lo && ohi == hi) {
+                atomicAdd(&s->count, add);
+                return true;
+            }
+        }
+        idx = (idx + 1) & mask;
+    }
+    return false;
+}
+
+// ------------------------------------------------------------------ rem[] = minimizers left in the read
+__global__ void __launch_bounds__(256) fill_rem_kernel(const uint64_t* offs, uint64_t read_lo, uint64_t read_hi,
+                                                       uint8_t* rem) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t r = read_lo + warp; r < read_hi; r += n_warps) {
+        const uint64_t b = offs[r], e = offs[r + 1];
+        for (uint64_t g = b + lane; g < e; g += 32) {
+            const uint64_t left = e - g;
+            rem[g] = (uint8_t)(left > 255 ? 255 : left);
+        }
+    }
+}
+
+void launch_fill_rem(const uint64_t* offs, uint64_t read_lo, uint64_t read_hi, uint8_t* rem, cudaStream_t s) {
+    if (read_hi <= read_lo) return;
+    uint64_t blocks = (read_hi - read_lo + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    fill_rem_kernel<<<(unsigned)blocks, 256, 0, s>>>(offs, read_lo, read_hi, rem);
+}
+
+// ------------------------------------------------------------------ insert: one thread per window
+// Window starting at flat minimizer index g exists iff the read still holds k
+// minimizers from g on (getKminmers_complete: i in [0, n-k]).
+template <int K_FIXED>
+__global__ void __launch_bounds__(256) insert_kernel(const InsertArgs a) {
+    const uint64_t g = a.g_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= a.g_hi) return;
+    const int k = K_FIXED ? K_FIXED : (int)a.k;
+    if ((int)a.rem[g] < k) return;
+    const uint32_t* w = a.mins + g;
+    // KmerVec::normalize (Commons.hpp:886-916): first differing pair decides,
+    // a palindromic vector counts as reversed.
+    bool rev = true;
+    for (int j = 0; j < k / 2; j++) {
+        const uint32_t x = w[j], y = w[k - 1 - j];
+        if (x != y) { rev = x > y; break; }
+    }
+    uint64_t h1, h2;
+    if (rev) murmur128_u32vec([&](int i) { return w[k - 1 - i]; }, k, h1, h2);
+    else murmur128_u32vec([&](int i) { return w[i]; }, k, h1, h2);
+    if (!table_add(a.table, a.mask, h2, h1, 1u, g | (rev ? REF_REV : 0ULL))) atomicExch(a.full_flag, 1u);
+}
+
+void launch_insert(const InsertArgs& a, cudaStream_t s) {
+    if (a.g_hi <= a.g_lo) return;
+    const uint64_t n = a.g_hi - a.g_lo;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    if (a.k == 4) insert_kernel<4><<<blocks, 256, 0, s>>>(a);
+    else insert_kernel<0><<<blocks, 256, 0, s>>>(a);
+}
+
+__global__ void __launch_bounds__(256) insert_vecs_kernel(const InsertVecArgs a) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const int k = (int)a.k;
+    const uint32_t* w = a.vecs + i * (uint64_t)k;
+    uint64_t h1, h2;
+    murmur128_u32vec([&](int j) { return w[j]; }, k, h1, h2);   // already normalized by the sender
+    if (!table_add(a.table, a.mask, h2, h1, a.counts[i], REF_FOREIGN | (a.foreign_base + i)))
+        atomicExch(a.full_flag, 1u);
+}
+
+void launch_insert_vecs(const InsertVecArgs& a, cudaStream_t s) {
+    if (a.n == 0) return;
+    insert_vecs_kernel<<<(unsigned)((a.n + 255) / 256), 256, 0, s>>>(a);
+}
+
+// ------------------------------------------------------------------ stats / emit
+__global__ void __launch_bounds__(256) table_stats_kernel(const Slot* table, uint64_t capacity, uint32_t min_count,
+                                                          TableStats* out) {
+    unsigned long long ne = 0, nd = 0, ni = 0, cs = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < capacity;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 q0 = reinterpret_cast<const uint4*>(table + i)[0];
+        const uint32_t count = reinterpret_cast<const uint4*>(table + i)[1].x;
+        const uint64_t lo = (uint64_t)q0.x | ((uint64_t)q0.y << 32);
+        const uint64_t hi = (uint64_t)q0.z | ((uint64_t)q0.w << 32);
+        if (lo | hi) {
+            nd++;
+            ni += count;
+            if (count >= min_count) { ne++; cs += (unsigned long long)count * lo; }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        ne += __shfl_down_sync(0xffffffffu, ne, d);
+        nd += __shfl_down_sync(0xffffffffu, nd, d);
+        ni += __shfl_down_sync(0xffffffffu, ni, d);
+        cs += __shfl_down_sync(0xffffffffu, cs, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (ne) atomicAdd(&out->n_entries, ne);
+        if (nd) atomicAdd(&out->n_distinct, nd);
+        if (ni) atomicAdd(&out->n_instances, ni);
+        if (cs) atomicAdd(&out->checksum, cs);
+    }
+}
+
+void launch_table_stats(const Slot* table, uint64_t capacity, uint32_t min_count, TableStats* d_stats, cudaStream_t s) {
+    cudaMemsetAsync(d_stats, 0, sizeof(TableStats), s);
+    uint64_t blocks = (capacity + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    table_stats_kernel<<<(unsigned)blocks, 256, 0, s>>>(table, capacity, min_count, d_stats);
+}
+
+__device__ __forceinline__ uint32_t vec_elem(const uint32_t* mins, const uint32_t* foreign, uint64_t ref, int k, int i) {
+    const uint64_t idx = ref & REF_INDEX_MASK;
+    if (ref & REF_FOREIGN) return foreign[idx * (uint64_t)k + i];
+    return (ref & REF_REV) ? mins[idx + k - 1 - i] : mins[idx + i];
+}
+
+__global__ void __launch_bounds__(256) table_emit_kernel(const EmitArgs a) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t rounds = (a.capacity + stride - 1) / stride;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint64_t it = 0; it < rounds; it++, i += stride) {
+        bool take = false;
+        uint64_t lo = 0, hi = 0, ref = 0;
+        uint32_t count = 0;
+        if (i < a.capacity) {
+            const Slot sl = a.table[i];
+            lo = sl.lo; hi = sl.hi; count = sl.count; ref = sl.ref;
+            take = (lo | hi) != 0 && count >= a.min_count;
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, take);
+        if (m == 0) continue;
+        unsigned long long base = 0;
+        if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(a.cursor, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (take) {
+            const uint64_t pos = base + __popc(m & ((1u << lane) - 1u));
+            a.out_hashes[2 * pos] = lo;
+            a.out_hashes[2 * pos + 1] = hi;
+            a.out_abund[pos] = count;
+            for (int j = 0; j < (int)a.k; j++)
+                a.out_vecs[pos * a.k + j] = vec_elem(a.mins, a.foreign_vecs, ref, (int)a.k, j);
+        }
+    }
+}
+
+void launch_table_emit(const EmitArgs& a, cudaStream_t s) {
+    uint64_t blocks = (a.capacity + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    table_emit_kernel<<<(unsigned)blocks, 256, 0, s>>>(a);
+}
+
+// ------------------------------------------------------------------ multi-GPU pack by owner rank
+__global__ void __launch_bounds__(256) table_pack_kernel(const PackArgs a) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.capacity;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const Slot sl = a.table[i];
+        if ((sl.lo | sl.hi) == 0) continue;
+        const uint32_t dst = owner_of(sl.hi, a.n_ranks);
+        const unsigned long long slot = atomicAdd(&a.bucket_count[dst], 1ULL);
+        if (a.pass == 2) {
+            const uint64_t pos = a.bucket_base[dst] + slot;
+            a.out_counts[pos] = sl.count;
+            for (int j = 0; j < (int)a.k; j++)
+                a.out_vecs[pos * a.k + j] = vec_elem(a.mins, a.foreign_vecs, sl.ref, (int)a.k, j);
+        }
+    }
+}
+
+void launch_table_pack(const PackArgs& a, cudaStream_t s) {
+    uint64_t blocks = (a.capacity + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    table_pack_kernel<<<(unsigned)blocks, 256, 0, s>>>(a);
+}
+
+}  // namespace mdbg

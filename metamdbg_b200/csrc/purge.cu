@@ -1,0 +1,157 @@
+// purge.cu -- K2: Commons::purgePalindrome (src/Commons.hpp:1617-1723) over the
+// device-resident minimizer-space reads, plus the synthetic-read generator.
+//
+// A palindromic window (KmerVec::isPalindrome, src/Commons.hpp:918-921) of
+// size k >= 2 needs m[c] == m[c+1] (even k) or m[c-1] == m[c+1] (odd k) at its
+// centre, so a one-pass neighbour test rules out almost every read; only
+// flagged reads run the exact (sequential, order-dependent) banning loop.
+#include "common.cuh"
+#include "engine.cuh"
+
+namespace mdbg {
+
+__global__ void __launch_bounds__(256) purge_flag_kernel(const uint32_t* mins, const uint64_t* offs, uint64_t n_reads,
+                                                         uint8_t* flags, unsigned long long* n_flagged) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t r = warp; r < n_reads; r += n_warps) {
+        const uint64_t b = offs[r], e = offs[r + 1];
+        bool hit = false;
+        for (uint64_t g = b + lane; g < e; g += 32) {
+            const uint32_t m = mins[g];
+            if (g + 1 < e && mins[g + 1] == m) hit = true;
+            if (g + 2 < e && mins[g + 2] == m) hit = true;
+        }
+        hit = __any_sync(0xffffffffu, hit);
+        if (lane == 0) {
+            flags[r] = hit ? 1 : 0;
+            if (hit) atomicAdd(n_flagged, 1ULL);
+        }
+    }
+}
+
+void launch_purge_flag(const uint32_t* mins, const uint64_t* offs, uint64_t n_reads, uint8_t* flags,
+                       unsigned long long* n_flagged, cudaStream_t s) {
+    if (n_reads == 0) return;
+    uint64_t blocks = (n_reads + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    purge_flag_kernel<<<(unsigned)blocks, 256, 0, s>>>(mins, offs, n_reads, flags, n_flagged);
+}
+
+// Exact restatement of the banning loop for one flagged read, executed by one
+// thread (flagged reads are rare).  keep[] is used as the banned bitmap.
+__global__ void __launch_bounds__(128) purge_exact_kernel(const uint32_t* mins, const uint64_t* offs, uint64_t n_reads,
+                                                          const uint8_t* flags, uint32_t first_k, uint32_t last_k,
+                                                          uint8_t* keep, uint32_t* new_cnt,
+                                                          unsigned long long* n_changed) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const uint64_t b = offs[r], e = offs[r + 1];
+    const long n = (long)(e - b);
+    if (!flags[r]) {
+        new_cnt[r] = (uint32_t)n;
+        return;
+    }
+    const uint32_t* m = mins + b;
+    uint8_t* kp = keep + b;                              // 1 = kept (pre-set by the caller)
+    for (;;) {                                           // Commons.hpp:1627
+        bool has = false;
+        for (long k = first_k; k < (long)last_k && !has; k++) {
+            const long i_max = n - k + 1;                // Commons.hpp:1635
+            for (long i = 0; i < i_max && !has; i++) {
+                if (!kp[i]) continue;
+                // the next k kept minimizers from i: positions idx[0..k)
+                // palindrome test needs pairs (t, k-1-t); gather lazily from both ends
+                long cnt = 0, j = i;
+                // find the k-th kept index from i (or fail)
+                long last_idx = -1;
+                for (; j < n; j++) {
+                    if (!kp[j]) continue;
+                    cnt++;
+                    if (cnt == k) { last_idx = j; break; }
+                }
+                if (last_idx < 0) continue;
+                long lo = i, hi = last_idx;
+                bool pal = true;
+                for (long t = 0; t < k / 2; t++) {
+                    if (m[lo] != m[hi]) { pal = false; break; }
+                    do { lo++; } while (!kp[lo]);
+                    do { hi--; } while (!kp[hi]);
+                }
+                if (pal) { kp[i] = 0; has = true; }      // Commons.hpp:1669 bans the window's first minimizer
+            }
+        }
+        if (!has) break;
+    }
+    uint32_t c = 0;
+    for (long i = 0; i < n; i++) c += kp[i];
+    new_cnt[r] = c;
+    if (c != (uint32_t)n) atomicAdd(n_changed, 1ULL);
+}
+
+void launch_purge_exact(const uint32_t* mins, const uint64_t* offs, uint64_t n_reads, const uint8_t* flags,
+                        uint32_t first_k, uint32_t last_k, uint8_t* keep, uint32_t* new_cnt,
+                        unsigned long long* n_changed, cudaStream_t s) {
+    if (n_reads == 0) return;
+    purge_exact_kernel<<<(unsigned)((n_reads + 127) / 128), 128, 0, s>>>(mins, offs, n_reads, flags, first_k, last_k,
+                                                                        keep, new_cnt, n_changed);
+}
+
+__global__ void __launch_bounds__(256) purge_compact_kernel(const uint32_t* mins, const uint64_t* offs,
+                                                            const uint64_t* new_offs, const uint8_t* keep,
+                                                            uint64_t n_reads, uint32_t* out_mins) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t r = warp; r < n_reads; r += n_warps) {
+        const uint64_t b = offs[r], e = offs[r + 1];
+        uint64_t dst = new_offs[r];
+        for (uint64_t g0 = b; g0 < e; g0 += 32) {
+            const uint64_t g = g0 + lane;
+            const bool k = (g < e) && keep[g];
+            const uint32_t mk = __ballot_sync(0xffffffffu, k);
+            if (k) out_mins[dst + __popc(mk & ((1u << lane) - 1u))] = mins[g];
+            dst += __popc(mk);
+        }
+    }
+}
+
+void launch_purge_compact(const uint32_t* mins, const uint64_t* offs, const uint64_t* new_offs, const uint8_t* keep,
+                          uint64_t n_reads, uint32_t* out_mins, cudaStream_t s) {
+    if (n_reads == 0) return;
+    uint64_t blocks = (n_reads + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    purge_compact_kernel<<<(unsigned)blocks, 256, 0, s>>>(mins, offs, new_offs, keep, n_reads, out_mins);
+}
+
+// ------------------------------------------------------------------ synthetic reads (metamdbg_b200/synth.py)
+__global__ void __launch_bounds__(256) synth_fill_kernel(uint8_t* bases, const uint64_t* offsets,
+                                                         const uint64_t* vstart, const uint8_t* strand,
+                                                         uint32_t n_reads, uint64_t read_index_base, uint64_t seed,
+                                                         uint32_t err_q24) {
+    const uint64_t GOLD = 0x9E3779B97F4A7C15ULL;
+    for (uint32_t r = blockIdx.x; r < n_reads; r += gridDim.x) {
+        const uint64_t b = offsets[r], n = offsets[r + 1] - b;
+        const uint64_t vs = vstart[r];
+        const bool rc = strand[r] != 0;
+        const uint64_t rid = read_index_base + r;
+        for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint64_t q = rc ? vs + (n - 1) - i : vs + i;
+            uint32_t x = (uint32_t)(mix64(q + seed) & 3);
+            if (rc) x = 3 - x;
+            const uint64_t e = mix64((rid * GOLD) ^ (i + seed * 0x632BE5ABULL));
+            if ((e & 0xFFFFFFULL) < (uint64_t)err_q24) x = (x + 1 + (uint32_t)((e >> 24) % 3)) & 3;
+            bases[b + i] = "ACGT"[x];
+        }
+    }
+}
+
+void launch_synth_fill(uint8_t* bases, const uint64_t* offsets, const uint64_t* vstart, const uint8_t* strand,
+                       uint32_t n_reads, uint64_t read_index_base, uint64_t seed, uint32_t err_q24, cudaStream_t s) {
+    if (n_reads == 0) return;
+    unsigned blocks = n_reads < 148u * 16u ? n_reads : 148u * 16u;
+    synth_fill_kernel<<<blocks, 256, 0, s>>>(bases, offsets, vstart, strand, n_reads, read_index_base, seed, err_q24);
+}
+
+}  // namespace mdbg

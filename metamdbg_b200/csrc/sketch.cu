@@ -1,0 +1,434 @@
+// sketch.cu -- K1: homopolymer compression + canonical l-mer roll + MurmurHash3
+// density-threshold selection, one warp per read.
+//
+// Replaces (reference, paths relative to the metaMDBG tree):
+//   EncoderRLE::execute          src/Commons.hpp:4163-4203
+//   KmerModel::iterate/first/next src/utils/kmer/Kmer.hpp:488-611
+//   MinimizerParser::parse       src/utils/kmer/Kmer.hpp:1373-1456
+//   MurmurHash3_x64_128          src/utils/MurmurHash3.cpp:246-325
+//
+// Data flow per warp (no block-level synchronisation anywhere):
+//   HBM --16 B/lane coalesced loads--> registers --keep-mask (SIMD byte compare,
+//   ballot-free warp scan)--> 2 KB shared-memory ring of HPC base codes
+//   --2 x LDS.128 per lane--> 16 consecutive l-mers per lane rolled in registers
+//   --Murmur + integer threshold--> selected (value, position, strand) written
+//   in position order to the read's output slot.
+#include "common.cuh"
+#include "engine.cuh"
+
+namespace mdbg {
+
+constexpr int WARPS_PER_CTA = 8;
+constexpr int RING = 2048;        // bytes of HPC codes per warp (power of two)
+constexpr int BLK = 512;          // l-mer positions per warp step (16 per lane)
+constexpr int CHUNK = 512;        // raw bytes per warp load step (16 per lane)
+
+// 4 byte-flags (0xFF/0x00 per byte) -> 4-bit mask
+__device__ __forceinline__ uint32_t nib(uint32_t bytes) {
+    return ((bytes & 0x01010101u) * 0x01020408u) >> 24;
+}
+__device__ __forceinline__ uint32_t nib16(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    return (nib(a) & 0xF) | ((nib(b) & 0xF) << 4) | ((nib(c) & 0xF) << 8) | ((nib(d) & 0xF) << 12);
+}
+
+__device__ __forceinline__ bool blacklisted(const uint32_t* bl, uint32_t n, uint32_t v) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (bl[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    return lo < n && bl[lo] == v;
+}
+
+// l-mer starting at HPC position p, read back from the ring (rare path).
+// key = canonical value, or ~0 when the window holds an invalid character
+// (Kmer.hpp:541-542, 579-580); dir as KmerCanonical::updateChoice (Kmer.hpp:427).
+__device__ __forceinline__ void lmer_at(const uint8_t* ring, uint32_t p, uint32_t l, uint64_t& key, uint32_t& dir) {
+    uint32_t fwd = 0, rc = 0, inv = 0;
+    for (uint32_t t = 0; t < l; t++) {
+        uint32_t b = ring[(p + t) & (RING - 1)];
+        uint32_t c = b & 3;
+        inv |= b & 4;
+        fwd = (fwd << 2) | c;
+        rc = (rc >> 2) | ((c ^ 2u) << (2 * l - 2));
+    }
+    if (l < 16) fwd &= (1u << (2 * l)) - 1;
+    dir = (fwd < rc) ? 0u : 1u;
+    key = inv ? ~0ULL : (uint64_t)(dir ? rc : fwd);
+}
+
+template <int L>
+__device__ __forceinline__ uint32_t byte_of(const uint32_t (&W)[8], int t) {
+    return (W[t >> 2] >> (8 * (t & 3))) & 0xFFu;
+}
+
+// Unrolled register path: 16 consecutive l-mers for this lane out of the
+// 32 ring bytes W (no invalid code present).  Returns the 16-bit selection
+// mask; the last selected (value, dir) is left in sel_val / sel_dir.
+template <int L>
+__device__ __forceinline__ uint32_t roll16_fast(const uint32_t (&W)[8], uint64_t threshold, uint32_t& sel_val,
+                                                uint32_t& sel_dir) {
+    constexpr uint32_t MASK = (L < 16) ? ((1u << (2 * L)) - 1u) : 0xFFFFFFFFu;
+    uint32_t fwd = 0, rc = 0;
+#pragma unroll
+    for (int t = 0; t < L - 1; t++) {
+        uint32_t c = byte_of<L>(W, t);
+        fwd = (fwd << 2) | c;
+        rc = (rc >> 2) | ((c ^ 2u) << (2 * L - 2));
+    }
+    uint32_t sel = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        uint32_t c = byte_of<L>(W, L - 1 + j);
+        fwd = ((fwd << 2) | c) & MASK;
+        rc = (rc >> 2) | ((c ^ 2u) << (2 * L - 2));
+        uint32_t val = min(fwd, rc);
+        uint64_t h = murmur_h1_u64((uint64_t)val);
+        if (h <= threshold) {
+            sel |= 1u << j;
+            sel_val = val;
+            sel_dir = (fwd < rc) ? 0u : 1u;
+        }
+    }
+    return sel;
+}
+
+// Generic path: runtime l, invalid characters tracked as the reference does
+// (indexBadChar, Kmer.hpp:552-556).
+__device__ __forceinline__ uint32_t roll16_generic(const uint8_t* ring, uint32_t p0, uint32_t l, uint64_t threshold,
+                                                   uint32_t valid_bits) {
+    const uint32_t mask = (l < 16) ? ((1u << (2 * l)) - 1u) : 0xFFFFFFFFu;
+    uint32_t fwd = 0, rc = 0, sel = 0;
+    int bad = -1;
+    for (uint32_t t = 0; t < l + 15; t++) {
+        uint32_t b = ring[(p0 + t) & (RING - 1)];
+        uint32_t c = b & 3;
+        bad = (b & 4) ? (int)l - 1 : bad - 1;
+        fwd = ((fwd << 2) | c) & mask;
+        rc = (rc >> 2) | ((c ^ 2u) << (2 * l - 2));
+        if (t >= l - 1) {
+            uint32_t j = t - (l - 1);
+            if ((valid_bits >> j) & 1u) {
+                uint64_t key = (bad < 0) ? (uint64_t)min(fwd, rc) : ~0ULL;
+                if (murmur_h1_u64(key) <= threshold) sel |= 1u << j;
+            }
+        }
+    }
+    return sel;
+}
+
+template <int L_FAST>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) sketch_kernel(const SketchArgs a) {
+    __shared__ __align__(16) uint8_t ring_all[WARPS_PER_CTA][RING];
+    const uint32_t lane = threadIdx.x & 31;
+    uint8_t* ring = ring_all[threadIdx.x >> 5];
+    const uint32_t l = a.l;
+
+    for (;;) {
+        uint32_t r = 0;
+        if (lane == 0) r = atomicAdd(a.cursor, 1u);
+        r = __shfl_sync(0xffffffffu, r, 0);
+        if (r >= a.n_reads) break;
+
+        const uint64_t start = a.offsets[r], end = a.offsets[r + 1];
+        const uint32_t len = (uint32_t)(end - start);
+        uint64_t slot_lo, slot_cap;
+        if (a.exact_off) {
+            slot_lo = a.exact_off[r];
+            slot_cap = a.exact_off[r + 1] - slot_lo;
+        } else {
+            slot_lo = (start >> a.cap_shift) + (uint64_t)r * a.cap_const;
+            slot_cap = ((end >> a.cap_shift) + (uint64_t)(r + 1) * a.cap_const) - slot_lo;
+        }
+        const uint8_t* base = a.bases + start;
+        const uint32_t skip = (uint32_t)((uintptr_t)base & 15);
+        const uint8_t* abase = base - skip;             // 16-byte aligned
+        const uint32_t x_end = skip + len;              // aligned-index space: x = skip + i
+        const uint32_t n_chunks = (x_end + CHUNK - 1) / CHUNK;
+
+        uint32_t avail = 0, done = 0, out_cnt = 0, chunk = 0;
+        uint32_t carry = '#';                           // EncoderRLE's lastChar sentinel
+
+        for (;;) {
+            // ---- fill: append HPC base codes to the ring ----------------------
+            while (chunk < n_chunks && avail - done < (uint32_t)BLK + l) {
+                const uint32_t x0 = chunk * CHUNK + lane * 16;
+                uint4 w = make_uint4(0, 0, 0, 0);
+                if (x0 < x_end && x0 + 16 > skip) {
+                    const uint8_t* p = abase + x0;
+                    if (p + 16 <= a.bases_end) {
+                        w = *reinterpret_cast<const uint4*>(p);
+                    } else {                             // last 16 bytes of the buffer: byte loads
+                        uint32_t t[4] = {0, 0, 0, 0};
+                        for (int j = 0; j < 16; j++)
+                            if (p + j < a.bases_end) t[j >> 2] |= (uint32_t)p[j] << (8 * (j & 3));
+                        w = make_uint4(t[0], t[1], t[2], t[3]);
+                    }
+                }
+                // validity of each of my 16 bytes: skip <= x0+j < x_end
+                const uint32_t lo = (skip > x0) ? min(skip - x0, 16u) : 0u;
+                const uint32_t hi = (x_end > x0) ? min(x_end - x0, 16u) : 0u;
+                const uint32_t vm = (hi > lo) ? (((1u << hi) - 1u) & ~((1u << lo) - 1u)) : 0u;
+                uint32_t pb = __shfl_up_sync(0xffffffffu, w.w >> 24, 1);
+                if (lane == 0) pb = carry;
+                carry = __shfl_sync(0xffffffffu, w.w >> 24, 31);
+
+                uint32_t keep = vm;
+                if (a.hpc) {
+                    const uint32_t e0 = __vcmpeq4(w.x, (w.x << 8) | pb);
+                    const uint32_t e1 = __vcmpeq4(w.y, (w.y << 8) | (w.x >> 24));
+                    const uint32_t e2 = __vcmpeq4(w.z, (w.z << 8) | (w.y >> 24));
+                    const uint32_t e3 = __vcmpeq4(w.w, (w.w << 8) | (w.z >> 24));
+                    const uint32_t h0 = __vcmpeq4(w.x, 0x23232323u), h1 = __vcmpeq4(w.y, 0x23232323u);
+                    const uint32_t h2 = __vcmpeq4(w.z, 0x23232323u), h3 = __vcmpeq4(w.w, 0x23232323u);
+                    uint32_t k16 = ~nib16(e0 | h0, e1 | h1, e2 | h2, e3 | h3) & 0xFFFFu;
+                    if (skip >= x0 && skip < x0 + 16) {  // first base of the read: previous char is the '#' sentinel
+                        const uint32_t fb = 1u << (skip - x0);
+                        k16 |= fb & ~nib16(h0, h1, h2, h3);
+                    }
+                    keep = k16 & vm;
+                }
+                const uint32_t cnt = __popc(keep);
+                const uint32_t incl = warp_inclusive_scan(cnt);
+                const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                uint32_t idx = avail + incl - cnt;
+                const uint32_t cw[4] = {(w.x >> 1) & 0x07070707u, (w.y >> 1) & 0x07070707u,
+                                        (w.z >> 1) & 0x07070707u, (w.w >> 1) & 0x07070707u};
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    if ((keep >> j) & 1u) {
+                        ring[idx & (RING - 1)] = (uint8_t)(cw[j >> 2] >> (8 * (j & 3)));
+                        idx++;
+                    }
+                }
+                avail += total;
+                chunk++;
+            }
+            __syncwarp();
+
+            // ---- roll + hash + select, 512 positions per step ------------------
+            const bool final_ = (chunk == n_chunks);
+            // Kmer.hpp:1395: positions 1 .. n-2 with n = L' - l + 1  =>  p <= L' - l - 1
+            const int pmax_final = (int)avail - (int)l - 1;
+            for (;;) {
+                int pmax;
+                if (avail - done >= (uint32_t)BLK + l) pmax = 0x7fffffff;
+                else if (final_ && (int)done <= pmax_final) pmax = pmax_final;
+                else break;
+
+                const uint32_t p0 = done + lane * 16;
+                int nv = 16;
+                if (pmax != 0x7fffffff) nv = max(0, min(16, pmax - (int)p0 + 1));
+                uint32_t valid_bits = (1u << nv) - 1u;
+                if (p0 == 0) valid_bits &= ~1u;          // position 0 is trimmed (Kmer.hpp:1362,1395)
+
+                uint32_t W[8];
+                {
+                    const uint4 u0 = *reinterpret_cast<const uint4*>(ring + (p0 & (RING - 1)));
+                    const uint4 u1 = *reinterpret_cast<const uint4*>(ring + ((p0 + 16) & (RING - 1)));
+                    W[0] = u0.x; W[1] = u0.y; W[2] = u0.z; W[3] = u0.w;
+                    W[4] = u1.x; W[5] = u1.y; W[6] = u1.z; W[7] = u1.w;
+                }
+                const uint32_t inv = (W[0] | W[1] | W[2] | W[3] | W[4] | W[5] | W[6] | W[7]) & 0x04040404u;
+                const bool fast = (L_FAST != 0) && (l == (uint32_t)L_FAST) && !__any_sync(0xffffffffu, inv != 0);
+
+                uint32_t sel, sel_val = 0, sel_dir = 0;
+                bool regs_ok = false;
+                if (a.select_none) {
+                    sel = 0;
+                } else if (fast) {
+                    sel = roll16_fast<(L_FAST ? L_FAST : 15)>(W, a.threshold, sel_val, sel_dir);
+                    regs_ok = (valid_bits == 0xFFFFu);
+                    sel &= valid_bits;
+                } else {
+                    sel = roll16_generic(ring, p0, l, a.threshold, valid_bits);
+                }
+                if (__any_sync(0xffffffffu, sel != 0)) {
+                    // rare: resolve values, apply the repetitive-minimizer blacklist, write in order
+                    uint32_t v0 = 0, v1 = 0, d0 = 0, d1 = 0;   // register cache for up to 2 hits
+                    uint32_t kept = 0;
+                    uint32_t scan_sel = sel;
+                    uint32_t nsel = 0;
+                    while (scan_sel) {
+                        const uint32_t j = __ffs(scan_sel) - 1;
+                        scan_sel &= scan_sel - 1;
+                        uint64_t key; uint32_t dir;
+                        if (regs_ok && __popc(sel) == 1) { key = sel_val; dir = sel_dir; }
+                        else lmer_at(ring, p0 + j, l, key, dir);
+                        const uint32_t v32 = (uint32_t)key;          // Kmer.hpp:1441 truncation
+                        if (a.n_blacklist && blacklisted(a.blacklist, a.n_blacklist, v32)) continue;
+                        kept |= 1u << j;
+                        if (nsel == 0) { v0 = v32; d0 = dir; }
+                        else if (nsel == 1) { v1 = v32; d1 = dir; }
+                        nsel++;
+                    }
+                    const uint32_t incl = warp_inclusive_scan(nsel);
+                    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                    uint64_t e = (uint64_t)out_cnt + incl - nsel;
+                    uint32_t i = 0;
+                    while (kept) {
+                        const uint32_t j = __ffs(kept) - 1;
+                        kept &= kept - 1;
+                        uint32_t v32, dir;
+                        if (i == 0) { v32 = v0; dir = d0; }
+                        else if (i == 1) { v32 = v1; dir = d1; }
+                        else { uint64_t key; lmer_at(ring, p0 + j, l, key, dir); v32 = (uint32_t)key; }
+                        if (e < slot_cap) {
+                            a.out_min[slot_lo + e] = v32;
+                            a.out_pos[slot_lo + e] = p0 + j;
+                            a.out_dir[slot_lo + e] = (uint8_t)dir;
+                        }
+                        e++; i++;
+                    }
+                    out_cnt += total;
+                }
+                done += BLK;
+            }
+            __syncwarp();
+            if (final_) break;
+        }
+        if (lane == 0) {
+            a.n_min[r] = out_cnt;
+            if ((uint64_t)out_cnt > slot_cap) atomicAdd(a.n_overflow, 1ULL);
+        }
+    }
+}
+
+void launch_sketch(const SketchArgs& a, int sm_count, cudaStream_t s) {
+    if (a.n_reads == 0) return;
+    // persistent grid: enough CTAs to fill every SM, reads are pulled dynamically
+    int per_sm = 0;
+    if (a.l == 15) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sketch_kernel<15>, WARPS_PER_CTA * 32, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sketch_kernel<0>, WARPS_PER_CTA * 32, 0);
+    if (per_sm < 1) per_sm = 1;
+    uint64_t want = ((uint64_t)a.n_reads + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    uint64_t grid = (uint64_t)sm_count * per_sm;
+    if (grid > want) grid = want;
+    if (a.l == 15) sketch_kernel<15><<<(unsigned)grid, WARPS_PER_CTA * 32, 0, s>>>(a);
+    else sketch_kernel<0><<<(unsigned)grid, WARPS_PER_CTA * 32, 0, s>>>(a);
+}
+
+// ------------------------------------------------------------------ scan
+constexpr int SCAN_T = 256, SCAN_E = 8, SCAN_TILE = SCAN_T * SCAN_E;
+
+size_t scan_scratch_elems(uint32_t n) { return (size_t)(n + SCAN_TILE - 1) / SCAN_TILE + 1; }
+
+__device__ __forceinline__ uint64_t block_exclusive_scan_u64(uint64_t v, uint64_t* total) {
+    __shared__ uint64_t wsum[SCAN_T / 32];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint64_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint64_t t = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= (uint32_t)d) x += t;
+    }
+    if (lane == 31) wsum[wid] = x;
+    __syncthreads();
+    uint64_t woff = 0, tot = 0;
+    for (int i = 0; i < SCAN_T / 32; i++) {
+        if (i < (int)wid) woff += wsum[i];
+        tot += wsum[i];
+    }
+    __syncthreads();
+    *total = tot;
+    return woff + x - v;
+}
+
+__global__ void __launch_bounds__(SCAN_T) scan_tile_sums(const uint32_t* counts, uint32_t n, uint64_t* tile_sums) {
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_E;
+    uint64_t s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_E; i++)
+        if (base + i < n) s += counts[base + i];
+    uint64_t tot;
+    block_exclusive_scan_u64(s, &tot);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(SCAN_T) scan_tile_prefix(uint64_t* tile_sums, uint32_t n_tiles) {
+    uint64_t running = 0;
+    for (uint32_t base = 0; base < n_tiles; base += SCAN_T) {
+        const uint32_t i = base + threadIdx.x;
+        const uint64_t v = (i < n_tiles) ? tile_sums[i] : 0;
+        uint64_t tot;
+        const uint64_t ex = block_exclusive_scan_u64(v, &tot);
+        if (i < n_tiles) tile_sums[i] = running + ex;
+        running += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tile_sums[n_tiles] = running;
+}
+
+__global__ void __launch_bounds__(SCAN_T) scan_write(const uint32_t* counts, uint32_t n, const uint64_t* tile_sums,
+                                                      uint32_t n_tiles, uint64_t* offsets) {
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_E;
+    uint32_t c[SCAN_E];
+    uint64_t s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_E; i++) {
+        c[i] = (base + i < n) ? counts[base + i] : 0;
+        s += c[i];
+    }
+    uint64_t tot;
+    uint64_t ex = block_exclusive_scan_u64(s, &tot) + tile_sums[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < SCAN_E; i++) {
+        if (base + i < n) offsets[base + i] = ex;
+        ex += c[i];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) offsets[n] = tile_sums[n_tiles];
+}
+
+void launch_scan_u32_to_u64(const uint32_t* counts, uint64_t* offsets, uint32_t n, uint64_t* scratch, cudaStream_t s) {
+    if (n == 0) {
+        cudaMemsetAsync(offsets, 0, sizeof(uint64_t), s);
+        return;
+    }
+    const uint32_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    scan_tile_sums<<<n_tiles, SCAN_T, 0, s>>>(counts, n, scratch);
+    scan_tile_prefix<<<1, SCAN_T, 0, s>>>(scratch, n_tiles);
+    scan_write<<<n_tiles, SCAN_T, 0, s>>>(counts, n, scratch, n_tiles, offsets);
+}
+
+// ------------------------------------------------------------------ compact padded slots -> tight CSR
+__global__ void __launch_bounds__(256) compact_kernel(const CompactArgs a) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t r = warp; r < a.n_reads; r += n_warps) {
+        const uint64_t start = a.base_offsets[r], end = a.base_offsets[r + 1];
+        const uint64_t slot_lo = (start >> a.cap_shift) + r * a.cap_const;
+        const uint64_t slot_cap = ((end >> a.cap_shift) + (r + 1) * a.cap_const) - slot_lo;
+        uint64_t n = a.n_min[r];
+        if (n > slot_cap) n = slot_cap;                  // overflowed read: the caller re-runs in exact mode
+        const uint64_t dst = a.tight_off[r];
+        for (uint64_t i = lane; i < n; i += 32) {
+            a.out_min[dst + i] = a.in_min[slot_lo + i];
+            a.out_pos[dst + i] = a.in_pos[slot_lo + i];
+            a.out_dir[dst + i] = a.in_dir[slot_lo + i];
+        }
+    }
+}
+
+void launch_compact(const CompactArgs& a, cudaStream_t s) {
+    if (a.n_reads == 0) return;
+    uint64_t blocks = ((uint64_t)a.n_reads + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    compact_kernel<<<(unsigned)blocks, 256, 0, s>>>(a);
+}
+
+__global__ void append_offsets_kernel(const uint64_t* batch_off, uint64_t* store_off, uint32_t n_reads,
+                                      uint64_t dst_read_base, uint64_t dst_min_base) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_reads) store_off[dst_read_base + 1 + i] = dst_min_base + batch_off[i + 1];
+    if (i == 0 && dst_read_base == 0) store_off[0] = 0;
+}
+
+void launch_append_offsets(const uint64_t* batch_off, uint64_t* store_off, uint32_t n_reads, uint64_t dst_read_base,
+                           uint64_t dst_min_base, cudaStream_t s) {
+    if (n_reads == 0) return;
+    append_offsets_kernel<<<(n_reads + 255) / 256, 256, 0, s>>>(batch_off, store_off, n_reads, dst_read_base,
+                                                                dst_min_base);
+}
+
+}  // namespace mdbg

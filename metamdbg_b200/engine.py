@@ -1,0 +1,258 @@
+"""Host-side mirror of the reference's operator interface for the hot path,
+implemented on top of the C ABI (include/mdbg_b200.h) -- every call below is a
+call into libmdbg_b200.so; no computation happens in Python.
+
+Naming follows metaMDBG (paths relative to its source tree):
+  * ``MinimizerParser.parse``   <- src/utils/kmer/Kmer.hpp:1339-1456 (with the
+    EncoderRLE step of src/Commons.hpp:4163-4203 folded in, as
+    ReadSelectionFunctor chains them, src/readSelection/ReadSelection.hpp:682-690)
+  * ``KminmerCounter``          <- src/graph/CreateMdbg.hpp:3591-3883
+  * ``purge_palindromes``       <- src/Commons.hpp:1617-1723
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _capi
+from ._capi import MdbgParams, SketchDev, SketchOut, TableOut
+
+STATUS = {0: "OK", 1: "CUDA", 2: "ARG", 3: "STATE", 4: "TABLE_FULL", 5: "NCCL", 6: "OOM"}
+
+
+class MdbgError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"mdbg status {STATUS.get(status, status)}: {message}")
+        self.status = status
+
+
+@dataclass
+class Sketch:
+    """CSR of one sketched batch (host copies)."""
+    min_offsets: np.ndarray   # uint64 [n_reads+1]
+    minimizers: np.ndarray    # uint32
+    positions: np.ndarray     # uint32
+    directions: np.ndarray    # uint8
+
+    @property
+    def n_reads(self) -> int:
+        return len(self.min_offsets) - 1
+
+    def read(self, r: int):
+        lo, hi = int(self.min_offsets[r]), int(self.min_offsets[r + 1])
+        return self.minimizers[lo:hi], self.positions[lo:hi], self.directions[lo:hi]
+
+
+@dataclass
+class CountTable:
+    """Finalised k-min-mer abundance table (unordered, like kminmerData_abundance.txt)."""
+    k: int
+    hashes: np.ndarray        # uint64 [n, 2]: (low64 = Murmur h2, high64 = Murmur h1), the on-disk u128 bytes
+    abundances: np.ndarray    # uint32 [n]
+    kminmers: np.ndarray      # uint32 [n, k]
+    n_instances: int
+    n_distinct: int
+    checksum: int
+
+    def as_dict(self) -> dict:
+        """{(h1, h2): abundance} with h1 = high 64 bits, h2 = low 64 bits."""
+        return {(int(h[1]), int(h[0])): int(a) for h, a in zip(self.hashes, self.abundances)}
+
+
+class Engine:
+    """One context = one GPU.  Not thread-safe (serialise calls, as the C ABI requires)."""
+
+    def __init__(self, minimizer_size: int = 15, density: float = 0.005, use_hpc: bool = True,
+                 blacklist: np.ndarray | None = None, device: int = 0):
+        self._lib = _capi.load()
+        self._ctx = C.c_void_p()
+        bl = None
+        if blacklist is not None and len(blacklist):
+            bl = np.ascontiguousarray(blacklist, dtype=np.uint32)
+        p = MdbgParams(minimizer_size, float(np.float32(density)), 1 if use_hpc else 0,
+                       bl.ctypes.data_as(_capi.u32p) if bl is not None else None, 0 if bl is None else len(bl))
+        st = self._lib.mdbg_ctx_create(device, C.byref(p), C.byref(self._ctx))
+        if st != 0:
+            raise MdbgError(st, self._lib.mdbg_last_error(None).decode())
+        self.minimizer_size, self.density, self.use_hpc, self.device = minimizer_size, density, use_hpc, device
+
+    # -- plumbing -------------------------------------------------------------
+    def _ck(self, st: int):
+        if st != 0:
+            raise MdbgError(st, self._lib.mdbg_last_error(self._ctx).decode())
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self._lib.mdbg_ctx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream: int | None):
+        self._ck(self._lib.mdbg_ctx_set_stream(self._ctx, C.c_void_p(cuda_stream or 0)))
+
+    def synchronize(self):
+        self._ck(self._lib.mdbg_ctx_synchronize(self._ctx))
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self._lib.mdbg_ctx_kernel_launches(self._ctx))
+
+    # -- sketch ---------------------------------------------------------------
+    @staticmethod
+    def _copy_sketch(out: SketchOut) -> Sketch:
+        n, t = out.n_reads, out.n_minimizers
+        mo = np.ctypeslib.as_array(out.min_offsets, shape=(n + 1,)).copy()
+        if t:
+            m = np.ctypeslib.as_array(out.minimizers, shape=(t,)).copy()
+            p = np.ctypeslib.as_array(out.positions, shape=(t,)).copy()
+            d = np.ctypeslib.as_array(out.directions, shape=(t,)).copy()
+        else:
+            m = np.zeros(0, np.uint32); p = np.zeros(0, np.uint32); d = np.zeros(0, np.uint8)
+        return Sketch(mo, m, p, d)
+
+    def sketch_batch(self, bases: np.ndarray, offsets: np.ndarray, append_to_store: bool = False,
+                     fetch: bool = True) -> Sketch | None:
+        """Host reads (ASCII uint8 + uint64 offsets[n+1]) -> minimizer CSR."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        out = SketchOut()
+        self._ck(self._lib.mdbg_sketch_batch(self._ctx, bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1,
+                                             int(append_to_store), C.byref(out) if fetch else None))
+        return self._copy_sketch(out) if fetch else None
+
+    def sketch_batch_device(self, d_bases_ptr: int, d_offsets_ptr: int, n_reads: int, n_bases: int,
+                            append_to_store: bool = False) -> SketchDev:
+        out = SketchDev()
+        self._ck(self._lib.mdbg_sketch_batch_device(self._ctx, C.c_void_p(d_bases_ptr), C.c_void_p(d_offsets_ptr),
+                                                    n_reads, n_bases, int(append_to_store), C.byref(out)))
+        return out
+
+    def sketch_fetch(self) -> Sketch:
+        out = SketchOut()
+        self._ck(self._lib.mdbg_sketch_fetch(self._ctx, C.byref(out)))
+        return self._copy_sketch(out)
+
+    # -- minimizer-space read store ----------------------------------------------
+    def store_clear(self):
+        self._ck(self._lib.mdbg_store_clear(self._ctx))
+
+    def store_append(self, minimizers: np.ndarray, min_offsets: np.ndarray):
+        minimizers = np.ascontiguousarray(minimizers, dtype=np.uint32)
+        min_offsets = np.ascontiguousarray(min_offsets, dtype=np.uint64)
+        self._ck(self._lib.mdbg_store_append(self._ctx, minimizers.ctypes.data, min_offsets.ctypes.data,
+                                             len(min_offsets) - 1))
+
+    def store_size(self) -> tuple[int, int]:
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self._ck(self._lib.mdbg_store_size(self._ctx, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def store_fetch(self) -> tuple[np.ndarray, np.ndarray]:
+        nr, nm = self.store_size()
+        offs = np.zeros(nr + 1, dtype=np.uint64)
+        mins = np.zeros(max(nm, 1), dtype=np.uint32)
+        self._ck(self._lib.mdbg_store_fetch(self._ctx, offs.ctypes.data, mins.ctypes.data))
+        return offs, mins[:nm]
+
+    def purge_palindromes(self, first_k: int, last_k: int) -> int:
+        n = C.c_uint64(0)
+        self._ck(self._lib.mdbg_purge_palindromes(self._ctx, first_k, last_k, C.byref(n)))
+        return int(n.value)
+
+    # -- count table ---------------------------------------------------------------
+    def count_begin(self, k: int, expected_distinct: int = 0):
+        self._ck(self._lib.mdbg_count_begin(self._ctx, k, expected_distinct))
+
+    def count_add_store(self, read_lo: int = 0, read_hi: int = 2 ** 64 - 1):
+        self._ck(self._lib.mdbg_count_add_store(self._ctx, read_lo, read_hi))
+
+    def count_add(self, minimizers: np.ndarray, min_offsets: np.ndarray):
+        minimizers = np.ascontiguousarray(minimizers, dtype=np.uint32)
+        min_offsets = np.ascontiguousarray(min_offsets, dtype=np.uint64)
+        self._ck(self._lib.mdbg_count_add(self._ctx, minimizers.ctypes.data, min_offsets.ctypes.data,
+                                          len(min_offsets) - 1))
+
+    def count_stats(self, min_abundance: int = 2) -> dict:
+        v = [C.c_uint64(0) for _ in range(4)]
+        self._ck(self._lib.mdbg_count_stats(self._ctx, min_abundance, *[C.byref(x) for x in v]))
+        return dict(n_entries=int(v[0].value), n_distinct=int(v[1].value), n_instances=int(v[2].value),
+                    checksum=int(v[3].value))
+
+    def count_finalize(self, min_abundance: int = 2) -> CountTable:
+        out = TableOut()
+        self._ck(self._lib.mdbg_count_finalize(self._ctx, min_abundance, C.byref(out)))
+        n, k = int(out.n_entries), int(out.k)
+        if n:
+            h = np.ctypeslib.as_array(out.hashes, shape=(2 * n,)).copy().reshape(n, 2)
+            a = np.ctypeslib.as_array(out.abundances, shape=(n,)).copy()
+            v = np.ctypeslib.as_array(out.kminmers, shape=(n * k,)).copy().reshape(n, k)
+        else:
+            h = np.zeros((0, 2), np.uint64); a = np.zeros(0, np.uint32); v = np.zeros((0, k), np.uint32)
+        return CountTable(k, h, a, v, int(out.n_instances), int(out.n_distinct), int(out.checksum))
+
+    # -- multi-GPU -----------------------------------------------------------------
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        lib = _capi.load()
+        buf = (C.c_uint8 * 128)()
+        st = lib.mdbg_nccl_unique_id(buf)
+        if st != 0:
+            raise MdbgError(st, lib.mdbg_last_error(None).decode())
+        return bytes(buf)
+
+    def comm_init(self, rank: int, n_ranks: int, unique_id: bytes):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._ck(self._lib.mdbg_comm_init(self._ctx, rank, n_ranks, buf))
+
+    def count_merge(self):
+        self._ck(self._lib.mdbg_count_merge(self._ctx))
+
+    # -- synthetic reads on the device ------------------------------------------------
+    def synth_fill_reads(self, d_bases_ptr: int, d_offsets_ptr: int, d_vstart_ptr: int, d_strand_ptr: int,
+                         n_reads: int, read_index_base: int, seed: int, err_q24: int):
+        self._ck(self._lib.mdbg_synth_fill_reads(self._ctx, C.c_void_p(d_bases_ptr), C.c_void_p(d_offsets_ptr),
+                                                 C.c_void_p(d_vstart_ptr), C.c_void_p(d_strand_ptr), n_reads,
+                                                 read_index_base, seed, err_q24))
+
+
+class MinimizerParser:
+    """``MinimizerParser(minimizerSize, density, repetitive)`` + ``parse`` of the
+    reference (Kmer.hpp:1351-1456), batched: one call sketches many reads."""
+
+    def __init__(self, minimizer_size: int, density: float, repetitive_minimizers: np.ndarray | None = None,
+                 use_homopolymer_compression: bool = True, device: int = 0):
+        self.engine = Engine(minimizer_size, density, use_homopolymer_compression, repetitive_minimizers, device)
+
+    def parse(self, seq: bytes):
+        """Single read -> (minimizers, positions, directions), the three vectors of the reference call."""
+        bases = np.frombuffer(seq, dtype=np.uint8)
+        sk = self.engine.sketch_batch(bases, np.array([0, len(seq)], dtype=np.uint64))
+        return sk.minimizers, sk.positions, sk.directions
+
+    def parse_batch(self, bases: np.ndarray, offsets: np.ndarray) -> Sketch:
+        return self.engine.sketch_batch(bases, offsets)
+
+
+class KminmerCounter:
+    """``CreateMdbg::KminmerCounter`` (CreateMdbg.hpp:3591-3883): feed minimizer-space
+    reads, get the solid k-min-mer table."""
+
+    def __init__(self, engine: Engine, k: int, expected_distinct: int = 0):
+        self.engine, self.k = engine, k
+        engine.count_begin(k, expected_distinct)
+
+    def add_reads(self, minimizers: np.ndarray, min_offsets: np.ndarray):
+        self.engine.count_add(minimizers, min_offsets)
+
+    def add_store(self):
+        self.engine.count_add_store()
+
+    def execute(self, min_abundance: int = 2) -> CountTable:
+        return self.engine.count_finalize(min_abundance)

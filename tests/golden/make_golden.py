@@ -1,0 +1,118 @@
+"""Mint golden input/output vectors for the sketch+count path from the
+REFERENCE'S OWN CODE (oracle/_ref/libmdbg_ref.so = metaMDBG sources compiled
+where they lie under /root/reference; see oracle/ref_shim.cpp).
+
+Run in the build container (needs /root/reference):
+    python tests/golden/make_golden.py
+The resulting tests/golden/*.npz files are committed; /root/reference is never
+read at test time.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from metamdbg_b200 import synth  # noqa: E402
+from oracle.pyoracle import Reference  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def sketch_all(ref, bases, offs, l, d, hpc, bl=None):
+    raw = bases.tobytes()
+    ms, ps, ds, mo = [], [], [], [0]
+    for r in range(len(offs) - 1):
+        m, p, dd = ref.sketch_read(raw[int(offs[r]):int(offs[r + 1])], l, d, hpc, bl)
+        ms.append(m); ps.append(p); ds.append(dd); mo.append(mo[-1] + len(m))
+    cat = lambda xs, t: np.concatenate(xs).astype(t) if xs else np.zeros(0, t)
+    return np.array(mo, np.uint64), cat(ms, np.uint32), cat(ps, np.uint32), cat(ds, np.uint8)
+
+
+def main():
+    ref = Reference()
+
+    # 1. HiFi-like: HPC on, l=15, d=0.005, k=4 count, abundance >= 2 (BASELINE config 0, scaled down)
+    rs = synth.make_readset(600, 6000, seed=101, n_genomes=2, genome_len_range=(90_000, 140_000), err=0.001)
+    bases, offs = synth.fill_reads(rs)
+    mo, m, p, d = sketch_all(ref, bases, offs, 15, 0.005, True)
+    purged, po = [], [0]
+    for r in range(len(mo) - 1):
+        q = ref.purge_palindrome(m[int(mo[r]):int(mo[r + 1])], 4, 60)
+        purged.append(q); po.append(po[-1] + len(q))
+    pm = np.concatenate(purged).astype(np.uint32)
+    po = np.array(po, np.uint64)
+    tabs = {}
+    for k in (4, 5, 7):
+        c = ref.count(pm, po, k, 2, threads=2)
+        tabs[f"k{k}_hashes"] = c["hashes"]; tabs[f"k{k}_abund"] = c["abundances"]; tabs[f"k{k}_vecs"] = c["vecs"]
+        tabs[f"k{k}_stats"] = np.array([c["n_instances"], c["n_distinct"]], np.uint64)
+    np.savez_compressed(os.path.join(HERE, "hifi_small.npz"), seed=101, bases=bases, offsets=offs,
+                        min_offsets=mo, minimizers=m, positions=p, directions=d,
+                        purged_offsets=po, purged_minimizers=pm, **tabs)
+
+    # 2. ONT-like: HPC off, d=0.025, 2 % substitutions, with a repetitive-minimizer blacklist
+    rs = synth.make_readset(300, 4000, seed=202, n_genomes=1, genome_len_range=(150_000, 150_001), err=0.02)
+    bases, offs = synth.fill_reads(rs)
+    mo0, m0, _, _ = sketch_all(ref, bases, offs, 15, 0.025, False)
+    vals, cnts = np.unique(m0, return_counts=True)
+    bl = vals[np.argsort(-cnts, kind="stable")[:5]].astype(np.uint32)
+    mo, m, p, d = sketch_all(ref, bases, offs, 15, 0.025, False, bl)
+    c = ref.count(m, mo, 4, 2, threads=2)
+    np.savez_compressed(os.path.join(HERE, "ont_small.npz"), seed=202, bases=bases, offsets=offs, blacklist=bl,
+                        min_offsets=mo, minimizers=m, positions=p, directions=d,
+                        k4_hashes=c["hashes"], k4_abund=c["abundances"], k4_vecs=c["vecs"],
+                        k4_stats=np.array([c["n_instances"], c["n_distinct"]], np.uint64))
+
+    # 3. edge cases: N, lower case, '#', empty / short reads, homopolymers, several l and densities
+    rng = np.random.default_rng(303)
+    reads = [b"", b"A", b"ACGT", b"A" * 300, b"AC" * 200, b"ACGTN" * 80, b"acgtACGT" * 60, b"#" * 10 + b"ACGGT" * 40,
+             b"ACG#TTGCA" * 50, bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), 15)),
+             bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), 16)),
+             bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), 17))]
+    for _ in range(40):
+        ln = int(rng.integers(1, 3000))
+        s = rng.choice(np.frombuffer(b"ACGTACGTACGTNacgt", np.uint8), ln)
+        rep = rng.integers(1, 5, size=ln)
+        reads.append(bytes(np.repeat(s, rep)[:ln]))
+    bases = np.frombuffer(b"".join(reads), np.uint8).copy()
+    offs = np.zeros(len(reads) + 1, np.uint64)
+    offs[1:] = np.cumsum([len(r) for r in reads])
+    out = dict(bases=bases, offsets=offs)
+    cases = []
+    for l in (5, 11, 15, 16):
+        for dens in (0.005, 0.05, 0.6):
+            for hpc in (0, 1):
+                mo, m, p, d = sketch_all(ref, bases, offs, l, dens, bool(hpc))
+                tag = f"l{l}_d{dens}_h{hpc}"
+                cases.append(tag)
+                out[tag + "_mo"] = mo; out[tag + "_m"] = m; out[tag + "_p"] = p; out[tag + "_d"] = d
+    out["cases"] = np.array(cases)
+    np.savez_compressed(os.path.join(HERE, "edge_cases.npz"), **out)
+
+    # 4. minimizer-space streams with many palindromes (tiny alphabet): purge + count for several k
+    reads = [rng.integers(0, 5, size=int(rng.integers(0, 70))).astype(np.uint32) for _ in range(500)]
+    offs = np.zeros(len(reads) + 1, np.uint64)
+    offs[1:] = np.cumsum([len(r) for r in reads])
+    mins = np.concatenate(reads).astype(np.uint32)
+    purged, po = [], [0]
+    for r in reads:
+        q = ref.purge_palindrome(r, 4, 12)
+        purged.append(q); po.append(po[-1] + len(q))
+    pm = np.concatenate(purged).astype(np.uint32)
+    po = np.array(po, np.uint64)
+    out = dict(minimizers=mins, offsets=offs, purged_minimizers=pm, purged_offsets=po)
+    for k in (4, 6, 9, 21):
+        c = ref.count(pm, po, k, 3, threads=2)
+        out[f"k{k}_hashes"] = c["hashes"]; out[f"k{k}_abund"] = c["abundances"]; out[f"k{k}_vecs"] = c["vecs"]
+        out[f"k{k}_stats"] = np.array([c["n_instances"], c["n_distinct"]], np.uint64)
+    np.savez_compressed(os.path.join(HERE, "minspace_palindromes.npz"), **out)
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))
+
+
+if __name__ == "__main__":
+    main()

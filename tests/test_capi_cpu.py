@@ -1,0 +1,72 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads, exports
+every symbol include/mdbg_b200.h declares, and refuses to run without a GPU
+(no CPU fallback).  No compute call is made here."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    g.build()
+    from metamdbg_b200 import _capi
+    return _capi.load()
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "mdbg_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mdbg_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_all_exported(lib):
+    from metamdbg_b200 import _capi
+    names = _header_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/mdbg_b200.h but not exported"
+    assert sorted(_capi.SYMBOLS) == names       # the ctypes table covers exactly the header
+
+
+def test_library_is_sm100a_only():
+    out = subprocess.run(["cuobjdump", "-lelf", os.path.join(ROOT, "metamdbg_b200", "libmdbg_b200.so")],
+                         capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    archs = set(re.findall(r"sm_\d+a?", out.stdout))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_product_does_not_link_or_import_oracle():
+    so = os.path.join(ROOT, "metamdbg_b200", "libmdbg_b200.so")
+    ldd = subprocess.run(["ldd", so], capture_output=True, text=True).stdout
+    assert "oracle" not in ldd and "mdbg_ref" not in ldd
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "metamdbg_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "pyoracle" not in txt and "mdbg_oracle" not in txt and "libmdbg_ref" not in txt, f
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from metamdbg_b200 import Engine, MdbgError
+    with pytest.raises(MdbgError) as e:
+        Engine(15, 0.005, True)
+    assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_bad_params_rejected(lib):
+    from metamdbg_b200 import _capi
+    p = _capi.MdbgParams(17, 0.005, 1, None, 0)
+    ctx = C.c_void_p()
+    assert lib.mdbg_ctx_create(0, C.byref(p), C.byref(ctx)) != 0
+    assert b"minimizer_size" in lib.mdbg_last_error(None)

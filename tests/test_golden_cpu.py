@@ -1,0 +1,67 @@
+"""The C restatement (oracle/) against the committed golden vectors minted from
+the reference's own code (tests/golden/make_golden.py).  Runs anywhere."""
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(GOLD, name))
+
+
+def table_dict(hashes, abund):
+    return {(int(h[0]), int(h[1])): int(a) for h, a in zip(hashes, abund)}
+
+
+def test_hifi_small_sketch_purge_count(oracle):
+    g = load("hifi_small.npz")
+    mo, m, p, d = oracle.sketch_batch(g["bases"], g["offsets"], 15, 0.005, True)
+    assert np.array_equal(mo, g["min_offsets"]) and np.array_equal(m, g["minimizers"])
+    assert np.array_equal(p, g["positions"]) and np.array_equal(d, g["directions"])
+    po = [0]; pm = []
+    for r in range(len(mo) - 1):
+        q, _ = oracle.purge_palindrome(m[int(mo[r]):int(mo[r + 1])], 4, 60)
+        pm.append(q); po.append(po[-1] + len(q))
+    assert np.array_equal(np.concatenate(pm), g["purged_minimizers"])
+    assert np.array_equal(np.array(po, np.uint64), g["purged_offsets"])
+    for k in (4, 5, 7):
+        c = oracle.count(g["purged_minimizers"], g["purged_offsets"], k, 2)
+        assert np.array_equal(c["vecs"], g[f"k{k}_vecs"])
+        assert np.array_equal(c["hashes"], g[f"k{k}_hashes"]) and np.array_equal(c["abundances"], g[f"k{k}_abund"])
+        assert [c["n_instances"], c["n_distinct"]] == list(g[f"k{k}_stats"])
+
+
+def test_ont_small(oracle):
+    g = load("ont_small.npz")
+    mo, m, p, d = oracle.sketch_batch(g["bases"], g["offsets"], 15, 0.025, False, g["blacklist"])
+    assert np.array_equal(mo, g["min_offsets"]) and np.array_equal(m, g["minimizers"])
+    assert np.array_equal(p, g["positions"]) and np.array_equal(d, g["directions"])
+    c = oracle.count(m, mo, 4, 2)
+    assert table_dict(c["hashes"], c["abundances"]) == table_dict(g["k4_hashes"], g["k4_abund"])
+
+
+def test_edge_cases(oracle):
+    g = load("edge_cases.npz")
+    for tag in g["cases"]:
+        tag = str(tag)
+        l = int(tag.split("_")[0][1:]); dens = float(tag.split("_")[1][1:]); hpc = tag.endswith("h1")
+        mo, m, p, d = oracle.sketch_batch(g["bases"], g["offsets"], l, dens, hpc)
+        assert np.array_equal(mo, g[tag + "_mo"]), tag
+        assert np.array_equal(m, g[tag + "_m"]) and np.array_equal(p, g[tag + "_p"]) and np.array_equal(d, g[tag + "_d"]), tag
+
+
+def test_minspace_palindromes(oracle):
+    g = load("minspace_palindromes.npz")
+    offs, mins = g["offsets"], g["minimizers"]
+    pm = []
+    for r in range(len(offs) - 1):
+        q, _ = oracle.purge_palindrome(mins[int(offs[r]):int(offs[r + 1])], 4, 12)
+        pm.append(q)
+    assert np.array_equal(np.concatenate(pm), g["purged_minimizers"])
+    for k in (4, 6, 9, 21):
+        c = oracle.count(g["purged_minimizers"], g["purged_offsets"], k, 3)
+        assert np.array_equal(c["hashes"], g[f"k{k}_hashes"]) and np.array_equal(c["abundances"], g[f"k{k}_abund"])
+        assert np.array_equal(c["vecs"], g[f"k{k}_vecs"])

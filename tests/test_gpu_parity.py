@@ -1,0 +1,274 @@
+"""GPU parity tests proper: libmdbg_b200.so (through the C ABI) against the CPU
+oracle on the same seeded inputs, against the golden vectors minted from the
+reference's code, and size-independent properties.  Bit-exact everywhere
+(integer / byte / index work)."""
+import os
+
+import numpy as np
+import pytest
+
+from metamdbg_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(GOLD, name))
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as g
+    g.build()
+    import torch
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    return True
+
+
+def engine(l=15, d=0.005, hpc=True, bl=None):
+    from metamdbg_b200 import Engine
+    return Engine(l, d, hpc, bl)
+
+
+def assert_sketch_equal(sk, mo, m, p, d, tag=""):
+    assert np.array_equal(sk.min_offsets, mo), f"min_offsets {tag}"
+    assert np.array_equal(sk.minimizers, m), f"minimizers {tag}"
+    assert np.array_equal(sk.positions, p), f"positions {tag}"
+    assert np.array_equal(sk.directions, d), f"directions {tag}"
+
+
+def table_dict(hashes_h1h2, abund):
+    return {(int(h[0]), int(h[1])): int(a) for h, a in zip(hashes_h1h2, abund)}
+
+
+def check_table(tab, ref_hashes, ref_abund, ref_vecs, stats=None):
+    assert tab.as_dict() == table_dict(ref_hashes, ref_abund)
+    got_vecs = {(int(h[1]), int(h[0])): tuple(int(x) for x in v) for h, v in zip(tab.hashes, tab.kminmers)}
+    want_vecs = {(int(h[0]), int(h[1])): tuple(int(x) for x in v) for h, v in zip(ref_hashes, ref_vecs)}
+    assert got_vecs == want_vecs
+    if stats is not None:
+        assert [tab.n_instances, tab.n_distinct] == [int(stats[0]), int(stats[1])]
+
+
+# ---------------------------------------------------------------- sketch
+
+def test_sketch_hifi_vs_oracle(built, oracle):
+    rs = synth.make_readset(2000, 9000, seed=5, n_genomes=3, genome_len_range=(200_000, 400_000))
+    bases, offs = synth.fill_reads(rs)
+    eng = engine()
+    sk = eng.sketch_batch(bases, offs)
+    assert_sketch_equal(sk, *oracle.sketch_batch(bases, offs, 15, 0.005, True))
+    assert sk.min_offsets[-1] > 20_000
+    eng.close()
+
+
+def test_sketch_ont_vs_oracle(built, oracle):
+    rs = synth.make_readset(1500, 8000, seed=6, n_genomes=2, genome_len_range=(200_000, 300_000), err=0.02)
+    bases, offs = synth.fill_reads(rs)
+    eng = engine(15, 0.025, False)
+    sk = eng.sketch_batch(bases, offs)
+    assert_sketch_equal(sk, *oracle.sketch_batch(bases, offs, 15, 0.025, False))
+    eng.close()
+
+
+def test_sketch_golden_hifi_and_ont(built):
+    g = load("hifi_small.npz")
+    eng = engine()
+    sk = eng.sketch_batch(g["bases"], g["offsets"])
+    assert_sketch_equal(sk, g["min_offsets"], g["minimizers"], g["positions"], g["directions"], "hifi golden")
+    eng.close()
+    g = load("ont_small.npz")
+    eng = engine(15, 0.025, False, g["blacklist"])
+    sk = eng.sketch_batch(g["bases"], g["offsets"])
+    assert_sketch_equal(sk, g["min_offsets"], g["minimizers"], g["positions"], g["directions"], "ont golden")
+    eng.close()
+
+
+def test_sketch_edge_cases_golden(built):
+    """N / lower case / '#' / empty / short / homopolymer reads, l in {5,11,15,16},
+    densities up to 0.6 (exercises the slot-overflow re-run), HPC on and off."""
+    g = load("edge_cases.npz")
+    for tag in g["cases"]:
+        tag = str(tag)
+        l = int(tag.split("_")[0][1:]); dens = float(tag.split("_")[1][1:]); hpc = tag.endswith("h1")
+        eng = engine(l, dens, hpc)
+        sk = eng.sketch_batch(g["bases"], g["offsets"])
+        assert_sketch_equal(sk, g[tag + "_mo"], g[tag + "_m"], g[tag + "_p"], g[tag + "_d"], tag)
+        eng.close()
+
+
+def test_sketch_long_and_ragged_reads(built, oracle):
+    """One 300 kbp read, many tiny reads, every start alignment 0..15."""
+    rng = np.random.default_rng(9)
+    reads = [bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), 300_000))]
+    for a in range(40):
+        reads.append(bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), int(rng.integers(0, 700)) + a)))
+    reads.append(bytes(np.repeat(rng.choice(np.frombuffer(b"ACGT", np.uint8), 5000), rng.integers(1, 9, 5000))))
+    bases = np.frombuffer(b"".join(reads), np.uint8).copy()
+    offs = np.zeros(len(reads) + 1, np.uint64)
+    offs[1:] = np.cumsum([len(r) for r in reads])
+    for hpc in (True, False):
+        eng = engine(15, 0.01, hpc)
+        sk = eng.sketch_batch(bases, offs)
+        assert_sketch_equal(sk, *oracle.sketch_batch(bases, offs, 15, 0.01, hpc), tag=f"hpc={hpc}")
+        eng.close()
+
+
+def test_sketch_empty_batch(built):
+    eng = engine()
+    sk = eng.sketch_batch(np.zeros(0, np.uint8), np.zeros(1, np.uint64))
+    assert sk.n_reads == 0 and len(sk.minimizers) == 0
+    eng.close()
+
+
+def test_sketch_reverse_complement_symmetry(built):
+    """Size-independent property: sketching the reverse complement yields the same
+    canonical minimizers mirrored, with flipped strands."""
+    rs = synth.make_readset(400, 12000, seed=12, n_genomes=1, genome_len_range=(500_000, 500_001))
+    bases, offs = synth.fill_reads(rs)
+    comp = np.zeros(256, np.uint8)
+    for a, b in zip(b"ACGT", b"TGCA"):
+        comp[a] = b
+    rc = np.empty_like(bases)
+    for r in range(len(offs) - 1):
+        lo, hi = int(offs[r]), int(offs[r + 1])
+        rc[lo:hi] = comp[bases[lo:hi]][::-1]
+    eng = engine(15, 0.005, False)          # no HPC: positions map exactly
+    a = eng.sketch_batch(bases, offs)
+    b = eng.sketch_batch(rc, offs)
+    n_checked = 0
+    for r in range(a.n_reads):
+        ma, pa, da = a.read(r)
+        mb, pb, db = b.read(r)
+        n_l = int(offs[r + 1] - offs[r]) - 15 + 1
+        assert np.array_equal(ma, mb[::-1])
+        assert np.array_equal(pa, (n_l - 1 - pb.astype(np.int64))[::-1])
+        pal = ma == 0  # never true; palindromic l-mers impossible for odd l
+        assert np.array_equal(da[~pal], (1 - db[::-1])[~pal])
+        n_checked += len(ma)
+    assert n_checked > 10_000
+    eng.close()
+
+
+# ---------------------------------------------------------------- store / purge / count
+
+def test_purge_and_count_minspace_golden(built):
+    g = load("minspace_palindromes.npz")
+    eng = engine()
+    eng.store_append(g["minimizers"], g["offsets"])
+    changed = eng.purge_palindromes(4, 12)
+    assert changed > 0
+    so, sm = eng.store_fetch()
+    assert np.array_equal(so, g["purged_offsets"]) and np.array_equal(sm, g["purged_minimizers"])
+    for k in (4, 6, 9, 21):
+        eng.count_begin(k)
+        eng.count_add_store()
+        tab = eng.count_finalize(3)
+        check_table(tab, g[f"k{k}_hashes"], g[f"k{k}_abund"], g[f"k{k}_vecs"], g[f"k{k}_stats"])
+    eng.close()
+
+
+def test_full_path_hifi_golden(built):
+    """Reads -> sketch -> store -> purge -> count(k=4,5,7) on the device, against
+    the reference-minted table."""
+    g = load("hifi_small.npz")
+    eng = engine()
+    eng.sketch_batch(g["bases"], g["offsets"], append_to_store=True, fetch=False)
+    eng.purge_palindromes(4, 60)
+    so, sm = eng.store_fetch()
+    assert np.array_equal(so, g["purged_offsets"]) and np.array_equal(sm, g["purged_minimizers"])
+    for k in (4, 5, 7):
+        eng.count_begin(k)
+        eng.count_add_store()
+        tab = eng.count_finalize(2)
+        check_table(tab, g[f"k{k}_hashes"], g[f"k{k}_abund"], g[f"k{k}_vecs"], g[f"k{k}_stats"])
+        st = eng.count_stats(2)
+        assert st["n_entries"] == len(tab.abundances) and st["checksum"] == tab.checksum
+    eng.close()
+
+
+def test_count_vs_oracle_multi_k_and_batches(built, oracle):
+    rs = synth.make_readset(3000, 9000, seed=31, n_genomes=1, genome_len_range=(300_000, 300_001))
+    bases, offs = synth.fill_reads(rs)
+    eng = engine()
+    half = 1500
+    eng.sketch_batch(bases[:int(offs[half])], offs[:half + 1], append_to_store=True, fetch=False)
+    eng.sketch_batch(bases[int(offs[half]):], offs[half:] - offs[half], append_to_store=True, fetch=False)
+    mo, m, p, d = oracle.sketch_batch(bases, offs, 15, 0.005, True)
+    so, sm = eng.store_fetch()
+    assert np.array_equal(so, mo) and np.array_equal(sm, m)
+    for k, min_ab in ((4, 2), (4, 5), (8, 0), (13, 2), (21, 2)):
+        eng.count_begin(k)
+        eng.count_add_store(0, half)            # two insert launches into one table
+        eng.count_add_store(half, 2 ** 63)
+        tab = eng.count_finalize(min_ab)
+        ref = oracle.count(m, mo, k, min_ab)
+        check_table(tab, ref["hashes"], ref["abundances"], ref["vecs"], [ref["n_instances"], ref["n_distinct"]])
+        assert tab.checksum == oracle.checksum(ref["hashes"], ref["abundances"])
+    eng.close()
+
+
+def test_count_add_host_reads(built, oracle):
+    rng = np.random.default_rng(3)
+    reads = [rng.integers(0, 50, size=int(rng.integers(0, 90))).astype(np.uint32) for _ in range(2000)]
+    offs = np.zeros(len(reads) + 1, np.uint64)
+    offs[1:] = np.cumsum([len(r) for r in reads])
+    mins = np.concatenate(reads).astype(np.uint32)
+    from metamdbg_b200 import KminmerCounter
+    eng = engine()
+    kc = KminmerCounter(eng, 5, expected_distinct=200_000)
+    kc.add_reads(mins[:int(offs[700])], offs[:701])
+    kc.add_reads(mins, offs[700:])               # offsets not starting at 0
+    tab = kc.execute(2)
+    ref = oracle.count(mins, offs, 5, 2)
+    check_table(tab, ref["hashes"], ref["abundances"], ref["vecs"])
+    eng.close()
+
+
+def test_table_full_is_reported(built):
+    from metamdbg_b200 import MdbgError
+    rng = np.random.default_rng(4)
+    mins = rng.integers(0, 2 ** 32, size=200_000, dtype=np.uint64).astype(np.uint32)
+    offs = np.array([0, len(mins)], np.uint64)
+    eng = engine()
+    eng.count_begin(4, expected_distinct=256)    # far too small
+    with pytest.raises(MdbgError) as e:
+        eng.count_add(mins, offs)
+    assert e.value.status == 4
+    eng.close()
+
+
+# ---------------------------------------------------------------- device-resident path + generator
+
+def test_device_generator_matches_numpy_and_device_sketch(built, oracle):
+    import torch
+    rs = synth.make_readset(500, 7000, seed=77, n_genomes=2, genome_len_range=(100_000, 200_000))
+    bases, offs = synth.fill_reads(rs)
+    eng = engine()
+    dev = torch.device("cuda:0")
+    d_off = torch.from_numpy(offs.astype(np.int64)).to(dev)
+    d_vs = torch.from_numpy(rs.vstart.astype(np.int64)).to(dev)
+    d_st = torch.from_numpy(rs.strand).to(dev)
+    d_bases = torch.empty(int(offs[-1]) + 64, dtype=torch.uint8, device=dev)
+    eng.synth_fill_reads(d_bases.data_ptr(), d_off.data_ptr(), d_vs.data_ptr(), d_st.data_ptr(), rs.n_reads, 0,
+                         rs.seed, rs.err_q24)
+    eng.synchronize()
+    assert np.array_equal(d_bases[:int(offs[-1])].cpu().numpy(), bases)
+    out = eng.sketch_batch_device(d_bases.data_ptr(), d_off.data_ptr(), rs.n_reads, int(offs[-1]), True)
+    sk = eng.sketch_fetch()
+    assert out.n_minimizers == len(sk.minimizers)
+    assert_sketch_equal(sk, *oracle.sketch_batch(bases, offs, 15, 0.005, True))
+    eng.close()
+
+
+def test_python_mirror_single_read(built, oracle):
+    from metamdbg_b200 import MinimizerParser
+    rs = synth.make_readset(3, 20000, seed=8, n_genomes=1, genome_len_range=(100_000, 100_001))
+    bases, offs = synth.fill_reads(rs)
+    mp = MinimizerParser(15, 0.005, None, True)
+    seq = bases[:int(offs[1])].tobytes()
+    m, p, d = mp.parse(seq)
+    rm, rp, rd = oracle.sketch_read(seq, 15, 0.005, True)
+    assert np.array_equal(m, rm) and np.array_equal(p, rp) and np.array_equal(d, rd)
+    mp.engine.close()
