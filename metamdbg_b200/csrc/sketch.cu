@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sketch_kernel(const Sketch
             const int pmax_final = (int)avail - (int)l - 1;
             for (;;) {
                 int pmax;
-                if (avail - done >= (uint32_t)BLK + l) pmax = 0x7fffffff;
+                if (avail >= done + (uint32_t)BLK + l) pmax = 0x7fffffff;   // (done may pass avail at the end)
                 else if (final_ && (int)done <= pmax_final) pmax = pmax_final;
                 else break;
 
