@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py -- Gbp/s through minimizer-sketch + k-min-mer count (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this engine
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU path (oracle/_ref)
+
+Workload (config.workload): BASELINE.json configs[1] per GPU -- 1 M synthetic
+HiFi reads x 15 kbp, l=15, d=0.005, HPC on, k=4, abundance >= 2.  A "step" is
+one pass of the hot path over that batch: sketch -> minimizer store ->
+purgePalindromes -> k-min-mer insert -> [NCCL owner merge for N>1] -> table
+statistics.  `value` times it with the reads resident in HBM; `e2e` times the
+same work through the host-buffer C ABI (H2D of the ASCII reads, D2H of the
+minimizer CSR and of the finalised table inside the timed region).  For N>1
+every rank processes its own shard of N x 1 M reads (weak scaling) and the only
+data-path collective is the owner-partitioned table merge.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+L, DENSITY, HPC, K, MIN_AB = 15, 0.005, True, 4, 2
+SEED = 20260924
+
+
+def workload_config(args):
+    return {
+        "workload": "cfg2: 1M synthetic HiFi reads x 15 kbp per GPU, l=15 d=0.005 HPC k=4 min-abundance 2"
+        if (args.reads == 1_000_000 and args.read_len == 15_000) else
+        f"{args.reads} synthetic HiFi reads x {args.read_len} bp per GPU, l=15 d=0.005 HPC k=4 min-abundance 2",
+        "reads_per_gpu": args.reads, "read_len_mean": args.read_len, "minimizer_size": L, "density": DENSITY,
+        "hpc": HPC, "k": K, "min_abundance": MIN_AB, "purge_last_k": purge_last_k(args),
+        "genomes": args.genomes, "substitution_rate": 0.001, "input_format": "ASCII bases (Read::_seq)",
+        "l2_policy": "inputs (>= 1 GB per step) are far larger than the 126 MB L2; no explicit flush",
+    }
+
+
+def purge_last_k(args):
+    # Commons::computeLastK (src/Commons.hpp:1726-1741): n50 * density * 2, at least firstK+2
+    return max(int(args.read_len * np.float32(DENSITY) * np.float32(2.0)), 6)
+
+
+# ---------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons, self.proc = index, [], set(), None
+        self.max_mhz = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                self.samples.append(float(f[0])); self.max_mhz = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(n)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ---------------------------------------------------------------- reference arm
+def run_reference(args, rank: int):
+    """The reference's own CPU implementation of the path (oracle/_ref = metaMDBG sources compiled
+    as they are; falls back to the C restatement when that library is absent), all host threads,
+    on a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    from metamdbg_b200 import synth
+    from oracle import pyoracle
+    cores = os.cpu_count() or 1
+    try:
+        ref = pyoracle.Reference()
+        kind = "reference"
+        threads = min(cores, ref.max_threads())
+    except (FileNotFoundError, OSError):
+        ref, kind, threads = None, "port", 1
+    n_sample = args.ref_reads or int(min(args.reads, max(2000, 400 * threads)))
+    rs = synth.make_readset(args.reads * max(1, args.gpus), args.read_len, seed=SEED, n_genomes=args.genomes)
+    sub = rs.subset(0, n_sample)
+    bases, offs = synth.fill_reads(sub)
+    n_bases = int(offs[-1])
+    lk = purge_last_k(args)
+
+    def one():
+        t0 = time.perf_counter()
+        if ref is not None:
+            res = ref.pipeline(bases, offs, L, DENSITY, HPC, K, purge_last_k=lk, min_abundance=MIN_AB, threads=threads)
+        else:
+            orc = pyoracle.Oracle()
+            mo, m, p, d = orc.sketch_batch(bases, offs, L, DENSITY, HPC)
+            c = orc.count(m, mo, K, MIN_AB)
+            res = dict(n_solid=len(c["abundances"]), n_minimizers=len(m))
+        return time.perf_counter() - t0, res
+
+    for _ in range(args.warmup):
+        one()
+    ts = []
+    for _ in range(args.steps):
+        t, res = one()
+        ts.append(t)
+    total = sum(ts)
+    gbps = n_bases * args.steps / total / 1e9
+    sample = f"first {n_sample} reads of the workload ({n_bases / 1e9:.3f} Gbp) per step"
+    line = {
+        "impl": "reference", "metric": "Gbp/s through minimizer-sketch + k-min-mer count", "value": gbps,
+        "unit": "Gbp/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic", "config": dict(workload_config(args), sample=sample),
+        "cpu_baseline": {"value": gbps, "unit": "Gbp/s", "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": gbps, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "check": {"n_minimizers": res.get("n_minimizers"), "n_solid": res.get("n_solid")},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------- this engine
+def run_ours(args, rank: int, local_rank: int, world: int):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+
+    ge.build()
+    from metamdbg_b200 import Engine, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: int) -> int:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return int(t.item())
+
+    # ---- synthetic reads, generated straight into HBM -------------------------------
+    rs_all = synth.make_readset(args.reads * world, args.read_len, seed=SEED, n_genomes=args.genomes)
+    rs = rs_all.shard(rank, world)
+    n_reads, n_bases = rs.n_reads, rs.n_bases
+    eng = Engine(L, DENSITY, HPC, device=local_rank)
+    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    eng.enable_timing(True)
+    d_off = torch.from_numpy(rs.offsets.astype(np.int64)).to(dev)
+    d_vs = torch.from_numpy(rs.vstart.astype(np.int64)).to(dev)
+    d_st = torch.from_numpy(rs.strand).to(dev)
+    d_bases = torch.empty(n_bases + 64, dtype=torch.uint8, device=dev)
+    eng.synth_fill_reads(d_bases.data_ptr(), d_off.data_ptr(), d_vs.data_ptr(), d_st.data_ptr(), n_reads,
+                         rs.index_base, rs.seed, rs.err_q24)
+    torch.cuda.synchronize()
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(Engine.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        eng.comm_init(rank, world, bytes(uid.cpu().numpy().tobytes()))
+    lk = purge_last_k(args)
+
+    def step_device():
+        eng.store_clear()
+        eng.sketch_batch_device(d_bases.data_ptr(), d_off.data_ptr(), n_reads, n_bases, True)
+        eng.purge_palindromes(4, lk)
+        eng.count_begin(K, 0)
+        eng.count_add_store()
+        if world > 1:
+            eng.count_merge()
+        return eng.count_stats(MIN_AB)
+
+    # ---- device-resident timing ---------------------------------------------------------
+    for _ in range(args.warmup):
+        stats = step_device()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sketch_ms, insert_ms = [], []
+    e0.record()
+    for _ in range(args.steps):
+        stats = step_device()
+        sketch_ms.append(eng.kernel_time_ms(0))
+        insert_ms.append(eng.kernel_time_ms(1))
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    launches = eng.kernel_launches - launches0
+    total_bases = sum_over_ranks(n_bases)
+    value = total_bases * args.steps / (ms_total * 1e-3) / 1e9
+    n_min_store = eng.store_size()[1]
+    solid_total = sum_over_ranks(stats["n_entries"])
+    checksum_local = stats["checksum"]
+
+    # ---- end to end through the host-buffer C ABI ---------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        e_reads = min(n_reads, args.e2e_reads or n_reads)
+        e_bases = int(rs.offsets[e_reads])
+        h_bases = torch.empty(e_bases, dtype=torch.uint8, pin_memory=True)
+        h_bases.copy_(d_bases[:e_bases])
+        h_offs = rs.offsets[:e_reads + 1].copy()
+        torch.cuda.synchronize()
+        batch = args.e2e_batch
+        d2h = [0]
+
+        def step_e2e():
+            d2h[0] = 0
+            eng.store_clear()
+            for lo in range(0, e_reads, batch):
+                hi = min(e_reads, lo + batch)
+                offs = h_offs[lo:hi + 1] - h_offs[lo]
+                sk = eng.sketch_batch_ptr(h_bases.data_ptr() + int(h_offs[lo]), offs, True)
+                d2h[0] += 8 * (hi - lo + 1) + 9 * sk
+            eng.purge_palindromes(4, lk)
+            eng.count_begin(K, 0)
+            eng.count_add_store()
+            if world > 1:
+                eng.count_merge()
+            tab = eng.count_finalize(MIN_AB)
+            d2h[0] += len(tab.abundances) * (16 + 4 + 4 * K)
+            return tab
+
+        for _ in range(max(1, min(args.warmup, 2))):
+            tab = step_e2e()
+        e_steps = max(1, min(args.steps, args.e2e_steps))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            tab = step_e2e()
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        e_total = sum_over_ranks(e_bases)
+        e2e = {"value": e_total * e_steps / dt / 1e9, "unit": "Gbp/s",
+               "h2d_bytes_per_step": int(e_bases + 8 * (e_reads + 1)), "d2h_bytes_per_step": int(d2h[0]),
+               "steps": e_steps, "reads_per_gpu": e_reads, "host_batch_reads": batch,
+               "timer": "host wall clock around synchronous C-ABI calls, max over ranks"}
+        if world == 1 and e_reads == n_reads:
+            assert tab.checksum == checksum_local, "e2e table differs from the device-resident table"
+        del h_bases
+
+    # ---- CPU baseline (rank 0, N=1 only) + parity spot check against it ------------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import pyoracle
+        cores = os.cpu_count() or 1
+        try:
+            ref = pyoracle.Reference()
+            kind, threads = "reference", min(cores, ref.max_threads())
+        except (FileNotFoundError, OSError):
+            ref, kind, threads = None, "port", 1
+        n_sample = int(min(n_reads, max(2000, 400 * threads)))
+        s_bases = d_bases[:int(rs.offsets[n_sample])].cpu().numpy()
+        s_offs = rs.offsets[:n_sample + 1].copy()
+        t0 = time.perf_counter()
+        if ref is not None:
+            res = ref.pipeline(s_bases, s_offs, L, DENSITY, HPC, K, purge_last_k=lk, min_abundance=MIN_AB,
+                               threads=threads)
+            ref_solid, ref_cs, ref_nmin = res["n_solid"], res["checksum"], res["n_minimizers"]
+        else:
+            orc = pyoracle.Oracle()
+            mo, m, p, d = orc.sketch_batch(s_bases, s_offs, L, DENSITY, HPC)
+            c = orc.count(m, mo, K, MIN_AB)
+            ref_solid, ref_cs, ref_nmin = len(c["abundances"]), orc.checksum(c["hashes"], c["abundances"]), len(m)
+        dt = time.perf_counter() - t0
+        # same sample through the GPU engine: bit-exact fingerprint must agree
+        eng.store_clear()
+        eng.sketch_batch_device(d_bases.data_ptr(), d_off.data_ptr(), n_sample, int(s_offs[-1]), True)
+        eng.purge_palindromes(4, lk)
+        eng.count_begin(K, 0)
+        eng.count_add_store()
+        g = eng.count_stats(MIN_AB)
+        ok = (g["n_entries"] == ref_solid and g["checksum"] == ref_cs and eng.store_size()[1] == ref_nmin)
+        if not ok:
+            raise SystemExit(f"bench.py: GPU result differs from the CPU {kind} on the sample: {g} vs "
+                             f"{ref_solid}/{ref_cs}/{ref_nmin}")
+        cpu_baseline = {"value": int(s_offs[-1]) / dt / 1e9, "unit": "Gbp/s", "cores": threads, "kind": kind,
+                        "sample": f"first {n_sample} reads ({int(s_offs[-1]) / 1e9:.3f} Gbp), one pass, "
+                                  f"GPU fingerprint (n_minimizers, n_solid, checksum) identical"}
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        sk_ms = float(np.mean(sketch_ms))
+        algo_bytes = n_bases * 1.0 + n_min_store * 9.0      # 1 B/bp ASCII in + 9 B per minimizer out
+        achieved = algo_bytes / (sk_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if tj.get("reads") == n_reads and tj.get("kernel") == "sketch_kernel":
+                traffic = tj.get("dram_bytes_per_launch")
+        line = {
+            "metric": "Gbp/s through minimizer-sketch + k-min-mer count", "value": value, "unit": "Gbp/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": workload_config(args), "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "sketch_kernel<15>", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "ms_per_launch": sk_ms, "algorithmic_bytes_per_launch": algo_bytes,
+                         "note": "integer-issue bound (one MurmurHash3_x64_128 per l-mer), see DESIGN.md",
+                         "share_of_step": sk_ms / (ms_total / args.steps)},
+            "kernels_ms": {"sketch": sk_ms, "insert": float(np.mean(insert_ms))},
+            "cpu_baseline": cpu_baseline,
+            "check": {"n_minimizers_rank0": int(n_min_store), "n_solid_total": int(solid_total),
+                      "checksum_rank0": int(checksum_local)},
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=1_000_000, help="reads per GPU")
+    ap.add_argument("--read-len", type=int, default=15_000)
+    ap.add_argument("--genomes", type=int, default=100)
+    ap.add_argument("--e2e-reads", type=int, default=0, help="reads per GPU in the e2e leg (0 = all)")
+    ap.add_argument("--e2e-batch", type=int, default=65_536, help="reads per host-buffer C-ABI call")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--ref-reads", type=int, default=0, help="sample size of the reference arm (0 = auto)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    args.warmup = max(args.warmup, 3)       # timing rule: at least 3 warm-up steps
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("bench.py: --gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

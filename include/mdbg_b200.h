@@ -117,6 +117,11 @@ mdbg_status mdbg_ctx_set_stream(mdbg_ctx* ctx, void* cuda_stream);
 mdbg_status mdbg_ctx_synchronize(mdbg_ctx* ctx);
 /* Number of this library's kernels launched on the context so far. */
 uint64_t    mdbg_ctx_kernel_launches(mdbg_ctx* ctx);
+/* Per-kernel device timing (CUDA events recorded on the context's stream around
+ * the launch).  which: 0 = sketch kernel (K1), 1 = k-min-mer insert kernel (K3).
+ * Returns the duration of the most recent launch of that kernel in ms. */
+mdbg_status mdbg_ctx_enable_timing(mdbg_ctx* ctx, int on);
+mdbg_status mdbg_ctx_kernel_time_ms(mdbg_ctx* ctx, int which, float* ms);
 
 /* ---- sketch (rows A1-A3 of SURVEY.md section 8a) -------------------------- */
 /* Host reads: read r = bases[offsets[r] .. offsets[r+1]) (ASCII, as Read::_seq).

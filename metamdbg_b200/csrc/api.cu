@@ -52,6 +52,9 @@ struct mdbg_ctx {
     cudaStream_t stream = nullptr;
     std::string error;
     uint64_t launches = 0;
+    bool timing = false;
+    cudaEvent_t ev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    bool ev_valid[2] = {false, false};
 
     // parameters
     uint32_t l = 15;
@@ -221,7 +224,9 @@ mdbg_status sketch_internal(mdbg_ctx* ctx, const uint8_t* d_bases, const uint64_
 
     CK(cudaMemsetAsync(&ctx->d_small->cursor, 0, sizeof(uint32_t), s));
     CK(cudaMemsetAsync(&ctx->d_small->n_overflow, 0, sizeof(unsigned long long), s));
+    if (ctx->timing) CK(cudaEventRecord(ctx->ev[0][0], s));
     launch_sketch(a, ctx->sm_count, s);
+    if (ctx->timing) { CK(cudaEventRecord(ctx->ev[0][1], s)); ctx->ev_valid[0] = true; }
     CKS(check_launch(ctx, "sketch_kernel", 1));
     launch_scan_u32_to_u64(ctx->n_min.as<uint32_t>(), ctx->b_off.as<uint64_t>(), n_reads,
                            ctx->scan_scratch.as<uint64_t>(), s);
@@ -409,6 +414,9 @@ void mdbg_ctx_destroy(mdbg_ctx* c) {
     if (c->d_small) cudaFree(c->d_small);
     if (c->h_small) cudaFreeHost(c->h_small);
     if (c->h_scalar) cudaFreeHost(c->h_scalar);
+    for (int i = 0; i < 2; i++)
+        for (int j = 0; j < 2; j++)
+            if (c->ev[i][j]) cudaEventDestroy(c->ev[i][j]);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -429,6 +437,24 @@ mdbg_status mdbg_ctx_synchronize(mdbg_ctx* ctx) {
 }
 
 uint64_t mdbg_ctx_kernel_launches(mdbg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+mdbg_status mdbg_ctx_enable_timing(mdbg_ctx* ctx, int on) {
+    if (!ctx) return MDBG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (on && !ctx->ev[0][0])
+        for (int i = 0; i < 2; i++)
+            for (int j = 0; j < 2; j++) CK(cudaEventCreate(&ctx->ev[i][j]));
+    ctx->timing = on != 0;
+    return MDBG_OK;
+}
+
+mdbg_status mdbg_ctx_kernel_time_ms(mdbg_ctx* ctx, int which, float* ms) {
+    if (!ctx || !ms || which < 0 || which > 1) return MDBG_ERR_ARG;
+    if (!ctx->ev_valid[which]) return fail(ctx, MDBG_ERR_STATE, "no timed launch of kernel %d yet", which);
+    CK(cudaEventSynchronize(ctx->ev[which][1]));
+    CK(cudaEventElapsedTime(ms, ctx->ev[which][0], ctx->ev[which][1]));
+    return MDBG_OK;
+}
 
 // ---- sketch -----------------------------------------------------------------------
 mdbg_status mdbg_sketch_batch_device(mdbg_ctx* ctx, const uint8_t* d_bases, const uint64_t* d_offsets,
@@ -643,7 +669,9 @@ mdbg_status mdbg_count_add_store(mdbg_ctx* ctx, uint64_t read_lo, uint64_t read_
     a.table = ctx->table.as<Slot>();
     a.mask = ctx->t_capacity - 1;
     a.full_flag = &ctx->d_small->full_flag;
+    if (ctx->timing) CK(cudaEventRecord(ctx->ev[1][0], s));
     launch_insert(a, s);
+    if (ctx->timing) { CK(cudaEventRecord(ctx->ev[1][1], s)); ctx->ev_valid[1] = true; }
     CKS(check_launch(ctx, "insert_kernel", g_hi > g_lo ? 1 : 0));
     CK(cudaMemcpyAsync(&ctx->h_small->full_flag, &ctx->d_small->full_flag, 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));

@@ -104,6 +104,15 @@ class Engine:
     def kernel_launches(self) -> int:
         return int(self._lib.mdbg_ctx_kernel_launches(self._ctx))
 
+    def enable_timing(self, on: bool = True):
+        self._ck(self._lib.mdbg_ctx_enable_timing(self._ctx, int(on)))
+
+    def kernel_time_ms(self, which: int) -> float:
+        """Device time of the last sketch (0) / insert (1) kernel launch."""
+        ms = C.c_float(0)
+        self._ck(self._lib.mdbg_ctx_kernel_time_ms(self._ctx, which, C.byref(ms)))
+        return float(ms.value)
+
     # -- sketch ---------------------------------------------------------------
     @staticmethod
     def _copy_sketch(out: SketchOut) -> Sketch:
@@ -126,6 +135,16 @@ class Engine:
         self._ck(self._lib.mdbg_sketch_batch(self._ctx, bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1,
                                              int(append_to_store), C.byref(out) if fetch else None))
         return self._copy_sketch(out) if fetch else None
+
+    def sketch_batch_ptr(self, bases_ptr: int, offsets: np.ndarray, append_to_store: bool = True,
+                         fetch: bool = True) -> int:
+        """Host reads given as a raw pointer (e.g. a pinned buffer) + uint64 offsets; the CSR lands in the
+        library's pinned result buffers (no numpy copy).  Returns the number of minimizers."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        out = SketchOut()
+        self._ck(self._lib.mdbg_sketch_batch(self._ctx, C.c_void_p(bases_ptr), offsets.ctypes.data, len(offsets) - 1,
+                                             int(append_to_store), C.byref(out) if fetch else None))
+        return int(out.n_minimizers) if fetch else 0
 
     def sketch_batch_device(self, d_bases_ptr: int, d_offsets_ptr: int, n_reads: int, n_bases: int,
                             append_to_store: bool = False) -> SketchDev:

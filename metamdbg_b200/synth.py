@@ -47,6 +47,7 @@ class ReadSet:
     strand: np.ndarray           # uint8  [n] 1 = reverse complement
     n_genomes: int
     genome_len: np.ndarray       # uint64 [G]
+    index_base: int = 0          # global index of this set's first read (error stream is keyed by global index)
 
     @property
     def n_reads(self) -> int:
@@ -60,14 +61,15 @@ class ReadSet:
         """Contiguous record range for one rank."""
         n = self.n_reads
         lo, hi = n * rank // world, n * (rank + 1) // world
-        off = self.offsets[lo:hi + 1] - self.offsets[lo]
-        return dataclasses.replace(self, offsets=off.copy(), vstart=self.vstart[lo:hi].copy(),
-                                   strand=self.strand[lo:hi].copy())
+        return self.subset(lo, hi)
 
     def subset(self, lo: int, hi: int) -> "ReadSet":
         off = self.offsets[lo:hi + 1] - self.offsets[lo]
-        return dataclasses.replace(self, offsets=off.copy(), vstart=self.vstart[lo:hi].copy(),
-                                   strand=self.strand[lo:hi].copy())
+        rs = dataclasses.replace(self, offsets=off.copy(), vstart=self.vstart[lo:hi].copy(),
+                                 strand=self.strand[lo:hi].copy(), index_base=self.index_base + lo)
+        if hasattr(self, "lengths"):
+            rs.lengths = self.lengths[lo:hi].copy()  # type: ignore[attr-defined]
+        return rs
 
 
 def make_readset(n_reads: int, mean_len: int, *, seed: int = 1, n_genomes: int = 1,
@@ -131,6 +133,7 @@ def fill_reads(rs: ReadSet, lo: int = 0, hi: int | None = None) -> tuple[np.ndar
     s = np.uint64(rs.seed)
     for j, r in enumerate(range(lo, hi)):
         n = int(lens[j])
+        rid = np.uint64(rs.index_base + r)
         i = np.arange(n, dtype=np.uint64)
         with np.errstate(over="ignore"):
             if rs.strand[r]:
@@ -140,7 +143,7 @@ def fill_reads(rs: ReadSet, lo: int = 0, hi: int | None = None) -> tuple[np.ndar
             b = (mix64(q + s) & np.uint64(3)).astype(np.uint8)
             if rs.strand[r]:
                 b = COMP_IDX[b]
-            e = mix64((np.uint64(r) * GOLD) ^ (i + s * np.uint64(0x632BE5AB)))
+            e = mix64((rid * GOLD) ^ (i + s * np.uint64(0x632BE5AB)))
             sub = (e & np.uint64(0xFFFFFF)) < np.uint64(rs.err_q24)
             shift = (np.uint64(1) + (e >> np.uint64(24)) % np.uint64(3)).astype(np.uint8)
             b = np.where(sub, (b + shift) & np.uint8(3), b).astype(np.uint8)
