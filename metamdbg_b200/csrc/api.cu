@@ -589,8 +589,8 @@ mdbg_status mdbg_purge_palindromes(mdbg_ctx* ctx, uint32_t first_k, uint32_t las
     cudaStream_t s = ctx->stream;
     CKS(ensure(ctx, ctx->p_flags, ctx->s_reads));
     CK(cudaMemsetAsync(&ctx->d_small->n_flagged, 0, 2 * sizeof(unsigned long long), s));   // n_flagged, n_changed
-    launch_purge_flag(ctx->s_min.as<uint32_t>(), ctx->s_off.as<uint64_t>(), ctx->s_reads, ctx->p_flags.as<uint8_t>(),
-                      &ctx->d_small->n_flagged, s);
+    launch_purge_flag(ctx->s_min.as<uint32_t>(), ctx->s_off.as<uint64_t>(), ctx->s_reads, first_k, last_k,
+                      ctx->p_flags.as<uint8_t>(), &ctx->d_small->n_flagged, s);
     CKS(check_launch(ctx, "purge_flag_kernel", 1));
     CK(cudaMemcpyAsync(&ctx->h_scalar[0], &ctx->d_small->n_flagged, 8, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));

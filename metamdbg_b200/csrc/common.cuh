@@ -39,6 +39,56 @@ __device__ __forceinline__ uint64_t murmur_h1_u64(uint64_t key) {
     return h1 + h2;
 }
 
+// Cheap superset test for "murmur_h1_u64(key) <= T" with a 32-bit key.
+//
+//   h1 + h2 = fmix64(A) + fmix64(B),  A = (k1 ^ 34) + 34,  B = A + 34
+//   (seed 42, len 8: h1 = 42 ^ k1 ^ 8, h2 = 42 ^ 8, then h1 += h2, h2 += h1).
+//
+// Only the HIGH words of the two fmix64 results are formed: with
+// s0 = hi(fmix(A)) + hi(fmix(B)) (mod 2^32) the true high word of the sum is s0
+// or s0 + 1 (carry out of the low words), so "hash <= T" implies s0 <= T_hi or
+// s0 == 0xFFFFFFFF, i.e. (s0 + 1) <= T_hi + 1 in unsigned arithmetic.  The two
+// +34 additions are done on the low word only; the 2^-26-rare case where one of
+// them carries into the high word is detected (B_lo < 68) and simply reported as
+// a candidate.  Callers confirm every candidate with the exact murmur_h1_u64.
+__device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c) { return a * b + c; }
+
+// fmix64 up to its second multiply: returns the two words (plo, phi) of
+// ((k ^ k>>33) * 0xff51afd7ed558ccd) ^ (.. >> 33); t = hi >> 1 and m = hi * 0xed558ccd are
+// shared by A and B (same high word)
+__device__ __forceinline__ void fmix64_front(uint32_t lo, uint32_t t, uint32_t m, uint32_t& plo, uint32_t& phi) {
+    lo ^= t;                                                   // k ^= k >> 33
+    const uint64_t p = (uint64_t)lo * 0xed558ccdu;             // k *= 0xff51afd7ed558ccd
+    phi = (uint32_t)(p >> 32) + mad_lo(lo, 0xff51afd7u, m);
+    plo = (uint32_t)p ^ (phi >> 1);                            // k ^= k >> 33
+}
+
+__device__ __forceinline__ bool murmur_candidate_u32(uint32_t key, uint32_t thr_hi_plus1) {
+    // k1 = key * c1 ; k1 = rotl64(k1, 31) ; k1 *= c2
+    uint64_t p = (uint64_t)key * 0x114253d5u;
+    uint32_t lo = (uint32_t)p;
+    uint32_t hi = mad_lo(key, 0x87c37b91u, (uint32_t)(p >> 32));
+    const uint32_t rlo = __funnelshift_l(hi, lo, 31);          // low word of (k1 << 31) | (k1 >> 33)
+    const uint32_t rhi = __funnelshift_l(lo, hi, 31);
+    p = (uint64_t)rlo * 0x2745937fu;
+    hi = (uint32_t)(p >> 32) + mad_lo(rlo, 0x4cf5ad43u, rhi * 0x2745937fu);
+    const uint32_t alo = ((uint32_t)p ^ 34u) + 34u;            // A (low word)
+    const uint32_t blo = alo + 34u;                            // B (low word)
+    const uint32_t t = hi >> 1;
+    const uint32_t m = hi * 0xed558ccdu;
+    uint32_t plo_a, phi_a, plo_b, phi_b;
+    fmix64_front(alo, t, m, plo_a, phi_a);
+    fmix64_front(blo, t, m, plo_b, phi_b);
+    // high words of k * 0xc4ceb9fe1a85ec53 for A and B, summed (+1): the final k ^= k >> 33
+    // only changes the low word
+    uint32_t acc = mad_lo(phi_a, 0x1a85ec53u, 1u);
+    acc = mad_lo(plo_a, 0xc4ceb9feu, acc);
+    acc = mad_lo(phi_b, 0x1a85ec53u, acc);
+    acc = mad_lo(plo_b, 0xc4ceb9feu, acc);
+    const uint32_t s1 = acc + __umulhi(plo_a, 0x1a85ec53u) + __umulhi(plo_b, 0x1a85ec53u);
+    return (s1 <= thr_hi_plus1) || (blo < 68u);
+}
+
 // MurmurHash3_x64_128_original(vec, 4*k bytes, seed 0) = KmerVec::hash128
 // (src/Commons.hpp:941-969).  `get(i)` returns the i-th u32 of the normalized
 // vector.  h1 -> high 64 bits of the u128, h2 -> low 64 bits.

@@ -53,8 +53,8 @@ void launch_append_offsets(const uint64_t* batch_off, uint64_t* store_off, uint3
 
 // ------------------------------------------------------------------ purge palindromes
 // flags[r] = 1 when read r may contain a palindromic window (cheap necessary test)
-void launch_purge_flag(const uint32_t* mins, const uint64_t* offs, uint64_t n_reads, uint8_t* flags,
-                       unsigned long long* n_flagged, cudaStream_t s);
+void launch_purge_flag(const uint32_t* mins, const uint64_t* offs, uint64_t n_reads, uint32_t first_k, uint32_t last_k,
+                       uint8_t* flags, unsigned long long* n_flagged, cudaStream_t s);
 // exact Commons::purgePalindrome on flagged reads: keep[g] = 0 for banned minimizers, new_cnt[r] = survivors
 void launch_purge_exact(const uint32_t* mins, const uint64_t* offs, uint64_t n_reads, const uint8_t* flags,
                         uint32_t first_k, uint32_t last_k, uint8_t* keep, uint32_t* new_cnt,

@@ -1,17 +1,32 @@
 // purge.cu -- K2: Commons::purgePalindrome (src/Commons.hpp:1617-1723) over the
 // device-resident minimizer-space reads, plus the synthetic-read generator.
 //
-// A palindromic window (KmerVec::isPalindrome, src/Commons.hpp:918-921) of
-// size k >= 2 needs m[c] == m[c+1] (even k) or m[c-1] == m[c+1] (odd k) at its
-// centre, so a one-pass neighbour test rules out almost every read; only
-// flagged reads run the exact (sequential, order-dependent) banning loop.
+// The reference bans, one at a time, the first minimizer of the first
+// palindromic window it finds scanning k = firstK..lastK-1 and then the start
+// index (KmerVec::isPalindrome, src/Commons.hpp:918-921).  Because a palindrome
+// of size k+2 always contains one of size k, only k = firstK and firstK+1 can
+// ever be found, which turns the O(n^2 lastK) loop into O(n) per banned
+// element; reads without such a window (almost all) are left untouched.
 #include "common.cuh"
 #include "engine.cuh"
 
 namespace mdbg {
 
+// True when the window of k minimizers starting at w is a palindrome
+// (KmerVec::isPalindrome, Commons.hpp:918-921).
+__device__ __forceinline__ bool window_is_palindrome(const uint32_t* w, uint32_t k) {
+    for (uint32_t t = 0; t < k / 2; t++)
+        if (w[t] != w[k - 1 - t]) return false;
+    return true;
+}
+
+// A palindromic window of size k+2 contains the palindromic window of size k
+// with the same centre, and the reference scans k in ascending order
+// (Commons.hpp:1631), so the first window it ever bans has size first_k or
+// first_k+1.  A read is untouched iff it holds no palindrome of those two sizes.
 __global__ void __launch_bounds__(256) purge_flag_kernel(const uint32_t* mins, const uint64_t* offs, uint64_t n_reads,
-                                                         uint8_t* flags, unsigned long long* n_flagged) {
+                                                         uint32_t first_k, uint32_t last_k, uint8_t* flags,
+                                                         unsigned long long* n_flagged) {
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -19,9 +34,8 @@ __global__ void __launch_bounds__(256) purge_flag_kernel(const uint32_t* mins, c
         const uint64_t b = offs[r], e = offs[r + 1];
         bool hit = false;
         for (uint64_t g = b + lane; g < e; g += 32) {
-            const uint32_t m = mins[g];
-            if (g + 1 < e && mins[g + 1] == m) hit = true;
-            if (g + 2 < e && mins[g + 2] == m) hit = true;
+            for (uint32_t k = first_k; k < last_k && k < first_k + 2; k++)
+                if (g + k <= e && window_is_palindrome(mins + g, k)) hit = true;
         }
         hit = __any_sync(0xffffffffu, hit);
         if (lane == 0) {
@@ -31,12 +45,12 @@ __global__ void __launch_bounds__(256) purge_flag_kernel(const uint32_t* mins, c
     }
 }
 
-void launch_purge_flag(const uint32_t* mins, const uint64_t* offs, uint64_t n_reads, uint8_t* flags,
-                       unsigned long long* n_flagged, cudaStream_t s) {
+void launch_purge_flag(const uint32_t* mins, const uint64_t* offs, uint64_t n_reads, uint32_t first_k, uint32_t last_k,
+                       uint8_t* flags, unsigned long long* n_flagged, cudaStream_t s) {
     if (n_reads == 0) return;
     uint64_t blocks = (n_reads + 7) / 8;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    purge_flag_kernel<<<(unsigned)blocks, 256, 0, s>>>(mins, offs, n_reads, flags, n_flagged);
+    purge_flag_kernel<<<(unsigned)blocks, 256, 0, s>>>(mins, offs, n_reads, first_k, last_k, flags, n_flagged);
 }
 
 // Exact restatement of the banning loop for one flagged read, executed by one
@@ -57,7 +71,8 @@ __global__ void __launch_bounds__(128) purge_exact_kernel(const uint32_t* mins, 
     uint8_t* kp = keep + b;                              // 1 = kept (pre-set by the caller)
     for (;;) {                                           // Commons.hpp:1627
         bool has = false;
-        for (long k = first_k; k < (long)last_k && !has; k++) {
+        // only sizes first_k and first_k+1 can be the first palindrome found (see purge_flag_kernel)
+        for (long k = first_k; k < (long)last_k && k < (long)first_k + 2 && !has; k++) {
             const long i_max = n - k + 1;                // Commons.hpp:1635
             for (long i = 0; i < i_max && !has; i++) {
                 if (!kp[i]) continue;

@@ -62,32 +62,41 @@ __device__ __forceinline__ uint32_t byte_of(const uint32_t (&W)[8], int t) {
     return (W[t >> 2] >> (8 * (t & 3))) & 0xFFu;
 }
 
-// Unrolled register path: 16 consecutive l-mers for this lane out of the
-// 32 ring bytes W (no invalid code present).  Returns the 16-bit selection
-// mask; the last selected (value, dir) is left in sel_val / sel_dir.
+// 4 base codes (one per byte, each < 4) -> 8 bits, first base most significant / least significant
+__device__ __forceinline__ uint32_t pack4_msb(uint32_t w) { return (w * 0x40100401u) >> 24; }
+__device__ __forceinline__ uint32_t pack4_lsb(uint32_t w) { return (w * 0x01041040u) >> 24; }
+
+// reverse complement of a 2L-bit l-mer value (A0 C1 T2 G3: complement = code ^ 2)
 template <int L>
-__device__ __forceinline__ uint32_t roll16_fast(const uint32_t (&W)[8], uint64_t threshold, uint32_t& sel_val,
-                                                uint32_t& sel_dir) {
+__device__ __forceinline__ uint32_t revcomp_lmer(uint32_t fwd) {
     constexpr uint32_t MASK = (L < 16) ? ((1u << (2 * L)) - 1u) : 0xFFFFFFFFu;
-    uint32_t fwd = 0, rc = 0;
-#pragma unroll
-    for (int t = 0; t < L - 1; t++) {
-        uint32_t c = byte_of<L>(W, t);
-        fwd = (fwd << 2) | c;
-        rc = (rc >> 2) | ((c ^ 2u) << (2 * L - 2));
-    }
+    uint32_t x = __brev(fwd ^ (0xAAAAAAAAu & MASK));
+    x = ((x & 0x55555555u) << 1) | ((x >> 1) & 0x55555555u);
+    return x >> (32 - 2 * L);
+}
+
+// Unrolled register path: 16 consecutive l-mers for this lane out of the
+// 32 ring bytes W (no invalid code present).  Returns the 16-bit CANDIDATE
+// mask (superset of the selected positions, see murmur_candidate_u32); the
+// forward l-mer of the last candidate is left in sel_fwd.
+template <int L>
+__device__ __forceinline__ uint32_t roll16_fast(const uint32_t (&W)[8], uint32_t thr_hi_plus1, uint32_t& sel_fwd) {
+    constexpr uint32_t MASK = (L < 16) ? ((1u << (2 * L)) - 1u) : 0xFFFFFFFFu;
+    constexpr uint32_t INIT_MASK = (1u << (2 * (L - 1))) - 1u;      // L-1 <= 15 bases
+    // state after the first L-1 bases, built with two multiplies per 4 bases instead of L-1 roll steps
+    const uint32_t pf = (pack4_msb(W[0]) << 24) | (pack4_msb(W[1]) << 16) | (pack4_msb(W[2]) << 8) | pack4_msb(W[3]);
+    const uint32_t pr = pack4_lsb(W[0]) | (pack4_lsb(W[1]) << 8) | (pack4_lsb(W[2]) << 16) | (pack4_lsb(W[3]) << 24);
+    uint32_t fwd = pf >> (2 * (16 - (L - 1)));
+    uint32_t rc = ((pr & INIT_MASK) ^ (0xAAAAAAAAu & INIT_MASK)) << 2;
     uint32_t sel = 0;
 #pragma unroll
     for (int j = 0; j < 16; j++) {
-        uint32_t c = byte_of<L>(W, L - 1 + j);
+        const uint32_t c = byte_of<L>(W, L - 1 + j);
         fwd = ((fwd << 2) | c) & MASK;
         rc = (rc >> 2) | ((c ^ 2u) << (2 * L - 2));
-        uint32_t val = min(fwd, rc);
-        uint64_t h = murmur_h1_u64((uint64_t)val);
-        if (h <= threshold) {
+        if (murmur_candidate_u32(min(fwd, rc), thr_hi_plus1)) {
             sel |= 1u << j;
-            sel_val = val;
-            sel_dir = (fwd < rc) ? 0u : 1u;
+            sel_fwd = fwd;
         }
     }
     return sel;
@@ -123,6 +132,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sketch_kernel(const Sketch
     const uint32_t lane = threadIdx.x & 31;
     uint8_t* ring = ring_all[threadIdx.x >> 5];
     const uint32_t l = a.l;
+    const uint32_t thr_hi_plus1 = (uint32_t)(a.threshold >> 32) + 1u;   // densities < 1: no overflow
 
     for (;;) {
         uint32_t r = 0;
@@ -230,31 +240,39 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sketch_kernel(const Sketch
                     W[4] = u1.x; W[5] = u1.y; W[6] = u1.z; W[7] = u1.w;
                 }
                 const uint32_t inv = (W[0] | W[1] | W[2] | W[3] | W[4] | W[5] | W[6] | W[7]) & 0x04040404u;
-                const bool fast = (L_FAST != 0) && (l == (uint32_t)L_FAST) && !__any_sync(0xffffffffu, inv != 0);
+                const bool fast = (L_FAST != 0) && (l == (uint32_t)L_FAST) && thr_hi_plus1 != 0 &&
+                                  !__any_sync(0xffffffffu, inv != 0);
 
-                uint32_t sel, sel_val = 0, sel_dir = 0;
+                uint32_t sel, sel_fwd = 0;
                 bool regs_ok = false;
                 if (a.select_none) {
                     sel = 0;
                 } else if (fast) {
-                    sel = roll16_fast<(L_FAST ? L_FAST : 15)>(W, a.threshold, sel_val, sel_dir);
+                    sel = roll16_fast<(L_FAST ? L_FAST : 15)>(W, thr_hi_plus1, sel_fwd);
                     regs_ok = (valid_bits == 0xFFFFu);
                     sel &= valid_bits;
                 } else {
                     sel = roll16_generic(ring, p0, l, a.threshold, valid_bits);
                 }
-                if (__any_sync(0xffffffffu, sel != 0)) {
-                    // rare: resolve values, apply the repetitive-minimizer blacklist, write in order
+                const uint32_t hit_lanes = __ballot_sync(0xffffffffu, sel != 0);
+                if (hit_lanes) {
+                    // rare: confirm candidates with the exact hash, apply the repetitive-minimizer
+                    // blacklist, write (value, position, strand) in position order
                     uint32_t v0 = 0, v1 = 0, d0 = 0, d1 = 0;   // register cache for up to 2 hits
-                    uint32_t kept = 0;
+                    uint32_t kept = 0, nsel = 0;
                     uint32_t scan_sel = sel;
-                    uint32_t nsel = 0;
                     while (scan_sel) {
                         const uint32_t j = __ffs(scan_sel) - 1;
                         scan_sel &= scan_sel - 1;
                         uint64_t key; uint32_t dir;
-                        if (regs_ok && __popc(sel) == 1) { key = sel_val; dir = sel_dir; }
-                        else lmer_at(ring, p0 + j, l, key, dir);
+                        if (regs_ok && __popc(sel) == 1) {
+                            const uint32_t rcv = revcomp_lmer<(L_FAST ? L_FAST : 15)>(sel_fwd);
+                            dir = (sel_fwd < rcv) ? 0u : 1u;
+                            key = dir ? rcv : sel_fwd;
+                        } else {
+                            lmer_at(ring, p0 + j, l, key, dir);
+                        }
+                        if (murmur_h1_u64(key) > a.threshold) continue;        // exact test (Kmer.hpp:1434)
                         const uint32_t v32 = (uint32_t)key;          // Kmer.hpp:1441 truncation
                         if (a.n_blacklist && blacklisted(a.blacklist, a.n_blacklist, v32)) continue;
                         kept |= 1u << j;
@@ -262,9 +280,18 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sketch_kernel(const Sketch
                         else if (nsel == 1) { v1 = v32; d1 = dir; }
                         nsel++;
                     }
-                    const uint32_t incl = warp_inclusive_scan(nsel);
-                    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-                    uint64_t e = (uint64_t)out_cnt + incl - nsel;
+                    uint32_t before, total;
+                    const uint32_t multi = __ballot_sync(0xffffffffu, nsel > 1);
+                    if (multi == 0) {                       // common: at most one hit per lane
+                        const uint32_t m1 = __ballot_sync(0xffffffffu, nsel == 1);
+                        before = __popc(m1 & ((1u << lane) - 1u));
+                        total = __popc(m1);
+                    } else {
+                        const uint32_t incl = warp_inclusive_scan(nsel);
+                        total = __shfl_sync(0xffffffffu, incl, 31);
+                        before = incl - nsel;
+                    }
+                    uint64_t e = (uint64_t)out_cnt + before;
                     uint32_t i = 0;
                     while (kept) {
                         const uint32_t j = __ffs(kept) - 1;
