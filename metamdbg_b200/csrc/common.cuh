@@ -49,8 +49,12 @@ __device__ __forceinline__ uint64_t murmur_h1_u64(uint64_t key) {
 // or s0 + 1 (carry out of the low words), so "hash <= T" implies s0 <= T_hi or
 // s0 == 0xFFFFFFFF, i.e. (s0 + 1) <= T_hi + 1 in unsigned arithmetic.  The two
 // +34 additions are done on the low word only; the 2^-26-rare case where one of
-// them carries into the high word is detected (B_lo < 68) and simply reported as
-// a candidate.  Callers confirm every candidate with the exact murmur_h1_u64.
+// them carries into the high word is detected (B_lo < 68) and reported as s1 = 0.
+//
+// murmur_s1_u32 returns s1 = s0 + 1 (or 0).  With T_hi = threshold >> 32:
+//   s1 >  T_hi + 1            -> certainly not selected
+//   1 <= s1 < T_hi            -> certainly selected (sum_hi <= s1 < T_hi)
+//   otherwise (s1 in {0, T_hi, T_hi + 1}) -> undecided: callers run the exact murmur_h1_u64.
 __device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c) { return a * b + c; }
 
 // fmix64 up to its second multiply: returns the two words (plo, phi) of
@@ -63,7 +67,7 @@ __device__ __forceinline__ void fmix64_front(uint32_t lo, uint32_t t, uint32_t m
     plo = (uint32_t)p ^ (phi >> 1);                            // k ^= k >> 33
 }
 
-__device__ __forceinline__ bool murmur_candidate_u32(uint32_t key, uint32_t thr_hi_plus1) {
+__device__ __forceinline__ uint32_t murmur_s1_u32(uint32_t key) {
     // k1 = key * c1 ; k1 = rotl64(k1, 31) ; k1 *= c2
     uint64_t p = (uint64_t)key * 0x114253d5u;
     uint32_t lo = (uint32_t)p;
@@ -86,7 +90,7 @@ __device__ __forceinline__ bool murmur_candidate_u32(uint32_t key, uint32_t thr_
     acc = mad_lo(phi_b, 0x1a85ec53u, acc);
     acc = mad_lo(plo_b, 0xc4ceb9feu, acc);
     const uint32_t s1 = acc + __umulhi(plo_a, 0x1a85ec53u) + __umulhi(plo_b, 0x1a85ec53u);
-    return (s1 <= thr_hi_plus1) || (blo < 68u);
+    return (blo < 68u) ? 0u : s1;                              // 0 = "undecided, run the exact hash"
 }
 
 // MurmurHash3_x64_128_original(vec, 4*k bytes, seed 0) = KmerVec::hash128

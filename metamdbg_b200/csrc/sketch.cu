@@ -31,6 +31,20 @@ __device__ __forceinline__ uint32_t nib16(uint32_t a, uint32_t b, uint32_t c, ui
     return (nib(a) & 0xF) | ((nib(b) & 0xF) << 4) | ((nib(c) & 0xF) << 8) | ((nib(d) & 0xF) << 12);
 }
 
+// 0x80 in every byte of x that is non-zero (exact for arbitrary bytes)
+__device__ __forceinline__ uint32_t nonzero_bytes(uint32_t x) {
+    return (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
+}
+// four words of per-byte 0x80 flags -> 16-bit mask (bit 4q+b = byte b of word q)
+__device__ __forceinline__ uint32_t flags_to_mask16(uint32_t f0, uint32_t f1, uint32_t f2, uint32_t f3) {
+    // multiply gathers bits 7,15,23,31 into bits 28..31
+    const uint32_t a = (f0 * 0x00204081u) >> 28;
+    const uint32_t b = (f1 * 0x00204081u) >> 24;
+    const uint32_t c = (f2 * 0x00204081u) >> 20;
+    const uint32_t d = (f3 * 0x00204081u) >> 16;
+    return a | (b & 0xF0u) | (c & 0xF00u) | (d & 0xF000u);
+}
+
 __device__ __forceinline__ bool blacklisted(const uint32_t* bl, uint32_t n, uint32_t v) {
     uint32_t lo = 0, hi = n;
     while (lo < hi) {
@@ -77,10 +91,11 @@ __device__ __forceinline__ uint32_t revcomp_lmer(uint32_t fwd) {
 
 // Unrolled register path: 16 consecutive l-mers for this lane out of the
 // 32 ring bytes W (no invalid code present).  Returns the 16-bit CANDIDATE
-// mask (superset of the selected positions, see murmur_candidate_u32); the
-// forward l-mer of the last candidate is left in sel_fwd.
+// mask (superset of the selected positions, see murmur_s1_u32); the forward
+// l-mer and the s1 value of the last candidate are left in sel_fwd / sel_s1.
 template <int L>
-__device__ __forceinline__ uint32_t roll16_fast(const uint32_t (&W)[8], uint32_t thr_hi_plus1, uint32_t& sel_fwd) {
+__device__ __forceinline__ uint32_t roll16_fast(const uint32_t (&W)[8], uint32_t thr_hi_plus1, uint32_t& sel_fwd,
+                                                uint32_t& sel_s1) {
     constexpr uint32_t MASK = (L < 16) ? ((1u << (2 * L)) - 1u) : 0xFFFFFFFFu;
     constexpr uint32_t INIT_MASK = (1u << (2 * (L - 1))) - 1u;      // L-1 <= 15 bases
     // state after the first L-1 bases, built with two multiplies per 4 bases instead of L-1 roll steps
@@ -94,9 +109,11 @@ __device__ __forceinline__ uint32_t roll16_fast(const uint32_t (&W)[8], uint32_t
         const uint32_t c = byte_of<L>(W, L - 1 + j);
         fwd = ((fwd << 2) | c) & MASK;
         rc = (rc >> 2) | ((c ^ 2u) << (2 * L - 2));
-        if (murmur_candidate_u32(min(fwd, rc), thr_hi_plus1)) {
+        const uint32_t s1 = murmur_s1_u32(min(fwd, rc));
+        if (s1 <= thr_hi_plus1) {
             sel |= 1u << j;
             sel_fwd = fwd;
+            sel_s1 = s1;
         }
     }
     return sel;
@@ -128,11 +145,12 @@ __device__ __forceinline__ uint32_t roll16_generic(const uint8_t* ring, uint32_t
 
 template <int L_FAST>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sketch_kernel(const SketchArgs a) {
-    __shared__ __align__(16) uint8_t ring_all[WARPS_PER_CTA][RING];
+    __shared__ __align__(16) uint8_t ring_all[WARPS_PER_CTA][RING + 16];   // +16: linear-write slack
     const uint32_t lane = threadIdx.x & 31;
     uint8_t* ring = ring_all[threadIdx.x >> 5];
     const uint32_t l = a.l;
-    const uint32_t thr_hi_plus1 = (uint32_t)(a.threshold >> 32) + 1u;   // densities < 1: no overflow
+    const uint32_t thr_hi_plus1 = (uint32_t)(a.threshold >> 32) + 1u;   // 0 (overflow) disables the fast path
+    const uint32_t sure_lim = thr_hi_plus1 >= 2u ? thr_hi_plus1 - 2u : 0u;
 
     for (;;) {
         uint32_t r = 0;
@@ -163,53 +181,79 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sketch_kernel(const Sketch
             // ---- fill: append HPC base codes to the ring ----------------------
             while (chunk < n_chunks && avail - done < (uint32_t)BLK + l) {
                 const uint32_t x0 = chunk * CHUNK + lane * 16;
+                // interior chunk: every byte of every lane belongs to the read (all but the first/last chunk)
+                const bool interior = (chunk * CHUNK >= skip) && ((chunk + 1) * CHUNK <= x_end);
                 uint4 w = make_uint4(0, 0, 0, 0);
-                if (x0 < x_end && x0 + 16 > skip) {
-                    const uint8_t* p = abase + x0;
-                    if (p + 16 <= a.bases_end) {
-                        w = *reinterpret_cast<const uint4*>(p);
-                    } else {                             // last 16 bytes of the buffer: byte loads
-                        uint32_t t[4] = {0, 0, 0, 0};
-                        for (int j = 0; j < 16; j++)
-                            if (p + j < a.bases_end) t[j >> 2] |= (uint32_t)p[j] << (8 * (j & 3));
-                        w = make_uint4(t[0], t[1], t[2], t[3]);
+                uint32_t vm = 0xFFFFu;
+                if (interior) {
+                    w = *reinterpret_cast<const uint4*>(abase + x0);
+                } else {
+                    if (x0 < x_end && x0 + 16 > skip) {
+                        const uint8_t* p = abase + x0;
+                        if (p + 16 <= a.bases_end) {
+                            w = *reinterpret_cast<const uint4*>(p);
+                        } else {                         // last 16 bytes of the buffer: byte loads
+                            uint32_t t[4] = {0, 0, 0, 0};
+                            for (int j = 0; j < 16; j++)
+                                if (p + j < a.bases_end) t[j >> 2] |= (uint32_t)p[j] << (8 * (j & 3));
+                            w = make_uint4(t[0], t[1], t[2], t[3]);
+                        }
                     }
+                    // validity of each of my 16 bytes: skip <= x0+j < x_end
+                    const uint32_t lo = (skip > x0) ? min(skip - x0, 16u) : 0u;
+                    const uint32_t hi = (x_end > x0) ? min(x_end - x0, 16u) : 0u;
+                    vm = (hi > lo) ? (((1u << hi) - 1u) & ~((1u << lo) - 1u)) : 0u;
                 }
-                // validity of each of my 16 bytes: skip <= x0+j < x_end
-                const uint32_t lo = (skip > x0) ? min(skip - x0, 16u) : 0u;
-                const uint32_t hi = (x_end > x0) ? min(x_end - x0, 16u) : 0u;
-                const uint32_t vm = (hi > lo) ? (((1u << hi) - 1u) & ~((1u << lo) - 1u)) : 0u;
                 uint32_t pb = __shfl_up_sync(0xffffffffu, w.w >> 24, 1);
                 if (lane == 0) pb = carry;
                 carry = __shfl_sync(0xffffffffu, w.w >> 24, 31);
 
                 uint32_t keep = vm;
                 if (a.hpc) {
-                    const uint32_t e0 = __vcmpeq4(w.x, (w.x << 8) | pb);
-                    const uint32_t e1 = __vcmpeq4(w.y, (w.y << 8) | (w.x >> 24));
-                    const uint32_t e2 = __vcmpeq4(w.z, (w.z << 8) | (w.y >> 24));
-                    const uint32_t e3 = __vcmpeq4(w.w, (w.w << 8) | (w.z >> 24));
-                    const uint32_t h0 = __vcmpeq4(w.x, 0x23232323u), h1 = __vcmpeq4(w.y, 0x23232323u);
-                    const uint32_t h2 = __vcmpeq4(w.z, 0x23232323u), h3 = __vcmpeq4(w.w, 0x23232323u);
-                    uint32_t k16 = ~nib16(e0 | h0, e1 | h1, e2 | h2, e3 | h3) & 0xFFFFu;
-                    if (skip >= x0 && skip < x0 + 16) {  // first base of the read: previous char is the '#' sentinel
-                        const uint32_t fb = 1u << (skip - x0);
-                        k16 |= fb & ~nib16(h0, h1, h2, h3);
+                    // EncoderRLE (Commons.hpp:4172-4190): a base survives iff it differs from the previous
+                    // char and is not the '#' sentinel.  x_q has a zero byte where byte == previous byte.
+                    const uint32_t x0w = w.x ^ ((w.x << 8) | pb);
+                    const uint32_t x1w = w.y ^ __funnelshift_l(w.x, w.y, 8);
+                    const uint32_t x2w = w.z ^ __funnelshift_l(w.y, w.z, 8);
+                    const uint32_t x3w = w.w ^ __funnelshift_l(w.z, w.w, 8);
+                    uint32_t n0 = nonzero_bytes(x0w), n1 = nonzero_bytes(x1w), n2 = nonzero_bytes(x2w),
+                             n3 = nonzero_bytes(x3w);
+                    // '#' (0x23) has bit 6 clear; reads made of letters never take this branch
+                    const uint32_t low = ~(w.x & w.y & w.z & w.w) & 0x40404040u;
+                    if (__any_sync(0xffffffffu, (low != 0) && (vm != 0))) {
+                        n0 &= nonzero_bytes(w.x ^ 0x23232323u);
+                        n1 &= nonzero_bytes(w.y ^ 0x23232323u);
+                        n2 &= nonzero_bytes(w.z ^ 0x23232323u);
+                        n3 &= nonzero_bytes(w.w ^ 0x23232323u);
+                    }
+                    uint32_t k16 = flags_to_mask16(n0, n1, n2, n3);
+                    if (!interior && skip >= x0 && skip < x0 + 16) {
+                        // first base of the read: the previous char is the '#' sentinel, not the byte before it
+                        const uint32_t sh = 8 * ((skip - x0) & 3);
+                        const uint32_t wq = (skip - x0) < 4 ? w.x : (skip - x0) < 8 ? w.y : (skip - x0) < 12 ? w.z : w.w;
+                        const bool is_hash = ((wq >> sh) & 0xFFu) == 0x23u;
+                        k16 = is_hash ? (k16 & ~(1u << (skip - x0))) : (k16 | (1u << (skip - x0)));
                     }
                     keep = k16 & vm;
                 }
                 const uint32_t cnt = __popc(keep);
                 const uint32_t incl = warp_inclusive_scan(cnt);
                 const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-                uint32_t idx = avail + incl - cnt;
+                const uint32_t base_idx = (avail + incl - cnt) & (RING - 1);
                 const uint32_t cw[4] = {(w.x >> 1) & 0x07070707u, (w.y >> 1) & 0x07070707u,
                                         (w.z >> 1) & 0x07070707u, (w.w >> 1) & 0x07070707u};
+                // the ring has 16 bytes of slack past RING: write linearly, then wrap the overhang
+                uint8_t* dst = ring + base_idx;
 #pragma unroll
                 for (int j = 0; j < 16; j++) {
                     if ((keep >> j) & 1u) {
-                        ring[idx & (RING - 1)] = (uint8_t)(cw[j >> 2] >> (8 * (j & 3)));
-                        idx++;
+                        *dst = (uint8_t)(cw[j >> 2] >> (8 * (j & 3)));
+                        dst++;
                     }
+                }
+                if (base_idx + cnt > (uint32_t)RING) {
+                    const uint32_t over = base_idx + cnt - RING;
+                    for (uint32_t i = 0; i < over; i++) ring[i] = ring[RING + i];
                 }
                 avail += total;
                 chunk++;
@@ -243,12 +287,12 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sketch_kernel(const Sketch
                 const bool fast = (L_FAST != 0) && (l == (uint32_t)L_FAST) && thr_hi_plus1 != 0 &&
                                   !__any_sync(0xffffffffu, inv != 0);
 
-                uint32_t sel, sel_fwd = 0;
+                uint32_t sel, sel_fwd = 0, sel_s1 = 0;
                 bool regs_ok = false;
                 if (a.select_none) {
                     sel = 0;
                 } else if (fast) {
-                    sel = roll16_fast<(L_FAST ? L_FAST : 15)>(W, thr_hi_plus1, sel_fwd);
+                    sel = roll16_fast<(L_FAST ? L_FAST : 15)>(W, thr_hi_plus1, sel_fwd, sel_s1);
                     regs_ok = (valid_bits == 0xFFFFu);
                     sel &= valid_bits;
                 } else {
@@ -265,14 +309,16 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sketch_kernel(const Sketch
                         const uint32_t j = __ffs(scan_sel) - 1;
                         scan_sel &= scan_sel - 1;
                         uint64_t key; uint32_t dir;
+                        bool sure = false;
                         if (regs_ok && __popc(sel) == 1) {
                             const uint32_t rcv = revcomp_lmer<(L_FAST ? L_FAST : 15)>(sel_fwd);
                             dir = (sel_fwd < rcv) ? 0u : 1u;
                             key = dir ? rcv : sel_fwd;
+                            sure = (sel_s1 - 1u) < sure_lim;             // 1 <= s1 < T_hi
                         } else {
                             lmer_at(ring, p0 + j, l, key, dir);
                         }
-                        if (murmur_h1_u64(key) > a.threshold) continue;        // exact test (Kmer.hpp:1434)
+                        if (!sure && murmur_h1_u64(key) > a.threshold) continue;   // exact test (Kmer.hpp:1434)
                         const uint32_t v32 = (uint32_t)key;          // Kmer.hpp:1441 truncation
                         if (a.n_blacklist && blacklisted(a.blacklist, a.n_blacklist, v32)) continue;
                         kept |= 1u << j;
