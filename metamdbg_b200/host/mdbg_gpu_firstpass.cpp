@@ -1,0 +1,109 @@
+// mdbg_gpu_firstpass -- C++ host driver over the C ABI: the GPU form of
+//   metaMDBG readSelection <tmp> ... ; metaMDBG graph <tmp> --firstpass --min-abundance n
+// for the part of those stages that is on the hot path (sketch -> purgePalindromes -> k-min-mer count).
+// Reads FASTA/FASTQ (plain or gzip, through zlib), writes read_data_corrected.txt,
+// kminmerData_min.txt and kminmerData_abundance.txt in the reference's formats.
+#include <zlib.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+
+#include "mdbg_host.hpp"
+
+using namespace mdbg_host;
+
+static bool getline_gz(gzFile f, std::string& line) {
+    line.clear();
+    char buf[1 << 16];
+    while (gzgets(f, buf, sizeof buf)) {
+        size_t n = strlen(buf);
+        bool eol = n && buf[n - 1] == '\n';
+        if (eol) n--;
+        if (n && buf[n - 1] == '\r') n--;
+        line.append(buf, n);
+        if (eol) return true;
+    }
+    return !line.empty();
+}
+
+int main(int argc, char** argv) {
+    if (argc < 3) {
+        std::cerr << "usage: mdbg_gpu_firstpass <reads.fa|fq[.gz]> <outDir> [--ont] [-l 15] [-d 0.005] [-k 4] "
+                     "[--min-abundance 2] [--last-k N] [--batch-mbp 1024]\n";
+        return 2;
+    }
+    std::string input = argv[1], outDir = argv[2];
+    bool hpc = true;
+    uint32_t l = 15, k = 4, minAb = 2, lastK = 0;
+    float density = 0.005f;
+    size_t batchMbp = 1024;
+    for (int i = 3; i < argc; i++) {
+        std::string a = argv[i];
+        auto next = [&]() { return std::string(i + 1 < argc ? argv[++i] : "0"); };
+        if (a == "--ont") hpc = false;
+        else if (a == "-l") l = (uint32_t)atoi(next().c_str());
+        else if (a == "-d") density = (float)atof(next().c_str());
+        else if (a == "-k") k = (uint32_t)atoi(next().c_str());
+        else if (a == "--min-abundance") minAb = (uint32_t)atoi(next().c_str());
+        else if (a == "--last-k") lastK = (uint32_t)atoi(next().c_str());
+        else if (a == "--batch-mbp") batchMbp = (size_t)atol(next().c_str());
+    }
+    try {
+        Context ctx(l, density, hpc);
+        std::vector<uint32_t> readLengths;
+        GpuReadSelectionFunctor functor(ctx, [&](const ReadMinimizers& r) { readLengths.push_back(r.readLength); },
+                                        batchMbp << 20);
+        gzFile f = gzopen(input.c_str(), "rb");
+        if (!f) throw std::runtime_error("cannot open " + input);
+        std::string line;
+        Read read;
+        uint64_t index = 0;
+        bool have = getline_gz(f, line);
+        while (have) {
+            if (line.empty()) { have = getline_gz(f, line); continue; }
+            if (line[0] == '>') {                        // FASTA, possibly multi-line
+                read._header = line.substr(1);
+                read._seq.clear();
+                while ((have = getline_gz(f, line)) && (line.empty() || line[0] != '>')) read._seq += line;
+                read._index = index++;
+                functor(read);
+            } else if (line[0] == '@') {                 // FASTQ, 4-line records
+                read._header = line.substr(1);
+                getline_gz(f, read._seq);
+                getline_gz(f, line);
+                getline_gz(f, read._qual);
+                read._index = index++;
+                functor(read);
+                have = getline_gz(f, line);
+            } else {
+                throw std::runtime_error("unrecognised record: " + line.substr(0, 40));
+            }
+        }
+        gzclose(f);
+        functor.flush();
+        if (lastK == 0) {                                // Commons::computeLastK with the N50 (Commons.hpp:1726-1741)
+            std::vector<uint32_t> s = readLengths;
+            std::sort(s.begin(), s.end(), std::greater<uint32_t>());
+            uint64_t total = 0, acc = 0;
+            for (uint32_t x : s) total += x;
+            uint32_t n50 = s.empty() ? 0 : s.back();
+            for (uint32_t x : s) { acc += x; if (acc >= total / 2) { n50 = x; break; } }
+            lastK = (uint32_t)(n50 * density * 2.0f);
+            if (lastK < 6) lastK = 6;
+        }
+        uint64_t changed = purgePalindromesAndWrite(ctx, 4, lastK, outDir + "/read_data_corrected.txt");
+        GpuKminmerCounter counter(ctx, k, minAb);
+        counter.execute(outDir + "/kminmerData_min.txt", outDir + "/kminmerData_abundance.txt");
+        std::cout << "reads " << functor.nbReads() << " bases " << functor.nbBases() << " minimizers "
+                  << functor.nbSelectedMinimizers() << " purged_reads " << changed << " kminmers " << counter._nbKminmers
+                  << " distinct " << counter._nbDistinct << " solid " << counter._nbSolidKminmers << " checksum "
+                  << counter._checksum << " lastK " << lastK << " kernel_launches "
+                  << mdbg_ctx_kernel_launches(ctx.get()) << std::endl;
+    } catch (const std::exception& e) {
+        std::cerr << "error: " << e.what() << std::endl;
+        return 1;
+    }
+    return 0;
+}

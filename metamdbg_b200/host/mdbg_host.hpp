@@ -1,0 +1,184 @@
+// mdbg_host.hpp -- C++ host-side mirror of the reference's functor interface for the
+// sketch + count path, on top of the C ABI (include/mdbg_b200.h).  Header-only, C++17.
+//
+// It mirrors (metaMDBG source tree):
+//   * ReadSelectionFunctor::operator()(const Read&)   src/readSelection/ReadSelection.hpp:669-1161
+//     (the EncoderRLE + MinimizerParser::parse part, lines 682-690) -> GpuReadSelectionFunctor
+//   * ReadSelection::purgePalindromes                  src/readSelection/ReadSelection.hpp:1374-1431
+//   * CreateMdbg::KminmerCounter::execute              src/graph/CreateMdbg.hpp:3634-3883 -> GpuKminmerCounter
+// and writes the reference's file formats:
+//   read_data_corrected.txt   u32 n, u8 isCircular(0), u32 minimizers[n]   (Commons.hpp:7405-7440 reader)
+//   kminmerData_min.txt       k * u32 per entry                            (Commons.hpp:4429-4446)
+//   kminmerData_abundance.txt u128 hash (LE) + u32 abundance = 20 bytes    (Commons.hpp:4463-4471)
+//
+// Threading contract = the C ABI's: ReadParserParallel calls the functor from several OpenMP
+// threads; feed() must be called under the parser's existing critical section (or from one thread).
+#pragma once
+
+#include <cstdint>
+#include <cstdio>
+#include <functional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/mdbg_b200.h"
+
+namespace mdbg_host {
+
+// Same fields as the reference's Read (src/Commons.hpp:92-98).
+struct Read {
+    uint64_t _index = 0;
+    std::string _header, _seq, _qual;
+    uint64_t _datasetIndex = 0;
+};
+
+inline void check(mdbg_ctx* ctx, mdbg_status st, const char* what) {
+    if (st != MDBG_OK) throw std::runtime_error(std::string(what) + ": " + mdbg_last_error(ctx));
+}
+
+class Context {
+public:
+    Context(uint32_t minimizerSize, float density, bool useHomopolymerCompression,
+            const std::vector<uint32_t>& repetitiveMinimizers = {}, int device = 0) {
+        mdbg_params p{};
+        p.minimizer_size = minimizerSize;
+        p.density = density;
+        p.use_hpc = useHomopolymerCompression ? 1 : 0;
+        p.blacklist = repetitiveMinimizers.empty() ? nullptr : repetitiveMinimizers.data();
+        p.n_blacklist = repetitiveMinimizers.size();
+        mdbg_status st = mdbg_ctx_create(device, &p, &_ctx);
+        if (st != MDBG_OK) throw std::runtime_error(std::string("mdbg_ctx_create: ") + mdbg_last_error(nullptr));
+    }
+    ~Context() { mdbg_ctx_destroy(_ctx); }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    mdbg_ctx* get() const { return _ctx; }
+
+private:
+    mdbg_ctx* _ctx = nullptr;
+};
+
+// Per-read result handed to the sink, in input order (what ReadSelection::writeRead receives).
+struct ReadMinimizers {
+    uint64_t readIndex;
+    uint32_t readLength;
+    uint32_t n;
+    const uint32_t* minimizers;
+    const uint32_t* positions;
+    const uint8_t* directions;
+};
+
+// Batching replacement of ReadSelectionFunctor: reads are buffered until `batchBases` bases are
+// pending, sketched on the GPU in one call, appended to the device-resident minimizer store and
+// reported read by read, in input order, to `sink`.
+class GpuReadSelectionFunctor {
+public:
+    using Sink = std::function<void(const ReadMinimizers&)>;
+
+    GpuReadSelectionFunctor(Context& ctx, Sink sink, size_t batchBases = size_t(1) << 30)
+        : _ctx(ctx), _sink(std::move(sink)), _batchBases(batchBases) {
+        _offsets.push_back(0);
+    }
+
+    void operator()(const Read& read) {                 // same call shape as the reference functor
+        _bases.insert(_bases.end(), read._seq.begin(), read._seq.end());
+        _offsets.push_back(_bases.size());
+        _indices.push_back(read._index);
+        _nbBases += read._seq.size();
+        if (_bases.size() >= _batchBases) flush();
+    }
+
+    void flush() {
+        const uint32_t n = (uint32_t)_indices.size();
+        if (n == 0) return;
+        mdbg_sketch_out out{};
+        check(_ctx.get(),
+              mdbg_sketch_batch(_ctx.get(), reinterpret_cast<const uint8_t*>(_bases.data()), _offsets.data(), n,
+                                /*append_to_store=*/1, &out),
+              "mdbg_sketch_batch");
+        for (uint32_t r = 0; r < n; r++) {
+            const uint64_t lo = out.min_offsets[r], hi = out.min_offsets[r + 1];
+            if (_sink)
+                _sink(ReadMinimizers{_indices[r], (uint32_t)(_offsets[r + 1] - _offsets[r]), (uint32_t)(hi - lo),
+                                     out.minimizers + lo, out.positions + lo, out.directions + lo});
+            _nbSelectedMinimizers += hi - lo;
+        }
+        _nbReads += n;
+        _bases.clear();
+        _offsets.assign(1, 0);
+        _indices.clear();
+    }
+
+    uint64_t nbReads() const { return _nbReads; }
+    uint64_t nbBases() const { return _nbBases; }
+    uint64_t nbSelectedMinimizers() const { return _nbSelectedMinimizers; }
+
+private:
+    Context& _ctx;
+    Sink _sink;
+    size_t _batchBases;
+    std::vector<char> _bases;
+    std::vector<uint64_t> _offsets;
+    std::vector<uint64_t> _indices;
+    uint64_t _nbReads = 0, _nbBases = 0, _nbSelectedMinimizers = 0;
+};
+
+// ReadSelection::purgePalindromes + the read_data_corrected.txt writer.
+inline uint64_t purgePalindromesAndWrite(Context& ctx, uint32_t firstK, uint32_t lastK, const std::string& filename) {
+    uint64_t changed = 0;
+    check(ctx.get(), mdbg_purge_palindromes(ctx.get(), firstK, lastK, &changed), "mdbg_purge_palindromes");
+    uint64_t nReads = 0, nMins = 0;
+    check(ctx.get(), mdbg_store_size(ctx.get(), &nReads, &nMins), "mdbg_store_size");
+    std::vector<uint64_t> offs(nReads + 1);
+    std::vector<uint32_t> mins(nMins + 1);
+    check(ctx.get(), mdbg_store_fetch(ctx.get(), offs.data(), mins.data()), "mdbg_store_fetch");
+    FILE* f = fopen(filename.c_str(), "wb");
+    if (!f) throw std::runtime_error("cannot open " + filename);
+    for (uint64_t r = 0; r < nReads; r++) {
+        const uint32_t size = (uint32_t)(offs[r + 1] - offs[r]);
+        const uint8_t isCircular = 0;                    // CONTIG_LINEAR
+        fwrite(&size, sizeof size, 1, f);
+        fwrite(&isCircular, 1, 1, f);
+        fwrite(mins.data() + offs[r], sizeof(uint32_t), size, f);
+    }
+    fclose(f);
+    return changed;
+}
+
+// CreateMdbg::KminmerCounter (first pass): counts every k-min-mer of the device-resident reads and
+// writes kminmerData_min.txt / kminmerData_abundance.txt.
+class GpuKminmerCounter {
+public:
+    GpuKminmerCounter(Context& ctx, uint32_t kminmerSize, uint32_t minAbundance)
+        : _ctx(ctx), _k(kminmerSize), _minAbundance(minAbundance) {}
+
+    void execute(const std::string& kminmerFile, const std::string& abundanceFile) {
+        check(_ctx.get(), mdbg_count_begin(_ctx.get(), _k, 0), "mdbg_count_begin");
+        check(_ctx.get(), mdbg_count_add_store(_ctx.get(), 0, UINT64_MAX), "mdbg_count_add_store");
+        mdbg_table_out t{};
+        check(_ctx.get(), mdbg_count_finalize(_ctx.get(), _minAbundance, &t), "mdbg_count_finalize");
+        FILE* fk = fopen(kminmerFile.c_str(), "wb");
+        FILE* fa = fopen(abundanceFile.c_str(), "wb");
+        if (!fk || !fa) throw std::runtime_error("cannot open output files");
+        fwrite(t.kminmers, sizeof(uint32_t), (size_t)t.n_entries * _k, fk);
+        for (uint64_t i = 0; i < t.n_entries; i++) {
+            fwrite(t.hashes + 2 * i, 16, 1, fa);         // u128 little-endian: low = Murmur h2, high = h1
+            fwrite(t.abundances + i, 4, 1, fa);
+        }
+        fclose(fk);
+        fclose(fa);
+        _nbSolidKminmers = t.n_entries;
+        _nbKminmers = t.n_instances;
+        _nbDistinct = t.n_distinct;
+        _checksum = t.checksum;
+    }
+
+    uint64_t _nbKminmers = 0, _nbSolidKminmers = 0, _nbDistinct = 0, _checksum = 0;
+
+private:
+    Context& _ctx;
+    uint32_t _k, _minAbundance;
+};
+
+}  // namespace mdbg_host

@@ -1,0 +1,60 @@
+"""The C++ host driver (metamdbg_b200/host, reference-language host side over the C ABI):
+FASTQ in, reference-format files out, compared with the CPU oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from metamdbg_b200 import synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "metamdbg_b200", "host", "mdbg_gpu_firstpass")
+
+
+def test_cpp_driver_files_match_oracle(tmp_path, oracle):
+    import __graft_entry__ as g
+    g.build()
+    assert os.path.exists(EXE), "C++ host driver not built"
+    rs = synth.make_readset(1200, 7000, seed=55, n_genomes=2, genome_len_range=(150_000, 250_000))
+    bases, offs = synth.fill_reads(rs)
+    fq = tmp_path / "reads.fastq"
+    with open(fq, "wb") as f:
+        raw = bases.tobytes()
+        for r in range(rs.n_reads):
+            s = raw[int(offs[r]):int(offs[r + 1])]
+            f.write(b"@r%d\n" % r + s + b"\n+\n" + b"I" * len(s) + b"\n")
+    out = subprocess.run([EXE, str(fq), str(tmp_path), "-k", "4", "--min-abundance", "2", "--batch-mbp", "3"],
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    stats = dict(zip(out.stdout.split()[::2], out.stdout.split()[1::2]))
+    # expected, from the oracle
+    mo, m, p, d = oracle.sketch_batch(bases, offs, 15, 0.005, True)
+    pm, po = [], [0]
+    for r in range(rs.n_reads):
+        q, _ = oracle.purge_palindrome(m[int(mo[r]):int(mo[r + 1])], 4, 60)
+        pm.append(q); po.append(po[-1] + len(q))
+    pm = np.concatenate(pm).astype(np.uint32)
+    po = np.array(po, np.uint64)
+    ref = oracle.count(pm, po, 4, 2)
+    # read_data_corrected.txt: u32 n, u8 0, u32[n]
+    buf = open(tmp_path / "read_data_corrected.txt", "rb").read()
+    pos, got = 0, []
+    for r in range(rs.n_reads):
+        n = int(np.frombuffer(buf, np.uint32, 1, pos)[0]); pos += 4
+        assert buf[pos] == 0; pos += 1
+        got.append(np.frombuffer(buf, np.uint32, n, pos)); pos += 4 * n
+    assert pos == len(buf)
+    assert np.array_equal(np.concatenate(got), pm)
+    # kminmerData_abundance.txt: 20-byte records (u128 LE hash, u32 abundance)
+    ab = np.frombuffer(open(tmp_path / "kminmerData_abundance.txt", "rb").read(), dtype=np.uint8).reshape(-1, 20)
+    lo = ab[:, 0:8].copy().view(np.uint64)[:, 0]; hi = ab[:, 8:16].copy().view(np.uint64)[:, 0]
+    cnt = ab[:, 16:20].copy().view(np.uint32)[:, 0]
+    got_tab = {(int(h), int(l)): int(c) for h, l, c in zip(hi, lo, cnt)}
+    want = {(int(h[0]), int(h[1])): int(a) for h, a in zip(ref["hashes"], ref["abundances"])}
+    assert got_tab == want and len(want) > 100
+    vec = np.frombuffer(open(tmp_path / "kminmerData_min.txt", "rb").read(), dtype=np.uint32).reshape(-1, 4)
+    assert sorted(map(tuple, vec.tolist())) == sorted(map(tuple, ref["vecs"].tolist()))
+    assert int(stats["solid"]) == len(want) and int(stats["reads"]) == rs.n_reads
+    assert int(stats["checksum"]) == oracle.checksum(ref["hashes"], ref["abundances"])
