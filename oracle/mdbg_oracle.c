@@ -343,8 +343,9 @@ size_t orc_count(const uint32_t* mins, const uint64_t* offs, size_t n_reads, int
         while (j < total && cmp_vec(all + i * (size_t)k, all + j * (size_t)k) == 0) j++;
         uint32_t ab = (uint32_t)(j - i);
         distinct++;
-        /* dumpKminmer CreateMdbg.hpp:3862-3869 (first pass) */
-        if (ab > 1 && ab >= min_abundance) {
+        /* dumpKminmer CreateMdbg.hpp:3862-3869 (first pass); min_abundance == UINT32_MAX is a
+         * test-only "keep every distinct k-min-mer" mode used to check the multi-GPU merge */
+        if (min_abundance == 0xFFFFFFFFu || (ab > 1 && ab >= min_abundance)) {
             memcpy(vecs + n_out * (size_t)k, all + i * (size_t)k, (size_t)k * sizeof(uint32_t));
             orc_hash128(all + i * (size_t)k, k, hashes + 2 * n_out);
             abs_[n_out] = ab;

@@ -172,8 +172,11 @@ class Oracle(_Lib):
         n = self.lib.orc_purge_palindrome(_p(m, _u32p), len(m), first_k, last_k, _p(out, _u32p), _p(keep, _u8p))
         return out[:n].copy(), keep[:len(m)].copy()
 
-    def count(self, mins: np.ndarray, offs: np.ndarray, k: int, min_abundance: int = 2):
-        """-> dict(vecs [n,k] u32, hashes [n,2] u64 (h1,h2), abundances [n] u32, n_instances, n_distinct)."""
+    def count(self, mins: np.ndarray, offs: np.ndarray, k: int, min_abundance: int = 2, keep_all: bool = False):
+        """-> dict(vecs [n,k] u32, hashes [n,2] u64 (h1,h2), abundances [n] u32, n_instances, n_distinct).
+        keep_all=True returns every distinct k-min-mer (abundance 1 included; multi-GPU merge tests)."""
+        if keep_all:
+            min_abundance = 0xFFFFFFFF
         mins = np.ascontiguousarray(mins, dtype=np.uint32)
         offs = np.ascontiguousarray(offs, dtype=np.uint64)
         v = _u32p(); h = _u64p(); a = _u32p()
