@@ -775,6 +775,7 @@ mdbg_status mdbg_nccl_unique_id(uint8_t id_out[128]) {
 
 mdbg_status mdbg_comm_init(mdbg_ctx* ctx, int rank, int n_ranks, const uint8_t id[128]) {
     if (!ctx || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return MDBG_ERR_ARG;
+    if (n_ranks > 64) return fail(ctx, MDBG_ERR_ARG, "at most 64 ranks are supported");
     std::string err;
     if (!load_nccl(err)) return fail(ctx, MDBG_ERR_NCCL, "%s", err.c_str());
     CK(cudaSetDevice(ctx->device));

@@ -183,12 +183,15 @@ __device__ __forceinline__ uint32_t vec_elem(const uint32_t* mins, const uint32_
     return (ref & REF_REV) ? mins[idx + k - 1 - i] : mins[idx + i];
 }
 
+// Block-aggregated compaction: one atomicAdd per 256-slot tile instead of one per warp/thread
+// (tens of millions of same-address atomics serialise in L2).
 __global__ void __launch_bounds__(256) table_emit_kernel(const EmitArgs a) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t rounds = (a.capacity + stride - 1) / stride;
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (uint64_t it = 0; it < rounds; it++, i += stride) {
+    __shared__ uint32_t wcnt[8];
+    __shared__ unsigned long long tile_base;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t n_tiles = (a.capacity + 255) / 256;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t i = tile * 256 + threadIdx.x;
         bool take = false;
         uint64_t lo = 0, hi = 0, ref = 0;
         uint32_t count = 0;
@@ -198,18 +201,23 @@ __global__ void __launch_bounds__(256) table_emit_kernel(const EmitArgs a) {
             take = (lo | hi) != 0 && count >= a.min_count;
         }
         const uint32_t m = __ballot_sync(0xffffffffu, take);
-        if (m == 0) continue;
-        unsigned long long base = 0;
-        if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(a.cursor, (unsigned long long)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (lane == 0) wcnt[warp] = __popc(m);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tot = 0;
+            for (int w = 0; w < 8; w++) { const uint32_t c = wcnt[w]; wcnt[w] = tot; tot += c; }
+            tile_base = tot ? atomicAdd(a.cursor, (unsigned long long)tot) : 0ULL;
+        }
+        __syncthreads();
         if (take) {
-            const uint64_t pos = base + __popc(m & ((1u << lane) - 1u));
+            const uint64_t pos = tile_base + wcnt[warp] + __popc(m & ((1u << lane) - 1u));
             a.out_hashes[2 * pos] = lo;
             a.out_hashes[2 * pos + 1] = hi;
             a.out_abund[pos] = count;
             for (int j = 0; j < (int)a.k; j++)
                 a.out_vecs[pos * a.k + j] = vec_elem(a.mins, a.foreign_vecs, ref, (int)a.k, j);
         }
+        __syncthreads();
     }
 }
 
@@ -220,19 +228,45 @@ void launch_table_emit(const EmitArgs& a, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------ multi-GPU pack by owner rank
+constexpr int PACK_MAX_RANKS = 64;
+
 __global__ void __launch_bounds__(256) table_pack_kernel(const PackArgs a) {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.capacity;
-         i += (uint64_t)gridDim.x * blockDim.x) {
-        const Slot sl = a.table[i];
-        if ((sl.lo | sl.hi) == 0) continue;
-        const uint32_t dst = owner_of(sl.hi, a.n_ranks);
-        const unsigned long long slot = atomicAdd(&a.bucket_count[dst], 1ULL);
-        if (a.pass == 2) {
-            const uint64_t pos = a.bucket_base[dst] + slot;
-            a.out_counts[pos] = sl.count;
-            for (int j = 0; j < (int)a.k; j++)
-                a.out_vecs[pos * a.k + j] = vec_elem(a.mins, a.foreign_vecs, sl.ref, (int)a.k, j);
+    __shared__ uint32_t wcnt[8][PACK_MAX_RANKS];          // per-warp counts -> exclusive offsets inside the tile
+    __shared__ unsigned long long bbase[PACK_MAX_RANKS];  // this tile's reservation in every bucket
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t R = a.n_ranks;
+    const uint64_t n_tiles = (a.capacity + 255) / 256;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t i = tile * 256 + threadIdx.x;
+        bool take = false;
+        uint32_t dst = 0, count = 0, my_prefix = 0;
+        uint64_t ref = 0;
+        if (i < a.capacity) {
+            const Slot sl = a.table[i];
+            take = (sl.lo | sl.hi) != 0;
+            dst = owner_of(sl.hi, R);
+            count = sl.count;
+            ref = sl.ref;
         }
+        for (uint32_t d = 0; d < R; d++) {
+            const uint32_t m = __ballot_sync(0xffffffffu, take && dst == d);
+            if (lane == 0) wcnt[warp][d] = __popc(m);
+            if (take && dst == d) my_prefix = __popc(m & ((1u << lane) - 1u));
+        }
+        __syncthreads();
+        if (threadIdx.x < R) {
+            uint32_t tot = 0;
+            for (int w = 0; w < 8; w++) { const uint32_t c = wcnt[w][threadIdx.x]; wcnt[w][threadIdx.x] = tot; tot += c; }
+            bbase[threadIdx.x] = tot ? atomicAdd(&a.bucket_count[threadIdx.x], (unsigned long long)tot) : 0ULL;
+        }
+        __syncthreads();
+        if (a.pass == 2 && take) {
+            const uint64_t pos = a.bucket_base[dst] + bbase[dst] + wcnt[warp][dst] + my_prefix;
+            a.out_counts[pos] = count;
+            for (int j = 0; j < (int)a.k; j++)
+                a.out_vecs[pos * a.k + j] = vec_elem(a.mins, a.foreign_vecs, ref, (int)a.k, j);
+        }
+        __syncthreads();
     }
 }
 
