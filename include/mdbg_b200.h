@@ -105,6 +105,7 @@ typedef struct {
     uint64_t n_instances;         /* k-min-mer occurrences inserted */
     uint64_t n_distinct;          /* distinct k-min-mers in the table (any abundance) */
     uint64_t checksum;            /* sum abundance * low64(hash) mod 2^64 (CreateMdbg.cpp:3321) */
+    uint64_t n_rescued;           /* abundance-1 entries kept by mdbg_count_rescue (included in n_entries) */
 } mdbg_table_out;
 
 /* ---- context ------------------------------------------------------------ */
@@ -166,6 +167,28 @@ mdbg_status mdbg_count_finalize(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_tabl
 /* Table statistics without the host copy (device-side reduction only). */
 mdbg_status mdbg_count_stats(mdbg_ctx* ctx, uint32_t min_abundance, uint64_t* n_entries,
                              uint64_t* n_distinct, uint64_t* n_instances, uint64_t* checksum);
+
+/* rescueKminmers / RescueKminmerFunctor (CreateMdbg.hpp:4517-4640; default mode, --min-abundance <= 1):
+ * second pass over the stored reads; reads whose median solid abundance m satisfies m * 0.1f <= 1 (and that
+ * hold at least one solid k-min-mer) keep their abundance-1 k-min-mers, which are then emitted by
+ * mdbg_count_finalize / counted by mdbg_count_stats next to the abundance >= 2 entries.  Single context only. */
+mdbg_status mdbg_count_rescue(mdbg_ctx* ctx, uint64_t* n_reads_rescued);
+
+/* ---- multi-k: previous-k abundance table and the k >= firstK+1 passes (rows A8/A9) ------------
+ * The reference derives the abundance of a k-min-mer from the table of the previous k
+ * (_kminmerAbundances, loaded by loadRefinedAbundances, CreateMdbg.cpp:3401-3709): minimum over its two
+ * (k-1)-min-mers, absent or 0 => 1, kept when > 1 (getRefinedAbundance CreateMdbg.hpp:3933-4005 for
+ * k = firstK+1; IndexKminmerFunctor CreateMdbg.hpp:988-1010,1240-1265,1268-1464 for k >= firstK+2). */
+/* previous-k table := the current table's emitted entries (abundance >= max(2,min_abundance) or rescued) */
+mdbg_status mdbg_prev_from_current(mdbg_ctx* ctx, uint32_t min_abundance);
+/* insert-or-assign host (hash, abundance) pairs, hashes laid out as in mdbg_table_out / on disk;
+ * clear != 0 starts from an empty table (e.g. kminmerData_abundance_prev.txt), clear == 0 patches the
+ * existing one (e.g. unitigGraph.nodes.refined_abundances) */
+mdbg_status mdbg_prev_load(mdbg_ctx* ctx, const uint64_t* hashes, const uint32_t* abundances, uint64_t n, int clear);
+/* after mdbg_count_begin(ctx, k, ...): insert-if-absent every k-min-mer of stored reads [read_lo, read_hi)
+ * whose derived abundance is > 1, with that abundance (unitig sequences are appended to the store by the
+ * host like reads). mdbg_count_finalize(ctx, 0, ..) then returns kminmerData_abundance.txt of this k. */
+mdbg_status mdbg_count_add_store_next_k(mdbg_ctx* ctx, uint64_t read_lo, uint64_t read_hi);
 
 /* ---- multi-GPU (one process per GPU) --------------------------------------- */
 /* NCCL is loaded at run time (dlopen libnccl.so.2).  Rank 0 creates an id,

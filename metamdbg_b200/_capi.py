@@ -35,7 +35,7 @@ class SketchDev(C.Structure):
 class TableOut(C.Structure):
     _fields_ = [("k", C.c_uint32), ("n_entries", C.c_uint64), ("hashes", u64p), ("abundances", u32p),
                 ("kminmers", u32p), ("n_instances", C.c_uint64), ("n_distinct", C.c_uint64),
-                ("checksum", C.c_uint64)]
+                ("checksum", C.c_uint64), ("n_rescued", C.c_uint64)]
 
 
 # every symbol include/mdbg_b200.h declares: name -> (restype, argtypes)
@@ -62,6 +62,10 @@ SYMBOLS = {
     "mdbg_count_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "mdbg_count_finalize": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(TableOut)]),
     "mdbg_count_stats": (C.c_int, [C.c_void_p, C.c_uint32, u64p, u64p, u64p, u64p]),
+    "mdbg_count_rescue": (C.c_int, [C.c_void_p, u64p]),
+    "mdbg_prev_from_current": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "mdbg_prev_load": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]),
+    "mdbg_count_add_store_next_k": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64]),
     "mdbg_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "mdbg_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "mdbg_count_merge": (C.c_int, [C.c_void_p]),

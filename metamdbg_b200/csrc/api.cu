@@ -91,6 +91,8 @@ struct mdbg_ctx {
     bool t_active = false;
     DevBuf foreign_vecs;
     uint64_t foreign_n = 0;
+    DevBuf prev_table, prev_stage_h, prev_stage_a;
+    uint64_t prev_capacity = 0;
     DevBuf o_hash, o_abund, o_vecs;
     PinBuf ho_hash, ho_abund, ho_vecs;
 
@@ -405,7 +407,7 @@ void mdbg_ctx_destroy(mdbg_ctx* c) {
     DevBuf* devs[] = {&c->d_blacklist, &c->d_bases, &c->d_offsets, &c->pad_min, &c->pad_pos, &c->pad_dir, &c->n_min,
                       &c->scan_scratch, &c->b_off, &c->b_min, &c->b_pos, &c->b_dir, &c->s_min, &c->s_off, &c->s_rem,
                       &c->p_flags, &c->p_keep, &c->p_cnt, &c->p_newoff, &c->p_newmin, &c->table, &c->foreign_vecs,
-                      &c->o_hash, &c->o_abund, &c->o_vecs, &c->m_send_vecs, &c->m_send_counts, &c->m_recv_vecs,
+                      &c->o_hash, &c->o_abund, &c->o_vecs, &c->prev_table, &c->prev_stage_h, &c->prev_stage_a, &c->m_send_vecs, &c->m_send_counts, &c->m_recv_vecs,
                       &c->m_recv_counts, &c->m_bucket};
     for (DevBuf* b : devs) release(*b);
     PinBuf* pins[] = {&c->h_off, &c->h_min, &c->h_pos, &c->h_dir, &c->ho_hash, &c->ho_abund, &c->ho_vecs};
@@ -761,7 +763,127 @@ mdbg_status mdbg_count_finalize(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_tabl
     out->n_instances = st.n_instances;
     out->n_distinct = st.n_distinct;
     out->checksum = st.checksum;
+    out->n_rescued = st.n_rescued;
     return MDBG_OK;
+}
+
+mdbg_status mdbg_count_rescue(mdbg_ctx* ctx, uint64_t* n_reads_rescued) {
+    if (!ctx) return MDBG_ERR_ARG;
+    if (n_reads_rescued) *n_reads_rescued = 0;
+    if (!ctx->t_active) return fail(ctx, MDBG_ERR_STATE, "mdbg_count_rescue before mdbg_count_begin");
+    if (ctx->n_ranks > 1) return fail(ctx, MDBG_ERR_STATE, "mdbg_count_rescue is single-context only");
+    if (ctx->s_reads == 0) return MDBG_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemsetAsync(&ctx->d_small->n_changed, 0, sizeof(unsigned long long), s));
+    RescueArgs a{};
+    a.mins = ctx->s_min.as<uint32_t>();
+    a.offs = ctx->s_off.as<uint64_t>();
+    a.n_reads = ctx->s_reads;
+    a.k = ctx->t_k;
+    a.table = ctx->table.as<Slot>();
+    a.mask = ctx->t_capacity - 1;
+    a.n_reads_rescued = &ctx->d_small->n_changed;
+    launch_rescue(a, s);
+    CKS(check_launch(ctx, "rescue_kernel", 1));
+    CK(cudaMemcpyAsync(&ctx->h_scalar[0], &ctx->d_small->n_changed, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (n_reads_rescued) *n_reads_rescued = ctx->h_scalar[0];
+    return MDBG_OK;
+}
+
+static mdbg_status prev_alloc(mdbg_ctx* ctx, uint64_t expect) {
+    if (expect < 512) expect = 512;
+    const uint64_t cap = pow2ceil(expect * 2);
+    CKS(ensure(ctx, ctx->prev_table, cap * sizeof(Slot)));
+    CK(cudaMemsetAsync(ctx->prev_table.p, 0, cap * sizeof(Slot), ctx->stream));
+    CK(cudaMemsetAsync(&ctx->d_small->full_flag, 0, sizeof(uint32_t), ctx->stream));
+    ctx->prev_capacity = cap;
+    return MDBG_OK;
+}
+
+static mdbg_status check_full(mdbg_ctx* ctx, const char* what) {
+    CK(cudaMemcpyAsync(&ctx->h_small->full_flag, &ctx->d_small->full_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_small->full_flag) return fail(ctx, MDBG_ERR_TABLE_FULL, "%s: table full", what);
+    return MDBG_OK;
+}
+
+mdbg_status mdbg_prev_from_current(mdbg_ctx* ctx, uint32_t min_abundance) {
+    if (!ctx) return MDBG_ERR_ARG;
+    if (!ctx->t_active) return fail(ctx, MDBG_ERR_STATE, "mdbg_prev_from_current without a count table");
+    CK(cudaSetDevice(ctx->device));
+    const uint32_t thr = count_threshold(min_abundance);
+    TableStats st;
+    CKS(table_stats(ctx, thr, &st));
+    CKS(prev_alloc(ctx, st.n_entries));
+    PrevFromTableArgs a{};
+    a.table = ctx->table.as<Slot>();
+    a.capacity = ctx->t_capacity;
+    a.min_count = thr;
+    a.prev = ctx->prev_table.as<Slot>();
+    a.prev_mask = ctx->prev_capacity - 1;
+    a.full_flag = &ctx->d_small->full_flag;
+    launch_prev_from_table(a, ctx->stream);
+    CKS(check_launch(ctx, "prev_from_table_kernel", 1));
+    return check_full(ctx, "mdbg_prev_from_current");
+}
+
+mdbg_status mdbg_prev_load(mdbg_ctx* ctx, const uint64_t* hashes, const uint32_t* abundances, uint64_t n, int clear) {
+    if (!ctx) return MDBG_ERR_ARG;
+    if (n && (!hashes || !abundances)) return fail(ctx, MDBG_ERR_ARG, "null table arrays");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    if (clear || ctx->prev_capacity == 0) CKS(prev_alloc(ctx, n));
+    if (n == 0) return MDBG_OK;
+    CKS(ensure(ctx, ctx->prev_stage_h, n * 16));
+    CKS(ensure(ctx, ctx->prev_stage_a, n * 4));
+    CK(cudaMemcpyAsync(ctx->prev_stage_h.p, hashes, n * 16, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->prev_stage_a.p, abundances, n * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(&ctx->d_small->full_flag, 0, sizeof(uint32_t), s));
+    PrevLoadArgs a{};
+    a.hashes = ctx->prev_stage_h.as<uint64_t>();
+    a.abund = ctx->prev_stage_a.as<uint32_t>();
+    a.n = n;
+    a.prev = ctx->prev_table.as<Slot>();
+    a.prev_mask = ctx->prev_capacity - 1;
+    a.full_flag = &ctx->d_small->full_flag;
+    launch_prev_load(a, s);
+    CKS(check_launch(ctx, "prev_load_kernel", 1));
+    return check_full(ctx, "mdbg_prev_load (patching needs free slots: load the base table with clear=1 first)");
+}
+
+mdbg_status mdbg_count_add_store_next_k(mdbg_ctx* ctx, uint64_t read_lo, uint64_t read_hi) {
+    if (!ctx) return MDBG_ERR_ARG;
+    if (!ctx->t_active) return fail(ctx, MDBG_ERR_STATE, "mdbg_count_add_store_next_k before mdbg_count_begin");
+    if (ctx->prev_capacity == 0) return fail(ctx, MDBG_ERR_STATE, "no previous-k table (mdbg_prev_load / mdbg_prev_from_current)");
+    if (ctx->t_k < 3) return fail(ctx, MDBG_ERR_ARG, "k must be >= 3 for a next-k pass");
+    if (read_hi > ctx->s_reads) read_hi = ctx->s_reads;
+    if (read_lo >= read_hi) return MDBG_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemcpyAsync(&ctx->h_scalar[0], ctx->s_off.as<uint64_t>() + read_lo, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&ctx->h_scalar[1], ctx->s_off.as<uint64_t>() + read_hi, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CKS(ensure(ctx, ctx->s_rem, ctx->s_mins + 1));
+    launch_fill_rem(ctx->s_off.as<uint64_t>(), read_lo, read_hi, ctx->s_rem.as<uint8_t>(), s);
+    CKS(check_launch(ctx, "fill_rem_kernel", 1));
+    NextKArgs a{};
+    a.mins = ctx->s_min.as<uint32_t>();
+    a.rem = ctx->s_rem.as<uint8_t>();
+    a.g_lo = ctx->h_scalar[0];
+    a.g_hi = ctx->h_scalar[1];
+    a.k = ctx->t_k;
+    a.prev = ctx->prev_table.as<Slot>();
+    a.prev_mask = ctx->prev_capacity - 1;
+    a.table = ctx->table.as<Slot>();
+    a.mask = ctx->t_capacity - 1;
+    a.full_flag = &ctx->d_small->full_flag;
+    if (ctx->timing) CK(cudaEventRecord(ctx->ev[1][0], s));
+    launch_next_k(a, s);
+    if (ctx->timing) { CK(cudaEventRecord(ctx->ev[1][1], s)); ctx->ev_valid[1] = true; }
+    CKS(check_launch(ctx, "next_k_kernel", a.g_hi > a.g_lo ? 1 : 0));
+    return check_full(ctx, "mdbg_count_add_store_next_k");
 }
 
 // ---- multi-GPU --------------------------------------------------------------------------

@@ -67,7 +67,7 @@ struct __align__(32) Slot {
     uint64_t lo;      // Murmur h2 = low 64 bits of KmerVec::hash128 (0,0 = empty)
     uint64_t hi;      // Murmur h1 = high 64 bits
     uint32_t count;   // abundance
-    uint32_t pad;
+    uint32_t flags;   // bit 0: rescued (abundance-1 k-min-mer kept by rescueKminmers)
     uint64_t ref;     // bit63: vector is the reversed window; bit62: index into foreign vecs; low bits: index
 };
 
@@ -101,11 +101,14 @@ struct InsertVecArgs {
 };
 void launch_insert_vecs(const InsertVecArgs& a, cudaStream_t s);
 
+constexpr uint32_t SLOT_RESCUED = 1u;
+
 struct TableStats {
-    unsigned long long n_entries;    // count >= threshold
+    unsigned long long n_entries;    // count >= threshold, or rescued
     unsigned long long n_distinct;   // occupied
     unsigned long long n_instances;  // sum of counts
     unsigned long long checksum;     // sum count*lo over qualifying entries
+    unsigned long long n_rescued;    // rescued entries among n_entries
 };
 void launch_table_stats(const Slot* table, uint64_t capacity, uint32_t min_count, TableStats* d_stats, cudaStream_t s);
 
@@ -122,6 +125,39 @@ struct EmitArgs {
     unsigned long long* cursor;    // zeroed before launch
 };
 void launch_table_emit(const EmitArgs& a, cudaStream_t s);
+
+// ---- rescue (RescueKminmerFunctor, CreateMdbg.hpp:4579-4637): flag the abundance-1 k-min-mers of reads whose
+// median solid abundance is <= 10
+struct RescueArgs {
+    const uint32_t* mins;
+    const uint64_t* offs;
+    uint64_t n_reads;
+    uint32_t k;
+    Slot* table;
+    uint64_t mask;
+    unsigned long long* n_reads_rescued;
+};
+void launch_rescue(const RescueArgs& a, cudaStream_t s);
+
+// ---- previous-k lookup table + next-k pass (getRefinedAbundance / IndexKminmerFunctor)
+struct PrevFromTableArgs {
+    const Slot* table; uint64_t capacity; uint32_t min_count;
+    Slot* prev; uint64_t prev_mask; uint32_t* full_flag;
+};
+void launch_prev_from_table(const PrevFromTableArgs& a, cudaStream_t s);
+struct PrevLoadArgs {
+    const uint64_t* hashes;   // [2n]: lo, hi
+    const uint32_t* abund;    // [n]
+    uint64_t n;
+    Slot* prev; uint64_t prev_mask; uint32_t* full_flag;
+};
+void launch_prev_load(const PrevLoadArgs& a, cudaStream_t s);
+struct NextKArgs {
+    const uint32_t* mins; const uint8_t* rem; uint64_t g_lo, g_hi; uint32_t k;
+    const Slot* prev; uint64_t prev_mask;
+    Slot* table; uint64_t mask; uint32_t* full_flag;
+};
+void launch_next_k(const NextKArgs& a, cudaStream_t s);
 
 // multi-GPU pack: bucket every occupied slot by owner rank
 struct PackArgs {

@@ -142,17 +142,19 @@ void launch_insert_vecs(const InsertVecArgs& a, cudaStream_t s) {
 // ------------------------------------------------------------------ stats / emit
 __global__ void __launch_bounds__(256) table_stats_kernel(const Slot* table, uint64_t capacity, uint32_t min_count,
                                                           TableStats* out) {
-    unsigned long long ne = 0, nd = 0, ni = 0, cs = 0;
+    unsigned long long ne = 0, nd = 0, ni = 0, cs = 0, nr = 0;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < capacity;
          i += (uint64_t)gridDim.x * blockDim.x) {
         const uint4 q0 = reinterpret_cast<const uint4*>(table + i)[0];
-        const uint32_t count = reinterpret_cast<const uint4*>(table + i)[1].x;
+        const uint4 q1 = reinterpret_cast<const uint4*>(table + i)[1];
+        const uint32_t count = q1.x, flags = q1.y;
         const uint64_t lo = (uint64_t)q0.x | ((uint64_t)q0.y << 32);
         const uint64_t hi = (uint64_t)q0.z | ((uint64_t)q0.w << 32);
         if (lo | hi) {
             nd++;
             ni += count;
             if (count >= min_count) { ne++; cs += (unsigned long long)count * lo; }
+            else if (flags & SLOT_RESCUED) { ne++; nr++; cs += (unsigned long long)count * lo; }
         }
     }
 #pragma unroll
@@ -161,12 +163,14 @@ __global__ void __launch_bounds__(256) table_stats_kernel(const Slot* table, uin
         nd += __shfl_down_sync(0xffffffffu, nd, d);
         ni += __shfl_down_sync(0xffffffffu, ni, d);
         cs += __shfl_down_sync(0xffffffffu, cs, d);
+        nr += __shfl_down_sync(0xffffffffu, nr, d);
     }
     if ((threadIdx.x & 31) == 0) {
         if (ne) atomicAdd(&out->n_entries, ne);
         if (nd) atomicAdd(&out->n_distinct, nd);
         if (ni) atomicAdd(&out->n_instances, ni);
         if (cs) atomicAdd(&out->checksum, cs);
+        if (nr) atomicAdd(&out->n_rescued, nr);
     }
 }
 
@@ -198,7 +202,7 @@ __global__ void __launch_bounds__(256) table_emit_kernel(const EmitArgs a) {
         if (i < a.capacity) {
             const Slot sl = a.table[i];
             lo = sl.lo; hi = sl.hi; count = sl.count; ref = sl.ref;
-            take = (lo | hi) != 0 && count >= a.min_count;
+            take = (lo | hi) != 0 && (count >= a.min_count || (sl.flags & SLOT_RESCUED));
         }
         const uint32_t m = __ballot_sync(0xffffffffu, take);
         if (lane == 0) wcnt[warp] = __popc(m);
@@ -225,6 +229,184 @@ void launch_table_emit(const EmitArgs& a, cudaStream_t s) {
     uint64_t blocks = (a.capacity + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     table_emit_kernel<<<(unsigned)blocks, 256, 0, s>>>(a);
+}
+
+// ------------------------------------------------------------------ lookups, rescue, next-k
+// normalized hash of the k-window starting at w
+__device__ __forceinline__ void window_hash(const uint32_t* w, int k, uint64_t& h1, uint64_t& h2, bool& rev) {
+    rev = true;
+    for (int j = 0; j < k / 2; j++) {
+        const uint32_t x = w[j], y = w[k - 1 - j];
+        if (x != y) { rev = x > y; break; }
+    }
+    if (rev) murmur128_u32vec([&](int i) { return w[k - 1 - i]; }, k, h1, h2);
+    else murmur128_u32vec([&](int i) { return w[i]; }, k, h1, h2);
+}
+
+// read-only probe (the table is not being modified while this runs)
+__device__ __forceinline__ Slot* table_find(Slot* table, uint64_t mask, uint64_t lo, uint64_t hi) {
+    uint64_t idx = lo & mask;
+    for (uint64_t probe = 0; probe <= mask && probe < 4096; probe++) {
+        Slot* s = table + idx;
+        const uint64_t clo = s->lo, chi = s->hi;
+        if (clo == lo && chi == hi) return s;
+        if ((clo | chi) == 0) return nullptr;
+        idx = (idx + 1) & mask;
+    }
+    return nullptr;
+}
+
+// RescueKminmerFunctor (CreateMdbg.hpp:4579-4637), one warp per read.  The decision only needs
+// "median * 0.1f > 1", which is unchanged when abundances are clamped at 22, so the median comes from a
+// 22-bin histogram held one bin per lane (Utils::compute_median, Commons.hpp:2973-2988).
+__global__ void __launch_bounds__(256) rescue_kernel(const RescueArgs a) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const int k = (int)a.k;
+    for (uint64_t r = warp; r < a.n_reads; r += n_warps) {
+        const uint64_t b = a.offs[r], e = a.offs[r + 1];
+        if (e - b < (uint64_t)k) continue;
+        const uint64_t nw = e - b - k + 1;
+        uint32_t bin = 0;                                  // lane v holds #windows with clamped abundance v
+        bool any_solid = false;
+        for (uint64_t i0 = 0; i0 < nw; i0 += 32) {
+            const uint64_t i = i0 + lane;
+            uint32_t c = 0;
+            if (i < nw) {
+                uint64_t h1, h2; bool rev;
+                window_hash(a.mins + b + i, k, h1, h2, rev);
+                const Slot* s = table_find(a.table, a.mask, h2, h1);
+                const uint32_t cnt = s ? s->count : 1u;
+                const uint32_t ab = cnt >= 2 ? cnt : 1u;   // solid = listed with abundance != 1 (CreateMdbg.hpp:4553-4556)
+                any_solid |= ab >= 2;
+                c = ab > 22u ? 22u : ab;
+            }
+            for (uint32_t v = 1; v <= 22; v++) {
+                const uint32_t m = __ballot_sync(0xffffffffu, c == v);
+                if (lane == v) bin += __popc(m);
+            }
+        }
+        if (!__any_sync(0xffffffffu, any_solid)) continue;  // allAbundanceOne
+        const uint32_t incl = warp_inclusive_scan(bin);      // #windows with clamped abundance <= lane
+        const uint64_t h = nw / 2;
+        // value at sorted index j = smallest v with incl[v] > j
+        const uint32_t hi_v = __ffs(__ballot_sync(0xffffffffu, incl > h)) - 1;
+        uint32_t median = hi_v;
+        if ((nw & 1) == 0) {
+            const uint32_t lo_v = __ffs(__ballot_sync(0xffffffffu, incl > h - 1)) - 1;
+            median = (lo_v + hi_v) / 2;
+        }
+        const double cutoff = (double)((float)median * 0.1f);    // CreateMdbg.hpp:4612
+        if (cutoff > 1) continue;
+        for (uint64_t i = lane; i < nw; i += 32) {
+            uint64_t h1, h2; bool rev;
+            window_hash(a.mins + b + i, k, h1, h2, rev);
+            Slot* s = table_find(a.table, a.mask, h2, h1);
+            if (s && s->count < 2) s->flags = SLOT_RESCUED;
+        }
+        if (lane == 0) atomicAdd(a.n_reads_rescued, 1ULL);
+    }
+}
+
+void launch_rescue(const RescueArgs& a, cudaStream_t s) {
+    if (a.n_reads == 0) return;
+    uint64_t blocks = (a.n_reads + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    rescue_kernel<<<(unsigned)blocks, 256, 0, s>>>(a);
+}
+
+// insert-or-assign into the previous-k lookup table (value in `count`)
+__device__ __forceinline__ bool prev_put(Slot* table, uint64_t mask, uint64_t lo, uint64_t hi, uint32_t value) {
+    uint64_t idx = lo & mask;
+    for (uint64_t probe = 0; probe <= mask && probe < 4096; probe++) {
+        Slot* s = table + idx;
+        uint64_t clo, chi;
+        load_key(s, clo, chi);
+        if (clo == lo && chi == hi && lo != 0 && hi != 0) { s->count = value; return true; }
+        if (clo == 0 || chi == 0) {
+            uint64_t olo, ohi;
+            cas_key(s, lo, hi, olo, ohi);
+            if ((olo == 0 && ohi == 0) || (olo == lo && ohi == hi)) { s->count = value; return true; }
+        }
+        idx = (idx + 1) & mask;
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(256) prev_from_table_kernel(const PrevFromTableArgs a) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.capacity;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const Slot sl = a.table[i];
+        if ((sl.lo | sl.hi) == 0) continue;
+        if (sl.count >= a.min_count || (sl.flags & SLOT_RESCUED))
+            if (!prev_put(a.prev, a.prev_mask, sl.lo, sl.hi, sl.count)) atomicExch(a.full_flag, 1u);
+    }
+}
+
+void launch_prev_from_table(const PrevFromTableArgs& a, cudaStream_t s) {
+    uint64_t blocks = (a.capacity + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    prev_from_table_kernel<<<(unsigned)blocks, 256, 0, s>>>(a);
+}
+
+__global__ void __launch_bounds__(256) prev_load_kernel(const PrevLoadArgs a) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    if (!prev_put(a.prev, a.prev_mask, a.hashes[2 * i], a.hashes[2 * i + 1], a.abund[i])) atomicExch(a.full_flag, 1u);
+}
+
+void launch_prev_load(const PrevLoadArgs& a, cudaStream_t s) {
+    if (a.n == 0) return;
+    prev_load_kernel<<<(unsigned)((a.n + 255) / 256), 256, 0, s>>>(a);
+}
+
+// k >= firstK+1: abundance of a k-min-mer = min over its two (k-1)-min-mers of the previous-k table,
+// absent (or 0) => 1; kept (insert-if-absent, value = that abundance) only when > 1.
+//   KminmerCounter::getRefinedAbundance  CreateMdbg.hpp:3933-4005  (k = firstK+1)
+//   IndexKminmerFunctor                  CreateMdbg.hpp:988-1010, 1240-1265, 1268-1464  (k >= firstK+2)
+__global__ void __launch_bounds__(256) next_k_kernel(const NextKArgs a) {
+    const uint64_t g = a.g_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= a.g_hi) return;
+    const int k = (int)a.k;
+    if ((int)a.rem[g] < k) return;
+    const uint32_t* w = a.mins + g;
+    uint32_t ab = 0xFFFFFFFFu;
+    for (int sub = 0; sub < 2; sub++) {
+        uint64_t h1, h2; bool rev;
+        window_hash(w + sub, k - 1, h1, h2, rev);
+        const Slot* s = table_find(const_cast<Slot*>(a.prev), a.prev_mask, h2, h1);
+        const uint32_t v = s ? s->count : 1u;
+        ab = v < ab ? v : ab;
+    }
+    if (ab <= 1) return;
+    uint64_t h1, h2; bool rev;
+    window_hash(w, k, h1, h2, rev);
+    // insert-if-absent: the value is a function of the key, so concurrent inserters write the same number
+    uint64_t idx = h2 & a.mask;
+    for (uint64_t probe = 0; probe <= a.mask && probe < 4096; probe++) {
+        Slot* s = a.table + idx;
+        uint64_t clo, chi;
+        load_key(s, clo, chi);
+        if (clo == h2 && chi == h1 && h2 != 0 && h1 != 0) return;
+        if (clo == 0 || chi == 0) {
+            uint64_t olo, ohi;
+            cas_key(s, h2, h1, olo, ohi);
+            if (olo == 0 && ohi == 0) {
+                s->ref = g | (rev ? REF_REV : 0ULL);
+                s->count = ab;
+                return;
+            }
+            if (olo == h2 && ohi == h1) return;
+        }
+        idx = (idx + 1) & a.mask;
+    }
+    atomicExch(a.full_flag, 1u);
+}
+
+void launch_next_k(const NextKArgs& a, cudaStream_t s) {
+    if (a.g_hi <= a.g_lo) return;
+    next_k_kernel<<<(unsigned)((a.g_hi - a.g_lo + 255) / 256), 256, 0, s>>>(a);
 }
 
 // ------------------------------------------------------------------ multi-GPU pack by owner rank

@@ -55,6 +55,7 @@ class CountTable:
     n_instances: int
     n_distinct: int
     checksum: int
+    n_rescued: int = 0
 
     def as_dict(self) -> dict:
         """{(h1, h2): abundance} with h1 = high 64 bits, h2 = low 64 bits."""
@@ -214,7 +215,27 @@ class Engine:
             v = np.ctypeslib.as_array(out.kminmers, shape=(n * k,)).copy().reshape(n, k)
         else:
             h = np.zeros((0, 2), np.uint64); a = np.zeros(0, np.uint32); v = np.zeros((0, k), np.uint32)
-        return CountTable(k, h, a, v, int(out.n_instances), int(out.n_distinct), int(out.checksum))
+        return CountTable(k, h, a, v, int(out.n_instances), int(out.n_distinct), int(out.checksum), int(out.n_rescued))
+
+    def count_rescue(self) -> int:
+        """rescueKminmers (CreateMdbg.hpp:4517-4640); returns the number of reads that rescued k-min-mers."""
+        n = C.c_uint64(0)
+        self._ck(self._lib.mdbg_count_rescue(self._ctx, C.byref(n)))
+        return int(n.value)
+
+    # -- multi-k ---------------------------------------------------------------------
+    def prev_from_current(self, min_abundance: int = 2):
+        self._ck(self._lib.mdbg_prev_from_current(self._ctx, min_abundance))
+
+    def prev_load(self, hashes: np.ndarray, abundances: np.ndarray, clear: bool = True):
+        """hashes: uint64 [n, 2] as in CountTable.hashes (low64, high64)."""
+        hashes = np.ascontiguousarray(hashes, dtype=np.uint64)
+        abundances = np.ascontiguousarray(abundances, dtype=np.uint32)
+        self._ck(self._lib.mdbg_prev_load(self._ctx, hashes.ctypes.data, abundances.ctypes.data, len(abundances),
+                                          int(clear)))
+
+    def count_add_store_next_k(self, read_lo: int = 0, read_hi: int = 2 ** 64 - 1):
+        self._ck(self._lib.mdbg_count_add_store_next_k(self._ctx, read_lo, read_hi))
 
     # -- multi-GPU -----------------------------------------------------------------
     @staticmethod

@@ -360,6 +360,152 @@ size_t orc_count(const uint32_t* mins, const uint64_t* offs, size_t n_reads, int
     return n_out;
 }
 
+/* ------------------------------------------------------- hash -> abundance lookup (sorted array) */
+
+typedef struct { uint64_t h1, h2; uint32_t ab; uint32_t idx; } HEntry;
+
+static int cmp_hentry(const void* a, const void* b) {
+    const HEntry* x = (const HEntry*)a; const HEntry* y = (const HEntry*)b;
+    if (x->h1 != y->h1) return x->h1 < y->h1 ? -1 : 1;
+    if (x->h2 != y->h2) return x->h2 < y->h2 ? -1 : 1;
+    return x->idx < y->idx ? -1 : (x->idx > y->idx ? 1 : 0);
+}
+
+static HEntry* build_lookup(const uint64_t* hashes, const uint32_t* ab, size_t n) {
+    HEntry* t = (HEntry*)malloc((n ? n : 1) * sizeof(HEntry));
+    for (size_t i = 0; i < n; i++) { t[i].h1 = hashes[2 * i]; t[i].h2 = hashes[2 * i + 1]; t[i].ab = ab[i]; t[i].idx = (uint32_t)i; }
+    qsort(t, n, sizeof(HEntry), cmp_hentry);
+    return t;
+}
+
+/* returns 1 and *ab when present (the LAST loaded duplicate wins, like map[key] = value) */
+static int lookup(const HEntry* t, size_t n, uint64_t h1, uint64_t h2, uint32_t* ab) {
+    size_t lo = 0, hi = n;
+    while (lo < hi) {                                /* upper bound of (h1,h2) */
+        size_t mid = (lo + hi) / 2;
+        if (t[mid].h1 < h1 || (t[mid].h1 == h1 && t[mid].h2 <= h2)) lo = mid + 1; else hi = mid;
+    }
+    if (lo == 0 || t[lo - 1].h1 != h1 || t[lo - 1].h2 != h2) return 0;
+    *ab = t[lo - 1].ab;
+    return 1;
+}
+
+static int cmp_u32(const void* a, const void* b) {
+    uint32_t x = *(const uint32_t*)a, y = *(const uint32_t*)b;
+    return x < y ? -1 : (x > y ? 1 : 0);
+}
+
+size_t orc_rescue(const uint32_t* mins, const uint64_t* offs, size_t n_reads, int k,
+                  const uint64_t* solid_hashes, const uint32_t* solid_ab, size_t n_solid,
+                  uint32_t** vecs_out, uint64_t** hashes_out, uint64_t* n_reads_rescued) {
+    HEntry* t = build_lookup(solid_hashes, solid_ab, n_solid);
+    size_t cap = 1024, n_out = 0, n_rr = 0;
+    uint32_t* vecs = (uint32_t*)malloc(cap * (size_t)k * 4);
+    uint64_t* hashes = (uint64_t*)malloc(cap * 16);
+    for (size_t r = 0; r < n_reads; r++) {
+        size_t n = (size_t)(offs[r + 1] - offs[r]);
+        if (n < (size_t)k) continue;
+        size_t nw = n - (size_t)k + 1;
+        uint32_t* w = (uint32_t*)malloc(nw * (size_t)k * 4);
+        uint32_t* ab = (uint32_t*)malloc(nw * 4);
+        uint32_t* sorted = (uint32_t*)malloc(nw * 4);
+        uint8_t* solid = (uint8_t*)malloc(nw);
+        orc_kminmers(mins + offs[r], n, k, w, NULL);
+        int all_one = 1;
+        for (size_t i = 0; i < nw; i++) {            /* CreateMdbg.hpp:4593-4607 */
+            uint64_t h[2]; uint32_t a;
+            orc_hash128(w + i * (size_t)k, k, h);
+            if (lookup(t, n_solid, h[0], h[1], &a)) { ab[i] = a; solid[i] = 1; all_one = 0; }
+            else { ab[i] = 1; solid[i] = 0; }
+            sorted[i] = ab[i];
+        }
+        qsort(sorted, nw, 4, cmp_u32);               /* Utils::compute_median, Commons.hpp:2973-2988 */
+        uint32_t median = (nw % 2 == 0) ? (uint32_t)(sorted[nw / 2 - 1] + sorted[nw / 2]) / 2 : sorted[nw / 2];
+        double cutoff = median * 0.1f;               /* CreateMdbg.hpp:4612: u32 * float */
+        if (!(cutoff > 1) && !all_one) {
+            n_rr++;
+            for (size_t i = 0; i < nw; i++) {
+                if (solid[i]) continue;
+                if (n_out == cap) {
+                    cap *= 2;
+                    vecs = (uint32_t*)realloc(vecs, cap * (size_t)k * 4);
+                    hashes = (uint64_t*)realloc(hashes, cap * 16);
+                }
+                memcpy(vecs + n_out * (size_t)k, w + i * (size_t)k, (size_t)k * 4);
+                orc_hash128(w + i * (size_t)k, k, hashes + 2 * n_out);
+                n_out++;
+            }
+        }
+        free(w); free(ab); free(sorted); free(solid);
+    }
+    free(t);
+    *vecs_out = vecs; *hashes_out = hashes;
+    if (n_reads_rescued) *n_reads_rescued = n_rr;
+    return n_out;
+}
+
+typedef struct { uint64_t h1, h2; uint32_t ab; const uint32_t* vec; } NEntry;
+static int cmp_nentry(const void* a, const void* b) {
+    const NEntry* x = (const NEntry*)a; const NEntry* y = (const NEntry*)b;
+    if (x->h1 != y->h1) return x->h1 < y->h1 ? -1 : 1;
+    if (x->h2 != y->h2) return x->h2 < y->h2 ? -1 : 1;
+    return 0;
+}
+
+size_t orc_next_k(const uint32_t* mins, const uint64_t* offs, size_t n_reads, int k,
+                  const uint64_t* prev_hashes, const uint32_t* prev_ab, size_t n_prev,
+                  uint32_t** vecs_out, uint64_t** hashes_out, uint32_t** abundances_out) {
+    HEntry* t = build_lookup(prev_hashes, prev_ab, n_prev);
+    size_t total = 0;
+    for (size_t r = 0; r < n_reads; r++) {
+        size_t n = (size_t)(offs[r + 1] - offs[r]);
+        if (n >= (size_t)k) total += n - (size_t)k + 1;
+    }
+    uint32_t* all = (uint32_t*)malloc((total ? total : 1) * (size_t)k * 4);
+    NEntry* ent = (NEntry*)malloc((total ? total : 1) * sizeof(NEntry));
+    size_t ne = 0, wpos = 0;
+    for (size_t r = 0; r < n_reads; r++) {
+        size_t n = (size_t)(offs[r + 1] - offs[r]);
+        if (n < (size_t)k) continue;
+        size_t nw = n - (size_t)k + 1, np = n - (size_t)k + 2;     /* (k-1)-windows */
+        uint32_t* sub = (uint32_t*)malloc(np * (size_t)(k - 1) * 4);
+        uint32_t* prev = (uint32_t*)malloc(np * 4);
+        orc_kminmers(mins + offs[r], n, k - 1, sub, NULL);          /* getPrevAbundances, CreateMdbg.hpp:1240-1265 */
+        for (size_t i = 0; i < np; i++) {
+            uint64_t h[2]; uint32_t a;
+            orc_hash128(sub + i * (size_t)(k - 1), k - 1, h);
+            prev[i] = lookup(t, n_prev, h[0], h[1], &a) ? a : 1;
+        }
+        orc_kminmers(mins + offs[r], n, k, all + wpos * (size_t)k, NULL);
+        for (size_t i = 0; i < nw; i++) {
+            uint32_t a = prev[i] < prev[i + 1] ? prev[i] : prev[i + 1];   /* getAbundance, CreateMdbg.hpp:988-1010 */
+            if (a <= 1) continue;                                           /* CreateMdbg.hpp:1429-1431 */
+            NEntry* e = &ent[ne++];
+            e->vec = all + (wpos + i) * (size_t)k;
+            uint64_t h[2];
+            orc_hash128(e->vec, k, h);
+            e->h1 = h[0]; e->h2 = h[1]; e->ab = a;
+        }
+        wpos += nw;
+        free(sub); free(prev);
+    }
+    qsort(ent, ne, sizeof(NEntry), cmp_nentry);
+    uint32_t* vecs = (uint32_t*)malloc((ne ? ne : 1) * (size_t)k * 4);
+    uint64_t* hashes = (uint64_t*)malloc((ne ? ne : 1) * 16);
+    uint32_t* abs_ = (uint32_t*)malloc((ne ? ne : 1) * 4);
+    size_t n_out = 0;
+    for (size_t i = 0; i < ne; i++) {                /* lazy_emplace_l: first insertion wins (all equal anyway) */
+        if (i > 0 && ent[i].h1 == ent[i - 1].h1 && ent[i].h2 == ent[i - 1].h2) continue;
+        memcpy(vecs + n_out * (size_t)k, ent[i].vec, (size_t)k * 4);
+        hashes[2 * n_out] = ent[i].h1; hashes[2 * n_out + 1] = ent[i].h2;
+        abs_[n_out] = ent[i].ab;
+        n_out++;
+    }
+    free(all); free(ent); free(t);
+    *vecs_out = vecs; *hashes_out = hashes; *abundances_out = abs_;
+    return n_out;
+}
+
 uint64_t orc_table_checksum(const uint64_t* hashes, const uint32_t* abundances, size_t n) {
     uint64_t s = 0;
     for (size_t i = 0; i < n; i++) s += (uint64_t)abundances[i] * hashes[2 * i + 1];

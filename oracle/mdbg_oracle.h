@@ -88,6 +88,25 @@ size_t orc_count(const uint32_t* mins, const uint64_t* offs, size_t n_reads, int
                  uint32_t min_abundance, uint32_t** vecs, uint64_t** hashes,
                  uint32_t** abundances, uint64_t* n_instances, uint64_t* n_distinct);
 
+/* rescueKminmers / RescueKminmerFunctor (src/graph/CreateMdbg.hpp:4517-4640), default mode.
+ * solid_hashes (n_solid x {h1,h2}) / solid_ab = the abundance >= 2 table.  For every read whose
+ * median abundance m (solid abundance, else 1; Utils::compute_median, src/Commons.hpp:2973-2988)
+ * satisfies m * 0.1f <= 1 and that has at least one solid k-min-mer, the non-solid k-min-mers are
+ * emitted with abundance 1, in read order.  Outputs malloc'ed: vecs (n*k), hashes (n*2: h1,h2).
+ * Returns n; *n_reads_rescued = number of qualifying reads. */
+size_t orc_rescue(const uint32_t* mins, const uint64_t* offs, size_t n_reads, int k,
+                  const uint64_t* solid_hashes, const uint32_t* solid_ab, size_t n_solid,
+                  uint32_t** vecs, uint64_t** hashes, uint64_t* n_reads_rescued);
+
+/* k >= firstK+1 pass: KminmerCounter::getRefinedAbundance (src/graph/CreateMdbg.hpp:3933-4005)
+ * and IndexKminmerFunctor (src/graph/CreateMdbg.hpp:988-1010, 1240-1265, 1268-1464) give the same
+ * table: every distinct k-min-mer of the reads whose min over its two (k-1)-min-mers of the previous
+ * table (absent or 0 => 1) is > 1, with that value.  prev_hashes: n_prev x {h1,h2}.  Outputs
+ * malloc'ed and sorted by (h1,h2): vecs (n*k), hashes (n*2), abundances (n).  Returns n. */
+size_t orc_next_k(const uint32_t* mins, const uint64_t* offs, size_t n_reads, int k,
+                  const uint64_t* prev_hashes, const uint32_t* prev_ab, size_t n_prev,
+                  uint32_t** vecs, uint64_t** hashes, uint32_t** abundances);
+
 /* Order-free fingerprint used by the reference's debug log
  * (src/graph/CreateMdbg.cpp:3321): sum abundance * (u64)hash128 mod 2^64,
  * where (u64)hash128 = low 64 bits = h2. */

@@ -29,7 +29,8 @@ def build(force: bool = False) -> None:
         subprocess.run(["make", "-s", "-C", HERE, os.path.join(HERE, "libmdbg_oracle.so")], check=True)
     if os.path.exists("/root/reference/src/Commons.hpp"):
         if force or not os.path.exists(REF_SO) or \
-                os.path.getmtime(REF_SO) < os.path.getmtime(os.path.join(HERE, "ref_shim.cpp")):
+                os.path.getmtime(REF_SO) < max(os.path.getmtime(os.path.join(HERE, "ref_shim.cpp")),
+                                               os.path.getmtime(os.path.join(HERE, "Makefile"))):
             subprocess.run(["make", "-s", "-C", HERE, "ref"], check=True)
 
 
@@ -140,6 +141,12 @@ class Oracle(_Lib):
         L.orc_sketch_batch.restype = C.c_size_t
         L.orc_sketch_batch.argtypes = [C.c_void_p, _u64p, C.c_size_t, C.c_int, C.c_float, C.c_int, _u32p, C.c_size_t,
                                        _u64p, _u32p, _u32p, _u8p, C.c_size_t]
+        L.orc_rescue.restype = C.c_size_t
+        L.orc_rescue.argtypes = [_u32p, _u64p, C.c_size_t, C.c_int, _u64p, _u32p, C.c_size_t, C.POINTER(_u32p),
+                                 C.POINTER(_u64p), _u64p]
+        L.orc_next_k.restype = C.c_size_t
+        L.orc_next_k.argtypes = [_u32p, _u64p, C.c_size_t, C.c_int, _u64p, _u32p, C.c_size_t, C.POINTER(_u32p),
+                                 C.POINTER(_u64p), C.POINTER(_u32p)]
         L.orc_table_checksum.restype = C.c_uint64
         L.orc_table_checksum.argtypes = [_u64p, _u32p, C.c_size_t]
 
@@ -188,6 +195,26 @@ class Oracle(_Lib):
         abund = self._take(a, n, np.uint32)
         return dict(vecs=vecs, hashes=hashes, abundances=abund, n_instances=int(ni.value), n_distinct=int(nd.value))
 
+    def rescue(self, mins, offs, k, solid_hashes, solid_ab):
+        """-> dict(vecs [n,k], hashes [n,2] (h1,h2), n_reads_rescued); rescued abundance is always 1."""
+        mins = np.ascontiguousarray(mins, dtype=np.uint32); offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        sh = np.ascontiguousarray(solid_hashes, dtype=np.uint64); sa = np.ascontiguousarray(solid_ab, dtype=np.uint32)
+        v = _u32p(); h = _u64p(); nr = C.c_uint64(0)
+        n = self.lib.orc_rescue(_p(mins, _u32p), _p(offs, _u64p), len(offs) - 1, k, _p(sh, _u64p), _p(sa, _u32p), len(sa),
+                                C.byref(v), C.byref(h), C.byref(nr))
+        return dict(vecs=self._take(v, n * k, np.uint32).reshape(n, k), hashes=self._take(h, 2 * n, np.uint64).reshape(n, 2),
+                    n_reads_rescued=int(nr.value))
+
+    def next_k(self, mins, offs, k, prev_hashes, prev_ab):
+        """-> dict(vecs, hashes (h1,h2), abundances), sorted by hash."""
+        mins = np.ascontiguousarray(mins, dtype=np.uint32); offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        ph = np.ascontiguousarray(prev_hashes, dtype=np.uint64); pa = np.ascontiguousarray(prev_ab, dtype=np.uint32)
+        v = _u32p(); h = _u64p(); a = _u32p()
+        n = self.lib.orc_next_k(_p(mins, _u32p), _p(offs, _u64p), len(offs) - 1, k, _p(ph, _u64p), _p(pa, _u32p), len(pa),
+                                C.byref(v), C.byref(h), C.byref(a))
+        return dict(vecs=self._take(v, n * k, np.uint32).reshape(n, k), hashes=self._take(h, 2 * n, np.uint64).reshape(n, 2),
+                    abundances=self._take(a, n, np.uint32))
+
     def checksum(self, hashes: np.ndarray, abundances: np.ndarray) -> int:
         hashes = np.ascontiguousarray(hashes, dtype=np.uint64)
         abundances = np.ascontiguousarray(abundances, dtype=np.uint32)
@@ -213,6 +240,13 @@ class Reference(_Lib):
         L.ref_pipeline.argtypes = [C.c_void_p, _u64p, C.c_size_t, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
                                    C.c_uint32, C.c_int, _u64p, _u64p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.ref_max_threads.restype = C.c_int
+        L.ref_graph_firstpass.restype = C.c_size_t
+        L.ref_graph_firstpass.argtypes = [_u32p, _u64p, C.c_size_t, C.c_int, C.c_uint32, C.c_int, C.c_char_p,
+                                          C.POINTER(_u32p), C.POINTER(_u64p), C.POINTER(_u32p), _u64p, _u64p,
+                                          C.POINTER(C.c_double)]
+        L.ref_graph_next_k.restype = C.c_size_t
+        L.ref_graph_next_k.argtypes = [_u32p, _u64p, C.c_size_t, C.c_int, _u64p, _u32p, C.c_size_t, C.c_int, C.c_int,
+                                       C.c_char_p, C.POINTER(_u32p), C.POINTER(_u64p), C.POINTER(_u32p)]
 
     def purge_palindrome(self, m: np.ndarray, first_k: int, last_k: int):
         m = np.ascontiguousarray(m, dtype=np.uint32)
@@ -231,6 +265,33 @@ class Reference(_Lib):
         hashes = self._take(h, n * 2, np.uint64).reshape(n, 2)
         abund = self._take(a, n, np.uint32)
         return dict(vecs=vecs, hashes=hashes, abundances=abund, n_instances=int(ni.value), n_distinct=int(nd.value))
+
+    def graph_firstpass(self, mins, offs, k, min_abundance=0, threads=1):
+        """The reference's own KminmerCounter (+ rescueKminmers when min_abundance <= 1) in a scratch dir."""
+        import tempfile
+        mins = np.ascontiguousarray(mins, dtype=np.uint32); offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        v = _u32p(); h = _u64p(); a = _u32p()
+        ns = C.c_uint64(0); nr = C.c_uint64(0); sec = C.c_double(0)
+        with tempfile.TemporaryDirectory() as d:
+            n = self.lib.ref_graph_firstpass(_p(mins, _u32p), _p(offs, _u64p), len(offs) - 1, k, min_abundance, threads,
+                                             d.encode(), C.byref(v), C.byref(h), C.byref(a), C.byref(ns), C.byref(nr),
+                                             C.byref(sec))
+        return dict(vecs=self._take(v, n * k, np.uint32).reshape(n, k), hashes=self._take(h, 2 * n, np.uint64).reshape(n, 2),
+                    abundances=self._take(a, n, np.uint32), n_solid=int(ns.value), n_rescued=int(nr.value),
+                    seconds=float(sec.value))
+
+    def graph_next_k(self, mins, offs, k, prev_hashes, prev_ab, use_counter=False, threads=1):
+        import tempfile
+        mins = np.ascontiguousarray(mins, dtype=np.uint32); offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        ph = np.ascontiguousarray(prev_hashes, dtype=np.uint64); pa = np.ascontiguousarray(prev_ab, dtype=np.uint32)
+        v = _u32p(); h = _u64p(); a = _u32p()
+        with tempfile.TemporaryDirectory() as d:
+            n = self.lib.ref_graph_next_k(_p(mins, _u32p), _p(offs, _u64p), len(offs) - 1, k, _p(ph, _u64p), _p(pa, _u32p),
+                                          len(pa), int(use_counter), threads, d.encode(), C.byref(v), C.byref(h),
+                                          C.byref(a))
+        vecs = self._take(v, n * k, np.uint32).reshape(n, k)
+        return dict(vecs=vecs if use_counter else None, hashes=self._take(h, 2 * n, np.uint64).reshape(n, 2),
+                    abundances=self._take(a, n, np.uint32))
 
     def max_threads(self) -> int:
         return int(self.lib.ref_max_threads())

@@ -18,12 +18,15 @@
  *   MDBG::getKminmers_complete     src/Commons.hpp:5150-5367
  *   KmerVec::{normalize,hash128,operator<}  src/Commons.hpp:740-1005
  *   Commons::sortParallel          src/Commons.hpp:1537-1574
- * The only logic written here is the run-length count + ">=2" filter of
- * KminmerCounter::dereplicatePartition/dumpKminmer (src/graph/CreateMdbg.hpp:
- * 3744-3883), whose file I/O is replaced by in-memory vectors (this favours
- * the reference when it is timed).
+ *   CreateMdbg::KminmerCounter     src/graph/CreateMdbg.hpp:3591-4007   (ref_graph_firstpass, ref_graph_next_k)
+ *   CreateMdbg::rescueKminmers     src/graph/CreateMdbg.hpp:4517-4640   (ref_graph_firstpass)
+ *   CreateMdbg::IndexKminmerFunctor src/graph/CreateMdbg.hpp:951-1465   (ref_graph_next_k)
+ * ref_count (in-memory sort/count) is the only place where logic is written here: the run-length
+ * count + ">=2" filter of KminmerCounter::dereplicatePartition/dumpKminmer without its file I/O;
+ * ref_graph_* drive the reference's own classes through their file contract in a scratch directory.
  */
 #include "Commons.hpp"
+#include "graph/CreateMdbg.hpp"
 
 #include <cstdint>
 #include <cstdlib>
@@ -226,6 +229,130 @@ size_t ref_pipeline(const char* bases, const uint64_t* offsets, size_t n_reads, 
     if (seconds_sketch) *seconds_sketch = duration<double>(t1 - t0).count();
     if (seconds_count) *seconds_count = duration<double>(t2 - t1).count();
     return n;
+}
+
+// ---- the reference's own graph-stage classes, driven through their file contract -----------------
+
+static void write_read_data(const string& filename, const uint32_t* mins, const uint64_t* offs, size_t n_reads) {
+    // record format read by KminmerParserParallel (src/Commons.hpp:7405-7440): u32 n, u8 isCircular, u32[n]
+    ofstream f(filename, std::ios::binary);
+    for (size_t r = 0; r < n_reads; r++) {
+        u_int32_t size = (u_int32_t)(offs[r + 1] - offs[r]);
+        u_int8_t isCircular = 0;
+        f.write((const char*)&size, sizeof(size));
+        f.write((const char*)&isCircular, sizeof(isCircular));
+        f.write((const char*)(mins + offs[r]), size * sizeof(u_int32_t));
+    }
+}
+
+static size_t read_tables(const string& dir, int k, bool with_vecs, uint32_t** vecs_out, uint64_t** hashes_out,
+                          uint32_t** abundances_out) {
+    vector<uint64_t> hashes;
+    vector<uint32_t> abs_;
+    ifstream fa(dir + "/kminmerData_abundance.txt", std::ios::binary);
+    while (true) {
+        u_int128_t vecHash;
+        AbundanceType abundance;
+        bool iseof = MDBG::readKminmerAbundance(vecHash, abundance, fa);
+        if (iseof) break;
+        hashes.push_back((uint64_t)(vecHash >> 64));
+        hashes.push_back((uint64_t)vecHash);
+        abs_.push_back(abundance);
+    }
+    size_t n = abs_.size();
+    *hashes_out = (uint64_t*)malloc((hashes.size() + 1) * 8);
+    *abundances_out = (uint32_t*)malloc((n + 1) * 4);
+    memcpy(*hashes_out, hashes.data(), hashes.size() * 8);
+    memcpy(*abundances_out, abs_.data(), n * 4);
+    *vecs_out = (uint32_t*)malloc((n * (size_t)k + 1) * 4);
+    if (with_vecs) {
+        ifstream fk(dir + "/kminmerData_min.txt", std::ios::binary);
+        fk.read((char*)*vecs_out, n * (size_t)k * 4);
+    }
+    return n;
+}
+
+/* CreateMdbg::createMDBG first pass (src/graph/CreateMdbg.cpp:284-326): KminmerCounter::execute
+ * (disk partitions, sortParallel, dump) then rescueKminmers when min_abundance <= 1.
+ * Entries come back in file order: the n_solid counted entries first, rescued ones after. */
+size_t ref_graph_firstpass(const uint32_t* mins, const uint64_t* offs, size_t n_reads, int k, uint32_t min_abundance,
+                           int n_threads, const char* tmp_dir, uint32_t** vecs_out, uint64_t** hashes_out,
+                           uint32_t** abundances_out, uint64_t* n_solid, uint64_t* n_rescued, double* seconds) {
+    if (n_threads < 1) n_threads = 1;
+    const string dir(tmp_dir);
+    write_read_data(dir + "/read_data_corrected.txt", mins, offs, n_reads);
+    auto t0 = high_resolution_clock::now();
+    CreateMdbg c;
+    c._outputDir = dir;
+    c._kminmerSize = k;
+    c._nbCores = n_threads;
+    c._nbPartitions = n_threads;                       // CreateMdbg.cpp:223-226: max(nbBases/20e9, nbCores, 1)
+    c._isFirstPass = true;
+    c._minAbundance = min_abundance;
+    c._kminmerFile = ofstream(dir + "/kminmerData_min.txt");
+    c._kminmerAbundanceFile = ofstream(dir + "/kminmerData_abundance.txt");
+    {
+        CreateMdbg::KminmerCounter kminmerCounter(c);
+        kminmerCounter.execute();
+        if (n_solid) *n_solid = kminmerCounter._nbSolidKminmers;
+    }
+    c._kminmerFile.close();
+    c._kminmerAbundanceFile.close();
+    c._nbRescuedKminmers = 0;
+    if (min_abundance <= 1) {                          // CreateMdbg.cpp:309-319
+        c._kminmerFile.open(dir + "/kminmerData_min.txt", std::ios_base::app);
+        c._kminmerAbundanceFile.open(dir + "/kminmerData_abundance.txt", std::ios_base::app);
+        c.rescueKminmers();
+        c._kminmerFile.close();
+        c._kminmerAbundanceFile.close();
+    }
+    if (n_rescued) *n_rescued = c._nbRescuedKminmers;
+    if (seconds) *seconds = duration<double>(high_resolution_clock::now() - t0).count();
+    return read_tables(dir, k, true, vecs_out, hashes_out, abundances_out);
+}
+
+/* createMDBG for k > firstK (src/graph/CreateMdbg.cpp:386-468) with _kminmerAbundances given:
+ * use_counter != 0 -> the KminmerCounter + getRefinedAbundance path (k == firstK+1),
+ * else             -> the IndexKminmerFunctor path (k >= firstK+2).  unitig_data.txt is empty. */
+size_t ref_graph_next_k(const uint32_t* mins, const uint64_t* offs, size_t n_reads, int k, const uint64_t* prev_hashes,
+                        const uint32_t* prev_ab, size_t n_prev, int use_counter, int n_threads, const char* tmp_dir,
+                        uint32_t** vecs_out, uint64_t** hashes_out, uint32_t** abundances_out) {
+    if (n_threads < 1) n_threads = 1;
+    const string dir(tmp_dir);
+    write_read_data(dir + "/read_data_corrected.txt", mins, offs, n_reads);
+    { ofstream empty(dir + "/unitig_data.txt", std::ios::binary); }
+    CreateMdbg c;
+    c._outputDir = dir;
+    c._kminmerSize = k;
+    c._kminmerSizePrev = k - 1;
+    c._kminmerSizeFirst = 4;
+    c._nbCores = n_threads;
+    c._nbPartitions = n_threads;
+    c._isFirstPass = false;
+    c._minAbundance = 0;
+    for (size_t i = 0; i < n_prev; i++) {
+        u_int128_t h = ((u_int128_t)prev_hashes[2 * i] << 64) | prev_hashes[2 * i + 1];
+        c._kminmerAbundances[h] = prev_ab[i];
+    }
+    if (use_counter) {
+        c._kminmerFile.open(dir + "/kminmerData_min.txt");
+        c._kminmerAbundanceFile.open(dir + "/kminmerData_abundance.txt");
+        CreateMdbg::KminmerCounter kminmerCounter(c);
+        kminmerCounter.execute();
+        c._kminmerFile.close();
+        c._kminmerAbundanceFile.close();
+        return read_tables(dir, k, true, vecs_out, hashes_out, abundances_out);
+    }
+    KminmerParserParallel parser2(dir + "/read_data_corrected.txt", 0, k, false, false, n_threads);
+    parser2.parse(CreateMdbg::IndexKminmerFunctor(c, false));
+    c._kminmerAbundanceFile.open(dir + "/kminmerData_abundance.txt");
+    for (const auto& it : c._mdbgNodesLight) {          // CreateMdbg.cpp:453-464
+        u_int128_t vecHash = it.first;
+        u_int32_t abundance = it.second;
+        MDBG::writeKminmerAbundance(vecHash, abundance, c._kminmerAbundanceFile);
+    }
+    c._kminmerAbundanceFile.close();
+    return read_tables(dir, k, false, vecs_out, hashes_out, abundances_out);
 }
 
 int ref_max_threads() { return omp_get_max_threads(); }

@@ -109,6 +109,29 @@ def main():
         out[f"k{k}_hashes"] = c["hashes"]; out[f"k{k}_abund"] = c["abundances"]; out[f"k{k}_vecs"] = c["vecs"]
         out[f"k{k}_stats"] = np.array([c["n_instances"], c["n_distinct"]], np.uint64)
     np.savez_compressed(os.path.join(HERE, "minspace_palindromes.npz"), **out)
+    # 5. default-mode first pass (KminmerCounter + rescueKminmers) and the k=5,6 passes, from the reference's
+    #    own CreateMdbg classes (oracle/ref_shim.cpp: ref_graph_firstpass / ref_graph_next_k)
+    base = rng.integers(0, 400, size=6000).astype(np.uint32)
+    reads = []
+    for _ in range(900):
+        ln = int(rng.integers(0, 90)); st = int(rng.integers(0, len(base) - 90))
+        r = base[st:st + ln].copy()
+        if ln and rng.random() < 0.3:
+            r[rng.integers(0, ln)] = rng.integers(0, 400)
+        if rng.random() < 0.5:
+            r = r[::-1].copy()
+        reads.append(r)
+    offs = np.zeros(len(reads) + 1, np.uint64)
+    offs[1:] = np.cumsum([len(r) for r in reads])
+    mins = np.concatenate(reads).astype(np.uint32)
+    g4 = ref.graph_firstpass(mins, offs, 4, min_abundance=0, threads=2)
+    g5 = ref.graph_next_k(mins, offs, 5, g4["hashes"], g4["abundances"], use_counter=True, threads=2)
+    g6 = ref.graph_next_k(mins, offs, 6, g5["hashes"], g5["abundances"], use_counter=False, threads=2)
+    np.savez_compressed(os.path.join(HERE, "minspace_multik.npz"), minimizers=mins, offsets=offs,
+                        k4_hashes=g4["hashes"], k4_abund=g4["abundances"], k4_vecs=g4["vecs"],
+                        k4_n_solid=g4["n_solid"], k4_n_rescued=g4["n_rescued"],
+                        k5_hashes=g5["hashes"], k5_abund=g5["abundances"], k5_vecs=g5["vecs"],
+                        k6_hashes=g6["hashes"], k6_abund=g6["abundances"])
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -65,3 +65,21 @@ def test_minspace_palindromes(oracle):
         c = oracle.count(g["purged_minimizers"], g["purged_offsets"], k, 3)
         assert np.array_equal(c["hashes"], g[f"k{k}_hashes"]) and np.array_equal(c["abundances"], g[f"k{k}_abund"])
         assert np.array_equal(c["vecs"], g[f"k{k}_vecs"])
+
+
+def test_minspace_multik(oracle):
+    """Default-mode first pass (count + rescue) and the k=5 / k=6 passes against vectors minted from the
+    reference's own KminmerCounter / rescueKminmers / IndexKminmerFunctor."""
+    g = load("minspace_multik.npz")
+    mins, offs = g["minimizers"], g["offsets"]
+    ns = int(g["k4_n_solid"])
+    c = oracle.count(mins, offs, 4, 2)
+    assert table_dict(c["hashes"], c["abundances"]) == table_dict(g["k4_hashes"][:ns], g["k4_abund"][:ns])
+    r = oracle.rescue(mins, offs, 4, c["hashes"], c["abundances"])
+    assert len(r["hashes"]) == int(g["k4_n_rescued"]) > 0
+    assert sorted(map(tuple, r["hashes"].tolist())) == sorted(map(tuple, g["k4_hashes"][ns:].tolist()))
+    t5 = oracle.next_k(mins, offs, 5, g["k4_hashes"], g["k4_abund"])
+    assert table_dict(t5["hashes"], t5["abundances"]) == table_dict(g["k5_hashes"], g["k5_abund"])
+    t6 = oracle.next_k(mins, offs, 6, g["k5_hashes"], g["k5_abund"])
+    assert table_dict(t6["hashes"], t6["abundances"]) == table_dict(g["k6_hashes"], g["k6_abund"])
+    assert len(t6["abundances"]) > 20

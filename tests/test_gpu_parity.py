@@ -272,3 +272,85 @@ def test_python_mirror_single_read(built, oracle):
     rm, rp, rd = oracle.sketch_read(seq, 15, 0.005, True)
     assert np.array_equal(m, rm) and np.array_equal(p, rp) and np.array_equal(d, rd)
     mp.engine.close()
+
+
+# ---------------------------------------------------------------- rescue (A7b) and next-k passes (A8/A9)
+
+def _h1h2(tab):
+    """CountTable.hashes (low, high) -> list of (h1, h2) tuples."""
+    return [(int(h[1]), int(h[0])) for h in tab.hashes]
+
+
+def test_rescue_and_next_k_golden(built):
+    g = load("minspace_multik.npz")
+    mins, offs = g["minimizers"], g["offsets"]
+    ns = int(g["k4_n_solid"])
+    eng = engine()
+    eng.store_append(mins, offs)
+    # default mode: count, rescue, finalize -> solid + rescued entries
+    eng.count_begin(4)
+    eng.count_add_store()
+    n_reads_rescued = eng.count_rescue()
+    tab = eng.count_finalize(0)
+    assert n_reads_rescued > 0 and tab.n_rescued == int(g["k4_n_rescued"])
+    assert tab.as_dict() == table_dict(g["k4_hashes"], g["k4_abund"])
+    want_vecs = {(int(h[0]), int(h[1])): tuple(int(x) for x in v) for h, v in zip(g["k4_hashes"], g["k4_vecs"])}
+    got_vecs = {hh: tuple(int(x) for x in v) for hh, v in zip(_h1h2(tab), tab.kminmers)}
+    assert got_vecs == want_vecs
+    # k = 5 from the table just built (device side), k = 6 from the k = 5 table
+    eng.prev_from_current(0)
+    eng.count_begin(5)
+    eng.count_add_store_next_k()
+    t5 = eng.count_finalize(0)
+    assert t5.as_dict() == table_dict(g["k5_hashes"], g["k5_abund"])
+    want_vecs = {(int(h[0]), int(h[1])): tuple(int(x) for x in v) for h, v in zip(g["k5_hashes"], g["k5_vecs"])}
+    assert {hh: tuple(int(x) for x in v) for hh, v in zip(_h1h2(t5), t5.kminmers)} == want_vecs
+    eng.prev_from_current(0)
+    eng.count_begin(6)
+    eng.count_add_store_next_k()
+    t6 = eng.count_finalize(0)
+    assert t6.as_dict() == table_dict(g["k6_hashes"], g["k6_abund"]) and len(t6.abundances) > 20
+    eng.close()
+
+
+def test_next_k_with_host_loaded_and_patched_prev_table(built, oracle):
+    """prev table from host pairs (kminmerData_abundance_prev.txt) + a patch (refined abundances incl. zeros)."""
+    rs = synth.make_readset(2500, 9000, seed=61, n_genomes=1, genome_len_range=(250_000, 250_001))
+    bases, offs = synth.fill_reads(rs)
+    eng = engine()
+    eng.sketch_batch(bases, offs, append_to_store=True, fetch=False)
+    so, sm = eng.store_fetch()
+    prev = oracle.count(sm, so, 4, 2)
+    rng = np.random.default_rng(5)
+    patch_idx = np.nonzero(rng.random(len(prev["abundances"])) < 0.2)[0]
+    patched = prev["abundances"].copy()
+    patched[patch_idx] = rng.integers(0, 4, size=len(patch_idx)).astype(np.uint32)
+    lohi = np.stack([prev["hashes"][:, 1], prev["hashes"][:, 0]], axis=1)       # (low, high) as on disk
+    eng.prev_load(lohi, prev["abundances"], clear=True)
+    eng.prev_load(lohi[patch_idx], patched[patch_idx], clear=False)
+    for k in (5,):
+        eng.count_begin(k)
+        eng.count_add_store_next_k()
+        tab = eng.count_finalize(0)
+        want = oracle.next_k(sm, so, k, prev["hashes"], patched)
+        assert tab.as_dict() == table_dict(want["hashes"], want["abundances"]) and len(want["abundances"]) > 1000
+    eng.close()
+
+
+def test_rescue_on_sketched_reads_vs_oracle(built, oracle):
+    rs = synth.make_readset(3000, 8000, seed=62, n_genomes=3, genome_len_range=(150_000, 600_000), err=0.004)
+    bases, offs = synth.fill_reads(rs)
+    eng = engine()
+    eng.sketch_batch(bases, offs, append_to_store=True, fetch=False)
+    so, sm = eng.store_fetch()
+    eng.count_begin(4)
+    eng.count_add_store()
+    eng.count_rescue()
+    tab = eng.count_finalize(0)
+    c = oracle.count(sm, so, 4, 2)
+    r = oracle.rescue(sm, so, 4, c["hashes"], c["abundances"])
+    want = table_dict(c["hashes"], c["abundances"])
+    for h in r["hashes"]:
+        want[(int(h[0]), int(h[1]))] = 1
+    assert tab.as_dict() == want and tab.n_rescued == len(r["hashes"]) > 0
+    eng.close()

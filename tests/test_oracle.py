@@ -226,3 +226,72 @@ def test_ref_pipeline_checksum(oracle, reference):
     assert res["n_minimizers"] == len(m)
     assert res["n_solid"] == len(c["abundances"]) and res["n_solid"] > 10
     assert res["checksum"] == oracle.checksum(c["hashes"], c["abundances"])
+
+
+# ---- rows A7 (real KminmerCounter with disk partitions), A7b rescue, A8/A9 next-k: restatement vs the
+# ---- reference's own CreateMdbg classes driven through their file contract
+
+def _table(hashes, abund):
+    return {(int(h[0]), int(h[1])): int(a) for h, a in zip(hashes, abund)}
+
+
+def _minspace_reads(seed, n_reads=600, alphabet=400, max_len=80):
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, alphabet, size=5000).astype(np.uint32)       # a "genome" in minimizer space
+    reads = []
+    for _ in range(n_reads):
+        ln = int(rng.integers(0, max_len))
+        st = int(rng.integers(0, len(base) - max_len))
+        r = base[st:st + ln].copy()
+        if ln and rng.random() < 0.3:
+            r[rng.integers(0, ln)] = rng.integers(0, alphabet)           # an "error"
+        if rng.random() < 0.5:
+            r = r[::-1].copy()
+        reads.append(r)
+    offs = np.zeros(len(reads) + 1, np.uint64)
+    offs[1:] = np.cumsum([len(r) for r in reads])
+    return np.concatenate(reads).astype(np.uint32), offs
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("k", [4, 7])
+def test_ref_graph_firstpass_counter_and_rescue(oracle, reference, k):
+    mins, offs = _minspace_reads(41)
+    # --min-abundance 2: pure count, no rescue
+    g = reference.graph_firstpass(mins, offs, k, min_abundance=2, threads=3)
+    c = oracle.count(mins, offs, k, 2)
+    assert g["n_rescued"] == 0 and g["n_solid"] == len(c["abundances"]) > 50
+    assert _table(g["hashes"], g["abundances"]) == _table(c["hashes"], c["abundances"])
+    assert sorted(map(tuple, g["vecs"].tolist())) == sorted(map(tuple, c["vecs"].tolist()))
+    # default mode (--min-abundance 0): solid entries, then the rescued abundance-1 entries
+    g = reference.graph_firstpass(mins, offs, k, min_abundance=0, threads=2)
+    ns = g["n_solid"]
+    assert _table(g["hashes"][:ns], g["abundances"][:ns]) == _table(c["hashes"], c["abundances"])
+    r = oracle.rescue(mins, offs, k, c["hashes"], c["abundances"])
+    assert g["n_rescued"] == len(r["hashes"]) > 0
+    assert np.all(g["abundances"][ns:] == 1)
+    assert sorted(map(tuple, g["hashes"][ns:].tolist())) == sorted(map(tuple, r["hashes"].tolist()))
+    assert sorted(map(tuple, g["vecs"][ns:].tolist())) == sorted(map(tuple, r["vecs"].tolist()))
+    assert len(set(map(tuple, r["hashes"].tolist()))) == len(r["hashes"])       # rescued keys are unique
+
+
+@pytest.mark.ref
+def test_ref_graph_next_k_both_paths(oracle, reference):
+    mins, offs = _minspace_reads(42)
+    prev = oracle.count(mins, offs, 4, 2)
+    rng = np.random.default_rng(0)
+    prev_ab = prev["abundances"].copy()
+    prev_ab[rng.random(len(prev_ab)) < 0.1] = 0           # "refined" abundances may be 0 (treated as <= 1)
+    for k, use_counter in ((5, True), (5, False)):
+        want = oracle.next_k(mins, offs, k, prev["hashes"], prev_ab)
+        got = reference.graph_next_k(mins, offs, k, prev["hashes"], prev_ab, use_counter=use_counter, threads=2)
+        assert _table(got["hashes"], got["abundances"]) == _table(want["hashes"], want["abundances"])
+        assert len(want["abundances"]) > 50 and want["abundances"].min() >= 2
+        if use_counter:
+            assert sorted(map(tuple, got["vecs"].tolist())) == sorted(map(tuple, want["vecs"].tolist()))
+    # chain: k=5 table feeds k=6 (IndexKminmerFunctor path)
+    t5 = oracle.next_k(mins, offs, 5, prev["hashes"], prev["abundances"])
+    want = oracle.next_k(mins, offs, 6, t5["hashes"], t5["abundances"])
+    got = reference.graph_next_k(mins, offs, 6, t5["hashes"], t5["abundances"], use_counter=False, threads=3)
+    assert _table(got["hashes"], got["abundances"]) == _table(want["hashes"], want["abundances"])
+    assert len(want["abundances"]) > 20
