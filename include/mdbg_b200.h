@@ -139,6 +139,24 @@ mdbg_status mdbg_sketch_batch_device(mdbg_ctx* ctx, const uint8_t* d_bases, cons
 /* Copy the last batch's CSR to pinned host memory (after *_device). */
 mdbg_status mdbg_sketch_fetch(mdbg_ctx* ctx, mdbg_sketch_out* out);
 
+/* ---- read side outputs (row A3b: ReadSelection.hpp:870-920, 1047-1138, 1171-1228, 1302-1320) ------------
+ * What ReadSelectionFunctor hands to writeRead besides the sketch.  Host pointers are library-owned. */
+typedef struct {
+    uint32_t n_reads;
+    const float*   mean_quality;    /* [n_reads] meanReadQuality; NaN when the batch has no qualities */
+    const double*  complexity;      /* [n_reads] computeSequenceComplexity(seq, 64, 32) */
+    const uint8_t* low_complexity;  /* [n_reads] 1 = complexity > 5 (minimizers cleared when the filter is on) */
+    const uint8_t* qualities;       /* [n_minimizers] per-minimizer min base quality, aligned with mdbg_sketch_out
+                                       (all 1 when the batch has no qualities, ReadSelection.hpp:1049-1053) */
+} mdbg_aux_out;
+
+/* filter_low_complexity != 0: reads with complexity > 5 lose their minimizers (ReadSelection.hpp:894-903), as the
+ * reference always does.  Only applied by mdbg_sketch_batch_q.  --min-read-quality > 0 is not supported. */
+mdbg_status mdbg_ctx_set_read_filters(mdbg_ctx* ctx, int filter_low_complexity);
+/* mdbg_sketch_batch plus the side outputs.  quals = Read::_qual bytes laid out like bases (NULL for FASTA). */
+mdbg_status mdbg_sketch_batch_q(mdbg_ctx* ctx, const uint8_t* bases, const uint8_t* quals, const uint64_t* offsets,
+                                uint32_t n_reads, int append_to_store, mdbg_sketch_out* out, mdbg_aux_out* aux);
+
 /* ---- minimizer-space read store (device-resident read_data_*.txt) -------- */
 mdbg_status mdbg_store_clear(mdbg_ctx* ctx);
 /* Append host minimizer-space reads (what KminmerParserParallel would read). */

@@ -38,6 +38,11 @@ class TableOut(C.Structure):
                 ("checksum", C.c_uint64), ("n_rescued", C.c_uint64)]
 
 
+class AuxOut(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32), ("mean_quality", C.POINTER(C.c_float)), ("complexity", C.POINTER(C.c_double)),
+                ("low_complexity", u8p), ("qualities", u8p)]
+
+
 # every symbol include/mdbg_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "mdbg_ctx_create": (C.c_int, [C.c_int, C.POINTER(MdbgParams), C.POINTER(C.c_void_p)]),
@@ -52,6 +57,9 @@ SYMBOLS = {
     "mdbg_sketch_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_int,
                                            C.POINTER(SketchDev)]),
     "mdbg_sketch_fetch": (C.c_int, [C.c_void_p, C.POINTER(SketchOut)]),
+    "mdbg_ctx_set_read_filters": (C.c_int, [C.c_void_p, C.c_int]),
+    "mdbg_sketch_batch_q": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int,
+                                      C.POINTER(SketchOut), C.POINTER(AuxOut)]),
     "mdbg_store_clear": (C.c_int, [C.c_void_p]),
     "mdbg_store_append": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "mdbg_store_size": (C.c_int, [C.c_void_p, u64p, u64p]),

@@ -79,6 +79,12 @@ struct mdbg_ctx {
     uint64_t b_total = 0;
     PinBuf h_off, h_min, h_pos, h_dir;
 
+    // read side outputs (row A3b)
+    bool filter_low_complexity = false;
+    DevBuf d_quals, pad_qual, pad_raw_a, pad_raw_b, b_qual, x_sum_lo, x_sum_hi, x_lmin, x_cplx, x_low, d_err_fixed, d_err_tz;
+    PinBuf hx_sum_lo, hx_sum_hi, hx_lmin, hx_cplx, hx_low, hx_meanq, h_qual;
+    bool aux_valid = false, aux_has_quals = false;
+
     // minimizer-space read store
     DevBuf s_min, s_off, s_rem;
     uint64_t s_reads = 0, s_mins = 0;
@@ -186,11 +192,50 @@ mdbg_status check_launch(mdbg_ctx* ctx, const char* what, int n_kernels) {
 }
 
 // ---- sketch of a device-resident batch into the tight CSR b_* -------------------
+// error-rate table of ReadSelection::execute (ReadSelection.hpp:101-104): pow(10.0f, -q/10.0f) as float, handed
+// to the device as exact integers (value * 2^ERR_SHIFT)
+mdbg_status ensure_err_table(mdbg_ctx* ctx) {
+    if (ctx->d_err_fixed.p) return MDBG_OK;
+    uint64_t fixed[256];
+    uint8_t tz[256];
+    for (int c = 0; c < 256; c++) {
+        float e = 0.0f;
+        if (c >= 33 && c <= 127) { float q = (float)(uint8_t)(c - 33); e = powf(10.0f, -q / 10.0f); }   // Commons.hpp:2338-2341
+        const long double scaled = ldexpl((long double)e, ERR_SHIFT);
+        fixed[c] = (uint64_t)scaled;
+        tz[c] = fixed[c] ? (uint8_t)__builtin_ctzll(fixed[c]) : 255;
+    }
+    CKS(ensure(ctx, ctx->d_err_fixed, sizeof fixed));
+    CKS(ensure(ctx, ctx->d_err_tz, sizeof tz));
+    CK(cudaMemcpy(ctx->d_err_fixed.p, fixed, sizeof fixed, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_err_tz.p, tz, sizeof tz, cudaMemcpyHostToDevice));
+    return MDBG_OK;
+}
+
+mdbg_status run_aux(mdbg_ctx* ctx, const uint8_t* d_bases, const uint8_t* d_quals, const uint64_t* d_offsets,
+                    uint32_t n_reads, uint64_t n_bases, const uint64_t* exact_off, const uint32_t* pos, uint8_t* qual_out) {
+    AuxArgs x{};
+    x.bases = d_bases; x.bases_end = d_bases + n_bases; x.quals = d_quals;
+    x.offsets = d_offsets; x.n_reads = n_reads; x.l = ctx->l; x.hpc = ctx->hpc;
+    x.err_fixed = ctx->d_err_fixed.as<uint64_t>(); x.err_tz = ctx->d_err_tz.as<uint8_t>();
+    x.exact_off = exact_off; x.cap_shift = ctx->cap_shift; x.cap_const = ctx->cap_const;
+    x.n_min = ctx->n_min.as<uint32_t>(); x.pad_pos = pos;
+    x.pad_raw_a = ctx->pad_raw_a.as<uint32_t>(); x.pad_raw_b = ctx->pad_raw_b.as<uint32_t>();
+    x.out_qual = qual_out;
+    x.err_sum_lo = ctx->x_sum_lo.as<uint64_t>(); x.err_sum_hi = ctx->x_sum_hi.as<uint64_t>();
+    x.err_lmin = ctx->x_lmin.as<uint8_t>(); x.complexity = ctx->x_cplx.as<double>();
+    x.low_complexity = ctx->x_low.as<uint8_t>();
+    x.filter_low_complexity = ctx->filter_low_complexity ? 1 : 0;
+    launch_read_aux(x, ctx->stream);
+    return check_launch(ctx, "read_aux_kernel", 1);
+}
+
 mdbg_status sketch_internal(mdbg_ctx* ctx, const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t n_reads,
-                            uint64_t n_bases, int append) {
+                            uint64_t n_bases, int append, bool want_aux = false, const uint8_t* d_quals = nullptr) {
     cudaStream_t s = ctx->stream;
     ctx->b_reads = n_reads;
     ctx->b_total = 0;
+    ctx->aux_valid = false;
     CKS(ensure(ctx, ctx->b_off, ((size_t)n_reads + 1) * sizeof(uint64_t)));
     if (n_reads == 0) {
         CK(cudaMemsetAsync(ctx->b_off.p, 0, sizeof(uint64_t), s));
@@ -230,6 +275,21 @@ mdbg_status sketch_internal(mdbg_ctx* ctx, const uint8_t* d_bases, const uint64_
     launch_sketch(a, ctx->sm_count, s);
     if (ctx->timing) { CK(cudaEventRecord(ctx->ev[0][1], s)); ctx->ev_valid[0] = true; }
     CKS(check_launch(ctx, "sketch_kernel", 1));
+    if (want_aux) {
+        CKS(ensure_err_table(ctx));
+        CKS(ensure(ctx, ctx->pad_qual, pad_cap));
+        CKS(ensure(ctx, ctx->pad_raw_a, pad_cap * 4));
+        CKS(ensure(ctx, ctx->pad_raw_b, pad_cap * 4));
+        CKS(ensure(ctx, ctx->x_sum_lo, (size_t)n_reads * 8));
+        CKS(ensure(ctx, ctx->x_sum_hi, (size_t)n_reads * 8));
+        CKS(ensure(ctx, ctx->x_lmin, n_reads));
+        CKS(ensure(ctx, ctx->x_cplx, (size_t)n_reads * 8));
+        CKS(ensure(ctx, ctx->x_low, n_reads));
+        CKS(run_aux(ctx, d_bases, d_quals, d_offsets, n_reads, n_bases, nullptr, ctx->pad_pos.as<uint32_t>(),
+                    ctx->pad_qual.as<uint8_t>()));
+        ctx->aux_valid = true;
+        ctx->aux_has_quals = d_quals != nullptr;
+    }
     launch_scan_u32_to_u64(ctx->n_min.as<uint32_t>(), ctx->b_off.as<uint64_t>(), n_reads,
                            ctx->scan_scratch.as<uint64_t>(), s);
     CKS(check_launch(ctx, "scan", 3));
@@ -243,6 +303,7 @@ mdbg_status sketch_internal(mdbg_ctx* ctx, const uint8_t* d_bases, const uint64_
     CKS(ensure(ctx, ctx->b_min, (total + 1) * 4));
     CKS(ensure(ctx, ctx->b_pos, (total + 1) * 4));
     CKS(ensure(ctx, ctx->b_dir, total + 1));
+    if (want_aux) CKS(ensure(ctx, ctx->b_qual, total + 1));
     if (n_over == 0) {
         CompactArgs c{};
         c.base_offsets = d_offsets;
@@ -257,6 +318,8 @@ mdbg_status sketch_internal(mdbg_ctx* ctx, const uint8_t* d_bases, const uint64_
         c.out_pos = ctx->b_pos.as<uint32_t>();
         c.out_dir = ctx->b_dir.as<uint8_t>();
         c.n_reads = n_reads;
+        c.in_qual = want_aux ? ctx->pad_qual.as<uint8_t>() : nullptr;
+        c.out_qual = want_aux ? ctx->b_qual.as<uint8_t>() : nullptr;
         launch_compact(c, s);
         CKS(check_launch(ctx, "compact_kernel", 1));
     } else {
@@ -271,6 +334,14 @@ mdbg_status sketch_internal(mdbg_ctx* ctx, const uint8_t* d_bases, const uint64_
         CK(cudaMemsetAsync(&ctx->d_small->n_overflow, 0, sizeof(unsigned long long), s));
         launch_sketch(a, ctx->sm_count, s);
         CKS(check_launch(ctx, "sketch_kernel(exact)", 1));
+        if (want_aux) {
+            // qualities again on the exact slots (the filter was already applied to n_min; a filtered read has an
+            // empty exact slot, and the re-sketch writes nothing into it)
+            CKS(ensure(ctx, ctx->pad_raw_a, (total + 1) * 4));
+            CKS(ensure(ctx, ctx->pad_raw_b, (total + 1) * 4));
+            CKS(run_aux(ctx, d_bases, d_quals, d_offsets, n_reads, n_bases, ctx->b_off.as<uint64_t>(),
+                        ctx->b_pos.as<uint32_t>(), ctx->b_qual.as<uint8_t>()));
+        }
     }
     if (append) {
         CKS(ensure(ctx, ctx->s_min, (ctx->s_mins + total + 1) * 4, true));
@@ -407,10 +478,10 @@ void mdbg_ctx_destroy(mdbg_ctx* c) {
     DevBuf* devs[] = {&c->d_blacklist, &c->d_bases, &c->d_offsets, &c->pad_min, &c->pad_pos, &c->pad_dir, &c->n_min,
                       &c->scan_scratch, &c->b_off, &c->b_min, &c->b_pos, &c->b_dir, &c->s_min, &c->s_off, &c->s_rem,
                       &c->p_flags, &c->p_keep, &c->p_cnt, &c->p_newoff, &c->p_newmin, &c->table, &c->foreign_vecs,
-                      &c->o_hash, &c->o_abund, &c->o_vecs, &c->prev_table, &c->prev_stage_h, &c->prev_stage_a, &c->m_send_vecs, &c->m_send_counts, &c->m_recv_vecs,
+                      &c->o_hash, &c->o_abund, &c->o_vecs, &c->d_quals, &c->pad_qual, &c->pad_raw_a, &c->pad_raw_b, &c->b_qual, &c->x_sum_lo, &c->x_sum_hi, &c->x_lmin, &c->x_cplx, &c->x_low, &c->d_err_fixed, &c->d_err_tz, &c->prev_table, &c->prev_stage_h, &c->prev_stage_a, &c->m_send_vecs, &c->m_send_counts, &c->m_recv_vecs,
                       &c->m_recv_counts, &c->m_bucket};
     for (DevBuf* b : devs) release(*b);
-    PinBuf* pins[] = {&c->h_off, &c->h_min, &c->h_pos, &c->h_dir, &c->ho_hash, &c->ho_abund, &c->ho_vecs};
+    PinBuf* pins[] = {&c->h_off, &c->h_min, &c->h_pos, &c->h_dir, &c->ho_hash, &c->ho_abund, &c->ho_vecs, &c->hx_sum_lo, &c->hx_sum_hi, &c->hx_lmin, &c->hx_cplx, &c->hx_low, &c->hx_meanq, &c->h_qual};
     for (PinBuf* b : pins) release(*b);
     if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
     if (c->d_small) cudaFree(c->d_small);
@@ -520,6 +591,67 @@ mdbg_status mdbg_sketch_batch(mdbg_ctx* ctx, const uint8_t* bases, const uint64_
     CKS(sketch_internal(ctx, ctx->d_bases.as<uint8_t>(), ctx->d_offsets.as<uint64_t>(), n_reads, n_bases,
                         append_to_store));
     if (out) return mdbg_sketch_fetch(ctx, out);
+    return MDBG_OK;
+}
+
+mdbg_status mdbg_ctx_set_read_filters(mdbg_ctx* ctx, int filter_low_complexity) {
+    if (!ctx) return MDBG_ERR_ARG;
+    ctx->filter_low_complexity = filter_low_complexity != 0;
+    return MDBG_OK;
+}
+
+mdbg_status mdbg_sketch_batch_q(mdbg_ctx* ctx, const uint8_t* bases, const uint8_t* quals, const uint64_t* offsets,
+                                uint32_t n_reads, int append_to_store, mdbg_sketch_out* out, mdbg_aux_out* aux) {
+    if (!ctx) return MDBG_ERR_ARG;
+    if (n_reads && (!bases || !offsets)) return fail(ctx, MDBG_ERR_ARG, "null host buffer");
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t n_bases = n_reads ? offsets[n_reads] : 0;
+    if (n_reads && offsets[0] != 0) return fail(ctx, MDBG_ERR_ARG, "offsets[0] must be 0");
+    CKS(ensure(ctx, ctx->d_bases, n_bases + 64));
+    CKS(ensure(ctx, ctx->d_offsets, ((size_t)n_reads + 1) * 8));
+    if (quals) CKS(ensure(ctx, ctx->d_quals, n_bases + 64));
+    cudaStream_t s = ctx->stream;
+    if (n_reads) {
+        CK(cudaMemcpyAsync(ctx->d_bases.p, bases, n_bases, cudaMemcpyHostToDevice, s));
+        if (quals) CK(cudaMemcpyAsync(ctx->d_quals.p, quals, n_bases, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->d_offsets.p, offsets, ((size_t)n_reads + 1) * 8, cudaMemcpyHostToDevice, s));
+    }
+    CKS(sketch_internal(ctx, ctx->d_bases.as<uint8_t>(), ctx->d_offsets.as<uint64_t>(), n_reads, n_bases,
+                        append_to_store, true, quals ? ctx->d_quals.as<uint8_t>() : nullptr));
+    if (out) CKS(mdbg_sketch_fetch(ctx, out));
+    if (aux) {
+        const uint64_t t = ctx->b_total;
+        CKS(ensure_pin(ctx, ctx->hx_sum_lo, (size_t)n_reads * 8 + 8));
+        CKS(ensure_pin(ctx, ctx->hx_sum_hi, (size_t)n_reads * 8 + 8));
+        CKS(ensure_pin(ctx, ctx->hx_lmin, n_reads + 1));
+        CKS(ensure_pin(ctx, ctx->hx_cplx, (size_t)n_reads * 8 + 8));
+        CKS(ensure_pin(ctx, ctx->hx_low, n_reads + 1));
+        CKS(ensure_pin(ctx, ctx->hx_meanq, (size_t)n_reads * 4 + 4));
+        CKS(ensure_pin(ctx, ctx->h_qual, t + 1));
+        if (n_reads) {
+            CK(cudaMemcpyAsync(ctx->hx_sum_lo.p, ctx->x_sum_lo.p, (size_t)n_reads * 8, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(ctx->hx_sum_hi.p, ctx->x_sum_hi.p, (size_t)n_reads * 8, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(ctx->hx_cplx.p, ctx->x_cplx.p, (size_t)n_reads * 8, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(ctx->hx_low.p, ctx->x_low.p, n_reads, cudaMemcpyDeviceToHost, s));
+        }
+        if (t) CK(cudaMemcpyAsync(ctx->h_qual.p, ctx->b_qual.p, t, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        // ReadSelection.hpp:870-879 on the exact error sum, with the reference's own operand types
+        float* mq = ctx->hx_meanq.as<float>();
+        for (uint32_t r = 0; r < n_reads; r++) {
+            const uint64_t len = offsets[r + 1] - offsets[r];
+            if (!quals) { long double z = 0; float e = z / (long double)0; mq[r] = -10.0f * log10f(e); continue; }
+            long double errorSum = ldexpl((long double)ctx->hx_sum_hi.as<uint64_t>()[r], 64 - ERR_SHIFT) +
+                                   ldexpl((long double)ctx->hx_sum_lo.as<uint64_t>()[r], -ERR_SHIFT);
+            float meanReadError = errorSum / len;
+            mq[r] = -10.0f * log10f(meanReadError);
+        }
+        aux->n_reads = n_reads;
+        aux->mean_quality = mq;
+        aux->complexity = ctx->hx_cplx.as<double>();
+        aux->low_complexity = ctx->hx_low.as<uint8_t>();
+        aux->qualities = ctx->h_qual.as<uint8_t>();
+    }
     return MDBG_OK;
 }
 

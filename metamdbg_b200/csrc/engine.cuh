@@ -44,12 +44,33 @@ struct CompactArgs {
     const uint32_t* in_min; const uint32_t* in_pos; const uint8_t* in_dir;
     uint32_t* out_min; uint32_t* out_pos; uint8_t* out_dir;
     uint32_t n_reads;
+    const uint8_t* in_qual; uint8_t* out_qual;   // optional per-minimizer qualities (nullptr = none)
 };
 void launch_compact(const CompactArgs& a, cudaStream_t s);
 
 // store_off[dst_read_base + 1 + i] = dst_min_base + batch_off[i + 1]
 void launch_append_offsets(const uint64_t* batch_off, uint64_t* store_off, uint32_t n_reads, uint64_t dst_read_base,
                            uint64_t dst_min_base, cudaStream_t s);
+
+// ------------------------------------------------------------------ read side outputs (row A3b)
+constexpr int ERR_SHIFT = 60;   // error rates are handed over as exact integers: float value * 2^60
+struct AuxArgs {
+    const uint8_t* bases; const uint8_t* bases_end; const uint8_t* quals;   // quals may be nullptr
+    const uint64_t* offsets; uint32_t n_reads;
+    uint32_t l, hpc;
+    const uint64_t* err_fixed;   // [256]
+    const uint8_t* err_tz;       // [256] index of the lowest set bit of err_fixed (255 for zero)
+    const uint64_t* exact_off;   // tight slots (after an overflow re-sketch) or nullptr = padded formula
+    uint32_t cap_shift, cap_const;
+    uint32_t* n_min;             // in/out: zeroed for filtered reads
+    const uint32_t* pad_pos;
+    uint32_t* pad_raw_a; uint32_t* pad_raw_b;   // scratch, padded layout
+    uint8_t* out_qual;           // padded layout, may be nullptr
+    uint64_t* err_sum_lo; uint64_t* err_sum_hi; uint8_t* err_lmin;
+    double* complexity; uint8_t* low_complexity;
+    uint32_t filter_low_complexity;
+};
+void launch_read_aux(const AuxArgs& a, cudaStream_t s);
 
 // ------------------------------------------------------------------ purge palindromes
 // flags[r] = 1 when read r may contain a palindromic window (cheap necessary test)

@@ -479,6 +479,7 @@ __global__ void __launch_bounds__(256) compact_kernel(const CompactArgs a) {
             a.out_min[dst + i] = a.in_min[slot_lo + i];
             a.out_pos[dst + i] = a.in_pos[slot_lo + i];
             a.out_dir[dst + i] = a.in_dir[slot_lo + i];
+            if (a.out_qual) a.out_qual[dst + i] = a.in_qual[slot_lo + i];
         }
     }
 }

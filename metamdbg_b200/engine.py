@@ -17,7 +17,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _capi
-from ._capi import MdbgParams, SketchDev, SketchOut, TableOut
+from ._capi import AuxOut, MdbgParams, SketchDev, SketchOut, TableOut
 
 STATUS = {0: "OK", 1: "CUDA", 2: "ARG", 3: "STATE", 4: "TABLE_FULL", 5: "NCCL", 6: "OOM"}
 
@@ -136,6 +136,27 @@ class Engine:
         self._ck(self._lib.mdbg_sketch_batch(self._ctx, bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1,
                                              int(append_to_store), C.byref(out) if fetch else None))
         return self._copy_sketch(out) if fetch else None
+
+    def set_read_filters(self, filter_low_complexity: bool = True):
+        self._ck(self._lib.mdbg_ctx_set_read_filters(self._ctx, int(filter_low_complexity)))
+
+    def sketch_batch_q(self, bases: np.ndarray, quals: np.ndarray | None, offsets: np.ndarray,
+                       append_to_store: bool = False):
+        """Sketch + the side outputs of ReadSelectionFunctor (mean quality, complexity, per-minimizer quality).
+        Returns (Sketch, dict)."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        if quals is not None:
+            quals = np.ascontiguousarray(quals, dtype=np.uint8)
+        out, aux = SketchOut(), AuxOut()
+        self._ck(self._lib.mdbg_sketch_batch_q(self._ctx, bases.ctypes.data, quals.ctypes.data if quals is not None else None,
+                                               offsets.ctypes.data, len(offsets) - 1, int(append_to_store),
+                                               C.byref(out), C.byref(aux)))
+        sk = self._copy_sketch(out)
+        n, t = sk.n_reads, len(sk.minimizers)
+        take = lambda p, m, dt: np.ctypeslib.as_array(p, shape=(m,)).copy() if m else np.zeros(0, dt)
+        return sk, dict(mean_quality=take(aux.mean_quality, n, np.float32), complexity=take(aux.complexity, n, np.float64),
+                        low_complexity=take(aux.low_complexity, n, np.uint8), qualities=take(aux.qualities, t, np.uint8))
 
     def sketch_batch_ptr(self, bases_ptr: int, offsets: np.ndarray, append_to_store: bool = True,
                          fetch: bool = True) -> int:

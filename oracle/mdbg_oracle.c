@@ -10,6 +10,7 @@
  */
 #include "mdbg_oracle.h"
 
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -229,6 +230,70 @@ size_t orc_sketch_batch(const char* bases, const uint64_t* offsets, size_t n_rea
     }
     min_offsets[n_reads] = total;
     return total;
+}
+
+/* ---------------------------------------------------------------- side outputs */
+
+void orc_read_aux(const char* seq, const char* qual, size_t len, size_t qual_len, int l, int hpc,
+                  const uint32_t* positions, size_t n_minimizers,
+                  float* mean_quality, double* complexity, uint8_t* qualities) {
+    /* ReadSelection.hpp:870-879 */
+    long double error_sum = 0;
+    for (size_t i = 0; i < qual_len; i++) {
+        unsigned char c = (unsigned char)qual[i];
+        float e = 0.0f;                              /* table is zero outside 33..127 (ReadSelection.hpp:101-104) */
+        if (c >= 33 && c <= 127) { float q = (float)(unsigned char)(c - 33); e = powf(10.0f, -q / 10.0f); }
+        error_sum += e;
+    }
+    float mean_err = (float)(error_sum / (long double)qual_len);
+    *mean_quality = -10.0f * log10f(mean_err);
+
+    /* computeSequenceComplexity(seq, 64, 32), ReadSelection.hpp:1171-1228 */
+    {
+        const size_t w = 64, step = 32;
+        const double lw = (double)w - 2;
+        size_t nk = len >= 3 ? len - 2 : 0;
+        double nb_windows = 0, sum = 0;
+        for (size_t ii = 0; ii < nk; ii += step) {
+            double counts[64];
+            for (int i = 0; i < 64; i++) counts[i] = 0;
+            size_t n = 0;
+            for (size_t i = ii; i < nk; i++) {
+                unsigned c0 = ((unsigned char)seq[i] >> 1) & 3, c1 = ((unsigned char)seq[i + 1] >> 1) & 3,
+                         c2 = ((unsigned char)seq[i + 2] >> 1) & 3;
+                counts[(c0 << 4) | (c1 << 2) | c2] += 1;
+                if (++n == w) break;
+            }
+            if (n < w) continue;
+            double score = 0;
+            for (int i = 0; i < 64; i++) score += counts[i] * (counts[i] - 1) / 2.0;
+            score /= (lw - 1);
+            nb_windows += 1;
+            sum += score;
+        }
+        *complexity = sum / nb_windows;
+    }
+
+    /* per-minimizer min quality */
+    if (n_minimizers == 0) return;
+    if (qual_len == 0) {
+        for (size_t j = 0; j < n_minimizers; j++) qualities[j] = 1;
+        return;
+    }
+    char* hs = (char*)malloc(len + 1);
+    uint64_t* rle = (uint64_t*)malloc((len + 2) * sizeof(uint64_t));
+    size_t hl = orc_hpc(seq, len, hpc, hs, rle);
+    if (!hpc) rle[hl] = len;
+    for (size_t j = 0; j < n_minimizers; j++) {
+        size_t a = (size_t)rle[positions[j]], b = (size_t)rle[positions[j] + (size_t)l];
+        uint8_t mq = 255;
+        for (size_t i = a; i < b; i++) {
+            uint8_t q = (uint8_t)((unsigned char)qual[i] - 33);
+            if (q < mq) mq = q;
+        }
+        qualities[j] = mq;
+    }
+    free(hs); free(rle);
 }
 
 /* -------------------------------------------------------- purge palindromes */

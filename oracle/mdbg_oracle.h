@@ -63,6 +63,17 @@ size_t orc_sketch_batch(const char* bases, const uint64_t* offsets, size_t n_rea
                         uint64_t* min_offsets, uint32_t* minimizers, uint32_t* positions,
                         uint8_t* directions, size_t cap);
 
+/* Side outputs of ReadSelectionFunctor::operator() (src/readSelection/ReadSelection.hpp):
+ *   mean_quality  = -10.0f * log10f((float)(errorSum / n)) with errorSum the long double sum of
+ *                   pow(10.0f, -(q-33)/10.0f) over the quality bytes (:870-879; NaN when qual is empty)
+ *   complexity    = computeSequenceComplexity(seq, 64, 32) (:1171-1228), the read is dropped when > 5
+ *   qualities[j]  = getMinQuality over raw [rlePos[pos_j], rlePos[pos_j + l]) (:1135, :1302-1320), or 1
+ *                   when qual is empty (:1049-1053)
+ * positions = HPC positions of the read's minimizers (as returned by orc_sketch_read). */
+void orc_read_aux(const char* seq, const char* qual, size_t len, size_t qual_len, int l, int hpc,
+                  const uint32_t* positions, size_t n_minimizers,
+                  float* mean_quality, double* complexity, uint8_t* qualities);
+
 /* Commons::purgePalindrome, src/Commons.hpp:1617-1723.  out holds n entries;
  * keep (may be NULL) receives 0/1 per input position.  Returns n'. */
 size_t orc_purge_palindrome(const uint32_t* m, size_t n, size_t first_k, size_t last_k,

@@ -34,6 +34,35 @@ def build(force: bool = False) -> None:
             subprocess.run(["make", "-s", "-C", HERE, "ref"], check=True)
 
 
+def parse_read_data(path: str, has_quality: bool):
+    """read_data_init.txt (has_quality) / read_data_corrected.txt records
+    (ReadSelection.hpp:415-467): u32 n, u8 isCircular, u32 min[n] [, u32 pos[n], u8 dir[n], u8 qual[n], f32 meanQ, u32 len]."""
+    buf = open(path, "rb").read()
+    pos, recs = 0, []
+    while pos < len(buf):
+        n = int(np.frombuffer(buf, np.uint32, 1, pos)[0]); pos += 4
+        circ = buf[pos]; pos += 1
+        rec = dict(circular=circ, minimizers=np.frombuffer(buf, np.uint32, n, pos).copy()); pos += 4 * n
+        if has_quality:
+            rec["positions"] = np.frombuffer(buf, np.uint32, n, pos).copy(); pos += 4 * n
+            rec["directions"] = np.frombuffer(buf, np.uint8, n, pos).copy(); pos += n
+            rec["qualities"] = np.frombuffer(buf, np.uint8, n, pos).copy(); pos += n
+            rec["mean_quality"] = np.frombuffer(buf, np.float32, 1, pos)[0]; pos += 4
+            rec["read_length"] = int(np.frombuffer(buf, np.uint32, 1, pos)[0]); pos += 4
+        recs.append(rec)
+    return recs
+
+
+def parse_read_stats(path: str):
+    """read_stats.txt (ReadSelection.hpp:305-384): u64 nbReads, u32 n50, f32 density, u64 nbBases, f32 avgQ,
+    u32 meanLen, u64 nbSelectedMinimizers."""
+    b = open(path, "rb").read()
+    return dict(n_reads=int(np.frombuffer(b, np.uint64, 1, 0)[0]), n50=int(np.frombuffer(b, np.uint32, 1, 8)[0]),
+                density=float(np.frombuffer(b, np.float32, 1, 12)[0]), n_bases=int(np.frombuffer(b, np.uint64, 1, 16)[0]),
+                avg_quality=float(np.frombuffer(b, np.float32, 1, 24)[0]), mean_length=int(np.frombuffer(b, np.uint32, 1, 28)[0]),
+                n_minimizers=int(np.frombuffer(b, np.uint64, 1, 32)[0]))
+
+
 def _p(a: np.ndarray, t):
     return a.ctypes.data_as(t)
 
@@ -141,6 +170,9 @@ class Oracle(_Lib):
         L.orc_sketch_batch.restype = C.c_size_t
         L.orc_sketch_batch.argtypes = [C.c_void_p, _u64p, C.c_size_t, C.c_int, C.c_float, C.c_int, _u32p, C.c_size_t,
                                        _u64p, _u32p, _u32p, _u8p, C.c_size_t]
+        L.orc_read_aux.restype = None
+        L.orc_read_aux.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, _u32p, C.c_size_t,
+                                   C.POINTER(C.c_float), C.POINTER(C.c_double), _u8p]
         L.orc_rescue.restype = C.c_size_t
         L.orc_rescue.argtypes = [_u32p, _u64p, C.c_size_t, C.c_int, _u64p, _u32p, C.c_size_t, C.POINTER(_u32p),
                                  C.POINTER(_u64p), _u64p]
@@ -195,6 +227,15 @@ class Oracle(_Lib):
         abund = self._take(a, n, np.uint32)
         return dict(vecs=vecs, hashes=hashes, abundances=abund, n_instances=int(ni.value), n_distinct=int(nd.value))
 
+    def read_aux(self, seq: bytes, qual: bytes, l: int, hpc: bool, positions: np.ndarray):
+        """-> (mean_quality f32, complexity f64, qualities u8[n])."""
+        positions = np.ascontiguousarray(positions, dtype=np.uint32)
+        mq = C.c_float(0); cx = C.c_double(0)
+        q = np.zeros(len(positions) + 1, dtype=np.uint8)
+        self.lib.orc_read_aux(seq, qual, len(seq), len(qual), l, int(hpc), _p(positions, _u32p), len(positions),
+                              C.byref(mq), C.byref(cx), _p(q, _u8p))
+        return np.float32(mq.value), float(cx.value), q[:len(positions)].copy()
+
     def rescue(self, mins, offs, k, solid_hashes, solid_ab):
         """-> dict(vecs [n,k], hashes [n,2] (h1,h2), n_reads_rescued); rescued abundance is always 1."""
         mins = np.ascontiguousarray(mins, dtype=np.uint32); offs = np.ascontiguousarray(offs, dtype=np.uint64)
@@ -240,6 +281,9 @@ class Reference(_Lib):
         L.ref_pipeline.argtypes = [C.c_void_p, _u64p, C.c_size_t, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
                                    C.c_uint32, C.c_int, _u64p, _u64p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.ref_max_threads.restype = C.c_int
+        L.ref_read_selection.restype = C.c_int
+        L.ref_read_selection.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
+                                         C.POINTER(C.c_double)]
         L.ref_graph_firstpass.restype = C.c_size_t
         L.ref_graph_firstpass.argtypes = [_u32p, _u64p, C.c_size_t, C.c_int, C.c_uint32, C.c_int, C.c_char_p,
                                           C.POINTER(_u32p), C.POINTER(_u64p), C.POINTER(_u32p), _u64p, _u64p,
@@ -292,6 +336,29 @@ class Reference(_Lib):
         vecs = self._take(v, n * k, np.uint32).reshape(n, k)
         return dict(vecs=vecs if use_counter else None, hashes=self._take(h, 2 * n, np.uint64).reshape(n, 2),
                     abundances=self._take(a, n, np.uint32))
+
+    def read_selection(self, fastq_paths, l=15, density=0.005, hpc=True, threads=1, skip_correction=False,
+                       workdir=None):
+        """The reference's whole readSelection stage on FASTA/FASTQ files.  Returns the parsed
+        read_data_init.txt records, read_stats.txt and read_data_corrected.txt."""
+        import tempfile
+        ctx = tempfile.TemporaryDirectory() if workdir is None else None
+        d = ctx.name if ctx else workdir
+        with open(os.path.join(d, "input.txt"), "w") as f:
+            for pth in fastq_paths:
+                f.write(str(pth) + "\n")
+        sec = C.c_double(0)
+        self.lib.ref_read_selection(os.path.join(d, "input.txt").encode(), d.encode(), l, density, int(hpc), threads,
+                                    int(skip_correction), C.byref(sec))
+        out = dict(seconds=float(sec.value), records=parse_read_data(os.path.join(d, "read_data_init.txt"), True),
+                   stats=parse_read_stats(os.path.join(d, "read_stats.txt")))
+        bl = os.path.join(d, "repetitiveMinimizers.bin")            # u32 list (ReadSelection.hpp:553-556)
+        out["blacklist"] = np.fromfile(bl, dtype=np.uint32) if os.path.exists(bl) else np.zeros(0, np.uint32)
+        cp = os.path.join(d, "read_data_corrected.txt")
+        out["corrected"] = parse_read_data(cp, False) if os.path.exists(cp) else None
+        if ctx:
+            ctx.cleanup()
+        return out
 
     def max_threads(self) -> int:
         return int(self.lib.ref_max_threads())

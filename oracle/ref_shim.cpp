@@ -27,6 +27,7 @@
  */
 #include "Commons.hpp"
 #include "graph/CreateMdbg.hpp"
+#include "readSelection/ReadSelection.hpp"
 
 #include <cstdint>
 #include <cstdlib>
@@ -353,6 +354,33 @@ size_t ref_graph_next_k(const uint32_t* mins, const uint64_t* offs, size_t n_rea
     }
     c._kminmerAbundanceFile.close();
     return read_tables(dir, k, false, vecs_out, hashes_out, abundances_out);
+}
+
+/* The reference's whole readSelection stage (ReadSelection::execute, src/readSelection/ReadSelection.hpp:92-303):
+ * kseq FASTA/FASTQ parsing, HPC, sketch, complexity / quality side outputs, ordered record writer, read stats,
+ * purgePalindromes.  `input_list` is the text file listing the read files (what `metaMDBG asm` writes as input.txt).
+ * Writes <dir>/read_data_init.txt, read_stats.txt, repetitiveMinimizers.bin, read_data_corrected.txt. */
+int ref_read_selection(const char* input_list, const char* dir, int l, float density, int hpc, int n_threads,
+                       int skip_correction, double* seconds) {
+    auto t0 = high_resolution_clock::now();
+    ReadSelection rs;
+    rs._inputFilename = input_list;
+    rs._inputDir = dir;
+    rs._outputFilename = string(dir) + "/read_data_init.txt";
+    rs._nbCores = n_threads < 1 ? 1 : n_threads;
+    rs._minReadQuality = 0;                              // default of --min-read-quality (ReadSelection.hpp:163)
+    rs._outputQuality = true;                            // ReadSelection.hpp:196
+    rs._skipCorrection = skip_correction != 0;
+    rs._params._minimizerSize = l;
+    rs._params._minimizerDensity_assembly = density;
+    rs._params._minimizerDensity_correction = 0.025f;
+    rs._params._useHomopolymerCompression = hpc != 0;
+    rs._params._kminmerSize = 4;
+    rs._params._kminmerSizeFirst = 4;
+    rs._params._kminmerSizePrev = 3;
+    rs.execute();
+    if (seconds) *seconds = duration<double>(high_resolution_clock::now() - t0).count();
+    return 0;
 }
 
 int ref_max_threads() { return omp_get_max_threads(); }

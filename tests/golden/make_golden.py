@@ -132,6 +132,42 @@ def main():
                         k4_n_solid=g4["n_solid"], k4_n_rescued=g4["n_rescued"],
                         k5_hashes=g5["hashes"], k5_abund=g5["abundances"], k5_vecs=g5["vecs"],
                         k6_hashes=g6["hashes"], k6_abund=g6["abundances"])
+    # 6. the whole readSelection stage (real ReadSelection::execute on a FASTQ): side outputs + record fields
+    import tempfile
+    rs = synth.make_readset(150, 5000, seed=404, n_genomes=1, genome_len_range=(90_000, 90_001))
+    b6, o6 = synth.fill_reads(rs)
+    raw = b6.tobytes()
+    rd = [raw[int(o6[r]):int(o6[r + 1])] for r in range(rs.n_reads)]
+    # (no read with N here: computeSequenceComplexity indexes kmerCounts[-1] for invalid 3-mers upstream -- heap corruption)
+    rd += [b"AC" * 1500, b"A" * 800 + b"ACGTTGCA" * 300, b"ACG" * 900, b"ACGT" * 10]
+    ql = []
+    for sq in rd:
+        q = rng.integers(2, 60, size=len(sq)).astype(np.uint8) + 33
+        q[rng.random(len(sq)) < 0.01] = 33 + 93
+        ql.append(q.tobytes())
+    for tag, hpc, dens in (("hifi", True, 0.005), ("ont", False, 0.025)):
+        with tempfile.TemporaryDirectory() as d:
+            fq = os.path.join(d, "reads.fastq")
+            with open(fq, "wb") as f:
+                for i, (sq, q) in enumerate(zip(rd, ql)):
+                    f.write(b"@r%d\n" % i + sq + b"\n+\n" + q + b"\n")
+            res = ref.read_selection([fq], 15, dens, hpc, threads=2, skip_correction=True, workdir=d)
+        recs = res["records"]
+        mo = np.zeros(len(recs) + 1, np.uint64)
+        mo[1:] = np.cumsum([len(r["minimizers"]) for r in recs])
+        cat = lambda key, t: np.concatenate([r[key] for r in recs]).astype(t)
+        offs6 = np.zeros(len(rd) + 1, np.uint64)
+        offs6[1:] = np.cumsum([len(x) for x in rd])
+        np.savez_compressed(os.path.join(HERE, f"readselection_{tag}.npz"),
+                            bases=np.frombuffer(b"".join(rd), np.uint8), quals=np.frombuffer(b"".join(ql), np.uint8),
+                            offsets=offs6, blacklist=res["blacklist"], min_offsets=mo,
+                            minimizers=cat("minimizers", np.uint32), positions=cat("positions", np.uint32),
+                            directions=cat("directions", np.uint8), qualities=cat("qualities", np.uint8),
+                            mean_quality=np.array([r["mean_quality"] for r in recs], np.float32),
+                            read_length=np.array([r["read_length"] for r in recs], np.uint32),
+                            stats=np.array([res["stats"]["n_reads"], res["stats"]["n50"], res["stats"]["n_bases"],
+                                            res["stats"]["mean_length"], res["stats"]["n_minimizers"]], np.uint64),
+                            stats_f=np.array([res["stats"]["density"], res["stats"]["avg_quality"]], np.float32))
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

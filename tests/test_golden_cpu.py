@@ -83,3 +83,24 @@ def test_minspace_multik(oracle):
     t6 = oracle.next_k(mins, offs, 6, g["k5_hashes"], g["k5_abund"])
     assert table_dict(t6["hashes"], t6["abundances"]) == table_dict(g["k6_hashes"], g["k6_abund"])
     assert len(t6["abundances"]) > 20
+
+
+@pytest.mark.parametrize("tag,hpc,dens", [("hifi", True, 0.005), ("ont", False, 0.025)])
+def test_readselection_stage_golden(oracle, tag, hpc, dens):
+    """Rows A3b/A3c: record fields of read_data_init.txt minted by the reference's whole readSelection stage."""
+    g = load(f"readselection_{tag}.npz")
+    raw, qraw, offs, mo = g["bases"].tobytes(), g["quals"].tobytes(), g["offsets"], g["min_offsets"]
+    n_low = 0
+    for r in range(len(offs) - 1):
+        s, q = raw[int(offs[r]):int(offs[r + 1])], qraw[int(offs[r]):int(offs[r + 1])]
+        m, p, d = oracle.sketch_read(s, 15, dens, hpc, g["blacklist"])
+        mq, cx, mins_q = oracle.read_aux(s, q, 15, hpc, p)
+        if cx > 5:
+            n_low += 1
+            m, p, d, mins_q = m[:0], p[:0], d[:0], mins_q[:0]
+        lo, hi = int(mo[r]), int(mo[r + 1])
+        assert np.array_equal(g["minimizers"][lo:hi], m) and np.array_equal(g["positions"][lo:hi], p)
+        assert np.array_equal(g["directions"][lo:hi], d) and np.array_equal(g["qualities"][lo:hi], mins_q)
+        assert np.float32(g["mean_quality"][r]).tobytes() == np.float32(mq).tobytes()
+        assert int(g["read_length"][r]) == len(s)
+    assert n_low >= 2

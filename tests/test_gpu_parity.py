@@ -354,3 +354,46 @@ def test_rescue_on_sketched_reads_vs_oracle(built, oracle):
         want[(int(h[0]), int(h[1]))] = 1
     assert tab.as_dict() == want and tab.n_rescued == len(r["hashes"]) > 0
     eng.close()
+
+
+# ---------------------------------------------------------------- side outputs (A3b) against the real readSelection stage
+
+@pytest.mark.parametrize("tag,hpc,dens", [("hifi", True, 0.005), ("ont", False, 0.025)])
+def test_side_outputs_golden(built, tag, hpc, dens):
+    g = load(f"readselection_{tag}.npz")
+    eng = engine(15, dens, hpc, g["blacklist"])
+    eng.set_read_filters(True)
+    sk, aux = eng.sketch_batch_q(g["bases"], g["quals"], g["offsets"])
+    assert_sketch_equal(sk, g["min_offsets"], g["minimizers"], g["positions"], g["directions"], tag)
+    assert np.array_equal(aux["qualities"], g["qualities"])
+    assert aux["mean_quality"].tobytes() == g["mean_quality"].tobytes()         # bit-exact floats
+    assert aux["low_complexity"].sum() >= 2
+    # filtered reads are exactly the empty records of long reads
+    lens = np.diff(g["offsets"].astype(np.int64))
+    empty = np.diff(g["min_offsets"].astype(np.int64)) == 0
+    assert np.all(aux["low_complexity"][lens > 2000] == empty[lens > 2000])
+    # without qualities (FASTA): per-minimizer quality is 1 and the mean quality is NaN
+    sk2, aux2 = eng.sketch_batch_q(g["bases"], None, g["offsets"])
+    assert np.array_equal(sk2.minimizers, g["minimizers"]) and np.all(aux2["qualities"] == 1)
+    assert np.all(np.isnan(aux2["mean_quality"]))
+    eng.close()
+
+
+def test_side_outputs_vs_oracle_with_overflow(built, oracle):
+    """density 0.5 overflows the padded slots: qualities must survive the exact re-sketch."""
+    rng = np.random.default_rng(17)
+    rs = synth.make_readset(60, 3000, seed=88, n_genomes=1, genome_len_range=(50_000, 50_001))
+    bases, offs = synth.fill_reads(rs)
+    quals = (rng.integers(1, 70, size=len(bases)).astype(np.uint8) + 33)
+    eng = engine(15, 0.5, True)
+    sk, aux = eng.sketch_batch_q(bases, quals, offs)
+    raw, qraw = bases.tobytes(), quals.tobytes()
+    for r in range(rs.n_reads):
+        s, q = raw[int(offs[r]):int(offs[r + 1])], qraw[int(offs[r]):int(offs[r + 1])]
+        m, p, d = oracle.sketch_read(s, 15, 0.5, True)
+        mq, cx, mins_q = oracle.read_aux(s, q, 15, True, p)
+        lo, hi = int(sk.min_offsets[r]), int(sk.min_offsets[r + 1])
+        assert np.array_equal(sk.minimizers[lo:hi], m) and np.array_equal(aux["qualities"][lo:hi], mins_q)
+        assert np.float32(aux["mean_quality"][r]).tobytes() == np.float32(mq).tobytes()
+        assert aux["complexity"][r] == cx or (np.isnan(cx) and np.isnan(aux["complexity"][r]))
+    eng.close()

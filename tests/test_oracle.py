@@ -295,3 +295,58 @@ def test_ref_graph_next_k_both_paths(oracle, reference):
     got = reference.graph_next_k(mins, offs, 6, t5["hashes"], t5["abundances"], use_counter=False, threads=3)
     assert _table(got["hashes"], got["abundances"]) == _table(want["hashes"], want["abundances"])
     assert len(want["abundances"]) > 20
+
+
+# ---- rows A3b / A3c: side outputs and the record writer, against the reference's whole readSelection stage
+
+def _write_fastq(path, reads, quals):
+    with open(path, "wb") as f:
+        for i, (s, q) in enumerate(zip(reads, quals)):
+            f.write(b"@r%d\n" % i + s + b"\n+\n" + q + b"\n")
+
+
+def _aux_reads(seed):
+    rng = np.random.default_rng(seed)
+    rs = synth.make_readset(120, 5000, seed=seed, n_genomes=1, genome_len_range=(80_000, 80_001))
+    bases, offs = synth.fill_reads(rs)
+    raw = bases.tobytes()
+    reads = [raw[int(offs[r]):int(offs[r + 1])] for r in range(rs.n_reads)]
+    reads += [b"AC" * 1500, b"A" * 800 + b"ACGTTGCA" * 300, b"ACG" * 900, b"ACGT" * 10]   # low complexity / short
+    quals = []
+    for s in reads:
+        q = rng.integers(2, 60, size=len(s)).astype(np.uint8) + 33
+        q[rng.random(len(s)) < 0.01] = 33 + 93
+        quals.append(q.tobytes())
+    return reads, quals
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("hpc", [True, False])
+def test_ref_read_selection_side_outputs(tmp_path, oracle, reference, hpc):
+    reads, quals = _aux_reads(71)
+    fq = tmp_path / "reads.fastq"
+    _write_fastq(fq, reads, quals)
+    dens = 0.005 if hpc else 0.025
+    res = reference.read_selection([fq], 15, dens, hpc, threads=3, skip_correction=True, workdir=str(tmp_path))
+    assert len(res["records"]) == len(reads)
+    n_low = 0
+    for r, (s, q) in enumerate(zip(reads, quals)):
+        rec = res["records"][r]
+        m, p, d = oracle.sketch_read(s, 15, dens, hpc, res["blacklist"])   # ONT: the stage's own blacklist
+        mq, cx, mins_q = oracle.read_aux(s, q, 15, hpc, p)
+        if cx > 5:                                            # low-complexity filter clears the record
+            n_low += 1
+            m, p, d, mins_q = m[:0], p[:0], d[:0], mins_q[:0]
+        assert np.array_equal(rec["minimizers"], m) and np.array_equal(rec["positions"], p), r
+        assert np.array_equal(rec["directions"], d) and np.array_equal(rec["qualities"], mins_q), r
+        assert rec["read_length"] == len(s)
+        assert np.float32(rec["mean_quality"]).tobytes() == np.float32(mq).tobytes(), r     # bit-exact float
+    assert n_low >= 2 and (hpc or len(res["blacklist"]) >= 1)
+    assert res["stats"]["n_reads"] == len(reads) and res["stats"]["n_bases"] == sum(len(s) for s in reads)
+    # purged stream (thread-completion order upstream => compare as multisets)
+    want = []
+    for rec in res["records"]:
+        q, _ = oracle.purge_palindrome(rec["minimizers"], 4, 50)
+        want.append(tuple(int(x) for x in q))
+    got = [tuple(int(x) for x in rec["minimizers"]) for rec in res["corrected"]]
+    assert sorted(got) == sorted(want)
