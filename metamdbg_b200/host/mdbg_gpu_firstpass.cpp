@@ -1,8 +1,9 @@
 // mdbg_gpu_firstpass -- C++ host driver over the C ABI: the GPU form of
 //   metaMDBG readSelection <tmp> ... ; metaMDBG graph <tmp> --firstpass --min-abundance n
-// for the part of those stages that is on the hot path (sketch -> purgePalindromes -> k-min-mer count).
-// Reads FASTA/FASTQ (plain or gzip, through zlib), writes read_data_corrected.txt,
-// kminmerData_min.txt and kminmerData_abundance.txt in the reference's formats.
+// for the part of those stages that is on the hot path (sketch + side outputs -> purgePalindromes ->
+// k-min-mer count).  Reads FASTA/FASTQ (plain or gzip, through zlib), writes read_data_init.txt,
+// read_stats.txt, read_data_corrected.txt, kminmerData_min.txt and kminmerData_abundance.txt in the
+// reference's formats.
 #include <zlib.h>
 
 #include <algorithm>
@@ -53,8 +54,11 @@ int main(int argc, char** argv) {
     try {
         Context ctx(l, density, hpc);
         std::vector<uint32_t> readLengths;
-        GpuReadSelectionFunctor functor(ctx, [&](const ReadMinimizers& r) { readLengths.push_back(r.readLength); },
-                                        batchMbp << 20);
+        ReadDataWriter writer(outDir + "/read_data_init.txt", l);     // readSelection's record file + read_stats.txt
+        GpuReadSelectionFunctor functor(ctx, [&](const ReadMinimizers& r) {
+            readLengths.push_back(r.readLength);
+            writer.write(r);
+        }, batchMbp << 20, /*sideOutputs=*/true);
         gzFile f = gzopen(input.c_str(), "rb");
         if (!f) throw std::runtime_error("cannot open " + input);
         std::string line;
@@ -83,6 +87,8 @@ int main(int argc, char** argv) {
         }
         gzclose(f);
         functor.flush();
+        writer.close();
+        writer.writeReadStats(outDir + "/read_stats.txt");
         if (lastK == 0) {                                // Commons::computeLastK with the N50 (Commons.hpp:1726-1741)
             std::vector<uint32_t> s = readLengths;
             std::sort(s.begin(), s.end(), std::greater<uint32_t>());

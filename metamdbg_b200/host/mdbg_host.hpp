@@ -15,6 +15,7 @@
 // threads; feed() must be called under the parser's existing critical section (or from one thread).
 #pragma once
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <functional>
@@ -67,6 +68,9 @@ struct ReadMinimizers {
     const uint32_t* minimizers;
     const uint32_t* positions;
     const uint8_t* directions;
+    const uint8_t* qualities;      // per-minimizer min base quality (nullptr unless side outputs are on)
+    float meanReadQuality;         // NaN without qualities
+    bool lowComplexity;
 };
 
 // Batching replacement of ReadSelectionFunctor: reads are buffered until `batchBases` bases are
@@ -76,12 +80,23 @@ class GpuReadSelectionFunctor {
 public:
     using Sink = std::function<void(const ReadMinimizers&)>;
 
-    GpuReadSelectionFunctor(Context& ctx, Sink sink, size_t batchBases = size_t(1) << 30)
-        : _ctx(ctx), _sink(std::move(sink)), _batchBases(batchBases) {
+    // sideOutputs = also compute mean read quality, the low-complexity filter and per-minimizer qualities
+    // (the rest of ReadSelectionFunctor::operator(), ReadSelection.hpp:870-920, 1047-1138)
+    GpuReadSelectionFunctor(Context& ctx, Sink sink, size_t batchBases = size_t(1) << 30, bool sideOutputs = false)
+        : _ctx(ctx), _sink(std::move(sink)), _batchBases(batchBases), _sideOutputs(sideOutputs) {
         _offsets.push_back(0);
+        if (_sideOutputs) check(_ctx.get(), mdbg_ctx_set_read_filters(_ctx.get(), 1), "mdbg_ctx_set_read_filters");
     }
 
     void operator()(const Read& read) {                 // same call shape as the reference functor
+        if (_sideOutputs) {
+            if (!read._qual.empty() && read._qual.size() != read._seq.size())
+                throw std::runtime_error("quality/sequence length mismatch in read " + read._header);
+            if (_indices.empty()) _haveQual = !read._qual.empty();
+            else if (_haveQual != !read._qual.empty()) flush();      // FASTA and FASTQ records never share a batch
+            if (_indices.empty()) _haveQual = !read._qual.empty();
+            if (_haveQual) _quals.insert(_quals.end(), read._qual.begin(), read._qual.end());
+        }
         _bases.insert(_bases.end(), read._seq.begin(), read._seq.end());
         _offsets.push_back(_bases.size());
         _indices.push_back(read._index);
@@ -93,18 +108,30 @@ public:
         const uint32_t n = (uint32_t)_indices.size();
         if (n == 0) return;
         mdbg_sketch_out out{};
-        check(_ctx.get(),
-              mdbg_sketch_batch(_ctx.get(), reinterpret_cast<const uint8_t*>(_bases.data()), _offsets.data(), n,
-                                /*append_to_store=*/1, &out),
-              "mdbg_sketch_batch");
+        mdbg_aux_out aux{};
+        if (_sideOutputs)
+            check(_ctx.get(),
+                  mdbg_sketch_batch_q(_ctx.get(), reinterpret_cast<const uint8_t*>(_bases.data()),
+                                      _haveQual ? reinterpret_cast<const uint8_t*>(_quals.data()) : nullptr,
+                                      _offsets.data(), n, /*append_to_store=*/1, &out, &aux),
+                  "mdbg_sketch_batch_q");
+        else
+            check(_ctx.get(),
+                  mdbg_sketch_batch(_ctx.get(), reinterpret_cast<const uint8_t*>(_bases.data()), _offsets.data(), n,
+                                    /*append_to_store=*/1, &out),
+                  "mdbg_sketch_batch");
         for (uint32_t r = 0; r < n; r++) {
             const uint64_t lo = out.min_offsets[r], hi = out.min_offsets[r + 1];
             if (_sink)
                 _sink(ReadMinimizers{_indices[r], (uint32_t)(_offsets[r + 1] - _offsets[r]), (uint32_t)(hi - lo),
-                                     out.minimizers + lo, out.positions + lo, out.directions + lo});
+                                     out.minimizers + lo, out.positions + lo, out.directions + lo,
+                                     _sideOutputs ? aux.qualities + lo : nullptr,
+                                     _sideOutputs ? aux.mean_quality[r] : 0.0f,
+                                     _sideOutputs ? aux.low_complexity[r] != 0 : false});
             _nbSelectedMinimizers += hi - lo;
         }
         _nbReads += n;
+        _quals.clear();
         _bases.clear();
         _offsets.assign(1, 0);
         _indices.clear();
@@ -118,10 +145,92 @@ private:
     Context& _ctx;
     Sink _sink;
     size_t _batchBases;
+    bool _sideOutputs = false, _haveQual = false;
+    std::vector<char> _quals;
     std::vector<char> _bases;
     std::vector<uint64_t> _offsets;
     std::vector<uint64_t> _indices;
     uint64_t _nbReads = 0, _nbBases = 0, _nbSelectedMinimizers = 0;
+};
+
+// ReadSelection::writeRead + computeReadStats (ReadSelection.hpp:305-491): read_data_init.txt records
+//   u32 n, u8 isCircular, u32 min[n], u32 pos[n], u8 dir[n], u8 qual[n], f32 meanReadQuality, u32 readLength
+// and read_stats.txt (u64 nbReads, u32 n50, f32 density, u64 nbBases, f32 avgQuality, u32 meanLength,
+// u64 nbSelectedMinimizers).  Records arrive in input order, so no re-ordering queue is needed.
+class ReadDataWriter {
+public:
+    ReadDataWriter(const std::string& filename, uint32_t minimizerSize) : _minimizerSize(minimizerSize) {
+        _f = fopen(filename.c_str(), "wb");
+        if (!_f) throw std::runtime_error("cannot open " + filename);
+    }
+    ~ReadDataWriter() { if (_f) fclose(_f); }
+
+    void write(const ReadMinimizers& r) {
+        const uint32_t size = r.n;
+        const uint8_t isCircular = 0;
+        fwrite(&size, 4, 1, _f);
+        fwrite(&isCircular, 1, 1, _f);
+        fwrite(r.minimizers, 4, size, _f);
+        fwrite(r.positions, 4, size, _f);
+        fwrite(r.directions, 1, size, _f);
+        fwrite(r.qualities, 1, size, _f);
+        fwrite(&r.meanReadQuality, 4, 1, _f);
+        fwrite(&r.readLength, 4, 1, _f);
+        _allReadSizes.push_back(r.readLength);
+        _nbSelectedMinimizers += size;
+        _nbKmers += (uint64_t)r.readLength - _minimizerSize + 1;     // ReadSelection.hpp:474 (unsigned wrap kept)
+        _nbBases += r.readLength;
+        if (!(r.meanReadQuality < 0.0f)) {                           // ReadSelection.hpp:906-917, minReadQuality = 0
+            _readQualitySum += r.meanReadQuality;
+            _readQualityN += 1;
+        }
+    }
+
+    void close() { if (_f) { fclose(_f); _f = nullptr; } }
+
+    static uint32_t computeN50(std::vector<uint32_t> lengths) {     // Utils::computeN50, Commons.hpp:2291-2322
+        if (lengths.empty()) return 0;
+        std::sort(lengths.begin(), lengths.end(), std::greater<uint32_t>());
+        std::vector<uint64_t> cumuls;
+        uint64_t cumul = 0;
+        for (uint32_t x : lengths) { cumul += x; cumuls.push_back(cumul); }
+        std::reverse(lengths.begin(), lengths.end());
+        std::reverse(cumuls.begin(), cumuls.end());
+        uint32_t n50 = lengths.back();
+        const uint64_t halfsize = cumuls[0] / 2;
+        for (size_t i = 0; i < lengths.size(); i++)
+            if (cumuls[i] < halfsize) { n50 = lengths[i]; break; }
+        return n50;
+    }
+
+    uint32_t n50() const { return computeN50(_allReadSizes); }
+
+    void writeReadStats(const std::string& filename) {
+        const uint64_t nbReads = _allReadSizes.size();
+        const uint32_t n50v = n50();
+        long double sum = 0, cnt = 0;                                 // Utils::computeMeanLength, Commons.hpp:2324-2336
+        for (uint32_t x : _allReadSizes) { sum += x; cnt += 1; }
+        const uint32_t meanLength = (uint32_t)(uint64_t)(sum / cnt);
+        const float minimizerDensity = (long double)_nbSelectedMinimizers / (long double)_nbKmers;
+        const float averageQuality = _readQualitySum / _readQualityN;
+        FILE* f = fopen(filename.c_str(), "wb");
+        if (!f) throw std::runtime_error("cannot open " + filename);
+        fwrite(&nbReads, 8, 1, f);
+        fwrite(&n50v, 4, 1, f);
+        fwrite(&minimizerDensity, 4, 1, f);
+        fwrite(&_nbBases, 8, 1, f);
+        fwrite(&averageQuality, 4, 1, f);
+        fwrite(&meanLength, 4, 1, f);
+        fwrite(&_nbSelectedMinimizers, 8, 1, f);
+        fclose(f);
+    }
+
+private:
+    FILE* _f = nullptr;
+    uint32_t _minimizerSize;
+    std::vector<uint32_t> _allReadSizes;
+    uint64_t _nbSelectedMinimizers = 0, _nbKmers = 0, _nbBases = 0;
+    long double _readQualitySum = 0, _readQualityN = 0;
 };
 
 // ReadSelection::purgePalindromes + the read_data_corrected.txt writer.

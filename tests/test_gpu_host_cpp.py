@@ -58,3 +58,39 @@ def test_cpp_driver_files_match_oracle(tmp_path, oracle):
     assert sorted(map(tuple, vec.tolist())) == sorted(map(tuple, ref["vecs"].tolist()))
     assert int(stats["solid"]) == len(want) and int(stats["reads"]) == rs.n_reads
     assert int(stats["checksum"]) == oracle.checksum(ref["hashes"], ref["abundances"])
+
+
+def test_cpp_driver_read_data_init_is_byte_identical(tmp_path):
+    """Row A3c: read_data_init.txt written by the C++ host driver equals, byte for byte, the file the reference's
+    readSelection stage wrote for the same FASTQ (golden minted from ReadSelection::execute); read_stats.txt
+    fields match (the average quality is a racy long double sum upstream: compared to 1e-5)."""
+    import __graft_entry__ as g
+    g.build()
+    z = np.load(os.path.join(ROOT, "tests", "golden", "readselection_hifi.npz"))
+    raw, qraw, offs = z["bases"].tobytes(), z["quals"].tobytes(), z["offsets"]
+    fq = tmp_path / "reads.fastq"
+    with open(fq, "wb") as f:
+        for r in range(len(offs) - 1):
+            lo, hi = int(offs[r]), int(offs[r + 1])
+            f.write(b"@r%d\n" % r + raw[lo:hi] + b"\n+\n" + qraw[lo:hi] + b"\n")
+    out = subprocess.run([EXE, str(fq), str(tmp_path), "--batch-mbp", "1"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    want = bytearray()
+    mo = z["min_offsets"]
+    for r in range(len(offs) - 1):
+        lo, hi = int(mo[r]), int(mo[r + 1])
+        want += np.uint32(hi - lo).tobytes() + b"\x00"
+        want += z["minimizers"][lo:hi].tobytes() + z["positions"][lo:hi].tobytes()
+        want += z["directions"][lo:hi].tobytes() + z["qualities"][lo:hi].tobytes()
+        want += np.float32(z["mean_quality"][r]).tobytes() + np.uint32(z["read_length"][r]).tobytes()
+    got = open(tmp_path / "read_data_init.txt", "rb").read()
+    assert got == bytes(want)
+    b = open(tmp_path / "read_stats.txt", "rb").read()
+    assert len(b) == 40
+    n_reads = int(np.frombuffer(b, np.uint64, 1, 0)[0]); n50 = int(np.frombuffer(b, np.uint32, 1, 8)[0])
+    dens = np.frombuffer(b, np.float32, 1, 12)[0]; n_bases = int(np.frombuffer(b, np.uint64, 1, 16)[0])
+    avgq = np.frombuffer(b, np.float32, 1, 24)[0]; mean_len = int(np.frombuffer(b, np.uint32, 1, 28)[0])
+    n_min = int(np.frombuffer(b, np.uint64, 1, 32)[0])
+    assert [n_reads, n50, n_bases, mean_len, n_min] == [int(x) for x in z["stats"]]
+    assert np.float32(dens).tobytes() == np.float32(z["stats_f"][0]).tobytes()
+    assert abs(float(avgq) - float(z["stats_f"][1])) <= 1e-5 * abs(float(z["stats_f"][1]))
