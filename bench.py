@@ -131,8 +131,18 @@ def run_reference(args, rank: int):
             res = dict(n_solid=len(c["abundances"]), n_minimizers=len(m))
         return time.perf_counter() - t0, res
 
-    for _ in range(args.warmup):
-        one()
+    # the warm-up steps also pick the thread count: all logical CPUs or one per physical core, whichever is faster
+    if ref is not None and args.warmup >= 2 and threads >= 4:
+        t_all, _ = one()
+        full, threads = threads, max(1, threads // 2)
+        t_half, _ = one()
+        if t_all < t_half:
+            threads = full
+        for _ in range(args.warmup - 2):
+            one()
+    else:
+        for _ in range(args.warmup):
+            one()
     ts = []
     for _ in range(args.steps):
         t, res = one()
@@ -149,7 +159,35 @@ def run_reference(args, rank: int):
         "e2e": {"value": gbps, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "check": {"n_minimizers": res.get("n_minimizers"), "n_solid": res.get("n_solid")},
     }
+    if ref is not None and not args.no_stages:
+        line["reference_stages"] = reference_stages(ref, bases, offs, threads, n_bases)
     print(json.dumps(line), flush=True)
+
+
+def reference_stages(ref, bases, offs, threads, n_bases):
+    """Extra, not the headline: the reference's real stage code on the same sample -- ReadSelection::execute on a
+    FASTQ in tmpfs (kseq parsing, side outputs, record writer, purgePalindromes) then CreateMdbg::KminmerCounter
+    with its disk partitions -- i.e. what `metaMDBG readSelection` + `graph --firstpass` spend on this path."""
+    import tempfile
+    from oracle import pyoracle
+    base_dir = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    with tempfile.TemporaryDirectory(dir=base_dir) as d:
+        fq = os.path.join(d, "reads.fastq")
+        raw = bases.tobytes()
+        with open(fq, "wb") as f:
+            for r in range(len(offs) - 1):
+                s = raw[int(offs[r]):int(offs[r + 1])]
+                f.write(b"@r%d\n" % r + s + b"\n+\n" + b"I" * len(s) + b"\n")
+        t0 = time.perf_counter()
+        res = ref.read_selection([fq], L, DENSITY, HPC, threads=threads, skip_correction=False, workdir=d)
+        t_rs = time.perf_counter() - t0
+        mins = np.concatenate([r["minimizers"] for r in res["corrected"]]) if res["corrected"] else np.zeros(0, np.uint32)
+        mo = np.zeros(len(res["corrected"]) + 1, np.uint64)
+        mo[1:] = np.cumsum([len(r["minimizers"]) for r in res["corrected"]])
+        g = ref.graph_firstpass(mins, mo, K, min_abundance=MIN_AB, threads=threads)
+    return {"readSelection_s": res["seconds"], "graph_firstpass_count_s": g["seconds"],
+            "value": n_bases / (res["seconds"] + g["seconds"]) / 1e9, "unit": "Gbp/s", "threads": threads,
+            "n_solid": g["n_solid"], "wall_incl_parsing_the_outputs_s": t_rs}
 
 
 # ---------------------------------------------------------------- this engine
@@ -382,6 +420,7 @@ def main():
     ap.add_argument("--ref-reads", type=int, default=0, help="sample size of the reference arm (0 = auto)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stages", action="store_true", help="reference arm: skip the extra real-stage timing")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank = int(os.environ.get("RANK", "0"))

@@ -33,8 +33,11 @@ struct PinBuf {
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+constexpr int MAX_SUB = 64;       // H2D/compute pipeline depth of one host batch
+
 struct SmallDev {                 // device-side scalars, one allocation
     uint32_t cursor;
+    uint32_t sub_cursor[MAX_SUB];
     uint32_t full_flag;
     unsigned long long n_overflow;
     unsigned long long n_flagged;
@@ -50,6 +53,9 @@ struct mdbg_ctx {
     int sm_count = 148;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t sub_ev[MAX_SUB] = {};
+    cudaEvent_t copy_gate = nullptr;
     std::string error;
     uint64_t launches = 0;
     bool timing = false;
@@ -230,8 +236,11 @@ mdbg_status run_aux(mdbg_ctx* ctx, const uint8_t* d_bases, const uint8_t* d_qual
     return check_launch(ctx, "read_aux_kernel", 1);
 }
 
+struct SubRange { uint32_t r0, r1; };
+
 mdbg_status sketch_internal(mdbg_ctx* ctx, const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t n_reads,
-                            uint64_t n_bases, int append, bool want_aux = false, const uint8_t* d_quals = nullptr) {
+                            uint64_t n_bases, int append, bool want_aux = false, const uint8_t* d_quals = nullptr,
+                            const std::vector<SubRange>* subs = nullptr) {
     cudaStream_t s = ctx->stream;
     ctx->b_reads = n_reads;
     ctx->b_total = 0;
@@ -253,6 +262,8 @@ mdbg_status sketch_internal(mdbg_ctx* ctx, const uint8_t* d_bases, const uint64_
     a.bases_end = d_bases + n_bases;
     a.offsets = d_offsets;
     a.n_reads = n_reads;
+    a.read_begin = 0;
+    a.read_end = n_reads;
     a.l = ctx->l;
     a.hpc = ctx->hpc;
     a.threshold = ctx->threshold;
@@ -269,12 +280,27 @@ mdbg_status sketch_internal(mdbg_ctx* ctx, const uint8_t* d_bases, const uint64_
     a.cursor = &ctx->d_small->cursor;
     a.n_overflow = &ctx->d_small->n_overflow;
 
-    CK(cudaMemsetAsync(&ctx->d_small->cursor, 0, sizeof(uint32_t), s));
+    CK(cudaMemsetAsync(&ctx->d_small->cursor, 0, sizeof(uint32_t) * (1 + MAX_SUB), s));
     CK(cudaMemsetAsync(&ctx->d_small->n_overflow, 0, sizeof(unsigned long long), s));
-    if (ctx->timing) CK(cudaEventRecord(ctx->ev[0][0], s));
-    launch_sketch(a, ctx->sm_count, s);
-    if (ctx->timing) { CK(cudaEventRecord(ctx->ev[0][1], s)); ctx->ev_valid[0] = true; }
-    CKS(check_launch(ctx, "sketch_kernel", 1));
+    if (subs && !subs->empty()) {
+        // host batch arriving in pieces on the copy stream: one launch per piece, each gated by its H2D event
+        for (size_t i = 0; i < subs->size(); i++) {
+            CK(cudaStreamWaitEvent(s, ctx->sub_ev[i], 0));
+            a.read_begin = (*subs)[i].r0;
+            a.read_end = (*subs)[i].r1;
+            a.cursor = &ctx->d_small->sub_cursor[i];
+            launch_sketch(a, ctx->sm_count, s);
+            CKS(check_launch(ctx, "sketch_kernel", 1));
+        }
+        a.read_begin = 0;
+        a.read_end = n_reads;
+        a.cursor = &ctx->d_small->cursor;
+    } else {
+        if (ctx->timing) CK(cudaEventRecord(ctx->ev[0][0], s));
+        launch_sketch(a, ctx->sm_count, s);
+        if (ctx->timing) { CK(cudaEventRecord(ctx->ev[0][1], s)); ctx->ev_valid[0] = true; }
+        CKS(check_launch(ctx, "sketch_kernel", 1));
+    }
     if (want_aux) {
         CKS(ensure_err_table(ctx));
         CKS(ensure(ctx, ctx->pad_qual, pad_cap));
@@ -451,6 +477,16 @@ mdbg_status mdbg_ctx_create(int device, const mdbg_params* p, mdbg_ctx** out) {
     cudaError_t e2 = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
     if (e2 != cudaSuccess) { delete c; return fail(nullptr, MDBG_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e2)); }
     c->stream = c->own_stream;
+    if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->copy_gate, cudaEventDisableTiming) != cudaSuccess) {
+        mdbg_ctx_destroy(c);
+        return fail(nullptr, MDBG_ERR_CUDA, "copy stream creation failed");
+    }
+    for (int i = 0; i < MAX_SUB; i++)
+        if (cudaEventCreateWithFlags(&c->sub_ev[i], cudaEventDisableTiming) != cudaSuccess) {
+            mdbg_ctx_destroy(c);
+            return fail(nullptr, MDBG_ERR_CUDA, "event creation failed");
+        }
     if (cudaMalloc((void**)&c->d_small, sizeof(SmallDev)) != cudaSuccess ||
         cudaMallocHost((void**)&c->h_small, sizeof(SmallDev)) != cudaSuccess ||
         cudaMallocHost((void**)&c->h_scalar, 8 * sizeof(uint64_t)) != cudaSuccess) {
@@ -490,6 +526,10 @@ void mdbg_ctx_destroy(mdbg_ctx* c) {
     for (int i = 0; i < 2; i++)
         for (int j = 0; j < 2; j++)
             if (c->ev[i][j]) cudaEventDestroy(c->ev[i][j]);
+    for (int i = 0; i < MAX_SUB; i++)
+        if (c->sub_ev[i]) cudaEventDestroy(c->sub_ev[i]);
+    if (c->copy_gate) cudaEventDestroy(c->copy_gate);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -528,6 +568,9 @@ mdbg_status mdbg_ctx_kernel_time_ms(mdbg_ctx* ctx, int which, float* ms) {
     CK(cudaEventElapsedTime(ms, ctx->ev[which][0], ctx->ev[which][1]));
     return MDBG_OK;
 }
+
+static mdbg_status upload_batch(mdbg_ctx* ctx, const uint8_t* bases, const uint8_t* quals, const uint64_t* offsets,
+                                uint32_t n_reads, uint64_t n_bases, std::vector<SubRange>& subs);
 
 // ---- sketch -----------------------------------------------------------------------
 mdbg_status mdbg_sketch_batch_device(mdbg_ctx* ctx, const uint8_t* d_bases, const uint64_t* d_offsets,
@@ -583,14 +626,41 @@ mdbg_status mdbg_sketch_batch(mdbg_ctx* ctx, const uint8_t* bases, const uint64_
     if (n_reads && offsets[0] != 0) return fail(ctx, MDBG_ERR_ARG, "offsets[0] must be 0");
     CKS(ensure(ctx, ctx->d_bases, n_bases + 64));
     CKS(ensure(ctx, ctx->d_offsets, ((size_t)n_reads + 1) * 8));
-    cudaStream_t s = ctx->stream;
-    if (n_reads) {
-        CK(cudaMemcpyAsync(ctx->d_bases.p, bases, n_bases, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(ctx->d_offsets.p, offsets, ((size_t)n_reads + 1) * 8, cudaMemcpyHostToDevice, s));
-    }
+    std::vector<SubRange> subs;
+    CKS(upload_batch(ctx, bases, nullptr, offsets, n_reads, n_bases, subs));
     CKS(sketch_internal(ctx, ctx->d_bases.as<uint8_t>(), ctx->d_offsets.as<uint64_t>(), n_reads, n_bases,
-                        append_to_store));
+                        append_to_store, false, nullptr, &subs));
     if (out) return mdbg_sketch_fetch(ctx, out);
+    return MDBG_OK;
+}
+
+// Host batch -> device in up to MAX_SUB pieces on the copy stream, so that the sketch of piece i overlaps the
+// transfer of piece i+1 (pieces end on read boundaries).  Falls back to one piece for small batches.
+static mdbg_status upload_batch(mdbg_ctx* ctx, const uint8_t* bases, const uint8_t* quals, const uint64_t* offsets,
+                                uint32_t n_reads, uint64_t n_bases, std::vector<SubRange>& subs) {
+    subs.clear();
+    if (n_reads == 0) return MDBG_OK;
+    cudaStream_t s = ctx->stream, cs = ctx->copy_stream;
+    // the copy stream must not overwrite buffers the compute stream is still reading
+    CK(cudaEventRecord(ctx->copy_gate, s));
+    CK(cudaStreamWaitEvent(cs, ctx->copy_gate, 0));
+    CK(cudaMemcpyAsync(ctx->d_offsets.p, offsets, ((size_t)n_reads + 1) * 8, cudaMemcpyHostToDevice, cs));
+    const uint64_t piece = std::max<uint64_t>(uint64_t(128) << 20, (n_bases + MAX_SUB - 1) / MAX_SUB);
+    uint32_t r0 = 0;
+    while (r0 < n_reads) {
+        const uint64_t target = offsets[r0] + piece;
+        uint32_t r1 = (uint32_t)(std::upper_bound(offsets + r0 + 1, offsets + n_reads + 1, target) - offsets);
+        if (r1 <= r0 + 1) r1 = r0 + 1; else r1 -= 1;
+        if (r1 > n_reads || subs.size() + 1 == (size_t)MAX_SUB) r1 = n_reads;
+        const uint64_t lo = offsets[r0], hi = offsets[r1];
+        if (hi > lo) {
+            CK(cudaMemcpyAsync(ctx->d_bases.as<uint8_t>() + lo, bases + lo, hi - lo, cudaMemcpyHostToDevice, cs));
+            if (quals) CK(cudaMemcpyAsync(ctx->d_quals.as<uint8_t>() + lo, quals + lo, hi - lo, cudaMemcpyHostToDevice, cs));
+        }
+        CK(cudaEventRecord(ctx->sub_ev[subs.size()], cs));
+        subs.push_back(SubRange{r0, r1});
+        r0 = r1;
+    }
     return MDBG_OK;
 }
 
@@ -611,13 +681,10 @@ mdbg_status mdbg_sketch_batch_q(mdbg_ctx* ctx, const uint8_t* bases, const uint8
     CKS(ensure(ctx, ctx->d_offsets, ((size_t)n_reads + 1) * 8));
     if (quals) CKS(ensure(ctx, ctx->d_quals, n_bases + 64));
     cudaStream_t s = ctx->stream;
-    if (n_reads) {
-        CK(cudaMemcpyAsync(ctx->d_bases.p, bases, n_bases, cudaMemcpyHostToDevice, s));
-        if (quals) CK(cudaMemcpyAsync(ctx->d_quals.p, quals, n_bases, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(ctx->d_offsets.p, offsets, ((size_t)n_reads + 1) * 8, cudaMemcpyHostToDevice, s));
-    }
+    std::vector<SubRange> subs;
+    CKS(upload_batch(ctx, bases, quals, offsets, n_reads, n_bases, subs));
     CKS(sketch_internal(ctx, ctx->d_bases.as<uint8_t>(), ctx->d_offsets.as<uint64_t>(), n_reads, n_bases,
-                        append_to_store, true, quals ? ctx->d_quals.as<uint8_t>() : nullptr));
+                        append_to_store, true, quals ? ctx->d_quals.as<uint8_t>() : nullptr, &subs));
     if (out) CKS(mdbg_sketch_fetch(ctx, out));
     if (aux) {
         const uint64_t t = ctx->b_total;
@@ -640,7 +707,12 @@ mdbg_status mdbg_sketch_batch_q(mdbg_ctx* ctx, const uint8_t* bases, const uint8
         float* mq = ctx->hx_meanq.as<float>();
         for (uint32_t r = 0; r < n_reads; r++) {
             const uint64_t len = offsets[r + 1] - offsets[r];
-            if (!quals) { long double z = 0; float e = z / (long double)0; mq[r] = -10.0f * log10f(e); continue; }
+            if (!quals) {                                  // empty _qual: errorSum / 0 = NaN, carried through log10f
+                volatile long double z = 0, n0 = 0;
+                float e = z / n0;
+                mq[r] = -10.0f * log10f(e);
+                continue;
+            }
             long double errorSum = ldexpl((long double)ctx->hx_sum_hi.as<uint64_t>()[r], 64 - ERR_SHIFT) +
                                    ldexpl((long double)ctx->hx_sum_lo.as<uint64_t>()[r], -ERR_SHIFT);
             float meanReadError = errorSum / len;

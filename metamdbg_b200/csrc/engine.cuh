@@ -12,6 +12,7 @@ struct SketchArgs {
     const uint8_t* bases_end;    // bases + n_bases: bytes at/after this address are never dereferenced
     const uint64_t* offsets;     // [n_reads+1]
     uint32_t n_reads;
+    uint32_t read_begin, read_end;   // this launch handles reads [read_begin, read_end) (H2D/compute pipelining)
     uint32_t l;                  // minimizer size (2..16)
     uint32_t hpc;                // homopolymer compression on/off
     uint64_t threshold;          // select iff murmur_h1 <= threshold ...

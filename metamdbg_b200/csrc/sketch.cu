@@ -154,9 +154,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sketch_kernel(const Sketch
 
     for (;;) {
         uint32_t r = 0;
-        if (lane == 0) r = atomicAdd(a.cursor, 1u);
+        if (lane == 0) r = a.read_begin + atomicAdd(a.cursor, 1u);
         r = __shfl_sync(0xffffffffu, r, 0);
-        if (r >= a.n_reads) break;
+        if (r >= a.read_end) break;
 
         const uint64_t start = a.offsets[r], end = a.offsets[r + 1];
         const uint32_t len = (uint32_t)(end - start);
@@ -368,13 +368,13 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sketch_kernel(const Sketch
 }
 
 void launch_sketch(const SketchArgs& a, int sm_count, cudaStream_t s) {
-    if (a.n_reads == 0) return;
+    if (a.read_end <= a.read_begin) return;
     // persistent grid: enough CTAs to fill every SM, reads are pulled dynamically
     int per_sm = 0;
     if (a.l == 15) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sketch_kernel<15>, WARPS_PER_CTA * 32, 0);
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sketch_kernel<0>, WARPS_PER_CTA * 32, 0);
     if (per_sm < 1) per_sm = 1;
-    uint64_t want = ((uint64_t)a.n_reads + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    uint64_t want = ((uint64_t)(a.read_end - a.read_begin) + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     uint64_t grid = (uint64_t)sm_count * per_sm;
     if (grid > want) grid = want;
     if (a.l == 15) sketch_kernel<15><<<(unsigned)grid, WARPS_PER_CTA * 32, 0, s>>>(a);
