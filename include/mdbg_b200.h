@@ -131,6 +131,10 @@ mdbg_status mdbg_ctx_kernel_time_ms(mdbg_ctx* ctx, int which, float* ms);
  * store when append_to_store != 0. */
 mdbg_status mdbg_sketch_batch(mdbg_ctx* ctx, const uint8_t* bases, const uint64_t* offsets,
                               uint32_t n_reads, int append_to_store, mdbg_sketch_out* out);
+/* Host batches without qualities cross PCIe 2-bit packed (worker threads + AVX2 inside the library, unpacked again
+ * by the sketch kernel; reads holding a byte outside "ACGT" stay ASCII, so results are identical).  on = 0 sends the
+ * ASCII bytes as they are.  Default: on. */
+mdbg_status mdbg_ctx_set_host_packing(mdbg_ctx* ctx, int on);
 /* Same with the reads already in HBM.  d_bases must be 16-byte aligned;
  * nothing is copied to the host.  `out` may be NULL. */
 mdbg_status mdbg_sketch_batch_device(mdbg_ctx* ctx, const uint8_t* d_bases, const uint64_t* d_offsets,

@@ -54,6 +54,7 @@ SYMBOLS = {
     "mdbg_ctx_enable_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "mdbg_ctx_kernel_time_ms": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     "mdbg_sketch_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.POINTER(SketchOut)]),
+    "mdbg_ctx_set_host_packing": (C.c_int, [C.c_void_p, C.c_int]),
     "mdbg_sketch_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_int,
                                            C.POINTER(SketchDev)]),
     "mdbg_sketch_fetch": (C.c_int, [C.c_void_p, C.POINTER(SketchOut)]),

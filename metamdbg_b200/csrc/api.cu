@@ -14,6 +14,8 @@
 
 #include "../../include/mdbg_b200.h"
 #include "engine.cuh"
+#include "pack_host.hpp"
+#include <functional>
 
 using namespace mdbg;
 
@@ -54,6 +56,10 @@ struct mdbg_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
+    bool host_packing = true;          // 2-bit pack ASCII host batches before H2D (transfer compression)
+    HostPool* pool = nullptr;
+    DevBuf d_pack, d_src;
+    PinBuf h_pack, h_src, h_asc;
     cudaEvent_t sub_ev[MAX_SUB] = {};
     cudaEvent_t copy_gate = nullptr;
     std::string error;
@@ -237,10 +243,13 @@ mdbg_status run_aux(mdbg_ctx* ctx, const uint8_t* d_bases, const uint8_t* d_qual
 }
 
 struct SubRange { uint32_t r0, r1; };
+// A feeder enqueues the sketch launches itself (host batches arriving in pieces); it may edit the argument block
+// (input pointers) and must leave read_begin/read_end/cursor covering the whole batch when it returns.
+using Feeder = std::function<mdbg_status(SketchArgs&)>;
 
 mdbg_status sketch_internal(mdbg_ctx* ctx, const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t n_reads,
                             uint64_t n_bases, int append, bool want_aux = false, const uint8_t* d_quals = nullptr,
-                            const std::vector<SubRange>* subs = nullptr) {
+                            const Feeder* feeder = nullptr) {
     cudaStream_t s = ctx->stream;
     ctx->b_reads = n_reads;
     ctx->b_total = 0;
@@ -282,16 +291,8 @@ mdbg_status sketch_internal(mdbg_ctx* ctx, const uint8_t* d_bases, const uint64_
 
     CK(cudaMemsetAsync(&ctx->d_small->cursor, 0, sizeof(uint32_t) * (1 + MAX_SUB), s));
     CK(cudaMemsetAsync(&ctx->d_small->n_overflow, 0, sizeof(unsigned long long), s));
-    if (subs && !subs->empty()) {
-        // host batch arriving in pieces on the copy stream: one launch per piece, each gated by its H2D event
-        for (size_t i = 0; i < subs->size(); i++) {
-            CK(cudaStreamWaitEvent(s, ctx->sub_ev[i], 0));
-            a.read_begin = (*subs)[i].r0;
-            a.read_end = (*subs)[i].r1;
-            a.cursor = &ctx->d_small->sub_cursor[i];
-            launch_sketch(a, ctx->sm_count, s);
-            CKS(check_launch(ctx, "sketch_kernel", 1));
-        }
+    if (feeder) {
+        CKS((*feeder)(a));
         a.read_begin = 0;
         a.read_end = n_reads;
         a.cursor = &ctx->d_small->cursor;
@@ -514,10 +515,10 @@ void mdbg_ctx_destroy(mdbg_ctx* c) {
     DevBuf* devs[] = {&c->d_blacklist, &c->d_bases, &c->d_offsets, &c->pad_min, &c->pad_pos, &c->pad_dir, &c->n_min,
                       &c->scan_scratch, &c->b_off, &c->b_min, &c->b_pos, &c->b_dir, &c->s_min, &c->s_off, &c->s_rem,
                       &c->p_flags, &c->p_keep, &c->p_cnt, &c->p_newoff, &c->p_newmin, &c->table, &c->foreign_vecs,
-                      &c->o_hash, &c->o_abund, &c->o_vecs, &c->d_quals, &c->pad_qual, &c->pad_raw_a, &c->pad_raw_b, &c->b_qual, &c->x_sum_lo, &c->x_sum_hi, &c->x_lmin, &c->x_cplx, &c->x_low, &c->d_err_fixed, &c->d_err_tz, &c->prev_table, &c->prev_stage_h, &c->prev_stage_a, &c->m_send_vecs, &c->m_send_counts, &c->m_recv_vecs,
+                      &c->o_hash, &c->o_abund, &c->o_vecs, &c->d_pack, &c->d_src, &c->d_quals, &c->pad_qual, &c->pad_raw_a, &c->pad_raw_b, &c->b_qual, &c->x_sum_lo, &c->x_sum_hi, &c->x_lmin, &c->x_cplx, &c->x_low, &c->d_err_fixed, &c->d_err_tz, &c->prev_table, &c->prev_stage_h, &c->prev_stage_a, &c->m_send_vecs, &c->m_send_counts, &c->m_recv_vecs,
                       &c->m_recv_counts, &c->m_bucket};
     for (DevBuf* b : devs) release(*b);
-    PinBuf* pins[] = {&c->h_off, &c->h_min, &c->h_pos, &c->h_dir, &c->ho_hash, &c->ho_abund, &c->ho_vecs, &c->hx_sum_lo, &c->hx_sum_hi, &c->hx_lmin, &c->hx_cplx, &c->hx_low, &c->hx_meanq, &c->h_qual};
+    PinBuf* pins[] = {&c->h_off, &c->h_min, &c->h_pos, &c->h_dir, &c->ho_hash, &c->ho_abund, &c->ho_vecs, &c->hx_sum_lo, &c->hx_sum_hi, &c->hx_lmin, &c->hx_cplx, &c->hx_low, &c->hx_meanq, &c->h_qual, &c->h_pack, &c->h_src, &c->h_asc};
     for (PinBuf* b : pins) release(*b);
     if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
     if (c->d_small) cudaFree(c->d_small);
@@ -526,6 +527,7 @@ void mdbg_ctx_destroy(mdbg_ctx* c) {
     for (int i = 0; i < 2; i++)
         for (int j = 0; j < 2; j++)
             if (c->ev[i][j]) cudaEventDestroy(c->ev[i][j]);
+    if (c->pool) host_pool_destroy(c->pool);
     for (int i = 0; i < MAX_SUB; i++)
         if (c->sub_ev[i]) cudaEventDestroy(c->sub_ev[i]);
     if (c->copy_gate) cudaEventDestroy(c->copy_gate);
@@ -569,8 +571,8 @@ mdbg_status mdbg_ctx_kernel_time_ms(mdbg_ctx* ctx, int which, float* ms) {
     return MDBG_OK;
 }
 
-static mdbg_status upload_batch(mdbg_ctx* ctx, const uint8_t* bases, const uint8_t* quals, const uint64_t* offsets,
-                                uint32_t n_reads, uint64_t n_bases, std::vector<SubRange>& subs);
+static mdbg_status sketch_host_batch(mdbg_ctx* ctx, const uint8_t* bases, const uint8_t* quals, const uint64_t* offsets,
+                                     uint32_t n_reads, uint64_t n_bases, int append, bool want_aux);
 
 // ---- sketch -----------------------------------------------------------------------
 mdbg_status mdbg_sketch_batch_device(mdbg_ctx* ctx, const uint8_t* d_bases, const uint64_t* d_offsets,
@@ -626,25 +628,17 @@ mdbg_status mdbg_sketch_batch(mdbg_ctx* ctx, const uint8_t* bases, const uint64_
     if (n_reads && offsets[0] != 0) return fail(ctx, MDBG_ERR_ARG, "offsets[0] must be 0");
     CKS(ensure(ctx, ctx->d_bases, n_bases + 64));
     CKS(ensure(ctx, ctx->d_offsets, ((size_t)n_reads + 1) * 8));
-    std::vector<SubRange> subs;
-    CKS(upload_batch(ctx, bases, nullptr, offsets, n_reads, n_bases, subs));
-    CKS(sketch_internal(ctx, ctx->d_bases.as<uint8_t>(), ctx->d_offsets.as<uint64_t>(), n_reads, n_bases,
-                        append_to_store, false, nullptr, &subs));
+    CKS(sketch_host_batch(ctx, bases, nullptr, offsets, n_reads, n_bases, append_to_store, false));
     if (out) return mdbg_sketch_fetch(ctx, out);
     return MDBG_OK;
 }
 
 // Host batch -> device in up to MAX_SUB pieces on the copy stream, so that the sketch of piece i overlaps the
-// transfer of piece i+1 (pieces end on read boundaries).  Falls back to one piece for small batches.
-static mdbg_status upload_batch(mdbg_ctx* ctx, const uint8_t* bases, const uint8_t* quals, const uint64_t* offsets,
-                                uint32_t n_reads, uint64_t n_bases, std::vector<SubRange>& subs) {
+// transfer of piece i+1 (pieces end on read boundaries).  Without qualities the pieces travel 2-bit packed
+// (pack_host.cpp, AVX2 + worker threads): 4x fewer PCIe bytes; reads holding a byte outside "ACGT" keep their
+// ASCII form so that the result is unchanged.
+static void split_pieces(const uint64_t* offsets, uint32_t n_reads, uint64_t n_bases, std::vector<SubRange>& subs) {
     subs.clear();
-    if (n_reads == 0) return MDBG_OK;
-    cudaStream_t s = ctx->stream, cs = ctx->copy_stream;
-    // the copy stream must not overwrite buffers the compute stream is still reading
-    CK(cudaEventRecord(ctx->copy_gate, s));
-    CK(cudaStreamWaitEvent(cs, ctx->copy_gate, 0));
-    CK(cudaMemcpyAsync(ctx->d_offsets.p, offsets, ((size_t)n_reads + 1) * 8, cudaMemcpyHostToDevice, cs));
     const uint64_t piece = std::max<uint64_t>(uint64_t(128) << 20, (n_bases + MAX_SUB - 1) / MAX_SUB);
     uint32_t r0 = 0;
     while (r0 < n_reads) {
@@ -652,15 +646,119 @@ static mdbg_status upload_batch(mdbg_ctx* ctx, const uint8_t* bases, const uint8
         uint32_t r1 = (uint32_t)(std::upper_bound(offsets + r0 + 1, offsets + n_reads + 1, target) - offsets);
         if (r1 <= r0 + 1) r1 = r0 + 1; else r1 -= 1;
         if (r1 > n_reads || subs.size() + 1 == (size_t)MAX_SUB) r1 = n_reads;
-        const uint64_t lo = offsets[r0], hi = offsets[r1];
-        if (hi > lo) {
-            CK(cudaMemcpyAsync(ctx->d_bases.as<uint8_t>() + lo, bases + lo, hi - lo, cudaMemcpyHostToDevice, cs));
-            if (quals) CK(cudaMemcpyAsync(ctx->d_quals.as<uint8_t>() + lo, quals + lo, hi - lo, cudaMemcpyHostToDevice, cs));
-        }
-        CK(cudaEventRecord(ctx->sub_ev[subs.size()], cs));
         subs.push_back(SubRange{r0, r1});
         r0 = r1;
     }
+}
+
+static mdbg_status sketch_host_batch(mdbg_ctx* ctx, const uint8_t* bases, const uint8_t* quals, const uint64_t* offsets,
+                                     uint32_t n_reads, uint64_t n_bases, int append, bool want_aux) {
+    cudaStream_t s = ctx->stream, cs = ctx->copy_stream;
+    CKS(ensure(ctx, ctx->d_offsets, ((size_t)n_reads + 1) * 8));
+    if (n_reads == 0)
+        return sketch_internal(ctx, nullptr, ctx->d_offsets.as<uint64_t>(), 0, 0, append, want_aux, nullptr);
+    std::vector<SubRange> subs;
+    split_pieces(offsets, n_reads, n_bases, subs);
+    // the copy stream must not overwrite buffers the compute stream is still reading
+    CK(cudaEventRecord(ctx->copy_gate, s));
+    CK(cudaStreamWaitEvent(cs, ctx->copy_gate, 0));
+    CK(cudaMemcpyAsync(ctx->d_offsets.p, offsets, ((size_t)n_reads + 1) * 8, cudaMemcpyHostToDevice, cs));
+
+    const bool packed = ctx->host_packing && !quals && !want_aux && n_bases >= (uint64_t(1) << 20);
+    if (!packed) {
+        CKS(ensure(ctx, ctx->d_bases, n_bases + 64));
+        if (quals) CKS(ensure(ctx, ctx->d_quals, n_bases + 64));
+        const Feeder feeder = [&](SketchArgs& a) -> mdbg_status {
+            for (size_t i = 0; i < subs.size(); i++) {
+                const uint64_t lo = offsets[subs[i].r0], hi = offsets[subs[i].r1];
+                if (hi > lo) {
+                    CK(cudaMemcpyAsync(ctx->d_bases.as<uint8_t>() + lo, bases + lo, hi - lo, cudaMemcpyHostToDevice, cs));
+                    if (quals)
+                        CK(cudaMemcpyAsync(ctx->d_quals.as<uint8_t>() + lo, quals + lo, hi - lo, cudaMemcpyHostToDevice, cs));
+                }
+                CK(cudaEventRecord(ctx->sub_ev[i], cs));
+                CK(cudaStreamWaitEvent(s, ctx->sub_ev[i], 0));
+                a.read_begin = subs[i].r0;
+                a.read_end = subs[i].r1;
+                a.cursor = &ctx->d_small->sub_cursor[i];
+                launch_sketch(a, ctx->sm_count, s);
+                CKS(check_launch(ctx, "sketch_kernel", 1));
+            }
+            return MDBG_OK;
+        };
+        return sketch_internal(ctx, ctx->d_bases.as<uint8_t>(), ctx->d_offsets.as<uint64_t>(), n_reads, n_bases, append,
+                               want_aux, quals ? ctx->d_quals.as<uint8_t>() : nullptr, &feeder);
+    }
+
+    // ---- packed transfer ----------------------------------------------------------------------------------------
+    if (!ctx->pool) ctx->pool = host_pool_create(0);
+    std::vector<uint64_t> pk_off((size_t)n_reads + 1);
+    pk_off[0] = 0;
+    for (uint32_t r = 0; r < n_reads; r++) pk_off[r + 1] = pk_off[r] + ((offsets[r + 1] - offsets[r] + 15) >> 4);
+    const uint64_t n_words = pk_off[n_reads];
+    const uint64_t asc_cap = n_bases + 16ull * n_reads + 64;                 // worst case: every read kept as ASCII
+    CKS(ensure_pin(ctx, ctx->h_pack, (n_words + 1) * 4));
+    CKS(ensure_pin(ctx, ctx->h_src, (size_t)n_reads * 8));
+    CKS(ensure(ctx, ctx->d_pack, (n_words + 1) * 4));
+    CKS(ensure(ctx, ctx->d_src, (size_t)n_reads * 8));
+    // ASCII spill: pinned staging grows on demand (reads with N / lower case are rare), device side is reserved lazily too
+    std::atomic<uint64_t> asc_cursor{0};
+    uint64_t asc_sent = 0;
+    const Feeder feeder = [&](SketchArgs& a) -> mdbg_status {
+        a.read_src = ctx->d_src.as<uint64_t>();
+        a.packed = ctx->d_pack.as<uint32_t>();
+        for (size_t i = 0; i < subs.size(); i++) {
+            const uint32_t r0 = subs[i].r0, r1 = subs[i].r1;
+            // worst-case ASCII spill of this piece must fit the pinned staging before the workers start
+            const uint64_t piece_bytes = offsets[r1] - offsets[r0] + 16ull * (r1 - r0);
+            if (ctx->h_asc.cap < asc_cursor.load() + piece_bytes) {
+                PinBuf bigger;
+                CKS(ensure_pin(ctx, bigger, asc_cursor.load() + piece_bytes));
+                if (ctx->h_asc.p && asc_cursor.load()) {
+                    CK(cudaStreamSynchronize(cs));                           // earlier spill copies still read the old buffer
+                    memcpy(bigger.p, ctx->h_asc.p, asc_cursor.load());
+                }
+                release(ctx->h_asc);
+                ctx->h_asc = bigger;
+            }
+            host_pack_reads(ctx->pool, bases, offsets, r0, r1, pk_off.data(), ctx->h_pack.as<uint32_t>(),
+                            ctx->h_src.as<uint64_t>(), ctx->h_asc.as<uint8_t>(), &asc_cursor);
+            const uint64_t w0 = pk_off[r0], w1 = pk_off[r1];
+            if (w1 > w0)
+                CK(cudaMemcpyAsync(ctx->d_pack.as<uint32_t>() + w0, ctx->h_pack.as<uint32_t>() + w0, (w1 - w0) * 4,
+                                   cudaMemcpyHostToDevice, cs));
+            CK(cudaMemcpyAsync(ctx->d_src.as<uint64_t>() + r0, ctx->h_src.as<uint64_t>() + r0, (size_t)(r1 - r0) * 8,
+                               cudaMemcpyHostToDevice, cs));
+            const uint64_t asc_now = asc_cursor.load();
+            if (asc_now > asc_sent) {
+                if (ctx->d_bases.cap < asc_now + 64) {                       // grow, keeping what earlier pieces spilled
+                    CK(cudaStreamSynchronize(cs));
+                    CK(cudaStreamSynchronize(s));
+                    CKS(ensure(ctx, ctx->d_bases, std::min<uint64_t>(asc_cap, 2 * asc_now + (uint64_t(64) << 20)), true));
+                }
+                CK(cudaMemcpyAsync(ctx->d_bases.as<uint8_t>() + asc_sent, ctx->h_asc.as<uint8_t>() + asc_sent,
+                                   asc_now - asc_sent, cudaMemcpyHostToDevice, cs));
+                asc_sent = asc_now;
+            }
+            CK(cudaEventRecord(ctx->sub_ev[i], cs));
+            CK(cudaStreamWaitEvent(s, ctx->sub_ev[i], 0));
+            a.bases = ctx->d_bases.as<uint8_t>();
+            a.bases_end = ctx->d_bases.p ? ctx->d_bases.as<uint8_t>() + ctx->d_bases.cap - 32 : nullptr;
+            a.read_begin = r0;
+            a.read_end = r1;
+            a.cursor = &ctx->d_small->sub_cursor[i];
+            launch_sketch(a, ctx->sm_count, s);
+            CKS(check_launch(ctx, "sketch_kernel", 1));
+        }
+        return MDBG_OK;
+    };
+    return sketch_internal(ctx, ctx->d_bases.as<uint8_t>(), ctx->d_offsets.as<uint64_t>(), n_reads, n_bases, append,
+                           false, nullptr, &feeder);
+}
+
+mdbg_status mdbg_ctx_set_host_packing(mdbg_ctx* ctx, int on) {
+    if (!ctx) return MDBG_ERR_ARG;
+    ctx->host_packing = on != 0;
     return MDBG_OK;
 }
 
@@ -679,12 +777,8 @@ mdbg_status mdbg_sketch_batch_q(mdbg_ctx* ctx, const uint8_t* bases, const uint8
     if (n_reads && offsets[0] != 0) return fail(ctx, MDBG_ERR_ARG, "offsets[0] must be 0");
     CKS(ensure(ctx, ctx->d_bases, n_bases + 64));
     CKS(ensure(ctx, ctx->d_offsets, ((size_t)n_reads + 1) * 8));
-    if (quals) CKS(ensure(ctx, ctx->d_quals, n_bases + 64));
     cudaStream_t s = ctx->stream;
-    std::vector<SubRange> subs;
-    CKS(upload_batch(ctx, bases, quals, offsets, n_reads, n_bases, subs));
-    CKS(sketch_internal(ctx, ctx->d_bases.as<uint8_t>(), ctx->d_offsets.as<uint64_t>(), n_reads, n_bases,
-                        append_to_store, true, quals ? ctx->d_quals.as<uint8_t>() : nullptr, &subs));
+    CKS(sketch_host_batch(ctx, bases, quals, offsets, n_reads, n_bases, append_to_store, true));
     if (out) CKS(mdbg_sketch_fetch(ctx, out));
     if (aux) {
         const uint64_t t = ctx->b_total;

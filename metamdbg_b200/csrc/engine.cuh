@@ -11,6 +11,11 @@ struct SketchArgs {
     const uint8_t* bases;        // concatenated ASCII reads (16-byte aligned allocation)
     const uint8_t* bases_end;    // bases + n_bases: bytes at/after this address are never dereferenced
     const uint64_t* offsets;     // [n_reads+1]
+    // optional per-read source table of a host batch that travelled 2-bit packed (bit 63 clear: index of the
+    // read's first u32 in `packed`, 16 bases per word, base j at bits [2j,2j+1], code (c>>1)&3; bit 63 set: byte
+    // offset in `bases` of a read holding a character outside "ACGT", kept as ASCII).  nullptr = plain ASCII batch.
+    const uint64_t* read_src;
+    const uint32_t* packed;
     uint32_t n_reads;
     uint32_t read_begin, read_end;   // this launch handles reads [read_begin, read_end) (H2D/compute pipelining)
     uint32_t l;                  // minimizer size (2..16)
@@ -93,6 +98,7 @@ struct __align__(32) Slot {
     uint64_t ref;     // bit63: vector is the reversed window; bit62: index into foreign vecs; low bits: index
 };
 
+constexpr uint64_t SRC_ASCII = 1ULL << 63;
 constexpr uint64_t REF_REV = 1ULL << 63;
 constexpr uint64_t REF_FOREIGN = 1ULL << 62;
 constexpr uint64_t REF_INDEX_MASK = (1ULL << 62) - 1;

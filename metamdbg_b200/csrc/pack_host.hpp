@@ -1,0 +1,21 @@
+// pack_host.hpp -- host-side 2-bit packing of ASCII reads before they cross PCIe (transfer compression only:
+// the packed bases are unpacked again inside the sketch kernel; no part of the result is computed here).
+#pragma once
+
+#include <atomic>
+#include <cstdint>
+
+namespace mdbg {
+
+class HostPool;                                   // persistent worker threads
+HostPool* host_pool_create(int n_threads);        // n_threads <= 0: one per hardware thread, at most 32
+void host_pool_destroy(HostPool* p);
+
+// Pack reads [r0, r1) of an ASCII batch.  Read r goes to pack_out[pk_off[r] ...] (16 bases per u32, base j at bits
+// [2j, 2j+1], code (c >> 1) & 3) and src_out[r] = pk_off[r]; a read holding any byte outside "ACGT" is instead
+// copied verbatim to asc_out (16-byte aligned slot reserved from *asc_cursor) and src_out[r] = (1 << 63) | offset.
+void host_pack_reads(HostPool* pool, const uint8_t* bases, const uint64_t* offsets, uint32_t r0, uint32_t r1,
+                     const uint64_t* pk_off, uint32_t* pack_out, uint64_t* src_out, uint8_t* asc_out,
+                     std::atomic<uint64_t>* asc_cursor);
+
+}  // namespace mdbg

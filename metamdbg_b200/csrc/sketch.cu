@@ -45,6 +45,15 @@ __device__ __forceinline__ uint32_t flags_to_mask16(uint32_t f0, uint32_t f1, ui
     return a | (b & 0xF0u) | (c & 0xF00u) | (d & 0xF000u);
 }
 
+// gather the 16 even bits of x into the low 16 bits
+__device__ __forceinline__ uint32_t even_bits16(uint32_t x) {
+    x &= 0x55555555u;
+    x = (x | (x >> 1)) & 0x33333333u;
+    x = (x | (x >> 2)) & 0x0F0F0F0Fu;
+    x = (x | (x >> 4)) & 0x00FF00FFu;
+    return (x | (x >> 8)) & 0xFFFFu;
+}
+
 __device__ __forceinline__ bool blacklisted(const uint32_t* bl, uint32_t n, uint32_t v) {
     uint32_t lo = 0, hi = n;
     while (lo < hi) {
@@ -168,8 +177,15 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sketch_kernel(const Sketch
             slot_lo = (start >> a.cap_shift) + (uint64_t)r * a.cap_const;
             slot_cap = ((end >> a.cap_shift) + (uint64_t)(r + 1) * a.cap_const) - slot_lo;
         }
+        // where this read's bases live: the ASCII batch, or (host batches) its 2-bit packed copy
+        const uint32_t* pk = nullptr;
         const uint8_t* base = a.bases + start;
-        const uint32_t skip = (uint32_t)((uintptr_t)base & 15);
+        if (a.read_src) {
+            const uint64_t src = a.read_src[r];
+            if (src & SRC_ASCII) base = a.bases + (src & ~SRC_ASCII);
+            else pk = a.packed + src;
+        }
+        const uint32_t skip = pk ? 0u : (uint32_t)((uintptr_t)base & 15);
         const uint8_t* abase = base - skip;             // 16-byte aligned
         const uint32_t x_end = skip + len;              // aligned-index space: x = skip + i
         const uint32_t n_chunks = (x_end + CHUNK - 1) / CHUNK;
@@ -181,6 +197,41 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sketch_kernel(const Sketch
             // ---- fill: append HPC base codes to the ring ----------------------
             while (chunk < n_chunks && avail - done < (uint32_t)BLK + l) {
                 const uint32_t x0 = chunk * CHUNK + lane * 16;
+                if (pk) {
+                    // ---- 2-bit packed source: one u32 = my 16 bases (clean reads: only A, C, G, T) ----------
+                    const uint32_t w = (x0 < len) ? pk[chunk * 32 + lane] : 0u;
+                    const uint32_t nvalid = (len > x0) ? min(len - x0, 16u) : 0u;
+                    const uint32_t vm = (1u << nvalid) - 1u;
+                    uint32_t prev = __shfl_up_sync(0xffffffffu, w >> 30, 1);
+                    if (lane == 0) prev = carry;
+                    carry = __shfl_sync(0xffffffffu, w >> 30, 31);
+                    uint32_t keep = vm;
+                    if (a.hpc) {
+                        const uint32_t x = w ^ ((w << 2) | (prev & 3u));
+                        uint32_t k16 = even_bits16(x | (x >> 1));      // base differs from the previous base
+                        if (x0 == 0) k16 |= 1u;                        // first base: previous char is the '#' sentinel
+                        keep = k16 & vm;
+                    }
+                    const uint32_t cnt = __popc(keep);
+                    const uint32_t incl = warp_inclusive_scan(cnt);
+                    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                    const uint32_t base_idx = (avail + incl - cnt) & (RING - 1);
+                    uint8_t* dst = ring + base_idx;
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        if ((keep >> j) & 1u) {
+                            *dst = (uint8_t)((w >> (2 * j)) & 3u);
+                            dst++;
+                        }
+                    }
+                    if (base_idx + cnt > (uint32_t)RING) {
+                        const uint32_t over = base_idx + cnt - RING;
+                        for (uint32_t i = 0; i < over; i++) ring[i] = ring[RING + i];
+                    }
+                    avail += total;
+                    chunk++;
+                    continue;
+                }
                 // interior chunk: every byte of every lane belongs to the read (all but the first/last chunk)
                 const bool interior = (chunk * CHUNK >= skip) && ((chunk + 1) * CHUNK <= x_end);
                 uint4 w = make_uint4(0, 0, 0, 0);

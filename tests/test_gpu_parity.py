@@ -397,3 +397,42 @@ def test_side_outputs_vs_oracle_with_overflow(built, oracle):
         assert np.float32(aux["mean_quality"][r]).tobytes() == np.float32(mq).tobytes()
         assert aux["complexity"][r] == cx or (np.isnan(cx) and np.isnan(aux["complexity"][r]))
     eng.close()
+
+
+# ---------------------------------------------------------------- host batches travel 2-bit packed
+
+def test_packed_host_transfer_with_dirty_reads(built, oracle):
+    """> 1 MB host batches are 2-bit packed before H2D; reads with N / lower case / '#' keep their ASCII form.
+    Results must equal the oracle and the unpacked transfer, HPC on and off."""
+    rng = np.random.default_rng(23)
+    rs = synth.make_readset(700, 6000, seed=23, n_genomes=2, genome_len_range=(100_000, 200_000))
+    bases, offs = synth.fill_reads(rs)
+    reads = [bytearray(bases[int(offs[r]):int(offs[r + 1])].tobytes()) for r in range(rs.n_reads)]
+    for r in range(0, rs.n_reads, 7):                      # every 7th read gets something outside "ACGT"
+        rd = reads[r]
+        kind = (r // 7) % 4
+        pos = int(rng.integers(0, len(rd)))
+        if kind == 0:
+            rd[pos:pos + 3] = b"NNN"[:len(rd) - pos]
+        elif kind == 1:
+            rd[pos] = ord("acgt"[int(rng.integers(0, 4))])
+        elif kind == 2:
+            rd[pos] = ord("#")
+        else:
+            rd[0] = ord("n")
+    reads += [bytearray(b""), bytearray(b"ACGT"), bytearray(b"A" * 5000), bytearray(b"N" * 100)]
+    flat = np.frombuffer(b"".join(bytes(x) for x in reads), np.uint8).copy()
+    o2 = np.zeros(len(reads) + 1, np.uint64)
+    o2[1:] = np.cumsum([len(x) for x in reads])
+    assert len(flat) > (1 << 21)
+    for hpc, dens in ((True, 0.005), (False, 0.02)):
+        want = oracle.sketch_batch(flat, o2, 15, dens, hpc)
+        eng = engine(15, dens, hpc)
+        sk_packed = eng.sketch_batch(flat, o2, append_to_store=True)
+        assert_sketch_equal(sk_packed, *want, tag=f"packed hpc={hpc}")
+        eng.set_host_packing(False)
+        sk_ascii = eng.sketch_batch(flat, o2)
+        assert_sketch_equal(sk_ascii, *want, tag=f"ascii hpc={hpc}")
+        so, sm = eng.store_fetch()
+        assert np.array_equal(so, want[0]) and np.array_equal(sm, want[1])
+        eng.close()
