@@ -316,14 +316,19 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             tab = step_e2e()
         e_steps = max(1, min(args.steps, args.e2e_steps))
         barrier()
+        moved0 = eng.bytes_moved()
         t0 = time.perf_counter()
         for _ in range(e_steps):
             tab = step_e2e()
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
+        moved1 = eng.bytes_moved()
         e_total = sum_over_ranks(e_bases)
         e2e = {"value": e_total * e_steps / dt / 1e9, "unit": "Gbp/s",
-               "h2d_bytes_per_step": int(e_bases + 8 * (e_reads + 1)), "d2h_bytes_per_step": int(d2h[0]),
+               "h2d_bytes_per_step": int((moved1[0] - moved0[0]) // e_steps),
+               "d2h_bytes_per_step": int((moved1[1] - moved0[1]) // e_steps),
+               "host_input_bytes_per_step": int(e_bases + 8 * (e_reads + 1)),
+               "transfer": "ASCII reads are 2-bit packed by the library's host threads before H2D",
                "steps": e_steps, "reads_per_gpu": e_reads, "host_batch_reads": batch,
                "timer": "host wall clock around synchronous C-ABI calls, max over ranks"}
         if world == 1 and e_reads == n_reads:

@@ -118,6 +118,8 @@ mdbg_status mdbg_ctx_set_stream(mdbg_ctx* ctx, void* cuda_stream);
 mdbg_status mdbg_ctx_synchronize(mdbg_ctx* ctx);
 /* Number of this library's kernels launched on the context so far. */
 uint64_t    mdbg_ctx_kernel_launches(mdbg_ctx* ctx);
+/* Bytes the host-buffer entry points (sketch batches, fetches, finalize) have sent over PCIe so far. */
+mdbg_status mdbg_ctx_bytes_moved(mdbg_ctx* ctx, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
 /* Per-kernel device timing (CUDA events recorded on the context's stream around
  * the launch).  which: 0 = sketch kernel (K1), 1 = k-min-mer insert kernel (K3).
  * Returns the duration of the most recent launch of that kernel in ms. */

@@ -64,6 +64,7 @@ struct mdbg_ctx {
     cudaEvent_t copy_gate = nullptr;
     std::string error;
     uint64_t launches = 0;
+    uint64_t h2d_bytes = 0, d2h_bytes = 0;   // bytes enqueued across PCIe by the host-buffer entry points
     bool timing = false;
     cudaEvent_t ev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     bool ev_valid[2] = {false, false};
@@ -553,6 +554,13 @@ mdbg_status mdbg_ctx_synchronize(mdbg_ctx* ctx) {
 
 uint64_t mdbg_ctx_kernel_launches(mdbg_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+mdbg_status mdbg_ctx_bytes_moved(mdbg_ctx* ctx, uint64_t* h2d_bytes, uint64_t* d2h_bytes) {
+    if (!ctx) return MDBG_ERR_ARG;
+    if (h2d_bytes) *h2d_bytes = ctx->h2d_bytes;
+    if (d2h_bytes) *d2h_bytes = ctx->d2h_bytes;
+    return MDBG_OK;
+}
+
 mdbg_status mdbg_ctx_enable_timing(mdbg_ctx* ctx, int on) {
     if (!ctx) return MDBG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
@@ -610,6 +618,7 @@ mdbg_status mdbg_sketch_fetch(mdbg_ctx* ctx, mdbg_sketch_out* out) {
         CK(cudaMemcpyAsync(ctx->h_dir.p, ctx->b_dir.p, t, cudaMemcpyDeviceToHost, s));
     }
     CK(cudaStreamSynchronize(s));
+    ctx->d2h_bytes += ((uint64_t)n + 1) * 8 + t * 9;
     out->n_reads = n;
     out->n_minimizers = t;
     out->min_offsets = ctx->h_off.as<uint64_t>();
@@ -663,6 +672,7 @@ static mdbg_status sketch_host_batch(mdbg_ctx* ctx, const uint8_t* bases, const 
     CK(cudaEventRecord(ctx->copy_gate, s));
     CK(cudaStreamWaitEvent(cs, ctx->copy_gate, 0));
     CK(cudaMemcpyAsync(ctx->d_offsets.p, offsets, ((size_t)n_reads + 1) * 8, cudaMemcpyHostToDevice, cs));
+    ctx->h2d_bytes += ((uint64_t)n_reads + 1) * 8;
 
     const bool packed = ctx->host_packing && !quals && !want_aux && n_bases >= (uint64_t(1) << 20);
     if (!packed) {
@@ -675,6 +685,7 @@ static mdbg_status sketch_host_batch(mdbg_ctx* ctx, const uint8_t* bases, const 
                     CK(cudaMemcpyAsync(ctx->d_bases.as<uint8_t>() + lo, bases + lo, hi - lo, cudaMemcpyHostToDevice, cs));
                     if (quals)
                         CK(cudaMemcpyAsync(ctx->d_quals.as<uint8_t>() + lo, quals + lo, hi - lo, cudaMemcpyHostToDevice, cs));
+                    ctx->h2d_bytes += (hi - lo) * (quals ? 2 : 1);
                 }
                 CK(cudaEventRecord(ctx->sub_ev[i], cs));
                 CK(cudaStreamWaitEvent(s, ctx->sub_ev[i], 0));
@@ -729,6 +740,7 @@ static mdbg_status sketch_host_batch(mdbg_ctx* ctx, const uint8_t* bases, const 
                                    cudaMemcpyHostToDevice, cs));
             CK(cudaMemcpyAsync(ctx->d_src.as<uint64_t>() + r0, ctx->h_src.as<uint64_t>() + r0, (size_t)(r1 - r0) * 8,
                                cudaMemcpyHostToDevice, cs));
+            ctx->h2d_bytes += (w1 - w0) * 4 + (uint64_t)(r1 - r0) * 8;
             const uint64_t asc_now = asc_cursor.load();
             if (asc_now > asc_sent) {
                 if (ctx->d_bases.cap < asc_now + 64) {                       // grow, keeping what earlier pieces spilled
@@ -738,6 +750,7 @@ static mdbg_status sketch_host_batch(mdbg_ctx* ctx, const uint8_t* bases, const 
                 }
                 CK(cudaMemcpyAsync(ctx->d_bases.as<uint8_t>() + asc_sent, ctx->h_asc.as<uint8_t>() + asc_sent,
                                    asc_now - asc_sent, cudaMemcpyHostToDevice, cs));
+                ctx->h2d_bytes += asc_now - asc_sent;
                 asc_sent = asc_now;
             }
             CK(cudaEventRecord(ctx->sub_ev[i], cs));
@@ -1053,6 +1066,7 @@ mdbg_status mdbg_count_finalize(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_tabl
         CK(cudaMemcpyAsync(ctx->ho_vecs.p, ctx->o_vecs.p, n * 4 * k, cudaMemcpyDeviceToHost, s));
     }
     CK(cudaStreamSynchronize(s));
+    ctx->d2h_bytes += n * (16 + 4 + 4ull * k);
     out->k = k;
     out->n_entries = n;
     out->hashes = ctx->ho_hash.as<uint64_t>();

@@ -4,6 +4,7 @@
 #include <immintrin.h>
 
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <mutex>
@@ -16,9 +17,18 @@ class HostPool {
 public:
     explicit HostPool(int n) {
         if (n <= 0) {
-            n = (int)std::thread::hardware_concurrency();
-            if (n <= 0) n = 4;
-            if (n > 32) n = 32;
+            // one worker per hardware thread this process may fairly use: MDBG_HOST_THREADS overrides, else
+            // hardware threads / ranks on this node (torchrun exports LOCAL_WORLD_SIZE), at most 64
+            const char* env = getenv("MDBG_HOST_THREADS");
+            if (env && atoi(env) > 0) n = atoi(env);
+            else {
+                n = (int)std::thread::hardware_concurrency();
+                if (n <= 0) n = 4;
+                const char* lws = getenv("LOCAL_WORLD_SIZE");
+                if (lws && atoi(lws) > 1) n /= atoi(lws);
+                if (n > 64) n = 64;
+                if (n < 2) n = 2;
+            }
         }
         for (int i = 0; i < n; i++) workers_.emplace_back([this, i] { loop(i); });
     }
@@ -103,6 +113,20 @@ __attribute__((target("avx2"))) bool pack_avx2(const uint8_t* s, uint64_t len, u
                                              0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1);
     uint64_t i = 0;
     __m256i bad = _mm256_setzero_si256();
+    const __m256i pick = _mm256_setr_epi32(0, 4, 0, 4, 0, 4, 0, 4);
+    for (; i + 64 <= len; i += 64) {
+        const __m256i v0 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + i));
+        const __m256i v1 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + i + 32));
+        const __m256i c0 = _mm256_and_si256(_mm256_srli_epi16(v0, 1), three);
+        const __m256i c1 = _mm256_and_si256(_mm256_srli_epi16(v1, 1), three);
+        bad = _mm256_or_si256(bad, _mm256_or_si256(_mm256_xor_si256(_mm256_shuffle_epi8(lut, c0), v0),
+                                                   _mm256_xor_si256(_mm256_shuffle_epi8(lut, c1), v1)));
+        const __m256i q0 = _mm256_shuffle_epi8(_mm256_madd_epi16(_mm256_maddubs_epi16(c0, w2), w4), gather);
+        const __m256i q1 = _mm256_shuffle_epi8(_mm256_madd_epi16(_mm256_maddubs_epi16(c1, w2), w4), gather);
+        const __m128i lo = _mm256_castsi256_si128(_mm256_permutevar8x32_epi32(q0, pick));   // words 0,1
+        const __m128i hi = _mm256_castsi256_si128(_mm256_permutevar8x32_epi32(q1, pick));   // words 2,3
+        _mm_storeu_si128(reinterpret_cast<__m128i*>(dst + (i >> 4)), _mm_unpacklo_epi64(lo, hi));
+    }
     for (; i + 32 <= len; i += 32) {
         const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + i));
         const __m256i code = _mm256_and_si256(_mm256_srli_epi16(v, 1), three);

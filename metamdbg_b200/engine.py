@@ -105,6 +105,12 @@ class Engine:
     def kernel_launches(self) -> int:
         return int(self._lib.mdbg_ctx_kernel_launches(self._ctx))
 
+    def bytes_moved(self) -> tuple[int, int]:
+        """(H2D, D2H) bytes enqueued by the host-buffer entry points so far."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self._ck(self._lib.mdbg_ctx_bytes_moved(self._ctx, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def enable_timing(self, on: bool = True):
         self._ck(self._lib.mdbg_ctx_enable_timing(self._ctx, int(on)))
 
