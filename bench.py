@@ -46,6 +46,18 @@ def workload_config(args):
     }
 
 
+def usable_cpus() -> int:
+    """CPUs this process can really use: affinity mask capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, -(-int(quota) // int(period))))
+    except (OSError, ValueError):
+        pass
+    return max(1, n)
+
+
 def purge_last_k(args):
     # Commons::computeLastK (src/Commons.hpp:1726-1741): n50 * density * 2, at least firstK+2
     return max(int(args.read_len * np.float32(DENSITY) * np.float32(2.0)), 6)
@@ -131,14 +143,20 @@ def run_reference(args, rank: int):
             res = dict(n_solid=len(c["abundances"]), n_minimizers=len(m))
         return time.perf_counter() - t0, res
 
-    # the warm-up steps also pick the thread count: all logical CPUs or one per physical core, whichever is faster
-    if ref is not None and args.warmup >= 2 and threads >= 4:
-        t_all, _ = one()
-        full, threads = threads, max(1, threads // 2)
-        t_half, _ = one()
-        if t_all < t_half:
-            threads = full
-        for _ in range(args.warmup - 2):
+    # the warm-up steps also pick the thread count: candidates from the usable CPUs (cgroup quota) up to every
+    # logical CPU; the fastest is used for the timed steps ("all the host threads it can use")
+    if ref is not None and args.warmup >= 1:
+        eff = usable_cpus()
+        cands = sorted({max(1, min(threads, c)) for c in (eff, 2 * eff, max(1, cores // 2), cores)})
+        cands = cands[:max(1, args.warmup)] if len(cands) > args.warmup else cands
+        best = None
+        for c in cands:
+            threads = c
+            t, _ = one()
+            if best is None or t < best[0]:
+                best = (t, c)
+        threads = best[1]
+        for _ in range(args.warmup - len(cands)):
             one()
     else:
         for _ in range(args.warmup):
@@ -342,10 +360,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         cores = os.cpu_count() or 1
         try:
             ref = pyoracle.Reference()
-            kind, threads = "reference", min(cores, ref.max_threads())
+            kind, threads = "reference", min(cores, 2 * usable_cpus())
         except (FileNotFoundError, OSError):
             ref, kind, threads = None, "port", 1
-        n_sample = int(min(n_reads, max(2000, 400 * threads)))
+        n_sample = int(min(n_reads, max(2000, 800 * threads)))
         s_bases = d_bases[:int(rs.offsets[n_sample])].cpu().numpy()
         s_offs = rs.offsets[:n_sample + 1].copy()
         t0 = time.perf_counter()

@@ -135,7 +135,8 @@ mdbg_status mdbg_sketch_batch(mdbg_ctx* ctx, const uint8_t* bases, const uint64_
                               uint32_t n_reads, int append_to_store, mdbg_sketch_out* out);
 /* Host batches without qualities cross PCIe 2-bit packed (worker threads + AVX2 inside the library, unpacked again
  * by the sketch kernel; reads holding a byte outside "ACGT" stay ASCII, so results are identical).  on = 0 sends the
- * ASCII bytes as they are.  Default: on. */
+ * ASCII bytes as they are, on = 1 always packs, on = -1 (default) packs when the process has at least 12 usable CPUs
+ * (cgroup quota and ranks-per-node aware), i.e. when packing outruns the PCIe transfer it saves. */
 mdbg_status mdbg_ctx_set_host_packing(mdbg_ctx* ctx, int on);
 /* Same with the reads already in HBM.  d_bases must be 16-byte aligned;
  * nothing is copied to the host.  `out` may be NULL. */

@@ -56,7 +56,7 @@ struct mdbg_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
-    bool host_packing = true;          // 2-bit pack ASCII host batches before H2D (transfer compression)
+    int host_packing = -1;             // 2-bit pack ASCII host batches before H2D: -1 auto, 0 off, 1 on
     HostPool* pool = nullptr;
     DevBuf d_pack, d_src;
     PinBuf h_pack, h_src, h_asc;
@@ -674,7 +674,13 @@ static mdbg_status sketch_host_batch(mdbg_ctx* ctx, const uint8_t* bases, const 
     CK(cudaMemcpyAsync(ctx->d_offsets.p, offsets, ((size_t)n_reads + 1) * 8, cudaMemcpyHostToDevice, cs));
     ctx->h2d_bytes += ((uint64_t)n_reads + 1) * 8;
 
-    const bool packed = ctx->host_packing && !quals && !want_aux && n_bases >= (uint64_t(1) << 20);
+    // auto: packing pays when the host can pack faster than PCIe moves ASCII (~55 GB/s), i.e. with >= 12 usable CPUs
+    bool want_pack = ctx->host_packing == 1;
+    if (ctx->host_packing < 0) {
+        const char* env = getenv("MDBG_HOST_THREADS");
+        want_pack = ((env && atoi(env) > 0) ? atoi(env) : host_default_threads()) >= 12;
+    }
+    const bool packed = want_pack && !quals && !want_aux && n_bases >= (uint64_t(1) << 20);
     if (!packed) {
         CKS(ensure(ctx, ctx->d_bases, n_bases + 64));
         if (quals) CKS(ensure(ctx, ctx->d_quals, n_bases + 64));
@@ -771,7 +777,7 @@ static mdbg_status sketch_host_batch(mdbg_ctx* ctx, const uint8_t* bases, const 
 
 mdbg_status mdbg_ctx_set_host_packing(mdbg_ctx* ctx, int on) {
     if (!ctx) return MDBG_ERR_ARG;
-    ctx->host_packing = on != 0;
+    ctx->host_packing = on < 0 ? -1 : (on != 0);
     return MDBG_OK;
 }
 

@@ -4,6 +4,7 @@
 #include <immintrin.h>
 
 #include <condition_variable>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
@@ -13,6 +14,30 @@
 
 namespace mdbg {
 
+// CPUs this process may actually use: hardware threads, capped by the cgroup CPU quota (containers), divided
+// by the ranks sharing the node (torchrun exports LOCAL_WORLD_SIZE); at most 64.
+int host_default_threads() {
+    int n = (int)std::thread::hardware_concurrency();
+    if (n <= 0) n = 4;
+    if (FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+        char quota[32];
+        long period = 0;
+        if (fscanf(f, "%31s %ld", quota, &period) == 2 && strcmp(quota, "max") != 0 && period > 0) {
+            const long q = atol(quota);
+            if (q > 0) {
+                const int cap = (int)((q + period - 1) / period);
+                if (cap < n) n = cap;
+            }
+        }
+        fclose(f);
+    }
+    const char* lws = getenv("LOCAL_WORLD_SIZE");
+    if (lws && atoi(lws) > 1) n /= atoi(lws);
+    if (n > 64) n = 64;
+    if (n < 1) n = 1;
+    return n;
+}
+
 class HostPool {
 public:
     explicit HostPool(int n) {
@@ -21,14 +46,7 @@ public:
             // hardware threads / ranks on this node (torchrun exports LOCAL_WORLD_SIZE), at most 64
             const char* env = getenv("MDBG_HOST_THREADS");
             if (env && atoi(env) > 0) n = atoi(env);
-            else {
-                n = (int)std::thread::hardware_concurrency();
-                if (n <= 0) n = 4;
-                const char* lws = getenv("LOCAL_WORLD_SIZE");
-                if (lws && atoi(lws) > 1) n /= atoi(lws);
-                if (n > 64) n = 64;
-                if (n < 2) n = 2;
-            }
+            else n = host_default_threads();
         }
         for (int i = 0; i < n; i++) workers_.emplace_back([this, i] { loop(i); });
     }
@@ -82,6 +100,7 @@ private:
 };
 
 HostPool* host_pool_create(int n_threads) { return new HostPool(n_threads); }
+int host_pool_size(const HostPool* p) { return p->size(); }
 void host_pool_destroy(HostPool* p) { delete p; }
 
 namespace {

@@ -8,7 +8,9 @@
 namespace mdbg {
 
 class HostPool;                                   // persistent worker threads
-HostPool* host_pool_create(int n_threads);        // n_threads <= 0: one per hardware thread, at most 32
+int host_default_threads();                       // CPUs this process can really use (cgroup quota, ranks per node)
+HostPool* host_pool_create(int n_threads);        // n_threads <= 0: MDBG_HOST_THREADS or host_default_threads()
+int host_pool_size(const HostPool* p);
 void host_pool_destroy(HostPool* p);
 
 // Pack reads [r0, r1) of an ASCII batch.  Read r goes to pack_out[pk_off[r] ...] (16 bases per u32, base j at bits
