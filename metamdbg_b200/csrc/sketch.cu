@@ -8,11 +8,12 @@
 //   MurmurHash3_x64_128          src/utils/MurmurHash3.cpp:246-325
 //
 // Data flow per warp (no block-level synchronisation anywhere):
-//   HBM --16 B/lane coalesced loads--> registers --keep-mask (SIMD byte compare,
-//   ballot-free warp scan)--> 2 KB shared-memory ring of HPC base codes
+//   HBM --16 B/lane coalesced loads (ASCII) or 4 B/lane (2-bit packed host batches)--> registers
+//   --keep-mask (SIMD-in-register compare, warp scan)--> 2 KB shared-memory ring of HPC base codes
 //   --2 x LDS.128 per lane--> 16 consecutive l-mers per lane rolled in registers
-//   --Murmur + integer threshold--> selected (value, position, strand) written
-//   in position order to the read's output slot.
+//   --high-word Murmur test--> candidates appended in position order to a 64-entry per-warp list
+//   --32 at a time: exact hash, blacklist, ballot compaction--> coalesced (value, position, strand)
+//   writes into the read's output slot.
 #include "common.cuh"
 #include "engine.cuh"
 
@@ -22,14 +23,6 @@ constexpr int WARPS_PER_CTA = 8;
 constexpr int RING = 2048;        // bytes of HPC codes per warp (power of two)
 constexpr int BLK = 512;          // l-mer positions per warp step (16 per lane)
 constexpr int CHUNK = 512;        // raw bytes per warp load step (16 per lane)
-
-// 4 byte-flags (0xFF/0x00 per byte) -> 4-bit mask
-__device__ __forceinline__ uint32_t nib(uint32_t bytes) {
-    return ((bytes & 0x01010101u) * 0x01020408u) >> 24;
-}
-__device__ __forceinline__ uint32_t nib16(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    return (nib(a) & 0xF) | ((nib(b) & 0xF) << 4) | ((nib(c) & 0xF) << 8) | ((nib(d) & 0xF) << 12);
-}
 
 // 0x80 in every byte of x that is non-zero (exact for arbitrary bytes)
 __device__ __forceinline__ uint32_t nonzero_bytes(uint32_t x) {
@@ -63,21 +56,65 @@ __device__ __forceinline__ bool blacklisted(const uint32_t* bl, uint32_t n, uint
     return lo < n && bl[lo] == v;
 }
 
-// l-mer starting at HPC position p, read back from the ring (rare path).
-// key = canonical value, or ~0 when the window holds an invalid character
-// (Kmer.hpp:541-542, 579-580); dir as KmerCanonical::updateChoice (Kmer.hpp:427).
-__device__ __forceinline__ void lmer_at(const uint8_t* ring, uint32_t p, uint32_t l, uint64_t& key, uint32_t& dir) {
-    uint32_t fwd = 0, rc = 0, inv = 0;
+// The fill phase writes each lane's bases linearly (the ring has 16 bytes of slack past RING).  When this chunk
+// crosses the end of the ring exactly one lane straddles it; its overhang is copied back to the ring start by the
+// first lanes of the warp (warp-uniform test, one byte per lane).
+__device__ __forceinline__ void wrap_overhang(uint8_t* ring, uint32_t avail, uint32_t total, uint32_t base_idx,
+                                              uint32_t cnt, uint32_t lane) {
+    if ((avail & (RING - 1)) + total <= (uint32_t)RING) return;            // uniform
+    const bool straddle = base_idx < (uint32_t)RING && base_idx + cnt > (uint32_t)RING;
+    const uint32_t who = __ballot_sync(0xffffffffu, straddle);
+    if (who == 0) return;                                                  // the boundary fell between two lanes
+    const uint32_t over = __shfl_sync(0xffffffffu, base_idx + cnt - RING, __ffs(who) - 1);
+    __syncwarp();
+    if (lane < over) ring[lane] = ring[RING + lane];
+}
+
+// forward l-mer (2-bit codes of all l characters, valid or not) starting at HPC position p; inv != 0 when the
+// window holds an invalid character
+__device__ __forceinline__ uint32_t fwd_at(const uint8_t* ring, uint32_t p, uint32_t l, uint32_t& inv) {
+    uint32_t fwd = 0;
+    inv = 0;
     for (uint32_t t = 0; t < l; t++) {
-        uint32_t b = ring[(p + t) & (RING - 1)];
-        uint32_t c = b & 3;
-        inv |= b & 4;
-        fwd = (fwd << 2) | c;
-        rc = (rc >> 2) | ((c ^ 2u) << (2 * l - 2));
+        const uint32_t b = ring[(p + t) & (RING - 1)];
+        inv |= b & 4u;
+        fwd = (fwd << 2) | (b & 3u);
     }
-    if (l < 16) fwd &= (1u << (2 * l)) - 1;
-    dir = (fwd < rc) ? 0u : 1u;
-    key = inv ? ~0ULL : (uint64_t)(dir ? rc : fwd);
+    if (l < 16) fwd &= (1u << (2 * l)) - 1u;
+    return fwd;
+}
+
+// One candidate-list entry per lane (lane < cnt): exact selection test, blacklist, then the survivors of the
+// warp are written in list (= position) order with consecutive indices.  Returns the number written.
+__device__ __forceinline__ uint32_t flush_candidates(const SketchArgs& a, const uint2* cand, uint32_t cnt, uint32_t lane,
+                                                     uint64_t slot_lo, uint64_t slot_cap, uint32_t out_cnt) {
+    const uint32_t l = a.l;
+    bool ok = lane < cnt;
+    uint32_t pos = 0, v32 = 0, dir = 0;
+    if (ok) {
+        const uint2 e = cand[lane];
+        pos = e.x & 0x7FFFFFFFu;
+        const uint32_t fwd = e.y;
+        const uint32_t mask = (l < 16) ? ((1u << (2 * l)) - 1u) : 0xFFFFFFFFu;
+        uint32_t x = __brev(fwd ^ (0xAAAAAAAAu & mask));               // reverse complement (code ^ 2, reversed)
+        x = ((x & 0x55555555u) << 1) | ((x >> 1) & 0x55555555u);
+        const uint32_t rc = x >> (32 - 2 * l);
+        dir = (fwd < rc) ? 0u : 1u;                                     // KmerCanonical::updateChoice, Kmer.hpp:427
+        const uint64_t key = (e.x >> 31) ? ~0ULL : (uint64_t)(dir ? rc : fwd);
+        v32 = (uint32_t)key;                                            // Kmer.hpp:1441 truncation
+        ok = murmur_h1_u64(key) <= a.threshold;                         // exact test, Kmer.hpp:1434
+        if (ok && a.n_blacklist) ok = !blacklisted(a.blacklist, a.n_blacklist, v32);
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, ok);
+    if (ok) {
+        const uint64_t idx = (uint64_t)out_cnt + __popc(m & ((1u << lane) - 1u));
+        if (idx < slot_cap) {
+            a.out_min[slot_lo + idx] = v32;
+            a.out_pos[slot_lo + idx] = pos;
+            a.out_dir[slot_lo + idx] = (uint8_t)dir;
+        }
+    }
+    return __popc(m);
 }
 
 template <int L>
@@ -101,10 +138,9 @@ __device__ __forceinline__ uint32_t revcomp_lmer(uint32_t fwd) {
 // Unrolled register path: 16 consecutive l-mers for this lane out of the
 // 32 ring bytes W (no invalid code present).  Returns the 16-bit CANDIDATE
 // mask (superset of the selected positions, see murmur_s1_u32); the forward
-// l-mer and the s1 value of the last candidate are left in sel_fwd / sel_s1.
+// l-mer of the last candidate is left in sel_fwd.
 template <int L>
-__device__ __forceinline__ uint32_t roll16_fast(const uint32_t (&W)[8], uint32_t thr_hi_plus1, uint32_t& sel_fwd,
-                                                uint32_t& sel_s1) {
+__device__ __forceinline__ uint32_t roll16_fast(const uint32_t (&W)[8], uint32_t thr_hi_plus1, uint32_t& sel_fwd) {
     constexpr uint32_t MASK = (L < 16) ? ((1u << (2 * L)) - 1u) : 0xFFFFFFFFu;
     constexpr uint32_t INIT_MASK = (1u << (2 * (L - 1))) - 1u;      // L-1 <= 15 bases
     // state after the first L-1 bases, built with two multiplies per 4 bases instead of L-1 roll steps
@@ -122,7 +158,6 @@ __device__ __forceinline__ uint32_t roll16_fast(const uint32_t (&W)[8], uint32_t
         if (s1 <= thr_hi_plus1) {
             sel |= 1u << j;
             sel_fwd = fwd;
-            sel_s1 = s1;
         }
     }
     return sel;
@@ -155,11 +190,13 @@ __device__ __forceinline__ uint32_t roll16_generic(const uint8_t* ring, uint32_t
 template <int L_FAST>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sketch_kernel(const SketchArgs a) {
     __shared__ __align__(16) uint8_t ring_all[WARPS_PER_CTA][RING + 16];   // +16: linear-write slack
+    __shared__ uint2 cand_all[WARPS_PER_CTA][64];                           // pending candidates: (pos | invalid<<31, fwd)
     const uint32_t lane = threadIdx.x & 31;
     uint8_t* ring = ring_all[threadIdx.x >> 5];
+    uint2* cand = cand_all[threadIdx.x >> 5];
+    uint32_t n_list = 0;
     const uint32_t l = a.l;
     const uint32_t thr_hi_plus1 = (uint32_t)(a.threshold >> 32) + 1u;   // 0 (overflow) disables the fast path
-    const uint32_t sure_lim = thr_hi_plus1 >= 2u ? thr_hi_plus1 - 2u : 0u;
 
     for (;;) {
         uint32_t r = 0;
@@ -224,10 +261,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sketch_kernel(const Sketch
                             dst++;
                         }
                     }
-                    if (base_idx + cnt > (uint32_t)RING) {
-                        const uint32_t over = base_idx + cnt - RING;
-                        for (uint32_t i = 0; i < over; i++) ring[i] = ring[RING + i];
-                    }
+                    wrap_overhang(ring, avail, total, base_idx, cnt, lane);
                     avail += total;
                     chunk++;
                     continue;
@@ -302,10 +336,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sketch_kernel(const Sketch
                         dst++;
                     }
                 }
-                if (base_idx + cnt > (uint32_t)RING) {
-                    const uint32_t over = base_idx + cnt - RING;
-                    for (uint32_t i = 0; i < over; i++) ring[i] = ring[RING + i];
-                }
+                wrap_overhang(ring, avail, total, base_idx, cnt, lane);
                 avail += total;
                 chunk++;
             }
@@ -338,12 +369,12 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sketch_kernel(const Sketch
                 const bool fast = (L_FAST != 0) && (l == (uint32_t)L_FAST) && thr_hi_plus1 != 0 &&
                                   !__any_sync(0xffffffffu, inv != 0);
 
-                uint32_t sel, sel_fwd = 0, sel_s1 = 0;
+                uint32_t sel, sel_fwd = 0;
                 bool regs_ok = false;
                 if (a.select_none) {
                     sel = 0;
                 } else if (fast) {
-                    sel = roll16_fast<(L_FAST ? L_FAST : 15)>(W, thr_hi_plus1, sel_fwd, sel_s1);
+                    sel = roll16_fast<(L_FAST ? L_FAST : 15)>(W, thr_hi_plus1, sel_fwd);
                     regs_ok = (valid_bits == 0xFFFFu);
                     sel &= valid_bits;
                 } else {
@@ -351,65 +382,54 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sketch_kernel(const Sketch
                 }
                 const uint32_t hit_lanes = __ballot_sync(0xffffffffu, sel != 0);
                 if (hit_lanes) {
-                    // rare: confirm candidates with the exact hash, apply the repetitive-minimizer
-                    // blacklist, write (value, position, strand) in position order
-                    uint32_t v0 = 0, v1 = 0, d0 = 0, d1 = 0;   // register cache for up to 2 hits
-                    uint32_t kept = 0, nsel = 0;
-                    uint32_t scan_sel = sel;
-                    while (scan_sel) {
-                        const uint32_t j = __ffs(scan_sel) - 1;
-                        scan_sel &= scan_sel - 1;
-                        uint64_t key; uint32_t dir;
-                        bool sure = false;
-                        if (regs_ok && __popc(sel) == 1) {
-                            const uint32_t rcv = revcomp_lmer<(L_FAST ? L_FAST : 15)>(sel_fwd);
-                            dir = (sel_fwd < rcv) ? 0u : 1u;
-                            key = dir ? rcv : sel_fwd;
-                            sure = (sel_s1 - 1u) < sure_lim;             // 1 <= s1 < T_hi
-                        } else {
-                            lmer_at(ring, p0 + j, l, key, dir);
-                        }
-                        if (!sure && murmur_h1_u64(key) > a.threshold) continue;   // exact test (Kmer.hpp:1434)
-                        const uint32_t v32 = (uint32_t)key;          // Kmer.hpp:1441 truncation
-                        if (a.n_blacklist && blacklisted(a.blacklist, a.n_blacklist, v32)) continue;
-                        kept |= 1u << j;
-                        if (nsel == 0) { v0 = v32; d0 = dir; }
-                        else if (nsel == 1) { v1 = v32; d1 = dir; }
-                        nsel++;
-                    }
+                    // Candidates (~2 per 512 positions) are appended, in position order, to a small per-warp list;
+                    // the list is resolved 32 entries at a time with every lane busy (flush_candidates).
+                    const uint32_t n_c = __popc(sel);
                     uint32_t before, total;
-                    const uint32_t multi = __ballot_sync(0xffffffffu, nsel > 1);
-                    if (multi == 0) {                       // common: at most one hit per lane
-                        const uint32_t m1 = __ballot_sync(0xffffffffu, nsel == 1);
-                        before = __popc(m1 & ((1u << lane) - 1u));
-                        total = __popc(m1);
+                    if (__ballot_sync(0xffffffffu, n_c > 1) == 0) {
+                        before = __popc(hit_lanes & ((1u << lane) - 1u));
+                        total = __popc(hit_lanes);
                     } else {
-                        const uint32_t incl = warp_inclusive_scan(nsel);
+                        const uint32_t incl = warp_inclusive_scan(n_c);
                         total = __shfl_sync(0xffffffffu, incl, 31);
-                        before = incl - nsel;
+                        before = incl - n_c;
                     }
-                    uint64_t e = (uint64_t)out_cnt + before;
-                    uint32_t i = 0;
-                    while (kept) {
-                        const uint32_t j = __ffs(kept) - 1;
-                        kept &= kept - 1;
-                        uint32_t v32, dir;
-                        if (i == 0) { v32 = v0; dir = d0; }
-                        else if (i == 1) { v32 = v1; dir = d1; }
-                        else { uint64_t key; lmer_at(ring, p0 + j, l, key, dir); v32 = (uint32_t)key; }
-                        if (e < slot_cap) {
-                            a.out_min[slot_lo + e] = v32;
-                            a.out_pos[slot_lo + e] = p0 + j;
-                            a.out_dir[slot_lo + e] = (uint8_t)dir;
+                    for (uint32_t base_rank = 0; base_rank < total; base_rank += 32) {   // one pass unless > 32 candidates
+                        uint32_t rest = sel, rank = before;
+                        while (rest) {
+                            const uint32_t j = __ffs(rest) - 1;
+                            rest &= rest - 1;
+                            if (rank >= base_rank && rank < base_rank + 32) {
+                                uint32_t fwd, inv = 0;
+                                if (regs_ok && n_c == 1) fwd = sel_fwd;
+                                else fwd = fwd_at(ring, p0 + j, l, inv);
+                                cand[n_list + (rank - base_rank)] = make_uint2((p0 + j) | (inv ? 0x80000000u : 0u), fwd);
+                            }
+                            rank++;
                         }
-                        e++; i++;
+                        n_list += min(32u, total - base_rank);
+                        __syncwarp();
+                        if (n_list >= 32) {
+                            out_cnt += flush_candidates(a, cand, 32, lane, slot_lo, slot_cap, out_cnt);
+                            __syncwarp();
+                            uint2 keep_e = make_uint2(0, 0);
+                            if (32 + lane < n_list) keep_e = cand[32 + lane];
+                            __syncwarp();
+                            if (32 + lane < n_list) cand[lane] = keep_e;
+                            n_list -= 32;
+                            __syncwarp();
+                        }
                     }
-                    out_cnt += total;
                 }
                 done += BLK;
             }
             __syncwarp();
             if (final_) break;
+        }
+        if (n_list) {
+            out_cnt += flush_candidates(a, cand, n_list, lane, slot_lo, slot_cap, out_cnt);
+            n_list = 0;
+            __syncwarp();
         }
         if (lane == 0) {
             a.n_min[r] = out_cnt;
