@@ -401,12 +401,13 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         sk_ms = float(np.mean(sketch_ms))
         algo_bytes = n_bases * 1.0 + n_min_store * 9.0      # 1 B/bp ASCII in + 9 B per minimizer out
         achieved = algo_bytes / (sk_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, ncu_pipes = None, None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
             if tj.get("reads") == n_reads and tj.get("kernel") == "sketch_kernel":
-                traffic = tj.get("dram_bytes_per_launch")
+                traffic = tj.get("dram_bytes_per_launch")       # one `ncu --set full` capture of this launch shape
+                ncu_pipes = tj.get("ncu")
         line = {
             "metric": "Gbp/s through minimizer-sketch + k-min-mer count", "value": value, "unit": "Gbp/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
@@ -416,6 +417,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "ms_per_launch": sk_ms, "algorithmic_bytes_per_launch": algo_bytes,
                          "note": "integer-issue bound (one MurmurHash3_x64_128 per l-mer), see DESIGN.md",
+                         "binding_pipes_ncu": ncu_pipes,
                          "share_of_step": sk_ms / (ms_total / args.steps)},
             "kernels_ms": {"sketch": sk_ms, "insert": float(np.mean(insert_ms))},
             "cpu_baseline": cpu_baseline,
