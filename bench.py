@@ -440,7 +440,7 @@ def main():
     ap.add_argument("--read-len", type=int, default=15_000)
     ap.add_argument("--genomes", type=int, default=100)
     ap.add_argument("--e2e-reads", type=int, default=0, help="reads per GPU in the e2e leg (0 = all)")
-    ap.add_argument("--e2e-batch", type=int, default=65_536, help="reads per host-buffer C-ABI call")
+    ap.add_argument("--e2e-batch", type=int, default=262_144, help="reads per host-buffer C-ABI call")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--ref-reads", type=int, default=0, help="sample size of the reference arm (0 = auto)")
     ap.add_argument("--no-e2e", action="store_true")
