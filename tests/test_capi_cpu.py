@@ -70,3 +70,16 @@ def test_bad_params_rejected(lib):
     ctx = C.c_void_p()
     assert lib.mdbg_ctx_create(0, C.byref(p), C.byref(ctx)) != 0
     assert b"minimizer_size" in lib.mdbg_last_error(None)
+
+
+def test_host_packer_cpp(tmp_path):
+    """The host-side 2-bit packer (transfer compression of host batches) is plain C++: unit-tested on the CPU."""
+    import __graft_entry__ as g
+    g.build()
+    exe = tmp_path / "pack_host_test"
+    obj = os.path.join(ROOT, "metamdbg_b200", "csrc", "pack_host.o")
+    assert os.path.exists(obj)
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-pthread", "-o", str(exe),
+                    os.path.join(ROOT, "tests", "cpp", "pack_host_test.cpp"), obj], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
