@@ -176,6 +176,11 @@ mdbg_status mdbg_store_fetch(mdbg_ctx* ctx, uint64_t* min_offsets, uint32_t* min
 mdbg_status mdbg_purge_palindromes(mdbg_ctx* ctx, uint32_t first_k, uint32_t last_k,
                                    uint64_t* n_reads_changed);
 
+/* Utils::applyDensityThreshold (src/Commons.hpp:2507-2550) on every stored read, in place: keeps the minimizers
+ * whose Murmur hash (of the stored u32 value) is below density * 2^64 -- how reads sketched at the correction
+ * density (0.025) are parsed at the assembly density (0.005), src/Commons.hpp:7457. */
+mdbg_status mdbg_store_apply_density(mdbg_ctx* ctx, float density, uint64_t* n_reads_changed);
+
 /* ---- k-min-mer count table (rows A5-A7) ----------------------------------- */
 /* expected_distinct = 0 sizes the table from the store (upper bound: one slot
  * pair per k-min-mer occurrence). */

@@ -66,6 +66,7 @@ SYMBOLS = {
     "mdbg_store_append": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "mdbg_store_size": (C.c_int, [C.c_void_p, u64p, u64p]),
     "mdbg_store_fetch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mdbg_store_apply_density": (C.c_int, [C.c_void_p, C.c_float, u64p]),
     "mdbg_purge_palindromes": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, u64p]),
     "mdbg_count_begin": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64]),
     "mdbg_count_add_store": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64]),

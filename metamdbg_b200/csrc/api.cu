@@ -947,6 +947,45 @@ mdbg_status mdbg_purge_palindromes(mdbg_ctx* ctx, uint32_t first_k, uint32_t las
     return MDBG_OK;
 }
 
+mdbg_status mdbg_store_apply_density(mdbg_ctx* ctx, float density, uint64_t* n_reads_changed) {
+    if (!ctx) return MDBG_ERR_ARG;
+    if (n_reads_changed) *n_reads_changed = 0;
+    if (ctx->s_reads == 0) return MDBG_OK;
+    if (ctx->s_reads > 0xFFFFFFFFull) return fail(ctx, MDBG_ERR_ARG, "store too large");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    uint32_t none = 0;
+    const uint64_t thr = threshold_from_density(density, &none);
+    CKS(ensure(ctx, ctx->p_keep, ctx->s_mins + 1));
+    CKS(ensure(ctx, ctx->p_cnt, ctx->s_reads * 4));
+    CK(cudaMemsetAsync(&ctx->d_small->n_changed, 0, sizeof(unsigned long long), s));
+    launch_density_filter(ctx->s_min.as<uint32_t>(), ctx->s_off.as<uint64_t>(), ctx->s_reads, thr, none,
+                          ctx->p_keep.as<uint8_t>(), ctx->p_cnt.as<uint32_t>(), &ctx->d_small->n_changed, s);
+    CKS(check_launch(ctx, "density_filter_kernel", 1));
+    CK(cudaMemcpyAsync(&ctx->h_scalar[1], &ctx->d_small->n_changed, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const uint64_t changed = ctx->h_scalar[1];
+    if (n_reads_changed) *n_reads_changed = changed;
+    if (changed == 0) return MDBG_OK;
+    CKS(ensure(ctx, ctx->p_newoff, (ctx->s_reads + 2) * 8));
+    CKS(ensure(ctx, ctx->scan_scratch, scan_scratch_elems((uint32_t)ctx->s_reads) * 8));
+    launch_scan_u32_to_u64(ctx->p_cnt.as<uint32_t>(), ctx->p_newoff.as<uint64_t>(), (uint32_t)ctx->s_reads,
+                           ctx->scan_scratch.as<uint64_t>(), s);
+    CKS(check_launch(ctx, "scan", 3));
+    CK(cudaMemcpyAsync(&ctx->h_scalar[2], ctx->p_newoff.as<uint64_t>() + ctx->s_reads, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const uint64_t new_total = ctx->h_scalar[2];
+    CKS(ensure(ctx, ctx->p_newmin, (new_total + 1) * 4));
+    launch_purge_compact(ctx->s_min.as<uint32_t>(), ctx->s_off.as<uint64_t>(), ctx->p_newoff.as<uint64_t>(),
+                         ctx->p_keep.as<uint8_t>(), ctx->s_reads, ctx->p_newmin.as<uint32_t>(), s);
+    CKS(check_launch(ctx, "purge_compact_kernel", 1));
+    CK(cudaStreamSynchronize(s));
+    std::swap(ctx->s_min, ctx->p_newmin);
+    std::swap(ctx->s_off, ctx->p_newoff);
+    ctx->s_mins = new_total;
+    return MDBG_OK;
+}
+
 // ---- count table --------------------------------------------------------------------
 mdbg_status mdbg_count_begin(mdbg_ctx* ctx, uint32_t k, uint64_t expected_distinct) {
     if (!ctx) return MDBG_ERR_ARG;

@@ -86,6 +86,9 @@ void launch_purge_flag(const uint32_t* mins, const uint64_t* offs, uint64_t n_re
 void launch_purge_exact(const uint32_t* mins, const uint64_t* offs, uint64_t n_reads, const uint8_t* flags,
                         uint32_t first_k, uint32_t last_k, uint8_t* keep, uint32_t* new_cnt,
                         unsigned long long* n_changed, cudaStream_t s);
+void launch_density_filter(const uint32_t* mins, const uint64_t* offs, uint64_t n_reads, uint64_t threshold,
+                           uint32_t select_none, uint8_t* keep, uint32_t* new_cnt, unsigned long long* n_changed,
+                           cudaStream_t s);
 void launch_purge_compact(const uint32_t* mins, const uint64_t* offs, const uint64_t* new_offs, const uint8_t* keep,
                           uint64_t n_reads, uint32_t* out_mins, cudaStream_t s);
 

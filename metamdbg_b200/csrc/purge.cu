@@ -113,6 +113,43 @@ void launch_purge_exact(const uint32_t* mins, const uint64_t* offs, uint64_t n_r
                                                                         keep, new_cnt, n_changed);
 }
 
+// Utils::applyDensityThreshold (src/Commons.hpp:2507-2550): re-hash every stored minimizer value (u32 widened to
+// u64, seed 42) and keep it iff hash < density * 2^64; keep[] / new_cnt[] feed the same scan + compaction as the purge.
+__global__ void __launch_bounds__(256) density_filter_kernel(const uint32_t* mins, const uint64_t* offs, uint64_t n_reads,
+                                                             uint64_t threshold, uint32_t select_none, uint8_t* keep,
+                                                             uint32_t* new_cnt, unsigned long long* n_changed) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t r = warp; r < n_reads; r += n_warps) {
+        const uint64_t b = offs[r], e = offs[r + 1];
+        uint32_t cnt = 0;
+        for (uint64_t g0 = b; g0 < e; g0 += 32) {
+            const uint64_t g = g0 + lane;
+            bool k = false;
+            if (g < e) {
+                k = !select_none && murmur_h1_u64((uint64_t)mins[g]) <= threshold;
+                keep[g] = k ? 1 : 0;
+            }
+            cnt += __popc(__ballot_sync(0xffffffffu, k));
+        }
+        if (lane == 0) {
+            new_cnt[r] = cnt;
+            if ((uint64_t)cnt != e - b) atomicAdd(n_changed, 1ULL);
+        }
+    }
+}
+
+void launch_density_filter(const uint32_t* mins, const uint64_t* offs, uint64_t n_reads, uint64_t threshold,
+                           uint32_t select_none, uint8_t* keep, uint32_t* new_cnt, unsigned long long* n_changed,
+                           cudaStream_t s) {
+    if (n_reads == 0) return;
+    uint64_t blocks = (n_reads + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    density_filter_kernel<<<(unsigned)blocks, 256, 0, s>>>(mins, offs, n_reads, threshold, select_none, keep, new_cnt,
+                                                           n_changed);
+}
+
 __global__ void __launch_bounds__(256) purge_compact_kernel(const uint32_t* mins, const uint64_t* offs,
                                                             const uint64_t* new_offs, const uint8_t* keep,
                                                             uint64_t n_reads, uint32_t* out_mins) {

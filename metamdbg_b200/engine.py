@@ -212,6 +212,12 @@ class Engine:
         self._ck(self._lib.mdbg_store_fetch(self._ctx, offs.ctypes.data, mins.ctypes.data))
         return offs, mins[:nm]
 
+    def store_apply_density(self, density: float) -> int:
+        """Utils::applyDensityThreshold on every stored read; returns the number of reads that lost minimizers."""
+        n = C.c_uint64(0)
+        self._ck(self._lib.mdbg_store_apply_density(self._ctx, float(np.float32(density)), C.byref(n)))
+        return int(n.value)
+
     def purge_palindromes(self, first_k: int, last_k: int) -> int:
         n = C.c_uint64(0)
         self._ck(self._lib.mdbg_purge_palindromes(self._ctx, first_k, last_k, C.byref(n)))

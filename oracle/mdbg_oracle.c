@@ -296,6 +296,18 @@ void orc_read_aux(const char* seq, const char* qual, size_t len, size_t qual_len
     free(hs); free(rle);
 }
 
+size_t orc_apply_density(const uint32_t* m, size_t n, float density, uint32_t* out) {
+    uint64_t max_hash = (uint64_t)-1;
+    double bound = density * max_hash;              /* Commons.hpp:2515-2516: float * u64 -> float, widened */
+    size_t o = 0;
+    for (size_t i = 0; i < n; i++) {
+        uint64_t v = m[i];
+        uint64_t h = orc_murmur3_x64_128_h1(&v, 8, 42);
+        if (h < bound) out[o++] = m[i];
+    }
+    return o;
+}
+
 /* -------------------------------------------------------- purge palindromes */
 
 /* KmerVec::isPalindrome, Commons.hpp:918-921: first size/2 entries equal the

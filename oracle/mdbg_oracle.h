@@ -74,6 +74,10 @@ void orc_read_aux(const char* seq, const char* qual, size_t len, size_t qual_len
                   const uint32_t* positions, size_t n_minimizers,
                   float* mean_quality, double* complexity, uint8_t* qualities);
 
+/* Utils::applyDensityThreshold, src/Commons.hpp:2507-2550: keep[i] = 1 iff Murmur(u64(m[i]), seed 42) < density*2^64.
+ * Returns the number kept (written to out in order). */
+size_t orc_apply_density(const uint32_t* m, size_t n, float density, uint32_t* out);
+
 /* Commons::purgePalindrome, src/Commons.hpp:1617-1723.  out holds n entries;
  * keep (may be NULL) receives 0/1 per input position.  Returns n'. */
 size_t orc_purge_palindrome(const uint32_t* m, size_t n, size_t first_k, size_t last_k,

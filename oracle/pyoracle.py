@@ -81,6 +81,7 @@ class _Lib:
         f = getattr(L, p + "lmers"); f.restype = C.c_size_t; f.argtypes = [C.c_char_p, C.c_size_t, C.c_int, _u64p, _u8p]
         f = getattr(L, p + "sketch_read"); f.restype = C.c_size_t
         f.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_float, C.c_int, _u32p, C.c_size_t, _u32p, _u32p, _u8p, C.c_size_t]
+        f = getattr(L, p + "apply_density"); f.restype = C.c_size_t; f.argtypes = [_u32p, C.c_size_t, C.c_float, _u32p]
         f = getattr(L, p + "kminmers"); f.restype = C.c_size_t; f.argtypes = [_u32p, C.c_size_t, C.c_int, _u32p, _u8p]
         f = getattr(L, p + "hash128"); f.restype = None; f.argtypes = [_u32p, C.c_int, _u64p]
         getattr(L, p + "free").argtypes = [C.c_void_p]
@@ -131,6 +132,12 @@ class _Lib:
             ms.append(m); ps.append(p); ds.append(d); offs.append(offs[-1] + len(m))
         cat = lambda xs, t: np.concatenate(xs).astype(t) if xs else np.zeros(0, t)
         return (np.array(offs, dtype=np.uint64), cat(ms, np.uint32), cat(ps, np.uint32), cat(ds, np.uint8))
+
+    def apply_density(self, m: np.ndarray, density: float) -> np.ndarray:
+        m = np.ascontiguousarray(m, dtype=np.uint32)
+        out = np.zeros(len(m) + 1, dtype=np.uint32)
+        n = getattr(self.lib, self.prefix + "apply_density")(_p(m, _u32p), len(m), density, _p(out, _u32p))
+        return out[:n].copy()
 
     def kminmers(self, m: np.ndarray, k: int):
         m = np.ascontiguousarray(m, dtype=np.uint32)

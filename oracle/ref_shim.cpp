@@ -107,6 +107,15 @@ size_t ref_purge_palindrome(const uint32_t* m, size_t n, size_t first_k, size_t 
     return r.size();
 }
 
+size_t ref_apply_density(const uint32_t* m, size_t n, float density, uint32_t* out) {
+    vector<MinimizerType> mins(m, m + n), f;
+    vector<u_int32_t> pos, fp;
+    vector<u_int8_t> dirs, quals, fd, fq;
+    Utils::applyDensityThreshold(density, mins, pos, dirs, quals, f, fp, fd, fq);     // src/Commons.hpp:2507-2550
+    memcpy(out, f.data(), f.size() * sizeof(MinimizerType));
+    return f.size();
+}
+
 size_t ref_kminmers(const uint32_t* m, size_t n, int k, uint32_t* vecs, uint8_t* reversed) {
     vector<MinimizerType> mins(m, m + n);
     vector<u_int32_t> pos(n, 0);

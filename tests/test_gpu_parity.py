@@ -436,3 +436,26 @@ def test_packed_host_transfer_with_dirty_reads(built, oracle):
         so, sm = eng.store_fetch()
         assert np.array_equal(so, want[0]) and np.array_equal(sm, want[1])
         eng.close()
+
+
+def test_ont_density_rethreshold_and_count(built, oracle):
+    """BASELINE config 3 shape: ONT reads (no HPC) sketched at the correction density 0.025, re-thresholded to the
+    assembly density 0.005 (Utils::applyDensityThreshold), then counted at k=4."""
+    rs = synth.make_readset(2500, 8000, seed=33, n_genomes=2, genome_len_range=(150_000, 250_000), err=0.02)
+    bases, offs = synth.fill_reads(rs)
+    eng = engine(15, 0.025, False)
+    eng.sketch_batch(bases, offs, append_to_store=True, fetch=False)
+    mo, m, p, d = oracle.sketch_batch(bases, offs, 15, 0.025, False)
+    changed = eng.store_apply_density(0.005)
+    so, sm = eng.store_fetch()
+    want, wo = [], [0]
+    for r in range(rs.n_reads):
+        q = oracle.apply_density(m[int(mo[r]):int(mo[r + 1])], 0.005)
+        want.append(q); wo.append(wo[-1] + len(q))
+    assert changed > 0 and np.array_equal(sm, np.concatenate(want)) and np.array_equal(so, np.array(wo, np.uint64))
+    eng.count_begin(4)
+    eng.count_add_store()
+    tab = eng.count_finalize(2)
+    ref = oracle.count(sm, so, 4, 2)
+    check_table(tab, ref["hashes"], ref["abundances"], ref["vecs"], [ref["n_instances"], ref["n_distinct"]])
+    eng.close()

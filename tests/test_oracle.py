@@ -350,3 +350,17 @@ def test_ref_read_selection_side_outputs(tmp_path, oracle, reference, hpc):
         want.append(tuple(int(x) for x in q))
     got = [tuple(int(x) for x in rec["minimizers"]) for rec in res["corrected"]]
     assert sorted(got) == sorted(want)
+
+
+@pytest.mark.ref
+def test_ref_apply_density(oracle, reference):
+    rs = synth.make_readset(30, 6000, seed=13, n_genomes=1, genome_len_range=(60_000, 60_001), err=0.02)
+    bases, offs = synth.fill_reads(rs)
+    mo, m, p, d = oracle.sketch_batch(bases, offs, 15, 0.025, False)
+    for dens in (0.005, 0.01, 0.025, 0.5):
+        a, b = oracle.apply_density(m, dens), reference.apply_density(m, dens)
+        assert np.array_equal(a, b)
+    low = oracle.apply_density(m, 0.005)
+    assert 0 < len(low) < len(m)
+    # sketching at 0.025 then thresholding at 0.005 == sketching at 0.005 (same hash, same bound)
+    assert np.array_equal(low, oracle.sketch_batch(bases, offs, 15, 0.005, False)[1])
