@@ -32,15 +32,19 @@ static bool getline_gz(gzFile f, std::string& line) {
 int main(int argc, char** argv) {
     if (argc < 3) {
         std::cerr << "usage: mdbg_gpu_firstpass <reads.fa|fq[.gz]> <outDir> [--ont] [-l 15] [-d 0.005] [-k 4] "
-                     "[--min-abundance 2] [--last-k N] [--batch-mbp 1024]\n";
+                     "[--min-abundance 2] [--last-k N] [--batch-mbp 1024]\n"
+                     "       mdbg_gpu_firstpass --from-read-data <read_data_corrected.txt> <outDir> [-k 4] [--min-abundance 2]\n"
+                     "         (the `graph --firstpass` seam alone: count the minimizer-space reads of an existing file)\n";
         return 2;
     }
-    std::string input = argv[1], outDir = argv[2];
+    bool fromReadData = std::string(argv[1]) == "--from-read-data";
+    if (fromReadData && argc < 4) { std::cerr << "--from-read-data needs <file> <outDir>\n"; return 2; }
+    std::string input = fromReadData ? argv[2] : argv[1], outDir = fromReadData ? argv[3] : argv[2];
     bool hpc = true;
     uint32_t l = 15, k = 4, minAb = 2, lastK = 0;
     float density = 0.005f;
     size_t batchMbp = 1024;
-    for (int i = 3; i < argc; i++) {
+    for (int i = fromReadData ? 4 : 3; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&]() { return std::string(i + 1 < argc ? argv[++i] : "0"); };
         if (a == "--ont") hpc = false;
@@ -53,6 +57,15 @@ int main(int argc, char** argv) {
     }
     try {
         Context ctx(l, density, hpc);
+        if (fromReadData) {
+            const uint64_t nReads = loadReadData(ctx, input);
+            GpuKminmerCounter counter(ctx, k, minAb);
+            counter.execute(outDir + "/kminmerData_min.txt", outDir + "/kminmerData_abundance.txt");
+            std::cout << "reads " << nReads << " kminmers " << counter._nbKminmers << " distinct " << counter._nbDistinct
+                      << " solid " << counter._nbSolidKminmers << " rescued " << counter._nbRescuedKminmers << " checksum "
+                      << counter._checksum << std::endl;
+            return 0;
+        }
         std::vector<uint32_t> readLengths;
         ReadDataWriter writer(outDir + "/read_data_init.txt", l);     // readSelection's record file + read_stats.txt
         GpuReadSelectionFunctor functor(ctx, [&](const ReadMinimizers& r) {
@@ -104,7 +117,8 @@ int main(int argc, char** argv) {
         counter.execute(outDir + "/kminmerData_min.txt", outDir + "/kminmerData_abundance.txt");
         std::cout << "reads " << functor.nbReads() << " bases " << functor.nbBases() << " minimizers "
                   << functor.nbSelectedMinimizers() << " purged_reads " << changed << " kminmers " << counter._nbKminmers
-                  << " distinct " << counter._nbDistinct << " solid " << counter._nbSolidKminmers << " checksum "
+                  << " distinct " << counter._nbDistinct << " solid " << counter._nbSolidKminmers << " rescued "
+                  << counter._nbRescuedKminmers << " checksum "
                   << counter._checksum << " lastK " << lastK << " kernel_launches "
                   << mdbg_ctx_kernel_launches(ctx.get()) << std::endl;
     } catch (const std::exception& e) {

@@ -255,6 +255,38 @@ inline uint64_t purgePalindromesAndWrite(Context& ctx, uint32_t firstK, uint32_t
     return changed;
 }
 
+// KminmerParserParallel's input side (src/Commons.hpp:7367-7495, records u32 n, u8 isCircular, u32[n]): load a
+// read_data_corrected.txt (or unitig_data.txt) into the context's device store, 256 MB of minimizers at a time.
+inline uint64_t loadReadData(Context& ctx, const std::string& filename) {
+    FILE* f = fopen(filename.c_str(), "rb");
+    if (!f) throw std::runtime_error("cannot open " + filename);
+    std::vector<uint32_t> mins;
+    std::vector<uint64_t> offs{0};
+    uint64_t nReads = 0;
+    auto flush = [&]() {
+        if (offs.size() > 1)
+            check(ctx.get(), mdbg_store_append(ctx.get(), mins.data(), offs.data(), (uint32_t)(offs.size() - 1)),
+                  "mdbg_store_append");
+        mins.clear();
+        offs.assign(1, 0);
+    };
+    for (;;) {
+        uint32_t size;
+        uint8_t isCircular;
+        if (fread(&size, 4, 1, f) != 1) break;
+        if (fread(&isCircular, 1, 1, f) != 1) throw std::runtime_error("truncated record in " + filename);
+        const size_t at = mins.size();
+        mins.resize(at + size);
+        if (size && fread(mins.data() + at, 4, size, f) != size) throw std::runtime_error("truncated record in " + filename);
+        offs.push_back(mins.size());
+        nReads++;
+        if (mins.size() > (size_t(64) << 20)) flush();
+    }
+    fclose(f);
+    flush();
+    return nReads;
+}
+
 // CreateMdbg::KminmerCounter (first pass): counts every k-min-mer of the device-resident reads and
 // writes kminmerData_min.txt / kminmerData_abundance.txt.
 class GpuKminmerCounter {
@@ -262,9 +294,12 @@ public:
     GpuKminmerCounter(Context& ctx, uint32_t kminmerSize, uint32_t minAbundance)
         : _ctx(ctx), _k(kminmerSize), _minAbundance(minAbundance) {}
 
+    // minAbundance <= 1 is metaMDBG's default mode: the abundance >= 2 entries are followed by the rescued
+    // abundance-1 entries (CreateMdbg.cpp:309-319, rescueKminmers)
     void execute(const std::string& kminmerFile, const std::string& abundanceFile) {
         check(_ctx.get(), mdbg_count_begin(_ctx.get(), _k, 0), "mdbg_count_begin");
         check(_ctx.get(), mdbg_count_add_store(_ctx.get(), 0, UINT64_MAX), "mdbg_count_add_store");
+        if (_minAbundance <= 1) check(_ctx.get(), mdbg_count_rescue(_ctx.get(), &_nbReadsRescued), "mdbg_count_rescue");
         mdbg_table_out t{};
         check(_ctx.get(), mdbg_count_finalize(_ctx.get(), _minAbundance, &t), "mdbg_count_finalize");
         FILE* fk = fopen(kminmerFile.c_str(), "wb");
@@ -277,13 +312,15 @@ public:
         }
         fclose(fk);
         fclose(fa);
-        _nbSolidKminmers = t.n_entries;
+        _nbSolidKminmers = t.n_entries - t.n_rescued;
+        _nbRescuedKminmers = t.n_rescued;
         _nbKminmers = t.n_instances;
         _nbDistinct = t.n_distinct;
         _checksum = t.checksum;
     }
 
-    uint64_t _nbKminmers = 0, _nbSolidKminmers = 0, _nbDistinct = 0, _checksum = 0;
+    uint64_t _nbKminmers = 0, _nbSolidKminmers = 0, _nbRescuedKminmers = 0, _nbReadsRescued = 0, _nbDistinct = 0,
+             _checksum = 0;
 
 private:
     Context& _ctx;

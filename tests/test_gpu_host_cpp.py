@@ -94,3 +94,45 @@ def test_cpp_driver_read_data_init_is_byte_identical(tmp_path):
     assert [n_reads, n50, n_bases, mean_len, n_min] == [int(x) for x in z["stats"]]
     assert np.float32(dens).tobytes() == np.float32(z["stats_f"][0]).tobytes()
     assert abs(float(avgq) - float(z["stats_f"][1])) <= 1e-5 * abs(float(z["stats_f"][1]))
+
+
+def test_cpp_driver_graph_seam_and_default_mode(tmp_path, oracle):
+    """`--from-read-data`: the graph --firstpass seam alone, on a read_data_corrected.txt written by stage one; with
+    --min-abundance 0 (metaMDBG's default mode) the table carries the rescued abundance-1 entries."""
+    import __graft_entry__ as g
+    g.build()
+    rs = synth.make_readset(1500, 7000, seed=56, n_genomes=2, genome_len_range=(150_000, 250_000), err=0.004)
+    bases, offs = synth.fill_reads(rs)
+    fa = tmp_path / "reads.fasta"
+    raw = bases.tobytes()
+    with open(fa, "wb") as f:
+        for r in range(rs.n_reads):
+            s = raw[int(offs[r]):int(offs[r + 1])]
+            f.write(b">r%d\n" % r)
+            for i in range(0, len(s), 80):                 # multi-line FASTA
+                f.write(s[i:i + 80] + b"\n")
+    d1, d2 = tmp_path / "one", tmp_path / "two"
+    d1.mkdir(); d2.mkdir()
+    out = subprocess.run([EXE, str(fa), str(d1), "--batch-mbp", "4"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    out = subprocess.run([EXE, "--from-read-data", str(d1 / "read_data_corrected.txt"), str(d2), "--min-abundance", "0"],
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    stats = dict(zip(out.stdout.split()[::2], out.stdout.split()[1::2]))
+    mo, m, p, d = oracle.sketch_batch(bases, offs, 15, 0.005, True)
+    c = oracle.count(m, mo, 4, 2)
+    r = oracle.rescue(m, mo, 4, c["hashes"], c["abundances"])
+    want = {(int(h[0]), int(h[1])): int(a) for h, a in zip(c["hashes"], c["abundances"])}
+    for h in r["hashes"]:
+        want[(int(h[0]), int(h[1]))] = 1
+    ab = np.frombuffer(open(d2 / "kminmerData_abundance.txt", "rb").read(), dtype=np.uint8).reshape(-1, 20)
+    lo = ab[:, 0:8].copy().view(np.uint64)[:, 0]; hi = ab[:, 8:16].copy().view(np.uint64)[:, 0]
+    cnt = ab[:, 16:20].copy().view(np.uint32)[:, 0]
+    got = {(int(h), int(l)): int(c_) for h, l, c_ in zip(hi, lo, cnt)}
+    assert got == want
+    assert int(stats["solid"]) == len(c["abundances"]) and int(stats["rescued"]) == len(r["hashes"]) > 0
+    # FASTA input: no qualities -> per-minimizer quality 1 and NaN mean quality in read_data_init.txt
+    from oracle.pyoracle import parse_read_data
+    recs = parse_read_data(str(d1 / "read_data_init.txt"), True)
+    assert len(recs) == rs.n_reads and all(np.all(x["qualities"] == 1) for x in recs[:50])
+    assert all(np.isnan(x["mean_quality"]) for x in recs[:50])
