@@ -58,6 +58,7 @@ struct mdbg_ctx {
     cudaStream_t copy_stream = nullptr;
     int host_packing = -1;             // 2-bit pack ASCII host batches before H2D: -1 auto, 0 off, 1 on
     HostPool* pool = nullptr;
+    uint64_t last_direct_pieces = 0, last_pieces = 0;   // hybrid transfer statistics of the last host batch
     DevBuf d_pack, d_src;
     PinBuf h_pack, h_src, h_asc;
     cudaEvent_t sub_ev[MAX_SUB] = {};
@@ -718,46 +719,80 @@ static mdbg_status sketch_host_batch(mdbg_ctx* ctx, const uint8_t* bases, const 
     CKS(ensure_pin(ctx, ctx->h_src, (size_t)n_reads * 8));
     CKS(ensure(ctx, ctx->d_pack, (n_words + 1) * 4));
     CKS(ensure(ctx, ctx->d_src, (size_t)n_reads * 8));
-    // ASCII spill: pinned staging grows on demand (reads with N / lower case are rare), device side is reserved lazily too
+    // Hybrid transfer: when the caller's buffer is pinned, a piece can also travel as plain ASCII by DMA alone
+    // (no CPU work).  Each piece picks its mode by looking at the copy stream: if the previous pieces have already
+    // landed, PCIe is idle and the piece is sent as it is; otherwise the host threads use the waiting time to pack
+    // it.  Both resources (copy engine, CPU packer) stay busy and the split adapts to the machine.
+    bool can_direct = false;
+    {
+        cudaPointerAttributes attr{};
+        if (cudaPointerGetAttributes(&attr, bases) == cudaSuccess && attr.type == cudaMemoryTypeHost) can_direct = true;
+        else cudaGetLastError();                                         // pageable memory: not an error
+    }
+    // device ASCII area: [0, n_bases) mirrors the batch (direct pieces), the spill of packed pieces follows it
+    const uint64_t spill_base = can_direct ? ((n_bases + 15) & ~uint64_t(15)) : 0;
+    if (can_direct) CKS(ensure(ctx, ctx->d_bases, spill_base + (uint64_t(16) << 20)));
     std::atomic<uint64_t> asc_cursor{0};
     uint64_t asc_sent = 0;
+    uint64_t n_direct_pieces = 0;
     const Feeder feeder = [&](SketchArgs& a) -> mdbg_status {
         a.read_src = ctx->d_src.as<uint64_t>();
         a.packed = ctx->d_pack.as<uint32_t>();
         for (size_t i = 0; i < subs.size(); i++) {
             const uint32_t r0 = subs[i].r0, r1 = subs[i].r1;
-            // worst-case ASCII spill of this piece must fit the pinned staging before the workers start
-            const uint64_t piece_bytes = offsets[r1] - offsets[r0] + 16ull * (r1 - r0);
-            if (ctx->h_asc.cap < asc_cursor.load() + piece_bytes) {
-                PinBuf bigger;
-                CKS(ensure_pin(ctx, bigger, asc_cursor.load() + piece_bytes));
-                if (ctx->h_asc.p && asc_cursor.load()) {
-                    CK(cudaStreamSynchronize(cs));                           // earlier spill copies still read the old buffer
-                    memcpy(bigger.p, ctx->h_asc.p, asc_cursor.load());
-                }
-                release(ctx->h_asc);
-                ctx->h_asc = bigger;
-            }
-            host_pack_reads(ctx->pool, bases, offsets, r0, r1, pk_off.data(), ctx->h_pack.as<uint32_t>(),
-                            ctx->h_src.as<uint64_t>(), ctx->h_asc.as<uint8_t>(), &asc_cursor);
-            const uint64_t w0 = pk_off[r0], w1 = pk_off[r1];
-            if (w1 > w0)
-                CK(cudaMemcpyAsync(ctx->d_pack.as<uint32_t>() + w0, ctx->h_pack.as<uint32_t>() + w0, (w1 - w0) * 4,
+            bool direct = false;
+            if (can_direct) direct = (i == 0) || cudaEventQuery(ctx->sub_ev[i - 1]) == cudaSuccess;
+            if (direct) {
+                uint64_t* src = ctx->h_src.as<uint64_t>();
+                for (uint32_t r = r0; r < r1; r++) src[r] = SRC_ASCII | offsets[r];
+                const uint64_t lo = offsets[r0], hi = offsets[r1];
+                if (hi > lo)
+                    CK(cudaMemcpyAsync(ctx->d_bases.as<uint8_t>() + lo, bases + lo, hi - lo, cudaMemcpyHostToDevice, cs));
+                CK(cudaMemcpyAsync(ctx->d_src.as<uint64_t>() + r0, src + r0, (size_t)(r1 - r0) * 8,
                                    cudaMemcpyHostToDevice, cs));
-            CK(cudaMemcpyAsync(ctx->d_src.as<uint64_t>() + r0, ctx->h_src.as<uint64_t>() + r0, (size_t)(r1 - r0) * 8,
-                               cudaMemcpyHostToDevice, cs));
-            ctx->h2d_bytes += (w1 - w0) * 4 + (uint64_t)(r1 - r0) * 8;
-            const uint64_t asc_now = asc_cursor.load();
-            if (asc_now > asc_sent) {
-                if (ctx->d_bases.cap < asc_now + 64) {                       // grow, keeping what earlier pieces spilled
-                    CK(cudaStreamSynchronize(cs));
-                    CK(cudaStreamSynchronize(s));
-                    CKS(ensure(ctx, ctx->d_bases, std::min<uint64_t>(asc_cap, 2 * asc_now + (uint64_t(64) << 20)), true));
+                ctx->h2d_bytes += (hi - lo) + (uint64_t)(r1 - r0) * 8;
+                n_direct_pieces++;
+            } else {
+                // worst-case ASCII spill of this piece must fit the pinned staging before the workers start
+                const uint64_t piece_bytes = offsets[r1] - offsets[r0] + 16ull * (r1 - r0);
+                if (ctx->h_asc.cap < asc_cursor.load() + piece_bytes) {
+                    PinBuf bigger;
+                    CKS(ensure_pin(ctx, bigger, asc_cursor.load() + piece_bytes));
+                    if (ctx->h_asc.p && asc_cursor.load()) {
+                        CK(cudaStreamSynchronize(cs));                       // earlier spill copies still read the old buffer
+                        memcpy(bigger.p, ctx->h_asc.p, asc_cursor.load());
+                    }
+                    release(ctx->h_asc);
+                    ctx->h_asc = bigger;
                 }
-                CK(cudaMemcpyAsync(ctx->d_bases.as<uint8_t>() + asc_sent, ctx->h_asc.as<uint8_t>() + asc_sent,
-                                   asc_now - asc_sent, cudaMemcpyHostToDevice, cs));
-                ctx->h2d_bytes += asc_now - asc_sent;
-                asc_sent = asc_now;
+                host_pack_reads(ctx->pool, bases, offsets, r0, r1, pk_off.data(), ctx->h_pack.as<uint32_t>(),
+                                ctx->h_src.as<uint64_t>(), ctx->h_asc.as<uint8_t>(), &asc_cursor);
+                if (spill_base) {                                            // spilled reads live behind the mirror area
+                    uint64_t* src = ctx->h_src.as<uint64_t>();
+                    for (uint32_t r = r0; r < r1; r++)
+                        if (src[r] & SRC_ASCII) src[r] = SRC_ASCII | (spill_base + (src[r] & ~SRC_ASCII));
+                }
+                const uint64_t w0 = pk_off[r0], w1 = pk_off[r1];
+                if (w1 > w0)
+                    CK(cudaMemcpyAsync(ctx->d_pack.as<uint32_t>() + w0, ctx->h_pack.as<uint32_t>() + w0, (w1 - w0) * 4,
+                                       cudaMemcpyHostToDevice, cs));
+                CK(cudaMemcpyAsync(ctx->d_src.as<uint64_t>() + r0, ctx->h_src.as<uint64_t>() + r0, (size_t)(r1 - r0) * 8,
+                                   cudaMemcpyHostToDevice, cs));
+                ctx->h2d_bytes += (w1 - w0) * 4 + (uint64_t)(r1 - r0) * 8;
+                const uint64_t asc_now = asc_cursor.load();
+                if (asc_now > asc_sent) {
+                    if (ctx->d_bases.cap < spill_base + asc_now + 64) {      // grow, keeping what is already there
+                        CK(cudaStreamSynchronize(cs));
+                        CK(cudaStreamSynchronize(s));
+                        CKS(ensure(ctx, ctx->d_bases,
+                                   std::min<uint64_t>(spill_base + asc_cap, spill_base + 2 * asc_now + (uint64_t(64) << 20)),
+                                   true));
+                    }
+                    CK(cudaMemcpyAsync(ctx->d_bases.as<uint8_t>() + spill_base + asc_sent,
+                                       ctx->h_asc.as<uint8_t>() + asc_sent, asc_now - asc_sent, cudaMemcpyHostToDevice, cs));
+                    ctx->h2d_bytes += asc_now - asc_sent;
+                    asc_sent = asc_now;
+                }
             }
             CK(cudaEventRecord(ctx->sub_ev[i], cs));
             CK(cudaStreamWaitEvent(s, ctx->sub_ev[i], 0));
@@ -771,8 +806,12 @@ static mdbg_status sketch_host_batch(mdbg_ctx* ctx, const uint8_t* bases, const 
         }
         return MDBG_OK;
     };
-    return sketch_internal(ctx, ctx->d_bases.as<uint8_t>(), ctx->d_offsets.as<uint64_t>(), n_reads, n_bases, append,
-                           false, nullptr, &feeder);
+    ctx->last_direct_pieces = 0;
+    const mdbg_status st = sketch_internal(ctx, ctx->d_bases.as<uint8_t>(), ctx->d_offsets.as<uint64_t>(), n_reads, n_bases,
+                                           append, false, nullptr, &feeder);
+    ctx->last_direct_pieces = n_direct_pieces;
+    ctx->last_pieces = subs.size();
+    return st;
 }
 
 mdbg_status mdbg_ctx_set_host_packing(mdbg_ctx* ctx, int on) {

@@ -459,3 +459,42 @@ def test_ont_density_rethreshold_and_count(built, oracle):
     ref = oracle.count(sm, so, 4, 2)
     check_table(tab, ref["hashes"], ref["abundances"], ref["vecs"], [ref["n_instances"], ref["n_distinct"]])
     eng.close()
+
+
+def test_hybrid_transfer_from_pinned_host_memory(built, oracle):
+    """Pinned caller buffers: pieces travel either as ASCII by DMA (PCIe idle) or 2-bit packed (PCIe busy); both
+    modes -- and dirty reads inside packed pieces -- must give the oracle's sketch."""
+    import torch
+    rs = synth.make_readset(40_000, 9000, seed=29, n_genomes=3, genome_len_range=(300_000, 600_000))
+    sub = rs.subset(0, 40_000)
+    dev = torch.device("cuda:0")
+    eng = engine()
+    d_off = torch.from_numpy(sub.offsets.astype(np.int64)).to(dev)
+    d_vs = torch.from_numpy(sub.vstart.astype(np.int64)).to(dev)
+    d_st = torch.from_numpy(sub.strand).to(dev)
+    d_bases = torch.empty(sub.n_bases + 64, dtype=torch.uint8, device=dev)
+    eng.synth_fill_reads(d_bases.data_ptr(), d_off.data_ptr(), d_vs.data_ptr(), d_st.data_ptr(), sub.n_reads, 0,
+                         sub.seed, sub.err_q24)
+    eng.synchronize()
+    h = torch.empty(sub.n_bases, dtype=torch.uint8, pin_memory=True)
+    h.copy_(d_bases[:sub.n_bases])
+    torch.cuda.synchronize()
+    hb = h.numpy()
+    for r in range(0, sub.n_reads, 501):                     # a few dirty reads
+        hb[int(sub.offsets[r]) + 7] = ord("N")
+    assert sub.n_bases > 300 * (1 << 20)                      # several 128 MB pieces
+    eng.set_host_packing(True)
+    n = eng.sketch_batch_ptr(h.data_ptr(), sub.offsets, append_to_store=True)
+    sk = eng.sketch_fetch()
+    assert n == len(sk.minimizers)
+    # oracle on a sample of reads (incl. the dirty ones) + device-resident path on everything
+    raw = hb.tobytes()
+    for r in list(range(0, sub.n_reads, 501)) + list(range(1, sub.n_reads, 997)):
+        m, p, d = oracle.sketch_read(raw[int(sub.offsets[r]):int(sub.offsets[r + 1])], 15, 0.005, True)
+        gm, gp, gd = sk.read(r)
+        assert np.array_equal(gm, m) and np.array_equal(gp, p) and np.array_equal(gd, d), r
+    d_bases[:sub.n_bases].copy_(h)
+    eng.sketch_batch_device(d_bases.data_ptr(), d_off.data_ptr(), sub.n_reads, sub.n_bases, False)
+    ref = eng.sketch_fetch()
+    assert_sketch_equal(sk, ref.min_offsets, ref.minimizers, ref.positions, ref.directions, "hybrid vs device-resident")
+    eng.close()
