@@ -136,7 +136,9 @@ mdbg_status mdbg_sketch_batch(mdbg_ctx* ctx, const uint8_t* bases, const uint64_
 /* Host batches without qualities cross PCIe 2-bit packed (worker threads + AVX2 inside the library, unpacked again
  * by the sketch kernel; reads holding a byte outside "ACGT" stay ASCII, so results are identical).  on = 0 sends the
  * ASCII bytes as they are, on = 1 always packs, on = -1 (default) packs when the process has at least 12 usable CPUs
- * (cgroup quota and ranks-per-node aware), i.e. when packing outruns the PCIe transfer it saves. */
+ * (cgroup quota and ranks-per-node aware), i.e. when packing outruns the PCIe transfer it saves.  on = 2
+ * (experimental, pinned caller buffers only) additionally sends a piece as plain ASCII whenever the copy engine
+ * is idle, so that DMA and the packer work side by side. */
 mdbg_status mdbg_ctx_set_host_packing(mdbg_ctx* ctx, int on);
 /* Same with the reads already in HBM.  d_bases must be 16-byte aligned;
  * nothing is copied to the host.  `out` may be NULL. */

@@ -56,7 +56,7 @@ struct mdbg_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
-    int host_packing = -1;             // 2-bit pack ASCII host batches before H2D: -1 auto, 0 off, 1 on
+    int host_packing = -1;             // 2-bit pack ASCII host batches before H2D: -1 auto, 0 off, 1 on, 2 hybrid
     HostPool* pool = nullptr;
     uint64_t last_direct_pieces = 0, last_pieces = 0;   // hybrid transfer statistics of the last host batch
     DevBuf d_pack, d_src;
@@ -676,7 +676,7 @@ static mdbg_status sketch_host_batch(mdbg_ctx* ctx, const uint8_t* bases, const 
     ctx->h2d_bytes += ((uint64_t)n_reads + 1) * 8;
 
     // auto: packing pays when the host can pack faster than PCIe moves ASCII (~55 GB/s), i.e. with >= 12 usable CPUs
-    bool want_pack = ctx->host_packing == 1;
+    bool want_pack = ctx->host_packing >= 1;
     if (ctx->host_packing < 0) {
         const char* env = getenv("MDBG_HOST_THREADS");
         want_pack = ((env && atoi(env) > 0) ? atoi(env) : host_default_threads()) >= 12;
@@ -724,7 +724,7 @@ static mdbg_status sketch_host_batch(mdbg_ctx* ctx, const uint8_t* bases, const 
     // landed, PCIe is idle and the piece is sent as it is; otherwise the host threads use the waiting time to pack
     // it.  Both resources (copy engine, CPU packer) stay busy and the split adapts to the machine.
     bool can_direct = false;
-    {
+    if (ctx->host_packing == 2) {      // opt-in: on the round-1 test box the DMA reads slowed the packer more than they saved
         cudaPointerAttributes attr{};
         if (cudaPointerGetAttributes(&attr, bases) == cudaSuccess && attr.type == cudaMemoryTypeHost) can_direct = true;
         else cudaGetLastError();                                         // pageable memory: not an error
@@ -816,7 +816,7 @@ static mdbg_status sketch_host_batch(mdbg_ctx* ctx, const uint8_t* bases, const 
 
 mdbg_status mdbg_ctx_set_host_packing(mdbg_ctx* ctx, int on) {
     if (!ctx) return MDBG_ERR_ARG;
-    ctx->host_packing = on < 0 ? -1 : (on != 0);
+    ctx->host_packing = on < 0 ? -1 : (on > 2 ? 1 : on);
     return MDBG_OK;
 }
 

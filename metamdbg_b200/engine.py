@@ -143,8 +143,8 @@ class Engine:
                                              int(append_to_store), C.byref(out) if fetch else None))
         return self._copy_sketch(out) if fetch else None
 
-    def set_host_packing(self, on: bool | None = True):
-        """2-bit pack host batches before H2D: True / False / None = automatic (default)."""
+    def set_host_packing(self, on: bool | int | None = True):
+        """2-bit pack host batches before H2D: True / False / None = automatic (default) / 2 = hybrid (experimental)."""
         self._ck(self._lib.mdbg_ctx_set_host_packing(self._ctx, -1 if on is None else int(on)))
 
     def set_read_filters(self, filter_low_complexity: bool = True):

@@ -483,10 +483,15 @@ def test_hybrid_transfer_from_pinned_host_memory(built, oracle):
     for r in range(0, sub.n_reads, 501):                     # a few dirty reads
         hb[int(sub.offsets[r]) + 7] = ord("N")
     assert sub.n_bases > 300 * (1 << 20)                      # several 128 MB pieces
-    eng.set_host_packing(True)
+    eng.set_host_packing(2)                                   # hybrid: ASCII-by-DMA and packed pieces mixed
     n = eng.sketch_batch_ptr(h.data_ptr(), sub.offsets, append_to_store=True)
     sk = eng.sketch_fetch()
     assert n == len(sk.minimizers)
+    eng.set_host_packing(True)                                # packed pieces only
+    n2 = eng.sketch_batch_ptr(h.data_ptr(), sub.offsets, append_to_store=False)
+    sk2 = eng.sketch_fetch()
+    assert n2 == n
+    assert_sketch_equal(sk2, sk.min_offsets, sk.minimizers, sk.positions, sk.directions, "packed vs hybrid")
     # oracle on a sample of reads (incl. the dirty ones) + device-resident path on everything
     raw = hb.tobytes()
     for r in list(range(0, sub.n_reads, 501)) + list(range(1, sub.n_reads, 997)):
