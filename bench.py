@@ -300,6 +300,14 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     n_min_store = eng.store_size()[1]
     solid_total = sum_over_ranks(stats["n_entries"])
     checksum_local = stats["checksum"]
+    # size-independent property at full size: every k-min-mer occurrence of every read is in exactly one table
+    # (after the owner merge): sum of all abundances over all ranks == sum over reads of max(0, n_minimizers - k + 1)
+    so, _ = eng.store_fetch()
+    per_read = np.diff(so.astype(np.int64))
+    expect_instances = sum_over_ranks(int(np.maximum(per_read - K + 1, 0).sum()))
+    got_instances = sum_over_ranks(stats["n_instances"])
+    if expect_instances != got_instances:
+        raise SystemExit(f"bench.py: occurrence conservation violated: {got_instances} != {expect_instances}")
 
     # ---- end to end through the host-buffer C ABI ---------------------------------------------
     e2e = None
@@ -422,7 +430,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "kernels_ms": {"sketch": sk_ms, "insert": float(np.mean(insert_ms))},
             "cpu_baseline": cpu_baseline,
             "check": {"n_minimizers_rank0": int(n_min_store), "n_solid_total": int(solid_total),
-                      "checksum_rank0": int(checksum_local)},
+                      "checksum_rank0": int(checksum_local), "kminmer_occurrences_total": int(got_instances),
+                      "occurrences_conserved": True},
         }
         print(json.dumps(line), flush=True)
     eng.close()
