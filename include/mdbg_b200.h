@@ -145,6 +145,12 @@ mdbg_status mdbg_ctx_set_host_packing(mdbg_ctx* ctx, int on);
 mdbg_status mdbg_sketch_batch_device(mdbg_ctx* ctx, const uint8_t* d_bases, const uint64_t* d_offsets,
                                      uint32_t n_reads, uint64_t n_bases, int append_to_store,
                                      mdbg_sketch_dev* out);
+/* Reads resident in HBM in 2-bit packed form: 16 bases per u32, base j of a word at bits [2j, 2j+1], code
+ * (c >> 1) & 3 (A=0 C=1 T=2 G=3); read r starts at word d_word_offsets[r] and has d_offsets[r+1] - d_offsets[r]
+ * bases.  Only for reads made of the letters A, C, G, T (anything else must use the ASCII entry points). */
+mdbg_status mdbg_sketch_batch_device_packed(mdbg_ctx* ctx, const uint32_t* d_packed, const uint64_t* d_word_offsets,
+                                            const uint64_t* d_offsets, uint32_t n_reads, uint64_t n_bases,
+                                            int append_to_store, mdbg_sketch_dev* out);
 /* Copy the last batch's CSR to pinned host memory (after *_device). */
 mdbg_status mdbg_sketch_fetch(mdbg_ctx* ctx, mdbg_sketch_out* out);
 

@@ -602,6 +602,34 @@ mdbg_status mdbg_sketch_batch_device(mdbg_ctx* ctx, const uint8_t* d_bases, cons
     return MDBG_OK;
 }
 
+mdbg_status mdbg_sketch_batch_device_packed(mdbg_ctx* ctx, const uint32_t* d_packed, const uint64_t* d_word_offsets,
+                                            const uint64_t* d_offsets, uint32_t n_reads, uint64_t n_bases,
+                                            int append_to_store, mdbg_sketch_dev* out) {
+    if (!ctx) return MDBG_ERR_ARG;
+    if (n_reads && (!d_packed || !d_word_offsets || !d_offsets)) return fail(ctx, MDBG_ERR_ARG, "null device buffer");
+    CK(cudaSetDevice(ctx->device));
+    const Feeder feeder = [&](SketchArgs& a) -> mdbg_status {
+        a.read_src = d_word_offsets;            // bit 63 clear everywhere: every read is packed
+        a.packed = d_packed;
+        a.bases = nullptr;
+        a.bases_end = nullptr;
+        if (ctx->timing) CK(cudaEventRecord(ctx->ev[0][0], ctx->stream));
+        launch_sketch(a, ctx->sm_count, ctx->stream);
+        if (ctx->timing) { CK(cudaEventRecord(ctx->ev[0][1], ctx->stream)); ctx->ev_valid[0] = true; }
+        return check_launch(ctx, "sketch_kernel", 1);
+    };
+    CKS(sketch_internal(ctx, nullptr, d_offsets, n_reads, n_bases, append_to_store, false, nullptr, &feeder));
+    if (out) {
+        out->n_reads = n_reads;
+        out->n_minimizers = ctx->b_total;
+        out->d_min_offsets = ctx->b_off.as<uint64_t>();
+        out->d_minimizers = ctx->b_min.as<uint32_t>();
+        out->d_positions = ctx->b_pos.as<uint32_t>();
+        out->d_directions = ctx->b_dir.as<uint8_t>();
+    }
+    return MDBG_OK;
+}
+
 mdbg_status mdbg_sketch_fetch(mdbg_ctx* ctx, mdbg_sketch_out* out) {
     if (!ctx || !out) return MDBG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));

@@ -185,6 +185,15 @@ class Engine:
                                                     n_reads, n_bases, int(append_to_store), C.byref(out)))
         return out
 
+    def sketch_batch_device_packed(self, d_packed_ptr: int, d_word_offsets_ptr: int, d_offsets_ptr: int, n_reads: int,
+                                   n_bases: int, append_to_store: bool = False) -> SketchDev:
+        """Reads resident in HBM as 2-bit codes (16 bases per u32, see include/mdbg_b200.h)."""
+        out = SketchDev()
+        self._ck(self._lib.mdbg_sketch_batch_device_packed(self._ctx, C.c_void_p(d_packed_ptr),
+                                                           C.c_void_p(d_word_offsets_ptr), C.c_void_p(d_offsets_ptr),
+                                                           n_reads, n_bases, int(append_to_store), C.byref(out)))
+        return out
+
     def sketch_fetch(self) -> Sketch:
         out = SketchOut()
         self._ck(self._lib.mdbg_sketch_fetch(self._ctx, C.byref(out)))

@@ -149,3 +149,23 @@ def fill_reads(rs: ReadSet, lo: int = 0, hi: int | None = None) -> tuple[np.ndar
             b = np.where(sub, (b + shift) & np.uint8(3), b).astype(np.uint8)
         out[int(offs[j]):int(offs[j + 1])] = LETTERS[b]
     return out, offs
+
+
+def pack_2bit(bases: np.ndarray, offsets: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+    """ASCII reads (letters A, C, G, T only) -> (uint32 words, uint64 word offset per read) in the 2-bit layout of
+    include/mdbg_b200.h: 16 bases per word, base j at bits [2j, 2j+1], code (c >> 1) & 3."""
+    n = len(offsets) - 1
+    lens = np.diff(offsets.astype(np.int64))
+    words_per = (lens + 15) // 16
+    woff = np.zeros(n + 1, dtype=np.uint64)
+    woff[1:] = np.cumsum(words_per).astype(np.uint64)
+    out = np.zeros(int(woff[-1]) + 1, dtype=np.uint32)
+    codes = ((bases >> np.uint8(1)) & np.uint8(3)).astype(np.uint32)
+    for r in range(n):
+        c = codes[int(offsets[r]):int(offsets[r + 1])]
+        pad = (-len(c)) % 16
+        if pad:
+            c = np.concatenate([c, np.zeros(pad, np.uint32)])
+        c = c.reshape(-1, 16)
+        out[int(woff[r]):int(woff[r]) + len(c)] = (c << (2 * np.arange(16, dtype=np.uint32))).sum(axis=1, dtype=np.uint64).astype(np.uint32)
+    return out[:int(woff[-1])], woff[:n].copy()

@@ -503,3 +503,23 @@ def test_hybrid_transfer_from_pinned_host_memory(built, oracle):
     ref = eng.sketch_fetch()
     assert_sketch_equal(sk, ref.min_offsets, ref.minimizers, ref.positions, ref.directions, "hybrid vs device-resident")
     eng.close()
+
+
+def test_device_resident_packed_input(built, oracle):
+    """Reads kept 2-bit packed in HBM (the layout the design brief names) sketch to the same CSR as ASCII reads."""
+    import torch
+    rs = synth.make_readset(1500, 7000, seed=44, n_genomes=2, genome_len_range=(100_000, 200_000))
+    bases, offs = synth.fill_reads(rs)
+    words, woff = synth.pack_2bit(bases, offs)
+    dev = torch.device("cuda:0")
+    d_words = torch.from_numpy(words.astype(np.int64).astype(np.uint32).view(np.int32)).to(dev)
+    d_woff = torch.from_numpy(woff.astype(np.int64)).to(dev)
+    d_off = torch.from_numpy(offs.astype(np.int64)).to(dev)
+    for hpc in (True, False):
+        eng = engine(15, 0.005, hpc)
+        out = eng.sketch_batch_device_packed(d_words.data_ptr(), d_woff.data_ptr(), d_off.data_ptr(), rs.n_reads,
+                                             int(offs[-1]), True)
+        sk = eng.sketch_fetch()
+        assert out.n_minimizers == len(sk.minimizers)
+        assert_sketch_equal(sk, *oracle.sketch_batch(bases, offs, 15, 0.005, hpc), tag=f"packed device hpc={hpc}")
+        eng.close()
