@@ -385,6 +385,24 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sketch_kernel(const Sketch
                     // Candidates (~2 per 512 positions) are appended, in position order, to a small per-warp list;
                     // the list is resolved 32 entries at a time with every lane busy (flush_candidates).
                     const uint32_t n_c = __popc(sel);
+                    // common case: at most one candidate per lane, all from the register path -> one store per hit lane
+                    if (__all_sync(0xffffffffu, n_c <= 1 && (regs_ok || n_c == 0))) {
+                        if (n_c) cand[n_list + __popc(hit_lanes & ((1u << lane) - 1u))] = make_uint2(p0 + __ffs(sel) - 1, sel_fwd);
+                        n_list += __popc(hit_lanes);
+                        __syncwarp();
+                        if (n_list >= 32) {
+                            out_cnt += flush_candidates(a, cand, 32, lane, slot_lo, slot_cap, out_cnt);
+                            __syncwarp();
+                            uint2 keep_e = make_uint2(0, 0);
+                            if (32 + lane < n_list) keep_e = cand[32 + lane];
+                            __syncwarp();
+                            if (32 + lane < n_list) cand[lane] = keep_e;
+                            n_list -= 32;
+                            __syncwarp();
+                        }
+                        done += BLK;
+                        continue;
+                    }
                     uint32_t before, total;
                     if (__ballot_sync(0xffffffffu, n_c > 1) == 0) {
                         before = __popc(hit_lanes & ((1u << lane) - 1u));
