@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -59,6 +60,8 @@ struct mdbg_ctx {
     int host_packing = -1;             // 2-bit pack ASCII host batches before H2D: -1 auto, 0 off, 1 on, 2 hybrid
     HostPool* pool = nullptr;
     uint64_t last_direct_pieces = 0, last_pieces = 0;   // hybrid transfer statistics of the last host batch
+    double last_pack_gbs = 0;          // host packer throughput of the last packed batch (raw GB/s)
+    int auto_pack_pause = 0;           // auto mode: batches still to send as ASCII after the packer proved too slow
     DevBuf d_pack, d_src;
     PinBuf h_pack, h_src, h_asc;
     cudaEvent_t sub_ev[MAX_SUB] = {};
@@ -708,6 +711,8 @@ static mdbg_status sketch_host_batch(mdbg_ctx* ctx, const uint8_t* bases, const 
     if (ctx->host_packing < 0) {
         const char* env = getenv("MDBG_HOST_THREADS");
         want_pack = ((env && atoi(env) > 0) ? atoi(env) : host_default_threads()) >= 12;
+        // ... and only while the packer keeps ahead of what PCIe would move as ASCII (busy or NUMA-remote hosts)
+        if (want_pack && ctx->auto_pack_pause > 0) { ctx->auto_pack_pause--; want_pack = false; }
     }
     const bool packed = want_pack && !quals && !want_aux && n_bases >= (uint64_t(1) << 20);
     if (!packed) {
@@ -763,6 +768,8 @@ static mdbg_status sketch_host_batch(mdbg_ctx* ctx, const uint8_t* bases, const 
     std::atomic<uint64_t> asc_cursor{0};
     uint64_t asc_sent = 0;
     uint64_t n_direct_pieces = 0;
+    double pack_seconds = 0;
+    uint64_t pack_bytes = 0;
     const Feeder feeder = [&](SketchArgs& a) -> mdbg_status {
         a.read_src = ctx->d_src.as<uint64_t>();
         a.packed = ctx->d_pack.as<uint32_t>();
@@ -793,8 +800,11 @@ static mdbg_status sketch_host_batch(mdbg_ctx* ctx, const uint8_t* bases, const 
                     release(ctx->h_asc);
                     ctx->h_asc = bigger;
                 }
+                const auto t_pack = std::chrono::steady_clock::now();
                 host_pack_reads(ctx->pool, bases, offsets, r0, r1, pk_off.data(), ctx->h_pack.as<uint32_t>(),
                                 ctx->h_src.as<uint64_t>(), ctx->h_asc.as<uint8_t>(), &asc_cursor);
+                pack_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_pack).count();
+                pack_bytes += offsets[r1] - offsets[r0];
                 if (spill_base) {                                            // spilled reads live behind the mirror area
                     uint64_t* src = ctx->h_src.as<uint64_t>();
                     for (uint32_t r = r0; r < r1; r++)
@@ -839,6 +849,11 @@ static mdbg_status sketch_host_batch(mdbg_ctx* ctx, const uint8_t* bases, const 
                                            append, false, nullptr, &feeder);
     ctx->last_direct_pieces = n_direct_pieces;
     ctx->last_pieces = subs.size();
+    if (pack_seconds > 0) {
+        ctx->last_pack_gbs = (double)pack_bytes / pack_seconds / 1e9;
+        // slower than the ~48 GB/s the pipelined ASCII path sustains over PCIe: stop packing for a while
+        if (ctx->host_packing < 0 && pack_bytes >= (uint64_t(256) << 20) && ctx->last_pack_gbs < 45.0) ctx->auto_pack_pause = 16;
+    }
     return st;
 }
 
