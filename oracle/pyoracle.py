@@ -28,6 +28,11 @@ def build(force: bool = False) -> None:
             os.path.getmtime(ORACLE_SO) < os.path.getmtime(os.path.join(HERE, "mdbg_oracle.c")):
         subprocess.run(["make", "-s", "-C", HERE, os.path.join(HERE, "libmdbg_oracle.so")], check=True)
     if os.path.exists("/root/reference/src/Commons.hpp"):
+        integrated = os.path.join(HERE, "_ref", "mdbg_ref_integrated")
+        engine = os.path.join(HERE, "..", "metamdbg_b200", "libmdbg_b200.so")
+        if os.path.exists(REF_SO) and os.path.exists(engine) and (
+                not os.path.exists(integrated) or os.path.getmtime(integrated) < os.path.getmtime(engine)):
+            subprocess.run(["make", "-s", "-C", HERE, "ref"], check=True)
         if force or not os.path.exists(REF_SO) or \
                 os.path.getmtime(REF_SO) < max(os.path.getmtime(os.path.join(HERE, "ref_shim.cpp")),
                                                os.path.getmtime(os.path.join(HERE, "Makefile"))):

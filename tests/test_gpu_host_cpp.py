@@ -141,3 +141,40 @@ def test_cpp_driver_graph_seam_and_default_mode(tmp_path, oracle):
     recs = parse_read_data(str(d1 / "read_data_init.txt"), True)
     assert len(recs) == rs.n_reads and all(np.all(x["qualities"] == 1) for x in recs[:50])
     assert all(np.isnan(x["mean_quality"]) for x in recs[:50])
+
+
+def test_reference_stage_driven_by_gpu_functor(tmp_path):
+    """metaMDBG's own readSelection stage code (kseq FASTQ parser, ReadSelection::writeRead with its re-ordering queue,
+    computeReadStats) with the GPU functor of INTEGRATION.md plugged in (oracle/_ref/mdbg_ref_integrated = reference
+    sources + libmdbg_b200.so).  Its read_data_init.txt must be byte-identical to the file the unmodified stage
+    wrote (golden), with the reads arriving from several parser threads."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "mdbg_ref_integrated")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/mdbg_ref_integrated not built (needs the reference sources)")
+    z = np.load(os.path.join(ROOT, "tests", "golden", "readselection_hifi.npz"))
+    raw, qraw, offs = z["bases"].tobytes(), z["quals"].tobytes(), z["offsets"]
+    fq = tmp_path / "reads.fastq"
+    with open(fq, "wb") as f:
+        for r in range(len(offs) - 1):
+            lo, hi = int(offs[r]), int(offs[r + 1])
+            f.write(b"@r%d\n" % r + raw[lo:hi] + b"\n+\n" + qraw[lo:hi] + b"\n")
+    with open(tmp_path / "input.txt", "w") as f:
+        f.write(str(fq) + "\n")
+    out = subprocess.run([exe, str(tmp_path / "input.txt"), str(tmp_path), "15", "0.005", "1", "4"],
+                         capture_output=True, text=True, timeout=180)
+    assert out.returncode == 0, out.stderr[-2000:]
+    want = bytearray()
+    mo = z["min_offsets"]
+    for r in range(len(offs) - 1):
+        lo, hi = int(mo[r]), int(mo[r + 1])
+        want += np.uint32(hi - lo).tobytes() + b"\x00"
+        want += z["minimizers"][lo:hi].tobytes() + z["positions"][lo:hi].tobytes()
+        want += z["directions"][lo:hi].tobytes() + z["qualities"][lo:hi].tobytes()
+        want += np.float32(z["mean_quality"][r]).tobytes() + np.uint32(z["read_length"][r]).tobytes()
+    assert open(tmp_path / "read_data_init.txt", "rb").read() == bytes(want)
+    b = open(tmp_path / "read_stats.txt", "rb").read()
+    got = [int(np.frombuffer(b, np.uint64, 1, 0)[0]), int(np.frombuffer(b, np.uint32, 1, 8)[0]),
+           int(np.frombuffer(b, np.uint64, 1, 16)[0]), int(np.frombuffer(b, np.uint32, 1, 28)[0]),
+           int(np.frombuffer(b, np.uint64, 1, 32)[0])]
+    assert got == [int(x) for x in z["stats"]]
+    assert os.path.getsize(tmp_path / "read_data_corrected.txt") > 0
