@@ -523,3 +523,22 @@ def test_device_resident_packed_input(built, oracle):
         assert out.n_minimizers == len(sk.minimizers)
         assert_sketch_equal(sk, *oracle.sketch_batch(bases, offs, 15, 0.005, hpc), tag=f"packed device hpc={hpc}")
         eng.close()
+
+
+@pytest.mark.parametrize("dens", [0.0, 1.0, 0.999])
+def test_sketch_extreme_densities(built, oracle, dens):
+    """density 0 selects nothing; density >= 1 overflows the 32-bit high-word test and must fall back to the exact
+    path (every position but the trimmed first/last is selected)."""
+    rng = np.random.default_rng(3)
+    reads = [bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), n)) for n in (0, 14, 15, 16, 17, 700, 2500)]
+    reads.append(b"ACGTNACGT" * 60)
+    bases = np.frombuffer(b"".join(reads), np.uint8).copy()
+    offs = np.zeros(len(reads) + 1, np.uint64)
+    offs[1:] = np.cumsum([len(r) for r in reads])
+    for hpc in (True, False):
+        eng = engine(15, dens, hpc)
+        sk = eng.sketch_batch(bases, offs)
+        assert_sketch_equal(sk, *oracle.sketch_batch(bases, offs, 15, dens, hpc), tag=f"d={dens} hpc={hpc}")
+        if dens == 0.0:
+            assert len(sk.minimizers) == 0
+        eng.close()
