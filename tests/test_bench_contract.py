@@ -1,0 +1,45 @@
+"""bench.py contract checks that need no GPU: the reference arm prints one well-formed JSON line, and the GPU arm
+refuses to run without a device (no CPU path)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.ref
+def test_reference_arm_json_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2",
+                          "--warmup", "1", "--reads", "600", "--read-len", "4000", "--genomes", "2", "--no-stages"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["unit"] == "Gbp/s" and j["higher_is_better"] is True
+    assert j["value"] > 0 and j["steps"] == 2 and j["n_gpus"] == 1 and j["gpu_launches"] == 0
+    assert j["cpu_baseline"]["kind"] in ("reference", "port") and j["cpu_baseline"]["cores"] >= 1
+    assert j["cpu_baseline"]["value"] == j["value"] and "sample" in j["cpu_baseline"]
+    assert j["e2e"] == {"value": j["value"], "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert j["config"]["k"] == 4 and j["config"]["minimizer_size"] == 15 and "workload" in j["config"]
+    assert j["check"]["n_solid"] > 0
+
+
+def test_reference_arm_other_ranks_are_silent():
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                         capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_gpu_arm_has_no_cpu_path():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--reads", "100"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode != 0
+    assert "no CUDA device" in (out.stderr + out.stdout) or "CUDA" in (out.stderr + out.stdout)
