@@ -58,6 +58,25 @@ def usable_cpus() -> int:
     return max(1, n)
 
 
+def host_bytes_available() -> int:
+    """Host memory this process may still take: MemAvailable capped by the cgroup's remaining allowance."""
+    avail = 1 << 62
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable:"):
+                avail = int(ln.split()[1]) * 1024
+                break
+    except OSError:
+        pass
+    try:
+        lim = open("/sys/fs/cgroup/memory.max").read().strip()
+        if lim != "max":
+            avail = min(avail, int(lim) - int(open("/sys/fs/cgroup/memory.current").read()))
+    except (OSError, ValueError):
+        pass
+    return max(0, avail)
+
+
 def purge_last_k(args):
     # Commons::computeLastK (src/Commons.hpp:1726-1741): n50 * density * 2, at least firstK+2
     return max(int(args.read_len * np.float32(DENSITY) * np.float32(2.0)), 6)
@@ -313,8 +332,21 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     e2e = None
     if not args.no_e2e:
         e_reads = min(n_reads, args.e2e_reads or n_reads)
-        e_bases = int(rs.offsets[e_reads])
-        h_bases = torch.empty(e_bases, dtype=torch.uint8, pin_memory=True)
+        # the pinned host copy of this rank's reads must fit beside the other ranks' (one node): use at most half of
+        # what the host still has, split over the local ranks; fewer reads in the e2e leg is reported, not hidden
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+        share = host_bytes_available() // (2 * max(1, local_world))
+        while e_reads > args.e2e_batch and int(rs.offsets[e_reads]) > share:
+            e_reads = max(args.e2e_batch, e_reads // 2)
+        h_bases = None
+        while h_bases is None:
+            e_bases = int(rs.offsets[e_reads])
+            try:
+                h_bases = torch.empty(e_bases, dtype=torch.uint8, pin_memory=True)
+            except RuntimeError:
+                if e_reads <= 1024:
+                    raise
+                e_reads //= 2
         h_bases.copy_(d_bases[:e_bases])
         h_offs = rs.offsets[:e_reads + 1].copy()
         torch.cuda.synchronize()
