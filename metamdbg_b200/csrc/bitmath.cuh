@@ -1,0 +1,78 @@
+// bitmath.cuh -- pure SIMD-in-register helpers of the sketch kernel (K1).  Host+device so that
+// tests/cpp/device_math_test.cu can check them on a CPU against naive loops; the kernel itself is in sketch.cu.
+#pragma once
+
+#include "common.cuh"
+
+namespace mdbg {
+
+// 0x80 in every byte of x that is non-zero (exact for arbitrary bytes)
+MDBG_HD uint32_t nonzero_bytes(uint32_t x) {
+    return (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
+}
+// four words of per-byte 0x80 flags -> 16-bit mask (bit 4q+b = byte b of word q)
+MDBG_HD uint32_t flags_to_mask16(uint32_t f0, uint32_t f1, uint32_t f2, uint32_t f3) {
+    // multiply gathers bits 7,15,23,31 into bits 28..31
+    const uint32_t a = (f0 * 0x00204081u) >> 28;
+    const uint32_t b = (f1 * 0x00204081u) >> 24;
+    const uint32_t c = (f2 * 0x00204081u) >> 20;
+    const uint32_t d = (f3 * 0x00204081u) >> 16;
+    return a | (b & 0xF0u) | (c & 0xF00u) | (d & 0xF000u);
+}
+
+// gather the 16 even bits of x into the low 16 bits
+MDBG_HD uint32_t even_bits16(uint32_t x) {
+    x &= 0x55555555u;
+    x = (x | (x >> 1)) & 0x33333333u;
+    x = (x | (x >> 2)) & 0x0F0F0F0Fu;
+    x = (x | (x >> 4)) & 0x00FF00FFu;
+    return (x | (x >> 8)) & 0xFFFFu;
+}
+
+template <int L>
+MDBG_HD uint32_t byte_of(const uint32_t (&W)[8], int t) {
+    return (W[t >> 2] >> (8 * (t & 3))) & 0xFFu;
+}
+
+// 4 base codes (one per byte, each < 4) -> 8 bits, first base most significant / least significant
+MDBG_HD uint32_t pack4_msb(uint32_t w) { return (w * 0x40100401u) >> 24; }
+MDBG_HD uint32_t pack4_lsb(uint32_t w) { return (w * 0x01041040u) >> 24; }
+
+// reverse complement of a 2L-bit l-mer value (A0 C1 T2 G3: complement = code ^ 2)
+template <int L>
+MDBG_HD uint32_t revcomp_lmer(uint32_t fwd) {
+    constexpr uint32_t MASK = (L < 16) ? ((1u << (2 * L)) - 1u) : 0xFFFFFFFFu;
+    uint32_t x = brev32(fwd ^ (0xAAAAAAAAu & MASK));
+    x = ((x & 0x55555555u) << 1) | ((x >> 1) & 0x55555555u);
+    return x >> (32 - 2 * L);
+}
+
+// Unrolled register path: 16 consecutive l-mers for this lane out of the
+// 32 ring bytes W (no invalid code present).  Returns the 16-bit CANDIDATE
+// mask (superset of the selected positions, see murmur_s1_u32); the forward
+// l-mer of the last candidate is left in sel_fwd.
+template <int L>
+MDBG_HD uint32_t roll16_fast(const uint32_t (&W)[8], uint32_t thr_hi_plus1, uint32_t& sel_fwd) {
+    constexpr uint32_t MASK = (L < 16) ? ((1u << (2 * L)) - 1u) : 0xFFFFFFFFu;
+    constexpr uint32_t INIT_MASK = (1u << (2 * (L - 1))) - 1u;      // L-1 <= 15 bases
+    // state after the first L-1 bases, built with two multiplies per 4 bases instead of L-1 roll steps
+    const uint32_t pf = (pack4_msb(W[0]) << 24) | (pack4_msb(W[1]) << 16) | (pack4_msb(W[2]) << 8) | pack4_msb(W[3]);
+    const uint32_t pr = pack4_lsb(W[0]) | (pack4_lsb(W[1]) << 8) | (pack4_lsb(W[2]) << 16) | (pack4_lsb(W[3]) << 24);
+    uint32_t fwd = pf >> (2 * (16 - (L - 1)));
+    uint32_t rc = ((pr & INIT_MASK) ^ (0xAAAAAAAAu & INIT_MASK)) << 2;
+    uint32_t sel = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const uint32_t c = byte_of<L>(W, L - 1 + j);
+        fwd = ((fwd << 2) | c) & MASK;
+        rc = (rc >> 2) | ((c ^ 2u) << (2 * L - 2));
+        const uint32_t s1 = murmur_s1_u32(min(fwd, rc));
+        if (s1 <= thr_hi_plus1) {
+            sel |= 1u << j;
+            sel_fwd = fwd;
+        }
+    }
+    return sel;
+}
+
+}  // namespace mdbg

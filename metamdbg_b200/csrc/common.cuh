@@ -4,14 +4,44 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Pure arithmetic helpers are host+device so that tests/cpp/device_math_test.cu can run them on a CPU (exhaustively
+// for the 32-bit candidate test); the device code is unchanged by this (same intrinsics under __CUDA_ARCH__).
+#define MDBG_HD __host__ __device__ __forceinline__
+
 namespace mdbg {
+
+MDBG_HD uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t s) {      // high word of (hi:lo) << s, s < 32
+#ifdef __CUDA_ARCH__
+    return __funnelshift_l(lo, hi, s);
+#else
+    return (uint32_t)((((uint64_t)hi << 32 | lo) << (s & 31)) >> 32);
+#endif
+}
+MDBG_HD uint32_t umulhi32(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+MDBG_HD uint32_t brev32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return __brev(x);
+#else
+    x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+    x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+    x = ((x >> 4) & 0x0F0F0F0Fu) | ((x & 0x0F0F0F0Fu) << 4);
+    x = ((x >> 8) & 0x00FF00FFu) | ((x & 0x00FF00FFu) << 8);
+    return (x >> 16) | (x << 16);
+#endif
+}
 
 // ------------------------------------------------------------------ MurmurHash3
 // Arithmetic of MurmurHash3_x64_128 (reference: src/utils/MurmurHash3.cpp:246-405).
 
-__device__ __forceinline__ uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+MDBG_HD uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
 
-__device__ __forceinline__ uint64_t fmix64(uint64_t k) {
+MDBG_HD uint64_t fmix64(uint64_t k) {
     k ^= k >> 33;
     k *= 0xff51afd7ed558ccdULL;
     k ^= k >> 33;
@@ -26,7 +56,7 @@ constexpr uint64_t MURMUR_C2 = 0x4cf5ad432745937fULL;
 // h1 of MurmurHash3_x64_128(&key, 8, seed=42): the 8-byte key takes the "tail"
 // branch only (case 8..1), no body block (MurmurHash3.cpp:246-325, call site
 // src/utils/kmer/Kmer.hpp:1421).
-__device__ __forceinline__ uint64_t murmur_h1_u64(uint64_t key) {
+MDBG_HD uint64_t murmur_h1_u64(uint64_t key) {
     uint64_t k1 = key * MURMUR_C1;
     k1 = rotl64(k1, 31);
     k1 *= MURMUR_C2;
@@ -55,25 +85,25 @@ __device__ __forceinline__ uint64_t murmur_h1_u64(uint64_t key) {
 //   s1 >  T_hi + 1            -> certainly not selected
 //   1 <= s1 < T_hi            -> certainly selected (sum_hi <= s1 < T_hi)
 //   otherwise (s1 in {0, T_hi, T_hi + 1}) -> undecided: callers run the exact murmur_h1_u64.
-__device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c) { return a * b + c; }
+MDBG_HD uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c) { return a * b + c; }
 
 // fmix64 up to its second multiply: returns the two words (plo, phi) of
 // ((k ^ k>>33) * 0xff51afd7ed558ccd) ^ (.. >> 33); t = hi >> 1 and m = hi * 0xed558ccd are
 // shared by A and B (same high word)
-__device__ __forceinline__ void fmix64_front(uint32_t lo, uint32_t t, uint32_t m, uint32_t& plo, uint32_t& phi) {
+MDBG_HD void fmix64_front(uint32_t lo, uint32_t t, uint32_t m, uint32_t& plo, uint32_t& phi) {
     lo ^= t;                                                   // k ^= k >> 33
     const uint64_t p = (uint64_t)lo * 0xed558ccdu;             // k *= 0xff51afd7ed558ccd
     phi = (uint32_t)(p >> 32) + mad_lo(lo, 0xff51afd7u, m);
     plo = (uint32_t)p ^ (phi >> 1);                            // k ^= k >> 33
 }
 
-__device__ __forceinline__ uint32_t murmur_s1_u32(uint32_t key) {
+MDBG_HD uint32_t murmur_s1_u32(uint32_t key) {
     // k1 = key * c1 ; k1 = rotl64(k1, 31) ; k1 *= c2
     uint64_t p = (uint64_t)key * 0x114253d5u;
     uint32_t lo = (uint32_t)p;
     uint32_t hi = mad_lo(key, 0x87c37b91u, (uint32_t)(p >> 32));
-    const uint32_t rlo = __funnelshift_l(hi, lo, 31);          // low word of (k1 << 31) | (k1 >> 33)
-    const uint32_t rhi = __funnelshift_l(lo, hi, 31);
+    const uint32_t rlo = funnel_l(hi, lo, 31);          // low word of (k1 << 31) | (k1 >> 33)
+    const uint32_t rhi = funnel_l(lo, hi, 31);
     p = (uint64_t)rlo * 0x2745937fu;
     hi = (uint32_t)(p >> 32) + mad_lo(rlo, 0x4cf5ad43u, rhi * 0x2745937fu);
     const uint32_t alo = ((uint32_t)p ^ 34u) + 34u;            // A (low word)
@@ -89,7 +119,7 @@ __device__ __forceinline__ uint32_t murmur_s1_u32(uint32_t key) {
     acc = mad_lo(plo_a, 0xc4ceb9feu, acc);
     acc = mad_lo(phi_b, 0x1a85ec53u, acc);
     acc = mad_lo(plo_b, 0xc4ceb9feu, acc);
-    const uint32_t s1 = acc + __umulhi(plo_a, 0x1a85ec53u) + __umulhi(plo_b, 0x1a85ec53u);
+    const uint32_t s1 = acc + umulhi32(plo_a, 0x1a85ec53u) + umulhi32(plo_b, 0x1a85ec53u);
     return (blo < 68u) ? 0u : s1;                              // 0 = "undecided, run the exact hash"
 }
 
@@ -97,7 +127,7 @@ __device__ __forceinline__ uint32_t murmur_s1_u32(uint32_t key) {
 // (src/Commons.hpp:941-969).  `get(i)` returns the i-th u32 of the normalized
 // vector.  h1 -> high 64 bits of the u128, h2 -> low 64 bits.
 template <typename Get>
-__device__ __forceinline__ void murmur128_u32vec(Get get, int k, uint64_t& o1, uint64_t& o2) {
+MDBG_HD void murmur128_u32vec(Get get, int k, uint64_t& o1, uint64_t& o2) {
     uint64_t h1 = 0, h2 = 0;
     const int nblocks = k >> 2;                      // 16-byte blocks = 4 u32
     for (int b = 0; b < nblocks; b++) {
@@ -141,7 +171,7 @@ __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v) {
 }
 
 // splitmix64 finaliser (synthetic-read generator only)
-__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+MDBG_HD uint64_t mix64(uint64_t x) {
     x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
     x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
     return x ^ (x >> 31);
