@@ -130,7 +130,10 @@ mdbg_status mdbg_ctx_kernel_time_ms(mdbg_ctx* ctx, int which, float* ms);
 /* Host reads: read r = bases[offsets[r] .. offsets[r+1]) (ASCII, as Read::_seq).
  * The batch is copied to the device, sketched, the CSR is copied back into
  * `out`, and the minimizer-space reads are appended to the context's device
- * store when append_to_store != 0. */
+ * store when append_to_store != 0.  offsets[0] must be 0, offsets must not
+ * decrease and a read must be shorter than 2^31 bases (MDBG_ERR_ARG otherwise;
+ * positions are u32 as upstream).  The device-buffer variants trust their
+ * offsets. */
 mdbg_status mdbg_sketch_batch(mdbg_ctx* ctx, const uint8_t* bases, const uint64_t* offsets,
                               uint32_t n_reads, int append_to_store, mdbg_sketch_out* out);
 /* Host batches without qualities cross PCIe 2-bit packed (worker threads + AVX2 inside the library, unpacked again

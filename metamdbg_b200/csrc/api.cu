@@ -586,6 +586,17 @@ mdbg_status mdbg_ctx_kernel_time_ms(mdbg_ctx* ctx, int which, float* ms) {
 static mdbg_status sketch_host_batch(mdbg_ctx* ctx, const uint8_t* bases, const uint8_t* quals, const uint64_t* offsets,
                                      uint32_t n_reads, uint64_t n_bases, int append, bool want_aux);
 
+// Host CSR offsets: start at 0, never decrease, and no read reaches 2^31 bases (positions are u32 and the candidate
+// list keeps a flag in bit 31).  A bad array would otherwise turn into out-of-range device addresses.
+static mdbg_status check_host_offsets(mdbg_ctx* ctx, const uint64_t* offsets, uint32_t n_reads) {
+    if (n_reads == 0) return MDBG_OK;
+    if (offsets[0] != 0) return fail(ctx, MDBG_ERR_ARG, "offsets[0] must be 0");
+    uint64_t bad = 0;
+    for (uint32_t r = 0; r < n_reads; r++) bad |= (offsets[r + 1] - offsets[r]) >> 31;      // wraps if decreasing
+    if (bad) return fail(ctx, MDBG_ERR_ARG, "offsets must be non-decreasing with reads shorter than 2^31 bases");
+    return MDBG_OK;
+}
+
 // ---- sketch -----------------------------------------------------------------------
 mdbg_status mdbg_sketch_batch_device(mdbg_ctx* ctx, const uint8_t* d_bases, const uint64_t* d_offsets,
                                      uint32_t n_reads, uint64_t n_bases, int append_to_store, mdbg_sketch_dev* out) {
@@ -665,8 +676,8 @@ mdbg_status mdbg_sketch_batch(mdbg_ctx* ctx, const uint8_t* bases, const uint64_
     if (!ctx) return MDBG_ERR_ARG;
     if (n_reads && (!bases || !offsets)) return fail(ctx, MDBG_ERR_ARG, "null host buffer");
     CK(cudaSetDevice(ctx->device));
+    CKS(check_host_offsets(ctx, offsets, n_reads));
     const uint64_t n_bases = n_reads ? offsets[n_reads] : 0;
-    if (n_reads && offsets[0] != 0) return fail(ctx, MDBG_ERR_ARG, "offsets[0] must be 0");
     CKS(ensure(ctx, ctx->d_bases, n_bases + 64));
     CKS(ensure(ctx, ctx->d_offsets, ((size_t)n_reads + 1) * 8));
     CKS(sketch_host_batch(ctx, bases, nullptr, offsets, n_reads, n_bases, append_to_store, false));
@@ -874,8 +885,8 @@ mdbg_status mdbg_sketch_batch_q(mdbg_ctx* ctx, const uint8_t* bases, const uint8
     if (!ctx) return MDBG_ERR_ARG;
     if (n_reads && (!bases || !offsets)) return fail(ctx, MDBG_ERR_ARG, "null host buffer");
     CK(cudaSetDevice(ctx->device));
+    CKS(check_host_offsets(ctx, offsets, n_reads));
     const uint64_t n_bases = n_reads ? offsets[n_reads] : 0;
-    if (n_reads && offsets[0] != 0) return fail(ctx, MDBG_ERR_ARG, "offsets[0] must be 0");
     CKS(ensure(ctx, ctx->d_bases, n_bases + 64));
     CKS(ensure(ctx, ctx->d_offsets, ((size_t)n_reads + 1) * 8));
     cudaStream_t s = ctx->stream;
@@ -935,6 +946,9 @@ mdbg_status mdbg_store_append(mdbg_ctx* ctx, const uint32_t* minimizers, const u
     if (!ctx) return MDBG_ERR_ARG;
     if (n_reads == 0) return MDBG_OK;
     if (!min_offsets) return fail(ctx, MDBG_ERR_ARG, "null min_offsets");
+    for (uint32_t r = 0; r < n_reads; r++)
+        if (min_offsets[r + 1] < min_offsets[r]) return fail(ctx, MDBG_ERR_ARG, "min_offsets must be non-decreasing");
+    if (min_offsets[n_reads] > min_offsets[0] && !minimizers) return fail(ctx, MDBG_ERR_ARG, "null minimizers");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     const uint64_t total = min_offsets[n_reads] - min_offsets[0];

@@ -542,3 +542,62 @@ def test_sketch_extreme_densities(built, oracle, dens):
         if dens == 0.0:
             assert len(sk.minimizers) == 0
         eng.close()
+
+
+def test_sketch_arbitrary_bytes(built, oracle):
+    """Reads of arbitrary bytes 0..255 (zero and >= 0x80 included): the keep-mask compares raw bytes, the base code
+    is (c >> 1) & 3 with bit 3 = invalid for ANY byte (Kmer.hpp:505-556), host buffers take the ASCII route for
+    such reads even when 2-bit packing is on.  Both transfer modes, both HPC modes, fast (l=15) and generic l."""
+    rng = np.random.default_rng(21)
+    reads = []
+    for i in range(60):
+        n = int(rng.integers(0, 3000))
+        kind = i % 4
+        if kind == 0:
+            s = rng.integers(0, 256, n).astype(np.uint8)
+        elif kind == 1:                                         # runs of arbitrary bytes (HPC on raw bytes)
+            runs = rng.geometric(0.4, max(1, n // 2))
+            s = np.repeat(rng.integers(0, 256, len(runs)).astype(np.uint8), runs)[:n]
+        elif kind == 2:                                         # ACGT with valid-coded non-ACGT bytes ('a', 'e', 0x00 ...)
+            s = rng.choice(np.frombuffer(b"ACGTacgtBEDF\x00\x02\x04\x06\xe1\xe3", np.uint8), n)
+        else:
+            s = rng.choice(np.frombuffer(b"ACGT", np.uint8), n)
+        reads.append(s.tobytes())
+    bases = np.frombuffer(b"".join(reads), np.uint8).copy()
+    offs = np.zeros(len(reads) + 1, np.uint64)
+    offs[1:] = np.cumsum([len(r) for r in reads])
+    for l, dens in ((15, 0.05), (11, 0.02)):
+        for hpc in (True, False):
+            want = oracle.sketch_batch(bases, offs, l, dens, hpc)
+            assert int(want[0][-1]) > 50
+            for packing in (0, 1):
+                eng = engine(l, dens, hpc)
+                eng.set_host_packing(packing)
+                sk = eng.sketch_batch(bases, offs)
+                assert_sketch_equal(sk, *want, tag=f"l={l} hpc={hpc} packing={packing}")
+                eng.close()
+
+
+def test_bad_host_arrays_are_rejected(built):
+    """Error behaviour of the boundary: malformed CSR arrays come back as MDBG_ERR_ARG (status 2) with a message,
+    nothing is launched, and the context stays usable."""
+    from metamdbg_b200.engine import MdbgError
+    eng = engine(15, 0.05, True)
+    bases = np.frombuffer(b"ACGTTGCAAGGCTTAACCGGTTAACG" * 8, np.uint8).copy()
+    good = np.array([0, 100, len(bases)], np.uint64)
+    launches0 = eng.kernel_launches
+    for offs in (np.array([4, 100, 200], np.uint64),           # does not start at 0
+                 np.array([0, 150, 100], np.uint64),           # decreasing
+                 np.array([0, 1 << 31, (1 << 31) + 5], np.uint64)):   # a read of 2^31 bases
+        with pytest.raises(MdbgError) as ei:
+            eng.sketch_batch(bases, offs)
+        assert ei.value.status == 2 and "offsets" in str(ei.value)
+        with pytest.raises(MdbgError):
+            eng.sketch_batch_q(bases, None, offs)
+    with pytest.raises(MdbgError) as ei:
+        eng.store_append(np.arange(10, dtype=np.uint32), np.array([0, 7, 3], np.uint64))
+    assert ei.value.status == 2 and "non-decreasing" in str(ei.value)
+    assert eng.kernel_launches == launches0
+    sk = eng.sketch_batch(bases, good)                          # still works afterwards
+    assert sk.n_reads == 2
+    eng.close()
