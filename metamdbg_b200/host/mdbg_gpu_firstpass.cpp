@@ -66,14 +66,17 @@ int main(int argc, char** argv) {
                       << counter._checksum << std::endl;
             return 0;
         }
-        std::vector<uint32_t> readLengths;
         ReadDataWriter writer(outDir + "/read_data_init.txt", l);     // readSelection's record file + read_stats.txt
-        GpuReadSelectionFunctor functor(ctx, [&](const ReadMinimizers& r) {
-            readLengths.push_back(r.readLength);
-            writer.write(r);
-        }, batchMbp << 20, /*sideOutputs=*/true);
-        gzFile f = gzopen(input.c_str(), "rb");
-        if (!f) throw std::runtime_error("cannot open " + input);
+        GpuReadSelectionFunctor functor(ctx, [&](const ReadMinimizers& r) { writer.write(r); }, batchMbp << 20,
+                                        /*sideOutputs=*/true);
+        struct GzIn {                                    // closes on every exit path
+            gzFile f;
+            explicit GzIn(const std::string& name) : f(gzopen(name.c_str(), "rb")) {
+                if (!f) throw std::runtime_error("cannot open " + name);
+            }
+            ~GzIn() { gzclose(f); }
+        } gz(input);
+        gzFile f = gz.f;
         std::string line;
         Read read;
         uint64_t index = 0;
@@ -98,20 +101,10 @@ int main(int argc, char** argv) {
                 throw std::runtime_error("unrecognised record: " + line.substr(0, 40));
             }
         }
-        gzclose(f);
         functor.flush();
         writer.close();
         writer.writeReadStats(outDir + "/read_stats.txt");
-        if (lastK == 0) {                                // Commons::computeLastK with the N50 (Commons.hpp:1726-1741)
-            std::vector<uint32_t> s = readLengths;
-            std::sort(s.begin(), s.end(), std::greater<uint32_t>());
-            uint64_t total = 0, acc = 0;
-            for (uint32_t x : s) total += x;
-            uint32_t n50 = s.empty() ? 0 : s.back();
-            for (uint32_t x : s) { acc += x; if (acc >= total / 2) { n50 = x; break; } }
-            lastK = (uint32_t)(n50 * density * 2.0f);
-            if (lastK < 6) lastK = 6;
-        }
+        if (lastK == 0) lastK = computeLastK(density, writer.n50(), 4);   // on read_stats' N50, as upstream
         uint64_t changed = purgePalindromesAndWrite(ctx, 4, lastK, outDir + "/read_data_corrected.txt");
         GpuKminmerCounter counter(ctx, k, minAb);
         counter.execute(outDir + "/kminmerData_min.txt", outDir + "/kminmerData_abundance.txt");

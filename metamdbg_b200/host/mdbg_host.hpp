@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <functional>
 #include <stdexcept>
 #include <string>
@@ -37,6 +38,34 @@ struct Read {
 inline void check(mdbg_ctx* ctx, mdbg_status st, const char* what) {
     if (st != MDBG_OK) throw std::runtime_error(std::string(what) + ": " + mdbg_last_error(ctx));
 }
+
+// stdio handle that closes itself (read or write mode); put() throws on a short write (disk full, quota) instead of leaving a truncated
+// read_data / kminmerData file behind for the next stage to misparse
+class File {
+public:
+    File() = default;
+    explicit File(const std::string& filename, const char* mode = "wb") : _name(filename) {
+        _f = fopen(filename.c_str(), mode);
+        if (!_f) throw std::runtime_error("cannot open " + filename);
+    }
+    ~File() { if (_f) fclose(_f); }
+    File(const File&) = delete;
+    File& operator=(const File&) = delete;
+    FILE* get() const { return _f; }
+    void put(const void* data, size_t size, size_t count) {
+        if (count && fwrite(data, size, count, _f) != count) throw std::runtime_error("write failed: " + _name);
+    }
+    void close() {
+        if (!_f) return;
+        const int rc = fclose(_f);
+        _f = nullptr;
+        if (rc != 0) throw std::runtime_error("close failed: " + _name);
+    }
+
+private:
+    FILE* _f = nullptr;
+    std::string _name;
+};
 
 class Context {
 public:
@@ -159,23 +188,20 @@ private:
 // u64 nbSelectedMinimizers).  Records arrive in input order, so no re-ordering queue is needed.
 class ReadDataWriter {
 public:
-    ReadDataWriter(const std::string& filename, uint32_t minimizerSize) : _minimizerSize(minimizerSize) {
-        _f = fopen(filename.c_str(), "wb");
-        if (!_f) throw std::runtime_error("cannot open " + filename);
-    }
-    ~ReadDataWriter() { if (_f) fclose(_f); }
+    ReadDataWriter(const std::string& filename, uint32_t minimizerSize) : _f(filename), _minimizerSize(minimizerSize) {}
 
     void write(const ReadMinimizers& r) {
         const uint32_t size = r.n;
         const uint8_t isCircular = 0;
-        fwrite(&size, 4, 1, _f);
-        fwrite(&isCircular, 1, 1, _f);
-        fwrite(r.minimizers, 4, size, _f);
-        fwrite(r.positions, 4, size, _f);
-        fwrite(r.directions, 1, size, _f);
-        fwrite(r.qualities, 1, size, _f);
-        fwrite(&r.meanReadQuality, 4, 1, _f);
-        fwrite(&r.readLength, 4, 1, _f);
+        if (size && !r.qualities) throw std::runtime_error("ReadDataWriter needs the side outputs (sideOutputs = true)");
+        _f.put(&size, 4, 1);
+        _f.put(&isCircular, 1, 1);
+        _f.put(r.minimizers, 4, size);
+        _f.put(r.positions, 4, size);
+        _f.put(r.directions, 1, size);
+        _f.put(r.qualities, 1, size);
+        _f.put(&r.meanReadQuality, 4, 1);
+        _f.put(&r.readLength, 4, 1);
         _allReadSizes.push_back(r.readLength);
         _nbSelectedMinimizers += size;
         _nbKmers += (uint64_t)r.readLength - _minimizerSize + 1;     // ReadSelection.hpp:474 (unsigned wrap kept)
@@ -186,7 +212,7 @@ public:
         }
     }
 
-    void close() { if (_f) { fclose(_f); _f = nullptr; } }
+    void close() { _f.close(); }
 
     static uint32_t computeN50(std::vector<uint32_t> lengths) {     // Utils::computeN50, Commons.hpp:2291-2322
         if (lengths.empty()) return 0;
@@ -203,35 +229,45 @@ public:
         return n50;
     }
 
+    static uint64_t computeMeanLength(const std::vector<uint32_t>& lengths) {   // Utils::computeMeanLength, Commons.hpp:2324-2336
+        long double sum = 0, cnt = 0;
+        for (uint32_t x : lengths) { sum += x; cnt += 1; }
+        return (uint64_t)(sum / cnt);                                 // 0/0 -> NaN -> conversion as upstream
+    }
+
     uint32_t n50() const { return computeN50(_allReadSizes); }
 
     void writeReadStats(const std::string& filename) {
         const uint64_t nbReads = _allReadSizes.size();
         const uint32_t n50v = n50();
-        long double sum = 0, cnt = 0;                                 // Utils::computeMeanLength, Commons.hpp:2324-2336
-        for (uint32_t x : _allReadSizes) { sum += x; cnt += 1; }
-        const uint32_t meanLength = (uint32_t)(uint64_t)(sum / cnt);
+        const uint32_t meanLength = (uint32_t)computeMeanLength(_allReadSizes);
         const float minimizerDensity = (long double)_nbSelectedMinimizers / (long double)_nbKmers;
         const float averageQuality = _readQualitySum / _readQualityN;
-        FILE* f = fopen(filename.c_str(), "wb");
-        if (!f) throw std::runtime_error("cannot open " + filename);
-        fwrite(&nbReads, 8, 1, f);
-        fwrite(&n50v, 4, 1, f);
-        fwrite(&minimizerDensity, 4, 1, f);
-        fwrite(&_nbBases, 8, 1, f);
-        fwrite(&averageQuality, 4, 1, f);
-        fwrite(&meanLength, 4, 1, f);
-        fwrite(&_nbSelectedMinimizers, 8, 1, f);
-        fclose(f);
+        File f(filename);
+        f.put(&nbReads, 8, 1);
+        f.put(&n50v, 4, 1);
+        f.put(&minimizerDensity, 4, 1);
+        f.put(&_nbBases, 8, 1);
+        f.put(&averageQuality, 4, 1);
+        f.put(&meanLength, 4, 1);
+        f.put(&_nbSelectedMinimizers, 8, 1);
+        f.close();
     }
 
 private:
-    FILE* _f = nullptr;
+    File _f;
     uint32_t _minimizerSize;
     std::vector<uint32_t> _allReadSizes;
     uint64_t _nbSelectedMinimizers = 0, _nbKmers = 0, _nbBases = 0;
     long double _readQualitySum = 0, _readQualityN = 0;
 };
+
+// Commons::computeLastK (Commons.hpp:1726-1741) as ReadSelection::purgePalindromes calls it (ReadSelection.hpp:1376,
+// maxK = 0): size_t * float * 2.0f truncated, at least firstK + 2.
+inline uint32_t computeLastK(float minimizerDensityAssembly, size_t n50ReadLength, size_t firstK) {
+    const size_t lastK = n50ReadLength * minimizerDensityAssembly * 2.0f;
+    return (uint32_t)std::max(lastK, firstK + 2);
+}
 
 // ReadSelection::purgePalindromes + the read_data_corrected.txt writer.
 inline uint64_t purgePalindromesAndWrite(Context& ctx, uint32_t firstK, uint32_t lastK, const std::string& filename) {
@@ -242,24 +278,23 @@ inline uint64_t purgePalindromesAndWrite(Context& ctx, uint32_t firstK, uint32_t
     std::vector<uint64_t> offs(nReads + 1);
     std::vector<uint32_t> mins(nMins + 1);
     check(ctx.get(), mdbg_store_fetch(ctx.get(), offs.data(), mins.data()), "mdbg_store_fetch");
-    FILE* f = fopen(filename.c_str(), "wb");
-    if (!f) throw std::runtime_error("cannot open " + filename);
+    File f(filename);
     for (uint64_t r = 0; r < nReads; r++) {
         const uint32_t size = (uint32_t)(offs[r + 1] - offs[r]);
         const uint8_t isCircular = 0;                    // CONTIG_LINEAR
-        fwrite(&size, sizeof size, 1, f);
-        fwrite(&isCircular, 1, 1, f);
-        fwrite(mins.data() + offs[r], sizeof(uint32_t), size, f);
+        f.put(&size, sizeof size, 1);
+        f.put(&isCircular, 1, 1);
+        f.put(mins.data() + offs[r], sizeof(uint32_t), size);
     }
-    fclose(f);
+    f.close();
     return changed;
 }
 
 // KminmerParserParallel's input side (src/Commons.hpp:7367-7495, records u32 n, u8 isCircular, u32[n]): load a
 // read_data_corrected.txt (or unitig_data.txt) into the context's device store, 256 MB of minimizers at a time.
 inline uint64_t loadReadData(Context& ctx, const std::string& filename) {
-    FILE* f = fopen(filename.c_str(), "rb");
-    if (!f) throw std::runtime_error("cannot open " + filename);
+    File in(filename, "rb");
+    FILE* f = in.get();
     std::vector<uint32_t> mins;
     std::vector<uint64_t> offs{0};
     uint64_t nReads = 0;
@@ -282,7 +317,6 @@ inline uint64_t loadReadData(Context& ctx, const std::string& filename) {
         nReads++;
         if (mins.size() > (size_t(64) << 20)) flush();
     }
-    fclose(f);
     flush();
     return nReads;
 }
@@ -302,16 +336,16 @@ public:
         if (_minAbundance <= 1) check(_ctx.get(), mdbg_count_rescue(_ctx.get(), &_nbReadsRescued), "mdbg_count_rescue");
         mdbg_table_out t{};
         check(_ctx.get(), mdbg_count_finalize(_ctx.get(), _minAbundance, &t), "mdbg_count_finalize");
-        FILE* fk = fopen(kminmerFile.c_str(), "wb");
-        FILE* fa = fopen(abundanceFile.c_str(), "wb");
-        if (!fk || !fa) throw std::runtime_error("cannot open output files");
-        fwrite(t.kminmers, sizeof(uint32_t), (size_t)t.n_entries * _k, fk);
+        File fk(kminmerFile), fa(abundanceFile);
+        fk.put(t.kminmers, sizeof(uint32_t), (size_t)t.n_entries * _k);
+        std::vector<unsigned char> rec((size_t)t.n_entries * 20);     // 20-byte records, written in one go
         for (uint64_t i = 0; i < t.n_entries; i++) {
-            fwrite(t.hashes + 2 * i, 16, 1, fa);         // u128 little-endian: low = Murmur h2, high = h1
-            fwrite(t.abundances + i, 4, 1, fa);
+            memcpy(&rec[i * 20], t.hashes + 2 * i, 16);    // u128 little-endian: low = Murmur h2, high = h1
+            memcpy(&rec[i * 20 + 16], t.abundances + i, 4);
         }
-        fclose(fk);
-        fclose(fa);
+        fa.put(rec.data(), 20, (size_t)t.n_entries);
+        fk.close();
+        fa.close();
         _nbSolidKminmers = t.n_entries - t.n_rescued;
         _nbRescuedKminmers = t.n_rescued;
         _nbKminmers = t.n_instances;

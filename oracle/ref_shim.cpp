@@ -392,6 +392,18 @@ int ref_read_selection(const char* input_list, const char* dir, int l, float den
     return 0;
 }
 
+// Utils::computeN50 / computeMeanLength (Commons.hpp:2291-2336) and Commons::computeLastK (Commons.hpp:1726-1741):
+// the scalars ReadSelection derives from the read lengths (read_stats.txt, purgePalindromes' lastK)
+uint64_t ref_compute_n50(const uint32_t* lengths, size_t n) {
+    return Utils::computeN50(std::vector<u_int32_t>(lengths, lengths + n));
+}
+uint64_t ref_compute_mean_length(const uint32_t* lengths, size_t n) {
+    return Utils::computeMeanLength(std::vector<u_int32_t>(lengths, lengths + n));
+}
+int ref_compute_last_k(float density, size_t n50, size_t first_k, size_t max_k) {
+    return Commons::computeLastK(density, n50, first_k, max_k);
+}
+
 int ref_max_threads() { return omp_get_max_threads(); }
 
 void ref_free(void* p) { free(p); }

@@ -83,3 +83,21 @@ def test_host_packer_cpp(tmp_path):
                     os.path.join(ROOT, "tests", "cpp", "pack_host_test.cpp"), obj], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
+
+
+@pytest.mark.ref
+def test_host_glue_scalars_vs_reference(tmp_path):
+    """mdbg_host.hpp's read_stats scalars (N50, mean length, purge lastK) against the reference's own
+    Utils::computeN50 / computeMeanLength / Commons::computeLastK, and the file helper's error paths."""
+    from oracle import pyoracle
+    pyoracle.build()
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.exists(os.path.join(ref_dir, "libmdbg_ref.so")):
+        pytest.skip("oracle/_ref not built")
+    exe = tmp_path / "host_glue_test"
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-I" + os.path.join(ROOT, "include"),
+                    "-I" + os.path.join(ROOT, "metamdbg_b200", "host"), "-o", str(exe),
+                    os.path.join(ROOT, "tests", "cpp", "host_glue_test.cpp"), "-L" + ref_dir, "-lmdbg_ref",
+                    "-Wl,-rpath," + ref_dir], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout + out.stderr
