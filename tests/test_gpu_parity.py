@@ -545,21 +545,23 @@ def test_sketch_extreme_densities(built, oracle, dens):
 
 
 def test_sketch_arbitrary_bytes(built, oracle):
-    """Reads of arbitrary bytes 0..255 (zero and >= 0x80 included): the keep-mask compares raw bytes, the base code
-    is (c >> 1) & 3 with bit 3 = invalid for ANY byte (Kmer.hpp:505-556), host buffers take the ASCII route for
-    such reads even when 2-bit packing is on.  Both transfer modes, both HPC modes, fast (l=15) and generic l."""
+    """Reads of arbitrary bytes 1..255 (>= 0x80 included): the keep-mask compares raw bytes, the base code is
+    (c >> 1) & 3 with bit 3 = invalid for ANY byte (Kmer.hpp:505-556), host buffers take the ASCII route for such
+    reads even when 2-bit packing is on.  Both transfer modes, both HPC modes, fast (l=15) and generic l.
+    NUL is excluded: reads are NUL-free by contract (the reference's non-HPC branch builds a
+    C string and would stop at it, its FASTQ parser never produces one)."""
     rng = np.random.default_rng(21)
     reads = []
     for i in range(60):
         n = int(rng.integers(0, 3000))
         kind = i % 4
         if kind == 0:
-            s = rng.integers(0, 256, n).astype(np.uint8)
+            s = rng.integers(1, 256, n).astype(np.uint8)
         elif kind == 1:                                         # runs of arbitrary bytes (HPC on raw bytes)
             runs = rng.geometric(0.4, max(1, n // 2))
-            s = np.repeat(rng.integers(0, 256, len(runs)).astype(np.uint8), runs)[:n]
-        elif kind == 2:                                         # ACGT with valid-coded non-ACGT bytes ('a', 'e', 0x00 ...)
-            s = rng.choice(np.frombuffer(b"ACGTacgtBEDF\x00\x02\x04\x06\xe1\xe3", np.uint8), n)
+            s = np.repeat(rng.integers(1, 256, len(runs)).astype(np.uint8), runs)[:n]
+        elif kind == 2:                                         # ACGT with valid-coded non-ACGT bytes ('a', 'e', 0x02 ...)
+            s = rng.choice(np.frombuffer(b"ACGTacgtBEDF\x02\x04\x06\xe1\xe3", np.uint8), n)
         else:
             s = rng.choice(np.frombuffer(b"ACGT", np.uint8), n)
         reads.append(s.tobytes())
