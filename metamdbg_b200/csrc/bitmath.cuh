@@ -52,7 +52,7 @@ MDBG_HD uint32_t revcomp_lmer(uint32_t fwd) {
 // mask (superset of the selected positions, see murmur_s1_u32); the forward
 // l-mer of the last candidate is left in sel_fwd.
 template <int L>
-MDBG_HD uint32_t roll16_fast(const uint32_t (&W)[8], uint32_t thr_hi_plus1, uint32_t& sel_fwd) {
+MDBG_HD uint32_t roll16_fast(const uint32_t (&W)[8], uint32_t thr_cand, uint32_t& sel_fwd) {
     constexpr uint32_t MASK = (L < 16) ? ((1u << (2 * L)) - 1u) : 0xFFFFFFFFu;
     constexpr uint32_t INIT_MASK = (1u << (2 * (L - 1))) - 1u;      // L-1 <= 15 bases
     // state after the first L-1 bases, built with two multiplies per 4 bases instead of L-1 roll steps
@@ -67,7 +67,7 @@ MDBG_HD uint32_t roll16_fast(const uint32_t (&W)[8], uint32_t thr_hi_plus1, uint
         fwd = ((fwd << 2) | c) & MASK;
         rc = (rc >> 2) | ((c ^ 2u) << (2 * L - 2));
         const uint32_t s1 = murmur_s1_u32(min(fwd, rc));
-        if (s1 <= thr_hi_plus1) {
+        if (s1 <= thr_cand) {
             sel |= 1u << j;
             sel_fwd = fwd;
         }

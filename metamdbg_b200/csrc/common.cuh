@@ -74,18 +74,28 @@ MDBG_HD uint64_t murmur_h1_u64(uint64_t key) {
 //   h1 + h2 = fmix64(A) + fmix64(B),  A = (k1 ^ 34) + 34,  B = A + 34
 //   (seed 42, len 8: h1 = 42 ^ k1 ^ 8, h2 = 42 ^ 8, then h1 += h2, h2 += h1).
 //
-// Only the HIGH words of the two fmix64 results are formed: with
-// s0 = hi(fmix(A)) + hi(fmix(B)) (mod 2^32) the true high word of the sum is s0
-// or s0 + 1 (carry out of the low words), so "hash <= T" implies s0 <= T_hi or
-// s0 == 0xFFFFFFFF, i.e. (s0 + 1) <= T_hi + 1 in unsigned arithmetic.  The two
-// +34 additions are done on the low word only; the 2^-26-rare case where one of
-// them carries into the high word is detected (B_lo < 68) and reported as s1 = 0.
+// Only the HIGH words of the two fmix64 results are formed.  With s0 = hi(fmix(A)) + hi(fmix(B)) (mod 2^32) the
+// true high word of the sum is s0 or s0 + 1 (carry out of the low words).  murmur_s1_u32 forms s' = s0 or s0 + 1
+// (its low x low partial products are accumulated in one 64-bit multiply-add, whose own low-word carry is not the
+// exact sum's) and returns s1 = s' + 1 (mod 2^32), so that
 //
-// murmur_s1_u32 returns s1 = s0 + 1 (or 0).  With T_hi = threshold >> 32:
-//   s1 >  T_hi + 1            -> certainly not selected
-//   1 <= s1 < T_hi            -> certainly selected (sum_hi <= s1 < T_hi)
-//   otherwise (s1 in {0, T_hi, T_hi + 1}) -> undecided: callers run the exact murmur_h1_u64.
-MDBG_HD uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c) { return a * b + c; }
+//   hash <= T   implies   s1 <= T_hi + S1_SLACK      (unsigned, T_hi = T >> 32, when T_hi + S1_SLACK does not wrap)
+//
+// including the wrap case s0 = 0xFFFFFFFF with a carry (true high word 0, s1 in {0, 1}).  The two +34 additions
+// are done on the low word only; the 2^-26-rare case where one of them carries into the high word is detected
+// (B_lo < 68) and reported as s1 = 0, which is always a candidate.  Callers confirm every candidate with the exact
+// murmur_h1_u64 (tests/cpp/device_math_test.cu walks all 2^32 keys: no selected key is ever rejected).
+constexpr uint32_t S1_SLACK = 2;
+
+MDBG_HD uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c) {
+#ifdef __CUDA_ARCH__
+    uint32_t d;                                                  // pinned: NVVM would re-associate a * b + c
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+#else
+    return a * b + c;
+#endif
+}
 
 // fmix64 up to its second multiply: returns the two words (plo, phi) of
 // ((k ^ k>>33) * 0xff51afd7ed558ccd) ^ (.. >> 33); t = hi >> 1 and m = hi * 0xed558ccd are
@@ -105,7 +115,7 @@ MDBG_HD uint32_t murmur_s1_u32(uint32_t key) {
     const uint32_t rlo = funnel_l(hi, lo, 31);          // low word of (k1 << 31) | (k1 >> 33)
     const uint32_t rhi = funnel_l(lo, hi, 31);
     p = (uint64_t)rlo * 0x2745937fu;
-    hi = (uint32_t)(p >> 32) + mad_lo(rlo, 0x4cf5ad43u, rhi * 0x2745937fu);
+    hi = mad_lo(rlo, 0x4cf5ad43u, mad_lo(rhi, 0x2745937fu, (uint32_t)(p >> 32)));
     const uint32_t alo = ((uint32_t)p ^ 34u) + 34u;            // A (low word)
     const uint32_t blo = alo + 34u;                            // B (low word)
     const uint32_t t = hi >> 1;
@@ -113,13 +123,21 @@ MDBG_HD uint32_t murmur_s1_u32(uint32_t key) {
     uint32_t plo_a, phi_a, plo_b, phi_b;
     fmix64_front(alo, t, m, plo_a, phi_a);
     fmix64_front(blo, t, m, plo_b, phi_b);
-    // high words of k * 0xc4ceb9fe1a85ec53 for A and B, summed (+1): the final k ^= k >> 33
-    // only changes the low word
-    uint32_t acc = mad_lo(phi_a, 0x1a85ec53u, 1u);
+    // high words of k * 0xc4ceb9fe1a85ec53 for A and B, summed; the final k ^= k >> 33 only changes the low word.
+    // The two low x low products are accumulated as one 64-bit multiply-add, so their high words arrive together
+    // with a carry of the low words that the exact sum may or may not have: s' is s0 or s0 + 1.
+#ifdef __CUDA_ARCH__
+    uint32_t ll_lo, ll_hi;                                     // pinned as mul.wide + mad.wide on one register pair
+    asm("{\n\t.reg .b64 q;\n\tmul.wide.u32 q, %2, %4;\n\tmad.wide.u32 q, %3, %4, q;\n\tmov.b64 {%0, %1}, q;\n\t}"
+        : "=r"(ll_lo), "=r"(ll_hi) : "r"(plo_a), "r"(plo_b), "r"(0x1a85ec53u));
+#else
+    const uint32_t ll_hi = (uint32_t)(((uint64_t)plo_b * 0x1a85ec53u + (uint64_t)plo_a * 0x1a85ec53u) >> 32);
+#endif
+    uint32_t acc = mad_lo(phi_a, 0x1a85ec53u, ll_hi);
     acc = mad_lo(plo_a, 0xc4ceb9feu, acc);
     acc = mad_lo(phi_b, 0x1a85ec53u, acc);
     acc = mad_lo(plo_b, 0xc4ceb9feu, acc);
-    const uint32_t s1 = acc + umulhi32(plo_a, 0x1a85ec53u) + umulhi32(plo_b, 0x1a85ec53u);
+    const uint32_t s1 = acc + 1u;
     return (blo < 68u) ? 0u : s1;                              // 0 = "undecided, run the exact hash"
 }
 

@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sketch_kernel(const Sketch
     uint2* cand = cand_all[threadIdx.x >> 5];
     uint32_t n_list = 0;
     const uint32_t l = a.l;
-    const uint32_t thr_hi_plus1 = (uint32_t)(a.threshold >> 32) + 1u;   // 0 (overflow) disables the fast path
+    const uint32_t thr_cand = (uint32_t)(a.threshold >> 32) + S1_SLACK;   // wrapped (< S1_SLACK) disables the fast path
 
     for (;;) {
         uint32_t r = 0;
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sketch_kernel(const Sketch
                     W[4] = u1.x; W[5] = u1.y; W[6] = u1.z; W[7] = u1.w;
                 }
                 const uint32_t inv = (W[0] | W[1] | W[2] | W[3] | W[4] | W[5] | W[6] | W[7]) & 0x04040404u;
-                const bool fast = (L_FAST != 0) && (l == (uint32_t)L_FAST) && thr_hi_plus1 != 0 &&
+                const bool fast = (L_FAST != 0) && (l == (uint32_t)L_FAST) && thr_cand >= S1_SLACK &&
                                   !__any_sync(0xffffffffu, inv != 0);
 
                 uint32_t sel, sel_fwd = 0;
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sketch_kernel(const Sketch
                 if (a.select_none) {
                     sel = 0;
                 } else if (fast) {
-                    sel = roll16_fast<(L_FAST ? L_FAST : 15)>(W, thr_hi_plus1, sel_fwd);
+                    sel = roll16_fast<(L_FAST ? L_FAST : 15)>(W, thr_cand, sel_fwd);
                     regs_ok = (valid_bits == 0xFFFFu);
                     sel &= valid_bits;
                 } else {

