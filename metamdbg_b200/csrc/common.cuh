@@ -17,6 +17,13 @@ MDBG_HD uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t s) {      // high w
     return (uint32_t)((((uint64_t)hi << 32 | lo) << (s & 31)) >> 32);
 #endif
 }
+MDBG_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) {      // low word of (hi:lo) >> s, s < 32
+#ifdef __CUDA_ARCH__
+    return __funnelshift_r(lo, hi, s);
+#else
+    return (uint32_t)(((uint64_t)hi << 32 | lo) >> (s & 31));
+#endif
+}
 MDBG_HD uint32_t umulhi32(uint32_t a, uint32_t b) {
 #ifdef __CUDA_ARCH__
     return __umulhi(a, b);
@@ -82,10 +89,12 @@ MDBG_HD uint64_t murmur_h1_u64(uint64_t key) {
 //   hash <= T   implies   s1 <= T_hi + S1_SLACK      (unsigned, T_hi = T >> 32, when T_hi + S1_SLACK does not wrap)
 //
 // including the wrap case s0 = 0xFFFFFFFF with a carry (true high word 0, s1 in {0, 1}).  The two +34 additions
-// are done on the low word only; the 2^-26-rare case where one of them carries into the high word is detected
-// (B_lo < 68) and reported as s1 = 0, which is always a candidate.  Callers confirm every candidate with the exact
-// murmur_h1_u64 (tests/cpp/device_math_test.cu walks all 2^32 keys: no selected key is ever rejected).
+// are done on the low word only; the 2^-26-rare case where one of them carries into the high word makes s1
+// meaningless and is reported through `risk`: the caller keeps risk = max(risk, ...) over as many keys as it
+// likes and must treat ALL of them as candidates when risk >= S1_RISK.  Callers confirm every candidate with the
+// exact murmur_h1_u64 (tests/cpp/device_math_test.cu walks all 2^32 keys: no selected key is ever rejected).
 constexpr uint32_t S1_SLACK = 2;
+constexpr uint32_t S1_RISK = 0xFFFFFFBCu;                      // (k1_lo ^ 34) + 68 wraps
 
 MDBG_HD uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c) {
 #ifdef __CUDA_ARCH__
@@ -107,7 +116,7 @@ MDBG_HD void fmix64_front(uint32_t lo, uint32_t t, uint32_t m, uint32_t& plo, ui
     plo = (uint32_t)p ^ (phi >> 1);                            // k ^= k >> 33
 }
 
-MDBG_HD uint32_t murmur_s1_u32(uint32_t key) {
+MDBG_HD uint32_t murmur_s1_u32(uint32_t key, uint32_t& risk) {
     // k1 = key * c1 ; k1 = rotl64(k1, 31) ; k1 *= c2
     uint64_t p = (uint64_t)key * 0x114253d5u;
     uint32_t lo = (uint32_t)p;
@@ -116,8 +125,10 @@ MDBG_HD uint32_t murmur_s1_u32(uint32_t key) {
     const uint32_t rhi = funnel_l(lo, hi, 31);
     p = (uint64_t)rlo * 0x2745937fu;
     hi = mad_lo(rlo, 0x4cf5ad43u, mad_lo(rhi, 0x2745937fu, (uint32_t)(p >> 32)));
-    const uint32_t alo = ((uint32_t)p ^ 34u) + 34u;            // A (low word)
-    const uint32_t blo = alo + 34u;                            // B (low word)
+    const uint32_t x34 = (uint32_t)p ^ 34u;
+    risk = max(risk, x34);
+    const uint32_t alo = x34 + 34u;                            // A (low word)
+    const uint32_t blo = x34 + 68u;                            // B (low word)
     const uint32_t t = hi >> 1;
     const uint32_t m = hi * 0xed558ccdu;
     uint32_t plo_a, phi_a, plo_b, phi_b;
@@ -137,8 +148,7 @@ MDBG_HD uint32_t murmur_s1_u32(uint32_t key) {
     acc = mad_lo(plo_a, 0xc4ceb9feu, acc);
     acc = mad_lo(phi_b, 0x1a85ec53u, acc);
     acc = mad_lo(plo_b, 0xc4ceb9feu, acc);
-    const uint32_t s1 = acc + 1u;
-    return (blo < 68u) ? 0u : s1;                              // 0 = "undecided, run the exact hash"
+    return acc + 1u;
 }
 
 // MurmurHash3_x64_128_original(vec, 4*k bytes, seed 0) = KmerVec::hash128

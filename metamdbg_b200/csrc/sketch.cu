@@ -120,7 +120,7 @@ __device__ __forceinline__ uint32_t roll16_generic(const uint8_t* ring, uint32_t
 }
 
 template <int L_FAST>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) sketch_kernel(const SketchArgs a) {
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) sketch_kernel(const SketchArgs a) {
     __shared__ __align__(16) uint8_t ring_all[WARPS_PER_CTA][RING + 16];   // +16: linear-write slack
     __shared__ uint2 cand_all[WARPS_PER_CTA][64];                           // pending candidates: (pos | invalid<<31, fwd)
     const uint32_t lane = threadIdx.x & 31;
@@ -301,12 +301,12 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sketch_kernel(const Sketch
                 const bool fast = (L_FAST != 0) && (l == (uint32_t)L_FAST) && thr_cand >= S1_SLACK &&
                                   !__any_sync(0xffffffffu, inv != 0);
 
-                uint32_t sel, sel_fwd = 0;
+                uint32_t sel, s_hi = 0, s_lo = 0;
                 bool regs_ok = false;
                 if (a.select_none) {
                     sel = 0;
                 } else if (fast) {
-                    sel = roll16_fast<(L_FAST ? L_FAST : 15)>(W, thr_cand, sel_fwd);
+                    sel = roll16_fast<(L_FAST ? L_FAST : 15)>(W, thr_cand, s_hi, s_lo);
                     regs_ok = (valid_bits == 0xFFFFu);
                     sel &= valid_bits;
                 } else {
@@ -319,7 +319,11 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sketch_kernel(const Sketch
                     const uint32_t n_c = __popc(sel);
                     // common case: at most one candidate per lane, all from the register path -> one store per hit lane
                     if (__all_sync(0xffffffffu, n_c <= 1 && (regs_ok || n_c == 0))) {
-                        if (n_c) cand[n_list + __popc(hit_lanes & ((1u << lane) - 1u))] = make_uint2(p0 + __ffs(sel) - 1, sel_fwd);
+                        if (n_c) {
+                            const uint32_t j = __ffs(sel) - 1;
+                            cand[n_list + __popc(hit_lanes & ((1u << lane) - 1u))] =
+                                make_uint2(p0 + j, lmer_from_packed<(L_FAST ? L_FAST : 15)>(s_hi, s_lo, j));
+                        }
                         n_list += __popc(hit_lanes);
                         __syncwarp();
                         if (n_list >= 32) {
@@ -351,7 +355,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sketch_kernel(const Sketch
                             rest &= rest - 1;
                             if (rank >= base_rank && rank < base_rank + 32) {
                                 uint32_t fwd, inv = 0;
-                                if (regs_ok && n_c == 1) fwd = sel_fwd;
+                                if (regs_ok) fwd = lmer_from_packed<(L_FAST ? L_FAST : 15)>(s_hi, s_lo, j);
                                 else fwd = fwd_at(ring, p0 + j, l, inv);
                                 cand[n_list + (rank - base_rank)] = make_uint2((p0 + j) | (inv ? 0x80000000u : 0u), fwd);
                             }

@@ -51,10 +51,11 @@ static void cand_range(uint64_t lo, uint64_t hi, uint64_t step, uint64_t T, Cand
     CandStats s;
     for (uint64_t k = lo; k < hi; k += step) {
         const uint32_t key = (uint32_t)k;
-        const uint32_t s1 = murmur_s1_u32(key);
-        const bool cand = s1 <= thp1;
+        uint32_t risk = 0;
+        const uint32_t s1 = murmur_s1_u32(key, risk);
+        const bool cand = s1 <= thp1 || risk >= S1_RISK;
         const bool sel = murmur_h1_u64((uint64_t)key) <= T;
-        s.keys++; s.selected += sel; s.candidates += cand; s.undecided0 += (s1 == 0);
+        s.keys++; s.selected += sel; s.candidates += cand; s.undecided0 += (risk >= S1_RISK);
         if (sel && !cand) s.missed++;
     }
     *st = s;
@@ -78,7 +79,7 @@ static void test_candidates(bool exhaustive) {
         CandStats s;
         for (auto& x : st) { s.keys += x.keys; s.selected += x.selected; s.candidates += x.candidates;
                              s.undecided0 += x.undecided0; s.missed += x.missed; }
-        printf("density %-8g T=%016llx keys %llu%s selected %llu candidates %llu (s1==0: %llu) misclassified %llu\n",
+        printf("density %-8g T=%016llx keys %llu%s selected %llu candidates %llu (carry case: %llu) misclassified %llu\n",
                densities[d], (unsigned long long)T, (unsigned long long)s.keys, full ? " (all)" : "",
                (unsigned long long)s.selected, (unsigned long long)s.candidates, (unsigned long long)s.undecided0,
                (unsigned long long)s.missed);
@@ -139,21 +140,19 @@ static void test_roll(uint64_t T) {
         uint64_t vals[32]; uint8_t dirs[32];
         const size_t n = orc_lmers(seq, L + 15, L, vals, dirs);
         CHECK(n == 16, "orc_lmers returned %zu", n);
-        uint32_t sel_fwd = 0xDEADBEEF;
-        const uint32_t cand = roll16_fast<L>(W, thp1, sel_fwd);
-        uint32_t exact = 0, last = 0;
-        for (int j = 0; j < 16; j++) {
+        uint32_t s_hi = 0, s_lo = 0;
+        const uint32_t cand = roll16_fast<L>(W, thp1, s_hi, s_lo);
+        uint32_t exact = 0;
+        for (int j = 0; j < 16; j++)
             if (orc_murmur3_x64_128_h1(&vals[j], 8, 42) <= T) exact |= 1u << j;
-            if ((cand >> j) & 1u) last = j;
-        }
         CHECK((exact & ~cand) == 0, "roll16_fast<%d> lost a selected position (%04x vs %04x)", L, cand, exact);
-        if (cand) {                                                     // sel_fwd = forward l-mer of the last candidate
+        for (int j = 0; j < 16; j++) {                                  // every position's l-mer from the packed codes
             uint32_t fwd = 0;
-            for (int t = 0; t < L; t++) fwd = (fwd << 2) | ((W[(last + t) >> 2] >> (8 * ((last + t) & 3))) & 3u);
-            if (L < 16) fwd &= (1u << (2 * L)) - 1u;
-            CHECK(sel_fwd == fwd, "sel_fwd");
+            for (int t = 0; t < L; t++) fwd = (fwd << 2) | ((W[(j + t) >> 2] >> (8 * ((j + t) & 3))) & 3u);
+            if (L < 16) fwd &= (1u << ((2 * L) & 31)) - 1u;
+            CHECK(lmer_from_packed<L>(s_hi, s_lo, j) == fwd, "lmer_from_packed j=%d", j);
             const uint32_t rc = revcomp_lmer<L>(fwd);
-            CHECK((uint64_t)(fwd < rc ? fwd : rc) == vals[last] && dirs[last] == (fwd < rc ? 0 : 1), "canonical/dir");
+            CHECK((uint64_t)(fwd < rc ? fwd : rc) == vals[j] && dirs[j] == (fwd < rc ? 0 : 1), "canonical/dir");
         }
         n_sel += __builtin_popcount(exact); n_cand += __builtin_popcount(cand);
     }
