@@ -1,0 +1,199 @@
+// sketch_emu_test.cpp -- runs the REAL sketch kernel source (metamdbg_b200/csrc/sketch.cu, its launch lines
+// removed by the build step) on the CPU inside the warp emulator and compares every read's minimizers with the
+// oracle.  This is a CPU regression test of the GPU kernel's logic (HPC fill, ring, roll, candidate list, flush,
+// slot overflow + exact re-run, packed 2-bit input); it says nothing about speed.
+//
+//   sketch_emu_test            exit 0 = identical to the oracle on every case
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "warp_emu.hpp"
+#include SKETCH_SOURCE                       // the kernel source, `<<<...>>>` launches stripped
+
+extern "C" {
+#include "../../oracle/mdbg_oracle.h"
+}
+
+using namespace mdbg;
+
+static int fails = 0;
+#define CHECK(c, ...) do { if (!(c)) { if (fails++ < 20) { printf("FAIL line %d: ", __LINE__); printf(__VA_ARGS__); printf("\n"); } } } while (0)
+
+struct Batch {
+    std::vector<uint8_t> bases;
+    std::vector<uint64_t> offsets{0};
+    void add(const std::string& s) { bases.insert(bases.end(), s.begin(), s.end()); offsets.push_back(bases.size()); }
+    uint32_t n() const { return (uint32_t)offsets.size() - 1; }
+};
+
+static uint64_t threshold_of(float density, uint32_t* none) {
+    int nn = 0;
+    const uint64_t t = orc_minimizer_threshold(density, &nn);
+    *none = (uint32_t)nn;
+    return t;
+}
+
+struct Result { std::vector<uint64_t> off; std::vector<uint32_t> min, pos; std::vector<uint8_t> dir; };
+
+// what api.cu's sketch_internal does around the kernel, on host memory: padded slots, overflow -> exact re-run
+static Result run_kernel(const Batch& b, uint32_t l, float density, int hpc, const std::vector<uint32_t>& blacklist,
+                         bool packed, uint64_t* n_overflow_seen) {
+    const uint32_t n = b.n();
+    uint32_t none = 0;
+    SketchArgs a{};
+    std::vector<uint8_t> bases = b.bases;
+    bases.resize(bases.size() + 64, 0);                       // the library allocates n_bases + 64
+    // the device buffer is 16-byte aligned; keep that property
+    std::vector<uint8_t> store(bases.size() + 16);
+    uint8_t* aligned = store.data() + ((16 - ((uintptr_t)store.data() & 15)) & 15);
+    memcpy(aligned, bases.data(), bases.size());
+    a.bases = aligned;
+    a.bases_end = aligned + b.bases.size();
+    a.offsets = b.offsets.data();
+    a.n_reads = n;
+    a.read_begin = 0;
+    a.read_end = n;
+    a.l = l;
+    a.hpc = hpc;
+    a.threshold = threshold_of(density, &none);
+    a.select_none = none;
+    a.blacklist = blacklist.empty() ? nullptr : blacklist.data();
+    a.n_blacklist = (uint32_t)blacklist.size();
+    int shift = 0;
+    while (shift < 8 && 1.0 / (double)(1u << (shift + 1)) >= 4.0 * (double)density) shift++;
+    a.cap_shift = (uint32_t)shift;
+    a.cap_const = 32;
+    const uint64_t pad_cap = (b.bases.size() >> a.cap_shift) + (uint64_t)n * a.cap_const + 1;
+    std::vector<uint32_t> pad_min(pad_cap), pad_pos(pad_cap), n_min(n + 1);
+    std::vector<uint8_t> pad_dir(pad_cap);
+    a.out_min = pad_min.data(); a.out_pos = pad_pos.data(); a.out_dir = pad_dir.data();
+    a.n_min = n_min.data();
+    uint32_t cursor = 0;
+    unsigned long long n_overflow = 0;
+    a.cursor = &cursor;
+    a.n_overflow = &n_overflow;
+    // packed input: every clean read as 2-bit words, dirty reads stay ASCII (what host_pack_reads produces)
+    std::vector<uint32_t> words;
+    std::vector<uint64_t> src(n);
+    if (packed) {
+        for (uint32_t r = 0; r < n; r++) {
+            const uint64_t lo = b.offsets[r], hi = b.offsets[r + 1];
+            bool clean = true;
+            for (uint64_t i = lo; i < hi; i++) clean &= (b.bases[i] == 'A' || b.bases[i] == 'C' || b.bases[i] == 'G' || b.bases[i] == 'T');
+            if (!clean) { src[r] = SRC_ASCII | lo; continue; }
+            src[r] = words.size();
+            for (uint64_t i = lo; i < hi; i += 16) {
+                uint32_t w = 0;
+                for (uint64_t j = i; j < hi && j < i + 16; j++) w |= (uint32_t)((b.bases[j] >> 1) & 3) << (2 * (j - i));
+                words.push_back(w);
+            }
+        }
+        words.resize(words.size() + 64, 0);
+        a.read_src = src.data();
+        a.packed = words.data();
+    }
+    auto launch = [&]() {
+        cursor = 0;
+        if (l == 15) emu::run_warp([&] { sketch_kernel<15>(a); });
+        else emu::run_warp([&] { sketch_kernel<0>(a); });
+    };
+    launch();
+    Result res;
+    res.off.assign(n + 1, 0);
+    for (uint32_t r = 0; r < n; r++) res.off[r + 1] = res.off[r] + n_min[r];
+    const uint64_t total = res.off[n];
+    res.min.resize(total + 1); res.pos.resize(total + 1); res.dir.resize(total + 1);
+    *n_overflow_seen = n_overflow;
+    if (n_overflow == 0) {
+        for (uint32_t r = 0; r < n; r++) {                   // compact_kernel's job
+            const uint64_t slot = (b.offsets[r] >> a.cap_shift) + (uint64_t)r * a.cap_const;
+            for (uint32_t i = 0; i < n_min[r]; i++) {
+                res.min[res.off[r] + i] = pad_min[slot + i];
+                res.pos[res.off[r] + i] = pad_pos[slot + i];
+                res.dir[res.off[r] + i] = pad_dir[slot + i];
+            }
+        }
+    } else {                                                  // exact re-run straight into the tight CSR
+        a.exact_off = res.off.data();
+        a.out_min = res.min.data(); a.out_pos = res.pos.data(); a.out_dir = res.dir.data();
+        n_overflow = 0;
+        launch();
+        CHECK(n_overflow == 0, "overflow in the exact re-run");
+    }
+    res.min.resize(total); res.pos.resize(total); res.dir.resize(total);
+    return res;
+}
+
+static void compare(const Batch& b, uint32_t l, float density, int hpc, const std::vector<uint32_t>& bl, bool packed,
+                    const char* tag, uint64_t* totals) {
+    uint64_t n_over = 0;
+    const Result got = run_kernel(b, l, density, hpc, bl, packed, &n_over);
+    std::vector<uint32_t> bls = bl;
+    std::sort(bls.begin(), bls.end());
+    for (uint32_t r = 0; r < b.n(); r++) {
+        const uint64_t lo = b.offsets[r], len = b.offsets[r + 1] - lo;
+        std::vector<uint32_t> m(len + 1), p(len + 1);
+        std::vector<uint8_t> d(len + 1);
+        const size_t nm = orc_sketch_read((const char*)b.bases.data() + lo, len, (int)l, density, hpc,
+                                          bls.empty() ? nullptr : bls.data(), bls.size(), m.data(), p.data(), d.data(), len + 1);
+        const uint64_t g0 = got.off[r], gn = got.off[r + 1] - g0;
+        CHECK(gn == nm, "%s read %u: %llu minimizers, oracle %zu", tag, r, (unsigned long long)gn, nm);
+        if (gn != nm) continue;
+        for (size_t i = 0; i < nm; i++)
+            CHECK(got.min[g0 + i] == m[i] && got.pos[g0 + i] == p[i] && got.dir[g0 + i] == d[i],
+                  "%s read %u minimizer %zu", tag, r, i);
+        totals[0] += nm;
+    }
+    totals[1] += n_over;
+}
+
+int main() {
+    std::mt19937_64 rng(2024);
+    auto rnd_read = [&](size_t n, int kind) {
+        std::string s(n, 'A');
+        static const char* alpha = "ACGT";
+        for (size_t i = 0; i < n; i++) s[i] = alpha[rng() & 3];
+        if (kind == 1) for (size_t i = 0; i < n; i++) if (rng() % 3 == 0 && i) s[i] = s[i - 1];           // homopolymers
+        if (kind == 2) for (size_t i = 0; i < n; i += 1 + rng() % 97) s[i] = "NnacgtRY#"[rng() % 9];      // dirty
+        if (kind == 3) { const size_t u = 1 + rng() % 6; for (size_t i = u; i < n; i++) s[i] = s[i - u]; } // tandem repeat
+        return s;
+    };
+    Batch b;
+    for (size_t n : {0u, 1u, 14u, 15u, 16u, 17u, 31u, 32u, 33u, 511u, 512u, 513u, 527u, 528u, 1039u, 2047u, 2048u, 2049u})
+        b.add(rnd_read(n, 0));
+    for (int i = 0; i < 40; i++) b.add(rnd_read(rng() % 6000, i % 4));
+    b.add(rnd_read(40000, 0));                                   // many ring wraps
+    b.add(rnd_read(9000, 1));
+    b.add(std::string(3000, 'A'));
+    b.add("####ACGTACGGTCA#ACGTTTGACCATGACCAGTAGGACCATTAGGGACCCATAGAC");
+    uint64_t totals[2] = {0, 0};
+    std::vector<uint32_t> none;
+    for (int hpc = 0; hpc < 2; hpc++) {
+        compare(b, 15, 0.005f, hpc, none, false, "l15 d0.005", totals);
+        compare(b, 15, 0.05f, hpc, none, false, "l15 d0.05", totals);
+        compare(b, 15, 0.05f, hpc, none, true, "l15 d0.05 packed", totals);
+        compare(b, 15, 0.6f, hpc, none, false, "l15 d0.6 (slot overflow)", totals);
+        compare(b, 11, 0.02f, hpc, none, false, "l11 generic", totals);
+        compare(b, 16, 0.02f, hpc, none, true, "l16 generic packed", totals);
+        compare(b, 15, 1.0f, hpc, none, false, "l15 d1.0 (exact path)", totals);
+        compare(b, 15, 0.0f, hpc, none, false, "l15 d0 (select none)", totals);
+    }
+    {                                                            // blacklist = every third minimizer of a plain run
+        uint64_t n_over = 0;
+        const Result r0 = run_kernel(b, 15, 0.05f, 1, none, false, &n_over);
+        std::vector<uint32_t> bl;
+        for (size_t i = 0; i < r0.min.size(); i += 3) bl.push_back(r0.min[i]);
+        std::sort(bl.begin(), bl.end());
+        bl.erase(std::unique(bl.begin(), bl.end()), bl.end());
+        compare(b, 15, 0.05f, 1, bl, false, "blacklist", totals);
+    }
+    printf("%llu minimizers compared, %llu slot overflows exercised\n", (unsigned long long)totals[0],
+           (unsigned long long)totals[1]);
+    CHECK(totals[0] > 20000 && totals[1] > 0, "coverage too small");
+    printf(fails ? "FAILED (%d)\n" : "OK\n", fails);
+    return fails ? 1 : 0;
+}
