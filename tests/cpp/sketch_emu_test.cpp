@@ -1,7 +1,9 @@
-// sketch_emu_test.cpp -- runs the REAL sketch kernel source (metamdbg_b200/csrc/sketch.cu, its launch lines
-// removed by the build step) on the CPU inside the warp emulator and compares every read's minimizers with the
+// sketch_emu_test.cpp -- runs the REAL sketch / scan / compact kernel sources (metamdbg_b200/csrc/sketch.cu) on the CPU inside the warp emulator and compares every read's minimizers with the
 // oracle.  This is a CPU regression test of the GPU kernel's logic (HPC fill, ring, roll, candidate list, flush,
 // slot overflow + exact re-run, packed 2-bit input); it says nothing about speed.
+//
+// The kernels are started through the product's own launch_* functions (grid sizing included); `<<<...>>>` is
+// rewritten to emu::launch by tests/_emu.py.
 //
 //   sketch_emu_test            exit 0 = identical to the oracle on every case
 #include <cstdio>
@@ -98,25 +100,25 @@ static Result run_kernel(const Batch& b, uint32_t l, float density, int hpc, con
     }
     auto launch = [&]() {
         cursor = 0;
-        if (l == 15) emu::run_warp([&] { sketch_kernel<15>(a); });
-        else emu::run_warp([&] { sketch_kernel<0>(a); });
+        launch_sketch(a, /*sm_count=*/2, nullptr);            // 2 "SMs" x 2 CTAs x 8 warps, reads pulled dynamically
     };
     launch();
     Result res;
     res.off.assign(n + 1, 0);
-    for (uint32_t r = 0; r < n; r++) res.off[r + 1] = res.off[r] + n_min[r];
+    std::vector<uint64_t> scratch(scan_scratch_elems(n) + 1);
+    launch_scan_u32_to_u64(n_min.data(), res.off.data(), n, scratch.data(), nullptr);      // the real 3-kernel scan
+    for (uint32_t r = 0, acc = 0; r < n; r++) { CHECK(res.off[r] == acc, "scan at %u", r); acc += n_min[r]; }
     const uint64_t total = res.off[n];
     res.min.resize(total + 1); res.pos.resize(total + 1); res.dir.resize(total + 1);
     *n_overflow_seen = n_overflow;
     if (n_overflow == 0) {
-        for (uint32_t r = 0; r < n; r++) {                   // compact_kernel's job
-            const uint64_t slot = (b.offsets[r] >> a.cap_shift) + (uint64_t)r * a.cap_const;
-            for (uint32_t i = 0; i < n_min[r]; i++) {
-                res.min[res.off[r] + i] = pad_min[slot + i];
-                res.pos[res.off[r] + i] = pad_pos[slot + i];
-                res.dir[res.off[r] + i] = pad_dir[slot + i];
-            }
-        }
+        CompactArgs c{};                                      // the real compact_kernel
+        c.base_offsets = b.offsets.data(); c.cap_shift = a.cap_shift; c.cap_const = a.cap_const;
+        c.n_min = n_min.data(); c.tight_off = res.off.data();
+        c.in_min = pad_min.data(); c.in_pos = pad_pos.data(); c.in_dir = pad_dir.data();
+        c.out_min = res.min.data(); c.out_pos = res.pos.data(); c.out_dir = res.dir.data();
+        c.n_reads = n;
+        launch_compact(c, nullptr);
     } else {                                                  // exact re-run straight into the tight CSR
         a.exact_off = res.off.data();
         a.out_min = res.min.data(); a.out_pos = res.pos.data(); a.out_dir = res.dir.data();
