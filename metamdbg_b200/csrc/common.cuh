@@ -83,8 +83,8 @@ MDBG_HD uint64_t murmur_h1_u64(uint64_t key) {
 //
 // Only the HIGH words of the two fmix64 results are formed.  With s0 = hi(fmix(A)) + hi(fmix(B)) (mod 2^32) the
 // true high word of the sum is s0 or s0 + 1 (carry out of the low words).  murmur_s1_u32 forms s' = s0 or s0 + 1
-// (its low x low partial products are accumulated in one 64-bit multiply-add, whose own low-word carry is not the
-// exact sum's) and returns s1 = s' + 1 (mod 2^32), so that
+// (the last multiply is applied once, to the SUM of the two pre-images; its low-word carry is not the exact
+// sum's) and returns s1 = s' + 1 (mod 2^32), so that
 //
 //   hash <= T   implies   s1 <= T_hi + S1_SLACK      (unsigned, T_hi = T >> 32, when T_hi + S1_SLACK does not wrap)
 //
@@ -134,20 +134,19 @@ MDBG_HD uint32_t murmur_s1_u32(uint32_t key, uint32_t& risk) {
     uint32_t plo_a, phi_a, plo_b, phi_b;
     fmix64_front(alo, t, m, plo_a, phi_a);
     fmix64_front(blo, t, m, plo_b, phi_b);
-    // high words of k * 0xc4ceb9fe1a85ec53 for A and B, summed; the final k ^= k >> 33 only changes the low word.
-    // The two low x low products are accumulated as one 64-bit multiply-add, so their high words arrive together
-    // with a carry of the low words that the exact sum may or may not have: s' is s0 or s0 + 1.
+    // fmix64's last multiply and xor-shift: h = (P_a ^ P_a >> 33) + (P_b ^ P_b >> 33) with P = k * 0xc4ceb9fe1a85ec53.
+    // The xor-shifts only touch the low words, so the high word of h is hi(P_a) + hi(P_b) plus a carry out of the
+    // low words; by linearity (k_a + k_b) * M has the same two high words plus ITS low-word carry.  One 64-bit add
+    // and the high word of one 64 x 64 product therefore give s' = s0 or s0 + 1.
+    uint32_t klo, khi;
 #ifdef __CUDA_ARCH__
-    uint32_t ll_lo, ll_hi;                                     // pinned as mul.wide + mad.wide on one register pair
-    asm("{\n\t.reg .b64 q;\n\tmul.wide.u32 q, %2, %4;\n\tmad.wide.u32 q, %3, %4, q;\n\tmov.b64 {%0, %1}, q;\n\t}"
-        : "=r"(ll_lo), "=r"(ll_hi) : "r"(plo_a), "r"(plo_b), "r"(0x1a85ec53u));
+    asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, %5;" : "=r"(klo), "=r"(khi) : "r"(plo_a), "r"(plo_b), "r"(phi_a), "r"(phi_b));
 #else
-    const uint32_t ll_hi = (uint32_t)(((uint64_t)plo_b * 0x1a85ec53u + (uint64_t)plo_a * 0x1a85ec53u) >> 32);
+    klo = plo_a + plo_b;
+    khi = phi_a + phi_b + (klo < plo_a ? 1u : 0u);
 #endif
-    uint32_t acc = mad_lo(phi_a, 0x1a85ec53u, ll_hi);
-    acc = mad_lo(plo_a, 0xc4ceb9feu, acc);
-    acc = mad_lo(phi_b, 0x1a85ec53u, acc);
-    acc = mad_lo(plo_b, 0xc4ceb9feu, acc);
+    uint32_t acc = mad_lo(klo, 0xc4ceb9feu, umulhi32(klo, 0x1a85ec53u));
+    acc = mad_lo(khi, 0x1a85ec53u, acc);
     return acc + 1u;
 }
 
