@@ -82,18 +82,18 @@ MDBG_HD uint64_t murmur_h1_u64(uint64_t key) {
 //   (seed 42, len 8: h1 = 42 ^ k1 ^ 8, h2 = 42 ^ 8, then h1 += h2, h2 += h1).
 //
 // Only the HIGH words of the two fmix64 results are formed.  With s0 = hi(fmix(A)) + hi(fmix(B)) (mod 2^32) the
-// true high word of the sum is s0 or s0 + 1 (carry out of the low words).  murmur_s1_u32 forms s' = s0 or s0 + 1
+// true high word of the sum is s0 or s0 + 1 (carry out of the low words).  murmur_s1_u32 returns s' = s0 or s0 + 1
 // (the last multiply is applied once, to the SUM of the two pre-images; its low-word carry is not the exact
-// sum's) and returns s1 = s' + 1 (mod 2^32), so that
+// sum's), so that for a selected key (hash <= T, T_hi = T >> 32)
 //
-//   hash <= T   implies   s1 <= T_hi + S1_SLACK      (unsigned, T_hi = T >> 32, when T_hi + S1_SLACK does not wrap)
+//   s' <= T_hi + S1_SLACK     or     s' = 0xFFFFFFFF  (s0 = 0xFFFFFFFF with a carry: true high word 0)
 //
-// including the wrap case s0 = 0xFFFFFFFF with a carry (true high word 0, s1 in {0, 1}).  The two +34 additions
-// are done on the low word only; the 2^-26-rare case where one of them carries into the high word makes s1
-// meaningless and is reported through `risk`: the caller keeps risk = max(risk, ...) over as many keys as it
-// likes and must treat ALL of them as candidates when risk >= S1_RISK.  Callers confirm every candidate with the
-// exact murmur_h1_u64 (tests/cpp/device_math_test.cu walks all 2^32 keys: no selected key is ever rejected).
-constexpr uint32_t S1_SLACK = 2;
+// The second case, and the 2^-26-rare case where one of the two +34 additions (done on the low word only) carries
+// into the high word and makes s' meaningless, are reported through `risk`: murmur_s1_u32 keeps
+// risk = max(risk, ...) and the caller must treat ALL keys that went into a `risk` as candidates when
+// risk >= S1_RISK (probability 2^-26 per key).  Callers confirm every candidate with the exact murmur_h1_u64
+// (tests/cpp/device_math_test.cu walks all 2^32 keys: no selected key is ever rejected).
+constexpr uint32_t S1_SLACK = 1;
 constexpr uint32_t S1_RISK = 0xFFFFFFBCu;                      // (k1_lo ^ 34) + 68 wraps
 
 MDBG_HD uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c) {
@@ -126,7 +126,6 @@ MDBG_HD uint32_t murmur_s1_u32(uint32_t key, uint32_t& risk) {
     p = (uint64_t)rlo * 0x2745937fu;
     hi = mad_lo(rlo, 0x4cf5ad43u, mad_lo(rhi, 0x2745937fu, (uint32_t)(p >> 32)));
     const uint32_t x34 = (uint32_t)p ^ 34u;
-    risk = max(risk, x34);
     const uint32_t alo = x34 + 34u;                            // A (low word)
     const uint32_t blo = x34 + 68u;                            // B (low word)
     const uint32_t t = hi >> 1;
@@ -147,7 +146,8 @@ MDBG_HD uint32_t murmur_s1_u32(uint32_t key, uint32_t& risk) {
 #endif
     uint32_t acc = mad_lo(klo, 0xc4ceb9feu, umulhi32(klo, 0x1a85ec53u));
     acc = mad_lo(khi, 0x1a85ec53u, acc);
-    return acc + 1u;
+    risk = max(risk, max(x34, acc));                           // acc >= S1_RISK also covers the wrap s' = 0xFFFFFFFF
+    return acc;
 }
 
 // MurmurHash3_x64_128_original(vec, 4*k bytes, seed 0) = KmerVec::hash128
