@@ -55,3 +55,29 @@ def build_and_run(tmp_path, test_cpp: str, sources: dict, extra_flags=(), timeou
     run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=timeout)
     assert run.returncode == 0 and run.stdout.strip().endswith("OK"), run.stdout[-3000:] + run.stderr[-2000:]
     return run.stdout
+
+
+def build_emulated_library(out_dir) -> str:
+    """The whole C-ABI library for the CPU emulator (TEST ONLY, never shipped or loaded by the product): api.cu is
+    compiled unchanged against the synchronous runtime stub, the four kernel files with their launches rewritten,
+    pack_host.cpp as it is.  Returns the path of libmdbg_b200_emu.so inside out_dir."""
+    out_dir = str(out_dir)
+    objs = []
+    stub = os.path.join(ROOT, "tests", "cpp", "emu_stub")
+    common = ["/usr/bin/g++", "-O1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-Wno-unknown-pragmas", "-w",
+              "-I" + stub, "-I" + os.path.join(ROOT, "tests", "cpp"), "-I" + CSRC, "-I" + os.path.join(ROOT, "include")]
+    for name in ("sketch.cu", "kminmer.cu", "purge.cu", "aux.cu"):
+        inc = os.path.join(out_dir, name.replace(".cu", "_emu.cpp"))
+        with open(inc, "w") as f:
+            f.write(emulated_source(name))
+        objs.append(inc)
+    api = os.path.join(out_dir, "api_emu.cpp")
+    src = open(os.path.join(CSRC, "api.cu")).read()
+    src = src.replace('#include "../../include/mdbg_b200.h"', '#include "mdbg_b200.h"')     # same header, found through -I
+    with open(api, "w") as f:
+        f.write(src)
+    lib = os.path.join(out_dir, "libmdbg_b200_emu.so")
+    cmd = common + ["-shared", "-o", lib, api, *objs, os.path.join(CSRC, "pack_host.cpp"), "-ldl", "-lpthread"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-4000:]
+    return lib

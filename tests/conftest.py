@@ -8,6 +8,15 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# tests/test_capi_emulated_cpu.py re-runs the GPU parity tests against the CPU-emulated build of the C-ABI library
+# (tests/_emu.py: api.cu + the kernels compiled by g++ against tests/cpp/warp_emu.hpp).  The product never looks at
+# this variable; it only redirects the ctypes loader inside that child pytest process.
+EMULATED_LIB = os.environ.get("MDBG_EMU_LIB")
+if EMULATED_LIB:
+    from metamdbg_b200 import _capi
+    _capi.LIB_PATH = EMULATED_LIB
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
     config.addinivalue_line("markers", "ref: needs oracle/_ref/libmdbg_ref.so (reference sources compiled)")

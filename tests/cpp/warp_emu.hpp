@@ -34,7 +34,7 @@ static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) {
 #if defined(__x86_64__) && !defined(EMU_USE_UCONTEXT)
 extern "C" void emu_switch_x86(void** from_sp, void** to_sp);
 asm(".text\n"
-    ".globl emu_switch_x86\n"
+    ".weak emu_switch_x86\n"
     ".type emu_switch_x86,@function\n"
     "emu_switch_x86:\n"
     "    pushq %rbp\n    pushq %rbx\n    pushq %r12\n    pushq %r13\n    pushq %r14\n    pushq %r15\n"

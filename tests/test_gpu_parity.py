@@ -17,13 +17,23 @@ def load(name):
     return np.load(os.path.join(GOLD, name))
 
 
+EMULATED = bool(os.environ.get("MDBG_EMU_LIB"))      # child run of tests/test_capi_emulated_cpu.py (see conftest.py)
+
+
 @pytest.fixture(scope="module")
 def built():
+    if EMULATED:
+        return True
     import __graft_entry__ as g
     g.build()
     import torch
     assert torch.cuda.is_available(), "gpu tests need a CUDA device"
     return True
+
+
+def real_gpu_only():
+    if EMULATED:
+        pytest.skip("uses torch device tensors: real GPU only")
 
 
 def engine(l=15, d=0.005, hpc=True, bl=None):
@@ -242,6 +252,7 @@ def test_table_full_is_reported(built):
 # ---------------------------------------------------------------- device-resident path + generator
 
 def test_device_generator_matches_numpy_and_device_sketch(built, oracle):
+    real_gpu_only()
     import torch
     rs = synth.make_readset(500, 7000, seed=77, n_genomes=2, genome_len_range=(100_000, 200_000))
     bases, offs = synth.fill_reads(rs)
@@ -464,6 +475,7 @@ def test_ont_density_rethreshold_and_count(built, oracle):
 def test_hybrid_transfer_from_pinned_host_memory(built, oracle):
     """Pinned caller buffers: pieces travel either as ASCII by DMA (PCIe idle) or 2-bit packed (PCIe busy); both
     modes -- and dirty reads inside packed pieces -- must give the oracle's sketch."""
+    real_gpu_only()
     import torch
     rs = synth.make_readset(40_000, 9000, seed=29, n_genomes=3, genome_len_range=(300_000, 600_000))
     sub = rs.subset(0, 40_000)
@@ -507,6 +519,7 @@ def test_hybrid_transfer_from_pinned_host_memory(built, oracle):
 
 def test_device_resident_packed_input(built, oracle):
     """Reads kept 2-bit packed in HBM (the layout the design brief names) sketch to the same CSR as ASCII reads."""
+    real_gpu_only()
     import torch
     rs = synth.make_readset(1500, 7000, seed=44, n_genomes=2, genome_len_range=(100_000, 200_000))
     bases, offs = synth.fill_reads(rs)
