@@ -139,7 +139,7 @@ MDBG_HD uint32_t murmur_s1_u32(uint32_t key, uint32_t& risk) {
     // and the high word of one 64 x 64 product therefore give s' = s0 or s0 + 1.
     uint32_t klo, khi;
 #ifdef __CUDA_ARCH__
-    asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, %5;" : "=r"(klo), "=r"(khi) : "r"(plo_a), "r"(plo_b), "r"(phi_a), "r"(phi_b));
+    asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, %5;" : "=&r"(klo), "=r"(khi) : "r"(plo_a), "r"(plo_b), "r"(phi_a), "r"(phi_b));
 #else
     klo = plo_a + plo_b;
     khi = phi_a + phi_b + (klo < plo_a ? 1u : 0u);
