@@ -90,6 +90,14 @@ def main():
                 eng.sketch_batch_device(buf.ctypes.data + sh, offs.ctypes.data, len(offs) - 1, len(bases), True)
                 sk = eng.sketch_fetch()
             else:                                             # side outputs, with or without qualities
+                if hpc and (bases == ord("#")).any():         # refused by design (EncoderRLE's sentinel)
+                    try:
+                        eng.sketch_batch_q(bases, None, offs)
+                        raise AssertionError(("'#' accepted", scen))
+                    except Exception as e:
+                        assert "'#'" in str(e), e
+                    bases = np.where(bases == ord("#"), ord("N"), bases).astype(np.uint8)
+                    want = orc.sketch_batch(bases, offs, l, dens, hpc)
                 q = None
                 if rng.integers(0, 2):
                     q = rng.integers(33, 90, len(bases)).astype(np.uint8)

@@ -5,7 +5,7 @@ runtime (tests/cpp/emu_stub/cuda_runtime.h: device memory = host memory, async w
 the four kernel files against tests/cpp/warp_emu.hpp, pack_host.cpp as it is -- into a throw-away
 libmdbg_b200_emu.so, and a child pytest re-runs the GPU parity suites against it:
 
-  * tests/test_gpu_parity.py   every test that talks to the library through host arrays (26 of 29; the three that
+  * tests/test_gpu_parity.py   every test that talks to the library through host arrays (27 of 30; the three that
                                hand torch CUDA tensors to the device-pointer entry points need a real GPU)
   * tests/test_gpu_host_cpp.py the C++ host driver and metaMDBG's own readSelection stage with the GPU functor
                                plugged in (the binaries pick the emulated library up through LD_LIBRARY_PATH)
@@ -39,4 +39,4 @@ def test_gpu_parity_suites_against_the_emulated_library(tmp_path):
     last = run.stdout.strip().splitlines()[-1]
     assert "passed" in last and "failed" not in last, tail
     n_passed = int(last.split(" passed")[0].split()[-1])
-    assert n_passed >= 30, tail                  # 26 parity + 4 host-driver tests
+    assert n_passed >= 31, tail                  # 27 parity + 4 host-driver tests
