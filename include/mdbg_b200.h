@@ -171,7 +171,10 @@ typedef struct {
 /* filter_low_complexity != 0: reads with complexity > 5 lose their minimizers (ReadSelection.hpp:894-903), as the
  * reference always does.  Only applied by mdbg_sketch_batch_q.  --min-read-quality > 0 is not supported. */
 mdbg_status mdbg_ctx_set_read_filters(mdbg_ctx* ctx, int filter_low_complexity);
-/* mdbg_sketch_batch plus the side outputs.  quals = Read::_qual bytes laid out like bases (NULL for FASTA). */
+/* mdbg_sketch_batch plus the side outputs.  quals = Read::_qual bytes laid out like bases (NULL for FASTA).
+ * With HPC on, a base string containing '#' (EncoderRLE's internal sentinel, never produced by a FASTA/FASTQ
+ * parser) is refused with MDBG_ERR_ARG: the reference records shifted rlePositions after a '#', which the quality
+ * windows here would not reproduce.  The plain sketch entry points accept such reads and stay bit-exact. */
 mdbg_status mdbg_sketch_batch_q(mdbg_ctx* ctx, const uint8_t* bases, const uint8_t* quals, const uint64_t* offsets,
                                 uint32_t n_reads, int append_to_store, mdbg_sketch_out* out, mdbg_aux_out* aux);
 

@@ -887,6 +887,12 @@ mdbg_status mdbg_sketch_batch_q(mdbg_ctx* ctx, const uint8_t* bases, const uint8
     CK(cudaSetDevice(ctx->device));
     CKS(check_host_offsets(ctx, offsets, n_reads));
     const uint64_t n_bases = n_reads ? offsets[n_reads] : 0;
+    // '#' is EncoderRLE's internal sentinel (Commons.hpp:4172): a base string holding it makes the reference record
+    // shifted rlePositions, which the quality windows of the side outputs do not reproduce.  No FASTA/FASTQ parser
+    // produces it, so such a batch is refused here instead of returning windows that differ (the plain sketch entry
+    // points accept it and stay bit-exact).
+    if (ctx->hpc && n_bases && memchr(bases, '#', n_bases))
+        return fail(ctx, MDBG_ERR_ARG, "a read contains '#': not supported by the side-output entry point with HPC on");
     CKS(ensure(ctx, ctx->d_bases, n_bases + 64));
     CKS(ensure(ctx, ctx->d_offsets, ((size_t)n_reads + 1) * 8));
     cudaStream_t s = ctx->stream;

@@ -90,11 +90,11 @@ struct Block {
     Dim3 block_idx, block_dim, grid_dim;
 };
 
-inline Block*& current() { static Block* b = nullptr; return b; }
+inline Block*& current() { static thread_local Block* b = nullptr; return b; }   // one emulated GPU per OS thread
 inline bool outer_running() { return current() != nullptr; }
 constexpr size_t STACK_BYTES = 256 * 1024;
 inline char* fiber_stack(int i) {                           // stacks are reused by every block of every launch
-    static std::vector<std::vector<char>> pool(MAX_THREADS);
+    static thread_local std::vector<std::vector<char>> pool(MAX_THREADS);
     if (pool[i].empty()) pool[i].resize(STACK_BYTES);
     return pool[i].data();
 }
@@ -221,7 +221,7 @@ struct GridDimT { struct X { operator unsigned() const { return current()->grid_
 #define __device__
 #define __host__
 #define __forceinline__ inline
-#define __shared__ static
+#define __shared__ static thread_local      /* per OS thread: several emulated ranks may run the same kernel */
 #define __align__(n) __attribute__((aligned(n)))
 #define __launch_bounds__(...)
 #define __restrict__

@@ -5,13 +5,14 @@ runtime (tests/cpp/emu_stub/cuda_runtime.h: device memory = host memory, async w
 the four kernel files against tests/cpp/warp_emu.hpp, pack_host.cpp as it is -- into a throw-away
 libmdbg_b200_emu.so, and a child pytest re-runs the GPU parity suites against it:
 
-  * tests/test_gpu_parity.py   every test that talks to the library through host arrays (26 of 29; the three that
+  * tests/test_gpu_parity.py   every test that talks to the library through host arrays (27 of 30; the three that
                                hand torch CUDA tensors to the device-pointer entry points need a real GPU)
   * tests/test_gpu_host_cpp.py the C++ host driver and metaMDBG's own readSelection stage with the GPU functor
                                plugged in (the binaries pick the emulated library up through LD_LIBRARY_PATH)
 
 So the host-side sequencing of api.cu (pieces, 2-bit packed transfer, slot overflow re-run, store, purge, count,
-rescue, next-k, finalize, error paths) is checked here without a GPU.  The emulated library is test infrastructure:
+rescue, next-k, finalize, error paths, and the multi-rank owner merge over an in-process fake NCCL) is checked here
+without a GPU.  The emulated library is test infrastructure:
 it is built into a temporary directory, nothing in metamdbg_b200/ can load it, and the product still refuses to
 run without a CUDA device (tests/test_capi_cpu.py)."""
 import os
@@ -24,13 +25,38 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import _emu  # noqa: E402
 
 
-def test_gpu_parity_suites_against_the_emulated_library(tmp_path):
+import pytest  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def emulated(tmp_path_factory):
+    """(library path, environment for child processes): the emulated library under its own name and under the
+    soname the C++ binaries ask for, plus the in-process fake libnccl.so.2, all in one temporary directory."""
     import __graft_entry__ as g
     g.build()                                    # the host driver binaries (they are re-pointed at run time)
-    lib = _emu.build_emulated_library(tmp_path)
-    shutil.copy(lib, os.path.join(str(tmp_path), "libmdbg_b200.so"))     # the soname the C++ binaries ask for
-    env = dict(os.environ, MDBG_EMU_LIB=lib,
-               LD_LIBRARY_PATH=str(tmp_path) + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    d = str(tmp_path_factory.mktemp("emu"))
+    lib = _emu.build_emulated_library(d)
+    shutil.copy(lib, os.path.join(d, "libmdbg_b200.so"))
+    subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-o", os.path.join(d, "libnccl.so.2"),
+                    os.path.join(ROOT, "tests", "cpp", "fake_nccl.cpp"), "-lpthread"], check=True)
+    env = dict(os.environ, MDBG_EMU_LIB=lib, LD_LIBRARY_PATH=d + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    return lib, env
+
+
+@pytest.mark.parametrize("n_ranks,k", [(2, 4), (3, 5), (8, 4)])
+def test_owner_merge_on_the_emulator(emulated, n_ranks, k):
+    """mdbg_comm_init + mdbg_count_merge with N ranks = N threads of one process, each with its own emulated
+    context, exchanging through tests/cpp/fake_nccl.cpp (an in-process libnccl.so.2: barriers + memcpy).  The union
+    of the ranks' tables is the oracle's table of the whole read set, every key sits on its owner, occurrences are
+    conserved -- the N = 8 sequencing of the merge is exercised here although the round's GPU runs stopped at 4."""
+    _, env = emulated
+    run = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu_multirank_child.py"), str(n_ranks), str(k)],
+                         env=env, capture_output=True, text=True, timeout=900)
+    assert run.returncode == 0 and run.stdout.strip().endswith("OK"), run.stdout[-2000:] + run.stderr[-3000:]
+
+
+def test_gpu_parity_suites_against_the_emulated_library(emulated):
+    lib, env = emulated
     run = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "tests/test_gpu_host_cpp.py", "-m", "gpu",
                           "-q", "-x", "-p", "no:cacheprovider"], cwd=ROOT, env=env, capture_output=True, text=True,
                          timeout=3000)
@@ -39,4 +65,4 @@ def test_gpu_parity_suites_against_the_emulated_library(tmp_path):
     last = run.stdout.strip().splitlines()[-1]
     assert "passed" in last and "failed" not in last, tail
     n_passed = int(last.split(" passed")[0].split()[-1])
-    assert n_passed >= 30, tail                  # 26 parity + 4 host-driver tests
+    assert n_passed >= 31, tail                  # 27 parity + 4 host-driver tests

@@ -616,3 +616,33 @@ def test_bad_host_arrays_are_rejected(built):
     sk = eng.sketch_batch(bases, good)                          # still works afterwards
     assert sk.n_reads == 2
     eng.close()
+
+
+def test_side_outputs_refuse_the_hpc_sentinel_in_reads(built, oracle):
+    """'#' is EncoderRLE's internal sentinel: with HPC on the side-output entry point refuses a base string that
+    holds it (MDBG_ERR_ARG) instead of returning quality windows that differ from the reference's shifted
+    rlePositions; the plain sketch of the same batch stays bit-exact, and with HPC off the batch is accepted."""
+    from metamdbg_b200.engine import MdbgError
+    rng = np.random.default_rng(8)
+    reads = [bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), 900)) for _ in range(4)]
+    reads[2] = reads[2][:400] + b"#" + reads[2][401:]
+    bases = np.frombuffer(b"".join(reads), np.uint8).copy()
+    offs = np.zeros(len(reads) + 1, np.uint64)
+    offs[1:] = np.cumsum([len(r) for r in reads])
+    quals = rng.integers(40, 70, len(bases)).astype(np.uint8)
+    eng = engine(15, 0.05, True)
+    with pytest.raises(MdbgError) as ei:
+        eng.sketch_batch_q(bases, quals, offs)
+    assert ei.value.status == 2 and "'#'" in str(ei.value)
+    assert_sketch_equal(eng.sketch_batch(bases, offs), *oracle.sketch_batch(bases, offs, 15, 0.05, True), tag="plain sketch")
+    eng.close()
+    eng = engine(15, 0.05, False)
+    sk, aux = eng.sketch_batch_q(bases, quals, offs)
+    assert_sketch_equal(sk, *oracle.sketch_batch(bases, offs, 15, 0.05, False), tag="hpc off")
+    raw = bases.tobytes()
+    for r in range(len(reads)):
+        lo, hi = int(offs[r]), int(offs[r + 1])
+        pos = sk.positions[int(sk.min_offsets[r]):int(sk.min_offsets[r + 1])]
+        _, _, ql = oracle.read_aux(raw[lo:hi], quals[lo:hi].tobytes(), 15, False, pos)
+        assert np.array_equal(aux["qualities"][int(sk.min_offsets[r]):int(sk.min_offsets[r + 1])], ql)
+    eng.close()
