@@ -52,11 +52,15 @@ int main() {
             continue;
         }
         if (!clean || src[r] != pk[r]) { bad++; continue; }
-        for (size_t j = 0; j < s.size(); j++) {
-            const uint32_t w = pack[pk[r] + j / 16];
-            if (((w >> (2 * (j % 16))) & 3) != (((unsigned char)s[j] >> 1) & 3u)) { bad++; break; }
+        // exact words: base j at bits [2j, 2j+1] of word j/16, padding bits of the last word zero
+        for (size_t w = 0; w < (s.size() + 15) / 16; w++) {
+            uint32_t want = 0;
+            for (size_t j = 16 * w; j < s.size() && j < 16 * w + 16; j++)
+                want |= (((unsigned char)s[j] >> 1) & 3u) << (2 * (j % 16));
+            if (pack[pk[r] + w] != want) { bad++; break; }
         }
     }
-    printf("reads %zu dirty %d bad %d threads_default %d\n", reads.size(), dirty, bad, host_default_threads());
+    for (size_t w = pk.back(); w < pack.size(); w++) if (pack[w] != 0xFFFFFFFFu) bad++;    // nothing written past the end
+    printf("reads %zu dirty %d bad %d threads_default %d isa %s\n", reads.size(), dirty, bad, host_default_threads(), host_pack_isa());
     return bad == 0 && dirty > 20 ? 0 : 1;
 }
