@@ -283,6 +283,15 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         dist.broadcast(uid, 0)
         eng.comm_init(rank, world, bytes(uid.cpu().numpy().tobytes()))
     lk = purge_last_k(args)
+    # engine set-up, outside every timed region: both arithmetic variants of the sketch kernel on this rank's own
+    # reads, complete outputs compared on the device; the faster identical one stays active (variant 0 otherwise)
+    tune = eng.autotune_sketch(d_bases.data_ptr(), d_off.data_ptr(), n_reads, n_bases)
+    if args.sketch_variant >= 0:
+        if not tune["identical"][args.sketch_variant]:
+            raise SystemExit(f"bench.py: sketch variant {args.sketch_variant} does not reproduce variant 0: {tune}")
+        eng.set_sketch_variant(args.sketch_variant)
+        tune["chosen"] = args.sketch_variant
+        tune["forced"] = True
 
     def step_device():
         eng.store_clear()
@@ -453,13 +462,15 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": workload_config(args), "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "sketch_kernel<15>", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": f"sketch_kernel<15, {tune['chosen']}>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "ms_per_launch": sk_ms, "algorithmic_bytes_per_launch": algo_bytes,
                          "note": "integer-issue bound (one MurmurHash3_x64_128 per l-mer), see DESIGN.md",
                          "binding_pipes_ncu": ncu_pipes,
                          "share_of_step": sk_ms / (ms_total / args.steps)},
             "kernels_ms": {"sketch": sk_ms, "insert": float(np.mean(insert_ms))},
+            "sketch_autotune": dict(tune, note="ms = sketch + scan + compaction of the full batch, best of 2; a variant is "
+                                               "eligible only if its whole output equals variant 0's on the device"),
             "cpu_baseline": cpu_baseline,
             "check": {"n_minimizers_rank0": int(n_min_store), "n_solid_total": int(solid_total),
                       "checksum_rank0": int(checksum_local), "kminmer_occurrences_total": int(got_instances),
@@ -484,6 +495,7 @@ def main():
     ap.add_argument("--e2e-batch", type=int, default=262_144, help="reads per host-buffer C-ABI call")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--ref-reads", type=int, default=0, help="sample size of the reference arm (0 = auto)")
+    ap.add_argument("--sketch-variant", type=int, default=-1, help="force a sketch-kernel variant (-1 = autotune)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stages", action="store_true", help="reference arm: skip the extra real-stage timing")

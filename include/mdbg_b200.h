@@ -148,6 +148,25 @@ mdbg_status mdbg_ctx_set_host_packing(mdbg_ctx* ctx, int on);
 mdbg_status mdbg_sketch_batch_device(mdbg_ctx* ctx, const uint8_t* d_bases, const uint64_t* d_offsets,
                                      uint32_t n_reads, uint64_t n_bases, int append_to_store,
                                      mdbg_sketch_dev* out);
+/* The sketch kernel's unrolled l = 15 block exists in MDBG_SKETCH_VARIANTS arithmetic variants with identical
+ * results (sketch.cu: 0 = one roll step + candidate filter per position, 1 = funnel-shift l-mers from packed codes,
+ * one final hash multiply on the summed pre-images, carry-chain accept bits).  Variant 0 is the default; the
+ * environment variable MDBG_SKETCH_VARIANT presets it at context creation.  mdbg_ctx_autotune_sketch runs every
+ * variant on the caller's own device-resident batch (nothing is appended to the store), compares the complete
+ * results with variant 0 byte for byte ON THE DEVICE, and keeps the fastest variant that is identical. */
+#define MDBG_SKETCH_VARIANTS 2
+typedef struct mdbg_autotune_out {
+    int32_t n_variants;
+    int32_t chosen;                                  /* variant now active in the context */
+    int32_t identical[4];                            /* [v]: 1 when variant v reproduced variant 0 exactly */
+    float ms[4];                                     /* [v]: best-of-2 time of sketch + scan + compaction */
+    uint32_t n_reads;
+    uint64_t n_minimizers;
+} mdbg_autotune_out;
+mdbg_status mdbg_ctx_set_sketch_variant(mdbg_ctx* ctx, int variant);
+mdbg_status mdbg_ctx_get_sketch_variant(mdbg_ctx* ctx, int* variant);
+mdbg_status mdbg_ctx_autotune_sketch(mdbg_ctx* ctx, const uint8_t* d_bases, const uint64_t* d_offsets,
+                                     uint32_t n_reads, uint64_t n_bases, mdbg_autotune_out* out);
 /* Reads resident in HBM in 2-bit packed form: 16 bases per u32, base j of a word at bits [2j, 2j+1], code
  * (c >> 1) & 3 (A=0 C=1 T=2 G=3); read r starts at word d_word_offsets[r] and has d_offsets[r+1] - d_offsets[r]
  * bases.  Only for reads made of the letters A, C, G, T (anything else must use the ASCII entry points). */

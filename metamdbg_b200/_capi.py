@@ -43,6 +43,11 @@ class AuxOut(C.Structure):
                 ("low_complexity", u8p), ("qualities", u8p)]
 
 
+class AutotuneOut(C.Structure):
+    _fields_ = [("n_variants", C.c_int32), ("chosen", C.c_int32), ("identical", C.c_int32 * 4), ("ms", C.c_float * 4),
+                ("n_reads", C.c_uint32), ("n_minimizers", C.c_uint64)]
+
+
 # every symbol include/mdbg_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "mdbg_ctx_create": (C.c_int, [C.c_int, C.POINTER(MdbgParams), C.POINTER(C.c_void_p)]),
@@ -58,6 +63,10 @@ SYMBOLS = {
     "mdbg_ctx_set_host_packing": (C.c_int, [C.c_void_p, C.c_int]),
     "mdbg_sketch_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_int,
                                            C.POINTER(SketchDev)]),
+    "mdbg_ctx_set_sketch_variant": (C.c_int, [C.c_void_p, C.c_int]),
+    "mdbg_ctx_get_sketch_variant": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "mdbg_ctx_autotune_sketch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64,
+                                           C.POINTER(AutotuneOut)]),
     "mdbg_sketch_batch_device_packed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                                   C.c_uint64, C.c_int, C.POINTER(SketchDev)]),
     "mdbg_sketch_fetch": (C.c_int, [C.c_void_p, C.POINTER(SketchOut)]),

@@ -57,6 +57,7 @@ struct mdbg_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
+    int sketch_variant = 0;            // arithmetic variant of the unrolled l = 15 block (sketch.cu); same results
     int host_packing = -1;             // 2-bit pack ASCII host batches before H2D: -1 auto, 0 off, 1 on, 2 hybrid
     HostPool* pool = nullptr;
     uint64_t last_direct_pieces = 0, last_pieces = 0;   // hybrid transfer statistics of the last host batch
@@ -293,6 +294,7 @@ mdbg_status sketch_internal(mdbg_ctx* ctx, const uint8_t* d_bases, const uint64_
     a.n_min = ctx->n_min.as<uint32_t>();
     a.cursor = &ctx->d_small->cursor;
     a.n_overflow = &ctx->d_small->n_overflow;
+    a.variant = (uint32_t)ctx->sketch_variant;
 
     CK(cudaMemsetAsync(&ctx->d_small->cursor, 0, sizeof(uint32_t) * (1 + MAX_SUB), s));
     CK(cudaMemsetAsync(&ctx->d_small->n_overflow, 0, sizeof(unsigned long long), s));
@@ -500,6 +502,10 @@ mdbg_status mdbg_ctx_create(int device, const mdbg_params* p, mdbg_ctx** out) {
         return fail(nullptr, MDBG_ERR_OOM, "context allocation failed");
     }
     cudaMemset(c->d_small, 0, sizeof(SmallDev));
+    if (const char* v = getenv("MDBG_SKETCH_VARIANT")) {
+        const int want = atoi(v);
+        if (want >= 0 && want < SKETCH_VARIANTS) c->sketch_variant = want;
+    }
     if (p->blacklist && p->n_blacklist) {
         std::vector<uint32_t> bl(p->blacklist, p->blacklist + p->n_blacklist);
         std::sort(bl.begin(), bl.end());
@@ -614,6 +620,99 @@ mdbg_status mdbg_sketch_batch_device(mdbg_ctx* ctx, const uint8_t* d_bases, cons
         out->d_directions = ctx->b_dir.as<uint8_t>();
     }
     return MDBG_OK;
+}
+
+mdbg_status mdbg_ctx_set_sketch_variant(mdbg_ctx* ctx, int variant) {
+    if (!ctx) return MDBG_ERR_ARG;
+    if (variant < 0 || variant >= SKETCH_VARIANTS) return fail(ctx, MDBG_ERR_ARG, "sketch variant %d unknown (0..%d)", variant, SKETCH_VARIANTS - 1);
+    ctx->sketch_variant = variant;
+    return MDBG_OK;
+}
+
+mdbg_status mdbg_ctx_get_sketch_variant(mdbg_ctx* ctx, int* variant) {
+    if (!ctx || !variant) return MDBG_ERR_ARG;
+    *variant = ctx->sketch_variant;
+    return MDBG_OK;
+}
+
+// Runs every arithmetic variant of the sketch kernel on the caller's own device batch, compares the complete
+// results (offsets, minimizers, positions, strands) with variant 0 byte for byte on the device, and keeps the
+// fastest variant whose output is identical.  Variant 0 is the reference point and the fallback.
+mdbg_status mdbg_ctx_autotune_sketch(mdbg_ctx* ctx, const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t n_reads,
+                                     uint64_t n_bases, mdbg_autotune_out* out) {
+    if (!ctx || !out) return MDBG_ERR_ARG;
+    if (n_reads == 0 || !d_bases || !d_offsets) return fail(ctx, MDBG_ERR_ARG, "autotune needs a non-empty device batch");
+    if ((uintptr_t)d_bases & 15) return fail(ctx, MDBG_ERR_ARG, "d_bases must be 16-byte aligned");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const int before = ctx->sketch_variant;
+    memset(out, 0, sizeof *out);
+    out->n_variants = SKETCH_VARIANTS;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    DevBuf r_off, r_min, r_pos, r_dir;                            // variant 0's result
+    uint64_t r_total = 0;
+    mdbg_status st = MDBG_OK;
+    auto run = [&](int v, float* ms) -> mdbg_status {
+        ctx->sketch_variant = v;
+        CKS(sketch_internal(ctx, d_bases, d_offsets, n_reads, n_bases, 0));      // warm-up (allocations, caches)
+        float best = 0;
+        for (int rep = 0; rep < 2; rep++) {
+            CK(cudaEventRecord(e0, s));
+            CKS(sketch_internal(ctx, d_bases, d_offsets, n_reads, n_bases, 0));
+            CK(cudaEventRecord(e1, s));
+            CK(cudaEventSynchronize(e1));
+            float t = 0;
+            CK(cudaEventElapsedTime(&t, e0, e1));
+            if (rep == 0 || t < best) best = t;
+        }
+        *ms = best;
+        return MDBG_OK;
+    };
+    auto body = [&]() -> mdbg_status {
+        CKS(run(0, &out->ms[0]));
+        out->identical[0] = 1;
+        r_total = ctx->b_total;
+        CKS(ensure(ctx, r_off, ((size_t)n_reads + 1) * 8));
+        CKS(ensure(ctx, r_min, (r_total + 1) * 4));
+        CKS(ensure(ctx, r_pos, (r_total + 1) * 4));
+        CKS(ensure(ctx, r_dir, r_total + 1));
+        CK(cudaMemcpyAsync(r_off.p, ctx->b_off.p, ((size_t)n_reads + 1) * 8, cudaMemcpyDeviceToDevice, s));
+        CK(cudaMemcpyAsync(r_min.p, ctx->b_min.p, r_total * 4, cudaMemcpyDeviceToDevice, s));
+        CK(cudaMemcpyAsync(r_pos.p, ctx->b_pos.p, r_total * 4, cudaMemcpyDeviceToDevice, s));
+        CK(cudaMemcpyAsync(r_dir.p, ctx->b_dir.p, r_total, cudaMemcpyDeviceToDevice, s));
+        int best_v = 0;
+        for (int v = 1; v < SKETCH_VARIANTS; v++) {
+            CKS(run(v, &out->ms[v]));
+            unsigned long long* n_diff = &ctx->d_small->n_changed;
+            CK(cudaMemsetAsync(n_diff, 0, sizeof(unsigned long long), s));
+            bool same = ctx->b_total == r_total;
+            if (same) {
+                launch_count_diff(r_off.p, ctx->b_off.p, ((size_t)n_reads + 1) * 8, n_diff, s);
+                launch_count_diff(r_min.p, ctx->b_min.p, r_total * 4, n_diff, s);
+                launch_count_diff(r_pos.p, ctx->b_pos.p, r_total * 4, n_diff, s);
+                launch_count_diff(r_dir.p, ctx->b_dir.p, r_total, n_diff, s);
+                CKS(check_launch(ctx, "count_diff_kernel", 4));
+                CK(cudaMemcpyAsync(&ctx->h_scalar[2], n_diff, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+                CK(cudaStreamSynchronize(s));
+                same = ctx->h_scalar[2] == 0;
+            }
+            out->identical[v] = same ? 1 : 0;
+            if (same && out->ms[v] < 0.99f * out->ms[best_v]) best_v = v;
+        }
+        out->chosen = best_v;
+        return MDBG_OK;
+    };
+    st = body();
+    ctx->sketch_variant = (st == MDBG_OK) ? out->chosen : before;
+    out->n_reads = n_reads;
+    out->n_minimizers = r_total;
+    cudaStreamSynchronize(s);
+    release(r_off); release(r_min); release(r_pos); release(r_dir);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return st;
 }
 
 mdbg_status mdbg_sketch_batch_device_packed(mdbg_ctx* ctx, const uint32_t* d_packed, const uint64_t* d_word_offsets,

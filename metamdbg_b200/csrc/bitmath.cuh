@@ -47,10 +47,40 @@ MDBG_HD uint32_t revcomp_lmer(uint32_t fwd) {
     return x >> (32 - 2 * L);
 }
 
-// Unrolled register path: 16 consecutive l-mers for this lane out of the 32 ring bytes W (no invalid code
-// present).  Returns the 16-bit CANDIDATE mask (superset of the selected positions, see murmur_s1_u32) and leaves
-// the lane's 32 codes packed in (s_hi:s_lo), first base most significant (code i at bits 63-2i, 62-2i), from which
-// lmer_from_packed() re-derives the forward l-mer of a candidate.
+// Unrolled register path: 16 consecutive l-mers for this lane out of the
+// 32 ring bytes W (no invalid code present).  Returns the 16-bit CANDIDATE
+// mask (superset of the selected positions, see murmur_s1_u32); the forward
+// l-mer of the last candidate is left in sel_fwd.
+template <int L>
+MDBG_HD uint32_t roll16_fast(const uint32_t (&W)[8], uint32_t thr_hi_plus1, uint32_t& sel_fwd) {
+    constexpr uint32_t MASK = (L < 16) ? ((1u << (2 * L)) - 1u) : 0xFFFFFFFFu;
+    constexpr uint32_t INIT_MASK = (1u << (2 * (L - 1))) - 1u;      // L-1 <= 15 bases
+    // state after the first L-1 bases, built with two multiplies per 4 bases instead of L-1 roll steps
+    const uint32_t pf = (pack4_msb(W[0]) << 24) | (pack4_msb(W[1]) << 16) | (pack4_msb(W[2]) << 8) | pack4_msb(W[3]);
+    const uint32_t pr = pack4_lsb(W[0]) | (pack4_lsb(W[1]) << 8) | (pack4_lsb(W[2]) << 16) | (pack4_lsb(W[3]) << 24);
+    uint32_t fwd = pf >> (2 * (16 - (L - 1)));
+    uint32_t rc = ((pr & INIT_MASK) ^ (0xAAAAAAAAu & INIT_MASK)) << 2;
+    uint32_t sel = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const uint32_t c = byte_of<L>(W, L - 1 + j);
+        fwd = ((fwd << 2) | c) & MASK;
+        rc = (rc >> 2) | ((c ^ 2u) << (2 * L - 2));
+        const uint32_t s1 = murmur_s1_u32(min(fwd, rc));
+        if (s1 <= thr_hi_plus1) {
+            sel |= 1u << j;
+            sel_fwd = fwd;
+        }
+    }
+    return sel;
+}
+
+// ---- variant 1 of the register path: the lane's 32 codes are packed ONCE into (s_hi:s_lo), first base most
+// significant (code i at bits 63-2i, 62-2i), and into the complemented, reversed (r_hi:r_lo); every forward /
+// reverse-complement l-mer is then one funnel shift + mask instead of a roll step, and the accept bits are
+// collected by an add-with-carry chain.  lmer_from_packed() re-derives the forward l-mer of any position.
+namespace k1v1 {
+
 template <int L>
 MDBG_HD uint32_t lmer_from_packed(uint32_t s_hi, uint32_t s_lo, uint32_t j) {
     constexpr uint32_t MASK = (L < 16) ? ((1u << (2 * L)) - 1u) : 0xFFFFFFFFu;
@@ -61,8 +91,6 @@ MDBG_HD uint32_t lmer_from_packed(uint32_t s_hi, uint32_t s_lo, uint32_t j) {
 template <int L>
 MDBG_HD uint32_t roll16_fast(const uint32_t (&W)[8], uint32_t thr_cand, uint32_t& s_hi, uint32_t& s_lo) {
     constexpr uint32_t MASK = (L < 16) ? ((1u << (2 * L)) - 1u) : 0xFFFFFFFFu;
-    // S = (s_hi:s_lo) as above; R holds the complements first-base-least-significant (code i ^ 2 at bits 2i, 2i+1).
-    // Every forward l-mer is one 64-bit shift of S, every reverse complement one 64-bit shift of R.
     s_hi = (pack4_msb(W[0]) << 24) | (pack4_msb(W[1]) << 16) | (pack4_msb(W[2]) << 8) | pack4_msb(W[3]);
     s_lo = (pack4_msb(W[4]) << 24) | (pack4_msb(W[5]) << 16) | (pack4_msb(W[6]) << 8) | pack4_msb(W[7]);
     uint32_t r_lo = brev32(s_hi ^ 0xAAAAAAAAu), r_hi = brev32(s_lo ^ 0xAAAAAAAAu);   // bit order reversed ...
@@ -80,7 +108,7 @@ MDBG_HD uint32_t roll16_fast(const uint32_t (&W)[8], uint32_t thr_cand, uint32_t
         const uint32_t s1 = murmur_s1_u32(min(fwd, rc), risk);
 #ifdef __CUDA_ARCH__
         uint32_t scratch;
-        asm("add.cc.u32 %1, %2, %3;\n\taddc.u32 %0, %0, %0;" : "+r"(rej), "=r"(scratch) : "r"(s1), "r"(not_thr));
+        asm("add.cc.u32 %1, %2, %3;\n\taddc.u32 %0, %0, %0;" : "+r"(rej), "=&r"(scratch) : "r"(s1), "r"(not_thr));
 #else
         rej = 2u * rej + (s1 > thr_cand ? 1u : 0u);
 #endif
@@ -88,5 +116,7 @@ MDBG_HD uint32_t roll16_fast(const uint32_t (&W)[8], uint32_t thr_cand, uint32_t
     if (risk >= S1_RISK) return 0xFFFFu;                            // 2^-26 per key: let the exact test decide all 16
     return brev32(~rej) >> 16;                                      // accepted positions, position j in bit j
 }
+
+}  // namespace k1v1
 
 }  // namespace mdbg

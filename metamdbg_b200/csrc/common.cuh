@@ -81,18 +81,69 @@ MDBG_HD uint64_t murmur_h1_u64(uint64_t key) {
 //   h1 + h2 = fmix64(A) + fmix64(B),  A = (k1 ^ 34) + 34,  B = A + 34
 //   (seed 42, len 8: h1 = 42 ^ k1 ^ 8, h2 = 42 ^ 8, then h1 += h2, h2 += h1).
 //
-// Only the HIGH words of the two fmix64 results are formed.  With s0 = hi(fmix(A)) + hi(fmix(B)) (mod 2^32) the
-// true high word of the sum is s0 or s0 + 1 (carry out of the low words).  murmur_s1_u32 returns s' = s0 or s0 + 1
-// (the last multiply is applied once, to the SUM of the two pre-images; its low-word carry is not the exact
-// sum's), so that for a selected key (hash <= T, T_hi = T >> 32)
+// Only the HIGH words of the two fmix64 results are formed: with
+// s0 = hi(fmix(A)) + hi(fmix(B)) (mod 2^32) the true high word of the sum is s0
+// or s0 + 1 (carry out of the low words), so "hash <= T" implies s0 <= T_hi or
+// s0 == 0xFFFFFFFF, i.e. (s0 + 1) <= T_hi + 1 in unsigned arithmetic.  The two
+// +34 additions are done on the low word only; the 2^-26-rare case where one of
+// them carries into the high word is detected (B_lo < 68) and reported as s1 = 0.
 //
-//   s' <= T_hi + S1_SLACK     or     s' = 0xFFFFFFFF  (s0 = 0xFFFFFFFF with a carry: true high word 0)
+// murmur_s1_u32 returns s1 = s0 + 1 (or 0).  With T_hi = threshold >> 32:
+//   s1 >  T_hi + 1            -> certainly not selected
+//   1 <= s1 < T_hi            -> certainly selected (sum_hi <= s1 < T_hi)
+//   otherwise (s1 in {0, T_hi, T_hi + 1}) -> undecided: callers run the exact murmur_h1_u64.
+MDBG_HD uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c) { return a * b + c; }
+
+// fmix64 up to its second multiply: returns the two words (plo, phi) of
+// ((k ^ k>>33) * 0xff51afd7ed558ccd) ^ (.. >> 33); t = hi >> 1 and m = hi * 0xed558ccd are
+// shared by A and B (same high word)
+MDBG_HD void fmix64_front(uint32_t lo, uint32_t t, uint32_t m, uint32_t& plo, uint32_t& phi) {
+    lo ^= t;                                                   // k ^= k >> 33
+    const uint64_t p = (uint64_t)lo * 0xed558ccdu;             // k *= 0xff51afd7ed558ccd
+    phi = (uint32_t)(p >> 32) + mad_lo(lo, 0xff51afd7u, m);
+    plo = (uint32_t)p ^ (phi >> 1);                            // k ^= k >> 33
+}
+
+MDBG_HD uint32_t murmur_s1_u32(uint32_t key) {
+    // k1 = key * c1 ; k1 = rotl64(k1, 31) ; k1 *= c2
+    uint64_t p = (uint64_t)key * 0x114253d5u;
+    uint32_t lo = (uint32_t)p;
+    uint32_t hi = mad_lo(key, 0x87c37b91u, (uint32_t)(p >> 32));
+    const uint32_t rlo = funnel_l(hi, lo, 31);          // low word of (k1 << 31) | (k1 >> 33)
+    const uint32_t rhi = funnel_l(lo, hi, 31);
+    p = (uint64_t)rlo * 0x2745937fu;
+    hi = (uint32_t)(p >> 32) + mad_lo(rlo, 0x4cf5ad43u, rhi * 0x2745937fu);
+    const uint32_t alo = ((uint32_t)p ^ 34u) + 34u;            // A (low word)
+    const uint32_t blo = alo + 34u;                            // B (low word)
+    const uint32_t t = hi >> 1;
+    const uint32_t m = hi * 0xed558ccdu;
+    uint32_t plo_a, phi_a, plo_b, phi_b;
+    fmix64_front(alo, t, m, plo_a, phi_a);
+    fmix64_front(blo, t, m, plo_b, phi_b);
+    // high words of k * 0xc4ceb9fe1a85ec53 for A and B, summed (+1): the final k ^= k >> 33
+    // only changes the low word
+    uint32_t acc = mad_lo(phi_a, 0x1a85ec53u, 1u);
+    acc = mad_lo(plo_a, 0xc4ceb9feu, acc);
+    acc = mad_lo(phi_b, 0x1a85ec53u, acc);
+    acc = mad_lo(plo_b, 0xc4ceb9feu, acc);
+    const uint32_t s1 = acc + umulhi32(plo_a, 0x1a85ec53u) + umulhi32(plo_b, 0x1a85ec53u);
+    return (blo < 68u) ? 0u : s1;                              // 0 = "undecided, run the exact hash"
+}
+
+// ---- variant 1 of the candidate filter (sketch kernel variant 1, see sketch.cu) -------------------------------------
+// Same superset contract, fewer instructions.  The last fmix64 multiply is applied ONCE, to the sum of the two
+// pre-images: h = (P_a ^ P_a >> 33) + (P_b ^ P_b >> 33) with P = k * 0xc4ceb9fe1a85ec53; the xor-shifts only touch
+// the low words, so hi(h) = hi(P_a) + hi(P_b) + carry, and by linearity (k_a + k_b) * M has the same two high
+// words plus ITS low-word carry.  s1(key) returns s' = s0 or s0 + 1, so that for a selected key (hash <= T)
+//
+//   s' <= T_hi + S1_SLACK     or     s' = 0xFFFFFFFF  (s0 = 0xFFFFFFFF with a carry: true high word 0).
 //
 // The second case, and the 2^-26-rare case where one of the two +34 additions (done on the low word only) carries
-// into the high word and makes s' meaningless, are reported through `risk`: murmur_s1_u32 keeps
-// risk = max(risk, ...) and the caller must treat ALL keys that went into a `risk` as candidates when
-// risk >= S1_RISK (probability 2^-26 per key).  Callers confirm every candidate with the exact murmur_h1_u64
-// (tests/cpp/device_math_test.cu walks all 2^32 keys: no selected key is ever rejected).
+// into the high word, are reported through `risk`: s1 keeps risk = max(risk, ...) and the caller must treat ALL
+// keys that went into one `risk` as candidates when risk >= S1_RISK.  Callers confirm every candidate with the
+// exact murmur_h1_u64 (tests/cpp/device_math_test.cu walks all 2^32 keys: no selected key is ever rejected).
+namespace k1v1 {
+
 constexpr uint32_t S1_SLACK = 1;
 constexpr uint32_t S1_RISK = 0xFFFFFFBCu;                      // (k1_lo ^ 34) + 68 wraps
 
@@ -106,9 +157,6 @@ MDBG_HD uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c) {
 #endif
 }
 
-// fmix64 up to its second multiply: returns the two words (plo, phi) of
-// ((k ^ k>>33) * 0xff51afd7ed558ccd) ^ (.. >> 33); t = hi >> 1 and m = hi * 0xed558ccd are
-// shared by A and B (same high word)
 MDBG_HD void fmix64_front(uint32_t lo, uint32_t t, uint32_t m, uint32_t& plo, uint32_t& phi) {
     lo ^= t;                                                   // k ^= k >> 33
     const uint64_t p = (uint64_t)lo * 0xed558ccdu;             // k *= 0xff51afd7ed558ccd
@@ -117,11 +165,10 @@ MDBG_HD void fmix64_front(uint32_t lo, uint32_t t, uint32_t m, uint32_t& plo, ui
 }
 
 MDBG_HD uint32_t murmur_s1_u32(uint32_t key, uint32_t& risk) {
-    // k1 = key * c1 ; k1 = rotl64(k1, 31) ; k1 *= c2
     uint64_t p = (uint64_t)key * 0x114253d5u;
     uint32_t lo = (uint32_t)p;
     uint32_t hi = mad_lo(key, 0x87c37b91u, (uint32_t)(p >> 32));
-    const uint32_t rlo = funnel_l(hi, lo, 31);          // low word of (k1 << 31) | (k1 >> 33)
+    const uint32_t rlo = funnel_l(hi, lo, 31);
     const uint32_t rhi = funnel_l(lo, hi, 31);
     p = (uint64_t)rlo * 0x2745937fu;
     hi = mad_lo(rlo, 0x4cf5ad43u, mad_lo(rhi, 0x2745937fu, (uint32_t)(p >> 32)));
@@ -133,10 +180,6 @@ MDBG_HD uint32_t murmur_s1_u32(uint32_t key, uint32_t& risk) {
     uint32_t plo_a, phi_a, plo_b, phi_b;
     fmix64_front(alo, t, m, plo_a, phi_a);
     fmix64_front(blo, t, m, plo_b, phi_b);
-    // fmix64's last multiply and xor-shift: h = (P_a ^ P_a >> 33) + (P_b ^ P_b >> 33) with P = k * 0xc4ceb9fe1a85ec53.
-    // The xor-shifts only touch the low words, so the high word of h is hi(P_a) + hi(P_b) plus a carry out of the
-    // low words; by linearity (k_a + k_b) * M has the same two high words plus ITS low-word carry.  One 64-bit add
-    // and the high word of one 64 x 64 product therefore give s' = s0 or s0 + 1.
     uint32_t klo, khi;
 #ifdef __CUDA_ARCH__
     asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, %5;" : "=&r"(klo), "=r"(khi) : "r"(plo_a), "r"(plo_b), "r"(phi_a), "r"(phi_b));
@@ -149,6 +192,8 @@ MDBG_HD uint32_t murmur_s1_u32(uint32_t key, uint32_t& risk) {
     risk = max(risk, max(x34, acc));                           // acc >= S1_RISK also covers the wrap s' = 0xFFFFFFFF
     return acc;
 }
+
+}  // namespace k1v1
 
 // MurmurHash3_x64_128_original(vec, 4*k bytes, seed 0) = KmerVec::hash128
 // (src/Commons.hpp:941-969).  `get(i)` returns the i-th u32 of the normalized

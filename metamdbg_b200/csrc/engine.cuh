@@ -34,9 +34,14 @@ struct SketchArgs {
     uint32_t* n_min;             // [n_reads] true minimizer count per read
     uint32_t* cursor;            // dynamic read scheduler (zeroed before launch)
     unsigned long long* n_overflow;  // reads whose slot was too small (zeroed before launch)
+    uint32_t variant;            // arithmetic of the unrolled l = 15 block: 0 or 1 (sketch.cu; identical results)
 };
+constexpr int SKETCH_VARIANTS = 2;
 
 void launch_sketch(const SketchArgs& a, int sm_count, cudaStream_t s);
+
+// *n_diff += number of bytes at which a[0..n_bytes) and b[0..n_bytes) differ (autotune's identity check)
+void launch_count_diff(const void* a, const void* b, size_t n_bytes, unsigned long long* n_diff, cudaStream_t s);
 
 // counts (u32[n]) -> exclusive offsets (u64[n+1]); scratch must hold ceil(n/2048)+1 u64
 void launch_scan_u32_to_u64(const uint32_t* counts, uint64_t* offsets, uint32_t n, uint64_t* scratch, cudaStream_t s);

@@ -14,6 +14,8 @@
 //   --high-word Murmur test--> candidates appended in position order to a 64-entry per-warp list
 //   --32 at a time: exact hash, blacklist, ballot compaction--> coalesced (value, position, strand)
 //   writes into the read's output slot.
+#include <algorithm>
+
 #include "common.cuh"
 #include "engine.cuh"
 #include "bitmath.cuh"
@@ -119,8 +121,14 @@ __device__ __forceinline__ uint32_t roll16_generic(const uint8_t* ring, uint32_t
     return sel;
 }
 
-template <int L_FAST>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) sketch_kernel(const SketchArgs a) {
+// V selects the arithmetic of the unrolled register block (everything else is shared):
+//   V = 0  roll step per position + murmur_s1_u32          (47.5 instructions per l-mer, 23.1 on the FMA pipe)
+//   V = 1  k1v1:: funnel-shift l-mers from packed codes, one final fmix multiply on the summed pre-images,
+//          carry-chain accept bits                         (40.6 instructions per l-mer, 18.1 on the FMA pipe)
+// Both are supersets confirmed by the exact hash in flush_candidates, so their outputs are identical;
+// mdbg_ctx_autotune_sketch() verifies that on the caller's own batch and keeps the faster one.
+template <int L_FAST, int V>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, V ? 5 : 0) sketch_kernel(const SketchArgs a) {
     __shared__ __align__(16) uint8_t ring_all[WARPS_PER_CTA][RING + 16];   // +16: linear-write slack
     __shared__ uint2 cand_all[WARPS_PER_CTA][64];                           // pending candidates: (pos | invalid<<31, fwd)
     const uint32_t lane = threadIdx.x & 31;
@@ -128,7 +136,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) sketch_kernel(const Ske
     uint2* cand = cand_all[threadIdx.x >> 5];
     uint32_t n_list = 0;
     const uint32_t l = a.l;
-    const uint32_t thr_cand = (uint32_t)(a.threshold >> 32) + S1_SLACK;   // wrapped (< S1_SLACK) disables the fast path
+    // V = 0: T_hi + 1, V = 1: T_hi + S1_SLACK; a wrapped value (overflow) disables the fast path
+    const uint32_t thr_cand = (uint32_t)(a.threshold >> 32) + (V ? k1v1::S1_SLACK : 1u);
+    constexpr uint32_t THR_MIN = V ? k1v1::S1_SLACK : 1u;
 
     for (;;) {
         uint32_t r = 0;
@@ -298,15 +308,17 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) sketch_kernel(const Ske
                     W[4] = u1.x; W[5] = u1.y; W[6] = u1.z; W[7] = u1.w;
                 }
                 const uint32_t inv = (W[0] | W[1] | W[2] | W[3] | W[4] | W[5] | W[6] | W[7]) & 0x04040404u;
-                const bool fast = (L_FAST != 0) && (l == (uint32_t)L_FAST) && thr_cand >= S1_SLACK &&
+                const bool fast = (L_FAST != 0) && (l == (uint32_t)L_FAST) && thr_cand >= THR_MIN &&
                                   !__any_sync(0xffffffffu, inv != 0);
 
-                uint32_t sel, s_hi = 0, s_lo = 0;
+                uint32_t sel, sel_fwd = 0;           // V = 0: forward l-mer of the last candidate
+                uint32_t s_hi = 0, s_lo = 0;         // V = 1: the lane's 32 codes, packed
                 bool regs_ok = false;
                 if (a.select_none) {
                     sel = 0;
                 } else if (fast) {
-                    sel = roll16_fast<(L_FAST ? L_FAST : 15)>(W, thr_cand, s_hi, s_lo);
+                    if constexpr (V == 0) sel = roll16_fast<(L_FAST ? L_FAST : 15)>(W, thr_cand, sel_fwd);
+                    else sel = k1v1::roll16_fast<(L_FAST ? L_FAST : 15)>(W, thr_cand, s_hi, s_lo);
                     regs_ok = (valid_bits == 0xFFFFu);
                     sel &= valid_bits;
                 } else {
@@ -321,8 +333,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) sketch_kernel(const Ske
                     if (__all_sync(0xffffffffu, n_c <= 1 && (regs_ok || n_c == 0))) {
                         if (n_c) {
                             const uint32_t j = __ffs(sel) - 1;
-                            cand[n_list + __popc(hit_lanes & ((1u << lane) - 1u))] =
-                                make_uint2(p0 + j, lmer_from_packed<(L_FAST ? L_FAST : 15)>(s_hi, s_lo, j));
+                            if constexpr (V != 0) sel_fwd = k1v1::lmer_from_packed<(L_FAST ? L_FAST : 15)>(s_hi, s_lo, j);
+                            cand[n_list + __popc(hit_lanes & ((1u << lane) - 1u))] = make_uint2(p0 + j, sel_fwd);
                         }
                         n_list += __popc(hit_lanes);
                         __syncwarp();
@@ -355,7 +367,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) sketch_kernel(const Ske
                             rest &= rest - 1;
                             if (rank >= base_rank && rank < base_rank + 32) {
                                 uint32_t fwd, inv = 0;
-                                if (regs_ok) fwd = lmer_from_packed<(L_FAST ? L_FAST : 15)>(s_hi, s_lo, j);
+                                if (V == 0 && regs_ok && n_c == 1) fwd = sel_fwd;
+                                else if (V != 0 && regs_ok) fwd = k1v1::lmer_from_packed<(L_FAST ? L_FAST : 15)>(s_hi, s_lo, j);
                                 else fwd = fwd_at(ring, p0 + j, l, inv);
                                 cand[n_list + (rank - base_rank)] = make_uint2((p0 + j) | (inv ? 0x80000000u : 0u), fwd);
                             }
@@ -392,18 +405,38 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) sketch_kernel(const Ske
     }
 }
 
-void launch_sketch(const SketchArgs& a, int sm_count, cudaStream_t s) {
-    if (a.read_end <= a.read_begin) return;
+template <int L_FAST, int V>
+static void launch_sketch_as(const SketchArgs& a, int sm_count, cudaStream_t s) {
     // persistent grid: enough CTAs to fill every SM, reads are pulled dynamically
     int per_sm = 0;
-    if (a.l == 15) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sketch_kernel<15>, WARPS_PER_CTA * 32, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sketch_kernel<0>, WARPS_PER_CTA * 32, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (sketch_kernel<L_FAST, V>), WARPS_PER_CTA * 32, 0);
     if (per_sm < 1) per_sm = 1;
     uint64_t want = ((uint64_t)(a.read_end - a.read_begin) + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     uint64_t grid = (uint64_t)sm_count * per_sm;
     if (grid > want) grid = want;
-    if (a.l == 15) sketch_kernel<15><<<(unsigned)grid, WARPS_PER_CTA * 32, 0, s>>>(a);
-    else sketch_kernel<0><<<(unsigned)grid, WARPS_PER_CTA * 32, 0, s>>>(a);
+    sketch_kernel<L_FAST, V><<<(unsigned)grid, WARPS_PER_CTA * 32, 0, s>>>(a);
+}
+
+void launch_sketch(const SketchArgs& a, int sm_count, cudaStream_t s) {
+    if (a.read_end <= a.read_begin) return;
+    if (a.l != 15) launch_sketch_as<0, 0>(a, sm_count, s);          // generic l: no unrolled register block at all
+    else if (a.variant == 1) launch_sketch_as<15, 1>(a, sm_count, s);
+    else launch_sketch_as<15, 0>(a, sm_count, s);
+}
+
+// ------------------------------------------------------------------ byte-wise comparison of two device arrays
+__global__ void __launch_bounds__(256) count_diff_kernel(const uint8_t* a, const uint8_t* b, size_t n, unsigned long long* n_diff) {
+    unsigned long long mine = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        mine += a[i] != b[i];
+    for (int d = 16; d; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(n_diff, mine);
+}
+
+void launch_count_diff(const void* a, const void* b, size_t n_bytes, unsigned long long* n_diff, cudaStream_t s) {
+    if (n_bytes == 0) return;
+    const uint64_t grid = std::min<uint64_t>((n_bytes + 255) / 256, 148 * 8);
+    count_diff_kernel<<<(unsigned)grid, 256, 0, s>>>(reinterpret_cast<const uint8_t*>(a), reinterpret_cast<const uint8_t*>(b), n_bytes, n_diff);
 }
 
 // ------------------------------------------------------------------ scan

@@ -17,7 +17,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _capi
-from ._capi import AuxOut, MdbgParams, SketchDev, SketchOut, TableOut
+from ._capi import AutotuneOut, AuxOut, MdbgParams, SketchDev, SketchOut, TableOut
 
 STATUS = {0: "OK", 1: "CUDA", 2: "ARG", 3: "STATE", 4: "TABLE_FULL", 5: "NCCL", 6: "OOM"}
 
@@ -184,6 +184,27 @@ class Engine:
         self._ck(self._lib.mdbg_sketch_batch_device(self._ctx, C.c_void_p(d_bases_ptr), C.c_void_p(d_offsets_ptr),
                                                     n_reads, n_bases, int(append_to_store), C.byref(out)))
         return out
+
+    def set_sketch_variant(self, variant: int):
+        """Arithmetic variant of the sketch kernel's unrolled l = 15 block (identical results, sketch.cu)."""
+        self._ck(self._lib.mdbg_ctx_set_sketch_variant(self._ctx, int(variant)))
+
+    @property
+    def sketch_variant(self) -> int:
+        v = C.c_int(0)
+        self._ck(self._lib.mdbg_ctx_get_sketch_variant(self._ctx, C.byref(v)))
+        return v.value
+
+    def autotune_sketch(self, d_bases_ptr: int, d_offsets_ptr: int, n_reads: int, n_bases: int) -> dict:
+        """Run every sketch-kernel variant on this device batch, compare the results byte for byte on the device
+        and keep the fastest identical one (variant 0 is the fallback)."""
+        out = AutotuneOut()
+        self._ck(self._lib.mdbg_ctx_autotune_sketch(self._ctx, C.c_void_p(d_bases_ptr), C.c_void_p(d_offsets_ptr),
+                                                    n_reads, n_bases, C.byref(out)))
+        n = out.n_variants
+        return {"chosen": int(out.chosen), "identical": [bool(out.identical[i]) for i in range(n)],
+                "ms": [float(out.ms[i]) for i in range(n)], "n_reads": int(out.n_reads),
+                "n_minimizers": int(out.n_minimizers)}
 
     def sketch_batch_device_packed(self, d_packed_ptr: int, d_word_offsets_ptr: int, d_offsets_ptr: int, n_reads: int,
                                    n_bases: int, append_to_store: bool = False) -> SketchDev:

@@ -18,6 +18,12 @@ extern "C" {
 }
 
 using namespace mdbg;
+#ifndef MDBG_TEST_VARIANT
+#define MDBG_TEST_VARIANT 0                  // which arithmetic variant of the sketch kernel's register block is tested
+#endif
+#if MDBG_TEST_VARIANT == 1
+using namespace mdbg::k1v1;                  // murmur_s1_u32(key, risk), roll16_fast(W, thr, s_hi, s_lo), lmer_from_packed
+#endif
 
 static uint64_t rng_state = 0x9E3779B97F4A7C15ull;
 static uint64_t rnd() { rng_state += 0x9E3779B97F4A7C15ull; return mix64(rng_state); }
@@ -47,16 +53,34 @@ static void test_murmur() {
 struct CandStats { uint64_t keys = 0, selected = 0, candidates = 0, undecided0 = 0, missed = 0; };
 
 static void cand_range(uint64_t lo, uint64_t hi, uint64_t step, uint64_t T, CandStats* st) {
+#if MDBG_TEST_VARIANT == 0
+    const uint32_t thp1 = (uint32_t)(T >> 32) + 1u;
+#else
     const uint32_t thp1 = (uint32_t)(T >> 32) + S1_SLACK;
+#endif
     CandStats s;
     for (uint64_t k = lo; k < hi; k += step) {
         const uint32_t key = (uint32_t)k;
+#if MDBG_TEST_VARIANT == 0
+        const uint32_t s1 = murmur_s1_u32(key);
+        const bool cand = s1 <= thp1;
+#else
         uint32_t risk = 0;
         const uint32_t s1 = murmur_s1_u32(key, risk);
         const bool cand = s1 <= thp1 || risk >= S1_RISK;
+#endif
         const bool sel = murmur_h1_u64((uint64_t)key) <= T;
+#if MDBG_TEST_VARIANT == 0
+        s.keys++; s.selected += sel; s.candidates += cand; s.undecided0 += (s1 == 0);
+#else
         s.keys++; s.selected += sel; s.candidates += cand; s.undecided0 += (risk >= S1_RISK);
+#endif
         if (sel && !cand) s.missed++;
+#if MDBG_TEST_VARIANT == 0
+        // documented three-way classification (common.cuh): 1 <= s1 < T_hi  =>  certainly selected
+        if (s1 >= 1 && s1 < (uint32_t)(T >> 32) && !sel) s.missed++;
+#else
+#endif
     }
     *st = s;
 }
@@ -79,7 +103,11 @@ static void test_candidates(bool exhaustive) {
         CandStats s;
         for (auto& x : st) { s.keys += x.keys; s.selected += x.selected; s.candidates += x.candidates;
                              s.undecided0 += x.undecided0; s.missed += x.missed; }
+#if MDBG_TEST_VARIANT == 0
+        printf("density %-8g T=%016llx keys %llu%s selected %llu candidates %llu (s1==0: %llu) misclassified %llu\n",
+#else
         printf("density %-8g T=%016llx keys %llu%s selected %llu candidates %llu (carry case: %llu) misclassified %llu\n",
+#endif
                densities[d], (unsigned long long)T, (unsigned long long)s.keys, full ? " (all)" : "",
                (unsigned long long)s.selected, (unsigned long long)s.candidates, (unsigned long long)s.undecided0,
                (unsigned long long)s.missed);
@@ -123,7 +151,11 @@ static void test_bits() {
 template <int L>
 static void test_roll(uint64_t T) {
     static const char ALPHA[4] = {'A', 'C', 'T', 'G'};                  // code = (c >> 1) & 3
+#if MDBG_TEST_VARIANT == 0
+    const uint32_t thp1 = (uint32_t)(T >> 32) + 1u;
+#else
     const uint32_t thp1 = (uint32_t)(T >> 32) + S1_SLACK;
+#endif
     uint64_t n_sel = 0, n_cand = 0;
     for (int rep = 0; rep < 200000; rep++) {
         uint32_t W[8];
@@ -140,19 +172,45 @@ static void test_roll(uint64_t T) {
         uint64_t vals[32]; uint8_t dirs[32];
         const size_t n = orc_lmers(seq, L + 15, L, vals, dirs);
         CHECK(n == 16, "orc_lmers returned %zu", n);
+#if MDBG_TEST_VARIANT == 0
+        uint32_t sel_fwd = 0xDEADBEEF;
+        const uint32_t cand = roll16_fast<L>(W, thp1, sel_fwd);
+        uint32_t exact = 0, last = 0;
+        for (int j = 0; j < 16; j++) {
+#else
         uint32_t s_hi = 0, s_lo = 0;
         const uint32_t cand = roll16_fast<L>(W, thp1, s_hi, s_lo);
         uint32_t exact = 0;
         for (int j = 0; j < 16; j++)
+#endif
             if (orc_murmur3_x64_128_h1(&vals[j], 8, 42) <= T) exact |= 1u << j;
+#if MDBG_TEST_VARIANT == 0
+            if ((cand >> j) & 1u) last = j;
+        }
+#else
+#endif
         CHECK((exact & ~cand) == 0, "roll16_fast<%d> lost a selected position (%04x vs %04x)", L, cand, exact);
+#if MDBG_TEST_VARIANT == 0
+        if (cand) {                                                     // sel_fwd = forward l-mer of the last candidate
+#else
         for (int j = 0; j < 16; j++) {                                  // every position's l-mer from the packed codes
+#endif
             uint32_t fwd = 0;
+#if MDBG_TEST_VARIANT == 0
+            for (int t = 0; t < L; t++) fwd = (fwd << 2) | ((W[(last + t) >> 2] >> (8 * ((last + t) & 3))) & 3u);
+            if (L < 16) fwd &= (1u << (2 * L)) - 1u;
+            CHECK(sel_fwd == fwd, "sel_fwd");
+#else
             for (int t = 0; t < L; t++) fwd = (fwd << 2) | ((W[(j + t) >> 2] >> (8 * ((j + t) & 3))) & 3u);
             if (L < 16) fwd &= (1u << ((2 * L) & 31)) - 1u;
             CHECK(lmer_from_packed<L>(s_hi, s_lo, j) == fwd, "lmer_from_packed j=%d", j);
+#endif
             const uint32_t rc = revcomp_lmer<L>(fwd);
+#if MDBG_TEST_VARIANT == 0
+            CHECK((uint64_t)(fwd < rc ? fwd : rc) == vals[last] && dirs[last] == (fwd < rc ? 0 : 1), "canonical/dir");
+#else
             CHECK((uint64_t)(fwd < rc ? fwd : rc) == vals[j] && dirs[j] == (fwd < rc ? 0 : 1), "canonical/dir");
+#endif
         }
         n_sel += __builtin_popcount(exact); n_cand += __builtin_popcount(cand);
     }

@@ -65,4 +65,19 @@ def test_gpu_parity_suites_against_the_emulated_library(emulated):
     last = run.stdout.strip().splitlines()[-1]
     assert "passed" in last and "failed" not in last, tail
     n_passed = int(last.split(" passed")[0].split()[-1])
-    assert n_passed >= 31, tail                  # 27 parity + 4 host-driver tests
+    assert n_passed >= 33, tail                  # 29 parity + 4 host-driver tests
+
+
+def test_sketch_variant_1_through_the_emulated_library(emulated):
+    """The sketch-heavy GPU parity tests once more with MDBG_SKETCH_VARIANT=1: variant 1 of the unrolled register
+    block (k1v1:: in common.cuh / bitmath.cuh) behind the whole host-side sequencing."""
+    lib, env = emulated
+    env = dict(env, MDBG_SKETCH_VARIANT="1")
+    run = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "-m", "gpu", "-q", "-x",
+                          "-p", "no:cacheprovider", "-k", "sketch or packed or full_path or side_outputs"],
+                         cwd=ROOT, env=env, capture_output=True, text=True, timeout=3000)
+    tail = run.stdout[-2500:] + run.stderr[-1500:]
+    assert run.returncode == 0, tail
+    last = run.stdout.strip().splitlines()[-1]
+    assert "passed" in last and "failed" not in last, tail
+    assert int(last.split(" passed")[0].split()[-1]) >= 15, tail

@@ -17,13 +17,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.mark.skipif(shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"),
                     reason="nvcc not available")
-def test_device_math_on_host(tmp_path):
+@pytest.mark.parametrize("variant", [0, 1])
+def test_device_math_on_host(tmp_path, variant):
     from oracle import pyoracle
     pyoracle.build()
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     exe = str(tmp_path / "device_math_test")
     odir = os.path.join(ROOT, "oracle")
-    cmd = [nvcc, "-O2", "-std=c++17", "-w", "-Xcompiler", "-pthread", "-o", exe,
+    cmd = [nvcc, "-O2", "-std=c++17", "-w", f"-DMDBG_TEST_VARIANT={variant}", "-Xcompiler", "-pthread", "-o", exe,
            os.path.join(ROOT, "tests", "cpp", "device_math_test.cu"), "-L" + odir, "-lmdbg_oracle",
            "-Xlinker", "-rpath=" + odir]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)

@@ -36,6 +36,22 @@ def real_gpu_only():
         pytest.skip("uses torch device tensors: real GPU only")
 
 
+def device_array(arr: np.ndarray, pad: int = 0):
+    """(device pointer, owner) of a copy of `arr` (+ pad bytes): a torch CUDA tensor on the GPU box; under the CPU
+    emulator device memory is host memory, so a 16-byte aligned numpy copy plays the part."""
+    raw = np.ascontiguousarray(arr).view(np.uint8).ravel()
+    if EMULATED:
+        store = np.zeros(len(raw) + pad + 16, np.uint8)
+        shift = (-store.ctypes.data) % 16
+        view = store[shift:shift + len(raw) + pad]
+        view[:len(raw)] = raw
+        return view.ctypes.data, (store, view)
+    import torch
+    t = torch.zeros(len(raw) + pad, dtype=torch.uint8, device="cuda:0")
+    t[:len(raw)] = torch.from_numpy(raw.copy()).to("cuda:0")
+    return t.data_ptr(), t
+
+
 def engine(l=15, d=0.005, hpc=True, bl=None):
     from metamdbg_b200 import Engine
     return Engine(l, d, hpc, bl)
@@ -271,6 +287,41 @@ def test_device_generator_matches_numpy_and_device_sketch(built, oracle):
     assert out.n_minimizers == len(sk.minimizers)
     assert_sketch_equal(sk, *oracle.sketch_batch(bases, offs, 15, 0.005, True))
     eng.close()
+
+
+@pytest.mark.parametrize("hpc,dens", [(True, 0.005), (False, 0.025)])
+def test_sketch_kernel_variants_and_autotune(built, oracle, hpc, dens):
+    """Every arithmetic variant of the sketch kernel's unrolled block gives the oracle's sketch, and
+    mdbg_ctx_autotune_sketch only ever activates a variant whose complete output matched variant 0 on the device."""
+    import warnings
+    rs = synth.make_readset(1500, 8000, seed=314, n_genomes=2, genome_len_range=(150_000, 250_000), err=0.01)
+    bases, offs = synth.fill_reads(rs)
+    bases = bases.copy()
+    rng = np.random.default_rng(9)
+    for r in rng.choice(rs.n_reads, 40, replace=False):                       # some blocks leave the fast path
+        lo, hi = int(offs[r]), int(offs[r + 1])
+        if hi - lo > 10:
+            bases[lo + int(rng.integers(0, hi - lo))] = ord("N")
+    want = oracle.sketch_batch(bases, offs, 15, dens, hpc)
+    eng = engine(15, dens, hpc)
+    assert eng.sketch_variant == int(os.environ.get("MDBG_SKETCH_VARIANT", "0"))
+    p_b, keep_b = device_array(bases, pad=64)
+    p_o, keep_o = device_array(offs.astype(np.uint64))
+    res = eng.autotune_sketch(p_b, p_o, rs.n_reads, int(offs[-1]))
+    assert res["identical"][0] and res["n_minimizers"] == len(want[1]) and res["n_reads"] == rs.n_reads
+    assert res["identical"][res["chosen"]] and eng.sketch_variant == res["chosen"]
+    assert eng.store_size() == (0, 0)                                         # autotune appends nothing
+    assert_sketch_equal(eng.sketch_batch(bases, offs), *want, tag=f"autotuned variant {res['chosen']}")
+    for v, same in enumerate(res["identical"]):
+        if not same:                                   # never activated by autotune; say so instead of hiding it
+            warnings.warn(f"sketch variant {v} differs from variant 0 on this device (times {res['ms']})")
+            continue
+        eng.set_sketch_variant(v)
+        assert_sketch_equal(eng.sketch_batch(bases, offs), *want, tag=f"forced variant {v}")
+    with pytest.raises(Exception):
+        eng.set_sketch_variant(len(res["identical"]))
+    eng.close()
+    del keep_b, keep_o
 
 
 def test_python_mirror_single_read(built, oracle):
