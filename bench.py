@@ -395,8 +395,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                "h2d_bytes_per_step": int((moved1[0] - moved0[0]) // e_steps),
                "d2h_bytes_per_step": int((moved1[1] - moved0[1]) // e_steps),
                "host_input_bytes_per_step": int(e_bases + 8 * (e_reads + 1)),
-               "transfer": "ASCII reads are 2-bit packed by the library's host threads before H2D",
+               "transfer": "ASCII reads are 2-bit packed by the library's host threads before H2D; scan, compaction and "
+                           "the CSR's D2H run piece by piece behind each piece's sketch",
                "steps": e_steps, "reads_per_gpu": e_reads, "host_batch_reads": batch,
+               "last_host_batch": eng.last_batch_info(),
                "timer": "host wall clock around synchronous C-ABI calls, max over ranks"}
         if world == 1 and e_reads == n_reads:
             assert tab.checksum == checksum_local, "e2e table differs from the device-resident table"

@@ -143,6 +143,18 @@ mdbg_status mdbg_sketch_batch(mdbg_ctx* ctx, const uint8_t* bases, const uint64_
  * (experimental, pinned caller buffers only) additionally sends a piece as plain ASCII whenever the copy engine
  * is idle, so that DMA and the packer work side by side. */
 mdbg_status mdbg_ctx_set_host_packing(mdbg_ctx* ctx, int on);
+/* How the last host batch (mdbg_sketch_batch / _q) travelled: pieces it was cut into, pieces whose scan /
+ * compaction / CSR copy ran piece-wise behind their sketch (all of them unless a read overflowed its padded slot,
+ * which sends the whole batch through the exact re-sketch: overflow_fallback = 1), buffer growths with copies in
+ * flight, and the host packer's throughput on the raw ASCII bytes. */
+typedef struct mdbg_batch_info {
+    uint64_t n_pieces, n_pieces_pipelined, n_buffer_growths, n_direct_pieces;
+    int32_t overflow_fallback, packed;
+    double pack_gb_per_s;
+    const char* pack_isa;                            /* "avx512" | "avx2" | "scalar" */
+    int32_t host_threads;
+} mdbg_batch_info;
+mdbg_status mdbg_ctx_last_batch_info(mdbg_ctx* ctx, mdbg_batch_info* info);
 /* Same with the reads already in HBM.  d_bases must be 16-byte aligned;
  * nothing is copied to the host.  `out` may be NULL. */
 mdbg_status mdbg_sketch_batch_device(mdbg_ctx* ctx, const uint8_t* d_bases, const uint64_t* d_offsets,

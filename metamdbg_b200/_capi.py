@@ -43,6 +43,12 @@ class AuxOut(C.Structure):
                 ("low_complexity", u8p), ("qualities", u8p)]
 
 
+class BatchInfo(C.Structure):
+    _fields_ = [("n_pieces", C.c_uint64), ("n_pieces_pipelined", C.c_uint64), ("n_buffer_growths", C.c_uint64),
+                ("n_direct_pieces", C.c_uint64), ("overflow_fallback", C.c_int32), ("packed", C.c_int32),
+                ("pack_gb_per_s", C.c_double), ("pack_isa", C.c_char_p), ("host_threads", C.c_int32)]
+
+
 class AutotuneOut(C.Structure):
     _fields_ = [("n_variants", C.c_int32), ("chosen", C.c_int32), ("identical", C.c_int32 * 4), ("ms", C.c_float * 4),
                 ("n_reads", C.c_uint32), ("n_minimizers", C.c_uint64)]
@@ -61,6 +67,7 @@ SYMBOLS = {
     "mdbg_ctx_kernel_time_ms": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     "mdbg_sketch_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.POINTER(SketchOut)]),
     "mdbg_ctx_set_host_packing": (C.c_int, [C.c_void_p, C.c_int]),
+    "mdbg_ctx_last_batch_info": (C.c_int, [C.c_void_p, C.POINTER(BatchInfo)]),
     "mdbg_sketch_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_int,
                                            C.POINTER(SketchDev)]),
     "mdbg_ctx_set_sketch_variant": (C.c_int, [C.c_void_p, C.c_int]),

@@ -62,11 +62,19 @@ struct mdbg_ctx {
     HostPool* pool = nullptr;
     uint64_t last_direct_pieces = 0, last_pieces = 0;   // hybrid transfer statistics of the last host batch
     double last_pack_gbs = 0;          // host packer throughput of the last packed batch (raw GB/s)
+    uint64_t last_pipelined = 0, last_grows = 0;   // piece pipeline: pieces finished piece-wise, mid-batch buffer growths
+    int last_overflow_fallback = 0, last_packed = 0;
     int auto_pack_pause = 0;           // auto mode: batches still to send as ASCII after the packer proved too slow
     DevBuf d_pack, d_src;
     PinBuf h_pack, h_src, h_asc;
     cudaEvent_t sub_ev[MAX_SUB] = {};
     cudaEvent_t copy_gate = nullptr;
+    // piece pipeline of a host batch: per-piece scan / compaction / D2H of the CSR behind the sketch of that piece
+    cudaStream_t d2h_stream = nullptr;
+    cudaEvent_t tot_ev[MAX_SUB] = {}, cmp_ev[MAX_SUB] = {};
+    uint64_t* h_piece = nullptr;       // pinned, [MAX_SUB][2]: minimizers of the piece, overflow counter snapshot
+    DevBuf loc_off;                    // piece-local exclusive offsets: u64 [n_reads + n_pieces]
+    bool piece_pipeline = true;        // MDBG_PIECE_PIPELINE=0 restores the whole-batch tail
     std::string error;
     uint64_t launches = 0;
     uint64_t h2d_bytes = 0, d2h_bytes = 0;   // bytes enqueued across PCIe by the host-buffer entry points
@@ -96,6 +104,7 @@ struct mdbg_ctx {
     uint32_t b_reads = 0;
     uint64_t b_total = 0;
     PinBuf h_off, h_min, h_pos, h_dir;
+    bool host_csr_valid = false;                // the piece pipeline already copied this batch's CSR into h_*
 
     // read side outputs (row A3b)
     bool filter_low_complexity = false;
@@ -249,17 +258,152 @@ mdbg_status run_aux(mdbg_ctx* ctx, const uint8_t* d_bases, const uint8_t* d_qual
 }
 
 struct SubRange { uint32_t r0, r1; };
+
+// Per-piece tail of a host batch.  A host batch reaches the device in pieces (sketch_host_batch); instead of
+// waiting for the last piece before the scan / compaction / device-to-host copy of the minimizer CSR start, every
+// piece gets its own scan right behind its sketch launch, and LAG pieces later -- when its total has long landed
+// in pinned memory, so the host does not block -- its compaction into the tight CSR at the running offset and, if
+// the caller wants the CSR on the host, its D2H copy on a third stream.  What is left after the last piece is
+// one piece's worth of work.  A read that overflows its padded slot (low-complexity sequence) cancels the
+// pipeline: the whole batch then takes the classic tail (global scan, exact re-sketch), results unchanged.
+struct PiecePipeline {
+    static constexpr size_t LAG = 2;
+    mdbg_ctx* ctx;
+    const uint64_t* d_offsets;           // device: read byte offsets of the batch
+    const std::vector<SubRange>* subs;
+    uint32_t n_reads;
+    bool fetch;                          // also copy the CSR to the pinned host arrays h_off / h_min / h_pos / h_dir
+    uint64_t run_total = 0;
+    size_t launched_n = 0, finished_n = 0;
+    bool overflow = false;
+    bool in_flight = false;              // begin() is over: growth from here on happens with copies in flight
+
+    mdbg_status grow_dev(DevBuf& b, size_t bytes) {
+        if (bytes <= b.cap && b.p) return MDBG_OK;
+        CK(cudaStreamSynchronize(ctx->d2h_stream));               // a copy may still read the old allocation
+        if (in_flight) ctx->last_grows++;
+        return ensure(ctx, b, bytes + bytes / 4, true);
+    }
+    mdbg_status grow_pin(PinBuf& b, size_t bytes, size_t keep_bytes) {
+        if (bytes <= b.cap && b.p) return MDBG_OK;
+        CK(cudaStreamSynchronize(ctx->d2h_stream));
+        if (in_flight) ctx->last_grows++;
+        PinBuf bigger;
+        CKS(ensure_pin(ctx, bigger, bytes + bytes / 4));
+        if (b.p && keep_bytes) memcpy(bigger.p, b.p, keep_bytes);
+        release(b);
+        b = bigger;
+        return MDBG_OK;
+    }
+    // sizes everything for the expected number of minimizers, so that growing mid-batch is the exception
+    mdbg_status begin(uint64_t n_bases) {
+        const uint64_t est = (uint64_t)((double)n_bases * (double)ctx->density * 1.25) + 1024;
+        CKS(ensure(ctx, ctx->loc_off, ((size_t)n_reads + subs->size() + 1) * sizeof(uint64_t)));
+        CKS(grow_dev(ctx->b_min, (est + 1) * 4));
+        CKS(grow_dev(ctx->b_pos, (est + 1) * 4));
+        CKS(grow_dev(ctx->b_dir, est + 1));
+        if (fetch) {
+            CKS(grow_pin(ctx->h_off, ((size_t)n_reads + 1) * 8, 0));
+            CKS(grow_pin(ctx->h_min, (est + 1) * 4, 0));
+            CKS(grow_pin(ctx->h_pos, (est + 1) * 4, 0));
+            CKS(grow_pin(ctx->h_dir, est + 1, 0));
+            ctx->h_off.as<uint64_t>()[0] = 0;
+        }
+        in_flight = true;
+        ctx->last_pipelined = ctx->last_grows = 0;
+        ctx->last_overflow_fallback = 0;
+        return MDBG_OK;
+    }
+    // call right after the sketch launch of piece i (pieces are launched in order)
+    mdbg_status launched(size_t i) {
+        cudaStream_t s = ctx->stream;
+        const SubRange& sr = (*subs)[i];
+        const uint32_t np = sr.r1 - sr.r0;
+        uint64_t* loc = ctx->loc_off.as<uint64_t>() + sr.r0 + i;                  // np + 1 entries
+        launch_scan_u32_to_u64(ctx->n_min.as<uint32_t>() + sr.r0, loc, np, ctx->scan_scratch.as<uint64_t>(), s);
+        CKS(check_launch(ctx, "scan", np ? 3 : 0));
+        CK(cudaMemcpyAsync(&ctx->h_piece[2 * i], loc + np, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(&ctx->h_piece[2 * i + 1], &ctx->d_small->n_overflow, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        CK(cudaEventRecord(ctx->tot_ev[i], s));
+        launched_n = i + 1;
+        while (finished_n + LAG < launched_n) CKS(finish(finished_n));
+        return MDBG_OK;
+    }
+    mdbg_status finish(size_t j) {
+        cudaStream_t s = ctx->stream, ds = ctx->d2h_stream;
+        finished_n = j + 1;
+        CK(cudaEventSynchronize(ctx->tot_ev[j]));
+        const uint64_t total = ctx->h_piece[2 * j];
+        if (ctx->h_piece[2 * j + 1] != 0) overflow = true;
+        if (overflow) { ctx->last_overflow_fallback = 1; return MDBG_OK; }        // the classic tail redoes the batch
+        ctx->last_pipelined++;
+        const SubRange& sr = (*subs)[j];
+        const uint32_t np = sr.r1 - sr.r0;
+        const uint64_t* loc = ctx->loc_off.as<uint64_t>() + sr.r0 + j;
+        CKS(grow_dev(ctx->b_min, (run_total + total + 1) * 4));
+        CKS(grow_dev(ctx->b_pos, (run_total + total + 1) * 4));
+        CKS(grow_dev(ctx->b_dir, run_total + total + 1));
+        CompactArgs c{};
+        c.base_offsets = d_offsets;
+        c.cap_shift = ctx->cap_shift;
+        c.cap_const = ctx->cap_const;
+        c.n_min = ctx->n_min.as<uint32_t>();
+        c.tight_off = loc;
+        c.tight_base = run_total;
+        c.read_begin = sr.r0;
+        c.n_reads = np;
+        c.in_min = ctx->pad_min.as<uint32_t>();
+        c.in_pos = ctx->pad_pos.as<uint32_t>();
+        c.in_dir = ctx->pad_dir.as<uint8_t>();
+        c.out_min = ctx->b_min.as<uint32_t>();
+        c.out_pos = ctx->b_pos.as<uint32_t>();
+        c.out_dir = ctx->b_dir.as<uint8_t>();
+        launch_compact(c, s);
+        CKS(check_launch(ctx, "compact_kernel", np ? 1 : 0));
+        // b_off[r0 + 1 + t] = run_total + loc[t + 1]  (and b_off[0] = 0 with the first piece)
+        launch_append_offsets(loc, ctx->b_off.as<uint64_t>(), np, sr.r0, run_total, s);
+        CKS(check_launch(ctx, "append_offsets_kernel", np ? 1 : 0));
+        if (fetch) {
+            CKS(grow_pin(ctx->h_min, (run_total + total + 1) * 4, run_total * 4));
+            CKS(grow_pin(ctx->h_pos, (run_total + total + 1) * 4, run_total * 4));
+            CKS(grow_pin(ctx->h_dir, run_total + total + 1, run_total));
+            CK(cudaEventRecord(ctx->cmp_ev[j], s));
+            CK(cudaStreamWaitEvent(ds, ctx->cmp_ev[j], 0));
+            if (np)
+                CK(cudaMemcpyAsync(ctx->h_off.as<uint64_t>() + sr.r0 + 1, ctx->b_off.as<uint64_t>() + sr.r0 + 1, (size_t)np * 8,
+                                   cudaMemcpyDeviceToHost, ds));
+            if (total) {
+                CK(cudaMemcpyAsync(ctx->h_min.as<uint32_t>() + run_total, ctx->b_min.as<uint32_t>() + run_total, total * 4,
+                                   cudaMemcpyDeviceToHost, ds));
+                CK(cudaMemcpyAsync(ctx->h_pos.as<uint32_t>() + run_total, ctx->b_pos.as<uint32_t>() + run_total, total * 4,
+                                   cudaMemcpyDeviceToHost, ds));
+                CK(cudaMemcpyAsync(ctx->h_dir.as<uint8_t>() + run_total, ctx->b_dir.as<uint8_t>() + run_total, total,
+                                   cudaMemcpyDeviceToHost, ds));
+            }
+            ctx->d2h_bytes += (uint64_t)np * 8 + total * 9;
+        }
+        run_total += total;
+        return MDBG_OK;
+    }
+    // after the last piece: the remaining tails; the caller then checks `overflow`
+    mdbg_status drain() {
+        while (finished_n < launched_n) CKS(finish(finished_n));
+        return MDBG_OK;
+    }
+};
 // A feeder enqueues the sketch launches itself (host batches arriving in pieces); it may edit the argument block
 // (input pointers) and must leave read_begin/read_end/cursor covering the whole batch when it returns.
 using Feeder = std::function<mdbg_status(SketchArgs&)>;
 
+
 mdbg_status sketch_internal(mdbg_ctx* ctx, const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t n_reads,
                             uint64_t n_bases, int append, bool want_aux = false, const uint8_t* d_quals = nullptr,
-                            const Feeder* feeder = nullptr) {
+                            const Feeder* feeder = nullptr, PiecePipeline* pipe = nullptr) {
     cudaStream_t s = ctx->stream;
     ctx->b_reads = n_reads;
     ctx->b_total = 0;
     ctx->aux_valid = false;
+    ctx->host_csr_valid = false;
     CKS(ensure(ctx, ctx->b_off, ((size_t)n_reads + 1) * sizeof(uint64_t)));
     if (n_reads == 0) {
         CK(cudaMemsetAsync(ctx->b_off.p, 0, sizeof(uint64_t), s));
@@ -299,7 +443,9 @@ mdbg_status sketch_internal(mdbg_ctx* ctx, const uint8_t* d_bases, const uint64_
     CK(cudaMemsetAsync(&ctx->d_small->cursor, 0, sizeof(uint32_t) * (1 + MAX_SUB), s));
     CK(cudaMemsetAsync(&ctx->d_small->n_overflow, 0, sizeof(unsigned long long), s));
     if (feeder) {
+        if (pipe) CKS(pipe->begin(n_bases));
         CKS((*feeder)(a));
+        if (pipe) CKS(pipe->drain());
         a.read_begin = 0;
         a.read_end = n_reads;
         a.cursor = &ctx->d_small->cursor;
@@ -324,21 +470,34 @@ mdbg_status sketch_internal(mdbg_ctx* ctx, const uint8_t* d_bases, const uint64_
         ctx->aux_valid = true;
         ctx->aux_has_quals = d_quals != nullptr;
     }
-    launch_scan_u32_to_u64(ctx->n_min.as<uint32_t>(), ctx->b_off.as<uint64_t>(), n_reads,
-                           ctx->scan_scratch.as<uint64_t>(), s);
-    CKS(check_launch(ctx, "scan", 3));
-    CK(cudaMemcpyAsync(&ctx->h_scalar[0], ctx->b_off.as<uint64_t>() + n_reads, sizeof(uint64_t),
-                       cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(&ctx->h_scalar[1], &ctx->d_small->n_overflow, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    const uint64_t total = ctx->h_scalar[0];
-    const uint64_t n_over = ctx->h_scalar[1];
-    ctx->b_total = total;
-    CKS(ensure(ctx, ctx->b_min, (total + 1) * 4));
-    CKS(ensure(ctx, ctx->b_pos, (total + 1) * 4));
-    CKS(ensure(ctx, ctx->b_dir, total + 1));
-    if (want_aux) CKS(ensure(ctx, ctx->b_qual, total + 1));
-    if (n_over == 0) {
+    const bool piecewise_done = pipe && !pipe->overflow;          // every piece already sits in the tight CSR
+    uint64_t total = 0, n_over = 0;
+    if (piecewise_done) {
+        total = pipe->run_total;
+        ctx->b_total = total;
+    } else {
+        if (pipe) {                                                // cancelled by a slot overflow: classic tail, no D2H yet
+            CK(cudaStreamSynchronize(ctx->d2h_stream));
+            pipe->fetch = false;
+        }
+        launch_scan_u32_to_u64(ctx->n_min.as<uint32_t>(), ctx->b_off.as<uint64_t>(), n_reads,
+                               ctx->scan_scratch.as<uint64_t>(), s);
+        CKS(check_launch(ctx, "scan", 3));
+        CK(cudaMemcpyAsync(&ctx->h_scalar[0], ctx->b_off.as<uint64_t>() + n_reads, sizeof(uint64_t),
+                           cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(&ctx->h_scalar[1], &ctx->d_small->n_overflow, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        total = ctx->h_scalar[0];
+        n_over = ctx->h_scalar[1];
+        ctx->b_total = total;
+        CKS(ensure(ctx, ctx->b_min, (total + 1) * 4));
+        CKS(ensure(ctx, ctx->b_pos, (total + 1) * 4));
+        CKS(ensure(ctx, ctx->b_dir, total + 1));
+        if (want_aux) CKS(ensure(ctx, ctx->b_qual, total + 1));
+    }
+    if (piecewise_done) {
+        // nothing left to do before the store append
+    } else if (n_over == 0) {
         CompactArgs c{};
         c.base_offsets = d_offsets;
         c.cap_shift = ctx->cap_shift;
@@ -491,10 +650,18 @@ mdbg_status mdbg_ctx_create(int device, const mdbg_params* p, mdbg_ctx** out) {
         return fail(nullptr, MDBG_ERR_CUDA, "copy stream creation failed");
     }
     for (int i = 0; i < MAX_SUB; i++)
-        if (cudaEventCreateWithFlags(&c->sub_ev[i], cudaEventDisableTiming) != cudaSuccess) {
+        if (cudaEventCreateWithFlags(&c->sub_ev[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->tot_ev[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->cmp_ev[i], cudaEventDisableTiming) != cudaSuccess) {
             mdbg_ctx_destroy(c);
             return fail(nullptr, MDBG_ERR_CUDA, "event creation failed");
         }
+    if (cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMallocHost((void**)&c->h_piece, 2 * MAX_SUB * sizeof(uint64_t)) != cudaSuccess) {
+        mdbg_ctx_destroy(c);
+        return fail(nullptr, MDBG_ERR_CUDA, "piece pipeline allocation failed");
+    }
+    if (const char* v = getenv("MDBG_PIECE_PIPELINE")) c->piece_pipeline = atoi(v) != 0;
     if (cudaMalloc((void**)&c->d_small, sizeof(SmallDev)) != cudaSuccess ||
         cudaMallocHost((void**)&c->h_small, sizeof(SmallDev)) != cudaSuccess ||
         cudaMallocHost((void**)&c->h_scalar, 8 * sizeof(uint64_t)) != cudaSuccess) {
@@ -527,7 +694,7 @@ void mdbg_ctx_destroy(mdbg_ctx* c) {
                       &c->scan_scratch, &c->b_off, &c->b_min, &c->b_pos, &c->b_dir, &c->s_min, &c->s_off, &c->s_rem,
                       &c->p_flags, &c->p_keep, &c->p_cnt, &c->p_newoff, &c->p_newmin, &c->table, &c->foreign_vecs,
                       &c->o_hash, &c->o_abund, &c->o_vecs, &c->d_pack, &c->d_src, &c->d_quals, &c->pad_qual, &c->pad_raw_a, &c->pad_raw_b, &c->b_qual, &c->x_sum_lo, &c->x_sum_hi, &c->x_lmin, &c->x_cplx, &c->x_low, &c->d_err_fixed, &c->d_err_tz, &c->prev_table, &c->prev_stage_h, &c->prev_stage_a, &c->m_send_vecs, &c->m_send_counts, &c->m_recv_vecs,
-                      &c->m_recv_counts, &c->m_bucket};
+                      &c->m_recv_counts, &c->m_bucket, &c->loc_off};
     for (DevBuf* b : devs) release(*b);
     PinBuf* pins[] = {&c->h_off, &c->h_min, &c->h_pos, &c->h_dir, &c->ho_hash, &c->ho_abund, &c->ho_vecs, &c->hx_sum_lo, &c->hx_sum_hi, &c->hx_lmin, &c->hx_cplx, &c->hx_low, &c->hx_meanq, &c->h_qual, &c->h_pack, &c->h_src, &c->h_asc};
     for (PinBuf* b : pins) release(*b);
@@ -539,8 +706,13 @@ void mdbg_ctx_destroy(mdbg_ctx* c) {
         for (int j = 0; j < 2; j++)
             if (c->ev[i][j]) cudaEventDestroy(c->ev[i][j]);
     if (c->pool) host_pool_destroy(c->pool);
-    for (int i = 0; i < MAX_SUB; i++)
+    for (int i = 0; i < MAX_SUB; i++) {
         if (c->sub_ev[i]) cudaEventDestroy(c->sub_ev[i]);
+        if (c->tot_ev[i]) cudaEventDestroy(c->tot_ev[i]);
+        if (c->cmp_ev[i]) cudaEventDestroy(c->cmp_ev[i]);
+    }
+    if (c->h_piece) cudaFreeHost(c->h_piece);
+    if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     if (c->copy_gate) cudaEventDestroy(c->copy_gate);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -590,7 +762,7 @@ mdbg_status mdbg_ctx_kernel_time_ms(mdbg_ctx* ctx, int which, float* ms) {
 }
 
 static mdbg_status sketch_host_batch(mdbg_ctx* ctx, const uint8_t* bases, const uint8_t* quals, const uint64_t* offsets,
-                                     uint32_t n_reads, uint64_t n_bases, int append, bool want_aux);
+                                     uint32_t n_reads, uint64_t n_bases, int append, bool want_aux, bool fetch = false);
 
 // Host CSR offsets: start at 0, never decrease, and no read reaches 2^31 bases (positions are u32 and the candidate
 // list keeps a flag in bit 31).  A bad array would otherwise turn into out-of-range device addresses.
@@ -748,6 +920,16 @@ mdbg_status mdbg_sketch_fetch(mdbg_ctx* ctx, mdbg_sketch_out* out) {
     CK(cudaSetDevice(ctx->device));
     const uint32_t n = ctx->b_reads;
     const uint64_t t = ctx->b_total;
+    if (ctx->host_csr_valid) {                  // copied piece by piece behind the sketch: wait for the last copies
+        CK(cudaStreamSynchronize(ctx->d2h_stream));
+        out->n_reads = n;
+        out->n_minimizers = t;
+        out->min_offsets = ctx->h_off.as<uint64_t>();
+        out->minimizers = ctx->h_min.as<uint32_t>();
+        out->positions = ctx->h_pos.as<uint32_t>();
+        out->directions = ctx->h_dir.as<uint8_t>();
+        return MDBG_OK;
+    }
     CKS(ensure_pin(ctx, ctx->h_off, ((size_t)n + 1) * 8));
     CKS(ensure_pin(ctx, ctx->h_min, (t + 1) * 4));
     CKS(ensure_pin(ctx, ctx->h_pos, (t + 1) * 4));
@@ -779,7 +961,7 @@ mdbg_status mdbg_sketch_batch(mdbg_ctx* ctx, const uint8_t* bases, const uint64_
     const uint64_t n_bases = n_reads ? offsets[n_reads] : 0;
     CKS(ensure(ctx, ctx->d_bases, n_bases + 64));
     CKS(ensure(ctx, ctx->d_offsets, ((size_t)n_reads + 1) * 8));
-    CKS(sketch_host_batch(ctx, bases, nullptr, offsets, n_reads, n_bases, append_to_store, false));
+    CKS(sketch_host_batch(ctx, bases, nullptr, offsets, n_reads, n_bases, append_to_store, false, out != nullptr));
     if (out) return mdbg_sketch_fetch(ctx, out);
     return MDBG_OK;
 }
@@ -790,7 +972,11 @@ mdbg_status mdbg_sketch_batch(mdbg_ctx* ctx, const uint8_t* bases, const uint64_
 // ASCII form so that the result is unchanged.
 static void split_pieces(const uint64_t* offsets, uint32_t n_reads, uint64_t n_bases, std::vector<SubRange>& subs) {
     subs.clear();
-    const uint64_t piece = std::max<uint64_t>(uint64_t(128) << 20, (n_bases + MAX_SUB - 1) / MAX_SUB);
+    // pieces of at least 128 MB (MDBG_PIECE_BYTES overrides the floor: tests use it to cut small batches into many
+    // pieces), at most MAX_SUB of them
+    uint64_t floor_bytes = uint64_t(128) << 20;
+    if (const char* e = getenv("MDBG_PIECE_BYTES")) { const long long v = atoll(e); if (v > 0) floor_bytes = (uint64_t)v; }
+    const uint64_t piece = std::max<uint64_t>(floor_bytes, (n_bases + MAX_SUB - 1) / MAX_SUB);
     uint32_t r0 = 0;
     while (r0 < n_reads) {
         const uint64_t target = offsets[r0] + piece;
@@ -803,13 +989,20 @@ static void split_pieces(const uint64_t* offsets, uint32_t n_reads, uint64_t n_b
 }
 
 static mdbg_status sketch_host_batch(mdbg_ctx* ctx, const uint8_t* bases, const uint8_t* quals, const uint64_t* offsets,
-                                     uint32_t n_reads, uint64_t n_bases, int append, bool want_aux) {
+                                     uint32_t n_reads, uint64_t n_bases, int append, bool want_aux, bool fetch) {
     cudaStream_t s = ctx->stream, cs = ctx->copy_stream;
+    ctx->host_csr_valid = false;
     CKS(ensure(ctx, ctx->d_offsets, ((size_t)n_reads + 1) * 8));
     if (n_reads == 0)
         return sketch_internal(ctx, nullptr, ctx->d_offsets.as<uint64_t>(), 0, 0, append, want_aux, nullptr);
     std::vector<SubRange> subs;
     split_pieces(offsets, n_reads, n_bases, subs);
+    PiecePipeline pipeline{ctx, ctx->d_offsets.as<uint64_t>(), &subs, n_reads, fetch};
+    PiecePipeline* pipe = (ctx->piece_pipeline && !quals && !want_aux) ? &pipeline : nullptr;
+    const auto done = [&](mdbg_status st) {
+        if (st == MDBG_OK && pipe && !pipe->overflow && pipe->fetch) ctx->host_csr_valid = true;
+        return st;
+    };
     // the copy stream must not overwrite buffers the compute stream is still reading
     CK(cudaEventRecord(ctx->copy_gate, s));
     CK(cudaStreamWaitEvent(cs, ctx->copy_gate, 0));
@@ -825,6 +1018,9 @@ static mdbg_status sketch_host_batch(mdbg_ctx* ctx, const uint8_t* bases, const 
         if (want_pack && ctx->auto_pack_pause > 0) { ctx->auto_pack_pause--; want_pack = false; }
     }
     const bool packed = want_pack && !quals && !want_aux && n_bases >= (uint64_t(1) << 20);
+    ctx->last_packed = packed ? 1 : 0;
+    ctx->last_pieces = subs.size();
+    if (!pipe) { ctx->last_pipelined = ctx->last_grows = 0; ctx->last_overflow_fallback = 0; }
     if (!packed) {
         CKS(ensure(ctx, ctx->d_bases, n_bases + 64));
         if (quals) CKS(ensure(ctx, ctx->d_quals, n_bases + 64));
@@ -844,11 +1040,12 @@ static mdbg_status sketch_host_batch(mdbg_ctx* ctx, const uint8_t* bases, const 
                 a.cursor = &ctx->d_small->sub_cursor[i];
                 launch_sketch(a, ctx->sm_count, s);
                 CKS(check_launch(ctx, "sketch_kernel", 1));
+                if (pipe) CKS(pipe->launched(i));
             }
             return MDBG_OK;
         };
-        return sketch_internal(ctx, ctx->d_bases.as<uint8_t>(), ctx->d_offsets.as<uint64_t>(), n_reads, n_bases, append,
-                               want_aux, quals ? ctx->d_quals.as<uint8_t>() : nullptr, &feeder);
+        return done(sketch_internal(ctx, ctx->d_bases.as<uint8_t>(), ctx->d_offsets.as<uint64_t>(), n_reads, n_bases, append,
+                                    want_aux, quals ? ctx->d_quals.as<uint8_t>() : nullptr, &feeder, pipe));
     }
 
     // ---- packed transfer ----------------------------------------------------------------------------------------
@@ -951,12 +1148,13 @@ static mdbg_status sketch_host_batch(mdbg_ctx* ctx, const uint8_t* bases, const 
             a.cursor = &ctx->d_small->sub_cursor[i];
             launch_sketch(a, ctx->sm_count, s);
             CKS(check_launch(ctx, "sketch_kernel", 1));
+            if (pipe) CKS(pipe->launched(i));
         }
         return MDBG_OK;
     };
     ctx->last_direct_pieces = 0;
-    const mdbg_status st = sketch_internal(ctx, ctx->d_bases.as<uint8_t>(), ctx->d_offsets.as<uint64_t>(), n_reads, n_bases,
-                                           append, false, nullptr, &feeder);
+    const mdbg_status st = done(sketch_internal(ctx, ctx->d_bases.as<uint8_t>(), ctx->d_offsets.as<uint64_t>(), n_reads, n_bases,
+                                                append, false, nullptr, &feeder, pipe));
     ctx->last_direct_pieces = n_direct_pieces;
     ctx->last_pieces = subs.size();
     if (pack_seconds > 0) {
@@ -965,6 +1163,20 @@ static mdbg_status sketch_host_batch(mdbg_ctx* ctx, const uint8_t* bases, const 
         if (ctx->host_packing < 0 && pack_bytes >= (uint64_t(256) << 20) && ctx->last_pack_gbs < 45.0) ctx->auto_pack_pause = 16;
     }
     return st;
+}
+
+mdbg_status mdbg_ctx_last_batch_info(mdbg_ctx* ctx, mdbg_batch_info* info) {
+    if (!ctx || !info) return MDBG_ERR_ARG;
+    info->n_pieces = ctx->last_pieces;
+    info->n_pieces_pipelined = ctx->last_pipelined;
+    info->n_buffer_growths = ctx->last_grows;
+    info->n_direct_pieces = ctx->last_direct_pieces;
+    info->overflow_fallback = ctx->last_overflow_fallback;
+    info->packed = ctx->last_packed;
+    info->pack_gb_per_s = ctx->last_packed ? ctx->last_pack_gbs : 0.0;
+    info->pack_isa = host_pack_isa();
+    info->host_threads = ctx->pool ? host_pool_size(ctx->pool) : 0;
+    return MDBG_OK;
 }
 
 mdbg_status mdbg_ctx_set_host_packing(mdbg_ctx* ctx, int on) {

@@ -56,6 +56,10 @@ struct CompactArgs {
     uint32_t* out_min; uint32_t* out_pos; uint8_t* out_dir;
     uint32_t n_reads;
     const uint8_t* in_qual; uint8_t* out_qual;   // optional per-minimizer qualities (nullptr = none)
+    // piece-wise compaction of a host batch (api.cu, PiecePipeline): reads [read_begin, read_begin + n_reads) only,
+    // tight_off = the piece's own exclusive offsets (indexed from 0), destination shifted by tight_base
+    uint32_t read_begin;
+    uint64_t tight_base;
 };
 void launch_compact(const CompactArgs& a, cudaStream_t s);
 

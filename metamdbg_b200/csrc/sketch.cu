@@ -526,13 +526,14 @@ __global__ void __launch_bounds__(256) compact_kernel(const CompactArgs a) {
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    for (uint64_t r = warp; r < a.n_reads; r += n_warps) {
+    for (uint64_t i_read = warp; i_read < a.n_reads; i_read += n_warps) {
+        const uint64_t r = a.read_begin + i_read;
         const uint64_t start = a.base_offsets[r], end = a.base_offsets[r + 1];
         const uint64_t slot_lo = (start >> a.cap_shift) + r * a.cap_const;
         const uint64_t slot_cap = ((end >> a.cap_shift) + (r + 1) * a.cap_const) - slot_lo;
         uint64_t n = a.n_min[r];
         if (n > slot_cap) n = slot_cap;                  // overflowed read: the caller re-runs in exact mode
-        const uint64_t dst = a.tight_off[r];
+        const uint64_t dst = a.tight_base + a.tight_off[i_read];
         for (uint64_t i = lane; i < n; i += 32) {
             a.out_min[dst + i] = a.in_min[slot_lo + i];
             a.out_pos[dst + i] = a.in_pos[slot_lo + i];

@@ -17,7 +17,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _capi
-from ._capi import AutotuneOut, AuxOut, MdbgParams, SketchDev, SketchOut, TableOut
+from ._capi import AutotuneOut, AuxOut, BatchInfo, MdbgParams, SketchDev, SketchOut, TableOut
 
 STATUS = {0: "OK", 1: "CUDA", 2: "ARG", 3: "STATE", 4: "TABLE_FULL", 5: "NCCL", 6: "OOM"}
 
@@ -146,6 +146,16 @@ class Engine:
     def set_host_packing(self, on: bool | int | None = True):
         """2-bit pack host batches before H2D: True / False / None = automatic (default) / 2 = hybrid (experimental)."""
         self._ck(self._lib.mdbg_ctx_set_host_packing(self._ctx, -1 if on is None else int(on)))
+
+    def last_batch_info(self) -> dict:
+        """How the last host batch travelled (pieces, piece-wise tails, packer throughput); see mdbg_batch_info."""
+        b = BatchInfo()
+        self._ck(self._lib.mdbg_ctx_last_batch_info(self._ctx, C.byref(b)))
+        return {"n_pieces": int(b.n_pieces), "n_pieces_pipelined": int(b.n_pieces_pipelined),
+                "n_buffer_growths": int(b.n_buffer_growths), "n_direct_pieces": int(b.n_direct_pieces),
+                "overflow_fallback": bool(b.overflow_fallback), "packed": bool(b.packed),
+                "pack_gb_per_s": float(b.pack_gb_per_s), "pack_isa": (b.pack_isa or b"").decode(),
+                "host_threads": int(b.host_threads)}
 
     def set_read_filters(self, filter_low_complexity: bool = True):
         self._ck(self._lib.mdbg_ctx_set_read_filters(self._ctx, int(filter_low_complexity)))

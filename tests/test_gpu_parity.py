@@ -324,6 +324,84 @@ def test_sketch_kernel_variants_and_autotune(built, oracle, hpc, dens):
     del keep_b, keep_o
 
 
+def _selected_lmer(oracle, l, dens):
+    """(bases of) one l-mer the density threshold selects, found by sketching random sequence with the oracle."""
+    rng = np.random.default_rng(4)
+    seq = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 20000)]
+    mo, m, p, d = oracle.sketch_batch(seq, np.array([0, len(seq)], np.uint64), l, dens, False)
+    assert len(p) > 3
+    return seq[int(p[1]):int(p[1]) + l].copy()
+
+
+@pytest.mark.parametrize("packing", [0, 1])
+def test_piece_pipeline_many_pieces(built, oracle, packing, monkeypatch):
+    """Host batches cut into many pieces (MDBG_PIECE_BYTES): per-piece scan / compaction / D2H behind each piece's
+    sketch gives the same CSR and store as the whole-batch tail -- plain reads, reads whose minimizer count exceeds
+    the up-front estimate (buffers grow mid-batch), a slot overflow in a late piece (pipeline cancelled, exact
+    re-sketch), empty reads, and the next batch appended behind it."""
+    monkeypatch.setenv("MDBG_PIECE_BYTES", "60000")
+    rs = synth.make_readset(700, 6000, seed=91, n_genomes=2, genome_len_range=(150_000, 250_000))
+    bases, offs = synth.fill_reads(rs)
+    want = oracle.sketch_batch(bases, offs, 15, 0.005, True)
+    eng = engine(15, 0.005, True)
+    eng.set_host_packing(packing)
+    sk = eng.sketch_batch(bases, offs, append_to_store=True)
+    assert_sketch_equal(sk, *want, tag="many pieces")
+    info = eng.last_batch_info()
+    assert info["n_pieces"] >= 40 and info["n_pieces_pipelined"] == info["n_pieces"] and not info["overflow_fallback"]
+    assert info["packed"] == bool(packing)
+    # a second batch with empty and tiny reads between the pieces, appended to the same store
+    rs2 = synth.make_readset(300, 5000, seed=92, n_genomes=1, genome_len_range=(150_000, 250_000))
+    b2, o2 = synth.fill_reads(rs2)
+    lens = np.diff(o2.astype(np.int64))
+    lens[::7] = 0
+    lens[3::11] = 9
+    o2b = np.zeros(len(lens) + 1, np.uint64)
+    o2b[1:] = np.cumsum(lens)
+    b2b = np.concatenate([b2[int(o2[r]):int(o2[r]) + int(lens[r])] for r in range(len(lens))])
+    want2 = oracle.sketch_batch(b2b, o2b, 15, 0.005, True)
+    assert_sketch_equal(eng.sketch_batch(b2b, o2b, append_to_store=True), *want2, tag="ragged second batch")
+    so, sm = eng.store_fetch()
+    assert np.array_equal(sm, np.concatenate([want[1], want2[1]]))
+    assert np.array_equal(so, np.concatenate([want[0], want2[0][1:] + want[0][-1]]))
+    # same batch without fetching the CSR (store only), then fetched afterwards
+    eng.store_clear()
+    assert eng.sketch_batch(bases, offs, append_to_store=True, fetch=False) is None
+    assert_sketch_equal(eng.sketch_fetch(), *want, tag="deferred fetch")
+    assert np.array_equal(eng.store_fetch()[1], want[1])
+    eng.close()
+
+    # minimizer-rich reads: 3-4 x the nominal density (tandem repeats of a selected l-mer), HPC off -> the
+    # estimate-sized buffers must grow while copies are in flight; one read far above its slot -> overflow fallback
+    lm = _selected_lmer(oracle, 15, 0.005)
+    unit = np.concatenate([lm, np.frombuffer(b"ACGTA", np.uint8)])
+    rng = np.random.default_rng(12)
+    reads = []
+    for r in range(400):
+        rnd = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 4200)]
+        reads.append(np.concatenate([rnd[:2100], np.tile(unit, 90), rnd[2100:]]))
+    for with_overflow in (False, True):
+        rr = list(reads)
+        if with_overflow:
+            rr[377] = np.tile(unit, 300)
+        bb = np.concatenate(rr)
+        oo = np.zeros(len(rr) + 1, np.uint64)
+        oo[1:] = np.cumsum([len(x) for x in rr])
+        want3 = oracle.sketch_batch(bb, oo, 15, 0.005, False)
+        assert len(want3[1]) > 2.5 * 0.005 * len(bb)
+        eng = engine(15, 0.005, False)
+        eng.set_host_packing(packing)
+        assert_sketch_equal(eng.sketch_batch(bb, oo, append_to_store=True), *want3, tag=f"rich reads overflow={with_overflow}")
+        info = eng.last_batch_info()
+        assert info["n_pieces"] >= 30 and info["overflow_fallback"] == with_overflow
+        if not with_overflow:
+            assert info["n_buffer_growths"] >= 1 and info["n_pieces_pipelined"] == info["n_pieces"]
+        else:
+            assert 0 < info["n_pieces_pipelined"] < info["n_pieces"]
+        assert np.array_equal(eng.store_fetch()[1], want3[1])
+        eng.close()
+
+
 def test_python_mirror_single_read(built, oracle):
     from metamdbg_b200 import MinimizerParser
     rs = synth.make_readset(3, 20000, seed=8, n_genomes=1, genome_len_range=(100_000, 100_001))
