@@ -246,7 +246,10 @@ mdbg_status mdbg_count_stats(mdbg_ctx* ctx, uint32_t min_abundance, uint64_t* n_
 /* rescueKminmers / RescueKminmerFunctor (CreateMdbg.hpp:4517-4640; default mode, --min-abundance <= 1):
  * second pass over the stored reads; reads whose median solid abundance m satisfies m * 0.1f <= 1 (and that
  * hold at least one solid k-min-mer) keep their abundance-1 k-min-mers, which are then emitted by
- * mdbg_count_finalize / counted by mdbg_count_stats next to the abundance >= 2 entries.  Single context only. */
+ * mdbg_count_finalize / counted by mdbg_count_stats next to the abundance >= 2 entries.
+ * With more than one rank (mdbg_comm_init) the call is COLLECTIVE and must follow mdbg_count_merge: the solid
+ * k-min-mers of all ranks are replicated for the per-read decision, every rank decides for its own reads, and
+ * the abundance-1 k-min-mers of rescued reads are sent to their owner ranks, which flag them. */
 mdbg_status mdbg_count_rescue(mdbg_ctx* ctx, uint64_t* n_reads_rescued);
 
 /* ---- multi-k: previous-k abundance table and the k >= firstK+1 passes (rows A8/A9) ------------
@@ -254,7 +257,11 @@ mdbg_status mdbg_count_rescue(mdbg_ctx* ctx, uint64_t* n_reads_rescued);
  * (_kminmerAbundances, loaded by loadRefinedAbundances, CreateMdbg.cpp:3401-3709): minimum over its two
  * (k-1)-min-mers, absent or 0 => 1, kept when > 1 (getRefinedAbundance CreateMdbg.hpp:3933-4005 for
  * k = firstK+1; IndexKminmerFunctor CreateMdbg.hpp:988-1010,1240-1265,1268-1464 for k >= firstK+2). */
-/* previous-k table := the current table's emitted entries (abundance >= max(2,min_abundance) or rescued) */
+/* previous-k table := the current table's emitted entries (abundance >= max(2,min_abundance) or rescued).
+ * With more than one rank the call is COLLECTIVE and must follow mdbg_count_merge: every rank's owned entries
+ * are exchanged so that each rank holds the complete previous-k table (20 B per entry); the next-k pass then
+ * runs on the rank's own reads and mdbg_count_merge moves the resulting (k-min-mer -> abundance) entries to
+ * their owners without adding them up (the abundance is a function of the key). */
 mdbg_status mdbg_prev_from_current(mdbg_ctx* ctx, uint32_t min_abundance);
 /* insert-or-assign host (hash, abundance) pairs, hashes laid out as in mdbg_table_out / on disk;
  * clear != 0 starts from an empty table (e.g. kminmerData_abundance_prev.txt), clear == 0 patches the
@@ -272,7 +279,8 @@ mdbg_status mdbg_nccl_unique_id(uint8_t id_out[128]);
 mdbg_status mdbg_comm_init(mdbg_ctx* ctx, int rank, int n_ranks, const uint8_t id[128]);
 /* Owner-partitioned all-to-all of the local table's (k-min-mer, count) pairs
  * followed by reduce-by-key: afterwards this context's table holds exactly the
- * keys it owns with their global abundances.  Collective over all ranks. */
+ * keys it owns with their global abundances.  Collective over all ranks.  Tables filled by
+ * mdbg_count_add_store_next_k hold abundance VALUES: equal keys from several ranks are kept once, not summed. */
 mdbg_status mdbg_count_merge(mdbg_ctx* ctx);
 
 /* ---- synthetic input (benchmark/test support, device side) ------------------ */

@@ -122,6 +122,8 @@ struct mdbg_ctx {
     uint64_t t_capacity = 0;
     uint32_t t_k = 0;
     bool t_active = false;
+    bool t_value_mode = false;         // the table was filled by the next-k pass: `count` is a value, not an occurrence count
+    bool t_merged = false;             // multi-rank: mdbg_count_merge has moved every key to its owner
     DevBuf foreign_vecs;
     uint64_t foreign_n = 0;
     DevBuf prev_table, prev_stage_h, prev_stage_a;
@@ -1413,6 +1415,8 @@ mdbg_status mdbg_count_begin(mdbg_ctx* ctx, uint32_t k, uint64_t expected_distin
     ctx->t_capacity = cap;
     ctx->t_k = k;
     ctx->t_active = true;
+    ctx->t_value_mode = false;
+    ctx->t_merged = false;
     ctx->foreign_n = 0;
     return MDBG_OK;
 }
@@ -1440,6 +1444,7 @@ mdbg_status mdbg_count_add_store(mdbg_ctx* ctx, uint64_t read_lo, uint64_t read_
     a.table = ctx->table.as<Slot>();
     a.mask = ctx->t_capacity - 1;
     a.full_flag = &ctx->d_small->full_flag;
+    ctx->t_merged = false;
     if (ctx->timing) CK(cudaEventRecord(ctx->ev[1][0], s));
     launch_insert(a, s);
     if (ctx->timing) { CK(cudaEventRecord(ctx->ev[1][1], s)); ctx->ev_valid[1] = true; }
@@ -1537,11 +1542,116 @@ mdbg_status mdbg_count_finalize(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_tabl
     return MDBG_OK;
 }
 
+static mdbg_status prev_from_current_all_ranks(mdbg_ctx* ctx, uint32_t thr);
+
+// Multi-rank rescue (collective, after mdbg_count_merge).  The decision per read needs the abundance of every
+// window, the flag belongs to the window's owner:
+//   1. the solid k-min-mers (abundance >= 2) of all ranks are replicated into the lookup table (the same exchange
+//      the next-k pass uses);
+//   2. every rank runs the rescue decision on ITS reads against that table and collects the normalized vectors of
+//      the non-solid windows of rescued reads (each occurs exactly once in the whole read set);
+//   3. the vectors are bucketed by owner rank and exchanged in one grouped all-to-all;
+//   4. the owner flags the slots (count 1) of the vectors it received.
+static mdbg_status count_rescue_all_ranks(mdbg_ctx* ctx, uint64_t* n_reads_rescued) {
+    if (!ctx->nccl_comm) return fail(ctx, MDBG_ERR_STATE, "mdbg_count_rescue before mdbg_comm_init");
+    if (!ctx->t_merged || ctx->t_value_mode)
+        return fail(ctx, MDBG_ERR_STATE, "multi-rank mdbg_count_rescue needs the merged count table: call mdbg_count_merge first");
+    cudaStream_t s = ctx->stream;
+    const uint32_t R = (uint32_t)ctx->n_ranks, k = ctx->t_k;
+    CKS(prev_from_current_all_ranks(ctx, 2));                       // step 1 (lookup table = ctx->prev_table)
+    // step 2
+    const uint64_t max_windows = ctx->s_mins + 1;
+    CKS(ensure(ctx, ctx->m_recv_vecs, max_windows * 4 * k));        // flat list of collected vectors
+    CK(cudaMemsetAsync(&ctx->d_small->n_changed, 0, sizeof(unsigned long long), s));
+    CK(cudaMemsetAsync(&ctx->d_small->emit_cursor, 0, sizeof(unsigned long long), s));
+    if (ctx->s_reads) {
+        RescueArgs a{};
+        a.mins = ctx->s_min.as<uint32_t>();
+        a.offs = ctx->s_off.as<uint64_t>();
+        a.n_reads = ctx->s_reads;
+        a.k = k;
+        a.table = ctx->prev_table.as<Slot>();
+        a.mask = ctx->prev_capacity - 1;
+        a.n_reads_rescued = &ctx->d_small->n_changed;
+        a.out_vecs = ctx->m_recv_vecs.as<uint32_t>();
+        a.out_cursor = &ctx->d_small->emit_cursor;
+        launch_rescue(a, s);
+        CKS(check_launch(ctx, "rescue_kernel(collect)", 1));
+    }
+    CK(cudaMemcpyAsync(&ctx->h_scalar[0], &ctx->d_small->n_changed, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&ctx->h_scalar[1], &ctx->d_small->emit_cursor, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (n_reads_rescued) *n_reads_rescued = ctx->h_scalar[0];
+    const uint64_t n_list = ctx->h_scalar[1];
+    // step 3: bucket by owner, exchange
+    CKS(ensure(ctx, ctx->m_bucket, (size_t)(2 * R + R * R) * 8));
+    uint64_t* d_cnt = ctx->m_bucket.as<uint64_t>();
+    uint64_t* d_base = d_cnt + R;
+    uint64_t* d_all = d_cnt + 2 * R;
+    CK(cudaMemsetAsync(d_cnt, 0, R * 8, s));
+    BucketVecArgs b{};
+    b.vecs = ctx->m_recv_vecs.as<uint32_t>();
+    b.n = n_list;
+    b.k = k;
+    b.n_ranks = R;
+    b.bucket_count = reinterpret_cast<unsigned long long*>(d_cnt);
+    b.pass = 1;
+    launch_bucket_vecs(b, s);
+    CKS(check_launch(ctx, "bucket_vecs_kernel(count)", n_list ? 1 : 0));
+    NK(g_nccl.AllGather(d_cnt, d_all, R, NCCL_UINT64, ctx->nccl_comm, s));
+    std::vector<uint64_t> all((size_t)R * R);
+    CK(cudaMemcpyAsync(all.data(), d_all, (size_t)R * R * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    std::vector<uint64_t> send_cnt(R), send_base(R), recv_cnt(R), recv_base(R);
+    uint64_t send_total = 0, recv_total = 0;
+    for (uint32_t d = 0; d < R; d++) {
+        send_cnt[d] = all[(size_t)ctx->rank * R + d];
+        send_base[d] = send_total;
+        send_total += send_cnt[d];
+        recv_cnt[d] = all[(size_t)d * R + ctx->rank];
+        recv_base[d] = recv_total;
+        recv_total += recv_cnt[d];
+    }
+    CKS(ensure(ctx, ctx->m_send_vecs, (send_total + 1) * 4 * k));
+    CKS(ensure(ctx, ctx->o_vecs, (recv_total + 1) * 4 * k));       // receive side
+    CK(cudaMemcpyAsync(d_base, send_base.data(), R * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(d_cnt, 0, R * 8, s));
+    b.bucket_base = d_base;
+    b.out_vecs = ctx->m_send_vecs.as<uint32_t>();
+    b.pass = 2;
+    launch_bucket_vecs(b, s);
+    CKS(check_launch(ctx, "bucket_vecs_kernel(scatter)", n_list ? 1 : 0));
+    NK(g_nccl.GroupStart());
+    for (uint32_t d = 0; d < R; d++) {
+        if (send_cnt[d])
+            NK(g_nccl.Send(ctx->m_send_vecs.as<uint32_t>() + send_base[d] * k, send_cnt[d] * 4 * k, NCCL_UINT8, (int)d,
+                           ctx->nccl_comm, s));
+        if (recv_cnt[d])
+            NK(g_nccl.Recv(ctx->o_vecs.as<uint32_t>() + recv_base[d] * k, recv_cnt[d] * 4 * k, NCCL_UINT8, (int)d,
+                           ctx->nccl_comm, s));
+    }
+    NK(g_nccl.GroupEnd());
+    // step 4
+    CK(cudaMemsetAsync(&ctx->d_small->n_flagged, 0, sizeof(unsigned long long), s));
+    launch_rescue_flag(ctx->o_vecs.as<uint32_t>(), recv_total, k, ctx->table.as<Slot>(), ctx->t_capacity - 1,
+                       &ctx->d_small->n_flagged, s);
+    CKS(check_launch(ctx, "rescue_flag_kernel", recv_total ? 1 : 0));
+    CK(cudaMemcpyAsync(&ctx->h_scalar[2], &ctx->d_small->n_flagged, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (ctx->h_scalar[2])
+        return fail(ctx, MDBG_ERR_STATE, "multi-rank rescue: %llu rescued k-min-mers have no slot on their owner "
+                    "(were reads added after mdbg_count_merge?)", (unsigned long long)ctx->h_scalar[2]);
+    return MDBG_OK;
+}
+
 mdbg_status mdbg_count_rescue(mdbg_ctx* ctx, uint64_t* n_reads_rescued) {
     if (!ctx) return MDBG_ERR_ARG;
     if (n_reads_rescued) *n_reads_rescued = 0;
     if (!ctx->t_active) return fail(ctx, MDBG_ERR_STATE, "mdbg_count_rescue before mdbg_count_begin");
-    if (ctx->n_ranks > 1) return fail(ctx, MDBG_ERR_STATE, "mdbg_count_rescue is single-context only");
+    if (ctx->n_ranks > 1) {
+        CK(cudaSetDevice(ctx->device));
+        return count_rescue_all_ranks(ctx, n_reads_rescued);
+    }
     if (ctx->s_reads == 0) return MDBG_OK;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
@@ -1579,11 +1689,89 @@ static mdbg_status check_full(mdbg_ctx* ctx, const char* what) {
     return MDBG_OK;
 }
 
+// Multi-rank: after mdbg_count_merge every rank holds the keys it owns with their global abundances.  The next-k
+// pass looks up arbitrary (k-1)-min-mers, so the qualifying (hash, abundance) pairs of all ranks are replicated:
+// local emit -> all-gather of the counts -> one grouped exchange of the pairs over NVLink -> insert into the
+// previous-k table of every rank ("replicate if it fits": 20 B per solid k-min-mer).
+static mdbg_status prev_from_current_all_ranks(mdbg_ctx* ctx, uint32_t thr) {
+    if (!ctx->nccl_comm) return fail(ctx, MDBG_ERR_STATE, "mdbg_prev_from_current before mdbg_comm_init");
+    if (!ctx->t_merged)
+        return fail(ctx, MDBG_ERR_STATE, "multi-rank mdbg_prev_from_current needs the merged table: call mdbg_count_merge first");
+    cudaStream_t s = ctx->stream;
+    const uint32_t R = (uint32_t)ctx->n_ranks;
+    TableStats st;
+    CKS(table_stats(ctx, thr, &st));
+    const uint64_t n_local = st.n_entries;
+    CKS(ensure(ctx, ctx->o_hash, (n_local + 1) * 16));
+    CKS(ensure(ctx, ctx->o_abund, (n_local + 1) * 4));
+    CK(cudaMemsetAsync(&ctx->d_small->emit_cursor, 0, 8, s));
+    EmitArgs e{};
+    e.table = ctx->table.as<Slot>();
+    e.capacity = ctx->t_capacity;
+    e.min_count = thr;
+    e.k = ctx->t_k;
+    e.mins = ctx->s_min.as<uint32_t>();
+    e.foreign_vecs = ctx->foreign_vecs.as<uint32_t>();
+    e.out_hashes = ctx->o_hash.as<uint64_t>();
+    e.out_abund = ctx->o_abund.as<uint32_t>();
+    e.out_vecs = nullptr;
+    e.cursor = &ctx->d_small->emit_cursor;
+    launch_table_emit(e, s);
+    CKS(check_launch(ctx, "table_emit_kernel", 1));
+    // every rank's pair count
+    CKS(ensure(ctx, ctx->m_bucket, (size_t)(2 * R + R * R) * 8));
+    uint64_t* d_mine = ctx->m_bucket.as<uint64_t>();
+    uint64_t* d_all = d_mine + R;
+    ctx->h_scalar[3] = n_local;
+    CK(cudaMemcpyAsync(d_mine, &ctx->h_scalar[3], 8, cudaMemcpyHostToDevice, s));
+    NK(g_nccl.AllGather(d_mine, d_all, 1, NCCL_UINT64, ctx->nccl_comm, s));
+    std::vector<uint64_t> cnt(R), base(R);
+    CK(cudaMemcpyAsync(cnt.data(), d_all, (size_t)R * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    uint64_t total = 0;
+    for (uint32_t d = 0; d < R; d++) { base[d] = total; total += cnt[d]; }
+    CKS(ensure(ctx, ctx->prev_stage_h, (total + 1) * 16));
+    CKS(ensure(ctx, ctx->prev_stage_a, (total + 1) * 4));
+    uint64_t* g_hash = ctx->prev_stage_h.as<uint64_t>();
+    uint32_t* g_abund = ctx->prev_stage_a.as<uint32_t>();
+    NK(g_nccl.GroupStart());
+    for (uint32_t d = 0; d < R; d++) {
+        if ((int)d == ctx->rank) continue;
+        if (n_local) {
+            NK(g_nccl.Send(ctx->o_hash.p, n_local * 16, NCCL_UINT8, (int)d, ctx->nccl_comm, s));
+            NK(g_nccl.Send(ctx->o_abund.p, n_local * 4, NCCL_UINT8, (int)d, ctx->nccl_comm, s));
+        }
+        if (cnt[d]) {
+            NK(g_nccl.Recv(g_hash + 2 * base[d], cnt[d] * 16, NCCL_UINT8, (int)d, ctx->nccl_comm, s));
+            NK(g_nccl.Recv(g_abund + base[d], cnt[d] * 4, NCCL_UINT8, (int)d, ctx->nccl_comm, s));
+        }
+    }
+    NK(g_nccl.GroupEnd());
+    if (n_local) {
+        CK(cudaMemcpyAsync(g_hash + 2 * base[ctx->rank], ctx->o_hash.p, n_local * 16, cudaMemcpyDeviceToDevice, s));
+        CK(cudaMemcpyAsync(g_abund + base[ctx->rank], ctx->o_abund.p, n_local * 4, cudaMemcpyDeviceToDevice, s));
+    }
+    CKS(prev_alloc(ctx, total));
+    if (total) {
+        PrevLoadArgs a{};
+        a.hashes = g_hash;
+        a.abund = g_abund;
+        a.n = total;
+        a.prev = ctx->prev_table.as<Slot>();
+        a.prev_mask = ctx->prev_capacity - 1;
+        a.full_flag = &ctx->d_small->full_flag;
+        launch_prev_load(a, s);
+        CKS(check_launch(ctx, "prev_load_kernel", 1));
+    }
+    return check_full(ctx, "mdbg_prev_from_current (all ranks)");
+}
+
 mdbg_status mdbg_prev_from_current(mdbg_ctx* ctx, uint32_t min_abundance) {
     if (!ctx) return MDBG_ERR_ARG;
     if (!ctx->t_active) return fail(ctx, MDBG_ERR_STATE, "mdbg_prev_from_current without a count table");
     CK(cudaSetDevice(ctx->device));
     const uint32_t thr = count_threshold(min_abundance);
+    if (ctx->n_ranks > 1) return prev_from_current_all_ranks(ctx, thr);
     TableStats st;
     CKS(table_stats(ctx, thr, &st));
     CKS(prev_alloc(ctx, st.n_entries));
@@ -1649,6 +1837,8 @@ mdbg_status mdbg_count_add_store_next_k(mdbg_ctx* ctx, uint64_t read_lo, uint64_
     a.table = ctx->table.as<Slot>();
     a.mask = ctx->t_capacity - 1;
     a.full_flag = &ctx->d_small->full_flag;
+    ctx->t_value_mode = true;
+    ctx->t_merged = false;
     if (ctx->timing) CK(cudaEventRecord(ctx->ev[1][0], s));
     launch_next_k(a, s);
     if (ctx->timing) { CK(cudaEventRecord(ctx->ev[1][1], s)); ctx->ev_valid[1] = true; }
@@ -1763,11 +1953,13 @@ mdbg_status mdbg_count_merge(mdbg_ctx* ctx) {
     iv.table = ctx->table.as<Slot>();
     iv.mask = cap - 1;
     iv.full_flag = &ctx->d_small->full_flag;
+    iv.assign = ctx->t_value_mode ? 1u : 0u;      // next-k abundances are values (equal on every rank), not counts to add
     launch_insert_vecs(iv, s);
     CKS(check_launch(ctx, "insert_vecs_kernel", recv_total ? 1 : 0));
     CK(cudaMemcpyAsync(&ctx->h_small->full_flag, &ctx->d_small->full_flag, 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     if (ctx->h_small->full_flag) return fail(ctx, MDBG_ERR_TABLE_FULL, "merged table full");
+    ctx->t_merged = true;
     return MDBG_OK;
 }
 

@@ -138,6 +138,7 @@ struct InsertVecArgs {
     Slot* table;
     uint64_t mask;
     uint32_t* full_flag;
+    uint32_t assign;        // 0: counts are added (occurrence counts); 1: insert-if-absent with the value (next-k tables)
 };
 void launch_insert_vecs(const InsertVecArgs& a, cudaStream_t s);
 
@@ -161,7 +162,7 @@ struct EmitArgs {
     const uint32_t* foreign_vecs;  // merged-in vectors (may be nullptr)
     uint64_t* out_hashes;          // [2n]: lo, hi
     uint32_t* out_abund;           // [n]
-    uint32_t* out_vecs;            // [n*k]
+    uint32_t* out_vecs;            // [n*k], or nullptr when only (hash, abundance) pairs are wanted
     unsigned long long* cursor;    // zeroed before launch
 };
 void launch_table_emit(const EmitArgs& a, cudaStream_t s);
@@ -173,11 +174,27 @@ struct RescueArgs {
     const uint64_t* offs;
     uint64_t n_reads;
     uint32_t k;
-    Slot* table;
+    Slot* table;                 // one context: the count table; multi-rank: the replicated table of solid k-min-mers
     uint64_t mask;
     unsigned long long* n_reads_rescued;
+    // multi-rank only (nullptr otherwise): normalized vectors of the rescued, non-solid windows, appended through
+    // *out_cursor (zeroed before launch; capacity = number of windows of the local reads)
+    uint32_t* out_vecs;
+    unsigned long long* out_cursor;
 };
 void launch_rescue(const RescueArgs& a, cudaStream_t s);
+
+struct BucketVecArgs {
+    const uint32_t* vecs; uint64_t n; uint32_t k; uint32_t n_ranks;
+    unsigned long long* bucket_count;   // [n_ranks], zeroed before each pass
+    const uint64_t* bucket_base;        // [n_ranks], pass 2
+    uint32_t* out_vecs;                 // pass 2
+    int pass;
+};
+void launch_bucket_vecs(const BucketVecArgs& a, cudaStream_t s);
+// flags = SLOT_RESCUED on the slot of every vector (count < 2); *n_missing counts vectors without a slot
+void launch_rescue_flag(const uint32_t* vecs, uint64_t n, uint32_t k, Slot* table, uint64_t mask,
+                        unsigned long long* n_missing, cudaStream_t s);
 
 // ---- previous-k lookup table + next-k pass (getRefinedAbundance / IndexKminmerFunctor)
 struct PrevFromTableArgs {

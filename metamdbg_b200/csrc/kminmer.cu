@@ -123,6 +123,33 @@ void launch_insert(const InsertArgs& a, cudaStream_t s) {
     else insert_kernel<0><<<blocks, 256, 0, s>>>(a);
 }
 
+// Insert-if-absent with a VALUE (next-k tables: the abundance is a function of the key -- min over the two
+// (k-1)-min-mers of the replicated previous-k table -- so every rank that met the key computed the same number
+// and the first writer wins).
+__device__ __forceinline__ bool table_put(Slot* table, uint64_t mask, uint64_t lo, uint64_t hi, uint32_t value,
+                                          uint64_t ref) {
+    uint64_t idx = lo & mask;
+    const uint64_t max_probe = (mask + 1 < 4096) ? mask + 1 : 4096;
+    for (uint64_t probe = 0; probe < max_probe; probe++) {
+        Slot* s = table + idx;
+        uint64_t clo, chi;
+        load_key(s, clo, chi);
+        if (clo == lo && chi == hi && lo != 0 && hi != 0) return true;
+        if (clo == 0 || chi == 0) {
+            uint64_t olo, ohi;
+            cas_key(s, lo, hi, olo, ohi);
+            if (olo == 0 && ohi == 0) {                  // claimed
+                s->ref = ref;
+                s->count = value;
+                return true;
+            }
+            if (olo == lo && ohi == hi) return true;
+        }
+        idx = (idx + 1) & mask;
+    }
+    return false;
+}
+
 __global__ void __launch_bounds__(256) insert_vecs_kernel(const InsertVecArgs a) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
@@ -130,8 +157,10 @@ __global__ void __launch_bounds__(256) insert_vecs_kernel(const InsertVecArgs a)
     const uint32_t* w = a.vecs + i * (uint64_t)k;
     uint64_t h1, h2;
     murmur128_u32vec([&](int j) { return w[j]; }, k, h1, h2);   // already normalized by the sender
-    if (!table_add(a.table, a.mask, h2, h1, a.counts[i], REF_FOREIGN | (a.foreign_base + i)))
-        atomicExch(a.full_flag, 1u);
+    const uint64_t ref = REF_FOREIGN | (a.foreign_base + i);
+    const bool ok = a.assign ? table_put(a.table, a.mask, h2, h1, a.counts[i], ref)
+                             : table_add(a.table, a.mask, h2, h1, a.counts[i], ref);
+    if (!ok) atomicExch(a.full_flag, 1u);
 }
 
 void launch_insert_vecs(const InsertVecArgs& a, cudaStream_t s) {
@@ -218,8 +247,9 @@ __global__ void __launch_bounds__(256) table_emit_kernel(const EmitArgs a) {
             a.out_hashes[2 * pos] = lo;
             a.out_hashes[2 * pos + 1] = hi;
             a.out_abund[pos] = count;
-            for (int j = 0; j < (int)a.k; j++)
-                a.out_vecs[pos * a.k + j] = vec_elem(a.mins, a.foreign_vecs, ref, (int)a.k, j);
+            if (a.out_vecs)
+                for (int j = 0; j < (int)a.k; j++)
+                    a.out_vecs[pos * a.k + j] = vec_elem(a.mins, a.foreign_vecs, ref, (int)a.k, j);
         }
         __syncthreads();
     }
@@ -259,6 +289,11 @@ __device__ __forceinline__ Slot* table_find(Slot* table, uint64_t mask, uint64_t
 // RescueKminmerFunctor (CreateMdbg.hpp:4579-4637), one warp per read.  The decision only needs
 // "median * 0.1f > 1", which is unchanged when abundances are clamped at 22, so the median comes from a
 // 22-bin histogram held one bin per lane (Utils::compute_median, Commons.hpp:2973-2988).
+// REMOTE = false: one context; the abundance-1 windows of a rescued read are flagged in the table itself.
+// REMOTE = true : multi-rank; abundances come from the replicated table of solid k-min-mers (a.table; absent => 1),
+//                 and the non-solid windows of a rescued read are appended as normalized vectors to a.out_vecs --
+//                 their slots live on the owner rank, which flags them (rescue_flag_kernel) after the exchange.
+template <bool REMOTE>
 __global__ void __launch_bounds__(256) rescue_kernel(const RescueArgs a) {
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -299,11 +334,32 @@ __global__ void __launch_bounds__(256) rescue_kernel(const RescueArgs a) {
         }
         const double cutoff = (double)((float)median * 0.1f);    // CreateMdbg.hpp:4612
         if (cutoff > 1) continue;
-        for (uint64_t i = lane; i < nw; i += 32) {
-            uint64_t h1, h2; bool rev;
-            window_hash(a.mins + b + i, k, h1, h2, rev);
-            Slot* s = table_find(a.table, a.mask, h2, h1);
-            if (s && s->count < 2) s->flags = SLOT_RESCUED;
+        if constexpr (!REMOTE) {
+            for (uint64_t i = lane; i < nw; i += 32) {
+                uint64_t h1, h2; bool rev;
+                window_hash(a.mins + b + i, k, h1, h2, rev);
+                Slot* s = table_find(a.table, a.mask, h2, h1);
+                if (s && s->count < 2) s->flags = SLOT_RESCUED;
+            }
+        } else {
+            for (uint64_t i0 = 0; i0 < nw; i0 += 32) {
+                const uint64_t i = i0 + lane;
+                bool emit = false, rev = false;
+                if (i < nw) {
+                    uint64_t h1, h2;
+                    window_hash(a.mins + b + i, k, h1, h2, rev);
+                    emit = table_find(a.table, a.mask, h2, h1) == nullptr;      // not solid: exactly one occurrence
+                }
+                const uint32_t m = __ballot_sync(0xffffffffu, emit);
+                unsigned long long base = 0;
+                if (lane == 0 && m) base = atomicAdd(a.out_cursor, (unsigned long long)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (emit) {
+                    const uint64_t pos = base + __popc(m & ((1u << lane) - 1u));
+                    const uint32_t* w = a.mins + b + i;
+                    for (int j = 0; j < k; j++) a.out_vecs[pos * k + j] = rev ? w[k - 1 - j] : w[j];
+                }
+            }
         }
         if (lane == 0) atomicAdd(a.n_reads_rescued, 1ULL);
     }
@@ -313,7 +369,48 @@ void launch_rescue(const RescueArgs& a, cudaStream_t s) {
     if (a.n_reads == 0) return;
     uint64_t blocks = (a.n_reads + 7) / 8;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    rescue_kernel<<<(unsigned)blocks, 256, 0, s>>>(a);
+    if (a.out_vecs) rescue_kernel<true><<<(unsigned)blocks, 256, 0, s>>>(a);
+    else rescue_kernel<false><<<(unsigned)blocks, 256, 0, s>>>(a);
+}
+
+// ---- multi-rank rescue: bucket the collected vectors by owner rank (pass 1 counts, pass 2 scatters; the order
+// inside a bucket is irrelevant), and on the owner flag the slot of every received vector
+__global__ void __launch_bounds__(256) bucket_vecs_kernel(const BucketVecArgs a) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const int k = (int)a.k;
+    const uint32_t* w = a.vecs + i * (uint64_t)k;
+    uint64_t h1, h2;
+    murmur128_u32vec([&](int j) { return w[j]; }, k, h1, h2);
+    const uint32_t dst = owner_of(h1, a.n_ranks);
+    const unsigned long long slot = atomicAdd(&a.bucket_count[dst], 1ULL);
+    if (a.pass == 2) {
+        const uint64_t pos = a.bucket_base[dst] + slot;
+        for (int j = 0; j < k; j++) a.out_vecs[pos * k + j] = w[j];
+    }
+}
+
+void launch_bucket_vecs(const BucketVecArgs& a, cudaStream_t s) {
+    if (a.n == 0) return;
+    bucket_vecs_kernel<<<(unsigned)((a.n + 255) / 256), 256, 0, s>>>(a);
+}
+
+__global__ void __launch_bounds__(256) rescue_flag_kernel(const uint32_t* vecs, uint64_t n, uint32_t k, Slot* table,
+                                                          uint64_t mask, unsigned long long* n_missing) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t* w = vecs + i * (uint64_t)k;
+    uint64_t h1, h2;
+    murmur128_u32vec([&](int j) { return w[j]; }, (int)k, h1, h2);
+    Slot* sl = table_find(table, mask, h2, h1);
+    if (!sl) { atomicAdd(n_missing, 1ULL); return; }            // every occurrence is in its owner's merged table
+    if (sl->count < 2) sl->flags = SLOT_RESCUED;
+}
+
+void launch_rescue_flag(const uint32_t* vecs, uint64_t n, uint32_t k, Slot* table, uint64_t mask,
+                        unsigned long long* n_missing, cudaStream_t s) {
+    if (n == 0) return;
+    rescue_flag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(vecs, n, k, table, mask, n_missing);
 }
 
 // insert-or-assign into the previous-k lookup table (value in `count`)

@@ -25,6 +25,8 @@ def main():
     bases, offs = synth.fill_reads(rs)
     uid = Engine.nccl_unique_id()                       # loads the (fake) NCCL once, before the threads start
     results, errors = [None] * n_ranks, []
+    next_results = [None] * n_ranks
+    rescue_results = [None] * n_ranks
 
     def rank_main(rank):
         try:
@@ -38,6 +40,19 @@ def main():
             eng.count_add_store()
             eng.count_merge()
             results[rank] = (eng.count_finalize(2), eng.count_stats(2))
+            # default mode (--min-abundance 0): rescue across ranks, then the table with the rescued abundance-1 entries
+            n_resc = eng.count_rescue()
+            rescue_results[rank] = (n_resc, eng.count_finalize(0))
+            # multi-k on the device: previous-k table replicated from the owners, next-k pass on this rank's reads,
+            # owner merge of the (key -> value) tables, twice
+            chain = []
+            for kk in (k + 1, k + 2):
+                eng.prev_from_current(2)
+                eng.count_begin(kk, 0)
+                eng.count_add_store_next_k()
+                eng.count_merge()
+                chain.append(eng.count_finalize(0))
+            next_results[rank] = chain
             eng.close()
         except Exception as e:                           # noqa: BLE001
             errors.append((rank, repr(e)))
@@ -67,6 +82,36 @@ def main():
         instances += st["n_instances"]; distinct += st["n_distinct"]
     assert merged == want and len(want) > 3000, (len(merged), len(want))
     assert instances == ref["n_instances"] and distinct == ref["n_distinct"], "occurrences not conserved"
+    # rescue: solid + rescued entries over all ranks = the oracle's table of the whole read set
+    resc = orc.rescue(pm, po, k, ref["hashes"], ref["abundances"])
+    want_r = dict(want)
+    for h in resc["hashes"]:
+        want_r[(int(h[0]), int(h[1]))] = 1
+    got_r, reads_rescued, n_rescued = {}, 0, 0
+    for rank, (n_resc, tab) in enumerate(rescue_results):
+        reads_rescued += n_resc
+        n_rescued += tab.n_rescued
+        for key, ab in tab.as_dict().items():
+            assert owner_of(key[0], n_ranks) == rank and key not in got_r
+            got_r[key] = ab
+    assert got_r == want_r and n_rescued == len(resc["hashes"]) > 50, (len(got_r), len(want_r), n_rescued)
+    assert reads_rescued == resc["n_reads_rescued"], (reads_rescued, resc["n_reads_rescued"])
+    print(f"  rescue: {n_rescued} abundance-1 k-min-mers of {reads_rescued} reads flagged on their owners")
+    # the multi-k chain against the oracle's next-k restatement (IndexKminmerFunctor / getRefinedAbundance); the
+    # previous-k table holds the solid AND the rescued entries, as kminmerData_abundance.txt does in default mode
+    prev_h = np.concatenate([ref["hashes"], resc["hashes"]]) if len(resc["hashes"]) else ref["hashes"]
+    prev_a = np.concatenate([ref["abundances"], np.ones(len(resc["hashes"]), np.uint32)])
+    for step, kk in enumerate((k + 1, k + 2)):
+        nk = orc.next_k(pm, po, kk, prev_h, prev_a)
+        want_k = {(int(h[0]), int(h[1])): int(a) for h, a in zip(nk["hashes"], nk["abundances"])}
+        got_k = {}
+        for rank in range(n_ranks):
+            for key, ab in next_results[rank][step].as_dict().items():
+                assert owner_of(key[0], n_ranks) == rank and key not in got_k
+                got_k[key] = ab
+        assert got_k == want_k and len(want_k) > 1000, (kk, len(got_k), len(want_k))
+        prev_h, prev_a = nk["hashes"], nk["abundances"]
+        print(f"  next-k {kk}: {len(want_k)} entries identical over {n_ranks} ranks")
     print(f"{n_ranks} ranks, k={k}: {len(want)} solid k-min-mers, {instances} occurrences conserved")
     print("OK")
 
