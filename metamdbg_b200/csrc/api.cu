@@ -284,14 +284,14 @@ struct PiecePipeline {
         if (bytes <= b.cap && b.p) return MDBG_OK;
         CK(cudaStreamSynchronize(ctx->d2h_stream));               // a copy may still read the old allocation
         if (in_flight) ctx->last_grows++;
-        return ensure(ctx, b, bytes + bytes / 4, true);
+        return ensure(ctx, b, in_flight ? 2 * bytes : bytes, true);   // the estimate was low: double, do not creep
     }
     mdbg_status grow_pin(PinBuf& b, size_t bytes, size_t keep_bytes) {
         if (bytes <= b.cap && b.p) return MDBG_OK;
         CK(cudaStreamSynchronize(ctx->d2h_stream));
         if (in_flight) ctx->last_grows++;
         PinBuf bigger;
-        CKS(ensure_pin(ctx, bigger, bytes + bytes / 4));
+        CKS(ensure_pin(ctx, bigger, in_flight ? 2 * bytes : bytes));
         if (b.p && keep_bytes) memcpy(bigger.p, b.p, keep_bytes);
         release(b);
         b = bigger;

@@ -3,6 +3,14 @@
 // collectives are memcpy between threads behind barriers.  Only what libmdbg_b200 dlsym()s is provided:
 // ncclGetUniqueId, ncclCommInitRank, ncclCommDestroy, ncclAllGather, ncclGroupStart/End + ncclSend/Recv,
 // ncclGetErrorString.  Built as libnccl.so.2 into a temporary directory that is put first on LD_LIBRARY_PATH.
+//
+// With -DFAKE_NCCL_CUDA (scripts/gpu_selftest.sh) the buffers are real device memory: N ranks = N threads sharing
+// ONE GPU (real NCCL refuses two ranks on one device), each collective first drains the rank's stream and then
+// copies with cudaMemcpy.  That runs the product's multi-rank kernels and host sequencing on real hardware when
+// only a single GPU is available; it is not a performance path.
+#ifdef FAKE_NCCL_CUDA
+#include <cuda_runtime.h>
+#endif
 #include <condition_variable>
 #include <cstdint>
 #include <cstring>
@@ -12,6 +20,14 @@
 #include <vector>
 
 namespace {
+
+#ifdef FAKE_NCCL_CUDA
+inline void copy_bytes(void* d, const void* s, size_t n) { cudaMemcpy(d, s, n, cudaMemcpyDefault); }
+inline void drain(void* stream) { cudaStreamSynchronize((cudaStream_t)stream); }
+#else
+inline void copy_bytes(void* d, const void* s, size_t n) { memcpy(d, s, n); }
+inline void drain(void*) {}
+#endif
 
 struct Barrier {
     std::mutex m; std::condition_variable cv; int n = 0, waiting = 0; uint64_t gen = 0;
@@ -38,6 +54,7 @@ uint64_t g_next_id = 1;
 thread_local std::vector<PendingOp> t_ops;
 thread_local int t_depth = 0;
 thread_local Comm* t_comm = nullptr;
+thread_local void* t_stream = nullptr;
 
 size_t dtype_size(int t) { static const size_t s[] = {1, 1, 4, 4, 8, 8, 2, 4, 8, 2}; return (t >= 0 && t < 10) ? s[t] : 1; }
 
@@ -47,6 +64,7 @@ int flush_group_ops() {
     const int me = t_comm->rank;
     for (const PendingOp& op : t_ops)
         if (op.send) g->box[me][op.peer].push_back(Msg{op.sp, op.bytes});
+    drain(t_stream);                                         // what this rank sends has been produced
     g->bar.wait();                                           // everybody has posted
     std::vector<size_t> next(g->n, 0);
     int rc = 0;
@@ -54,7 +72,7 @@ int flush_group_ops() {
         if (!op.send) {
             auto& q = g->box[op.peer][me];
             if (next[op.peer] >= q.size() || q[next[op.peer]].bytes != op.bytes) { rc = 3; continue; }   // mismatched send/recv
-            memcpy(op.rp, q[next[op.peer]].p, op.bytes);
+            copy_bytes(op.rp, q[next[op.peer]].p, op.bytes);
             next[op.peer]++;
         }
     g->bar.wait();                                           // everybody has copied
@@ -102,13 +120,14 @@ int ncclCommInitRank(void** comm, int nranks, ncclUniqueId id, int rank) {
 
 int ncclCommDestroy(void* comm) { delete (Comm*)comm; return 0; }
 
-int ncclAllGather(const void* send, void* recv, size_t count, int dtype, void* comm, void*) {
+int ncclAllGather(const void* send, void* recv, size_t count, int dtype, void* comm, void* stream) {
     Comm* c = (Comm*)comm;
     t_comm = c;
+    drain(stream);
     const size_t bytes = count * dtype_size(dtype);
     c->g->gather_src[c->rank] = send;
     c->g->bar.wait();
-    for (int r = 0; r < c->g->n; r++) memcpy((char*)recv + (size_t)r * bytes, c->g->gather_src[r], bytes);
+    for (int r = 0; r < c->g->n; r++) copy_bytes((char*)recv + (size_t)r * bytes, c->g->gather_src[r], bytes);
     c->g->bar.wait();
     return 0;
 }
@@ -116,13 +135,15 @@ int ncclAllGather(const void* send, void* recv, size_t count, int dtype, void* c
 int ncclGroupStart() { t_depth++; return 0; }
 int ncclGroupEnd() { if (--t_depth == 0) return flush_group_ops(); return 0; }
 
-int ncclSend(const void* p, size_t count, int dtype, int peer, void* comm, void*) {
+int ncclSend(const void* p, size_t count, int dtype, int peer, void* comm, void* stream) {
     t_comm = (Comm*)comm;
+    t_stream = stream;
     t_ops.push_back(PendingOp{true, p, nullptr, count * dtype_size(dtype), peer});
     return t_depth ? 0 : flush_group_ops();
 }
-int ncclRecv(void* p, size_t count, int dtype, int peer, void* comm, void*) {
+int ncclRecv(void* p, size_t count, int dtype, int peer, void* comm, void* stream) {
     t_comm = (Comm*)comm;
+    t_stream = stream;
     t_ops.push_back(PendingOp{false, nullptr, p, count * dtype_size(dtype), peer});
     return t_depth ? 0 : flush_group_ops();
 }
