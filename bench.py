@@ -313,11 +313,13 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     launches0 = eng.kernel_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sketch_ms, insert_ms = [], []
+    step_checksums = {stats["checksum"]} if args.warmup else set()
     e0.record()
     for _ in range(args.steps):
         stats = step_device()
         sketch_ms.append(eng.kernel_time_ms(0))
         insert_ms.append(eng.kernel_time_ms(1))
+        step_checksums.add(stats["checksum"])
     e1.record()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
@@ -379,16 +381,23 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             d2h[0] += len(tab.abundances) * (16 + 4 + 4 * K)
             return tab
 
+        # parity of every e2e step (warm-up steps included): the finalised table of the host-buffer path must carry
+        # the checksum of the device-resident leg (same reads, same merge); reported, never silently skipped
+        comparable = e_reads == n_reads
+        e2e_checks = []
         for _ in range(max(1, min(args.warmup, 2))):
             tab = step_e2e()
+            e2e_checks.append(tab.checksum == checksum_local)
         e_steps = max(1, min(args.steps, args.e2e_steps))
         barrier()
         moved0 = eng.bytes_moved()
         t0 = time.perf_counter()
         for _ in range(e_steps):
             tab = step_e2e()
+            e2e_checks.append(tab.checksum == checksum_local)
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
+        bad_steps = sum_over_ranks(sum(1 for ok in e2e_checks if not ok)) if comparable else None
         moved1 = eng.bytes_moved()
         e_total = sum_over_ranks(e_bases)
         e2e = {"value": e_total * e_steps / dt / 1e9, "unit": "Gbp/s",
@@ -399,9 +408,14 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                            "the CSR's D2H run piece by piece behind each piece's sketch",
                "steps": e_steps, "reads_per_gpu": e_reads, "host_batch_reads": batch,
                "last_host_batch": eng.last_batch_info(),
-               "timer": "host wall clock around synchronous C-ABI calls, max over ranks"}
-        if world == 1 and e_reads == n_reads:
-            assert tab.checksum == checksum_local, "e2e table differs from the device-resident table"
+               "timer": "host wall clock around synchronous C-ABI calls, max over ranks",
+               "table_checks": {"steps_checked": len(e2e_checks) * world if comparable else 0,
+                                "steps_differing_from_device_leg": bad_steps,
+                                "what": "checksum (sum abundance*hash) of the finalised table of every e2e step, warm-up "
+                                        "included, against the device-resident leg on the same reads"}}
+        if comparable and bad_steps:
+            print(f"bench.py: WARNING: {bad_steps} e2e step(s) produced a table that differs from the device-resident leg",
+                  file=sys.stderr, flush=True)
         del h_bases
 
     # ---- CPU baseline (rank 0, N=1 only) + parity spot check against it ------------------------
@@ -476,7 +490,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "cpu_baseline": cpu_baseline,
             "check": {"n_minimizers_rank0": int(n_min_store), "n_solid_total": int(solid_total),
                       "checksum_rank0": int(checksum_local), "kminmer_occurrences_total": int(got_instances),
-                      "occurrences_conserved": True},
+                      "occurrences_conserved": True,
+                      "device_steps_same_checksum": len(step_checksums) == 1},
         }
         print(json.dumps(line), flush=True)
     eng.close()

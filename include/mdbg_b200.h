@@ -165,7 +165,9 @@ mdbg_status mdbg_sketch_batch_device(mdbg_ctx* ctx, const uint8_t* d_bases, cons
  * one final hash multiply on the summed pre-images, carry-chain accept bits).  Variant 0 is the default; the
  * environment variable MDBG_SKETCH_VARIANT presets it at context creation.  mdbg_ctx_autotune_sketch runs every
  * variant on the caller's own device-resident batch (nothing is appended to the store), compares the complete
- * results with variant 0 byte for byte ON THE DEVICE, and keeps the fastest variant that is identical. */
+ * results with variant 0 byte for byte ON THE DEVICE, and keeps the fastest variant that is identical.  Every
+ * variant is run twice: once as one launch (timed), once in launches of 2048 reads with the shared memory of all
+ * SMs overwritten in between, so that a variant depending on stale shared memory fails the comparison. */
 #define MDBG_SKETCH_VARIANTS 2
 typedef struct mdbg_autotune_out {
     int32_t n_variants;

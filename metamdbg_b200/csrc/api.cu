@@ -844,6 +844,38 @@ mdbg_status mdbg_ctx_autotune_sketch(mdbg_ctx* ctx, const uint8_t* d_bases, cons
         *ms = best;
         return MDBG_OK;
     };
+    // second opinion: the same batch in launches of at most 2048 reads with the shared memory of every SM
+    // scrambled in between -- every read then meets a ring it did not write (fresh-CTA conditions, 500 times per
+    // million reads instead of once), which a whole-batch launch hardly ever exercises
+    const Feeder stress_feeder = [&](SketchArgs& a) -> mdbg_status {
+        const uint32_t step = 2048;
+        uint32_t it = 0;
+        for (uint32_t r0 = 0; r0 < n_reads; r0 += step, it++) {
+            launch_smem_scramble(ctx->sm_count, it, &ctx->d_small->full_flag, s);
+            CK(cudaMemsetAsync(&ctx->d_small->cursor, 0, sizeof(uint32_t), s));
+            a.read_begin = r0;
+            a.read_end = std::min<uint64_t>(n_reads, (uint64_t)r0 + step);
+            a.cursor = &ctx->d_small->cursor;
+            launch_sketch(a, ctx->sm_count, s);
+            CKS(check_launch(ctx, "sketch_kernel(stress)", 2));
+        }
+        return MDBG_OK;
+    };
+    auto same_as_reference = [&](bool* same) -> mdbg_status {
+        unsigned long long* n_diff = &ctx->d_small->n_changed;
+        CK(cudaMemsetAsync(n_diff, 0, sizeof(unsigned long long), s));
+        *same = ctx->b_total == r_total;
+        if (!*same) return MDBG_OK;
+        launch_count_diff(r_off.p, ctx->b_off.p, ((size_t)n_reads + 1) * 8, n_diff, s);
+        launch_count_diff(r_min.p, ctx->b_min.p, r_total * 4, n_diff, s);
+        launch_count_diff(r_pos.p, ctx->b_pos.p, r_total * 4, n_diff, s);
+        launch_count_diff(r_dir.p, ctx->b_dir.p, r_total, n_diff, s);
+        CKS(check_launch(ctx, "count_diff_kernel", 4));
+        CK(cudaMemcpyAsync(&ctx->h_scalar[2], n_diff, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        *same = ctx->h_scalar[2] == 0;
+        return MDBG_OK;
+    };
     auto body = [&]() -> mdbg_status {
         CKS(run(0, &out->ms[0]));
         out->identical[0] = 1;
@@ -857,20 +889,19 @@ mdbg_status mdbg_ctx_autotune_sketch(mdbg_ctx* ctx, const uint8_t* d_bases, cons
         CK(cudaMemcpyAsync(r_pos.p, ctx->b_pos.p, r_total * 4, cudaMemcpyDeviceToDevice, s));
         CK(cudaMemcpyAsync(r_dir.p, ctx->b_dir.p, r_total, cudaMemcpyDeviceToDevice, s));
         int best_v = 0;
+        {   // the reference itself must survive the stress run, or the batch is not a usable yardstick
+            bool same = false;
+            CKS(sketch_internal(ctx, d_bases, d_offsets, n_reads, n_bases, 0, false, nullptr, &stress_feeder));
+            CKS(same_as_reference(&same));
+            if (!same) return fail(ctx, MDBG_ERR_STATE, "autotune: variant 0 is not reproducible under the fresh-CTA stress run");
+        }
         for (int v = 1; v < SKETCH_VARIANTS; v++) {
             CKS(run(v, &out->ms[v]));
-            unsigned long long* n_diff = &ctx->d_small->n_changed;
-            CK(cudaMemsetAsync(n_diff, 0, sizeof(unsigned long long), s));
-            bool same = ctx->b_total == r_total;
+            bool same = false;
+            CKS(same_as_reference(&same));
             if (same) {
-                launch_count_diff(r_off.p, ctx->b_off.p, ((size_t)n_reads + 1) * 8, n_diff, s);
-                launch_count_diff(r_min.p, ctx->b_min.p, r_total * 4, n_diff, s);
-                launch_count_diff(r_pos.p, ctx->b_pos.p, r_total * 4, n_diff, s);
-                launch_count_diff(r_dir.p, ctx->b_dir.p, r_total, n_diff, s);
-                CKS(check_launch(ctx, "count_diff_kernel", 4));
-                CK(cudaMemcpyAsync(&ctx->h_scalar[2], n_diff, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-                CK(cudaStreamSynchronize(s));
-                same = ctx->h_scalar[2] == 0;
+                CKS(sketch_internal(ctx, d_bases, d_offsets, n_reads, n_bases, 0, false, nullptr, &stress_feeder));
+                CKS(same_as_reference(&same));
             }
             out->identical[v] = same ? 1 : 0;
             if (same && out->ms[v] < 0.99f * out->ms[best_v]) best_v = v;

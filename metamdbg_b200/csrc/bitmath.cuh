@@ -91,8 +91,12 @@ MDBG_HD uint32_t lmer_from_packed(uint32_t s_hi, uint32_t s_lo, uint32_t j) {
 template <int L>
 MDBG_HD uint32_t roll16_fast(const uint32_t (&W)[8], uint32_t thr_cand, uint32_t& s_hi, uint32_t& s_lo) {
     constexpr uint32_t MASK = (L < 16) ? ((1u << (2 * L)) - 1u) : 0xFFFFFFFFu;
-    s_hi = (pack4_msb(W[0]) << 24) | (pack4_msb(W[1]) << 16) | (pack4_msb(W[2]) << 8) | pack4_msb(W[3]);
-    s_lo = (pack4_msb(W[4]) << 24) | (pack4_msb(W[5]) << 16) | (pack4_msb(W[6]) << 8) | pack4_msb(W[7]);
+    // The ring bytes past the read's last base are whatever shared memory held (not necessarily codes, and not
+    // necessarily flagged by the bit-2 test): keep 2 bits of every byte, or pack4's multiply lets such a byte carry
+    // into the fields of the codes before it -- codes that valid positions of this lane still need.
+    constexpr uint32_t M = 0x03030303u;
+    s_hi = (pack4_msb(W[0] & M) << 24) | (pack4_msb(W[1] & M) << 16) | (pack4_msb(W[2] & M) << 8) | pack4_msb(W[3] & M);
+    s_lo = (pack4_msb(W[4] & M) << 24) | (pack4_msb(W[5] & M) << 16) | (pack4_msb(W[6] & M) << 8) | pack4_msb(W[7] & M);
     uint32_t r_lo = brev32(s_hi ^ 0xAAAAAAAAu), r_hi = brev32(s_lo ^ 0xAAAAAAAAu);   // bit order reversed ...
     r_lo = ((r_lo & 0x55555555u) << 1) | ((r_lo >> 1) & 0x55555555u);                // ... pairs put back
     r_hi = ((r_hi & 0x55555555u) << 1) | ((r_hi >> 1) & 0x55555555u);

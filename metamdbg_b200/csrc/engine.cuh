@@ -40,6 +40,9 @@ constexpr int SKETCH_VARIANTS = 2;
 
 void launch_sketch(const SketchArgs& a, int sm_count, cudaStream_t s);
 
+// fills the shared memory of every SM with non-code bytes (verification aid of the autotuner, see sketch.cu)
+void launch_smem_scramble(int sm_count, uint32_t seed, uint32_t* sink, cudaStream_t s);
+
 // *n_diff += number of bytes at which a[0..n_bytes) and b[0..n_bytes) differ (autotune's identity check)
 void launch_count_diff(const void* a, const void* b, size_t n_bytes, unsigned long long* n_diff, cudaStream_t s);
 

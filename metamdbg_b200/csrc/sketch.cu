@@ -136,6 +136,13 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, V ? 5 : 0) sketch_kernel(c
     uint2* cand = cand_all[threadIdx.x >> 5];
     uint32_t n_list = 0;
     const uint32_t l = a.l;
+#ifdef MDBG_POISON_SMEM
+    // test builds only (tests/cpp/sketch_emu_test.cpp): shared memory is NOT zero when a CTA starts on a real SM --
+    // it holds whatever the previous CTA left there.  Fill the ring with non-code bytes that pass the bit-2
+    // "invalid character" test, so that any dependence on bytes past `avail` shows up as a wrong sketch.
+    for (uint32_t i = lane; i < (uint32_t)RING + 16; i += 32) ring[i] = (uint8_t)(0x18u + 0x20u * (i % 7u) + (i & 3u));
+    __syncwarp();
+#endif
     // V = 0: T_hi + 1, V = 1: T_hi + S1_SLACK; a wrapped value (overflow) disables the fast path
     const uint32_t thr_cand = (uint32_t)(a.threshold >> 32) + (V ? k1v1::S1_SLACK : 1u);
     constexpr uint32_t THR_MIN = V ? k1v1::S1_SLACK : 1u;
@@ -422,6 +429,27 @@ void launch_sketch(const SketchArgs& a, int sm_count, cudaStream_t s) {
     if (a.l != 15) launch_sketch_as<0, 0>(a, sm_count, s);          // generic l: no unrolled register block at all
     else if (a.variant == 1) launch_sketch_as<15, 1>(a, sm_count, s);
     else launch_sketch_as<15, 0>(a, sm_count, s);
+}
+
+// ------------------------------------------------------------------ shared-memory scrambler (verification aid)
+// A CTA starts with whatever the previous CTA on that SM left in shared memory.  mdbg_ctx_autotune_sketch runs
+// every kernel variant once more in many small launches with this kernel in between: it fills the shared memory
+// of every SM with bytes that are neither base codes nor caught by the bit-2 "invalid character" test, so a
+// variant whose result depends on ring bytes it never wrote is caught by the identity check instead of in
+// production (that is how the first version of variant 1 failed: once per ~10^6 reads, only in multi-launch runs).
+__global__ void __launch_bounds__(256) smem_scramble_kernel(uint32_t seed, uint32_t* sink) {
+    __shared__ uint32_t buf[12 * 1024];                           // 48 KB static; 4 CTAs cover 192 KB of an SM
+    for (uint32_t i = threadIdx.x; i < 12 * 1024; i += blockDim.x) {
+        const uint32_t b = 0x18u + 0x20u * ((i + seed) % 7u);     // bit 2 clear, value >= 0x18 in every byte
+        buf[i] = (b | (b << 8) | (b << 16) | (b << 24)) ^ ((i * 0x01010101u) & 0x03030303u);
+    }
+    __syncthreads();
+    if (seed == 0xFFFFFFFFu) *sink = buf[threadIdx.x];             // never true: keeps the stores alive
+}
+
+void launch_smem_scramble(int sm_count, uint32_t seed, uint32_t* sink, cudaStream_t s) {
+    const unsigned grid = (unsigned)sm_count * 4u;
+    smem_scramble_kernel<<<grid, 256, 0, s>>>(seed & 0x7FFFFFFFu, sink);
 }
 
 // ------------------------------------------------------------------ byte-wise comparison of two device arrays

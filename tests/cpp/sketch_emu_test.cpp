@@ -24,6 +24,7 @@ using namespace mdbg;
 
 static int fails = 0;
 static uint32_t g_variant = 0;             // arithmetic variant of the unrolled l = 15 block under test
+static bool g_per_read = false;            // one launch per read: every read is the first one a (poisoned) ring sees
 #define CHECK(c, ...) do { if (!(c)) { if (fails++ < 20) { printf("FAIL line %d: ", __LINE__); printf(__VA_ARGS__); printf("\n"); } } } while (0)
 
 struct Batch {
@@ -101,6 +102,15 @@ static Result run_kernel(const Batch& b, uint32_t l, float density, int hpc, con
         a.packed = words.data();
     }
     auto launch = [&]() {
+        if (g_per_read) {
+            for (uint32_t r = 0; r < n; r++) {
+                cursor = 0;
+                a.read_begin = r; a.read_end = r + 1;
+                launch_sketch(a, 2, nullptr);
+            }
+            a.read_begin = 0; a.read_end = n;
+            return;
+        }
         cursor = 0;
         launch_sketch(a, /*sm_count=*/2, nullptr);            // 2 "SMs" x 2 CTAs x 8 warps, reads pulled dynamically
     };
@@ -196,6 +206,23 @@ int main() {
         bl.erase(std::unique(bl.begin(), bl.end()), bl.end());
         compare(b, 15, 0.05f, 1, bl, false, "blacklist", totals);
     }
+#ifdef MDBG_POISON_SMEM
+    // Shared memory is not zero when a CTA starts: with the ring poisoned at kernel start and one launch per read,
+    // every read meets bytes past `avail` that are neither codes nor flagged invalid.  Reads whose HPC length puts
+    // `avail` exactly on a block boundary + l (the only non-final case) are included on purpose.
+    {
+        Batch pb;
+        for (size_t n : {527u, 528u, 529u, 1039u, 1040u, 1041u, 1551u, 1552u, 2063u, 2064u, 3000u}) pb.add(rnd_read(n, 0));
+        for (int i = 0; i < 300; i++) pb.add(rnd_read(500 + rng() % 2200, 0));
+        g_per_read = true;
+        for (g_variant = 0; g_variant < (uint32_t)SKETCH_VARIANTS; g_variant++)
+            for (int hpc = 0; hpc < 2; hpc++) {
+                compare(pb, 15, 0.02f, hpc, none, false, "poisoned ring", totals);
+                compare(pb, 15, 0.02f, hpc, none, true, "poisoned ring packed", totals);
+            }
+        g_per_read = false;
+    }
+#endif
     printf("%llu minimizers compared, %llu slot overflows exercised\n", (unsigned long long)totals[0],
            (unsigned long long)totals[1]);
     CHECK(totals[0] > 40000 && totals[1] > 0, "coverage too small");

@@ -26,6 +26,16 @@ def test_sketch_scan_compact_kernels_in_emulator(tmp_path):
     assert "slot overflows exercised" in out
 
 
+def test_sketch_kernel_does_not_depend_on_stale_shared_memory(tmp_path):
+    """Same suite with -DMDBG_POISON_SMEM: every warp's ring is filled with non-code bytes when the kernel starts
+    (a real SM hands a CTA whatever the previous CTA left in shared memory) and one launch is made per read, so a
+    result that depends on ring bytes past `avail` differs from the oracle.  (Found on a B200: variant 1 packed the
+    lane's 32 ring bytes with a multiply that let a garbage byte 31 carry into the codes of positions 14 / 15.)"""
+    out = _emu.build_and_run(tmp_path, "sketch_emu_test.cpp", {"SKETCH_SOURCE": "sketch.cu"},
+                             extra_flags=("-DMDBG_POISON_SMEM",))
+    assert "slot overflows exercised" in out
+
+
 def test_read_aux_kernel_in_emulator(tmp_path):
     """read_aux_kernel: exact error sums -> mean read quality (bit-exact float), DUST-like complexity (bit-exact
     double) + the low-complexity filter, per-minimizer minimum quality through the HPC -> raw coordinate re-scan."""
