@@ -339,6 +339,24 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     if expect_instances != got_instances:
         raise SystemExit(f"bench.py: occurrence conservation violated: {got_instances} != {expect_instances}")
 
+    # ---- extra (not the headline): the multi-k loop k = 4 .. 21 on the resident store (BASELINE config 4's shape on
+    # this workload): k = 4 counted, every further k derived from the previous table on the device.  Single GPU by
+    # default; --multi-k-ranks also runs it with the collective previous-k replication + value merge for N > 1.
+    multi_k = None
+    if args.multi_k > K and (world == 1 or args.multi_k_ranks):
+        try:
+            from metamdbg_b200 import multi_k_sweep
+            sweeps = [multi_k_sweep(eng, K, args.multi_k, MIN_AB, merge=world > 1) for _ in range(2)]   # 2nd = warm
+            per_k = [round(1e3 * max_over_ranks(r["seconds"]), 3) for r in sweeps[1]]
+            total_s = sum(per_k) * 1e-3
+            multi_k = {"k_first": K, "k_last": args.multi_k, "ms_per_k": per_k, "ms_total": round(sum(per_k), 3),
+                       "value": total_bases / total_s / 1e9, "unit": "Gbp/s (input bases / time of the k-loop alone; the "
+                       "sketch is not repeated, as in the reference)", "n_entries_rank0": [r["n_entries"] for r in sweeps[1]],
+                       "timer": "host wall clock per k around device work ending in a D2H of the table statistics",
+                       "same_tables_both_sweeps": [r["checksum"] for r in sweeps[0]] == [r["checksum"] for r in sweeps[1]]}
+        except Exception as e:                                # noqa: BLE001  -- an extra must not cost the headline line
+            multi_k = {"error": repr(e)}
+
     # ---- end to end through the host-buffer C ABI ---------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -485,6 +503,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                          "binding_pipes_ncu": ncu_pipes,
                          "share_of_step": sk_ms / (ms_total / args.steps)},
             "kernels_ms": {"sketch": sk_ms, "insert": float(np.mean(insert_ms))},
+            "multi_k": multi_k,
             "sketch_autotune": dict(tune, note="ms = sketch + scan + compaction of the full batch, best of 2; a variant is "
                                                "eligible only if its whole output equals variant 0's on the device"),
             "cpu_baseline": cpu_baseline,
@@ -513,6 +532,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--ref-reads", type=int, default=0, help="sample size of the reference arm (0 = auto)")
     ap.add_argument("--sketch-variant", type=int, default=-1, help="force a sketch-kernel variant (-1 = autotune)")
+    ap.add_argument("--multi-k", type=int, default=21, help="extra: multi-k loop up to this k on the resident store (0 = off)")
+    ap.add_argument("--multi-k-ranks", action="store_true", help="run the multi-k extra for N > 1 as well (collectives)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stages", action="store_true", help="reference arm: skip the extra real-stage timing")

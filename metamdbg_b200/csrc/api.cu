@@ -1031,7 +1031,9 @@ static mdbg_status sketch_host_batch(mdbg_ctx* ctx, const uint8_t* bases, const 
     std::vector<SubRange> subs;
     split_pieces(offsets, n_reads, n_bases, subs);
     PiecePipeline pipeline{ctx, ctx->d_offsets.as<uint64_t>(), &subs, n_reads, fetch};
-    PiecePipeline* pipe = (ctx->piece_pipeline && !quals && !want_aux) ? &pipeline : nullptr;
+    bool want_pipe = ctx->piece_pipeline;
+    if (const char* e = getenv("MDBG_PIECE_PIPELINE")) want_pipe = atoi(e) != 0;            // A/B runs, tests
+    PiecePipeline* pipe = (want_pipe && !quals && !want_aux) ? &pipeline : nullptr;
     const auto done = [&](mdbg_status st) {
         if (st == MDBG_OK && pipe && !pipe->overflow && pipe->fetch) ctx->host_csr_valid = true;
         return st;
@@ -1050,7 +1052,9 @@ static mdbg_status sketch_host_batch(mdbg_ctx* ctx, const uint8_t* bases, const 
         // ... and only while the packer keeps ahead of what PCIe would move as ASCII (busy or NUMA-remote hosts)
         if (want_pack && ctx->auto_pack_pause > 0) { ctx->auto_pack_pause--; want_pack = false; }
     }
-    const bool packed = want_pack && !quals && !want_aux && n_bases >= (uint64_t(1) << 20);
+    uint64_t pack_floor = uint64_t(1) << 20;            // below 1 MB the transfer is not worth a pass over the bases
+    if (const char* e = getenv("MDBG_PACK_MIN_BYTES")) { const long long v = atoll(e); if (v >= 0) pack_floor = (uint64_t)v; }   // tests
+    const bool packed = want_pack && !quals && !want_aux && n_bases >= pack_floor;
     ctx->last_packed = packed ? 1 : 0;
     ctx->last_pieces = subs.size();
     if (!pipe) { ctx->last_pipelined = ctx->last_grows = 0; ctx->last_overflow_fallback = 0; }

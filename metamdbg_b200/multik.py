@@ -1,0 +1,52 @@
+"""The multi-k loop of the hot path, on the device-resident minimizer store.
+
+metaMDBG re-runs its `graph` stage for k = firstK, firstK+1, ... on the SAME minimizer-space reads
+(src/pipeline/AssemblyPipeline.hpp drives it; src/graph/CreateMdbg.cpp:386-468 is the k > firstK branch):
+
+  * k = firstK      KminmerCounter::execute   (CreateMdbg.hpp:3591-3883)  -> occurrence counts, abundance >= 2
+                    [+ rescueKminmers, CreateMdbg.hpp:4517-4640, in default mode]
+  * k > firstK      abundance of a k-min-mer = min over its two (k-1)-min-mers of the previous k's table
+                    (getRefinedAbundance / IndexKminmerFunctor, CreateMdbg.hpp:3933-4005, 951-1465)
+
+Upstream patches the previous-k table with refined unitig abundances from the contig stage between two k's; that
+stage is outside this engine (mdbg_prev_load takes such patches), so the loop below is the part that can stay on the
+device: every call is a call into libmdbg_b200.so, nothing is computed in Python.  With more than one rank the
+three collective calls (merge, rescue, previous-k replication) are made by every rank in the same order.
+"""
+from __future__ import annotations
+
+import time
+
+
+def multi_k_sweep(engine, first_k: int = 4, last_k: int = 21, min_abundance: int = 2, rescue: bool = False,
+                  merge: bool = False, on_table=None, synchronize: bool = True) -> list[dict]:
+    """Count k = first_k on the engine's store, then derive k = first_k+1 .. last_k from the previous table.
+
+    on_table(k, engine) is called while the table of k is current (e.g. to finalize it into kminmerData files);
+    returns one dict per k: k, seconds (host wall clock around the device work of that k) and the table statistics.
+    """
+    out = []
+    for k in range(first_k, last_k + 1):
+        if synchronize:
+            engine.synchronize()
+        t0 = time.perf_counter()
+        if k == first_k:
+            engine.count_begin(k, 0)
+            engine.count_add_store()
+            if merge:
+                engine.count_merge()
+            n_rescued_reads = engine.count_rescue() if rescue else 0
+        else:
+            engine.prev_from_current(min_abundance)
+            engine.count_begin(k, 0)
+            engine.count_add_store_next_k()
+            if merge:
+                engine.count_merge()
+            n_rescued_reads = 0
+        stats = engine.count_stats(min_abundance)         # device-side reduction + one small D2H: ends the k's work
+        dt = time.perf_counter() - t0
+        if on_table is not None:
+            on_table(k, engine)
+        out.append(dict(k=k, seconds=dt, n_entries=stats["n_entries"], checksum=stats["checksum"],
+                        n_reads_rescued=n_rescued_reads))
+    return out

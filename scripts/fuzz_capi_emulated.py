@@ -72,8 +72,18 @@ def main():
         dens = float(rng.choice([0.005, 0.005, 0.05, 0.0025, 0.3, 0.7]))
         hpc = bool(rng.integers(0, 2))
         bl = None
+        # host-batch plumbing knobs: piece size (many pieces even for small batches), piece pipeline on/off, packed
+        # transfer for small batches too, and the arithmetic variant of the sketch kernel
+        for key, choices in (("MDBG_PIECE_BYTES", [None, "3000", "20000", "200000"]), ("MDBG_PIECE_PIPELINE", [None, "0", "1"]),
+                             ("MDBG_PACK_MIN_BYTES", [None, "0", "5000"])):
+            v = choices[int(rng.integers(0, len(choices)))]
+            if v is None:
+                os.environ.pop(key, None)
+            else:
+                os.environ[key] = v
         eng = Engine(l, dens, hpc)
         eng.set_host_packing(int(rng.choice([-1, 0, 1])))
+        eng.set_sketch_variant(int(rng.integers(0, 2)))
         all_m, all_off = [], [0]
         scen = (l, dens, hpc)
         for b in range(int(rng.integers(1, 4))):
@@ -87,6 +97,10 @@ def main():
                 buf = np.zeros(len(bases) + 64 + 16, np.uint8)
                 sh = (-buf.ctypes.data) % 16
                 buf[sh:sh + len(bases)] = bases
+                if len(offs) > 1 and rng.integers(0, 4) == 0:  # autotune on this batch first (appends nothing)
+                    tune = eng.autotune_sketch(buf.ctypes.data + sh, offs.ctypes.data, len(offs) - 1, len(bases))
+                    assert all(tune["identical"]), ("autotune", scen, tune)
+                    eng.set_sketch_variant(int(rng.integers(0, 2)))
                 eng.sketch_batch_device(buf.ctypes.data + sh, offs.ctypes.data, len(offs) - 1, len(bases), True)
                 sk = eng.sketch_fetch()
             else:                                             # side outputs, with or without qualities

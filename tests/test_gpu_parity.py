@@ -402,6 +402,36 @@ def test_piece_pipeline_many_pieces(built, oracle, packing, monkeypatch):
         eng.close()
 
 
+def test_multi_k_sweep_on_device_vs_oracle(built, oracle):
+    """multi_k_sweep: k = 4 counted (+ rescue), k = 5..9 each derived from the previous table, all on the device-resident
+    store; every k's table equals the oracle's chain (count -> rescue -> next_k -> next_k ...)."""
+    from metamdbg_b200 import multi_k_sweep
+    rs = synth.make_readset(1200, 7000, seed=23, n_genomes=2, genome_len_range=(120_000, 200_000))
+    bases, offs = synth.fill_reads(rs)
+    eng = engine()
+    eng.sketch_batch(bases, offs, append_to_store=True, fetch=False)
+    so, sm = eng.store_fetch()
+    for rescue in (False, True):
+        tables = {}
+        res = multi_k_sweep(eng, 4, 9, min_abundance=0 if rescue else 2, rescue=rescue,
+                            on_table=lambda k, e: tables.__setitem__(k, e.count_finalize(0 if rescue else 2)))
+        assert [r["k"] for r in res] == list(range(4, 10))
+        prev = oracle.count(sm, so, 4, 2)
+        ph, pa = prev["hashes"], prev["abundances"]
+        if rescue:
+            rr = oracle.rescue(sm, so, 4, ph, pa)
+            assert res[0]["n_reads_rescued"] == rr["n_reads_rescued"]
+            ph = np.concatenate([ph, rr["hashes"]]) if len(rr["hashes"]) else ph
+            pa = np.concatenate([pa, np.ones(len(rr["hashes"]), np.uint32)])
+        assert tables[4].as_dict() == table_dict(ph, pa)
+        for k in range(5, 10):
+            nk = oracle.next_k(sm, so, k, ph, pa)
+            assert tables[k].as_dict() == table_dict(nk["hashes"], nk["abundances"]), f"k={k} rescue={rescue}"
+            assert res[k - 4]["n_entries"] == len(nk["abundances"]) > 500
+            ph, pa = nk["hashes"], nk["abundances"]
+    eng.close()
+
+
 def test_python_mirror_single_read(built, oracle):
     from metamdbg_b200 import MinimizerParser
     rs = synth.make_readset(3, 20000, seed=8, n_genomes=1, genome_len_range=(100_000, 100_001))
