@@ -289,10 +289,22 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, V ? 5 : 0) sketch_kernel(c
                 avail += total;
                 chunk++;
             }
+            if (chunk == n_chunks) {                    // all raw bases are in (reached exactly once per read)
+                // EncoderRLE drops every run of '#' (its "no previous char" sentinel) EXCEPT a run that ends the
+                // read: the final `rleSequence += lastChar` (Commons.hpp:4186) is unconditional.  Such a read is one
+                // base longer in HPC space, which moves the last selectable position (n - 2) by one.  The base is
+                // only ever part of the trimmed last l-mer; its code is (0x23 >> 1) & 7 = 1.  Packed reads hold
+                // only A, C, G, T.
+                if (a.hpc && !pk && len > 0 && base[len - 1] == '#') {
+                    if (lane == 0) ring[avail & (RING - 1)] = 1;
+                    avail += 1;
+                }
+                chunk = n_chunks + 1;
+            }
             __syncwarp();
 
             // ---- roll + hash + select, 512 positions per step ------------------
-            const bool final_ = (chunk == n_chunks);
+            const bool final_ = (chunk > n_chunks);
             // Kmer.hpp:1395: positions 1 .. n-2 with n = L' - l + 1  =>  p <= L' - l - 1
             const int pmax_final = (int)avail - (int)l - 1;
             for (;;) {

@@ -85,7 +85,8 @@ def main():
         eng.set_host_packing(int(rng.choice([-1, 0, 1])))
         eng.set_sketch_variant(int(rng.integers(0, 2)))
         all_m, all_off = [], [0]
-        scen = (l, dens, hpc)
+        scen = (l, dens, hpc, {k: os.environ.get(k) for k in ("MDBG_PIECE_BYTES", "MDBG_PIECE_PIPELINE", "MDBG_PACK_MIN_BYTES")},
+                "variant", eng.sketch_variant)
         for b in range(int(rng.integers(1, 4))):
             big = rng.integers(0, 6) == 0
             bases, offs = make_batch(rng, int(rng.integers(1, 60)), 150_000 if big else 4000)
@@ -101,6 +102,7 @@ def main():
                     tune = eng.autotune_sketch(buf.ctypes.data + sh, offs.ctypes.data, len(offs) - 1, len(bases))
                     assert all(tune["identical"]), ("autotune", scen, tune)
                     eng.set_sketch_variant(int(rng.integers(0, 2)))
+                    scen = scen + ("autotuned, variant now", eng.sketch_variant)
                 eng.sketch_batch_device(buf.ctypes.data + sh, offs.ctypes.data, len(offs) - 1, len(bases), True)
                 sk = eng.sketch_fetch()
             else:                                             # side outputs, with or without qualities
@@ -130,8 +132,10 @@ def main():
                         assert np.float32(aux["mean_quality"][r]).tobytes() == np.float32(mq).tobytes(), ("mean q", scen, r)
                     c_got = aux["complexity"][r]
                     assert (np.isnan(c_got) and np.isnan(cx)) or c_got == cx, ("complexity", scen, r, c_got, cx)
-            for x, y, nm in zip((sk.min_offsets, sk.minimizers, sk.positions, sk.directions), want, "omp d".split(" ") + ["d"]):
-                assert np.array_equal(x, y), ("sketch", scen, b, mode)
+            for x, y, nm in zip((sk.min_offsets, sk.minimizers, sk.positions, sk.directions), want, ("offsets", "minimizers", "positions", "directions")):
+                if not np.array_equal(x, y):
+                    np.savez(os.path.join(tempfile.gettempdir(), "fuzz_capi_failure.npz"), bases=bases, offs=offs)
+                assert np.array_equal(x, y), ("sketch", scen, b, mode, nm, len(x), len(y))
             n["minimizers"] += len(want[1])
             all_m.append(want[1])
             for r in range(len(offs) - 1):

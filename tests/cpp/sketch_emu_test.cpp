@@ -184,6 +184,10 @@ int main() {
     b.add(rnd_read(9000, 1));
     b.add(std::string(3000, 'A'));
     b.add("####ACGTACGGTCA#ACGTTTGACCATGACCAGTAGGACCATTAGGGACCCATAGAC");
+    // EncoderRLE keeps a '#' run that ENDS the read (its final push is unconditional): one more HPC base, so the last
+    // selectable position moves by one.  Dense selections below make that position count.
+    for (int i = 0; i < 24; i++) b.add(rnd_read(40 + rng() % 1500, i % 3 == 1 ? 2 : 0) + (i % 2 ? "#" : "###"));
+    b.add("#"); b.add("###"); b.add("ACGTACGTTGCATGCA#"); b.add(rnd_read(527, 0) + "#"); b.add(rnd_read(511 + 15, 0) + "##");
     uint64_t totals[2] = {0, 0};
     std::vector<uint32_t> none;
     for (g_variant = 0; g_variant < (uint32_t)SKETCH_VARIANTS; g_variant++)

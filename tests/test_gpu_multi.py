@@ -40,6 +40,15 @@ def _worker(rank, world, port, out_dir):
         tab = eng.count_finalize(2)
         np.savez(os.path.join(out_dir, f"rank{rank}_k{k}.npz"), hashes=tab.hashes, abund=tab.abundances,
                  vecs=tab.kminmers)
+    # default mode + multi-k over NCCL: rescue across ranks, then k = 5, 6 from the replicated previous-k table
+    from metamdbg_b200 import multi_k_sweep
+
+    def keep(k, e):
+        tab = e.count_finalize(0)
+        np.savez(os.path.join(out_dir, f"chain_rank{rank}_k{k}.npz"), hashes=tab.hashes, abund=tab.abundances)
+
+    res = multi_k_sweep(eng, K, K + 2, min_abundance=0, rescue=True, merge=True, on_table=keep)
+    np.save(os.path.join(out_dir, f"chain_rank{rank}_rescued.npy"), np.array([res[0]["n_reads_rescued"]]))
     eng.close()
     dist.barrier()
     dist.destroy_process_group()
@@ -69,3 +78,27 @@ def test_two_gpu_merge_matches_oracle(tmp_path, oracle):
         want = {(int(h[0]), int(h[1])): (int(a), tuple(int(x) for x in v))
                 for h, a, v in zip(ref["hashes"], ref["abundances"], ref["vecs"])}
         assert got == want and len(want) > 100
+    # the chain: solid + rescued at k = 4, then two next-k passes (oracle restatement of the whole read set)
+    pm, po = [], [0]
+    for r in range(rs.n_reads):
+        q, _ = oracle.purge_palindrome(m[int(mo[r]):int(mo[r + 1])], 4, 80)
+        pm.append(q); po.append(po[-1] + len(q))
+    pm = np.concatenate(pm).astype(np.uint32); po = np.array(po, np.uint64)
+    solid = oracle.count(pm, po, K, 2)
+    resc = oracle.rescue(pm, po, K, solid["hashes"], solid["abundances"])
+    assert sum(int(np.load(tmp_path / f"chain_rank{r}_rescued.npy")[0]) for r in range(world)) == resc["n_reads_rescued"]
+    ph = np.concatenate([solid["hashes"], resc["hashes"]]) if len(resc["hashes"]) else solid["hashes"]
+    pa = np.concatenate([solid["abundances"], np.ones(len(resc["hashes"]), np.uint32)])
+    for k in (K, K + 1, K + 2):
+        if k > K:
+            nk = oracle.next_k(pm, po, k, ph, pa)
+            ph, pa = nk["hashes"], nk["abundances"]
+        want = {(int(h[0]), int(h[1])): int(a) for h, a in zip(ph, pa)}
+        got = {}
+        for r in range(world):
+            z = np.load(tmp_path / f"chain_rank{r}_k{k}.npz")
+            for h, a in zip(z["hashes"], z["abund"]):
+                key = (int(h[1]), int(h[0]))
+                assert key not in got
+                got[key] = int(a)
+        assert got == want and len(want) > 100, f"chain k={k}"

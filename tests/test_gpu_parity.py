@@ -432,6 +432,35 @@ def test_multi_k_sweep_on_device_vs_oracle(built, oracle):
     eng.close()
 
 
+def test_sketch_reads_ending_in_the_hpc_sentinel(built, oracle):
+    """EncoderRLE (Commons.hpp:4172-4190) swallows every run of '#' except one that ends the read -- its final
+    `rleSequence += lastChar` is unconditional -- so such a read is one HPC base longer and its last selectable
+    position moves by one (found by scripts/fuzz_capi_emulated.py).  Dense selection makes that position count."""
+    rng = np.random.default_rng(77)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    reads = []
+    for i in range(300):
+        body = rng.choice(acgt, int(rng.integers(0, 1800)))
+        if i % 5 == 0 and len(body) > 10:
+            body[rng.integers(0, len(body), 3)] = ord("#")              # interior sentinels too
+        tail = np.frombuffer((b"#", b"##", b"", b"N#", b"#A")[i % 5], np.uint8)
+        reads.append(np.concatenate([body, tail]).astype(np.uint8))
+    reads += [np.frombuffer(x, np.uint8) for x in (b"#", b"###", b"ACGTACGTTGCATGCA#")]
+    offs = np.zeros(len(reads) + 1, np.uint64)
+    offs[1:] = np.cumsum([len(r) for r in reads])
+    bases = np.concatenate(reads)
+    for l, dens in ((15, 0.3), (15, 0.005), (11, 0.3)):
+        for packing in (0, 1):                                          # dirty reads of a packed batch stay ASCII
+            eng = engine(l, dens, True)
+            eng.set_host_packing(packing)
+            assert_sketch_equal(eng.sketch_batch(bases, offs), *oracle.sketch_batch(bases, offs, l, dens, True),
+                                tag=f"l={l} d={dens} packing={packing}")
+            eng.close()
+        eng = engine(l, dens, False)                                    # without HPC '#' is an ordinary character
+        assert_sketch_equal(eng.sketch_batch(bases, offs), *oracle.sketch_batch(bases, offs, l, dens, False))
+        eng.close()
+
+
 def test_python_mirror_single_read(built, oracle):
     from metamdbg_b200 import MinimizerParser
     rs = synth.make_readset(3, 20000, seed=8, n_genomes=1, genome_len_range=(100_000, 100_001))

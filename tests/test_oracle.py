@@ -42,6 +42,8 @@ def test_hpc_edge_cases(oracle):
     assert oracle.hpc(b"aA")[0] == b"aA"                # case-sensitive byte compare
     assert oracle.hpc(b"ANNNC")[0] == b"ANC"
     assert oracle.hpc(b"A#C")[0] == b"AC"               # '#' is the sentinel and vanishes
+    assert oracle.hpc(b"AC#")[0] == b"AC#"              # ... except a run that ends the read (unconditional last push)
+    assert oracle.hpc(b"AC###")[0] == b"AC#" and oracle.hpc(b"###")[0] == b"#" and oracle.hpc(b"#AC")[0] == b"AC"
     assert oracle.hpc(b"AACC", hpc=False)[0] == b"AACC"
 
 
@@ -364,3 +366,17 @@ def test_ref_apply_density(oracle, reference):
     assert 0 < len(low) < len(m)
     # sketching at 0.025 then thresholding at 0.005 == sketching at 0.005 (same hash, same bound)
     assert np.array_equal(low, oracle.sketch_batch(bases, offs, 15, 0.005, False)[1])
+
+
+@pytest.mark.ref
+def test_ref_reads_ending_in_the_hpc_sentinel(oracle, reference):
+    """A '#' run at the END of a read survives EncoderRLE (Commons.hpp:4186), which moves the last selectable
+    position by one; the restatement and the reference's own MinimizerParser agree on it."""
+    rng = np.random.default_rng(5)
+    for i in range(300):
+        body = bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), int(rng.integers(0, 600))))
+        s = body + [b"#", b"##", b"N#", b"#A", b"a#"][i % 5]
+        assert oracle.hpc(s)[0] == reference.hpc(s)[0]
+        for l, d in ((15, 0.3), (11, 0.3), (15, 0.005)):
+            for x, y in zip(oracle.sketch_read(s, l, d, True), reference.sketch_read(s, l, d, True)):
+                assert np.array_equal(x, y)
