@@ -346,7 +346,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     if args.multi_k > K and (world == 1 or args.multi_k_ranks):
         try:
             from metamdbg_b200 import multi_k_sweep
-            sweeps = [multi_k_sweep(eng, K, args.multi_k, MIN_AB, merge=world > 1) for _ in range(2)]   # 2nd = warm
+            sweeps = [multi_k_sweep(eng, K, args.multi_k, MIN_AB, merge=world > 1, world=world) for _ in range(2)]   # 2nd = warm
             per_k = [round(1e3 * max_over_ranks(r["seconds"]), 3) for r in sweeps[1]]
             total_s = sum(per_k) * 1e-3
             multi_k = {"k_first": K, "k_last": args.multi_k, "ms_per_k": per_k, "ms_total": round(sum(per_k), 3),

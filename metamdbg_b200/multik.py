@@ -19,13 +19,22 @@ import time
 
 
 def multi_k_sweep(engine, first_k: int = 4, last_k: int = 21, min_abundance: int = 2, rescue: bool = False,
-                  merge: bool = False, on_table=None, synchronize: bool = True) -> list[dict]:
+                  merge: bool = False, on_table=None, synchronize: bool = True, world: int = 1,
+                  table_headroom: float = 2.0) -> list[dict]:
     """Count k = first_k on the engine's store, then derive k = first_k+1 .. last_k from the previous table.
 
     on_table(k, engine) is called while the table of k is current (e.g. to finalize it into kminmerData files);
     returns one dict per k: k, seconds (host wall clock around the device work of that k) and the table statistics.
+
+    Table sizing: the first table is sized for the worst case (every window distinct).  A k > first_k table holds
+    k-min-mers whose two (k-1)-min-mers are both in the previous table, i.e. about as many entries as that table, so
+    it is sized for table_headroom x (previous entries x world) instead -- the per-k clear / statistics / previous-k
+    passes then touch megabytes, not the gigabytes of the worst-case table.  The next-k pass is idempotent, so if
+    such a table does fill up (MDBG_ERR_TABLE_FULL) the k is simply redone with the worst-case size.
     """
+    from .engine import MdbgError
     out = []
+    n_prev_entries = 0
     for k in range(first_k, last_k + 1):
         if synchronize:
             engine.synchronize()
@@ -38,8 +47,15 @@ def multi_k_sweep(engine, first_k: int = 4, last_k: int = 21, min_abundance: int
             n_rescued_reads = engine.count_rescue() if rescue else 0
         else:
             engine.prev_from_current(min_abundance)
-            engine.count_begin(k, 0)
-            engine.count_add_store_next_k()
+            expected = int(table_headroom * max(n_prev_entries, 256) * max(1, world)) if table_headroom > 0 else 0
+            try:
+                engine.count_begin(k, expected)
+                engine.count_add_store_next_k()
+            except MdbgError as e:
+                if e.status != 4 or expected == 0:            # 4 = MDBG_ERR_TABLE_FULL
+                    raise
+                engine.count_begin(k, 0)                      # worst-case size; the pass is idempotent
+                engine.count_add_store_next_k()
             if merge:
                 engine.count_merge()
             n_rescued_reads = 0
@@ -47,6 +63,7 @@ def multi_k_sweep(engine, first_k: int = 4, last_k: int = 21, min_abundance: int
         dt = time.perf_counter() - t0
         if on_table is not None:
             on_table(k, engine)
+        n_prev_entries = stats["n_entries"]
         out.append(dict(k=k, seconds=dt, n_entries=stats["n_entries"], checksum=stats["checksum"],
                         n_reads_rescued=n_rescued_reads))
     return out

@@ -429,6 +429,11 @@ def test_multi_k_sweep_on_device_vs_oracle(built, oracle):
             assert tables[k].as_dict() == table_dict(nk["hashes"], nk["abundances"]), f"k={k} rescue={rescue}"
             assert res[k - 4]["n_entries"] == len(nk["abundances"]) > 500
             ph, pa = nk["hashes"], nk["abundances"]
+    # right-sized next-k tables: a table sized far too small fills up, the k is redone at the worst-case size
+    # (the pass is idempotent), and the tables do not change
+    want_sums = [r["checksum"] for r in multi_k_sweep(eng, 4, 7, table_headroom=0)]
+    assert [r["checksum"] for r in multi_k_sweep(eng, 4, 7, table_headroom=0.001)] == want_sums
+    assert [r["checksum"] for r in multi_k_sweep(eng, 4, 7)] == want_sums
     eng.close()
 
 
