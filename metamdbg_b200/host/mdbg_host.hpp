@@ -361,4 +361,52 @@ private:
     uint32_t _k, _minAbundance;
 };
 
+// `graph` at k > firstK (CreateMdbg.cpp:386-468): the abundance of a k-min-mer is the minimum over its two
+// (k-1)-min-mers of the previous k's table (_kminmerAbundances; getRefinedAbundance CreateMdbg.hpp:3933-4005 for
+// k = firstK+1, IndexKminmerFunctor CreateMdbg.hpp:951-1465 beyond), kept when > 1.  The previous table is the one
+// the context holds from the k before (optionally patched with the contig stage's refined abundances through
+// mdbg_prev_load between two calls); the reads stay in the device-resident store the whole time.
+class GpuNextKCounter {
+public:
+    GpuNextKCounter(Context& ctx, uint32_t minAbundance) : _ctx(ctx), _minAbundance(minAbundance) {}
+
+    // Derives the table of k from the context's current table (which must be the one of k-1) and writes
+    // kminmerData_min / kminmerData_abundance for this k.  The table is sized from the previous table's entry
+    // count; the pass is idempotent, so a table that fills up is redone at the worst-case size.
+    void execute(uint32_t k, const std::string& kminmerFile, const std::string& abundanceFile) {
+        uint64_t prevEntries = 0;
+        check(_ctx.get(), mdbg_count_stats(_ctx.get(), _minAbundance, &prevEntries, nullptr, nullptr, nullptr), "mdbg_count_stats");
+        check(_ctx.get(), mdbg_prev_from_current(_ctx.get(), _minAbundance), "mdbg_prev_from_current");
+        const uint64_t expected = 2 * (prevEntries < 256 ? 256 : prevEntries);
+        check(_ctx.get(), mdbg_count_begin(_ctx.get(), k, expected), "mdbg_count_begin");
+        mdbg_status st = mdbg_count_add_store_next_k(_ctx.get(), 0, UINT64_MAX);
+        if (st == MDBG_ERR_TABLE_FULL) {
+            check(_ctx.get(), mdbg_count_begin(_ctx.get(), k, 0), "mdbg_count_begin");
+            st = mdbg_count_add_store_next_k(_ctx.get(), 0, UINT64_MAX);
+            _nbResized++;
+        }
+        check(_ctx.get(), st, "mdbg_count_add_store_next_k");
+        mdbg_table_out t{};
+        check(_ctx.get(), mdbg_count_finalize(_ctx.get(), _minAbundance, &t), "mdbg_count_finalize");
+        File fk(kminmerFile), fa(abundanceFile);
+        fk.put(t.kminmers, sizeof(uint32_t), (size_t)t.n_entries * k);
+        std::vector<unsigned char> rec((size_t)t.n_entries * 20);
+        for (uint64_t i = 0; i < t.n_entries; i++) {
+            memcpy(&rec[i * 20], t.hashes + 2 * i, 16);
+            memcpy(&rec[i * 20 + 16], t.abundances + i, 4);
+        }
+        fa.put(rec.data(), 20, (size_t)t.n_entries);
+        fk.close();
+        fa.close();
+        _nbKminmers = t.n_entries;
+        _checksum = t.checksum;
+    }
+
+    uint64_t _nbKminmers = 0, _checksum = 0, _nbResized = 0;
+
+private:
+    Context& _ctx;
+    uint32_t _minAbundance;
+};
+
 }  // namespace mdbg_host
