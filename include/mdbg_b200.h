@@ -274,6 +274,23 @@ mdbg_status mdbg_prev_load(mdbg_ctx* ctx, const uint64_t* hashes, const uint32_t
  * host like reads). mdbg_count_finalize(ctx, 0, ..) then returns kminmerData_abundance.txt of this k. */
 mdbg_status mdbg_count_add_store_next_k(mdbg_ctx* ctx, uint64_t read_lo, uint64_t read_hi);
 
+/* ---- edge keys of the node set (first step beyond the count table) ----------------
+ * CreateMdbg::EdgeIndexer (src/graph/CreateMdbg.hpp:4010-4232, called first by CreateMdbg::indexEdges,
+ * src/graph/CreateMdbg.cpp:1177-1187): every node of the current table (entries mdbg_count_finalize would emit, in
+ * their normalized orientation) contributes the hash128 of its normalized (k-1)-prefix and (k-1)-suffix; the
+ * dereplicated keys are what the reference writes to edges.bin and builds its edge MPHF over.  hashes[2*i] = low
+ * 64 bits, hashes[2*i+1] = high 64 bits (the u128 as it lies in edges.bin); order unspecified; n_edges =
+ * EdgeIndexer::_nbEdges; checksum = EdgeIndexer::_checksum (sum of the keys truncated to 64 bits).  The arrays
+ * stay valid until the next call on the context.  Single context only. */
+typedef struct {
+    uint32_t k;
+    uint64_t n_nodes;             /* table entries that contributed */
+    uint64_t n_edges;
+    const uint64_t* hashes;       /* [2*n_edges] */
+    uint64_t checksum;
+} mdbg_edges_out;
+mdbg_status mdbg_edges_index(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_edges_out* out);
+
 /* ---- multi-GPU (one process per GPU) --------------------------------------- */
 /* NCCL is loaded at run time (dlopen libnccl.so.2).  Rank 0 creates an id,
  * the host distributes its 128 bytes to every rank by its own means. */

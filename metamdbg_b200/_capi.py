@@ -49,6 +49,11 @@ class BatchInfo(C.Structure):
                 ("pack_gb_per_s", C.c_double), ("pack_isa", C.c_char_p), ("host_threads", C.c_int32)]
 
 
+class EdgesOut(C.Structure):
+    _fields_ = [("k", C.c_uint32), ("n_nodes", C.c_uint64), ("n_edges", C.c_uint64), ("hashes", u64p),
+                ("checksum", C.c_uint64)]
+
+
 class AutotuneOut(C.Structure):
     _fields_ = [("n_variants", C.c_int32), ("chosen", C.c_int32), ("identical", C.c_int32 * 4), ("ms", C.c_float * 4),
                 ("n_reads", C.c_uint32), ("n_minimizers", C.c_uint64)]
@@ -95,6 +100,7 @@ SYMBOLS = {
     "mdbg_prev_from_current": (C.c_int, [C.c_void_p, C.c_uint32]),
     "mdbg_prev_load": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]),
     "mdbg_count_add_store_next_k": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64]),
+    "mdbg_edges_index": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(EdgesOut)]),
     "mdbg_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "mdbg_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "mdbg_count_merge": (C.c_int, [C.c_void_p]),

@@ -127,6 +127,7 @@ struct mdbg_ctx {
     DevBuf foreign_vecs;
     uint64_t foreign_n = 0;
     DevBuf prev_table, prev_stage_h, prev_stage_a;
+    DevBuf edge_table;
     uint64_t prev_capacity = 0;
     DevBuf o_hash, o_abund, o_vecs;
     PinBuf ho_hash, ho_abund, ho_vecs;
@@ -696,7 +697,7 @@ void mdbg_ctx_destroy(mdbg_ctx* c) {
                       &c->scan_scratch, &c->b_off, &c->b_min, &c->b_pos, &c->b_dir, &c->s_min, &c->s_off, &c->s_rem,
                       &c->p_flags, &c->p_keep, &c->p_cnt, &c->p_newoff, &c->p_newmin, &c->table, &c->foreign_vecs,
                       &c->o_hash, &c->o_abund, &c->o_vecs, &c->d_pack, &c->d_src, &c->d_quals, &c->pad_qual, &c->pad_raw_a, &c->pad_raw_b, &c->b_qual, &c->x_sum_lo, &c->x_sum_hi, &c->x_lmin, &c->x_cplx, &c->x_low, &c->d_err_fixed, &c->d_err_tz, &c->prev_table, &c->prev_stage_h, &c->prev_stage_a, &c->m_send_vecs, &c->m_send_counts, &c->m_recv_vecs,
-                      &c->m_recv_counts, &c->m_bucket, &c->loc_off};
+                      &c->m_recv_counts, &c->m_bucket, &c->loc_off, &c->edge_table};
     for (DevBuf* b : devs) release(*b);
     PinBuf* pins[] = {&c->h_off, &c->h_min, &c->h_pos, &c->h_dir, &c->ho_hash, &c->ho_abund, &c->ho_vecs, &c->hx_sum_lo, &c->hx_sum_hi, &c->hx_lmin, &c->hx_cplx, &c->hx_low, &c->hx_meanq, &c->h_qual, &c->h_pack, &c->h_src, &c->h_asc};
     for (PinBuf* b : pins) release(*b);
@@ -1879,6 +1880,70 @@ mdbg_status mdbg_count_add_store_next_k(mdbg_ctx* ctx, uint64_t read_lo, uint64_
     if (ctx->timing) { CK(cudaEventRecord(ctx->ev[1][1], s)); ctx->ev_valid[1] = true; }
     CKS(check_launch(ctx, "next_k_kernel", a.g_hi > a.g_lo ? 1 : 0));
     return check_full(ctx, "mdbg_count_add_store_next_k");
+}
+
+// CreateMdbg::EdgeIndexer (CreateMdbg.hpp:4010-4232; first step of indexEdges, CreateMdbg.cpp:1177-1187): the
+// dereplicated hash128 of the normalized (k-1)-prefix and (k-1)-suffix of every node of the current table.
+mdbg_status mdbg_edges_index(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_edges_out* out) {
+    if (!ctx || !out) return MDBG_ERR_ARG;
+    if (!ctx->t_active) return fail(ctx, MDBG_ERR_STATE, "mdbg_edges_index before mdbg_count_begin");
+    if (ctx->t_k < 2) return fail(ctx, MDBG_ERR_ARG, "k must be >= 2");
+    if (ctx->n_ranks > 1)
+        return fail(ctx, MDBG_ERR_STATE, "mdbg_edges_index is single-context (the keys of several ranks would need an owner exchange)");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const uint32_t thr = count_threshold(min_abundance);
+    TableStats st;
+    CKS(table_stats(ctx, thr, &st));
+    uint64_t expect = 2 * st.n_entries;                          // at most two keys per node
+    if (expect < 512) expect = 512;
+    const uint64_t cap = pow2ceil(expect * 2);
+    CKS(ensure(ctx, ctx->edge_table, cap * sizeof(Slot)));
+    CK(cudaMemsetAsync(ctx->edge_table.p, 0, cap * sizeof(Slot), s));
+    CK(cudaMemsetAsync(&ctx->d_small->full_flag, 0, sizeof(uint32_t), s));
+    EdgeArgs e{};
+    e.table = ctx->table.as<Slot>();
+    e.capacity = ctx->t_capacity;
+    e.min_count = thr;
+    e.k = ctx->t_k;
+    e.mins = ctx->s_min.as<uint32_t>();
+    e.foreign_vecs = ctx->foreign_vecs.as<uint32_t>();
+    e.edges = ctx->edge_table.as<Slot>();
+    e.edge_mask = cap - 1;
+    e.full_flag = &ctx->d_small->full_flag;
+    launch_edge_insert(e, s);
+    CKS(check_launch(ctx, "edge_insert_kernel", 1));
+    CKS(check_full(ctx, "mdbg_edges_index"));
+    // the set's statistics and contents: every entry has value 1
+    launch_table_stats(ctx->edge_table.as<Slot>(), cap, 1u, &ctx->d_small->stats, s);
+    CKS(check_launch(ctx, "table_stats_kernel", 1));
+    CK(cudaMemcpyAsync(&ctx->h_small->stats, &ctx->d_small->stats, sizeof(TableStats), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const uint64_t n = ctx->h_small->stats.n_entries;
+    CKS(ensure(ctx, ctx->o_hash, (n + 1) * 16));
+    CKS(ensure(ctx, ctx->o_abund, (n + 1) * 4));
+    CKS(ensure_pin(ctx, ctx->ho_hash, (n + 1) * 16));
+    CK(cudaMemsetAsync(&ctx->d_small->emit_cursor, 0, 8, s));
+    EmitArgs em{};
+    em.table = ctx->edge_table.as<Slot>();
+    em.capacity = cap;
+    em.min_count = 1;
+    em.k = ctx->t_k - 1;
+    em.out_hashes = ctx->o_hash.as<uint64_t>();
+    em.out_abund = ctx->o_abund.as<uint32_t>();
+    em.out_vecs = nullptr;
+    em.cursor = &ctx->d_small->emit_cursor;
+    launch_table_emit(em, s);
+    CKS(check_launch(ctx, "table_emit_kernel", 1));
+    if (n) CK(cudaMemcpyAsync(ctx->ho_hash.p, ctx->o_hash.p, n * 16, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    ctx->d2h_bytes += n * 16;
+    out->k = ctx->t_k;
+    out->n_edges = n;
+    out->hashes = ctx->ho_hash.as<uint64_t>();
+    out->checksum = ctx->h_small->stats.checksum;                // sum of the low words (value 1 each)
+    out->n_nodes = st.n_entries;
+    return MDBG_OK;
 }
 
 // ---- multi-GPU --------------------------------------------------------------------------

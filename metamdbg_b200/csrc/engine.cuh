@@ -219,6 +219,14 @@ struct NextKArgs {
 };
 void launch_next_k(const NextKArgs& a, cudaStream_t s);
 
+// ---- edge keys (CreateMdbg::EdgeIndexer): prefix / suffix hashes of every emitted node into a set table
+struct EdgeArgs {
+    const Slot* table; uint64_t capacity; uint32_t min_count; uint32_t k;
+    const uint32_t* mins; const uint32_t* foreign_vecs;
+    Slot* edges; uint64_t edge_mask; uint32_t* full_flag;
+};
+void launch_edge_insert(const EdgeArgs& a, cudaStream_t s);
+
 // multi-GPU pack: bucket every occupied slot by owner rank
 struct PackArgs {
     const Slot* table;

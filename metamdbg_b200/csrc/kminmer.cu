@@ -506,6 +506,39 @@ void launch_next_k(const NextKArgs& a, cudaStream_t s) {
     next_k_kernel<<<(unsigned)((a.g_hi - a.g_lo + 255) / 256), 256, 0, s>>>(a);
 }
 
+// ------------------------------------------------------------------ edge keys of the node set (row F1)
+// CreateMdbg::EdgeIndexer (src/graph/CreateMdbg.hpp:4010-4232): every node -- an emitted table entry, in the
+// normalized orientation it is dumped in -- contributes the hash128 of its normalized (k-1)-prefix and
+// (k-1)-suffix (partitionNode :4106-4120); the reference sorts and dereplicates them on disk, here they go into a
+// second open-addressing table used as a set (value 1), one thread per table slot.
+__global__ void __launch_bounds__(256) edge_insert_kernel(const EdgeArgs a) {
+    const int k = (int)a.k, km = k - 1;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.capacity;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const Slot sl = a.table[i];
+        if ((sl.lo | sl.hi) == 0) continue;
+        if (!(sl.count >= a.min_count || (sl.flags & SLOT_RESCUED))) continue;
+        for (int side = 0; side < 2; side++) {            // 0: prefix = elements 0 .. k-2, 1: suffix = 1 .. k-1
+            bool rev = true;                              // KmerVec::normalize on the k-1 elements
+            for (int j = 0; j < km / 2; j++) {
+                const uint32_t x = vec_elem(a.mins, a.foreign_vecs, sl.ref, k, side + j);
+                const uint32_t y = vec_elem(a.mins, a.foreign_vecs, sl.ref, k, side + km - 1 - j);
+                if (x != y) { rev = x > y; break; }
+            }
+            uint64_t h1, h2;
+            if (rev) murmur128_u32vec([&](int t) { return vec_elem(a.mins, a.foreign_vecs, sl.ref, k, side + km - 1 - t); }, km, h1, h2);
+            else murmur128_u32vec([&](int t) { return vec_elem(a.mins, a.foreign_vecs, sl.ref, k, side + t); }, km, h1, h2);
+            if (!table_put(a.edges, a.edge_mask, h2, h1, 1u, 0ULL)) atomicExch(a.full_flag, 1u);
+        }
+    }
+}
+
+void launch_edge_insert(const EdgeArgs& a, cudaStream_t s) {
+    uint64_t blocks = (a.capacity + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    edge_insert_kernel<<<(unsigned)blocks, 256, 0, s>>>(a);
+}
+
 // ------------------------------------------------------------------ multi-GPU pack by owner rank
 constexpr int PACK_MAX_RANKS = 64;
 

@@ -17,7 +17,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _capi
-from ._capi import AutotuneOut, AuxOut, BatchInfo, MdbgParams, SketchDev, SketchOut, TableOut
+from ._capi import AutotuneOut, AuxOut, BatchInfo, EdgesOut, MdbgParams, SketchDev, SketchOut, TableOut
 
 STATUS = {0: "OK", 1: "CUDA", 2: "ARG", 3: "STATE", 4: "TABLE_FULL", 5: "NCCL", 6: "OOM"}
 
@@ -313,6 +313,16 @@ class Engine:
 
     def count_add_store_next_k(self, read_lo: int = 0, read_hi: int = 2 ** 64 - 1):
         self._ck(self._lib.mdbg_count_add_store_next_k(self._ctx, read_lo, read_hi))
+
+    # -- edge keys (CreateMdbg::EdgeIndexer, src/graph/CreateMdbg.hpp:4010-4232) ------
+    def edges_index(self, min_abundance: int = 2) -> dict:
+        """Distinct hash128 of the normalized (k-1)-prefix / suffix of every node of the current table.
+        -> dict(hashes uint64 [n,2] (low64, high64), n_edges, n_nodes, checksum)."""
+        out = EdgesOut()
+        self._ck(self._lib.mdbg_edges_index(self._ctx, min_abundance, C.byref(out)))
+        n = int(out.n_edges)
+        h = np.ctypeslib.as_array(out.hashes, shape=(2 * n,)).reshape(n, 2).copy() if n else np.zeros((0, 2), np.uint64)
+        return dict(hashes=h, n_edges=n, n_nodes=int(out.n_nodes), checksum=int(out.checksum))
 
     # -- multi-GPU -----------------------------------------------------------------
     @staticmethod

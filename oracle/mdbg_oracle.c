@@ -583,6 +583,60 @@ size_t orc_next_k(const uint32_t* mins, const uint64_t* offs, size_t n_reads, in
     return n_out;
 }
 
+/* ------------------------------------------------------- edge keys of the node set (row F1)
+ * CreateMdbg::EdgeIndexer (src/graph/CreateMdbg.hpp:4010-4232): every node (normalized k-min-mer, as dumped to
+ * kminmerData_min.txt) contributes the hash128 of its normalized prefix (first k-1 minimizers, KmerVec::prefix
+ * Commons.hpp:851-856) and of its normalized suffix (last k-1, :858-862) -- partitionNode :4106-4120; the hashes
+ * are sorted and dereplicated per partition (:4140-4200).  The partition order is not observable in the key set,
+ * so the restatement returns the distinct keys sorted by (h1,h2); _nbEdges = their number, _checksum = sum of the
+ * keys truncated to 64 bits (u_int64_t += u_int128_t), i.e. the sum of the low words (h2). */
+typedef struct { uint64_t h1, h2; } EKey;
+static int cmp_ekey(const void* a, const void* b) {
+    const EKey* x = (const EKey*)a; const EKey* y = (const EKey*)b;
+    if (x->h1 != y->h1) return x->h1 < y->h1 ? -1 : 1;
+    if (x->h2 != y->h2) return x->h2 < y->h2 ? -1 : (x->h2 > y->h2 ? 1 : 0);
+    return 0;
+}
+
+size_t orc_edge_index(const uint32_t* vecs, size_t n, int k, uint64_t** hashes, uint64_t* checksum) {
+    const int km = k - 1;
+    EKey* keys = (EKey*)malloc((2 * n + 1) * sizeof(EKey));
+    uint32_t* tmp = (uint32_t*)malloc((size_t)(km > 0 ? km : 1) * sizeof(uint32_t));
+    size_t m = 0;
+    for (size_t i = 0; i < n; i++) {
+        for (int side = 1; side >= 0; side--) {          /* suffix first, then prefix (order is irrelevant) */
+            const uint32_t* w = vecs + i * (size_t)k + side;
+            int rev = 1;                                  /* KmerVec::normalize, Commons.hpp:886-916 */
+            for (int j = 0; j < km; j++) {
+                uint32_t a = w[j], b = w[km - 1 - j];
+                if (a == b) continue;
+                rev = (a < b) ? 0 : 1;
+                break;
+            }
+            for (int j = 0; j < km; j++) tmp[j] = rev ? w[km - 1 - j] : w[j];
+            uint64_t h[2];
+            orc_hash128(tmp, km, h);
+            keys[m].h1 = h[0]; keys[m].h2 = h[1];
+            m++;
+        }
+    }
+    qsort(keys, m, sizeof(EKey), cmp_ekey);
+    uint64_t* out = (uint64_t*)malloc((2 * m + 2) * sizeof(uint64_t));
+    size_t n_out = 0;
+    uint64_t cs = 0;
+    for (size_t i = 0; i < m; i++) {
+        if (i && keys[i].h1 == keys[i - 1].h1 && keys[i].h2 == keys[i - 1].h2) continue;
+        out[2 * n_out] = keys[i].h1; out[2 * n_out + 1] = keys[i].h2;
+        cs += keys[i].h2;
+        n_out++;
+    }
+    free(keys);
+    free(tmp);
+    *hashes = out;
+    if (checksum) *checksum = cs;
+    return n_out;
+}
+
 uint64_t orc_table_checksum(const uint64_t* hashes, const uint32_t* abundances, size_t n) {
     uint64_t s = 0;
     for (size_t i = 0; i < n; i++) s += (uint64_t)abundances[i] * hashes[2 * i + 1];

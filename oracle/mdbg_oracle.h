@@ -122,6 +122,11 @@ size_t orc_next_k(const uint32_t* mins, const uint64_t* offs, size_t n_reads, in
                   const uint64_t* prev_hashes, const uint32_t* prev_ab, size_t n_prev,
                   uint32_t** vecs, uint64_t** hashes, uint32_t** abundances);
 
+/* CreateMdbg::EdgeIndexer (CreateMdbg.hpp:4010-4232): the distinct hash128 of the normalized (k-1)-prefix and
+ * (k-1)-suffix of every node.  vecs: n normalized k-min-mers (kminmerData_min.txt rows).  *hashes: malloc'ed
+ * n_edges x {h1,h2} sorted by (h1,h2); *checksum = sum of the low words.  Returns n_edges (_nbEdges). */
+size_t orc_edge_index(const uint32_t* vecs, size_t n, int k, uint64_t** hashes, uint64_t* checksum);
+
 /* Order-free fingerprint used by the reference's debug log
  * (src/graph/CreateMdbg.cpp:3321): sum abundance * (u64)hash128 mod 2^64,
  * where (u64)hash128 = low 64 bits = h2. */

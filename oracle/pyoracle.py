@@ -191,6 +191,8 @@ class Oracle(_Lib):
         L.orc_next_k.restype = C.c_size_t
         L.orc_next_k.argtypes = [_u32p, _u64p, C.c_size_t, C.c_int, _u64p, _u32p, C.c_size_t, C.POINTER(_u32p),
                                  C.POINTER(_u64p), C.POINTER(_u32p)]
+        L.orc_edge_index.restype = C.c_size_t
+        L.orc_edge_index.argtypes = [_u32p, C.c_size_t, C.c_int, C.POINTER(_u64p), C.POINTER(C.c_uint64)]
         L.orc_table_checksum.restype = C.c_uint64
         L.orc_table_checksum.argtypes = [_u64p, _u32p, C.c_size_t]
 
@@ -268,6 +270,14 @@ class Oracle(_Lib):
         return dict(vecs=self._take(v, n * k, np.uint32).reshape(n, k), hashes=self._take(h, 2 * n, np.uint64).reshape(n, 2),
                     abundances=self._take(a, n, np.uint32))
 
+    def edge_index(self, vecs, k):
+        """EdgeIndexer: distinct hash128 of the normalized (k-1)-prefix / suffix of every node.
+        -> dict(hashes [n,2] (h1,h2) sorted, checksum)."""
+        vecs = np.ascontiguousarray(vecs, dtype=np.uint32).reshape(-1, k)
+        h = _u64p(); cs = C.c_uint64(0)
+        n = self.lib.orc_edge_index(_p(vecs, _u32p), len(vecs), k, C.byref(h), C.byref(cs))
+        return dict(hashes=self._take(h, 2 * n, np.uint64).reshape(n, 2), checksum=int(cs.value))
+
     def checksum(self, hashes: np.ndarray, abundances: np.ndarray) -> int:
         hashes = np.ascontiguousarray(hashes, dtype=np.uint64)
         abundances = np.ascontiguousarray(abundances, dtype=np.uint32)
@@ -300,6 +310,9 @@ class Reference(_Lib):
         L.ref_graph_firstpass.argtypes = [_u32p, _u64p, C.c_size_t, C.c_int, C.c_uint32, C.c_int, C.c_char_p,
                                           C.POINTER(_u32p), C.POINTER(_u64p), C.POINTER(_u32p), _u64p, _u64p,
                                           C.POINTER(C.c_double)]
+        L.ref_edge_index.restype = C.c_size_t
+        L.ref_edge_index.argtypes = [_u32p, C.c_size_t, C.c_int, C.c_int, C.c_char_p, C.POINTER(_u64p),
+                                     C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.ref_graph_next_k.restype = C.c_size_t
         L.ref_graph_next_k.argtypes = [_u32p, _u64p, C.c_size_t, C.c_int, _u64p, _u32p, C.c_size_t, C.c_int, C.c_int,
                                        C.c_char_p, C.POINTER(_u32p), C.POINTER(_u64p), C.POINTER(_u32p)]
@@ -335,6 +348,17 @@ class Reference(_Lib):
         return dict(vecs=self._take(v, n * k, np.uint32).reshape(n, k), hashes=self._take(h, 2 * n, np.uint64).reshape(n, 2),
                     abundances=self._take(a, n, np.uint32), n_solid=int(ns.value), n_rescued=int(nr.value),
                     seconds=float(sec.value))
+
+    def edge_index(self, vecs, k, threads=1):
+        """The reference's own CreateMdbg::EdgeIndexer on a node file (disk partitions + sortParallel) in a scratch
+        dir -> dict(hashes [n,2] (h1,h2) in edges.bin order, nb_edges, checksum)."""
+        import tempfile
+        vecs = np.ascontiguousarray(vecs, dtype=np.uint32).reshape(-1, k)
+        h = _u64p(); ne = C.c_uint64(0); cs = C.c_uint64(0)
+        with tempfile.TemporaryDirectory() as d:
+            n = self.lib.ref_edge_index(_p(vecs, _u32p), len(vecs), k, threads, d.encode(), C.byref(h), C.byref(ne),
+                                        C.byref(cs))
+        return dict(hashes=self._take(h, 2 * n, np.uint64).reshape(n, 2), nb_edges=int(ne.value), checksum=int(cs.value))
 
     def graph_next_k(self, mins, offs, k, prev_hashes, prev_ab, use_counter=False, threads=1):
         import tempfile

@@ -365,6 +365,40 @@ size_t ref_graph_next_k(const uint32_t* mins, const uint64_t* offs, size_t n_rea
     return read_tables(dir, k, false, vecs_out, hashes_out, abundances_out);
 }
 
+/* CreateMdbg::indexEdges' first step (src/graph/CreateMdbg.cpp:1177-1187): EdgeIndexer::execute on the node file
+ * kminmerData_min.txt -- disk partitions by hash128 % P, sortParallel, dereplication into edges.bin.
+ * Returns the keys of edges.bin in file order ({high, low} words), _nbEdges and _checksum. */
+size_t ref_edge_index(const uint32_t* vecs, size_t n, int k, int n_threads, const char* tmp_dir, uint64_t** hashes_out,
+                      uint64_t* nb_edges, uint64_t* checksum) {
+    if (n_threads < 1) n_threads = 1;
+    const string dir(tmp_dir);
+    {
+        ofstream f(dir + "/kminmerData_min.txt", std::ios::binary);
+        f.write((const char*)vecs, (std::streamsize)(n * (size_t)k * sizeof(uint32_t)));
+    }
+    CreateMdbg c;
+    c._outputDir = dir;
+    c._kminmerSize = k;
+    c._nbCores = n_threads;
+    c._nbPartitions = n_threads;
+    CreateMdbg::EdgeIndexer edgeIndexer(c);
+    edgeIndexer.execute();
+    if (nb_edges) *nb_edges = edgeIndexer._nbEdges;
+    if (checksum) *checksum = edgeIndexer._checksum;
+    vector<uint64_t> keys;
+    ifstream fe(edgeIndexer.getOutputFilename(), std::ios::binary);
+    while (true) {
+        u_int128_t e;
+        fe.read((char*)&e, sizeof e);
+        if (fe.eof()) break;
+        keys.push_back((uint64_t)(e >> 64));
+        keys.push_back((uint64_t)e);
+    }
+    *hashes_out = (uint64_t*)malloc((keys.size() + 2) * 8);
+    memcpy(*hashes_out, keys.data(), keys.size() * 8);
+    return keys.size() / 2;
+}
+
 /* The reference's whole readSelection stage (ReadSelection::execute, src/readSelection/ReadSelection.hpp:92-303):
  * kseq FASTA/FASTQ parsing, HPC, sketch, complexity / quality side outputs, ordered record writer, read stats,
  * purgePalindromes.  `input_list` is the text file listing the read files (what `metaMDBG asm` writes as input.txt).

@@ -466,6 +466,40 @@ def test_sketch_reads_ending_in_the_hpc_sentinel(built, oracle):
         eng.close()
 
 
+def test_edge_index_vs_oracle(built, oracle):
+    """Row F1 (CreateMdbg::EdgeIndexer): the dereplicated prefix / suffix keys of the node set, for the first-pass
+    table, the default-mode table (rescued nodes included) and a next-k table; set, count and checksum as the
+    oracle's restatement (pinned against the reference's own EdgeIndexer in tests/test_oracle.py)."""
+    rs = synth.make_readset(1500, 7000, seed=29, n_genomes=2, genome_len_range=(120_000, 200_000), err=0.003)
+    bases, offs = synth.fill_reads(rs)
+    eng = engine()
+    eng.sketch_batch(bases, offs, append_to_store=True, fetch=False)
+
+    def check(k, min_ab):
+        tab = eng.count_finalize(min_ab)
+        got = eng.edges_index(min_ab)
+        want = oracle.edge_index(tab.kminmers, k)
+        assert got["n_nodes"] == len(tab.abundances) and got["n_edges"] == len(want["hashes"]) > 500
+        assert got["checksum"] == want["checksum"]
+        assert {(int(h[1]), int(h[0])) for h in got["hashes"]} == {(int(h[0]), int(h[1])) for h in want["hashes"]}
+        assert len(got["hashes"]) == len({(int(h[0]), int(h[1])) for h in got["hashes"]})      # no duplicate key
+
+    eng.count_begin(4)
+    eng.count_add_store()
+    check(4, 2)
+    eng.count_rescue()
+    check(4, 0)
+    eng.prev_from_current(0)
+    eng.count_begin(5)
+    eng.count_add_store_next_k()
+    check(5, 0)
+    for k in (2, 3, 9):
+        eng.count_begin(k)
+        eng.count_add_store()
+        check(k, 2)
+    eng.close()
+
+
 def test_python_mirror_single_read(built, oracle):
     from metamdbg_b200 import MinimizerParser
     rs = synth.make_readset(3, 20000, seed=8, n_genomes=1, genome_len_range=(100_000, 100_001))

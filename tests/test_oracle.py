@@ -380,3 +380,23 @@ def test_ref_reads_ending_in_the_hpc_sentinel(oracle, reference):
         for l, d in ((15, 0.3), (11, 0.3), (15, 0.005)):
             for x, y in zip(oracle.sketch_read(s, l, d, True), reference.sketch_read(s, l, d, True)):
                 assert np.array_equal(x, y)
+
+
+@pytest.mark.ref
+def test_ref_edge_indexer(oracle, reference):
+    """Row F1: the restatement of CreateMdbg::EdgeIndexer against the reference's own class (disk partitions,
+    sortParallel, dereplication into edges.bin): same key set, _nbEdges and _checksum, for the node set of a real
+    count table and for small-alphabet vectors (palindromic prefixes / suffixes, shared keys)."""
+    rng = np.random.default_rng(3)
+    for k in (2, 3, 4, 5, 21):
+        vecs = rng.integers(0, 40, (2500, k)).astype(np.uint32)
+        a = oracle.edge_index(vecs, k)
+        b = reference.edge_index(vecs, k, threads=3)
+        assert b["nb_edges"] == len(b["hashes"]) == len(a["hashes"])
+        assert set(map(tuple, a["hashes"].tolist())) == set(map(tuple, b["hashes"].tolist()))
+        assert a["checksum"] == b["checksum"]
+    reads, offs = _minspace_reads(11)
+    nodes = oracle.count(reads, offs, 4, 2)["vecs"]
+    a = oracle.edge_index(nodes, 4); b = reference.edge_index(nodes, 4, threads=2)
+    assert len(nodes) > 500 and set(map(tuple, a["hashes"].tolist())) == set(map(tuple, b["hashes"].tolist()))
+    assert a["checksum"] == b["checksum"] and b["nb_edges"] == len(a["hashes"])
