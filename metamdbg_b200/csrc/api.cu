@@ -1852,6 +1852,9 @@ mdbg_status mdbg_count_add_store_next_k(mdbg_ctx* ctx, uint64_t read_lo, uint64_
     if (!ctx->t_active) return fail(ctx, MDBG_ERR_STATE, "mdbg_count_add_store_next_k before mdbg_count_begin");
     if (ctx->prev_capacity == 0) return fail(ctx, MDBG_ERR_STATE, "no previous-k table (mdbg_prev_load / mdbg_prev_from_current)");
     if (ctx->t_k < 3) return fail(ctx, MDBG_ERR_ARG, "k must be >= 3 for a next-k pass");
+    // the table now holds abundance VALUES (also on a rank that has no read to add: it still owns keys in the merge)
+    ctx->t_value_mode = true;
+    ctx->t_merged = false;
     if (read_hi > ctx->s_reads) read_hi = ctx->s_reads;
     if (read_lo >= read_hi) return MDBG_OK;
     CK(cudaSetDevice(ctx->device));
@@ -1873,8 +1876,6 @@ mdbg_status mdbg_count_add_store_next_k(mdbg_ctx* ctx, uint64_t read_lo, uint64_
     a.table = ctx->table.as<Slot>();
     a.mask = ctx->t_capacity - 1;
     a.full_flag = &ctx->d_small->full_flag;
-    ctx->t_value_mode = true;
-    ctx->t_merged = false;
     if (ctx->timing) CK(cudaEventRecord(ctx->ev[1][0], s));
     launch_next_k(a, s);
     if (ctx->timing) { CK(cudaEventRecord(ctx->ev[1][1], s)); ctx->ev_valid[1] = true; }

@@ -21,7 +21,8 @@ def main():
     n_ranks = int(sys.argv[1])
     k = int(sys.argv[2])
     orc = pyoracle.Oracle()
-    rs = synth.make_readset(260, 5000, seed=13, n_genomes=2, genome_len_range=(60_000, 90_000))
+    n_reads = int(sys.argv[3]) if len(sys.argv) > 3 else 260        # fewer reads than ranks: some ranks hold no read at all
+    rs = synth.make_readset(n_reads, 5000, seed=13, n_genomes=2, genome_len_range=(60_000, 90_000))
     bases, offs = synth.fill_reads(rs)
     uid = Engine.nccl_unique_id()                       # loads the (fake) NCCL once, before the threads start
     results, errors = [None] * n_ranks, []
@@ -80,7 +81,7 @@ def main():
             assert key not in merged, "key on two owners"
             merged[key] = ab
         instances += st["n_instances"]; distinct += st["n_distinct"]
-    assert merged == want and len(want) > 3000, (len(merged), len(want))
+    assert merged == want and (len(want) > 3000 or n_reads < 260), (len(merged), len(want))
     assert instances == ref["n_instances"] and distinct == ref["n_distinct"], "occurrences not conserved"
     # rescue: solid + rescued entries over all ranks = the oracle's table of the whole read set
     resc = orc.rescue(pm, po, k, ref["hashes"], ref["abundances"])
@@ -94,7 +95,7 @@ def main():
         for key, ab in tab.as_dict().items():
             assert owner_of(key[0], n_ranks) == rank and key not in got_r
             got_r[key] = ab
-    assert got_r == want_r and n_rescued == len(resc["hashes"]) > 50, (len(got_r), len(want_r), n_rescued)
+    assert got_r == want_r and n_rescued == len(resc["hashes"]) and (n_rescued > 50 or n_reads < 260), (len(got_r), len(want_r), n_rescued)
     assert reads_rescued == resc["n_reads_rescued"], (reads_rescued, resc["n_reads_rescued"])
     print(f"  rescue: {n_rescued} abundance-1 k-min-mers of {reads_rescued} reads flagged on their owners")
     # the multi-k chain against the oracle's next-k restatement (IndexKminmerFunctor / getRefinedAbundance); the
@@ -109,7 +110,7 @@ def main():
             for key, ab in next_results[rank][step].as_dict().items():
                 assert owner_of(key[0], n_ranks) == rank and key not in got_k
                 got_k[key] = ab
-        assert got_k == want_k and len(want_k) > 1000, (kk, len(got_k), len(want_k))
+        assert got_k == want_k and (len(want_k) > 1000 or n_reads < 260), (kk, len(got_k), len(want_k))
         prev_h, prev_a = nk["hashes"], nk["abundances"]
         print(f"  next-k {kk}: {len(want_k)} entries identical over {n_ranks} ranks")
     print(f"{n_ranks} ranks, k={k}: {len(want)} solid k-min-mers, {instances} occurrences conserved")

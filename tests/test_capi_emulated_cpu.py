@@ -43,14 +43,16 @@ def emulated(tmp_path_factory):
     return lib, env
 
 
-@pytest.mark.parametrize("n_ranks,k", [(2, 4), (3, 5), (8, 4)])
-def test_owner_merge_on_the_emulator(emulated, n_ranks, k):
+@pytest.mark.parametrize("n_ranks,k,n_reads", [(2, 4, 260), (3, 5, 260), (8, 4, 260), (8, 4, 5)])
+def test_owner_merge_on_the_emulator(emulated, n_ranks, k, n_reads):
     """mdbg_comm_init + mdbg_count_merge with N ranks = N threads of one process, each with its own emulated
     context, exchanging through tests/cpp/fake_nccl.cpp (an in-process libnccl.so.2: barriers + memcpy).  The union
     of the ranks' tables is the oracle's table of the whole read set, every key sits on its owner, occurrences are
     conserved -- the N = 8 sequencing of the merge is exercised here although the round's GPU runs stopped at 4."""
     _, env = emulated
-    run = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu_multirank_child.py"), str(n_ranks), str(k)],
+    # (8 ranks, 5 reads): three ranks hold no read at all but still take part in every collective and own keys
+    run = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu_multirank_child.py"), str(n_ranks), str(k),
+                          str(n_reads)],
                          env=env, capture_output=True, text=True, timeout=900)
     assert run.returncode == 0 and run.stdout.strip().endswith("OK"), run.stdout[-2000:] + run.stderr[-3000:]
 
