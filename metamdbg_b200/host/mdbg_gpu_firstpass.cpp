@@ -32,7 +32,7 @@ static bool getline_gz(gzFile f, std::string& line) {
 int main(int argc, char** argv) {
     if (argc < 3) {
         std::cerr << "usage: mdbg_gpu_firstpass <reads.fa|fq[.gz]> <outDir> [--ont] [-l 15] [-d 0.005] [-k 4] "
-                     "[--min-abundance 2] [--last-k N] [--batch-mbp 1024] [--max-k K]\n"
+                     "[--min-abundance 2] [--last-k N] [--batch-mbp 1024] [--max-k K] [--edges]\n"
                      "       mdbg_gpu_firstpass --from-read-data <read_data_corrected.txt> <outDir> [-k 4] [--min-abundance 2]\n"
                      "         (the `graph --firstpass` seam alone: count the minimizer-space reads of an existing file)\n"
                      "       --max-k K: also derive k+1 .. K from the previous table on the device (the k > firstK `graph`\n"
@@ -44,6 +44,7 @@ int main(int argc, char** argv) {
     std::string input = fromReadData ? argv[2] : argv[1], outDir = fromReadData ? argv[3] : argv[2];
     bool hpc = true;
     uint32_t l = 15, k = 4, minAb = 2, lastK = 0, maxK = 0;
+    bool writeEdges = false;
     float density = 0.005f;
     size_t batchMbp = 1024;
     for (int i = fromReadData ? 4 : 3; i < argc; i++) {
@@ -56,10 +57,17 @@ int main(int argc, char** argv) {
         else if (a == "--min-abundance") minAb = (uint32_t)atoi(next().c_str());
         else if (a == "--last-k") lastK = (uint32_t)atoi(next().c_str());
         else if (a == "--max-k") maxK = (uint32_t)atoi(next().c_str());
+        else if (a == "--edges") writeEdges = true;
         else if (a == "--batch-mbp") batchMbp = (size_t)atol(next().c_str());
     }
     try {
         Context ctx(l, density, hpc);
+        auto edgeKeys = [&](const std::string& file) {   // EdgeIndexer on the table the context holds
+            if (!writeEdges) return;
+            GpuEdgeIndexer edges(ctx, minAb);
+            edges.execute(file);
+            std::cout << "edges " << edges._nbEdges << " edge_checksum " << edges._checksum << "\n";
+        };
         auto nextKPasses = [&]() {                       // k+1 .. maxK from the table the context holds
             GpuNextKCounter nextK(ctx, minAb);
             for (uint32_t kk = k + 1; kk <= maxK; kk++) {
@@ -72,6 +80,7 @@ int main(int argc, char** argv) {
             const uint64_t nReads = loadReadData(ctx, input);
             GpuKminmerCounter counter(ctx, k, minAb);
             counter.execute(outDir + "/kminmerData_min.txt", outDir + "/kminmerData_abundance.txt");
+            edgeKeys(outDir + "/edges.bin");
             nextKPasses();
             std::cout << "reads " << nReads << " kminmers " << counter._nbKminmers << " distinct " << counter._nbDistinct
                       << " solid " << counter._nbSolidKminmers << " rescued " << counter._nbRescuedKminmers << " checksum "
@@ -120,6 +129,7 @@ int main(int argc, char** argv) {
         uint64_t changed = purgePalindromesAndWrite(ctx, 4, lastK, outDir + "/read_data_corrected.txt");
         GpuKminmerCounter counter(ctx, k, minAb);
         counter.execute(outDir + "/kminmerData_min.txt", outDir + "/kminmerData_abundance.txt");
+        edgeKeys(outDir + "/edges.bin");
         nextKPasses();
         std::cout << "reads " << functor.nbReads() << " bases " << functor.nbBases() << " minimizers "
                   << functor.nbSelectedMinimizers() << " purged_reads " << changed << " kminmers " << counter._nbKminmers

@@ -409,4 +409,28 @@ private:
     uint32_t _minAbundance;
 };
 
+// CreateMdbg::EdgeIndexer (CreateMdbg.hpp:4010-4232): the dereplicated hash128 keys of the (k-1)-prefixes / suffixes of
+// the nodes of the context's current table, written as edges.bin is (16-byte little-endian u128 per key; the
+// reference builds its edge MPHF over this file, so the key order is irrelevant).
+class GpuEdgeIndexer {
+public:
+    GpuEdgeIndexer(Context& ctx, uint32_t minAbundance) : _ctx(ctx), _minAbundance(minAbundance) {}
+
+    void execute(const std::string& edgeFile) {
+        mdbg_edges_out e{};
+        check(_ctx.get(), mdbg_edges_index(_ctx.get(), _minAbundance, &e), "mdbg_edges_index");
+        File f(edgeFile);
+        f.put(e.hashes, 16, (size_t)e.n_edges);            // {low, high} words = the u128 as it lies on disk
+        f.close();
+        _nbEdges = e.n_edges;
+        _checksum = e.checksum;
+    }
+
+    uint64_t _nbEdges = 0, _checksum = 0;
+
+private:
+    Context& _ctx;
+    uint32_t _minAbundance;
+};
+
 }  // namespace mdbg_host

@@ -144,6 +144,18 @@ def main():
         moff = np.array(all_off, np.uint64)
         so, sm = eng.store_fetch()
         assert np.array_equal(so, moff) and np.array_equal(sm, mins), ("store", scen)
+        # ONT-style density re-threshold on the store (Utils::applyDensityThreshold), sometimes
+        if rng.integers(0, 3) == 0 and len(mins):
+            d2 = float(rng.choice([dens / 5, dens / 2, dens]))
+            eng.store_apply_density(d2)
+            pm, po = [], [0]
+            for r in range(len(moff) - 1):
+                qv = orc.apply_density(mins[int(moff[r]):int(moff[r + 1])], d2)
+                pm.append(qv); po.append(po[-1] + len(qv))
+            mins = np.concatenate(pm).astype(np.uint32) if pm else np.zeros(0, np.uint32)
+            moff = np.array(po, np.uint64)
+            so, sm = eng.store_fetch()
+            assert np.array_equal(so, moff) and np.array_equal(sm, mins), ("apply_density", scen, d2)
         # purge (sometimes), then count / rescue / next-k at a random k
         if rng.integers(0, 2):
             lk = int(rng.integers(5, 40))
@@ -168,6 +180,11 @@ def main():
         assert tab.as_dict() == want_t, ("count", scen, k, min_ab, len(want_t))
         assert (tab.n_instances, tab.n_distinct) == (ref["n_instances"], ref["n_distinct"]), ("count totals", scen, k)
         n["table_entries"] += len(want_t)
+        if k >= 2 and rng.integers(0, 2):                     # edge keys of the node set (CreateMdbg::EdgeIndexer)
+            ed = eng.edges_index(min_ab)
+            we = orc.edge_index(tab.kminmers, k)
+            assert ed["n_edges"] == len(we["hashes"]) and ed["checksum"] == we["checksum"], ("edges", scen, k)
+            assert {(int(h[1]), int(h[0])) for h in ed["hashes"]} == {(int(h[0]), int(h[1])) for h in we["hashes"]}, ("edge set", scen, k)
         if rng.integers(0, 2):                                # default mode: rescue on top of the >= 2 table
             solid = orc.count(mins, moff, k, 2)
             resc = orc.rescue(mins, moff, k, solid["hashes"], solid["abundances"])

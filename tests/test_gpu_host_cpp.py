@@ -141,8 +141,15 @@ def test_cpp_driver_graph_seam_and_default_mode(tmp_path, oracle):
     d3 = tmp_path / "three"
     d3.mkdir()
     out = subprocess.run([EXE, "--from-read-data", str(d1 / "read_data_corrected.txt"), str(d3), "--min-abundance", "0",
-                          "--max-k", "7"], capture_output=True, text=True, timeout=120)
+                          "--max-k", "7", "--edges"], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr
+    # --edges: edges.bin of the k = 4 node set (GpuEdgeIndexer) = the oracle's EdgeIndexer key set
+    nodes = np.frombuffer(open(d3 / "kminmerData_min.txt", "rb").read(), dtype=np.uint32).reshape(-1, 4)
+    we = oracle.edge_index(nodes, 4)
+    eb = np.frombuffer(open(d3 / "edges.bin", "rb").read(), dtype=np.uint64).reshape(-1, 2)       # {low, high}
+    assert {(int(h[1]), int(h[0])) for h in eb} == {(int(h[0]), int(h[1])) for h in we["hashes"]} and len(eb) == len(we["hashes"]) > 500
+    words = out.stdout.split()
+    assert int(words[words.index("edges") + 1]) == len(eb) and int(words[words.index("edge_checksum") + 1]) == we["checksum"]
     ph = np.concatenate([c["hashes"], r["hashes"]]); pa = np.concatenate([c["abundances"], np.ones(len(r["hashes"]), np.uint32)])
     for kk in (5, 6, 7):
         nk = oracle.next_k(m, mo, kk, ph, pa)
