@@ -4,6 +4,9 @@
     python bench.py --gpus N --steps K --warmup W            # this engine
     python bench.py --impl reference --gpus N --steps K ...  # reference CPU path (oracle/_ref)
 
+`--workload cfg3` switches to BASELINE.json configs[2] (2 M ONT reads x 8 kbp: no HPC, sketch at the correction
+density 0.025, density re-threshold of the store to 0.005, purge, k = 4 count), same JSON line.
+
 Workload (config.workload): BASELINE.json configs[1] per GPU -- 1 M synthetic
 HiFi reads x 15 kbp, l=15, d=0.005, HPC on, k=4, abundance >= 2.  A "step" is
 one pass of the hot path over that batch: sketch -> minimizer store ->
@@ -31,17 +34,42 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 L, DENSITY, HPC, K, MIN_AB = 15, 0.005, True, 4, 2
+ASM_DENSITY, ERR = 0.0, 0.001          # ONT (cfg3): sketch at DENSITY, then re-threshold the store at ASM_DENSITY
 SEED = 20260924
+
+# BASELINE.json configs that fit one GPU.  cfg2 is the configuration the metric is quoted on (the default); cfg3 is
+# the ONT shape: no homopolymer compression, sketch at the correction density 0.025 ("nanoMDBG density"), then
+# Utils::applyDensityThreshold(0.005) on the minimizer store, purge, k = 4 count.
+WORKLOADS = {
+    "cfg2": dict(reads=1_000_000, read_len=15_000, density=0.005, hpc=True, asm_density=0.0, err=0.001,
+                 label="cfg2: 1M synthetic HiFi reads x 15 kbp per GPU, l=15 d=0.005 HPC k=4 min-abundance 2"),
+    "cfg3": dict(reads=2_000_000, read_len=8_000, density=0.025, hpc=False, asm_density=0.005, err=0.02,
+                 label="cfg3: 2M synthetic ONT reads x 8 kbp per GPU, l=15 sketch d=0.025 (no HPC) -> density 0.005, "
+                       "k=4 min-abundance 2"),
+}
+
+
+def select_workload(args):
+    """Set the module-level workload constants from --workload and fill the size defaults."""
+    global DENSITY, HPC, ASM_DENSITY, ERR
+    w = WORKLOADS[args.workload]
+    DENSITY, HPC, ASM_DENSITY, ERR = w["density"], w["hpc"], w["asm_density"], w["err"]
+    if args.reads <= 0:
+        args.reads = w["reads"]
+    if args.read_len <= 0:
+        args.read_len = w["read_len"]
 
 
 def workload_config(args):
     return {
-        "workload": "cfg2: 1M synthetic HiFi reads x 15 kbp per GPU, l=15 d=0.005 HPC k=4 min-abundance 2"
-        if (args.reads == 1_000_000 and args.read_len == 15_000) else
-        f"{args.reads} synthetic HiFi reads x {args.read_len} bp per GPU, l=15 d=0.005 HPC k=4 min-abundance 2",
+        "workload": WORKLOADS[args.workload]["label"]
+        if (args.reads == WORKLOADS[args.workload]["reads"] and args.read_len == WORKLOADS[args.workload]["read_len"]) else
+        f"{args.reads} synthetic reads x {args.read_len} bp per GPU, parameters of {args.workload}: l=15 d={DENSITY} "
+        f"hpc={HPC} assembly-density={ASM_DENSITY or DENSITY} k=4 min-abundance 2",
         "reads_per_gpu": args.reads, "read_len_mean": args.read_len, "minimizer_size": L, "density": DENSITY,
+        "assembly_density": ASM_DENSITY or DENSITY,
         "hpc": HPC, "k": K, "min_abundance": MIN_AB, "purge_last_k": purge_last_k(args),
-        "genomes": args.genomes, "substitution_rate": 0.001, "input_format": "ASCII bases (Read::_seq)",
+        "genomes": args.genomes, "substitution_rate": ERR, "input_format": "ASCII bases (Read::_seq)",
         "l2_policy": "inputs (>= 1 GB per step) are far larger than the 126 MB L2; no explicit flush",
     }
 
@@ -79,7 +107,7 @@ def host_bytes_available() -> int:
 
 def purge_last_k(args):
     # Commons::computeLastK (src/Commons.hpp:1726-1741): n50 * density * 2, at least firstK+2
-    return max(int(args.read_len * np.float32(DENSITY) * np.float32(2.0)), 6)
+    return max(int(args.read_len * np.float32(ASM_DENSITY or DENSITY) * np.float32(2.0)), 6)
 
 
 # ---------------------------------------------------------------- clocks sampler
@@ -145,7 +173,7 @@ def run_reference(args, rank: int):
     except (FileNotFoundError, OSError):
         ref, kind, threads = None, "port", 1
     n_sample = args.ref_reads or int(min(args.reads, max(2000, 400 * threads)))
-    rs = synth.make_readset(args.reads * max(1, args.gpus), args.read_len, seed=SEED, n_genomes=args.genomes)
+    rs = synth.make_readset(args.reads * max(1, args.gpus), args.read_len, seed=SEED, n_genomes=args.genomes, err=ERR)
     sub = rs.subset(0, n_sample)
     bases, offs = synth.fill_reads(sub)
     n_bases = int(offs[-1])
@@ -154,12 +182,10 @@ def run_reference(args, rank: int):
     def one():
         t0 = time.perf_counter()
         if ref is not None:
-            res = ref.pipeline(bases, offs, L, DENSITY, HPC, K, purge_last_k=lk, min_abundance=MIN_AB, threads=threads)
+            res = ref.pipeline(bases, offs, L, DENSITY, HPC, K, purge_last_k=lk, min_abundance=MIN_AB, threads=threads,
+                               assembly_density=ASM_DENSITY)
         else:
-            orc = pyoracle.Oracle()
-            mo, m, p, d = orc.sketch_batch(bases, offs, L, DENSITY, HPC)
-            c = orc.count(m, mo, K, MIN_AB)
-            res = dict(n_solid=len(c["abundances"]), n_minimizers=len(m))
+            res = oracle_port_pipeline(pyoracle.Oracle(), bases, offs, lk)
         return time.perf_counter() - t0, res
 
     # the warm-up steps also pick the thread count: candidates from the usable CPUs (cgroup quota) up to every
@@ -196,9 +222,24 @@ def run_reference(args, rank: int):
         "e2e": {"value": gbps, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "check": {"n_minimizers": res.get("n_minimizers"), "n_solid": res.get("n_solid")},
     }
-    if ref is not None and not args.no_stages:
+    if ref is not None and not args.no_stages and args.workload == "cfg2":
         line["reference_stages"] = reference_stages(ref, bases, offs, threads, n_bases)
     print(json.dumps(line), flush=True)
+
+
+def oracle_port_pipeline(orc, bases, offs, lk):
+    """The path on the C restatement (single thread): sketch, [density re-threshold], purge, count."""
+    mo, m, p, d = orc.sketch_batch(bases, offs, L, DENSITY, HPC)
+    pm, po = [], [0]
+    for r in range(len(offs) - 1):
+        q = m[int(mo[r]):int(mo[r + 1])]
+        if ASM_DENSITY:
+            q = orc.apply_density(q, ASM_DENSITY)
+        q, _ = orc.purge_palindrome(q, 4, lk)
+        pm.append(q); po.append(po[-1] + len(q))
+    pm = np.concatenate(pm).astype(np.uint32) if pm else np.zeros(0, np.uint32)
+    c = orc.count(pm, np.array(po, np.uint64), K, MIN_AB)
+    return dict(n_solid=len(c["abundances"]), n_minimizers=len(pm), checksum=orc.checksum(c["hashes"], c["abundances"]))
 
 
 def reference_stages(ref, bases, offs, threads, n_bases):
@@ -263,7 +304,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         return int(t.item())
 
     # ---- synthetic reads, generated straight into HBM -------------------------------
-    rs_all = synth.make_readset(args.reads * world, args.read_len, seed=SEED, n_genomes=args.genomes)
+    rs_all = synth.make_readset(args.reads * world, args.read_len, seed=SEED, n_genomes=args.genomes, err=ERR)
     rs = rs_all.shard(rank, world)
     n_reads, n_bases = rs.n_reads, rs.n_bases
     eng = Engine(L, DENSITY, HPC, device=local_rank)
@@ -293,9 +334,13 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         tune["chosen"] = args.sketch_variant
         tune["forced"] = True
 
+    n_sketched = [0]
+
     def step_device():
         eng.store_clear()
-        eng.sketch_batch_device(d_bases.data_ptr(), d_off.data_ptr(), n_reads, n_bases, True)
+        n_sketched[0] = int(eng.sketch_batch_device(d_bases.data_ptr(), d_off.data_ptr(), n_reads, n_bases, True).n_minimizers)
+        if ASM_DENSITY:
+            eng.store_apply_density(ASM_DENSITY)
         eng.purge_palindromes(4, lk)
         eng.count_begin(K, 0)
         eng.count_add_store()
@@ -390,6 +435,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                 offs = h_offs[lo:hi + 1] - h_offs[lo]
                 sk = eng.sketch_batch_ptr(h_bases.data_ptr() + int(h_offs[lo]), offs, True)
                 d2h[0] += 8 * (hi - lo + 1) + 9 * sk
+            if ASM_DENSITY:
+                eng.store_apply_density(ASM_DENSITY)
             eng.purge_palindromes(4, lk)
             eng.count_begin(K, 0)
             eng.count_add_store()
@@ -452,17 +499,16 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         t0 = time.perf_counter()
         if ref is not None:
             res = ref.pipeline(s_bases, s_offs, L, DENSITY, HPC, K, purge_last_k=lk, min_abundance=MIN_AB,
-                               threads=threads)
-            ref_solid, ref_cs, ref_nmin = res["n_solid"], res["checksum"], res["n_minimizers"]
+                               threads=threads, assembly_density=ASM_DENSITY)
         else:
-            orc = pyoracle.Oracle()
-            mo, m, p, d = orc.sketch_batch(s_bases, s_offs, L, DENSITY, HPC)
-            c = orc.count(m, mo, K, MIN_AB)
-            ref_solid, ref_cs, ref_nmin = len(c["abundances"]), orc.checksum(c["hashes"], c["abundances"]), len(m)
+            res = oracle_port_pipeline(pyoracle.Oracle(), s_bases, s_offs, lk)
+        ref_solid, ref_cs, ref_nmin = res["n_solid"], res["checksum"], res["n_minimizers"]
         dt = time.perf_counter() - t0
         # same sample through the GPU engine: bit-exact fingerprint must agree
         eng.store_clear()
         eng.sketch_batch_device(d_bases.data_ptr(), d_off.data_ptr(), n_sample, int(s_offs[-1]), True)
+        if ASM_DENSITY:
+            eng.store_apply_density(ASM_DENSITY)
         eng.purge_palindromes(4, lk)
         eng.count_begin(K, 0)
         eng.count_add_store()
@@ -482,7 +528,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         sk_ms = float(np.mean(sketch_ms))
-        algo_bytes = n_bases * 1.0 + n_min_store * 9.0      # 1 B/bp ASCII in + 9 B per minimizer out
+        algo_bytes = n_bases * 1.0 + n_sketched[0] * 9.0    # 1 B/bp ASCII in + 9 B per minimizer the sketch writes
         achieved = algo_bytes / (sk_ms * 1e-3) / 1e9
         traffic, ncu_pipes = None, None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -524,8 +570,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--reads", type=int, default=1_000_000, help="reads per GPU")
-    ap.add_argument("--read-len", type=int, default=15_000)
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS), help="BASELINE.json config (default: the one the metric is quoted on)")
+    ap.add_argument("--reads", type=int, default=0, help="reads per GPU (0 = the workload's)")
+    ap.add_argument("--read-len", type=int, default=0, help="mean read length (0 = the workload's)")
     ap.add_argument("--genomes", type=int, default=100)
     ap.add_argument("--e2e-reads", type=int, default=0, help="reads per GPU in the e2e leg (0 = all)")
     ap.add_argument("--e2e-batch", type=int, default=262_144, help="reads per host-buffer C-ABI call")
@@ -539,6 +586,7 @@ def main():
     ap.add_argument("--no-stages", action="store_true", help="reference arm: skip the extra real-stage timing")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    select_workload(args)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

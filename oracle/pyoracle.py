@@ -400,10 +400,20 @@ class Reference(_Lib):
         return int(self.lib.ref_max_threads())
 
     def pipeline(self, bases: np.ndarray, offsets: np.ndarray, l: int, density: float, hpc: bool, k: int,
-                 purge_last_k: int = 0, min_abundance: int = 2, threads: int = 1):
+                 purge_last_k: int = 0, min_abundance: int = 2, threads: int = 1, assembly_density: float = 0.0):
         bases = np.ascontiguousarray(bases, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         nm = C.c_uint64(0); cs = C.c_uint64(0); ts = C.c_double(0); tc = C.c_double(0)
+        if assembly_density > 0:                  # ONT: sketch at `density`, Utils::applyDensityThreshold, purge, count
+            f = self.lib.ref_pipeline2
+            f.restype = C.c_size_t
+            f.argtypes = [C.c_void_p, _u64p, C.c_size_t, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, C.c_int, C.c_uint32,
+                          C.c_int] + [C.POINTER(C.c_uint64)] * 3 + [C.POINTER(C.c_double)] * 2
+            ns = C.c_uint64(0)
+            n = f(bases.ctypes.data, _p(offsets, _u64p), len(offsets) - 1, l, density, int(hpc), assembly_density, k,
+                  purge_last_k, min_abundance, threads, C.byref(ns), C.byref(nm), C.byref(cs), C.byref(ts), C.byref(tc))
+            return dict(n_solid=int(n), n_minimizers=int(nm.value), n_minimizers_sketch=int(ns.value), checksum=int(cs.value),
+                        seconds_sketch=float(ts.value), seconds_count=float(tc.value))
         n = self.lib.ref_pipeline(bases.ctypes.data, _p(offsets, _u64p), len(offsets) - 1, l, density, int(hpc), k,
                                   purge_last_k, min_abundance, threads, C.byref(nm), C.byref(cs), C.byref(ts), C.byref(tc))
         return dict(n_solid=int(n), n_minimizers=int(nm.value), checksum=int(cs.value),

@@ -241,6 +241,59 @@ size_t ref_pipeline(const char* bases, const uint64_t* offsets, size_t n_reads, 
     return n;
 }
 
+/* Same with the ONT-style density re-threshold between sketch and purge: reads are sketched at `density`
+ * (--density-correction), Utils::applyDensityThreshold (src/Commons.hpp:2507-2550) keeps the minimizers that also
+ * pass `assembly_density`, then purgePalindrome and the count. */
+size_t ref_pipeline2(const char* bases, const uint64_t* offsets, size_t n_reads, int l, float density, int hpc,
+                     float assembly_density, int k, int purge_last_k, uint32_t min_abundance, int n_threads,
+                     uint64_t* n_minimizers_sketch, uint64_t* n_minimizers, uint64_t* checksum, double* seconds_sketch,
+                     double* seconds_count) {
+    if (n_threads < 1) n_threads = 1;
+    vector<vector<MinimizerType>> per_read(n_reads);
+    unordered_set<MinimizerType> bl;
+    uint64_t n_sketch = 0;
+    auto t0 = high_resolution_clock::now();
+#pragma omp parallel num_threads(n_threads) reduction(+ : n_sketch)
+    {
+        MinimizerParser parser(l, density, bl);
+        EncoderRLE enc;
+        vector<MinimizerType> mins, minsF;
+        vector<u_int32_t> pos, posF;
+        vector<u_int8_t> dirs, dirsF, quals, qualsF;
+#pragma omp for schedule(dynamic, 16)
+        for (size_t r = 0; r < n_reads; r++) {
+            sketch_one(enc, parser, bases + offsets[r], offsets[r + 1] - offsets[r], hpc, mins, pos, dirs);
+            n_sketch += mins.size();
+            const vector<MinimizerType>* use = &mins;
+            if (assembly_density > 0) {
+                Utils::applyDensityThreshold(assembly_density, mins, pos, dirs, quals, minsF, posF, dirsF, qualsF);
+                use = &minsF;
+            }
+            if (purge_last_k > 0) per_read[r] = Commons::purgePalindrome(*use, 4, purge_last_k);
+            else per_read[r] = *use;
+        }
+    }
+    auto t1 = high_resolution_clock::now();
+    vector<uint64_t> offs(n_reads + 1, 0);
+    for (size_t r = 0; r < n_reads; r++) offs[r + 1] = offs[r] + per_read[r].size();
+    vector<uint32_t> flat(offs[n_reads] + 1);
+    for (size_t r = 0; r < n_reads; r++)
+        if (!per_read[r].empty()) memcpy(flat.data() + offs[r], per_read[r].data(), per_read[r].size() * 4);
+    uint32_t* v; uint64_t* h; uint32_t* a;
+    uint64_t ni, nd;
+    size_t n = ref_count(flat.data(), offs.data(), n_reads, k, min_abundance, n_threads, &v, &h, &a, &ni, &nd);
+    auto t2 = high_resolution_clock::now();
+    uint64_t cs = 0;
+    for (size_t i = 0; i < n; i++) cs += (uint64_t)a[i] * h[2 * i + 1];
+    free(v); free(h); free(a);
+    if (n_minimizers_sketch) *n_minimizers_sketch = n_sketch;
+    if (n_minimizers) *n_minimizers = offs[n_reads];
+    if (checksum) *checksum = cs;
+    if (seconds_sketch) *seconds_sketch = duration<double>(t1 - t0).count();
+    if (seconds_count) *seconds_count = duration<double>(t2 - t1).count();
+    return n;
+}
+
 // ---- the reference's own graph-stage classes, driven through their file contract -----------------
 
 static void write_read_data(const string& filename, const uint32_t* mins, const uint64_t* offs, size_t n_reads) {
