@@ -873,3 +873,11 @@ def test_side_outputs_refuse_the_hpc_sentinel_in_reads(built, oracle):
         _, _, ql = oracle.read_aux(raw[lo:hi], quals[lo:hi].tobytes(), 15, False, pos)
         assert np.array_equal(aux["qualities"][int(sk.min_offsets[r]):int(sk.min_offsets[r + 1])], ql)
     eng.close()
+
+
+def test_graft_entry_smoke(built, capsys):
+    """__graft_entry__.smoke(): the driver's one small invocation of the hot path, checked against the oracle."""
+    import __graft_entry__ as g
+    g.smoke()
+    out = capsys.readouterr().out
+    assert "smoke OK" in out                     # (the line also reports whether variant 1 matched: informational)
