@@ -68,6 +68,48 @@ def _worker(rank, world, port, out_dir):
     solid = {k: v for k, v in merged.items() if v >= 2}         # filter AFTER the merge
     np.save(os.path.join(out_dir, f"rank{rank}.npy"),
             np.array([list(k) + [v] for k, v in solid.items()], dtype=np.int64).reshape(-1, K + 1))
+
+    # ---- the multi-k step of the protocol: the previous-k table is REPLICATED (all-gather of
+    # the owners' solid (hash, abundance) pairs), the next-k pass runs on the local reads, and the resulting
+    # (vector -> value) entries go to their owners where equal keys are kept once, never summed
+    pairs = np.array([list(orc.hash128(np.array(k, dtype=np.uint32))) + [v] for k, v in solid.items()],
+                     dtype=np.uint64).reshape(-1, 3)
+    n_pairs = torch.tensor([len(pairs)], dtype=torch.int64)
+    all_n = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(all_n, n_pairs)
+    cap = int(max(int(x) for x in all_n))
+    padded = torch.zeros((cap, 3), dtype=torch.int64)
+    padded[:len(pairs)] = torch.from_numpy(pairs.view(np.int64))
+    gathered = [torch.zeros((cap, 3), dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(gathered, padded)
+    prev = np.concatenate([g.numpy()[:int(n)].view(np.uint64) for g, n in zip(gathered, all_n)])
+    nk = orc.next_k(m, mo, K + 1, prev[:, :2].copy(), prev[:, 2].astype(np.uint32))      # local reads, replicated table
+    own = owner_of(nk["hashes"][:, 0], world)
+    send = []
+    for d in range(world):
+        sel = own == d
+        rec = np.concatenate([nk["vecs"][sel].astype(np.int64), nk["abundances"][sel, None].astype(np.int64)], 1)
+        send.append(torch.from_numpy(rec.reshape(-1, K + 2)))
+    counts = torch.tensor([len(x) for x in send], dtype=torch.int64)
+    all_counts = [torch.zeros(world, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(all_counts, counts)
+    recv = [torch.zeros((int(all_counts[s_][rank]), K + 2), dtype=torch.int64) for s_ in range(world)]
+    reqs = []
+    for d in range(world):
+        if d == rank:
+            recv[d].copy_(send[d])
+        else:
+            reqs.append(dist.isend(send[d], d))
+            reqs.append(dist.irecv(recv[d], d))
+    for r_ in reqs:
+        r_.wait()
+    table = {}
+    for t in recv:
+        for row in t.numpy():
+            key = tuple(int(x) for x in row[:K + 1])
+            assert table.setdefault(key, int(row[K + 1])) == int(row[K + 1])      # same key, same value on every rank
+    np.save(os.path.join(out_dir, f"next_rank{rank}.npy"),
+            np.array([list(k) + [v] for k, v in table.items()], dtype=np.int64).reshape(-1, K + 2))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -87,6 +129,16 @@ def test_owner_partitioned_merge_gloo(tmp_path, oracle):
     ref = oracle.count(m, mo, K, 2)
     want = {tuple(int(x) for x in v): int(a) for v, a in zip(ref["vecs"], ref["abundances"])}
     assert got == want and len(want) > 50
+    # the next-k tables of the two owners = the oracle's next-k table of the whole read set
+    nk = oracle.next_k(m, mo, K + 1, ref["hashes"], ref["abundances"])
+    want_n = {tuple(int(x) for x in v): int(a) for v, a in zip(nk["vecs"], nk["abundances"])}
+    got_n = {}
+    for r in range(world):
+        for row in np.load(tmp_path / f"next_rank{r}.npy"):
+            key = tuple(int(x) for x in row[:K + 1])
+            assert key not in got_n
+            got_n[key] = int(row[K + 1])
+    assert got_n == want_n and len(want_n) > 30
 
 
 def test_owner_of_matches_header_formula():
