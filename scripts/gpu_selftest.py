@@ -7,7 +7,9 @@ on a fresh box).  Everything goes through the C ABI (ctypes) and is compared wit
   ranks N    N ranks = N threads on ONE GPU over tests/cpp/fake_nccl.cpp built with -DFAKE_NCCL_CUDA: owner merge,
              multi-rank rescue, replicated previous-k table and two next-k passes (tests/emu_multirank_child.py)
 
-usage: gpu_selftest.py pieces | ranks N         (prints one JSON line, exit code 0 = identical to the oracle)
+  variants   sketch variant 1 in many small launches, reads ending in '#', edge keys (late round-1 kernel changes)
+
+usage: gpu_selftest.py pieces | variants | ranks N         (prints one JSON line, exit code 0 = identical to the oracle)
 """
 import json
 import os
@@ -75,6 +77,59 @@ def pieces():
     return out
 
 
+def variants():
+    """Sketch variant 1 in MANY small launches (the condition under which its first version went wrong), reads that
+    end in EncoderRLE's '#' sentinel, and the edge keys of a count table -- the three kernel changes made after the
+    last GPU run of round 1."""
+    os.environ["MDBG_PIECE_BYTES"] = "20000"
+    os.environ["MDBG_PACK_MIN_BYTES"] = "0"
+    from metamdbg_b200 import Engine, synth
+    from oracle.pyoracle import Oracle
+    orc = Oracle()
+    out = {}
+    rs = synth.make_readset(900, 4000, seed=5, n_genomes=2, genome_len_range=(150_000, 250_000))
+    bases, offs = synth.fill_reads(rs)
+    want = orc.sketch_batch(bases, offs, 15, 0.005, True)
+
+    def same(sk, w):
+        return all(np.array_equal(a, b) for a, b in zip((sk.min_offsets, sk.minimizers, sk.positions, sk.directions), w))
+
+    for v in (1, 0):
+        for packing in (1, 0):
+            eng = Engine(15, 0.005, True)
+            eng.set_sketch_variant(v)
+            eng.set_host_packing(packing)
+            ok = all(same(eng.sketch_batch(bases, offs), want) for _ in range(3))      # repeated: fresh CTAs every time
+            out[f"variant{v}_packing{packing}_{eng.last_batch_info()['n_pieces']}pieces"] = bool(ok)
+            eng.close()
+    rng = np.random.default_rng(77)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    reads = [np.concatenate([rng.choice(acgt, int(rng.integers(0, 1800))), np.frombuffer((b"#", b"##", b"", b"N#", b"#A")[i % 5], np.uint8)])
+             for i in range(300)]
+    o2 = np.zeros(len(reads) + 1, np.uint64)
+    o2[1:] = np.cumsum([len(r) for r in reads])
+    b2 = np.concatenate(reads).astype(np.uint8)
+    for l, d in ((15, 0.3), (11, 0.3), (15, 0.005)):
+        eng = Engine(l, d, True)
+        out[f"sentinel_l{l}_d{d}"] = bool(same(eng.sketch_batch(b2, o2), orc.sketch_batch(b2, o2, l, d, True)))
+        eng.close()
+    eng = Engine(15, 0.005, True)
+    eng.sketch_batch(bases, offs, append_to_store=True, fetch=False)
+    for k, rescue in ((4, False), (4, True), (6, False)):
+        eng.count_begin(k)
+        eng.count_add_store()
+        if rescue:
+            eng.count_rescue()
+        tab = eng.count_finalize(0 if rescue else 2)
+        got = eng.edges_index(0 if rescue else 2)
+        we = orc.edge_index(tab.kminmers, k)
+        out[f"edges_k{k}_rescue{int(rescue)}"] = bool(
+            got["n_edges"] == len(we["hashes"]) and got["checksum"] == we["checksum"] and
+            {(int(h[1]), int(h[0])) for h in got["hashes"]} == {(int(h[0]), int(h[1])) for h in we["hashes"]})
+    eng.close()
+    return out
+
+
 def ranks(n):
     os.environ.setdefault("MDBG_EMU_LIB", os.path.join(ROOT, "metamdbg_b200", "libmdbg_b200.so"))     # the REAL library
     sys.argv = ["emu_multirank_child.py", str(n), "4"]
@@ -93,7 +148,7 @@ if __name__ == "__main__":
     t0 = time.time()
     what = sys.argv[1]
     try:
-        res = pieces() if what == "pieces" else ranks(int(sys.argv[2]))
+        res = pieces() if what == "pieces" else variants() if what == "variants" else ranks(int(sys.argv[2]))
         ok = all(v for k, v in res.items() if isinstance(v, bool))
     except Exception as e:  # noqa: BLE001
         res, ok = {"error": repr(e)}, False
