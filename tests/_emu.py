@@ -1,7 +1,7 @@
 """Build helper for the warp-emulator tests: turns a kernel source file into something g++ can compile against
 tests/cpp/warp_emu.hpp WITHOUT editing the product source.  Only host-side constructs are rewritten:
 
-  kernel<<<grid, block, 0, s>>>(args);   ->  emu::launch(grid, block, [&] { kernel(args); });
+  kernel<<<grid, block, 0, s>>>(args);   ->  emu::launch(grid, block, s, [=] { kernel(args); });
   the two inline-PTX slot primitives of kminmer.cu (ld.relaxed.v2.u64, atom.cas.b128) -> their plain C meaning
   (the emulator is single threaded, so a plain load and a plain compare-and-swap are exact).
 
@@ -25,7 +25,7 @@ __device__ __forceinline__ void cas_key(Slot* s, uint64_t new_lo, uint64_t new_h
 def emulated_source(name: str) -> str:
     src = open(os.path.join(CSRC, name)).read()
     src, n = re.subn(r"(\w+(?:<[^<>;]*>)?)<<<([^;]*?),\s*([^;,]*?),\s*0,\s*s>>>\(([^;]*?)\);",
-                     r"emu::launch(\2, \3, [&] { \1(\4); });", src, flags=re.S)
+                     r"emu::launch(\2, \3, s, [=] { \1(\4); });", src, flags=re.S)
     assert n > 0 and "<<<" not in src, f"{name}: kernel launches not rewritten"
     if "asm volatile" in src:
         src, n1 = re.subn(r"__device__ __forceinline__ void load_key\(.*?\n}\n", "", src, count=1, flags=re.S)

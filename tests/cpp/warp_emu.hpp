@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <functional>
 #include <vector>
 
@@ -192,6 +193,42 @@ inline void launch(unsigned grid, unsigned block, const std::function<void()>& b
     for (unsigned bx = 0; bx < grid; bx++) { Dim3 bi; bi.x = bx; run_block((int)block, body, bi, g); }
 }
 
+// ---- streams ------------------------------------------------------------------------------------------------------
+// Default build: every enqueued operation runs at once (a valid serialisation of stream semantics).
+// -DEMU_DEFERRED: the ADVERSARIAL serialisation -- work enqueued on a stream sits in that stream's queue until the
+// host (or another stream, through an event) actually waits for it, so a missing synchronisation shows up as stale
+// or poisoned data instead of being hidden by eager execution.  Streams belong to the thread that created them.
+struct Stream {
+    std::deque<std::function<void()>> q;
+    uint64_t submitted = 0, executed = 0;
+};
+inline std::vector<Stream*>& my_streams() { static thread_local std::vector<Stream*> v; return v; }
+inline void drain(Stream* s, uint64_t upto) {
+    while (s && s->executed < upto && !s->q.empty()) {
+        std::function<void()> f = std::move(s->q.front());
+        s->q.pop_front();
+        s->executed++;
+        f();
+    }
+}
+inline void drain_all() { for (Stream* s : my_streams()) drain(s, s->submitted); }
+inline void enqueue(void* stream, std::function<void()> f) {
+#ifdef EMU_DEFERRED
+    if (stream) {
+        Stream* s = (Stream*)stream;
+        s->q.push_back(std::move(f));
+        s->submitted++;
+        return;
+    }
+#endif
+    (void)stream;
+    f();
+}
+// kernel<<<grid, block, 0, stream>>>(args): the body must hold its arguments by value (tests/_emu.py writes [=])
+inline void launch(unsigned grid, unsigned block, void* stream, std::function<void()> body) {
+    enqueue(stream, [grid, block, body]() { launch(grid, block, body); });
+}
+
 inline int tid() { return current()->cur; }
 inline int lane() { return current()->cur & (W - 1); }
 inline int warp_base() { return current()->cur & ~(W - 1); }
@@ -233,7 +270,7 @@ static emu::GridDimT gridDim;
 typedef void* cudaStream_t;
 // the two runtime calls the launch_* functions make
 #define cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, kernel, threads, smem) (*(out) = 2)
-static inline int cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return 0; }
+static inline int cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t s) { emu::enqueue(s, [=]() { memset(p, v, n); }); return 0; }
 
 template <typename T> static inline uint64_t emu_raw(T v) { static_assert(sizeof(T) <= 8, "payload"); uint64_t r = 0; memcpy(&r, &v, sizeof(T)); return r; }
 template <typename T> static inline T emu_val(uint64_t r) { T v; memcpy(&v, &r, sizeof(T)); return v; }

@@ -83,3 +83,29 @@ def test_sketch_variant_1_through_the_emulated_library(emulated):
     last = run.stdout.strip().splitlines()[-1]
     assert "passed" in last and "failed" not in last, tail
     assert int(last.split(" passed")[0].split()[-1]) >= 15, tail
+
+
+def test_gpu_parity_suite_with_deferred_stream_execution(tmp_path):
+    """The same library on the ADVERSARIAL serialisation of stream semantics (-DEMU_DEFERRED, see
+    tests/cpp/emu_stub/cuda_runtime.h): asynchronous copies and kernels stay queued until the host, or another stream
+    through an event, really waits for them; pinned memory is read / written only when the copy executes.  A host
+    read of a result, or a reuse of a staging buffer, that is not ordered by a real synchronisation then sees
+    poisoned or stale bytes and the parity tests fail.  (Removing the d2h-stream synchronisation of the piece
+    pipeline makes this test fail while the eager emulator still passes.)"""
+    os.environ["MDBG_EMU_EXTRA_FLAGS"] = "-DEMU_DEFERRED"
+    try:
+        lib = _emu.build_emulated_library(str(tmp_path))
+    finally:
+        del os.environ["MDBG_EMU_EXTRA_FLAGS"]
+    env = dict(os.environ, MDBG_EMU_LIB=lib)
+    # the tests that exercise host-side sequencing (the kernels themselves are covered by the eager run above)
+    pick = ("piece or packed or count or rescue or next_k or multi_k or edge or full_path or side_outputs_vs or sentinel "
+            "or variants or table_full or bad_host or empty or smoke or density")
+    run = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "-m", "gpu", "-q", "-x",
+                          "-p", "no:cacheprovider", "-k", pick], cwd=ROOT, env=env, capture_output=True, text=True,
+                         timeout=3000)
+    tail = run.stdout[-2500:] + run.stderr[-1500:]
+    assert run.returncode == 0, tail
+    last = run.stdout.strip().splitlines()[-1]
+    assert "passed" in last and "failed" not in last, tail
+    assert int(last.split(" passed")[0].split()[-1]) >= 20, tail
