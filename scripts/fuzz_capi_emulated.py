@@ -56,7 +56,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=120)
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--deferred", action="store_true", help="adversarial stream execution (-DEMU_DEFERRED)")
     a = ap.parse_args()
+    if a.deferred:
+        os.environ["MDBG_EMU_EXTRA_FLAGS"] = (os.environ.get("MDBG_EMU_EXTRA_FLAGS", "") + " -DEMU_DEFERRED").strip()
     import _emu
     from metamdbg_b200 import _capi
     tmp = tempfile.mkdtemp(prefix="mdbg_emu_")

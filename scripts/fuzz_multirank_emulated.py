@@ -32,7 +32,7 @@ def main():
         tmp = tempfile.mkdtemp(prefix="mdbg_emu_mr_")
         lib = _emu.build_emulated_library(tmp)
         subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-o", os.path.join(tmp, "libnccl.so.2"),
-                        os.path.join(ROOT, "tests", "cpp", "fake_nccl.cpp"), "-lpthread"], check=True)
+                        os.path.join(ROOT, "tests", "cpp", "fake_nccl.cpp"), "-lpthread", "-ldl"], check=True)
         env = dict(os.environ, MDBG_FUZZ_CHILD="1", MDBG_EMU_LIB=lib,
                    LD_LIBRARY_PATH=tmp + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
         sys.exit(subprocess.run([sys.executable] + sys.argv, env=env).returncode)

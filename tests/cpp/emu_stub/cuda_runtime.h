@@ -77,6 +77,10 @@ static inline cudaError_t cudaStreamSynchronize(cudaStream_t st) {
     if (s) emu::drain(s, s->submitted);
     return cudaSuccess;
 }
+// hook for tests/cpp/fake_nccl.cpp (found with dlsym): a collective first drains the rank's stream, as the CUDA-aware
+// build does with cudaStreamSynchronize
+extern "C" __attribute__((used, visibility("default"))) inline void emu_stream_synchronize(void* st) { cudaStreamSynchronize((cudaStream_t)st); }
+
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind kind, cudaStream_t st) {
 #ifdef EMU_DEFERRED
     if (st && n) {

@@ -11,6 +11,8 @@
 #ifdef FAKE_NCCL_CUDA
 #include <cuda_runtime.h>
 #endif
+#include <dlfcn.h>
+
 #include <condition_variable>
 #include <cstdint>
 #include <cstring>
@@ -26,7 +28,11 @@ inline void copy_bytes(void* d, const void* s, size_t n) { cudaMemcpy(d, s, n, c
 inline void drain(void* stream) { cudaStreamSynchronize((cudaStream_t)stream); }
 #else
 inline void copy_bytes(void* d, const void* s, size_t n) { memcpy(d, s, n); }
-inline void drain(void*) {}
+// the emulated library built with -DEMU_DEFERRED queues stream work; it exports a hook to flush a stream
+inline void drain(void* stream) {
+    static void (*hook)(void*) = (void (*)(void*))dlsym(RTLD_DEFAULT, "emu_stream_synchronize");
+    if (hook && stream) hook(stream);
+}
 #endif
 
 struct Barrier {

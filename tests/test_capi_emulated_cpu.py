@@ -38,7 +38,7 @@ def emulated(tmp_path_factory):
     lib = _emu.build_emulated_library(d)
     shutil.copy(lib, os.path.join(d, "libmdbg_b200.so"))
     subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-o", os.path.join(d, "libnccl.so.2"),
-                    os.path.join(ROOT, "tests", "cpp", "fake_nccl.cpp"), "-lpthread"], check=True)
+                    os.path.join(ROOT, "tests", "cpp", "fake_nccl.cpp"), "-lpthread", "-ldl"], check=True)
     env = dict(os.environ, MDBG_EMU_LIB=lib, LD_LIBRARY_PATH=d + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
     return lib, env
 
@@ -98,6 +98,13 @@ def test_gpu_parity_suite_with_deferred_stream_execution(tmp_path):
     finally:
         del os.environ["MDBG_EMU_EXTRA_FLAGS"]
     env = dict(os.environ, MDBG_EMU_LIB=lib)
+    # three ranks over the fake NCCL (it flushes the rank's stream through the library's emu_stream_synchronize hook)
+    subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-o", str(tmp_path / "libnccl.so.2"),
+                    os.path.join(ROOT, "tests", "cpp", "fake_nccl.cpp"), "-lpthread", "-ldl"], check=True)
+    mr = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu_multirank_child.py"), "3", "4", "120"],
+                        env=dict(env, LD_LIBRARY_PATH=str(tmp_path) + os.pathsep + os.environ.get("LD_LIBRARY_PATH", "")),
+                        capture_output=True, text=True, timeout=900)
+    assert mr.returncode == 0 and mr.stdout.strip().endswith("OK"), mr.stdout[-2000:] + mr.stderr[-3000:]
     # the tests that exercise host-side sequencing (the kernels themselves are covered by the eager run above)
     pick = ("piece or packed or count or rescue or next_k or multi_k or edge or full_path or side_outputs_vs or sentinel "
             "or variants or table_full or bad_host or empty or smoke or density")
