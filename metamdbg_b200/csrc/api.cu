@@ -1115,6 +1115,93 @@ static mdbg_status sketch_host_batch(mdbg_ctx* ctx, const uint8_t* bases, const 
     uint64_t n_direct_pieces = 0;
     double pack_seconds = 0;
     uint64_t pack_bytes = 0;
+    // worst-case ASCII spill of a piece must fit the pinned staging before the workers start on it
+    const auto reserve_spill = [&](uint32_t r0, uint32_t r1, uint64_t asc_used) -> mdbg_status {
+        const uint64_t piece_bytes = offsets[r1] - offsets[r0] + 16ull * (r1 - r0);
+        if (ctx->h_asc.cap < asc_used + piece_bytes) {
+            PinBuf bigger;
+            CKS(ensure_pin(ctx, bigger, asc_used + piece_bytes));
+            if (ctx->h_asc.p && asc_used) {
+                CK(cudaStreamSynchronize(cs));                           // earlier spill copies still read the old buffer
+                memcpy(bigger.p, ctx->h_asc.p, asc_used);
+            }
+            release(ctx->h_asc);
+            ctx->h_asc = bigger;
+        }
+        return MDBG_OK;
+    };
+    const auto start_pack = [&](uint32_t r0, uint32_t r1) {
+        return host_pack_start(ctx->pool, bases, offsets, r0, r1, pk_off.data(), ctx->h_pack.as<uint32_t>(),
+                               ctx->h_src.as<uint64_t>(), ctx->h_asc.as<uint8_t>(), &asc_cursor);
+    };
+    // copies of a packed piece [r0, r1) whose spill area ends at asc_end, then its sketch launch
+    const auto enqueue_packed_piece = [&](SketchArgs& a, size_t i, uint32_t r0, uint32_t r1, uint64_t asc_end) -> mdbg_status {
+        if (spill_base) {                                                // spilled reads live behind the mirror area
+            uint64_t* src = ctx->h_src.as<uint64_t>();
+            for (uint32_t r = r0; r < r1; r++)
+                if (src[r] & SRC_ASCII) src[r] = SRC_ASCII | (spill_base + (src[r] & ~SRC_ASCII));
+        }
+        const uint64_t w0 = pk_off[r0], w1 = pk_off[r1];
+        if (w1 > w0)
+            CK(cudaMemcpyAsync(ctx->d_pack.as<uint32_t>() + w0, ctx->h_pack.as<uint32_t>() + w0, (w1 - w0) * 4,
+                               cudaMemcpyHostToDevice, cs));
+        CK(cudaMemcpyAsync(ctx->d_src.as<uint64_t>() + r0, ctx->h_src.as<uint64_t>() + r0, (size_t)(r1 - r0) * 8,
+                           cudaMemcpyHostToDevice, cs));
+        ctx->h2d_bytes += (w1 - w0) * 4 + (uint64_t)(r1 - r0) * 8;
+        if (asc_end > asc_sent) {
+            if (ctx->d_bases.cap < spill_base + asc_end + 64) {          // grow, keeping what is already there
+                CK(cudaStreamSynchronize(cs));
+                CK(cudaStreamSynchronize(s));
+                CKS(ensure(ctx, ctx->d_bases,
+                           std::min<uint64_t>(spill_base + asc_cap, spill_base + 2 * asc_end + (uint64_t(64) << 20)), true));
+            }
+            CK(cudaMemcpyAsync(ctx->d_bases.as<uint8_t>() + spill_base + asc_sent, ctx->h_asc.as<uint8_t>() + asc_sent,
+                               asc_end - asc_sent, cudaMemcpyHostToDevice, cs));
+            ctx->h2d_bytes += asc_end - asc_sent;
+            asc_sent = asc_end;
+        }
+        CK(cudaEventRecord(ctx->sub_ev[i], cs));
+        CK(cudaStreamWaitEvent(s, ctx->sub_ev[i], 0));
+        a.bases = ctx->d_bases.as<uint8_t>();
+        a.bases_end = ctx->d_bases.p ? ctx->d_bases.as<uint8_t>() + ctx->d_bases.cap - 32 : nullptr;
+        a.read_begin = r0;
+        a.read_end = r1;
+        a.cursor = &ctx->d_small->sub_cursor[i];
+        launch_sketch(a, ctx->sm_count, s);
+        CKS(check_launch(ctx, "sketch_kernel", 1));
+        if (pipe) CKS(pipe->launched(i));
+        return MDBG_OK;
+    };
+    // Plain packed transfer: piece i+1 is handed to the workers BEFORE piece i's copies, launches and piece-pipeline
+    // bookkeeping are enqueued (~20 driver calls, ~0.1 ms: 8 % of a piece's packing time on 16 threads), so the
+    // packer -- the bottleneck of the host path -- never waits for the enqueuing thread.
+    PackJob* job_in_flight = nullptr;
+    struct JobGuard {                                                    // an early error return must not leave workers
+        HostPool*& pool; PackJob*& job;                                  // running on the caller's buffers
+        ~JobGuard() { if (job) { host_pack_wait(pool, job); job = nullptr; } }
+    } job_guard{ctx->pool, job_in_flight};
+    const Feeder overlapped_feeder = [&](SketchArgs& a) -> mdbg_status {
+        a.read_src = ctx->d_src.as<uint64_t>();
+        a.packed = ctx->d_pack.as<uint32_t>();
+        CKS(reserve_spill(subs[0].r0, subs[0].r1, 0));
+        auto t_pack = std::chrono::steady_clock::now();
+        job_in_flight = start_pack(subs[0].r0, subs[0].r1);
+        for (size_t i = 0; i < subs.size(); i++) {
+            const uint32_t r0 = subs[i].r0, r1 = subs[i].r1;
+            host_pack_wait(ctx->pool, job_in_flight);
+            job_in_flight = nullptr;
+            pack_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_pack).count();
+            pack_bytes += offsets[r1] - offsets[r0];
+            const uint64_t asc_end = asc_cursor.load();                  // spill of pieces 0 .. i, complete
+            if (i + 1 < subs.size()) {
+                CKS(reserve_spill(subs[i + 1].r0, subs[i + 1].r1, asc_end));
+                t_pack = std::chrono::steady_clock::now();
+                job_in_flight = start_pack(subs[i + 1].r0, subs[i + 1].r1);
+            }
+            CKS(enqueue_packed_piece(a, i, r0, r1, asc_end));
+        }
+        return MDBG_OK;
+    };
     const Feeder feeder = [&](SketchArgs& a) -> mdbg_status {
         a.read_src = ctx->d_src.as<uint64_t>();
         a.packed = ctx->d_pack.as<uint32_t>();
@@ -1132,67 +1219,31 @@ static mdbg_status sketch_host_batch(mdbg_ctx* ctx, const uint8_t* bases, const 
                                    cudaMemcpyHostToDevice, cs));
                 ctx->h2d_bytes += (hi - lo) + (uint64_t)(r1 - r0) * 8;
                 n_direct_pieces++;
+                CK(cudaEventRecord(ctx->sub_ev[i], cs));
+                CK(cudaStreamWaitEvent(s, ctx->sub_ev[i], 0));
+                a.bases = ctx->d_bases.as<uint8_t>();
+                a.bases_end = ctx->d_bases.p ? ctx->d_bases.as<uint8_t>() + ctx->d_bases.cap - 32 : nullptr;
+                a.read_begin = r0;
+                a.read_end = r1;
+                a.cursor = &ctx->d_small->sub_cursor[i];
+                launch_sketch(a, ctx->sm_count, s);
+                CKS(check_launch(ctx, "sketch_kernel", 1));
+                if (pipe) CKS(pipe->launched(i));
             } else {
-                // worst-case ASCII spill of this piece must fit the pinned staging before the workers start
-                const uint64_t piece_bytes = offsets[r1] - offsets[r0] + 16ull * (r1 - r0);
-                if (ctx->h_asc.cap < asc_cursor.load() + piece_bytes) {
-                    PinBuf bigger;
-                    CKS(ensure_pin(ctx, bigger, asc_cursor.load() + piece_bytes));
-                    if (ctx->h_asc.p && asc_cursor.load()) {
-                        CK(cudaStreamSynchronize(cs));                       // earlier spill copies still read the old buffer
-                        memcpy(bigger.p, ctx->h_asc.p, asc_cursor.load());
-                    }
-                    release(ctx->h_asc);
-                    ctx->h_asc = bigger;
-                }
+                CKS(reserve_spill(r0, r1, asc_cursor.load()));
                 const auto t_pack = std::chrono::steady_clock::now();
                 host_pack_reads(ctx->pool, bases, offsets, r0, r1, pk_off.data(), ctx->h_pack.as<uint32_t>(),
                                 ctx->h_src.as<uint64_t>(), ctx->h_asc.as<uint8_t>(), &asc_cursor);
                 pack_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_pack).count();
                 pack_bytes += offsets[r1] - offsets[r0];
-                if (spill_base) {                                            // spilled reads live behind the mirror area
-                    uint64_t* src = ctx->h_src.as<uint64_t>();
-                    for (uint32_t r = r0; r < r1; r++)
-                        if (src[r] & SRC_ASCII) src[r] = SRC_ASCII | (spill_base + (src[r] & ~SRC_ASCII));
-                }
-                const uint64_t w0 = pk_off[r0], w1 = pk_off[r1];
-                if (w1 > w0)
-                    CK(cudaMemcpyAsync(ctx->d_pack.as<uint32_t>() + w0, ctx->h_pack.as<uint32_t>() + w0, (w1 - w0) * 4,
-                                       cudaMemcpyHostToDevice, cs));
-                CK(cudaMemcpyAsync(ctx->d_src.as<uint64_t>() + r0, ctx->h_src.as<uint64_t>() + r0, (size_t)(r1 - r0) * 8,
-                                   cudaMemcpyHostToDevice, cs));
-                ctx->h2d_bytes += (w1 - w0) * 4 + (uint64_t)(r1 - r0) * 8;
-                const uint64_t asc_now = asc_cursor.load();
-                if (asc_now > asc_sent) {
-                    if (ctx->d_bases.cap < spill_base + asc_now + 64) {      // grow, keeping what is already there
-                        CK(cudaStreamSynchronize(cs));
-                        CK(cudaStreamSynchronize(s));
-                        CKS(ensure(ctx, ctx->d_bases,
-                                   std::min<uint64_t>(spill_base + asc_cap, spill_base + 2 * asc_now + (uint64_t(64) << 20)),
-                                   true));
-                    }
-                    CK(cudaMemcpyAsync(ctx->d_bases.as<uint8_t>() + spill_base + asc_sent,
-                                       ctx->h_asc.as<uint8_t>() + asc_sent, asc_now - asc_sent, cudaMemcpyHostToDevice, cs));
-                    ctx->h2d_bytes += asc_now - asc_sent;
-                    asc_sent = asc_now;
-                }
+                CKS(enqueue_packed_piece(a, i, r0, r1, asc_cursor.load()));
             }
-            CK(cudaEventRecord(ctx->sub_ev[i], cs));
-            CK(cudaStreamWaitEvent(s, ctx->sub_ev[i], 0));
-            a.bases = ctx->d_bases.as<uint8_t>();
-            a.bases_end = ctx->d_bases.p ? ctx->d_bases.as<uint8_t>() + ctx->d_bases.cap - 32 : nullptr;
-            a.read_begin = r0;
-            a.read_end = r1;
-            a.cursor = &ctx->d_small->sub_cursor[i];
-            launch_sketch(a, ctx->sm_count, s);
-            CKS(check_launch(ctx, "sketch_kernel", 1));
-            if (pipe) CKS(pipe->launched(i));
         }
         return MDBG_OK;
     };
     ctx->last_direct_pieces = 0;
     const mdbg_status st = done(sketch_internal(ctx, ctx->d_bases.as<uint8_t>(), ctx->d_offsets.as<uint64_t>(), n_reads, n_bases,
-                                                append, false, nullptr, &feeder, pipe));
+                                                append, false, nullptr, can_direct ? &feeder : &overlapped_feeder, pipe));
     ctx->last_direct_pieces = n_direct_pieces;
     ctx->last_pieces = subs.size();
     if (pack_seconds > 0) {

@@ -64,6 +64,12 @@ public:
     // kernel launch enqueued in between, so both sides first spin for a moment (~100 us) before they sleep on the
     // condition variable: a futex round trip per worker per piece otherwise costs ~0.2 ms of a ~1.5 ms piece.
     void run(const std::function<void(int)>& f) {
+        start(f);
+        wait();
+    }
+    // start() hands f to every worker and returns; wait() blocks until all of them are done with it.  One job at a
+    // time; f must stay alive until wait() returns.
+    void start(const std::function<void(int)>& f) {
         {
             std::lock_guard<std::mutex> g(m_);
             job_ = &f;
@@ -71,6 +77,8 @@ public:
             gen_.fetch_add(1, std::memory_order_release);
         }
         cv_.notify_all();
+    }
+    void wait() {
         for (int spin = 0; spin < kSpin && pending_.load(std::memory_order_acquire) != 0; spin++) _mm_pause();
         if (pending_.load(std::memory_order_acquire) != 0) {
             std::unique_lock<std::mutex> g(m_);
@@ -269,14 +277,22 @@ inline bool pack_read(const uint8_t* s, uint64_t len, uint32_t* dst) {
 
 const char* host_pack_isa() { return g_isa == 2 ? "avx512" : g_isa == 1 ? "avx2" : "scalar"; }
 
-void host_pack_reads(HostPool* pool, const uint8_t* bases, const uint64_t* offsets, uint32_t r0, uint32_t r1,
-                     const uint64_t* pk_off, uint32_t* pack_out, uint64_t* src_out, uint8_t* asc_out,
-                     std::atomic<uint64_t>* asc_cursor) {
-    std::atomic<uint32_t> next{r0};
-    const uint32_t grain = 32;
-    const std::function<void(int)> body = [&](int) {
+// one piece being packed: lives on the heap so that the workers can go on while the caller enqueues the previous
+// piece's copies and launches
+struct PackJob {
+    std::atomic<uint32_t> next;
+    std::function<void(int)> body;
+};
+
+PackJob* host_pack_start(HostPool* pool, const uint8_t* bases, const uint64_t* offsets, uint32_t r0, uint32_t r1,
+                         const uint64_t* pk_off, uint32_t* pack_out, uint64_t* src_out, uint8_t* asc_out,
+                         std::atomic<uint64_t>* asc_cursor) {
+    PackJob* job = new PackJob();
+    job->next.store(r0);
+    job->body = [=](int) {
+        const uint32_t grain = 32;
         for (;;) {
-            const uint32_t b = next.fetch_add(grain);
+            const uint32_t b = job->next.fetch_add(grain);
             if (b >= r1) break;
             const uint32_t e = b + grain < r1 ? b + grain : r1;
             for (uint32_t r = b; r < e; r++) {
@@ -292,7 +308,20 @@ void host_pack_reads(HostPool* pool, const uint8_t* bases, const uint64_t* offse
             }
         }
     };
-    pool->run(body);
+    pool->start(job->body);
+    return job;
+}
+
+void host_pack_wait(HostPool* pool, PackJob* job) {
+    if (!job) return;
+    pool->wait();
+    delete job;
+}
+
+void host_pack_reads(HostPool* pool, const uint8_t* bases, const uint64_t* offsets, uint32_t r0, uint32_t r1,
+                     const uint64_t* pk_off, uint32_t* pack_out, uint64_t* src_out, uint8_t* asc_out,
+                     std::atomic<uint64_t>* asc_cursor) {
+    host_pack_wait(pool, host_pack_start(pool, bases, offsets, r0, r1, pk_off, pack_out, src_out, asc_out, asc_cursor));
 }
 
 }  // namespace mdbg

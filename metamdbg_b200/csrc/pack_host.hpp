@@ -21,4 +21,13 @@ void host_pack_reads(HostPool* pool, const uint8_t* bases, const uint64_t* offse
                      const uint64_t* pk_off, uint32_t* pack_out, uint64_t* src_out, uint8_t* asc_out,
                      std::atomic<uint64_t>* asc_cursor);
 
+// The same in two halves: host_pack_start hands the piece to the workers and returns, host_pack_wait blocks until
+// it is packed (and frees the job).  One job per pool at a time.  The host-batch path uses this to enqueue piece
+// i's copies and kernel launches (~20 driver calls) while piece i+1 is already being packed.
+struct PackJob;
+PackJob* host_pack_start(HostPool* pool, const uint8_t* bases, const uint64_t* offsets, uint32_t r0, uint32_t r1,
+                         const uint64_t* pk_off, uint32_t* pack_out, uint64_t* src_out, uint8_t* asc_out,
+                         std::atomic<uint64_t>* asc_cursor);
+void host_pack_wait(HostPool* pool, PackJob* job);
+
 }  // namespace mdbg

@@ -39,8 +39,38 @@ int main() {
                     asc.data(), &cur);                               // two ranges, like two pipeline pieces
     host_pack_reads(pool, bases.data(), offs.data(), (uint32_t)reads.size() / 2, (uint32_t)reads.size(), pk.data(),
                     pack.data(), src.data(), asc.data(), &cur);
+    // the two-halves form the host-batch path uses: piece i+1 is already being packed while piece i is consumed
+    std::vector<uint32_t> pack2(pk.back() + 16, 0xFFFFFFFFu);
+    std::vector<uint64_t> src2(reads.size());
+    std::vector<uint8_t> asc2(asc.size());
+    std::atomic<uint64_t> cur2{0};
+    int bad_overlap = 0;
+    {
+        const uint32_t n_pieces = 16, per = (uint32_t)reads.size() / n_pieces;
+        auto lo = [&](uint32_t p) { return p * per; };
+        auto hi = [&](uint32_t p) { return p + 1 == n_pieces ? (uint32_t)reads.size() : (p + 1) * per; };
+        PackJob* job = host_pack_start(pool, bases.data(), offs.data(), lo(0), hi(0), pk.data(), pack2.data(), src2.data(),
+                                       asc2.data(), &cur2);
+        for (uint32_t p = 0; p < n_pieces; p++) {
+            host_pack_wait(pool, job);
+            job = nullptr;
+            const uint64_t asc_end = cur2.load();
+            if (p + 1 < n_pieces)
+                job = host_pack_start(pool, bases.data(), offs.data(), lo(p + 1), hi(p + 1), pk.data(), pack2.data(),
+                                      src2.data(), asc2.data(), &cur2);
+            for (uint32_t r = lo(p); r < hi(p); r++) {                // "enqueue piece p": its data must be final by now
+                if (src2[r] >> 63) { if ((src2[r] & ~(1ull << 63)) + reads[r].size() > asc_end) bad_overlap++; continue; }
+                for (size_t w = 0; w < (reads[r].size() + 15) / 16; w++) {
+                    uint32_t want = 0;
+                    for (size_t j = 16 * w; j < reads[r].size() && j < 16 * w + 16; j++)
+                        want |= (((unsigned char)reads[r][j] >> 1) & 3u) << (2 * (j % 16));
+                    if (pack2[pk[r] + w] != want) { bad_overlap++; break; }
+                }
+            }
+        }
+    }
     host_pool_destroy(pool);
-    int bad = 0, dirty = 0;
+    int bad = bad_overlap, dirty = 0;
     for (size_t r = 0; r < reads.size(); r++) {
         const std::string& s = reads[r];
         bool clean = true;
