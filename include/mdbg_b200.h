@@ -281,7 +281,10 @@ mdbg_status mdbg_count_add_store_next_k(mdbg_ctx* ctx, uint64_t read_lo, uint64_
  * dereplicated keys are what the reference writes to edges.bin and builds its edge MPHF over.  hashes[2*i] = low
  * 64 bits, hashes[2*i+1] = high 64 bits (the u128 as it lies in edges.bin); order unspecified; n_edges =
  * EdgeIndexer::_nbEdges; checksum = EdgeIndexer::_checksum (sum of the keys truncated to 64 bits).  The arrays
- * stay valid until the next call on the context.  Single context only. */
+ * stay valid until the next call on the context.  With more than one rank the call is COLLECTIVE and must follow
+ * mdbg_count_merge: every rank derives the keys of the nodes it owns, the distinct local keys travel to their owner
+ * rank (same owner function as the count table) and are dereplicated there; each rank returns the keys it owns, and
+ * the union over the ranks is the reference's key set (n_edges and checksum add up). */
 typedef struct {
     uint32_t k;
     uint64_t n_nodes;             /* table entries that contributed */

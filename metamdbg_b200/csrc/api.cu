@@ -1940,8 +1940,8 @@ mdbg_status mdbg_edges_index(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_edges_o
     if (!ctx || !out) return MDBG_ERR_ARG;
     if (!ctx->t_active) return fail(ctx, MDBG_ERR_STATE, "mdbg_edges_index before mdbg_count_begin");
     if (ctx->t_k < 2) return fail(ctx, MDBG_ERR_ARG, "k must be >= 2");
-    if (ctx->n_ranks > 1)
-        return fail(ctx, MDBG_ERR_STATE, "mdbg_edges_index is single-context (the keys of several ranks would need an owner exchange)");
+    if (ctx->n_ranks > 1 && (!ctx->nccl_comm || !ctx->t_merged))
+        return fail(ctx, MDBG_ERR_STATE, "multi-rank mdbg_edges_index needs the merged table: call mdbg_count_merge first");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     const uint32_t thr = count_threshold(min_abundance);
@@ -1966,8 +1966,88 @@ mdbg_status mdbg_edges_index(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_edges_o
     launch_edge_insert(e, s);
     CKS(check_launch(ctx, "edge_insert_kernel", 1));
     CKS(check_full(ctx, "mdbg_edges_index"));
+    uint64_t set_cap = cap;
+    if (ctx->n_ranks > 1) {
+        // Several ranks: the nodes a rank owns give it a local key set; a key can come from nodes of different
+        // ranks, so the distinct local keys travel to owner(key) in one grouped all-to-all and the owner
+        // dereplicates what it receives.  Afterwards every rank holds (and returns) the keys it owns.
+        const uint32_t R = (uint32_t)ctx->n_ranks;
+        launch_table_stats(ctx->edge_table.as<Slot>(), cap, 1u, &ctx->d_small->stats, s);
+        CKS(check_launch(ctx, "table_stats_kernel", 1));
+        CK(cudaMemcpyAsync(&ctx->h_small->stats, &ctx->d_small->stats, sizeof(TableStats), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        const uint64_t n_local = ctx->h_small->stats.n_entries;
+        CKS(ensure(ctx, ctx->o_hash, (n_local + 1) * 16));
+        CKS(ensure(ctx, ctx->o_abund, (n_local + 1) * 4));
+        CK(cudaMemsetAsync(&ctx->d_small->emit_cursor, 0, 8, s));
+        EmitArgs el{};
+        el.table = ctx->edge_table.as<Slot>();
+        el.capacity = cap;
+        el.min_count = 1;
+        el.k = ctx->t_k - 1;
+        el.out_hashes = ctx->o_hash.as<uint64_t>();
+        el.out_abund = ctx->o_abund.as<uint32_t>();
+        el.out_vecs = nullptr;
+        el.cursor = &ctx->d_small->emit_cursor;
+        launch_table_emit(el, s);
+        CKS(check_launch(ctx, "table_emit_kernel", 1));
+        CKS(ensure(ctx, ctx->m_bucket, (size_t)(2 * R + R * R) * 8));
+        uint64_t* d_cnt = ctx->m_bucket.as<uint64_t>();
+        uint64_t* d_base = d_cnt + R;
+        uint64_t* d_all = d_cnt + 2 * R;
+        CK(cudaMemsetAsync(d_cnt, 0, R * 8, s));
+        BucketKeyArgs b{};
+        b.keys = ctx->o_hash.as<uint64_t>();
+        b.n = n_local;
+        b.n_ranks = R;
+        b.bucket_count = reinterpret_cast<unsigned long long*>(d_cnt);
+        b.pass = 1;
+        launch_bucket_keys(b, s);
+        CKS(check_launch(ctx, "bucket_keys_kernel(count)", n_local ? 1 : 0));
+        NK(g_nccl.AllGather(d_cnt, d_all, R, NCCL_UINT64, ctx->nccl_comm, s));
+        std::vector<uint64_t> all((size_t)R * R);
+        CK(cudaMemcpyAsync(all.data(), d_all, (size_t)R * R * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        std::vector<uint64_t> send_cnt(R), send_base(R), recv_cnt(R), recv_base(R);
+        uint64_t send_total = 0, recv_total = 0;
+        for (uint32_t d = 0; d < R; d++) {
+            send_cnt[d] = all[(size_t)ctx->rank * R + d];
+            send_base[d] = send_total;
+            send_total += send_cnt[d];
+            recv_cnt[d] = all[(size_t)d * R + ctx->rank];
+            recv_base[d] = recv_total;
+            recv_total += recv_cnt[d];
+        }
+        CKS(ensure(ctx, ctx->prev_stage_h, (send_total + 1) * 16));        // send side (free at this point of the flow)
+        CKS(ensure(ctx, ctx->m_recv_vecs, (recv_total + 1) * 16));         // receive side
+        CK(cudaMemcpyAsync(d_base, send_base.data(), R * 8, cudaMemcpyHostToDevice, s));
+        CK(cudaMemsetAsync(d_cnt, 0, R * 8, s));
+        b.bucket_base = d_base;
+        b.out_keys = ctx->prev_stage_h.as<uint64_t>();
+        b.pass = 2;
+        launch_bucket_keys(b, s);
+        CKS(check_launch(ctx, "bucket_keys_kernel(scatter)", n_local ? 1 : 0));
+        NK(g_nccl.GroupStart());
+        for (uint32_t d = 0; d < R; d++) {
+            if (send_cnt[d])
+                NK(g_nccl.Send(ctx->prev_stage_h.as<uint64_t>() + 2 * send_base[d], send_cnt[d] * 16, NCCL_UINT8, (int)d,
+                               ctx->nccl_comm, s));
+            if (recv_cnt[d])
+                NK(g_nccl.Recv(ctx->m_recv_vecs.as<uint64_t>() + 2 * recv_base[d], recv_cnt[d] * 16, NCCL_UINT8, (int)d,
+                               ctx->nccl_comm, s));
+        }
+        NK(g_nccl.GroupEnd());
+        set_cap = pow2ceil((recv_total < 512 ? 512 : recv_total) * 2);
+        CKS(ensure(ctx, ctx->edge_table, set_cap * sizeof(Slot)));
+        CK(cudaMemsetAsync(ctx->edge_table.p, 0, set_cap * sizeof(Slot), s));
+        CK(cudaMemsetAsync(&ctx->d_small->full_flag, 0, sizeof(uint32_t), s));
+        launch_insert_keys(ctx->m_recv_vecs.as<uint64_t>(), recv_total, ctx->edge_table.as<Slot>(), set_cap - 1,
+                           &ctx->d_small->full_flag, s);
+        CKS(check_launch(ctx, "insert_keys_kernel", recv_total ? 1 : 0));
+        CKS(check_full(ctx, "mdbg_edges_index (owner side)"));
+    }
     // the set's statistics and contents: every entry has value 1
-    launch_table_stats(ctx->edge_table.as<Slot>(), cap, 1u, &ctx->d_small->stats, s);
+    launch_table_stats(ctx->edge_table.as<Slot>(), set_cap, 1u, &ctx->d_small->stats, s);
     CKS(check_launch(ctx, "table_stats_kernel", 1));
     CK(cudaMemcpyAsync(&ctx->h_small->stats, &ctx->d_small->stats, sizeof(TableStats), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -1978,7 +2058,7 @@ mdbg_status mdbg_edges_index(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_edges_o
     CK(cudaMemsetAsync(&ctx->d_small->emit_cursor, 0, 8, s));
     EmitArgs em{};
     em.table = ctx->edge_table.as<Slot>();
-    em.capacity = cap;
+    em.capacity = set_cap;
     em.min_count = 1;
     em.k = ctx->t_k - 1;
     em.out_hashes = ctx->o_hash.as<uint64_t>();

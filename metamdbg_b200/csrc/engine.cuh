@@ -226,6 +226,15 @@ struct EdgeArgs {
     Slot* edges; uint64_t edge_mask; uint32_t* full_flag;
 };
 void launch_edge_insert(const EdgeArgs& a, cudaStream_t s);
+struct BucketKeyArgs {
+    const uint64_t* keys; uint64_t n; uint32_t n_ranks;      // keys: [2n] {lo, hi}
+    unsigned long long* bucket_count;                        // [n_ranks], zeroed before each pass
+    const uint64_t* bucket_base;                             // [n_ranks], pass 2
+    uint64_t* out_keys;                                      // pass 2
+    int pass;
+};
+void launch_bucket_keys(const BucketKeyArgs& a, cudaStream_t s);
+void launch_insert_keys(const uint64_t* keys, uint64_t n, Slot* table, uint64_t mask, uint32_t* full_flag, cudaStream_t s);
 
 // multi-GPU pack: bucket every occupied slot by owner rank
 struct PackArgs {

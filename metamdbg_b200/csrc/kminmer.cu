@@ -539,6 +539,38 @@ void launch_edge_insert(const EdgeArgs& a, cudaStream_t s) {
     edge_insert_kernel<<<(unsigned)blocks, 256, 0, s>>>(a);
 }
 
+// multi-rank edge keys: bucket the local distinct keys by owner rank (pass 1 counts, pass 2 scatters), and on the
+// owner insert what arrived into a fresh set table -- a key produced by nodes of several ranks is kept once
+__global__ void __launch_bounds__(256) bucket_keys_kernel(const BucketKeyArgs a) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const uint64_t lo = a.keys[2 * i], hi = a.keys[2 * i + 1];
+    const uint32_t dst = owner_of(hi, a.n_ranks);
+    const unsigned long long slot = atomicAdd(&a.bucket_count[dst], 1ULL);
+    if (a.pass == 2) {
+        const uint64_t pos = a.bucket_base[dst] + slot;
+        a.out_keys[2 * pos] = lo;
+        a.out_keys[2 * pos + 1] = hi;
+    }
+}
+
+void launch_bucket_keys(const BucketKeyArgs& a, cudaStream_t s) {
+    if (a.n == 0) return;
+    bucket_keys_kernel<<<(unsigned)((a.n + 255) / 256), 256, 0, s>>>(a);
+}
+
+__global__ void __launch_bounds__(256) insert_keys_kernel(const uint64_t* keys, uint64_t n, Slot* table, uint64_t mask,
+                                                          uint32_t* full_flag) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (!table_put(table, mask, keys[2 * i], keys[2 * i + 1], 1u, 0ULL)) atomicExch(full_flag, 1u);
+}
+
+void launch_insert_keys(const uint64_t* keys, uint64_t n, Slot* table, uint64_t mask, uint32_t* full_flag, cudaStream_t s) {
+    if (n == 0) return;
+    insert_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(keys, n, table, mask, full_flag);
+}
+
 // ------------------------------------------------------------------ multi-GPU pack by owner rank
 constexpr int PACK_MAX_RANKS = 64;
 

@@ -65,6 +65,7 @@ def main():
         scen = dict(world=world, n_reads=n_reads, k=k, dens=dens, rescue=rescue, chain=chain, bounds=bounds)
         uid = Engine.nccl_unique_id()
         tables, errors = [None] * world, []
+        edges = [None] * world
 
         def rank_main(rank):
             try:
@@ -80,6 +81,7 @@ def main():
                 if rescue:
                     eng.count_rescue()
                 got.append(eng.count_finalize(min_ab))
+                edges[rank] = eng.edges_index(min_ab)                    # collective: keys travel to their owners
                 for kk in range(k + 1, k + 1 + chain):
                     eng.prev_from_current(min_ab)
                     eng.count_begin(kk, 0)
@@ -104,6 +106,17 @@ def main():
             rr = orc.rescue(m, mo, k, ph, pa)
             if len(rr["hashes"]):
                 ph = np.concatenate([ph, rr["hashes"]]); pa = np.concatenate([pa, np.ones(len(rr["hashes"]), np.uint32)])
+        if k >= 2:                                                        # edge keys of the first table's nodes
+            nodes = np.concatenate([tables[r][0].kminmers for r in range(world)]) if sum(len(tables[r][0].abundances) for r in range(world)) else np.zeros((0, k), np.uint32)
+            we = orc.edge_index(nodes, k)
+            got_e = set()
+            for rank in range(world):
+                for h in edges[rank]["hashes"]:
+                    key = (int(h[1]), int(h[0]))
+                    assert int(owner_of(np.uint64(key[0]), world)) == rank and key not in got_e, ("edge owner", scen)
+                    got_e.add(key)
+            assert got_e == {(int(h[0]), int(h[1])) for h in we["hashes"]}, ("edges", scen, len(got_e), len(we["hashes"]))
+            assert sum(e["checksum"] for e in edges) % 2 ** 64 == we["checksum"], ("edge checksum", scen)
         for step in range(chain + 1):
             if step:
                 nk = orc.next_k(m, mo, k + step, ph, pa)

@@ -28,6 +28,7 @@ def main():
     results, errors = [None] * n_ranks, []
     next_results = [None] * n_ranks
     rescue_results = [None] * n_ranks
+    edge_results = [None] * n_ranks
 
     def rank_main(rank):
         try:
@@ -41,6 +42,7 @@ def main():
             eng.count_add_store()
             eng.count_merge()
             results[rank] = (eng.count_finalize(2), eng.count_stats(2))
+            edge_results[rank] = eng.edges_index(2)          # collective: keys of the owned nodes -> their owner ranks
             # default mode (--min-abundance 0): rescue across ranks, then the table with the rescued abundance-1 entries
             n_resc = eng.count_rescue()
             rescue_results[rank] = (n_resc, eng.count_finalize(0))
@@ -83,6 +85,18 @@ def main():
         instances += st["n_instances"]; distinct += st["n_distinct"]
     assert merged == want and (len(want) > 3000 or n_reads < 260), (len(merged), len(want))
     assert instances == ref["n_instances"] and distinct == ref["n_distinct"], "occurrences not conserved"
+    # edge keys (CreateMdbg::EdgeIndexer) of the solid nodes: disjoint per owner, union = the oracle's key set
+    we = orc.edge_index(ref["vecs"], k)
+    got_e = set()
+    for rank, ed in enumerate(edge_results):
+        for h in ed["hashes"]:
+            key = (int(h[1]), int(h[0]))
+            assert owner_of(key[0], n_ranks) == rank and key not in got_e
+            got_e.add(key)
+    assert got_e == {(int(h[0]), int(h[1])) for h in we["hashes"]}, (len(got_e), len(we["hashes"]))
+    assert sum(ed["checksum"] for ed in edge_results) % 2 ** 64 == we["checksum"]
+    assert sum(ed["n_nodes"] for ed in edge_results) == len(ref["abundances"])
+    print(f"  edge keys: {len(got_e)} distinct over {n_ranks} owners")
     # rescue: solid + rescued entries over all ranks = the oracle's table of the whole read set
     resc = orc.rescue(pm, po, k, ref["hashes"], ref["abundances"])
     want_r = dict(want)
