@@ -136,7 +136,11 @@ mdbg_status mdbg_ctx_kernel_time_ms(mdbg_ctx* ctx, int which, float* ms);
  * offsets. */
 mdbg_status mdbg_sketch_batch(mdbg_ctx* ctx, const uint8_t* bases, const uint64_t* offsets,
                               uint32_t n_reads, int append_to_store, mdbg_sketch_out* out);
-/* Host batches without qualities cross PCIe 2-bit packed (worker threads + AVX2 inside the library, unpacked again
+/* A host batch is cut into pieces of >= 128 MB on read boundaries; packing / copying piece i+1, sketching piece i and
+ * the scan, compaction and device-to-host copy of piece i-2's share of the CSR overlap, so `out` is complete shortly
+ * after the last piece has been sketched.  `out` arrays live in pinned memory owned by the context and stay valid
+ * until the next call on it.
+ * Host batches without qualities cross PCIe 2-bit packed (worker threads + AVX-512 / AVX2 inside the library, unpacked again
  * by the sketch kernel; reads holding a byte outside "ACGT" stay ASCII, so results are identical).  on = 0 sends the
  * ASCII bytes as they are, on = 1 always packs, on = -1 (default) packs when the process has at least 12 usable CPUs
  * (cgroup quota and ranks-per-node aware), i.e. when packing outruns the PCIe transfer it saves.  on = 2
