@@ -637,6 +637,77 @@ size_t orc_edge_index(const uint32_t* vecs, size_t n, int k, uint64_t** hashes, 
     return n_out;
 }
 
+/* ------------------------------------------------------- edge values of the node set (row F1, second step)
+ * CreateMdbg::indexEdge + successorExists (src/graph/CreateMdbg.cpp:1277-1500), order-free form.  Every node offers
+ *   to the key of its normalized SUFFIX : (minimizer = first element, isReversed = suffix was reversed, isPrefix = 0)
+ *   to the key of its normalized PREFIX : (minimizer = last element,  isReversed = prefix was reversed, isPrefix = 1)
+ * successorExists folds an offer into an existing slot when the key's vector is a palindrome, or when
+ * (isReversed, isPrefix) equals the slot's or is its exact complement -- i.e. there are two orientation classes,
+ * A = {(0,0),(1,1)} and B = {(0,1),(1,0)} (a palindromic key has one class) -- and then only marks
+ * hasMultipleSuccessors; which offer of a class was recorded first depends on the thread arrival order upstream,
+ * and the consumers (getSuccessors_unitig / getPredecessors_unitig, :2039-2130, :2287-2380) use the recorded
+ * minimizer only while the class is not marked.  Canonical value per (key, class): count = 0, 1 or 2 (= two or
+ * more), and for count == 1 the single offer's minimizer / isReversed / isPrefix. */
+typedef struct { uint64_t h1, h2; uint32_t cls, min, rev, pre; } EOffer;
+static int cmp_eoffer(const void* a, const void* b) {
+    const EOffer* x = (const EOffer*)a; const EOffer* y = (const EOffer*)b;
+    if (x->h1 != y->h1) return x->h1 < y->h1 ? -1 : 1;
+    if (x->h2 != y->h2) return x->h2 < y->h2 ? -1 : 1;
+    if (x->cls != y->cls) return x->cls < y->cls ? -1 : 1;
+    return 0;
+}
+
+size_t orc_edge_values(const uint32_t* vecs, size_t n, int k, uint64_t** hashes, uint32_t** values) {
+    const int km = k - 1;
+    EOffer* of = (EOffer*)malloc((2 * n + 1) * sizeof(EOffer));
+    uint32_t* tmp = (uint32_t*)malloc((size_t)(km > 0 ? km : 1) * sizeof(uint32_t));
+    size_t m = 0;
+    for (size_t i = 0; i < n; i++) {
+        const uint32_t* v = vecs + i * (size_t)k;
+        for (int side = 1; side >= 0; side--) {          /* 1: suffix (isPrefix = 0), 0: prefix (isPrefix = 1) */
+            const uint32_t* w = v + side;
+            int rev = 1, pal = 1;
+            for (int j = 0; j < km; j++) {
+                uint32_t a = w[j], b = w[km - 1 - j];
+                if (a == b) continue;
+                rev = (a < b) ? 0 : 1;
+                break;
+            }
+            for (int j = 0; j < km / 2; j++) if (w[j] != w[km - 1 - j]) { pal = 0; break; }   /* KmerVec::isPalindrome */
+            for (int j = 0; j < km; j++) tmp[j] = rev ? w[km - 1 - j] : w[j];
+            uint64_t h[2];
+            orc_hash128(tmp, km, h);
+            const uint32_t pre = side ? 0u : 1u;
+            of[m].h1 = h[0]; of[m].h2 = h[1];
+            of[m].cls = pal ? 0u : (((uint32_t)rev == pre) ? 0u : 1u);
+            of[m].min = side ? v[0] : v[k - 1];
+            of[m].rev = (uint32_t)rev; of[m].pre = pre;
+            m++;
+        }
+    }
+    qsort(of, m, sizeof(EOffer), cmp_eoffer);
+    uint64_t* hk = (uint64_t*)malloc((2 * m + 2) * sizeof(uint64_t));
+    uint32_t* val = (uint32_t*)calloc(8 * m + 8, sizeof(uint32_t));      /* per key: 2 classes x {count, min, rev, pre} */
+    size_t ne = 0;
+    for (size_t i = 0; i < m;) {
+        size_t j = i;
+        while (j < m && of[j].h1 == of[i].h1 && of[j].h2 == of[i].h2) j++;
+        hk[2 * ne] = of[i].h1; hk[2 * ne + 1] = of[i].h2;
+        for (size_t t = i; t < j; t++) {
+            uint32_t* c = val + 8 * ne + 4 * of[t].cls;
+            if (c[0] == 0) { c[0] = 1; c[1] = of[t].min; c[2] = of[t].rev; c[3] = of[t].pre; }
+            else { c[0] = 2; c[1] = c[2] = c[3] = 0; }
+        }
+        ne++;
+        i = j;
+    }
+    free(of);
+    free(tmp);
+    *hashes = hk;
+    *values = val;
+    return ne;
+}
+
 uint64_t orc_table_checksum(const uint64_t* hashes, const uint32_t* abundances, size_t n) {
     uint64_t s = 0;
     for (size_t i = 0; i < n; i++) s += (uint64_t)abundances[i] * hashes[2 * i + 1];

@@ -127,6 +127,11 @@ size_t orc_next_k(const uint32_t* mins, const uint64_t* offs, size_t n_reads, in
  * n_edges x {h1,h2} sorted by (h1,h2); *checksum = sum of the low words.  Returns n_edges (_nbEdges). */
 size_t orc_edge_index(const uint32_t* vecs, size_t n, int k, uint64_t** hashes, uint64_t* checksum);
 
+/* CreateMdbg::indexEdge / successorExists (CreateMdbg.cpp:1277-1500) in order-free form: per distinct edge key
+ * (sorted by (h1,h2)) two orientation classes x {count (0, 1, 2 = two or more), minimizer, isReversed, isPrefix};
+ * the last three are those of the single offer when count == 1, else 0.  *values: n_edges x 8 u32. */
+size_t orc_edge_values(const uint32_t* vecs, size_t n, int k, uint64_t** hashes, uint32_t** values);
+
 /* Order-free fingerprint used by the reference's debug log
  * (src/graph/CreateMdbg.cpp:3321): sum abundance * (u64)hash128 mod 2^64,
  * where (u64)hash128 = low 64 bits = h2. */

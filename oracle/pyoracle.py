@@ -193,6 +193,8 @@ class Oracle(_Lib):
                                  C.POINTER(_u64p), C.POINTER(_u32p)]
         L.orc_edge_index.restype = C.c_size_t
         L.orc_edge_index.argtypes = [_u32p, C.c_size_t, C.c_int, C.POINTER(_u64p), C.POINTER(C.c_uint64)]
+        L.orc_edge_values.restype = C.c_size_t
+        L.orc_edge_values.argtypes = [_u32p, C.c_size_t, C.c_int, C.POINTER(_u64p), C.POINTER(_u32p)]
         L.orc_table_checksum.restype = C.c_uint64
         L.orc_table_checksum.argtypes = [_u64p, _u32p, C.c_size_t]
 
@@ -278,6 +280,14 @@ class Oracle(_Lib):
         n = self.lib.orc_edge_index(_p(vecs, _u32p), len(vecs), k, C.byref(h), C.byref(cs))
         return dict(hashes=self._take(h, 2 * n, np.uint64).reshape(n, 2), checksum=int(cs.value))
 
+    def edge_values(self, vecs, k):
+        """indexEdge in order-free form -> dict(hashes [n,2] (h1,h2) sorted, values [n,2,4]: per orientation class
+        (count 0/1/2+, minimizer, isReversed, isPrefix))."""
+        vecs = np.ascontiguousarray(vecs, dtype=np.uint32).reshape(-1, k)
+        h = _u64p(); v = _u32p()
+        n = self.lib.orc_edge_values(_p(vecs, _u32p), len(vecs), k, C.byref(h), C.byref(v))
+        return dict(hashes=self._take(h, 2 * n, np.uint64).reshape(n, 2), values=self._take(v, 8 * n, np.uint32).reshape(n, 2, 4))
+
     def checksum(self, hashes: np.ndarray, abundances: np.ndarray) -> int:
         hashes = np.ascontiguousarray(hashes, dtype=np.uint64)
         abundances = np.ascontiguousarray(abundances, dtype=np.uint32)
@@ -313,6 +323,9 @@ class Reference(_Lib):
         L.ref_edge_index.restype = C.c_size_t
         L.ref_edge_index.argtypes = [_u32p, C.c_size_t, C.c_int, C.c_int, C.c_char_p, C.POINTER(_u64p),
                                      C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.ref_edge_values.restype = C.c_size_t
+        L.ref_edge_values.argtypes = [_u32p, C.c_size_t, C.c_int, C.c_int, C.c_char_p, C.POINTER(_u64p), C.POINTER(_u8p),
+                                      C.POINTER(_u32p), C.POINTER(_u8p)]
         L.ref_graph_next_k.restype = C.c_size_t
         L.ref_graph_next_k.argtypes = [_u32p, _u64p, C.c_size_t, C.c_int, _u64p, _u32p, C.c_size_t, C.c_int, C.c_int,
                                        C.c_char_p, C.POINTER(_u32p), C.POINTER(_u64p), C.POINTER(_u32p)]
@@ -359,6 +372,19 @@ class Reference(_Lib):
             n = self.lib.ref_edge_index(_p(vecs, _u32p), len(vecs), k, threads, d.encode(), C.byref(h), C.byref(ne),
                                         C.byref(cs))
         return dict(hashes=self._take(h, 2 * n, np.uint64).reshape(n, 2), nb_edges=int(ne.value), checksum=int(cs.value))
+
+    def edge_values(self, vecs, k, threads=1):
+        """The reference's own CreateMdbg::indexEdges (EdgeIndexer, BooPHF, indexEdge over all nodes) in a scratch
+        dir -> dict(hashes [n,2] (h1,h2), palindrome [n], minimizers [n,2], flags [n,2]): the raw KminmerEdge33
+        slots (flags: 1 isReversed, 2 isPrefix, 4 hasMultipleSuccessors; minimizer 0xFFFFFFFF = empty slot)."""
+        import tempfile
+        vecs = np.ascontiguousarray(vecs, dtype=np.uint32).reshape(-1, k)
+        h = _u64p(); pal = _u8p(); mn = _u32p(); fl = _u8p()
+        with tempfile.TemporaryDirectory() as d:
+            n = self.lib.ref_edge_values(_p(vecs, _u32p), len(vecs), k, threads, d.encode(), C.byref(h), C.byref(pal),
+                                         C.byref(mn), C.byref(fl))
+        return dict(hashes=self._take(h, 2 * n, np.uint64).reshape(n, 2), palindrome=self._take(pal, n, np.uint8),
+                    minimizers=self._take(mn, 2 * n, np.uint32).reshape(n, 2), flags=self._take(fl, 2 * n, np.uint8).reshape(n, 2))
 
     def graph_next_k(self, mins, offs, k, prev_hashes, prev_ab, use_counter=False, threads=1):
         import tempfile
@@ -418,3 +444,21 @@ class Reference(_Lib):
                                   purge_last_k, min_abundance, threads, C.byref(nm), C.byref(cs), C.byref(ts), C.byref(tc))
         return dict(n_solid=int(n), n_minimizers=int(nm.value), checksum=int(cs.value),
                     seconds_sketch=float(ts.value), seconds_count=float(tc.value))
+
+
+def canonical_edge_values(raw: dict) -> dict:
+    """Order-free content of the reference's KminmerEdge33 slots (Reference.edge_values): {(h1, h2): ((count, minimizer,
+    isReversed, isPrefix) of class A, ... of class B)} with class A = {(r,p): r == p} (and every slot of a
+    palindromic key), class B = {r != p}; count 2 = hasMultipleSuccessors, whose recorded minimizer is arbitrary."""
+    out = {}
+    for h, pal, mins, flags in zip(raw["hashes"], raw["palindrome"], raw["minimizers"], raw["flags"]):
+        cls = [(0, 0, 0, 0), (0, 0, 0, 0)]
+        for m, f in zip(mins, flags):
+            if int(m) == 0xFFFFFFFF:
+                continue
+            r, p, multi = int(f) & 1, (int(f) >> 1) & 1, (int(f) >> 2) & 1
+            c = 0 if (pal or r == p) else 1
+            assert cls[c][0] == 0, "two slots of one orientation class"
+            cls[c] = (2, 0, 0, 0) if multi else (1, int(m), r, p)
+        out[(int(h[0]), int(h[1]))] = tuple(cls)
+    return out

@@ -452,6 +452,65 @@ size_t ref_edge_index(const uint32_t* vecs, size_t n, int k, int n_threads, cons
     return keys.size() / 2;
 }
 
+/* CreateMdbg::indexEdges (src/graph/CreateMdbg.cpp:1177-1275): EdgeIndexer, the BooPHF over edges.bin, then indexEdge
+ * (:1277-1420) for every node of kminmerData_min.txt, with n_threads OpenMP threads.  Returns, per distinct edge key
+ * (in first-seen order of the node file), the key {high, low}, whether the key's (k-1)-min-mer is a palindrome, and the
+ * raw KminmerEdge33 slots as the reference left them: minimizer (0xFFFFFFFF = empty) and flags bit0 isReversed, bit1
+ * isPrefix, bit2 hasMultipleSuccessors.  Which node is recorded in a slot depends on the thread arrival order; the
+ * order-free content is derived from this by oracle/pyoracle.py::canonical_edge_values. */
+size_t ref_edge_values(const uint32_t* vecs, size_t n, int k, int n_threads, const char* tmp_dir, uint64_t** keys_out,
+                       uint8_t** palindrome_out, uint32_t** minimizers_out, uint8_t** flags_out) {
+    if (n_threads < 1) n_threads = 1;
+    const string dir(tmp_dir);
+    {
+        ofstream f(dir + "/kminmerData_min.txt", std::ios::binary);
+        f.write((const char*)vecs, (std::streamsize)(n * (size_t)k * sizeof(uint32_t)));
+    }
+    CreateMdbg c;
+    c._outputDir = dir;
+    c._kminmerSize = k;
+    c._nbCores = n_threads;
+    c._nbPartitions = n_threads;
+    c._mutexes.resize(1000);
+    for (size_t i = 0; i < c._mutexes.size(); i++) omp_init_lock(&c._mutexes[i]);
+    c.indexEdges();
+    vector<uint64_t> keys;
+    vector<uint8_t> pal, flags;
+    vector<uint32_t> mins;
+    unordered_set<string> seen;
+    for (size_t i = 0; i < n; i++) {
+        KmerVec vec;
+        vec._kmers.assign(vecs + i * (size_t)k, vecs + (i + 1) * (size_t)k);
+        for (int side = 0; side < 2; side++) {
+            bool rev;
+            const KmerVec e = side ? vec.suffix().normalize(rev) : vec.prefix().normalize(rev);
+            const u_int128_t h = e.hash128();
+            const string hs((const char*)&h, sizeof h);
+            if (!seen.insert(hs).second) continue;
+            const KminmerEdge33& v = c._mdbgEdges10._values[c._mdbgEdges10._keys->lookup(h)];
+            keys.push_back((uint64_t)(h >> 64));
+            keys.push_back((uint64_t)h);
+            pal.push_back(e.isPalindrome() ? 1 : 0);
+            mins.push_back(v._minimizer1);
+            flags.push_back(v._minimizer1 == (MinimizerType)-1 ? 0 : (uint8_t)((v._isReversed1 ? 1 : 0) | (v._isPrefix1 ? 2 : 0) | (v._hasMultipleSuccessors1 ? 4 : 0)));
+            mins.push_back(v._minimizer2);
+            flags.push_back(v._minimizer2 == (MinimizerType)-1 ? 0 : (uint8_t)((v._isReversed2 ? 1 : 0) | (v._isPrefix2 ? 2 : 0) | (v._hasMultipleSuccessors2 ? 4 : 0)));
+        }
+    }
+    for (size_t i = 0; i < c._mutexes.size(); i++) omp_destroy_lock(&c._mutexes[i]);
+    c._mdbgEdges10.clear();
+    const size_t ne = pal.size();
+    *keys_out = (uint64_t*)malloc((2 * ne + 2) * 8);
+    memcpy(*keys_out, keys.data(), 2 * ne * 8);
+    *palindrome_out = (uint8_t*)malloc(ne + 1);
+    memcpy(*palindrome_out, pal.data(), ne);
+    *minimizers_out = (uint32_t*)malloc((2 * ne + 2) * 4);
+    memcpy(*minimizers_out, mins.data(), 2 * ne * 4);
+    *flags_out = (uint8_t*)malloc(2 * ne + 2);
+    memcpy(*flags_out, flags.data(), 2 * ne);
+    return ne;
+}
+
 /* The reference's whole readSelection stage (ReadSelection::execute, src/readSelection/ReadSelection.hpp:92-303):
  * kseq FASTA/FASTQ parsing, HPC, sketch, complexity / quality side outputs, ordered record writer, read stats,
  * purgePalindromes.  `input_list` is the text file listing the read files (what `metaMDBG asm` writes as input.txt).

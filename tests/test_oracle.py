@@ -400,3 +400,26 @@ def test_ref_edge_indexer(oracle, reference):
     a = oracle.edge_index(nodes, 4); b = reference.edge_index(nodes, 4, threads=2)
     assert len(nodes) > 500 and set(map(tuple, a["hashes"].tolist())) == set(map(tuple, b["hashes"].tolist()))
     assert a["checksum"] == b["checksum"] and b["nb_edges"] == len(a["hashes"])
+
+
+@pytest.mark.ref
+def test_ref_edge_values_order_free_form(oracle, reference):
+    """Row F1, second step: CreateMdbg::indexEdges run for real (EdgeIndexer, BooPHF, indexEdge over every node, 1 and
+    4 OpenMP threads); its KminmerEdge33 slots, reduced to their order-free content (pyoracle.canonical_edge_values),
+    equal the oracle's restatement -- two orientation classes per key with count 0 / 1 / 2+ and the single offer's
+    minimizer and flags.  Small alphabets give palindromic keys and many branching ones."""
+    from oracle.pyoracle import canonical_edge_values
+    rng = np.random.default_rng(3)
+    for k, alpha in ((4, 30), (5, 30), (3, 12), (2, 8), (7, 50), (4, 6), (21, 40)):
+        vecs = rng.integers(0, alpha, (2500, k)).astype(np.uint32)
+        nodes = np.unique(np.array([oracle.kminmers(v, k)[0][0] for v in vecs], dtype=np.uint32), axis=0)
+        a = oracle.edge_values(nodes, k)
+        want = {(int(h[0]), int(h[1])): tuple(tuple(int(x) for x in c) for c in v) for h, v in zip(a["hashes"], a["values"])}
+        assert len(want) == len(oracle.edge_index(nodes, k)["hashes"])
+        for threads in (1, 4):
+            assert canonical_edge_values(reference.edge_values(nodes, k, threads=threads)) == want, (k, alpha, threads)
+    reads, offs = _minspace_reads(11)
+    nodes = oracle.count(reads, offs, 4, 2)["vecs"]
+    a = oracle.edge_values(nodes, 4)
+    want = {(int(h[0]), int(h[1])): tuple(tuple(int(x) for x in c) for c in v) for h, v in zip(a["hashes"], a["values"])}
+    assert canonical_edge_values(reference.edge_values(nodes, 4, threads=3)) == want and len(want) > 500
