@@ -51,7 +51,7 @@ class BatchInfo(C.Structure):
 
 class EdgesOut(C.Structure):
     _fields_ = [("k", C.c_uint32), ("n_nodes", C.c_uint64), ("n_edges", C.c_uint64), ("hashes", u64p),
-                ("checksum", C.c_uint64)]
+                ("checksum", C.c_uint64), ("values", u64p)]
 
 
 class AutotuneOut(C.Structure):

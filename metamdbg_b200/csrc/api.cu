@@ -127,7 +127,8 @@ struct mdbg_ctx {
     DevBuf foreign_vecs;
     uint64_t foreign_n = 0;
     DevBuf prev_table, prev_stage_h, prev_stage_a;
-    DevBuf edge_table;
+    DevBuf edge_table, edge_vals, o_edge_vals;
+    PinBuf ho_edge_vals;
     uint64_t prev_capacity = 0;
     DevBuf o_hash, o_abund, o_vecs;
     PinBuf ho_hash, ho_abund, ho_vecs;
@@ -697,9 +698,9 @@ void mdbg_ctx_destroy(mdbg_ctx* c) {
                       &c->scan_scratch, &c->b_off, &c->b_min, &c->b_pos, &c->b_dir, &c->s_min, &c->s_off, &c->s_rem,
                       &c->p_flags, &c->p_keep, &c->p_cnt, &c->p_newoff, &c->p_newmin, &c->table, &c->foreign_vecs,
                       &c->o_hash, &c->o_abund, &c->o_vecs, &c->d_pack, &c->d_src, &c->d_quals, &c->pad_qual, &c->pad_raw_a, &c->pad_raw_b, &c->b_qual, &c->x_sum_lo, &c->x_sum_hi, &c->x_lmin, &c->x_cplx, &c->x_low, &c->d_err_fixed, &c->d_err_tz, &c->prev_table, &c->prev_stage_h, &c->prev_stage_a, &c->m_send_vecs, &c->m_send_counts, &c->m_recv_vecs,
-                      &c->m_recv_counts, &c->m_bucket, &c->loc_off, &c->edge_table};
+                      &c->m_recv_counts, &c->m_bucket, &c->loc_off, &c->edge_table, &c->edge_vals, &c->o_edge_vals};
     for (DevBuf* b : devs) release(*b);
-    PinBuf* pins[] = {&c->h_off, &c->h_min, &c->h_pos, &c->h_dir, &c->ho_hash, &c->ho_abund, &c->ho_vecs, &c->hx_sum_lo, &c->hx_sum_hi, &c->hx_lmin, &c->hx_cplx, &c->hx_low, &c->hx_meanq, &c->h_qual, &c->h_pack, &c->h_src, &c->h_asc};
+    PinBuf* pins[] = {&c->h_off, &c->h_min, &c->h_pos, &c->h_dir, &c->ho_hash, &c->ho_abund, &c->ho_vecs, &c->hx_sum_lo, &c->hx_sum_hi, &c->hx_lmin, &c->hx_cplx, &c->hx_low, &c->hx_meanq, &c->h_qual, &c->h_pack, &c->h_src, &c->h_asc, &c->ho_edge_vals};
     for (PinBuf* b : pins) release(*b);
     if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
     if (c->d_small) cudaFree(c->d_small);
@@ -2065,8 +2066,28 @@ mdbg_status mdbg_edges_index(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_edges_o
     em.out_abund = ctx->o_abund.as<uint32_t>();
     em.out_vecs = nullptr;
     em.cursor = &ctx->d_small->emit_cursor;
-    launch_table_emit(em, s);
-    CKS(check_launch(ctx, "table_emit_kernel", 1));
+    out->values = nullptr;
+    if (ctx->n_ranks == 1) {
+        // one context: the keys come out together with their order-free edge values (indexEdge / successorExists)
+        CKS(ensure(ctx, ctx->edge_vals, set_cap * 16));
+        CKS(ensure(ctx, ctx->o_edge_vals, (n + 1) * 16));
+        CKS(ensure_pin(ctx, ctx->ho_edge_vals, (n + 1) * 16));
+        CK(cudaMemsetAsync(ctx->edge_vals.p, 0, set_cap * 16, s));
+        CK(cudaMemsetAsync(&ctx->d_small->full_flag, 0, sizeof(uint32_t), s));
+        e.edge_vals = ctx->edge_vals.as<unsigned long long>();
+        launch_edge_values(e, s);
+        CKS(check_launch(ctx, "edge_values_kernel", 1));
+        CKS(check_full(ctx, "mdbg_edges_index (values: a key is missing from the set)"));
+        launch_edge_emit(ctx->edge_table.as<Slot>(), ctx->edge_vals.as<unsigned long long>(), set_cap, ctx->o_hash.as<uint64_t>(),
+                         ctx->o_edge_vals.as<unsigned long long>(), &ctx->d_small->emit_cursor, s);
+        CKS(check_launch(ctx, "edge_emit_kernel", 1));
+        if (n) CK(cudaMemcpyAsync(ctx->ho_edge_vals.p, ctx->o_edge_vals.p, n * 16, cudaMemcpyDeviceToHost, s));
+        out->values = ctx->ho_edge_vals.as<uint64_t>();
+        ctx->d2h_bytes += n * 16;
+    } else {
+        launch_table_emit(em, s);
+        CKS(check_launch(ctx, "table_emit_kernel", 1));
+    }
     if (n) CK(cudaMemcpyAsync(ctx->ho_hash.p, ctx->o_hash.p, n * 16, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     ctx->d2h_bytes += n * 16;

@@ -224,8 +224,13 @@ struct EdgeArgs {
     const Slot* table; uint64_t capacity; uint32_t min_count; uint32_t k;
     const uint32_t* mins; const uint32_t* foreign_vecs;
     Slot* edges; uint64_t edge_mask; uint32_t* full_flag;
+    unsigned long long* edge_vals;      // launch_edge_values only: [2 * edge capacity], zeroed
 };
 void launch_edge_insert(const EdgeArgs& a, cudaStream_t s);
+constexpr unsigned long long EDGE_VALID = 1ULL << 63, EDGE_MULTI = 1ULL << 34;
+void launch_edge_values(const EdgeArgs& a, cudaStream_t s);
+void launch_edge_emit(const Slot* edges, const unsigned long long* vals, uint64_t capacity, uint64_t* out_hashes,
+                      unsigned long long* out_vals, unsigned long long* cursor, cudaStream_t s);
 struct BucketKeyArgs {
     const uint64_t* keys; uint64_t n; uint32_t n_ranks;      // keys: [2n] {lo, hi}
     unsigned long long* bucket_count;                        // [n_ranks], zeroed before each pass

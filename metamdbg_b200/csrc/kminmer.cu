@@ -539,6 +539,84 @@ void launch_edge_insert(const EdgeArgs& a, cudaStream_t s) {
     edge_insert_kernel<<<(unsigned)blocks, 256, 0, s>>>(a);
 }
 
+// Edge VALUES (CreateMdbg::indexEdge + successorExists, src/graph/CreateMdbg.cpp:1277-1500) in order-free form.
+// Every node offers (extending minimizer, isReversed, isPrefix) to the key of its normalized suffix (first element,
+// isPrefix = 0) and of its normalized prefix (last element, isPrefix = 1).  Offers to one key fall into two
+// orientation classes, A = {isReversed == isPrefix} and B = {isReversed != isPrefix}; a palindromic key has only
+// class A.  Upstream records the first offer of a class and marks hasMultipleSuccessors on any further one (which
+// offer is "first" depends on its thread arrival order; its consumers use the recorded minimizer only while the
+// mark is clear), so the order-free value of (key, class) is: empty, ONE offer with its fields, or "two or more".
+//   vals[2 * slot + class]: bit 63 valid, bit 34 multi, bit 33 isPrefix, bit 32 isReversed, bits 0-31 minimizer
+__global__ void __launch_bounds__(256) edge_values_kernel(const EdgeArgs a) {
+    const int k = (int)a.k, km = k - 1;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.capacity;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const Slot sl = a.table[i];
+        if ((sl.lo | sl.hi) == 0) continue;
+        if (!(sl.count >= a.min_count || (sl.flags & SLOT_RESCUED))) continue;
+        for (int side = 0; side < 2; side++) {            // 0: prefix (isPrefix = 1), 1: suffix (isPrefix = 0)
+            bool rev = true, pal = true;
+            for (int j = 0; j < km / 2; j++) {
+                const uint32_t x = vec_elem(a.mins, a.foreign_vecs, sl.ref, k, side + j);
+                const uint32_t y = vec_elem(a.mins, a.foreign_vecs, sl.ref, k, side + km - 1 - j);
+                if (x != y) { rev = x > y; pal = false; break; }
+            }
+            uint64_t h1, h2;
+            if (rev) murmur128_u32vec([&](int t) { return vec_elem(a.mins, a.foreign_vecs, sl.ref, k, side + km - 1 - t); }, km, h1, h2);
+            else murmur128_u32vec([&](int t) { return vec_elem(a.mins, a.foreign_vecs, sl.ref, k, side + t); }, km, h1, h2);
+            const Slot* es = table_find(a.edges, a.edge_mask, h2, h1);
+            if (!es) { atomicExch(a.full_flag, 1u); continue; }        // every key was inserted by edge_insert_kernel
+            const uint32_t pre = side ? 0u : 1u, r = rev ? 1u : 0u;
+            const uint32_t cls = pal ? 0u : (r == pre ? 0u : 1u);
+            const uint32_t ext = vec_elem(a.mins, a.foreign_vecs, sl.ref, k, side ? 0 : k - 1);
+            const unsigned long long one = EDGE_VALID | ((unsigned long long)pre << 33) | ((unsigned long long)r << 32) | ext;
+            unsigned long long* w = a.edge_vals + 2 * (uint64_t)(es - a.edges) + cls;
+            if (atomicCAS(w, 0ULL, one) != 0ULL) atomicExch(w, EDGE_VALID | EDGE_MULTI);
+        }
+    }
+}
+
+void launch_edge_values(const EdgeArgs& a, cudaStream_t s) {
+    uint64_t blocks = (a.capacity + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    edge_values_kernel<<<(unsigned)blocks, 256, 0, s>>>(a);
+}
+
+// keys and their two value words, in one (unspecified) order
+__global__ void __launch_bounds__(256) edge_emit_kernel(const Slot* edges, const unsigned long long* vals, uint64_t capacity,
+                                                        uint64_t* out_hashes, unsigned long long* out_vals,
+                                                        unsigned long long* cursor) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t n_rounds = (capacity + (uint64_t)gridDim.x * blockDim.x - 1) / ((uint64_t)gridDim.x * blockDim.x);
+    for (uint64_t round = 0; round < n_rounds; round++) {
+        const uint64_t i = round * gridDim.x * blockDim.x + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        bool take = false;
+        uint64_t lo = 0, hi = 0;
+        if (i < capacity) { lo = edges[i].lo; hi = edges[i].hi; take = (lo | hi) != 0; }
+        const uint32_t m = __ballot_sync(0xffffffffu, take);
+        unsigned long long base = 0;
+        if (lane == 0 && m) base = atomicAdd(cursor, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (take) {
+            const uint64_t pos = base + __popc(m & ((1u << lane) - 1u));
+            out_hashes[2 * pos] = lo;
+            out_hashes[2 * pos + 1] = hi;
+            unsigned long long a0 = vals[2 * i], b0 = vals[2 * i + 1];
+            if (a0 & EDGE_MULTI) a0 = EDGE_VALID | EDGE_MULTI;        // canonical: nothing but the mark
+            if (b0 & EDGE_MULTI) b0 = EDGE_VALID | EDGE_MULTI;
+            out_vals[2 * pos] = a0;
+            out_vals[2 * pos + 1] = b0;
+        }
+    }
+}
+
+void launch_edge_emit(const Slot* edges, const unsigned long long* vals, uint64_t capacity, uint64_t* out_hashes,
+                      unsigned long long* out_vals, unsigned long long* cursor, cudaStream_t s) {
+    uint64_t blocks = (capacity + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    edge_emit_kernel<<<(unsigned)blocks, 256, 0, s>>>(edges, vals, capacity, out_hashes, out_vals, cursor);
+}
+
 // multi-rank edge keys: bucket the local distinct keys by owner rank (pass 1 counts, pass 2 scatters), and on the
 // owner insert what arrived into a fresh set table -- a key produced by nodes of several ranks is kept once
 __global__ void __launch_bounds__(256) bucket_keys_kernel(const BucketKeyArgs a) {

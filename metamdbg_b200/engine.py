@@ -322,7 +322,17 @@ class Engine:
         self._ck(self._lib.mdbg_edges_index(self._ctx, min_abundance, C.byref(out)))
         n = int(out.n_edges)
         h = np.ctypeslib.as_array(out.hashes, shape=(2 * n,)).reshape(n, 2).copy() if n else np.zeros((0, 2), np.uint64)
-        return dict(hashes=h, n_edges=n, n_nodes=int(out.n_nodes), checksum=int(out.checksum))
+        vals = None
+        if out.values:                      # single context: order-free edge values, two orientation classes per key
+            w = np.ctypeslib.as_array(out.values, shape=(2 * n,)).reshape(n, 2).copy() if n else np.zeros((0, 2), np.uint64)
+            valid, multi = (w >> np.uint64(63)) & np.uint64(1), (w >> np.uint64(34)) & np.uint64(1)
+            single = (valid == 1) & (multi == 0)
+            vals = np.zeros((n, 2, 4), np.uint32)          # (count 0/1/2+, minimizer, isReversed, isPrefix)
+            vals[..., 0] = np.where(valid == 1, np.where(multi == 1, 2, 1), 0)
+            vals[..., 1] = np.where(single, w & np.uint64(0xFFFFFFFF), 0)
+            vals[..., 2] = np.where(single, (w >> np.uint64(32)) & np.uint64(1), 0)
+            vals[..., 3] = np.where(single, (w >> np.uint64(33)) & np.uint64(1), 0)
+        return dict(hashes=h, n_edges=n, n_nodes=int(out.n_nodes), checksum=int(out.checksum), values=vals)
 
     # -- multi-GPU -----------------------------------------------------------------
     @staticmethod

@@ -188,6 +188,9 @@ def main():
             we = orc.edge_index(tab.kminmers, k)
             assert ed["n_edges"] == len(we["hashes"]) and ed["checksum"] == we["checksum"], ("edges", scen, k)
             assert {(int(h[1]), int(h[0])) for h in ed["hashes"]} == {(int(h[0]), int(h[1])) for h in we["hashes"]}, ("edge set", scen, k)
+            wv = orc.edge_values(tab.kminmers, k)
+            assert {(int(h[1]), int(h[0])): v.tolist() for h, v in zip(ed["hashes"], ed["values"])} == \
+                {(int(h[0]), int(h[1])): v.tolist() for h, v in zip(wv["hashes"], wv["values"])}, ("edge values", scen, k)
         if rng.integers(0, 2):                                # default mode: rescue on top of the >= 2 table
             solid = orc.count(mins, moff, k, 2)
             resc = orc.rescue(mins, moff, k, solid["hashes"], solid["abundances"])

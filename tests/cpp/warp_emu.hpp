@@ -329,6 +329,7 @@ static inline unsigned __fns(unsigned mask, unsigned base, int offset) {     // 
 static inline double __ddiv_rn(double a, double b) { return a / b; }          // build with -ffp-contract=off
 static inline double __dadd_rn(double a, double b) { return a + b; }
 template <typename T> static inline T atomicExch(T* p, T v) { T old = *p; *p = v; return old; }
+template <typename T> static inline T atomicCAS(T* p, T cmp, T v) { T old = *p; if (old == cmp) *p = v; return old; }
 template <typename T, typename U> static inline T atomicAdd(T* p, U v) { T old = *p; *p = (T)(old + (T)v); return old; }
 
 static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }

@@ -483,6 +483,11 @@ def test_edge_index_vs_oracle(built, oracle):
         assert got["checksum"] == want["checksum"]
         assert {(int(h[1]), int(h[0])) for h in got["hashes"]} == {(int(h[0]), int(h[1])) for h in want["hashes"]}
         assert len(got["hashes"]) == len({(int(h[0]), int(h[1])) for h in got["hashes"]})      # no duplicate key
+        # edge values (indexEdge / successorExists, order-free): two orientation classes per key
+        wv = oracle.edge_values(tab.kminmers, k)
+        want_v = {(int(h[0]), int(h[1])): v.tolist() for h, v in zip(wv["hashes"], wv["values"])}
+        got_v = {(int(h[1]), int(h[0])): v.tolist() for h, v in zip(got["hashes"], got["values"])}
+        assert got_v == want_v
 
     eng.count_begin(4)
     eng.count_add_store()
