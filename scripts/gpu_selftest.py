@@ -126,6 +126,10 @@ def variants():
         out[f"edges_k{k}_rescue{int(rescue)}"] = bool(
             got["n_edges"] == len(we["hashes"]) and got["checksum"] == we["checksum"] and
             {(int(h[1]), int(h[0])) for h in got["hashes"]} == {(int(h[0]), int(h[1])) for h in we["hashes"]})
+        wv = orc.edge_values(tab.kminmers, k)
+        out[f"edge_values_k{k}_rescue{int(rescue)}"] = bool(
+            {(int(h[1]), int(h[0])): v.tolist() for h, v in zip(got["hashes"], got["values"])} ==
+            {(int(h[0]), int(h[1])): v.tolist() for h, v in zip(wv["hashes"], wv["values"])})
     eng.close()
     return out
 
