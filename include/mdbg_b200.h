@@ -295,14 +295,15 @@ typedef struct {
     uint64_t n_edges;
     const uint64_t* hashes;       /* [2*n_edges] */
     uint64_t checksum;
-    /* Edge values, single context only (NULL with several ranks): CreateMdbg::indexEdge / successorExists
+    /* Edge values (with several ranks: the offers of a rank's nodes travel to the owner of their key, which folds them):
+     * CreateMdbg::indexEdge / successorExists
      * (src/graph/CreateMdbg.cpp:1277-1500) in order-free form.  values[2*i + c], c = orientation class of the offers a
      * key received (0: isReversed == isPrefix, and every offer to a palindromic key; 1: isReversed != isPrefix):
      *   0                               no node extends the key in this class
      *   bit 63 set, bit 34 clear        exactly one node: bits 0-31 = the extending minimizer (KminmerEdge33::_minimizer),
      *                                   bit 32 = _isReversed, bit 33 = _isPrefix
      *   bit 63 and bit 34 set           two or more nodes (_hasMultipleSuccessors; upstream keeps whichever arrived first) */
-    const uint64_t* values;       /* [2*n_edges] or NULL */
+    const uint64_t* values;       /* [2*n_edges] */
 } mdbg_edges_out;
 mdbg_status mdbg_edges_index(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_edges_out* out);
 

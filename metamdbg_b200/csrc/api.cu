@@ -2001,6 +2001,7 @@ mdbg_status mdbg_edges_index(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_edges_o
         b.keys = ctx->o_hash.as<uint64_t>();
         b.n = n_local;
         b.n_ranks = R;
+        b.rec_words = 2;
         b.bucket_count = reinterpret_cast<unsigned long long*>(d_cnt);
         b.pass = 1;
         launch_bucket_keys(b, s);
@@ -2057,37 +2058,89 @@ mdbg_status mdbg_edges_index(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_edges_o
     CKS(ensure(ctx, ctx->o_abund, (n + 1) * 4));
     CKS(ensure_pin(ctx, ctx->ho_hash, (n + 1) * 16));
     CK(cudaMemsetAsync(&ctx->d_small->emit_cursor, 0, 8, s));
-    EmitArgs em{};
-    em.table = ctx->edge_table.as<Slot>();
-    em.capacity = set_cap;
-    em.min_count = 1;
-    em.k = ctx->t_k - 1;
-    em.out_hashes = ctx->o_hash.as<uint64_t>();
-    em.out_abund = ctx->o_abund.as<uint32_t>();
-    em.out_vecs = nullptr;
-    em.cursor = &ctx->d_small->emit_cursor;
-    out->values = nullptr;
+    // the keys come out together with their order-free edge values (indexEdge / successorExists)
+    CKS(ensure(ctx, ctx->edge_vals, set_cap * 16));
+    CKS(ensure(ctx, ctx->o_edge_vals, (n + 1) * 16));
+    CKS(ensure_pin(ctx, ctx->ho_edge_vals, (n + 1) * 16));
+    CK(cudaMemsetAsync(ctx->edge_vals.p, 0, set_cap * 16, s));
+    CK(cudaMemsetAsync(&ctx->d_small->full_flag, 0, sizeof(uint32_t), s));
     if (ctx->n_ranks == 1) {
-        // one context: the keys come out together with their order-free edge values (indexEdge / successorExists)
-        CKS(ensure(ctx, ctx->edge_vals, set_cap * 16));
-        CKS(ensure(ctx, ctx->o_edge_vals, (n + 1) * 16));
-        CKS(ensure_pin(ctx, ctx->ho_edge_vals, (n + 1) * 16));
-        CK(cudaMemsetAsync(ctx->edge_vals.p, 0, set_cap * 16, s));
-        CK(cudaMemsetAsync(&ctx->d_small->full_flag, 0, sizeof(uint32_t), s));
         e.edge_vals = ctx->edge_vals.as<unsigned long long>();
         launch_edge_values(e, s);
         CKS(check_launch(ctx, "edge_values_kernel", 1));
         CKS(check_full(ctx, "mdbg_edges_index (values: a key is missing from the set)"));
-        launch_edge_emit(ctx->edge_table.as<Slot>(), ctx->edge_vals.as<unsigned long long>(), set_cap, ctx->o_hash.as<uint64_t>(),
-                         ctx->o_edge_vals.as<unsigned long long>(), &ctx->d_small->emit_cursor, s);
-        CKS(check_launch(ctx, "edge_emit_kernel", 1));
-        if (n) CK(cudaMemcpyAsync(ctx->ho_edge_vals.p, ctx->o_edge_vals.p, n * 16, cudaMemcpyDeviceToHost, s));
-        out->values = ctx->ho_edge_vals.as<uint64_t>();
-        ctx->d2h_bytes += n * 16;
     } else {
-        launch_table_emit(em, s);
-        CKS(check_launch(ctx, "table_emit_kernel", 1));
+        // several ranks: the two offers of every owned node travel to the owner of their key as 3-word records and
+        // are folded into that key's class words there
+        const uint32_t R = (uint32_t)ctx->n_ranks;
+        const uint64_t off_cap = 2 * st.n_entries;
+        CKS(ensure(ctx, ctx->m_send_vecs, (off_cap + 1) * 24));
+        CK(cudaMemsetAsync(&ctx->d_small->emit_cursor, 0, 8, s));
+        launch_edge_offers(e, ctx->m_send_vecs.as<uint64_t>(), &ctx->d_small->emit_cursor, s);
+        CKS(check_launch(ctx, "edge_offers_kernel", 1));
+        CK(cudaMemcpyAsync(&ctx->h_scalar[4], &ctx->d_small->emit_cursor, 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (ctx->h_scalar[4] != off_cap)
+            return fail(ctx, MDBG_ERR_STATE, "mdbg_edges_index: %llu offers for %llu nodes", (unsigned long long)ctx->h_scalar[4],
+                        (unsigned long long)st.n_entries);
+        uint64_t* d_cnt = ctx->m_bucket.as<uint64_t>();
+        uint64_t* d_base = d_cnt + R;
+        uint64_t* d_all = d_cnt + 2 * R;
+        CK(cudaMemsetAsync(d_cnt, 0, R * 8, s));
+        BucketKeyArgs b{};
+        b.keys = ctx->m_send_vecs.as<uint64_t>();
+        b.n = off_cap;
+        b.n_ranks = R;
+        b.rec_words = 3;
+        b.bucket_count = reinterpret_cast<unsigned long long*>(d_cnt);
+        b.pass = 1;
+        launch_bucket_keys(b, s);
+        CKS(check_launch(ctx, "bucket_keys_kernel(count)", off_cap ? 1 : 0));
+        NK(g_nccl.AllGather(d_cnt, d_all, R, NCCL_UINT64, ctx->nccl_comm, s));
+        std::vector<uint64_t> all((size_t)R * R);
+        CK(cudaMemcpyAsync(all.data(), d_all, (size_t)R * R * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        std::vector<uint64_t> send_cnt(R), send_base(R), recv_cnt(R), recv_base(R);
+        uint64_t send_total = 0, recv_total = 0;
+        for (uint32_t d = 0; d < R; d++) {
+            send_cnt[d] = all[(size_t)ctx->rank * R + d];
+            send_base[d] = send_total;
+            send_total += send_cnt[d];
+            recv_cnt[d] = all[(size_t)d * R + ctx->rank];
+            recv_base[d] = recv_total;
+            recv_total += recv_cnt[d];
+        }
+        CKS(ensure(ctx, ctx->prev_stage_h, (send_total + 1) * 24));
+        CKS(ensure(ctx, ctx->m_recv_vecs, (recv_total + 1) * 24));
+        CK(cudaMemcpyAsync(d_base, send_base.data(), R * 8, cudaMemcpyHostToDevice, s));
+        CK(cudaMemsetAsync(d_cnt, 0, R * 8, s));
+        b.bucket_base = d_base;
+        b.out_keys = ctx->prev_stage_h.as<uint64_t>();
+        b.pass = 2;
+        launch_bucket_keys(b, s);
+        CKS(check_launch(ctx, "bucket_keys_kernel(scatter)", off_cap ? 1 : 0));
+        NK(g_nccl.GroupStart());
+        for (uint32_t d = 0; d < R; d++) {
+            if (send_cnt[d])
+                NK(g_nccl.Send(ctx->prev_stage_h.as<uint64_t>() + 3 * send_base[d], send_cnt[d] * 24, NCCL_UINT8, (int)d,
+                               ctx->nccl_comm, s));
+            if (recv_cnt[d])
+                NK(g_nccl.Recv(ctx->m_recv_vecs.as<uint64_t>() + 3 * recv_base[d], recv_cnt[d] * 24, NCCL_UINT8, (int)d,
+                               ctx->nccl_comm, s));
+        }
+        NK(g_nccl.GroupEnd());
+        launch_edge_apply_offers(ctx->m_recv_vecs.as<uint64_t>(), recv_total, ctx->edge_table.as<Slot>(), set_cap - 1,
+                                 ctx->edge_vals.as<unsigned long long>(), &ctx->d_small->full_flag, s);
+        CKS(check_launch(ctx, "edge_apply_offers_kernel", recv_total ? 1 : 0));
+        CKS(check_full(ctx, "mdbg_edges_index (values: an offer arrived for a key its owner does not hold)"));
+        CK(cudaMemsetAsync(&ctx->d_small->emit_cursor, 0, 8, s));
     }
+    launch_edge_emit(ctx->edge_table.as<Slot>(), ctx->edge_vals.as<unsigned long long>(), set_cap, ctx->o_hash.as<uint64_t>(),
+                     ctx->o_edge_vals.as<unsigned long long>(), &ctx->d_small->emit_cursor, s);
+    CKS(check_launch(ctx, "edge_emit_kernel", 1));
+    if (n) CK(cudaMemcpyAsync(ctx->ho_edge_vals.p, ctx->o_edge_vals.p, n * 16, cudaMemcpyDeviceToHost, s));
+    out->values = ctx->ho_edge_vals.as<uint64_t>();
+    ctx->d2h_bytes += n * 16;
     if (n) CK(cudaMemcpyAsync(ctx->ho_hash.p, ctx->o_hash.p, n * 16, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     ctx->d2h_bytes += n * 16;

@@ -232,7 +232,8 @@ void launch_edge_values(const EdgeArgs& a, cudaStream_t s);
 void launch_edge_emit(const Slot* edges, const unsigned long long* vals, uint64_t capacity, uint64_t* out_hashes,
                       unsigned long long* out_vals, unsigned long long* cursor, cudaStream_t s);
 struct BucketKeyArgs {
-    const uint64_t* keys; uint64_t n; uint32_t n_ranks;      // keys: [2n] {lo, hi}
+    const uint64_t* keys; uint64_t n; uint32_t n_ranks;      // records: [rec_words * n], {lo, hi[, value word]}
+    uint32_t rec_words;                                      // 2 or 3
     unsigned long long* bucket_count;                        // [n_ranks], zeroed before each pass
     const uint64_t* bucket_base;                             // [n_ranks], pass 2
     uint64_t* out_keys;                                      // pass 2
@@ -240,6 +241,10 @@ struct BucketKeyArgs {
 };
 void launch_bucket_keys(const BucketKeyArgs& a, cudaStream_t s);
 void launch_insert_keys(const uint64_t* keys, uint64_t n, Slot* table, uint64_t mask, uint32_t* full_flag, cudaStream_t s);
+// multi-rank edge values: offers of the owned nodes as 3-word records, folded into the class words on the key's owner
+void launch_edge_offers(const EdgeArgs& a, uint64_t* out_recs, unsigned long long* cursor, cudaStream_t s);
+void launch_edge_apply_offers(const uint64_t* recs, uint64_t n, const Slot* edges, uint64_t mask, unsigned long long* vals,
+                              uint32_t* full_flag, cudaStream_t s);
 
 // multi-GPU pack: bucket every occupied slot by owner rank
 struct PackArgs {

@@ -622,13 +622,13 @@ void launch_edge_emit(const Slot* edges, const unsigned long long* vals, uint64_
 __global__ void __launch_bounds__(256) bucket_keys_kernel(const BucketKeyArgs a) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
-    const uint64_t lo = a.keys[2 * i], hi = a.keys[2 * i + 1];
-    const uint32_t dst = owner_of(hi, a.n_ranks);
+    const uint32_t W = a.rec_words;                       // 2: bare keys {lo, hi}; 3: offers {lo, hi, value word}
+    const uint64_t* rec = a.keys + (uint64_t)W * i;
+    const uint32_t dst = owner_of(rec[1], a.n_ranks);
     const unsigned long long slot = atomicAdd(&a.bucket_count[dst], 1ULL);
     if (a.pass == 2) {
         const uint64_t pos = a.bucket_base[dst] + slot;
-        a.out_keys[2 * pos] = lo;
-        a.out_keys[2 * pos + 1] = hi;
+        for (uint32_t w = 0; w < W; w++) a.out_keys[(uint64_t)W * pos + w] = rec[w];
     }
 }
 
@@ -642,6 +642,75 @@ __global__ void __launch_bounds__(256) insert_keys_kernel(const uint64_t* keys, 
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (!table_put(table, mask, keys[2 * i], keys[2 * i + 1], 1u, 0ULL)) atomicExch(full_flag, 1u);
+}
+
+// multi-rank edge values.  edge_offers_kernel: the two offers of every owned node as records {key lo, key hi, value
+// word | class << 36}; after the owner exchange edge_apply_offers_kernel folds each record into the class word of
+// its key exactly as edge_values_kernel does locally.
+constexpr unsigned long long EDGE_CLASS_B = 1ULL << 36;
+
+__global__ void __launch_bounds__(256) edge_offers_kernel(const EdgeArgs a, uint64_t* out_recs, unsigned long long* cursor) {
+    const int k = (int)a.k, km = k - 1;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n_rounds = (a.capacity + stride - 1) / stride;
+    for (uint64_t round = 0; round < n_rounds; round++) {
+        const uint64_t i = round * stride + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        bool take = false;
+        Slot sl{};
+        if (i < a.capacity) {
+            sl = a.table[i];
+            take = (sl.lo | sl.hi) != 0 && (sl.count >= a.min_count || (sl.flags & SLOT_RESCUED));
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, take);
+        unsigned long long base = 0;
+        if (lane == 0 && m) base = atomicAdd(cursor, 2ULL * __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (!take) continue;
+        const uint64_t pos0 = base + 2ULL * __popc(m & ((1u << lane) - 1u));
+        for (int side = 0; side < 2; side++) {
+            bool rev = true, pal = true;
+            for (int j = 0; j < km / 2; j++) {
+                const uint32_t x = vec_elem(a.mins, a.foreign_vecs, sl.ref, k, side + j);
+                const uint32_t y = vec_elem(a.mins, a.foreign_vecs, sl.ref, k, side + km - 1 - j);
+                if (x != y) { rev = x > y; pal = false; break; }
+            }
+            uint64_t h1, h2;
+            if (rev) murmur128_u32vec([&](int t) { return vec_elem(a.mins, a.foreign_vecs, sl.ref, k, side + km - 1 - t); }, km, h1, h2);
+            else murmur128_u32vec([&](int t) { return vec_elem(a.mins, a.foreign_vecs, sl.ref, k, side + t); }, km, h1, h2);
+            const uint32_t pre = side ? 0u : 1u, r = rev ? 1u : 0u;
+            const uint32_t cls = pal ? 0u : (r == pre ? 0u : 1u);
+            const uint32_t ext = vec_elem(a.mins, a.foreign_vecs, sl.ref, k, side ? 0 : k - 1);
+            uint64_t* rec = out_recs + 3 * (pos0 + side);
+            rec[0] = h2;
+            rec[1] = h1;
+            rec[2] = EDGE_VALID | ((unsigned long long)pre << 33) | ((unsigned long long)r << 32) | ext | (cls ? EDGE_CLASS_B : 0ULL);
+        }
+    }
+}
+
+void launch_edge_offers(const EdgeArgs& a, uint64_t* out_recs, unsigned long long* cursor, cudaStream_t s) {
+    uint64_t blocks = (a.capacity + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    edge_offers_kernel<<<(unsigned)blocks, 256, 0, s>>>(a, out_recs, cursor);
+}
+
+__global__ void __launch_bounds__(256) edge_apply_offers_kernel(const uint64_t* recs, uint64_t n, const Slot* edges, uint64_t mask,
+                                                                unsigned long long* vals, uint32_t* full_flag) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t* rec = recs + 3 * i;
+    const Slot* es = table_find(const_cast<Slot*>(edges), mask, rec[0], rec[1]);
+    if (!es) { atomicExch(full_flag, 1u); return; }                  // the owner holds every key its ranks produced
+    const unsigned long long one = rec[2] & ~EDGE_CLASS_B;
+    unsigned long long* w = vals + 2 * (uint64_t)(es - edges) + ((rec[2] & EDGE_CLASS_B) ? 1 : 0);
+    if (atomicCAS(w, 0ULL, one) != 0ULL) atomicExch(w, EDGE_VALID | EDGE_MULTI);
+}
+
+void launch_edge_apply_offers(const uint64_t* recs, uint64_t n, const Slot* edges, uint64_t mask, unsigned long long* vals,
+                              uint32_t* full_flag, cudaStream_t s) {
+    if (n == 0) return;
+    edge_apply_offers_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(recs, n, edges, mask, vals, full_flag);
 }
 
 void launch_insert_keys(const uint64_t* keys, uint64_t n, Slot* table, uint64_t mask, uint32_t* full_flag, cudaStream_t s) {

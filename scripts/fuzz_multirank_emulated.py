@@ -117,6 +117,12 @@ def main():
                     got_e.add(key)
             assert got_e == {(int(h[0]), int(h[1])) for h in we["hashes"]}, ("edges", scen, len(got_e), len(we["hashes"]))
             assert sum(e["checksum"] for e in edges) % 2 ** 64 == we["checksum"], ("edge checksum", scen)
+            wv = orc.edge_values(nodes, k)
+            got_v = {}
+            for e in edges:
+                for h, v in zip(e["hashes"], e["values"]):
+                    got_v[(int(h[1]), int(h[0]))] = v.tolist()
+            assert got_v == {(int(h[0]), int(h[1])): v.tolist() for h, v in zip(wv["hashes"], wv["values"])}, ("edge values", scen)
         for step in range(chain + 1):
             if step:
                 nk = orc.next_k(m, mo, k + step, ph, pa)

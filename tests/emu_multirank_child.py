@@ -96,7 +96,14 @@ def main():
     assert got_e == {(int(h[0]), int(h[1])) for h in we["hashes"]}, (len(got_e), len(we["hashes"]))
     assert sum(ed["checksum"] for ed in edge_results) % 2 ** 64 == we["checksum"]
     assert sum(ed["n_nodes"] for ed in edge_results) == len(ref["abundances"])
-    print(f"  edge keys: {len(got_e)} distinct over {n_ranks} owners")
+    wv = orc.edge_values(ref["vecs"], k)                  # order-free indexEdge content, folded on the key's owner
+    want_v = {(int(h[0]), int(h[1])): v.tolist() for h, v in zip(wv["hashes"], wv["values"])}
+    got_v = {}
+    for ed in edge_results:
+        for h, v in zip(ed["hashes"], ed["values"]):
+            got_v[(int(h[1]), int(h[0]))] = v.tolist()
+    assert got_v == want_v, "edge values"
+    print(f"  edge keys: {len(got_e)} distinct over {n_ranks} owners, values identical")
     # rescue: solid + rescued entries over all ranks = the oracle's table of the whole read set
     resc = orc.rescue(pm, po, k, ref["hashes"], ref["abundances"])
     want_r = dict(want)

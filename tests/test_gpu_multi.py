@@ -40,7 +40,8 @@ def _worker(rank, world, port, out_dir):
         tab = eng.count_finalize(2)
         ed = eng.edges_index(2)                          # collective: edge keys of the owned nodes -> their owners
         np.savez(os.path.join(out_dir, f"rank{rank}_k{k}.npz"), hashes=tab.hashes, abund=tab.abundances,
-                 vecs=tab.kminmers, edge_keys=ed["hashes"], edge_checksum=np.array([ed["checksum"]], np.uint64))
+                 vecs=tab.kminmers, edge_keys=ed["hashes"], edge_values=ed["values"],
+                 edge_checksum=np.array([ed["checksum"]], np.uint64))
     # default mode + multi-k over NCCL: rescue across ranks, then k = 5, 6 from the replicated previous-k table
     from metamdbg_b200 import multi_k_sweep
 
@@ -80,14 +81,17 @@ def test_two_gpu_merge_matches_oracle(tmp_path, oracle):
                 for h, a, v in zip(ref["hashes"], ref["abundances"], ref["vecs"])}
         assert got == want and len(want) > 100
         we = oracle.edge_index(ref["vecs"], k)            # CreateMdbg::EdgeIndexer key set of this node set
-        keys, cs = set(), 0
+        wv = oracle.edge_values(ref["vecs"], k)
+        keys, cs, vals = set(), 0, {}
         for r in range(world):
             z = np.load(tmp_path / f"rank{r}_k{k}.npz")
-            for h in z["edge_keys"]:
+            for h, v in zip(z["edge_keys"], z["edge_values"]):
                 assert (int(h[1]), int(h[0])) not in keys
                 keys.add((int(h[1]), int(h[0])))
+                vals[(int(h[1]), int(h[0]))] = v.tolist()
             cs = (cs + int(z["edge_checksum"][0])) % 2 ** 64
         assert keys == {(int(h[0]), int(h[1])) for h in we["hashes"]} and cs == we["checksum"]
+        assert vals == {(int(h[0]), int(h[1])): v.tolist() for h, v in zip(wv["hashes"], wv["values"])}
     # the chain: solid + rescued at k = 4, then two next-k passes (oracle restatement of the whole read set)
     pm, po = [], [0]
     for r in range(rs.n_reads):
