@@ -387,6 +387,24 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     # ---- extra (not the headline): the multi-k loop k = 4 .. 21 on the resident store (BASELINE config 4's shape on
     # this workload): k = 4 counted, every further k derived from the previous table on the device.  Single GPU by
     # default; --multi-k-ranks also runs it with the collective previous-k replication + value merge for N > 1.
+    # ---- extra: edge keys + order-free edge values of the k = 4 node set (CreateMdbg::EdgeIndexer / indexEdge), the
+    # first step beyond the count table; the table of the last timed step is still current here
+    edges_extra = None
+    if world == 1 and not args.no_edges:
+        try:
+            t_e = []
+            for _ in range(2):                              # 2nd = warm
+                eng.synchronize()
+                t0 = time.perf_counter()
+                ed = eng.edges_index(MIN_AB)
+                t_e.append(time.perf_counter() - t0)
+            edges_extra = {"k": K, "n_nodes": ed["n_nodes"], "n_edges": ed["n_edges"], "checksum": ed["checksum"],
+                           "ms": round(1e3 * t_e[1], 3), "d2h_bytes": ed["n_edges"] * 32,
+                           "branching_keys": int((ed["values"][..., 0] == 2).any(axis=1).sum()),
+                           "timer": "host wall clock around mdbg_edges_index incl. the D2H of keys and values"}
+        except Exception as e:                                # noqa: BLE001
+            edges_extra = {"error": repr(e)}
+
     multi_k = None
     if args.multi_k > K and (world == 1 or args.multi_k_ranks):
         try:
@@ -549,7 +567,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                          "binding_pipes_ncu": ncu_pipes,
                          "share_of_step": sk_ms / (ms_total / args.steps)},
             "kernels_ms": {"sketch": sk_ms, "insert": float(np.mean(insert_ms))},
-            "multi_k": multi_k,
+            "multi_k": multi_k, "edges": edges_extra,
             "sketch_autotune": dict(tune, note="ms = sketch + scan + compaction of the full batch, best of 2; a variant is "
                                                "eligible only if its whole output equals variant 0's on the device"),
             "cpu_baseline": cpu_baseline,
@@ -581,6 +599,7 @@ def main():
     ap.add_argument("--sketch-variant", type=int, default=-1, help="force a sketch-kernel variant (-1 = autotune)")
     ap.add_argument("--multi-k", type=int, default=21, help="extra: multi-k loop up to this k on the resident store (0 = off)")
     ap.add_argument("--multi-k-ranks", action="store_true", help="run the multi-k extra for N > 1 as well (collectives)")
+    ap.add_argument("--no-edges", action="store_true", help="skip the edge-key extra")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stages", action="store_true", help="reference arm: skip the extra real-stage timing")

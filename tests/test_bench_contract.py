@@ -70,5 +70,6 @@ def test_gpu_arm_runs_on_the_emulator(tmp_path):
         assert d["e2e"]["table_checks"]["steps_differing_from_device_leg"] == 0 and d["e2e"]["table_checks"]["steps_checked"] == 4
         assert d["check"]["occurrences_conserved"] and d["check"]["device_steps_same_checksum"]
         assert all(d["sketch_autotune"]["identical"]) and d["multi_k"]["same_tables_both_sweeps"]
+        assert d["edges"]["n_edges"] > 0 and d["edges"]["n_nodes"] == d["check"]["n_solid_total"]
         assert d["cpu_baseline"]["kind"] in ("reference", "port") and "identical" in d["cpu_baseline"]["sample"]
         assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
