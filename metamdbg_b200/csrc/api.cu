@@ -1011,10 +1011,21 @@ static void split_pieces(const uint64_t* offsets, uint32_t n_reads, uint64_t n_b
     // pieces), at most MAX_SUB of them
     uint64_t floor_bytes = uint64_t(128) << 20;
     if (const char* e = getenv("MDBG_PIECE_BYTES")) { const long long v = atoll(e); if (v > 0) floor_bytes = (uint64_t)v; }
-    const uint64_t piece = std::max<uint64_t>(floor_bytes, (n_bases + MAX_SUB - 1) / MAX_SUB);
+    const uint64_t piece = std::max<uint64_t>(floor_bytes, (n_bases + (MAX_SUB - 8) - 1) / (MAX_SUB - 8));
+    // Ramp: nothing overlaps the packing of the first piece, and nothing overlaps the copy / sketch / scan / compaction
+    // of the last one, so a batch of several pieces starts with a quarter and a half piece and ends by halving what
+    // is left (down to an eighth): at most 6 extra pieces.
+    const bool ramp = n_bases >= 4 * piece;
     uint32_t r0 = 0;
     while (r0 < n_reads) {
-        const uint64_t target = offsets[r0] + piece;
+        uint64_t size = piece;
+        if (ramp) {
+            const uint64_t rem = n_bases - offsets[r0];
+            if (subs.size() == 0) size = piece / 4;
+            else if (subs.size() == 1) size = piece / 2;
+            else if (rem < 2 * piece) size = rem / 2 >= piece / 8 ? rem / 2 : rem;
+        }
+        const uint64_t target = offsets[r0] + std::max<uint64_t>(size, 1);
         uint32_t r1 = (uint32_t)(std::upper_bound(offsets + r0 + 1, offsets + n_reads + 1, target) - offsets);
         if (r1 <= r0 + 1) r1 = r0 + 1; else r1 -= 1;
         if (r1 > n_reads || subs.size() + 1 == (size_t)MAX_SUB) r1 = n_reads;
