@@ -606,6 +606,58 @@ constexpr int NCCL_UINT64 = 5;   // ncclUint64
         if (r_ != 0) return fail(ctx, MDBG_ERR_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r_)); \
     } while (0)
 
+// Owner-partitioned all-to-all, host side.  After a bucket-count pass has left this rank's per-destination record
+// counts in m_bucket[0, R), plan() all-gathers the R x R count matrix and derives what this rank sends to and
+// receives from everybody; run() moves records of rec_bytes each in one grouped ncclSend / ncclRecv.
+struct OwnerExchange {
+    std::vector<uint64_t> send_cnt, send_base, recv_cnt, recv_base;
+    uint64_t send_total = 0, recv_total = 0;
+
+    mdbg_status plan(mdbg_ctx* ctx) {
+        cudaStream_t s = ctx->stream;
+        const uint32_t R = (uint32_t)ctx->n_ranks;
+        uint64_t* d_cnt = ctx->m_bucket.as<uint64_t>();
+        uint64_t* d_all = d_cnt + 2 * R;
+        NK(g_nccl.AllGather(d_cnt, d_all, R, NCCL_UINT64, ctx->nccl_comm, s));
+        std::vector<uint64_t> all((size_t)R * R);
+        CK(cudaMemcpyAsync(all.data(), d_all, (size_t)R * R * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        send_cnt.assign(R, 0); send_base.assign(R, 0); recv_cnt.assign(R, 0); recv_base.assign(R, 0);
+        send_total = recv_total = 0;
+        for (uint32_t d = 0; d < R; d++) {
+            send_cnt[d] = all[(size_t)ctx->rank * R + d];
+            send_base[d] = send_total;
+            send_total += send_cnt[d];
+            recv_cnt[d] = all[(size_t)d * R + ctx->rank];
+            recv_base[d] = recv_total;
+            recv_total += recv_cnt[d];
+        }
+        return MDBG_OK;
+    }
+    // bucket bases for the scatter pass (m_bucket[R, 2R)) and fresh cursors (m_bucket[0, R))
+    mdbg_status upload_bases(mdbg_ctx* ctx) {
+        const uint32_t R = (uint32_t)ctx->n_ranks;
+        uint64_t* d_cnt = ctx->m_bucket.as<uint64_t>();
+        CK(cudaMemcpyAsync(d_cnt + R, send_base.data(), R * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemsetAsync(d_cnt, 0, R * 8, ctx->stream));
+        return MDBG_OK;
+    }
+    mdbg_status run(mdbg_ctx* ctx, const void* send, void* recv, size_t rec_bytes) {
+        const uint32_t R = (uint32_t)ctx->n_ranks;
+        NK(g_nccl.GroupStart());
+        for (uint32_t d = 0; d < R; d++) {
+            if (send_cnt[d])
+                NK(g_nccl.Send((const char*)send + send_base[d] * rec_bytes, send_cnt[d] * rec_bytes, NCCL_UINT8, (int)d,
+                               ctx->nccl_comm, ctx->stream));
+            if (recv_cnt[d])
+                NK(g_nccl.Recv((char*)recv + recv_base[d] * rec_bytes, recv_cnt[d] * rec_bytes, NCCL_UINT8, (int)d,
+                               ctx->nccl_comm, ctx->stream));
+        }
+        NK(g_nccl.GroupEnd());
+        return MDBG_OK;
+    }
+};
+
 }  // namespace
 
 // =====================================================================================
@@ -1686,7 +1738,6 @@ static mdbg_status count_rescue_all_ranks(mdbg_ctx* ctx, uint64_t* n_reads_rescu
     CKS(ensure(ctx, ctx->m_bucket, (size_t)(2 * R + R * R) * 8));
     uint64_t* d_cnt = ctx->m_bucket.as<uint64_t>();
     uint64_t* d_base = d_cnt + R;
-    uint64_t* d_all = d_cnt + 2 * R;
     CK(cudaMemsetAsync(d_cnt, 0, R * 8, s));
     BucketVecArgs b{};
     b.vecs = ctx->m_recv_vecs.as<uint32_t>();
@@ -1697,39 +1748,18 @@ static mdbg_status count_rescue_all_ranks(mdbg_ctx* ctx, uint64_t* n_reads_rescu
     b.pass = 1;
     launch_bucket_vecs(b, s);
     CKS(check_launch(ctx, "bucket_vecs_kernel(count)", n_list ? 1 : 0));
-    NK(g_nccl.AllGather(d_cnt, d_all, R, NCCL_UINT64, ctx->nccl_comm, s));
-    std::vector<uint64_t> all((size_t)R * R);
-    CK(cudaMemcpyAsync(all.data(), d_all, (size_t)R * R * 8, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    std::vector<uint64_t> send_cnt(R), send_base(R), recv_cnt(R), recv_base(R);
-    uint64_t send_total = 0, recv_total = 0;
-    for (uint32_t d = 0; d < R; d++) {
-        send_cnt[d] = all[(size_t)ctx->rank * R + d];
-        send_base[d] = send_total;
-        send_total += send_cnt[d];
-        recv_cnt[d] = all[(size_t)d * R + ctx->rank];
-        recv_base[d] = recv_total;
-        recv_total += recv_cnt[d];
-    }
-    CKS(ensure(ctx, ctx->m_send_vecs, (send_total + 1) * 4 * k));
+    OwnerExchange xr;
+    CKS(xr.plan(ctx));
+    const uint64_t recv_total = xr.recv_total;
+    CKS(ensure(ctx, ctx->m_send_vecs, (xr.send_total + 1) * 4 * k));
     CKS(ensure(ctx, ctx->o_vecs, (recv_total + 1) * 4 * k));       // receive side
-    CK(cudaMemcpyAsync(d_base, send_base.data(), R * 8, cudaMemcpyHostToDevice, s));
-    CK(cudaMemsetAsync(d_cnt, 0, R * 8, s));
+    CKS(xr.upload_bases(ctx));
     b.bucket_base = d_base;
     b.out_vecs = ctx->m_send_vecs.as<uint32_t>();
     b.pass = 2;
     launch_bucket_vecs(b, s);
     CKS(check_launch(ctx, "bucket_vecs_kernel(scatter)", n_list ? 1 : 0));
-    NK(g_nccl.GroupStart());
-    for (uint32_t d = 0; d < R; d++) {
-        if (send_cnt[d])
-            NK(g_nccl.Send(ctx->m_send_vecs.as<uint32_t>() + send_base[d] * k, send_cnt[d] * 4 * k, NCCL_UINT8, (int)d,
-                           ctx->nccl_comm, s));
-        if (recv_cnt[d])
-            NK(g_nccl.Recv(ctx->o_vecs.as<uint32_t>() + recv_base[d] * k, recv_cnt[d] * 4 * k, NCCL_UINT8, (int)d,
-                           ctx->nccl_comm, s));
-    }
-    NK(g_nccl.GroupEnd());
+    CKS(xr.run(ctx, ctx->m_send_vecs.p, ctx->o_vecs.p, (size_t)4 * k));
     // step 4
     CK(cudaMemsetAsync(&ctx->d_small->n_flagged, 0, sizeof(unsigned long long), s));
     launch_rescue_flag(ctx->o_vecs.as<uint32_t>(), recv_total, k, ctx->table.as<Slot>(), ctx->t_capacity - 1,
@@ -2006,7 +2036,6 @@ mdbg_status mdbg_edges_index(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_edges_o
         CKS(ensure(ctx, ctx->m_bucket, (size_t)(2 * R + R * R) * 8));
         uint64_t* d_cnt = ctx->m_bucket.as<uint64_t>();
         uint64_t* d_base = d_cnt + R;
-        uint64_t* d_all = d_cnt + 2 * R;
         CK(cudaMemsetAsync(d_cnt, 0, R * 8, s));
         BucketKeyArgs b{};
         b.keys = ctx->o_hash.as<uint64_t>();
@@ -2017,39 +2046,18 @@ mdbg_status mdbg_edges_index(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_edges_o
         b.pass = 1;
         launch_bucket_keys(b, s);
         CKS(check_launch(ctx, "bucket_keys_kernel(count)", n_local ? 1 : 0));
-        NK(g_nccl.AllGather(d_cnt, d_all, R, NCCL_UINT64, ctx->nccl_comm, s));
-        std::vector<uint64_t> all((size_t)R * R);
-        CK(cudaMemcpyAsync(all.data(), d_all, (size_t)R * R * 8, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        std::vector<uint64_t> send_cnt(R), send_base(R), recv_cnt(R), recv_base(R);
-        uint64_t send_total = 0, recv_total = 0;
-        for (uint32_t d = 0; d < R; d++) {
-            send_cnt[d] = all[(size_t)ctx->rank * R + d];
-            send_base[d] = send_total;
-            send_total += send_cnt[d];
-            recv_cnt[d] = all[(size_t)d * R + ctx->rank];
-            recv_base[d] = recv_total;
-            recv_total += recv_cnt[d];
-        }
-        CKS(ensure(ctx, ctx->prev_stage_h, (send_total + 1) * 16));        // send side (free at this point of the flow)
+        OwnerExchange xk;
+        CKS(xk.plan(ctx));
+        const uint64_t recv_total = xk.recv_total;
+        CKS(ensure(ctx, ctx->prev_stage_h, (xk.send_total + 1) * 16));     // send side (free at this point of the flow)
         CKS(ensure(ctx, ctx->m_recv_vecs, (recv_total + 1) * 16));         // receive side
-        CK(cudaMemcpyAsync(d_base, send_base.data(), R * 8, cudaMemcpyHostToDevice, s));
-        CK(cudaMemsetAsync(d_cnt, 0, R * 8, s));
+        CKS(xk.upload_bases(ctx));
         b.bucket_base = d_base;
         b.out_keys = ctx->prev_stage_h.as<uint64_t>();
         b.pass = 2;
         launch_bucket_keys(b, s);
         CKS(check_launch(ctx, "bucket_keys_kernel(scatter)", n_local ? 1 : 0));
-        NK(g_nccl.GroupStart());
-        for (uint32_t d = 0; d < R; d++) {
-            if (send_cnt[d])
-                NK(g_nccl.Send(ctx->prev_stage_h.as<uint64_t>() + 2 * send_base[d], send_cnt[d] * 16, NCCL_UINT8, (int)d,
-                               ctx->nccl_comm, s));
-            if (recv_cnt[d])
-                NK(g_nccl.Recv(ctx->m_recv_vecs.as<uint64_t>() + 2 * recv_base[d], recv_cnt[d] * 16, NCCL_UINT8, (int)d,
-                               ctx->nccl_comm, s));
-        }
-        NK(g_nccl.GroupEnd());
+        CKS(xk.run(ctx, ctx->prev_stage_h.p, ctx->m_recv_vecs.p, 16));
         set_cap = pow2ceil((recv_total < 512 ? 512 : recv_total) * 2);
         CKS(ensure(ctx, ctx->edge_table, set_cap * sizeof(Slot)));
         CK(cudaMemsetAsync(ctx->edge_table.p, 0, set_cap * sizeof(Slot), s));
@@ -2096,7 +2104,6 @@ mdbg_status mdbg_edges_index(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_edges_o
                         (unsigned long long)st.n_entries);
         uint64_t* d_cnt = ctx->m_bucket.as<uint64_t>();
         uint64_t* d_base = d_cnt + R;
-        uint64_t* d_all = d_cnt + 2 * R;
         CK(cudaMemsetAsync(d_cnt, 0, R * 8, s));
         BucketKeyArgs b{};
         b.keys = ctx->m_send_vecs.as<uint64_t>();
@@ -2107,39 +2114,18 @@ mdbg_status mdbg_edges_index(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_edges_o
         b.pass = 1;
         launch_bucket_keys(b, s);
         CKS(check_launch(ctx, "bucket_keys_kernel(count)", off_cap ? 1 : 0));
-        NK(g_nccl.AllGather(d_cnt, d_all, R, NCCL_UINT64, ctx->nccl_comm, s));
-        std::vector<uint64_t> all((size_t)R * R);
-        CK(cudaMemcpyAsync(all.data(), d_all, (size_t)R * R * 8, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        std::vector<uint64_t> send_cnt(R), send_base(R), recv_cnt(R), recv_base(R);
-        uint64_t send_total = 0, recv_total = 0;
-        for (uint32_t d = 0; d < R; d++) {
-            send_cnt[d] = all[(size_t)ctx->rank * R + d];
-            send_base[d] = send_total;
-            send_total += send_cnt[d];
-            recv_cnt[d] = all[(size_t)d * R + ctx->rank];
-            recv_base[d] = recv_total;
-            recv_total += recv_cnt[d];
-        }
-        CKS(ensure(ctx, ctx->prev_stage_h, (send_total + 1) * 24));
+        OwnerExchange xo;
+        CKS(xo.plan(ctx));
+        const uint64_t recv_total = xo.recv_total;
+        CKS(ensure(ctx, ctx->prev_stage_h, (xo.send_total + 1) * 24));
         CKS(ensure(ctx, ctx->m_recv_vecs, (recv_total + 1) * 24));
-        CK(cudaMemcpyAsync(d_base, send_base.data(), R * 8, cudaMemcpyHostToDevice, s));
-        CK(cudaMemsetAsync(d_cnt, 0, R * 8, s));
+        CKS(xo.upload_bases(ctx));
         b.bucket_base = d_base;
         b.out_keys = ctx->prev_stage_h.as<uint64_t>();
         b.pass = 2;
         launch_bucket_keys(b, s);
         CKS(check_launch(ctx, "bucket_keys_kernel(scatter)", off_cap ? 1 : 0));
-        NK(g_nccl.GroupStart());
-        for (uint32_t d = 0; d < R; d++) {
-            if (send_cnt[d])
-                NK(g_nccl.Send(ctx->prev_stage_h.as<uint64_t>() + 3 * send_base[d], send_cnt[d] * 24, NCCL_UINT8, (int)d,
-                               ctx->nccl_comm, s));
-            if (recv_cnt[d])
-                NK(g_nccl.Recv(ctx->m_recv_vecs.as<uint64_t>() + 3 * recv_base[d], recv_cnt[d] * 24, NCCL_UINT8, (int)d,
-                               ctx->nccl_comm, s));
-        }
-        NK(g_nccl.GroupEnd());
+        CKS(xo.run(ctx, ctx->prev_stage_h.p, ctx->m_recv_vecs.p, 24));
         launch_edge_apply_offers(ctx->m_recv_vecs.as<uint64_t>(), recv_total, ctx->edge_table.as<Slot>(), set_cap - 1,
                                  ctx->edge_vals.as<unsigned long long>(), &ctx->d_small->full_flag, s);
         CKS(check_launch(ctx, "edge_apply_offers_kernel", recv_total ? 1 : 0));
