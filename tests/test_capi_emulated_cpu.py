@@ -59,7 +59,7 @@ def test_owner_merge_on_the_emulator(emulated, n_ranks, k, n_reads):
 
 def test_gpu_parity_suites_against_the_emulated_library(emulated):
     lib, env = emulated
-    run = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "tests/test_gpu_host_cpp.py", "-m", "gpu",
+    run = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "tests/test_gpu_host_cpp.py", "tests/test_gpu_z_new_paths.py", "-m", "gpu",
                           "-q", "-x", "-p", "no:cacheprovider"], cwd=ROOT, env=env, capture_output=True, text=True,
                          timeout=3000)
     tail = run.stdout[-2500:] + run.stderr[-1500:]
@@ -67,7 +67,7 @@ def test_gpu_parity_suites_against_the_emulated_library(emulated):
     last = run.stdout.strip().splitlines()[-1]
     assert "passed" in last and "failed" not in last, tail
     n_passed = int(last.split(" passed")[0].split()[-1])
-    assert n_passed >= 33, tail                  # 29 parity + 4 host-driver tests
+    assert n_passed >= 39, tail                  # parity + host-driver + the paths added after the last GPU run
 
 
 def test_sketch_variant_1_through_the_emulated_library(emulated):
@@ -75,7 +75,7 @@ def test_sketch_variant_1_through_the_emulated_library(emulated):
     block (k1v1:: in common.cuh / bitmath.cuh) behind the whole host-side sequencing."""
     lib, env = emulated
     env = dict(env, MDBG_SKETCH_VARIANT="1")
-    run = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "-m", "gpu", "-q", "-x",
+    run = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "tests/test_gpu_z_new_paths.py", "-m", "gpu", "-q", "-x",
                           "-p", "no:cacheprovider", "-k", "sketch_hifi or sketch_ont or sketch_golden or sketch_edge or sketch_long or packed_host or full_path or piece_pipeline or sentinel"],
                          cwd=ROOT, env=env, capture_output=True, text=True, timeout=3000)
     tail = run.stdout[-2500:] + run.stderr[-1500:]
@@ -108,8 +108,8 @@ def test_gpu_parity_suite_with_deferred_stream_execution(tmp_path):
     # the tests that exercise host-side sequencing (the kernels themselves are covered by the eager run above)
     pick = ("piece or packed or count or rescue or next_k or multi_k or edge or full_path or side_outputs_vs or sentinel "
             "or variants or table_full or bad_host or empty or smoke or density")
-    run = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "-m", "gpu", "-q", "-x",
-                          "-p", "no:cacheprovider", "-k", pick], cwd=ROOT, env=env, capture_output=True, text=True,
+    run = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "tests/test_gpu_z_new_paths.py", "-m", "gpu",
+                          "-q", "-x", "-p", "no:cacheprovider", "-k", pick], cwd=ROOT, env=env, capture_output=True, text=True,
                          timeout=3000)
     tail = run.stdout[-2500:] + run.stderr[-1500:]
     assert run.returncode == 0, tail

@@ -136,31 +136,6 @@ def test_cpp_driver_graph_seam_and_default_mode(tmp_path, oracle):
     got = {(int(h), int(l)): int(c_) for h, l, c_ in zip(hi, lo, cnt)}
     assert got == want
     assert int(stats["solid"]) == len(c["abundances"]) and int(stats["rescued"]) == len(r["hashes"]) > 0
-    # --max-k: the k > firstK passes (GpuNextKCounter) from the table the context holds, default mode: the previous
-    # table of k = 5 carries the rescued entries, as kminmerData_abundance.txt does upstream
-    d3 = tmp_path / "three"
-    d3.mkdir()
-    out = subprocess.run([EXE, "--from-read-data", str(d1 / "read_data_corrected.txt"), str(d3), "--min-abundance", "0",
-                          "--max-k", "7", "--edges"], capture_output=True, text=True, timeout=120)
-    assert out.returncode == 0, out.stderr
-    # --edges: edges.bin of the k = 4 node set (GpuEdgeIndexer) = the oracle's EdgeIndexer key set
-    nodes = np.frombuffer(open(d3 / "kminmerData_min.txt", "rb").read(), dtype=np.uint32).reshape(-1, 4)
-    we = oracle.edge_index(nodes, 4)
-    eb = np.frombuffer(open(d3 / "edges.bin", "rb").read(), dtype=np.uint64).reshape(-1, 2)       # {low, high}
-    assert {(int(h[1]), int(h[0])) for h in eb} == {(int(h[0]), int(h[1])) for h in we["hashes"]} and len(eb) == len(we["hashes"]) > 500
-    words = out.stdout.split()
-    assert int(words[words.index("edges") + 1]) == len(eb) and int(words[words.index("edge_checksum") + 1]) == we["checksum"]
-    ph = np.concatenate([c["hashes"], r["hashes"]]); pa = np.concatenate([c["abundances"], np.ones(len(r["hashes"]), np.uint32)])
-    for kk in (5, 6, 7):
-        nk = oracle.next_k(m, mo, kk, ph, pa)
-        ab = np.frombuffer(open(d3 / f"kminmerData_abundance_k{kk}.txt", "rb").read(), dtype=np.uint8).reshape(-1, 20)
-        lo = ab[:, 0:8].copy().view(np.uint64)[:, 0]; hi = ab[:, 8:16].copy().view(np.uint64)[:, 0]
-        cnt = ab[:, 16:20].copy().view(np.uint32)[:, 0]
-        assert {(int(h), int(l)): int(c_) for h, l, c_ in zip(hi, lo, cnt)} == \
-            {(int(h[0]), int(h[1])): int(a) for h, a in zip(nk["hashes"], nk["abundances"])}, f"k={kk}"
-        vec = np.frombuffer(open(d3 / f"kminmerData_min_k{kk}.txt", "rb").read(), dtype=np.uint32).reshape(-1, kk)
-        assert sorted(map(tuple, vec.tolist())) == sorted(map(tuple, nk["vecs"].tolist())) and len(vec) > 500
-        ph, pa = nk["hashes"], nk["abundances"]
     # FASTA input: no qualities -> per-minimizer quality 1 and NaN mean quality in read_data_init.txt
     from oracle.pyoracle import parse_read_data
     recs = parse_read_data(str(d1 / "read_data_init.txt"), True)
