@@ -164,15 +164,20 @@ mdbg_status mdbg_ctx_last_batch_info(mdbg_ctx* ctx, mdbg_batch_info* info);
 mdbg_status mdbg_sketch_batch_device(mdbg_ctx* ctx, const uint8_t* d_bases, const uint64_t* d_offsets,
                                      uint32_t n_reads, uint64_t n_bases, int append_to_store,
                                      mdbg_sketch_dev* out);
-/* The sketch kernel's unrolled l = 15 block exists in MDBG_SKETCH_VARIANTS arithmetic variants with identical
- * results (sketch.cu: 0 = one roll step + candidate filter per position, 1 = funnel-shift l-mers from packed codes,
- * one final hash multiply on the summed pre-images, carry-chain accept bits).  Variant 0 is the default; the
- * environment variable MDBG_SKETCH_VARIANT presets it at context creation.  mdbg_ctx_autotune_sketch runs every
- * variant on the caller's own device-resident batch (nothing is appended to the store), compares the complete
- * results with variant 0 byte for byte ON THE DEVICE, and keeps the fastest variant that is identical.  Every
- * variant is run twice: once as one launch (timed), once in launches of 2048 reads with the shared memory of all
- * SMs overwritten in between, so that a variant depending on stale shared memory fails the comparison. */
-#define MDBG_SKETCH_VARIANTS 2
+/* The sketch kernel exists in MDBG_SKETCH_VARIANTS variants with identical results (sketch.cu):
+ *   2 (default)  the packed kernel: 2-bit bases fetched by bulk copy (TMA) into shared memory, homopolymer
+ *                compression by table lookups in registers, bit-packed ring, funnel-shift l-mers.  ASCII input is
+ *                turned into the 2-bit layout by one streaming pass on the device first; reads holding a byte
+ *                outside "ACGT", minimizer sizes other than 15 and degenerate densities use the byte-ring kernel.
+ *   0 / 1        the byte-ring kernel on ASCII bytes (0 = one roll step + candidate filter per position, 1 =
+ *                funnel-shift l-mers from codes packed in registers, one final hash multiply on the summed
+ *                pre-images, carry-chain accept bits).
+ * The environment variable MDBG_SKETCH_VARIANT presets the variant at context creation.  mdbg_ctx_autotune_sketch
+ * runs every variant on the caller's own device-resident batch (nothing is appended to the store), compares the
+ * complete results with variant 0 byte for byte ON THE DEVICE, and keeps the fastest variant that is identical.
+ * Every variant is run twice: once as one launch (timed), once in launches of 2048 reads with the shared memory of
+ * all SMs overwritten in between, so that a variant depending on stale shared memory fails the comparison. */
+#define MDBG_SKETCH_VARIANTS 3
 typedef struct mdbg_autotune_out {
     int32_t n_variants;
     int32_t chosen;                                  /* variant now active in the context */
@@ -191,6 +196,24 @@ mdbg_status mdbg_ctx_autotune_sketch(mdbg_ctx* ctx, const uint8_t* d_bases, cons
 mdbg_status mdbg_sketch_batch_device_packed(mdbg_ctx* ctx, const uint32_t* d_packed, const uint64_t* d_word_offsets,
                                             const uint64_t* d_offsets, uint32_t n_reads, uint64_t n_bases,
                                             int append_to_store, mdbg_sketch_dev* out);
+/* The packed layout is the device-resident input format of the sketch (0.25 B per base).  d_packed must be
+ * 16-byte aligned and readable up to the next multiple of 16 bytes behind the last word of the last read (any
+ * cudaMalloc'ed buffer is): the kernel fetches each read with 16-byte granular bulk copies.  Reads that start on a
+ * 16-byte boundary (word offset % 4 == 0, what mdbg_pack_device produces) avoid a slower first step.
+ *
+ * mdbg_pack_device: ASCII reads in HBM -> that layout, one streaming pass (1 B/bp read, 0.25 B/bp written).
+ *   d_packed_out      caller-owned, mdbg_pack_device_words(n_bases, n_reads) u32
+ *   d_read_src_out    [n_reads]: word offset of the read, or MDBG_SRC_ASCII | byte offset in d_bases for a read
+ *                     holding a byte outside "ACGT" (not representable; it stays ASCII)
+ * mdbg_sketch_batch_device_packed2 takes exactly these two arrays plus the ASCII buffer the flagged reads live in
+ * (d_bases may be NULL when no entry is flagged). */
+#define MDBG_SRC_ASCII (1ULL << 63)
+uint64_t    mdbg_pack_device_words(uint64_t n_bases, uint64_t n_reads);
+mdbg_status mdbg_pack_device(mdbg_ctx* ctx, const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t n_reads,
+                             uint64_t n_bases, uint32_t* d_packed_out, uint64_t* d_read_src_out);
+mdbg_status mdbg_sketch_batch_device_packed2(mdbg_ctx* ctx, const uint32_t* d_packed, const uint64_t* d_read_src,
+                                             const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t n_reads,
+                                             uint64_t n_bases, int append_to_store, mdbg_sketch_dev* out);
 /* Copy the last batch's CSR to pinned host memory (after *_device). */
 mdbg_status mdbg_sketch_fetch(mdbg_ctx* ctx, mdbg_sketch_out* out);
 

@@ -81,6 +81,10 @@ SYMBOLS = {
                                            C.POINTER(AutotuneOut)]),
     "mdbg_sketch_batch_device_packed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                                   C.c_uint64, C.c_int, C.POINTER(SketchDev)]),
+    "mdbg_pack_device_words": (C.c_uint64, [C.c_uint64, C.c_uint64]),
+    "mdbg_pack_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "mdbg_sketch_batch_device_packed2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                                   C.c_uint64, C.c_int, C.POINTER(SketchDev)]),
     "mdbg_sketch_fetch": (C.c_int, [C.c_void_p, C.POINTER(SketchOut)]),
     "mdbg_ctx_set_read_filters": (C.c_int, [C.c_void_p, C.c_int]),
     "mdbg_sketch_batch_q": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int,

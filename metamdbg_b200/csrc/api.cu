@@ -41,6 +41,8 @@ constexpr int MAX_SUB = 64;       // H2D/compute pipeline depth of one host batc
 struct SmallDev {                 // device-side scalars, one allocation
     uint32_t cursor;
     uint32_t sub_cursor[MAX_SUB];
+    uint32_t dirty_n[1 + MAX_SUB];       // variant 2: reads left to the byte-ring kernel, whole batch [0] / per piece [1 + i]
+    uint32_t dirty_cur[1 + MAX_SUB];     // ... and the list-mode cursors
     uint32_t full_flag;
     unsigned long long n_overflow;
     unsigned long long n_flagged;
@@ -57,7 +59,8 @@ struct mdbg_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
-    int sketch_variant = 0;            // arithmetic variant of the unrolled l = 15 block (sketch.cu); same results
+    int sketch_variant = 2;            // sketch kernel variant (sketch.cu): 2 = packed kernel (default), 0 / 1 = byte-ring
+                                       // kernel with the two arithmetic forms of the l = 15 block; same results
     int host_packing = -1;             // 2-bit pack ASCII host batches before H2D: -1 auto, 0 off, 1 on, 2 hybrid
     HostPool* pool = nullptr;
     uint64_t last_direct_pieces = 0, last_pieces = 0;   // hybrid transfer statistics of the last host batch
@@ -65,7 +68,7 @@ struct mdbg_ctx {
     uint64_t last_pipelined = 0, last_grows = 0;   // piece pipeline: pieces finished piece-wise, mid-batch buffer growths
     int last_overflow_fallback = 0, last_packed = 0;
     int auto_pack_pause = 0;           // auto mode: batches still to send as ASCII after the packer proved too slow
-    DevBuf d_pack, d_src;
+    DevBuf d_pack, d_src, d_dirty;
     PinBuf h_pack, h_src, h_asc;
     cudaEvent_t sub_ev[MAX_SUB] = {};
     cudaEvent_t copy_gate = nullptr;
@@ -400,6 +403,33 @@ struct PiecePipeline {
 using Feeder = std::function<mdbg_status(SketchArgs&)>;
 
 
+// Variant 2 on ASCII bytes that are already in HBM (device batches, host batches that travelled unpacked): buffers
+// for the 2-bit copy, and the streaming pack pass over a read range (launched right in front of that range's sketch).
+mdbg_status device_pack_prepare(mdbg_ctx* ctx, SketchArgs& a, uint32_t n_reads, uint64_t n_bases) {
+    CKS(ensure(ctx, ctx->d_pack, pack_words_capacity(n_bases, n_reads) * 4 + 64));
+    CKS(ensure(ctx, ctx->d_src, (size_t)n_reads * 8));
+    a.packed = ctx->d_pack.as<uint32_t>();
+    a.read_src = ctx->d_src.as<uint64_t>();
+    return MDBG_OK;
+}
+mdbg_status device_pack_range(mdbg_ctx* ctx, const SketchArgs& a, uint32_t r0, uint32_t r1, cudaStream_t s) {
+    PackArgsAscii pa{};
+    pa.bases = a.bases; pa.bases_end = a.bases_end; pa.offsets = a.offsets;
+    pa.read_begin = r0; pa.read_end = r1;
+    pa.packed = ctx->d_pack.as<uint32_t>(); pa.read_src = ctx->d_src.as<uint64_t>();
+    launch_pack_ascii(pa, ctx->sm_count, s);
+    return check_launch(ctx, "pack_ascii_kernel", r1 > r0 ? 1 : 0);
+}
+// per-piece launches of a host batch: each piece has its own cursor, dirty list segment and counters
+void piece_args(mdbg_ctx* ctx, SketchArgs& a, size_t i, uint32_t r0, uint32_t r1) {
+    a.read_begin = r0;
+    a.read_end = r1;
+    a.cursor = &ctx->d_small->sub_cursor[i];
+    a.dirty_list = ctx->d_dirty.as<uint32_t>() + r0;
+    a.dirty_count = &ctx->d_small->dirty_n[1 + i];
+    a.dirty_cursor = &ctx->d_small->dirty_cur[1 + i];
+}
+
 mdbg_status sketch_internal(mdbg_ctx* ctx, const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t n_reads,
                             uint64_t n_bases, int append, bool want_aux = false, const uint8_t* d_quals = nullptr,
                             const Feeder* feeder = nullptr, PiecePipeline* pipe = nullptr) {
@@ -443,9 +473,19 @@ mdbg_status sketch_internal(mdbg_ctx* ctx, const uint8_t* d_bases, const uint64_
     a.cursor = &ctx->d_small->cursor;
     a.n_overflow = &ctx->d_small->n_overflow;
     a.variant = (uint32_t)ctx->sketch_variant;
+    CKS(ensure(ctx, ctx->d_dirty, (size_t)n_reads * 4));
+    a.dirty_list = ctx->d_dirty.as<uint32_t>();
+    a.dirty_count = &ctx->d_small->dirty_n[0];
+    a.dirty_cursor = &ctx->d_small->dirty_cur[0];
 
-    CK(cudaMemsetAsync(&ctx->d_small->cursor, 0, sizeof(uint32_t) * (1 + MAX_SUB), s));
+    // cursor, sub_cursor[], dirty_n[], dirty_cur[] are adjacent
+    CK(cudaMemsetAsync(&ctx->d_small->cursor, 0, sizeof(uint32_t) * (1 + MAX_SUB + 2 * (1 + MAX_SUB)), s));
     CK(cudaMemsetAsync(&ctx->d_small->n_overflow, 0, sizeof(unsigned long long), s));
+    if (!feeder && d_bases && a.variant == 2 && sketch_packed_eligible(a)) {
+        // ASCII batch resident in HBM: one streaming pass turns it into the 2-bit layout the packed kernel reads
+        CKS(device_pack_prepare(ctx, a, n_reads, n_bases));
+        CKS(device_pack_range(ctx, a, 0, n_reads, s));
+    }
     if (feeder) {
         if (pipe) CKS(pipe->begin(n_bases));
         CKS((*feeder)(a));
@@ -453,11 +493,14 @@ mdbg_status sketch_internal(mdbg_ctx* ctx, const uint8_t* d_bases, const uint64_
         a.read_begin = 0;
         a.read_end = n_reads;
         a.cursor = &ctx->d_small->cursor;
+        a.dirty_list = ctx->d_dirty.as<uint32_t>();
+        a.dirty_count = &ctx->d_small->dirty_n[0];
+        a.dirty_cursor = &ctx->d_small->dirty_cur[0];
     } else {
         if (ctx->timing) CK(cudaEventRecord(ctx->ev[0][0], s));
-        launch_sketch(a, ctx->sm_count, s);
+        const int n_k = launch_sketch(a, ctx->sm_count, s);
         if (ctx->timing) { CK(cudaEventRecord(ctx->ev[0][1], s)); ctx->ev_valid[0] = true; }
-        CKS(check_launch(ctx, "sketch_kernel", 1));
+        CKS(check_launch(ctx, "sketch_kernel", n_k + 0));
     }
     if (want_aux) {
         CKS(ensure_err_table(ctx));
@@ -527,10 +570,13 @@ mdbg_status sketch_internal(mdbg_ctx* ctx, const uint8_t* d_bases, const uint64_
         a.out_min = ctx->b_min.as<uint32_t>();
         a.out_pos = ctx->b_pos.as<uint32_t>();
         a.out_dir = ctx->b_dir.as<uint8_t>();
-        CK(cudaMemsetAsync(&ctx->d_small->cursor, 0, sizeof(uint32_t), s));
+        a.dirty_list = ctx->d_dirty.as<uint32_t>();
+        a.dirty_count = &ctx->d_small->dirty_n[0];
+        a.dirty_cursor = &ctx->d_small->dirty_cur[0];
+        CK(cudaMemsetAsync(&ctx->d_small->cursor, 0, sizeof(uint32_t) * (1 + MAX_SUB + 2 * (1 + MAX_SUB)), s));
         CK(cudaMemsetAsync(&ctx->d_small->n_overflow, 0, sizeof(unsigned long long), s));
-        launch_sketch(a, ctx->sm_count, s);
-        CKS(check_launch(ctx, "sketch_kernel(exact)", 1));
+        const int n_k = launch_sketch(a, ctx->sm_count, s);
+        CKS(check_launch(ctx, "sketch_kernel(exact)", n_k + 0));
         if (want_aux) {
             // qualities again on the exact slots (the filter was already applied to n_min; a filtered read has an
             // empty exact slot, and the re-sketch writes nothing into it)
@@ -749,7 +795,7 @@ void mdbg_ctx_destroy(mdbg_ctx* c) {
     DevBuf* devs[] = {&c->d_blacklist, &c->d_bases, &c->d_offsets, &c->pad_min, &c->pad_pos, &c->pad_dir, &c->n_min,
                       &c->scan_scratch, &c->b_off, &c->b_min, &c->b_pos, &c->b_dir, &c->s_min, &c->s_off, &c->s_rem,
                       &c->p_flags, &c->p_keep, &c->p_cnt, &c->p_newoff, &c->p_newmin, &c->table, &c->foreign_vecs,
-                      &c->o_hash, &c->o_abund, &c->o_vecs, &c->d_pack, &c->d_src, &c->d_quals, &c->pad_qual, &c->pad_raw_a, &c->pad_raw_b, &c->b_qual, &c->x_sum_lo, &c->x_sum_hi, &c->x_lmin, &c->x_cplx, &c->x_low, &c->d_err_fixed, &c->d_err_tz, &c->prev_table, &c->prev_stage_h, &c->prev_stage_a, &c->m_send_vecs, &c->m_send_counts, &c->m_recv_vecs,
+                      &c->o_hash, &c->o_abund, &c->o_vecs, &c->d_pack, &c->d_src, &c->d_dirty, &c->d_quals, &c->pad_qual, &c->pad_raw_a, &c->pad_raw_b, &c->b_qual, &c->x_sum_lo, &c->x_sum_hi, &c->x_lmin, &c->x_cplx, &c->x_low, &c->d_err_fixed, &c->d_err_tz, &c->prev_table, &c->prev_stage_h, &c->prev_stage_a, &c->m_send_vecs, &c->m_send_counts, &c->m_recv_vecs,
                       &c->m_recv_counts, &c->m_bucket, &c->loc_off, &c->edge_table, &c->edge_vals, &c->o_edge_vals};
     for (DevBuf* b : devs) release(*b);
     PinBuf* pins[] = {&c->h_off, &c->h_min, &c->h_pos, &c->h_dir, &c->ho_hash, &c->ho_abund, &c->ho_vecs, &c->hx_sum_lo, &c->hx_sum_hi, &c->hx_lmin, &c->hx_cplx, &c->hx_low, &c->hx_meanq, &c->h_qual, &c->h_pack, &c->h_src, &c->h_asc, &c->ho_edge_vals};
@@ -907,11 +953,17 @@ mdbg_status mdbg_ctx_autotune_sketch(mdbg_ctx* ctx, const uint8_t* d_bases, cons
         for (uint32_t r0 = 0; r0 < n_reads; r0 += step, it++) {
             launch_smem_scramble(ctx->sm_count, it, &ctx->d_small->full_flag, s);
             CK(cudaMemsetAsync(&ctx->d_small->cursor, 0, sizeof(uint32_t), s));
+            CK(cudaMemsetAsync(&ctx->d_small->dirty_n[0], 0, sizeof(uint32_t), s));
+            CK(cudaMemsetAsync(&ctx->d_small->dirty_cur[0], 0, sizeof(uint32_t), s));
             a.read_begin = r0;
             a.read_end = std::min<uint64_t>(n_reads, (uint64_t)r0 + step);
             a.cursor = &ctx->d_small->cursor;
-            launch_sketch(a, ctx->sm_count, s);
-            CKS(check_launch(ctx, "sketch_kernel(stress)", 2));
+            if (it == 0 && a.variant == 2 && sketch_packed_eligible(a)) {
+                CKS(device_pack_prepare(ctx, a, n_reads, n_bases));
+                CKS(device_pack_range(ctx, a, 0, n_reads, s));
+            }
+            const int n_k = launch_sketch(a, ctx->sm_count, s);
+            CKS(check_launch(ctx, "sketch_kernel(stress)", n_k + 1));
         }
         return MDBG_OK;
     };
@@ -979,6 +1031,7 @@ mdbg_status mdbg_sketch_batch_device_packed(mdbg_ctx* ctx, const uint32_t* d_pac
                                             int append_to_store, mdbg_sketch_dev* out) {
     if (!ctx) return MDBG_ERR_ARG;
     if (n_reads && (!d_packed || !d_word_offsets || !d_offsets)) return fail(ctx, MDBG_ERR_ARG, "null device buffer");
+    if ((uintptr_t)d_packed & 15) return fail(ctx, MDBG_ERR_ARG, "d_packed must be 16-byte aligned");
     CK(cudaSetDevice(ctx->device));
     const Feeder feeder = [&](SketchArgs& a) -> mdbg_status {
         a.read_src = d_word_offsets;            // bit 63 clear everywhere: every read is packed
@@ -986,9 +1039,55 @@ mdbg_status mdbg_sketch_batch_device_packed(mdbg_ctx* ctx, const uint32_t* d_pac
         a.bases = nullptr;
         a.bases_end = nullptr;
         if (ctx->timing) CK(cudaEventRecord(ctx->ev[0][0], ctx->stream));
-        launch_sketch(a, ctx->sm_count, ctx->stream);
+        const int n_k = launch_sketch(a, ctx->sm_count, ctx->stream);
         if (ctx->timing) { CK(cudaEventRecord(ctx->ev[0][1], ctx->stream)); ctx->ev_valid[0] = true; }
-        return check_launch(ctx, "sketch_kernel", 1);
+        return check_launch(ctx, "sketch_kernel", n_k + 0);
+    };
+    CKS(sketch_internal(ctx, nullptr, d_offsets, n_reads, n_bases, append_to_store, false, nullptr, &feeder));
+    if (out) {
+        out->n_reads = n_reads;
+        out->n_minimizers = ctx->b_total;
+        out->d_min_offsets = ctx->b_off.as<uint64_t>();
+        out->d_minimizers = ctx->b_min.as<uint32_t>();
+        out->d_positions = ctx->b_pos.as<uint32_t>();
+        out->d_directions = ctx->b_dir.as<uint8_t>();
+    }
+    return MDBG_OK;
+}
+
+uint64_t mdbg_pack_device_words(uint64_t n_bases, uint64_t n_reads) { return pack_words_capacity(n_bases, n_reads) + 16; }
+
+mdbg_status mdbg_pack_device(mdbg_ctx* ctx, const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t n_reads,
+                             uint64_t n_bases, uint32_t* d_packed_out, uint64_t* d_read_src_out) {
+    if (!ctx) return MDBG_ERR_ARG;
+    if (n_reads == 0) return MDBG_OK;
+    if (!d_bases || !d_offsets || !d_packed_out || !d_read_src_out) return fail(ctx, MDBG_ERR_ARG, "null device buffer");
+    if (((uintptr_t)d_bases & 15) || ((uintptr_t)d_packed_out & 15)) return fail(ctx, MDBG_ERR_ARG, "d_bases and d_packed_out must be 16-byte aligned");
+    CK(cudaSetDevice(ctx->device));
+    PackArgsAscii pa{};
+    pa.bases = d_bases; pa.bases_end = d_bases + n_bases; pa.offsets = d_offsets;
+    pa.read_begin = 0; pa.read_end = n_reads;
+    pa.packed = d_packed_out; pa.read_src = d_read_src_out;
+    launch_pack_ascii(pa, ctx->sm_count, ctx->stream);
+    return check_launch(ctx, "pack_ascii_kernel", 1);
+}
+
+mdbg_status mdbg_sketch_batch_device_packed2(mdbg_ctx* ctx, const uint32_t* d_packed, const uint64_t* d_read_src,
+                                             const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t n_reads,
+                                             uint64_t n_bases, int append_to_store, mdbg_sketch_dev* out) {
+    if (!ctx) return MDBG_ERR_ARG;
+    if (n_reads && (!d_packed || !d_read_src || !d_offsets)) return fail(ctx, MDBG_ERR_ARG, "null device buffer");
+    if (((uintptr_t)d_packed & 15) || ((uintptr_t)d_bases & 15)) return fail(ctx, MDBG_ERR_ARG, "d_packed and d_bases must be 16-byte aligned");
+    CK(cudaSetDevice(ctx->device));
+    const Feeder feeder = [&](SketchArgs& a) -> mdbg_status {
+        a.read_src = d_read_src;
+        a.packed = d_packed;
+        a.bases = d_bases;
+        a.bases_end = d_bases ? d_bases + n_bases : nullptr;
+        if (ctx->timing) CK(cudaEventRecord(ctx->ev[0][0], ctx->stream));
+        const int n_k = launch_sketch(a, ctx->sm_count, ctx->stream);
+        if (ctx->timing) { CK(cudaEventRecord(ctx->ev[0][1], ctx->stream)); ctx->ev_valid[0] = true; }
+        return check_launch(ctx, "sketch_kernel", n_k);
     };
     CKS(sketch_internal(ctx, nullptr, d_offsets, n_reads, n_bases, append_to_store, false, nullptr, &feeder));
     if (out) {
@@ -1127,6 +1226,9 @@ static mdbg_status sketch_host_batch(mdbg_ctx* ctx, const uint8_t* bases, const 
         CKS(ensure(ctx, ctx->d_bases, n_bases + 64));
         if (quals) CKS(ensure(ctx, ctx->d_quals, n_bases + 64));
         const Feeder feeder = [&](SketchArgs& a) -> mdbg_status {
+            // the ASCII bytes are packed on the device, piece by piece, in front of the packed kernel (variant 2)
+            const bool dev_pack = a.variant == 2 && sketch_packed_eligible(a);
+            if (dev_pack) CKS(device_pack_prepare(ctx, a, n_reads, n_bases));
             for (size_t i = 0; i < subs.size(); i++) {
                 const uint64_t lo = offsets[subs[i].r0], hi = offsets[subs[i].r1];
                 if (hi > lo) {
@@ -1137,11 +1239,10 @@ static mdbg_status sketch_host_batch(mdbg_ctx* ctx, const uint8_t* bases, const 
                 }
                 CK(cudaEventRecord(ctx->sub_ev[i], cs));
                 CK(cudaStreamWaitEvent(s, ctx->sub_ev[i], 0));
-                a.read_begin = subs[i].r0;
-                a.read_end = subs[i].r1;
-                a.cursor = &ctx->d_small->sub_cursor[i];
-                launch_sketch(a, ctx->sm_count, s);
-                CKS(check_launch(ctx, "sketch_kernel", 1));
+                piece_args(ctx, a, i, subs[i].r0, subs[i].r1);
+                if (dev_pack) CKS(device_pack_range(ctx, a, subs[i].r0, subs[i].r1, s));
+                const int n_k = launch_sketch(a, ctx->sm_count, s);
+                CKS(check_launch(ctx, "sketch_kernel", n_k + 0));
                 if (pipe) CKS(pipe->launched(i));
             }
             return MDBG_OK;
@@ -1154,12 +1255,13 @@ static mdbg_status sketch_host_batch(mdbg_ctx* ctx, const uint8_t* bases, const 
     if (!ctx->pool) ctx->pool = host_pool_create(0);
     std::vector<uint64_t> pk_off((size_t)n_reads + 1);
     pk_off[0] = 0;
-    for (uint32_t r = 0; r < n_reads; r++) pk_off[r + 1] = pk_off[r] + ((offsets[r + 1] - offsets[r] + 15) >> 4);
+    // every read starts on a 16-byte boundary of the packed buffer: the packed kernel fetches it by bulk copy
+    for (uint32_t r = 0; r < n_reads; r++) pk_off[r + 1] = pk_off[r] + (((offsets[r + 1] - offsets[r] + 63) >> 6) << 2);
     const uint64_t n_words = pk_off[n_reads];
     const uint64_t asc_cap = n_bases + 16ull * n_reads + 64;                 // worst case: every read kept as ASCII
     CKS(ensure_pin(ctx, ctx->h_pack, (n_words + 1) * 4));
     CKS(ensure_pin(ctx, ctx->h_src, (size_t)n_reads * 8));
-    CKS(ensure(ctx, ctx->d_pack, (n_words + 1) * 4));
+    CKS(ensure(ctx, ctx->d_pack, (n_words + 1) * 4 + 64));
     CKS(ensure(ctx, ctx->d_src, (size_t)n_reads * 8));
     // Hybrid transfer: when the caller's buffer is pinned, a piece can also travel as plain ASCII by DMA alone
     // (no CPU work).  Each piece picks its mode by looking at the copy stream: if the previous pieces have already
@@ -1228,11 +1330,9 @@ static mdbg_status sketch_host_batch(mdbg_ctx* ctx, const uint8_t* bases, const 
         CK(cudaStreamWaitEvent(s, ctx->sub_ev[i], 0));
         a.bases = ctx->d_bases.as<uint8_t>();
         a.bases_end = ctx->d_bases.p ? ctx->d_bases.as<uint8_t>() + ctx->d_bases.cap - 32 : nullptr;
-        a.read_begin = r0;
-        a.read_end = r1;
-        a.cursor = &ctx->d_small->sub_cursor[i];
-        launch_sketch(a, ctx->sm_count, s);
-        CKS(check_launch(ctx, "sketch_kernel", 1));
+        piece_args(ctx, a, i, r0, r1);
+        const int n_k = launch_sketch(a, ctx->sm_count, s);
+        CKS(check_launch(ctx, "sketch_kernel", n_k + 0));
         if (pipe) CKS(pipe->launched(i));
         return MDBG_OK;
     };
@@ -1287,11 +1387,9 @@ static mdbg_status sketch_host_batch(mdbg_ctx* ctx, const uint8_t* bases, const 
                 CK(cudaStreamWaitEvent(s, ctx->sub_ev[i], 0));
                 a.bases = ctx->d_bases.as<uint8_t>();
                 a.bases_end = ctx->d_bases.p ? ctx->d_bases.as<uint8_t>() + ctx->d_bases.cap - 32 : nullptr;
-                a.read_begin = r0;
-                a.read_end = r1;
-                a.cursor = &ctx->d_small->sub_cursor[i];
-                launch_sketch(a, ctx->sm_count, s);
-                CKS(check_launch(ctx, "sketch_kernel", 1));
+                piece_args(ctx, a, i, r0, r1);
+                const int n_k = launch_sketch(a, ctx->sm_count, s);
+                CKS(check_launch(ctx, "sketch_kernel", n_k + 0));
                 if (pipe) CKS(pipe->launched(i));
             } else {
                 CKS(reserve_spill(r0, r1, asc_cursor.load()));

@@ -88,18 +88,11 @@ MDBG_HD uint32_t lmer_from_packed(uint32_t s_hi, uint32_t s_lo, uint32_t j) {
     return (sh >= 32u ? (s_hi >> (sh - 32u)) : funnel_r(s_lo, s_hi, sh)) & MASK;
 }
 
+// core of variant 1 / 2: 16 consecutive l-mers out of (s_hi:s_lo) = the lane's 32 codes, first base most significant,
+// and (r_lo, r_hi) = the same codes complemented, first base LEAST significant (r_lo = codes 0..15)
 template <int L>
-MDBG_HD uint32_t roll16_fast(const uint32_t (&W)[8], uint32_t thr_cand, uint32_t& s_hi, uint32_t& s_lo) {
+MDBG_HD uint32_t roll16_core(uint32_t s_hi, uint32_t s_lo, uint32_t r_lo, uint32_t r_hi, uint32_t thr_cand) {
     constexpr uint32_t MASK = (L < 16) ? ((1u << (2 * L)) - 1u) : 0xFFFFFFFFu;
-    // The ring bytes past the read's last base are whatever shared memory held (not necessarily codes, and not
-    // necessarily flagged by the bit-2 test): keep 2 bits of every byte, or pack4's multiply lets such a byte carry
-    // into the fields of the codes before it -- codes that valid positions of this lane still need.
-    constexpr uint32_t M = 0x03030303u;
-    s_hi = (pack4_msb(W[0] & M) << 24) | (pack4_msb(W[1] & M) << 16) | (pack4_msb(W[2] & M) << 8) | pack4_msb(W[3] & M);
-    s_lo = (pack4_msb(W[4] & M) << 24) | (pack4_msb(W[5] & M) << 16) | (pack4_msb(W[6] & M) << 8) | pack4_msb(W[7] & M);
-    uint32_t r_lo = brev32(s_hi ^ 0xAAAAAAAAu), r_hi = brev32(s_lo ^ 0xAAAAAAAAu);   // bit order reversed ...
-    r_lo = ((r_lo & 0x55555555u) << 1) | ((r_lo >> 1) & 0x55555555u);                // ... pairs put back
-    r_hi = ((r_hi & 0x55555555u) << 1) | ((r_hi >> 1) & 0x55555555u);
     // rejected positions are shifted into `rej` (position 0 ends up in bit 15) by a carry chain: s1 + ~thr_cand
     // carries out of 32 bits exactly when s1 > thr_cand, and the add-with-carry doubles rej and takes the carry in
     uint32_t rej = 0, risk = 0;
@@ -119,6 +112,34 @@ MDBG_HD uint32_t roll16_fast(const uint32_t (&W)[8], uint32_t thr_cand, uint32_t
     }
     if (risk >= S1_RISK) return 0xFFFFu;                            // 2^-26 per key: let the exact test decide all 16
     return brev32(~rej) >> 16;                                      // accepted positions, position j in bit j
+}
+
+// bit-reverse a word of 16 two-bit codes code-wise: code i moves from bits [2i, 2i+1] to [30-2i, 31-2i]
+MDBG_HD uint32_t reverse_codes16(uint32_t x) {
+    x = brev32(x);
+    return ((x & 0x55555555u) << 1) | ((x >> 1) & 0x55555555u);
+}
+
+template <int L>
+MDBG_HD uint32_t roll16_fast(const uint32_t (&W)[8], uint32_t thr_cand, uint32_t& s_hi, uint32_t& s_lo) {
+    // The ring bytes past the read's last base are whatever shared memory held (not necessarily codes, and not
+    // necessarily flagged by the bit-2 test): keep 2 bits of every byte, or pack4's multiply lets such a byte carry
+    // into the fields of the codes before it -- codes that valid positions of this lane still need.
+    constexpr uint32_t M = 0x03030303u;
+    s_hi = (pack4_msb(W[0] & M) << 24) | (pack4_msb(W[1] & M) << 16) | (pack4_msb(W[2] & M) << 8) | pack4_msb(W[3] & M);
+    s_lo = (pack4_msb(W[4] & M) << 24) | (pack4_msb(W[5] & M) << 16) | (pack4_msb(W[6] & M) << 8) | pack4_msb(W[7] & M);
+    const uint32_t r_lo = reverse_codes16(s_hi ^ 0xAAAAAAAAu), r_hi = reverse_codes16(s_lo ^ 0xAAAAAAAAu);
+    return roll16_core<L>(s_hi, s_lo, r_lo, r_hi, thr_cand);
+}
+
+// variant 2 (packed ring): the ring already holds two-bit codes, 16 per word, first base in the low bits --
+// `lo` = codes 0..15 of the lane, `hi` = codes 16..31.  That IS the reverse-complement orientation (up to the
+// complement xor); the forward orientation is one code-wise reversal per word.
+template <int L>
+MDBG_HD uint32_t roll16_packed(uint32_t lo, uint32_t hi, uint32_t thr_cand, uint32_t& s_hi, uint32_t& s_lo) {
+    s_hi = reverse_codes16(lo);
+    s_lo = reverse_codes16(hi);
+    return roll16_core<L>(s_hi, s_lo, lo ^ 0xAAAAAAAAu, hi ^ 0xAAAAAAAAu, thr_cand);
 }
 
 }  // namespace k1v1

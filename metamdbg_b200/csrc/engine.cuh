@@ -34,11 +34,37 @@ struct SketchArgs {
     uint32_t* n_min;             // [n_reads] true minimizer count per read
     uint32_t* cursor;            // dynamic read scheduler (zeroed before launch)
     unsigned long long* n_overflow;  // reads whose slot was too small (zeroed before launch)
-    uint32_t variant;            // arithmetic of the unrolled l = 15 block: 0 or 1 (sketch.cu; identical results)
+    uint32_t variant;            // 0 / 1: arithmetic of the unrolled l = 15 block of the byte-ring kernel; 2: the packed
+                                 // kernel (2-bit input by bulk copy, bit-packed ring) where it applies (sketch.cu)
+    // variant 2 only: reads the packed kernel cannot take (kept as ASCII because they hold a byte outside "ACGT") are
+    // appended here and sketched by the byte-ring kernel in list mode right behind it.  dirty_list has room for
+    // read_end - read_begin indices; the two counters are zeroed before the launch.
+    uint32_t* dirty_list;
+    uint32_t* dirty_count;
+    uint32_t* dirty_cursor;
+    // list mode of the byte-ring kernel (set by launch_sketch): reads read_list[0 .. *read_list_n) instead of a range
+    const uint32_t* read_list;
+    const uint32_t* read_list_n;
 };
-constexpr int SKETCH_VARIANTS = 2;
+constexpr int SKETCH_VARIANTS = 3;
 
-void launch_sketch(const SketchArgs& a, int sm_count, cudaStream_t s);
+// true when variant 2's packed kernel can run this configuration (l = 15, a usable 32-bit candidate threshold,
+// something to select); everything else stays on the byte-ring kernel
+bool sketch_packed_eligible(const SketchArgs& a);
+
+// ASCII reads -> the 2-bit device layout of SketchArgs::packed (16 bases per u32, base j at bits [2j, 2j+1], code
+// (c >> 1) & 3); read r starts at word pack_word_offset(offsets[r], r) (16-byte aligned, closed form, no prefix sum).
+// read_src[r] = that word offset, or SRC_ASCII | offsets[r] for a read holding a byte outside "ACGT".
+__host__ __device__ inline uint64_t pack_word_offset(uint64_t base_offset, uint64_t r) { return ((base_offset >> 6) + r) << 2; }
+inline uint64_t pack_words_capacity(uint64_t n_bases, uint64_t n_reads) { return ((n_bases >> 6) + n_reads + 2) << 2; }
+struct PackArgsAscii {
+    const uint8_t* bases; const uint8_t* bases_end; const uint64_t* offsets;
+    uint32_t read_begin, read_end;
+    uint32_t* packed; uint64_t* read_src;
+};
+void launch_pack_ascii(const PackArgsAscii& a, int sm_count, cudaStream_t s);
+
+int launch_sketch(const SketchArgs& a, int sm_count, cudaStream_t s);   // returns the number of kernels launched
 
 // fills the shared memory of every SM with non-code bytes (verification aid of the autotuner, see sketch.cu)
 void launch_smem_scramble(int sm_count, uint32_t seed, uint32_t* sink, cudaStream_t s);

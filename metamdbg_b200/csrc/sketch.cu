@@ -15,6 +15,7 @@
 //   --32 at a time: exact hash, blacklist, ballot compaction--> coalesced (value, position, strand)
 //   writes into the read's output slot.
 #include <algorithm>
+#include <cstring>
 
 #include "common.cuh"
 #include "engine.cuh"
@@ -147,9 +148,14 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, V ? 5 : 0) sketch_kernel(c
     const uint32_t thr_cand = (uint32_t)(a.threshold >> 32) + (V ? k1v1::S1_SLACK : 1u);
     constexpr uint32_t THR_MIN = V ? k1v1::S1_SLACK : 1u;
 
+    const uint32_t list_n = a.read_list ? *a.read_list_n : 0u;    // list mode: the reads variant 2 left behind
     for (;;) {
         uint32_t r = 0;
-        if (lane == 0) r = a.read_begin + atomicAdd(a.cursor, 1u);
+        if (lane == 0) {
+            r = atomicAdd(a.cursor, 1u);
+            if (a.read_list) r = r < list_n ? a.read_list[r] : 0xFFFFFFFFu;
+            else r += a.read_begin;
+        }
         r = __shfl_sync(0xffffffffu, r, 0);
         if (r >= a.read_end) break;
 
@@ -424,6 +430,306 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, V ? 5 : 0) sketch_kernel(c
     }
 }
 
+
+// ------------------------------------------------------------------ K1, packed form (variant 2)
+// Same result as sketch_kernel, different data path -- the layout north_star names:
+//   HBM: 2-bit packed bases (16 per u32)  --cp.async.bulk (TMA) 1 KB tiles, mbarrier, double buffered per warp-->
+//   shared-memory stage  --LDS.64 per lane (32 bases)-->  in-register homopolymer compaction: four 10-bit lookups
+//   per word in a 2 KB table ((previous code, 4 codes) -> compacted codes + count), warp prefix sum, and the lane's
+//   compacted string is OR-ed at its bit offset into a 512-byte ring of two-bit codes (no byte stores, no per-base
+//   predicates)  --2 x LDS.32 per lane-->  the variant-1 arithmetic on 16 consecutive l-mers, whose funnel-shift
+//   form wants exactly this packed string (no pack multiplies)  -->  candidate list / exact confirm as before.
+// No lane issues a global load or address arithmetic in the fill; one elected lane issues the bulk copies.
+// Reads the host kept as ASCII (a byte outside "ACGT") are appended to a list for the byte-ring kernel.
+constexpr int P_RING_WORDS = 128;                // 2048 codes per warp (power of two)
+constexpr int P_TILE_WORDS = 256;                // one bulk copy: 1 KB = 4096 bases
+constexpr int P_STEP_WORDS = 64;                 // one fill step: 2 words (32 bases) per lane = 1024 bases
+constexpr int P_STEPS_PER_TILE = P_TILE_WORDS / P_STEP_WORDS;
+
+struct __align__(16) PackedWarpSmem {
+    uint32_t stage[2][P_TILE_WORDS];
+    uint32_t ring[P_RING_WORDS];
+    uint2 cand[64];
+    unsigned long long bar[2];
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// arm the barrier with the byte count, then start the bulk copy global -> shared that completes it
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "MDBG_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra MDBG_DONE;\n\t"
+        "bra MDBG_WAIT;\n\t"
+        "MDBG_DONE:\n\t"
+        "}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+#else   // CPU emulator (tests/cpp/warp_emu.hpp): the copy completes when it is issued, waiting is a warp rendezvous
+static inline void mbar_init(unsigned long long*, uint32_t) {}
+static inline void mbar_init_fence() {}
+static inline void bulk_load(void* dst, const void* src, uint32_t bytes, unsigned long long*) { memcpy(dst, src, bytes); }
+static inline void mbar_wait(unsigned long long*, uint32_t) { __syncwarp(); }
+#endif
+
+// hpc_lut[prev | c0 << 2 | c1 << 4 | c2 << 6 | c3 << 8] = surviving codes (first survivor in the low bits) | 2 * count << 8
+__device__ __forceinline__ uint32_t hpc_lut_entry(uint32_t idx) {
+    uint32_t p = idx & 3u, out = 0, n = 0;
+    for (int t = 0; t < 4; t++) {
+        const uint32_t c = (idx >> (2 + 2 * t)) & 3u;
+        if (c != p) { out |= c << (2 * n); n++; }
+        p = c;
+    }
+    return out | (2u * n) << 8;
+}
+
+// four table entries (one word of 16 bases) -> compacted codes; n_bits = 2 * survivors
+__device__ __forceinline__ uint32_t hpc_merge4(uint32_t e0, uint32_t e1, uint32_t e2, uint32_t e3, uint32_t& n_bits) {
+    uint32_t acc = e3 & 0xFFu;
+    acc = (acc << (e2 >> 8)) | (e2 & 0xFFu);
+    acc = (acc << (e1 >> 8)) | (e1 & 0xFFu);
+    acc = (acc << (e0 >> 8)) | (e0 & 0xFFu);
+    n_bits = (e0 >> 8) + (e1 >> 8) + (e2 >> 8) + (e3 >> 8);
+    return acc;
+}
+
+template <int L>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) sketch_packed_kernel(const SketchArgs a) {
+    __shared__ PackedWarpSmem smem_all[WARPS_PER_CTA];
+    __shared__ __align__(16) uint16_t hpc_lut[1024];
+    const uint32_t lane = threadIdx.x & 31;
+    PackedWarpSmem& sm = smem_all[threadIdx.x >> 5];
+    uint32_t* ring = sm.ring;
+    uint2* cand = sm.cand;
+    const uint8_t* lut_bytes = reinterpret_cast<const uint8_t*>(hpc_lut);
+    for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) hpc_lut[i] = (uint16_t)hpc_lut_entry(i);
+    if (lane == 0) {
+        mbar_init(&sm.bar[0], 1);
+        mbar_init(&sm.bar[1], 1);
+        mbar_init_fence();
+    }
+#ifdef MDBG_POISON_SMEM
+    for (uint32_t i = lane; i < 2 * P_TILE_WORDS; i += 32) sm.stage[0][i] = 0x9E3779B9u * (i + 1);   // test builds: stale stage
+    for (uint32_t i = lane; i < P_RING_WORDS; i += 32) ring[i] = 0xDEADBEEFu + i;
+#endif
+    __syncthreads();
+    uint32_t n_list = 0, phase = 0;                     // bit s of phase: parity the next wait on stage s uses
+    const uint32_t thr_cand = (uint32_t)(a.threshold >> 32) + k1v1::S1_SLACK;
+
+    for (;;) {
+        uint32_t r = 0;
+        if (lane == 0) r = a.read_begin + atomicAdd(a.cursor, 1u);
+        r = __shfl_sync(0xffffffffu, r, 0);
+        if (r >= a.read_end) break;
+        const uint64_t src = a.read_src[r];
+        if (src & SRC_ASCII) {                          // not packable: the byte-ring kernel takes it (list mode)
+            if (lane == 0) a.dirty_list[atomicAdd(a.dirty_count, 1u)] = r;
+            continue;
+        }
+        const uint64_t start = a.offsets[r], end = a.offsets[r + 1];
+        const uint32_t len = (uint32_t)(end - start);
+        uint64_t slot_lo, slot_cap;
+        if (a.exact_off) {
+            slot_lo = a.exact_off[r];
+            slot_cap = a.exact_off[r + 1] - slot_lo;
+        } else {
+            slot_lo = (start >> a.cap_shift) + (uint64_t)r * a.cap_const;
+            slot_cap = ((end >> a.cap_shift) + (uint64_t)(r + 1) * a.cap_const) - slot_lo;
+        }
+        // stage coordinates: word x of the 16-byte aligned copy; base b = 16 x + j; the read is [b_lo, b_hi)
+        const uint32_t skipw = (uint32_t)(src & 3u);
+        const uint32_t* gsrc = a.packed + (src - skipw);
+        const uint32_t b_lo = 16u * skipw, b_hi = b_lo + len;
+        const uint32_t tot_words = len ? skipw + ((len + 15u) >> 4) : 0u;
+        const uint32_t tot_bytes = ((tot_words + 3u) & ~3u) * 4u;            // bulk copies move multiples of 16 bytes
+        const uint32_t n_tiles = (tot_words + P_TILE_WORDS - 1) / P_TILE_WORDS;
+        const uint32_t n_steps = (tot_words + P_STEP_WORDS - 1) / P_STEP_WORDS;
+
+        // the ring is written by OR: it must be all zero where codes are going to land
+        *reinterpret_cast<uint4*>(ring + 4 * lane) = make_uint4(0, 0, 0, 0);
+        __syncwarp();                                   // every lane is done with the previous read's stage and ring
+        if (lane == 0) {
+            if (n_tiles > 0) bulk_load(sm.stage[0], gsrc, min(tot_bytes, (uint32_t)P_TILE_WORDS * 4u), &sm.bar[0]);
+            if (n_tiles > 1) bulk_load(sm.stage[1], gsrc + P_TILE_WORDS, min(tot_bytes - P_TILE_WORDS * 4u, (uint32_t)P_TILE_WORDS * 4u), &sm.bar[1]);
+        }
+
+        uint32_t avail = 0, done = 0, out_cnt = 0, step = 0;
+        uint32_t carry = 0;                             // last code of the previous step (lane 31)
+
+        for (;;) {
+            // ---- fill: append compacted codes to the ring --------------------------
+            while (step < n_steps && avail - done < (uint32_t)BLK + (uint32_t)L) {
+                const uint32_t tile = step / P_STEPS_PER_TILE, sub = step % P_STEPS_PER_TILE, st = tile & 1u;
+                if (sub == 0) {
+                    mbar_wait(&sm.bar[st], (phase >> st) & 1u);
+                    phase ^= 1u << st;
+                }
+                const uint2 w = *reinterpret_cast<const uint2*>(&sm.stage[st][sub * P_STEP_WORDS + 2 * lane]);
+                const uint32_t b0 = step * (P_STEP_WORDS * 16u) + lane * 32u;           // my first base, stage coordinates
+                const bool interior = step * (P_STEP_WORDS * 16u) >= b_lo && (step + 1) * (P_STEP_WORDS * 16u) <= b_hi;
+                uint32_t prev = __shfl_up_sync(0xffffffffu, w.y >> 30, 1);
+                if (lane == 0) prev = carry;
+                carry = __shfl_sync(0xffffffffu, w.y >> 30, 31);
+                uint32_t lo, hi, cnt;
+                if (interior) {
+                    if (a.hpc) {
+                        if (b0 == b_lo) prev = (w.x & 3u) ^ 1u;                        // first base of the read: always kept
+                        const uint32_t X0 = (w.x << 2) | prev;
+                        const uint32_t X1 = __funnelshift_l(w.x, w.y, 2);
+#define MDBG_LUT(addr) ((uint32_t) * reinterpret_cast<const uint16_t*>(lut_bytes + (addr)))
+                        const uint32_t e0 = MDBG_LUT((X0 << 1) & 0x7FEu), e1 = MDBG_LUT((X0 >> 7) & 0x7FEu);
+                        const uint32_t e2 = MDBG_LUT((X0 >> 15) & 0x7FEu), e3 = MDBG_LUT(__funnelshift_r(X0, X1, 23) & 0x7FEu);
+                        const uint32_t e4 = MDBG_LUT((X1 << 1) & 0x7FEu), e5 = MDBG_LUT((X1 >> 7) & 0x7FEu);
+                        const uint32_t e6 = MDBG_LUT((X1 >> 15) & 0x7FEu), e7 = MDBG_LUT((w.y >> 21) & 0x7FEu);
+#undef MDBG_LUT
+                        uint32_t n0, n1;
+                        const uint32_t a0 = hpc_merge4(e0, e1, e2, e3, n0), a1 = hpc_merge4(e4, e5, e6, e7, n1);
+                        const uint64_t v = (uint64_t)a0 | ((uint64_t)a1 << n0);        // n0 <= 32
+                        lo = (uint32_t)v; hi = (uint32_t)(v >> 32);
+                        cnt = (n0 + n1) >> 1;
+                    } else {
+                        lo = w.x; hi = w.y; cnt = 32;
+                    }
+                } else {
+                    // first / last step of the read (ragged ends): base by base
+                    uint64_t v = 0;
+                    cnt = 0;
+                    uint32_t pc = prev;
+#pragma unroll 4
+                    for (uint32_t j = 0; j < 32; j++) {
+                        const uint32_t b = b0 + j;
+                        const uint32_t c = ((j < 16 ? w.x >> (2 * j) : w.y >> (2 * j - 32)) & 3u);
+                        if (b >= b_lo && b < b_hi && (!a.hpc || b == b_lo || c != pc)) {
+                            v |= (uint64_t)c << (2 * cnt);
+                            cnt++;
+                        }
+                        pc = c;
+                    }
+                    lo = (uint32_t)v; hi = (uint32_t)(v >> 32);
+                }
+                const uint32_t incl = warp_inclusive_scan(cnt);
+                const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                const uint32_t bit = (2u * (avail + incl - cnt)) & (P_RING_WORDS * 32u - 1u);
+                const uint32_t wi = bit >> 5, sh = bit & 31u;
+                const uint32_t p0 = lo << sh, p1 = __funnelshift_l(lo, hi, sh), p2 = __funnelshift_l(hi, 0u, sh);
+                if (p0) atomicOr(&ring[wi], p0);
+                if (p1) atomicOr(&ring[(wi + 1) & (P_RING_WORDS - 1)], p1);
+                if (p2) atomicOr(&ring[(wi + 2) & (P_RING_WORDS - 1)], p2);
+                avail += total;
+                step++;
+                if (sub == P_STEPS_PER_TILE - 1 || step == n_steps) {      // the stage has been read completely: refill it
+                    __syncwarp();
+                    if (lane == 0 && tile + 2 < n_tiles) {
+                        const uint32_t off = (tile + 2) * P_TILE_WORDS;
+                        bulk_load(sm.stage[st], gsrc + off, min(tot_bytes - off * 4u, (uint32_t)P_TILE_WORDS * 4u), &sm.bar[st]);
+                    }
+                }
+            }
+            __syncwarp();                               // the ORs of every lane have landed before the ring is read
+
+            // ---- roll + hash + select, 512 positions per step ------------------
+            const bool final_ = (step == n_steps);
+            const int pmax_final = (int)avail - L - 1;          // Kmer.hpp:1395: positions 1 .. n-2, n = L' - l + 1
+            for (;;) {
+                int pmax;
+                if (avail >= done + (uint32_t)BLK + (uint32_t)L) pmax = 0x7fffffff;
+                else if (final_ && (int)done <= pmax_final) pmax = pmax_final;
+                else break;
+                const uint32_t p0 = done + lane * 16;
+                int nv = 16;
+                if (pmax != 0x7fffffff) nv = max(0, min(16, pmax - (int)p0 + 1));
+                uint32_t valid_bits = (1u << nv) - 1u;
+                if (p0 == 0) valid_bits &= ~1u;                 // position 0 is trimmed (Kmer.hpp:1362,1395)
+                const uint32_t wi = ((done >> 4) + lane) & (P_RING_WORDS - 1);
+                const uint32_t lo = ring[wi], hi = ring[(wi + 1) & (P_RING_WORDS - 1)];
+                uint32_t s_hi, s_lo;
+                const uint32_t sel = k1v1::roll16_packed<L>(lo, hi, thr_cand, s_hi, s_lo) & valid_bits;
+                const uint32_t hit_lanes = __ballot_sync(0xffffffffu, sel != 0);
+                ring[wi] = 0;                                    // consumed: ready for the ORs of a later fill
+                if (hit_lanes) {
+                    const uint32_t n_c = __popc(sel);
+                    if (__all_sync(0xffffffffu, n_c <= 1)) {     // common case: one store per hit lane
+                        if (n_c) {
+                            const uint32_t j = __ffs(sel) - 1;
+                            cand[n_list + __popc(hit_lanes & ((1u << lane) - 1u))] =
+                                make_uint2(p0 + j, k1v1::lmer_from_packed<L>(s_hi, s_lo, j));
+                        }
+                        n_list += __popc(hit_lanes);
+                    } else {
+                        const uint32_t incl = warp_inclusive_scan(n_c);
+                        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                        const uint32_t before = incl - n_c;
+                        for (uint32_t base_rank = 0; base_rank < total; base_rank += 32) {
+                            uint32_t rest = sel, rank = before;
+                            while (rest) {
+                                const uint32_t j = __ffs(rest) - 1;
+                                rest &= rest - 1;
+                                if (rank >= base_rank && rank < base_rank + 32)
+                                    cand[n_list + (rank - base_rank)] = make_uint2(p0 + j, k1v1::lmer_from_packed<L>(s_hi, s_lo, j));
+                                rank++;
+                            }
+                            n_list += min(32u, total - base_rank);
+                            __syncwarp();
+                            if (n_list >= 32 && base_rank + 32 < total) {        // make room for the next 32
+                                out_cnt += flush_candidates(a, cand, 32, lane, slot_lo, slot_cap, out_cnt);
+                                __syncwarp();
+                                uint2 keep_e = make_uint2(0, 0);
+                                if (32 + lane < n_list) keep_e = cand[32 + lane];
+                                __syncwarp();
+                                if (32 + lane < n_list) cand[lane] = keep_e;
+                                n_list -= 32;
+                                __syncwarp();
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (n_list >= 32) {
+                        out_cnt += flush_candidates(a, cand, 32, lane, slot_lo, slot_cap, out_cnt);
+                        __syncwarp();
+                        uint2 keep_e = make_uint2(0, 0);
+                        if (32 + lane < n_list) keep_e = cand[32 + lane];
+                        __syncwarp();
+                        if (32 + lane < n_list) cand[lane] = keep_e;
+                        n_list -= 32;
+                        __syncwarp();
+                    }
+                }
+                done += BLK;
+            }
+            __syncwarp();                               // the zeroing stores are ordered before the next fill's ORs
+            if (final_) break;
+        }
+        if (n_list) {
+            out_cnt += flush_candidates(a, cand, n_list, lane, slot_lo, slot_cap, out_cnt);
+            n_list = 0;
+            __syncwarp();
+        }
+        if (lane == 0) {
+            a.n_min[r] = out_cnt;
+            if ((uint64_t)out_cnt > slot_cap) atomicAdd(a.n_overflow, 1ULL);
+        }
+    }
+}
+
+bool sketch_packed_eligible(const SketchArgs& a) {
+    const uint32_t t_hi = (uint32_t)(a.threshold >> 32);
+    return a.l == 15 && !a.select_none && t_hi + k1v1::S1_SLACK >= k1v1::S1_SLACK;
+}
+
 template <int L_FAST, int V>
 static void launch_sketch_as(const SketchArgs& a, int sm_count, cudaStream_t s) {
     // persistent grid: enough CTAs to fill every SM, reads are pulled dynamically
@@ -436,11 +742,103 @@ static void launch_sketch_as(const SketchArgs& a, int sm_count, cudaStream_t s) 
     sketch_kernel<L_FAST, V><<<(unsigned)grid, WARPS_PER_CTA * 32, 0, s>>>(a);
 }
 
-void launch_sketch(const SketchArgs& a, int sm_count, cudaStream_t s) {
-    if (a.read_end <= a.read_begin) return;
+static void launch_byte_ring(const SketchArgs& a, int sm_count, cudaStream_t s) {
     if (a.l != 15) launch_sketch_as<0, 0>(a, sm_count, s);          // generic l: no unrolled register block at all
-    else if (a.variant == 1) launch_sketch_as<15, 1>(a, sm_count, s);
-    else launch_sketch_as<15, 0>(a, sm_count, s);
+    else if (a.variant == 0) launch_sketch_as<15, 0>(a, sm_count, s);
+    else launch_sketch_as<15, 1>(a, sm_count, s);
+}
+
+int launch_sketch(const SketchArgs& a, int sm_count, cudaStream_t s) {
+    if (a.read_end <= a.read_begin) return 0;
+    if (a.variant == 2 && a.read_src && a.packed && a.dirty_list && sketch_packed_eligible(a)) {
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (sketch_packed_kernel<15>), WARPS_PER_CTA * 32, 0);
+        if (per_sm < 1) per_sm = 1;
+        const uint64_t want = ((uint64_t)(a.read_end - a.read_begin) + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+        const uint64_t grid = std::min<uint64_t>((uint64_t)sm_count * per_sm, want);
+        sketch_packed_kernel<15><<<(unsigned)grid, WARPS_PER_CTA * 32, 0, s>>>(a);
+        // the reads it could not take (ASCII spill of the host packer): byte-ring kernel over the list, a few CTAs
+        SketchArgs b = a;
+        b.variant = 1;
+        b.read_list = a.dirty_list;
+        b.read_list_n = a.dirty_count;
+        b.cursor = a.dirty_cursor;
+        b.read_begin = 0;                                   // list entries are absolute read indices
+        b.read_end = a.n_reads;
+        launch_byte_ring(b, sm_count, s);
+        return 2;
+    }
+    launch_byte_ring(a, sm_count, s);
+    return 1;
+}
+
+// ------------------------------------------------------------------ ASCII -> 2-bit device layout (variant 2's input)
+// One warp per read, 16 bases -> one u32 per lane and step.  HBM-streaming: 1 B/bp in, 0.25 B/bp out.  A read holding
+// any byte outside "ACGT" (N, IUPAC, lower case, '#') is left to the byte-ring kernel: read_src = SRC_ASCII | offset.
+__global__ void __launch_bounds__(256) pack_ascii_kernel(const PackArgsAscii a) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t r = a.read_begin + warp; r < a.read_end; r += n_warps) {
+        const uint64_t start = a.offsets[r], end = a.offsets[r + 1];
+        const uint32_t len = (uint32_t)(end - start);
+        const uint64_t w_off = pack_word_offset(start, r);
+        const uint8_t* base = a.bases + start;
+        const uint32_t skip = (uint32_t)((uintptr_t)base & 15);
+        const uint8_t* abase = base - skip;                       // 16-byte aligned
+        const uint32_t sh8 = 8 * (skip & 3), k = skip >> 2;       // warp-uniform realignment
+        uint32_t bad = 0;
+        for (uint32_t j0 = 0; j0 < len; j0 += 512) {
+            const uint32_t j = j0 + lane * 16;                    // my 16 bases start at read index j
+            if (j < len) {
+                // two aligned 16-byte loads cover bases [j, j + 16) at any alignment
+                const uint8_t* p = abase + j;
+                uint32_t q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                if (p + 32 <= a.bases_end) {
+                    const uint4 u0 = *reinterpret_cast<const uint4*>(p), u1 = *reinterpret_cast<const uint4*>(p + 16);
+                    q[0] = u0.x; q[1] = u0.y; q[2] = u0.z; q[3] = u0.w; q[4] = u1.x; q[5] = u1.y; q[6] = u1.z; q[7] = u1.w;
+                } else {
+                    for (int t = 0; t < 32; t++)
+                        if (p + t < a.bases_end) q[t >> 2] |= (uint32_t)p[t] << (8 * (t & 3));
+                }
+                uint32_t x[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint32_t lo = k == 0 ? q[i] : k == 1 ? q[i + 1] : k == 2 ? q[i + 2] : q[i + 3];
+                    const uint32_t hi = k == 0 ? q[i + 1] : k == 1 ? q[i + 2] : k == 2 ? q[i + 3] : q[i + 4];
+                    x[i] = __funnelshift_r(lo, hi, sh8);
+                }
+                const uint32_t nvalid = min(16u, len - j);
+                uint32_t word = 0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    // exact "is one of A C G T": rebuild the byte from its two code bits and compare
+                    const uint32_t c0 = (x[i] >> 1) & 0x01010101u, c1 = (x[i] >> 2) & 0x01010101u;
+                    const uint32_t g = c1 & c0, t = c1 ^ g;
+                    const uint32_t expect = 0x41414141u ^ (c0 << 1) ^ (g << 2) ^ (t * 0x15u);
+                    uint32_t diff = x[i] ^ expect;
+                    uint32_t codes = (x[i] >> 1) & 0x03030303u;
+                    const int nb = (int)nvalid - 4 * i;                  // valid bytes of this word
+                    if (nb < 4) {
+                        const uint32_t m = nb <= 0 ? 0u : (1u << (8 * nb)) - 1u;
+                        diff &= m; codes &= m;
+                    }
+                    bad |= diff;
+                    word |= pack4_lsb(codes) << (8 * i);
+                }
+                a.packed[w_off + (j >> 4)] = word;
+            }
+        }
+        const bool dirty = __any_sync(0xffffffffu, bad != 0);
+        if (lane == 0) a.read_src[r] = dirty ? (SRC_ASCII | start) : w_off;
+    }
+}
+
+void launch_pack_ascii(const PackArgsAscii& a, int sm_count, cudaStream_t s) {
+    if (a.read_end <= a.read_begin) return;
+    uint64_t blocks = ((uint64_t)(a.read_end - a.read_begin) + 7) / 8;
+    if (blocks > (uint64_t)sm_count * 8) blocks = (uint64_t)sm_count * 8;
+    pack_ascii_kernel<<<(unsigned)blocks, 256, 0, s>>>(a);
 }
 
 // ------------------------------------------------------------------ shared-memory scrambler (verification aid)

@@ -225,6 +225,26 @@ class Engine:
                                                            n_reads, n_bases, int(append_to_store), C.byref(out)))
         return out
 
+    def pack_device_words(self, n_bases: int, n_reads: int) -> int:
+        """u32 words the packed copy of an ASCII device batch needs (closed form, 16-byte aligned read starts)."""
+        return int(self._lib.mdbg_pack_device_words(n_bases, n_reads))
+
+    def pack_device(self, d_bases_ptr: int, d_offsets_ptr: int, n_reads: int, n_bases: int, d_packed_ptr: int,
+                    d_read_src_ptr: int):
+        """ASCII reads in HBM -> the 2-bit device layout (one streaming kernel); reads with a byte outside ACGT are
+        flagged in d_read_src (bit 63 | byte offset) and stay ASCII."""
+        self._ck(self._lib.mdbg_pack_device(self._ctx, C.c_void_p(d_bases_ptr), C.c_void_p(d_offsets_ptr), n_reads, n_bases,
+                                            C.c_void_p(d_packed_ptr), C.c_void_p(d_read_src_ptr)))
+
+    def sketch_batch_device_packed2(self, d_packed_ptr: int, d_read_src_ptr: int, d_bases_ptr: int, d_offsets_ptr: int,
+                                    n_reads: int, n_bases: int, append_to_store: bool = False) -> SketchDev:
+        """Sketch of a batch resident in HBM in the packed layout; flagged reads are taken from the ASCII buffer."""
+        out = SketchDev()
+        self._ck(self._lib.mdbg_sketch_batch_device_packed2(self._ctx, C.c_void_p(d_packed_ptr), C.c_void_p(d_read_src_ptr),
+                                                            C.c_void_p(d_bases_ptr), C.c_void_p(d_offsets_ptr), n_reads,
+                                                            n_bases, int(append_to_store), C.byref(out)))
+        return out
+
     def sketch_fetch(self) -> Sketch:
         out = SketchOut()
         self._ck(self._lib.mdbg_sketch_fetch(self._ctx, C.byref(out)))

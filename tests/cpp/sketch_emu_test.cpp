@@ -101,17 +101,36 @@ static Result run_kernel(const Batch& b, uint32_t l, float density, int hpc, con
         a.read_src = src.data();
         a.packed = words.data();
     }
+    // variant 2 (packed kernel + byte-ring kernel over the dirty list): an ASCII batch goes through the device-side
+    // packer first (16-byte aligned read starts); the host-style packing above gives it arbitrary word alignment
+    std::vector<uint32_t> dirty(n + 1);
+    uint32_t dirty_n = 0, dirty_cur = 0;
+    a.dirty_list = dirty.data(); a.dirty_count = &dirty_n; a.dirty_cursor = &dirty_cur;
+    if (g_variant == 2 && !packed) {
+        words.assign(pack_words_capacity(b.bases.size(), n) + 64, 0xA5A5A5A5u);
+        PackArgsAscii pa{};
+        pa.bases = a.bases; pa.bases_end = a.bases_end; pa.offsets = a.offsets;
+        pa.read_begin = 0; pa.read_end = n; pa.packed = words.data(); pa.read_src = src.data();
+        launch_pack_ascii(pa, 2, nullptr);
+        for (uint32_t r = 0; r < n; r++) {
+            bool clean = true;
+            for (uint64_t i = b.offsets[r]; i < b.offsets[r + 1]; i++) clean &= (b.bases[i] == 'A' || b.bases[i] == 'C' || b.bases[i] == 'G' || b.bases[i] == 'T');
+            CHECK(src[r] == (clean ? pack_word_offset(b.offsets[r], r) : (SRC_ASCII | b.offsets[r])), "pack kernel: read_src of read %u", r);
+        }
+        a.read_src = src.data();
+        a.packed = words.data();
+    }
     auto launch = [&]() {
         if (g_per_read) {
             for (uint32_t r = 0; r < n; r++) {
-                cursor = 0;
+                cursor = 0; dirty_n = 0; dirty_cur = 0;
                 a.read_begin = r; a.read_end = r + 1;
                 launch_sketch(a, 2, nullptr);
             }
             a.read_begin = 0; a.read_end = n;
             return;
         }
-        cursor = 0;
+        cursor = 0; dirty_n = 0; dirty_cur = 0;
         launch_sketch(a, /*sm_count=*/2, nullptr);            // 2 "SMs" x 2 CTAs x 8 warps, reads pulled dynamically
     };
     launch();

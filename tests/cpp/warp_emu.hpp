@@ -331,6 +331,7 @@ static inline double __dadd_rn(double a, double b) { return a + b; }
 template <typename T> static inline T atomicExch(T* p, T v) { T old = *p; *p = v; return old; }
 template <typename T> static inline T atomicCAS(T* p, T cmp, T v) { T old = *p; if (old == cmp) *p = v; return old; }
 template <typename T, typename U> static inline T atomicAdd(T* p, U v) { T old = *p; *p = (T)(old + (T)v); return old; }
+template <typename T, typename U> static inline T atomicOr(T* p, U v) { T old = *p; *p = (T)(old | (T)v); return old; }
 
 static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
 static inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }

@@ -59,7 +59,7 @@ def test_owner_merge_on_the_emulator(emulated, n_ranks, k, n_reads):
 
 def test_gpu_parity_suites_against_the_emulated_library(emulated):
     lib, env = emulated
-    run = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "tests/test_gpu_host_cpp.py", "tests/test_gpu_z_new_paths.py", "-m", "gpu",
+    run = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "tests/test_gpu_host_cpp.py", "tests/test_gpu_z_new_paths.py", "tests/test_gpu_zz_round2.py", "-m", "gpu",
                           "-q", "-x", "-p", "no:cacheprovider"], cwd=ROOT, env=env, capture_output=True, text=True,
                          timeout=3000)
     tail = run.stdout[-2500:] + run.stderr[-1500:]
@@ -108,7 +108,7 @@ def test_gpu_parity_suite_with_deferred_stream_execution(tmp_path):
     # the tests that exercise host-side sequencing (the kernels themselves are covered by the eager run above)
     pick = ("(piece or packed or count or rescue or next_k or multi_k or edge or full_path or side_outputs_vs or sentinel "
             "or variants or table_full or bad_host or empty or smoke or density) and not cpp_driver")
-    run = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "tests/test_gpu_z_new_paths.py", "-m", "gpu",
+    run = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "tests/test_gpu_z_new_paths.py", "tests/test_gpu_zz_round2.py", "-m", "gpu",
                           "-q", "-x", "-p", "no:cacheprovider", "-k", pick], cwd=ROOT, env=env, capture_output=True, text=True,
                          timeout=3000)
     tail = run.stdout[-2500:] + run.stderr[-1500:]

@@ -30,7 +30,7 @@ def test_sketch_kernel_variants_and_autotune(built, oracle, hpc, dens):
             bases[lo + int(rng.integers(0, hi - lo))] = ord("N")
     want = oracle.sketch_batch(bases, offs, 15, dens, hpc)
     eng = engine(15, dens, hpc)
-    assert eng.sketch_variant == int(os.environ.get("MDBG_SKETCH_VARIANT", "0"))
+    assert eng.sketch_variant == int(os.environ.get("MDBG_SKETCH_VARIANT", "2"))
     p_b, keep_b = device_array(bases, pad=64)
     p_o, keep_o = device_array(offs.astype(np.uint64))
     res = eng.autotune_sketch(p_b, p_o, rs.n_reads, int(offs[-1]))

@@ -1,0 +1,132 @@
+"""GPU parity tests of the round-2 paths: the packed sketch kernel (variant 2: bulk-copy staged 2-bit input, table
+compaction, bit-packed ring), the device-side ASCII -> 2-bit packer, and what was rebuilt around the count table.
+All through the C ABI, all bit-exact against the oracle.  They also run on the CPU emulator
+(tests/test_capi_emulated_cpu.py) wherever they only need device_array()."""
+import os
+
+import numpy as np
+import pytest
+
+from metamdbg_b200 import synth
+from tests.test_gpu_parity import (EMULATED, assert_sketch_equal, built, device_array, engine, table_dict)  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC_ASCII = 1 << 63
+
+
+def _edge_case_reads(rng):
+    """Lengths around every boundary of the packed kernel: 16 (word), 64 (16-byte group), 512 (roll block), 1024 (fill
+    step), 4096 (bulk-copy tile), plus homopolymer-rich, tandem and dirty reads."""
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    reads = []
+    for n in (0, 1, 2, 14, 15, 16, 17, 31, 32, 33, 63, 64, 65, 511, 512, 513, 526, 527, 528, 1023, 1024, 1025, 1039, 2047,
+              2048, 2049, 4095, 4096, 4097, 8191, 8192, 8193, 12288, 20000):
+        reads.append(acgt[rng.integers(0, 4, n)])
+    for i in range(30):
+        n = int(rng.integers(30, 9000))
+        s = acgt[rng.integers(0, 4, n)].copy()
+        if i % 3 == 0:                                      # homopolymer runs, some of them hundreds long
+            j = 0
+            while j < n:
+                run = int(rng.integers(1, 300 if i % 6 == 0 else 6))
+                s[j:j + run] = s[j]
+                j += run
+        if i % 5 == 1:                                      # dirty: N, lower case, IUPAC -> stays ASCII
+            for p in rng.integers(0, n, 3):
+                s[p] = rng.choice(np.frombuffer(b"NnacgtRY", np.uint8))
+        if i % 7 == 2:
+            u = int(rng.integers(1, 7))
+            s[u:] = np.resize(s[:u], n - u)                 # tandem repeat
+        reads.append(s)
+    reads.append(np.full(5000, ord("A"), np.uint8))         # one HPC base
+    reads.append(np.tile(np.frombuffer(b"AC", np.uint8), 3000))
+    bases = np.concatenate(reads).astype(np.uint8)
+    offs = np.zeros(len(reads) + 1, np.uint64)
+    offs[1:] = np.cumsum([len(r) for r in reads])
+    return bases, offs
+
+
+@pytest.mark.parametrize("hpc,dens", [(True, 0.005), (True, 0.05), (False, 0.025), (True, 0.6)])
+def test_packed_kernel_edge_cases_device_batch(built, oracle, hpc, dens):
+    """ASCII batch in device memory -> pack pass -> packed kernel (+ byte-ring kernel for the dirty reads) equals the
+    oracle on reads whose lengths sit on every internal boundary; density 0.6 forces the slot-overflow re-sketch."""
+    bases, offs = _edge_case_reads(np.random.default_rng(77))
+    want = oracle.sketch_batch(bases, offs, 15, dens, hpc)
+    eng = engine(15, dens, hpc)
+    assert eng.sketch_variant == int(os.environ.get("MDBG_SKETCH_VARIANT", "2"))
+    p_b, keep_b = device_array(bases, pad=64)
+    p_o, keep_o = device_array(offs.astype(np.uint64))
+    for v in (2, 1, 0):
+        eng.set_sketch_variant(v)
+        out = eng.sketch_batch_device(p_b, p_o, len(offs) - 1, int(offs[-1]), False)
+        sk = eng.sketch_fetch()
+        assert out.n_minimizers == len(want[1])
+        assert_sketch_equal(sk, *want, tag=f"device batch, variant {v}, hpc={hpc}, d={dens}")
+    eng.close()
+    del keep_b, keep_o
+
+
+@pytest.mark.parametrize("hpc", [True, False])
+def test_pack_device_and_packed2(built, oracle, hpc):
+    """mdbg_pack_device writes the documented layout (word offsets in closed form, dirty reads flagged), and
+    mdbg_sketch_batch_device_packed2 on it equals the oracle; the same words at UNALIGNED word offsets (the host
+    style layout of round 1) go through the kernel's realigned first step."""
+    bases, offs = _edge_case_reads(np.random.default_rng(5))
+    n = len(offs) - 1
+    want = oracle.sketch_batch(bases, offs, 15, 0.01, hpc)
+    eng = engine(15, 0.01, hpc)
+    p_b, keep_b = device_array(bases, pad=64)
+    p_o, keep_o = device_array(offs.astype(np.uint64))
+    n_words = eng.pack_device_words(int(offs[-1]), n)
+    p_w, keep_w = device_array(np.full(n_words, 0xA5A5A5A5, np.uint32))
+    p_s, keep_s = device_array(np.zeros(n, np.uint64))
+    eng.pack_device(p_b, p_o, n, int(offs[-1]), p_w, p_s)
+    eng.sketch_batch_device_packed2(p_w, p_s, p_b, p_o, n, int(offs[-1]), False)
+    assert_sketch_equal(eng.sketch_fetch(), *want, tag=f"pack_device + packed2 hpc={hpc}")
+    eng.synchronize()
+    if EMULATED:                                            # device memory is host memory: look at the layout itself
+        src = keep_s[1].view(np.uint64)
+        words = keep_w[1].view(np.uint32)
+        for r in range(n):
+            lo, hi = int(offs[r]), int(offs[r + 1])
+            s = bases[lo:hi]
+            clean = bool(np.isin(s, np.frombuffer(b"ACGT", np.uint8)).all())
+            if not clean:
+                assert int(src[r]) == SRC_ASCII | lo
+                continue
+            w0 = ((lo >> 6) + r) << 2
+            assert int(src[r]) == w0
+            codes = ((s >> 1) & 3).astype(np.uint64)
+            for j in range(0, hi - lo, 16):
+                c = codes[j:j + 16]
+                assert int(words[w0 + j // 16]) == int((c << (2 * np.arange(len(c), dtype=np.uint64))).sum()), (r, j)
+    # host-style contiguous packing: arbitrary word alignment of the read starts
+    clean_mask = np.array([bool(np.isin(bases[int(offs[r]):int(offs[r + 1])], np.frombuffer(b"ACGT", np.uint8)).all())
+                           for r in range(n)])
+    words, woff = synth.pack_2bit(bases, offs)
+    src2 = woff[:n].astype(np.uint64).copy()
+    src2[~clean_mask] = np.uint64(SRC_ASCII) | offs[:n][~clean_mask]
+    p_w2, keep_w2 = device_array(np.concatenate([words.astype(np.uint32), np.zeros(8, np.uint32)]))
+    p_s2, keep_s2 = device_array(src2)
+    eng.sketch_batch_device_packed2(p_w2, p_s2, p_b, p_o, n, int(offs[-1]), False)
+    assert_sketch_equal(eng.sketch_fetch(), *want, tag=f"unaligned packed layout hpc={hpc}")
+    eng.close()
+    del keep_b, keep_o, keep_w, keep_s, keep_w2, keep_s2
+
+
+def test_packed_kernel_host_batches_with_dirty_reads(built, oracle, monkeypatch):
+    """Host batches: packed by the host threads (16-byte aligned read starts, ASCII spill for dirty reads) or sent as
+    ASCII and packed on the device, in many pieces -- the dirty list of every piece reaches the byte-ring kernel."""
+    monkeypatch.setenv("MDBG_PIECE_BYTES", "60000")
+    monkeypatch.setenv("MDBG_PACK_MIN_BYTES", "0")
+    bases, offs = _edge_case_reads(np.random.default_rng(11))
+    want = oracle.sketch_batch(bases, offs, 15, 0.005, True)
+    for packing in (1, 0):
+        eng = engine(15, 0.005, True)
+        eng.set_host_packing(packing)
+        sk = eng.sketch_batch(bases, offs)
+        info = eng.last_batch_info()
+        assert info["n_pieces"] > 3
+        assert_sketch_equal(sk, *want, tag=f"host batch packing={packing}")
+        eng.close()
