@@ -48,6 +48,7 @@ struct SmallDev {                 // device-side scalars, one allocation
     unsigned long long n_flagged;
     unsigned long long n_changed;
     unsigned long long emit_cursor;
+    unsigned long long t_claims;         // claimed slots (= distinct keys) of the current count table
     TableStats stats;
 };
 
@@ -127,9 +128,22 @@ struct mdbg_ctx {
     bool t_active = false;
     bool t_value_mode = false;         // the table was filled by the next-k pass: `count` is a value, not an occurrence count
     bool t_merged = false;             // multi-rank: mdbg_count_merge has moved every key to its owner
+    // The table is sized for the EXPECTED number of distinct k-min-mers (load factor <= 0.6), not for the worst case
+    // "every window distinct": a pass that outgrows it is abandoned early (kernels watch the claim counter) and the
+    // table is rebuilt 4x larger from the store ranges inserted so far -- both kinds of pass are reproducible from
+    // the store.  distinct_ratio remembers distinct keys per stored minimizer of the last first-pass table, so
+    // steady-state batches are sized right the first time.
+    struct Range { uint64_t read_lo, read_hi; };
+    std::vector<Range> t_ranges;       // store ranges inserted into the current table (rebuild recipe)
+    bool t_rebuildable = false;        // false once foreign vectors were merged in
+    bool t_autogrow = true;            // MDBG_TABLE_AUTOGROW=0: report MDBG_ERR_TABLE_FULL instead of rebuilding (tests)
+    uint64_t t_claim_limit = 0;
+    double distinct_ratio = 0.0;
+    uint64_t store_gen = 0, rem_gen = ~0ull;   // s_rem (minimizers left in the read) is valid for this store generation
+    uint32_t prev_min_count = 0;       // lookup-time filter of the previous-k table (see mdbg_prev_from_current)
     DevBuf foreign_vecs;
     uint64_t foreign_n = 0;
-    DevBuf prev_table, prev_stage_h, prev_stage_a;
+    DevBuf prev_table, prev_stage_h, prev_stage_a, rescue_table;
     DevBuf edge_table, edge_vals, o_edge_vals;
     PinBuf ho_edge_vals;
     uint64_t prev_capacity = 0;
@@ -597,6 +611,7 @@ mdbg_status sketch_internal(mdbg_ctx* ctx, const uint8_t* d_bases, const uint64_
         CKS(check_launch(ctx, "append_offsets_kernel", 1));
         ctx->s_reads += n_reads;
         ctx->s_mins += total;
+        ctx->store_gen++;
     }
     return MDBG_OK;
 }
@@ -771,6 +786,7 @@ mdbg_status mdbg_ctx_create(int device, const mdbg_params* p, mdbg_ctx** out) {
         return fail(nullptr, MDBG_ERR_OOM, "context allocation failed");
     }
     cudaMemset(c->d_small, 0, sizeof(SmallDev));
+    if (const char* v = getenv("MDBG_TABLE_AUTOGROW")) c->t_autogrow = atoi(v) != 0;
     if (const char* v = getenv("MDBG_SKETCH_VARIANT")) {
         const int want = atoi(v);
         if (want >= 0 && want < SKETCH_VARIANTS) c->sketch_variant = want;
@@ -795,7 +811,7 @@ void mdbg_ctx_destroy(mdbg_ctx* c) {
     DevBuf* devs[] = {&c->d_blacklist, &c->d_bases, &c->d_offsets, &c->pad_min, &c->pad_pos, &c->pad_dir, &c->n_min,
                       &c->scan_scratch, &c->b_off, &c->b_min, &c->b_pos, &c->b_dir, &c->s_min, &c->s_off, &c->s_rem,
                       &c->p_flags, &c->p_keep, &c->p_cnt, &c->p_newoff, &c->p_newmin, &c->table, &c->foreign_vecs,
-                      &c->o_hash, &c->o_abund, &c->o_vecs, &c->d_pack, &c->d_src, &c->d_dirty, &c->d_quals, &c->pad_qual, &c->pad_raw_a, &c->pad_raw_b, &c->b_qual, &c->x_sum_lo, &c->x_sum_hi, &c->x_lmin, &c->x_cplx, &c->x_low, &c->d_err_fixed, &c->d_err_tz, &c->prev_table, &c->prev_stage_h, &c->prev_stage_a, &c->m_send_vecs, &c->m_send_counts, &c->m_recv_vecs,
+                      &c->o_hash, &c->o_abund, &c->o_vecs, &c->d_pack, &c->d_src, &c->d_dirty, &c->d_quals, &c->pad_qual, &c->pad_raw_a, &c->pad_raw_b, &c->b_qual, &c->x_sum_lo, &c->x_sum_hi, &c->x_lmin, &c->x_cplx, &c->x_low, &c->d_err_fixed, &c->d_err_tz, &c->prev_table, &c->prev_stage_h, &c->prev_stage_a, &c->rescue_table, &c->m_send_vecs, &c->m_send_counts, &c->m_recv_vecs,
                       &c->m_recv_counts, &c->m_bucket, &c->loc_off, &c->edge_table, &c->edge_vals, &c->o_edge_vals};
     for (DevBuf* b : devs) release(*b);
     PinBuf* pins[] = {&c->h_off, &c->h_min, &c->h_pos, &c->h_dir, &c->ho_hash, &c->ho_abund, &c->ho_vecs, &c->hx_sum_lo, &c->hx_sum_hi, &c->hx_lmin, &c->hx_cplx, &c->hx_low, &c->hx_meanq, &c->h_qual, &c->h_pack, &c->h_src, &c->h_asc, &c->ho_edge_vals};
@@ -1502,10 +1518,20 @@ mdbg_status mdbg_sketch_batch_q(mdbg_ctx* ctx, const uint8_t* bases, const uint8
 }
 
 // ---- store ------------------------------------------------------------------------
+// The slots of a count table reference positions of the store (Slot::ref): anything that rewrites the store ends
+// the current table -- finalize / merge / edges first, then clear or purge (mdbg_store_append keeps positions).
+static void store_rewritten(mdbg_ctx* ctx) {
+    ctx->t_active = false;
+    ctx->t_ranges.clear();
+    ctx->store_gen++;
+}
+
 mdbg_status mdbg_store_clear(mdbg_ctx* ctx) {
     if (!ctx) return MDBG_ERR_ARG;
+    store_rewritten(ctx);
     ctx->s_reads = 0;
     ctx->s_mins = 0;
+    ctx->store_gen++;
     return MDBG_OK;
 }
 
@@ -1536,6 +1562,7 @@ mdbg_status mdbg_store_append(mdbg_ctx* ctx, const uint32_t* minimizers, const u
     ctx->b_total = 0;
     ctx->s_reads += n_reads;
     ctx->s_mins += total;
+    ctx->store_gen++;
     return MDBG_OK;
 }
 
@@ -1608,6 +1635,7 @@ mdbg_status mdbg_purge_palindromes(mdbg_ctx* ctx, uint32_t first_k, uint32_t las
     std::swap(ctx->s_min, ctx->p_newmin);
     std::swap(ctx->s_off, ctx->p_newoff);
     ctx->s_mins = new_total;
+    store_rewritten(ctx);
     return MDBG_OK;
 }
 
@@ -1647,26 +1675,134 @@ mdbg_status mdbg_store_apply_density(mdbg_ctx* ctx, float density, uint64_t* n_r
     std::swap(ctx->s_min, ctx->p_newmin);
     std::swap(ctx->s_off, ctx->p_newoff);
     ctx->s_mins = new_total;
+    store_rewritten(ctx);
     return MDBG_OK;
 }
 
 // ---- count table --------------------------------------------------------------------
+// capacity for `expect` distinct keys at load factor <= 0.6, and the claim count at which a pass gives up (0.8)
+static uint64_t table_capacity_for(uint64_t expect) {
+    if (expect < 512) expect = 512;
+    return pow2ceil(expect + (expect * 2) / 3 + 1);
+}
+
+static mdbg_status table_reset(mdbg_ctx* ctx, uint64_t cap) {
+    CKS(ensure(ctx, ctx->table, cap * sizeof(Slot)));
+    CK(cudaMemsetAsync(ctx->table.p, 0, cap * sizeof(Slot), ctx->stream));
+    CK(cudaMemsetAsync(&ctx->d_small->full_flag, 0, sizeof(uint32_t), ctx->stream));
+    CK(cudaMemsetAsync(&ctx->d_small->t_claims, 0, sizeof(unsigned long long), ctx->stream));
+    ctx->t_capacity = cap;
+    ctx->t_claim_limit = cap - cap / 5;
+    return MDBG_OK;
+}
+
 mdbg_status mdbg_count_begin(mdbg_ctx* ctx, uint32_t k, uint64_t expected_distinct) {
     if (!ctx) return MDBG_ERR_ARG;
     if (k < 2 || k > 255) return fail(ctx, MDBG_ERR_ARG, "k=%u unsupported (2..255)", k);
     CK(cudaSetDevice(ctx->device));
-    uint64_t expect = expected_distinct ? expected_distinct : ctx->s_mins;
-    if (expect < 512) expect = 512;
-    const uint64_t cap = pow2ceil(expect * 2);
-    CKS(ensure(ctx, ctx->table, cap * sizeof(Slot)));
-    CK(cudaMemsetAsync(ctx->table.p, 0, cap * sizeof(Slot), ctx->stream));
-    CK(cudaMemsetAsync(&ctx->d_small->full_flag, 0, sizeof(uint32_t), ctx->stream));
-    ctx->t_capacity = cap;
+    // expected_distinct = 0: distinct k-min-mers per stored minimizer as the last first-pass table saw them (+ 15 %),
+    // a quarter of the windows before anything is known; a table that turns out too small is rebuilt (count_pass)
+    uint64_t expect = expected_distinct;
+    if (!expect) {
+        const double ratio = ctx->distinct_ratio > 0 ? ctx->distinct_ratio * 1.15 : 0.25;
+        expect = (uint64_t)((double)ctx->s_mins * ratio) + 1024;
+        if (expect > ctx->s_mins + 1024) expect = ctx->s_mins + 1024;
+    }
+    CKS(table_reset(ctx, table_capacity_for(expect)));
     ctx->t_k = k;
     ctx->t_active = true;
     ctx->t_value_mode = false;
     ctx->t_merged = false;
+    ctx->t_ranges.clear();
+    ctx->t_rebuildable = true;
     ctx->foreign_n = 0;
+    return MDBG_OK;
+}
+
+// minimizers-left-in-the-read array of the store, rebuilt only when the store changed
+static mdbg_status ensure_rem(mdbg_ctx* ctx) {
+    if (ctx->rem_gen == ctx->store_gen && ctx->s_rem.p) return MDBG_OK;
+    CKS(ensure(ctx, ctx->s_rem, ctx->s_mins + 1));
+    launch_fill_rem(ctx->s_off.as<uint64_t>(), 0, ctx->s_reads, ctx->s_rem.as<uint8_t>(), ctx->stream);
+    CKS(check_launch(ctx, "fill_rem_kernel", ctx->s_reads ? 1 : 0));
+    ctx->rem_gen = ctx->store_gen;
+    return MDBG_OK;
+}
+
+// flat minimizer range of a read range (no device round trip for the usual "whole store")
+static mdbg_status flat_range(mdbg_ctx* ctx, uint64_t read_lo, uint64_t read_hi, uint64_t* g_lo, uint64_t* g_hi) {
+    if (read_lo == 0 && read_hi == ctx->s_reads) { *g_lo = 0; *g_hi = ctx->s_mins; return MDBG_OK; }
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemcpyAsync(&ctx->h_scalar[0], ctx->s_off.as<uint64_t>() + read_lo, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&ctx->h_scalar[1], ctx->s_off.as<uint64_t>() + read_hi, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    *g_lo = ctx->h_scalar[0]; *g_hi = ctx->h_scalar[1];
+    return MDBG_OK;
+}
+
+// one pass over a store range into the current table: occurrence counts (first pass) or next-k values
+static mdbg_status launch_pass(mdbg_ctx* ctx, uint64_t g_lo, uint64_t g_hi, bool next_k, bool timed) {
+    cudaStream_t s = ctx->stream;
+    if (timed && ctx->timing) CK(cudaEventRecord(ctx->ev[1][0], s));
+    if (!next_k) {
+        InsertArgs a{};
+        a.mins = ctx->s_min.as<uint32_t>();
+        a.rem = ctx->s_rem.as<uint8_t>();
+        a.g_lo = g_lo; a.g_hi = g_hi;
+        a.k = ctx->t_k;
+        a.table = ctx->table.as<Slot>();
+        a.mask = ctx->t_capacity - 1;
+        a.full_flag = &ctx->d_small->full_flag;
+        a.claims = &ctx->d_small->t_claims;
+        a.claim_limit = ctx->t_claim_limit;
+        launch_insert(a, s);
+    } else {
+        NextKArgs a{};
+        a.mins = ctx->s_min.as<uint32_t>();
+        a.rem = ctx->s_rem.as<uint8_t>();
+        a.g_lo = g_lo; a.g_hi = g_hi;
+        a.k = ctx->t_k;
+        a.prev = ctx->prev_table.as<Slot>();
+        a.prev_mask = ctx->prev_capacity - 1;
+        a.prev_min_count = ctx->prev_min_count;
+        a.table = ctx->table.as<Slot>();
+        a.mask = ctx->t_capacity - 1;
+        a.full_flag = &ctx->d_small->full_flag;
+        a.claims = &ctx->d_small->t_claims;
+        a.claim_limit = ctx->t_claim_limit;
+        launch_next_k(a, s);
+    }
+    if (timed && ctx->timing) { CK(cudaEventRecord(ctx->ev[1][1], s)); ctx->ev_valid[1] = true; }
+    return check_launch(ctx, next_k ? "next_k_kernel" : "insert_kernel", g_hi > g_lo ? 1 : 0);
+}
+
+// Runs the pass for [read_lo, read_hi); when the table proves too small (probe limit or load limit hit -- the
+// kernels abandon the pass early) it is rebuilt 4x larger from every range inserted so far and the pass is redone.
+static mdbg_status count_pass(mdbg_ctx* ctx, uint64_t read_lo, uint64_t read_hi, bool next_k) {
+    cudaStream_t s = ctx->stream;
+    CKS(ensure_rem(ctx));
+    uint64_t g_lo, g_hi;
+    CKS(flat_range(ctx, read_lo, read_hi, &g_lo, &g_hi));
+    CKS(launch_pass(ctx, g_lo, g_hi, next_k, true));
+    for (int attempt = 0;; attempt++) {
+        CK(cudaMemcpyAsync(&ctx->h_small->full_flag, &ctx->d_small->full_flag, 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(&ctx->h_small->t_claims, &ctx->d_small->t_claims, 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (!ctx->h_small->full_flag) break;
+        const uint64_t worst = table_capacity_for(ctx->s_mins + 1024);
+        if (!ctx->t_rebuildable || !ctx->t_autogrow || ctx->t_capacity >= worst || attempt >= 16)
+            return fail(ctx, MDBG_ERR_TABLE_FULL, "count table (capacity %llu slots) is full; raise expected_distinct",
+                        (unsigned long long)ctx->t_capacity);
+        CKS(table_reset(ctx, std::min<uint64_t>(ctx->t_capacity * 4, worst)));
+        for (const mdbg_ctx::Range& r : ctx->t_ranges) {
+            uint64_t a_lo, a_hi;
+            CKS(flat_range(ctx, r.read_lo, r.read_hi, &a_lo, &a_hi));
+            CKS(launch_pass(ctx, a_lo, a_hi, next_k, false));
+        }
+        CKS(launch_pass(ctx, g_lo, g_hi, next_k, true));
+    }
+    ctx->t_ranges.push_back(mdbg_ctx::Range{read_lo, read_hi});
+    if (!next_k && ctx->s_mins) ctx->distinct_ratio = (double)ctx->h_small->t_claims / (double)ctx->s_mins;
     return MDBG_OK;
 }
 
@@ -1676,34 +1812,8 @@ mdbg_status mdbg_count_add_store(mdbg_ctx* ctx, uint64_t read_lo, uint64_t read_
     if (read_hi > ctx->s_reads) read_hi = ctx->s_reads;
     if (read_lo >= read_hi) return MDBG_OK;
     CK(cudaSetDevice(ctx->device));
-    cudaStream_t s = ctx->stream;
-    CK(cudaMemcpyAsync(&ctx->h_scalar[0], ctx->s_off.as<uint64_t>() + read_lo, 8, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(&ctx->h_scalar[1], ctx->s_off.as<uint64_t>() + read_hi, 8, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    const uint64_t g_lo = ctx->h_scalar[0], g_hi = ctx->h_scalar[1];
-    CKS(ensure(ctx, ctx->s_rem, ctx->s_mins + 1));
-    launch_fill_rem(ctx->s_off.as<uint64_t>(), read_lo, read_hi, ctx->s_rem.as<uint8_t>(), s);
-    CKS(check_launch(ctx, "fill_rem_kernel", 1));
-    InsertArgs a{};
-    a.mins = ctx->s_min.as<uint32_t>();
-    a.rem = ctx->s_rem.as<uint8_t>();
-    a.g_lo = g_lo;
-    a.g_hi = g_hi;
-    a.k = ctx->t_k;
-    a.table = ctx->table.as<Slot>();
-    a.mask = ctx->t_capacity - 1;
-    a.full_flag = &ctx->d_small->full_flag;
     ctx->t_merged = false;
-    if (ctx->timing) CK(cudaEventRecord(ctx->ev[1][0], s));
-    launch_insert(a, s);
-    if (ctx->timing) { CK(cudaEventRecord(ctx->ev[1][1], s)); ctx->ev_valid[1] = true; }
-    CKS(check_launch(ctx, "insert_kernel", g_hi > g_lo ? 1 : 0));
-    CK(cudaMemcpyAsync(&ctx->h_small->full_flag, &ctx->d_small->full_flag, 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    if (ctx->h_small->full_flag)
-        return fail(ctx, MDBG_ERR_TABLE_FULL, "count table (capacity %llu slots) is full; raise expected_distinct",
-                    (unsigned long long)ctx->t_capacity);
-    return MDBG_OK;
+    return count_pass(ctx, read_lo, read_hi, false);
 }
 
 mdbg_status mdbg_count_add(mdbg_ctx* ctx, const uint32_t* minimizers, const uint64_t* min_offsets, uint32_t n_reads) {
@@ -1726,7 +1836,12 @@ static mdbg_status table_stats(mdbg_ctx* ctx, uint32_t thr, TableStats* st) {
 
 // dumpKminmer (CreateMdbg.hpp:3862-3869): drop abundance <= 1, and on the first
 // pass abundance < min_abundance.
-static uint32_t count_threshold(uint32_t min_abundance) { return min_abundance > 2 ? min_abundance : 2; }
+// Later passes (value tables of the next-k pass) keep every k-min-mer with refined abundance > 1 whatever
+// --min-abundance says (`_isFirstPass && abundance < _minAbundance`, CreateMdbg.hpp:3868-3869).
+static uint32_t count_threshold(const mdbg_ctx* ctx, uint32_t min_abundance) {
+    if (ctx->t_value_mode) return 2;
+    return min_abundance > 2 ? min_abundance : 2;
+}
 
 mdbg_status mdbg_count_stats(mdbg_ctx* ctx, uint32_t min_abundance, uint64_t* n_entries, uint64_t* n_distinct,
                              uint64_t* n_instances, uint64_t* checksum) {
@@ -1734,7 +1849,7 @@ mdbg_status mdbg_count_stats(mdbg_ctx* ctx, uint32_t min_abundance, uint64_t* n_
     if (!ctx->t_active) return fail(ctx, MDBG_ERR_STATE, "no active count table");
     CK(cudaSetDevice(ctx->device));
     TableStats st;
-    CKS(table_stats(ctx, count_threshold(min_abundance), &st));
+    CKS(table_stats(ctx, count_threshold(ctx, min_abundance), &st));
     if (n_entries) *n_entries = st.n_entries;
     if (n_distinct) *n_distinct = st.n_distinct;
     if (n_instances) *n_instances = st.n_instances;
@@ -1747,7 +1862,7 @@ mdbg_status mdbg_count_finalize(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_tabl
     if (!ctx->t_active) return fail(ctx, MDBG_ERR_STATE, "mdbg_count_finalize before mdbg_count_begin");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
-    const uint32_t thr = count_threshold(min_abundance);
+    const uint32_t thr = count_threshold(ctx, min_abundance);
     const uint32_t k = ctx->t_k;
     TableStats st;
     CKS(table_stats(ctx, thr, &st));
@@ -1807,7 +1922,16 @@ static mdbg_status count_rescue_all_ranks(mdbg_ctx* ctx, uint64_t* n_reads_rescu
         return fail(ctx, MDBG_ERR_STATE, "multi-rank mdbg_count_rescue needs the merged count table: call mdbg_count_merge first");
     cudaStream_t s = ctx->stream;
     const uint32_t R = (uint32_t)ctx->n_ranks, k = ctx->t_k;
-    CKS(prev_from_current_all_ranks(ctx, 2));                       // step 1 (lookup table = ctx->prev_table)
+    // step 1: the lookup table is built in ctx->prev_table; a previous-k table the caller loaded is set aside and
+    // put back at the end (mdbg_prev_load + refined-abundance patches survive a rescue)
+    struct PrevStash {
+        mdbg_ctx* c; DevBuf table; uint64_t cap; uint32_t thr;
+        explicit PrevStash(mdbg_ctx* ctx) : c(ctx), table(ctx->prev_table), cap(ctx->prev_capacity), thr(ctx->prev_min_count) {
+            c->prev_table = c->rescue_table; c->prev_capacity = 0;
+        }
+        ~PrevStash() { c->rescue_table = c->prev_table; c->prev_table = table; c->prev_capacity = cap; c->prev_min_count = thr; }
+    } stash(ctx);
+    CKS(prev_from_current_all_ranks(ctx, 2));
     // step 2
     const uint64_t max_windows = ctx->s_mins + 1;
     CKS(ensure(ctx, ctx->m_recv_vecs, max_windows * 4 * k));        // flat list of collected vectors
@@ -1906,6 +2030,7 @@ static mdbg_status prev_alloc(mdbg_ctx* ctx, uint64_t expect) {
     CK(cudaMemsetAsync(ctx->prev_table.p, 0, cap * sizeof(Slot), ctx->stream));
     CK(cudaMemsetAsync(&ctx->d_small->full_flag, 0, sizeof(uint32_t), ctx->stream));
     ctx->prev_capacity = cap;
+    ctx->prev_min_count = 0;           // a table built from listed pairs: every entry counts
     return MDBG_OK;
 }
 
@@ -1997,21 +2122,18 @@ mdbg_status mdbg_prev_from_current(mdbg_ctx* ctx, uint32_t min_abundance) {
     if (!ctx) return MDBG_ERR_ARG;
     if (!ctx->t_active) return fail(ctx, MDBG_ERR_STATE, "mdbg_prev_from_current without a count table");
     CK(cudaSetDevice(ctx->device));
-    const uint32_t thr = count_threshold(min_abundance);
+    const uint32_t thr = count_threshold(ctx, min_abundance);
     if (ctx->n_ranks > 1) return prev_from_current_all_ranks(ctx, thr);
-    TableStats st;
-    CKS(table_stats(ctx, thr, &st));
-    CKS(prev_alloc(ctx, st.n_entries));
-    PrevFromTableArgs a{};
-    a.table = ctx->table.as<Slot>();
-    a.capacity = ctx->t_capacity;
-    a.min_count = thr;
-    a.prev = ctx->prev_table.as<Slot>();
-    a.prev_mask = ctx->prev_capacity - 1;
-    a.full_flag = &ctx->d_small->full_flag;
-    launch_prev_from_table(a, ctx->stream);
-    CKS(check_launch(ctx, "prev_from_table_kernel", 1));
-    return check_full(ctx, "mdbg_prev_from_current");
+    // One context: the current table BECOMES the previous-k table -- no copy, no scan.  Entries the reference
+    // would not have dumped (abundance below the threshold and not rescued) are skipped at lookup time
+    // (NextKArgs::prev_min_count).  The old previous-k buffer is recycled as the next current table.
+    std::swap(ctx->prev_table, ctx->table);
+    ctx->prev_capacity = ctx->t_capacity;
+    ctx->prev_min_count = thr;
+    ctx->t_capacity = 0;
+    ctx->t_active = false;
+    ctx->t_ranges.clear();
+    return MDBG_OK;
 }
 
 mdbg_status mdbg_prev_load(mdbg_ctx* ctx, const uint64_t* hashes, const uint32_t* abundances, uint64_t n, int clear) {
@@ -2049,29 +2171,7 @@ mdbg_status mdbg_count_add_store_next_k(mdbg_ctx* ctx, uint64_t read_lo, uint64_
     if (read_hi > ctx->s_reads) read_hi = ctx->s_reads;
     if (read_lo >= read_hi) return MDBG_OK;
     CK(cudaSetDevice(ctx->device));
-    cudaStream_t s = ctx->stream;
-    CK(cudaMemcpyAsync(&ctx->h_scalar[0], ctx->s_off.as<uint64_t>() + read_lo, 8, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(&ctx->h_scalar[1], ctx->s_off.as<uint64_t>() + read_hi, 8, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    CKS(ensure(ctx, ctx->s_rem, ctx->s_mins + 1));
-    launch_fill_rem(ctx->s_off.as<uint64_t>(), read_lo, read_hi, ctx->s_rem.as<uint8_t>(), s);
-    CKS(check_launch(ctx, "fill_rem_kernel", 1));
-    NextKArgs a{};
-    a.mins = ctx->s_min.as<uint32_t>();
-    a.rem = ctx->s_rem.as<uint8_t>();
-    a.g_lo = ctx->h_scalar[0];
-    a.g_hi = ctx->h_scalar[1];
-    a.k = ctx->t_k;
-    a.prev = ctx->prev_table.as<Slot>();
-    a.prev_mask = ctx->prev_capacity - 1;
-    a.table = ctx->table.as<Slot>();
-    a.mask = ctx->t_capacity - 1;
-    a.full_flag = &ctx->d_small->full_flag;
-    if (ctx->timing) CK(cudaEventRecord(ctx->ev[1][0], s));
-    launch_next_k(a, s);
-    if (ctx->timing) { CK(cudaEventRecord(ctx->ev[1][1], s)); ctx->ev_valid[1] = true; }
-    CKS(check_launch(ctx, "next_k_kernel", a.g_hi > a.g_lo ? 1 : 0));
-    return check_full(ctx, "mdbg_count_add_store_next_k");
+    return count_pass(ctx, read_lo, read_hi, true);
 }
 
 // CreateMdbg::EdgeIndexer (CreateMdbg.hpp:4010-4232; first step of indexEdges, CreateMdbg.cpp:1177-1187): the
@@ -2084,7 +2184,7 @@ mdbg_status mdbg_edges_index(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_edges_o
         return fail(ctx, MDBG_ERR_STATE, "multi-rank mdbg_edges_index needs the merged table: call mdbg_count_merge first");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
-    const uint32_t thr = count_threshold(min_abundance);
+    const uint32_t thr = count_threshold(ctx, min_abundance);
     TableStats st;
     CKS(table_stats(ctx, thr, &st));
     uint64_t expect = 2 * st.n_entries;                          // at most two keys per node

@@ -99,9 +99,20 @@ MDBG_HD uint32_t roll16_core(uint32_t s_hi, uint32_t s_lo, uint32_t r_lo, uint32
     const uint32_t not_thr = ~thr_cand;
 #pragma unroll
     for (int j = 0; j < 16; j++) {
-        const int sh = 64 - 2 * j - 2 * L;                          // S >> sh, low 2L bits
-        const uint32_t fwd = (sh >= 32 ? (s_hi >> (sh - 32)) : funnel_r(s_lo, s_hi, sh)) & MASK;
-        const uint32_t rc = (j == 0 ? r_lo : funnel_r(r_lo, r_hi, 2 * j)) & MASK;
+        uint32_t fwd, rc;
+        if constexpr (L == 15) {
+            // a 32-bit window holds 16 codes = TWO consecutive 15-mers: one funnel shift per pair of positions and
+            // orientation, then a shift (no mask needed) for one l-mer and a mask for the other
+            const int e = j & ~1;
+            const uint32_t wf = e == 0 ? s_hi : funnel_r(s_lo, s_hi, 32 - 2 * e);      // codes e .. e+15, first base on top
+            const uint32_t wr = e == 0 ? r_lo : funnel_r(r_lo, r_hi, 2 * e);           // same codes, first base at the bottom
+            fwd = (j & 1) ? (wf & MASK) : (wf >> 2);
+            rc = (j & 1) ? (wr >> 2) : (wr & MASK);
+        } else {
+            const int sh = 64 - 2 * j - 2 * L;                      // S >> sh, low 2L bits
+            fwd = (sh >= 32 ? (s_hi >> (sh - 32)) : funnel_r(s_lo, s_hi, sh)) & MASK;
+            rc = (j == 0 ? r_lo : funnel_r(r_lo, r_hi, 2 * j)) & MASK;
+        }
         const uint32_t s1 = murmur_s1_u32(min(fwd, rc), risk);
 #ifdef __CUDA_ARCH__
         uint32_t scratch;

@@ -153,7 +153,9 @@ struct InsertArgs {
     uint32_t k;
     Slot* table;
     uint64_t mask;          // capacity - 1 (power of two)
-    uint32_t* full_flag;
+    uint32_t* full_flag;    // raised when a probe sequence ran out or the table passed claim_limit distinct keys
+    unsigned long long* claims;        // running number of claimed slots (= distinct keys) of the table
+    unsigned long long claim_limit;
 };
 void launch_insert(const InsertArgs& a, cudaStream_t s);
 
@@ -241,7 +243,9 @@ void launch_prev_load(const PrevLoadArgs& a, cudaStream_t s);
 struct NextKArgs {
     const uint32_t* mins; const uint8_t* rem; uint64_t g_lo, g_hi; uint32_t k;
     const Slot* prev; uint64_t prev_mask;
+    uint32_t prev_min_count;           // previous-table entries below it (and not rescued) count as absent
     Slot* table; uint64_t mask; uint32_t* full_flag;
+    unsigned long long* claims; unsigned long long claim_limit;
 };
 void launch_next_k(const NextKArgs& a, cudaStream_t s);
 

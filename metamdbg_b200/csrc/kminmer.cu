@@ -36,9 +36,10 @@ __device__ __forceinline__ void cas_key(Slot* s, uint64_t new_lo, uint64_t new_h
         : "memory");
 }
 
-// Insert-or-add.  Returns false when the probe limit is hit (table full).
-__device__ __forceinline__ bool table_add(Slot* table, uint64_t mask, uint64_t lo, uint64_t hi, uint32_t add,
-                                          uint64_t ref) {
+// Insert-or-add.  Returns 0 when the probe limit is hit (table full), 1 when the key was there, 2 when this call
+// claimed a fresh slot for it (callers count claims: that is the number of distinct keys, and the load factor).
+__device__ __forceinline__ int table_add(Slot* table, uint64_t mask, uint64_t lo, uint64_t hi, uint32_t add,
+                                         uint64_t ref) {
     uint64_t idx = lo & mask;
     const uint64_t max_probe = (mask + 1 < 4096) ? mask + 1 : 4096;
     for (uint64_t probe = 0; probe < max_probe; probe++) {
@@ -50,7 +51,7 @@ __device__ __forceinline__ bool table_add(Slot* table, uint64_t mask, uint64_t l
         // half is re-examined by the atomic CAS.
         if (clo == lo && chi == hi && lo != 0 && hi != 0) {
             atomicAdd(&s->count, add);
-            return true;
+            return 1;
         }
         if (clo == 0 || chi == 0) {
             uint64_t olo, ohi;
@@ -58,16 +59,38 @@ __device__ __forceinline__ bool table_add(Slot* table, uint64_t mask, uint64_t l
             if (olo == 0 && ohi == 0) {                  // claimed
                 s->ref = ref;
                 atomicAdd(&s->count, add);
-                return true;
+                return 2;
             }
             if (olo == lo && ohi == hi) {
                 atomicAdd(&s->count, add);
-                return true;
+                return 1;
             }
         }
         idx = (idx + 1) & mask;
     }
-    return false;
+    return 0;
+}
+
+// Block-wide bookkeeping of an insert pass: adds the block's number of claimed slots to *claims and raises *full_flag
+// when a probe sequence ran out or the table passed its load limit (the host then rebuilds a larger table; blocks
+// that start after the flag is up skip their work).  Every thread of the block must call it.
+__device__ __forceinline__ void block_claims(int status, bool active, unsigned long long* claims, unsigned long long claim_limit,
+                                             uint32_t* full_flag) {
+    __shared__ uint32_t s_claims, s_fail;
+    if (threadIdx.x == 0) { s_claims = 0; s_fail = 0; }
+    __syncthreads();
+    const uint32_t mc = __ballot_sync(0xffffffffu, active && status == 2);
+    const uint32_t mf = __ballot_sync(0xffffffffu, active && status == 0);
+    if ((threadIdx.x & 31) == 0) {
+        if (mc) atomicAdd(&s_claims, (uint32_t)__popc(mc));
+        if (mf) atomicAdd(&s_fail, 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        bool full = s_fail != 0;
+        if (s_claims) full |= atomicAdd(claims, (unsigned long long)s_claims) + s_claims > claim_limit;
+        if (full) atomicExch(full_flag, 1u);
+    }
 }
 
 // ------------------------------------------------------------------ rem[] = minimizers left in the read
@@ -97,22 +120,26 @@ void launch_fill_rem(const uint64_t* offs, uint64_t read_lo, uint64_t read_hi, u
 // minimizers from g on (getKminmers_complete: i in [0, n-k]).
 template <int K_FIXED>
 __global__ void __launch_bounds__(256) insert_kernel(const InsertArgs a) {
+    if (*reinterpret_cast<volatile uint32_t*>(a.full_flag)) return;          // the pass is being abandoned (block-uniform)
     const uint64_t g = a.g_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= a.g_hi) return;
     const int k = K_FIXED ? K_FIXED : (int)a.k;
-    if ((int)a.rem[g] < k) return;
-    const uint32_t* w = a.mins + g;
-    // KmerVec::normalize (Commons.hpp:886-916): first differing pair decides,
-    // a palindromic vector counts as reversed.
-    bool rev = true;
-    for (int j = 0; j < k / 2; j++) {
-        const uint32_t x = w[j], y = w[k - 1 - j];
-        if (x != y) { rev = x > y; break; }
+    const bool active = g < a.g_hi && (int)a.rem[g] >= k;
+    int status = 1;
+    if (active) {
+        const uint32_t* w = a.mins + g;
+        // KmerVec::normalize (Commons.hpp:886-916): first differing pair decides,
+        // a palindromic vector counts as reversed.
+        bool rev = true;
+        for (int j = 0; j < k / 2; j++) {
+            const uint32_t x = w[j], y = w[k - 1 - j];
+            if (x != y) { rev = x > y; break; }
+        }
+        uint64_t h1, h2;
+        if (rev) murmur128_u32vec([&](int i) { return w[k - 1 - i]; }, k, h1, h2);
+        else murmur128_u32vec([&](int i) { return w[i]; }, k, h1, h2);
+        status = table_add(a.table, a.mask, h2, h1, 1u, g | (rev ? REF_REV : 0ULL));
     }
-    uint64_t h1, h2;
-    if (rev) murmur128_u32vec([&](int i) { return w[k - 1 - i]; }, k, h1, h2);
-    else murmur128_u32vec([&](int i) { return w[i]; }, k, h1, h2);
-    if (!table_add(a.table, a.mask, h2, h1, 1u, g | (rev ? REF_REV : 0ULL))) atomicExch(a.full_flag, 1u);
+    block_claims(status, active, a.claims, a.claim_limit, a.full_flag);
 }
 
 void launch_insert(const InsertArgs& a, cudaStream_t s) {
@@ -126,28 +153,28 @@ void launch_insert(const InsertArgs& a, cudaStream_t s) {
 // Insert-if-absent with a VALUE (next-k tables: the abundance is a function of the key -- min over the two
 // (k-1)-min-mers of the replicated previous-k table -- so every rank that met the key computed the same number
 // and the first writer wins).
-__device__ __forceinline__ bool table_put(Slot* table, uint64_t mask, uint64_t lo, uint64_t hi, uint32_t value,
-                                          uint64_t ref) {
+__device__ __forceinline__ int table_put(Slot* table, uint64_t mask, uint64_t lo, uint64_t hi, uint32_t value,
+                                         uint64_t ref) {
     uint64_t idx = lo & mask;
     const uint64_t max_probe = (mask + 1 < 4096) ? mask + 1 : 4096;
     for (uint64_t probe = 0; probe < max_probe; probe++) {
         Slot* s = table + idx;
         uint64_t clo, chi;
         load_key(s, clo, chi);
-        if (clo == lo && chi == hi && lo != 0 && hi != 0) return true;
+        if (clo == lo && chi == hi && lo != 0 && hi != 0) return 1;
         if (clo == 0 || chi == 0) {
             uint64_t olo, ohi;
             cas_key(s, lo, hi, olo, ohi);
             if (olo == 0 && ohi == 0) {                  // claimed
                 s->ref = ref;
                 s->count = value;
-                return true;
+                return 2;
             }
-            if (olo == lo && ohi == hi) return true;
+            if (olo == lo && ohi == hi) return 1;
         }
         idx = (idx + 1) & mask;
     }
-    return false;
+    return 0;
 }
 
 __global__ void __launch_bounds__(256) insert_vecs_kernel(const InsertVecArgs a) {
@@ -158,8 +185,8 @@ __global__ void __launch_bounds__(256) insert_vecs_kernel(const InsertVecArgs a)
     uint64_t h1, h2;
     murmur128_u32vec([&](int j) { return w[j]; }, k, h1, h2);   // already normalized by the sender
     const uint64_t ref = REF_FOREIGN | (a.foreign_base + i);
-    const bool ok = a.assign ? table_put(a.table, a.mask, h2, h1, a.counts[i], ref)
-                             : table_add(a.table, a.mask, h2, h1, a.counts[i], ref);
+    const int ok = a.assign ? table_put(a.table, a.mask, h2, h1, a.counts[i], ref)
+                            : table_add(a.table, a.mask, h2, h1, a.counts[i], ref);
     if (!ok) atomicExch(a.full_flag, 1u);
 }
 
@@ -420,11 +447,13 @@ __device__ __forceinline__ bool prev_put(Slot* table, uint64_t mask, uint64_t lo
         Slot* s = table + idx;
         uint64_t clo, chi;
         load_key(s, clo, chi);
-        if (clo == lo && chi == hi && lo != 0 && hi != 0) { s->count = value; return true; }
+        // SLOT_RESCUED = "listed whatever its count": a pair loaded or patched by the host is never hidden by the
+        // lookup-time abundance filter of a table that used to be a count table
+        if (clo == lo && chi == hi && lo != 0 && hi != 0) { s->count = value; s->flags = SLOT_RESCUED; return true; }
         if (clo == 0 || chi == 0) {
             uint64_t olo, ohi;
             cas_key(s, lo, hi, olo, ohi);
-            if ((olo == 0 && ohi == 0) || (olo == lo && ohi == hi)) { s->count = value; return true; }
+            if ((olo == 0 && ohi == 0) || (olo == lo && ohi == hi)) { s->count = value; s->flags = SLOT_RESCUED; return true; }
         }
         idx = (idx + 1) & mask;
     }
@@ -462,48 +491,46 @@ void launch_prev_load(const PrevLoadArgs& a, cudaStream_t s) {
 // absent (or 0) => 1; kept (insert-if-absent, value = that abundance) only when > 1.
 //   KminmerCounter::getRefinedAbundance  CreateMdbg.hpp:3933-4005  (k = firstK+1)
 //   IndexKminmerFunctor                  CreateMdbg.hpp:988-1010, 1240-1265, 1268-1464  (k >= firstK+2)
+// One thread per read POSITION: the (k-1)-min-mer starting there is hashed and looked up once; the k-min-mer starting
+// at the same position takes its second value from the next lane (__shfl_down).  A warp covers 31 windows with 32
+// positions, so every lookup but one per warp is used twice -- half the hashes and random reads of one thread per
+// window.  prev_min_count filters the previous table at lookup time (an entry below it that is not rescued counts
+// as absent), which lets the previous-k table BE the table of the previous pass, unfiltered and uncopied.
 __global__ void __launch_bounds__(256) next_k_kernel(const NextKArgs a) {
-    const uint64_t g = a.g_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= a.g_hi) return;
+    if (*reinterpret_cast<volatile uint32_t*>(a.full_flag)) return;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t g = a.g_lo + warp * 31 + lane;
     const int k = (int)a.k;
-    if ((int)a.rem[g] < k) return;
+    const uint32_t rem = g < a.g_hi ? (uint32_t)a.rem[g] : 0u;
     const uint32_t* w = a.mins + g;
-    uint32_t ab = 0xFFFFFFFFu;
-    for (int sub = 0; sub < 2; sub++) {
+    uint32_t v = 1;
+    if ((int)rem >= k - 1) {
         uint64_t h1, h2; bool rev;
-        window_hash(w + sub, k - 1, h1, h2, rev);
+        window_hash(w, k - 1, h1, h2, rev);
         const Slot* s = table_find(const_cast<Slot*>(a.prev), a.prev_mask, h2, h1);
-        const uint32_t v = s ? s->count : 1u;
-        ab = v < ab ? v : ab;
+        if (s && (s->count >= a.prev_min_count || (s->flags & SLOT_RESCUED))) v = s->count;
+        if (v == 0) v = 1;
     }
-    if (ab <= 1) return;
-    uint64_t h1, h2; bool rev;
-    window_hash(w, k, h1, h2, rev);
-    // insert-if-absent: the value is a function of the key, so concurrent inserters write the same number
-    uint64_t idx = h2 & a.mask;
-    for (uint64_t probe = 0; probe <= a.mask && probe < 4096; probe++) {
-        Slot* s = a.table + idx;
-        uint64_t clo, chi;
-        load_key(s, clo, chi);
-        if (clo == h2 && chi == h1 && h2 != 0 && h1 != 0) return;
-        if (clo == 0 || chi == 0) {
-            uint64_t olo, ohi;
-            cas_key(s, h2, h1, olo, ohi);
-            if (olo == 0 && ohi == 0) {
-                s->ref = g | (rev ? REF_REV : 0ULL);
-                s->count = ab;
-                return;
-            }
-            if (olo == h2 && ohi == h1) return;
+    const uint32_t v_next = __shfl_down_sync(0xffffffffu, v, 1);
+    const bool active = lane < 31 && (int)rem >= k;              // (rem >= k implies the next position has rem >= k - 1)
+    int status = 1;
+    if (active) {
+        const uint32_t ab = v < v_next ? v : v_next;
+        if (ab > 1) {
+            uint64_t h1, h2; bool rev;
+            window_hash(w, k, h1, h2, rev);
+            // insert-if-absent: the value is a function of the key, so concurrent inserters write the same number
+            status = table_put(a.table, a.mask, h2, h1, ab, g | (rev ? REF_REV : 0ULL));
         }
-        idx = (idx + 1) & a.mask;
     }
-    atomicExch(a.full_flag, 1u);
+    block_claims(status, active, a.claims, a.claim_limit, a.full_flag);
 }
 
 void launch_next_k(const NextKArgs& a, cudaStream_t s) {
     if (a.g_hi <= a.g_lo) return;
-    next_k_kernel<<<(unsigned)((a.g_hi - a.g_lo + 255) / 256), 256, 0, s>>>(a);
+    const uint64_t n_warps = (a.g_hi - a.g_lo + 30) / 31;
+    next_k_kernel<<<(unsigned)((n_warps + 7) / 8), 256, 0, s>>>(a);
 }
 
 // ------------------------------------------------------------------ edge keys of the node set (row F1)

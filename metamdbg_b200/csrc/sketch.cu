@@ -580,21 +580,36 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) sketch_packed_kernel(co
                 }
                 const uint2 w = *reinterpret_cast<const uint2*>(&sm.stage[st][sub * P_STEP_WORDS + 2 * lane]);
                 const uint32_t b0 = step * (P_STEP_WORDS * 16u) + lane * 32u;           // my first base, stage coordinates
-                const bool interior = step * (P_STEP_WORDS * 16u) >= b_lo && (step + 1) * (P_STEP_WORDS * 16u) <= b_hi;
+                const uint32_t step_lo = step * (P_STEP_WORDS * 16u);
+                const bool head_ok = step_lo >= b_lo;                   // no foreign bases in front of mine (aligned read start)
+                const bool interior = head_ok && step_lo + P_STEP_WORDS * 16u <= b_hi;
                 uint32_t prev = __shfl_up_sync(0xffffffffu, w.y >> 30, 1);
                 if (lane == 0) prev = carry;
                 carry = __shfl_sync(0xffffffffu, w.y >> 30, 31);
                 uint32_t lo, hi, cnt;
-                if (interior) {
+                if (head_ok) {
+                    uint32_t wx = w.x, wy = w.y, nvalid = 32;
+                    if (!interior) {
+                        // last step of the read: the bases behind its end become copies of its last base -- homopolymer
+                        // compression drops them, and without it the count cuts them off
+                        nvalid = b_hi > b0 ? min(32u, b_hi - b0) : 0u;
+                        if (nvalid > 0 && nvalid < 32) {
+                            const uint64_t v = (uint64_t)wx | ((uint64_t)wy << 32);
+                            const uint64_t m = (1ULL << (2 * nvalid)) - 1ULL;
+                            const uint64_t fill = ((v >> (2 * nvalid - 2)) & 3ULL) * 0x5555555555555555ULL;
+                            const uint64_t u = (v & m) | (fill & ~m);
+                            wx = (uint32_t)u; wy = (uint32_t)(u >> 32);
+                        }
+                    }
                     if (a.hpc) {
-                        if (b0 == b_lo) prev = (w.x & 3u) ^ 1u;                        // first base of the read: always kept
-                        const uint32_t X0 = (w.x << 2) | prev;
-                        const uint32_t X1 = __funnelshift_l(w.x, w.y, 2);
+                        if (b0 == b_lo) prev = (wx & 3u) ^ 1u;                         // first base of the read: always kept
+                        const uint32_t X0 = (wx << 2) | prev;
+                        const uint32_t X1 = __funnelshift_l(wx, wy, 2);
 #define MDBG_LUT(addr) ((uint32_t) * reinterpret_cast<const uint16_t*>(lut_bytes + (addr)))
                         const uint32_t e0 = MDBG_LUT((X0 << 1) & 0x7FEu), e1 = MDBG_LUT((X0 >> 7) & 0x7FEu);
                         const uint32_t e2 = MDBG_LUT((X0 >> 15) & 0x7FEu), e3 = MDBG_LUT(__funnelshift_r(X0, X1, 23) & 0x7FEu);
                         const uint32_t e4 = MDBG_LUT((X1 << 1) & 0x7FEu), e5 = MDBG_LUT((X1 >> 7) & 0x7FEu);
-                        const uint32_t e6 = MDBG_LUT((X1 >> 15) & 0x7FEu), e7 = MDBG_LUT((w.y >> 21) & 0x7FEu);
+                        const uint32_t e6 = MDBG_LUT((X1 >> 15) & 0x7FEu), e7 = MDBG_LUT((wy >> 21) & 0x7FEu);
 #undef MDBG_LUT
                         uint32_t n0, n1;
                         const uint32_t a0 = hpc_merge4(e0, e1, e2, e3, n0), a1 = hpc_merge4(e4, e5, e6, e7, n1);
@@ -602,10 +617,15 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) sketch_packed_kernel(co
                         lo = (uint32_t)v; hi = (uint32_t)(v >> 32);
                         cnt = (n0 + n1) >> 1;
                     } else {
-                        lo = w.x; hi = w.y; cnt = 32;
+                        lo = wx; hi = wy; cnt = nvalid;
+                        if (nvalid < 32) {
+                            const uint64_t u = ((uint64_t)wx | ((uint64_t)wy << 32)) & ((1ULL << (2 * nvalid)) - 1ULL);
+                            lo = (uint32_t)u; hi = (uint32_t)(u >> 32);
+                        }
                     }
+                    if (nvalid == 0) { lo = 0; hi = 0; cnt = 0; }
                 } else {
-                    // first / last step of the read (ragged ends): base by base
+                    // first step of a read that does not start on a 16-byte boundary of the packed buffer: base by base
                     uint64_t v = 0;
                     cnt = 0;
                     uint32_t pc = prev;

@@ -4,6 +4,7 @@
 //   scripts/k1_probe [n_reads=200000] [read_len=15000]
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -38,9 +39,41 @@ int main(int argc, char** argv) {
         mdbg_ctx_synchronize(ctx) != MDBG_OK) { printf("{\"error\": \"%s\"}\n", mdbg_last_error(ctx)); return 1; }
     mdbg_autotune_out o{};
     if (mdbg_ctx_autotune_sketch(ctx, d_bases, d_off, n, n * len, &o) != MDBG_OK) { printf("{\"error\": \"%s\"}\n", mdbg_last_error(ctx)); return 1; }
-    printf("{\"n_reads\": %u, \"read_len\": %llu, \"n_minimizers\": %llu, \"chosen\": %d, \"identical\": [%d, %d], \"ms\": [%.3f, %.3f], "
-           "\"gbp_per_s\": [%.1f, %.1f]}\n", n, (unsigned long long)len, (unsigned long long)o.n_minimizers, o.chosen, o.identical[0],
-           o.identical[1], o.ms[0], o.ms[1], n * len / (o.ms[0] * 1e6), n * len / (o.ms[1] * 1e6));
+    printf("{\"n_reads\": %u, \"read_len\": %llu, \"n_minimizers\": %llu, \"chosen\": %d, \"identical\": [%d, %d, %d], \"ms\": [%.3f, %.3f, %.3f], "
+           "\"gbp_per_s\": [%.1f, %.1f, %.1f]", n, (unsigned long long)len, (unsigned long long)o.n_minimizers, o.chosen, o.identical[0],
+           o.identical[1], o.identical[2], o.ms[0], o.ms[1], o.ms[2], n * len / (o.ms[0] * 1e6), n * len / (o.ms[1] * 1e6), n * len / (o.ms[2] * 1e6));
+    // packed-resident input: the pack pass alone, then the packed kernel alone (mdbg_ctx_kernel_time_ms(0))
+    {
+        uint32_t* d_words; uint64_t* d_src;
+        const uint64_t n_words = mdbg_pack_device_words(n * len, n);
+        if (cudaMalloc(&d_words, n_words * 4) || cudaMalloc(&d_src, (uint64_t)n * 8)) { printf(", \"error\": \"cudaMalloc packed\"}\n"); return 1; }
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        float pack_ms = 1e9f, k_ms = 1e9f, all_ms = 1e9f;
+        mdbg_ctx_set_sketch_variant(ctx, 2);
+        mdbg_ctx_enable_timing(ctx, 1);
+        for (int rep = 0; rep < 3; rep++) {
+            mdbg_ctx_synchronize(ctx);
+            cudaEventRecord(e0, 0);                       // legacy default stream synchronises with the context's blocking... not: use sync
+            cudaDeviceSynchronize();
+            auto t0 = std::chrono::steady_clock::now();
+            if (mdbg_pack_device(ctx, d_bases, d_off, n, n * len, d_words, d_src) != MDBG_OK) { printf(", \"error\": \"%s\"}\n", mdbg_last_error(ctx)); return 1; }
+            mdbg_ctx_synchronize(ctx);
+            const float t = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            if (t < pack_ms) pack_ms = t;
+            t0 = std::chrono::steady_clock::now();
+            mdbg_sketch_dev sd{};
+            if (mdbg_sketch_batch_device_packed2(ctx, d_words, d_src, d_bases, d_off, n, n * len, 0, &sd) != MDBG_OK) { printf(", \"error\": \"%s\"}\n", mdbg_last_error(ctx)); return 1; }
+            mdbg_ctx_synchronize(ctx);
+            const float ta = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            if (ta < all_ms) all_ms = ta;
+            float km = 0; mdbg_ctx_kernel_time_ms(ctx, 0, &km);
+            if (km < k_ms) k_ms = km;
+            if (sd.n_minimizers != o.n_minimizers) { printf(", \"error\": \"packed2 gave %llu minimizers\"}\n", (unsigned long long)sd.n_minimizers); return 1; }
+        }
+        printf(", \"pack_device_ms_wall\": %.3f, \"packed_kernels_ms\": %.3f, \"packed2_call_ms_wall\": %.3f, \"packed_gbp_per_s\": %.1f",
+               pack_ms, k_ms, all_ms, n * len / (k_ms * 1e6));
+    }
+    printf("}\n");
     mdbg_ctx_destroy(ctx);
     return 0;
 }

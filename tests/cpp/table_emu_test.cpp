@@ -76,7 +76,8 @@ static void insert_store(DevTable& t, const Store& s, uint64_t read_lo, uint64_t
     uint32_t full = 0;
     InsertArgs a{};
     a.mins = s.mins.data(); a.rem = rem.data(); a.g_lo = s.offs[read_lo]; a.g_hi = s.offs[read_hi]; a.k = t.k;
-    a.table = t.slots.data(); a.mask = t.cap - 1; a.full_flag = &full;
+    static unsigned long long claims; claims = 0;
+    a.table = t.slots.data(); a.mask = t.cap - 1; a.full_flag = &full; a.claims = &claims; a.claim_limit = t.cap;
     launch_insert(a, nullptr);
     CHECK(full == 0, "table full");
 }
@@ -216,7 +217,7 @@ static void test_tables(std::mt19937_64& rng) {
                 Table want;
                 for (size_t i = 0; i < nn; i++) want[Key(nh[2 * i], nh[2 * i + 1])] = Entry{na[i], std::vector<uint32_t>(nv + i * (k + 1), nv + (i + 1) * (k + 1))};
                 orc_free(nv); orc_free(nh); orc_free(na);
-                for (int mode = 0; mode < 2; mode++) {
+                for (int mode = 0; mode < 3; mode++) {            // 2: the count table itself as previous-k table (lookup-time filter)
                     const uint64_t pcap = pow2ceil(std::max<uint64_t>(want2.size(), 512) * 2);
                     std::vector<Slot> prev(pcap, Slot{});
                     uint32_t full = 0;
@@ -224,7 +225,7 @@ static void test_tables(std::mt19937_64& rng) {
                         PrevFromTableArgs pf{};
                         pf.table = t.slots.data(); pf.capacity = t.cap; pf.min_count = 2; pf.prev = prev.data(); pf.prev_mask = pcap - 1; pf.full_flag = &full;
                         launch_prev_from_table(pf, nullptr);
-                    } else {                                      // device layout of hashes: lo = h2, hi = h1
+                    } else if (mode == 1) {                       // device layout of hashes: lo = h2, hi = h1
                         std::vector<uint64_t> lohi; for (size_t i = 0; i < pa.size(); i++) { lohi.push_back(ph[2 * i + 1]); lohi.push_back(ph[2 * i]); }
                         PrevLoadArgs pl{};
                         pl.hashes = lohi.data(); pl.abund = pa.data(); pl.n = pa.size(); pl.prev = prev.data(); pl.prev_mask = pcap - 1; pl.full_flag = &full;
@@ -238,9 +239,11 @@ static void test_tables(std::mt19937_64& rng) {
                     NextKArgs nk{};
                     nk.mins = s.mins.data(); nk.rem = rem.data(); nk.g_lo = 0; nk.g_hi = s.offs[s.n()]; nk.k = (uint32_t)k + 1;
                     nk.prev = prev.data(); nk.prev_mask = pcap - 1; nk.table = t3.slots.data(); nk.mask = t3.cap - 1; nk.full_flag = &full;
+                    unsigned long long nk_claims = 0; nk.claims = &nk_claims; nk.claim_limit = t3.cap; nk.prev_min_count = 0;
+                    if (mode == 2) { nk.prev = t.slots.data(); nk.prev_mask = t.cap - 1; nk.prev_min_count = 2; }
                     launch_next_k(nk, nullptr);
                     CHECK(full == 0, "next-k table full");
-                    expect_equal(emit(t3, s, 2), want, mode ? "next-k (loaded prev)" : "next-k (device prev)");
+                    expect_equal(emit(t3, s, 2), want, mode == 2 ? "next-k (count table as prev)" : mode ? "next-k (loaded prev)" : "next-k (device prev)");
                     cov_nextk += want.size();
                 }
             }

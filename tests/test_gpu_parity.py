@@ -252,16 +252,27 @@ def test_count_add_host_reads(built, oracle):
     eng.close()
 
 
-def test_table_full_is_reported(built):
+def test_table_full_is_reported(built, monkeypatch):
+    """A table that is too small for its keys is rebuilt larger (round 2); with that switched off the pass reports
+    MDBG_ERR_TABLE_FULL as before, and the context stays usable."""
     from metamdbg_b200 import MdbgError
     rng = np.random.default_rng(4)
     mins = rng.integers(0, 2 ** 32, size=200_000, dtype=np.uint64).astype(np.uint32)
     offs = np.array([0, len(mins)], np.uint64)
     eng = engine()
-    eng.count_begin(4, expected_distinct=256)    # far too small
+    eng.count_begin(4, expected_distinct=256)    # far too small: grows
+    eng.count_add(mins, offs)
+    assert eng.count_stats(2)["n_distinct"] == len(mins) - 3
+    eng.close()
+    monkeypatch.setenv("MDBG_TABLE_AUTOGROW", "0")
+    eng = engine()
+    eng.count_begin(4, expected_distinct=256)
     with pytest.raises(MdbgError) as e:
         eng.count_add(mins, offs)
     assert e.value.status == 4
+    eng.count_begin(4, expected_distinct=len(mins))
+    eng.count_add_store()
+    assert eng.count_stats(2)["n_distinct"] == len(mins) - 3
     eng.close()
 
 

@@ -130,3 +130,97 @@ def test_packed_kernel_host_batches_with_dirty_reads(built, oracle, monkeypatch)
         assert info["n_pieces"] > 3
         assert_sketch_equal(sk, *want, tag=f"host batch packing={packing}")
         eng.close()
+
+
+# ---------------------------------------------------------------- count table: sizing, rebuild, later passes
+
+def test_table_grows_when_the_estimate_is_too_small(built, oracle):
+    """The table is sized for the expected number of distinct k-min-mers; a store of (almost) all-distinct windows
+    outgrows the default estimate (a quarter of the windows), the pass is abandoned and the table rebuilt larger --
+    also when the store was inserted in several ranges, and for a next-k pass."""
+    rng = np.random.default_rng(12)
+    n_reads, per = 600, 300
+    mins = rng.integers(0, 2**32 - 1, size=n_reads * per, dtype=np.uint64).astype(np.uint32)
+    offs = (np.arange(n_reads + 1) * per).astype(np.uint64)
+    mins[per * 10:per * 20] = mins[:per * 10]                     # some repeated reads: solid k-min-mers exist
+    mins[per * 20:per * 30] = mins[:per * 10]
+    want = oracle.count(mins, offs, 4, 2)
+    eng = engine()
+    eng.store_append(mins, offs)
+    eng.count_begin(4, 0)
+    eng.count_add_store(0, 200)                                   # three ranges: the rebuild re-inserts all of them
+    eng.count_add_store(200, 450)
+    eng.count_add_store(450, n_reads)
+    tab = eng.count_finalize(2)
+    assert tab.as_dict() == table_dict(want["hashes"], want["abundances"]) and len(want["abundances"]) > 2000
+    assert tab.n_distinct > 0.8 * (n_reads * (per - 3))          # the estimate (1/4 of the windows) was far too small
+    # explicit, much too small expectation
+    eng.count_begin(4, 1000)
+    eng.count_add_store()
+    assert eng.count_finalize(2).as_dict() == table_dict(want["hashes"], want["abundances"])
+    # next-k pass into a table sized for 1000 entries
+    eng.prev_from_current(2)
+    eng.count_begin(5, 600)
+    eng.count_add_store_next_k()
+    t5 = eng.count_finalize(2)
+    w5 = oracle.next_k(mins, offs, 5, want["hashes"], want["abundances"])
+    assert t5.as_dict() == table_dict(w5["hashes"], w5["abundances"]) and len(w5["abundances"]) > 1500
+    eng.close()
+
+
+def test_min_abundance_applies_to_the_first_pass_only(built, oracle):
+    """--min-abundance >= 3: the first pass drops abundance-2 k-min-mers, later passes keep every k-min-mer with a
+    derived abundance > 1 (CreateMdbg.hpp:3868-3869) -- visible once the previous-k table carries refined
+    abundances of 2 (patches from the contig stage)."""
+    rs = synth.make_readset(2500, 9000, seed=63, n_genomes=1, genome_len_range=(250_000, 250_001))
+    bases, offs = synth.fill_reads(rs)
+    eng = engine()
+    eng.sketch_batch(bases, offs, append_to_store=True, fetch=False)
+    so, sm = eng.store_fetch()
+    first = oracle.count(sm, so, 4, 3)                            # first pass, min abundance 3
+    eng.count_begin(4)
+    eng.count_add_store()
+    assert eng.count_finalize(3).as_dict() == table_dict(first["hashes"], first["abundances"])
+    eng.prev_from_current(3)                                      # the count table itself, filtered at lookup time
+    rng = np.random.default_rng(6)
+    patch_idx = np.nonzero(rng.random(len(first["abundances"])) < 0.3)[0]
+    patched = first["abundances"].copy()
+    patched[patch_idx] = rng.integers(0, 4, size=len(patch_idx)).astype(np.uint32)     # 0, 1, 2, 3
+    lohi = np.stack([first["hashes"][:, 1], first["hashes"][:, 0]], axis=1)
+    eng.prev_load(lohi[patch_idx], patched[patch_idx], clear=False)
+    prev_h, prev_a = first["hashes"], patched
+    for k in (5, 6):
+        eng.count_begin(k)
+        eng.count_add_store_next_k()
+        want = oracle.next_k(sm, so, k, prev_h, prev_a)
+        assert (want["abundances"] == 2).sum() > 50               # entries a min-abundance-3 filter would drop
+        st = eng.count_stats(3)
+        assert st["n_entries"] == len(want["abundances"])
+        tab = eng.count_finalize(3)
+        assert tab.as_dict() == table_dict(want["hashes"], want["abundances"]), k
+        eng.prev_from_current(3)
+        prev_h, prev_a = want["hashes"], want["abundances"]
+    eng.close()
+
+
+def test_store_rewrite_ends_the_table(built):
+    """Slots reference store positions: clearing or purging the store ends the current table instead of leaving
+    dangling references behind (finalize then reports a state error, nothing is read out of bounds)."""
+    from metamdbg_b200.engine import MdbgError
+    rng = np.random.default_rng(2)
+    mins = rng.integers(0, 50, size=4000, dtype=np.uint64).astype(np.uint32)
+    offs = (np.arange(41) * 100).astype(np.uint64)
+    eng = engine()
+    eng.store_append(mins, offs)
+    eng.count_begin(4)
+    eng.count_add_store()
+    assert len(eng.count_finalize(2).abundances) > 0
+    eng.store_clear()
+    with pytest.raises(MdbgError) as e:
+        eng.count_finalize(2)
+    assert e.value.status == 3                                    # MDBG_ERR_STATE
+    eng.store_append(mins, offs)                                  # and the context is still usable
+    eng.count_begin(4)
+    eng.count_add_store()
+    assert len(eng.count_finalize(2).abundances) > 0
+    eng.close()
