@@ -2,20 +2,25 @@
 """bench.py -- Gbp/s through minimizer-sketch + k-min-mer count (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W            # this engine
-    python bench.py --impl reference --gpus N --steps K ...  # reference CPU path (oracle/_ref)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU stages (oracle/_ref)
 
-`--workload cfg3` switches to BASELINE.json configs[2] (2 M ONT reads x 8 kbp: no HPC, sketch at the correction
-density 0.025, density re-threshold of the store to 0.005, purge, k = 4 count), same JSON line.
+Headline workload (config.workload): BASELINE.json configs[1] per GPU -- 1 M synthetic HiFi reads x 15 kbp, l=15,
+d=0.005, HPC on, k=4, abundance >= 2.  A "step" is one pass of the hot path over that batch:
 
-Workload (config.workload): BASELINE.json configs[1] per GPU -- 1 M synthetic
-HiFi reads x 15 kbp, l=15, d=0.005, HPC on, k=4, abundance >= 2.  A "step" is
-one pass of the hot path over that batch: sketch -> minimizer store ->
-purgePalindromes -> k-min-mer insert -> [NCCL owner merge for N>1] -> table
-statistics.  `value` times it with the reads resident in HBM; `e2e` times the
-same work through the host-buffer C ABI (H2D of the ASCII reads, D2H of the
-minimizer CSR and of the finalised table inside the timed region).  For N>1
-every rank processes its own shard of N x 1 M reads (weak scaling) and the only
-data-path collective is the owner-partitioned table merge.
+    sketch (2-bit packed reads resident in HBM) -> minimizer store -> purgePalindromes -> k-min-mer insert
+    -> [NCCL owner merge for N>1] -> statistics + on-device emit of (hash128, abundance, k-min-mer) arrays
+
+`value` times it with the reads resident in HBM in the packed layout the design brief names (`ascii_resident` is the
+same step on ASCII bytes, i.e. with the device-side pack pass in it); `e2e` times the same work through the
+host-buffer C ABI (ASCII in pinned host memory -> 2-bit packing by the library's host threads -> H2D; D2H of the
+minimizer CSR and of the finalised table inside the timed region).  For N>1 every rank processes its own shard of
+N x 1 M reads (weak scaling) and the only data-path collective of the step is the owner-partitioned table merge.
+
+Extras in the same JSON line (each with its own timing, none of them part of `value`): the multi-k loop k = 4..21 on
+the resident store (collective for N>1), edge indexing, and the other BASELINE.json configs -- cfg3 (ONT, N=1),
+cfg4 (5 M reads TOTAL, k = 4..21, strong scaling) and cfg5 (20 M reads TOTAL in 3 samples, strong scaling).  For N>1 a
+parity leg runs first: count -> merge -> rescue -> two next-k passes -> edge index over real NCCL on a shared read
+set, every stage compared with the CPU oracle of the whole set; a mismatch ends the run.
 """
 from __future__ import annotations
 
@@ -33,45 +38,32 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-L, DENSITY, HPC, K, MIN_AB = 15, 0.005, True, 4, 2
-ASM_DENSITY, ERR = 0.0, 0.001          # ONT (cfg3): sketch at DENSITY, then re-threshold the store at ASM_DENSITY
+L, K, MIN_AB = 15, 4, 2
 SEED = 20260924
+METRIC = "Gbp/s through minimizer-sketch + k-min-mer count"
 
-# BASELINE.json configs that fit one GPU.  cfg2 is the configuration the metric is quoted on (the default); cfg3 is
-# the ONT shape: no homopolymer compression, sketch at the correction density 0.025 ("nanoMDBG density"), then
-# Utils::applyDensityThreshold(0.005) on the minimizer store, purge, k = 4 count.
+# BASELINE.json configs.  cfg2 is the configuration the metric is quoted on (the default headline); cfg3 is the ONT
+# shape: no homopolymer compression, sketch at the correction density 0.025 ("nanoMDBG density"), then
+# Utils::applyDensityThreshold(0.005) on the minimizer store, purge, k = 4 count.  cfg4 / cfg5 fix the
+# TOTAL number of reads (strong scaling): the 5 M-read multi-k sweep and the 20 M-read 3-sample co-assembly.
 WORKLOADS = {
-    "cfg2": dict(reads=1_000_000, read_len=15_000, density=0.005, hpc=True, asm_density=0.0, err=0.001,
+    "cfg2": dict(reads=1_000_000, per_gpu=True, read_len=15_000, density=0.005, hpc=True, asm_density=0.0, err=0.001,
+                 samples=1, last_k=4,
                  label="cfg2: 1M synthetic HiFi reads x 15 kbp per GPU, l=15 d=0.005 HPC k=4 min-abundance 2"),
-    "cfg3": dict(reads=2_000_000, read_len=8_000, density=0.025, hpc=False, asm_density=0.005, err=0.02,
+    "cfg3": dict(reads=2_000_000, per_gpu=True, read_len=8_000, density=0.025, hpc=False, asm_density=0.005, err=0.02,
+                 samples=1, last_k=4,
                  label="cfg3: 2M synthetic ONT reads x 8 kbp per GPU, l=15 sketch d=0.025 (no HPC) -> density 0.005, "
                        "k=4 min-abundance 2"),
+    "cfg4": dict(reads=5_000_000, per_gpu=False, read_len=15_000, density=0.005, hpc=True, asm_density=0.0, err=0.001,
+                 samples=1, last_k=21,
+                 label="cfg4: 5M synthetic HiFi reads x 15 kbp in TOTAL (strong scaling), l=15 d=0.005 HPC, sketch + purge + "
+                       "k=4 count + next-k passes k=5..21 (previous-k tables, collectives for N>1), min-abundance 2"),
+    "cfg5": dict(reads=20_000_000, per_gpu=False, read_len=15_000, density=0.005, hpc=True, asm_density=0.0, err=0.001,
+                 samples=3, last_k=4,
+                 label="cfg5: 20M synthetic HiFi reads x 15 kbp in TOTAL, 3 samples (datasetIndex 0-2, different abundance "
+                       "profiles of one genome set) pooled as in the reference (strong scaling), k=4 min-abundance 2, "
+                       "NCCL owner merge of the count tables"),
 }
-
-
-def select_workload(args):
-    """Set the module-level workload constants from --workload and fill the size defaults."""
-    global DENSITY, HPC, ASM_DENSITY, ERR
-    w = WORKLOADS[args.workload]
-    DENSITY, HPC, ASM_DENSITY, ERR = w["density"], w["hpc"], w["asm_density"], w["err"]
-    if args.reads <= 0:
-        args.reads = w["reads"]
-    if args.read_len <= 0:
-        args.read_len = w["read_len"]
-
-
-def workload_config(args):
-    return {
-        "workload": WORKLOADS[args.workload]["label"]
-        if (args.reads == WORKLOADS[args.workload]["reads"] and args.read_len == WORKLOADS[args.workload]["read_len"]) else
-        f"{args.reads} synthetic reads x {args.read_len} bp per GPU, parameters of {args.workload}: l=15 d={DENSITY} "
-        f"hpc={HPC} assembly-density={ASM_DENSITY or DENSITY} k=4 min-abundance 2",
-        "reads_per_gpu": args.reads, "read_len_mean": args.read_len, "minimizer_size": L, "density": DENSITY,
-        "assembly_density": ASM_DENSITY or DENSITY,
-        "hpc": HPC, "k": K, "min_abundance": MIN_AB, "purge_last_k": purge_last_k(args),
-        "genomes": args.genomes, "substitution_rate": ERR, "input_format": "ASCII bases (Read::_seq)",
-        "l2_policy": "inputs (>= 1 GB per step) are far larger than the 126 MB L2; no explicit flush",
-    }
 
 
 def usable_cpus() -> int:
@@ -105,9 +97,41 @@ def host_bytes_available() -> int:
     return max(0, avail)
 
 
-def purge_last_k(args):
+def purge_last_k(read_len: int, w: dict) -> int:
     # Commons::computeLastK (src/Commons.hpp:1726-1741): n50 * density * 2, at least firstK+2
-    return max(int(args.read_len * np.float32(ASM_DENSITY or DENSITY) * np.float32(2.0)), 6)
+    return max(int(read_len * np.float32(w["asm_density"] or w["density"]) * np.float32(2.0)), 6)
+
+
+def workload_config(name: str, reads: int, read_len: int, genomes: int, world: int) -> dict:
+    w = WORKLOADS[name]
+    default = reads == w["reads"] and read_len == w["read_len"]
+    return {
+        "workload": w["label"] if default else
+        f"{reads} synthetic reads x {read_len} bp {'per GPU' if w['per_gpu'] else 'in total'}, parameters of {name}: l=15 "
+        f"d={w['density']} hpc={w['hpc']} assembly-density={w['asm_density'] or w['density']} k=4..{w['last_k']} min-abundance 2",
+        "reads_per_gpu": reads if w["per_gpu"] else reads // max(1, world), "reads_total": reads * world if w["per_gpu"] else reads,
+        "read_len_mean": read_len, "minimizer_size": L, "density": w["density"],
+        "assembly_density": w["asm_density"] or w["density"], "hpc": w["hpc"], "k": K, "last_k": w["last_k"],
+        "min_abundance": MIN_AB, "purge_last_k": purge_last_k(read_len, w), "genomes": genomes, "samples": w["samples"],
+        "substitution_rate": w["err"],
+        "input_format": "2-bit packed bases resident in HBM (16 per u32, 16-byte aligned reads); e2e: ASCII bases (Read::_seq) in pinned host memory",
+        "l2_policy": "inputs (>= 1 GB per step) are far larger than the 126 MB L2; no explicit flush",
+    }
+
+
+def make_readsets(name: str, reads_total: int, read_len: int, genomes: int):
+    """The read sets of a workload: one per sample (cfg5: three abundance profiles over the same genome set)."""
+    from metamdbg_b200 import synth
+    w = WORKLOADS[name]
+    if w["samples"] == 1:
+        return [synth.make_readset(reads_total, read_len, seed=SEED, n_genomes=genomes, err=w["err"])]
+    out, base = [], 0
+    for s in range(w["samples"]):
+        n = reads_total * (s + 1) // w["samples"] - reads_total * s // w["samples"]
+        rs = synth.make_readset(n, read_len, seed=SEED, n_genomes=genomes, err=w["err"], sample=s, index_base=base)
+        out.append(rs)
+        base += n
+    return out
 
 
 # ---------------------------------------------------------------- clocks sampler
@@ -157,131 +181,245 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------- reference arm
+def write_fastq(path: str, bases: np.ndarray, offs: np.ndarray):
+    raw = bases.tobytes()
+    with open(path, "wb", buffering=1 << 24) as f:
+        for r in range(len(offs) - 1):
+            s = raw[int(offs[r]):int(offs[r + 1])]
+            f.write(b"@r%d\n" % r + s + b"\n+\n" + b"I" * len(s) + b"\n")
+
+
 def run_reference(args, rank: int):
-    """The reference's own CPU implementation of the path (oracle/_ref = metaMDBG sources compiled
-    as they are; falls back to the C restatement when that library is absent), all host threads,
-    on a bounded sample of the same workload."""
+    """The reference's own CPU implementation of the path, all host threads, on a bounded sample of the workload.
+
+    Headline (kind "reference"): the STOCK stages -- ReadSelection::execute on a FASTQ in tmpfs (kseq parsing, sketch,
+    side outputs, ordered record writer, purgePalindromes; src/readSelection/ReadSelection.hpp:92-111) followed by
+    CreateMdbg::KminmerCounter with its disk partitions + parallel sort (src/graph/CreateMdbg.hpp:3634-3642), i.e. what
+    `metaMDBG readSelection` + `graph --firstpass` spend on this path; value = sample bases / (stage seconds).
+    Extra: the same reference primitives driven in memory (no FASTQ, no disk), and the reference's multi-k loop.
+    The thread count does not depend on OMP_NUM_THREADS (torch.distributed.run exports OMP_NUM_THREADS=1): every
+    parallel region of the shim and of the stages takes its thread count as an argument."""
     if rank != 0:
         return
     from metamdbg_b200 import synth
     from oracle import pyoracle
+    name = args.workload
+    w = WORKLOADS[name]
     cores = os.cpu_count() or 1
     try:
         ref = pyoracle.Reference()
         kind = "reference"
-        threads = min(cores, ref.max_threads())
     except (FileNotFoundError, OSError):
-        ref, kind, threads = None, "port", 1
-    n_sample = args.ref_reads or int(min(args.reads, max(2000, 400 * threads)))
-    rs = synth.make_readset(args.reads * max(1, args.gpus), args.read_len, seed=SEED, n_genomes=args.genomes, err=ERR)
-    sub = rs.subset(0, n_sample)
-    bases, offs = synth.fill_reads(sub)
+        ref, kind = None, "port"
+    world = max(1, args.gpus)
+    reads_total = args.reads * world if w["per_gpu"] else args.reads
+    n_sample = int(min(reads_total, args.ref_reads or 100_000))
+    rs = make_readsets(name, reads_total, args.read_len, args.genomes)[0]
+    n_sample = min(n_sample, rs.n_reads)
+    bases, offs = synth.fill_reads(rs.subset(0, n_sample))
     n_bases = int(offs[-1])
-    lk = purge_last_k(args)
+    lk = purge_last_k(args.read_len, w)
+    stock = ref is not None and not args.no_stages and name != "cfg3"      # ONT: the correction stage is out of scope
+    tmp_base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    import tempfile
+    tmp = tempfile.TemporaryDirectory(dir=tmp_base)
+    fq = os.path.join(tmp.name, "reads.fastq")
+    if stock:
+        write_fastq(fq, bases, offs)
+    threads = max(1, usable_cpus())
+    state = {}
 
-    def one():
+    def one(t: int):
+        if stock:
+            with tempfile.TemporaryDirectory(dir=tmp.name) as d:
+                res = ref.read_selection([fq], L, w["density"], w["hpc"], threads=t, skip_correction=False, workdir=d)
+            corr = res["corrected"]
+            mins = np.concatenate([r["minimizers"] for r in corr]) if corr else np.zeros(0, np.uint32)
+            mo = np.zeros(len(corr) + 1, np.uint64)
+            mo[1:] = np.cumsum([len(r["minimizers"]) for r in corr])
+            g = ref.graph_firstpass(mins, mo, K, min_abundance=MIN_AB, threads=t)
+            state.update(mins=mins, mo=mo, table=g)
+            return res["seconds"] + g["seconds"], dict(n_solid=g["n_solid"], n_minimizers=int(len(mins)),
+                                                       readSelection_s=res["seconds"], graph_firstpass_count_s=g["seconds"])
         t0 = time.perf_counter()
         if ref is not None:
-            res = ref.pipeline(bases, offs, L, DENSITY, HPC, K, purge_last_k=lk, min_abundance=MIN_AB, threads=threads,
-                               assembly_density=ASM_DENSITY)
+            res = ref.pipeline(bases, offs, L, w["density"], w["hpc"], K, purge_last_k=lk, min_abundance=MIN_AB, threads=t,
+                               assembly_density=w["asm_density"])
         else:
-            res = oracle_port_pipeline(pyoracle.Oracle(), bases, offs, lk)
+            res = oracle_port_pipeline(pyoracle.Oracle(), bases, offs, lk, w)
         return time.perf_counter() - t0, res
 
     # the warm-up steps also pick the thread count: candidates from the usable CPUs (cgroup quota) up to every
     # logical CPU; the fastest is used for the timed steps ("all the host threads it can use")
     if ref is not None and args.warmup >= 1:
         eff = usable_cpus()
-        cands = sorted({max(1, min(threads, c)) for c in (eff, 2 * eff, max(1, cores // 2), cores)})
-        cands = cands[:max(1, args.warmup)] if len(cands) > args.warmup else cands
+        cands = sorted({max(1, min(cores, c)) for c in (eff, 2 * eff, cores)})
+        cands = cands[:max(1, args.warmup)]
         best = None
         for c in cands:
-            threads = c
-            t, _ = one()
+            t, _ = one(c)
             if best is None or t < best[0]:
                 best = (t, c)
         threads = best[1]
         for _ in range(args.warmup - len(cands)):
-            one()
+            one(threads)
     else:
+        threads = 1 if ref is None else threads
         for _ in range(args.warmup):
-            one()
+            one(threads)
     ts = []
     for _ in range(args.steps):
-        t, res = one()
+        t, res = one(threads)
         ts.append(t)
     total = sum(ts)
     gbps = n_bases * args.steps / total / 1e9
-    sample = f"first {n_sample} reads of the workload ({n_bases / 1e9:.3f} Gbp) per step"
+    sample = (f"first {n_sample} reads of the workload ({n_bases / 1e9:.3f} Gbp) per step; "
+              + ("stock stages: ReadSelection::execute on a tmpfs FASTQ + KminmerCounter (disk partitions + sort), stage-internal seconds"
+                 if stock else "reference primitives driven in memory (no FASTQ, no disk)"))
     line = {
-        "impl": "reference", "metric": "Gbp/s through minimizer-sketch + k-min-mer count", "value": gbps,
+        "impl": "reference", "metric": METRIC, "value": gbps,
         "unit": "Gbp/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u64", "data": "synthetic", "config": dict(workload_config(args), sample=sample),
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+        "scaling": "weak" if w["per_gpu"] else "strong", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic",
+        "config": dict(workload_config(name, args.reads, args.read_len, args.genomes, world), sample=sample),
         "cpu_baseline": {"value": gbps, "unit": "Gbp/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": gbps, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "check": {"n_minimizers": res.get("n_minimizers"), "n_solid": res.get("n_solid")},
+        "host": {"logical_cpus": cores, "usable_cpus": usable_cpus(), "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS")},
     }
-    if ref is not None and not args.no_stages and args.workload == "cfg2":
-        line["reference_stages"] = reference_stages(ref, bases, offs, threads, n_bases)
+    if stock:
+        line["reference_stages"] = {k: res[k] for k in ("readSelection_s", "graph_firstpass_count_s")}
+        # extra: the same sample through the reference's primitives in memory (round 1's headline)
+        t0 = time.perf_counter()
+        mem = ref.pipeline(bases, offs, L, w["density"], w["hpc"], K, purge_last_k=lk, min_abundance=MIN_AB, threads=threads,
+                           assembly_density=w["asm_density"])
+        dt = time.perf_counter() - t0
+        line["reference_in_memory"] = {"value": n_bases / dt / 1e9, "unit": "Gbp/s", "threads": threads,
+                                       "same_table_as_stock_stages": mem["n_solid"] == res["n_solid"]}
+    if ref is not None and args.multi_k > K and state.get("table") is not None and not args.no_ref_multi_k:
+        # extra: the reference's multi-k loop on the same sample (CreateMdbg.cpp:386-468 driven per k by
+        # AssemblyPipeline.hpp:606-671): k = 4 first pass above, then every k from the previous k's table --
+        # getRefinedAbundance (k = 5, through KminmerCounter) and IndexKminmerFunctor (k >= 6)
+        prev_h, prev_a = state["table"]["hashes"], state["table"]["abundances"]
+        per_k = []
+        for k in range(K + 1, args.multi_k + 1):
+            t0 = time.perf_counter()
+            nk = ref.graph_next_k(state["mins"], state["mo"], k, prev_h, prev_a, use_counter=(k == K + 1), threads=threads)
+            per_k.append(round(time.perf_counter() - t0, 4))
+            prev_h, prev_a = nk["hashes"], nk["abundances"]
+        tot = res["graph_firstpass_count_s"] + sum(per_k)
+        line["reference_multi_k"] = {"k_first": K, "k_last": args.multi_k, "seconds_per_k": [res["graph_firstpass_count_s"]] + per_k,
+                                     "seconds_total": tot, "value": n_bases / tot / 1e9,
+                                     "unit": "Gbp/s (sample bases / time of the k-loop alone)", "threads": threads,
+                                     "n_entries_last_k": int(len(prev_a)),
+                                     "timer": "host wall clock per k around the reference's graph stage code (incl. its file I/O)"}
     print(json.dumps(line), flush=True)
+    tmp.cleanup()
 
 
-def oracle_port_pipeline(orc, bases, offs, lk):
+def oracle_port_pipeline(orc, bases, offs, lk, w):
     """The path on the C restatement (single thread): sketch, [density re-threshold], purge, count."""
-    mo, m, p, d = orc.sketch_batch(bases, offs, L, DENSITY, HPC)
+    mo, m, p, d = orc.sketch_batch(bases, offs, L, w["density"], w["hpc"])
     pm, po = [], [0]
     for r in range(len(offs) - 1):
         q = m[int(mo[r]):int(mo[r + 1])]
-        if ASM_DENSITY:
-            q = orc.apply_density(q, ASM_DENSITY)
+        if w["asm_density"]:
+            q = orc.apply_density(q, w["asm_density"])
         q, _ = orc.purge_palindrome(q, 4, lk)
         pm.append(q); po.append(po[-1] + len(q))
     pm = np.concatenate(pm).astype(np.uint32) if pm else np.zeros(0, np.uint32)
     c = orc.count(pm, np.array(po, np.uint64), K, MIN_AB)
-    return dict(n_solid=len(c["abundances"]), n_minimizers=len(pm), checksum=orc.checksum(c["hashes"], c["abundances"]))
-
-
-def reference_stages(ref, bases, offs, threads, n_bases):
-    """Extra, not the headline: the reference's real stage code on the same sample -- ReadSelection::execute on a
-    FASTQ in tmpfs (kseq parsing, side outputs, record writer, purgePalindromes) then CreateMdbg::KminmerCounter
-    with its disk partitions -- i.e. what `metaMDBG readSelection` + `graph --firstpass` spend on this path."""
-    import tempfile
-    from oracle import pyoracle
-    base_dir = "/dev/shm" if os.path.isdir("/dev/shm") else None
-    with tempfile.TemporaryDirectory(dir=base_dir) as d:
-        fq = os.path.join(d, "reads.fastq")
-        raw = bases.tobytes()
-        with open(fq, "wb") as f:
-            for r in range(len(offs) - 1):
-                s = raw[int(offs[r]):int(offs[r + 1])]
-                f.write(b"@r%d\n" % r + s + b"\n+\n" + b"I" * len(s) + b"\n")
-        t0 = time.perf_counter()
-        res = ref.read_selection([fq], L, DENSITY, HPC, threads=threads, skip_correction=False, workdir=d)
-        t_rs = time.perf_counter() - t0
-        mins = np.concatenate([r["minimizers"] for r in res["corrected"]]) if res["corrected"] else np.zeros(0, np.uint32)
-        mo = np.zeros(len(res["corrected"]) + 1, np.uint64)
-        mo[1:] = np.cumsum([len(r["minimizers"]) for r in res["corrected"]])
-        g = ref.graph_firstpass(mins, mo, K, min_abundance=MIN_AB, threads=threads)
-    return {"readSelection_s": res["seconds"], "graph_firstpass_count_s": g["seconds"],
-            "value": n_bases / (res["seconds"] + g["seconds"]) / 1e9, "unit": "Gbp/s", "threads": threads,
-            "n_solid": g["n_solid"], "wall_incl_parsing_the_outputs_s": t_rs}
+    return dict(n_solid=len(c["abundances"]), n_minimizers=len(pm), checksum=orc.checksum(c["hashes"], c["abundances"]),
+                mins=pm, offs=np.array(po, np.uint64), table=c)
 
 
 # ---------------------------------------------------------------- this engine
+class DeviceReads:
+    """A rank's shard of a workload, resident in HBM in the packed 2-bit layout (chunks of <= chunk_reads reads; each
+    chunk optionally keeps its ASCII bytes).  Generated on the device, chunk by chunk, through one ASCII scratch."""
+
+    def __init__(self, torch, dev, eng, readsets, rank, world, chunk_reads, keep_ascii):
+        self.chunks, self.n_reads, self.n_bases = [], 0, 0
+        scratch = None
+        for rs_all in readsets:
+            rs = rs_all.shard(rank, world)
+            for lo in range(0, rs.n_reads, chunk_reads):
+                sub = rs.subset(lo, min(rs.n_reads, lo + chunk_reads))
+                n, nb = sub.n_reads, sub.n_bases
+                d_off = torch.from_numpy(sub.offsets.astype(np.int64)).to(dev)
+                d_vs = torch.from_numpy(sub.vstart.astype(np.int64)).to(dev)
+                d_st = torch.from_numpy(sub.strand).to(dev)
+                if keep_ascii:
+                    d_bases = torch.empty(nb + 64, dtype=torch.uint8, device=dev)
+                else:
+                    if scratch is None or scratch.numel() < nb + 64:
+                        scratch = None
+                        scratch = torch.empty(int(1.05 * nb) + 64, dtype=torch.uint8, device=dev)
+                    d_bases = scratch
+                eng.synth_fill_reads(d_bases.data_ptr(), d_off.data_ptr(), d_vs.data_ptr(), d_st.data_ptr(), n,
+                                     sub.index_base, sub.seed, sub.err_q24)
+                d_words = torch.empty(eng.pack_device_words(nb, n) * 4, dtype=torch.uint8, device=dev)
+                d_src = torch.empty(n * 8, dtype=torch.uint8, device=dev)
+                eng.pack_device(d_bases.data_ptr(), d_off.data_ptr(), n, nb, d_words.data_ptr(), d_src.data_ptr())
+                eng.synchronize()
+                self.chunks.append(dict(n=n, n_bases=nb, off=d_off, words=d_words, src=d_src, offsets=sub.offsets,
+                                        bases=d_bases if keep_ascii else None))
+                self.n_reads += n
+                self.n_bases += nb
+        del scratch
+
+    def sketch_all(self, eng, ascii_input=False):
+        n_min = 0
+        for c in self.chunks:
+            if ascii_input:
+                n_min += int(eng.sketch_batch_device(c["bases"].data_ptr(), c["off"].data_ptr(), c["n"], c["n_bases"], True).n_minimizers)
+            else:
+                # synthetic reads hold only A, C, G, T: no read is flagged for the ASCII buffer
+                n_min += int(eng.sketch_batch_device_packed2(c["words"].data_ptr(), c["src"].data_ptr(),
+                                                             c["bases"].data_ptr() if c["bases"] is not None else 0,
+                                                             c["off"].data_ptr(), c["n"], c["n_bases"], True).n_minimizers)
+        return n_min
+
+
+def hot_path(eng, dr, w, lk, world, ascii_input=False, last_k=4):
+    """One step.  Returns (statistics of the LAST table incl. the on-device emit, minimizers sketched, per-k entries)."""
+    eng.store_clear()
+    n_min = dr.sketch_all(eng, ascii_input)
+    if w["asm_density"]:
+        eng.store_apply_density(w["asm_density"])
+    eng.purge_palindromes(4, lk)
+    eng.count_begin(K, 0)
+    eng.count_add_store()
+    if world > 1:
+        eng.count_merge()
+    tab = eng.count_finalize_device(MIN_AB)            # statistics + (hash128, abundance, k-min-mer) arrays left in HBM
+    per_k = [tab["n_entries"]]
+    for k in range(K + 1, last_k + 1):                 # multi-k: every further k from the previous k's table, on the device
+        eng.prev_from_current(MIN_AB)
+        eng.count_begin(k, 2 * max(256, per_k[-1]) * world)
+        eng.count_add_store_next_k()
+        if world > 1:
+            eng.count_merge()
+        tab = eng.count_finalize_device(MIN_AB)
+        per_k.append(tab["n_entries"])
+    return tab, n_min, per_k
+
+
 def run_ours(args, rank: int, local_rank: int, world: int):
     import torch
-    import torch.distributed as dist
     import __graft_entry__ as ge
 
     ge.build()
-    from metamdbg_b200 import Engine, synth
+    from metamdbg_b200 import Engine
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- this engine has no CPU path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    dist = None
     if world > 1:
+        import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -298,57 +436,77 @@ def run_ours(args, rank: int, local_rank: int, world: int):
 
     def sum_over_ranks(x: int) -> int:
         if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.int64, device=dev)
+            return int(x)
+        t = torch.tensor([int(x)], dtype=torch.int64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return int(t.item())
 
-    # ---- synthetic reads, generated straight into HBM -------------------------------
-    rs_all = synth.make_readset(args.reads * world, args.read_len, seed=SEED, n_genomes=args.genomes, err=ERR)
-    rs = rs_all.shard(rank, world)
-    n_reads, n_bases = rs.n_reads, rs.n_bases
-    eng = Engine(L, DENSITY, HPC, device=local_rank)
-    eng.set_stream(torch.cuda.current_stream().cuda_stream)
-    eng.enable_timing(True)
-    d_off = torch.from_numpy(rs.offsets.astype(np.int64)).to(dev)
-    d_vs = torch.from_numpy(rs.vstart.astype(np.int64)).to(dev)
-    d_st = torch.from_numpy(rs.strand).to(dev)
-    d_bases = torch.empty(n_bases + 64, dtype=torch.uint8, device=dev)
-    eng.synth_fill_reads(d_bases.data_ptr(), d_off.data_ptr(), d_vs.data_ptr(), d_st.data_ptr(), n_reads,
-                         rs.index_base, rs.seed, rs.err_q24)
-    torch.cuda.synchronize()
-    if world > 1:
-        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            uid.copy_(torch.frombuffer(bytearray(Engine.nccl_unique_id()), dtype=torch.uint8))
-        dist.broadcast(uid, 0)
-        eng.comm_init(rank, world, bytes(uid.cpu().numpy().tobytes()))
-    lk = purge_last_k(args)
-    # engine set-up, outside every timed region: both arithmetic variants of the sketch kernel on this rank's own
-    # reads, complete outputs compared on the device; the faster identical one stays active (variant 0 otherwise)
-    tune = eng.autotune_sketch(d_bases.data_ptr(), d_off.data_ptr(), n_reads, n_bases)
-    if args.sketch_variant >= 0:
-        if not tune["identical"][args.sketch_variant]:
-            raise SystemExit(f"bench.py: sketch variant {args.sketch_variant} does not reproduce variant 0: {tune}")
-        eng.set_sketch_variant(args.sketch_variant)
-        tune["chosen"] = args.sketch_variant
-        tune["forced"] = True
+    def sum_u64_over_ranks(x: int) -> int:
+        """sum mod 2^64 (checksums): the two 32-bit halves travel separately, so nothing overflows on the way"""
+        if world == 1:
+            return int(x) % (1 << 64)
+        t = torch.tensor([int(x) & 0xFFFFFFFF, (int(x) >> 32) & 0xFFFFFFFF], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        lo, hi = int(t[0].item()), int(t[1].item())
+        return (lo + (hi << 32)) % (1 << 64)
+
+    def new_engine(w):
+        e = Engine(L, w["density"], w["hpc"], device=local_rank)
+        e.set_stream(torch.cuda.current_stream().cuda_stream)
+        e.enable_timing(True)
+        if world > 1:
+            uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+            if rank == 0:
+                uid.copy_(torch.frombuffer(bytearray(Engine.nccl_unique_id()), dtype=torch.uint8))
+            dist.broadcast(uid, 0)
+            e.comm_init(rank, world, bytes(uid.cpu().numpy().tobytes()))
+        return e
+
+    def timed(fn, warmup: int, steps: int):
+        """W warm-up calls, then K calls timed with CUDA events on the launching stream between two barriers; max over ranks."""
+        out = None
+        for _ in range(warmup):
+            out = fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / steps, out
+
+    name = args.workload
+    w = WORKLOADS[name]
+    reads_total = args.reads * world if w["per_gpu"] else args.reads
+    lk = purge_last_k(args.read_len, w)
+    eng = new_engine(w)
+
+    # ---- N > 1: parity of every collective stage over real NCCL, before anything is timed --------------------------
+    parity = None
+    if world > 1 and not args.no_parity:
+        parity = multi_gpu_parity(args, eng, torch, dev, rank, world, sum_over_ranks, sum_u64_over_ranks, barrier)
+
+    # ---- synthetic reads, generated straight into HBM; 2-bit packed copy = the resident input of `value` ------------
+    readsets = make_readsets(name, reads_total, args.read_len, args.genomes)
+    dr = DeviceReads(torch, dev, eng, readsets, rank, world, args.chunk_reads, keep_ascii=True)
+    n_reads, n_bases = dr.n_reads, dr.n_bases
+    c0 = dr.chunks[0]
+    # engine set-up, outside every timed region: every sketch-kernel variant on this rank's first chunk (ASCII), complete
+    # outputs compared on the device; reported, and a variant that differs from variant 0 ends the run
+    tune = eng.autotune_sketch(c0["bases"].data_ptr(), c0["off"].data_ptr(), c0["n"], c0["n_bases"])
+    if not all(tune["identical"]):
+        raise SystemExit(f"bench.py: a sketch kernel variant does not reproduce variant 0 on this device: {tune}")
+    eng.set_sketch_variant(args.sketch_variant if args.sketch_variant >= 0 else 2)
+    active_variant = eng.sketch_variant
 
     n_sketched = [0]
 
     def step_device():
-        eng.store_clear()
-        n_sketched[0] = int(eng.sketch_batch_device(d_bases.data_ptr(), d_off.data_ptr(), n_reads, n_bases, True).n_minimizers)
-        if ASM_DENSITY:
-            eng.store_apply_density(ASM_DENSITY)
-        eng.purge_palindromes(4, lk)
-        eng.count_begin(K, 0)
-        eng.count_add_store()
-        if world > 1:
-            eng.count_merge()
-        return eng.count_stats(MIN_AB)
+        tab, n_sketched[0], _ = hot_path(eng, dr, w, lk, world, last_k=w["last_k"])
+        return tab
 
-    # ---- device-resident timing ---------------------------------------------------------
+    # ---- device-resident timing ---------------------------------------------------------------------------------------
     for _ in range(args.warmup):
         stats = step_device()
     sampler = ClockSampler(local_rank)
@@ -375,38 +533,57 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     n_min_store = eng.store_size()[1]
     solid_total = sum_over_ranks(stats["n_entries"])
     checksum_local = stats["checksum"]
+    checksum_total = sum_u64_over_ranks(checksum_local)
     # size-independent property at full size: every k-min-mer occurrence of every read is in exactly one table
     # (after the owner merge): sum of all abundances over all ranks == sum over reads of max(0, n_minimizers - k + 1)
-    so, _ = eng.store_fetch()
-    per_read = np.diff(so.astype(np.int64))
-    expect_instances = sum_over_ranks(int(np.maximum(per_read - K + 1, 0).sum()))
-    got_instances = sum_over_ranks(stats["n_instances"])
-    if expect_instances != got_instances:
-        raise SystemExit(f"bench.py: occurrence conservation violated: {got_instances} != {expect_instances}")
+    occ = None
+    if w["last_k"] == K:
+        so, _ = eng.store_fetch()
+        per_read = np.diff(so.astype(np.int64))
+        expect_instances = sum_over_ranks(int(np.maximum(per_read - K + 1, 0).sum()))
+        got_instances = sum_over_ranks(stats["n_instances"])
+        if expect_instances != got_instances:
+            raise SystemExit(f"bench.py: occurrence conservation violated: {got_instances} != {expect_instances}")
+        occ = int(got_instances)
 
-    # ---- extra (not the headline): the multi-k loop k = 4 .. 21 on the resident store (BASELINE config 4's shape on
-    # this workload): k = 4 counted, every further k derived from the previous table on the device.  Single GPU by
-    # default; --multi-k-ranks also runs it with the collective previous-k replication + value merge for N > 1.
+    # ---- extra: the same step with the reads resident as ASCII (device-side pack pass inside the step) ---------------
+    ascii_leg = None
+    if not args.no_ascii_leg and w["last_k"] == K:
+        def step_ascii():
+            return hot_path(eng, dr, w, lk, world, ascii_input=True)[0]
+        ms_a, st_a = timed(step_ascii, 2, max(1, min(args.steps, 3)))
+        ascii_leg = {"value": total_bases / (ms_a * 1e-3) / 1e9, "unit": "Gbp/s", "ms_per_step": ms_a,
+                     "same_table_as_packed_leg": st_a["checksum"] == checksum_local,
+                     "what": "identical step, reads resident as ASCII bytes: ASCII -> 2-bit pack kernel + packed sketch kernel"}
+        if st_a["checksum"] != checksum_local:
+            raise SystemExit("bench.py: the ASCII-resident step gives a different table than the packed-resident step")
+        step_device()                                   # leave the packed leg's table current for the extras below
+
     # ---- extra: edge keys + order-free edge values of the k = 4 node set (CreateMdbg::EdgeIndexer / indexEdge), the
-    # first step beyond the count table; the table of the last timed step is still current here
+    # first step beyond the count table; the table of the last step is still current here
     edges_extra = None
-    if world == 1 and not args.no_edges:
+    if not args.no_edges and w["last_k"] == K:
         try:
             t_e = []
             for _ in range(2):                              # 2nd = warm
-                eng.synchronize()
+                barrier()
                 t0 = time.perf_counter()
                 ed = eng.edges_index(MIN_AB)
-                t_e.append(time.perf_counter() - t0)
-            edges_extra = {"k": K, "n_nodes": ed["n_nodes"], "n_edges": ed["n_edges"], "checksum": ed["checksum"],
+                t_e.append(max_over_ranks(time.perf_counter() - t0))
+            edges_extra = {"k": K, "n_nodes": sum_over_ranks(ed["n_nodes"]), "n_edges": sum_over_ranks(ed["n_edges"]),
+                           "checksum": sum_u64_over_ranks(ed["checksum"]),
                            "ms": round(1e3 * t_e[1], 3), "d2h_bytes": ed["n_edges"] * 32,
-                           "branching_keys": int((ed["values"][..., 0] == 2).any(axis=1).sum()),
-                           "timer": "host wall clock around mdbg_edges_index incl. the D2H of keys and values"}
+                           "timer": "host wall clock around mdbg_edges_index incl. the D2H of keys and values, max over ranks"}
+            if ed["values"] is not None:
+                edges_extra["branching_keys"] = int((ed["values"][..., 0] == 2).any(axis=1).sum())
         except Exception as e:                                # noqa: BLE001
             edges_extra = {"error": repr(e)}
 
+    # ---- extra (not the headline): the multi-k loop k = 4 .. 21 on the resident store (BASELINE config 4's shape on
+    # this workload): k = 4 counted, every further k derived from the previous table on the device; collective
+    # previous-k replication + value merge for N > 1
     multi_k = None
-    if args.multi_k > K and (world == 1 or args.multi_k_ranks):
+    if args.multi_k > K and w["last_k"] == K:
         try:
             from metamdbg_b200 import multi_k_sweep
             sweeps = [multi_k_sweep(eng, K, args.multi_k, MIN_AB, merge=world > 1, world=world) for _ in range(2)]   # 2nd = warm
@@ -414,33 +591,35 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             total_s = sum(per_k) * 1e-3
             multi_k = {"k_first": K, "k_last": args.multi_k, "ms_per_k": per_k, "ms_total": round(sum(per_k), 3),
                        "value": total_bases / total_s / 1e9, "unit": "Gbp/s (input bases / time of the k-loop alone; the "
-                       "sketch is not repeated, as in the reference)", "n_entries_rank0": [r["n_entries"] for r in sweeps[1]],
-                       "timer": "host wall clock per k around device work ending in a D2H of the table statistics",
+                       "sketch is not repeated, as in the reference)",
+                       "n_entries_total": [sum_over_ranks(r["n_entries"]) for r in sweeps[1]],
+                       "timer": "host wall clock per k around device work ending in a D2H of the table statistics, max over ranks",
                        "same_tables_both_sweeps": [r["checksum"] for r in sweeps[0]] == [r["checksum"] for r in sweeps[1]]}
         except Exception as e:                                # noqa: BLE001  -- an extra must not cost the headline line
             multi_k = {"error": repr(e)}
 
     # ---- end to end through the host-buffer C ABI ---------------------------------------------
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and len(dr.chunks) == 1:
+        rs_off = c0["offsets"]
         e_reads = min(n_reads, args.e2e_reads or n_reads)
         # the pinned host copy of this rank's reads must fit beside the other ranks' (one node): use at most half of
         # what the host still has, split over the local ranks; fewer reads in the e2e leg is reported, not hidden
         local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
         share = host_bytes_available() // (2 * max(1, local_world))
-        while e_reads > args.e2e_batch and int(rs.offsets[e_reads]) > share:
+        while e_reads > args.e2e_batch and int(rs_off[e_reads]) > share:
             e_reads = max(args.e2e_batch, e_reads // 2)
         h_bases = None
         while h_bases is None:
-            e_bases = int(rs.offsets[e_reads])
+            e_bases = int(rs_off[e_reads])
             try:
                 h_bases = torch.empty(e_bases, dtype=torch.uint8, pin_memory=True)
             except RuntimeError:
                 if e_reads <= 1024:
                     raise
                 e_reads //= 2
-        h_bases.copy_(d_bases[:e_bases])
-        h_offs = rs.offsets[:e_reads + 1].copy()
+        h_bases.copy_(c0["bases"][:e_bases])
+        h_offs = rs_off[:e_reads + 1].copy()
         torch.cuda.synchronize()
         batch = args.e2e_batch
         d2h = [0]
@@ -453,8 +632,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                 offs = h_offs[lo:hi + 1] - h_offs[lo]
                 sk = eng.sketch_batch_ptr(h_bases.data_ptr() + int(h_offs[lo]), offs, True)
                 d2h[0] += 8 * (hi - lo + 1) + 9 * sk
-            if ASM_DENSITY:
-                eng.store_apply_density(ASM_DENSITY)
+            if w["asm_density"]:
+                eng.store_apply_density(w["asm_density"])
             eng.purge_palindromes(4, lk)
             eng.count_begin(K, 0)
             eng.count_add_store()
@@ -466,7 +645,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
 
         # parity of every e2e step (warm-up steps included): the finalised table of the host-buffer path must carry
         # the checksum of the device-resident leg (same reads, same merge); reported, never silently skipped
-        comparable = e_reads == n_reads
+        comparable = e_reads == n_reads and w["last_k"] == K
         e2e_checks = []
         for _ in range(max(1, min(args.warmup, 2))):
             tab = step_e2e()
@@ -487,8 +666,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                "h2d_bytes_per_step": int((moved1[0] - moved0[0]) // e_steps),
                "d2h_bytes_per_step": int((moved1[1] - moved0[1]) // e_steps),
                "host_input_bytes_per_step": int(e_bases + 8 * (e_reads + 1)),
-               "transfer": "ASCII reads are 2-bit packed by the library's host threads before H2D; scan, compaction and "
-                           "the CSR's D2H run piece by piece behind each piece's sketch",
+               "transfer": "ASCII reads are 2-bit packed by the library's host threads before H2D (ASCII + device-side pack "
+                           "pass when the process has too few CPUs); scan, compaction and the CSR's D2H run piece by piece "
+                           "behind each piece's sketch",
                "steps": e_steps, "reads_per_gpu": e_reads, "host_batch_reads": batch,
                "last_host_batch": eng.last_batch_info(),
                "timer": "host wall clock around synchronous C-ABI calls, max over ranks",
@@ -511,22 +691,23 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             kind, threads = "reference", min(cores, 2 * usable_cpus())
         except (FileNotFoundError, OSError):
             ref, kind, threads = None, "port", 1
-        n_sample = int(min(n_reads, max(2000, 800 * threads)))
-        s_bases = d_bases[:int(rs.offsets[n_sample])].cpu().numpy()
-        s_offs = rs.offsets[:n_sample + 1].copy()
+        n_sample = int(min(c0["n"], args.cpu_reads or (200_000 if ref is not None else 2_000)))
+        s_offs = c0["offsets"][:n_sample + 1].copy()
+        s_bases = c0["bases"][:int(s_offs[-1])].cpu().numpy()
         t0 = time.perf_counter()
         if ref is not None:
-            res = ref.pipeline(s_bases, s_offs, L, DENSITY, HPC, K, purge_last_k=lk, min_abundance=MIN_AB,
-                               threads=threads, assembly_density=ASM_DENSITY)
+            res = ref.pipeline(s_bases, s_offs, L, w["density"], w["hpc"], K, purge_last_k=lk, min_abundance=MIN_AB,
+                               threads=threads, assembly_density=w["asm_density"])
         else:
-            res = oracle_port_pipeline(pyoracle.Oracle(), s_bases, s_offs, lk)
+            res = oracle_port_pipeline(pyoracle.Oracle(), s_bases, s_offs, lk, w)
         ref_solid, ref_cs, ref_nmin = res["n_solid"], res["checksum"], res["n_minimizers"]
         dt = time.perf_counter() - t0
-        # same sample through the GPU engine: bit-exact fingerprint must agree
+        # same sample through the GPU engine (packed-resident input): bit-exact fingerprint must agree
         eng.store_clear()
-        eng.sketch_batch_device(d_bases.data_ptr(), d_off.data_ptr(), n_sample, int(s_offs[-1]), True)
-        if ASM_DENSITY:
-            eng.store_apply_density(ASM_DENSITY)
+        eng.sketch_batch_device_packed2(c0["words"].data_ptr(), c0["src"].data_ptr(), c0["bases"].data_ptr(), c0["off"].data_ptr(),
+                                        n_sample, int(s_offs[-1]), True)
+        if w["asm_density"]:
+            eng.store_apply_density(w["asm_density"])
         eng.purge_palindromes(4, lk)
         eng.count_begin(K, 0)
         eng.count_add_store()
@@ -536,8 +717,30 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             raise SystemExit(f"bench.py: GPU result differs from the CPU {kind} on the sample: {g} vs "
                              f"{ref_solid}/{ref_cs}/{ref_nmin}")
         cpu_baseline = {"value": int(s_offs[-1]) / dt / 1e9, "unit": "Gbp/s", "cores": threads, "kind": kind,
-                        "sample": f"first {n_sample} reads ({int(s_offs[-1]) / 1e9:.3f} Gbp), one pass, "
+                        "sample": f"first {n_sample} reads ({int(s_offs[-1]) / 1e9:.3f} Gbp), one pass of the reference's "
+                                  f"sketch + purge + count code driven in memory, "
                                   f"GPU fingerprint (n_minimizers, n_solid, checksum) identical"}
+
+    # ---- extras: the other BASELINE.json configs ---------------------------------------------------------------------
+    extras = {}
+    want_extras = [x for x in args.extras.split(",") if x] if args.extras != "auto" else (
+        (["cfg3"] if world == 1 else []) + ["cfg4", "cfg5"]
+        if (name == "cfg2" and args.reads == w["reads"] and args.read_len == w["read_len"]) else [])
+    if want_extras:
+        del dr, c0
+        if hasattr(torch.cuda, "empty_cache"):
+            torch.cuda.empty_cache()
+    for xn in want_extras:
+        if xn == name or xn not in WORKLOADS:
+            continue
+        try:
+            extras[xn] = run_extra(args, xn, torch, dev, rank, world, eng if WORKLOADS[xn]["density"] == w["density"] and
+                                   WORKLOADS[xn]["hpc"] == w["hpc"] else None, new_engine, timed, sum_over_ranks,
+                                   sum_u64_over_ranks)
+        except Exception as e:                                # noqa: BLE001  -- an extra must not cost the headline line
+            extras[xn] = {"error": repr(e)}
+        if hasattr(torch.cuda, "empty_cache"):
+            torch.cuda.empty_cache()
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -546,40 +749,167 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         sk_ms = float(np.mean(sketch_ms))
-        algo_bytes = n_bases * 1.0 + n_sketched[0] * 9.0    # 1 B/bp ASCII in + 9 B per minimizer the sketch writes
+        kernel = {2: "sketch_packed_kernel<15>", 1: "sketch_kernel<15, 1>", 0: "sketch_kernel<15, 0>"}[active_variant]
+        # SURVEY 8d / DESIGN.md: 0.25 B per input base read (2-bit packed) + 9 B per selected minimizer written
+        algo_bytes = n_bases * 0.25 + n_sketched[0] * 9.0
         achieved = algo_bytes / (sk_ms * 1e-3) / 1e9
-        traffic, ncu_pipes = None, None
+        traffic, ncu_pipes, int_issue = None, None, None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
-            if tj.get("reads") == n_reads and tj.get("kernel") == "sketch_kernel":
-                traffic = tj.get("dram_bytes_per_launch")       # one `ncu --set full` capture of this launch shape
+            # only a capture of THIS kernel at THIS launch shape may annotate the line
+            if tj.get("kernel") == kernel and tj.get("reads") == dr_reads_of(args, w, world) and len(sketch_ms):
+                traffic = tj.get("dram_bytes_per_launch")
                 ncu_pipes = tj.get("ncu")
+                inst = tj.get("warp_instructions_per_launch")
+                if inst and clocks and clocks.get("sm_mhz"):
+                    peak_issue = 148 * 4 * clocks["sm_mhz"] * 1e6          # warp instructions per second: 4 schedulers per SM
+                    ach = inst / (sk_ms * 1e-3)
+                    int_issue = {"what": "integer-issue roofline (SURVEY 8d): warp instructions executed per launch (ncu "
+                                         "smsp__inst_executed.sum of the committed capture) / live launch duration, against one "
+                                         "instruction per scheduler per cycle at the sampled SM clock",
+                                 "achieved_warp_inst_per_s": ach, "peak_warp_inst_per_s": peak_issue, "frac": ach / peak_issue,
+                                 "thread_instructions_per_lmer": tj.get("thread_instructions_per_lmer")}
         line = {
-            "metric": "Gbp/s through minimizer-sketch + k-min-mer count", "value": value, "unit": "Gbp/s",
+            "metric": METRIC, "value": value, "unit": "Gbp/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": workload_config(args), "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": f"sketch_kernel<15, {tune['chosen']}>", "achieved": achieved, "peak": peak,
+            "higher_is_better": True, "scaling": "weak" if w["per_gpu"] else "strong", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic",
+            "config": workload_config(name, args.reads, args.read_len, args.genomes, world), "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "ms_per_launch": sk_ms, "algorithmic_bytes_per_launch": algo_bytes,
-                         "note": "integer-issue bound (one MurmurHash3_x64_128 per l-mer), see DESIGN.md",
-                         "binding_pipes_ncu": ncu_pipes,
+                         "note": "the kernel is bound by integer issue (one MurmurHash3_x64_128 per l-mer), not by HBM: see "
+                                 "int_issue and DESIGN.md",
+                         "binding_pipes_ncu": ncu_pipes, "int_issue": int_issue,
                          "share_of_step": sk_ms / (ms_total / args.steps)},
             "kernels_ms": {"sketch": sk_ms, "insert": float(np.mean(insert_ms))},
-            "multi_k": multi_k, "edges": edges_extra,
-            "sketch_autotune": dict(tune, note="ms = sketch + scan + compaction of the full batch, best of 2; a variant is "
-                                               "eligible only if its whole output equals variant 0's on the device"),
+            "ascii_resident": ascii_leg, "multi_k": multi_k, "edges": edges_extra, "extras": extras,
+            "sketch_autotune": dict(tune, active=active_variant,
+                                    note="ms = sketch (+ pack pass for variant 2) + scan + compaction of an ASCII-resident batch, "
+                                         "best of 2; every variant's whole output must equal variant 0's on the device"),
             "cpu_baseline": cpu_baseline,
             "check": {"n_minimizers_rank0": int(n_min_store), "n_solid_total": int(solid_total),
-                      "checksum_rank0": int(checksum_local), "kminmer_occurrences_total": int(got_instances),
-                      "occurrences_conserved": True,
-                      "device_steps_same_checksum": len(step_checksums) == 1},
+                      "checksum_rank0": int(checksum_local), "checksum_total": int(checksum_total),
+                      "kminmer_occurrences_total": occ, "occurrences_conserved": occ is not None,
+                      "device_steps_same_checksum": len(step_checksums) == 1,
+                      "multi_gpu_parity": parity},
         }
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def dr_reads_of(args, w, world):
+    return args.reads if w["per_gpu"] else args.reads // max(1, world)
+
+
+def run_extra(args, xn, torch, dev, rank, world, eng, new_engine, timed, sum_over_ranks, sum_u64_over_ranks):
+    """Another BASELINE.json config through the same step (strong scaling for cfg4 / cfg5: the read count is the total)."""
+    w = WORKLOADS[xn]
+    scale = args.extra_scale
+    reads = max(64 * world, int(w["reads"] * scale))
+    reads_total = reads * world if w["per_gpu"] else reads
+    read_len = w["read_len"] if scale >= 0.01 else max(1500, w["read_len"] // 4)
+    lk = purge_last_k(read_len, w)
+    own = eng is None
+    if own:
+        eng = new_engine(w)
+    t0 = time.perf_counter()
+    dr = DeviceReads(torch, dev, eng, make_readsets(xn, reads_total, read_len, args.genomes), rank, world, args.chunk_reads,
+                     keep_ascii=False)
+    t_gen = time.perf_counter() - t0
+    last_k = min(w["last_k"], args.multi_k) if w["last_k"] > K else K
+    out = {}
+
+    def step():
+        tab, n_min, per_k = hot_path(eng, dr, w, lk, world, last_k=last_k)
+        out.update(tab=tab, n_min=n_min, per_k=per_k)
+        return tab
+
+    ms, tab = timed(step, 3, 2)
+    total_bases = sum_over_ranks(dr.n_bases)
+    res = {"config": workload_config(xn, reads, read_len, args.genomes, world), "scaling": "weak" if w["per_gpu"] else "strong",
+           "value": total_bases / (ms * 1e-3) / 1e9, "unit": "Gbp/s", "ms_per_step": ms, "steps": 2, "warmup": 3,
+           "n_bases_total": int(total_bases), "n_minimizers_total": sum_over_ranks(out["n_min"]),
+           "n_entries_per_k_total": [sum_over_ranks(x) for x in out["per_k"]], "k_last": last_k,
+           "checksum_total_last_k": sum_u64_over_ranks(tab["checksum"]), "resident_chunks_rank0": len(dr.chunks),
+           "generate_and_pack_s": round(t_gen, 2),
+           "timer": "CUDA events on the launching stream around 2 steps after 3 warm-up steps, barriers on both sides, max over ranks"}
+    del dr
+    if own:
+        eng.close()
+    return res
+
+
+def multi_gpu_parity(args, eng, torch, dev, rank, world, sum_over_ranks, sum_u64_over_ranks, barrier):
+    """All ranks shard ONE read set and run count -> merge -> rescue -> previous-k -> two next-k passes -> edge index
+    over real NCCL; per stage the all-reduced (entries, checksum) pair is compared on rank 0 with the CPU oracle of the
+    WHOLE set (oracle/: the C restatement, itself pinned against the reference's own code in tests/test_oracle.py).
+    Any mismatch ends the run."""
+    from metamdbg_b200 import synth
+    n_reads, read_len, last = args.parity_reads, args.parity_read_len, 80
+    rs = synth.make_readset(n_reads, read_len, seed=4242, n_genomes=3, genome_len_range=(300_000, 700_000), err=0.004)
+    bases, offs = synth.fill_reads(rs.shard(rank, world))
+    eng.store_clear()
+    eng.sketch_batch(bases, offs, append_to_store=True, fetch=False)
+    eng.purge_palindromes(4, last)
+    got = {}
+
+    def stage(tag, extra=0):
+        st = eng.count_stats(0)
+        got[tag] = (sum_over_ranks(st["n_entries"]), sum_u64_over_ranks(st["checksum"]), sum_over_ranks(extra))
+
+    eng.count_begin(K, 0)
+    eng.count_add_store()
+    eng.count_merge()
+    st2 = eng.count_stats(2)
+    got["count"] = (sum_over_ranks(st2["n_entries"]), sum_u64_over_ranks(st2["checksum"]), sum_over_ranks(st2["n_distinct"]))
+    n_resc = eng.count_rescue()
+    stage("rescue", n_resc)
+    ed = eng.edges_index(0)
+    got["edges"] = (sum_over_ranks(ed["n_edges"]), sum_u64_over_ranks(ed["checksum"]), sum_over_ranks(ed["n_nodes"]))
+    for k in (K + 1, K + 2):
+        eng.prev_from_current(0)
+        eng.count_begin(k, 0)
+        eng.count_add_store_next_k()
+        eng.count_merge()
+        stage(f"k{k}")
+    barrier()
+    verdict = None
+    if rank == 0:
+        from oracle.pyoracle import Oracle
+        orc = Oracle()
+        ab, ao = synth.fill_reads(rs)
+        mo, m, _, _ = orc.sketch_batch(ab, ao, L, WORKLOADS[args.workload]["density"], WORKLOADS[args.workload]["hpc"])
+        pm, po = [], [0]
+        for r in range(rs.n_reads):
+            q, _ = orc.purge_palindrome(m[int(mo[r]):int(mo[r + 1])], 4, last)
+            pm.append(q); po.append(po[-1] + len(q))
+        pm = np.concatenate(pm).astype(np.uint32); po = np.array(po, np.uint64)
+        allk = orc.count(pm, po, K, keep_all=True)
+        solid = orc.count(pm, po, K, 2)
+        resc = orc.rescue(pm, po, K, solid["hashes"], solid["abundances"])
+        ph = np.concatenate([solid["hashes"], resc["hashes"]]) if len(resc["hashes"]) else solid["hashes"]
+        pa = np.concatenate([solid["abundances"], np.ones(len(resc["hashes"]), np.uint32)])
+        pv = np.concatenate([solid["vecs"], resc["vecs"]]) if len(resc["hashes"]) else solid["vecs"]
+        want = {"count": (len(solid["abundances"]), orc.checksum(solid["hashes"], solid["abundances"]), len(allk["abundances"])),
+                "rescue": (len(pa), orc.checksum(ph, pa), resc["n_reads_rescued"])}
+        we = orc.edge_index(pv, K)
+        want["edges"] = (len(we["hashes"]), we["checksum"], len(pa))
+        for k in (K + 1, K + 2):
+            nk = orc.next_k(pm, po, k, ph, pa)
+            ph, pa = nk["hashes"], nk["abundances"]
+            want[f"k{k}"] = (len(pa), orc.checksum(ph, pa), 0)
+        verdict = {t: tuple(int(x) for x in got[t]) == tuple(int(x) for x in want[t]) for t in want}
+        verdict["reads"] = n_reads
+        verdict["what"] = ("(entries, sum abundance*hash, third figure: distinct keys / rescued reads / nodes) of every stage, "
+                           "all-reduced over the ranks, against the CPU oracle of the whole read set")
+        if not all(v for t, v in verdict.items() if t in want):
+            raise SystemExit(f"bench.py: multi-GPU parity FAILED: got {got} want {want}")
+    return verdict
 
 
 def main():
@@ -588,24 +918,36 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS), help="BASELINE.json config (default: the one the metric is quoted on)")
-    ap.add_argument("--reads", type=int, default=0, help="reads per GPU (0 = the workload's)")
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS), help="BASELINE.json config of the headline (default: the one the metric is quoted on)")
+    ap.add_argument("--reads", type=int, default=0, help="reads per GPU (cfg2/cfg3) or in total (cfg4/cfg5); 0 = the workload's")
     ap.add_argument("--read-len", type=int, default=0, help="mean read length (0 = the workload's)")
     ap.add_argument("--genomes", type=int, default=100)
+    ap.add_argument("--chunk-reads", type=int, default=1_000_000, help="reads per resident chunk (device generation / sketch call)")
+    ap.add_argument("--extras", default="auto", help="comma list of other configs to run as extras (auto: cfg3 at N=1, cfg4, cfg5 with the default headline; '' = none)")
+    ap.add_argument("--extra-scale", type=float, default=1.0, help="shrink the extras' read counts (tests)")
     ap.add_argument("--e2e-reads", type=int, default=0, help="reads per GPU in the e2e leg (0 = all)")
     ap.add_argument("--e2e-batch", type=int, default=262_144, help="reads per host-buffer C-ABI call")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--ref-reads", type=int, default=0, help="sample size of the reference arm (0 = auto)")
-    ap.add_argument("--sketch-variant", type=int, default=-1, help="force a sketch-kernel variant (-1 = autotune)")
-    ap.add_argument("--multi-k", type=int, default=21, help="extra: multi-k loop up to this k on the resident store (0 = off)")
-    ap.add_argument("--multi-k-ranks", action="store_true", help="run the multi-k extra for N > 1 as well (collectives)")
+    ap.add_argument("--ref-reads", type=int, default=0, help="sample size of the reference arm (0 = 100000)")
+    ap.add_argument("--cpu-reads", type=int, default=0, help="sample size of the cpu_baseline leg (0 = 200000)")
+    ap.add_argument("--parity-reads", type=int, default=20_000, help="N>1 parity leg: reads of the shared set")
+    ap.add_argument("--parity-read-len", type=int, default=6_000)
+    ap.add_argument("--sketch-variant", type=int, default=-1, help="force a sketch-kernel variant (-1 = the default, 2)")
+    ap.add_argument("--multi-k", type=int, default=21, help="multi-k loops run up to this k (0 = off)")
     ap.add_argument("--no-edges", action="store_true", help="skip the edge-key extra")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-ascii-leg", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="N>1: skip the parity leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-stages", action="store_true", help="reference arm: skip the extra real-stage timing")
+    ap.add_argument("--no-stages", action="store_true", help="reference arm: time the in-memory harness instead of the stock stages")
+    ap.add_argument("--no-ref-multi-k", action="store_true", help="reference arm: skip the multi-k extra")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
-    select_workload(args)
+    w = WORKLOADS[args.workload]
+    if args.reads <= 0:
+        args.reads = w["reads"]
+    if args.read_len <= 0:
+        args.read_len = w["read_len"]
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

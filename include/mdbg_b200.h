@@ -268,6 +268,17 @@ mdbg_status mdbg_count_add(mdbg_ctx* ctx, const uint32_t* minimizers, const uint
  * and copy the table to the host.  out->hashes etc. are in unspecified order
  * (as upstream, whose writer runs under an omp critical). */
 mdbg_status mdbg_count_finalize(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_table_out* out);
+/* The same output ((u128, u32)[n] + u32[n * k]) left in HBM: pointers into context-owned device memory,
+ * valid until the next finalize / edges call.  Nothing but the five statistics crosses PCIe. */
+typedef struct {
+    uint32_t k;
+    uint64_t n_entries;
+    const uint64_t* d_hashes;       /* [2*n_entries]: low 64 bits, high 64 bits */
+    const uint32_t* d_abundances;   /* [n_entries] */
+    const uint32_t* d_kminmers;     /* [n_entries*k] */
+    uint64_t n_instances, n_distinct, checksum, n_rescued;
+} mdbg_table_dev;
+mdbg_status mdbg_count_finalize_device(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_table_dev* out);
 /* Table statistics without the host copy (device-side reduction only). */
 mdbg_status mdbg_count_stats(mdbg_ctx* ctx, uint32_t min_abundance, uint64_t* n_entries,
                              uint64_t* n_distinct, uint64_t* n_instances, uint64_t* checksum);

@@ -38,6 +38,12 @@ class TableOut(C.Structure):
                 ("checksum", C.c_uint64), ("n_rescued", C.c_uint64)]
 
 
+class TableDev(C.Structure):
+    _fields_ = [("k", C.c_uint32), ("n_entries", C.c_uint64), ("d_hashes", C.c_void_p), ("d_abundances", C.c_void_p),
+                ("d_kminmers", C.c_void_p), ("n_instances", C.c_uint64), ("n_distinct", C.c_uint64),
+                ("checksum", C.c_uint64), ("n_rescued", C.c_uint64)]
+
+
 class AuxOut(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("mean_quality", C.POINTER(C.c_float)), ("complexity", C.POINTER(C.c_double)),
                 ("low_complexity", u8p), ("qualities", u8p)]
@@ -99,6 +105,7 @@ SYMBOLS = {
     "mdbg_count_add_store": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64]),
     "mdbg_count_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "mdbg_count_finalize": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(TableOut)]),
+    "mdbg_count_finalize_device": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(TableDev)]),
     "mdbg_count_stats": (C.c_int, [C.c_void_p, C.c_uint32, u64p, u64p, u64p, u64p]),
     "mdbg_count_rescue": (C.c_int, [C.c_void_p, u64p]),
     "mdbg_prev_from_current": (C.c_int, [C.c_void_p, C.c_uint32]),

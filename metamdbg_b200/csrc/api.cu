@@ -1857,12 +1857,9 @@ mdbg_status mdbg_count_stats(mdbg_ctx* ctx, uint32_t min_abundance, uint64_t* n_
     return MDBG_OK;
 }
 
-mdbg_status mdbg_count_finalize(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_table_out* out) {
-    if (!ctx || !out) return MDBG_ERR_ARG;
-    if (!ctx->t_active) return fail(ctx, MDBG_ERR_STATE, "mdbg_count_finalize before mdbg_count_begin");
-    CK(cudaSetDevice(ctx->device));
+// statistics + compaction of the qualifying entries into o_hash / o_abund / o_vecs (device); *st_out = the statistics
+static mdbg_status emit_table(mdbg_ctx* ctx, uint32_t thr, TableStats* st_out) {
     cudaStream_t s = ctx->stream;
-    const uint32_t thr = count_threshold(ctx, min_abundance);
     const uint32_t k = ctx->t_k;
     TableStats st;
     CKS(table_stats(ctx, thr, &st));
@@ -1870,9 +1867,6 @@ mdbg_status mdbg_count_finalize(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_tabl
     CKS(ensure(ctx, ctx->o_hash, (n + 1) * 16));
     CKS(ensure(ctx, ctx->o_abund, (n + 1) * 4));
     CKS(ensure(ctx, ctx->o_vecs, (n + 1) * 4 * k));
-    CKS(ensure_pin(ctx, ctx->ho_hash, (n + 1) * 16));
-    CKS(ensure_pin(ctx, ctx->ho_abund, (n + 1) * 4));
-    CKS(ensure_pin(ctx, ctx->ho_vecs, (n + 1) * 4 * k));
     CK(cudaMemsetAsync(&ctx->d_small->emit_cursor, 0, 8, s));
     EmitArgs e{};
     e.table = ctx->table.as<Slot>();
@@ -1887,6 +1881,40 @@ mdbg_status mdbg_count_finalize(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_tabl
     e.cursor = &ctx->d_small->emit_cursor;
     launch_table_emit(e, s);
     CKS(check_launch(ctx, "table_emit_kernel", 1));
+    *st_out = st;
+    return MDBG_OK;
+}
+
+mdbg_status mdbg_count_finalize_device(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_table_dev* out) {
+    if (!ctx || !out) return MDBG_ERR_ARG;
+    if (!ctx->t_active) return fail(ctx, MDBG_ERR_STATE, "mdbg_count_finalize_device before mdbg_count_begin");
+    CK(cudaSetDevice(ctx->device));
+    TableStats st;
+    CKS(emit_table(ctx, count_threshold(ctx, min_abundance), &st));
+    out->k = ctx->t_k;
+    out->n_entries = st.n_entries;
+    out->d_hashes = ctx->o_hash.as<uint64_t>();
+    out->d_abundances = ctx->o_abund.as<uint32_t>();
+    out->d_kminmers = ctx->o_vecs.as<uint32_t>();
+    out->n_instances = st.n_instances;
+    out->n_distinct = st.n_distinct;
+    out->checksum = st.checksum;
+    out->n_rescued = st.n_rescued;
+    return MDBG_OK;
+}
+
+mdbg_status mdbg_count_finalize(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_table_out* out) {
+    if (!ctx || !out) return MDBG_ERR_ARG;
+    if (!ctx->t_active) return fail(ctx, MDBG_ERR_STATE, "mdbg_count_finalize before mdbg_count_begin");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const uint32_t k = ctx->t_k;
+    TableStats st;
+    CKS(emit_table(ctx, count_threshold(ctx, min_abundance), &st));
+    const uint64_t n = st.n_entries;
+    CKS(ensure_pin(ctx, ctx->ho_hash, (n + 1) * 16));
+    CKS(ensure_pin(ctx, ctx->ho_abund, (n + 1) * 4));
+    CKS(ensure_pin(ctx, ctx->ho_vecs, (n + 1) * 4 * k));
     if (n) {
         CK(cudaMemcpyAsync(ctx->ho_hash.p, ctx->o_hash.p, n * 16, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(ctx->ho_abund.p, ctx->o_abund.p, n * 4, cudaMemcpyDeviceToHost, s));

@@ -646,9 +646,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) sketch_packed_kernel(co
                 const uint32_t bit = (2u * (avail + incl - cnt)) & (P_RING_WORDS * 32u - 1u);
                 const uint32_t wi = bit >> 5, sh = bit & 31u;
                 const uint32_t p0 = lo << sh, p1 = __funnelshift_l(lo, hi, sh), p2 = __funnelshift_l(hi, 0u, sh);
-                if (p0) atomicOr(&ring[wi], p0);
-                if (p1) atomicOr(&ring[(wi + 1) & (P_RING_WORDS - 1)], p1);
-                if (p2) atomicOr(&ring[(wi + 2) & (P_RING_WORDS - 1)], p2);
+                // unconditional: OR-ing a zero word is harmless and cheaper than a branch around each atomic
+                atomicOr(&ring[wi], p0);
+                atomicOr(&ring[(wi + 1) & (P_RING_WORDS - 1)], p1);
+                atomicOr(&ring[(wi + 2) & (P_RING_WORDS - 1)], p2);
                 avail += total;
                 step++;
                 if (sub == P_STEPS_PER_TILE - 1 || step == n_steps) {      // the stage has been read completely: refill it

@@ -17,7 +17,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _capi
-from ._capi import AutotuneOut, AuxOut, BatchInfo, EdgesOut, MdbgParams, SketchDev, SketchOut, TableOut
+from ._capi import AutotuneOut, AuxOut, BatchInfo, EdgesOut, MdbgParams, SketchDev, SketchOut, TableDev, TableOut
 
 STATUS = {0: "OK", 1: "CUDA", 2: "ARG", 3: "STATE", 4: "TABLE_FULL", 5: "NCCL", 6: "OOM"}
 
@@ -301,6 +301,14 @@ class Engine:
         self._ck(self._lib.mdbg_count_stats(self._ctx, min_abundance, *[C.byref(x) for x in v]))
         return dict(n_entries=int(v[0].value), n_distinct=int(v[1].value), n_instances=int(v[2].value),
                     checksum=int(v[3].value))
+
+    def count_finalize_device(self, min_abundance: int = 2) -> dict:
+        """Emit the table into device arrays (hashes, abundances, normalized vectors); only the statistics reach the host."""
+        out = TableDev()
+        self._ck(self._lib.mdbg_count_finalize_device(self._ctx, min_abundance, C.byref(out)))
+        return dict(k=int(out.k), n_entries=int(out.n_entries), d_hashes=out.d_hashes, d_abundances=out.d_abundances,
+                    d_kminmers=out.d_kminmers, n_instances=int(out.n_instances), n_distinct=int(out.n_distinct),
+                    checksum=int(out.checksum), n_rescued=int(out.n_rescued))
 
     def count_finalize(self, min_abundance: int = 2) -> CountTable:
         out = TableOut()

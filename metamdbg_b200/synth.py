@@ -75,11 +75,15 @@ class ReadSet:
 def make_readset(n_reads: int, mean_len: int, *, seed: int = 1, n_genomes: int = 1,
                  genome_len_range=(2_000_000, 6_000_000), err: float = 0.001,
                  len_sd_frac: float = 0.15, min_len: int = 1000, abundance_sigma: float = 1.0,
-                 align: int = 1) -> ReadSet:
+                 align: int = 1, sample: int = 0, index_base: int = 0) -> ReadSet:
     """Draw read placements (host, numpy).  ``align`` pads every read start to a
     multiple of ``align`` bytes in the concatenated buffer (padding bytes are
-    never part of a read)."""
+    never part of a read).  ``sample`` > 0 draws another SAMPLE of the same genome
+    set (same genomes and bases, its own abundance profile and read placements:
+    a co-assembly input, datasetIndex = sample); ``index_base`` is the global
+    index of its first read (keys the per-read error stream)."""
     s = np.uint64(seed)
+    smp = np.uint64(sample) * np.uint64(0x9E3779B1)
     g = np.arange(n_genomes, dtype=np.uint64)
     with np.errstate(over="ignore"):
         u = mix64(g * GOLD + s + np.uint64(0x1111))
@@ -87,13 +91,13 @@ def make_readset(n_reads: int, mean_len: int, *, seed: int = 1, n_genomes: int =
         glen = (np.uint64(lo) + u % np.uint64(max(1, hi - lo))).astype(np.uint64)
         gbase = np.concatenate([[np.uint64(0)], np.cumsum(glen)[:-1]]).astype(np.uint64)
         # log-normal abundance via Box-Muller on two hashed uniforms
-        u1 = (mix64(g * GOLD + s + np.uint64(0x2222)) >> np.uint64(11)).astype(np.float64) / 2.0**53
-        u2 = (mix64(g * GOLD + s + np.uint64(0x3333)) >> np.uint64(11)).astype(np.float64) / 2.0**53
+        u1 = (mix64(g * GOLD + s + np.uint64(0x2222) + smp) >> np.uint64(11)).astype(np.float64) / 2.0**53
+        u2 = (mix64(g * GOLD + s + np.uint64(0x3333) + smp) >> np.uint64(11)).astype(np.float64) / 2.0**53
         z = np.sqrt(-2.0 * np.log(np.maximum(u1, 1e-300))) * np.cos(2 * np.pi * u2)
         w = np.exp(abundance_sigma * z) * glen.astype(np.float64)
         cum = np.cumsum(w) / np.sum(w)
 
-        r = np.arange(n_reads, dtype=np.uint64)
+        r = np.arange(n_reads, dtype=np.uint64) + np.uint64(index_base)
         ug = (mix64(r * GOLD + s + np.uint64(0x4444)) >> np.uint64(11)).astype(np.float64) / 2.0**53
         gi = np.minimum(np.searchsorted(cum, ug, side="right"), n_genomes - 1)
         ul = mix64(r * GOLD + s + np.uint64(0x5555))
@@ -112,7 +116,7 @@ def make_readset(n_reads: int, mean_len: int, *, seed: int = 1, n_genomes: int =
     # offsets delimit padded slots; true length kept separately
     rs = ReadSet(seed=seed, err_q24=int(round(err * (1 << 24))), offsets=offsets,
                  vstart=(gbase[gi] + st).astype(np.uint64), strand=strand,
-                 n_genomes=n_genomes, genome_len=glen)
+                 n_genomes=n_genomes, genome_len=glen, index_base=index_base)
     rs.lengths = ln.astype(np.uint64)  # type: ignore[attr-defined]
     if align == 1:
         assert np.array_equal(np.diff(offsets.astype(np.int64)), ln)

@@ -15,6 +15,9 @@ class _T:
     def data_ptr(self):
         return self.a.ctypes.data
 
+    def numel(self):
+        return int(self.a.size)
+
     def to(self, _dev):
         return self
 

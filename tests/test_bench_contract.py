@@ -55,7 +55,7 @@ def test_gpu_arm_runs_on_the_emulator(tmp_path):
     import _emu
     lib = _emu.build_emulated_library(str(tmp_path))
     env = dict(os.environ, MDBG_EMU_LIB=lib)
-    for extra in ([], ["--workload", "cfg3"]):
+    for extra in (["--extras", "cfg4,cfg5", "--extra-scale", "0.00002"], ["--workload", "cfg3"]):
         run = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "bench_on_emulator.py"), "--reads", "240",
                               "--read-len", "3000", "--genomes", "2", "--steps", "2", "--warmup", "3", "--e2e-batch", "100",
                               "--multi-k", "6"] + extra, env=env, capture_output=True, text=True, timeout=900, cwd=ROOT)
@@ -73,3 +73,9 @@ def test_gpu_arm_runs_on_the_emulator(tmp_path):
         assert d["edges"]["n_edges"] > 0 and d["edges"]["n_nodes"] == d["check"]["n_solid_total"]
         assert d["cpu_baseline"]["kind"] in ("reference", "port") and "identical" in d["cpu_baseline"]["sample"]
         assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
+        assert d["ascii_resident"]["same_table_as_packed_leg"] and d["ascii_resident"]["value"] > 0
+        if "--extras" in extra:                      # the other BASELINE configs run through the same step, scaled down
+            x4, x5 = d["extras"]["cfg4"], d["extras"]["cfg5"]
+            assert "error" not in x4 and "error" not in x5, (x4, x5)
+            assert x4["scaling"] == "strong" and x4["k_last"] == 6 and len(x4["n_entries_per_k_total"]) == 3
+            assert x5["config"]["samples"] == 3 and x5["n_minimizers_total"] > 0 and x5["value"] > 0
