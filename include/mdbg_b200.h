@@ -159,6 +159,37 @@ typedef struct mdbg_batch_info {
     int32_t host_threads;
 } mdbg_batch_info;
 mdbg_status mdbg_ctx_last_batch_info(mdbg_ctx* ctx, mdbg_batch_info* info);
+/* Host batch that is ALREADY 2-bit packed (a reader that packs while it parses -- on all of its parser threads --
+ * hands over a quarter of the bytes and nothing is left for the library's packer to do):
+ *   mdbg_host_pack_read    packs one read on the calling thread (thread safe, stateless; AVX-512 / AVX2 / scalar):
+ *                          ceil(len / 16) words, base j of a word at bits [2j, 2j+1], code (c >> 1) & 3.  Returns 1, or
+ *                          0 when the read holds a byte outside "ACGT" (words undefined): such a read must travel as
+ *                          ASCII in the spill buffer.
+ *   mdbg_sketch_batch_packed  packed     host words of the batch, n_words of them
+ *                          read_src[r]   first word of read r (use multiples of 4: 16-byte aligned reads; must not
+ *                                        decrease with r), or MDBG_SRC_ASCII | byte offset of the read in `ascii`
+ *                          ascii         spill buffer of the reads that could not be packed (may be NULL)
+ *                          offsets       [n_reads+1] base offsets (read lengths), offsets[0] = 0
+ * Same pipelining, outputs and store behaviour as mdbg_sketch_batch. */
+int         mdbg_host_pack_read(const uint8_t* bases, uint64_t len, uint32_t* words_out);
+mdbg_status mdbg_sketch_batch_packed(mdbg_ctx* ctx, const uint32_t* packed, uint64_t n_words, const uint64_t* read_src,
+                                     const uint8_t* ascii, uint64_t n_ascii_bytes, const uint64_t* offsets,
+                                     uint32_t n_reads, int append_to_store, mdbg_sketch_out* out);
+/* Raw, uncompressed FASTQ / FASTA TEXT -> sketch: the record split runs on the device (newline index, sequence /
+ * quality line of every record, 2-bit packing straight from the text), replacing the parsing half of
+ * ReadParserParallel::parse (src/Commons.hpp:5846-5911, kseq on one thread inside an omp critical).  Supported:
+ * 4-line FASTQ and 2-line FASTA ('\n' or '\r\n'); any other shape returns MDBG_ERR_ARG and the caller uses its host
+ * parser.  The block may end inside a record: only complete records are sketched and info->consumed_bytes says where
+ * the next block must start (is_final != 0: a last line without a newline still ends its record).  Read r of `out`
+ * is record r of the block. */
+typedef struct {
+    uint64_t n_records;        /* complete records sketched */
+    uint64_t consumed_bytes;   /* text[0 .. consumed_bytes) was used */
+    uint64_t n_bases;
+    int32_t  format;           /* 1 = FASTQ, 2 = FASTA */
+} mdbg_fastx_info;
+mdbg_status mdbg_sketch_fastx(mdbg_ctx* ctx, const uint8_t* text, uint64_t n_bytes, int is_final, int append_to_store,
+                              mdbg_sketch_out* out, mdbg_fastx_info* info);
 /* Same with the reads already in HBM.  d_bases must be 16-byte aligned;
  * nothing is copied to the host.  `out` may be NULL. */
 mdbg_status mdbg_sketch_batch_device(mdbg_ctx* ctx, const uint8_t* d_bases, const uint64_t* d_offsets,

@@ -44,6 +44,10 @@ class TableDev(C.Structure):
                 ("checksum", C.c_uint64), ("n_rescued", C.c_uint64)]
 
 
+class FastxInfo(C.Structure):
+    _fields_ = [("n_records", C.c_uint64), ("consumed_bytes", C.c_uint64), ("n_bases", C.c_uint64), ("format", C.c_int32)]
+
+
 class AuxOut(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("mean_quality", C.POINTER(C.c_float)), ("complexity", C.POINTER(C.c_double)),
                 ("low_complexity", u8p), ("qualities", u8p)]
@@ -77,6 +81,11 @@ SYMBOLS = {
     "mdbg_ctx_enable_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "mdbg_ctx_kernel_time_ms": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     "mdbg_sketch_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.POINTER(SketchOut)]),
+    "mdbg_sketch_fastx": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.POINTER(SketchOut),
+                                    C.POINTER(FastxInfo)]),
+    "mdbg_host_pack_read": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
+    "mdbg_sketch_batch_packed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
+                                           C.c_uint32, C.c_int, C.POINTER(SketchOut)]),
     "mdbg_ctx_set_host_packing": (C.c_int, [C.c_void_p, C.c_int]),
     "mdbg_ctx_last_batch_info": (C.c_int, [C.c_void_p, C.POINTER(BatchInfo)]),
     "mdbg_sketch_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_int,

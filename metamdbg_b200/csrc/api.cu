@@ -70,6 +70,7 @@ struct mdbg_ctx {
     int last_overflow_fallback = 0, last_packed = 0;
     int auto_pack_pause = 0;           // auto mode: batches still to send as ASCII after the packer proved too slow
     DevBuf d_pack, d_src, d_dirty;
+    DevBuf f_raw, f_cnt, f_off, f_nl, f_start, f_len, f_qstart;   // FASTQ / FASTA text ingest (mdbg_sketch_fastx)
     PinBuf h_pack, h_src, h_asc;
     cudaEvent_t sub_ev[MAX_SUB] = {};
     cudaEvent_t copy_gate = nullptr;
@@ -811,7 +812,7 @@ void mdbg_ctx_destroy(mdbg_ctx* c) {
     DevBuf* devs[] = {&c->d_blacklist, &c->d_bases, &c->d_offsets, &c->pad_min, &c->pad_pos, &c->pad_dir, &c->n_min,
                       &c->scan_scratch, &c->b_off, &c->b_min, &c->b_pos, &c->b_dir, &c->s_min, &c->s_off, &c->s_rem,
                       &c->p_flags, &c->p_keep, &c->p_cnt, &c->p_newoff, &c->p_newmin, &c->table, &c->foreign_vecs,
-                      &c->o_hash, &c->o_abund, &c->o_vecs, &c->d_pack, &c->d_src, &c->d_dirty, &c->d_quals, &c->pad_qual, &c->pad_raw_a, &c->pad_raw_b, &c->b_qual, &c->x_sum_lo, &c->x_sum_hi, &c->x_lmin, &c->x_cplx, &c->x_low, &c->d_err_fixed, &c->d_err_tz, &c->prev_table, &c->prev_stage_h, &c->prev_stage_a, &c->rescue_table, &c->m_send_vecs, &c->m_send_counts, &c->m_recv_vecs,
+                      &c->o_hash, &c->o_abund, &c->o_vecs, &c->d_pack, &c->d_src, &c->d_dirty, &c->f_raw, &c->f_cnt, &c->f_off, &c->f_nl, &c->f_start, &c->f_len, &c->f_qstart, &c->d_quals, &c->pad_qual, &c->pad_raw_a, &c->pad_raw_b, &c->b_qual, &c->x_sum_lo, &c->x_sum_hi, &c->x_lmin, &c->x_cplx, &c->x_low, &c->d_err_fixed, &c->d_err_tz, &c->prev_table, &c->prev_stage_h, &c->prev_stage_a, &c->rescue_table, &c->m_send_vecs, &c->m_send_counts, &c->m_recv_vecs,
                       &c->m_recv_counts, &c->m_bucket, &c->loc_off, &c->edge_table, &c->edge_vals, &c->o_edge_vals};
     for (DevBuf* b : devs) release(*b);
     PinBuf* pins[] = {&c->h_off, &c->h_min, &c->h_pos, &c->h_dir, &c->ho_hash, &c->ho_abund, &c->ho_vecs, &c->hx_sum_lo, &c->hx_sum_hi, &c->hx_lmin, &c->hx_cplx, &c->hx_low, &c->hx_meanq, &c->h_qual, &c->h_pack, &c->h_src, &c->h_asc, &c->ho_edge_vals};
@@ -1430,6 +1431,193 @@ static mdbg_status sketch_host_batch(mdbg_ctx* ctx, const uint8_t* bases, const 
         if (ctx->host_packing < 0 && pack_bytes >= (uint64_t(256) << 20) && ctx->last_pack_gbs < 45.0) ctx->auto_pack_pause = 16;
     }
     return st;
+}
+
+// Raw FASTQ / FASTA text -> sketch, record split on the device (ingest.cu; row (f)3).
+mdbg_status mdbg_sketch_fastx(mdbg_ctx* ctx, const uint8_t* text, uint64_t n_bytes, int is_final, int append_to_store,
+                              mdbg_sketch_out* out, mdbg_fastx_info* info) {
+    if (!ctx || !info) return MDBG_ERR_ARG;
+    memset(info, 0, sizeof *info);
+    if (n_bytes && !text) return fail(ctx, MDBG_ERR_ARG, "null text buffer");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    ctx->host_csr_valid = false;
+    uint32_t lines = 0;
+    if (n_bytes) {
+        lines = text[0] == '@' ? 4u : text[0] == '>' ? 2u : 0u;
+        if (!lines) return fail(ctx, MDBG_ERR_ARG, "the text does not start with '@' (FASTQ) or '>' (FASTA)");
+    }
+    // a last line without '\n' at the end of the input still ends a record
+    const bool virtual_nl = is_final && n_bytes && text[n_bytes - 1] != '\n';
+    const uint64_t n_dev = n_bytes + (virtual_nl ? 1 : 0);
+    CKS(ensure(ctx, ctx->f_raw, n_dev + 64));
+    if (n_bytes) CK(cudaMemcpyAsync(ctx->f_raw.p, text, n_bytes, cudaMemcpyHostToDevice, s));
+    if (virtual_nl) CK(cudaMemsetAsync(ctx->f_raw.as<uint8_t>() + n_bytes, '\n', 1, s));
+    ctx->h2d_bytes += n_bytes;
+    const uint8_t* d_text = ctx->f_raw.as<uint8_t>();
+    uint64_t n_nl = 0;
+    if (n_dev) {
+        const uint64_t tiles = newline_tiles(n_dev);
+        if (tiles > 0xFFFFFFF0ull) return fail(ctx, MDBG_ERR_ARG, "text block too large");
+        CKS(ensure(ctx, ctx->f_cnt, tiles * 4));
+        CKS(ensure(ctx, ctx->f_off, (tiles + 1) * 8));
+        CKS(ensure(ctx, ctx->scan_scratch, scan_scratch_elems((uint32_t)tiles) * sizeof(uint64_t)));
+        launch_newline_count(d_text, n_dev, ctx->f_cnt.as<uint32_t>(), s);
+        launch_scan_u32_to_u64(ctx->f_cnt.as<uint32_t>(), ctx->f_off.as<uint64_t>(), (uint32_t)tiles, ctx->scan_scratch.as<uint64_t>(), s);
+        CKS(check_launch(ctx, "newline_count_kernel + scan", 4));
+        CK(cudaMemcpyAsync(&ctx->h_scalar[0], ctx->f_off.as<uint64_t>() + tiles, 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        n_nl = ctx->h_scalar[0];
+        CKS(ensure(ctx, ctx->f_nl, (n_nl + 1) * 8));
+        launch_newline_write(d_text, n_dev, ctx->f_off.as<uint64_t>(), ctx->f_nl.as<uint64_t>(), s);
+        CKS(check_launch(ctx, "newline_write_kernel", 1));
+    }
+    const uint64_t n_rec64 = lines ? n_nl / lines : 0;
+    if (n_rec64 > 0xFFFFFFF0ull) return fail(ctx, MDBG_ERR_ARG, "too many records in one block");
+    const uint32_t n_rec = (uint32_t)n_rec64;
+    CKS(ensure(ctx, ctx->d_offsets, ((size_t)n_rec + 1) * 8));
+    uint64_t n_bases = 0;
+    if (n_rec) {
+        CKS(ensure(ctx, ctx->f_start, (size_t)n_rec * 8));
+        CKS(ensure(ctx, ctx->f_len, (size_t)n_rec * 4));
+        CKS(ensure(ctx, ctx->f_qstart, (size_t)n_rec * 8));
+        CKS(ensure(ctx, ctx->scan_scratch, scan_scratch_elems(n_rec) * sizeof(uint64_t)));
+        CK(cudaMemsetAsync(&ctx->d_small->n_flagged, 0, sizeof(unsigned long long), s));
+        FastxArgs fa{};
+        fa.text = d_text; fa.nl = ctx->f_nl.as<uint64_t>(); fa.n_records = n_rec; fa.lines = lines;
+        fa.seq_start = ctx->f_start.as<uint64_t>(); fa.seq_len = ctx->f_len.as<uint32_t>();
+        fa.qual_start = ctx->f_qstart.as<uint64_t>(); fa.n_bad = &ctx->d_small->n_flagged;
+        launch_fastx_records(fa, s);
+        launch_scan_u32_to_u64(ctx->f_len.as<uint32_t>(), ctx->d_offsets.as<uint64_t>(), n_rec, ctx->scan_scratch.as<uint64_t>(), s);
+        CKS(check_launch(ctx, "fastx_records_kernel + scan", 4));
+        CK(cudaMemcpyAsync(&ctx->h_scalar[0], &ctx->d_small->n_flagged, 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(&ctx->h_scalar[1], ctx->f_nl.as<uint64_t>() + ((uint64_t)n_rec * lines - 1), 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(&ctx->h_scalar[2], ctx->d_offsets.as<uint64_t>() + n_rec, 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (ctx->h_scalar[0])
+            return fail(ctx, MDBG_ERR_ARG, "%llu of %u records are not well-formed 4-line FASTQ / 2-line FASTA (multi-line "
+                        "sequences need the host parser)", (unsigned long long)ctx->h_scalar[0], n_rec);
+        info->consumed_bytes = std::min<uint64_t>(ctx->h_scalar[1] + 1, n_bytes);
+        n_bases = ctx->h_scalar[2];
+    } else {
+        CK(cudaMemsetAsync(ctx->d_offsets.p, 0, 8, s));
+    }
+    info->n_records = n_rec;
+    info->n_bases = n_bases;
+    info->format = lines == 4 ? 1 : lines == 2 ? 2 : 0;
+    // sequence bytes -> 2-bit layout straight from the text; reads with a byte outside "ACGT" are sketched from the
+    // text itself (SRC_ASCII | position) by the byte-ring kernel
+    CKS(ensure(ctx, ctx->d_pack, pack_words_capacity(n_bases, n_rec) * 4 + 64));
+    CKS(ensure(ctx, ctx->d_src, (size_t)n_rec * 8 + 8));
+    if (n_rec) {
+        PackArgsAscii pa{};
+        pa.bases = d_text; pa.bases_end = d_text + n_dev; pa.offsets = ctx->d_offsets.as<uint64_t>();
+        pa.read_begin = 0; pa.read_end = n_rec;
+        pa.packed = ctx->d_pack.as<uint32_t>(); pa.read_src = ctx->d_src.as<uint64_t>();
+        pa.src_start = ctx->f_start.as<uint64_t>();
+        launch_pack_ascii(pa, ctx->sm_count, s);
+        CKS(check_launch(ctx, "pack_ascii_kernel", 1));
+    }
+    const Feeder feeder = [&](SketchArgs& a) -> mdbg_status {
+        a.read_src = ctx->d_src.as<uint64_t>();
+        a.packed = ctx->d_pack.as<uint32_t>();
+        a.bases = d_text;
+        a.bases_end = d_text + n_dev;
+        const int n_k = launch_sketch(a, ctx->sm_count, s);
+        return check_launch(ctx, "sketch_kernel", n_k);
+    };
+    CKS(sketch_internal(ctx, nullptr, ctx->d_offsets.as<uint64_t>(), n_rec, n_bases, append_to_store, false, nullptr, &feeder));
+    if (out) return mdbg_sketch_fetch(ctx, out);
+    return MDBG_OK;
+}
+
+int mdbg_host_pack_read(const uint8_t* bases, uint64_t len, uint32_t* words_out) {
+    return host_pack_one(bases, len, words_out) ? 1 : 0;
+}
+
+// Host batch handed over 2-bit packed: pieces of the word array cross PCIe on the copy stream while the packed kernel
+// works on the piece before; scan / compaction / D2H of the CSR piece by piece behind it (PiecePipeline).
+mdbg_status mdbg_sketch_batch_packed(mdbg_ctx* ctx, const uint32_t* packed, uint64_t n_words, const uint64_t* read_src,
+                                     const uint8_t* ascii, uint64_t n_ascii_bytes, const uint64_t* offsets,
+                                     uint32_t n_reads, int append_to_store, mdbg_sketch_out* out) {
+    if (!ctx) return MDBG_ERR_ARG;
+    if (n_reads && (!read_src || !offsets || (n_words && !packed))) return fail(ctx, MDBG_ERR_ARG, "null host buffer");
+    CK(cudaSetDevice(ctx->device));
+    CKS(check_host_offsets(ctx, offsets, n_reads));
+    const uint64_t n_bases = n_reads ? offsets[n_reads] : 0;
+    // every read must lie inside its buffer, packed reads in non-decreasing word order
+    uint64_t last_w = 0;
+    for (uint32_t r = 0; r < n_reads; r++) {
+        const uint64_t len = offsets[r + 1] - offsets[r], src = read_src[r];
+        if (src & SRC_ASCII) {
+            if ((src & ~SRC_ASCII) + len > n_ascii_bytes || !ascii) return fail(ctx, MDBG_ERR_ARG, "read %u lies outside the ASCII spill buffer", r);
+        } else {
+            if (src < last_w || src + ((len + 15) >> 4) > n_words) return fail(ctx, MDBG_ERR_ARG, "read %u: packed reads must follow each other without overlap inside the packed buffer", r);
+            last_w = src + ((len + 15) >> 4);
+        }
+    }
+    cudaStream_t s = ctx->stream, cs = ctx->copy_stream;
+    ctx->host_csr_valid = false;
+    CKS(ensure(ctx, ctx->d_offsets, ((size_t)n_reads + 1) * 8));
+    if (n_reads == 0) {
+        CKS(sketch_internal(ctx, nullptr, ctx->d_offsets.as<uint64_t>(), 0, 0, append_to_store));
+        return out ? mdbg_sketch_fetch(ctx, out) : MDBG_OK;
+    }
+    std::vector<SubRange> subs;
+    split_pieces(offsets, n_reads, n_bases, subs);
+    const bool fetch = out != nullptr;
+    PiecePipeline pipeline{ctx, ctx->d_offsets.as<uint64_t>(), &subs, n_reads, fetch};
+    bool want_pipe = ctx->piece_pipeline;
+    if (const char* e = getenv("MDBG_PIECE_PIPELINE")) want_pipe = atoi(e) != 0;
+    PiecePipeline* pipe = want_pipe ? &pipeline : nullptr;
+    CKS(ensure(ctx, ctx->d_pack, (n_words + 4) * 4 + 64));
+    CKS(ensure(ctx, ctx->d_src, (size_t)n_reads * 8));
+    CKS(ensure(ctx, ctx->d_bases, n_ascii_bytes + 64));
+    CK(cudaEventRecord(ctx->copy_gate, s));                          // the copy stream must not overwrite buffers still being read
+    CK(cudaStreamWaitEvent(cs, ctx->copy_gate, 0));
+    CK(cudaMemcpyAsync(ctx->d_offsets.p, offsets, ((size_t)n_reads + 1) * 8, cudaMemcpyHostToDevice, cs));
+    CK(cudaMemcpyAsync(ctx->d_src.p, read_src, (size_t)n_reads * 8, cudaMemcpyHostToDevice, cs));
+    if (n_ascii_bytes) CK(cudaMemcpyAsync(ctx->d_bases.p, ascii, n_ascii_bytes, cudaMemcpyHostToDevice, cs));
+    ctx->h2d_bytes += ((uint64_t)n_reads + 1) * 8 + (uint64_t)n_reads * 8 + n_ascii_bytes;
+    // first word of each piece = word offset of its first packed read
+    std::vector<uint64_t> piece_w(subs.size() + 1, n_words);
+    {
+        size_t i = subs.size();
+        uint64_t next = n_words;
+        while (i-- > 0) {
+            for (uint32_t r = subs[i].r1; r-- > subs[i].r0;)
+                if (!(read_src[r] & SRC_ASCII)) next = read_src[r];
+            piece_w[i] = next;
+        }
+        piece_w[0] = std::min<uint64_t>(piece_w[0], n_words);
+    }
+    ctx->last_packed = 0; ctx->last_pieces = subs.size(); ctx->last_direct_pieces = 0;
+    if (!pipe) { ctx->last_pipelined = ctx->last_grows = 0; ctx->last_overflow_fallback = 0; }
+    const Feeder feeder = [&](SketchArgs& a) -> mdbg_status {
+        a.read_src = ctx->d_src.as<uint64_t>();
+        a.packed = ctx->d_pack.as<uint32_t>();
+        a.bases = ctx->d_bases.as<uint8_t>();
+        a.bases_end = ctx->d_bases.as<uint8_t>() + n_ascii_bytes;
+        for (size_t i = 0; i < subs.size(); i++) {
+            const uint64_t w0 = (i == 0) ? 0 : piece_w[i], w1 = piece_w[i + 1];
+            if (w1 > w0) {
+                CK(cudaMemcpyAsync(ctx->d_pack.as<uint32_t>() + w0, packed + w0, (w1 - w0) * 4, cudaMemcpyHostToDevice, cs));
+                ctx->h2d_bytes += (w1 - w0) * 4;
+            }
+            CK(cudaEventRecord(ctx->sub_ev[i], cs));
+            CK(cudaStreamWaitEvent(s, ctx->sub_ev[i], 0));
+            piece_args(ctx, a, i, subs[i].r0, subs[i].r1);
+            const int n_k = launch_sketch(a, ctx->sm_count, s);
+            CKS(check_launch(ctx, "sketch_kernel", n_k));
+            if (pipe) CKS(pipe->launched(i));
+        }
+        return MDBG_OK;
+    };
+    CKS(sketch_internal(ctx, ctx->d_bases.as<uint8_t>(), ctx->d_offsets.as<uint64_t>(), n_reads, n_bases, append_to_store, false,
+                        nullptr, &feeder, pipe));
+    if (pipe && !pipe->overflow && pipe->fetch) ctx->host_csr_valid = true;
+    if (out) return mdbg_sketch_fetch(ctx, out);
+    return MDBG_OK;
 }
 
 mdbg_status mdbg_ctx_last_batch_info(mdbg_ctx* ctx, mdbg_batch_info* info) {

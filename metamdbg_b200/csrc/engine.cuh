@@ -61,8 +61,22 @@ struct PackArgsAscii {
     const uint8_t* bases; const uint8_t* bases_end; const uint64_t* offsets;
     uint32_t read_begin, read_end;
     uint32_t* packed; uint64_t* read_src;
+    // optional: read r's bytes start at bases[src_start[r]] instead of bases[offsets[r]] (reads located inside raw
+    // FASTQ text, ingest.cu); offsets still give the lengths and the packed layout
+    const uint64_t* src_start;
 };
 void launch_pack_ascii(const PackArgsAscii& a, int sm_count, cudaStream_t s);
+
+// ------------------------------------------------------------------ FASTQ / FASTA text on the device (ingest.cu)
+uint64_t newline_tiles(uint64_t n_bytes);                           // entries of the per-tile count array
+void launch_newline_count(const uint8_t* text, uint64_t n, uint32_t* counts, cudaStream_t s);
+void launch_newline_write(const uint8_t* text, uint64_t n, const uint64_t* tile_off, uint64_t* nl_pos, cudaStream_t s);
+struct FastxArgs {
+    const uint8_t* text; const uint64_t* nl; uint64_t n_records; uint32_t lines;   // lines per record: 4 (FASTQ) or 2 (FASTA)
+    uint64_t* seq_start; uint32_t* seq_len; uint64_t* qual_start;                 // qual_start may be nullptr
+    unsigned long long* n_bad;                                                    // records that are not well formed
+};
+void launch_fastx_records(const FastxArgs& a, cudaStream_t s);
 
 int launch_sketch(const SketchArgs& a, int sm_count, cudaStream_t s);   // returns the number of kernels launched
 

@@ -277,6 +277,8 @@ inline bool pack_read(const uint8_t* s, uint64_t len, uint32_t* dst) {
 
 const char* host_pack_isa() { return g_isa == 2 ? "avx512" : g_isa == 1 ? "avx2" : "scalar"; }
 
+bool host_pack_one(const uint8_t* bases, uint64_t len, uint32_t* words_out) { return pack_read(bases, len, words_out); }
+
 // one piece being packed: lives on the heap so that the workers can go on while the caller enqueues the previous
 // piece's copies and launches
 struct PackJob {

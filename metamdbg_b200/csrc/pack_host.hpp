@@ -13,6 +13,8 @@ HostPool* host_pool_create(int n_threads);        // n_threads <= 0: MDBG_HOST_T
 int host_pool_size(const HostPool* p);
 void host_pool_destroy(HostPool* p);
 const char* host_pack_isa();                      // "avx512" | "avx2" | "scalar": the packer the CPU (and MDBG_PACK_ISA) selects
+// one read on the calling thread: ceil(len / 16) words; false (words undefined) when it holds a byte outside "ACGT"
+bool host_pack_one(const uint8_t* bases, uint64_t len, uint32_t* words_out);
 
 // Pack reads [r0, r1) of an ASCII batch.  Read r goes to pack_out[pk_off[r] ...] (16 bases per u32, base j at bits
 // [2j, 2j+1], code (c >> 1) & 3) and src_out[r] = pk_off[r]; a read holding any byte outside "ACGT" is instead

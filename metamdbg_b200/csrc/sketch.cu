@@ -804,7 +804,8 @@ __global__ void __launch_bounds__(256) pack_ascii_kernel(const PackArgsAscii a) 
         const uint64_t start = a.offsets[r], end = a.offsets[r + 1];
         const uint32_t len = (uint32_t)(end - start);
         const uint64_t w_off = pack_word_offset(start, r);
-        const uint8_t* base = a.bases + start;
+        const uint64_t byte0 = a.src_start ? a.src_start[r] : start;       // where the read's bytes are
+        const uint8_t* base = a.bases + byte0;
         const uint32_t skip = (uint32_t)((uintptr_t)base & 15);
         const uint8_t* abase = base - skip;                       // 16-byte aligned
         const uint32_t sh8 = 8 * (skip & 3), k = skip >> 2;       // warp-uniform realignment
@@ -851,7 +852,7 @@ __global__ void __launch_bounds__(256) pack_ascii_kernel(const PackArgsAscii a) 
             }
         }
         const bool dirty = __any_sync(0xffffffffu, bad != 0);
-        if (lane == 0) a.read_src[r] = dirty ? (SRC_ASCII | start) : w_off;
+        if (lane == 0) a.read_src[r] = dirty ? (SRC_ASCII | byte0) : w_off;
     }
 }
 

@@ -17,7 +17,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _capi
-from ._capi import AutotuneOut, AuxOut, BatchInfo, EdgesOut, MdbgParams, SketchDev, SketchOut, TableDev, TableOut
+from ._capi import AutotuneOut, AuxOut, BatchInfo, EdgesOut, FastxInfo, MdbgParams, SketchDev, SketchOut, TableDev, TableOut
 
 STATUS = {0: "OK", 1: "CUDA", 2: "ARG", 3: "STATE", 4: "TABLE_FULL", 5: "NCCL", 6: "OOM"}
 
@@ -142,6 +142,64 @@ class Engine:
         self._ck(self._lib.mdbg_sketch_batch(self._ctx, bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1,
                                              int(append_to_store), C.byref(out) if fetch else None))
         return self._copy_sketch(out) if fetch else None
+
+    def sketch_fastx(self, text: bytes | np.ndarray, is_final: bool = True, append_to_store: bool = False):
+        """Raw FASTQ / FASTA text -> (Sketch of its complete records, info dict); record split on the device."""
+        buf = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray)) else np.ascontiguousarray(text, np.uint8)
+        out, info = SketchOut(), FastxInfo()
+        self._ck(self._lib.mdbg_sketch_fastx(self._ctx, buf.ctypes.data if len(buf) else None, len(buf), int(is_final),
+                                             int(append_to_store), C.byref(out), C.byref(info)))
+        return self._copy_sketch(out), dict(n_records=int(info.n_records), consumed_bytes=int(info.consumed_bytes),
+                                            n_bases=int(info.n_bases), format={1: "fastq", 2: "fasta"}.get(info.format))
+
+    def host_pack_reads(self, bases: np.ndarray, offsets: np.ndarray):
+        """What a packing reader does, read by read (mdbg_host_pack_read): -> (words u32, read_src u64, ascii spill u8).
+        Reads start on 16-byte boundaries of the word array; unpackable reads go to the spill."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        lens = np.diff(offsets.astype(np.int64))
+        woff = np.zeros(n + 1, np.int64)
+        woff[1:] = np.cumsum(((lens + 63) >> 6) << 2)
+        words = np.zeros(int(woff[-1]) + 4, np.uint32)
+        src = np.zeros(n, np.uint64)
+        spill, n_spill = [], 0
+        for r in range(n):
+            lo, ln = int(offsets[r]), int(lens[r])
+            ok = self._lib.mdbg_host_pack_read(C.c_void_p(bases.ctypes.data + lo), ln, C.c_void_p(words.ctypes.data + 4 * int(woff[r])))
+            if ok:
+                src[r] = woff[r]
+            else:
+                src[r] = (1 << 63) | n_spill
+                spill.append(bases[lo:lo + ln])
+                n_spill += (ln + 15) & ~15
+                spill.append(np.zeros(((ln + 15) & ~15) - ln, np.uint8))
+        asc = np.concatenate(spill).astype(np.uint8) if spill else np.zeros(0, np.uint8)
+        return words, src, asc
+
+    def sketch_batch_packed(self, words: np.ndarray, read_src: np.ndarray, ascii_spill: np.ndarray, offsets: np.ndarray,
+                            append_to_store: bool = False, fetch: bool = True):
+        """mdbg_sketch_batch_packed: a host batch that was 2-bit packed by the caller."""
+        words = np.ascontiguousarray(words, dtype=np.uint32)
+        read_src = np.ascontiguousarray(read_src, dtype=np.uint64)
+        ascii_spill = np.ascontiguousarray(ascii_spill, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        out = SketchOut()
+        self._ck(self._lib.mdbg_sketch_batch_packed(self._ctx, words.ctypes.data, len(words), read_src.ctypes.data,
+                                                    ascii_spill.ctypes.data if len(ascii_spill) else None, len(ascii_spill),
+                                                    offsets.ctypes.data, len(offsets) - 1, int(append_to_store),
+                                                    C.byref(out) if fetch else None))
+        return self._copy_sketch(out) if fetch else None
+
+    def sketch_batch_packed_ptr(self, words_ptr: int, n_words: int, read_src: np.ndarray, offsets: np.ndarray,
+                                append_to_store: bool = True) -> int:
+        """Same from raw (pinned) host pointers, clean reads only; returns the number of minimizers (bench e2e leg)."""
+        read_src = np.ascontiguousarray(read_src, dtype=np.uint64)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        out = SketchOut()
+        self._ck(self._lib.mdbg_sketch_batch_packed(self._ctx, C.c_void_p(words_ptr), n_words, read_src.ctypes.data, None, 0,
+                                                    offsets.ctypes.data, len(offsets) - 1, int(append_to_store), C.byref(out)))
+        return int(out.n_minimizers)
 
     def set_host_packing(self, on: bool | int | None = True):
         """2-bit pack host batches before H2D: True / False / None = automatic (default) / 2 = hybrid (experimental)."""

@@ -224,3 +224,85 @@ def test_store_rewrite_ends_the_table(built):
     eng.count_add_store()
     assert len(eng.count_finalize(2).abundances) > 0
     eng.close()
+
+
+def test_host_batch_handed_over_packed(built, oracle, monkeypatch):
+    """mdbg_host_pack_read + mdbg_sketch_batch_packed: a reader that packs while parsing hands over 2-bit words (dirty
+    reads in an ASCII spill); same CSR as the ASCII entry point, in many pieces and in one; bad layouts are refused."""
+    from metamdbg_b200.engine import MdbgError
+    bases, offs = _edge_case_reads(np.random.default_rng(21))
+    want = oracle.sketch_batch(bases, offs, 15, 0.005, True)
+    eng = engine(15, 0.005, True)
+    words, src, asc = eng.host_pack_reads(bases, offs)
+    assert (src >> np.uint64(63)).sum() >= 5 and len(asc) > 0          # the dirty reads travel as ASCII
+    for piece_bytes in ("50000", None):
+        if piece_bytes:
+            monkeypatch.setenv("MDBG_PIECE_BYTES", piece_bytes)
+        else:
+            monkeypatch.delenv("MDBG_PIECE_BYTES")
+        sk = eng.sketch_batch_packed(words, src, asc, offs, append_to_store=True)
+        assert_sketch_equal(sk, *want, tag=f"packed host batch, piece bytes {piece_bytes}")
+    assert eng.store_size() == (2 * (len(offs) - 1), 2 * len(want[1]))
+    bad = src.copy()
+    clean = np.nonzero((src >> np.uint64(63)) == 0)[0]
+    bad[clean[3]], bad[clean[4]] = bad[clean[4]], bad[clean[3]]          # decreasing word offsets
+    with pytest.raises(MdbgError) as e:
+        eng.sketch_batch_packed(words, bad, asc, offs)
+    assert e.value.status == 2
+    eng.close()
+
+
+# ---------------------------------------------------------------- (f)3: FASTQ / FASTA text, record split on the device
+
+def _fastq_text(reads, crlf=False, quals=None):
+    eol = b"\r\n" if crlf else b"\n"
+    out = []
+    for i, s in enumerate(reads):
+        q = quals[i] if quals is not None else b"I" * len(s)
+        out.append(b"@read_%d some description" % i + eol + bytes(s) + eol + b"+" + eol + q + eol)
+    return b"".join(out)
+
+
+@pytest.mark.parametrize("hpc", [True, False])
+def test_fastx_text_ingest(built, oracle, hpc):
+    """mdbg_sketch_fastx: the sketch of raw FASTQ / FASTA text (records split on the device) equals the sketch of the
+    reads a host parser extracts from it -- '\\n' and '\\r\\n' line ends, '@' inside quality lines, dirty reads, empty
+    reads, a block cut in the middle of a record (consumed_bytes), a last line without newline."""
+    from metamdbg_b200.engine import MdbgError
+    bases, offs = _edge_case_reads(np.random.default_rng(31))
+    reads = [bases[int(offs[r]):int(offs[r + 1])].tobytes() for r in range(len(offs) - 1)]
+    want = oracle.sketch_batch(bases, offs, 15, 0.01, hpc)
+    rng = np.random.default_rng(8)
+    quals = [bytes(rng.integers(33, 75, len(s), dtype=np.uint8)) for s in reads]
+    quals[3] = b"@" * len(reads[3]); quals[7] = b"+" * len(reads[7])         # quality lines that look like headers
+    eng = engine(15, 0.01, hpc)
+    for crlf in (False, True):
+        text = _fastq_text(reads, crlf, quals)
+        sk, info = eng.sketch_fastx(text)
+        assert info == dict(n_records=len(reads), consumed_bytes=len(text), n_bases=int(offs[-1]), format="fastq")
+        assert_sketch_equal(sk, *want, tag=f"fastq crlf={crlf} hpc={hpc}")
+    # FASTA, 2-line, last line without a newline
+    fa = b"".join(b">r%d\n" % i + s + b"\n" for i, s in enumerate(reads))[:-1]
+    sk, info = eng.sketch_fastx(fa, is_final=True)
+    assert info["n_records"] == len(reads) and info["format"] == "fasta" and info["consumed_bytes"] == len(fa)
+    assert_sketch_equal(sk, *want, tag="fasta")
+    # a block that ends inside record 40: records 0..39 are sketched, the caller continues at consumed_bytes
+    text = _fastq_text(reads, False, quals)
+    cut = text.index(b"@read_40 ") + 25
+    sk, info = eng.sketch_fastx(text[:cut], is_final=False, append_to_store=True)
+    assert info["n_records"] == 40 and text[info["consumed_bytes"]:].startswith(b"@read_40 ")
+    sk2, info2 = eng.sketch_fastx(text[info["consumed_bytes"]:], is_final=True, append_to_store=True)
+    assert info2["n_records"] == len(reads) - 40
+    assert np.array_equal(np.concatenate([sk.minimizers, sk2.minimizers]), want[1])
+    assert np.array_equal(np.concatenate([sk.positions, sk2.positions]), want[2])
+    so, sm = eng.store_fetch()
+    assert np.array_equal(sm, want[1]) and np.array_equal(so, want[0])
+    # multi-line FASTA is not handled on the device: reported, the caller falls back to its host parser
+    with pytest.raises(MdbgError) as e:
+        eng.sketch_fastx(b">a\nACGT\nACGT\n>b\nAC\n")
+    assert e.value.status == 2
+    with pytest.raises(MdbgError):
+        eng.sketch_fastx(b"ACGT\n")
+    sk, info = eng.sketch_fastx(b"")
+    assert info["n_records"] == 0 and len(sk.minimizers) == 0
+    eng.close()
