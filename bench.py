@@ -546,6 +546,12 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             raise SystemExit(f"bench.py: occurrence conservation violated: {got_instances} != {expect_instances}")
         occ = int(got_instances)
 
+    # exclusive phase times of one more step (diagnostic, not part of any timed region)
+    eng.phase_profile(True)
+    step_device()
+    step_phases = eng.phase_times()
+    eng.phase_profile(False)
+
     # ---- extra: the same step with the reads resident as ASCII (device-side pack pass inside the step) ---------------
     ascii_leg = None
     if not args.no_ascii_leg and w["last_k"] == K:
@@ -568,14 +574,14 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             for _ in range(2):                              # 2nd = warm
                 barrier()
                 t0 = time.perf_counter()
-                ed = eng.edges_index(MIN_AB)
+                ed = eng.edges_index(MIN_AB, decode=False)
                 t_e.append(max_over_ranks(time.perf_counter() - t0))
             edges_extra = {"k": K, "n_nodes": sum_over_ranks(ed["n_nodes"]), "n_edges": sum_over_ranks(ed["n_edges"]),
                            "checksum": sum_u64_over_ranks(ed["checksum"]),
                            "ms": round(1e3 * t_e[1], 3), "d2h_bytes": ed["n_edges"] * 32,
                            "timer": "host wall clock around mdbg_edges_index incl. the D2H of keys and values, max over ranks"}
-            if ed["values"] is not None:
-                edges_extra["branching_keys"] = int((ed["values"][..., 0] == 2).any(axis=1).sum())
+            if ed.get("raw_values") is not None:
+                edges_extra["branching_keys"] = int((((ed["raw_values"] >> np.uint64(34)) & np.uint64(1)) == 1).any(axis=1).sum())
         except Exception as e:                                # noqa: BLE001
             edges_extra = {"error": repr(e)}
 
@@ -595,6 +601,12 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                        "n_entries_total": [sum_over_ranks(r["n_entries"]) for r in sweeps[1]],
                        "timer": "host wall clock per k around device work ending in a D2H of the table statistics, max over ranks",
                        "same_tables_both_sweeps": [r["checksum"] for r in sweeps[0]] == [r["checksum"] for r in sweeps[1]]}
+            # where the loop's time goes: one more sweep with the library's phase profile on (exclusive phase times, every
+            # phase boundary synchronises the stream -- a diagnostic, slower than the timed sweep above)
+            eng.phase_profile(True)
+            multi_k_sweep(eng, K, args.multi_k, MIN_AB, merge=world > 1, world=world)
+            multi_k["phase_ms_profiled_sweep_rank0"] = eng.phase_times()
+            eng.phase_profile(False)
         except Exception as e:                                # noqa: BLE001  -- an extra must not cost the headline line
             multi_k = {"error": repr(e)}
 
@@ -680,6 +692,49 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             print(f"bench.py: WARNING: {bad_steps} e2e step(s) produced a table that differs from the device-resident leg",
                   file=sys.stderr, flush=True)
         del h_bases
+        # extra: the same leg with a host batch that is ALREADY 2-bit packed (mdbg_sketch_batch_packed: what a reader
+        # that packs while it parses hands over) -- PCIe carries a quarter of the bytes and no library thread packs
+        try:
+            src_all = np.frombuffer(c0["src"].cpu().numpy().tobytes(), dtype=np.uint64)[:e_reads + 1 if e_reads < n_reads else e_reads]
+            n_w = int(eng.pack_device_words(int(rs_off[e_reads]), e_reads))
+            h_words = torch.empty(n_w * 4, dtype=torch.uint8, pin_memory=True)
+            h_words.copy_(c0["words"][:n_w * 4])
+            torch.cuda.synchronize()
+
+            def step_e2e_packed():
+                eng.store_clear()
+                for lo in range(0, e_reads, batch):
+                    hi = min(e_reads, lo + batch)
+                    offs = h_offs[lo:hi + 1] - h_offs[lo]
+                    w_lo = int(src_all[lo])
+                    w_hi = int(src_all[hi]) if hi < len(src_all) else n_w
+                    eng.sketch_batch_packed_ptr(h_words.data_ptr() + 4 * w_lo, w_hi - w_lo, src_all[lo:hi] - np.uint64(w_lo), offs, True)
+                if w["asm_density"]:
+                    eng.store_apply_density(w["asm_density"])
+                eng.purge_palindromes(4, lk)
+                eng.count_begin(K, 0)
+                eng.count_add_store()
+                if world > 1:
+                    eng.count_merge()
+                return eng.count_finalize(MIN_AB)
+
+            ok_p = [step_e2e_packed().checksum == checksum_local for _ in range(2)]
+            barrier()
+            moved0 = eng.bytes_moved()
+            t0 = time.perf_counter()
+            for _ in range(e_steps):
+                ok_p.append(step_e2e_packed().checksum == checksum_local)
+            barrier()
+            dtp = max_over_ranks(time.perf_counter() - t0)
+            moved1 = eng.bytes_moved()
+            e2e["packed_host_input"] = {"value": e_total * e_steps / dtp / 1e9, "unit": "Gbp/s",
+                                        "h2d_bytes_per_step": int((moved1[0] - moved0[0]) // e_steps),
+                                        "d2h_bytes_per_step": int((moved1[1] - moved0[1]) // e_steps),
+                                        "same_table_as_device_leg": (all(ok_p) if comparable else None),
+                                        "what": "mdbg_sketch_batch_packed on pinned 2-bit words (16-byte aligned reads), otherwise the same leg"}
+            del h_words
+        except Exception as e:                                # noqa: BLE001
+            e2e["packed_host_input"] = {"error": repr(e)}
 
     # ---- CPU baseline (rank 0, N=1 only) + parity spot check against it ------------------------
     cpu_baseline = None
@@ -785,6 +840,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                          "binding_pipes_ncu": ncu_pipes, "int_issue": int_issue,
                          "share_of_step": sk_ms / (ms_total / args.steps)},
             "kernels_ms": {"sketch": sk_ms, "insert": float(np.mean(insert_ms))},
+            "table_phase_ms_profiled_step_rank0": step_phases,
             "ascii_resident": ascii_leg, "multi_k": multi_k, "edges": edges_extra, "extras": extras,
             "sketch_autotune": dict(tune, active=active_variant,
                                     note="ms = sketch (+ pack pass for variant 2) + scan + compaction of an ASCII-resident batch, "

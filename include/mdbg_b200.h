@@ -126,6 +126,14 @@ mdbg_status mdbg_ctx_bytes_moved(mdbg_ctx* ctx, uint64_t* h2d_bytes, uint64_t* d
 mdbg_status mdbg_ctx_enable_timing(mdbg_ctx* ctx, int on);
 mdbg_status mdbg_ctx_kernel_time_ms(mdbg_ctx* ctx, int which, float* ms);
 
+/* Per-phase wall-clock profile of the table and collective paths (merge: pack / plan / exchange / insert; previous-k
+ * replication; insert or next-k pass; statistics; emit; table reset).  While it is on, every phase boundary
+ * synchronises the stream: the figures are exclusive phase times in ms, accumulated since the profile was switched
+ * on, and the calls are slower -- a diagnostic, not for timed runs.  mdbg_ctx_phase_times returns the number of
+ * phases written (names are static strings). */
+mdbg_status mdbg_ctx_phase_profile(mdbg_ctx* ctx, int on);
+int         mdbg_ctx_phase_times(mdbg_ctx* ctx, double* ms_out, const char** names_out, int max_n);
+
 /* ---- sketch (rows A1-A3 of SURVEY.md section 8a) -------------------------- */
 /* Host reads: read r = bases[offsets[r] .. offsets[r+1]) (ASCII, as Read::_seq).
  * The batch is copied to the device, sketched, the CSR is copied back into

@@ -140,6 +140,8 @@ struct mdbg_ctx {
     bool t_autogrow = true;            // MDBG_TABLE_AUTOGROW=0: report MDBG_ERR_TABLE_FULL instead of rebuilding (tests)
     uint64_t t_claim_limit = 0;
     double distinct_ratio = 0.0;
+    bool phase_prof = false;
+    double phase_ms[16] = {};
     uint64_t store_gen = 0, rem_gen = ~0ull;   // s_rem (minimizers left in the read) is valid for this store generation
     uint32_t prev_min_count = 0;       // lookup-time filter of the previous-k table (see mdbg_prev_from_current)
     DevBuf foreign_vecs;
@@ -159,6 +161,20 @@ struct mdbg_ctx {
 
 namespace {
 
+// Optional per-phase wall-clock profile of the table / collective paths (mdbg_ctx_phase_profile): when enabled, every
+// phase boundary synchronises the stream, so the figures are exclusive phase times (and the run is slower).
+enum Phase { PH_MERGE_PACK_COUNT, PH_MERGE_PLAN, PH_MERGE_PACK_SCATTER, PH_MERGE_EXCHANGE, PH_MERGE_INSERT,
+             PH_PREV_EMIT, PH_PREV_PLAN, PH_PREV_EXCHANGE, PH_PREV_INSERT, PH_PASS, PH_STATS, PH_EMIT, PH_TABLE_RESET, PH_N };
+const char* const kPhaseNames[PH_N] = {"merge.pack_count", "merge.plan_allgather", "merge.pack_scatter", "merge.exchange",
+                                       "merge.insert", "prev.stats_emit", "prev.plan_allgather", "prev.exchange",
+                                       "prev.insert", "pass.insert_or_next_k", "table.stats", "table.emit", "table.reset"};
+struct PhaseClock {
+    mdbg_ctx* c;
+    std::chrono::steady_clock::time_point t0;
+    explicit PhaseClock(mdbg_ctx* ctx);
+    void lap(Phase p);
+};
+
 mdbg_status fail(mdbg_ctx* c, mdbg_status st, const char* fmt, ...) {
     char buf[512];
     va_list ap;
@@ -167,6 +183,17 @@ mdbg_status fail(mdbg_ctx* c, mdbg_status st, const char* fmt, ...) {
     va_end(ap);
     if (c) c->error = buf; else g_create_error = buf;
     return st;
+}
+
+PhaseClock::PhaseClock(mdbg_ctx* ctx) : c(ctx) {
+    if (c->phase_prof) { cudaStreamSynchronize(c->stream); t0 = std::chrono::steady_clock::now(); }
+}
+void PhaseClock::lap(Phase p) {
+    if (!c->phase_prof) return;
+    cudaStreamSynchronize(c->stream);
+    const auto t1 = std::chrono::steady_clock::now();
+    c->phase_ms[p] += std::chrono::duration<double, std::milli>(t1 - t0).count();
+    t0 = t1;
 }
 
 #define CK(call)                                                                                   \
@@ -860,6 +887,23 @@ mdbg_status mdbg_ctx_bytes_moved(mdbg_ctx* ctx, uint64_t* h2d_bytes, uint64_t* d
     if (h2d_bytes) *h2d_bytes = ctx->h2d_bytes;
     if (d2h_bytes) *d2h_bytes = ctx->d2h_bytes;
     return MDBG_OK;
+}
+
+mdbg_status mdbg_ctx_phase_profile(mdbg_ctx* ctx, int on) {
+    if (!ctx) return MDBG_ERR_ARG;
+    ctx->phase_prof = on != 0;
+    for (double& v : ctx->phase_ms) v = 0;
+    return MDBG_OK;
+}
+
+int mdbg_ctx_phase_times(mdbg_ctx* ctx, double* ms_out, const char** names_out, int max_n) {
+    if (!ctx) return 0;
+    int n = 0;
+    for (; n < PH_N && n < max_n; n++) {
+        if (ms_out) ms_out[n] = ctx->phase_ms[n];
+        if (names_out) names_out[n] = kPhaseNames[n];
+    }
+    return n;
 }
 
 mdbg_status mdbg_ctx_enable_timing(mdbg_ctx* ctx, int on) {
@@ -1875,12 +1919,14 @@ static uint64_t table_capacity_for(uint64_t expect) {
 }
 
 static mdbg_status table_reset(mdbg_ctx* ctx, uint64_t cap) {
+    PhaseClock clk(ctx);
     CKS(ensure(ctx, ctx->table, cap * sizeof(Slot)));
     CK(cudaMemsetAsync(ctx->table.p, 0, cap * sizeof(Slot), ctx->stream));
     CK(cudaMemsetAsync(&ctx->d_small->full_flag, 0, sizeof(uint32_t), ctx->stream));
     CK(cudaMemsetAsync(&ctx->d_small->t_claims, 0, sizeof(unsigned long long), ctx->stream));
     ctx->t_capacity = cap;
     ctx->t_claim_limit = cap - cap / 5;
+    clk.lap(PH_TABLE_RESET);
     return MDBG_OK;
 }
 
@@ -1971,6 +2017,7 @@ static mdbg_status count_pass(mdbg_ctx* ctx, uint64_t read_lo, uint64_t read_hi,
     CKS(ensure_rem(ctx));
     uint64_t g_lo, g_hi;
     CKS(flat_range(ctx, read_lo, read_hi, &g_lo, &g_hi));
+    PhaseClock clk(ctx);
     CKS(launch_pass(ctx, g_lo, g_hi, next_k, true));
     for (int attempt = 0;; attempt++) {
         CK(cudaMemcpyAsync(&ctx->h_small->full_flag, &ctx->d_small->full_flag, 4, cudaMemcpyDeviceToHost, s));
@@ -1989,6 +2036,7 @@ static mdbg_status count_pass(mdbg_ctx* ctx, uint64_t read_lo, uint64_t read_hi,
         }
         CKS(launch_pass(ctx, g_lo, g_hi, next_k, true));
     }
+    clk.lap(PH_PASS);
     ctx->t_ranges.push_back(mdbg_ctx::Range{read_lo, read_hi});
     if (!next_k && ctx->s_mins) ctx->distinct_ratio = (double)ctx->h_small->t_claims / (double)ctx->s_mins;
     return MDBG_OK;
@@ -2014,11 +2062,13 @@ mdbg_status mdbg_count_add(mdbg_ctx* ctx, const uint32_t* minimizers, const uint
 
 static mdbg_status table_stats(mdbg_ctx* ctx, uint32_t thr, TableStats* st) {
     cudaStream_t s = ctx->stream;
+    PhaseClock clk(ctx);
     launch_table_stats(ctx->table.as<Slot>(), ctx->t_capacity, thr, &ctx->d_small->stats, s);
     CKS(check_launch(ctx, "table_stats_kernel", 1));
     CK(cudaMemcpyAsync(&ctx->h_small->stats, &ctx->d_small->stats, sizeof(TableStats), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     *st = ctx->h_small->stats;
+    clk.lap(PH_STATS);
     return MDBG_OK;
 }
 
@@ -2067,8 +2117,10 @@ static mdbg_status emit_table(mdbg_ctx* ctx, uint32_t thr, TableStats* st_out) {
     e.out_abund = ctx->o_abund.as<uint32_t>();
     e.out_vecs = ctx->o_vecs.as<uint32_t>();
     e.cursor = &ctx->d_small->emit_cursor;
+    PhaseClock clk(ctx);
     launch_table_emit(e, s);
     CKS(check_launch(ctx, "table_emit_kernel", 1));
+    clk.lap(PH_EMIT);
     *st_out = st;
     return MDBG_OK;
 }
@@ -2267,6 +2319,7 @@ static mdbg_status prev_from_current_all_ranks(mdbg_ctx* ctx, uint32_t thr) {
         return fail(ctx, MDBG_ERR_STATE, "multi-rank mdbg_prev_from_current needs the merged table: call mdbg_count_merge first");
     cudaStream_t s = ctx->stream;
     const uint32_t R = (uint32_t)ctx->n_ranks;
+    PhaseClock clk(ctx);
     TableStats st;
     CKS(table_stats(ctx, thr, &st));
     const uint64_t n_local = st.n_entries;
@@ -2286,6 +2339,7 @@ static mdbg_status prev_from_current_all_ranks(mdbg_ctx* ctx, uint32_t thr) {
     e.cursor = &ctx->d_small->emit_cursor;
     launch_table_emit(e, s);
     CKS(check_launch(ctx, "table_emit_kernel", 1));
+    clk.lap(PH_PREV_EMIT);
     // every rank's pair count
     CKS(ensure(ctx, ctx->m_bucket, (size_t)(2 * R + R * R) * 8));
     uint64_t* d_mine = ctx->m_bucket.as<uint64_t>();
@@ -2302,6 +2356,7 @@ static mdbg_status prev_from_current_all_ranks(mdbg_ctx* ctx, uint32_t thr) {
     CKS(ensure(ctx, ctx->prev_stage_a, (total + 1) * 4));
     uint64_t* g_hash = ctx->prev_stage_h.as<uint64_t>();
     uint32_t* g_abund = ctx->prev_stage_a.as<uint32_t>();
+    clk.lap(PH_PREV_PLAN);
     NK(g_nccl.GroupStart());
     for (uint32_t d = 0; d < R; d++) {
         if ((int)d == ctx->rank) continue;
@@ -2319,6 +2374,7 @@ static mdbg_status prev_from_current_all_ranks(mdbg_ctx* ctx, uint32_t thr) {
         CK(cudaMemcpyAsync(g_hash + 2 * base[ctx->rank], ctx->o_hash.p, n_local * 16, cudaMemcpyDeviceToDevice, s));
         CK(cudaMemcpyAsync(g_abund + base[ctx->rank], ctx->o_abund.p, n_local * 4, cudaMemcpyDeviceToDevice, s));
     }
+    clk.lap(PH_PREV_EXCHANGE);
     CKS(prev_alloc(ctx, total));
     if (total) {
         PrevLoadArgs a{};
@@ -2331,7 +2387,9 @@ static mdbg_status prev_from_current_all_ranks(mdbg_ctx* ctx, uint32_t thr) {
         launch_prev_load(a, s);
         CKS(check_launch(ctx, "prev_load_kernel", 1));
     }
-    return check_full(ctx, "mdbg_prev_from_current (all ranks)");
+    const mdbg_status st_full = check_full(ctx, "mdbg_prev_from_current (all ranks)");
+    clk.lap(PH_PREV_INSERT);
+    return st_full;
 }
 
 mdbg_status mdbg_prev_from_current(mdbg_ctx* ctx, uint32_t min_abundance) {
@@ -2600,6 +2658,7 @@ mdbg_status mdbg_count_merge(mdbg_ctx* ctx) {
     uint64_t* d_base = d_cnt + R;
     uint64_t* d_all = d_cnt + 2 * R;
     CK(cudaMemsetAsync(d_cnt, 0, R * 8, s));
+    PhaseClock clk(ctx);
     PackArgs p{};
     p.table = ctx->table.as<Slot>();
     p.capacity = ctx->t_capacity;
@@ -2611,6 +2670,7 @@ mdbg_status mdbg_count_merge(mdbg_ctx* ctx) {
     p.pass = 1;
     launch_table_pack(p, s);
     CKS(check_launch(ctx, "table_pack_kernel(count)", 1));
+    clk.lap(PH_MERGE_PACK_COUNT);
     NK(g_nccl.AllGather(d_cnt, d_all, R, NCCL_UINT64, ctx->nccl_comm, s));
     std::vector<uint64_t> all((size_t)R * R);
     CK(cudaMemcpyAsync(all.data(), d_all, (size_t)R * R * 8, cudaMemcpyDeviceToHost, s));
@@ -2629,6 +2689,7 @@ mdbg_status mdbg_count_merge(mdbg_ctx* ctx) {
     CKS(ensure(ctx, ctx->m_send_counts, (send_total + 1) * 4));
     CKS(ensure(ctx, ctx->m_recv_vecs, (recv_total + 1) * 4 * k));
     CKS(ensure(ctx, ctx->m_recv_counts, (recv_total + 1) * 4));
+    clk.lap(PH_MERGE_PLAN);
     CK(cudaMemcpyAsync(d_base, send_base.data(), R * 8, cudaMemcpyHostToDevice, s));
     CK(cudaMemsetAsync(d_cnt, 0, R * 8, s));
     p.bucket_base = d_base;
@@ -2637,6 +2698,7 @@ mdbg_status mdbg_count_merge(mdbg_ctx* ctx) {
     p.pass = 2;
     launch_table_pack(p, s);
     CKS(check_launch(ctx, "table_pack_kernel(scatter)", 1));
+    clk.lap(PH_MERGE_PACK_SCATTER);
     // one grouped all-to-all over NVLink: vectors and counts
     NK(g_nccl.GroupStart());
     for (uint32_t d = 0; d < R; d++) {
@@ -2654,8 +2716,9 @@ mdbg_status mdbg_count_merge(mdbg_ctx* ctx) {
         }
     }
     NK(g_nccl.GroupEnd());
-    // rebuild the table with only the keys this rank owns
-    const uint64_t cap = pow2ceil((recv_total < 512 ? 512 : recv_total) * 2);
+    clk.lap(PH_MERGE_EXCHANGE);
+    // rebuild the table with only the keys this rank owns (recv_total bounds its distinct keys)
+    const uint64_t cap = table_capacity_for(recv_total);
     std::swap(ctx->foreign_vecs, ctx->m_recv_vecs);       // received vectors become the table's vector store
     ctx->foreign_n = recv_total;
     CKS(ensure(ctx, ctx->table, cap * sizeof(Slot)));
@@ -2676,7 +2739,11 @@ mdbg_status mdbg_count_merge(mdbg_ctx* ctx) {
     CK(cudaMemcpyAsync(&ctx->h_small->full_flag, &ctx->d_small->full_flag, 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     if (ctx->h_small->full_flag) return fail(ctx, MDBG_ERR_TABLE_FULL, "merged table full");
+    clk.lap(PH_MERGE_INSERT);
     ctx->t_merged = true;
+    ctx->t_rebuildable = false;            // the table now holds foreign vectors: it cannot be rebuilt from the store
+    ctx->t_ranges.clear();
+    ctx->t_claim_limit = cap;
     return MDBG_OK;
 }
 

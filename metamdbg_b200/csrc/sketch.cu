@@ -796,6 +796,16 @@ int launch_sketch(const SketchArgs& a, int sm_count, cudaStream_t s) {
 // ------------------------------------------------------------------ ASCII -> 2-bit device layout (variant 2's input)
 // One warp per read, 16 bases -> one u32 per lane and step.  HBM-streaming: 1 B/bp in, 0.25 B/bp out.  A read holding
 // any byte outside "ACGT" (N, IUPAC, lower case, '#') is left to the byte-ring kernel: read_src = SRC_ASCII | offset.
+// 4 ASCII bytes -> their four 2-bit codes in byte 3 of the result (pack4_lsb before the shift), and in `diff` a
+// non-zero byte for every input byte that is not one of A, C, G, T.  Exact: with y = x ^ 'A' the four letters are
+// 00, 02, 06, 15 (hex), i.e. everything outside the two code bits must be 0x00 -- or 0x11 exactly for T (code 2).
+__device__ __forceinline__ uint32_t pack4_checked(uint32_t x, uint32_t& diff) {
+    const uint32_t s1 = x >> 1, s2 = x >> 2;
+    const uint32_t t = s2 & ~s1 & 0x01010101u;                          // 1 where the code is 2 (T)
+    diff |= ((x & 0xF9F9F9F9u) ^ (t * 0x11u)) ^ 0x41414141u;
+    return (s1 & 0x03030303u) * 0x01041040u;                            // codes of bytes 0..3 in bits 24..31
+}
+
 __global__ void __launch_bounds__(256) pack_ascii_kernel(const PackArgsAscii a) {
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -808,47 +818,46 @@ __global__ void __launch_bounds__(256) pack_ascii_kernel(const PackArgsAscii a) 
         const uint8_t* base = a.bases + byte0;
         const uint32_t skip = (uint32_t)((uintptr_t)base & 15);
         const uint8_t* abase = base - skip;                       // 16-byte aligned
-        const uint32_t sh8 = 8 * (skip & 3), k = skip >> 2;       // warp-uniform realignment
+        // aligned 16-byte units of the text: unit m = bytes [16 m, 16 m + 16) of abase; the read is [skip, skip + len).
+        // Every lane packs ONE aligned unit (coalesced 16-byte loads); output word j = bases [16 j, 16 j + 16) of the
+        // read straddles units j and j + 1, so it is one funnel shift of the lane's word and its neighbour's: a warp
+        // step loads 32 units and writes 31 words.
+        const uint32_t x_end = skip + len, n_out = (len + 15) >> 4;
         uint32_t bad = 0;
-        for (uint32_t j0 = 0; j0 < len; j0 += 512) {
-            const uint32_t j = j0 + lane * 16;                    // my 16 bases start at read index j
-            if (j < len) {
-                // two aligned 16-byte loads cover bases [j, j + 16) at any alignment
-                const uint8_t* p = abase + j;
-                uint32_t q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                if (p + 32 <= a.bases_end) {
-                    const uint4 u0 = *reinterpret_cast<const uint4*>(p), u1 = *reinterpret_cast<const uint4*>(p + 16);
-                    q[0] = u0.x; q[1] = u0.y; q[2] = u0.z; q[3] = u0.w; q[4] = u1.x; q[5] = u1.y; q[6] = u1.z; q[7] = u1.w;
+        for (uint32_t m0 = 0; m0 < n_out; m0 += 31) {
+            const uint32_t m = m0 + lane;
+            uint32_t word = 0, diff = 0;
+            if (16 * m < x_end) {
+                const uint8_t* p = abase + 16 * (uint64_t)m;
+                uint4 u = make_uint4(0, 0, 0, 0);
+                if (p + 16 <= a.bases_end) {
+                    u = *reinterpret_cast<const uint4*>(p);
                 } else {
-                    for (int t = 0; t < 32; t++)
-                        if (p + t < a.bases_end) q[t >> 2] |= (uint32_t)p[t] << (8 * (t & 3));
+                    uint32_t t[4] = {0, 0, 0, 0};
+                    for (int j = 0; j < 16; j++)
+                        if (p + j < a.bases_end) t[j >> 2] |= (uint32_t)p[j] << (8 * (j & 3));
+                    u = make_uint4(t[0], t[1], t[2], t[3]);
                 }
-                uint32_t x[4];
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const uint32_t lo = k == 0 ? q[i] : k == 1 ? q[i + 1] : k == 2 ? q[i + 2] : q[i + 3];
-                    const uint32_t hi = k == 0 ? q[i + 1] : k == 1 ? q[i + 2] : k == 2 ? q[i + 3] : q[i + 4];
-                    x[i] = __funnelshift_r(lo, hi, sh8);
+                const uint32_t lo = m == 0 ? skip : 0u, hi = min(16u, x_end - 16 * m);
+                if (lo == 0 && hi == 16) {
+                    const uint32_t c0 = pack4_checked(u.x, diff), c1 = pack4_checked(u.y, diff);
+                    const uint32_t c2 = pack4_checked(u.z, diff), c3 = pack4_checked(u.w, diff);
+                    word = __byte_perm(__byte_perm(c0, c1, 0x0073), __byte_perm(c2, c3, 0x0073), 0x5410);
+                } else {                                          // first / last unit: only bytes [lo, hi) are the read's
+                    uint32_t d[4] = {0, 0, 0, 0};
+                    const uint32_t c0 = pack4_checked(u.x, d[0]), c1 = pack4_checked(u.y, d[1]);
+                    const uint32_t c2 = pack4_checked(u.z, d[2]), c3 = pack4_checked(u.w, d[3]);
+                    word = __byte_perm(__byte_perm(c0, c1, 0x0073), __byte_perm(c2, c3, 0x0073), 0x5410);
+                    for (uint32_t j = 0; j < 16; j++)
+                        if (j >= lo && j < hi) diff |= (d[j >> 2] >> (8 * (j & 3))) & 0xFFu;
                 }
-                const uint32_t nvalid = min(16u, len - j);
-                uint32_t word = 0;
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    // exact "is one of A C G T": rebuild the byte from its two code bits and compare
-                    const uint32_t c0 = (x[i] >> 1) & 0x01010101u, c1 = (x[i] >> 2) & 0x01010101u;
-                    const uint32_t g = c1 & c0, t = c1 ^ g;
-                    const uint32_t expect = 0x41414141u ^ (c0 << 1) ^ (g << 2) ^ (t * 0x15u);
-                    uint32_t diff = x[i] ^ expect;
-                    uint32_t codes = (x[i] >> 1) & 0x03030303u;
-                    const int nb = (int)nvalid - 4 * i;                  // valid bytes of this word
-                    if (nb < 4) {
-                        const uint32_t m = nb <= 0 ? 0u : (1u << (8 * nb)) - 1u;
-                        diff &= m; codes &= m;
-                    }
-                    bad |= diff;
-                    word |= pack4_lsb(codes) << (8 * i);
-                }
-                a.packed[w_off + (j >> 4)] = word;
+            }
+            bad |= diff;
+            const uint32_t next = __shfl_down_sync(0xffffffffu, word, 1);
+            if (lane < 31 && m < n_out) {
+                uint32_t out = skip ? __funnelshift_r(word, next, 2 * skip) : word;
+                if (m == n_out - 1 && (len & 15u)) out &= (1u << (2 * (len & 15u))) - 1u;   // unused bits of the last word: zero
+                a.packed[w_off + m] = out;
             }
         }
         const bool dirty = __any_sync(0xffffffffu, bad != 0);

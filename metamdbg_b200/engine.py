@@ -111,6 +111,16 @@ class Engine:
         self._ck(self._lib.mdbg_ctx_bytes_moved(self._ctx, C.byref(a), C.byref(b)))
         return int(a.value), int(b.value)
 
+    def phase_profile(self, on: bool = True):
+        """Exclusive per-phase times of the table / collective paths (diagnostic: adds stream synchronisations)."""
+        self._ck(self._lib.mdbg_ctx_phase_profile(self._ctx, int(on)))
+
+    def phase_times(self) -> dict:
+        ms = (C.c_double * 16)()
+        names = (C.c_char_p * 16)()
+        n = self._lib.mdbg_ctx_phase_times(self._ctx, ms, names, 16)
+        return {names[i].decode(): round(float(ms[i]), 3) for i in range(n) if ms[i] > 0}
+
     def enable_timing(self, on: bool = True):
         self._ck(self._lib.mdbg_ctx_enable_timing(self._ctx, int(on)))
 
@@ -401,7 +411,7 @@ class Engine:
         self._ck(self._lib.mdbg_count_add_store_next_k(self._ctx, read_lo, read_hi))
 
     # -- edge keys (CreateMdbg::EdgeIndexer, src/graph/CreateMdbg.hpp:4010-4232) ------
-    def edges_index(self, min_abundance: int = 2) -> dict:
+    def edges_index(self, min_abundance: int = 2, decode: bool = True) -> dict:
         """Distinct hash128 of the normalized (k-1)-prefix / suffix of every node of the current table.
         -> dict(hashes uint64 [n,2] (low64, high64), n_edges, n_nodes, checksum)."""
         out = EdgesOut()
@@ -409,6 +419,9 @@ class Engine:
         n = int(out.n_edges)
         h = np.ctypeslib.as_array(out.hashes, shape=(2 * n,)).reshape(n, 2).copy() if n else np.zeros((0, 2), np.uint64)
         vals = None
+        if out.values and not decode:       # raw class words (bit 63 valid, bit 34 multi, bit 33 isPrefix, bit 32 isReversed)
+            vals = np.ctypeslib.as_array(out.values, shape=(2 * n,)).reshape(n, 2) if n else np.zeros((0, 2), np.uint64)
+            return dict(hashes=h, n_edges=n, n_nodes=int(out.n_nodes), checksum=int(out.checksum), values=None, raw_values=vals)
         if out.values:                      # single context: order-free edge values, two orientation classes per key
             w = np.ctypeslib.as_array(out.values, shape=(2 * n,)).reshape(n, 2).copy() if n else np.zeros((0, 2), np.uint64)
             valid, multi = (w >> np.uint64(63)) & np.uint64(1), (w >> np.uint64(34)) & np.uint64(1)

@@ -320,6 +320,12 @@ static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned s) {
     return (unsigned)((((uint64_t)hi << 32) | lo) >> (s & 31));
 }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
+static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {     // selector nibbles 0..7 only (no sign replication)
+    const uint64_t v = ((uint64_t)y << 32) | x;
+    unsigned r = 0;
+    for (int i = 0; i < 4; i++) r |= (unsigned)((v >> (8 * ((s >> (4 * i)) & 7))) & 0xFF) << (8 * i);
+    return r;
+}
 static inline unsigned __fns(unsigned mask, unsigned base, int offset) {     // n-th set bit at/after base (offset > 0 only)
     if (offset <= 0) emu::die("__fns: only positive offsets are emulated");
     for (unsigned b = base; b < 32; b++)
