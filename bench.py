@@ -494,7 +494,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     c0 = dr.chunks[0]
     # engine set-up, outside every timed region: every sketch-kernel variant on this rank's first chunk (ASCII), complete
     # outputs compared on the device; reported, and a variant that differs from variant 0 ends the run
-    tune = eng.autotune_sketch(c0["bases"].data_ptr(), c0["off"].data_ptr(), c0["n"], c0["n_bases"])
+    if args.no_autotune:
+        tune = {"chosen": 2, "identical": [True], "ms": [], "skipped": True}
+    else:
+        tune = eng.autotune_sketch(c0["bases"].data_ptr(), c0["off"].data_ptr(), c0["n"], c0["n_bases"])
     if not all(tune["identical"]):
         raise SystemExit(f"bench.py: a sketch kernel variant does not reproduce variant 0 on this device: {tune}")
     eng.set_sketch_variant(args.sketch_variant if args.sketch_variant >= 0 else 2)
@@ -990,6 +993,7 @@ def main():
     ap.add_argument("--parity-read-len", type=int, default=6_000)
     ap.add_argument("--sketch-variant", type=int, default=-1, help="force a sketch-kernel variant (-1 = the default, 2)")
     ap.add_argument("--multi-k", type=int, default=21, help="multi-k loops run up to this k (0 = off)")
+    ap.add_argument("--no-autotune", action="store_true", help="skip the variant comparison of the sketch kernel (profiling runs)")
     ap.add_argument("--no-edges", action="store_true", help="skip the edge-key extra")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-ascii-leg", action="store_true")

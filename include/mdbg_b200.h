@@ -294,6 +294,26 @@ mdbg_status mdbg_purge_palindromes(mdbg_ctx* ctx, uint32_t first_k, uint32_t las
  * density (0.025) are parsed at the assembly density (0.005), src/Commons.hpp:7457. */
 mdbg_status mdbg_store_apply_density(mdbg_ctx* ctx, float density, uint64_t* n_reads_changed);
 
+/* ---- repetitive minimizers (ONT path; ReadSelection::determineRepetitiveMinimizers + CountMinimizerFunctor,
+ * src/readSelection/ReadSelection.hpp:497-625) ------------------------------------------------------------
+ * Counts every minimizer of the stored reads (upstream: the first 1 M reads sketched at the correction density with
+ * an empty blacklist) and returns the max(1, int(fraction * #distinct)) most frequent values with their counts,
+ * most frequent first -- the contents of repetitiveMinimizers.bin (fraction = 0.00001f upstream).  Upstream's choice
+ * among values of EQUAL count at the cut-off depends on the iteration order of an unordered_map; here the smaller
+ * value wins, and n_with_min_count / n_with_min_count_selected say whether the cut-off fell inside a tie.
+ * mdbg_ctx_set_blacklist installs such a list as the blacklist of all later sketches (copied; NULL / 0 clears it). */
+typedef struct {
+    uint64_t n_distinct;                 /* distinct minimizer values in the store */
+    uint64_t n_selected;
+    const uint32_t* minimizers;          /* [n_selected] host, library-owned, valid until the next call */
+    const uint32_t* counts;              /* [n_selected] */
+    uint32_t min_count_selected;         /* count of the last selected value */
+    uint64_t n_with_min_count;           /* values having exactly that count ... */
+    uint64_t n_with_min_count_selected;  /* ... and how many of them were selected */
+} mdbg_repeats_out;
+mdbg_status mdbg_store_repetitive_minimizers(mdbg_ctx* ctx, float fraction, mdbg_repeats_out* out);
+mdbg_status mdbg_ctx_set_blacklist(mdbg_ctx* ctx, const uint32_t* values, uint64_t n);
+
 /* ---- k-min-mer count table (rows A5-A7) ----------------------------------- */
 /* expected_distinct = 0 sizes the table from the store (upper bound: one slot
  * pair per k-min-mer occurrence). */

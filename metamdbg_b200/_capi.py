@@ -48,6 +48,11 @@ class FastxInfo(C.Structure):
     _fields_ = [("n_records", C.c_uint64), ("consumed_bytes", C.c_uint64), ("n_bases", C.c_uint64), ("format", C.c_int32)]
 
 
+class RepeatsOut(C.Structure):
+    _fields_ = [("n_distinct", C.c_uint64), ("n_selected", C.c_uint64), ("minimizers", u32p), ("counts", u32p),
+                ("min_count_selected", C.c_uint32), ("n_with_min_count", C.c_uint64), ("n_with_min_count_selected", C.c_uint64)]
+
+
 class AuxOut(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("mean_quality", C.POINTER(C.c_float)), ("complexity", C.POINTER(C.c_double)),
                 ("low_complexity", u8p), ("qualities", u8p)]
@@ -112,6 +117,8 @@ SYMBOLS = {
     "mdbg_store_fetch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "mdbg_store_apply_density": (C.c_int, [C.c_void_p, C.c_float, u64p]),
     "mdbg_purge_palindromes": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, u64p]),
+    "mdbg_store_repetitive_minimizers": (C.c_int, [C.c_void_p, C.c_float, C.POINTER(RepeatsOut)]),
+    "mdbg_ctx_set_blacklist": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "mdbg_count_begin": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64]),
     "mdbg_count_add_store": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64]),
     "mdbg_count_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),

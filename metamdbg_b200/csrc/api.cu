@@ -70,6 +70,8 @@ struct mdbg_ctx {
     int last_overflow_fallback = 0, last_packed = 0;
     int auto_pack_pause = 0;           // auto mode: batches still to send as ASCII after the packer proved too slow
     DevBuf d_pack, d_src, d_dirty;
+    DevBuf r_table, r_hist, r_out;                                // repetitive-minimizer histogram (K1b)
+    std::vector<uint32_t> r_sel_min, r_sel_cnt;
     DevBuf f_raw, f_cnt, f_off, f_nl, f_start, f_len, f_qstart;   // FASTQ / FASTA text ingest (mdbg_sketch_fastx)
     PinBuf h_pack, h_src, h_asc;
     cudaEvent_t sub_ev[MAX_SUB] = {};
@@ -144,6 +146,16 @@ struct mdbg_ctx {
     double phase_ms[16] = {};
     uint64_t store_gen = 0, rem_gen = ~0ull;   // s_rem (minimizers left in the read) is valid for this store generation
     uint32_t prev_min_count = 0;       // lookup-time filter of the previous-k table (see mdbg_prev_from_current)
+    // Per-position values of the last whole-store pass (kminmer.cu, next_k_stream_kernel): when the previous-k table is
+    // exactly that pass's table, the next pass needs no lookups -- and, with several ranks, no replicated table.
+    DevBuf val_a, val_b, prev_src;
+    bool val_valid = false;            // val_a holds the values of pass val_k over store generation val_gen
+    uint32_t val_k = 0;
+    uint64_t val_gen = 0;
+    bool t_whole = false;              // the current table = ONE pass over the whole store (nothing else inserted)
+    uint32_t prev_k = 0;               // k of the table that became the previous-k table
+    bool prev_pure = false;            // ... and it is that pass's table as it was (no host pairs loaded or patched in)
+    bool prev_replicated = true;       // several ranks: prev_table holds every rank's entries (false: only the owned ones)
     DevBuf foreign_vecs;
     uint64_t foreign_n = 0;
     DevBuf prev_table, prev_stage_h, prev_stage_a, rescue_table;
@@ -839,7 +851,7 @@ void mdbg_ctx_destroy(mdbg_ctx* c) {
     DevBuf* devs[] = {&c->d_blacklist, &c->d_bases, &c->d_offsets, &c->pad_min, &c->pad_pos, &c->pad_dir, &c->n_min,
                       &c->scan_scratch, &c->b_off, &c->b_min, &c->b_pos, &c->b_dir, &c->s_min, &c->s_off, &c->s_rem,
                       &c->p_flags, &c->p_keep, &c->p_cnt, &c->p_newoff, &c->p_newmin, &c->table, &c->foreign_vecs,
-                      &c->o_hash, &c->o_abund, &c->o_vecs, &c->d_pack, &c->d_src, &c->d_dirty, &c->f_raw, &c->f_cnt, &c->f_off, &c->f_nl, &c->f_start, &c->f_len, &c->f_qstart, &c->d_quals, &c->pad_qual, &c->pad_raw_a, &c->pad_raw_b, &c->b_qual, &c->x_sum_lo, &c->x_sum_hi, &c->x_lmin, &c->x_cplx, &c->x_low, &c->d_err_fixed, &c->d_err_tz, &c->prev_table, &c->prev_stage_h, &c->prev_stage_a, &c->rescue_table, &c->m_send_vecs, &c->m_send_counts, &c->m_recv_vecs,
+                      &c->o_hash, &c->o_abund, &c->o_vecs, &c->d_pack, &c->d_src, &c->d_dirty, &c->r_table, &c->r_hist, &c->r_out, &c->f_raw, &c->f_cnt, &c->f_off, &c->f_nl, &c->f_start, &c->f_len, &c->f_qstart, &c->d_quals, &c->pad_qual, &c->pad_raw_a, &c->pad_raw_b, &c->b_qual, &c->x_sum_lo, &c->x_sum_hi, &c->x_lmin, &c->x_cplx, &c->x_low, &c->d_err_fixed, &c->d_err_tz, &c->prev_table, &c->prev_stage_h, &c->prev_stage_a, &c->rescue_table, &c->val_a, &c->val_b, &c->prev_src, &c->m_send_vecs, &c->m_send_counts, &c->m_recv_vecs,
                       &c->m_recv_counts, &c->m_bucket, &c->loc_off, &c->edge_table, &c->edge_vals, &c->o_edge_vals};
     for (DevBuf* b : devs) release(*b);
     PinBuf* pins[] = {&c->h_off, &c->h_min, &c->h_pos, &c->h_dir, &c->ho_hash, &c->ho_abund, &c->ho_vecs, &c->hx_sum_lo, &c->hx_sum_hi, &c->hx_lmin, &c->hx_cplx, &c->hx_low, &c->hx_meanq, &c->h_qual, &c->h_pack, &c->h_src, &c->h_asc, &c->ho_edge_vals};
@@ -1911,6 +1923,96 @@ mdbg_status mdbg_store_apply_density(mdbg_ctx* ctx, float density, uint64_t* n_r
     return MDBG_OK;
 }
 
+// ---- repetitive minimizers (K1b) -------------------------------------------------------
+static mdbg_status check_full(mdbg_ctx* ctx, const char* what);
+
+mdbg_status mdbg_ctx_set_blacklist(mdbg_ctx* ctx, const uint32_t* values, uint64_t n) {
+    if (!ctx) return MDBG_ERR_ARG;
+    if (n && !values) return fail(ctx, MDBG_ERR_ARG, "null blacklist");
+    if (n > 0xFFFFFFFFull) return fail(ctx, MDBG_ERR_ARG, "blacklist too large");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<uint32_t> bl(values, values + n);
+    std::sort(bl.begin(), bl.end());
+    bl.erase(std::unique(bl.begin(), bl.end()), bl.end());
+    if (!bl.empty()) {
+        CKS(ensure(ctx, ctx->d_blacklist, bl.size() * 4));
+        CK(cudaMemcpy(ctx->d_blacklist.p, bl.data(), bl.size() * 4, cudaMemcpyHostToDevice));
+    }
+    ctx->n_blacklist = (uint32_t)bl.size();
+    return MDBG_OK;
+}
+
+mdbg_status mdbg_store_repetitive_minimizers(mdbg_ctx* ctx, float fraction, mdbg_repeats_out* out) {
+    if (!ctx || !out) return MDBG_ERR_ARG;
+    memset(out, 0, sizeof *out);
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const uint64_t n = ctx->s_mins;
+    if (n == 0) return MDBG_OK;
+    const uint64_t cap = pow2ceil(std::max<uint64_t>(1024, 2 * n));
+    constexpr uint32_t BINS = 65536;
+    CKS(ensure(ctx, ctx->r_table, cap * 8));
+    CKS(ensure(ctx, ctx->r_hist, (size_t)BINS * 8));
+    CK(cudaMemsetAsync(ctx->r_table.p, 0xFF, cap * 8, s));
+    CK(cudaMemsetAsync(ctx->r_hist.p, 0, (size_t)BINS * 8, s));
+    CK(cudaMemsetAsync(&ctx->d_small->n_changed, 0, 8, s));
+    CK(cudaMemsetAsync(&ctx->d_small->full_flag, 0, 4, s));
+    launch_mincount_insert(ctx->s_min.as<uint32_t>(), n, ctx->r_table.as<unsigned long long>(), cap - 1,
+                           &ctx->d_small->n_changed, &ctx->d_small->full_flag, s);
+    launch_mincount_hist(ctx->r_table.as<unsigned long long>(), cap, ctx->r_hist.as<unsigned long long>(), BINS, s);
+    CKS(check_launch(ctx, "mincount_insert_kernel + mincount_hist_kernel", 2));
+    std::vector<unsigned long long> hist(BINS);
+    CK(cudaMemcpyAsync(hist.data(), ctx->r_hist.p, (size_t)BINS * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&ctx->h_scalar[0], &ctx->d_small->n_changed, 8, cudaMemcpyDeviceToHost, s));
+    CKS(check_full(ctx, "mdbg_store_repetitive_minimizers"));
+    const uint64_t n_distinct = ctx->h_scalar[0];
+    // ReadSelection.hpp:524-525: int nb = fraction(float) * vec.size(); nb = max(nb, 1)
+    int nb = (int)(fraction * (float)n_distinct);
+    if (nb < 1) nb = 1;
+    uint64_t want = std::min<uint64_t>((uint64_t)nb, n_distinct);
+    // the smallest count still selected: largest T with #(count >= T) >= want
+    uint64_t ge = 0;
+    uint32_t T = 1;
+    for (uint32_t c = BINS - 1; c >= 1; c--) {
+        ge += hist[c];
+        if (ge >= want) { T = c; break; }
+    }
+    CKS(ensure(ctx, ctx->r_out, (ge + 1) * 8));
+    CK(cudaMemsetAsync(&ctx->d_small->emit_cursor, 0, 8, s));
+    launch_mincount_emit(ctx->r_table.as<unsigned long long>(), cap, T, ctx->r_out.as<unsigned long long>(),
+                         &ctx->d_small->emit_cursor, ge, s);
+    CKS(check_launch(ctx, "mincount_emit_kernel", 1));
+    std::vector<unsigned long long> cand(ge);
+    if (ge) CK(cudaMemcpyAsync(cand.data(), ctx->r_out.p, ge * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    ctx->d2h_bytes += ge * 8 + (uint64_t)BINS * 8;
+    // most frequent first; upstream's order among equal counts is whatever std::sort makes of an unordered_map's
+    // iteration order, here it is the smaller value first
+    std::sort(cand.begin(), cand.end(), [](unsigned long long a, unsigned long long b) {
+        const uint32_t ca = (uint32_t)a, cb = (uint32_t)b;
+        return ca != cb ? ca > cb : (a >> 32) < (b >> 32);
+    });
+    ctx->r_sel_min.resize(want);
+    ctx->r_sel_cnt.resize(want);
+    uint64_t ties_all = 0, ties_sel = 0;
+    const uint32_t c_last = want ? (uint32_t)cand[want - 1] : 0;
+    for (uint64_t i = 0; i < ge; i++) ties_all += (uint32_t)cand[i] == c_last;
+    for (uint64_t i = 0; i < want; i++) {
+        ctx->r_sel_min[i] = (uint32_t)(cand[i] >> 32);
+        ctx->r_sel_cnt[i] = (uint32_t)cand[i];
+        ties_sel += (uint32_t)cand[i] == c_last;
+    }
+    out->n_distinct = n_distinct;
+    out->n_selected = want;
+    out->minimizers = ctx->r_sel_min.data();
+    out->counts = ctx->r_sel_cnt.data();
+    out->min_count_selected = c_last;
+    out->n_with_min_count = ties_all;
+    out->n_with_min_count_selected = ties_sel;
+    return MDBG_OK;
+}
+
 // ---- count table --------------------------------------------------------------------
 // capacity for `expect` distinct keys at load factor <= 0.6, and the claim count at which a pass gives up (0.8)
 static uint64_t table_capacity_for(uint64_t expect) {
@@ -1949,6 +2051,7 @@ mdbg_status mdbg_count_begin(mdbg_ctx* ctx, uint32_t k, uint64_t expected_distin
     ctx->t_merged = false;
     ctx->t_ranges.clear();
     ctx->t_rebuildable = true;
+    ctx->t_whole = false;
     ctx->foreign_n = 0;
     return MDBG_OK;
 }
@@ -1975,7 +2078,8 @@ static mdbg_status flat_range(mdbg_ctx* ctx, uint64_t read_lo, uint64_t read_hi,
 }
 
 // one pass over a store range into the current table: occurrence counts (first pass) or next-k values
-static mdbg_status launch_pass(mdbg_ctx* ctx, uint64_t g_lo, uint64_t g_hi, bool next_k, bool timed) {
+static mdbg_status launch_pass(mdbg_ctx* ctx, uint64_t g_lo, uint64_t g_hi, bool next_k, bool timed,
+                               const uint32_t* val_in = nullptr, uint32_t* val_out = nullptr) {
     cudaStream_t s = ctx->stream;
     if (timed && ctx->timing) CK(cudaEventRecord(ctx->ev[1][0], s));
     if (!next_k) {
@@ -2004,6 +2108,8 @@ static mdbg_status launch_pass(mdbg_ctx* ctx, uint64_t g_lo, uint64_t g_hi, bool
         a.full_flag = &ctx->d_small->full_flag;
         a.claims = &ctx->d_small->t_claims;
         a.claim_limit = ctx->t_claim_limit;
+        a.val_in = val_in;
+        a.val_out = val_out;
         launch_next_k(a, s);
     }
     if (timed && ctx->timing) { CK(cudaEventRecord(ctx->ev[1][1], s)); ctx->ev_valid[1] = true; }
@@ -2012,13 +2118,34 @@ static mdbg_status launch_pass(mdbg_ctx* ctx, uint64_t g_lo, uint64_t g_hi, bool
 
 // Runs the pass for [read_lo, read_hi); when the table proves too small (probe limit or load limit hit -- the
 // kernels abandon the pass early) it is rebuilt 4x larger from every range inserted so far and the pass is redone.
+static mdbg_status replicate_into_prev(mdbg_ctx* ctx, const Slot* src, uint64_t src_cap, uint32_t thr);
+
 static mdbg_status count_pass(mdbg_ctx* ctx, uint64_t read_lo, uint64_t read_hi, bool next_k) {
     cudaStream_t s = ctx->stream;
     CKS(ensure_rem(ctx));
     uint64_t g_lo, g_hi;
     CKS(flat_range(ctx, read_lo, read_hi, &g_lo, &g_hi));
+    // a pass over the WHOLE store into a fresh table leaves per-position values for the next k (val_b), and can itself
+    // run without lookups when the previous-k table is nothing but the previous such pass's table
+    const bool whole = read_lo == 0 && read_hi == ctx->s_reads && ctx->t_ranges.empty() && ctx->foreign_n == 0;
+    const uint32_t* val_in = nullptr;
+    uint32_t* val_out = nullptr;
+    if (next_k) {
+        const bool stream = whole && ctx->val_valid && ctx->val_gen == ctx->store_gen && ctx->val_k + 1 == ctx->t_k &&
+                            ctx->prev_pure && ctx->prev_k + 1 == ctx->t_k && !getenv("MDBG_NO_STREAM_NEXT_K");
+        if (stream) val_in = ctx->val_a.as<uint32_t>();
+        else if (ctx->n_ranks > 1 && !ctx->prev_replicated) {
+            // the pass needs lookups in the COMPLETE previous-k table: collective exchange of the owned entries
+            std::swap(ctx->prev_table, ctx->prev_src);
+            CKS(replicate_into_prev(ctx, ctx->prev_src.as<Slot>(), ctx->prev_capacity, ctx->prev_min_count));
+        }
+        if (whole) {
+            CKS(ensure(ctx, ctx->val_b, (ctx->s_mins + 2) * 4));
+            val_out = ctx->val_b.as<uint32_t>();
+        }
+    }
     PhaseClock clk(ctx);
-    CKS(launch_pass(ctx, g_lo, g_hi, next_k, true));
+    CKS(launch_pass(ctx, g_lo, g_hi, next_k, true, val_in, val_out));
     for (int attempt = 0;; attempt++) {
         CK(cudaMemcpyAsync(&ctx->h_small->full_flag, &ctx->d_small->full_flag, 4, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(&ctx->h_small->t_claims, &ctx->d_small->t_claims, 8, cudaMemcpyDeviceToHost, s));
@@ -2034,10 +2161,19 @@ static mdbg_status count_pass(mdbg_ctx* ctx, uint64_t read_lo, uint64_t read_hi,
             CKS(flat_range(ctx, r.read_lo, r.read_hi, &a_lo, &a_hi));
             CKS(launch_pass(ctx, a_lo, a_hi, next_k, false));
         }
-        CKS(launch_pass(ctx, g_lo, g_hi, next_k, true));
+        CKS(launch_pass(ctx, g_lo, g_hi, next_k, true, val_in, val_out));
     }
     clk.lap(PH_PASS);
+    ctx->t_whole = whole;
     ctx->t_ranges.push_back(mdbg_ctx::Range{read_lo, read_hi});
+    if (val_out) {
+        std::swap(ctx->val_a, ctx->val_b);
+        ctx->val_valid = true;
+        ctx->val_k = ctx->t_k;
+        ctx->val_gen = ctx->store_gen;
+    } else {
+        ctx->val_valid = false;                            // (a count pass included: the next k looks its global counts up)
+    }
     if (!next_k && ctx->s_mins) ctx->distinct_ratio = (double)ctx->h_small->t_claims / (double)ctx->s_mins;
     return MDBG_OK;
 }
@@ -2060,10 +2196,11 @@ mdbg_status mdbg_count_add(mdbg_ctx* ctx, const uint32_t* minimizers, const uint
     return mdbg_count_add_store(ctx, lo, ctx->s_reads);
 }
 
-static mdbg_status table_stats(mdbg_ctx* ctx, uint32_t thr, TableStats* st) {
+static mdbg_status table_stats(mdbg_ctx* ctx, uint32_t thr, TableStats* st, const Slot* table = nullptr, uint64_t capacity = 0) {
     cudaStream_t s = ctx->stream;
     PhaseClock clk(ctx);
-    launch_table_stats(ctx->table.as<Slot>(), ctx->t_capacity, thr, &ctx->d_small->stats, s);
+    if (!table) { table = ctx->table.as<Slot>(); capacity = ctx->t_capacity; }
+    launch_table_stats(table, capacity, thr, &ctx->d_small->stats, s);
     CKS(check_launch(ctx, "table_stats_kernel", 1));
     CK(cudaMemcpyAsync(&ctx->h_small->stats, &ctx->d_small->stats, sizeof(TableStats), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -2174,7 +2311,7 @@ mdbg_status mdbg_count_finalize(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_tabl
     return MDBG_OK;
 }
 
-static mdbg_status prev_from_current_all_ranks(mdbg_ctx* ctx, uint32_t thr);
+static mdbg_status replicate_into_prev(mdbg_ctx* ctx, const Slot* src, uint64_t src_cap, uint32_t thr);
 
 // Multi-rank rescue (collective, after mdbg_count_merge).  The decision per read needs the abundance of every
 // window, the flag belongs to the window's owner:
@@ -2193,13 +2330,17 @@ static mdbg_status count_rescue_all_ranks(mdbg_ctx* ctx, uint64_t* n_reads_rescu
     // step 1: the lookup table is built in ctx->prev_table; a previous-k table the caller loaded is set aside and
     // put back at the end (mdbg_prev_load + refined-abundance patches survive a rescue)
     struct PrevStash {
-        mdbg_ctx* c; DevBuf table; uint64_t cap; uint32_t thr;
-        explicit PrevStash(mdbg_ctx* ctx) : c(ctx), table(ctx->prev_table), cap(ctx->prev_capacity), thr(ctx->prev_min_count) {
+        mdbg_ctx* c; DevBuf table; uint64_t cap; uint32_t thr, k; bool pure, repl;
+        explicit PrevStash(mdbg_ctx* ctx) : c(ctx), table(ctx->prev_table), cap(ctx->prev_capacity), thr(ctx->prev_min_count),
+                                            k(ctx->prev_k), pure(ctx->prev_pure), repl(ctx->prev_replicated) {
             c->prev_table = c->rescue_table; c->prev_capacity = 0;
         }
-        ~PrevStash() { c->rescue_table = c->prev_table; c->prev_table = table; c->prev_capacity = cap; c->prev_min_count = thr; }
+        ~PrevStash() {
+            c->rescue_table = c->prev_table; c->prev_table = table; c->prev_capacity = cap; c->prev_min_count = thr;
+            c->prev_k = k; c->prev_pure = pure; c->prev_replicated = repl;
+        }
     } stash(ctx);
-    CKS(prev_from_current_all_ranks(ctx, 2));
+    CKS(replicate_into_prev(ctx, ctx->table.as<Slot>(), ctx->t_capacity, 2));
     // step 2
     const uint64_t max_windows = ctx->s_mins + 1;
     CKS(ensure(ctx, ctx->m_recv_vecs, max_windows * 4 * k));        // flat list of collected vectors
@@ -2309,26 +2450,25 @@ static mdbg_status check_full(mdbg_ctx* ctx, const char* what) {
     return MDBG_OK;
 }
 
-// Multi-rank: after mdbg_count_merge every rank holds the keys it owns with their global abundances.  The next-k
-// pass looks up arbitrary (k-1)-min-mers, so the qualifying (hash, abundance) pairs of all ranks are replicated:
-// local emit -> all-gather of the counts -> one grouped exchange of the pairs over NVLink -> insert into the
-// previous-k table of every rank ("replicate if it fits": 20 B per solid k-min-mer).
-static mdbg_status prev_from_current_all_ranks(mdbg_ctx* ctx, uint32_t thr) {
-    if (!ctx->nccl_comm) return fail(ctx, MDBG_ERR_STATE, "mdbg_prev_from_current before mdbg_comm_init");
-    if (!ctx->t_merged)
-        return fail(ctx, MDBG_ERR_STATE, "multi-rank mdbg_prev_from_current needs the merged table: call mdbg_count_merge first");
+// Multi-rank: after mdbg_count_merge every rank holds the keys it owns with their global abundances.  A pass that
+// looks up arbitrary (k-1)-min-mers needs all of them, so the qualifying (hash, abundance) pairs of all ranks are
+// replicated: local emit -> all-gather of the counts -> one grouped exchange of the pairs over NVLink -> insert into
+// the previous-k table of every rank ("replicate if it fits": 20 B per solid k-min-mer).  `src` is the
+// rank's owned table (the current table, or the one mdbg_prev_from_current set aside); the result is ctx->prev_table.
+static mdbg_status replicate_into_prev(mdbg_ctx* ctx, const Slot* src, uint64_t src_cap, uint32_t thr) {
+    if (!ctx->nccl_comm) return fail(ctx, MDBG_ERR_STATE, "previous-k replication before mdbg_comm_init");
     cudaStream_t s = ctx->stream;
     const uint32_t R = (uint32_t)ctx->n_ranks;
     PhaseClock clk(ctx);
     TableStats st;
-    CKS(table_stats(ctx, thr, &st));
+    CKS(table_stats(ctx, thr, &st, src, src_cap));
     const uint64_t n_local = st.n_entries;
     CKS(ensure(ctx, ctx->o_hash, (n_local + 1) * 16));
     CKS(ensure(ctx, ctx->o_abund, (n_local + 1) * 4));
     CK(cudaMemsetAsync(&ctx->d_small->emit_cursor, 0, 8, s));
     EmitArgs e{};
-    e.table = ctx->table.as<Slot>();
-    e.capacity = ctx->t_capacity;
+    e.table = src;
+    e.capacity = src_cap;
     e.min_count = thr;
     e.k = ctx->t_k;
     e.mins = ctx->s_min.as<uint32_t>();
@@ -2387,23 +2527,29 @@ static mdbg_status prev_from_current_all_ranks(mdbg_ctx* ctx, uint32_t thr) {
         launch_prev_load(a, s);
         CKS(check_launch(ctx, "prev_load_kernel", 1));
     }
-    const mdbg_status st_full = check_full(ctx, "mdbg_prev_from_current (all ranks)");
+    const mdbg_status st_full = check_full(ctx, "previous-k replication (all ranks)");
     clk.lap(PH_PREV_INSERT);
+    ctx->prev_replicated = true;
     return st_full;
 }
 
 mdbg_status mdbg_prev_from_current(mdbg_ctx* ctx, uint32_t min_abundance) {
     if (!ctx) return MDBG_ERR_ARG;
     if (!ctx->t_active) return fail(ctx, MDBG_ERR_STATE, "mdbg_prev_from_current without a count table");
+    if (ctx->n_ranks > 1 && !ctx->t_merged)
+        return fail(ctx, MDBG_ERR_STATE, "multi-rank mdbg_prev_from_current needs the merged table: call mdbg_count_merge first");
     CK(cudaSetDevice(ctx->device));
     const uint32_t thr = count_threshold(ctx, min_abundance);
-    if (ctx->n_ranks > 1) return prev_from_current_all_ranks(ctx, thr);
-    // One context: the current table BECOMES the previous-k table -- no copy, no scan.  Entries the reference
-    // would not have dumped (abundance below the threshold and not rescued) are skipped at lookup time
-    // (NextKArgs::prev_min_count).  The old previous-k buffer is recycled as the next current table.
+    // The current table BECOMES the previous-k table -- no copy, no scan.  Entries the reference would not have dumped
+    // (abundance below the threshold and not rescued) are skipped at lookup time (NextKArgs::prev_min_count).  The
+    // old previous-k buffer is recycled as the next current table.  With several ranks the table holds the OWNED
+    // entries only; they are exchanged (replicate_into_prev) when -- and only when -- the next pass needs lookups.
     std::swap(ctx->prev_table, ctx->table);
     ctx->prev_capacity = ctx->t_capacity;
     ctx->prev_min_count = thr;
+    ctx->prev_k = ctx->t_k;
+    ctx->prev_pure = ctx->t_whole;
+    ctx->prev_replicated = ctx->n_ranks == 1;
     ctx->t_capacity = 0;
     ctx->t_active = false;
     ctx->t_ranges.clear();
@@ -2415,7 +2561,13 @@ mdbg_status mdbg_prev_load(mdbg_ctx* ctx, const uint64_t* hashes, const uint32_t
     if (n && (!hashes || !abundances)) return fail(ctx, MDBG_ERR_ARG, "null table arrays");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
+    ctx->prev_pure = false;                                // host pairs: the next pass must look them up
+    if (!clear && ctx->n_ranks > 1 && !ctx->prev_replicated && ctx->prev_capacity) {
+        std::swap(ctx->prev_table, ctx->prev_src);         // patches go on top of the COMPLETE table
+        CKS(replicate_into_prev(ctx, ctx->prev_src.as<Slot>(), ctx->prev_capacity, ctx->prev_min_count));
+    }
     if (clear || ctx->prev_capacity == 0) CKS(prev_alloc(ctx, n));
+    ctx->prev_replicated = true;
     if (n == 0) return MDBG_OK;
     CKS(ensure(ctx, ctx->prev_stage_h, n * 16));
     CKS(ensure(ctx, ctx->prev_stage_a, n * 4));
@@ -2443,7 +2595,9 @@ mdbg_status mdbg_count_add_store_next_k(mdbg_ctx* ctx, uint64_t read_lo, uint64_
     ctx->t_value_mode = true;
     ctx->t_merged = false;
     if (read_hi > ctx->s_reads) read_hi = ctx->s_reads;
-    if (read_lo >= read_hi) return MDBG_OK;
+    if (read_lo > read_hi) read_lo = read_hi;
+    // no early return for an empty range: with several ranks the pass may start with a collective (previous-k
+    // replication), and a rank without reads must take the same decisions as the others
     CK(cudaSetDevice(ctx->device));
     return count_pass(ctx, read_lo, read_hi, true);
 }

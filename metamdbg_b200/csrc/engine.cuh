@@ -260,6 +260,10 @@ struct NextKArgs {
     uint32_t prev_min_count;           // previous-table entries below it (and not rescued) count as absent
     Slot* table; uint64_t mask; uint32_t* full_flag;
     unsigned long long* claims; unsigned long long claim_limit;
+    // per-position values (kminmer.cu, next_k_stream_kernel): val_out[g] = what the next pass would look up for the
+    // k-min-mer starting at g (nullptr = not wanted); val_in != nullptr selects the lookup-free form of the pass,
+    // reading the previous pass's values instead of the previous-k table
+    uint32_t* val_out; const uint32_t* val_in;
 };
 void launch_next_k(const NextKArgs& a, cudaStream_t s);
 
@@ -309,6 +313,14 @@ void launch_table_pack(const PackArgs& a, cudaStream_t s);
 __host__ __device__ inline uint32_t owner_of(uint64_t hi, uint32_t n_ranks) {
     return (uint32_t)(((hi >> 32) * (uint64_t)n_ranks) >> 32);
 }
+
+// ------------------------------------------------------------------ repetitive minimizers (repeats.cu, K1b)
+// table: capacity 64-bit words, all ones = empty, else (minimizer << 32) | count
+void launch_mincount_insert(const uint32_t* mins, uint64_t n, unsigned long long* table, uint64_t mask,
+                            unsigned long long* n_distinct, uint32_t* full_flag, cudaStream_t s);
+void launch_mincount_hist(const unsigned long long* table, uint64_t capacity, unsigned long long* hist, uint32_t n_bins, cudaStream_t s);
+void launch_mincount_emit(const unsigned long long* table, uint64_t capacity, uint32_t min_count, unsigned long long* out,
+                          unsigned long long* cursor, uint64_t out_cap, cudaStream_t s);
 
 // ------------------------------------------------------------------ synthetic reads
 void launch_synth_fill(uint8_t* bases, const uint64_t* offsets, const uint64_t* vstart, const uint8_t* strand,

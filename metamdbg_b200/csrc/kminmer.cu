@@ -515,20 +515,56 @@ __global__ void __launch_bounds__(256) next_k_kernel(const NextKArgs a) {
     const uint32_t v_next = __shfl_down_sync(0xffffffffu, v, 1);
     const bool active = lane < 31 && (int)rem >= k;              // (rem >= k implies the next position has rem >= k - 1)
     int status = 1;
+    uint32_t out = 1;
     if (active) {
         const uint32_t ab = v < v_next ? v : v_next;
         if (ab > 1) {
+            out = ab;
             uint64_t h1, h2; bool rev;
             window_hash(w, k, h1, h2, rev);
             // insert-if-absent: the value is a function of the key, so concurrent inserters write the same number
             status = table_put(a.table, a.mask, h2, h1, ab, g | (rev ? REF_REV : 0ULL));
         }
     }
+    // value of the k-min-mer starting at g, as the NEXT pass would look it up (absent => 1): see next_k_stream_kernel
+    if (a.val_out && lane < 31 && g < a.g_hi) a.val_out[g] = out;
+    block_claims(status, active, a.claims, a.claim_limit, a.full_flag);
+}
+
+// The same pass without a single lookup.  The value a pass stores for a k-min-mer is a function of the key, and
+// every window of every read was offered to it -- so what the NEXT pass would find in the table for the k-min-mer
+// starting at position g is exactly what THIS pass computed at g (or "absent => 1" when that was <= 1).  When the
+// previous-k table is nothing but the previous pass's table (no host patches, same store), pass k + 1 therefore
+// reads val[g] and val[g + 1] -- two coalesced loads -- instead of hashing and probing two (k)-min-mers; the only
+// random access left per window is the insert into the new table.  Identical tables, by induction on k.
+__global__ void __launch_bounds__(256) next_k_stream_kernel(const NextKArgs a) {
+    if (*reinterpret_cast<volatile uint32_t*>(a.full_flag)) return;
+    const uint64_t g = a.g_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = (int)a.k;
+    const bool in_range = g < a.g_hi;
+    const bool active = in_range && (int)a.rem[g] >= k;
+    int status = 1;
+    uint32_t out = 1;
+    if (active) {
+        const uint32_t v = a.val_in[g], v_next = a.val_in[g + 1];
+        const uint32_t ab = v < v_next ? v : v_next;
+        if (ab > 1) {
+            out = ab;
+            uint64_t h1, h2; bool rev;
+            window_hash(a.mins + g, k, h1, h2, rev);
+            status = table_put(a.table, a.mask, h2, h1, ab, g | (rev ? REF_REV : 0ULL));
+        }
+    }
+    if (in_range) a.val_out[g] = out;
     block_claims(status, active, a.claims, a.claim_limit, a.full_flag);
 }
 
 void launch_next_k(const NextKArgs& a, cudaStream_t s) {
     if (a.g_hi <= a.g_lo) return;
+    if (a.val_in) {
+        next_k_stream_kernel<<<(unsigned)((a.g_hi - a.g_lo + 255) / 256), 256, 0, s>>>(a);
+        return;
+    }
     const uint64_t n_warps = (a.g_hi - a.g_lo + 30) / 31;
     next_k_kernel<<<(unsigned)((n_warps + 7) / 8), 256, 0, s>>>(a);
 }

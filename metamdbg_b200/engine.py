@@ -17,7 +17,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _capi
-from ._capi import AutotuneOut, AuxOut, BatchInfo, EdgesOut, FastxInfo, MdbgParams, SketchDev, SketchOut, TableDev, TableOut
+from ._capi import AutotuneOut, AuxOut, BatchInfo, EdgesOut, FastxInfo, MdbgParams, RepeatsOut, SketchDev, SketchOut, TableDev, TableOut
 
 STATUS = {0: "OK", 1: "CUDA", 2: "ARG", 3: "STATE", 4: "TABLE_FULL", 5: "NCCL", 6: "OOM"}
 
@@ -345,6 +345,20 @@ class Engine:
         n = C.c_uint64(0)
         self._ck(self._lib.mdbg_store_apply_density(self._ctx, float(np.float32(density)), C.byref(n)))
         return int(n.value)
+
+    def repetitive_minimizers(self, fraction: float = 0.00001) -> dict:
+        """determineRepetitiveMinimizers on the stored reads -> dict(minimizers, counts, n_distinct, ...)."""
+        out = RepeatsOut()
+        self._ck(self._lib.mdbg_store_repetitive_minimizers(self._ctx, C.c_float(fraction), C.byref(out)))
+        n = int(out.n_selected)
+        return dict(minimizers=np.ctypeslib.as_array(out.minimizers, shape=(n,)).copy() if n else np.zeros(0, np.uint32),
+                    counts=np.ctypeslib.as_array(out.counts, shape=(n,)).copy() if n else np.zeros(0, np.uint32),
+                    n_distinct=int(out.n_distinct), min_count_selected=int(out.min_count_selected),
+                    n_with_min_count=int(out.n_with_min_count), n_with_min_count_selected=int(out.n_with_min_count_selected))
+
+    def set_blacklist(self, values: np.ndarray | None):
+        v = np.ascontiguousarray(values if values is not None else np.zeros(0, np.uint32), dtype=np.uint32)
+        self._ck(self._lib.mdbg_ctx_set_blacklist(self._ctx, v.ctypes.data if len(v) else None, len(v)))
 
     def purge_palindromes(self, first_k: int, last_k: int) -> int:
         n = C.c_uint64(0)

@@ -306,3 +306,85 @@ def test_fastx_text_ingest(built, oracle, hpc):
     sk, info = eng.sketch_fastx(b"")
     assert info["n_records"] == 0 and len(sk.minimizers) == 0
     eng.close()
+
+
+# ---------------------------------------------------------------- lookup-free next-k passes, repetitive minimizers
+
+def test_next_k_without_lookups_equals_lookups(built, oracle, monkeypatch):
+    """k >= firstK + 2 on an unpatched previous table runs without lookups (per-position values of the previous pass);
+    tables are identical to the lookup form (MDBG_NO_STREAM_NEXT_K=1) and to the oracle, and a host patch of the
+    previous-k table switches the next pass back to lookups."""
+    from metamdbg_b200 import multi_k_sweep
+    rs = synth.make_readset(2500, 9000, seed=64, n_genomes=2, genome_len_range=(150_000, 300_000), err=0.003)
+    bases, offs = synth.fill_reads(rs)
+    runs = {}
+    for tag, env in (("stream", None), ("lookup", "1")):
+        if env:
+            monkeypatch.setenv("MDBG_NO_STREAM_NEXT_K", env)
+        eng = engine()
+        eng.sketch_batch(bases, offs, append_to_store=True, fetch=False)
+        tabs = {}
+        multi_k_sweep(eng, 4, 12, 0, rescue=True, on_table=lambda k, e: tabs.__setitem__(k, e.count_finalize(0).as_dict()))
+        runs[tag] = tabs
+        if tag == "stream":
+            so, sm = eng.store_fetch()
+            # patched previous table: k = 13 from the k = 12 table with some abundances lowered
+            t12 = eng.count_finalize(0)
+            eng.prev_from_current(0)
+            idx = np.arange(0, len(t12.abundances), 7)
+            eng.prev_load(t12.hashes[idx], np.ones(len(idx), np.uint32), clear=False)
+            eng.count_begin(13)
+            eng.count_add_store_next_k()
+            got13 = eng.count_finalize(0).as_dict()
+            pa = t12.abundances.copy(); pa[idx] = 1
+            ph = np.stack([t12.hashes[:, 1], t12.hashes[:, 0]], axis=1)          # (h1, h2) as the oracle takes them
+            want13 = oracle.next_k(sm, so, 13, ph, pa)
+            assert got13 == table_dict(want13["hashes"], want13["abundances"]) and len(got13) > 100
+        eng.close()
+    assert runs["stream"] == runs["lookup"] and all(len(runs["stream"][k]) > 200 for k in range(4, 13))
+    solid = oracle.count(sm, so, 4, 2)
+    resc = oracle.rescue(sm, so, 4, solid["hashes"], solid["abundances"])
+    ph = np.concatenate([solid["hashes"], resc["hashes"]]) if len(resc["hashes"]) else solid["hashes"]
+    pa = np.concatenate([solid["abundances"], np.ones(len(resc["hashes"]), np.uint32)])
+    for k in range(5, 13):
+        nk = oracle.next_k(sm, so, k, ph, pa)
+        ph, pa = nk["hashes"], nk["abundances"]
+        assert runs["stream"][k] == table_dict(ph, pa), k
+
+
+def test_repetitive_minimizers(built, oracle):
+    """determineRepetitiveMinimizers on the device: counts of every minimizer of the stored reads, the
+    max(1, int(1e-5f * distinct)) most frequent ones; installed as blacklist they disappear from later sketches."""
+    rng = np.random.default_rng(17)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    repeat = acgt[rng.integers(0, 4, 400)]
+    reads = []
+    for i in range(300):
+        s = acgt[rng.integers(0, 4, int(rng.integers(3000, 6000)))].copy()
+        for _ in range(int(rng.integers(0, 4))):              # a repeat element planted a few times per read
+            p = int(rng.integers(0, len(s) - 400))
+            s[p:p + 400] = repeat
+        reads.append(s)
+    bases = np.concatenate(reads)
+    offs = np.zeros(len(reads) + 1, np.uint64); offs[1:] = np.cumsum([len(r) for r in reads])
+    eng = engine(15, 0.025, False)
+    sk = eng.sketch_batch(bases, offs, append_to_store=True)
+    vals, counts = np.unique(sk.minimizers, return_counts=True)
+    for frac in (0.00001, 0.001, 0.5):
+        rep = eng.repetitive_minimizers(frac)
+        want_n = max(1, int(np.float32(frac) * np.float32(len(vals))))
+        assert rep["n_distinct"] == len(vals) and len(rep["minimizers"]) == min(want_n, len(vals))
+        order = np.lexsort((vals, -counts.astype(np.int64)))          # count descending, value ascending
+        assert np.array_equal(rep["minimizers"], vals[order][:want_n].astype(np.uint32))
+        assert np.array_equal(rep["counts"], counts[order][:want_n].astype(np.uint32))
+        assert rep["min_count_selected"] == counts[order][want_n - 1]
+        assert rep["n_with_min_count"] == int((counts == rep["min_count_selected"]).sum())
+    rep = eng.repetitive_minimizers(0.001)
+    eng.set_blacklist(rep["minimizers"])
+    sk2 = eng.sketch_batch(bases, offs)
+    want = oracle.sketch_batch(bases, offs, 15, 0.025, False, blacklist=np.sort(rep["minimizers"]))
+    assert_sketch_equal(sk2, *want, tag="sketch with the device-made blacklist")
+    assert len(sk2.minimizers) < len(sk.minimizers) and not np.isin(sk2.minimizers, rep["minimizers"]).any()
+    eng.set_blacklist(None)
+    assert_sketch_equal(eng.sketch_batch(bases, offs), sk.min_offsets, sk.minimizers, sk.positions, sk.directions, "blacklist cleared")
+    eng.close()
