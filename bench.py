@@ -400,7 +400,7 @@ def hot_path(eng, dr, w, lk, world, ascii_input=False, last_k=4):
         eng.count_begin(k, 2 * max(256, per_k[-1]) * world)
         eng.count_add_store_next_k()
         if world > 1:
-            eng.count_merge()
+            eng.count_merge_hashes()                   # (hash128, abundance) records: the k > 4 tables need no vectors on the owner
         tab = eng.count_finalize_device(MIN_AB)
         per_k.append(tab["n_entries"])
     return tab, n_min, per_k
@@ -595,7 +595,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     if args.multi_k > K and w["last_k"] == K:
         try:
             from metamdbg_b200 import multi_k_sweep
-            sweeps = [multi_k_sweep(eng, K, args.multi_k, MIN_AB, merge=world > 1, world=world) for _ in range(2)]   # 2nd = warm
+            mk_merge = "hashes" if world > 1 else False
+            sweeps = [multi_k_sweep(eng, K, args.multi_k, MIN_AB, merge=mk_merge, world=world) for _ in range(2)]   # 2nd = warm
             per_k = [round(1e3 * max_over_ranks(r["seconds"]), 3) for r in sweeps[1]]
             total_s = sum(per_k) * 1e-3
             multi_k = {"k_first": K, "k_last": args.multi_k, "ms_per_k": per_k, "ms_total": round(sum(per_k), 3),
@@ -607,8 +608,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             # where the loop's time goes: one more sweep with the library's phase profile on (exclusive phase times, every
             # phase boundary synchronises the stream -- a diagnostic, slower than the timed sweep above)
             eng.phase_profile(True)
-            multi_k_sweep(eng, K, args.multi_k, MIN_AB, merge=world > 1, world=world)
+            multi_k_sweep(eng, K, args.multi_k, MIN_AB, merge=mk_merge, world=world)
             multi_k["phase_ms_profiled_sweep_rank0"] = eng.phase_times()
+            multi_k["merge"] = "k = 4: owner merge with vectors; k > 4: keys-only owner merge (mdbg_count_merge_hashes)" if world > 1 else None
             eng.phase_profile(False)
         except Exception as e:                                # noqa: BLE001  -- an extra must not cost the headline line
             multi_k = {"error": repr(e)}
@@ -936,6 +938,17 @@ def multi_gpu_parity(args, eng, torch, dev, rank, world, sum_over_ranks, sum_u64
         eng.count_add_store_next_k()
         eng.count_merge()
         stage(f"k{k}")
+    # the same chain once more with the keys-only merge of the multi-k loop (k > 4)
+    eng.count_begin(K, 0)
+    eng.count_add_store()
+    eng.count_merge()
+    eng.count_rescue()
+    for k in (K + 1, K + 2, K + 3):
+        eng.prev_from_current(0)
+        eng.count_begin(k, 0)
+        eng.count_add_store_next_k()
+        eng.count_merge_hashes()
+        stage(f"k{k}_keys_only_merge")
     barrier()
     verdict = None
     if rank == 0:
@@ -958,10 +971,12 @@ def multi_gpu_parity(args, eng, torch, dev, rank, world, sum_over_ranks, sum_u64
                 "rescue": (len(pa), orc.checksum(ph, pa), resc["n_reads_rescued"])}
         we = orc.edge_index(pv, K)
         want["edges"] = (len(we["hashes"]), we["checksum"], len(pa))
-        for k in (K + 1, K + 2):
+        for k in (K + 1, K + 2, K + 3):
             nk = orc.next_k(pm, po, k, ph, pa)
             ph, pa = nk["hashes"], nk["abundances"]
-            want[f"k{k}"] = (len(pa), orc.checksum(ph, pa), 0)
+            if k <= K + 2:
+                want[f"k{k}"] = (len(pa), orc.checksum(ph, pa), 0)
+            want[f"k{k}_keys_only_merge"] = (len(pa), orc.checksum(ph, pa), 0)
         verdict = {t: tuple(int(x) for x in got[t]) == tuple(int(x) for x in want[t]) for t in want}
         verdict["reads"] = n_reads
         verdict["what"] = ("(entries, sum abundance*hash, third figure: distinct keys / rescued reads / nodes) of every stage, "

@@ -410,6 +410,12 @@ mdbg_status mdbg_comm_init(mdbg_ctx* ctx, int rank, int n_ranks, const uint8_t i
  * keys it owns with their global abundances.  Collective over all ranks.  Tables filled by
  * mdbg_count_add_store_next_k hold abundance VALUES: equal keys from several ranks are kept once, not summed. */
 mdbg_status mdbg_count_merge(mdbg_ctx* ctx);
+/* The same merge with (hash128, abundance) records only -- 24 bytes per entry instead of 4 k + 4, no vector gather on
+ * the sender, no re-hash on the owner.  The merged table carries no k-min-mer vectors: mdbg_count_finalize returns
+ * kminmers = NULL (hashes and abundances as usual), mdbg_edges_index and mdbg_count_rescue are refused.  For the per-k
+ * tables of a multi-k loop (the next pass needs no table of another rank, so the merge only has to place every key
+ * on exactly one rank). */
+mdbg_status mdbg_count_merge_hashes(mdbg_ctx* ctx);
 
 /* ---- synthetic input (benchmark/test support, device side) ------------------ */
 /* Fill d_bases with the reads described by (vstart, strand, offsets, lengths) using

@@ -133,6 +133,7 @@ SYMBOLS = {
     "mdbg_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "mdbg_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "mdbg_count_merge": (C.c_int, [C.c_void_p]),
+    "mdbg_count_merge_hashes": (C.c_int, [C.c_void_p]),
     "mdbg_synth_fill_reads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                         C.c_uint64, C.c_uint64, C.c_uint32]),
 }

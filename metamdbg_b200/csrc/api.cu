@@ -153,6 +153,7 @@ struct mdbg_ctx {
     uint32_t val_k = 0;
     uint64_t val_gen = 0;
     bool t_whole = false;              // the current table = ONE pass over the whole store (nothing else inserted)
+    bool t_no_vecs = false;            // keys-only merge: the slots carry no k-min-mer vectors (no kminmers output, no edges)
     uint32_t prev_k = 0;               // k of the table that became the previous-k table
     bool prev_pure = false;            // ... and it is that pass's table as it was (no host pairs loaded or patched in)
     bool prev_replicated = true;       // several ranks: prev_table holds every rank's entries (false: only the owned ones)
@@ -2052,6 +2053,7 @@ mdbg_status mdbg_count_begin(mdbg_ctx* ctx, uint32_t k, uint64_t expected_distin
     ctx->t_ranges.clear();
     ctx->t_rebuildable = true;
     ctx->t_whole = false;
+    ctx->t_no_vecs = false;
     ctx->foreign_n = 0;
     return MDBG_OK;
 }
@@ -2252,7 +2254,7 @@ static mdbg_status emit_table(mdbg_ctx* ctx, uint32_t thr, TableStats* st_out) {
     e.foreign_vecs = ctx->foreign_vecs.as<uint32_t>();
     e.out_hashes = ctx->o_hash.as<uint64_t>();
     e.out_abund = ctx->o_abund.as<uint32_t>();
-    e.out_vecs = ctx->o_vecs.as<uint32_t>();
+    e.out_vecs = ctx->t_no_vecs ? nullptr : ctx->o_vecs.as<uint32_t>();
     e.cursor = &ctx->d_small->emit_cursor;
     PhaseClock clk(ctx);
     launch_table_emit(e, s);
@@ -2272,7 +2274,7 @@ mdbg_status mdbg_count_finalize_device(mdbg_ctx* ctx, uint32_t min_abundance, md
     out->n_entries = st.n_entries;
     out->d_hashes = ctx->o_hash.as<uint64_t>();
     out->d_abundances = ctx->o_abund.as<uint32_t>();
-    out->d_kminmers = ctx->o_vecs.as<uint32_t>();
+    out->d_kminmers = ctx->t_no_vecs ? nullptr : ctx->o_vecs.as<uint32_t>();
     out->n_instances = st.n_instances;
     out->n_distinct = st.n_distinct;
     out->checksum = st.checksum;
@@ -2295,15 +2297,15 @@ mdbg_status mdbg_count_finalize(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_tabl
     if (n) {
         CK(cudaMemcpyAsync(ctx->ho_hash.p, ctx->o_hash.p, n * 16, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(ctx->ho_abund.p, ctx->o_abund.p, n * 4, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(ctx->ho_vecs.p, ctx->o_vecs.p, n * 4 * k, cudaMemcpyDeviceToHost, s));
+        if (!ctx->t_no_vecs) CK(cudaMemcpyAsync(ctx->ho_vecs.p, ctx->o_vecs.p, n * 4 * k, cudaMemcpyDeviceToHost, s));
     }
     CK(cudaStreamSynchronize(s));
-    ctx->d2h_bytes += n * (16 + 4 + 4ull * k);
+    ctx->d2h_bytes += n * (16 + 4 + (ctx->t_no_vecs ? 0ull : 4ull * k));
     out->k = k;
     out->n_entries = n;
     out->hashes = ctx->ho_hash.as<uint64_t>();
     out->abundances = ctx->ho_abund.as<uint32_t>();
-    out->kminmers = ctx->ho_vecs.as<uint32_t>();
+    out->kminmers = ctx->t_no_vecs ? nullptr : ctx->ho_vecs.as<uint32_t>();
     out->n_instances = st.n_instances;
     out->n_distinct = st.n_distinct;
     out->checksum = st.checksum;
@@ -2323,7 +2325,7 @@ static mdbg_status replicate_into_prev(mdbg_ctx* ctx, const Slot* src, uint64_t 
 //   4. the owner flags the slots (count 1) of the vectors it received.
 static mdbg_status count_rescue_all_ranks(mdbg_ctx* ctx, uint64_t* n_reads_rescued) {
     if (!ctx->nccl_comm) return fail(ctx, MDBG_ERR_STATE, "mdbg_count_rescue before mdbg_comm_init");
-    if (!ctx->t_merged || ctx->t_value_mode)
+    if (!ctx->t_merged || ctx->t_value_mode || ctx->t_no_vecs)
         return fail(ctx, MDBG_ERR_STATE, "multi-rank mdbg_count_rescue needs the merged count table: call mdbg_count_merge first");
     cudaStream_t s = ctx->stream;
     const uint32_t R = (uint32_t)ctx->n_ranks, k = ctx->t_k;
@@ -2608,6 +2610,7 @@ mdbg_status mdbg_edges_index(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_edges_o
     if (!ctx || !out) return MDBG_ERR_ARG;
     if (!ctx->t_active) return fail(ctx, MDBG_ERR_STATE, "mdbg_edges_index before mdbg_count_begin");
     if (ctx->t_k < 2) return fail(ctx, MDBG_ERR_ARG, "k must be >= 2");
+    if (ctx->t_no_vecs) return fail(ctx, MDBG_ERR_STATE, "mdbg_edges_index needs the k-min-mer vectors: merge with mdbg_count_merge, not mdbg_count_merge_hashes");
     if (ctx->n_ranks > 1 && (!ctx->nccl_comm || !ctx->t_merged))
         return fail(ctx, MDBG_ERR_STATE, "multi-rank mdbg_edges_index needs the merged table: call mdbg_count_merge first");
     CK(cudaSetDevice(ctx->device));
@@ -2898,6 +2901,67 @@ mdbg_status mdbg_count_merge(mdbg_ctx* ctx) {
     ctx->t_rebuildable = false;            // the table now holds foreign vectors: it cannot be rebuilt from the store
     ctx->t_ranges.clear();
     ctx->t_claim_limit = cap;
+    return MDBG_OK;
+}
+
+// Keys-only owner merge: (hash128, abundance) records of 24 bytes instead of (k-min-mer vector, abundance).  Afterwards
+// rank r holds exactly the keys it owns with their global abundances, as after mdbg_count_merge, but the slots carry no
+// vectors: finalize returns kminmers = NULL and mdbg_edges_index / mdbg_count_rescue are refused.  Made for the per-k
+// tables of a multi-k loop, where the next pass needs no table from other ranks at all (next_k_stream_kernel) and the
+// merge only has to put every key on one rank: 4.4 x fewer bytes over NVLink at k = 21, no vector gather, no re-hash.
+mdbg_status mdbg_count_merge_hashes(mdbg_ctx* ctx) {
+    if (!ctx) return MDBG_ERR_ARG;
+    if (!ctx->t_active) return fail(ctx, MDBG_ERR_STATE, "mdbg_count_merge_hashes before mdbg_count_begin");
+    if (ctx->n_ranks == 1) return MDBG_OK;
+    if (!ctx->nccl_comm) return fail(ctx, MDBG_ERR_STATE, "mdbg_count_merge_hashes before mdbg_comm_init");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const uint32_t R = (uint32_t)ctx->n_ranks;
+    CKS(ensure(ctx, ctx->m_bucket, (size_t)(2 * R + R * R) * 8));
+    uint64_t* d_cnt = ctx->m_bucket.as<uint64_t>();
+    uint64_t* d_base = d_cnt + R;
+    CK(cudaMemsetAsync(d_cnt, 0, R * 8, s));
+    PhaseClock clk(ctx);
+    PackArgs p{};
+    p.table = ctx->table.as<Slot>();
+    p.capacity = ctx->t_capacity;
+    p.k = ctx->t_k;
+    p.n_ranks = R;
+    p.bucket_count = reinterpret_cast<unsigned long long*>(d_cnt);
+    p.pass = 1;
+    launch_table_pack_hashes(p, nullptr, s);
+    CKS(check_launch(ctx, "table_pack_hashes_kernel(count)", 1));
+    clk.lap(PH_MERGE_PACK_COUNT);
+    OwnerExchange x;
+    CKS(x.plan(ctx));
+    CKS(ensure(ctx, ctx->m_send_vecs, (x.send_total + 1) * 24));
+    CKS(ensure(ctx, ctx->m_recv_vecs, (x.recv_total + 1) * 24));
+    clk.lap(PH_MERGE_PLAN);
+    CKS(x.upload_bases(ctx));
+    p.bucket_base = d_base;
+    p.pass = 2;
+    launch_table_pack_hashes(p, ctx->m_send_vecs.as<uint64_t>(), s);
+    CKS(check_launch(ctx, "table_pack_hashes_kernel(scatter)", 1));
+    clk.lap(PH_MERGE_PACK_SCATTER);
+    CKS(x.run(ctx, ctx->m_send_vecs.p, ctx->m_recv_vecs.p, 24));
+    clk.lap(PH_MERGE_EXCHANGE);
+    const uint64_t cap = table_capacity_for(x.recv_total);
+    CKS(ensure(ctx, ctx->table, cap * sizeof(Slot)));
+    CK(cudaMemsetAsync(ctx->table.p, 0, cap * sizeof(Slot), s));
+    ctx->t_capacity = cap;
+    launch_insert_hash_recs(ctx->m_recv_vecs.as<uint64_t>(), x.recv_total, ctx->table.as<Slot>(), cap - 1,
+                            ctx->t_value_mode ? 1u : 0u, &ctx->d_small->full_flag, s);
+    CKS(check_launch(ctx, "insert_hash_recs_kernel", x.recv_total ? 1 : 0));
+    CK(cudaMemcpyAsync(&ctx->h_small->full_flag, &ctx->d_small->full_flag, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (ctx->h_small->full_flag) return fail(ctx, MDBG_ERR_TABLE_FULL, "merged table full");
+    clk.lap(PH_MERGE_INSERT);
+    ctx->t_merged = true;
+    ctx->t_no_vecs = true;
+    ctx->t_rebuildable = false;
+    ctx->t_ranges.clear();
+    ctx->t_claim_limit = cap;
+    ctx->foreign_n = 0;
     return MDBG_OK;
 }
 

@@ -157,6 +157,7 @@ constexpr uint64_t SRC_ASCII = 1ULL << 63;
 constexpr uint64_t REF_REV = 1ULL << 63;
 constexpr uint64_t REF_FOREIGN = 1ULL << 62;
 constexpr uint64_t REF_INDEX_MASK = (1ULL << 62) - 1;
+constexpr uint64_t REF_NONE = ~0ULL;             // the slot's k-min-mer vector is not on this rank (keys-only merge)
 
 void launch_fill_rem(const uint64_t* offs, uint64_t read_lo, uint64_t read_hi, uint8_t* rem, cudaStream_t s);
 
@@ -309,6 +310,10 @@ struct PackArgs {
     int pass;                           // 1 = count, 2 = scatter
 };
 void launch_table_pack(const PackArgs& a, cudaStream_t s);
+// keys-only form: 24-byte records {hash lo, hash hi, count}; same two passes, same bucket arithmetic
+void launch_table_pack_hashes(const PackArgs& a, uint64_t* out_recs, cudaStream_t s);
+void launch_insert_hash_recs(const uint64_t* recs, uint64_t n, Slot* table, uint64_t mask, uint32_t assign, uint32_t* full_flag,
+                             cudaStream_t s);
 
 __host__ __device__ inline uint32_t owner_of(uint64_t hi, uint32_t n_ranks) {
     return (uint32_t)(((hi >> 32) * (uint64_t)n_ranks) >> 32);

@@ -830,4 +830,69 @@ void launch_table_pack(const PackArgs& a, cudaStream_t s) {
     table_pack_kernel<<<(unsigned)blocks, 256, 0, s>>>(a);
 }
 
+// ------------------------------------------------------------------ multi-GPU merge, keys only
+// For tables whose k-min-mer VECTORS are not wanted on the owner (the per-k tables of a multi-k loop: the next pass
+// needs no table at all, see next_k_stream_kernel): records of 24 bytes {hash lo, hash hi, count | 0} instead of
+// 4 k + 4 bytes, no gather of vectors on the sender, no re-hash on the owner.
+__global__ void __launch_bounds__(256) table_pack_hashes_kernel(const PackArgs a, uint64_t* out_recs) {
+    __shared__ uint32_t wcnt[8][PACK_MAX_RANKS];
+    __shared__ unsigned long long bbase[PACK_MAX_RANKS];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t R = a.n_ranks;
+    const uint64_t n_tiles = (a.capacity + 255) / 256;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t i = tile * 256 + threadIdx.x;
+        bool take = false;
+        uint32_t dst = 0, count = 0, my_prefix = 0;
+        uint64_t lo = 0, hi = 0;
+        if (i < a.capacity) {
+            const Slot sl = a.table[i];
+            take = (sl.lo | sl.hi) != 0;
+            dst = owner_of(sl.hi, R);
+            count = sl.count; lo = sl.lo; hi = sl.hi;
+        }
+        for (uint32_t d = 0; d < R; d++) {
+            const uint32_t m = __ballot_sync(0xffffffffu, take && dst == d);
+            if (lane == 0) wcnt[warp][d] = __popc(m);
+            if (take && dst == d) my_prefix = __popc(m & ((1u << lane) - 1u));
+        }
+        __syncthreads();
+        if (threadIdx.x < R) {
+            uint32_t tot = 0;
+            for (int w = 0; w < 8; w++) { const uint32_t c = wcnt[w][threadIdx.x]; wcnt[w][threadIdx.x] = tot; tot += c; }
+            bbase[threadIdx.x] = tot ? atomicAdd(&a.bucket_count[threadIdx.x], (unsigned long long)tot) : 0ULL;
+        }
+        __syncthreads();
+        if (a.pass == 2 && take) {
+            const uint64_t pos = a.bucket_base[dst] + bbase[dst] + wcnt[warp][dst] + my_prefix;
+            out_recs[3 * pos] = lo;
+            out_recs[3 * pos + 1] = hi;
+            out_recs[3 * pos + 2] = count;
+        }
+        __syncthreads();
+    }
+}
+
+void launch_table_pack_hashes(const PackArgs& a, uint64_t* out_recs, cudaStream_t s) {
+    uint64_t blocks = (a.capacity + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    table_pack_hashes_kernel<<<(unsigned)blocks, 256, 0, s>>>(a, out_recs);
+}
+
+__global__ void __launch_bounds__(256) insert_hash_recs_kernel(const uint64_t* recs, uint64_t n, Slot* table, uint64_t mask,
+                                                               uint32_t assign, uint32_t* full_flag) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t lo = recs[3 * i], hi = recs[3 * i + 1];
+    const uint32_t count = (uint32_t)recs[3 * i + 2];
+    const int ok = assign ? table_put(table, mask, lo, hi, count, REF_NONE) : table_add(table, mask, lo, hi, count, REF_NONE);
+    if (!ok) atomicExch(full_flag, 1u);
+}
+
+void launch_insert_hash_recs(const uint64_t* recs, uint64_t n, Slot* table, uint64_t mask, uint32_t assign, uint32_t* full_flag,
+                             cudaStream_t s) {
+    if (n == 0) return;
+    insert_hash_recs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(recs, n, table, mask, assign, full_flag);
+}
+
 }  // namespace mdbg

@@ -824,12 +824,12 @@ __global__ void __launch_bounds__(256) pack_ascii_kernel(const PackArgsAscii a) 
         // step loads 32 units and writes 31 words.
         const uint32_t x_end = skip + len, n_out = (len + 15) >> 4;
         uint32_t bad = 0;
-        for (uint32_t m0 = 0; m0 < n_out; m0 += 31) {
-            const uint32_t m = m0 + lane;
-            uint32_t word = 0, diff = 0;
-            if (16 * m < x_end) {
+        // aligned unit m of the text (zeros past the read / the buffer); loads of the NEXT step are issued before the
+        // current one is packed, so two 16-byte loads per lane are in flight (the kernel is latency-bound otherwise)
+        auto load_unit = [&](uint32_t m) -> uint4 {
+            uint4 u = make_uint4(0, 0, 0, 0);
+            if (16 * (uint64_t)m < x_end) {
                 const uint8_t* p = abase + 16 * (uint64_t)m;
-                uint4 u = make_uint4(0, 0, 0, 0);
                 if (p + 16 <= a.bases_end) {
                     u = *reinterpret_cast<const uint4*>(p);
                 } else {
@@ -838,6 +838,16 @@ __global__ void __launch_bounds__(256) pack_ascii_kernel(const PackArgsAscii a) 
                         if (p + j < a.bases_end) t[j >> 2] |= (uint32_t)p[j] << (8 * (j & 3));
                     u = make_uint4(t[0], t[1], t[2], t[3]);
                 }
+            }
+            return u;
+        };
+        uint4 u_next = load_unit(lane);
+        for (uint32_t m0 = 0; m0 < n_out; m0 += 31) {
+            const uint32_t m = m0 + lane;
+            const uint4 u = u_next;
+            if (m0 + 31 < n_out) u_next = load_unit(m + 31);
+            uint32_t word = 0, diff = 0;
+            if (16 * m < x_end) {
                 const uint32_t lo = m == 0 ? skip : 0u, hi = min(16u, x_end - 16 * m);
                 if (lo == 0 && hi == 16) {
                     const uint32_t c0 = pack4_checked(u.x, diff), c1 = pack4_checked(u.y, diff);

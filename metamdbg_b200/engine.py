@@ -399,7 +399,8 @@ class Engine:
         if n:
             h = np.ctypeslib.as_array(out.hashes, shape=(2 * n,)).copy().reshape(n, 2)
             a = np.ctypeslib.as_array(out.abundances, shape=(n,)).copy()
-            v = np.ctypeslib.as_array(out.kminmers, shape=(n * k,)).copy().reshape(n, k)
+            v = (np.ctypeslib.as_array(out.kminmers, shape=(n * k,)).copy().reshape(n, k) if out.kminmers
+                 else np.zeros((0, k), np.uint32))          # keys-only merge: no vectors on this rank
         else:
             h = np.zeros((0, 2), np.uint64); a = np.zeros(0, np.uint32); v = np.zeros((0, k), np.uint32)
         return CountTable(k, h, a, v, int(out.n_instances), int(out.n_distinct), int(out.checksum), int(out.n_rescued))
@@ -465,6 +466,10 @@ class Engine:
         self._ck(self._lib.mdbg_count_merge(self._ctx))
 
     # -- synthetic reads on the device ------------------------------------------------
+    def count_merge_hashes(self):
+        """Owner merge of (hash, abundance) only: no k-min-mer vectors on the owner afterwards (multi-k loops)."""
+        self._ck(self._lib.mdbg_count_merge_hashes(self._ctx))
+
     def synth_fill_reads(self, d_bases_ptr: int, d_offsets_ptr: int, d_vstart_ptr: int, d_strand_ptr: int,
                          n_reads: int, read_index_base: int, seed: int, err_q24: int):
         self._ck(self._lib.mdbg_synth_fill_reads(self._ctx, C.c_void_p(d_bases_ptr), C.c_void_p(d_offsets_ptr),

@@ -23,6 +23,9 @@ def multi_k_sweep(engine, first_k: int = 4, last_k: int = 21, min_abundance: int
                   table_headroom: float = 2.0) -> list[dict]:
     """Count k = first_k on the engine's store, then derive k = first_k+1 .. last_k from the previous table.
 
+    merge: False (one context), True (owner merge with the k-min-mer vectors after every k) or "hashes" (k > first_k:
+    mdbg_count_merge_hashes -- (hash, abundance) records only, the light collective of a pure table loop).
+
     on_table(k, engine) is called while the table of k is current (e.g. to finalize it into kminmerData files);
     returns one dict per k: k, seconds (host wall clock around the device work of that k) and the table statistics.
 
@@ -56,7 +59,9 @@ def multi_k_sweep(engine, first_k: int = 4, last_k: int = 21, min_abundance: int
                     raise
                 engine.count_begin(k, 0)                      # worst-case size; the pass is idempotent
                 engine.count_add_store_next_k()
-            if merge:
+            if merge == "hashes":                             # keys + abundances only: no vectors on the owners
+                engine.count_merge_hashes()
+            elif merge:
                 engine.count_merge()
             n_rescued_reads = 0
         stats = engine.count_stats(min_abundance)         # device-side reduction + one small D2H: ends the k's work

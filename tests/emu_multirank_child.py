@@ -29,6 +29,7 @@ def main():
     next_results = [None] * n_ranks
     rescue_results = [None] * n_ranks
     edge_results = [None] * n_ranks
+    light_results = [None] * n_ranks
 
     def rank_main(rank):
         try:
@@ -56,6 +57,21 @@ def main():
                 eng.count_merge()
                 chain.append(eng.count_finalize(0))
             next_results[rank] = chain
+            # the same two passes with the keys-only merge (no vectors on the owners), from a fresh first pass
+            eng.count_begin(k, 0)
+            eng.count_add_store()
+            eng.count_merge()
+            eng.count_rescue()
+            light = []
+            for kk in (k + 1, k + 2):
+                eng.prev_from_current(2)
+                eng.count_begin(kk, 0)
+                eng.count_add_store_next_k()
+                eng.count_merge_hashes()
+                t = eng.count_finalize(0)
+                assert t.kminmers.shape[0] == 0
+                light.append(t)
+            light_results[rank] = light
             eng.close()
         except Exception as e:                           # noqa: BLE001
             errors.append((rank, repr(e)))
@@ -132,6 +148,12 @@ def main():
                 assert owner_of(key[0], n_ranks) == rank and key not in got_k
                 got_k[key] = ab
         assert got_k == want_k and (len(want_k) > 1000 or n_reads < 260), (kk, len(got_k), len(want_k))
+        got_l = {}
+        for rank in range(n_ranks):
+            for key, ab in light_results[rank][step].as_dict().items():
+                assert owner_of(key[0], n_ranks) == rank and key not in got_l
+                got_l[key] = ab
+        assert got_l == want_k, ("keys-only merge", kk, len(got_l), len(want_k))
         prev_h, prev_a = nk["hashes"], nk["abundances"]
         print(f"  next-k {kk}: {len(want_k)} entries identical over {n_ranks} ranks")
     print(f"{n_ranks} ranks, k={k}: {len(want)} solid k-min-mers, {instances} occurrences conserved")

@@ -178,3 +178,91 @@ def test_reference_stage_driven_by_gpu_functor(tmp_path):
            int(np.frombuffer(b, np.uint64, 1, 32)[0])]
     assert got == [int(x) for x in z["stats"]]
     assert os.path.getsize(tmp_path / "read_data_corrected.txt") > 0
+
+
+def _write_parameters_gz(path, l=15, k=4, dens_asm=0.005, first_k=4, last_k=21, mean_len=0, dens_corr=0.025, hpc=True,
+                         data_type=0, snpmer=0):
+    """parameters.gz as AssemblyPipeline::writeParameters emits it (src/pipeline/AssemblyPipeline.hpp:1479-1517)."""
+    import gzip
+    import struct
+    spacing = np.float32(1) / np.float32(dens_asm)
+    len_mean = np.float32(spacing * np.float32(k - 1))
+    rec = struct.pack("<QQfQfffQQQf?iQ", l, k, dens_asm, first_k, float(spacing), float(len_mean),
+                      float(np.float32(len_mean - spacing)), first_k, last_k, mean_len, dens_corr, hpc, data_type, snpmer)
+    with gzip.open(path, "wb") as f:
+        f.write(rec)
+
+
+@pytest.mark.parametrize("hifi", [True, False])
+def test_cpp_driver_stage_compatible_subcommands(tmp_path, oracle, hifi):
+    """Row (f)2: `readSelection <tmpDir> <out> <input.txt>` and `graph <tmpDir> --firstpass --min-abundance n` with
+    metaMDBG's own positional command lines and parameters.gz; the files in <tmpDir> are the ones the next reference
+    stage reads: read_data_init.txt / read_stats.txt / repetitiveMinimizers.bin / read_data_corrected.txt, then
+    kminmerData_min.txt / kminmerData_abundance.txt (multiset-equal to the oracle's table)."""
+    import __graft_entry__ as g
+    g.build()
+    rs = synth.make_readset(900, 6000, seed=58, n_genomes=2, genome_len_range=(120_000, 200_000), err=0.002)
+    bases, offs = synth.fill_reads(rs)
+    raw = bases.tobytes()
+    files = []
+    for part, (lo, hi) in enumerate(((0, 500), (500, rs.n_reads))):      # two input files = two datasets
+        fq = tmp_path / f"reads{part}.fastq"
+        with open(fq, "wb") as f:
+            for r in range(lo, hi):
+                s = raw[int(offs[r]):int(offs[r + 1])]
+                f.write(b"@r%d\n" % r + s + b"\n+\n" + b"I" * len(s) + b"\n")
+        files.append(str(fq))
+    tmp = tmp_path / "tmp"
+    tmp.mkdir()
+    (tmp / "input.txt").write_text("\n".join(files) + "\n")
+    dens, corr = 0.005, 0.025
+    _write_parameters_gz(tmp / "parameters.gz", hpc=hifi, data_type=0 if hifi else 1, dens_asm=dens, dens_corr=corr)
+    out = subprocess.run([EXE, "readSelection", str(tmp), str(tmp / "read_data_init.txt"), str(tmp / "input.txt"), "--threads", "4",
+                          "--min-read-quality", "0", "--output-quality", "--skip-correction", "--batch-mbp", "2"],
+                         capture_output=True, text=True, timeout=180)
+    assert out.returncode == 0, out.stderr
+    for name in ("read_data_init.txt", "read_stats.txt", "repetitiveMinimizers.bin", "read_data_corrected.txt"):
+        assert (tmp / name).exists(), name
+    bl = np.fromfile(tmp / "repetitiveMinimizers.bin", dtype=np.uint32)
+    if hifi:
+        assert len(bl) == 0                                  # ReadSelection.hpp:501: nothing for HiFi
+    else:
+        # ONT: the most frequent minimizers of the sketch at the correction density (no blacklist, no HPC)
+        _, mc, _, _ = oracle.sketch_batch(bases, offs, 15, corr, False)
+        vals, counts = np.unique(mc, return_counts=True)
+        want_n = max(1, int(np.float32(0.00001) * np.float32(len(vals))))
+        assert len(bl) == want_n and counts[np.isin(vals, bl)].min() >= np.sort(counts)[-want_n]
+    mo, m, p, d = oracle.sketch_batch(bases, offs, 15, dens, hifi, blacklist=np.sort(bl) if len(bl) else None)
+    b = open(tmp / "read_stats.txt", "rb").read()
+    n50 = int(np.frombuffer(b, np.uint32, 1, 8)[0])
+    assert int(np.frombuffer(b, np.uint64, 1, 0)[0]) == rs.n_reads and int(np.frombuffer(b, np.uint64, 1, 32)[0]) == len(m)
+    last_k = max(int(np.float32(n50) * np.float32(dens) * np.float32(2.0)), 6)      # Commons::computeLastK
+    pm, po = [], [0]
+    for r in range(rs.n_reads):
+        q, _ = oracle.purge_palindrome(m[int(mo[r]):int(mo[r + 1])], 4, last_k)
+        pm.append(q); po.append(po[-1] + len(q))
+    pm = np.concatenate(pm).astype(np.uint32); po = np.array(po, np.uint64)
+    buf = open(tmp / "read_data_corrected.txt", "rb").read()
+    pos, got = 0, []
+    for r in range(rs.n_reads):
+        n = int(np.frombuffer(buf, np.uint32, 1, pos)[0]); pos += 5
+        got.append(np.frombuffer(buf, np.uint32, n, pos)); pos += 4 * n
+    assert pos == len(buf) and np.array_equal(np.concatenate(got), pm)
+    for min_ab in (2, 0):
+        out = subprocess.run([EXE, "graph", str(tmp), "--threads", "4", "--min-abundance", str(min_ab), "--firstpass"],
+                             capture_output=True, text=True, timeout=180)
+        assert out.returncode == 0, out.stderr
+        ref = oracle.count(pm, po, 4, 2)
+        want = {(int(h[0]), int(h[1])): int(a) for h, a in zip(ref["hashes"], ref["abundances"])}
+        if min_ab == 0:                                     # default mode: rescued abundance-1 entries ride along
+            for h in oracle.rescue(pm, po, 4, ref["hashes"], ref["abundances"])["hashes"]:
+                want[(int(h[0]), int(h[1]))] = 1
+        ab = np.frombuffer(open(tmp / "kminmerData_abundance.txt", "rb").read(), dtype=np.uint8).reshape(-1, 20)
+        lo = ab[:, 0:8].copy().view(np.uint64)[:, 0]; hi = ab[:, 8:16].copy().view(np.uint64)[:, 0]
+        cnt = ab[:, 16:20].copy().view(np.uint32)[:, 0]
+        assert {(int(h), int(l)): int(c) for h, l, c in zip(hi, lo, cnt)} == want and len(want) > 100
+        vec = np.frombuffer(open(tmp / "kminmerData_min.txt", "rb").read(), dtype=np.uint32).reshape(-1, 4)
+        assert len(vec) == len(want)
+    # a later pass needs the contig stage: refused with a message, not silently wrong
+    out = subprocess.run([EXE, "graph", str(tmp), "--threads", "4"], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 1 and "firstpass" in out.stderr
