@@ -382,8 +382,12 @@ class DeviceReads:
         return n_min
 
 
-def hot_path(eng, dr, w, lk, world, ascii_input=False, last_k=4):
-    """One step.  Returns (statistics of the LAST table incl. the on-device emit, minimizers sketched, per-k entries)."""
+def hot_path(eng, dr, w, lk, world, ascii_input=False, last_k=4, merge_every_k=True):
+    """One step.  Returns (statistics of the LAST table incl. the on-device emit, minimizers sketched, per-k entries).
+
+    merge_every_k=False (N > 1, multi-k): the tables of k = 5 .. last_k - 1 stay rank-local -- every rank holds the
+    k-min-mers of ITS reads with their (global) abundances, which is all the next pass needs (it reads per-position
+    values, no table) -- and only the first and the last table are merged to their owners."""
     eng.store_clear()
     n_min = dr.sketch_all(eng, ascii_input)
     if w["asm_density"]:
@@ -395,14 +399,17 @@ def hot_path(eng, dr, w, lk, world, ascii_input=False, last_k=4):
         eng.count_merge()
     tab = eng.count_finalize_device(MIN_AB)            # statistics + (hash128, abundance, k-min-mer) arrays left in HBM
     per_k = [tab["n_entries"]]
+    n_keys = tab["n_entries"] * world                  # keys a rank's table of the next k will hold (about as many as now)
     for k in range(K + 1, last_k + 1):                 # multi-k: every further k from the previous k's table, on the device
         eng.prev_from_current(MIN_AB)
-        eng.count_begin(k, 2 * max(256, per_k[-1]) * world)
+        eng.count_begin(k, int(1.3 * max(256, n_keys)))     # grows on demand
         eng.count_add_store_next_k()
-        if world > 1:
+        merged = world > 1 and (merge_every_k or k == last_k)
+        if merged:
             eng.count_merge_hashes()                   # (hash128, abundance) records: the k > 4 tables need no vectors on the owner
         tab = eng.count_finalize_device(MIN_AB)
         per_k.append(tab["n_entries"])
+        n_keys = tab["n_entries"] * (world if merged else 1)
     return tab, n_min, per_k
 
 
@@ -892,12 +899,25 @@ def run_extra(args, xn, torch, dev, rank, world, eng, new_engine, timed, sum_ove
 
     ms, tab = timed(step, 3, 2)
     total_bases = sum_over_ranks(dr.n_bases)
+    variant = None
+    if world > 1 and last_k > K + 1:
+        # the same loop with the tables of the intermediate k's left rank-local (merge at k = 4 and at the last k only)
+        def step_local():
+            return hot_path(eng, dr, w, lk, world, last_k=last_k, merge_every_k=False)[0]
+        ms_l, tab_l = timed(step_local, 2, 2)
+        variant = {"value": total_bases / (ms_l * 1e-3) / 1e9, "unit": "Gbp/s", "ms_per_step": ms_l,
+                   "checksum_total_last_k": sum_u64_over_ranks(tab_l["checksum"]),
+                   "same_last_table_as_per_k_merge": sum_u64_over_ranks(tab_l["checksum"]) == sum_u64_over_ranks(tab["checksum"]),
+                   "what": "tables of k = 5 .. last_k - 1 stay rank-local (k-min-mers of the rank's own reads with their global "
+                           "abundances; the next pass reads per-position values, no table); owner merge at k = 4 and at the last k"}
     res = {"config": workload_config(xn, reads, read_len, args.genomes, world), "scaling": "weak" if w["per_gpu"] else "strong",
            "value": total_bases / (ms * 1e-3) / 1e9, "unit": "Gbp/s", "ms_per_step": ms, "steps": 2, "warmup": 3,
            "n_bases_total": int(total_bases), "n_minimizers_total": sum_over_ranks(out["n_min"]),
            "n_entries_per_k_total": [sum_over_ranks(x) for x in out["per_k"]], "k_last": last_k,
            "checksum_total_last_k": sum_u64_over_ranks(tab["checksum"]), "resident_chunks_rank0": len(dr.chunks),
-           "generate_and_pack_s": round(t_gen, 2),
+           "generate_and_pack_s": round(t_gen, 2), "merge_at_first_and_last_k_only": variant,
+           "merge": ("k = 4: owner merge with vectors; every k > 4: keys-only owner merge (hash128, abundance)" if world > 1 and last_k > K else
+                     "owner merge with vectors" if world > 1 else None),
            "timer": "CUDA events on the launching stream around 2 steps after 3 warm-up steps, barriers on both sides, max over ranks"}
     del dr
     if own:

@@ -294,6 +294,25 @@ mdbg_status mdbg_purge_palindromes(mdbg_ctx* ctx, uint32_t first_k, uint32_t las
  * density (0.025) are parsed at the assembly density (0.005), src/Commons.hpp:7457. */
 mdbg_status mdbg_store_apply_density(mdbg_ctx* ctx, float density, uint64_t* n_reads_changed);
 
+/* ---- inverted index: k-min-mer -> (read, window) postings (row (f)4 of SURVEY.md section 8) -----------------------
+ * What ReadCorrection::indexReads builds over the low-density reads for the ONT all-vs-all chaining
+ * (IndexReadsFunctor, src/readSelection/ReadCorrection.hpp:3064-3130): for every emitted k-min-mer of the current
+ * occurrence-count table, the list of (read index in the store, window index = positionIndex) of its occurrences.
+ * CSR over the keys: list j is reads / windows[offsets[j] .. offsets[j+1]); its length is the k-min-mer's abundance;
+ * the order inside a list is unspecified (upstream: arrival order of the OpenMP threads).  Host arrays are pinned and
+ * library-owned; the d_* pointers are the same arrays in HBM.  Single context; the table must be the count of the
+ * whole store (mdbg_count_begin + one mdbg_count_add_store). */
+typedef struct {
+    uint32_t k;
+    uint64_t n_keys, n_postings;
+    const uint64_t* hashes;     /* [2*n_keys]: low 64 bits, high 64 bits */
+    const uint64_t* offsets;    /* [n_keys+1] */
+    const uint32_t* reads;      /* [n_postings] */
+    const uint32_t* windows;    /* [n_postings] */
+    const uint64_t* d_hashes; const uint64_t* d_offsets; const uint32_t* d_reads; const uint32_t* d_windows;
+} mdbg_postings_out;
+mdbg_status mdbg_count_postings(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_postings_out* out);
+
 /* ---- repetitive minimizers (ONT path; ReadSelection::determineRepetitiveMinimizers + CountMinimizerFunctor,
  * src/readSelection/ReadSelection.hpp:497-625) ------------------------------------------------------------
  * Counts every minimizer of the stored reads (upstream: the first 1 M reads sketched at the correction density with

@@ -70,6 +70,8 @@ struct mdbg_ctx {
     int last_overflow_fallback = 0, last_packed = 0;
     int auto_pack_pause = 0;           // auto mode: batches still to send as ASCII after the packer proved too slow
     DevBuf d_pack, d_src, d_dirty;
+    DevBuf pg_counts, pg_flags, pg_keyidx, pg_off, pg_readof, pg_hash, pg_koff, pg_reads, pg_wins;   // postings index
+    PinBuf hpg_hash, hpg_koff, hpg_reads, hpg_wins;
     DevBuf r_table, r_hist, r_out;                                // repetitive-minimizer histogram (K1b)
     std::vector<uint32_t> r_sel_min, r_sel_cnt;
     DevBuf f_raw, f_cnt, f_off, f_nl, f_start, f_len, f_qstart;   // FASTQ / FASTA text ingest (mdbg_sketch_fastx)
@@ -852,10 +854,10 @@ void mdbg_ctx_destroy(mdbg_ctx* c) {
     DevBuf* devs[] = {&c->d_blacklist, &c->d_bases, &c->d_offsets, &c->pad_min, &c->pad_pos, &c->pad_dir, &c->n_min,
                       &c->scan_scratch, &c->b_off, &c->b_min, &c->b_pos, &c->b_dir, &c->s_min, &c->s_off, &c->s_rem,
                       &c->p_flags, &c->p_keep, &c->p_cnt, &c->p_newoff, &c->p_newmin, &c->table, &c->foreign_vecs,
-                      &c->o_hash, &c->o_abund, &c->o_vecs, &c->d_pack, &c->d_src, &c->d_dirty, &c->r_table, &c->r_hist, &c->r_out, &c->f_raw, &c->f_cnt, &c->f_off, &c->f_nl, &c->f_start, &c->f_len, &c->f_qstart, &c->d_quals, &c->pad_qual, &c->pad_raw_a, &c->pad_raw_b, &c->b_qual, &c->x_sum_lo, &c->x_sum_hi, &c->x_lmin, &c->x_cplx, &c->x_low, &c->d_err_fixed, &c->d_err_tz, &c->prev_table, &c->prev_stage_h, &c->prev_stage_a, &c->rescue_table, &c->val_a, &c->val_b, &c->prev_src, &c->m_send_vecs, &c->m_send_counts, &c->m_recv_vecs,
+                      &c->o_hash, &c->o_abund, &c->o_vecs, &c->d_pack, &c->d_src, &c->d_dirty, &c->pg_counts, &c->pg_flags, &c->pg_keyidx, &c->pg_off, &c->pg_readof, &c->pg_hash, &c->pg_koff, &c->pg_reads, &c->pg_wins, &c->r_table, &c->r_hist, &c->r_out, &c->f_raw, &c->f_cnt, &c->f_off, &c->f_nl, &c->f_start, &c->f_len, &c->f_qstart, &c->d_quals, &c->pad_qual, &c->pad_raw_a, &c->pad_raw_b, &c->b_qual, &c->x_sum_lo, &c->x_sum_hi, &c->x_lmin, &c->x_cplx, &c->x_low, &c->d_err_fixed, &c->d_err_tz, &c->prev_table, &c->prev_stage_h, &c->prev_stage_a, &c->rescue_table, &c->val_a, &c->val_b, &c->prev_src, &c->m_send_vecs, &c->m_send_counts, &c->m_recv_vecs,
                       &c->m_recv_counts, &c->m_bucket, &c->loc_off, &c->edge_table, &c->edge_vals, &c->o_edge_vals};
     for (DevBuf* b : devs) release(*b);
-    PinBuf* pins[] = {&c->h_off, &c->h_min, &c->h_pos, &c->h_dir, &c->ho_hash, &c->ho_abund, &c->ho_vecs, &c->hx_sum_lo, &c->hx_sum_hi, &c->hx_lmin, &c->hx_cplx, &c->hx_low, &c->hx_meanq, &c->h_qual, &c->h_pack, &c->h_src, &c->h_asc, &c->ho_edge_vals};
+    PinBuf* pins[] = {&c->h_off, &c->h_min, &c->h_pos, &c->h_dir, &c->ho_hash, &c->ho_abund, &c->ho_vecs, &c->hx_sum_lo, &c->hx_sum_hi, &c->hx_lmin, &c->hx_cplx, &c->hx_low, &c->hx_meanq, &c->h_qual, &c->h_pack, &c->h_src, &c->h_asc, &c->ho_edge_vals, &c->hpg_hash, &c->hpg_koff, &c->hpg_reads, &c->hpg_wins};
     for (PinBuf* b : pins) release(*b);
     if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
     if (c->d_small) cudaFree(c->d_small);
@@ -2778,6 +2780,78 @@ mdbg_status mdbg_edges_index(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_edges_o
     return MDBG_OK;
 }
 
+// Inverted index over the current table: for every emitted k-min-mer the (read, window) pairs of its occurrences in
+// the stored reads (ReadCorrection::IndexReadsFunctor, src/readSelection/ReadCorrection.hpp:3064-3130).
+mdbg_status mdbg_count_postings(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_postings_out* out) {
+    if (!ctx || !out) return MDBG_ERR_ARG;
+    memset(out, 0, sizeof *out);
+    if (!ctx->t_active) return fail(ctx, MDBG_ERR_STATE, "mdbg_count_postings before mdbg_count_begin");
+    if (ctx->n_ranks > 1) return fail(ctx, MDBG_ERR_STATE, "mdbg_count_postings is a single-context call (postings refer to the rank's own reads)");
+    if (ctx->t_value_mode || !ctx->t_whole)
+        return fail(ctx, MDBG_ERR_STATE, "mdbg_count_postings needs the occurrence-count table of the whole store (one mdbg_count_add_store over all reads)");
+    if (ctx->t_capacity > 0xFFFFFFF0ull || ctx->s_reads > 0xFFFFFFF0ull) return fail(ctx, MDBG_ERR_ARG, "table too large for the postings scan");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const uint32_t thr = count_threshold(ctx, min_abundance);
+    const uint64_t cap = ctx->t_capacity;
+    CKS(ensure_rem(ctx));
+    CKS(ensure(ctx, ctx->pg_counts, cap * 4));
+    CKS(ensure(ctx, ctx->pg_flags, cap * 4));
+    CKS(ensure(ctx, ctx->pg_keyidx, (cap + 1) * 8));
+    CKS(ensure(ctx, ctx->pg_off, (cap + 1) * 8));
+    CKS(ensure(ctx, ctx->pg_readof, (ctx->s_mins + 1) * 4));
+    CKS(ensure(ctx, ctx->scan_scratch, scan_scratch_elems((uint32_t)cap) * sizeof(uint64_t)));
+    launch_posting_counts(ctx->table.as<Slot>(), cap, thr, ctx->pg_counts.as<uint32_t>(), ctx->pg_flags.as<uint32_t>(), s);
+    launch_scan_u32_to_u64(ctx->pg_flags.as<uint32_t>(), ctx->pg_keyidx.as<uint64_t>(), (uint32_t)cap, ctx->scan_scratch.as<uint64_t>(), s);
+    launch_scan_u32_to_u64(ctx->pg_counts.as<uint32_t>(), ctx->pg_off.as<uint64_t>(), (uint32_t)cap, ctx->scan_scratch.as<uint64_t>(), s);
+    launch_read_of(ctx->s_off.as<uint64_t>(), ctx->s_reads, ctx->pg_readof.as<uint32_t>(), s);
+    CKS(check_launch(ctx, "posting_counts_kernel + scans + read_of_kernel", 8));
+    CK(cudaMemcpyAsync(&ctx->h_scalar[0], ctx->pg_keyidx.as<uint64_t>() + cap, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&ctx->h_scalar[1], ctx->pg_off.as<uint64_t>() + cap, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const uint64_t n_keys = ctx->h_scalar[0], n_post = ctx->h_scalar[1];
+    CKS(ensure(ctx, ctx->pg_hash, (n_keys + 1) * 16));
+    CKS(ensure(ctx, ctx->pg_koff, (n_keys + 2) * 8));
+    CKS(ensure(ctx, ctx->pg_reads, (n_post + 1) * 4));
+    CKS(ensure(ctx, ctx->pg_wins, (n_post + 1) * 4));
+    launch_posting_keys(ctx->table.as<Slot>(), cap, ctx->pg_flags.as<uint32_t>(), ctx->pg_keyidx.as<uint64_t>(),
+                        ctx->pg_off.as<uint64_t>(), ctx->pg_hash.as<uint64_t>(), ctx->pg_koff.as<uint64_t>(), s);
+    CK(cudaMemsetAsync(ctx->pg_counts.p, 0, cap * 4, s));               // reused as the per-list fill cursors
+    PostingArgs pa{};
+    pa.mins = ctx->s_min.as<uint32_t>(); pa.rem = ctx->s_rem.as<uint8_t>(); pa.offs = ctx->s_off.as<uint64_t>();
+    pa.read_of = ctx->pg_readof.as<uint32_t>();
+    pa.g_lo = 0; pa.g_hi = ctx->s_mins; pa.k = ctx->t_k;
+    pa.table = ctx->table.as<Slot>(); pa.mask = cap - 1;
+    pa.flags = ctx->pg_flags.as<uint32_t>(); pa.post_off = ctx->pg_off.as<uint64_t>(); pa.cursors = ctx->pg_counts.as<uint32_t>();
+    pa.out_reads = ctx->pg_reads.as<uint32_t>(); pa.out_windows = ctx->pg_wins.as<uint32_t>();
+    launch_posting_fill(pa, s);
+    CKS(check_launch(ctx, "posting_keys_kernel + posting_fill_kernel", 2));
+    CKS(ensure_pin(ctx, ctx->hpg_hash, (n_keys + 1) * 16));
+    CKS(ensure_pin(ctx, ctx->hpg_koff, (n_keys + 2) * 8));
+    CKS(ensure_pin(ctx, ctx->hpg_reads, (n_post + 1) * 4));
+    CKS(ensure_pin(ctx, ctx->hpg_wins, (n_post + 1) * 4));
+    if (n_keys) CK(cudaMemcpyAsync(ctx->hpg_hash.p, ctx->pg_hash.p, n_keys * 16, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ctx->hpg_koff.p, ctx->pg_koff.p, (n_keys + 1) * 8, cudaMemcpyDeviceToHost, s));
+    if (n_post) {
+        CK(cudaMemcpyAsync(ctx->hpg_reads.p, ctx->pg_reads.p, n_post * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(ctx->hpg_wins.p, ctx->pg_wins.p, n_post * 4, cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    ctx->d2h_bytes += n_keys * 24 + n_post * 8;
+    out->k = ctx->t_k;
+    out->n_keys = n_keys;
+    out->n_postings = n_post;
+    out->hashes = ctx->hpg_hash.as<uint64_t>();
+    out->offsets = ctx->hpg_koff.as<uint64_t>();
+    out->reads = ctx->hpg_reads.as<uint32_t>();
+    out->windows = ctx->hpg_wins.as<uint32_t>();
+    out->d_hashes = ctx->pg_hash.as<uint64_t>();
+    out->d_offsets = ctx->pg_koff.as<uint64_t>();
+    out->d_reads = ctx->pg_reads.as<uint32_t>();
+    out->d_windows = ctx->pg_wins.as<uint32_t>();
+    return MDBG_OK;
+}
+
 // ---- multi-GPU --------------------------------------------------------------------------
 mdbg_status mdbg_nccl_unique_id(uint8_t id_out[128]) {
     mdbg_ctx* ctx = nullptr;
@@ -2919,30 +2993,35 @@ mdbg_status mdbg_count_merge_hashes(mdbg_ctx* ctx) {
     const uint32_t R = (uint32_t)ctx->n_ranks;
     CKS(ensure(ctx, ctx->m_bucket, (size_t)(2 * R + R * R) * 8));
     uint64_t* d_cnt = ctx->m_bucket.as<uint64_t>();
-    uint64_t* d_base = d_cnt + R;
     CK(cudaMemsetAsync(d_cnt, 0, R * 8, s));
     PhaseClock clk(ctx);
+    // ONE pack pass: a region of the send buffer per destination, each large enough for every key of the table (the
+    // number of distinct keys is known from the pass's claim counter; a table with foreign entries is scanned once)
+    uint64_t region_cap = ctx->h_small->t_claims;
+    if (!ctx->t_rebuildable || region_cap == 0 || region_cap > ctx->t_capacity) {
+        TableStats st;
+        CKS(table_stats(ctx, 2, &st));
+        region_cap = st.n_distinct;
+    }
+    region_cap += 1;
+    CKS(ensure(ctx, ctx->m_send_vecs, (size_t)R * region_cap * 24));
     PackArgs p{};
     p.table = ctx->table.as<Slot>();
     p.capacity = ctx->t_capacity;
     p.k = ctx->t_k;
     p.n_ranks = R;
     p.bucket_count = reinterpret_cast<unsigned long long*>(d_cnt);
-    p.pass = 1;
-    launch_table_pack_hashes(p, nullptr, s);
-    CKS(check_launch(ctx, "table_pack_hashes_kernel(count)", 1));
-    clk.lap(PH_MERGE_PACK_COUNT);
+    launch_table_pack_hashes(p, ctx->m_send_vecs.as<uint64_t>(), region_cap, s);
+    CKS(check_launch(ctx, "table_pack_hashes_kernel", 1));
+    clk.lap(PH_MERGE_PACK_SCATTER);
     OwnerExchange x;
-    CKS(x.plan(ctx));
-    CKS(ensure(ctx, ctx->m_send_vecs, (x.send_total + 1) * 24));
+    CKS(x.plan(ctx));                                               // all-gather of the R x R counts + one D2H
+    for (uint32_t d = 0; d < R; d++) {
+        if (x.send_cnt[d] > region_cap) return fail(ctx, MDBG_ERR_STATE, "keys-only merge: send region overflow");
+        x.send_base[d] = (uint64_t)d * region_cap;                  // regions, not a packed prefix
+    }
     CKS(ensure(ctx, ctx->m_recv_vecs, (x.recv_total + 1) * 24));
     clk.lap(PH_MERGE_PLAN);
-    CKS(x.upload_bases(ctx));
-    p.bucket_base = d_base;
-    p.pass = 2;
-    launch_table_pack_hashes(p, ctx->m_send_vecs.as<uint64_t>(), s);
-    CKS(check_launch(ctx, "table_pack_hashes_kernel(scatter)", 1));
-    clk.lap(PH_MERGE_PACK_SCATTER);
     CKS(x.run(ctx, ctx->m_send_vecs.p, ctx->m_recv_vecs.p, 24));
     clk.lap(PH_MERGE_EXCHANGE);
     const uint64_t cap = table_capacity_for(x.recv_total);

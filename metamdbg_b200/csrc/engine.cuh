@@ -295,6 +295,20 @@ void launch_edge_offers(const EdgeArgs& a, uint64_t* out_recs, unsigned long lon
 void launch_edge_apply_offers(const uint64_t* recs, uint64_t n, const Slot* edges, uint64_t mask, unsigned long long* vals,
                               uint32_t* full_flag, cudaStream_t s);
 
+// ---- postings (kminmer.cu): k-min-mer -> (read, window) lists over the count table
+struct PostingArgs {
+    const uint32_t* mins; const uint8_t* rem; const uint64_t* offs; const uint32_t* read_of;
+    uint64_t g_lo, g_hi; uint32_t k;
+    const Slot* table; uint64_t mask;
+    const uint32_t* flags; const uint64_t* post_off; uint32_t* cursors;
+    uint32_t* out_reads; uint32_t* out_windows;
+};
+void launch_posting_counts(const Slot* table, uint64_t capacity, uint32_t min_count, uint32_t* counts, uint32_t* flags, cudaStream_t s);
+void launch_posting_keys(const Slot* table, uint64_t capacity, const uint32_t* flags, const uint64_t* key_index,
+                         const uint64_t* post_off, uint64_t* out_hashes, uint64_t* out_offsets, cudaStream_t s);
+void launch_read_of(const uint64_t* offs, uint64_t n_reads, uint32_t* read_of, cudaStream_t s);
+void launch_posting_fill(const PostingArgs& a, cudaStream_t s);
+
 // multi-GPU pack: bucket every occupied slot by owner rank
 struct PackArgs {
     const Slot* table;
@@ -310,8 +324,8 @@ struct PackArgs {
     int pass;                           // 1 = count, 2 = scatter
 };
 void launch_table_pack(const PackArgs& a, cudaStream_t s);
-// keys-only form: 24-byte records {hash lo, hash hi, count}; same two passes, same bucket arithmetic
-void launch_table_pack_hashes(const PackArgs& a, uint64_t* out_recs, cudaStream_t s);
+// keys-only form, ONE pass: 24-byte records {hash lo, hash hi, count} appended to a fixed-capacity region per destination
+void launch_table_pack_hashes(const PackArgs& a, uint64_t* out_recs, uint64_t region_cap, cudaStream_t s);
 void launch_insert_hash_recs(const uint64_t* recs, uint64_t n, Slot* table, uint64_t mask, uint32_t assign, uint32_t* full_flag,
                              cudaStream_t s);
 

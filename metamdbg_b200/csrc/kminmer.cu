@@ -834,49 +834,47 @@ void launch_table_pack(const PackArgs& a, cudaStream_t s) {
 // For tables whose k-min-mer VECTORS are not wanted on the owner (the per-k tables of a multi-k loop: the next pass
 // needs no table at all, see next_k_stream_kernel): records of 24 bytes {hash lo, hash hi, count | 0} instead of
 // 4 k + 4 bytes, no gather of vectors on the sender, no re-hash on the owner.
-__global__ void __launch_bounds__(256) table_pack_hashes_kernel(const PackArgs a, uint64_t* out_recs) {
-    __shared__ uint32_t wcnt[8][PACK_MAX_RANKS];
-    __shared__ unsigned long long bbase[PACK_MAX_RANKS];
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// ONE pass: every destination has a fixed-capacity region of the send buffer (region_cap records; the host sizes it
+// for the table's number of distinct keys, so it cannot overflow), records are appended through one cursor per
+// destination -- warp-aggregated: lanes with the same destination share one atomicAdd.
+__global__ void __launch_bounds__(256) table_pack_hashes_kernel(const PackArgs a, uint64_t* out_recs, uint64_t region_cap) {
+    const uint32_t lane = threadIdx.x & 31;
     const uint32_t R = a.n_ranks;
-    const uint64_t n_tiles = (a.capacity + 255) / 256;
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint64_t i = tile * 256 + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n_rounds = (a.capacity + stride - 1) / stride;
+    for (uint64_t round = 0; round < n_rounds; round++) {
+        const uint64_t i = round * stride + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
         bool take = false;
-        uint32_t dst = 0, count = 0, my_prefix = 0;
+        uint32_t dst = 0xFFFFFFFFu, count = 0;
         uint64_t lo = 0, hi = 0;
         if (i < a.capacity) {
-            const Slot sl = a.table[i];
-            take = (sl.lo | sl.hi) != 0;
-            dst = owner_of(sl.hi, R);
-            count = sl.count; lo = sl.lo; hi = sl.hi;
+            const uint4 q0 = reinterpret_cast<const uint4*>(a.table + i)[0];
+            lo = (uint64_t)q0.x | ((uint64_t)q0.y << 32);
+            hi = (uint64_t)q0.z | ((uint64_t)q0.w << 32);
+            take = (lo | hi) != 0;
+            if (take) { dst = owner_of(hi, R); count = a.table[i].count; }
         }
-        for (uint32_t d = 0; d < R; d++) {
-            const uint32_t m = __ballot_sync(0xffffffffu, take && dst == d);
-            if (lane == 0) wcnt[warp][d] = __popc(m);
-            if (take && dst == d) my_prefix = __popc(m & ((1u << lane) - 1u));
+        if (!__any_sync(0xffffffffu, take)) continue;
+        const uint32_t peers = __match_any_sync(0xffffffffu, dst);           // lanes with my destination (idle lanes match each other)
+        const uint32_t leader = __ffs(peers) - 1, rank_in = __popc(peers & ((1u << lane) - 1u));
+        unsigned long long base = 0;
+        if (take && lane == leader) base = atomicAdd(&a.bucket_count[dst], (unsigned long long)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (take) {
+            const uint64_t pos = (uint64_t)dst * region_cap + base + rank_in;
+            if (base + rank_in < region_cap) {
+                out_recs[3 * pos] = lo;
+                out_recs[3 * pos + 1] = hi;
+                out_recs[3 * pos + 2] = count;
+            }
         }
-        __syncthreads();
-        if (threadIdx.x < R) {
-            uint32_t tot = 0;
-            for (int w = 0; w < 8; w++) { const uint32_t c = wcnt[w][threadIdx.x]; wcnt[w][threadIdx.x] = tot; tot += c; }
-            bbase[threadIdx.x] = tot ? atomicAdd(&a.bucket_count[threadIdx.x], (unsigned long long)tot) : 0ULL;
-        }
-        __syncthreads();
-        if (a.pass == 2 && take) {
-            const uint64_t pos = a.bucket_base[dst] + bbase[dst] + wcnt[warp][dst] + my_prefix;
-            out_recs[3 * pos] = lo;
-            out_recs[3 * pos + 1] = hi;
-            out_recs[3 * pos + 2] = count;
-        }
-        __syncthreads();
     }
 }
 
-void launch_table_pack_hashes(const PackArgs& a, uint64_t* out_recs, cudaStream_t s) {
+void launch_table_pack_hashes(const PackArgs& a, uint64_t* out_recs, uint64_t region_cap, cudaStream_t s) {
     uint64_t blocks = (a.capacity + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    table_pack_hashes_kernel<<<(unsigned)blocks, 256, 0, s>>>(a, out_recs);
+    table_pack_hashes_kernel<<<(unsigned)blocks, 256, 0, s>>>(a, out_recs, region_cap);
 }
 
 __global__ void __launch_bounds__(256) insert_hash_recs_kernel(const uint64_t* recs, uint64_t n, Slot* table, uint64_t mask,
@@ -893,6 +891,83 @@ void launch_insert_hash_recs(const uint64_t* recs, uint64_t n, Slot* table, uint
                              cudaStream_t s) {
     if (n == 0) return;
     insert_hash_recs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(recs, n, table, mask, assign, full_flag);
+}
+
+// ------------------------------------------------------------------ postings: k-min-mer -> (read, window) lists
+// Row (f)4: the inverted index the ONT correction stage builds over the low-density reads
+// (ReadCorrection::IndexReadsFunctor, src/readSelection/ReadCorrection.hpp:3064-3130: for every window i of every
+// read, _kminmer_to_readIndex[vec] gets (readIndex, positionIndex = i) when vec is a known k-min-mer).  Here the
+// count table IS the key set and its abundances are the list lengths: one scan over the slots gives every list its
+// place in one postings array (CSR), and one pass over the windows fills it.  Order inside a list is unspecified
+// (upstream's is the arrival order of its OpenMP threads).
+__global__ void __launch_bounds__(256) posting_counts_kernel(const Slot* table, uint64_t capacity, uint32_t min_count,
+                                                             uint32_t* counts, uint32_t* flags) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < capacity; i += (uint64_t)gridDim.x * blockDim.x) {
+        const Slot sl = table[i];
+        const bool take = (sl.lo | sl.hi) != 0 && (sl.count >= min_count || (sl.flags & SLOT_RESCUED));
+        counts[i] = take ? sl.count : 0u;
+        flags[i] = take ? 1u : 0u;
+    }
+}
+
+__global__ void __launch_bounds__(256) posting_keys_kernel(const Slot* table, uint64_t capacity, const uint32_t* flags,
+                                                           const uint64_t* key_index, const uint64_t* post_off,
+                                                           uint64_t* out_hashes, uint64_t* out_offsets) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < capacity; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (!flags[i]) continue;
+        const uint64_t j = key_index[i];
+        out_hashes[2 * j] = table[i].lo;
+        out_hashes[2 * j + 1] = table[i].hi;
+        out_offsets[j] = post_off[i];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) out_offsets[key_index[capacity]] = post_off[capacity];
+}
+
+__global__ void __launch_bounds__(256) read_of_kernel(const uint64_t* offs, uint64_t n_reads, uint32_t* read_of) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t r = warp; r < n_reads; r += n_warps)
+        for (uint64_t g = offs[r] + lane; g < offs[r + 1]; g += 32) read_of[g] = (uint32_t)r;
+}
+
+__global__ void __launch_bounds__(256) posting_fill_kernel(const PostingArgs a) {
+    const uint64_t g = a.g_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= a.g_hi) return;
+    const int k = (int)a.k;
+    if ((int)a.rem[g] < k) return;
+    uint64_t h1, h2; bool rev;
+    window_hash(a.mins + g, k, h1, h2, rev);
+    const Slot* s = table_find(const_cast<Slot*>(a.table), a.mask, h2, h1);
+    if (!s) return;
+    const uint64_t i = (uint64_t)(s - a.table);
+    if (!a.flags[i]) return;
+    const uint64_t p = a.post_off[i] + atomicAdd(&a.cursors[i], 1u);
+    const uint32_t r = a.read_of[g];
+    a.out_reads[p] = r;
+    a.out_windows[p] = (uint32_t)(g - a.offs[r]);
+}
+
+void launch_posting_counts(const Slot* table, uint64_t capacity, uint32_t min_count, uint32_t* counts, uint32_t* flags, cudaStream_t s) {
+    uint64_t blocks = (capacity + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    posting_counts_kernel<<<(unsigned)blocks, 256, 0, s>>>(table, capacity, min_count, counts, flags);
+}
+void launch_posting_keys(const Slot* table, uint64_t capacity, const uint32_t* flags, const uint64_t* key_index,
+                         const uint64_t* post_off, uint64_t* out_hashes, uint64_t* out_offsets, cudaStream_t s) {
+    uint64_t blocks = (capacity + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    posting_keys_kernel<<<(unsigned)blocks, 256, 0, s>>>(table, capacity, flags, key_index, post_off, out_hashes, out_offsets);
+}
+void launch_read_of(const uint64_t* offs, uint64_t n_reads, uint32_t* read_of, cudaStream_t s) {
+    if (n_reads == 0) return;
+    uint64_t blocks = (n_reads + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    read_of_kernel<<<(unsigned)blocks, 256, 0, s>>>(offs, n_reads, read_of);
+}
+void launch_posting_fill(const PostingArgs& a, cudaStream_t s) {
+    if (a.g_hi <= a.g_lo) return;
+    posting_fill_kernel<<<(unsigned)((a.g_hi - a.g_lo + 255) / 256), 256, 0, s>>>(a);
 }
 
 }  // namespace mdbg

@@ -17,7 +17,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _capi
-from ._capi import AutotuneOut, AuxOut, BatchInfo, EdgesOut, FastxInfo, MdbgParams, RepeatsOut, SketchDev, SketchOut, TableDev, TableOut
+from ._capi import AutotuneOut, AuxOut, BatchInfo, EdgesOut, FastxInfo, MdbgParams, PostingsOut, RepeatsOut, SketchDev, SketchOut, TableDev, TableOut
 
 STATUS = {0: "OK", 1: "CUDA", 2: "ARG", 3: "STATE", 4: "TABLE_FULL", 5: "NCCL", 6: "OOM"}
 
@@ -404,6 +404,17 @@ class Engine:
         else:
             h = np.zeros((0, 2), np.uint64); a = np.zeros(0, np.uint32); v = np.zeros((0, k), np.uint32)
         return CountTable(k, h, a, v, int(out.n_instances), int(out.n_distinct), int(out.checksum), int(out.n_rescued))
+
+    def count_postings(self, min_abundance: int = 2) -> dict:
+        """k-min-mer -> (read, window) postings of the current count table (CSR over the emitted keys)."""
+        out = PostingsOut()
+        self._ck(self._lib.mdbg_count_postings(self._ctx, min_abundance, C.byref(out)))
+        n, m = int(out.n_keys), int(out.n_postings)
+        return dict(k=int(out.k),
+                    hashes=np.ctypeslib.as_array(out.hashes, shape=(2 * n,)).copy().reshape(n, 2) if n else np.zeros((0, 2), np.uint64),
+                    offsets=np.ctypeslib.as_array(out.offsets, shape=(n + 1,)).copy(),
+                    reads=np.ctypeslib.as_array(out.reads, shape=(m,)).copy() if m else np.zeros(0, np.uint32),
+                    windows=np.ctypeslib.as_array(out.windows, shape=(m,)).copy() if m else np.zeros(0, np.uint32))
 
     def count_rescue(self) -> int:
         """rescueKminmers (CreateMdbg.hpp:4517-4640); returns the number of reads that rescued k-min-mers."""

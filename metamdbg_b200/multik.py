@@ -20,7 +20,7 @@ import time
 
 def multi_k_sweep(engine, first_k: int = 4, last_k: int = 21, min_abundance: int = 2, rescue: bool = False,
                   merge: bool = False, on_table=None, synchronize: bool = True, world: int = 1,
-                  table_headroom: float = 2.0) -> list[dict]:
+                  table_headroom: float = 1.3) -> list[dict]:
     """Count k = first_k on the engine's store, then derive k = first_k+1 .. last_k from the previous table.
 
     merge: False (one context), True (owner merge with the k-min-mer vectors after every k) or "hashes" (k > first_k:

@@ -293,6 +293,12 @@ template <typename T> static inline T __shfl_xor_sync(unsigned mask, T v, int la
     emu::collective(emu::OP_SHFL_XOR, emu_raw(v), mask);
     return emu_val<T>(emu::peer(emu::lane() ^ lane_mask));
 }
+template <typename T> static inline unsigned __match_any_sync(unsigned mask, T v) {    // lanes holding the same value as mine
+    emu::collective(emu::OP_SHFL, emu_raw(v), mask);
+    unsigned m = 0;
+    for (int i = 0; i < emu::W; i++) m |= (unsigned)(emu::peer(i) == emu_raw(v)) << i;
+    return m;
+}
 static inline unsigned __ballot_sync(unsigned mask, int pred) {
     emu::collective(emu::OP_BALLOT, pred ? 1 : 0, mask);
     unsigned b = 0;

@@ -388,3 +388,40 @@ def test_repetitive_minimizers(built, oracle):
     eng.set_blacklist(None)
     assert_sketch_equal(eng.sketch_batch(bases, offs), sk.min_offsets, sk.minimizers, sk.positions, sk.directions, "blacklist cleared")
     eng.close()
+
+
+def test_postings_index(built, oracle):
+    """mdbg_count_postings: for every solid k-min-mer the (read, window) pairs of its occurrences in the stored reads
+    (ReadCorrection::IndexReadsFunctor) -- list lengths are the abundances, lists hold exactly the occurrences."""
+    rs = synth.make_readset(400, 6000, seed=66, n_genomes=1, genome_len_range=(60_000, 60_001), err=0.002)
+    bases, offs = synth.fill_reads(rs)
+    eng = engine()
+    eng.sketch_batch(bases, offs, append_to_store=True, fetch=False)
+    so, sm = eng.store_fetch()
+    k = 4
+    eng.count_begin(k)
+    eng.count_add_store()
+    tab = eng.count_finalize(2)
+    post = eng.count_postings(2)
+    assert post["k"] == k and len(post["hashes"]) == len(tab.abundances) and len(post["reads"]) == int(tab.abundances.sum())
+    want_ab = {(int(h[0]), int(h[1])): int(a) for h, a in zip(tab.hashes, tab.abundances)}
+    # occurrences from the oracle's window enumeration: hash128 of every normalized window of every read
+    occ = {}
+    for r in range(rs.n_reads):
+        m = sm[int(so[r]):int(so[r + 1])]
+        if len(m) < k:
+            continue
+        vecs = oracle.kminmers(m, k)[0]
+        for i, v in enumerate(vecs):
+            h1, h2 = oracle.hash128(np.ascontiguousarray(v, np.uint32))
+            occ.setdefault((h2, h1), set()).add((r, i))
+    got_keys = set()
+    for j, h in enumerate(post["hashes"]):
+        key = (int(h[0]), int(h[1]))
+        lo, hi = int(post["offsets"][j]), int(post["offsets"][j + 1])
+        assert hi - lo == want_ab[key]
+        pairs = set(zip(post["reads"][lo:hi].tolist(), post["windows"][lo:hi].tolist()))
+        assert len(pairs) == hi - lo and pairs == occ[key], key
+        got_keys.add(key)
+    assert got_keys == set(want_ab) and len(got_keys) > 200
+    eng.close()
