@@ -294,6 +294,18 @@ mdbg_status mdbg_purge_palindromes(mdbg_ctx* ctx, uint32_t first_k, uint32_t las
  * density (0.025) are parsed at the assembly density (0.005), src/Commons.hpp:7457. */
 mdbg_status mdbg_store_apply_density(mdbg_ctx* ctx, float density, uint64_t* n_reads_changed);
 
+/* The whole multi-k loop in one call: count at first_k [merge, rescue], then for k = first_k + 1 .. last_k the
+ * previous-k table from the current one, the next-k pass over the store and [the merge].  merge_mode: 0 = none (one
+ * context), 1 = mdbg_count_merge after every k, 2 = mdbg_count_merge at first_k and mdbg_count_merge_hashes after every
+ * later k.  COLLECTIVE with several ranks.  stats_out has last_k - first_k + 1 entries; the table of last_k stays
+ * current (finalize / edges as usual).  Equivalent to the call sequence shown in INTEGRATION.md. */
+typedef struct {
+    uint32_t k;
+    uint64_t n_entries, n_distinct, n_instances, checksum, n_reads_rescued;
+} mdbg_k_stats;
+mdbg_status mdbg_multi_k_run(mdbg_ctx* ctx, uint32_t first_k, uint32_t last_k, uint32_t min_abundance, int rescue,
+                             int merge_mode, mdbg_k_stats* stats_out);
+
 /* ---- inverted index: k-min-mer -> (read, window) postings (row (f)4 of SURVEY.md section 8) -----------------------
  * What ReadCorrection::indexReads builds over the low-density reads for the ONT all-vs-all chaining
  * (IndexReadsFunctor, src/readSelection/ReadCorrection.hpp:3064-3130): for every emitted k-min-mer of the current

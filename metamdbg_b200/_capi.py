@@ -48,6 +48,11 @@ class FastxInfo(C.Structure):
     _fields_ = [("n_records", C.c_uint64), ("consumed_bytes", C.c_uint64), ("n_bases", C.c_uint64), ("format", C.c_int32)]
 
 
+class KStats(C.Structure):
+    _fields_ = [("k", C.c_uint32), ("n_entries", C.c_uint64), ("n_distinct", C.c_uint64), ("n_instances", C.c_uint64),
+                ("checksum", C.c_uint64), ("n_reads_rescued", C.c_uint64)]
+
+
 class PostingsOut(C.Structure):
     _fields_ = [("k", C.c_uint32), ("n_keys", C.c_uint64), ("n_postings", C.c_uint64), ("hashes", u64p), ("offsets", u64p),
                 ("reads", u32p), ("windows", u32p), ("d_hashes", C.c_void_p), ("d_offsets", C.c_void_p),
@@ -123,6 +128,7 @@ SYMBOLS = {
     "mdbg_store_fetch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "mdbg_store_apply_density": (C.c_int, [C.c_void_p, C.c_float, u64p]),
     "mdbg_purge_palindromes": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, u64p]),
+    "mdbg_multi_k_run": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.POINTER(KStats)]),
     "mdbg_count_postings": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(PostingsOut)]),
     "mdbg_store_repetitive_minimizers": (C.c_int, [C.c_void_p, C.c_float, C.POINTER(RepeatsOut)]),
     "mdbg_ctx_set_blacklist": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),

@@ -2540,7 +2540,11 @@ static mdbg_status replicate_into_prev(mdbg_ctx* ctx, const Slot* src, uint64_t 
 mdbg_status mdbg_prev_from_current(mdbg_ctx* ctx, uint32_t min_abundance) {
     if (!ctx) return MDBG_ERR_ARG;
     if (!ctx->t_active) return fail(ctx, MDBG_ERR_STATE, "mdbg_prev_from_current without a count table");
-    if (ctx->n_ranks > 1 && !ctx->t_merged)
+    // Several ranks: an occurrence-count table must be merged first (abundances are sums over all ranks).  A VALUE table
+    // of a whole-store pass may stay rank-local: its values are functions of the key, and every (k-1)-min-mer the
+    // rank's next pass can ask for is a window of the rank's own reads, i.e. already in this table.
+    const bool local_value_table = ctx->t_value_mode && ctx->t_whole && !ctx->t_merged;
+    if (ctx->n_ranks > 1 && !ctx->t_merged && !local_value_table)
         return fail(ctx, MDBG_ERR_STATE, "multi-rank mdbg_prev_from_current needs the merged table: call mdbg_count_merge first");
     CK(cudaSetDevice(ctx->device));
     const uint32_t thr = count_threshold(ctx, min_abundance);
@@ -2553,7 +2557,7 @@ mdbg_status mdbg_prev_from_current(mdbg_ctx* ctx, uint32_t min_abundance) {
     ctx->prev_min_count = thr;
     ctx->prev_k = ctx->t_k;
     ctx->prev_pure = ctx->t_whole;
-    ctx->prev_replicated = ctx->n_ranks == 1;
+    ctx->prev_replicated = ctx->n_ranks == 1 || local_value_table;
     ctx->t_capacity = 0;
     ctx->t_active = false;
     ctx->t_ranges.clear();
@@ -3004,7 +3008,10 @@ mdbg_status mdbg_count_merge_hashes(mdbg_ctx* ctx) {
         region_cap = st.n_distinct;
     }
     region_cap += 1;
-    CKS(ensure(ctx, ctx->m_send_vecs, (size_t)R * region_cap * 24));
+    {   // the tables of a multi-k loop grow a little with every k: allocate with headroom instead of re-allocating per k
+        const size_t need = (size_t)R * region_cap * 24;
+        if (need > ctx->m_send_vecs.cap) CKS(ensure(ctx, ctx->m_send_vecs, need + need / 2));
+    }
     PackArgs p{};
     p.table = ctx->table.as<Slot>();
     p.capacity = ctx->t_capacity;
@@ -3020,7 +3027,7 @@ mdbg_status mdbg_count_merge_hashes(mdbg_ctx* ctx) {
         if (x.send_cnt[d] > region_cap) return fail(ctx, MDBG_ERR_STATE, "keys-only merge: send region overflow");
         x.send_base[d] = (uint64_t)d * region_cap;                  // regions, not a packed prefix
     }
-    CKS(ensure(ctx, ctx->m_recv_vecs, (x.recv_total + 1) * 24));
+    if ((x.recv_total + 1) * 24 > ctx->m_recv_vecs.cap) CKS(ensure(ctx, ctx->m_recv_vecs, (x.recv_total + 1) * 36));
     clk.lap(PH_MERGE_PLAN);
     CKS(x.run(ctx, ctx->m_send_vecs.p, ctx->m_recv_vecs.p, 24));
     clk.lap(PH_MERGE_EXCHANGE);
@@ -3041,6 +3048,40 @@ mdbg_status mdbg_count_merge_hashes(mdbg_ctx* ctx) {
     ctx->t_ranges.clear();
     ctx->t_claim_limit = cap;
     ctx->foreign_n = 0;
+    return MDBG_OK;
+}
+
+// The multi-k loop as ONE library call (the host-side control of metaMDBG's `graph` passes, src/graph/CreateMdbg.cpp:386-468
+// driven per k by src/pipeline/AssemblyPipeline.hpp:606-671, without the contig stage in between): count at first_k
+// [+ merge, + rescue], then for every further k the previous-k table from the current one, the next-k pass over the
+// store and [the merge]; statistics of every k are returned, tables stay on the device (the last one is current).
+mdbg_status mdbg_multi_k_run(mdbg_ctx* ctx, uint32_t first_k, uint32_t last_k, uint32_t min_abundance, int rescue,
+                             int merge_mode, mdbg_k_stats* stats_out) {
+    if (!ctx || !stats_out) return MDBG_ERR_ARG;
+    if (first_k < 2 || last_k < first_k || last_k > 255) return fail(ctx, MDBG_ERR_ARG, "need 2 <= first_k <= last_k <= 255");
+    if (merge_mode < 0 || merge_mode > 2) return fail(ctx, MDBG_ERR_ARG, "merge_mode: 0 none, 1 with vectors, 2 keys only for k > first_k");
+    const int R = ctx->n_ranks;
+    uint64_t n_keys = 0;
+    for (uint32_t k = first_k; k <= last_k; k++) {
+        mdbg_k_stats& st = stats_out[k - first_k];
+        memset(&st, 0, sizeof st);
+        st.k = k;
+        if (k == first_k) {
+            CKS(mdbg_count_begin(ctx, k, 0));
+            CKS(mdbg_count_add_store(ctx, 0, UINT64_MAX));
+            if (merge_mode && R > 1) CKS(mdbg_count_merge(ctx));
+            if (rescue) CKS(mdbg_count_rescue(ctx, &st.n_reads_rescued));
+        } else {
+            CKS(mdbg_prev_from_current(ctx, min_abundance));
+            const uint64_t expect = (uint64_t)(1.3 * (double)std::max<uint64_t>(256, n_keys));
+            CKS(mdbg_count_begin(ctx, k, expect));
+            CKS(mdbg_count_add_store_next_k(ctx, 0, UINT64_MAX));
+            if (merge_mode == 1 && R > 1) CKS(mdbg_count_merge(ctx));
+            if (merge_mode == 2 && R > 1) CKS(mdbg_count_merge_hashes(ctx));
+        }
+        CKS(mdbg_count_stats(ctx, min_abundance, &st.n_entries, &st.n_distinct, &st.n_instances, &st.checksum));
+        n_keys = st.n_entries * (uint64_t)((merge_mode && R > 1) ? R : 1);       // keys a rank-local table of the next k will hold
+    }
     return MDBG_OK;
 }
 

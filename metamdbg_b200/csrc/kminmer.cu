@@ -835,39 +835,38 @@ void launch_table_pack(const PackArgs& a, cudaStream_t s) {
 // needs no table at all, see next_k_stream_kernel): records of 24 bytes {hash lo, hash hi, count | 0} instead of
 // 4 k + 4 bytes, no gather of vectors on the sender, no re-hash on the owner.
 // ONE pass: every destination has a fixed-capacity region of the send buffer (region_cap records; the host sizes it
-// for the table's number of distinct keys, so it cannot overflow), records are appended through one cursor per
-// destination -- warp-aggregated: lanes with the same destination share one atomicAdd.
+// for the table's number of distinct keys, so it cannot overflow).  Per 256-slot tile the records are counted per
+// destination in shared memory, the tile reserves its ranges with one global atomicAdd per destination, and the
+// records are written behind them.
 __global__ void __launch_bounds__(256) table_pack_hashes_kernel(const PackArgs a, uint64_t* out_recs, uint64_t region_cap) {
-    const uint32_t lane = threadIdx.x & 31;
+    __shared__ uint32_t cnt[PACK_MAX_RANKS];
+    __shared__ unsigned long long base[PACK_MAX_RANKS];
     const uint32_t R = a.n_ranks;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t n_rounds = (a.capacity + stride - 1) / stride;
-    for (uint64_t round = 0; round < n_rounds; round++) {
-        const uint64_t i = round * stride + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t n_tiles = (a.capacity + 255) / 256;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        if (threadIdx.x < R) cnt[threadIdx.x] = 0;
+        __syncthreads();
+        const uint64_t i = tile * 256 + threadIdx.x;
         bool take = false;
-        uint32_t dst = 0xFFFFFFFFu, count = 0;
+        uint32_t dst = 0, count = 0, my = 0;
         uint64_t lo = 0, hi = 0;
         if (i < a.capacity) {
             const uint4 q0 = reinterpret_cast<const uint4*>(a.table + i)[0];
             lo = (uint64_t)q0.x | ((uint64_t)q0.y << 32);
             hi = (uint64_t)q0.z | ((uint64_t)q0.w << 32);
             take = (lo | hi) != 0;
-            if (take) { dst = owner_of(hi, R); count = a.table[i].count; }
+            if (take) { dst = owner_of(hi, R); count = a.table[i].count; my = atomicAdd(&cnt[dst], 1u); }
         }
-        if (!__any_sync(0xffffffffu, take)) continue;
-        const uint32_t peers = __match_any_sync(0xffffffffu, dst);           // lanes with my destination (idle lanes match each other)
-        const uint32_t leader = __ffs(peers) - 1, rank_in = __popc(peers & ((1u << lane) - 1u));
-        unsigned long long base = 0;
-        if (take && lane == leader) base = atomicAdd(&a.bucket_count[dst], (unsigned long long)__popc(peers));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (take) {
-            const uint64_t pos = (uint64_t)dst * region_cap + base + rank_in;
-            if (base + rank_in < region_cap) {
-                out_recs[3 * pos] = lo;
-                out_recs[3 * pos + 1] = hi;
-                out_recs[3 * pos + 2] = count;
-            }
+        __syncthreads();
+        if (threadIdx.x < R) base[threadIdx.x] = cnt[threadIdx.x] ? atomicAdd(&a.bucket_count[threadIdx.x], (unsigned long long)cnt[threadIdx.x]) : 0ULL;
+        __syncthreads();
+        if (take && base[dst] + my < region_cap) {
+            const uint64_t pos = (uint64_t)dst * region_cap + base[dst] + my;
+            out_recs[3 * pos] = lo;
+            out_recs[3 * pos + 1] = hi;
+            out_recs[3 * pos + 2] = count;
         }
+        __syncthreads();
     }
 }
 

@@ -17,7 +17,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _capi
-from ._capi import AutotuneOut, AuxOut, BatchInfo, EdgesOut, FastxInfo, MdbgParams, PostingsOut, RepeatsOut, SketchDev, SketchOut, TableDev, TableOut
+from ._capi import AutotuneOut, AuxOut, BatchInfo, EdgesOut, FastxInfo, KStats, MdbgParams, PostingsOut, RepeatsOut, SketchDev, SketchOut, TableDev, TableOut
 
 STATUS = {0: "OK", 1: "CUDA", 2: "ARG", 3: "STATE", 4: "TABLE_FULL", 5: "NCCL", 6: "OOM"}
 
@@ -404,6 +404,15 @@ class Engine:
         else:
             h = np.zeros((0, 2), np.uint64); a = np.zeros(0, np.uint32); v = np.zeros((0, k), np.uint32)
         return CountTable(k, h, a, v, int(out.n_instances), int(out.n_distinct), int(out.checksum), int(out.n_rescued))
+
+    def multi_k_run(self, first_k: int = 4, last_k: int = 21, min_abundance: int = 2, rescue: bool = False,
+                    merge_mode: int = 0) -> list[dict]:
+        """mdbg_multi_k_run: the whole multi-k loop inside the library (merge_mode 0 none / 1 vectors / 2 keys only)."""
+        n = last_k - first_k + 1
+        st = (KStats * n)()
+        self._ck(self._lib.mdbg_multi_k_run(self._ctx, first_k, last_k, min_abundance, int(rescue), merge_mode, st))
+        return [dict(k=int(x.k), n_entries=int(x.n_entries), n_distinct=int(x.n_distinct), n_instances=int(x.n_instances),
+                     checksum=int(x.checksum), n_reads_rescued=int(x.n_reads_rescued)) for x in st]
 
     def count_postings(self, min_abundance: int = 2) -> dict:
         """k-min-mer -> (read, window) postings of the current count table (CSR over the emitted keys)."""

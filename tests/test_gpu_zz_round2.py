@@ -425,3 +425,18 @@ def test_postings_index(built, oracle):
         got_keys.add(key)
     assert got_keys == set(want_ab) and len(got_keys) > 200
     eng.close()
+
+
+def test_multi_k_run_in_the_library(built, oracle):
+    """mdbg_multi_k_run = the host loop of multik.py inside the library: same per-k statistics, last table current."""
+    from metamdbg_b200 import multi_k_sweep
+    rs = synth.make_readset(2000, 8000, seed=67, n_genomes=2, genome_len_range=(150_000, 250_000), err=0.003)
+    bases, offs = synth.fill_reads(rs)
+    eng = engine()
+    eng.sketch_batch(bases, offs, append_to_store=True, fetch=False)
+    want = multi_k_sweep(eng, 4, 10, 0, rescue=True)
+    got = eng.multi_k_run(4, 10, 0, rescue=True)
+    assert [(g["k"], g["n_entries"], g["checksum"]) for g in got] == [(w["k"], w["n_entries"], w["checksum"]) for w in want]
+    assert got[0]["n_reads_rescued"] == want[0]["n_reads_rescued"] > 0
+    assert eng.count_stats(0)["checksum"] == got[-1]["checksum"]          # the k = 10 table is current
+    eng.close()
