@@ -708,6 +708,208 @@ size_t orc_edge_values(const uint32_t* vecs, size_t n, int k, uint64_t** hashes,
     return ne;
 }
 
+/* ------------------------------------------------------- unitig nodes of the node set (row F1, third step)
+ * CreateMdbg::computeUnitigNodes / ComputeUnitigFunctor::computeUnitigNode2 (src/graph/CreateMdbg.cpp:1521-1598,
+ * CreateMdbg.hpp:2513-2916) followed by computeDeterministicUnitigs (CreateMdbg.cpp:1001-1043), run sequentially over
+ * the nodes in file order.  getNbSuccessors (CreateMdbg.cpp:1902-2135): the successors of an oriented node are the
+ * offers, in the orientation class that matches its (k-1)-suffix as written, to the key of that suffix -- exactly one
+ * (unmarked) offer <=> single successor = suffix + recorded minimizer; getNbPredecessors (:2227-2380) is the mirror
+ * image (predecessor of v = reverse of the successor of reverse(v)).  A unitig grows from its source node forwards
+ * while "single successor whose single predecessor exists", closes as a circle when the successor is the source
+ * again, else grows backwards; circular unitigs are rotated to start at their k-min-mer with the smallest normalized
+ * hash128, in that k-min-mer's normalized orientation.  computeDeterministicUnitigs normalizes every unitig's
+ * minimizer sequence (KmerVec::normalize), sorts by the hash128 of the sequence and numbers them 0, 2, 4, ...
+ * Returns the unitigs in that final order as a CSR (offs[n_unitigs + 1], mins). */
+typedef struct {
+    const uint32_t* vecs; size_t n; int k;
+    uint32_t* order;                 /* node ids sorted by vector */
+    const uint64_t* ekeys; const uint32_t* evals; size_t ne;
+} UCtx;
+static int g_ucmp_k;
+static const uint32_t* g_ucmp_vecs;
+static int cmp_node_idx(const void* a, const void* b) {
+    const uint32_t* x = g_ucmp_vecs + (size_t)(*(const uint32_t*)a) * g_ucmp_k;
+    const uint32_t* y = g_ucmp_vecs + (size_t)(*(const uint32_t*)b) * g_ucmp_k;
+    for (int j = 0; j < g_ucmp_k; j++) if (x[j] != y[j]) return x[j] < y[j] ? -1 : 1;
+    return 0;
+}
+/* KmerVec::normalize (Commons.hpp:886-916) of w[0..len): out = normalized, returns isReversed */
+static int u_normalize(const uint32_t* w, int len, uint32_t* out) {
+    int rev = 1;
+    for (int j = 0; j < len; j++) {
+        uint32_t a = w[j], b = w[len - 1 - j];
+        if (a == b) continue;
+        rev = (a < b) ? 0 : 1;
+        break;
+    }
+    for (int j = 0; j < len; j++) out[j] = rev ? w[len - 1 - j] : w[j];
+    return rev;
+}
+static long u_node_id(const UCtx* c, const uint32_t* vec) {           /* id of the node whose normalized form is norm(vec) */
+    uint32_t tmp[256];
+    u_normalize(vec, c->k, tmp);
+    size_t lo = 0, hi = c->n;
+    while (lo < hi) {
+        size_t mid = (lo + hi) / 2;
+        const uint32_t* y = c->vecs + (size_t)c->order[mid] * c->k;
+        int cmp = 0;
+        for (int j = 0; j < c->k; j++) if (tmp[j] != y[j]) { cmp = tmp[j] < y[j] ? -1 : 1; break; }
+        if (cmp == 0) return (long)c->order[mid];
+        if (cmp < 0) hi = mid; else lo = mid + 1;
+    }
+    return -1;
+}
+static int u_succ(const UCtx* c, const uint32_t* vec, uint32_t* out) {
+    const int km = c->k - 1;
+    uint32_t tmp[256];
+    const uint32_t* S = vec + 1;
+    const int rev = u_normalize(S, km, tmp);
+    int pal = 1;
+    for (int j = 0; j < km / 2; j++) if (S[j] != S[km - 1 - j]) { pal = 0; break; }
+    uint64_t h[2];
+    orc_hash128(tmp, km, h);
+    size_t lo = 0, hi = c->ne;
+    while (lo < hi) {
+        size_t mid = (lo + hi) / 2;
+        uint64_t a = c->ekeys[2 * mid], b = c->ekeys[2 * mid + 1];
+        if (a == h[0] && b == h[1]) { lo = mid; break; }
+        if (a < h[0] || (a == h[0] && b < h[1])) lo = mid + 1; else hi = mid;
+    }
+    if (lo >= c->ne || c->ekeys[2 * lo] != h[0] || c->ekeys[2 * lo + 1] != h[1]) return 0;
+    const uint32_t* cl = c->evals + 8 * lo + 4 * (pal ? 0 : (rev ? 0 : 1));
+    if (cl[0] != 1) return 0;
+    for (int j = 0; j < km; j++) out[j] = S[j];
+    out[km] = cl[1];
+    return 1;
+}
+static int u_pred(const UCtx* c, const uint32_t* vec, uint32_t* out) {
+    uint32_t r[256], t[256];
+    for (int j = 0; j < c->k; j++) r[j] = vec[c->k - 1 - j];
+    if (!u_succ(c, r, t)) return 0;
+    for (int j = 0; j < c->k; j++) out[j] = t[c->k - 1 - j];
+    return 1;
+}
+typedef struct { uint64_t h1, h2; uint32_t* m; uint32_t len; } UOut;
+static int cmp_uout(const void* a, const void* b) {
+    const UOut* x = (const UOut*)a; const UOut* y = (const UOut*)b;
+    if (x->h1 != y->h1) return x->h1 < y->h1 ? -1 : 1;
+    if (x->h2 != y->h2) return x->h2 < y->h2 ? -1 : 1;
+    return 0;
+}
+
+size_t orc_unitigs(const uint32_t* vecs, size_t n, int k, uint64_t** offs_out, uint32_t** mins_out, uint64_t** hashes_out) {
+    UCtx c; c.vecs = vecs; c.n = n; c.k = k;
+    c.order = (uint32_t*)malloc((n + 1) * sizeof(uint32_t));
+    for (size_t i = 0; i < n; i++) c.order[i] = (uint32_t)i;
+    g_ucmp_k = k; g_ucmp_vecs = vecs;
+    qsort(c.order, n, sizeof(uint32_t), cmp_node_idx);
+    uint64_t* ek; uint32_t* ev;
+    c.ne = orc_edge_values(vecs, n, k, &ek, &ev);
+    c.ekeys = ek; c.evals = ev;
+    uint8_t* marked = (uint8_t*)calloc(n + 1, 1);
+    UOut* outs = (UOut*)malloc((n + 1) * sizeof(UOut));
+    size_t n_out = 0;
+    uint32_t a[256], b[256], t[256];
+    for (size_t src = 0; src < n; src++) {
+        const uint32_t* source = vecs + src * (size_t)k;
+        if (marked[src]) continue;                                   /* isNodeUnitigged(source) || (sourceRC) */
+        size_t cap = (size_t)k + 16, len = (size_t)k;
+        uint32_t* u = (uint32_t*)malloc(cap * sizeof(uint32_t));
+        memcpy(u, source, (size_t)k * 4);
+        uint32_t start[256], end[256];
+        memcpy(start, source, (size_t)k * 4); memcpy(end, source, (size_t)k * 4);
+        int circular = 0;
+        for (;;) {                                                    /* forwards */
+            if (!u_succ(&c, end, a)) break;
+            if (!u_pred(&c, a, b)) break;
+            if (memcmp(a, source, (size_t)k * 4) == 0) { circular = 1; memcpy(end, a, (size_t)k * 4); memcpy(start, a, (size_t)k * 4); break; }
+            memcpy(end, a, (size_t)k * 4);
+            if (len + 1 > cap) { cap *= 2; u = (uint32_t*)realloc(u, cap * sizeof(uint32_t)); }
+            u[len++] = end[k - 1];
+        }
+        if (!circular) {                                              /* backwards */
+            size_t bcap = 16, blen = 0;
+            uint32_t* back = (uint32_t*)malloc(bcap * sizeof(uint32_t));
+            for (;;) {
+                if (!u_pred(&c, start, a)) break;
+                if (!u_succ(&c, a, b)) break;
+                memcpy(start, a, (size_t)k * 4);
+                if (blen + 1 > bcap) { bcap *= 2; back = (uint32_t*)realloc(back, bcap * sizeof(uint32_t)); }
+                back[blen++] = start[0];
+            }
+            uint32_t* full = (uint32_t*)malloc((len + blen + 1) * sizeof(uint32_t));
+            for (size_t i = 0; i < blen; i++) full[i] = back[blen - 1 - i];
+            memcpy(full + blen, u, len * 4);
+            free(u); free(back);
+            u = full; len += blen;
+        } else {
+            /* rotate to the window with the smallest normalized hash, in its normalized orientation */
+            const size_t nw = len - (size_t)k + 1;
+            uint64_t bh1 = ~0ULL, bh2 = ~0ULL; size_t bi = (size_t)-1; int brev = 0;
+            for (size_t i = 0; i < nw; i++) {
+                int r = u_normalize(u + i, k, t);
+                uint64_t h[2];
+                orc_hash128(t, k, h);
+                if (h[0] < bh1 || (h[0] == bh1 && h[1] < bh2)) { bh1 = h[0]; bh2 = h[1]; bi = i; brev = r; }
+            }
+            if (brev) {
+                for (size_t i = 0; i < len / 2; i++) { uint32_t x = u[i]; u[i] = u[len - 1 - i]; u[len - 1 - i] = x; }
+                for (size_t i = 0; i < nw; i++) {
+                    uint64_t h[2];
+                    orc_hash128(u + i, k, h);                         /* as written, not normalized */
+                    if (h[0] == bh1 && h[1] == bh2) { bi = i; break; }
+                }
+            }
+            uint32_t* rot = (uint32_t*)malloc((len + 1) * sizeof(uint32_t));
+            size_t rl = 0;
+            for (int j = 0; j < k; j++) rot[rl++] = u[bi + (size_t)j];
+            for (size_t i = bi + 1; i < nw; i++) rot[rl++] = u[i + (size_t)k - 1];
+            for (size_t i = 0; i < bi; i++) rot[rl++] = u[i + (size_t)k - 1];
+            free(u);
+            u = rot; len = rl;
+            u_normalize(u, k, start); memcpy(end, start, (size_t)k * 4);
+        }
+        /* isValid: none of start / end / their reverses is unitigged yet */
+        long is = u_node_id(&c, start), ie = u_node_id(&c, end);
+        if (is < 0 || ie < 0 || marked[is] || marked[ie]) { free(u); continue; }
+        for (size_t i = 0; i + (size_t)k <= len; i++) {
+            long id = u_node_id(&c, u + i);
+            if (id >= 0) marked[id] = 1;
+        }
+        outs[n_out].m = u; outs[n_out].len = (uint32_t)len;
+        n_out++;
+    }
+    /* computeDeterministicUnitigs */
+    size_t total = 0;
+    for (size_t i = 0; i < n_out; i++) {
+        uint32_t* nm = (uint32_t*)malloc(((size_t)outs[i].len + 1) * sizeof(uint32_t));
+        u_normalize(outs[i].m, (int)outs[i].len, nm);
+        free(outs[i].m);
+        outs[i].m = nm;
+        uint64_t h[2];
+        orc_hash128(nm, (int)outs[i].len, h);
+        outs[i].h1 = h[0]; outs[i].h2 = h[1];
+        total += outs[i].len;
+    }
+    qsort(outs, n_out, sizeof(UOut), cmp_uout);
+    uint64_t* offs = (uint64_t*)malloc((n_out + 2) * sizeof(uint64_t));
+    uint32_t* mins = (uint32_t*)malloc((total + 1) * sizeof(uint32_t));
+    uint64_t* hs = (uint64_t*)malloc((2 * n_out + 2) * sizeof(uint64_t));
+    size_t pos = 0;
+    for (size_t i = 0; i < n_out; i++) {
+        offs[i] = pos;
+        memcpy(mins + pos, outs[i].m, (size_t)outs[i].len * 4);
+        pos += outs[i].len;
+        hs[2 * i] = outs[i].h1; hs[2 * i + 1] = outs[i].h2;
+        free(outs[i].m);
+    }
+    offs[n_out] = pos;
+    free(outs); free(marked); free(c.order); free(ek); free(ev);
+    *offs_out = offs; *mins_out = mins;
+    if (hashes_out) *hashes_out = hs; else free(hs);
+    return n_out;
+}
+
 uint64_t orc_table_checksum(const uint64_t* hashes, const uint32_t* abundances, size_t n) {
     uint64_t s = 0;
     for (size_t i = 0; i < n; i++) s += (uint64_t)abundances[i] * hashes[2 * i + 1];

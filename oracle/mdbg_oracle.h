@@ -132,6 +132,12 @@ size_t orc_edge_index(const uint32_t* vecs, size_t n, int k, uint64_t** hashes, 
  * the last three are those of the single offer when count == 1, else 0.  *values: n_edges x 8 u32. */
 size_t orc_edge_values(const uint32_t* vecs, size_t n, int k, uint64_t** hashes, uint32_t** values);
 
+/* CreateMdbg::computeUnitigNodes + computeDeterministicUnitigs (CreateMdbg.cpp:1521-1598, 1001-1043; walker
+ * ComputeUnitigFunctor::computeUnitigNode2, CreateMdbg.hpp:2513-2916): the content of unitigGraph.nodes.bin -- every
+ * unitig's normalized minimizer sequence, sorted by the hash128 of that sequence (unitigIndex = 2 * position).
+ * *offs: n_unitigs + 1, *mins: concatenated sequences, *hashes (may be NULL): n_unitigs x {h1,h2}.  Returns n_unitigs. */
+size_t orc_unitigs(const uint32_t* vecs, size_t n, int k, uint64_t** offs, uint32_t** mins, uint64_t** hashes);
+
 /* Order-free fingerprint used by the reference's debug log
  * (src/graph/CreateMdbg.cpp:3321): sum abundance * (u64)hash128 mod 2^64,
  * where (u64)hash128 = low 64 bits = h2. */

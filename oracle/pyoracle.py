@@ -193,6 +193,8 @@ class Oracle(_Lib):
                                  C.POINTER(_u64p), C.POINTER(_u32p)]
         L.orc_edge_index.restype = C.c_size_t
         L.orc_edge_index.argtypes = [_u32p, C.c_size_t, C.c_int, C.POINTER(_u64p), C.POINTER(C.c_uint64)]
+        L.orc_unitigs.restype = C.c_size_t
+        L.orc_unitigs.argtypes = [_u32p, C.c_size_t, C.c_int, C.POINTER(_u64p), C.POINTER(_u32p), C.POINTER(_u64p)]
         L.orc_edge_values.restype = C.c_size_t
         L.orc_edge_values.argtypes = [_u32p, C.c_size_t, C.c_int, C.POINTER(_u64p), C.POINTER(_u32p)]
         L.orc_table_checksum.restype = C.c_uint64
@@ -288,6 +290,15 @@ class Oracle(_Lib):
         n = self.lib.orc_edge_values(_p(vecs, _u32p), len(vecs), k, C.byref(h), C.byref(v))
         return dict(hashes=self._take(h, 2 * n, np.uint64).reshape(n, 2), values=self._take(v, 8 * n, np.uint32).reshape(n, 2, 4))
 
+    def unitigs(self, vecs, k):
+        """computeUnitigNodes + computeDeterministicUnitigs -> dict(offsets [n+1], minimizers, hashes [n,2]): the records
+        of unitigGraph.nodes.bin in file order (unitigIndex = 2 * position)."""
+        vecs = np.ascontiguousarray(vecs, dtype=np.uint32).reshape(-1, k)
+        o = _u64p(); m = _u32p(); h = _u64p()
+        n = self.lib.orc_unitigs(_p(vecs, _u32p), len(vecs), k, C.byref(o), C.byref(m), C.byref(h))
+        offs = self._take(o, n + 1, np.uint64)
+        return dict(offsets=offs, minimizers=self._take(m, int(offs[-1]), np.uint32), hashes=self._take(h, 2 * n, np.uint64).reshape(n, 2))
+
     def checksum(self, hashes: np.ndarray, abundances: np.ndarray) -> int:
         hashes = np.ascontiguousarray(hashes, dtype=np.uint64)
         abundances = np.ascontiguousarray(abundances, dtype=np.uint32)
@@ -323,6 +334,8 @@ class Reference(_Lib):
         L.ref_edge_index.restype = C.c_size_t
         L.ref_edge_index.argtypes = [_u32p, C.c_size_t, C.c_int, C.c_int, C.c_char_p, C.POINTER(_u64p),
                                      C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.ref_unitig_nodes.restype = C.c_size_t
+        L.ref_unitig_nodes.argtypes = [_u32p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(_u64p), C.POINTER(_u32p)]
         L.ref_edge_values.restype = C.c_size_t
         L.ref_edge_values.argtypes = [_u32p, C.c_size_t, C.c_int, C.c_int, C.c_char_p, C.POINTER(_u64p), C.POINTER(_u8p),
                                       C.POINTER(_u32p), C.POINTER(_u8p)]
@@ -385,6 +398,18 @@ class Reference(_Lib):
                                          C.byref(mn), C.byref(fl))
         return dict(hashes=self._take(h, 2 * n, np.uint64).reshape(n, 2), palindrome=self._take(pal, n, np.uint8),
                     minimizers=self._take(mn, 2 * n, np.uint32).reshape(n, 2), flags=self._take(fl, 2 * n, np.uint8).reshape(n, 2))
+
+    def unitig_nodes(self, vecs, k, threads=1, deterministic=True):
+        """The reference's own indexEdges + computeUnitigNodes (+ computeDeterministicUnitigs) on a node file in a
+        scratch dir -> dict(offsets [n+1], minimizers): the records of unitigGraph.nodes.bin in file order."""
+        import tempfile
+        vecs = np.ascontiguousarray(vecs, dtype=np.uint32).reshape(-1, k)
+        o = _u64p(); m = _u32p()
+        with tempfile.TemporaryDirectory() as d:
+            n = self.lib.ref_unitig_nodes(_p(vecs, _u32p), len(vecs), k, threads, 1 if deterministic else 0, d.encode(),
+                                          C.byref(o), C.byref(m))
+        offs = self._take(o, n + 1, np.uint64)
+        return dict(offsets=offs, minimizers=self._take(m, int(offs[-1]), np.uint32))
 
     def graph_next_k(self, mins, offs, k, prev_hashes, prev_ab, use_counter=False, threads=1):
         import tempfile

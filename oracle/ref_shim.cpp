@@ -511,6 +511,58 @@ size_t ref_edge_values(const uint32_t* vecs, size_t n, int k, int n_threads, con
     return ne;
 }
 
+/* CreateMdbg::indexEdges + computeUnitigNodes (src/graph/CreateMdbg.cpp:1177-1275, 1521-1598; walker
+ * ComputeUnitigFunctor::computeUnitigNode2, CreateMdbg.hpp:2513-2916) and, when `deterministic`, computeDeterministicUnitigs
+ * (CreateMdbg.cpp:1001-1043), on the node file kminmerData_min.txt with n_threads OpenMP threads -- the same call
+ * sequence as createGfa (CreateMdbg.cpp:876-912).  Returns the records of unitigGraph.nodes.bin in file order as a CSR;
+ * the unitigIndex field of record i is checked to be 2 * i. */
+size_t ref_unitig_nodes(const uint32_t* vecs, size_t n, int k, int n_threads, int deterministic, const char* tmp_dir,
+                        uint64_t** offs_out, uint32_t** mins_out) {
+    if (n_threads < 1) n_threads = 1;
+    const string dir(tmp_dir);
+    {
+        ofstream f(dir + "/kminmerData_min.txt", std::ios::binary);
+        f.write((const char*)vecs, (std::streamsize)(n * (size_t)k * sizeof(uint32_t)));
+    }
+    CreateMdbg c;
+    c._outputDir = dir;
+    c._kminmerSize = k;
+    c._nbCores = n_threads;
+    c._nbPartitions = n_threads;
+    c._mutexes.resize(1000);
+    for (size_t i = 0; i < c._mutexes.size(); i++) omp_init_lock(&c._mutexes[i]);
+    c.indexEdges();
+    c._unitigGraphFile_nodes = ofstream(dir + "/unitigGraph.nodes.bin");
+    c.computeUnitigNodes();
+    c._unitigGraphFile_nodes.close();
+    c._mdbgEdges10.clear();
+    if (deterministic) c.computeDeterministicUnitigs();
+    for (size_t i = 0; i < c._mutexes.size(); i++) omp_destroy_lock(&c._mutexes[i]);
+    vector<uint64_t> offs;
+    vector<uint32_t> mins;
+    ifstream nf(dir + "/unitigGraph.nodes.bin", std::ios::binary);
+    size_t idx = 0;
+    while (true) {
+        u_int32_t size;
+        nf.read((char*)&size, sizeof size);
+        if (nf.eof()) break;
+        offs.push_back(mins.size());
+        const size_t at = mins.size();
+        mins.resize(at + size);
+        nf.read((char*)&mins[at], (std::streamsize)size * sizeof(MinimizerType));
+        UnitigType unitigIndex;
+        nf.read((char*)&unitigIndex, sizeof unitigIndex);
+        if (deterministic && (size_t)unitigIndex != 2 * idx) { fprintf(stderr, "ref_unitig_nodes: unitigIndex %llu at record %zu\n", (unsigned long long)unitigIndex, idx); abort(); }
+        idx++;
+    }
+    offs.push_back(mins.size());
+    *offs_out = (uint64_t*)malloc((offs.size() + 1) * 8);
+    memcpy(*offs_out, offs.data(), offs.size() * 8);
+    *mins_out = (uint32_t*)malloc((mins.size() + 1) * 4);
+    memcpy(*mins_out, mins.data(), mins.size() * 4);
+    return offs.size() - 1;
+}
+
 /* The reference's whole readSelection stage (ReadSelection::execute, src/readSelection/ReadSelection.hpp:92-303):
  * kseq FASTA/FASTQ parsing, HPC, sketch, complexity / quality side outputs, ordered record writer, read stats,
  * purgePalindromes.  `input_list` is the text file listing the read files (what `metaMDBG asm` writes as input.txt).
