@@ -431,6 +431,35 @@ typedef struct {
 } mdbg_edges_out;
 mdbg_status mdbg_edges_index(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_edges_out* out);
 
+/* ---- unitig nodes of the node set (third step) -------------------------------------
+ * CreateMdbg::computeUnitigNodes (src/graph/CreateMdbg.cpp:1521-1598; walker ComputeUnitigFunctor::computeUnitigNode2,
+ * src/graph/CreateMdbg.hpp:2513-2916, over getNbSuccessors / getNbPredecessors, CreateMdbg.cpp:1902-2380) followed by
+ * computeDeterministicUnitigs (CreateMdbg.cpp:1001-1043): the maximal non-branching paths of the node set of the current
+ * table (entries mdbg_count_finalize would emit), each as its minimizer sequence -- the first node's k minimizers, then
+ * the last minimizer of every further node; circular unitigs start at their k-min-mer with the smallest hash128, in
+ * that k-min-mer's normalized orientation -- normalized as a whole (KmerVec::normalize) and hashed (hash128 of the
+ * normalized sequence).  Unitig u = minimizers[offsets[u] .. offsets[u+1]); order[i] = the unitig the reference
+ * writes as record i of unitigGraph.nodes.bin (ascending u128 hash), i.e. with unitigIndex 2 * i.  hashes[2u] = low,
+ * hashes[2u+1] = high 64 bits.  Builds the edge set on the way (as mdbg_edges_index, nothing of it is copied to the
+ * host).  Single-context call (n_ranks == 1): with several ranks, gather the node set on one context first.  The
+ * arrays stay valid until the next unitigs call on the context. */
+typedef struct {
+    uint32_t k;
+    uint64_t n_nodes;
+    uint64_t n_unitigs;
+    uint64_t n_minimizers;        /* offsets[n_unitigs] */
+    uint64_t n_circular;          /* unitigs that close on themselves */
+    uint64_t n_cycle_nodes;       /* oriented nodes on cycles (diagnostic: 2 per node of a circular unitig) */
+    const uint64_t* offsets;      /* [n_unitigs + 1] */
+    const uint32_t* minimizers;   /* [n_minimizers] */
+    const uint64_t* hashes;       /* [2 * n_unitigs] */
+    const uint8_t* circular;      /* [n_unitigs] */
+    const uint32_t* order;        /* [n_unitigs] */
+    const uint64_t* d_offsets;    /* the same CSR in device memory */
+    const uint32_t* d_minimizers;
+} mdbg_unitigs_out;
+mdbg_status mdbg_unitigs_build(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_unitigs_out* out);
+
 /* ---- multi-GPU (one process per GPU) --------------------------------------- */
 /* NCCL is loaded at run time (dlopen libnccl.so.2).  Rank 0 creates an id,
  * the host distributes its 128 bytes to every rank by its own means. */

@@ -80,6 +80,13 @@ class EdgesOut(C.Structure):
                 ("checksum", C.c_uint64), ("values", u64p)]
 
 
+class UnitigsOut(C.Structure):
+    _fields_ = [("k", C.c_uint32), ("n_nodes", C.c_uint64), ("n_unitigs", C.c_uint64), ("n_minimizers", C.c_uint64),
+                ("n_circular", C.c_uint64), ("n_cycle_nodes", C.c_uint64), ("offsets", u64p), ("minimizers", C.POINTER(C.c_uint32)),
+                ("hashes", u64p), ("circular", C.POINTER(C.c_uint8)), ("order", C.POINTER(C.c_uint32)), ("d_offsets", C.c_void_p),
+                ("d_minimizers", C.c_void_p)]
+
+
 class AutotuneOut(C.Structure):
     _fields_ = [("n_variants", C.c_int32), ("chosen", C.c_int32), ("identical", C.c_int32 * 4), ("ms", C.c_float * 4),
                 ("n_reads", C.c_uint32), ("n_minimizers", C.c_uint64)]
@@ -143,6 +150,7 @@ SYMBOLS = {
     "mdbg_prev_load": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]),
     "mdbg_count_add_store_next_k": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64]),
     "mdbg_edges_index": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(EdgesOut)]),
+    "mdbg_unitigs_build": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(UnitigsOut)]),
     "mdbg_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "mdbg_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "mdbg_count_merge": (C.c_int, [C.c_void_p]),

@@ -164,6 +164,11 @@ struct mdbg_ctx {
     DevBuf prev_table, prev_stage_h, prev_stage_a, rescue_table;
     DevBuf edge_table, edge_vals, o_edge_vals;
     PinBuf ho_edge_vals;
+    uint64_t edge_cap = 0;             // slots of the device-resident edge set left by the last edges / unitigs call
+    // unitigs (mdbg_unitigs_build)
+    DevBuf u_slot_node, u_node_slot, u_next, u_pair, u_len, u_size, u_flag, u_cychead, u_seqoff, u_idx, u_cyclist, u_cycpos, u_best,
+        u_jump, u_mins, u_off, u_hash, u_rev, u_circ;
+    PinBuf hu_mins, hu_off, hu_hash, hu_circ, hu_order;
     uint64_t prev_capacity = 0;
     DevBuf o_hash, o_abund, o_vecs;
     PinBuf ho_hash, ho_abund, ho_vecs;
@@ -855,9 +860,13 @@ void mdbg_ctx_destroy(mdbg_ctx* c) {
                       &c->scan_scratch, &c->b_off, &c->b_min, &c->b_pos, &c->b_dir, &c->s_min, &c->s_off, &c->s_rem,
                       &c->p_flags, &c->p_keep, &c->p_cnt, &c->p_newoff, &c->p_newmin, &c->table, &c->foreign_vecs,
                       &c->o_hash, &c->o_abund, &c->o_vecs, &c->d_pack, &c->d_src, &c->d_dirty, &c->pg_counts, &c->pg_flags, &c->pg_keyidx, &c->pg_off, &c->pg_readof, &c->pg_hash, &c->pg_koff, &c->pg_reads, &c->pg_wins, &c->r_table, &c->r_hist, &c->r_out, &c->f_raw, &c->f_cnt, &c->f_off, &c->f_nl, &c->f_start, &c->f_len, &c->f_qstart, &c->d_quals, &c->pad_qual, &c->pad_raw_a, &c->pad_raw_b, &c->b_qual, &c->x_sum_lo, &c->x_sum_hi, &c->x_lmin, &c->x_cplx, &c->x_low, &c->d_err_fixed, &c->d_err_tz, &c->prev_table, &c->prev_stage_h, &c->prev_stage_a, &c->rescue_table, &c->val_a, &c->val_b, &c->prev_src, &c->m_send_vecs, &c->m_send_counts, &c->m_recv_vecs,
-                      &c->m_recv_counts, &c->m_bucket, &c->loc_off, &c->edge_table, &c->edge_vals, &c->o_edge_vals};
+                      &c->m_recv_counts, &c->m_bucket, &c->loc_off, &c->edge_table, &c->edge_vals, &c->o_edge_vals,
+                      &c->u_slot_node, &c->u_node_slot, &c->u_next, &c->u_pair, &c->u_len, &c->u_size, &c->u_flag, &c->u_cychead,
+                      &c->u_seqoff, &c->u_idx, &c->u_cyclist, &c->u_cycpos, &c->u_best, &c->u_jump, &c->u_mins, &c->u_off, &c->u_hash,
+                      &c->u_rev, &c->u_circ};
     for (DevBuf* b : devs) release(*b);
-    PinBuf* pins[] = {&c->h_off, &c->h_min, &c->h_pos, &c->h_dir, &c->ho_hash, &c->ho_abund, &c->ho_vecs, &c->hx_sum_lo, &c->hx_sum_hi, &c->hx_lmin, &c->hx_cplx, &c->hx_low, &c->hx_meanq, &c->h_qual, &c->h_pack, &c->h_src, &c->h_asc, &c->ho_edge_vals, &c->hpg_hash, &c->hpg_koff, &c->hpg_reads, &c->hpg_wins};
+    PinBuf* pins[] = {&c->h_off, &c->h_min, &c->h_pos, &c->h_dir, &c->ho_hash, &c->ho_abund, &c->ho_vecs, &c->hx_sum_lo, &c->hx_sum_hi, &c->hx_lmin, &c->hx_cplx, &c->hx_low, &c->hx_meanq, &c->h_qual, &c->h_pack, &c->h_src, &c->h_asc, &c->ho_edge_vals, &c->hpg_hash, &c->hpg_koff, &c->hpg_reads, &c->hpg_wins,
+                      &c->hu_mins, &c->hu_off, &c->hu_hash, &c->hu_circ, &c->hu_order};
     for (PinBuf* b : pins) release(*b);
     if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
     if (c->d_small) cudaFree(c->d_small);
@@ -2612,7 +2621,7 @@ mdbg_status mdbg_count_add_store_next_k(mdbg_ctx* ctx, uint64_t read_lo, uint64_
 
 // CreateMdbg::EdgeIndexer (CreateMdbg.hpp:4010-4232; first step of indexEdges, CreateMdbg.cpp:1177-1187): the
 // dereplicated hash128 of the normalized (k-1)-prefix and (k-1)-suffix of every node of the current table.
-mdbg_status mdbg_edges_index(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_edges_out* out) {
+static mdbg_status edges_index_impl(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_edges_out* out, bool to_host) {
     if (!ctx || !out) return MDBG_ERR_ARG;
     if (!ctx->t_active) return fail(ctx, MDBG_ERR_STATE, "mdbg_edges_index before mdbg_count_begin");
     if (ctx->t_k < 2) return fail(ctx, MDBG_ERR_ARG, "k must be >= 2");
@@ -2767,6 +2776,13 @@ mdbg_status mdbg_edges_index(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_edges_o
         CKS(check_full(ctx, "mdbg_edges_index (values: an offer arrived for a key its owner does not hold)"));
         CK(cudaMemsetAsync(&ctx->d_small->emit_cursor, 0, 8, s));
     }
+    ctx->edge_cap = set_cap;
+    if (!to_host) {                                              // the caller works on the device-resident set (unitigs)
+        out->k = ctx->t_k;
+        out->n_edges = n;
+        out->n_nodes = st.n_entries;
+        return MDBG_OK;
+    }
     launch_edge_emit(ctx->edge_table.as<Slot>(), ctx->edge_vals.as<unsigned long long>(), set_cap, ctx->o_hash.as<uint64_t>(),
                      ctx->o_edge_vals.as<unsigned long long>(), &ctx->d_small->emit_cursor, s);
     CKS(check_launch(ctx, "edge_emit_kernel", 1));
@@ -2781,6 +2797,168 @@ mdbg_status mdbg_edges_index(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_edges_o
     out->hashes = ctx->ho_hash.as<uint64_t>();
     out->checksum = ctx->h_small->stats.checksum;                // sum of the low words (value 1 each)
     out->n_nodes = st.n_entries;
+    return MDBG_OK;
+}
+
+mdbg_status mdbg_edges_index(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_edges_out* out) {
+    return edges_index_impl(ctx, min_abundance, out, true);
+}
+
+// CreateMdbg::computeUnitigNodes + computeDeterministicUnitigs (CreateMdbg.cpp:1521-1598, 1001-1043) on the device:
+// node ids -> edge set + class values (as mdbg_edges_index) -> unitig links between oriented nodes -> list ranking by
+// pointer jumping (cycles cut at their smallest hash128) -> minimizer sequences -> normalize + hash128 per unitig.
+// The host only sorts the unitig indices by hash (the reference's deterministic order).
+mdbg_status mdbg_unitigs_build(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_unitigs_out* out) {
+    if (!ctx || !out) return MDBG_ERR_ARG;
+    memset(out, 0, sizeof *out);
+    if (!ctx->t_active) return fail(ctx, MDBG_ERR_STATE, "mdbg_unitigs_build before mdbg_count_begin");
+    if (ctx->n_ranks > 1)
+        return fail(ctx, MDBG_ERR_STATE, "mdbg_unitigs_build is a single-context call (the walk needs the whole node set on one device)");
+    if (ctx->t_capacity > 0xFFFFFFF0ull) return fail(ctx, MDBG_ERR_ARG, "table too large for 32-bit node ids");
+    mdbg_edges_out eo;
+    memset(&eo, 0, sizeof eo);
+    CKS(edges_index_impl(ctx, min_abundance, &eo, false));       // device-resident edge set + class values
+    cudaStream_t s = ctx->stream;
+    const uint32_t thr = count_threshold(ctx, min_abundance);
+    const uint64_t cap = ctx->t_capacity;
+    const uint64_t n = eo.n_nodes;
+    if (2 * n + 2 > 0x7FFFFFF0ull) return fail(ctx, MDBG_ERR_ARG, "too many nodes for 32-bit oriented node ids");
+    const uint32_t n2 = (uint32_t)(2 * n);
+    out->k = ctx->t_k;
+    out->n_nodes = n;
+    CKS(ensure(ctx, ctx->u_slot_node, (cap + 1) * 4));
+    CKS(ensure(ctx, ctx->u_node_slot, (n + 1) * 4));
+    CKS(ensure(ctx, ctx->u_next, ((uint64_t)n2 + 1) * 4));
+    CKS(ensure(ctx, ctx->u_pair, ((uint64_t)n2 + 1) * 8));
+    CKS(ensure(ctx, ctx->u_len, ((uint64_t)n2 + 1) * 4));
+    CKS(ensure(ctx, ctx->u_size, ((uint64_t)n2 + 1) * 4));
+    CKS(ensure(ctx, ctx->u_flag, ((uint64_t)n2 + 1) * 4));
+    CKS(ensure(ctx, ctx->u_cychead, (uint64_t)n2 + 1));
+    CKS(ensure(ctx, ctx->u_seqoff, ((uint64_t)n2 + 2) * 8));
+    CKS(ensure(ctx, ctx->u_idx, ((uint64_t)n2 + 2) * 8));
+    CKS(ensure(ctx, ctx->scan_scratch, scan_scratch_elems(n2 + 1) * sizeof(uint64_t)));
+    CK(cudaMemsetAsync(&ctx->d_small->emit_cursor, 0, 8, s));
+    CK(cudaMemsetAsync(&ctx->d_small->full_flag, 0, sizeof(uint32_t), s));
+    CK(cudaMemsetAsync(ctx->u_cychead.p, 0, (uint64_t)n2 + 1, s));
+    launch_unitig_nodes(ctx->table.as<Slot>(), cap, thr, ctx->u_slot_node.as<uint32_t>(), ctx->u_node_slot.as<uint32_t>(),
+                        &ctx->d_small->emit_cursor, s);
+    UnitigArgs ua{};
+    ua.table = ctx->table.as<Slot>(); ua.mask = cap - 1;
+    ua.node_slot = ctx->u_node_slot.as<uint32_t>(); ua.slot_node = ctx->u_slot_node.as<uint32_t>();
+    ua.n_nodes = (uint32_t)n; ua.k = ctx->t_k;
+    ua.mins = ctx->s_min.as<uint32_t>(); ua.foreign_vecs = ctx->foreign_vecs.as<uint32_t>();
+    ua.edges = ctx->edge_table.as<Slot>(); ua.edge_mask = ctx->edge_cap - 1;
+    ua.edge_vals = ctx->edge_vals.as<unsigned long long>();
+    ua.next = ctx->u_next.as<uint32_t>(); ua.error_flag = &ctx->d_small->full_flag;
+    launch_unitig_link(ua, s);
+    unsigned long long* pair = ctx->u_pair.as<unsigned long long>();
+    launch_unitig_rank_init(ua.next, n2, pair, ctx->u_len.as<uint32_t>(), s);
+    CKS(check_launch(ctx, "unitig_nodes_kernel + unitig_link_kernel + unitig_rank_init_kernel", n ? 3 : 1));
+    CK(cudaMemcpyAsync(&ctx->h_scalar[0], &ctx->d_small->emit_cursor, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&ctx->h_small->full_flag, &ctx->d_small->full_flag, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (ctx->h_scalar[0] != n) return fail(ctx, MDBG_ERR_STATE, "mdbg_unitigs_build: %llu node ids for %llu nodes",
+                                           (unsigned long long)ctx->h_scalar[0], (unsigned long long)n);
+    if (ctx->h_small->full_flag)
+        return fail(ctx, MDBG_ERR_STATE, "mdbg_unitigs_build: %s", ctx->h_small->full_flag == 1 ? "a node's edge key is missing from the edge set"
+                                                                                                  : "an edge offer names a k-min-mer that is not a node");
+    // pointer jumping: the pointer distance of an open node at least doubles per launch, so paths are resolved after
+    // ceil(log2(2n)) launches; what is still open then lies on cycles
+    int max_rounds = 2;
+    while ((1ull << (max_rounds - 2)) < (uint64_t)n2 + 1) max_rounds++;
+    auto rank_all = [&](uint64_t* n_open_out) -> mdbg_status {
+        uint64_t n_open = n2;
+        for (int r = 0; r < max_rounds && n_open; r++) {
+            CK(cudaMemsetAsync(&ctx->d_small->n_flagged, 0, 8, s));
+            launch_unitig_jump(pair, n2, 2, &ctx->d_small->n_flagged, s);
+            CKS(check_launch(ctx, "unitig_jump_kernel", n2 ? 1 : 0));
+            CK(cudaMemcpyAsync(&ctx->h_scalar[1], &ctx->d_small->n_flagged, 8, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            n_open = ctx->h_scalar[1];
+        }
+        *n_open_out = n_open;
+        return MDBG_OK;
+    };
+    uint64_t n_open = 0;
+    CKS(rank_all(&n_open));
+    out->n_cycle_nodes = n_open;
+    if (n_open) {
+        const uint32_t m = (uint32_t)n_open;
+        CKS(ensure(ctx, ctx->u_cyclist, ((uint64_t)m + 1) * 4));
+        CKS(ensure(ctx, ctx->u_cycpos, ((uint64_t)n2 + 1) * 4));
+        CKS(ensure(ctx, ctx->u_best, 2 * ((uint64_t)m + 1) * 24));
+        CKS(ensure(ctx, ctx->u_jump, 2 * ((uint64_t)m + 1) * 4));
+        CK(cudaMemsetAsync(&ctx->d_small->emit_cursor, 0, 8, s));
+        launch_unitig_cycle_list(pair, n2, ctx->u_cyclist.as<uint32_t>(), ctx->u_cycpos.as<uint32_t>(), &ctx->d_small->emit_cursor, s);
+        uint64_t* best[2] = {ctx->u_best.as<uint64_t>(), ctx->u_best.as<uint64_t>() + 3 * ((uint64_t)m + 1)};
+        uint32_t* jump[2] = {ctx->u_jump.as<uint32_t>(), ctx->u_jump.as<uint32_t>() + ((uint64_t)m + 1)};
+        launch_unitig_cycle_init(ua, ctx->u_cyclist.as<uint32_t>(), ctx->u_cycpos.as<uint32_t>(), m, best[0], jump[0], s);
+        int cur = 0, rounds = 1;
+        while ((1ull << rounds) < (uint64_t)m + 1) rounds++;
+        for (int r = 0; r < rounds; r++, cur ^= 1)
+            launch_unitig_cycle_min(best[cur], jump[cur], m, best[cur ^ 1], jump[cur ^ 1], s);
+        launch_unitig_cycle_cut(ua.next, ctx->u_cyclist.as<uint32_t>(), best[cur], m, pair, ctx->u_cychead.as<uint8_t>(), s);
+        CKS(check_launch(ctx, "unitig_cycle_list/init/min/cut kernels", 3 + rounds));
+        CKS(rank_all(&n_open));
+        if (n_open) return fail(ctx, MDBG_ERR_STATE, "mdbg_unitigs_build: %llu oriented nodes are still unranked after the cycle cut",
+                                (unsigned long long)n_open);
+    }
+    launch_unitig_len(pair, n2, ctx->u_len.as<uint32_t>(), s);
+    launch_unitig_select(pair, ctx->u_cychead.as<uint8_t>(), ctx->u_len.as<uint32_t>(), n2, ctx->t_k, ctx->u_size.as<uint32_t>(),
+                         ctx->u_flag.as<uint32_t>(), s);
+    launch_scan_u32_to_u64(ctx->u_size.as<uint32_t>(), ctx->u_seqoff.as<uint64_t>(), n2, ctx->scan_scratch.as<uint64_t>(), s);
+    launch_scan_u32_to_u64(ctx->u_flag.as<uint32_t>(), ctx->u_idx.as<uint64_t>(), n2, ctx->scan_scratch.as<uint64_t>(), s);
+    CKS(check_launch(ctx, "unitig_len_kernel + unitig_select_kernel + scans", n2 ? 8 : 0));
+    CK(cudaMemcpyAsync(&ctx->h_scalar[2], ctx->u_seqoff.as<uint64_t>() + n2, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&ctx->h_scalar[3], ctx->u_idx.as<uint64_t>() + n2, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const uint64_t total = n2 ? ctx->h_scalar[2] : 0, nu = n2 ? ctx->h_scalar[3] : 0;
+    CKS(ensure(ctx, ctx->u_mins, (total + 1) * 4));
+    CKS(ensure(ctx, ctx->u_off, (nu + 2) * 8));
+    CKS(ensure(ctx, ctx->u_hash, (nu + 1) * 16));
+    CKS(ensure(ctx, ctx->u_rev, nu + 1));
+    CKS(ensure(ctx, ctx->u_circ, nu + 1));
+    launch_unitig_scatter(ua, pair, ctx->u_flag.as<uint32_t>(), ctx->u_seqoff.as<uint64_t>(), ctx->u_idx.as<uint64_t>(),
+                          ctx->u_mins.as<uint32_t>(), ctx->u_off.as<uint64_t>(), ctx->u_circ.as<uint8_t>(), ctx->u_cychead.as<uint8_t>(), s);
+    CK(cudaMemcpyAsync(ctx->u_off.as<uint64_t>() + nu, &ctx->h_scalar[2], 8, cudaMemcpyHostToDevice, s));
+    launch_unitig_hash(ctx->u_mins.as<uint32_t>(), ctx->u_off.as<uint64_t>(), nu, ctx->u_hash.as<uint64_t>(), ctx->u_rev.as<uint8_t>(), s);
+    launch_unitig_reverse(ctx->u_mins.as<uint32_t>(), ctx->u_off.as<uint64_t>(), nu, ctx->u_rev.as<uint8_t>(), s);
+    CKS(check_launch(ctx, "unitig_scatter_kernel + unitig_hash_kernel + unitig_reverse_kernel", nu ? 3 : 0));
+    CKS(ensure_pin(ctx, ctx->hu_mins, (total + 1) * 4));
+    CKS(ensure_pin(ctx, ctx->hu_off, (nu + 2) * 8));
+    CKS(ensure_pin(ctx, ctx->hu_hash, (nu + 1) * 16));
+    CKS(ensure_pin(ctx, ctx->hu_circ, nu + 1));
+    CKS(ensure_pin(ctx, ctx->hu_order, (nu + 1) * 4));
+    if (total) CK(cudaMemcpyAsync(ctx->hu_mins.p, ctx->u_mins.p, total * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ctx->hu_off.p, ctx->u_off.p, (nu + 1) * 8, cudaMemcpyDeviceToHost, s));
+    if (nu) {
+        CK(cudaMemcpyAsync(ctx->hu_hash.p, ctx->u_hash.p, nu * 16, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(ctx->hu_circ.p, ctx->u_circ.p, nu, cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    if (!nu) ctx->hu_off.as<uint64_t>()[0] = 0;
+    ctx->d2h_bytes += total * 4 + nu * 25 + 8;
+    // computeDeterministicUnitigs' order: ascending u128 hash = (high word, low word); unitigIndex = 2 * position
+    uint32_t* order = ctx->hu_order.as<uint32_t>();
+    const uint64_t* hh = ctx->hu_hash.as<uint64_t>();
+    for (uint64_t i = 0; i < nu; i++) order[i] = (uint32_t)i;
+    std::sort(order, order + nu, [hh](uint32_t x, uint32_t y) {
+        if (hh[2 * (uint64_t)x + 1] != hh[2 * (uint64_t)y + 1]) return hh[2 * (uint64_t)x + 1] < hh[2 * (uint64_t)y + 1];
+        if (hh[2 * (uint64_t)x] != hh[2 * (uint64_t)y]) return hh[2 * (uint64_t)x] < hh[2 * (uint64_t)y];
+        return x < y;
+    });
+    uint64_t n_circ = 0;
+    for (uint64_t i = 0; i < nu; i++) n_circ += ctx->hu_circ.as<uint8_t>()[i];
+    out->n_unitigs = nu;
+    out->n_minimizers = total;
+    out->n_circular = n_circ;
+    out->offsets = ctx->hu_off.as<uint64_t>();
+    out->minimizers = ctx->hu_mins.as<uint32_t>();
+    out->hashes = ctx->hu_hash.as<uint64_t>();
+    out->circular = ctx->hu_circ.as<uint8_t>();
+    out->order = order;
+    out->d_offsets = ctx->u_off.as<uint64_t>();
+    out->d_minimizers = ctx->u_mins.as<uint32_t>();
     return MDBG_OK;
 }
 

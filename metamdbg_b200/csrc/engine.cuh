@@ -295,6 +295,39 @@ void launch_edge_offers(const EdgeArgs& a, uint64_t* out_recs, unsigned long lon
 void launch_edge_apply_offers(const uint64_t* recs, uint64_t n, const Slot* edges, uint64_t mask, unsigned long long* vals,
                               uint32_t* full_flag, cudaStream_t s);
 
+// ---- unitigs (unitig.cu): oriented nodes x = 2 * node id + reversed; links, list ranking, sequences
+struct UnitigArgs {
+    const Slot* table; uint64_t mask;
+    const uint32_t* node_slot; const uint32_t* slot_node;      // node id <-> table slot
+    uint32_t n_nodes; uint32_t k;
+    const uint32_t* mins; const uint32_t* foreign_vecs;
+    const Slot* edges; uint64_t edge_mask; const unsigned long long* edge_vals;
+    uint32_t* next;                                              // [2 * n_nodes] linked successor or 0xFFFFFFFF
+    uint32_t* error_flag;
+};
+void launch_unitig_nodes(const Slot* table, uint64_t capacity, uint32_t min_count, uint32_t* slot_node, uint32_t* node_slot,
+                         unsigned long long* cursor, cudaStream_t s);
+void launch_unitig_link(const UnitigArgs& a, cudaStream_t s);
+void launch_unitig_rank_init(const uint32_t* next, uint32_t n2, unsigned long long* pair, uint32_t* len, cudaStream_t s);
+void launch_unitig_jump(unsigned long long* pair, uint32_t n2, int steps, unsigned long long* n_open, cudaStream_t s);
+void launch_unitig_cycle_list(const unsigned long long* pair, uint32_t n2, uint32_t* cyc_list, uint32_t* cyc_pos,
+                              unsigned long long* cursor, cudaStream_t s);
+void launch_unitig_cycle_init(const UnitigArgs& a, const uint32_t* cyc_list, const uint32_t* cyc_pos, uint32_t m, uint64_t* best,
+                              uint32_t* jump, cudaStream_t s);
+void launch_unitig_cycle_min(const uint64_t* best_in, const uint32_t* jump_in, uint32_t m, uint64_t* best_out, uint32_t* jump_out,
+                             cudaStream_t s);
+void launch_unitig_cycle_cut(const uint32_t* next, const uint32_t* cyc_list, const uint64_t* best, uint32_t m,
+                             unsigned long long* pair, uint8_t* is_cycle_head, cudaStream_t s);
+void launch_unitig_len(const unsigned long long* pair, uint32_t n2, uint32_t* len, cudaStream_t s);
+void launch_unitig_select(const unsigned long long* pair, const uint8_t* is_cycle_head, const uint32_t* len, uint32_t n2, uint32_t k,
+                          uint32_t* size, uint32_t* flag, cudaStream_t s);
+void launch_unitig_scatter(const UnitigArgs& a, const unsigned long long* pair, const uint32_t* flag, const uint64_t* seq_off,
+                           const uint64_t* unitig_idx, uint32_t* out_mins, uint64_t* out_off, uint8_t* out_circular,
+                           const uint8_t* is_cycle_head, cudaStream_t s);
+void launch_unitig_hash(const uint32_t* mins, const uint64_t* off, uint64_t n_unitigs, uint64_t* out_hashes, uint8_t* out_rev,
+                        cudaStream_t s);
+void launch_unitig_reverse(uint32_t* mins, const uint64_t* off, uint64_t n_unitigs, const uint8_t* rev, cudaStream_t s);
+
 // ---- postings (kminmer.cu): k-min-mer -> (read, window) lists over the count table
 struct PostingArgs {
     const uint32_t* mins; const uint8_t* rem; const uint64_t* offs; const uint32_t* read_of;

@@ -11,6 +11,7 @@
 // plus one 32-bit reduction, so the table is the only state.
 #include "common.cuh"
 #include "engine.cuh"
+#include "table.cuh"
 
 namespace mdbg {
 
@@ -237,12 +238,6 @@ void launch_table_stats(const Slot* table, uint64_t capacity, uint32_t min_count
     table_stats_kernel<<<(unsigned)blocks, 256, 0, s>>>(table, capacity, min_count, d_stats);
 }
 
-__device__ __forceinline__ uint32_t vec_elem(const uint32_t* mins, const uint32_t* foreign, uint64_t ref, int k, int i) {
-    const uint64_t idx = ref & REF_INDEX_MASK;
-    if (ref & REF_FOREIGN) return foreign[idx * (uint64_t)k + i];
-    return (ref & REF_REV) ? mins[idx + k - 1 - i] : mins[idx + i];
-}
-
 // Block-aggregated compaction: one atomicAdd per 256-slot tile instead of one per warp/thread
 // (tens of millions of same-address atomics serialise in L2).
 __global__ void __launch_bounds__(256) table_emit_kernel(const EmitArgs a) {
@@ -298,19 +293,6 @@ __device__ __forceinline__ void window_hash(const uint32_t* w, int k, uint64_t& 
     }
     if (rev) murmur128_u32vec([&](int i) { return w[k - 1 - i]; }, k, h1, h2);
     else murmur128_u32vec([&](int i) { return w[i]; }, k, h1, h2);
-}
-
-// read-only probe (the table is not being modified while this runs)
-__device__ __forceinline__ Slot* table_find(Slot* table, uint64_t mask, uint64_t lo, uint64_t hi) {
-    uint64_t idx = lo & mask;
-    for (uint64_t probe = 0; probe <= mask && probe < 4096; probe++) {
-        Slot* s = table + idx;
-        const uint64_t clo = s->lo, chi = s->hi;
-        if (clo == lo && chi == hi) return s;
-        if ((clo | chi) == 0) return nullptr;
-        idx = (idx + 1) & mask;
-    }
-    return nullptr;
 }
 
 // RescueKminmerFunctor (CreateMdbg.hpp:4579-4637), one warp per read.  The decision only needs

@@ -468,6 +468,34 @@ class Engine:
             vals[..., 3] = np.where(single, (w >> np.uint64(33)) & np.uint64(1), 0)
         return dict(hashes=h, n_edges=n, n_nodes=int(out.n_nodes), checksum=int(out.checksum), values=vals)
 
+    # -- unitig nodes (CreateMdbg::computeUnitigNodes + computeDeterministicUnitigs, CreateMdbg.cpp:1521-1598, 1001-1043) --
+    def unitigs_build(self, min_abundance: int = 2, copy: bool = True) -> dict:
+        """Maximal non-branching paths of the current table's node set as normalized minimizer sequences.
+        -> dict(offsets [n+1], minimizers, hashes [n,2] (low64, high64), circular [n], order [n]: order[i] = the unitig
+        the reference writes as record i of unitigGraph.nodes.bin (unitigIndex 2 * i), n_nodes, n_circular, n_cycle_nodes)."""
+        out = _capi.UnitigsOut()
+        self._ck(self._lib.mdbg_unitigs_build(self._ctx, min_abundance, C.byref(out)))
+        n, t = int(out.n_unitigs), int(out.n_minimizers)
+        arr = lambda p, shape, dt: (np.ctypeslib.as_array(p, shape=shape).copy() if copy else np.ctypeslib.as_array(p, shape=shape)) \
+            if shape[0] else np.zeros(shape, dt)
+        return dict(k=int(out.k), n_nodes=int(out.n_nodes), n_unitigs=n, n_circular=int(out.n_circular),
+                    n_cycle_nodes=int(out.n_cycle_nodes),
+                    offsets=np.ctypeslib.as_array(out.offsets, shape=(n + 1,)).copy(),
+                    minimizers=arr(out.minimizers, (t,), np.uint32),
+                    hashes=arr(out.hashes, (2 * n,), np.uint64).reshape(n, 2),
+                    circular=arr(out.circular, (n,), np.uint8), order=arr(out.order, (n,), np.uint32))
+
+    def unitig_records(self, min_abundance: int = 2) -> dict:
+        """The same unitigs in the reference's file order: dict(offsets [n+1], minimizers) = the records of
+        unitigGraph.nodes.bin (record i: u32 size, size x u32 minimizers, u32 unitigIndex = 2 * i)."""
+        u = self.unitigs_build(min_abundance)
+        lens = np.diff(u["offsets"]).astype(np.int64)[u["order"]]
+        offs = np.zeros(len(lens) + 1, np.uint64)
+        offs[1:] = np.cumsum(lens)
+        mins = np.concatenate([u["minimizers"][int(u["offsets"][i]):int(u["offsets"][i + 1])] for i in u["order"]]) \
+            if len(lens) else np.zeros(0, np.uint32)
+        return dict(offsets=offs, minimizers=mins.astype(np.uint32), n_circular=u["n_circular"], n_nodes=u["n_nodes"])
+
     # -- multi-GPU -----------------------------------------------------------------
     @staticmethod
     def nccl_unique_id() -> bytes:

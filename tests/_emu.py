@@ -68,7 +68,7 @@ def build_emulated_library(out_dir) -> str:
     common = ["/usr/bin/g++", "-O1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-Wno-unknown-pragmas", "-w",
               "-DMDBG_POISON_SMEM", *os.environ.get("MDBG_EMU_EXTRA_FLAGS", "").split(),   # e.g. -fsanitize=address -g
               "-I" + stub, "-I" + os.path.join(ROOT, "tests", "cpp"), "-I" + CSRC, "-I" + os.path.join(ROOT, "include")]
-    for name in ("sketch.cu", "kminmer.cu", "purge.cu", "aux.cu", "ingest.cu", "repeats.cu"):
+    for name in ("sketch.cu", "kminmer.cu", "purge.cu", "aux.cu", "ingest.cu", "repeats.cu", "unitig.cu"):
         inc = os.path.join(out_dir, name.replace(".cu", "_emu.cpp"))
         with open(inc, "w") as f:
             f.write(emulated_source(name))

@@ -344,6 +344,8 @@ template <typename T> static inline T atomicExch(T* p, T v) { T old = *p; *p = v
 template <typename T> static inline T atomicCAS(T* p, T cmp, T v) { T old = *p; if (old == cmp) *p = v; return old; }
 template <typename T, typename U> static inline T atomicAdd(T* p, U v) { T old = *p; *p = (T)(old + (T)v); return old; }
 template <typename T, typename U> static inline T atomicOr(T* p, U v) { T old = *p; *p = (T)(old | (T)v); return old; }
+template <typename T, typename U> static inline T atomicMax(T* p, U v) { T old = *p; if ((T)v > old) *p = (T)v; return old; }
+template <typename T, typename U> static inline T atomicMin(T* p, U v) { T old = *p; if ((T)v < old) *p = (T)v; return old; }
 
 static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
 static inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }

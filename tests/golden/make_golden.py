@@ -31,8 +31,64 @@ def sketch_all(ref, bases, offs, l, d, hpc, bl=None):
     return np.array(mo, np.uint64), cat(ms, np.uint32), cat(ps, np.uint32), cat(ds, np.uint8)
 
 
+def unitig_cases(seed=77):
+    """Minimizer-space read sets whose node sets exercise the unitig walk: long clean unitigs, small alphabets (palindromic
+    keys, hairpins, branching), circular genomes.  Every read is taken twice so that every window is solid at k."""
+    rng = np.random.default_rng(seed)
+    cases = []
+    for it in range(16):
+        k = int([3, 4, 5, 6, 8, 4, 21, 4][it % 8])
+        mode = it % 4
+        reads = []
+        if mode == 0:
+            g = rng.integers(1, 1 << 30, size=1200, dtype=np.uint32)
+            for _ in range(120):
+                st = int(rng.integers(0, 1100)); r = g[st:st + 90].copy()
+                if rng.random() < 0.5: r = r[::-1]
+                if rng.random() < 0.3: r[int(rng.integers(0, 90))] = rng.integers(1, 1 << 30)
+                reads.append(r)
+        elif mode == 1:
+            g = rng.integers(1, 12, size=300, dtype=np.uint32)
+            for _ in range(80):
+                st = int(rng.integers(0, 260)); r = g[st:st + 40].copy()
+                if rng.random() < 0.5: r = r[::-1]
+                reads.append(r)
+        elif mode == 2:
+            for _ in range(40): reads.append(rng.integers(1, 4, size=k + 8, dtype=np.uint32))
+        else:
+            for _ in range(3):
+                L = int(rng.integers(k, 200))
+                g = rng.integers(1, 1 << 30, size=L, dtype=np.uint32)
+                reads.append(np.concatenate([g, g[:k - 1]]))
+                if rng.random() < 0.5: reads.append(np.concatenate([g, g, g[:k - 1]])[::-1])
+            reads.append(rng.integers(1, 1 << 30, size=150, dtype=np.uint32))
+        reads = [np.ascontiguousarray(r, dtype=np.uint32) for r in reads + reads]
+        offs = np.zeros(len(reads) + 1, np.uint64)
+        offs[1:] = np.cumsum([len(r) for r in reads])
+        cases.append((k, np.concatenate(reads).astype(np.uint32), offs))
+    return cases
+
+
+def mint_unitigs(ref):
+    """7. unitig nodes: the reference's own indexEdges + computeUnitigNodes + computeDeterministicUnitigs
+    (oracle/ref_shim.cpp: ref_unitig_nodes) on the node set the reference's count gives for each case."""
+    out = {}
+    cases = unitig_cases()
+    out["n_cases"] = np.array(len(cases))
+    for i, (k, mins, offs) in enumerate(cases):
+        nodes = ref.count(mins, offs, k, 2, threads=2)["vecs"]
+        u = ref.unitig_nodes(nodes, k, threads=1 + (i % 2) * 3)
+        out[f"c{i}_k"] = np.array(k); out[f"c{i}_minimizers"] = mins; out[f"c{i}_offsets"] = offs
+        out[f"c{i}_nodes"] = nodes
+        out[f"c{i}_unitig_offsets"] = u["offsets"]; out[f"c{i}_unitig_minimizers"] = u["minimizers"]
+    np.savez_compressed(os.path.join(HERE, "minspace_unitigs.npz"), **out)
+
+
 def main():
     ref = Reference()
+    if "--only-unitigs" in sys.argv:
+        mint_unitigs(ref)
+        return
 
     # 1. HiFi-like: HPC on, l=15, d=0.005, k=4 count, abundance >= 2 (BASELINE config 0, scaled down)
     rs = synth.make_readset(600, 6000, seed=101, n_genomes=2, genome_len_range=(90_000, 140_000), err=0.001)
@@ -168,6 +224,7 @@ def main():
                             stats=np.array([res["stats"]["n_reads"], res["stats"]["n50"], res["stats"]["n_bases"],
                                             res["stats"]["mean_length"], res["stats"]["n_minimizers"]], np.uint64),
                             stats_f=np.array([res["stats"]["density"], res["stats"]["avg_quality"]], np.float32))
+    mint_unitigs(ref)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

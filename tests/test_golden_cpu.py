@@ -104,3 +104,19 @@ def test_readselection_stage_golden(oracle, tag, hpc, dens):
         assert np.float32(g["mean_quality"][r]).tobytes() == np.float32(mq).tobytes()
         assert int(g["read_length"][r]) == len(s)
     assert n_low >= 2
+
+
+def test_unitig_nodes_golden(oracle):
+    """Row F1, third step: the oracle's unitigs against unitigGraph.nodes.bin contents minted from the reference's own
+    indexEdges + computeUnitigNodes + computeDeterministicUnitigs (tests/golden/make_golden.py::mint_unitigs)."""
+    g = load("minspace_unitigs.npz")
+    n_multi = 0
+    for i in range(int(g["n_cases"])):
+        k = int(g[f"c{i}_k"])
+        nodes = oracle.count(g[f"c{i}_minimizers"], g[f"c{i}_offsets"], k, 2)["vecs"]
+        assert sorted(map(tuple, nodes.tolist())) == sorted(map(tuple, g[f"c{i}_nodes"].tolist()))
+        u = oracle.unitigs(g[f"c{i}_nodes"], k)
+        assert np.array_equal(u["offsets"], g[f"c{i}_unitig_offsets"]), i
+        assert np.array_equal(u["minimizers"], g[f"c{i}_unitig_minimizers"]), i
+        n_multi += int(np.any(np.diff(u["offsets"]) > k))
+    assert n_multi >= 8

@@ -440,3 +440,66 @@ def test_multi_k_run_in_the_library(built, oracle):
     assert got[0]["n_reads_rescued"] == want[0]["n_reads_rescued"] > 0
     assert eng.count_stats(0)["checksum"] == got[-1]["checksum"]          # the k = 10 table is current
     eng.close()
+
+
+def test_unitig_nodes_vs_oracle_and_golden(built, oracle):
+    """Row F1, third step (mdbg_unitigs_build): unitig links between oriented nodes, list ranking by pointer jumping,
+    cycle cut at the smallest hash128, normalized sequences and their hash128 -- the records of unitigGraph.nodes.bin
+    in the reference's deterministic order, against vectors minted from the reference's own computeUnitigNodes +
+    computeDeterministicUnitigs (clean paths, small alphabets with palindromic keys / hairpins, circular genomes) and,
+    on the node set of sketched reads (first pass, rescued nodes, a next-k table), against the oracle."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "minspace_unitigs.npz"))
+    eng = engine()
+    n_circ = 0
+    for i in range(int(g["n_cases"])):
+        k = int(g[f"c{i}_k"])
+        eng.store_clear()
+        eng.store_append(g[f"c{i}_minimizers"], g[f"c{i}_offsets"])
+        eng.count_begin(k)
+        eng.count_add_store()
+        got = eng.unitig_records(2)
+        assert got["n_nodes"] == len(g[f"c{i}_nodes"])
+        assert np.array_equal(got["offsets"], g[f"c{i}_unitig_offsets"]), i
+        assert np.array_equal(got["minimizers"], g[f"c{i}_unitig_minimizers"]), i
+        n_circ += got["n_circular"]
+    assert n_circ >= 4
+    eng.close()
+
+    rs = synth.make_readset(1500, 7000, seed=31, n_genomes=2, genome_len_range=(120_000, 200_000), err=0.003)
+    bases, offs = synth.fill_reads(rs)
+    eng = engine()
+    eng.sketch_batch(bases, offs, append_to_store=True, fetch=False)
+
+    def check(k, min_ab, at_least):
+        tab = eng.count_finalize(min_ab)
+        want = oracle.unitigs(tab.kminmers, k)
+        got = eng.unitigs_build(min_ab)
+        assert got["n_nodes"] == len(tab.abundances) and got["n_unitigs"] == len(want["offsets"]) - 1 >= at_least
+        rec = eng.unitig_records(min_ab)
+        assert np.array_equal(rec["offsets"], want["offsets"]) and np.array_equal(rec["minimizers"], want["minimizers"])
+        # hashes as the oracle's, order = ascending (high, low); every node lies in a unitig (a self-reverse-complementary
+        # path holds its nodes in both orientations, so the windows can outnumber the nodes)
+        hs = got["hashes"][got["order"]]
+        assert np.array_equal(hs[:, 1], want["hashes"][:, 0]) and np.array_equal(hs[:, 0], want["hashes"][:, 1])
+        assert int(np.sum(np.diff(got["offsets"]).astype(np.int64) - (k - 1))) >= got["n_nodes"]
+
+    eng.count_begin(4)
+    eng.count_add_store()
+    check(4, 2, 20)
+    eng.count_rescue()
+    check(4, 0, 20)
+    eng.prev_from_current(0)
+    eng.count_begin(5)
+    eng.count_add_store_next_k()
+    check(5, 0, 20)
+    for k in (2, 3, 9):
+        eng.count_begin(k)
+        eng.count_add_store()
+        check(k, 2, 1)
+    # an empty node set
+    eng.store_clear()
+    eng.count_begin(4)
+    eng.count_add_store()
+    e = eng.unitigs_build(2)
+    assert e["n_unitigs"] == 0 and e["n_nodes"] == 0 and len(e["offsets"]) == 1
+    eng.close()

@@ -1,10 +1,14 @@
 """CPU tests: the C restatement (oracle/mdbg_oracle.c) against the known-answer
 values of SURVEY.md section 8c and against the reference's own sources compiled
 into oracle/_ref (tests marked `ref` skip where that library is absent)."""
+import os
 import struct
+import sys
 
 import numpy as np
 import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 from metamdbg_b200 import synth
 
@@ -423,3 +427,27 @@ def test_ref_edge_values_order_free_form(oracle, reference):
     a = oracle.edge_values(nodes, 4)
     want = {(int(h[0]), int(h[1])): tuple(tuple(int(x) for x in c) for c in v) for h, v in zip(a["hashes"], a["values"])}
     assert canonical_edge_values(reference.edge_values(nodes, 4, threads=3)) == want and len(want) > 500
+
+
+@pytest.mark.ref
+def test_ref_unitig_nodes(oracle, reference):
+    """Row F1, third step: CreateMdbg::indexEdges + computeUnitigNodes + computeDeterministicUnitigs run for real (1 and 4
+    OpenMP threads) against the oracle's restatement: the records of unitigGraph.nodes.bin are identical -- same unitigs,
+    same normalized minimizer sequences, same order -- for clean paths, small alphabets (palindromic keys, hairpins,
+    branching everywhere) and circular genomes."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_golden import unitig_cases
+    n_circular_like = 0
+    for i, (k, mins, offs) in enumerate(unitig_cases(seed=5)):
+        nodes = oracle.count(mins, offs, k, 2)["vecs"]
+        a = oracle.unitigs(nodes, k)
+        for threads in (1, 4):
+            b = reference.unitig_nodes(nodes, k, threads=threads)
+            assert np.array_equal(a["offsets"], b["offsets"]) and np.array_equal(a["minimizers"], b["minimizers"]), (i, k, threads)
+        assert len(a["offsets"]) - 1 > 0
+        n_circular_like += int(i % 4 == 3)
+    reads, offs = _minspace_reads(11)
+    nodes = oracle.count(reads, offs, 4, 2)["vecs"]
+    a = oracle.unitigs(nodes, 4); b = reference.unitig_nodes(nodes, 4, threads=3)
+    assert len(nodes) > 500 and np.array_equal(a["offsets"], b["offsets"]) and np.array_equal(a["minimizers"], b["minimizers"])
+    assert n_circular_like >= 4
