@@ -595,6 +595,26 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         except Exception as e:                                # noqa: BLE001
             edges_extra = {"error": repr(e)}
 
+    # ---- extra: unitig nodes of the same node set (computeUnitigNodes + computeDeterministicUnitigs): edge set, links,
+    # list ranking, sequences, hashes on the device; the CSR's D2H and the host's sort of the unitig hashes are inside
+    unitigs_extra = None
+    if not args.no_edges and w["last_k"] == K and world == 1:
+        try:
+            t_u = []
+            for _ in range(2):
+                t0 = time.perf_counter()
+                un = eng.unitigs_build(MIN_AB, copy=False)
+                t_u.append(time.perf_counter() - t0)
+            lens = np.diff(un["offsets"]).astype(np.int64)
+            unitigs_extra = {"k": K, "n_nodes": un["n_nodes"], "n_unitigs": un["n_unitigs"], "n_circular": un["n_circular"],
+                             "n_minimizers": int(un["offsets"][-1]), "longest_unitig_nodes": int(lens.max() - (K - 1)) if len(lens) else 0,
+                             "ms": round(1e3 * t_u[1], 3), "d2h_bytes": int(un["offsets"][-1]) * 4 + un["n_unitigs"] * 25,
+                             "checksum_of_hashes": int(np.sum(un["hashes"][:, 0], dtype=np.uint64)) if un["n_unitigs"] else 0,
+                             "timer": "host wall clock around mdbg_unitigs_build (edge set + links + list ranking + sequences + "
+                                      "hash128 on the device, D2H of the CSR, host sort of the unitig hashes)"}
+        except Exception as e:                                # noqa: BLE001
+            unitigs_extra = {"error": repr(e)}
+
     # ---- extra (not the headline): the multi-k loop k = 4 .. 21 on the resident store (BASELINE config 4's shape on
     # this workload): k = 4 counted, every further k derived from the previous table on the device; collective
     # previous-k replication + value merge for N > 1
@@ -787,6 +807,29 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                         "sample": f"first {n_sample} reads ({int(s_offs[-1]) / 1e9:.3f} Gbp), one pass of the reference's "
                                   f"sketch + purge + count code driven in memory, "
                                   f"GPU fingerprint (n_minimizers, n_solid, checksum) identical"}
+        # the graph side of the same sample: the reference's indexEdges + computeUnitigNodes + computeDeterministicUnitigs
+        # on the sample's node set, against mdbg_unitigs_build -- the records of unitigGraph.nodes.bin must be identical
+        if ref is not None and unitigs_extra is not None and "error" not in unitigs_extra:
+            try:
+                nodes = eng.count_finalize(MIN_AB).kminmers
+                t0 = time.perf_counter()
+                gu = eng.unitig_records(MIN_AB)
+                t_gpu = time.perf_counter() - t0
+                t0 = time.perf_counter()
+                ru = ref.unitig_nodes(nodes, K, threads=threads)
+                t_ref = time.perf_counter() - t0
+                same = bool(np.array_equal(gu["offsets"], ru["offsets"]) and np.array_equal(gu["minimizers"], ru["minimizers"]))
+                if not same:
+                    raise SystemExit("bench.py: the unitigs of the GPU differ from the reference's unitigGraph.nodes.bin on the sample")
+                unitigs_extra["cpu_reference_on_sample"] = {
+                    "n_nodes": int(len(nodes)), "n_unitigs": int(len(ru["offsets"]) - 1), "seconds": round(t_ref, 3), "threads": threads,
+                    "gpu_seconds_same_sample": round(t_gpu, 4), "identical_records": same,
+                    "what": "CreateMdbg::indexEdges + computeUnitigNodes + computeDeterministicUnitigs of oracle/_ref through their "
+                            "file contract in a scratch directory, node set of the cpu_baseline sample"}
+            except SystemExit:
+                raise
+            except Exception as e:                            # noqa: BLE001
+                unitigs_extra["cpu_reference_on_sample"] = {"error": repr(e)}
 
     # ---- extras: the other BASELINE.json configs ---------------------------------------------------------------------
     extras = {}
@@ -853,7 +896,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                          "share_of_step": sk_ms / (ms_total / args.steps)},
             "kernels_ms": {"sketch": sk_ms, "insert": float(np.mean(insert_ms))},
             "table_phase_ms_profiled_step_rank0": step_phases,
-            "ascii_resident": ascii_leg, "multi_k": multi_k, "edges": edges_extra, "extras": extras,
+            "ascii_resident": ascii_leg, "multi_k": multi_k, "edges": edges_extra, "unitigs": unitigs_extra,
+            "extras": extras,
             "sketch_autotune": dict(tune, active=active_variant,
                                     note="ms = sketch (+ pack pass for variant 2) + scan + compaction of an ASCII-resident batch, "
                                          "best of 2; every variant's whole output must equal variant 0's on the device"),

@@ -455,6 +455,12 @@ typedef struct {
     const uint64_t* hashes;       /* [2 * n_unitigs] */
     const uint8_t* circular;      /* [n_unitigs] */
     const uint32_t* order;        /* [n_unitigs] */
+    /* dumpUnitigAbundances (CreateMdbg.cpp:3335-3390): the abundance of every k-min-mer of unitig u, in sequence order,
+     * at node_abundances[offsets[u] - u * (k - 1) ..] (offsets[u+1] - offsets[u] - (k - 1) of them) =
+     * the record of unitigGraph.nodes.abundances.bin */
+    const uint32_t* node_abundances;
+    uint64_t checksum_nodes;      /* "Checksum unitig nodes": sum over records of minimizer * size * unitigIndex (CreateMdbg.cpp:3380) */
+    uint64_t checksum_abundances; /* "Checksum unitig abundance": sum of abundance * number of abundances (CreateMdbg.cpp:3384) */
     const uint64_t* d_offsets;    /* the same CSR in device memory */
     const uint32_t* d_minimizers;
 } mdbg_unitigs_out;

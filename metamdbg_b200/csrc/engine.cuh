@@ -323,10 +323,11 @@ void launch_unitig_select(const unsigned long long* pair, const uint8_t* is_cycl
                           uint32_t* size, uint32_t* flag, cudaStream_t s);
 void launch_unitig_scatter(const UnitigArgs& a, const unsigned long long* pair, const uint32_t* flag, const uint64_t* seq_off,
                            const uint64_t* unitig_idx, uint32_t* out_mins, uint64_t* out_off, uint8_t* out_circular,
-                           const uint8_t* is_cycle_head, cudaStream_t s);
+                           const uint8_t* is_cycle_head, uint32_t* out_abund, cudaStream_t s);
 void launch_unitig_hash(const uint32_t* mins, const uint64_t* off, uint64_t n_unitigs, uint64_t* out_hashes, uint8_t* out_rev,
                         cudaStream_t s);
-void launch_unitig_reverse(uint32_t* mins, const uint64_t* off, uint64_t n_unitigs, const uint8_t* rev, cudaStream_t s);
+void launch_unitig_reverse(uint32_t* mins, const uint64_t* off, uint64_t n_unitigs, const uint8_t* rev, uint32_t* abund, uint32_t k,
+                           cudaStream_t s);
 
 // ---- postings (kminmer.cu): k-min-mer -> (read, window) lists over the count table
 struct PostingArgs {

@@ -299,15 +299,18 @@ void launch_unitig_select(const unsigned long long* pair, const uint8_t* is_cycl
 __global__ void __launch_bounds__(256) unitig_scatter_kernel(const UnitigArgs a, const unsigned long long* pair, const uint32_t* flag,
                                                              const uint64_t* seq_off, const uint64_t* unitig_idx,
                                                              uint32_t* out_mins, uint64_t* out_off, uint8_t* out_circular,
-                                                             const uint8_t* is_cycle_head) {
+                                                             const uint8_t* is_cycle_head, uint32_t* out_abund) {
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= 2 * a.n_nodes) return;
     const unsigned long long p = pair[x];
     const uint32_t h = (uint32_t)p & ~U_HEAD, r = (uint32_t)(p >> 32);
     if (!flag[h]) return;
     const uint64_t base = seq_off[h];
-    const uint64_t ref = a.table[a.node_slot[x >> 1]].ref;
+    const Slot* sl = a.table + a.node_slot[x >> 1];
+    const uint64_t ref = sl->ref;
     const int k = (int)a.k;
+    // dumpUnitigAbundances (CreateMdbg.cpp:3335-3390): the abundance of every k-min-mer of the unitig, in sequence order
+    out_abund[base - unitig_idx[h] * (uint64_t)(k - 1) + r] = sl->count;
     if (r == 0) {
         for (int j = 0; j < k; j++) out_mins[base + j] = onode_elem(a, ref, x & 1u, j);
         out_off[unitig_idx[h]] = base;
@@ -319,10 +322,10 @@ __global__ void __launch_bounds__(256) unitig_scatter_kernel(const UnitigArgs a,
 
 void launch_unitig_scatter(const UnitigArgs& a, const unsigned long long* pair, const uint32_t* flag, const uint64_t* seq_off,
                            const uint64_t* unitig_idx, uint32_t* out_mins, uint64_t* out_off, uint8_t* out_circular,
-                           const uint8_t* is_cycle_head, cudaStream_t s) {
+                           const uint8_t* is_cycle_head, uint32_t* out_abund, cudaStream_t s) {
     if (!a.n_nodes) return;
     unitig_scatter_kernel<<<(unsigned)((2 * (uint64_t)a.n_nodes + 255) / 256), 256, 0, s>>>(a, pair, flag, seq_off, unitig_idx, out_mins,
-                                                                                          out_off, out_circular, is_cycle_head);
+                                                                                          out_off, out_circular, is_cycle_head, out_abund);
 }
 
 // computeDeterministicUnitigs: KmerVec::normalize on the whole minimizer sequence, hash128 of the normalized sequence.
@@ -348,7 +351,7 @@ __global__ void __launch_bounds__(128) unitig_hash_kernel(const uint32_t* mins, 
 
 // sequences whose normalized form is the reversed one are reversed in place, one warp per unitig
 __global__ void __launch_bounds__(256) unitig_reverse_kernel(uint32_t* mins, const uint64_t* off, uint64_t n_unitigs,
-                                                             const uint8_t* rev) {
+                                                             const uint8_t* rev, uint32_t* abund, uint32_t k) {
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -361,6 +364,13 @@ __global__ void __launch_bounds__(256) unitig_reverse_kernel(uint32_t* mins, con
             w[j] = w[L - 1 - j];
             w[L - 1 - j] = t;
         }
+        uint32_t* ab = abund + (off[u] - u * (uint64_t)(k - 1));        // the k-min-mers of the reversed sequence, in its order
+        const uint64_t nw = L - (k - 1);
+        for (uint64_t j = lane; j < nw / 2; j += 32) {
+            const uint32_t t = ab[j];
+            ab[j] = ab[nw - 1 - j];
+            ab[nw - 1 - j] = t;
+        }
     }
 }
 
@@ -369,11 +379,12 @@ void launch_unitig_hash(const uint32_t* mins, const uint64_t* off, uint64_t n_un
     if (!n_unitigs) return;
     unitig_hash_kernel<<<(unsigned)((n_unitigs + 127) / 128), 128, 0, s>>>(mins, off, n_unitigs, out_hashes, out_rev);
 }
-void launch_unitig_reverse(uint32_t* mins, const uint64_t* off, uint64_t n_unitigs, const uint8_t* rev, cudaStream_t s) {
+void launch_unitig_reverse(uint32_t* mins, const uint64_t* off, uint64_t n_unitigs, const uint8_t* rev, uint32_t* abund, uint32_t k,
+                           cudaStream_t s) {
     if (!n_unitigs) return;
     uint64_t blocks = (n_unitigs + 7) / 8;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    unitig_reverse_kernel<<<(unsigned)blocks, 256, 0, s>>>(mins, off, n_unitigs, rev);
+    unitig_reverse_kernel<<<(unsigned)blocks, 256, 0, s>>>(mins, off, n_unitigs, rev, abund, k);
 }
 
 }  // namespace mdbg

@@ -483,7 +483,9 @@ class Engine:
                     offsets=np.ctypeslib.as_array(out.offsets, shape=(n + 1,)).copy(),
                     minimizers=arr(out.minimizers, (t,), np.uint32),
                     hashes=arr(out.hashes, (2 * n,), np.uint64).reshape(n, 2),
-                    circular=arr(out.circular, (n,), np.uint8), order=arr(out.order, (n,), np.uint32))
+                    circular=arr(out.circular, (n,), np.uint8), order=arr(out.order, (n,), np.uint32),
+                    node_abundances=arr(out.node_abundances, (t - n * (int(out.k) - 1),), np.uint32),
+                    checksum_nodes=int(out.checksum_nodes), checksum_abundances=int(out.checksum_abundances))
 
     def unitig_records(self, min_abundance: int = 2) -> dict:
         """The same unitigs in the reference's file order: dict(offsets [n+1], minimizers) = the records of
@@ -494,7 +496,11 @@ class Engine:
         offs[1:] = np.cumsum(lens)
         mins = np.concatenate([u["minimizers"][int(u["offsets"][i]):int(u["offsets"][i + 1])] for i in u["order"]]) \
             if len(lens) else np.zeros(0, np.uint32)
-        return dict(offsets=offs, minimizers=mins.astype(np.uint32), n_circular=u["n_circular"], n_nodes=u["n_nodes"])
+        km1 = u["k"] - 1
+        ab = [u["node_abundances"][int(u["offsets"][i]) - int(i) * km1:int(u["offsets"][i + 1]) - (int(i) + 1) * km1] for i in u["order"]]
+        return dict(offsets=offs, minimizers=mins.astype(np.uint32), n_circular=u["n_circular"], n_nodes=u["n_nodes"],
+                    abundances=np.concatenate(ab).astype(np.uint32) if ab else np.zeros(0, np.uint32),
+                    checksum_nodes=u["checksum_nodes"], checksum_abundances=u["checksum_abundances"])
 
     # -- multi-GPU -----------------------------------------------------------------
     @staticmethod

@@ -158,11 +158,12 @@ static int stageReadSelection(int argc, char** argv) {
 static int stageGraph(int argc, char** argv) {
     if (argc < 3) { std::cerr << "usage: graph <tmpDir> [--threads N] [--min-abundance n] [--firstpass]\n"; return 2; }
     const std::string tmpDir = argv[2];
-    bool firstPass = false;
+    bool firstPass = false, unitigs = false;
     uint32_t minAb = 0;
     for (int i = 3; i < argc; i++) {
         const std::string a = argv[i];
         if (a == "--firstpass") firstPass = true;
+        else if (a == "--unitigs") unitigs = true;
         else if (a == "--min-abundance" && i + 1 < argc) minAb = (uint32_t)atoi(argv[++i]);
         else if (a == "--threads") i++;
     }
@@ -177,6 +178,12 @@ static int stageGraph(int argc, char** argv) {
     counter.execute(tmpDir + "/kminmerData_min.txt", tmpDir + "/kminmerData_abundance.txt");
     std::cout << "reads " << nReads << " kminmers " << counter._nbKminmers << " distinct " << counter._nbDistinct << " solid "
               << counter._nbSolidKminmers << " rescued " << counter._nbRescuedKminmers << " checksum " << counter._checksum << std::endl;
+    if (unitigs) {                                       // createGfa's node side (CreateMdbg.cpp:876-925) on the table just built
+        GpuUnitigBuilder ub(ctx, minAb);
+        ub.execute(tmpDir + "/unitigGraph.nodes.bin", tmpDir + "/unitigGraph.nodes.abundances.bin");
+        std::cout << "unitigs " << ub._nbUnitigs << " circular " << ub._nbCircular << " checksum_unitig_nodes " << ub._checksumNodes
+                  << " checksum_unitig_abundance " << ub._checksumAbundances << std::endl;
+    }
     return 0;
 }
 
@@ -193,7 +200,7 @@ int main(int argc, char** argv) {
         std::cerr << "usage: mdbg_gpu_firstpass readSelection <tmpDir> <outputFile> <input.txt> [...]   (metaMDBG's stage command lines,\n"
                      "       mdbg_gpu_firstpass graph <tmpDir> --firstpass [--min-abundance n]            parameters.gz in <tmpDir>)\n"
                      "       mdbg_gpu_firstpass <reads.fa|fq[.gz]> <outDir> [--ont] [-l 15] [-d 0.005] [-k 4] "
-                     "[--min-abundance 2] [--last-k N] [--batch-mbp 1024] [--max-k K] [--edges]\n"
+                     "[--min-abundance 2] [--last-k N] [--batch-mbp 1024] [--max-k K] [--edges] [--unitigs]\n"
                      "       mdbg_gpu_firstpass --from-read-data <read_data_corrected.txt> <outDir> [-k 4] [--min-abundance 2]\n"
                      "         (the `graph --firstpass` seam alone: count the minimizer-space reads of an existing file)\n"
                      "       --max-k K: also derive k+1 .. K from the previous table on the device (the k > firstK `graph`\n"
@@ -205,7 +212,7 @@ int main(int argc, char** argv) {
     std::string input = fromReadData ? argv[2] : argv[1], outDir = fromReadData ? argv[3] : argv[2];
     bool hpc = true;
     uint32_t l = 15, k = 4, minAb = 2, lastK = 0, maxK = 0;
-    bool writeEdges = false;
+    bool writeEdges = false, writeUnitigs = false;
     float density = 0.005f;
     size_t batchMbp = 1024;
     for (int i = fromReadData ? 4 : 3; i < argc; i++) {
@@ -219,15 +226,23 @@ int main(int argc, char** argv) {
         else if (a == "--last-k") lastK = (uint32_t)atoi(next().c_str());
         else if (a == "--max-k") maxK = (uint32_t)atoi(next().c_str());
         else if (a == "--edges") writeEdges = true;
+        else if (a == "--unitigs") writeUnitigs = true;
         else if (a == "--batch-mbp") batchMbp = (size_t)atol(next().c_str());
     }
     try {
         Context ctx(l, density, hpc);
         auto edgeKeys = [&](const std::string& file) {   // EdgeIndexer on the table the context holds
-            if (!writeEdges) return;
-            GpuEdgeIndexer edges(ctx, minAb);
-            edges.execute(file);
-            std::cout << "edges " << edges._nbEdges << " edge_checksum " << edges._checksum << "\n";
+            if (writeEdges) {
+                GpuEdgeIndexer edges(ctx, minAb);
+                edges.execute(file);
+                std::cout << "edges " << edges._nbEdges << " edge_checksum " << edges._checksum << "\n";
+            }
+            if (!writeUnitigs) return;
+            GpuUnitigBuilder ub(ctx, minAb);
+            const std::string dir = file.substr(0, file.find_last_of('/'));
+            ub.execute(dir + "/unitigGraph.nodes.bin", dir + "/unitigGraph.nodes.abundances.bin");
+            std::cout << "unitigs " << ub._nbUnitigs << " circular " << ub._nbCircular << " checksum_unitig_nodes " << ub._checksumNodes
+                      << " checksum_unitig_abundance " << ub._checksumAbundances << "\n";
         };
         auto nextKPasses = [&]() {                       // k+1 .. maxK from the table the context holds
             GpuNextKCounter nextK(ctx, minAb);

@@ -433,4 +433,43 @@ private:
     uint32_t _minAbundance;
 };
 
+// CreateMdbg::computeUnitigNodes + computeDeterministicUnitigs + dumpUnitigAbundances (CreateMdbg.cpp:1521-1598,
+// 1001-1043, 3335-3390): the unitig nodes of the context's current table as the reference's two files --
+//   unitigGraph.nodes.bin             per unitig: u32 size, size x u32 minimizers, u32 unitigIndex (= 2 * record number)
+//   unitigGraph.nodes.abundances.bin  per unitig: u32 unitigIndex, u32 count, count x u32 abundance of its k-min-mers
+// in the reference's deterministic order (ascending hash128 of the normalized minimizer sequence).
+class GpuUnitigBuilder {
+public:
+    GpuUnitigBuilder(Context& ctx, uint32_t minAbundance) : _ctx(ctx), _minAbundance(minAbundance) {}
+
+    void execute(const std::string& nodeFile, const std::string& abundanceFile) {
+        mdbg_unitigs_out u{};
+        check(_ctx.get(), mdbg_unitigs_build(_ctx.get(), _minAbundance, &u), "mdbg_unitigs_build");
+        File fn(nodeFile), fa(abundanceFile);
+        const uint64_t km1 = u.k - 1;
+        for (uint64_t i = 0; i < u.n_unitigs; i++) {
+            const uint64_t j = u.order[i];
+            const uint32_t size = (uint32_t)(u.offsets[j + 1] - u.offsets[j]), index = (uint32_t)(2 * i), nb = size - (uint32_t)km1;
+            fn.put(&size, 4, 1);
+            fn.put(u.minimizers + u.offsets[j], 4, size);
+            fn.put(&index, 4, 1);
+            fa.put(&index, 4, 1);
+            fa.put(&nb, 4, 1);
+            fa.put(u.node_abundances + (u.offsets[j] - j * km1), 4, nb);
+        }
+        fn.close();
+        fa.close();
+        _nbUnitigs = u.n_unitigs;
+        _nbCircular = u.n_circular;
+        _checksumNodes = u.checksum_nodes;
+        _checksumAbundances = u.checksum_abundances;
+    }
+
+    uint64_t _nbUnitigs = 0, _nbCircular = 0, _checksumNodes = 0, _checksumAbundances = 0;
+
+private:
+    Context& _ctx;
+    uint32_t _minAbundance;
+};
+
 }  // namespace mdbg_host

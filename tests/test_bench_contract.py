@@ -71,6 +71,9 @@ def test_gpu_arm_runs_on_the_emulator(tmp_path):
         assert d["check"]["occurrences_conserved"] and d["check"]["device_steps_same_checksum"]
         assert all(d["sketch_autotune"]["identical"]) and d["multi_k"]["same_tables_both_sweeps"]
         assert d["edges"]["n_edges"] > 0 and d["edges"]["n_nodes"] == d["check"]["n_solid_total"]
+        if "--extras" in extra:
+            assert d["unitigs"]["n_nodes"] == d["edges"]["n_nodes"] and d["unitigs"]["n_unitigs"] > 0, d["unitigs"]
+            assert d["unitigs"].get("cpu_reference_on_sample", {}).get("identical_records", d["cpu_baseline"]["kind"] == "port"), d["unitigs"]
         assert d["cpu_baseline"]["kind"] in ("reference", "port") and "identical" in d["cpu_baseline"]["sample"]
         assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
         assert d["ascii_resident"]["same_table_as_packed_leg"] and d["ascii_resident"]["value"] > 0

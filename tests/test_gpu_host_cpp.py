@@ -249,7 +249,7 @@ def test_cpp_driver_stage_compatible_subcommands(tmp_path, oracle, hifi):
         got.append(np.frombuffer(buf, np.uint32, n, pos)); pos += 4 * n
     assert pos == len(buf) and np.array_equal(np.concatenate(got), pm)
     for min_ab in (2, 0):
-        out = subprocess.run([EXE, "graph", str(tmp), "--threads", "4", "--min-abundance", str(min_ab), "--firstpass"],
+        out = subprocess.run([EXE, "graph", str(tmp), "--threads", "4", "--min-abundance", str(min_ab), "--firstpass", "--unitigs"],
                              capture_output=True, text=True, timeout=180)
         assert out.returncode == 0, out.stderr
         ref = oracle.count(pm, po, 4, 2)
@@ -263,6 +263,12 @@ def test_cpp_driver_stage_compatible_subcommands(tmp_path, oracle, hifi):
         assert {(int(h), int(l)): int(c) for h, l, c in zip(hi, lo, cnt)} == want and len(want) > 100
         vec = np.frombuffer(open(tmp / "kminmerData_min.txt", "rb").read(), dtype=np.uint32).reshape(-1, 4)
         assert len(vec) == len(want)
+        # --unitigs: createGfa's node side on the table just built -- unitigGraph.nodes.bin as the reference writes it
+        wu = oracle.unitigs(vec, 4)
+        want_bytes = b"".join(np.uint32(int(wu["offsets"][i + 1] - wu["offsets"][i])).tobytes() +
+                              wu["minimizers"][int(wu["offsets"][i]):int(wu["offsets"][i + 1])].tobytes() + np.uint32(2 * i).tobytes()
+                              for i in range(len(wu["offsets"]) - 1))
+        assert open(tmp / "unitigGraph.nodes.bin", "rb").read() == want_bytes and len(wu["offsets"]) > 10
     # a later pass needs the contig stage: refused with a message, not silently wrong
     out = subprocess.run([EXE, "graph", str(tmp), "--threads", "4"], capture_output=True, text=True, timeout=60)
     assert out.returncode == 1 and "firstpass" in out.stderr

@@ -269,7 +269,7 @@ def test_cpp_driver_max_k_and_edges(tmp_path, oracle):
     d3 = tmp_path / "three"
     d3.mkdir()
     out = subprocess.run([EXE, "--from-read-data", str(d1 / "read_data_corrected.txt"), str(d3), "--min-abundance", "0",
-                          "--max-k", "7", "--edges"], capture_output=True, text=True, timeout=120)
+                          "--max-k", "7", "--edges", "--unitigs"], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr
     # --edges: edges.bin of the k = 4 node set (GpuEdgeIndexer) = the oracle's EdgeIndexer key set
     nodes = np.frombuffer(open(d3 / "kminmerData_min.txt", "rb").read(), dtype=np.uint32).reshape(-1, 4)
@@ -278,6 +278,22 @@ def test_cpp_driver_max_k_and_edges(tmp_path, oracle):
     assert {(int(h[1]), int(h[0])) for h in eb} == {(int(h[0]), int(h[1])) for h in we["hashes"]} and len(eb) == len(we["hashes"]) > 500
     words = out.stdout.split()
     assert int(words[words.index("edges") + 1]) == len(eb) and int(words[words.index("edge_checksum") + 1]) == we["checksum"]
+    # --unitigs: unitigGraph.nodes.bin of that node set (GpuUnitigBuilder) = the bytes computeUnitigNodes +
+    # computeDeterministicUnitigs write (oracle restatement, pinned against the reference's own run), and the per-node
+    # abundances of dumpUnitigAbundances
+    wu = oracle.unitigs(nodes, 4)
+    want_bytes, want_ab = b"", b""
+    abf = np.frombuffer(open(d3 / "kminmerData_abundance.txt", "rb").read(), dtype=np.uint8).reshape(-1, 20)
+    ab_of = {(int(h), int(l)): int(c_) for l, h, c_ in zip(abf[:, 0:8].copy().view(np.uint64)[:, 0], abf[:, 8:16].copy().view(np.uint64)[:, 0],
+                                                          abf[:, 16:20].copy().view(np.uint32)[:, 0])}
+    for i in range(len(wu["offsets"]) - 1):
+        seq = wu["minimizers"][int(wu["offsets"][i]):int(wu["offsets"][i + 1])]
+        want_bytes += np.uint32(len(seq)).tobytes() + seq.tobytes() + np.uint32(2 * i).tobytes()
+        a = np.array([ab_of[oracle.hash128(v)] for v in oracle.kminmers(seq, 4)[0]], np.uint32)
+        want_ab += np.uint32(2 * i).tobytes() + np.uint32(len(a)).tobytes() + a.tobytes()
+    assert open(d3 / "unitigGraph.nodes.bin", "rb").read() == want_bytes and len(wu["offsets"]) > 50
+    assert open(d3 / "unitigGraph.nodes.abundances.bin", "rb").read() == want_ab
+    assert int(words[words.index("unitigs") + 1]) == len(wu["offsets"]) - 1
     ph = np.concatenate([c["hashes"], r["hashes"]]); pa = np.concatenate([c["abundances"], np.ones(len(r["hashes"]), np.uint32)])
     for kk in (5, 6, 7):
         nk = oracle.next_k(m, mo, kk, ph, pa)

@@ -481,6 +481,19 @@ def test_unitig_nodes_vs_oracle_and_golden(built, oracle):
         # path holds its nodes in both orientations, so the windows can outnumber the nodes)
         hs = got["hashes"][got["order"]]
         assert np.array_equal(hs[:, 1], want["hashes"][:, 0]) and np.array_equal(hs[:, 0], want["hashes"][:, 1])
+        # dumpUnitigAbundances: the table's abundance of every k-min-mer of every unitig; the two checksums the reference logs
+        ab_of = tab.as_dict()
+        offs_r, mins_r = rec["offsets"], rec["minimizers"]
+        want_ab, cs_nodes, cs_ab = [], 0, 0
+        for i in range(len(offs_r) - 1):
+            seq = mins_r[int(offs_r[i]):int(offs_r[i + 1])]
+            vecs, _ = oracle.kminmers(seq, k)
+            a = [ab_of[oracle.hash128(v)] for v in vecs]
+            want_ab += a
+            cs_nodes = (cs_nodes + int(seq.astype(np.uint64).sum()) * len(seq) * (2 * i)) % 2 ** 64
+            cs_ab = (cs_ab + sum(a) * len(a)) % 2 ** 64
+        assert np.array_equal(rec["abundances"], np.array(want_ab, np.uint32))
+        assert rec["checksum_nodes"] == cs_nodes and rec["checksum_abundances"] == cs_ab
         assert int(np.sum(np.diff(got["offsets"]).astype(np.int64) - (k - 1))) >= got["n_nodes"]
 
     eng.count_begin(4)
