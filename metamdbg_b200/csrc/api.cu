@@ -167,7 +167,7 @@ struct mdbg_ctx {
     uint64_t edge_cap = 0;             // slots of the device-resident edge set left by the last edges / unitigs call
     // unitigs (mdbg_unitigs_build)
     DevBuf u_slot_node, u_node_slot, u_next, u_pair, u_len, u_size, u_flag, u_cychead, u_seqoff, u_idx, u_cyclist, u_cycpos, u_best,
-        u_jump, u_mins, u_off, u_hash, u_rev, u_circ, u_abund;
+        u_jump, u_mins, u_off, u_hash, u_rev, u_circ, u_abund, u_bcnt, u_boff, u_order, u_pos;
     PinBuf hu_mins, hu_off, hu_hash, hu_circ, hu_order, hu_abund;
     uint64_t prev_capacity = 0;
     DevBuf o_hash, o_abund, o_vecs;
@@ -863,7 +863,7 @@ void mdbg_ctx_destroy(mdbg_ctx* c) {
                       &c->m_recv_counts, &c->m_bucket, &c->loc_off, &c->edge_table, &c->edge_vals, &c->o_edge_vals,
                       &c->u_slot_node, &c->u_node_slot, &c->u_next, &c->u_pair, &c->u_len, &c->u_size, &c->u_flag, &c->u_cychead,
                       &c->u_seqoff, &c->u_idx, &c->u_cyclist, &c->u_cycpos, &c->u_best, &c->u_jump, &c->u_mins, &c->u_off, &c->u_hash,
-                      &c->u_rev, &c->u_circ, &c->u_abund};
+                      &c->u_rev, &c->u_circ, &c->u_abund, &c->u_bcnt, &c->u_boff, &c->u_order, &c->u_pos};
     for (DevBuf* b : devs) release(*b);
     PinBuf* pins[] = {&c->h_off, &c->h_min, &c->h_pos, &c->h_dir, &c->ho_hash, &c->ho_abund, &c->ho_vecs, &c->hx_sum_lo, &c->hx_sum_hi, &c->hx_lmin, &c->hx_cplx, &c->hx_low, &c->hx_meanq, &c->h_qual, &c->h_pack, &c->h_src, &c->h_asc, &c->ho_edge_vals, &c->hpg_hash, &c->hpg_koff, &c->hpg_reads, &c->hpg_wins,
                       &c->hu_mins, &c->hu_off, &c->hu_hash, &c->hu_circ, &c->hu_order, &c->hu_abund};
@@ -2928,63 +2928,44 @@ mdbg_status mdbg_unitigs_build(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_uniti
     launch_unitig_reverse(ctx->u_mins.as<uint32_t>(), ctx->u_off.as<uint64_t>(), nu, ctx->u_rev.as<uint8_t>(), ctx->u_abund.as<uint32_t>(),
                           ctx->t_k, s);
     CKS(check_launch(ctx, "unitig_scatter_kernel + unitig_hash_kernel + unitig_reverse_kernel", nu ? 3 : 0));
+    // computeDeterministicUnitigs' order (ascending u128 hash; unitigIndex = 2 * position) and the two checksums the
+    // reference logs for the stage, both on the device
+    uint32_t bucket_bits = 10;
+    while ((1ull << bucket_bits) < nu / 2 && bucket_bits < 28) bucket_bits++;
+    const uint64_t n_buckets = 1ull << bucket_bits;
+    CKS(ensure(ctx, ctx->u_bcnt, n_buckets * 4));
+    CKS(ensure(ctx, ctx->u_boff, (n_buckets + 1) * 8));
+    CKS(ensure(ctx, ctx->u_order, (nu + 1) * 4));
+    CKS(ensure(ctx, ctx->u_pos, (nu + 1) * 4));
+    CKS(ensure(ctx, ctx->scan_scratch, scan_scratch_elems((uint32_t)n_buckets) * sizeof(uint64_t)));
+    launch_unitig_sort(ctx->u_hash.as<uint64_t>(), nu, bucket_bits, ctx->u_bcnt.as<uint32_t>(), ctx->u_boff.as<uint64_t>(),
+                       ctx->scan_scratch.as<uint64_t>(), ctx->u_order.as<uint32_t>(), ctx->u_pos.as<uint32_t>(), s);
+    CK(cudaMemsetAsync(&ctx->d_small->n_flagged, 0, 2 * sizeof(unsigned long long), s));       // n_flagged, n_changed: the two sums
+    launch_unitig_checksum(ctx->u_mins.as<uint32_t>(), ctx->u_off.as<uint64_t>(), ctx->u_abund.as<uint32_t>(), ctx->u_pos.as<uint32_t>(),
+                           nu, ctx->t_k, &ctx->d_small->n_flagged, s);
+    CKS(check_launch(ctx, "unitig_bucket_count/fill/sort kernels + scan + unitig_checksum_kernel", nu ? 7 : 0));
     CKS(ensure_pin(ctx, ctx->hu_mins, (total + 1) * 4));
     CKS(ensure_pin(ctx, ctx->hu_off, (nu + 2) * 8));
     CKS(ensure_pin(ctx, ctx->hu_hash, (nu + 1) * 16));
     CKS(ensure_pin(ctx, ctx->hu_circ, nu + 1));
     CKS(ensure_pin(ctx, ctx->hu_order, (nu + 1) * 4));
     CKS(ensure_pin(ctx, ctx->hu_abund, (n_windows + 1) * 4));
-    // the hashes first: the host sorts them while the sequences are still on their way
     CK(cudaMemcpyAsync(ctx->hu_off.p, ctx->u_off.p, (nu + 1) * 8, cudaMemcpyDeviceToHost, s));
     if (nu) {
         CK(cudaMemcpyAsync(ctx->hu_hash.p, ctx->u_hash.p, nu * 16, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(ctx->hu_circ.p, ctx->u_circ.p, nu, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(ctx->hu_order.p, ctx->u_order.p, nu * 4, cudaMemcpyDeviceToHost, s));
     }
-    CK(cudaStreamSynchronize(s));
     if (total) CK(cudaMemcpyAsync(ctx->hu_mins.p, ctx->u_mins.p, total * 4, cudaMemcpyDeviceToHost, s));
     if (n_windows) CK(cudaMemcpyAsync(ctx->hu_abund.p, ctx->u_abund.p, n_windows * 4, cudaMemcpyDeviceToHost, s));
-    if (!nu) ctx->hu_off.as<uint64_t>()[0] = 0;
-    ctx->d2h_bytes += total * 4 + n_windows * 4 + nu * 25 + 8;
-    // computeDeterministicUnitigs' order: ascending u128 hash = (high word, low word); unitigIndex = 2 * position.
-    // Sorted as (high word, index) records -- contiguous keys instead of an indirect compare --, ties on the high word
-    // (practically none) are then ordered by the low word.
-    uint32_t* order = ctx->hu_order.as<uint32_t>();
-    const uint64_t* hh = ctx->hu_hash.as<uint64_t>();
-    {
-        std::vector<std::pair<uint64_t, uint32_t>> keys(nu);
-        for (uint64_t i = 0; i < nu; i++) keys[i] = {hh[2 * i + 1], (uint32_t)i};
-        std::sort(keys.begin(), keys.end());
-        for (uint64_t i = 0; i < nu;) {
-            uint64_t j = i + 1;
-            while (j < nu && keys[j].first == keys[i].first) j++;
-            if (j - i > 1)
-                std::sort(keys.begin() + i, keys.begin() + j, [hh](const std::pair<uint64_t, uint32_t>& x, const std::pair<uint64_t, uint32_t>& y) {
-                    if (hh[2 * (uint64_t)x.second] != hh[2 * (uint64_t)y.second]) return hh[2 * (uint64_t)x.second] < hh[2 * (uint64_t)y.second];
-                    return x.second < y.second;
-                });
-            i = j;
-        }
-        for (uint64_t i = 0; i < nu; i++) order[i] = keys[i].second;
-    }
+    CK(cudaMemcpyAsync(&ctx->h_scalar[4], &ctx->d_small->n_flagged, 16, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    // the two figures the reference logs for this stage (CreateMdbg.cpp:3380, 3384; "Checksum unitig nodes / abundance")
-    uint64_t n_circ = 0, cs_nodes = 0, cs_ab = 0;
-    {
-        const uint64_t* off = ctx->hu_off.as<uint64_t>();
-        const uint32_t* mm = ctx->hu_mins.as<uint32_t>();
-        const uint32_t* ab = ctx->hu_abund.as<uint32_t>();
-        const uint64_t km1 = ctx->t_k - 1;
-        for (uint64_t i = 0; i < nu; i++) {
-            const uint64_t u = order[i], L = off[u + 1] - off[u], nw = L - km1;
-            uint64_t sm = 0, sa = 0;
-            for (uint64_t j = off[u]; j < off[u + 1]; j++) sm += mm[j];
-            const uint32_t* a = ab + (off[u] - u * km1);
-            for (uint64_t j = 0; j < nw; j++) sa += a[j];
-            cs_nodes += sm * L * (uint64_t)(uint32_t)(2 * i);
-            cs_ab += sa * nw;
-            n_circ += ctx->hu_circ.as<uint8_t>()[u];
-        }
-    }
+    if (!nu) ctx->hu_off.as<uint64_t>()[0] = 0;
+    ctx->d2h_bytes += total * 4 + n_windows * 4 + nu * 29 + 24;
+    uint32_t* order = ctx->hu_order.as<uint32_t>();
+    const uint64_t cs_nodes = nu ? ctx->h_scalar[4] : 0, cs_ab = nu ? ctx->h_scalar[5] : 0;
+    uint64_t n_circ = 0;
+    for (uint64_t i = 0; i < nu; i++) n_circ += ctx->hu_circ.as<uint8_t>()[i];
     out->n_unitigs = nu;
     out->n_minimizers = total;
     out->n_circular = n_circ;

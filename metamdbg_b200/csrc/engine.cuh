@@ -329,6 +329,13 @@ void launch_unitig_hash(const uint32_t* mins, const uint64_t* off, uint64_t n_un
 void launch_unitig_reverse(uint32_t* mins, const uint64_t* off, uint64_t n_unitigs, const uint8_t* rev, uint32_t* abund, uint32_t k,
                            cudaStream_t s);
 
+// order[i] = unitig at position i of the ascending (high, low) hash order, pos_of = its inverse; cnt: 2^bucket_bits u32,
+// bucket_off: 2^bucket_bits + 1 u64
+void launch_unitig_sort(const uint64_t* hashes, uint64_t n, uint32_t bucket_bits, uint32_t* cnt, uint64_t* bucket_off,
+                        uint64_t* scan_scratch, uint32_t* order, uint32_t* pos_of, cudaStream_t s);
+void launch_unitig_checksum(const uint32_t* mins, const uint64_t* off, const uint32_t* abund, const uint32_t* pos_of, uint64_t n,
+                            uint32_t k, unsigned long long* sums, cudaStream_t s);
+
 // ---- postings (kminmer.cu): k-min-mer -> (read, window) lists over the count table
 struct PostingArgs {
     const uint32_t* mins; const uint8_t* rem; const uint64_t* offs; const uint32_t* read_of;

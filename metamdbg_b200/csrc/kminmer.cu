@@ -72,24 +72,37 @@ __device__ __forceinline__ int table_add(Slot* table, uint64_t mask, uint64_t lo
     return 0;
 }
 
-// Block-wide bookkeeping of an insert pass: adds the block's number of claimed slots to *claims and raises *full_flag
-// when a probe sequence ran out or the table passed its load limit (the host then rebuilds a larger table; blocks
-// that start after the flag is up skip their work).  Every thread of the block must call it.
-__device__ __forceinline__ void block_claims(int status, bool active, unsigned long long* claims, unsigned long long claim_limit,
-                                             uint32_t* full_flag) {
-    __shared__ uint32_t s_claims, s_fail;
-    if (threadIdx.x == 0) { s_claims = 0; s_fail = 0; }
+// Block-wide bookkeeping of an insert pass.  block_begin: thread 0 reads the abandon flag ONCE for the block (a
+// same-address load issued by every warp of a 200 000-block grid serialises in one L2 slice: 1.7 M requests at ~3
+// cycles each were the whole 2.7 ms of the round-2 insert kernel, whatever the table size) and zeroes the block's
+// counters; the caller does its independent loads and hashing, then block_ready() -- one barrier -- tells whether the
+// pass is being abandoned (table too small: the host rebuilds it; blocks that start afterwards skip their probes).
+// block_claims adds the block's number of claimed slots to *claims and raises *full_flag when a probe sequence ran out
+// or the table passed its load limit.  Every thread of the block must call all three.
+struct BlockPass { uint32_t claims, fail, abandon; };
+__device__ __forceinline__ void block_begin(BlockPass& st, const uint32_t* full_flag) {
+    if (threadIdx.x == 0) {
+        st.claims = 0;
+        st.fail = 0;
+        st.abandon = *reinterpret_cast<const volatile uint32_t*>(full_flag);
+    }
+}
+__device__ __forceinline__ bool block_ready(BlockPass& st) {
     __syncthreads();
+    return st.abandon == 0;
+}
+__device__ __forceinline__ void block_claims(BlockPass& st, int status, bool active, unsigned long long* claims,
+                                             unsigned long long claim_limit, uint32_t* full_flag) {
     const uint32_t mc = __ballot_sync(0xffffffffu, active && status == 2);
     const uint32_t mf = __ballot_sync(0xffffffffu, active && status == 0);
     if ((threadIdx.x & 31) == 0) {
-        if (mc) atomicAdd(&s_claims, (uint32_t)__popc(mc));
-        if (mf) atomicAdd(&s_fail, 1u);
+        if (mc) atomicAdd(&st.claims, (uint32_t)__popc(mc));
+        if (mf) atomicAdd(&st.fail, 1u);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        bool full = s_fail != 0;
-        if (s_claims) full |= atomicAdd(claims, (unsigned long long)s_claims) + s_claims > claim_limit;
+        bool full = st.fail != 0;
+        if (st.claims) full |= atomicAdd(claims, (unsigned long long)st.claims) + st.claims > claim_limit;
         if (full) atomicExch(full_flag, 1u);
     }
 }
@@ -121,26 +134,28 @@ void launch_fill_rem(const uint64_t* offs, uint64_t read_lo, uint64_t read_hi, u
 // minimizers from g on (getKminmers_complete: i in [0, n-k]).
 template <int K_FIXED>
 __global__ void __launch_bounds__(256) insert_kernel(const InsertArgs a) {
-    if (*reinterpret_cast<volatile uint32_t*>(a.full_flag)) return;          // the pass is being abandoned (block-uniform)
+    __shared__ BlockPass st;
+    block_begin(st, a.full_flag);
     const uint64_t g = a.g_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int k = K_FIXED ? K_FIXED : (int)a.k;
     const bool active = g < a.g_hi && (int)a.rem[g] >= k;
     int status = 1;
+    uint64_t h1 = 0, h2 = 0;
+    bool rev = true;
     if (active) {
         const uint32_t* w = a.mins + g;
         // KmerVec::normalize (Commons.hpp:886-916): first differing pair decides,
         // a palindromic vector counts as reversed.
-        bool rev = true;
         for (int j = 0; j < k / 2; j++) {
             const uint32_t x = w[j], y = w[k - 1 - j];
             if (x != y) { rev = x > y; break; }
         }
-        uint64_t h1, h2;
         if (rev) murmur128_u32vec([&](int i) { return w[k - 1 - i]; }, k, h1, h2);
         else murmur128_u32vec([&](int i) { return w[i]; }, k, h1, h2);
-        status = table_add(a.table, a.mask, h2, h1, 1u, g | (rev ? REF_REV : 0ULL));
     }
-    block_claims(status, active, a.claims, a.claim_limit, a.full_flag);
+    const bool go = block_ready(st);                                         // false: the pass is being abandoned
+    if (go && active) status = table_add(a.table, a.mask, h2, h1, 1u, g | (rev ? REF_REV : 0ULL));
+    block_claims(st, status, go && active, a.claims, a.claim_limit, a.full_flag);
 }
 
 void launch_insert(const InsertArgs& a, cudaStream_t s) {
@@ -479,7 +494,8 @@ void launch_prev_load(const PrevLoadArgs& a, cudaStream_t s) {
 // window.  prev_min_count filters the previous table at lookup time (an entry below it that is not rescued counts
 // as absent), which lets the previous-k table BE the table of the previous pass, unfiltered and uncopied.
 __global__ void __launch_bounds__(256) next_k_kernel(const NextKArgs a) {
-    if (*reinterpret_cast<volatile uint32_t*>(a.full_flag)) return;
+    __shared__ BlockPass st;
+    block_begin(st, a.full_flag);
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t g = a.g_lo + warp * 31 + lane;
@@ -498,19 +514,22 @@ __global__ void __launch_bounds__(256) next_k_kernel(const NextKArgs a) {
     const bool active = lane < 31 && (int)rem >= k;              // (rem >= k implies the next position has rem >= k - 1)
     int status = 1;
     uint32_t out = 1;
+    const bool go = block_ready(st);                             // false: the pass is being abandoned (it is redone as a whole)
     if (active) {
         const uint32_t ab = v < v_next ? v : v_next;
         if (ab > 1) {
             out = ab;
-            uint64_t h1, h2; bool rev;
-            window_hash(w, k, h1, h2, rev);
-            // insert-if-absent: the value is a function of the key, so concurrent inserters write the same number
-            status = table_put(a.table, a.mask, h2, h1, ab, g | (rev ? REF_REV : 0ULL));
+            if (go) {
+                uint64_t h1, h2; bool rev;
+                window_hash(w, k, h1, h2, rev);
+                // insert-if-absent: the value is a function of the key, so concurrent inserters write the same number
+                status = table_put(a.table, a.mask, h2, h1, ab, g | (rev ? REF_REV : 0ULL));
+            }
         }
     }
     // value of the k-min-mer starting at g, as the NEXT pass would look it up (absent => 1): see next_k_stream_kernel
     if (a.val_out && lane < 31 && g < a.g_hi) a.val_out[g] = out;
-    block_claims(status, active, a.claims, a.claim_limit, a.full_flag);
+    block_claims(st, status, go && active, a.claims, a.claim_limit, a.full_flag);
 }
 
 // The same pass without a single lookup.  The value a pass stores for a k-min-mer is a function of the key, and
@@ -520,25 +539,29 @@ __global__ void __launch_bounds__(256) next_k_kernel(const NextKArgs a) {
 // reads val[g] and val[g + 1] -- two coalesced loads -- instead of hashing and probing two (k)-min-mers; the only
 // random access left per window is the insert into the new table.  Identical tables, by induction on k.
 __global__ void __launch_bounds__(256) next_k_stream_kernel(const NextKArgs a) {
-    if (*reinterpret_cast<volatile uint32_t*>(a.full_flag)) return;
+    __shared__ BlockPass st;
+    block_begin(st, a.full_flag);
     const uint64_t g = a.g_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int k = (int)a.k;
     const bool in_range = g < a.g_hi;
     const bool active = in_range && (int)a.rem[g] >= k;
     int status = 1;
     uint32_t out = 1;
+    uint64_t h1 = 0, h2 = 0;
+    bool rev = true, put = false;
     if (active) {
         const uint32_t v = a.val_in[g], v_next = a.val_in[g + 1];
         const uint32_t ab = v < v_next ? v : v_next;
         if (ab > 1) {
             out = ab;
-            uint64_t h1, h2; bool rev;
+            put = true;
             window_hash(a.mins + g, k, h1, h2, rev);
-            status = table_put(a.table, a.mask, h2, h1, ab, g | (rev ? REF_REV : 0ULL));
         }
     }
     if (in_range) a.val_out[g] = out;
-    block_claims(status, active, a.claims, a.claim_limit, a.full_flag);
+    const bool go = block_ready(st);                             // false: the pass is being abandoned (it is redone as a whole)
+    if (go && put) status = table_put(a.table, a.mask, h2, h1, out, g | (rev ? REF_REV : 0ULL));
+    block_claims(st, status, go && active, a.claims, a.claim_limit, a.full_flag);
 }
 
 void launch_next_k(const NextKArgs& a, cudaStream_t s) {

@@ -162,8 +162,15 @@ __global__ void __launch_bounds__(256) unitig_jump_kernel(unsigned long long* pa
         if (changed) pair[x] = p;
         open = !((uint32_t)p & U_HEAD);
     }
+    // one atomic per block: in the first rounds every warp has open nodes, and 120 000 same-address atomics per launch
+    // would serialise in one L2 slice
+    __shared__ uint32_t s_open;
+    if (threadIdx.x == 0) s_open = 0;
+    __syncthreads();
     const uint32_t m = __ballot_sync(0xffffffffu, open);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_open, (unsigned long long)__popc(m));
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&s_open, (uint32_t)__popc(m));
+    __syncthreads();
+    if (threadIdx.x == 0 && s_open) atomicAdd(n_open, (unsigned long long)s_open);
 }
 
 void launch_unitig_jump(unsigned long long* pair, uint32_t n2, int steps, unsigned long long* n_open, cudaStream_t s) {
@@ -385,6 +392,88 @@ void launch_unitig_reverse(uint32_t* mins, const uint64_t* off, uint64_t n_uniti
     uint64_t blocks = (n_unitigs + 7) / 8;
     if (blocks > 148 * 16) blocks = 148 * 16;
     unitig_reverse_kernel<<<(unsigned)blocks, 256, 0, s>>>(mins, off, n_unitigs, rev, abund, k);
+}
+
+// ------------------------------------------------------------------ the reference's deterministic order, on the device
+// computeDeterministicUnitigs sorts the unitigs by the u128 hash of their normalized sequence.  The hashes are uniform,
+// so one counting pass over the top bits of the high word spreads n unitigs over >= n / 2 buckets of a few elements
+// each; a thread per bucket finishes with an insertion sort on (high, low, index).  order[i] = unitig at position i.
+__global__ void __launch_bounds__(256) unitig_bucket_count_kernel(const uint64_t* hashes, uint64_t n, uint32_t shift, uint32_t* cnt) {
+    const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < n) atomicAdd(cnt + (hashes[2 * u + 1] >> shift), 1u);
+}
+__global__ void __launch_bounds__(256) unitig_bucket_fill_kernel(const uint64_t* hashes, uint64_t n, uint32_t shift,
+                                                                 const uint64_t* bucket_off, uint32_t* cursor, uint32_t* order) {
+    const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n) return;
+    const uint64_t b = hashes[2 * u + 1] >> shift;
+    order[bucket_off[b] + atomicAdd(cursor + b, 1u)] = (uint32_t)u;
+}
+__global__ void __launch_bounds__(256) unitig_bucket_sort_kernel(const uint64_t* hashes, uint64_t n_buckets, const uint64_t* bucket_off,
+                                                                 uint32_t* order, uint32_t* pos_of) {
+    const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_buckets) return;
+    const uint64_t lo = bucket_off[b], hi = bucket_off[b + 1];
+    for (uint64_t i = lo + 1; i < hi; i++) {
+        const uint32_t x = order[i];
+        const uint64_t xh = hashes[2 * (uint64_t)x + 1], xl = hashes[2 * (uint64_t)x];
+        uint64_t j = i;
+        while (j > lo) {
+            const uint32_t y = order[j - 1];
+            const uint64_t yh = hashes[2 * (uint64_t)y + 1], yl = hashes[2 * (uint64_t)y];
+            const bool less = xh != yh ? xh < yh : (xl != yl ? xl < yl : x < y);
+            if (!less) break;
+            order[j] = y;
+            j--;
+        }
+        order[j] = x;
+    }
+    for (uint64_t i = lo; i < hi; i++) pos_of[order[i]] = (uint32_t)i;
+}
+
+// The two figures the reference logs for the stage: "Checksum unitig nodes" = sum over records of minimizer * size *
+// unitigIndex (CreateMdbg.cpp:3380, unitigIndex = 2 * position), "Checksum unitig abundance" = sum of abundance * number
+// of abundances (:3384).  One thread per unitig, one atomic per warp.
+__global__ void __launch_bounds__(256) unitig_checksum_kernel(const uint32_t* mins, const uint64_t* off, const uint32_t* abund,
+                                                              const uint32_t* pos_of, uint64_t n, uint32_t k,
+                                                              unsigned long long* sums) {
+    const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long cn = 0, ca = 0;
+    if (u < n) {
+        const uint64_t b = off[u], L = off[u + 1] - b, nw = L - (k - 1);
+        unsigned long long sm = 0, sa = 0;
+        for (uint64_t j = 0; j < L; j++) sm += mins[b + j];
+        const uint32_t* ab = abund + (b - u * (uint64_t)(k - 1));
+        for (uint64_t j = 0; j < nw; j++) sa += ab[j];
+        cn = sm * L * (unsigned long long)(uint32_t)(2u * pos_of[u]);
+        ca = sa * nw;
+    }
+    for (int d = 16; d; d >>= 1) {
+        cn += __shfl_down_sync(0xffffffffu, cn, d);
+        ca += __shfl_down_sync(0xffffffffu, ca, d);
+    }
+    if ((threadIdx.x & 31) == 0 && (cn | ca)) {
+        atomicAdd(sums, cn);
+        atomicAdd(sums + 1, ca);
+    }
+}
+
+void launch_unitig_sort(const uint64_t* hashes, uint64_t n, uint32_t bucket_bits, uint32_t* cnt, uint64_t* bucket_off,
+                        uint64_t* scan_scratch, uint32_t* order, uint32_t* pos_of, cudaStream_t s) {
+    if (!n) return;
+    const uint64_t nb = 1ull << bucket_bits;
+    const uint32_t shift = 64 - bucket_bits;
+    cudaMemsetAsync(cnt, 0, nb * 4, s);
+    unitig_bucket_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(hashes, n, shift, cnt);
+    launch_scan_u32_to_u64(cnt, bucket_off, (uint32_t)nb, scan_scratch, s);
+    cudaMemsetAsync(cnt, 0, nb * 4, s);
+    unitig_bucket_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(hashes, n, shift, bucket_off, cnt, order);
+    unitig_bucket_sort_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, s>>>(hashes, nb, bucket_off, order, pos_of);
+}
+void launch_unitig_checksum(const uint32_t* mins, const uint64_t* off, const uint32_t* abund, const uint32_t* pos_of, uint64_t n,
+                            uint32_t k, unsigned long long* sums, cudaStream_t s) {
+    if (!n) return;
+    unitig_checksum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(mins, off, abund, pos_of, n, k, sums);
 }
 
 }  // namespace mdbg
