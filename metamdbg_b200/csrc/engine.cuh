@@ -274,6 +274,8 @@ struct EdgeArgs {
     const uint32_t* mins; const uint32_t* foreign_vecs;
     Slot* edges; uint64_t edge_mask; uint32_t* full_flag;
     unsigned long long* edge_vals;      // launch_edge_values only: [2 * edge capacity], zeroed
+    const uint32_t* node_slot;          // optional: table slots of the emitted entries (launch_unitig_nodes); the insert /
+    uint64_t n_nodes;                   // values kernels then visit these instead of scanning the whole table
 };
 void launch_edge_insert(const EdgeArgs& a, cudaStream_t s);
 constexpr unsigned long long EDGE_VALID = 1ULL << 63, EDGE_MULTI = 1ULL << 34;

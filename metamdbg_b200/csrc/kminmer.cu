@@ -581,9 +581,12 @@ void launch_next_k(const NextKArgs& a, cudaStream_t s) {
 // second open-addressing table used as a set (value 1), one thread per table slot.
 __global__ void __launch_bounds__(256) edge_insert_kernel(const EdgeArgs a) {
     const int k = (int)a.k, km = k - 1;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.capacity;
+    // with a node list (slots of the emitted entries, unitig_nodes_kernel) the threads visit the nodes only; without
+    // one they scan the whole table
+    const uint64_t n_items = a.node_slot ? a.n_nodes : a.capacity;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_items;
          i += (uint64_t)gridDim.x * blockDim.x) {
-        const Slot sl = a.table[i];
+        const Slot sl = a.table[a.node_slot ? a.node_slot[i] : i];
         if ((sl.lo | sl.hi) == 0) continue;
         if (!(sl.count >= a.min_count || (sl.flags & SLOT_RESCUED))) continue;
         for (int side = 0; side < 2; side++) {            // 0: prefix = elements 0 .. k-2, 1: suffix = 1 .. k-1
@@ -602,8 +605,9 @@ __global__ void __launch_bounds__(256) edge_insert_kernel(const EdgeArgs a) {
 }
 
 void launch_edge_insert(const EdgeArgs& a, cudaStream_t s) {
-    uint64_t blocks = (a.capacity + 255) / 256;
+    uint64_t blocks = ((a.node_slot ? a.n_nodes : a.capacity) + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks == 0) return;
     edge_insert_kernel<<<(unsigned)blocks, 256, 0, s>>>(a);
 }
 
@@ -617,9 +621,12 @@ void launch_edge_insert(const EdgeArgs& a, cudaStream_t s) {
 //   vals[2 * slot + class]: bit 63 valid, bit 34 multi, bit 33 isPrefix, bit 32 isReversed, bits 0-31 minimizer
 __global__ void __launch_bounds__(256) edge_values_kernel(const EdgeArgs a) {
     const int k = (int)a.k, km = k - 1;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.capacity;
+    // with a node list (slots of the emitted entries, unitig_nodes_kernel) the threads visit the nodes only; without
+    // one they scan the whole table
+    const uint64_t n_items = a.node_slot ? a.n_nodes : a.capacity;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_items;
          i += (uint64_t)gridDim.x * blockDim.x) {
-        const Slot sl = a.table[i];
+        const Slot sl = a.table[a.node_slot ? a.node_slot[i] : i];
         if ((sl.lo | sl.hi) == 0) continue;
         if (!(sl.count >= a.min_count || (sl.flags & SLOT_RESCUED))) continue;
         for (int side = 0; side < 2; side++) {            // 0: prefix (isPrefix = 1), 1: suffix (isPrefix = 0)
@@ -645,8 +652,9 @@ __global__ void __launch_bounds__(256) edge_values_kernel(const EdgeArgs a) {
 }
 
 void launch_edge_values(const EdgeArgs& a, cudaStream_t s) {
-    uint64_t blocks = (a.capacity + 255) / 256;
+    uint64_t blocks = ((a.node_slot ? a.n_nodes : a.capacity) + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks == 0) return;
     edge_values_kernel<<<(unsigned)blocks, 256, 0, s>>>(a);
 }
 
@@ -654,19 +662,26 @@ void launch_edge_values(const EdgeArgs& a, cudaStream_t s) {
 __global__ void __launch_bounds__(256) edge_emit_kernel(const Slot* edges, const unsigned long long* vals, uint64_t capacity,
                                                         uint64_t* out_hashes, unsigned long long* out_vals,
                                                         unsigned long long* cursor) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint64_t n_rounds = (capacity + (uint64_t)gridDim.x * blockDim.x - 1) / ((uint64_t)gridDim.x * blockDim.x);
-    for (uint64_t round = 0; round < n_rounds; round++) {
-        const uint64_t i = round * gridDim.x * blockDim.x + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ uint32_t wcnt[8];
+    __shared__ unsigned long long tile_base;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t n_tiles = (capacity + 255) / 256;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {       // one cursor atomic per 256-slot tile
+        const uint64_t i = tile * 256 + threadIdx.x;
         bool take = false;
         uint64_t lo = 0, hi = 0;
         if (i < capacity) { lo = edges[i].lo; hi = edges[i].hi; take = (lo | hi) != 0; }
         const uint32_t m = __ballot_sync(0xffffffffu, take);
-        unsigned long long base = 0;
-        if (lane == 0 && m) base = atomicAdd(cursor, (unsigned long long)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lane == 0) wcnt[warp] = __popc(m);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tot = 0;
+            for (int w = 0; w < 8; w++) { const uint32_t c = wcnt[w]; wcnt[w] = tot; tot += c; }
+            tile_base = tot ? atomicAdd(cursor, (unsigned long long)tot) : 0ULL;
+        }
+        __syncthreads();
         if (take) {
-            const uint64_t pos = base + __popc(m & ((1u << lane) - 1u));
+            const uint64_t pos = tile_base + wcnt[warp] + __popc(m & ((1u << lane) - 1u));
             out_hashes[2 * pos] = lo;
             out_hashes[2 * pos + 1] = hi;
             unsigned long long a0 = vals[2 * i], b0 = vals[2 * i + 1];
@@ -675,6 +690,7 @@ __global__ void __launch_bounds__(256) edge_emit_kernel(const Slot* edges, const
             out_vals[2 * pos] = a0;
             out_vals[2 * pos + 1] = b0;
         }
+        __syncthreads();
     }
 }
 

@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(256) unitig_nodes_kernel(const Slot* table, ui
                 id = (uint32_t)(tile_base + wcnt[warp] + __popc(m & ((1u << lane) - 1u)));
                 node_slot[id] = (uint32_t)i;
             }
-            slot_node[i] = id;
+            if (slot_node) slot_node[i] = id;
         }
         __syncthreads();
     }
