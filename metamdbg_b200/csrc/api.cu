@@ -48,7 +48,7 @@ struct SmallDev {                 // device-side scalars, one allocation
     unsigned long long n_flagged;
     unsigned long long n_changed;
     unsigned long long emit_cursor;
-    unsigned long long t_claims[CLAIM_SHARDS];   // claimed slots of the current count table, sharded (sum = distinct keys)
+    unsigned long long t_claims;         // claimed slots (= distinct keys) of the current count table
     TableStats stats;
 };
 
@@ -2027,13 +2027,6 @@ mdbg_status mdbg_store_repetitive_minimizers(mdbg_ctx* ctx, float fraction, mdbg
 
 // ---- count table --------------------------------------------------------------------
 // capacity for `expect` distinct keys at load factor <= 0.6, and the claim count at which a pass gives up (0.8)
-// distinct keys of the current table as the last pass's claim counters (copied to the host by count_pass) saw them
-static uint64_t claims_total(const mdbg_ctx* ctx) {
-    uint64_t t = 0;
-    for (int i = 0; i < CLAIM_SHARDS; i++) t += ctx->h_small->t_claims[i];
-    return t;
-}
-
 static uint64_t table_capacity_for(uint64_t expect) {
     if (expect < 512) expect = 512;
     return pow2ceil(expect + (expect * 2) / 3 + 1);
@@ -2044,7 +2037,7 @@ static mdbg_status table_reset(mdbg_ctx* ctx, uint64_t cap) {
     CKS(ensure(ctx, ctx->table, cap * sizeof(Slot)));
     CK(cudaMemsetAsync(ctx->table.p, 0, cap * sizeof(Slot), ctx->stream));
     CK(cudaMemsetAsync(&ctx->d_small->full_flag, 0, sizeof(uint32_t), ctx->stream));
-    CK(cudaMemsetAsync(&ctx->d_small->t_claims[0], 0, sizeof(unsigned long long) * CLAIM_SHARDS, ctx->stream));
+    CK(cudaMemsetAsync(&ctx->d_small->t_claims, 0, sizeof(unsigned long long), ctx->stream));
     ctx->t_capacity = cap;
     ctx->t_claim_limit = cap - cap / 5;
     clk.lap(PH_TABLE_RESET);
@@ -2111,7 +2104,7 @@ static mdbg_status launch_pass(mdbg_ctx* ctx, uint64_t g_lo, uint64_t g_hi, bool
         a.table = ctx->table.as<Slot>();
         a.mask = ctx->t_capacity - 1;
         a.full_flag = &ctx->d_small->full_flag;
-        a.claims = &ctx->d_small->t_claims[0];
+        a.claims = &ctx->d_small->t_claims;
         a.claim_limit = ctx->t_claim_limit;
         launch_insert(a, s);
     } else {
@@ -2126,7 +2119,7 @@ static mdbg_status launch_pass(mdbg_ctx* ctx, uint64_t g_lo, uint64_t g_hi, bool
         a.table = ctx->table.as<Slot>();
         a.mask = ctx->t_capacity - 1;
         a.full_flag = &ctx->d_small->full_flag;
-        a.claims = &ctx->d_small->t_claims[0];
+        a.claims = &ctx->d_small->t_claims;
         a.claim_limit = ctx->t_claim_limit;
         a.val_in = val_in;
         a.val_out = val_out;
@@ -2168,7 +2161,7 @@ static mdbg_status count_pass(mdbg_ctx* ctx, uint64_t read_lo, uint64_t read_hi,
     CKS(launch_pass(ctx, g_lo, g_hi, next_k, true, val_in, val_out));
     for (int attempt = 0;; attempt++) {
         CK(cudaMemcpyAsync(&ctx->h_small->full_flag, &ctx->d_small->full_flag, 4, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(&ctx->h_small->t_claims[0], &ctx->d_small->t_claims[0], 8 * CLAIM_SHARDS, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(&ctx->h_small->t_claims, &ctx->d_small->t_claims, 8, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         if (!ctx->h_small->full_flag) break;
         const uint64_t worst = table_capacity_for(ctx->s_mins + 1024);
@@ -2194,7 +2187,7 @@ static mdbg_status count_pass(mdbg_ctx* ctx, uint64_t read_lo, uint64_t read_hi,
     } else {
         ctx->val_valid = false;                            // (a count pass included: the next k looks its global counts up)
     }
-    if (!next_k && ctx->s_mins) ctx->distinct_ratio = (double)claims_total(ctx) / (double)ctx->s_mins;
+    if (!next_k && ctx->s_mins) ctx->distinct_ratio = (double)ctx->h_small->t_claims / (double)ctx->s_mins;
     return MDBG_OK;
 }
 
@@ -3209,7 +3202,7 @@ mdbg_status mdbg_count_merge_hashes(mdbg_ctx* ctx) {
     PhaseClock clk(ctx);
     // ONE pack pass: a region of the send buffer per destination, each large enough for every key of the table (the
     // number of distinct keys is known from the pass's claim counter; a table with foreign entries is scanned once)
-    uint64_t region_cap = claims_total(ctx);
+    uint64_t region_cap = ctx->h_small->t_claims;
     if (!ctx->t_rebuildable || region_cap == 0 || region_cap > ctx->t_capacity) {
         TableStats st;
         CKS(table_stats(ctx, 2, &st));

@@ -161,8 +161,6 @@ constexpr uint64_t REF_NONE = ~0ULL;             // the slot's k-min-mer vector 
 
 void launch_fill_rem(const uint64_t* offs, uint64_t read_lo, uint64_t read_hi, uint8_t* rem, cudaStream_t s);
 
-constexpr int CLAIM_SHARDS = 64;     // the claim counter of a pass is spread over this many words (their sum = distinct keys)
-
 struct InsertArgs {
     const uint32_t* mins;   // store minimizers
     const uint8_t* rem;     // min(#minimizers from g to end of its read, 255)
@@ -171,7 +169,7 @@ struct InsertArgs {
     Slot* table;
     uint64_t mask;          // capacity - 1 (power of two)
     uint32_t* full_flag;    // raised when a probe sequence ran out or the table passed claim_limit distinct keys
-    unsigned long long* claims;        // [CLAIM_SHARDS] running number of claimed slots (sum = distinct keys) of the table
+    unsigned long long* claims;        // running number of claimed slots (= distinct keys) of the table
     unsigned long long claim_limit;
 };
 void launch_insert(const InsertArgs& a, cudaStream_t s);

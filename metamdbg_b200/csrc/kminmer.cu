@@ -72,55 +72,39 @@ __device__ __forceinline__ int table_add(Slot* table, uint64_t mask, uint64_t lo
     return 0;
 }
 
-// Bookkeeping of an insert pass, per WARP.  The pass kernels are persistent: every warp walks over 32-window tiles
-// (static stride) and nothing in them is block-synchronous -- with one window per thread and a block-wide barrier at
-// the end, a quarter of all warp time was spent waiting for the slowest warp of the block, and the 200 000 short blocks
-// of a pass each paid their own ramp.  Every CHECK_EVERY tiles a warp (lane 0) publishes the slots it claimed to one
-// of CLAIM_SHARDS counters -- their sum is the number of distinct keys; a shard passing its share of the load limit
-// raises *full_flag -- and reads the flag: a raised flag means the table is too small and the host will rebuild it, so
-// the warp stops (the pass is redone as a whole).  One same-address load per warp and 16 tiles instead of one per warp
-// and tile: that load, issued by every warp of a 200 000-block grid, serialised in one L2 slice and WAS the round-2
-// insert kernel's 2.7 ms, whatever the table size.
-constexpr int PASS_CHECK_EVERY = 16;
-struct WarpPass {
-    uint32_t pending;                                    // claims not yet published (warp-uniform)
-    uint32_t shard, n_shards;                            // a small grid fills only as many shards as it has warps
-    __device__ __forceinline__ void begin() {
-        pending = 0;
-        const uint64_t n_warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
-        shard = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & (CLAIM_SHARDS - 1);
-        n_shards = n_warps < (uint64_t)CLAIM_SHARDS ? (uint32_t)n_warps : (uint32_t)CLAIM_SHARDS;
+// Block-wide bookkeeping of an insert pass.  block_begin: thread 0 reads the abandon flag ONCE for the block (a
+// same-address load issued by every warp of a 200 000-block grid serialises in one L2 slice: 1.7 M requests at ~3
+// cycles each were the whole 2.7 ms of the round-2 insert kernel, whatever the table size) and zeroes the block's
+// counters; the caller does its independent loads and hashing, then block_ready() -- one barrier -- tells whether the
+// pass is being abandoned (table too small: the host rebuilds it; blocks that start afterwards skip their probes).
+// block_claims adds the block's number of claimed slots to *claims and raises *full_flag when a probe sequence ran out
+// or the table passed its load limit.  Every thread of the block must call all three.
+struct BlockPass { uint32_t claims, fail, abandon; };
+__device__ __forceinline__ void block_begin(BlockPass& st, const uint32_t* full_flag) {
+    if (threadIdx.x == 0) {
+        st.claims = 0;
+        st.fail = 0;
+        st.abandon = *reinterpret_cast<const volatile uint32_t*>(full_flag);
     }
-    // publishes the pending claims; true when the pass is being abandoned
-    __device__ __forceinline__ bool checkpoint(unsigned long long* claims, unsigned long long claim_limit, uint32_t* full_flag) {
-        uint32_t flag = 0;
-        if ((threadIdx.x & 31) == 0) {
-            if (pending) {
-                const unsigned long long now = atomicAdd(claims + shard, (unsigned long long)pending) + pending;
-                if (now * n_shards > claim_limit) atomicExch(full_flag, 1u);
-            }
-            flag = *reinterpret_cast<const volatile uint32_t*>(full_flag);
-        }
-        pending = 0;
-        return __shfl_sync(0xffffffffu, flag, 0) != 0;
-    }
-    // status of this lane's table operation (0 probe limit hit, 1 key was there, 2 slot claimed); false = table full
-    __device__ __forceinline__ bool note(int status, bool active, uint32_t* full_flag) {
-        const uint32_t mc = __ballot_sync(0xffffffffu, active && status == 2);
-        const uint32_t mf = __ballot_sync(0xffffffffu, active && status == 0);
-        pending += (uint32_t)__popc(mc);
-        if (mf && (threadIdx.x & 31) == 0) atomicExch(full_flag, 1u);
-        return mf == 0;
-    }
-};
-
-__device__ __forceinline__ void pass_geometry(uint64_t& warp_id, uint64_t& n_warps) {
-    warp_id = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    n_warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
 }
-static unsigned pass_blocks(uint64_t n_tiles) {
-    const uint64_t b = (n_tiles + 7) / 8;
-    return (unsigned)(b < 148 * 8 ? (b ? b : 1) : 148 * 8);
+__device__ __forceinline__ bool block_ready(BlockPass& st) {
+    __syncthreads();
+    return st.abandon == 0;
+}
+__device__ __forceinline__ void block_claims(BlockPass& st, int status, bool active, unsigned long long* claims,
+                                             unsigned long long claim_limit, uint32_t* full_flag) {
+    const uint32_t mc = __ballot_sync(0xffffffffu, active && status == 2);
+    const uint32_t mf = __ballot_sync(0xffffffffu, active && status == 0);
+    if ((threadIdx.x & 31) == 0) {
+        if (mc) atomicAdd(&st.claims, (uint32_t)__popc(mc));
+        if (mf) atomicAdd(&st.fail, 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        bool full = st.fail != 0;
+        if (st.claims) full |= atomicAdd(claims, (unsigned long long)st.claims) + st.claims > claim_limit;
+        if (full) atomicExch(full_flag, 1u);
+    }
 }
 
 // ------------------------------------------------------------------ rem[] = minimizers left in the read
@@ -149,42 +133,35 @@ void launch_fill_rem(const uint64_t* offs, uint64_t read_lo, uint64_t read_hi, u
 // Window starting at flat minimizer index g exists iff the read still holds k
 // minimizers from g on (getKminmers_complete: i in [0, n-k]).
 template <int K_FIXED>
-__global__ void __launch_bounds__(256, 8) insert_kernel(const InsertArgs a) {
-    const uint32_t lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(256) insert_kernel(const InsertArgs a) {
+    __shared__ BlockPass st;
+    block_begin(st, a.full_flag);
+    const uint64_t g = a.g_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int k = K_FIXED ? K_FIXED : (int)a.k;
-    uint64_t warp_id, n_warps;
-    pass_geometry(warp_id, n_warps);
-    const uint64_t n_tiles = (a.g_hi - a.g_lo + 31) / 32;
-    WarpPass wp;
-    wp.begin();
-    uint32_t it = 0;
-    for (uint64_t tile = warp_id; tile < n_tiles; tile += n_warps, it++) {
-        if ((it % PASS_CHECK_EVERY) == 0 && wp.checkpoint(a.claims, a.claim_limit, a.full_flag)) return;
-        const uint64_t g = a.g_lo + tile * 32 + lane;
-        const bool active = g < a.g_hi && (int)a.rem[g] >= k;
-        int status = 1;
-        if (active) {
-            const uint32_t* w = a.mins + g;
-            // KmerVec::normalize (Commons.hpp:886-916): first differing pair decides,
-            // a palindromic vector counts as reversed.
-            bool rev = true;
-            for (int j = 0; j < k / 2; j++) {
-                const uint32_t x = w[j], y = w[k - 1 - j];
-                if (x != y) { rev = x > y; break; }
-            }
-            uint64_t h1, h2;
-            if (rev) murmur128_u32vec([&](int i) { return w[k - 1 - i]; }, k, h1, h2);
-            else murmur128_u32vec([&](int i) { return w[i]; }, k, h1, h2);
-            status = table_add(a.table, a.mask, h2, h1, 1u, g | (rev ? REF_REV : 0ULL));
+    const bool active = g < a.g_hi && (int)a.rem[g] >= k;
+    int status = 1;
+    uint64_t h1 = 0, h2 = 0;
+    bool rev = true;
+    if (active) {
+        const uint32_t* w = a.mins + g;
+        // KmerVec::normalize (Commons.hpp:886-916): first differing pair decides,
+        // a palindromic vector counts as reversed.
+        for (int j = 0; j < k / 2; j++) {
+            const uint32_t x = w[j], y = w[k - 1 - j];
+            if (x != y) { rev = x > y; break; }
         }
-        if (!wp.note(status, active, a.full_flag)) break;
+        if (rev) murmur128_u32vec([&](int i) { return w[k - 1 - i]; }, k, h1, h2);
+        else murmur128_u32vec([&](int i) { return w[i]; }, k, h1, h2);
     }
-    wp.checkpoint(a.claims, a.claim_limit, a.full_flag);
+    const bool go = block_ready(st);                                         // false: the pass is being abandoned
+    if (go && active) status = table_add(a.table, a.mask, h2, h1, 1u, g | (rev ? REF_REV : 0ULL));
+    block_claims(st, status, go && active, a.claims, a.claim_limit, a.full_flag);
 }
 
 void launch_insert(const InsertArgs& a, cudaStream_t s) {
     if (a.g_hi <= a.g_lo) return;
-    const unsigned blocks = pass_blocks((a.g_hi - a.g_lo + 31) / 32);
+    const uint64_t n = a.g_hi - a.g_lo;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
     if (a.k == 4) insert_kernel<4><<<blocks, 256, 0, s>>>(a);
     else insert_kernel<0><<<blocks, 256, 0, s>>>(a);
 }
@@ -516,47 +493,43 @@ void launch_prev_load(const PrevLoadArgs& a, cudaStream_t s) {
 // positions, so every lookup but one per warp is used twice -- half the hashes and random reads of one thread per
 // window.  prev_min_count filters the previous table at lookup time (an entry below it that is not rescued counts
 // as absent), which lets the previous-k table BE the table of the previous pass, unfiltered and uncopied.
-__global__ void __launch_bounds__(256, 8) next_k_kernel(const NextKArgs a) {
+__global__ void __launch_bounds__(256) next_k_kernel(const NextKArgs a) {
+    __shared__ BlockPass st;
+    block_begin(st, a.full_flag);
     const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t g = a.g_lo + warp * 31 + lane;
     const int k = (int)a.k;
-    uint64_t warp_id, n_warps;
-    pass_geometry(warp_id, n_warps);
-    const uint64_t n_tiles = (a.g_hi - a.g_lo + 30) / 31;        // 32 positions = 31 windows per tile
-    WarpPass wp;
-    wp.begin();
-    uint32_t it = 0;
-    for (uint64_t tile = warp_id; tile < n_tiles; tile += n_warps, it++) {
-        if ((it % PASS_CHECK_EVERY) == 0 && wp.checkpoint(a.claims, a.claim_limit, a.full_flag)) return;
-        const uint64_t g = a.g_lo + tile * 31 + lane;
-        const uint32_t rem = g < a.g_hi ? (uint32_t)a.rem[g] : 0u;
-        const uint32_t* w = a.mins + g;
-        uint32_t v = 1;
-        if ((int)rem >= k - 1) {
-            uint64_t h1, h2; bool rev;
-            window_hash(w, k - 1, h1, h2, rev);
-            const Slot* s = table_find(const_cast<Slot*>(a.prev), a.prev_mask, h2, h1);
-            if (s && (s->count >= a.prev_min_count || (s->flags & SLOT_RESCUED))) v = s->count;
-            if (v == 0) v = 1;
-        }
-        const uint32_t v_next = __shfl_down_sync(0xffffffffu, v, 1);
-        const bool active = lane < 31 && (int)rem >= k;          // (rem >= k implies the next position has rem >= k - 1)
-        int status = 1;
-        uint32_t out = 1;
-        if (active) {
-            const uint32_t ab = v < v_next ? v : v_next;
-            if (ab > 1) {
-                out = ab;
+    const uint32_t rem = g < a.g_hi ? (uint32_t)a.rem[g] : 0u;
+    const uint32_t* w = a.mins + g;
+    uint32_t v = 1;
+    if ((int)rem >= k - 1) {
+        uint64_t h1, h2; bool rev;
+        window_hash(w, k - 1, h1, h2, rev);
+        const Slot* s = table_find(const_cast<Slot*>(a.prev), a.prev_mask, h2, h1);
+        if (s && (s->count >= a.prev_min_count || (s->flags & SLOT_RESCUED))) v = s->count;
+        if (v == 0) v = 1;
+    }
+    const uint32_t v_next = __shfl_down_sync(0xffffffffu, v, 1);
+    const bool active = lane < 31 && (int)rem >= k;              // (rem >= k implies the next position has rem >= k - 1)
+    int status = 1;
+    uint32_t out = 1;
+    const bool go = block_ready(st);                             // false: the pass is being abandoned (it is redone as a whole)
+    if (active) {
+        const uint32_t ab = v < v_next ? v : v_next;
+        if (ab > 1) {
+            out = ab;
+            if (go) {
                 uint64_t h1, h2; bool rev;
                 window_hash(w, k, h1, h2, rev);
                 // insert-if-absent: the value is a function of the key, so concurrent inserters write the same number
                 status = table_put(a.table, a.mask, h2, h1, ab, g | (rev ? REF_REV : 0ULL));
             }
         }
-        // value of the k-min-mer starting at g, as the NEXT pass would look it up (absent => 1): see next_k_stream_kernel
-        if (a.val_out && lane < 31 && g < a.g_hi) a.val_out[g] = out;
-        if (!wp.note(status, active, a.full_flag)) break;
     }
-    wp.checkpoint(a.claims, a.claim_limit, a.full_flag);
+    // value of the k-min-mer starting at g, as the NEXT pass would look it up (absent => 1): see next_k_stream_kernel
+    if (a.val_out && lane < 31 && g < a.g_hi) a.val_out[g] = out;
+    block_claims(st, status, go && active, a.claims, a.claim_limit, a.full_flag);
 }
 
 // The same pass without a single lookup.  The value a pass stores for a k-min-mer is a function of the key, and
@@ -565,45 +538,40 @@ __global__ void __launch_bounds__(256, 8) next_k_kernel(const NextKArgs a) {
 // previous-k table is nothing but the previous pass's table (no host patches, same store), pass k + 1 therefore
 // reads val[g] and val[g + 1] -- two coalesced loads -- instead of hashing and probing two (k)-min-mers; the only
 // random access left per window is the insert into the new table.  Identical tables, by induction on k.
-__global__ void __launch_bounds__(256, 8) next_k_stream_kernel(const NextKArgs a) {
-    const uint32_t lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(256) next_k_stream_kernel(const NextKArgs a) {
+    __shared__ BlockPass st;
+    block_begin(st, a.full_flag);
+    const uint64_t g = a.g_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int k = (int)a.k;
-    uint64_t warp_id, n_warps;
-    pass_geometry(warp_id, n_warps);
-    const uint64_t n_tiles = (a.g_hi - a.g_lo + 31) / 32;
-    WarpPass wp;
-    wp.begin();
-    uint32_t it = 0;
-    for (uint64_t tile = warp_id; tile < n_tiles; tile += n_warps, it++) {
-        if ((it % PASS_CHECK_EVERY) == 0 && wp.checkpoint(a.claims, a.claim_limit, a.full_flag)) return;
-        const uint64_t g = a.g_lo + tile * 32 + lane;
-        const bool in_range = g < a.g_hi;
-        const bool active = in_range && (int)a.rem[g] >= k;
-        int status = 1;
-        uint32_t out = 1;
-        if (active) {
-            const uint32_t v = a.val_in[g], v_next = a.val_in[g + 1];
-            const uint32_t ab = v < v_next ? v : v_next;
-            if (ab > 1) {
-                out = ab;
-                uint64_t h1, h2; bool rev;
-                window_hash(a.mins + g, k, h1, h2, rev);
-                status = table_put(a.table, a.mask, h2, h1, ab, g | (rev ? REF_REV : 0ULL));
-            }
+    const bool in_range = g < a.g_hi;
+    const bool active = in_range && (int)a.rem[g] >= k;
+    int status = 1;
+    uint32_t out = 1;
+    uint64_t h1 = 0, h2 = 0;
+    bool rev = true, put = false;
+    if (active) {
+        const uint32_t v = a.val_in[g], v_next = a.val_in[g + 1];
+        const uint32_t ab = v < v_next ? v : v_next;
+        if (ab > 1) {
+            out = ab;
+            put = true;
+            window_hash(a.mins + g, k, h1, h2, rev);
         }
-        if (in_range) a.val_out[g] = out;
-        if (!wp.note(status, active, a.full_flag)) break;
     }
-    wp.checkpoint(a.claims, a.claim_limit, a.full_flag);
+    if (in_range) a.val_out[g] = out;
+    const bool go = block_ready(st);                             // false: the pass is being abandoned (it is redone as a whole)
+    if (go && put) status = table_put(a.table, a.mask, h2, h1, out, g | (rev ? REF_REV : 0ULL));
+    block_claims(st, status, go && active, a.claims, a.claim_limit, a.full_flag);
 }
 
 void launch_next_k(const NextKArgs& a, cudaStream_t s) {
     if (a.g_hi <= a.g_lo) return;
     if (a.val_in) {
-        next_k_stream_kernel<<<pass_blocks((a.g_hi - a.g_lo + 31) / 32), 256, 0, s>>>(a);
+        next_k_stream_kernel<<<(unsigned)((a.g_hi - a.g_lo + 255) / 256), 256, 0, s>>>(a);
         return;
     }
-    next_k_kernel<<<pass_blocks((a.g_hi - a.g_lo + 30) / 31), 256, 0, s>>>(a);
+    const uint64_t n_warps = (a.g_hi - a.g_lo + 30) / 31;
+    next_k_kernel<<<(unsigned)((n_warps + 7) / 8), 256, 0, s>>>(a);
 }
 
 // ------------------------------------------------------------------ edge keys of the node set (row F1)

@@ -76,8 +76,8 @@ static void insert_store(DevTable& t, const Store& s, uint64_t read_lo, uint64_t
     uint32_t full = 0;
     InsertArgs a{};
     a.mins = s.mins.data(); a.rem = rem.data(); a.g_lo = s.offs[read_lo]; a.g_hi = s.offs[read_hi]; a.k = t.k;
-    static unsigned long long claims[CLAIM_SHARDS]; memset(claims, 0, sizeof claims);
-    a.table = t.slots.data(); a.mask = t.cap - 1; a.full_flag = &full; a.claims = claims; a.claim_limit = t.cap;
+    static unsigned long long claims; claims = 0;
+    a.table = t.slots.data(); a.mask = t.cap - 1; a.full_flag = &full; a.claims = &claims; a.claim_limit = t.cap;
     launch_insert(a, nullptr);
     CHECK(full == 0, "table full");
 }
@@ -239,7 +239,7 @@ static void test_tables(std::mt19937_64& rng) {
                     NextKArgs nk{};
                     nk.mins = s.mins.data(); nk.rem = rem.data(); nk.g_lo = 0; nk.g_hi = s.offs[s.n()]; nk.k = (uint32_t)k + 1;
                     nk.prev = prev.data(); nk.prev_mask = pcap - 1; nk.table = t3.slots.data(); nk.mask = t3.cap - 1; nk.full_flag = &full;
-                    unsigned long long nk_claims[CLAIM_SHARDS] = {0}; nk.claims = nk_claims; nk.claim_limit = t3.cap; nk.prev_min_count = 0;
+                    unsigned long long nk_claims = 0; nk.claims = &nk_claims; nk.claim_limit = t3.cap; nk.prev_min_count = 0;
                     if (mode == 2) { nk.prev = t.slots.data(); nk.prev_mask = t.cap - 1; nk.prev_min_count = 2; }
                     launch_next_k(nk, nullptr);
                     CHECK(full == 0, "next-k table full");
