@@ -610,8 +610,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                              "n_minimizers": int(un["offsets"][-1]), "longest_unitig_nodes": int(lens.max() - (K - 1)) if len(lens) else 0,
                              "ms": round(1e3 * t_u[1], 3), "d2h_bytes": int(un["offsets"][-1]) * 4 + un["n_unitigs"] * 25,
                              "checksum_of_hashes": int(np.sum(un["hashes"][:, 0], dtype=np.uint64)) if un["n_unitigs"] else 0,
-                             "timer": "host wall clock around mdbg_unitigs_build (edge set + links + list ranking + sequences + "
-                                      "hash128 on the device, D2H of the CSR, host sort of the unitig hashes)"}
+                             "n_unitig_edges": un["n_unitig_edges"], "checksum_unitig_edges": un["checksum_edges"],
+                             "checksum_unitig_nodes": un["checksum_nodes"], "checksum_unitig_abundances": un["checksum_abundances"],
+                             "timer": "host wall clock around mdbg_unitigs_build (edge set + links + list ranking + sequences + hash128 + "
+                                      "deterministic order + unitig graph edges on the device, D2H of the CSRs)"}
         except Exception as e:                                # noqa: BLE001
             unitigs_extra = {"error": repr(e)}
 
@@ -819,13 +821,24 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                 ru = ref.unitig_nodes(nodes, K, threads=threads)
                 t_ref = time.perf_counter() - t0
                 same = bool(np.array_equal(gu["offsets"], ru["offsets"]) and np.array_equal(gu["minimizers"], ru["minimizers"]))
+                t0 = time.perf_counter()
+                re_ = ref.unitig_edges(ru["offsets"], ru["minimizers"], K, threads=threads)
+                t_ref_e = time.perf_counter() - t0
+                lists = lambda d: [sorted(d["targets"][int(d["offsets"][x]):int(d["offsets"][x + 1])].tolist())
+                                   for x in range(len(d["offsets"]) - 1)]
+                same_e = bool(gu["n_unitig_edges"] == re_["n_edges"] and gu["checksum_edges"] == re_["checksum"] and
+                              lists(dict(offsets=gu["edge_offsets"], targets=gu["edge_targets"])) == lists(re_))
+                same = same and same_e
                 if not same:
-                    raise SystemExit("bench.py: the unitigs of the GPU differ from the reference's unitigGraph.nodes.bin on the sample")
+                    raise SystemExit("bench.py: the unitigs / unitig edges of the GPU differ from the reference's on the sample")
                 unitigs_extra["cpu_reference_on_sample"] = {
                     "n_nodes": int(len(nodes)), "n_unitigs": int(len(ru["offsets"]) - 1), "seconds": round(t_ref, 3), "threads": threads,
+                    "n_unitig_edges": int(re_["n_edges"]), "seconds_unitig_edges": round(t_ref_e, 3), "identical_edge_lists": same_e,
                     "gpu_seconds_same_sample": round(t_gpu, 4), "identical_records": same,
                     "what": "CreateMdbg::indexEdges + computeUnitigNodes + computeDeterministicUnitigs of oracle/_ref through their "
-                            "file contract in a scratch directory, node set of the cpu_baseline sample"}
+                            "file contract in a scratch directory, node set of the cpu_baseline sample; then indexUnitigEdges + "
+                            "computeUnitigEdges on those records (lists compared as multisets: the reference's order inside a list "
+                            "is its threads' arrival order)"}
             except SystemExit:
                 raise
             except Exception as e:                            # noqa: BLE001

@@ -459,6 +459,17 @@ typedef struct {
      * at node_abundances[offsets[u] - u * (k - 1) ..] (offsets[u+1] - offsets[u] - (k - 1) of them) =
      * the record of unitigGraph.nodes.abundances.bin */
     const uint32_t* node_abundances;
+    /* Unitig graph edges -- indexUnitigEdges + computeUnitigEdges (CreateMdbg.cpp:2915-3245; getSuccessors_unitig :2453-2530,
+     * getPredecessors_unitig :2631-2695, dumpUnitigEdge :2853-2912) -- as a CSR over ORIENTED unitigs in the reference's
+     * numbering (unitigIndex 2 i = record i = unitig order[i], 2 i + 1 = its reverse): edge_targets[edge_offsets[2 i] ..
+     * edge_offsets[2 i + 1]) = the successors of record i, edge_targets[edge_offsets[2 i + 1] .. edge_offsets[2 i + 2]) its
+     * predecessors, each list in the order one reference thread writes it (= the record of
+     * unitigGraph.edges.successors.bin).  n_unitig_edges = _nbUnitigEdges, checksum_edges = _checksum_unitigEdges.
+     * Computed for k <= 64; NULL / 0 beyond. */
+    uint64_t n_unitig_edges;
+    uint64_t checksum_edges;
+    const uint64_t* edge_offsets; /* [2 * n_unitigs + 1] */
+    const uint32_t* edge_targets; /* [n_unitig_edges] */
     uint64_t checksum_nodes;      /* "Checksum unitig nodes": sum over records of minimizer * size * unitigIndex (CreateMdbg.cpp:3380) */
     uint64_t checksum_abundances; /* "Checksum unitig abundance": sum of abundance * number of abundances (CreateMdbg.cpp:3384) */
     const uint64_t* d_offsets;    /* the same CSR in device memory */

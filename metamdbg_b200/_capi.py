@@ -84,7 +84,8 @@ class UnitigsOut(C.Structure):
     _fields_ = [("k", C.c_uint32), ("n_nodes", C.c_uint64), ("n_unitigs", C.c_uint64), ("n_minimizers", C.c_uint64),
                 ("n_circular", C.c_uint64), ("n_cycle_nodes", C.c_uint64), ("offsets", u64p), ("minimizers", C.POINTER(C.c_uint32)),
                 ("hashes", u64p), ("circular", C.POINTER(C.c_uint8)), ("order", C.POINTER(C.c_uint32)), ("node_abundances", C.POINTER(C.c_uint32)),
-                ("checksum_nodes", C.c_uint64), ("checksum_abundances", C.c_uint64), ("d_offsets", C.c_void_p),
+                ("n_unitig_edges", C.c_uint64), ("checksum_edges", C.c_uint64), ("edge_offsets", u64p),
+                ("edge_targets", C.POINTER(C.c_uint32)), ("checksum_nodes", C.c_uint64), ("checksum_abundances", C.c_uint64), ("d_offsets", C.c_void_p),
                 ("d_minimizers", C.c_void_p)]
 
 

@@ -167,8 +167,8 @@ struct mdbg_ctx {
     uint64_t edge_cap = 0;             // slots of the device-resident edge set left by the last edges / unitigs call
     // unitigs (mdbg_unitigs_build)
     DevBuf u_slot_node, u_node_slot, u_next, u_pair, u_len, u_size, u_flag, u_cychead, u_seqoff, u_idx, u_cyclist, u_cycpos, u_best,
-        u_jump, u_mins, u_off, u_hash, u_rev, u_circ, u_abund, u_bcnt, u_boff, u_order, u_pos;
-    PinBuf hu_mins, hu_off, hu_hash, hu_circ, hu_order, hu_abund;
+        u_jump, u_mins, u_off, u_hash, u_rev, u_circ, u_abund, u_bcnt, u_boff, u_order, u_pos, u_scnt, u_soff, u_ents, u_ecnt, u_eoff, u_etgt;
+    PinBuf hu_mins, hu_off, hu_hash, hu_circ, hu_order, hu_abund, hu_eoff, hu_etgt;
     uint64_t prev_capacity = 0;
     DevBuf o_hash, o_abund, o_vecs;
     PinBuf ho_hash, ho_abund, ho_vecs;
@@ -863,10 +863,11 @@ void mdbg_ctx_destroy(mdbg_ctx* c) {
                       &c->m_recv_counts, &c->m_bucket, &c->loc_off, &c->edge_table, &c->edge_vals, &c->o_edge_vals,
                       &c->u_slot_node, &c->u_node_slot, &c->u_next, &c->u_pair, &c->u_len, &c->u_size, &c->u_flag, &c->u_cychead,
                       &c->u_seqoff, &c->u_idx, &c->u_cyclist, &c->u_cycpos, &c->u_best, &c->u_jump, &c->u_mins, &c->u_off, &c->u_hash,
-                      &c->u_rev, &c->u_circ, &c->u_abund, &c->u_bcnt, &c->u_boff, &c->u_order, &c->u_pos};
+                      &c->u_rev, &c->u_circ, &c->u_abund, &c->u_bcnt, &c->u_boff, &c->u_order, &c->u_pos,
+                      &c->u_scnt, &c->u_soff, &c->u_ents, &c->u_ecnt, &c->u_eoff, &c->u_etgt};
     for (DevBuf* b : devs) release(*b);
     PinBuf* pins[] = {&c->h_off, &c->h_min, &c->h_pos, &c->h_dir, &c->ho_hash, &c->ho_abund, &c->ho_vecs, &c->hx_sum_lo, &c->hx_sum_hi, &c->hx_lmin, &c->hx_cplx, &c->hx_low, &c->hx_meanq, &c->h_qual, &c->h_pack, &c->h_src, &c->h_asc, &c->ho_edge_vals, &c->hpg_hash, &c->hpg_koff, &c->hpg_reads, &c->hpg_wins,
-                      &c->hu_mins, &c->hu_off, &c->hu_hash, &c->hu_circ, &c->hu_order, &c->hu_abund};
+                      &c->hu_mins, &c->hu_off, &c->hu_hash, &c->hu_circ, &c->hu_order, &c->hu_abund, &c->hu_eoff, &c->hu_etgt};
     for (PinBuf* b : pins) release(*b);
     if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
     if (c->d_small) cudaFree(c->d_small);
@@ -2947,6 +2948,52 @@ mdbg_status mdbg_unitigs_build(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_uniti
     launch_unitig_checksum(ctx->u_mins.as<uint32_t>(), ctx->u_off.as<uint64_t>(), ctx->u_abund.as<uint32_t>(), ctx->u_pos.as<uint32_t>(),
                            nu, ctx->t_k, &ctx->d_small->n_flagged, s);
     CKS(check_launch(ctx, "unitig_bucket_count/fill/sort kernels + scan + unitig_checksum_kernel", nu ? 7 : 0));
+    // unitig graph edges (indexUnitigEdges + computeUnitigEdges): end-node lists per edge-set slot, then the successor /
+    // predecessor lists of every unitig, in the order a single reference thread would write them
+    uint64_t n_uedges = 0;
+    const bool with_edges = nu > 0 && ctx->t_k <= 64;
+    if (with_edges) {
+        const uint64_t ecap = ctx->edge_cap;
+        CKS(ensure(ctx, ctx->u_scnt, ecap * 4));
+        CKS(ensure(ctx, ctx->u_soff, (ecap + 1) * 8));
+        CKS(ensure(ctx, ctx->u_ents, (4 * nu + 1) * 8));
+        CKS(ensure(ctx, ctx->u_ecnt, (2 * nu + 1) * 4));
+        CKS(ensure(ctx, ctx->u_eoff, (2 * nu + 2) * 8));
+        CKS(ensure(ctx, ctx->scan_scratch, scan_scratch_elems((uint32_t)std::max<uint64_t>(ecap, 2 * nu)) * sizeof(uint64_t)));
+        UnitigEdgeArgs ea{};
+        ea.mins = ctx->u_mins.as<uint32_t>(); ea.off = ctx->u_off.as<uint64_t>(); ea.n_unitigs = nu; ea.k = ctx->t_k;
+        ea.pos_of = ctx->u_pos.as<uint32_t>(); ea.order = ctx->u_order.as<uint32_t>();
+        ea.edges = ctx->edge_table.as<Slot>(); ea.edge_mask = ecap - 1;
+        ea.slot_cnt = ctx->u_scnt.as<uint32_t>(); ea.slot_off = ctx->u_soff.as<uint64_t>();
+        ea.entries = ctx->u_ents.as<unsigned long long>();
+        ea.edge_cnt = ctx->u_ecnt.as<uint32_t>(); ea.edge_off = ctx->u_eoff.as<uint64_t>();
+        ea.checksum = &ctx->d_small->emit_cursor; ea.error_flag = &ctx->d_small->full_flag;
+        CK(cudaMemsetAsync(ctx->u_scnt.p, 0, ecap * 4, s));
+        launch_unitig_end_offers(ea, 1, s);
+        launch_scan_u32_to_u64(ctx->u_scnt.as<uint32_t>(), ctx->u_soff.as<uint64_t>(), (uint32_t)ecap, ctx->scan_scratch.as<uint64_t>(), s);
+        CK(cudaMemsetAsync(ctx->u_scnt.p, 0, ecap * 4, s));
+        launch_unitig_end_offers(ea, 2, s);
+        launch_unitig_end_sort(ctx->u_soff.as<uint64_t>(), ecap, ctx->u_ents.as<unsigned long long>(), s);
+        launch_unitig_edges_query(ea, 1, s);
+        launch_scan_u32_to_u64(ctx->u_ecnt.as<uint32_t>(), ctx->u_eoff.as<uint64_t>(), (uint32_t)(2 * nu), ctx->scan_scratch.as<uint64_t>(), s);
+        CKS(check_launch(ctx, "unitig_end_offers/sort kernels + unitig_edges_query_kernel(count) + scans", 10));
+        CK(cudaMemcpyAsync(&ctx->h_scalar[6], ctx->u_eoff.as<uint64_t>() + 2 * nu, 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(&ctx->h_small->full_flag, &ctx->d_small->full_flag, 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (ctx->h_small->full_flag) return fail(ctx, MDBG_ERR_STATE, "mdbg_unitigs_build: a unitig end's key is missing from the edge set");
+        n_uedges = ctx->h_scalar[6];
+        CKS(ensure(ctx, ctx->u_etgt, (n_uedges + 1) * 4));
+        ea.edge_targets = ctx->u_etgt.as<uint32_t>();
+        CK(cudaMemsetAsync(&ctx->d_small->emit_cursor, 0, 8, s));
+        launch_unitig_edges_query(ea, 2, s);
+        CKS(check_launch(ctx, "unitig_edges_query_kernel(fill)", 1));
+        CKS(ensure_pin(ctx, ctx->hu_eoff, (2 * nu + 2) * 8));
+        CKS(ensure_pin(ctx, ctx->hu_etgt, (n_uedges + 1) * 4));
+        CK(cudaMemcpyAsync(ctx->hu_eoff.p, ctx->u_eoff.p, (2 * nu + 1) * 8, cudaMemcpyDeviceToHost, s));
+        if (n_uedges) CK(cudaMemcpyAsync(ctx->hu_etgt.p, ctx->u_etgt.p, n_uedges * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(&ctx->h_scalar[7], &ctx->d_small->emit_cursor, 8, cudaMemcpyDeviceToHost, s));
+        ctx->d2h_bytes += (2 * nu + 1) * 8 + n_uedges * 4 + 8;
+    }
     CKS(ensure_pin(ctx, ctx->hu_mins, (total + 1) * 4));
     CKS(ensure_pin(ctx, ctx->hu_off, (nu + 2) * 8));
     CKS(ensure_pin(ctx, ctx->hu_hash, (nu + 1) * 16));
@@ -2978,6 +3025,12 @@ mdbg_status mdbg_unitigs_build(mdbg_ctx* ctx, uint32_t min_abundance, mdbg_uniti
     out->circular = ctx->hu_circ.as<uint8_t>();
     out->order = order;
     out->node_abundances = ctx->hu_abund.as<uint32_t>();
+    if (with_edges) {
+        out->n_unitig_edges = n_uedges;
+        out->checksum_edges = ctx->h_scalar[7];
+        out->edge_offsets = ctx->hu_eoff.as<uint64_t>();
+        out->edge_targets = ctx->hu_etgt.as<uint32_t>();
+    }
     out->checksum_nodes = cs_nodes;
     out->checksum_abundances = cs_ab;
     out->d_offsets = ctx->u_off.as<uint64_t>();

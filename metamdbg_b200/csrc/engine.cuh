@@ -331,6 +331,19 @@ void launch_unitig_hash(const uint32_t* mins, const uint64_t* off, uint64_t n_un
 void launch_unitig_reverse(uint32_t* mins, const uint64_t* off, uint64_t n_unitigs, const uint8_t* rev, uint32_t* abund, uint32_t k,
                            cudaStream_t s);
 
+// unitig graph edges: lists of unitig end nodes per edge-set slot, successor / predecessor lists per oriented unitig
+struct UnitigEdgeArgs {
+    const uint32_t* mins; const uint64_t* off; uint64_t n_unitigs; uint32_t k;      // unitig sequences (unsorted index j)
+    const uint32_t* pos_of; const uint32_t* order;                                  // j -> position, position -> j
+    const Slot* edges; uint64_t edge_mask;
+    uint32_t* slot_cnt; const uint64_t* slot_off; unsigned long long* entries;      // per edge-set slot
+    uint32_t* edge_cnt; const uint64_t* edge_off; uint32_t* edge_targets;           // per oriented unitig x = 2 * position + reversed
+    unsigned long long* checksum; uint32_t* error_flag;
+};
+void launch_unitig_end_offers(const UnitigEdgeArgs& a, int pass, cudaStream_t s);   // pass 1: count, pass 2: fill (slot_cnt zeroed before each)
+void launch_unitig_end_sort(const uint64_t* slot_off, uint64_t n_slots, unsigned long long* entries, cudaStream_t s);
+void launch_unitig_edges_query(const UnitigEdgeArgs& a, int pass, cudaStream_t s);  // pass 1: edge_cnt, pass 2: edge_targets + checksum
+
 // order[i] = unitig at position i of the ascending (high, low) hash order, pos_of = its inverse; cnt: 2^bucket_bits u32,
 // bucket_off: 2^bucket_bits + 1 u64
 void launch_unitig_sort(const uint64_t* hashes, uint64_t n, uint32_t bucket_bits, uint32_t* cnt, uint64_t* bucket_off,

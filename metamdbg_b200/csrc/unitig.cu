@@ -458,6 +458,140 @@ __global__ void __launch_bounds__(256) unitig_checksum_kernel(const uint32_t* mi
     }
 }
 
+// ------------------------------------------------------------------ unitig graph edges
+// CreateMdbg::indexUnitigEdges / computeUnitigEdges (src/graph/CreateMdbg.cpp:2915-3245; getSuccessors_unitig :2453-2530,
+// getPredecessors_unitig :2631-2695).  The first and (when different) the last k-min-mer of every unitig, normalized, are
+// entered under their normalized (k-1)-prefix and (k-1)-suffix keys -- the keys are in the edge set already, so a list
+// per edge-set slot (count, scan, fill: a CSR) replaces the reference's second MPHF + vector-per-key map.  An entry is
+// (seq << 3) | nodeReversed << 2 | keyReversed << 1 | isPrefix with seq = ((2 * position + isLastNode) * 2 + isSuffixKey):
+// sorted by value, a list is in the order ONE reference thread would have pushed it (records in file order, first node
+// before last node, prefix entry before suffix entry), so the successor lists come out in the reference's own order.
+__device__ __forceinline__ void unitig_end_node(const uint32_t* seq, uint64_t L, uint32_t k, bool last, bool reversed_unitig,
+                                                uint32_t* out) {
+    // k-min-mer number 0 / L-k of the sequence, or of the reversed sequence
+    const uint64_t at = (last != reversed_unitig) ? L - k : 0;
+    for (uint32_t j = 0; j < k; j++) out[j] = reversed_unitig ? seq[at + k - 1 - j] : seq[at + j];
+}
+
+constexpr int UNITIG_MAX_K = 64;                                  // the end-node work areas live in registers / local memory
+
+__global__ void __launch_bounds__(128) unitig_end_offers_kernel(const UnitigEdgeArgs a, int pass) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= a.n_unitigs) return;
+    const uint32_t k = a.k, km = k - 1;
+    const uint32_t* seq = a.mins + a.off[j];
+    const uint64_t L = a.off[j + 1] - a.off[j];
+    const uint64_t pos = a.pos_of[j];
+    uint32_t node[UNITIG_MAX_K];
+    const bool single = L == k;                                   // startNode == endNode: entered once
+    bool same = single;
+    if (!single) {                                                // (equal vectors at both ends also count once)
+        same = true;
+        for (uint32_t t = 0; t < k; t++) if (seq[t] != seq[L - k + t]) { same = false; break; }
+    }
+    for (int end = 0; end < (same ? 1 : 2); end++) {
+        unitig_end_node(seq, L, k, end != 0, false, node);
+        bool nrev = true;                                         // KmerVec::normalize of the node
+        for (uint32_t t = 0; t < k / 2; t++) if (node[t] != node[k - 1 - t]) { nrev = node[t] > node[k - 1 - t]; break; }
+        if (nrev) for (uint32_t t = 0; t < k / 2; t++) { const uint32_t x = node[t]; node[t] = node[k - 1 - t]; node[k - 1 - t] = x; }
+        for (uint32_t side = 0; side < 2; side++) {               // prefix key, then suffix key (indexEdgeUnitig)
+            const uint32_t* w = node + side;
+            bool krev = true;
+            for (uint32_t t = 0; t < km / 2; t++) if (w[t] != w[km - 1 - t]) { krev = w[t] > w[km - 1 - t]; break; }
+            uint64_t h1, h2;
+            if (krev) murmur128_u32vec([&](int t) { return w[km - 1 - t]; }, (int)km, h1, h2);
+            else murmur128_u32vec([&](int t) { return w[t]; }, (int)km, h1, h2);
+            const Slot* es = table_find(const_cast<Slot*>(a.edges), a.edge_mask, h2, h1);
+            if (!es) { atomicExch(a.error_flag, 3u); continue; }
+            const uint64_t slot = (uint64_t)(es - a.edges);
+            if (pass == 1) {
+                atomicAdd(a.slot_cnt + slot, 1u);
+            } else {
+                const uint64_t seqno = (2 * pos + (uint64_t)end) * 2 + side;
+                a.entries[a.slot_off[slot] + atomicAdd(a.slot_cnt + slot, 1u)] =
+                    (seqno << 3) | ((unsigned long long)(nrev ? 1 : 0) << 2) | ((unsigned long long)(krev ? 1 : 0) << 1) | (side ? 0ULL : 1ULL);
+            }
+        }
+    }
+}
+
+// every list into ascending order (= the single-thread push order of the reference); lists are short
+__global__ void __launch_bounds__(256) unitig_end_sort_kernel(const uint64_t* slot_off, uint64_t n_slots, unsigned long long* entries) {
+    const uint64_t sl = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (sl >= n_slots) return;
+    const uint64_t lo = slot_off[sl], hi = slot_off[sl + 1];
+    for (uint64_t i = lo + 1; i < hi; i++) {
+        const unsigned long long x = entries[i];
+        uint64_t q = i;
+        while (q > lo && entries[q - 1] > x) { entries[q] = entries[q - 1]; q--; }
+        entries[q] = x;
+    }
+}
+
+// successors of oriented unitig x = 2 * position + reversed (the predecessors of a unitig are the successors of its
+// reverse): pass 1 counts, pass 2 writes targets and adds x * target to the checksum (_checksum_unitigEdges)
+__global__ void __launch_bounds__(128) unitig_edges_query_kernel(const UnitigEdgeArgs a, int pass) {
+    const uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long cs = 0;
+    if (x < 2 * a.n_unitigs) {
+        const uint32_t k = a.k, km = k - 1;
+        const uint64_t j = a.order[x >> 1];
+        const uint32_t* seq = a.mins + a.off[j];
+        const uint64_t L = a.off[j + 1] - a.off[j];
+        uint32_t node[UNITIG_MAX_K];
+        unitig_end_node(seq, L, k, true, (x & 1) != 0, node);    // the last k-min-mer of x as oriented
+        const uint32_t* S = node + 1;
+        bool srev = true, pal = true;
+        for (uint32_t t = 0; t < km / 2; t++) if (S[t] != S[km - 1 - t]) { srev = S[t] > S[km - 1 - t]; pal = false; break; }
+        uint64_t h1, h2;
+        if (srev) murmur128_u32vec([&](int t) { return S[km - 1 - t]; }, (int)km, h1, h2);
+        else murmur128_u32vec([&](int t) { return S[t]; }, (int)km, h1, h2);
+        const Slot* es = table_find(const_cast<Slot*>(a.edges), a.edge_mask, h2, h1);
+        uint32_t n = 0;
+        if (!es) {
+            atomicExch(a.error_flag, 3u);
+        } else {
+            const uint64_t slot = (uint64_t)(es - a.edges);
+            const uint64_t base = pass == 2 ? a.edge_off[x] : 0;
+            for (uint64_t e = a.slot_off[slot]; e < a.slot_off[slot + 1]; e++) {
+                const unsigned long long ent = a.entries[e];
+                const uint32_t idx = (uint32_t)(2 * (ent >> 5)) + (uint32_t)((ent >> 2) & 1);   // seq >> 2 = position
+                const bool krev = (ent >> 1) & 1, pre = ent & 1;
+                uint32_t target;
+                if (pre) {
+                    if (!(pal || krev == srev)) continue;         // getSuccessors_unitig: vec_suffix == v
+                    if ((uint32_t)x == (idx ^ 1u)) continue;
+                    target = idx;
+                } else {
+                    if (!(pal || krev != srev)) continue;         // vec_suffix == reverse(v)
+                    if ((uint32_t)x == idx) continue;
+                    target = idx ^ 1u;
+                }
+                if (pass == 2) { a.edge_targets[base + n] = target; cs += (unsigned long long)x * target; }
+                n++;
+            }
+        }
+        if (pass == 1) a.edge_cnt[x] = n;
+    }
+    if (pass == 2) {
+        for (int d = 16; d; d >>= 1) cs += __shfl_down_sync(0xffffffffu, cs, d);
+        if ((threadIdx.x & 31) == 0 && cs) atomicAdd(a.checksum, cs);
+    }
+}
+
+void launch_unitig_end_offers(const UnitigEdgeArgs& a, int pass, cudaStream_t s) {
+    if (!a.n_unitigs) return;
+    unitig_end_offers_kernel<<<(unsigned)((a.n_unitigs + 127) / 128), 128, 0, s>>>(a, pass);
+}
+void launch_unitig_end_sort(const uint64_t* slot_off, uint64_t n_slots, unsigned long long* entries, cudaStream_t s) {
+    if (!n_slots) return;
+    unitig_end_sort_kernel<<<(unsigned)((n_slots + 255) / 256), 256, 0, s>>>(slot_off, n_slots, entries);
+}
+void launch_unitig_edges_query(const UnitigEdgeArgs& a, int pass, cudaStream_t s) {
+    if (!a.n_unitigs) return;
+    unitig_edges_query_kernel<<<(unsigned)((2 * a.n_unitigs + 127) / 128), 128, 0, s>>>(a, pass);
+}
+
 void launch_unitig_sort(const uint64_t* hashes, uint64_t n, uint32_t bucket_bits, uint32_t* cnt, uint64_t* bucket_off,
                         uint64_t* scan_scratch, uint32_t* order, uint32_t* pos_of, cudaStream_t s) {
     if (!n) return;

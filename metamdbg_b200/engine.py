@@ -485,7 +485,10 @@ class Engine:
                     hashes=arr(out.hashes, (2 * n,), np.uint64).reshape(n, 2),
                     circular=arr(out.circular, (n,), np.uint8), order=arr(out.order, (n,), np.uint32),
                     node_abundances=arr(out.node_abundances, (t - n * (int(out.k) - 1),), np.uint32),
-                    checksum_nodes=int(out.checksum_nodes), checksum_abundances=int(out.checksum_abundances))
+                    checksum_nodes=int(out.checksum_nodes), checksum_abundances=int(out.checksum_abundances),
+                    n_unitig_edges=int(out.n_unitig_edges), checksum_edges=int(out.checksum_edges),
+                    edge_offsets=(np.ctypeslib.as_array(out.edge_offsets, shape=(2 * n + 1,)).copy() if out.edge_offsets else None),
+                    edge_targets=(arr(out.edge_targets, (int(out.n_unitig_edges),), np.uint32) if out.edge_offsets else None))
 
     def unitig_records(self, min_abundance: int = 2) -> dict:
         """The same unitigs in the reference's file order: dict(offsets [n+1], minimizers) = the records of
@@ -500,7 +503,9 @@ class Engine:
         ab = [u["node_abundances"][int(u["offsets"][i]) - int(i) * km1:int(u["offsets"][i + 1]) - (int(i) + 1) * km1] for i in u["order"]]
         return dict(offsets=offs, minimizers=mins.astype(np.uint32), n_circular=u["n_circular"], n_nodes=u["n_nodes"],
                     abundances=np.concatenate(ab).astype(np.uint32) if ab else np.zeros(0, np.uint32),
-                    checksum_nodes=u["checksum_nodes"], checksum_abundances=u["checksum_abundances"])
+                    checksum_nodes=u["checksum_nodes"], checksum_abundances=u["checksum_abundances"],
+                    edge_offsets=u["edge_offsets"], edge_targets=u["edge_targets"], n_unitig_edges=u["n_unitig_edges"],
+                    checksum_edges=u["checksum_edges"])
 
     # -- multi-GPU -----------------------------------------------------------------
     @staticmethod

@@ -180,9 +180,11 @@ static int stageGraph(int argc, char** argv) {
               << counter._nbSolidKminmers << " rescued " << counter._nbRescuedKminmers << " checksum " << counter._checksum << std::endl;
     if (unitigs) {                                       // createGfa's node side (CreateMdbg.cpp:876-925) on the table just built
         GpuUnitigBuilder ub(ctx, minAb);
-        ub.execute(tmpDir + "/unitigGraph.nodes.bin", tmpDir + "/unitigGraph.nodes.abundances.bin");
+        ub.execute(tmpDir + "/unitigGraph.nodes.bin", tmpDir + "/unitigGraph.nodes.abundances.bin",
+                   tmpDir + "/unitigGraph.edges.successors.bin");
         std::cout << "unitigs " << ub._nbUnitigs << " circular " << ub._nbCircular << " checksum_unitig_nodes " << ub._checksumNodes
-                  << " checksum_unitig_abundance " << ub._checksumAbundances << std::endl;
+                  << " checksum_unitig_abundance " << ub._checksumAbundances << " unitig_edges " << ub._nbUnitigEdges
+                  << " checksum_unitig_edges " << ub._checksumEdges << std::endl;
     }
     return 0;
 }
@@ -240,9 +242,10 @@ int main(int argc, char** argv) {
             if (!writeUnitigs) return;
             GpuUnitigBuilder ub(ctx, minAb);
             const std::string dir = file.substr(0, file.find_last_of('/'));
-            ub.execute(dir + "/unitigGraph.nodes.bin", dir + "/unitigGraph.nodes.abundances.bin");
+            ub.execute(dir + "/unitigGraph.nodes.bin", dir + "/unitigGraph.nodes.abundances.bin", dir + "/unitigGraph.edges.successors.bin");
             std::cout << "unitigs " << ub._nbUnitigs << " circular " << ub._nbCircular << " checksum_unitig_nodes " << ub._checksumNodes
-                      << " checksum_unitig_abundance " << ub._checksumAbundances << "\n";
+                      << " checksum_unitig_abundance " << ub._checksumAbundances << " unitig_edges " << ub._nbUnitigEdges
+                      << " checksum_unitig_edges " << ub._checksumEdges << "\n";
         };
         auto nextKPasses = [&]() {                       // k+1 .. maxK from the table the context holds
             GpuNextKCounter nextK(ctx, minAb);

@@ -437,14 +437,32 @@ private:
 // 1001-1043, 3335-3390): the unitig nodes of the context's current table as the reference's two files --
 //   unitigGraph.nodes.bin             per unitig: u32 size, size x u32 minimizers, u32 unitigIndex (= 2 * record number)
 //   unitigGraph.nodes.abundances.bin  per unitig: u32 unitigIndex, u32 count, count x u32 abundance of its k-min-mers
+//   unitigGraph.edges.successors.bin  per unitig: u32 unitigIndex, u32 nbSuccessors, successors, u32 nbPredecessors,
+//                                     predecessors (indexUnitigEdges + computeUnitigEdges, CreateMdbg.cpp:2915-3245)
 // in the reference's deterministic order (ascending hash128 of the normalized minimizer sequence).
 class GpuUnitigBuilder {
 public:
     GpuUnitigBuilder(Context& ctx, uint32_t minAbundance) : _ctx(ctx), _minAbundance(minAbundance) {}
 
-    void execute(const std::string& nodeFile, const std::string& abundanceFile) {
+    void execute(const std::string& nodeFile, const std::string& abundanceFile, const std::string& edgeFile = "") {
         mdbg_unitigs_out u{};
         check(_ctx.get(), mdbg_unitigs_build(_ctx.get(), _minAbundance, &u), "mdbg_unitigs_build");
+        if (!edgeFile.empty() && u.edge_offsets) {       // dumpUnitigEdge (CreateMdbg.cpp:2853-2912), record i = unitigIndex 2 i
+            File fe(edgeFile);
+            for (uint64_t i = 0; i < u.n_unitigs; i++) {
+                const uint32_t from = (uint32_t)(2 * i);
+                fe.put(&from, 4, 1);
+                for (int o = 0; o < 2; o++) {            // successors, then predecessors
+                    const uint64_t lo = u.edge_offsets[2 * i + o], hi = u.edge_offsets[2 * i + o + 1];
+                    const uint32_t nb = (uint32_t)(hi - lo);
+                    fe.put(&nb, 4, 1);
+                    fe.put(u.edge_targets + lo, 4, nb);
+                }
+            }
+            fe.close();
+            _nbUnitigEdges = u.n_unitig_edges;
+            _checksumEdges = u.checksum_edges;
+        }
         File fn(nodeFile), fa(abundanceFile);
         const uint64_t km1 = u.k - 1;
         for (uint64_t i = 0; i < u.n_unitigs; i++) {
@@ -465,7 +483,7 @@ public:
         _checksumAbundances = u.checksum_abundances;
     }
 
-    uint64_t _nbUnitigs = 0, _nbCircular = 0, _checksumNodes = 0, _checksumAbundances = 0;
+    uint64_t _nbUnitigs = 0, _nbCircular = 0, _checksumNodes = 0, _checksumAbundances = 0, _nbUnitigEdges = 0, _checksumEdges = 0;
 
 private:
     Context& _ctx;

@@ -910,6 +910,109 @@ size_t orc_unitigs(const uint32_t* vecs, size_t n, int k, uint64_t** offs_out, u
     return n_out;
 }
 
+/* ------------------------------------------------------- unitig graph edges (row F1, fourth step)
+ * CreateMdbg::indexUnitigEdges / indexUnitigEdge / indexEdgeUnitig (src/graph/CreateMdbg.cpp:2915-3086) and
+ * computeUnitigEdges / computeUnitigEdge / getSuccessors_unitig / getPredecessors_unitig / dumpUnitigEdge
+ * (:3088-3245, 2453-2530, 2631-2695, 2853-2912), run sequentially over unitigGraph.nodes.bin in file order (record i
+ * has unitigIndex 2 i; 2 i + 1 is its reverse).  Index: the first and (when different) the last k-min-mer of every unitig,
+ * normalized, enter the lists of their normalized (k-1)-prefix and (k-1)-suffix keys as {unitigIndex of the orientation
+ * in which the normalized k-min-mer appears, isReversed of the key, isPrefix}.  Query: the successors of a unitig are
+ * the entries of its last k-min-mer's suffix key whose oriented (k-1)-mer continues that suffix (isPrefix: the entry's
+ * unitig, unless that is the querying unitig's own reverse; else: the reverse of the entry's unitig, unless that is...
+ * the same exclusion seen from the other side); the predecessors are the successors of the reversed unitig.  Lists are
+ * returned in the order a single thread produces (file order of the offering unitigs, first node before last node,
+ * prefix entry before suffix entry).  CSR over ORIENTED unitigs: list 2 i = successors of record i, list 2 i + 1 = its
+ * predecessors.  *checksum = _checksum_unitigEdges (sum of from * to, predecessors with the reversed from index). */
+typedef struct { uint64_t h1, h2, seq; uint32_t idx, rev, pre; } UEnt;
+static int cmp_uent(const void* a, const void* b) {
+    const UEnt* x = (const UEnt*)a; const UEnt* y = (const UEnt*)b;
+    if (x->h1 != y->h1) return x->h1 < y->h1 ? -1 : 1;
+    if (x->h2 != y->h2) return x->h2 < y->h2 ? -1 : 1;
+    if (x->seq != y->seq) return x->seq < y->seq ? -1 : 1;
+    return 0;
+}
+static void ue_offer(UEnt* ents, size_t* m, const uint32_t* node, int k, uint32_t u, uint64_t seq) {
+    uint32_t nn[256], key[256];
+    const int nrev = u_normalize(node, k, nn);
+    const uint32_t idx = nrev ? u + 1 : u;
+    for (int side = 0; side < 2; side++) {               /* prefix entry first, then suffix entry (indexEdgeUnitig) */
+        const int rev = u_normalize(nn + side, k - 1, key);
+        uint64_t h[2];
+        orc_hash128(key, k - 1, h);
+        UEnt* e = ents + (*m)++;
+        e->h1 = h[0]; e->h2 = h[1]; e->seq = seq * 2 + (uint64_t)side; e->idx = idx; e->rev = (uint32_t)rev; e->pre = side ? 0u : 1u;
+    }
+}
+/* successors of oriented unitig x whose last k-min-mer (as oriented) is `end` */
+static size_t ue_succ(const UEnt* ents, size_t m, const uint32_t* end, int k, uint32_t x, uint32_t* out) {
+    const int km = k - 1;
+    uint32_t key[256];
+    const uint32_t* S = end + 1;
+    const int srev = u_normalize(S, km, key);
+    int pal = 1;
+    for (int j = 0; j < km / 2; j++) if (S[j] != S[km - 1 - j]) { pal = 0; break; }
+    uint64_t h[2];
+    orc_hash128(key, km, h);
+    size_t lo = 0, hi = m;
+    while (lo < hi) {
+        size_t mid = (lo + hi) / 2;
+        if (ents[mid].h1 < h[0] || (ents[mid].h1 == h[0] && ents[mid].h2 < h[1])) lo = mid + 1; else hi = mid;
+    }
+    size_t n = 0;
+    for (size_t i = lo; i < m && ents[i].h1 == h[0] && ents[i].h2 == h[1]; i++) {
+        const UEnt* e = ents + i;
+        if (e->pre) {
+            if (!(pal || (int)e->rev == srev)) continue;                  /* vec_suffix == v */
+            if (x == (e->idx ^ 1u)) continue;
+            out[n++] = e->idx;
+        } else {
+            if (!(pal || (int)e->rev != srev)) continue;                  /* vec_suffix == reverse(v) */
+            if (x == e->idx) continue;
+            out[n++] = e->idx ^ 1u;
+        }
+    }
+    return n;
+}
+
+size_t orc_unitig_edges(const uint32_t* mins, const uint64_t* offs, size_t n_unitigs, int k, uint64_t** eoff_out,
+                        uint32_t** etgt_out, uint64_t* checksum) {
+    UEnt* ents = (UEnt*)malloc((4 * n_unitigs + 1) * sizeof(UEnt));
+    size_t m = 0;
+    for (size_t i = 0; i < n_unitigs; i++) {
+        const uint32_t* u = mins + offs[i];
+        const size_t L = (size_t)(offs[i + 1] - offs[i]);
+        const uint32_t* start = u; const uint32_t* end = u + L - (size_t)k;
+        ue_offer(ents, &m, start, k, (uint32_t)(2 * i), 2 * (uint64_t)i);
+        if (memcmp(start, end, (size_t)k * 4) != 0) ue_offer(ents, &m, end, k, (uint32_t)(2 * i), 2 * (uint64_t)i + 1);
+    }
+    qsort(ents, m, sizeof(UEnt), cmp_uent);
+    uint64_t* eoff = (uint64_t*)malloc((2 * n_unitigs + 2) * sizeof(uint64_t));
+    size_t cap = 4 * n_unitigs + 16, tot = 0;
+    uint32_t* etgt = (uint32_t*)malloc(cap * sizeof(uint32_t));
+    uint32_t* tmp = (uint32_t*)malloc((m + 1) * sizeof(uint32_t));
+    uint32_t rc[256];
+    uint64_t cs = 0;
+    for (size_t i = 0; i < n_unitigs; i++) {
+        const uint32_t* u = mins + offs[i];
+        const size_t L = (size_t)(offs[i + 1] - offs[i]);
+        for (int o = 0; o < 2; o++) {
+            const uint32_t x = (uint32_t)(2 * i) + (uint32_t)o;
+            const uint32_t* end;
+            if (!o) end = u + L - (size_t)k;
+            else { for (int j = 0; j < k; j++) rc[j] = u[k - 1 - j]; end = rc; }     /* last k-min-mer of the reversed unitig */
+            const size_t n = ue_succ(ents, m, end, k, x, tmp);
+            eoff[2 * i + (size_t)o] = tot;
+            if (tot + n > cap) { cap = 2 * (tot + n); etgt = (uint32_t*)realloc(etgt, cap * sizeof(uint32_t)); }
+            for (size_t j = 0; j < n; j++) { etgt[tot++] = tmp[j]; cs += (uint64_t)x * (uint64_t)tmp[j]; }
+        }
+    }
+    eoff[2 * n_unitigs] = tot;
+    free(ents); free(tmp);
+    *eoff_out = eoff; *etgt_out = etgt;
+    if (checksum) *checksum = cs;
+    return tot;
+}
+
 uint64_t orc_table_checksum(const uint64_t* hashes, const uint32_t* abundances, size_t n) {
     uint64_t s = 0;
     for (size_t i = 0; i < n; i++) s += (uint64_t)abundances[i] * hashes[2 * i + 1];

@@ -138,6 +138,13 @@ size_t orc_edge_values(const uint32_t* vecs, size_t n, int k, uint64_t** hashes,
  * *offs: n_unitigs + 1, *mins: concatenated sequences, *hashes (may be NULL): n_unitigs x {h1,h2}.  Returns n_unitigs. */
 size_t orc_unitigs(const uint32_t* vecs, size_t n, int k, uint64_t** offs, uint32_t** mins, uint64_t** hashes);
 
+/* CreateMdbg::indexUnitigEdges + computeUnitigEdges (CreateMdbg.cpp:2915-3245, getSuccessors_unitig :2453-2530,
+ * getPredecessors_unitig :2631-2695, dumpUnitigEdge :2853-2912) on the records of unitigGraph.nodes.bin (mins / offs, record i
+ * = unitigIndex 2 i).  CSR over oriented unitigs: list 2 i = successors of record i, list 2 i + 1 = its predecessors, each
+ * in the order one thread produces.  Returns the number of edges (_nbUnitigEdges); *checksum = _checksum_unitigEdges. */
+size_t orc_unitig_edges(const uint32_t* mins, const uint64_t* offs, size_t n_unitigs, int k, uint64_t** edge_offs,
+                        uint32_t** edge_targets, uint64_t* checksum);
+
 /* Order-free fingerprint used by the reference's debug log
  * (src/graph/CreateMdbg.cpp:3321): sum abundance * (u64)hash128 mod 2^64,
  * where (u64)hash128 = low 64 bits = h2. */

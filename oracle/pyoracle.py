@@ -193,6 +193,8 @@ class Oracle(_Lib):
                                  C.POINTER(_u64p), C.POINTER(_u32p)]
         L.orc_edge_index.restype = C.c_size_t
         L.orc_edge_index.argtypes = [_u32p, C.c_size_t, C.c_int, C.POINTER(_u64p), C.POINTER(C.c_uint64)]
+        L.orc_unitig_edges.restype = C.c_size_t
+        L.orc_unitig_edges.argtypes = [_u32p, _u64p, C.c_size_t, C.c_int, C.POINTER(_u64p), C.POINTER(_u32p), C.POINTER(C.c_uint64)]
         L.orc_unitigs.restype = C.c_size_t
         L.orc_unitigs.argtypes = [_u32p, C.c_size_t, C.c_int, C.POINTER(_u64p), C.POINTER(_u32p), C.POINTER(_u64p)]
         L.orc_edge_values.restype = C.c_size_t
@@ -299,6 +301,17 @@ class Oracle(_Lib):
         offs = self._take(o, n + 1, np.uint64)
         return dict(offsets=offs, minimizers=self._take(m, int(offs[-1]), np.uint32), hashes=self._take(h, 2 * n, np.uint64).reshape(n, 2))
 
+    def unitig_edges(self, unitig_offsets, unitig_minimizers, k):
+        """indexUnitigEdges + computeUnitigEdges on the records of unitigGraph.nodes.bin -> dict(offsets [2n+1], targets,
+        n_edges, checksum): list 2i = successors of record i (unitigIndex 2i), list 2i+1 = its predecessors."""
+        offs = np.ascontiguousarray(unitig_offsets, dtype=np.uint64)
+        mins = np.ascontiguousarray(unitig_minimizers, dtype=np.uint32)
+        n = len(offs) - 1
+        eo = _u64p(); et = _u32p(); cs = C.c_uint64(0)
+        ne = self.lib.orc_unitig_edges(_p(mins, _u32p), _p(offs, _u64p), n, k, C.byref(eo), C.byref(et), C.byref(cs))
+        return dict(offsets=self._take(eo, 2 * n + 1, np.uint64), targets=self._take(et, ne, np.uint32), n_edges=int(ne),
+                    checksum=int(cs.value))
+
     def checksum(self, hashes: np.ndarray, abundances: np.ndarray) -> int:
         hashes = np.ascontiguousarray(hashes, dtype=np.uint64)
         abundances = np.ascontiguousarray(abundances, dtype=np.uint32)
@@ -334,6 +347,9 @@ class Reference(_Lib):
         L.ref_edge_index.restype = C.c_size_t
         L.ref_edge_index.argtypes = [_u32p, C.c_size_t, C.c_int, C.c_int, C.c_char_p, C.POINTER(_u64p),
                                      C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.ref_unitig_edges.restype = C.c_size_t
+        L.ref_unitig_edges.argtypes = [_u32p, _u64p, C.c_size_t, C.c_int, C.c_int, C.c_char_p, C.POINTER(_u64p), C.POINTER(_u32p),
+                                       C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.ref_unitig_nodes.restype = C.c_size_t
         L.ref_unitig_nodes.argtypes = [_u32p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(_u64p), C.POINTER(_u32p)]
         L.ref_edge_values.restype = C.c_size_t
@@ -410,6 +426,22 @@ class Reference(_Lib):
                                           C.byref(o), C.byref(m))
         offs = self._take(o, n + 1, np.uint64)
         return dict(offsets=offs, minimizers=self._take(m, int(offs[-1]), np.uint32))
+
+    def unitig_edges(self, unitig_offsets, unitig_minimizers, k, threads=1):
+        """The reference's own indexUnitigEdges + computeUnitigEdges on a unitigGraph.nodes.bin written from the given
+        records, in a scratch dir -> dict(offsets [2n+1], targets, n_edges, checksum) with the records of
+        unitigGraph.edges.successors.bin re-ordered by unitigIndex (list 2i successors, 2i+1 predecessors; the order inside
+        a list is the reference's arrival order: deterministic with one thread)."""
+        import tempfile
+        offs = np.ascontiguousarray(unitig_offsets, dtype=np.uint64)
+        mins = np.ascontiguousarray(unitig_minimizers, dtype=np.uint32)
+        n = len(offs) - 1
+        eo = _u64p(); et = _u32p(); ne = C.c_uint64(0); cs = C.c_uint64(0)
+        with tempfile.TemporaryDirectory() as d:
+            tot = self.lib.ref_unitig_edges(_p(mins, _u32p), _p(offs, _u64p), n, k, threads, d.encode(), C.byref(eo), C.byref(et),
+                                            C.byref(ne), C.byref(cs))
+        return dict(offsets=self._take(eo, 2 * n + 1, np.uint64), targets=self._take(et, tot, np.uint32), n_edges=int(ne.value),
+                    checksum=int(cs.value))
 
     def graph_next_k(self, mins, offs, k, prev_hashes, prev_ab, use_counter=False, threads=1):
         import tempfile

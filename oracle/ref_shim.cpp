@@ -563,6 +563,69 @@ size_t ref_unitig_nodes(const uint32_t* vecs, size_t n, int k, int n_threads, in
     return offs.size() - 1;
 }
 
+/* CreateMdbg::indexUnitigEdges + computeUnitigEdges (src/graph/CreateMdbg.cpp:2915-2994, 3088-3140; UnitigEdgeIndexer,
+ * BooPHF, indexUnitigEdge, computeUnitigEdge -> getSuccessors_unitig / getPredecessors_unitig -> dumpUnitigEdge) on a
+ * unitigGraph.nodes.bin written from the given records (record i: unitigIndex 2 i), with n_threads OpenMP threads -- the call
+ * sequence of createGfa (CreateMdbg.cpp:913-925).  Returns the records of unitigGraph.edges.successors.bin re-ordered by
+ * unitigIndex as a CSR over oriented unitigs (list 2 i = successors, 2 i + 1 = predecessors of record i; inside a list
+ * the file's order), *nb_edges = _nbUnitigEdges, *checksum = _checksum_unitigEdges. */
+size_t ref_unitig_edges(const uint32_t* mins, const uint64_t* offs, size_t n_unitigs, int k, int n_threads, const char* tmp_dir,
+                        uint64_t** eoff_out, uint32_t** etgt_out, uint64_t* nb_edges, uint64_t* checksum) {
+    if (n_threads < 1) n_threads = 1;
+    const string dir(tmp_dir);
+    {
+        ofstream f(dir + "/unitigGraph.nodes.bin", std::ios::binary);
+        for (size_t i = 0; i < n_unitigs; i++) {
+            const u_int32_t size = (u_int32_t)(offs[i + 1] - offs[i]);
+            const UnitigType index = (UnitigType)(2 * i);
+            f.write((const char*)&size, sizeof size);
+            f.write((const char*)(mins + offs[i]), (std::streamsize)size * sizeof(MinimizerType));
+            f.write((const char*)&index, sizeof index);
+        }
+    }
+    CreateMdbg c;
+    c._outputDir = dir;
+    c._kminmerSize = k;
+    c._nbCores = n_threads;
+    c._nbPartitions = n_threads;
+    c._mutexes.resize(1000);
+    for (size_t i = 0; i < c._mutexes.size(); i++) omp_init_lock(&c._mutexes[i]);
+    c._checksum_unitigEdges = 0;
+    c.indexUnitigEdges();
+    c._unitigGraphFile_edges_successors = ofstream(dir + "/unitigGraph.edges.successors.bin");
+    c.computeUnitigEdges();
+    c._unitigGraphFile_edges_successors.close();
+    for (size_t i = 0; i < c._mutexes.size(); i++) omp_destroy_lock(&c._mutexes[i]);
+    vector<vector<uint32_t>> lists(2 * n_unitigs);
+    ifstream ef(dir + "/unitigGraph.edges.successors.bin", std::ios::binary);
+    while (true) {
+        UnitigType from;
+        ef.read((char*)&from, sizeof from);
+        if (ef.eof()) break;
+        for (int o = 0; o < 2; o++) {
+            u_int32_t nb;
+            ef.read((char*)&nb, sizeof nb);
+            vector<uint32_t>& l = lists[(size_t)from + (size_t)o];
+            l.resize(nb);
+            if (nb) ef.read((char*)l.data(), (std::streamsize)nb * sizeof(UnitigType));
+        }
+    }
+    size_t tot = 0;
+    for (auto& l : lists) tot += l.size();
+    *eoff_out = (uint64_t*)malloc((2 * n_unitigs + 2) * 8);
+    *etgt_out = (uint32_t*)malloc((tot + 1) * 4);
+    size_t at = 0;
+    for (size_t x = 0; x < 2 * n_unitigs; x++) {
+        (*eoff_out)[x] = at;
+        memcpy(*etgt_out + at, lists[x].data(), lists[x].size() * 4);
+        at += lists[x].size();
+    }
+    (*eoff_out)[2 * n_unitigs] = at;
+    if (nb_edges) *nb_edges = c._nbUnitigEdges;
+    if (checksum) *checksum = c._checksum_unitigEdges;
+    return tot;
+}
+
 /* The reference's whole readSelection stage (ReadSelection::execute, src/readSelection/ReadSelection.hpp:92-303):
  * kseq FASTA/FASTQ parsing, HPC, sketch, complexity / quality side outputs, ordered record writer, read stats,
  * purgePalindromes.  `input_list` is the text file listing the read files (what `metaMDBG asm` writes as input.txt).

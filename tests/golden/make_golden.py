@@ -70,8 +70,9 @@ def unitig_cases(seed=77):
 
 
 def mint_unitigs(ref):
-    """7. unitig nodes: the reference's own indexEdges + computeUnitigNodes + computeDeterministicUnitigs
-    (oracle/ref_shim.cpp: ref_unitig_nodes) on the node set the reference's count gives for each case."""
+    """7. unitig nodes and unitig graph edges: the reference's own indexEdges + computeUnitigNodes +
+    computeDeterministicUnitigs (oracle/ref_shim.cpp: ref_unitig_nodes) on the node set the reference's count gives for
+    each case, then its indexUnitigEdges + computeUnitigEdges (ref_unitig_edges) on those records."""
     out = {}
     cases = unitig_cases()
     out["n_cases"] = np.array(len(cases))
@@ -81,6 +82,9 @@ def mint_unitigs(ref):
         out[f"c{i}_k"] = np.array(k); out[f"c{i}_minimizers"] = mins; out[f"c{i}_offsets"] = offs
         out[f"c{i}_nodes"] = nodes
         out[f"c{i}_unitig_offsets"] = u["offsets"]; out[f"c{i}_unitig_minimizers"] = u["minimizers"]
+        e = ref.unitig_edges(u["offsets"], u["minimizers"], k, threads=1)      # one thread: the file's list order is deterministic
+        out[f"c{i}_edge_offsets"] = e["offsets"]; out[f"c{i}_edge_targets"] = e["targets"]
+        out[f"c{i}_edge_stats"] = np.array([e["n_edges"], e["checksum"]], np.uint64)
     np.savez_compressed(os.path.join(HERE, "minspace_unitigs.npz"), **out)
 
 

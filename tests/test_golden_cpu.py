@@ -110,7 +110,7 @@ def test_unitig_nodes_golden(oracle):
     """Row F1, third step: the oracle's unitigs against unitigGraph.nodes.bin contents minted from the reference's own
     indexEdges + computeUnitigNodes + computeDeterministicUnitigs (tests/golden/make_golden.py::mint_unitigs)."""
     g = load("minspace_unitigs.npz")
-    n_multi = 0
+    n_multi = n_edges = 0
     for i in range(int(g["n_cases"])):
         k = int(g[f"c{i}_k"])
         nodes = oracle.count(g[f"c{i}_minimizers"], g[f"c{i}_offsets"], k, 2)["vecs"]
@@ -119,4 +119,8 @@ def test_unitig_nodes_golden(oracle):
         assert np.array_equal(u["offsets"], g[f"c{i}_unitig_offsets"]), i
         assert np.array_equal(u["minimizers"], g[f"c{i}_unitig_minimizers"]), i
         n_multi += int(np.any(np.diff(u["offsets"]) > k))
-    assert n_multi >= 8
+        e = oracle.unitig_edges(u["offsets"], u["minimizers"], k)           # unitigGraph.edges.successors.bin, 1-thread order
+        assert np.array_equal(e["offsets"], g[f"c{i}_edge_offsets"]) and np.array_equal(e["targets"], g[f"c{i}_edge_targets"]), i
+        assert [e["n_edges"], e["checksum"]] == [int(x) for x in g[f"c{i}_edge_stats"]]
+        n_edges += e["n_edges"]
+    assert n_multi >= 8 and n_edges > 500

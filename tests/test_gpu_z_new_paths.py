@@ -294,6 +294,16 @@ def test_cpp_driver_max_k_and_edges(tmp_path, oracle):
     assert open(d3 / "unitigGraph.nodes.bin", "rb").read() == want_bytes and len(wu["offsets"]) > 50
     assert open(d3 / "unitigGraph.nodes.abundances.bin", "rb").read() == want_ab
     assert int(words[words.index("unitigs") + 1]) == len(wu["offsets"]) - 1
+    # unitigGraph.edges.successors.bin: the records indexUnitigEdges + computeUnitigEdges write with one thread
+    we = oracle.unitig_edges(wu["offsets"], wu["minimizers"], 4)
+    want_e = b""
+    for i in range(len(wu["offsets"]) - 1):
+        want_e += np.uint32(2 * i).tobytes()
+        for o in (0, 1):
+            lst = we["targets"][int(we["offsets"][2 * i + o]):int(we["offsets"][2 * i + o + 1])]
+            want_e += np.uint32(len(lst)).tobytes() + lst.tobytes()
+    assert open(d3 / "unitigGraph.edges.successors.bin", "rb").read() == want_e and we["n_edges"] > 50
+    assert int(words[words.index("unitig_edges") + 1]) == we["n_edges"] and int(words[words.index("checksum_unitig_edges") + 1]) == we["checksum"]
     ph = np.concatenate([c["hashes"], r["hashes"]]); pa = np.concatenate([c["abundances"], np.ones(len(r["hashes"]), np.uint32)])
     for kk in (5, 6, 7):
         nk = oracle.next_k(m, mo, kk, ph, pa)

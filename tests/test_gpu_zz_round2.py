@@ -461,6 +461,10 @@ def test_unitig_nodes_vs_oracle_and_golden(built, oracle):
         assert got["n_nodes"] == len(g[f"c{i}_nodes"])
         assert np.array_equal(got["offsets"], g[f"c{i}_unitig_offsets"]), i
         assert np.array_equal(got["minimizers"], g[f"c{i}_unitig_minimizers"]), i
+        # unitig graph edges: the records of unitigGraph.edges.successors.bin as one reference thread writes them
+        assert np.array_equal(got["edge_offsets"], g[f"c{i}_edge_offsets"]), i
+        assert np.array_equal(got["edge_targets"], g[f"c{i}_edge_targets"]), i
+        assert [got["n_unitig_edges"], got["checksum_edges"]] == [int(x) for x in g[f"c{i}_edge_stats"]], i
         n_circ += got["n_circular"]
     assert n_circ >= 4
     eng.close()
@@ -493,6 +497,9 @@ def test_unitig_nodes_vs_oracle_and_golden(built, oracle):
             cs_nodes = (cs_nodes + int(seq.astype(np.uint64).sum()) * len(seq) * (2 * i)) % 2 ** 64
             cs_ab = (cs_ab + sum(a) * len(a)) % 2 ** 64
         assert np.array_equal(rec["abundances"], np.array(want_ab, np.uint32))
+        we = oracle.unitig_edges(want["offsets"], want["minimizers"], k)
+        assert np.array_equal(rec["edge_offsets"], we["offsets"]) and np.array_equal(rec["edge_targets"], we["targets"])
+        assert (rec["n_unitig_edges"], rec["checksum_edges"]) == (we["n_edges"], we["checksum"])
         assert rec["checksum_nodes"] == cs_nodes and rec["checksum_abundances"] == cs_ab
         assert int(np.sum(np.diff(got["offsets"]).astype(np.int64) - (k - 1))) >= got["n_nodes"]
 

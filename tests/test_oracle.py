@@ -446,6 +446,15 @@ def test_ref_unitig_nodes(oracle, reference):
             assert np.array_equal(a["offsets"], b["offsets"]) and np.array_equal(a["minimizers"], b["minimizers"]), (i, k, threads)
         assert len(a["offsets"]) - 1 > 0
         n_circular_like += int(i % 4 == 3)
+        # unitig graph edges: indexUnitigEdges + computeUnitigEdges for real; identical file content with one thread,
+        # identical lists up to the arrival order inside a list with four
+        e = oracle.unitig_edges(a["offsets"], a["minimizers"], k)
+        r1 = reference.unitig_edges(a["offsets"], a["minimizers"], k, threads=1)
+        assert np.array_equal(e["offsets"], r1["offsets"]) and np.array_equal(e["targets"], r1["targets"]), (i, k)
+        assert (e["n_edges"], e["checksum"]) == (r1["n_edges"], r1["checksum"])
+        r4 = reference.unitig_edges(a["offsets"], a["minimizers"], k, threads=4)
+        as_lists = lambda d: [sorted(d["targets"][int(d["offsets"][x]):int(d["offsets"][x + 1])].tolist()) for x in range(len(d["offsets"]) - 1)]
+        assert as_lists(e) == as_lists(r4) and e["checksum"] == r4["checksum"]
     reads, offs = _minspace_reads(11)
     nodes = oracle.count(reads, offs, 4, 2)["vecs"]
     a = oracle.unitigs(nodes, 4); b = reference.unitig_nodes(nodes, 4, threads=3)
