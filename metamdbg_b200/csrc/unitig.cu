@@ -567,7 +567,8 @@ __global__ void __launch_bounds__(128) unitig_edges_query_kernel(const UnitigEdg
                     if ((uint32_t)x == idx) continue;
                     target = idx ^ 1u;
                 }
-                if (pass == 2) { a.edge_targets[base + n] = target; cs += (unsigned long long)x * target; }
+                // (the reference multiplies two 32-bit UnitigType values: every product wraps at 2^32 before it is summed)
+                if (pass == 2) { a.edge_targets[base + n] = target; cs += (unsigned long long)(uint32_t)((uint32_t)x * target); }
                 n++;
             }
         }

@@ -1003,7 +1003,9 @@ size_t orc_unitig_edges(const uint32_t* mins, const uint64_t* offs, size_t n_uni
             const size_t n = ue_succ(ents, m, end, k, x, tmp);
             eoff[2 * i + (size_t)o] = tot;
             if (tot + n > cap) { cap = 2 * (tot + n); etgt = (uint32_t*)realloc(etgt, cap * sizeof(uint32_t)); }
-            for (size_t j = 0; j < n; j++) { etgt[tot++] = tmp[j]; cs += (uint64_t)x * (uint64_t)tmp[j]; }
+            /* dumpUnitigEdge: `_checksum_unitigEdges += unitigIndexFrom * unitigIndexTo` multiplies two 32-bit UnitigType
+             * values, so every product wraps at 2^32 before it is added to the 64-bit sum */
+            for (size_t j = 0; j < n; j++) { etgt[tot++] = tmp[j]; cs += (uint64_t)(uint32_t)(x * tmp[j]); }
         }
     }
     eoff[2 * n_unitigs] = tot;

@@ -455,6 +455,16 @@ def test_ref_unitig_nodes(oracle, reference):
         r4 = reference.unitig_edges(a["offsets"], a["minimizers"], k, threads=4)
         as_lists = lambda d: [sorted(d["targets"][int(d["offsets"][x]):int(d["offsets"][x + 1])].tolist()) for x in range(len(d["offsets"]) - 1)]
         assert as_lists(e) == as_lists(r4) and e["checksum"] == r4["checksum"]
+    # many unitigs with many edges between them: unitig indices beyond 2^16, so that the reference's 32-bit products in
+    # _checksum_unitigEdges wrap
+    rng = np.random.default_rng(9)
+    vecs = rng.integers(0, 40, (60000, 4)).astype(np.uint32)
+    nodes = np.unique(np.array([oracle.kminmers(v, 4)[0][0] for v in vecs], dtype=np.uint32), axis=0)
+    a = oracle.unitigs(nodes, 4); b = reference.unitig_nodes(nodes, 4, threads=4)
+    assert len(a["offsets"]) - 1 > 40000 and np.array_equal(a["offsets"], b["offsets"]) and np.array_equal(a["minimizers"], b["minimizers"])
+    e = oracle.unitig_edges(a["offsets"], a["minimizers"], 4); r1 = reference.unitig_edges(a["offsets"], a["minimizers"], 4, threads=1)
+    assert np.array_equal(e["offsets"], r1["offsets"]) and np.array_equal(e["targets"], r1["targets"]) and e["n_edges"] > 100000
+    assert e["checksum"] == r1["checksum"]
     reads, offs = _minspace_reads(11)
     nodes = oracle.count(reads, offs, 4, 2)["vecs"]
     a = oracle.unitigs(nodes, 4); b = reference.unitig_nodes(nodes, 4, threads=3)
