@@ -524,6 +524,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     if rank == 0:
         sampler.start()
     launches0 = eng.kernel_launches
+    allocs0 = eng.allocations()[0]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sketch_ms, insert_ms = [], []
     step_checksums = {stats["checksum"]} if args.warmup else set()
@@ -538,6 +539,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
     launches = eng.kernel_launches - launches0
+    allocs_timed = eng.allocations()[0] - allocs0            # steady state: the library must not allocate inside a step
     total_bases = sum_over_ranks(n_bases)
     value = total_bases * args.steps / (ms_total * 1e-3) / 1e9
     n_min_store = eng.store_size()[1]
@@ -625,7 +627,12 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         try:
             from metamdbg_b200 import multi_k_sweep
             mk_merge = "hashes" if world > 1 else False
-            sweeps = [multi_k_sweep(eng, K, args.multi_k, MIN_AB, merge=mk_merge, world=world) for _ in range(2)]   # 2nd = warm
+            sweeps, sweep_allocs = [], []
+            for _ in range(2):                                  # 2nd = warm
+                a0 = eng.allocations()
+                sweeps.append(multi_k_sweep(eng, K, args.multi_k, MIN_AB, merge=mk_merge, world=world))
+                a1 = eng.allocations()
+                sweep_allocs.append({"device_allocations": a1[0] - a0[0], "table_buffer_trades": a1[1] - a0[1]})
             per_k = [round(1e3 * max_over_ranks(r["seconds"]), 3) for r in sweeps[1]]
             total_s = sum(per_k) * 1e-3
             multi_k = {"k_first": K, "k_last": args.multi_k, "ms_per_k": per_k, "ms_total": round(sum(per_k), 3),
@@ -633,6 +640,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                        "sketch is not repeated, as in the reference)",
                        "n_entries_total": [sum_over_ranks(r["n_entries"]) for r in sweeps[1]],
                        "timer": "host wall clock per k around device work ending in a D2H of the table statistics, max over ranks",
+                       "ms_per_k_first_sweep": [round(1e3 * max_over_ranks(r["seconds"]), 3) for r in sweeps[0]],
+                       "allocations_rank0": {"first_sweep": sweep_allocs[0], "timed_sweep": sweep_allocs[1]},
                        "same_tables_both_sweeps": [r["checksum"] for r in sweeps[0]] == [r["checksum"] for r in sweeps[1]]}
             # where the loop's time goes: one more sweep with the library's phase profile on (exclusive phase times, every
             # phase boundary synchronises the stream -- a diagnostic, slower than the timed sweep above)
@@ -899,7 +908,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "higher_is_better": True, "scaling": "weak" if w["per_gpu"] else "strong", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic",
             "config": workload_config(name, args.reads, args.read_len, args.genomes, world), "e2e": e2e,
-            "gpu_launches": int(launches), "clocks": clocks,
+            "gpu_launches": int(launches), "device_allocations_in_timed_region": int(allocs_timed), "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "ms_per_launch": sk_ms, "algorithmic_bytes_per_launch": algo_bytes,

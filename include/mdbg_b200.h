@@ -120,6 +120,10 @@ mdbg_status mdbg_ctx_synchronize(mdbg_ctx* ctx);
 uint64_t    mdbg_ctx_kernel_launches(mdbg_ctx* ctx);
 /* Bytes the host-buffer entry points (sketch batches, fetches, finalize) have sent over PCIe so far. */
 mdbg_status mdbg_ctx_bytes_moved(mdbg_ctx* ctx, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
+/* Device buffers the context has (re)allocated so far (a steady-state loop must not add to it: cudaMalloc / cudaFree
+ * synchronise the device and cost milliseconds at these sizes), and how often the count table and the previous-k table
+ * traded buffers instead (see mdbg_prev_from_current). */
+mdbg_status mdbg_ctx_allocations(mdbg_ctx* ctx, uint64_t* n_device_allocations, uint64_t* n_table_buffer_trades);
 /* Per-kernel device timing (CUDA events recorded on the context's stream around
  * the launch).  which: 0 = sketch kernel (K1), 1 = k-min-mer insert kernel (K3).
  * Returns the duration of the most recent launch of that kernel in ms. */

@@ -103,6 +103,7 @@ SYMBOLS = {
     "mdbg_ctx_synchronize": (C.c_int, [C.c_void_p]),
     "mdbg_ctx_kernel_launches": (C.c_uint64, [C.c_void_p]),
     "mdbg_ctx_bytes_moved": (C.c_int, [C.c_void_p, u64p, u64p]),
+    "mdbg_ctx_allocations": (C.c_int, [C.c_void_p, u64p, u64p]),
     "mdbg_ctx_phase_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "mdbg_ctx_phase_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_char_p), C.c_int]),
     "mdbg_ctx_enable_timing": (C.c_int, [C.c_void_p, C.c_int]),

@@ -144,6 +144,8 @@ struct mdbg_ctx {
     bool t_autogrow = true;            // MDBG_TABLE_AUTOGROW=0: report MDBG_ERR_TABLE_FULL instead of rebuilding (tests)
     uint64_t t_claim_limit = 0;
     double distinct_ratio = 0.0;
+    uint64_t n_dev_allocs = 0;         // ensure(): device buffers (re)allocated so far
+    uint64_t n_table_trades = 0;       // table_reset: times the two table buffers traded places instead of a reallocation
     bool phase_prof = false;
     double phase_ms[16] = {};
     uint64_t store_gen = 0, rem_gen = ~0ull;   // s_rem (minimizers left in the read) is valid for this store generation
@@ -235,6 +237,7 @@ mdbg_status ensure(mdbg_ctx* ctx, DevBuf& b, size_t bytes, bool keep = false) {
     size_t want = bytes + bytes / 8 + 256;
     void* np = nullptr;
     CK(cudaMalloc(&np, want));
+    ctx->n_dev_allocs++;
     if (keep && b.p && b.cap) {
         CK(cudaMemcpyAsync(np, b.p, b.cap, cudaMemcpyDeviceToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
@@ -911,6 +914,13 @@ mdbg_status mdbg_ctx_bytes_moved(mdbg_ctx* ctx, uint64_t* h2d_bytes, uint64_t* d
     if (!ctx) return MDBG_ERR_ARG;
     if (h2d_bytes) *h2d_bytes = ctx->h2d_bytes;
     if (d2h_bytes) *d2h_bytes = ctx->d2h_bytes;
+    return MDBG_OK;
+}
+
+mdbg_status mdbg_ctx_allocations(mdbg_ctx* ctx, uint64_t* n_device_allocations, uint64_t* n_table_buffer_trades) {
+    if (!ctx) return MDBG_ERR_ARG;
+    if (n_device_allocations) *n_device_allocations = ctx->n_dev_allocs;
+    if (n_table_buffer_trades) *n_table_buffer_trades = ctx->n_table_trades;
     return MDBG_OK;
 }
 
@@ -2035,6 +2045,17 @@ static uint64_t table_capacity_for(uint64_t expect) {
 
 static mdbg_status table_reset(mdbg_ctx* ctx, uint64_t cap) {
     PhaseClock clk(ctx);
+    // mdbg_prev_from_current swaps the two table buffers, so a loop over k leaves the large first-pass buffer on either
+    // side.  When the current buffer is too small and the previous-k table sits in one that is large enough, its live
+    // slots move into the small one (a device copy of a few hundred MB) and the buffers trade places: no cudaMalloc /
+    // cudaFree in the loop (on the B200 boxes a reallocation of that size cost 5 - 70 ms, measured).
+    if (cap * sizeof(Slot) > ctx->table.cap && ctx->table.p && ctx->prev_table.p && ctx->prev_table.cap >= cap * sizeof(Slot) &&
+        ctx->prev_capacity * sizeof(Slot) <= ctx->table.cap) {
+        if (ctx->prev_capacity)
+            CK(cudaMemcpyAsync(ctx->table.p, ctx->prev_table.p, ctx->prev_capacity * sizeof(Slot), cudaMemcpyDeviceToDevice, ctx->stream));
+        std::swap(ctx->table, ctx->prev_table);
+        ctx->n_table_trades++;
+    }
     CKS(ensure(ctx, ctx->table, cap * sizeof(Slot)));
     CK(cudaMemsetAsync(ctx->table.p, 0, cap * sizeof(Slot), ctx->stream));
     CK(cudaMemsetAsync(&ctx->d_small->full_flag, 0, sizeof(uint32_t), ctx->stream));

@@ -111,6 +111,12 @@ class Engine:
         self._ck(self._lib.mdbg_ctx_bytes_moved(self._ctx, C.byref(a), C.byref(b)))
         return int(a.value), int(b.value)
 
+    def allocations(self) -> tuple[int, int]:
+        """(device buffers (re)allocated so far, times the two table buffers traded places instead of a reallocation)."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self._ck(self._lib.mdbg_ctx_allocations(self._ctx, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def phase_profile(self, on: bool = True):
         """Exclusive per-phase times of the table / collective paths (diagnostic: adds stream synchronisations)."""
         self._ck(self._lib.mdbg_ctx_phase_profile(self._ctx, int(on)))

@@ -442,6 +442,48 @@ def test_multi_k_run_in_the_library(built, oracle):
     eng.close()
 
 
+def test_table_buffers_trade_places_without_losing_the_previous_table(built, oracle):
+    """table_reset: when the current table's buffer is too small and the previous-k table sits in the large first-pass
+    buffer (mdbg_prev_from_current swaps the two every k), the previous table's live slots move into the small buffer
+    and the buffers trade places instead of a cudaMalloc / cudaFree pair.  The previous-k table must survive the move:
+    a next-k pass into a table far larger than needed gives the oracle's table, and so does a whole sweep right after."""
+    from metamdbg_b200 import multi_k_sweep
+    rs = synth.make_readset(1500, 8000, seed=71, n_genomes=2, genome_len_range=(150_000, 250_000), err=0.002)
+    bases, offs = synth.fill_reads(rs)
+    eng = engine()
+    eng.sketch_batch(bases, offs, append_to_store=True, fetch=False)
+    so, sm = eng.store_fetch()
+    first = multi_k_sweep(eng, 4, 7)
+    want = {}
+    prev = oracle.count(sm, so, 4, 2)
+    ph, pa = prev["hashes"], prev["abundances"]
+    for k in range(5, 8):
+        nk = oracle.next_k(sm, so, k, ph, pa)
+        ph, pa = nk["hashes"], nk["abundances"]
+        want[k] = table_dict(ph, pa)
+    eng2 = engine()
+    eng2.store_append(sm, so)
+    eng2.count_begin(4, 200_000)                     # L: a 16 MB buffer
+    eng2.count_add_store()
+    eng2.prev_from_current(2)                        # previous = k = 4 in L, no current buffer yet
+    eng2.count_begin(5, 1000)                        # S: a small buffer, grown on demand to what k = 5 needs
+    eng2.count_add_store_next_k()
+    eng2.prev_from_current(2)                        # previous = k = 5 in S, current = L
+    eng2.count_begin(6, 1000)                        # a few thousand slots of L
+    eng2.count_add_store_next_k()
+    assert eng2.count_finalize(2).as_dict() == want[6]
+    eng2.prev_from_current(2)                        # previous = k = 6 in L (a small part of it), current = S
+    allocs, trades = eng2.allocations()
+    eng2.count_begin(7, 150_000)                     # 8 MB: more than S, fits L -> k = 6 moves into S, the buffers trade places
+    assert eng2.allocations() == (allocs, trades + 1)
+    eng2.count_add_store_next_k()
+    assert eng2.count_finalize(2).as_dict() == want[7] and len(want[7]) > 300
+    eng2.close()
+    again = multi_k_sweep(eng, 4, 7)
+    assert [r["checksum"] for r in again] == [r["checksum"] for r in first]
+    eng.close()
+
+
 def test_unitig_nodes_vs_oracle_and_golden(built, oracle):
     """Row F1, third step (mdbg_unitigs_build): unitig links between oriented nodes, list ranking by pointer jumping,
     cycle cut at the smallest hash128, normalized sequences and their hash128 -- the records of unitigGraph.nodes.bin
