@@ -1082,6 +1082,7 @@ def main():
     ap.add_argument("--reads", type=int, default=0, help="reads per GPU (cfg2/cfg3) or in total (cfg4/cfg5); 0 = the workload's")
     ap.add_argument("--read-len", type=int, default=0, help="mean read length (0 = the workload's)")
     ap.add_argument("--genomes", type=int, default=100)
+    ap.add_argument("--err", type=float, default=-1.0, help="substitution rate of the synthetic reads (-1 = the workload's; experiments)")
     ap.add_argument("--chunk-reads", type=int, default=1_000_000, help="reads per resident chunk (device generation / sketch call)")
     ap.add_argument("--extras", default="auto", help="comma list of other configs to run as extras (auto: cfg3 at N=1, cfg4, cfg5 with the default headline; '' = none)")
     ap.add_argument("--extra-scale", type=float, default=1.0, help="shrink the extras' read counts (tests)")
@@ -1104,6 +1105,9 @@ def main():
     ap.add_argument("--no-ref-multi-k", action="store_true", help="reference arm: skip the multi-k extra")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    if args.err >= 0:
+        for wl in WORKLOADS.values():
+            wl["err"] = args.err
     w = WORKLOADS[args.workload]
     if args.reads <= 0:
         args.reads = w["reads"]

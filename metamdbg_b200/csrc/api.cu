@@ -163,7 +163,7 @@ struct mdbg_ctx {
     bool prev_replicated = true;       // several ranks: prev_table holds every rank's entries (false: only the owned ones)
     DevBuf foreign_vecs;
     uint64_t foreign_n = 0;
-    DevBuf prev_table, prev_stage_h, prev_stage_a, rescue_table;
+    DevBuf prev_table, prev_stage_h, prev_stage_a, rescue_table, pass_aux;
     DevBuf edge_table, edge_vals, o_edge_vals;
     PinBuf ho_edge_vals;
     uint64_t edge_cap = 0;             // slots of the device-resident edge set left by the last edges / unitigs call
@@ -862,7 +862,7 @@ void mdbg_ctx_destroy(mdbg_ctx* c) {
     DevBuf* devs[] = {&c->d_blacklist, &c->d_bases, &c->d_offsets, &c->pad_min, &c->pad_pos, &c->pad_dir, &c->n_min,
                       &c->scan_scratch, &c->b_off, &c->b_min, &c->b_pos, &c->b_dir, &c->s_min, &c->s_off, &c->s_rem,
                       &c->p_flags, &c->p_keep, &c->p_cnt, &c->p_newoff, &c->p_newmin, &c->table, &c->foreign_vecs,
-                      &c->o_hash, &c->o_abund, &c->o_vecs, &c->d_pack, &c->d_src, &c->d_dirty, &c->pg_counts, &c->pg_flags, &c->pg_keyidx, &c->pg_off, &c->pg_readof, &c->pg_hash, &c->pg_koff, &c->pg_reads, &c->pg_wins, &c->r_table, &c->r_hist, &c->r_out, &c->f_raw, &c->f_cnt, &c->f_off, &c->f_nl, &c->f_start, &c->f_len, &c->f_qstart, &c->d_quals, &c->pad_qual, &c->pad_raw_a, &c->pad_raw_b, &c->b_qual, &c->x_sum_lo, &c->x_sum_hi, &c->x_lmin, &c->x_cplx, &c->x_low, &c->d_err_fixed, &c->d_err_tz, &c->prev_table, &c->prev_stage_h, &c->prev_stage_a, &c->rescue_table, &c->val_a, &c->val_b, &c->prev_src, &c->m_send_vecs, &c->m_send_counts, &c->m_recv_vecs,
+                      &c->o_hash, &c->o_abund, &c->o_vecs, &c->d_pack, &c->d_src, &c->d_dirty, &c->pg_counts, &c->pg_flags, &c->pg_keyidx, &c->pg_off, &c->pg_readof, &c->pg_hash, &c->pg_koff, &c->pg_reads, &c->pg_wins, &c->r_table, &c->r_hist, &c->r_out, &c->f_raw, &c->f_cnt, &c->f_off, &c->f_nl, &c->f_start, &c->f_len, &c->f_qstart, &c->d_quals, &c->pad_qual, &c->pad_raw_a, &c->pad_raw_b, &c->b_qual, &c->x_sum_lo, &c->x_sum_hi, &c->x_lmin, &c->x_cplx, &c->x_low, &c->d_err_fixed, &c->d_err_tz, &c->prev_table, &c->prev_stage_h, &c->prev_stage_a, &c->rescue_table, &c->pass_aux, &c->val_a, &c->val_b, &c->prev_src, &c->m_send_vecs, &c->m_send_counts, &c->m_recv_vecs,
                       &c->m_recv_counts, &c->m_bucket, &c->loc_off, &c->edge_table, &c->edge_vals, &c->o_edge_vals,
                       &c->u_slot_node, &c->u_node_slot, &c->u_next, &c->u_pair, &c->u_len, &c->u_size, &c->u_flag, &c->u_cychead,
                       &c->u_seqoff, &c->u_idx, &c->u_cyclist, &c->u_cycpos, &c->u_best, &c->u_jump, &c->u_mins, &c->u_off, &c->u_hash,
@@ -2038,9 +2038,21 @@ mdbg_status mdbg_store_repetitive_minimizers(mdbg_ctx* ctx, float fraction, mdbg
 
 // ---- count table --------------------------------------------------------------------
 // capacity for `expect` distinct keys at load factor <= 0.6, and the claim count at which a pass gives up (0.8)
+// (any multiple of 1024 slots: the probes scale the hash to the capacity, table.cuh; MDBG_TABLE_POW2=1 restores the
+// power-of-two sizes of the earlier rounds for comparisons)
 static uint64_t table_capacity_for(uint64_t expect) {
+    static const bool pow2 = [] { const char* e = getenv("MDBG_TABLE_POW2"); return e && atoi(e) != 0; }();
     if (expect < 512) expect = 512;
-    return pow2ceil(expect + (expect * 2) / 3 + 1);
+    const uint64_t want = expect + (expect * 2) / 3 + 1;
+    return pow2 ? pow2ceil(want) : (want + 1023) & ~uint64_t(1023);
+}
+
+// claim-counter shards of the warp-form passes: one per 16 k slots, at most 64 (a shard's share of the load limit must
+// be large against the 32 claims a warp can add at once and against the imbalance between shards)
+static uint32_t pass_shards(uint64_t cap) {
+    uint32_t n = 1;
+    while (n < 64 && (uint64_t)n * 2 * 16384 <= cap) n *= 2;
+    return n;
 }
 
 static mdbg_status table_reset(mdbg_ctx* ctx, uint64_t cap) {
@@ -2060,6 +2072,8 @@ static mdbg_status table_reset(mdbg_ctx* ctx, uint64_t cap) {
     CK(cudaMemsetAsync(ctx->table.p, 0, cap * sizeof(Slot), ctx->stream));
     CK(cudaMemsetAsync(&ctx->d_small->full_flag, 0, sizeof(uint32_t), ctx->stream));
     CK(cudaMemsetAsync(&ctx->d_small->t_claims, 0, sizeof(unsigned long long), ctx->stream));
+    CKS(ensure(ctx, ctx->pass_aux, sizeof(PassAux)));
+    CK(cudaMemsetAsync(ctx->pass_aux.p, 0, sizeof(PassAux), ctx->stream));
     ctx->t_capacity = cap;
     ctx->t_claim_limit = cap - cap / 5;
     clk.lap(PH_TABLE_RESET);
@@ -2128,6 +2142,8 @@ static mdbg_status launch_pass(mdbg_ctx* ctx, uint64_t g_lo, uint64_t g_hi, bool
         a.full_flag = &ctx->d_small->full_flag;
         a.claims = &ctx->d_small->t_claims;
         a.claim_limit = ctx->t_claim_limit;
+        a.aux = ctx->pass_aux.as<PassAux>();
+        a.aux_shards = pass_shards(ctx->t_capacity);
         launch_insert(a, s);
     } else {
         NextKArgs a{};
@@ -2145,6 +2161,8 @@ static mdbg_status launch_pass(mdbg_ctx* ctx, uint64_t g_lo, uint64_t g_hi, bool
         a.claim_limit = ctx->t_claim_limit;
         a.val_in = val_in;
         a.val_out = val_out;
+        a.aux = ctx->pass_aux.as<PassAux>();
+        a.aux_shards = pass_shards(ctx->t_capacity);
         launch_next_k(a, s);
     }
     if (timed && ctx->timing) { CK(cudaEventRecord(ctx->ev[1][1], s)); ctx->ev_valid[1] = true; }

@@ -161,16 +161,24 @@ constexpr uint64_t REF_NONE = ~0ULL;             // the slot's k-min-mer vector 
 
 void launch_fill_rem(const uint64_t* offs, uint64_t read_lo, uint64_t read_hi, uint8_t* rem, cudaStream_t s);
 
+// Warp-form passes (kminmer.cu): 64 copies of the abandon flag and 64 shards of the claim counter, one 128-byte line each
+struct PassAux {
+    uint32_t flag[64][32];
+    unsigned long long claims[64][16];
+};
+
 struct InsertArgs {
     const uint32_t* mins;   // store minimizers
     const uint8_t* rem;     // min(#minimizers from g to end of its read, 255)
     uint64_t g_lo, g_hi;    // flat minimizer range
     uint32_t k;
     Slot* table;
-    uint64_t mask;          // capacity - 1 (power of two)
+    uint64_t mask;          // capacity - 1 (any capacity: slot_of() in table.cuh scales the hash to it)
     uint32_t* full_flag;    // raised when a probe sequence ran out or the table passed claim_limit distinct keys
     unsigned long long* claims;        // running number of claimed slots (= distinct keys) of the table
     unsigned long long claim_limit;
+    PassAux* aux;           // warp-form bookkeeping (nullptr: block form), zeroed with the table
+    uint32_t aux_shards;    // claim-counter shards in use: a power of two <= 64
 };
 void launch_insert(const InsertArgs& a, cudaStream_t s);
 
@@ -265,6 +273,7 @@ struct NextKArgs {
     // k-min-mer starting at g (nullptr = not wanted); val_in != nullptr selects the lookup-free form of the pass,
     // reading the previous pass's values instead of the previous-k table
     uint32_t* val_out; const uint32_t* val_in;
+    PassAux* aux; uint32_t aux_shards;  // warp-form bookkeeping, as in InsertArgs
 };
 void launch_next_k(const NextKArgs& a, cudaStream_t s);
 

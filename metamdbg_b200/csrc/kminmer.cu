@@ -41,7 +41,7 @@ __device__ __forceinline__ void cas_key(Slot* s, uint64_t new_lo, uint64_t new_h
 // claimed a fresh slot for it (callers count claims: that is the number of distinct keys, and the load factor).
 __device__ __forceinline__ int table_add(Slot* table, uint64_t mask, uint64_t lo, uint64_t hi, uint32_t add,
                                          uint64_t ref) {
-    uint64_t idx = lo & mask;
+    uint64_t idx = slot_of(lo, mask);
     const uint64_t max_probe = (mask + 1 < 4096) ? mask + 1 : 4096;
     for (uint64_t probe = 0; probe < max_probe; probe++) {
         Slot* s = table + idx;
@@ -67,7 +67,7 @@ __device__ __forceinline__ int table_add(Slot* table, uint64_t mask, uint64_t lo
                 return 1;
             }
         }
-        idx = (idx + 1) & mask;
+        idx = next_slot(idx, mask);
     }
     return 0;
 }
@@ -107,6 +107,88 @@ __device__ __forceinline__ void block_claims(BlockPass& st, int status, bool act
     }
 }
 
+// Warp-wide bookkeeping of a pass, without any block barrier (PassAux, engine.cuh).  The abandon flag exists in 64
+// copies, each in its own 128-byte line: lane 0 of every warp reads the copy of its warp index -- 1.7 M reads spread
+// over 64 addresses instead of one (a single address is served by one L2 slice at about one request per 3 cycles).  The
+// claim counter is sharded the same way; a shard that passes its share of the load limit raises every copy of the
+// flag.  pass_fold_kernel folds the shards into *claims and the flag into *full_flag after the pass, which is what
+// the host reads.  `shards` is a power of two <= 64 (1 for small tables, where a share would be a handful of slots).
+__device__ __forceinline__ uint32_t warp_abandon(const PassAux* x, uint32_t wid) {
+    uint32_t f = 0;
+    if ((threadIdx.x & 31) == 0) f = *reinterpret_cast<const volatile uint32_t*>(&x->flag[wid & 63][0]);
+    return __shfl_sync(0xffffffffu, f, 0);
+}
+__device__ __forceinline__ void warp_claims(PassAux* x, uint32_t shards, uint32_t wid, int status, bool active,
+                                            unsigned long long claim_limit) {
+    const uint32_t mc = __ballot_sync(0xffffffffu, active && status == 2);
+    const uint32_t mf = __ballot_sync(0xffffffffu, active && status == 0);
+    if ((mc | mf) == 0) return;
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t full = mf != 0;
+    if (lane == 0 && mc) {
+        const uint32_t c = (uint32_t)__popc(mc);
+        full |= atomicAdd(&x->claims[wid & (shards - 1)][0], (unsigned long long)c) + c > claim_limit / shards;
+    }
+    if (__shfl_sync(0xffffffffu, full, 0)) {
+        *reinterpret_cast<volatile uint32_t*>(&x->flag[lane][0]) = 1u;
+        *reinterpret_cast<volatile uint32_t*>(&x->flag[lane + 32][0]) = 1u;
+    }
+}
+__global__ void __launch_bounds__(64) pass_fold_kernel(PassAux* x, unsigned long long* claims, uint32_t* full_flag) {
+    unsigned long long c = x->claims[threadIdx.x][0];
+    uint32_t f = x->flag[threadIdx.x][0];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        c += __shfl_down_sync(0xffffffffu, c, d);
+        f |= __shfl_down_sync(0xffffffffu, f, d);
+    }
+    __shared__ unsigned long long sc[2];
+    __shared__ uint32_t sf[2];
+    if ((threadIdx.x & 31) == 0) { sc[threadIdx.x >> 5] = c; sf[threadIdx.x >> 5] = f; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *claims = sc[0] + sc[1];                           // the shards are cumulative over the passes into this table
+        if (sf[0] | sf[1]) *full_flag = 1u;
+    }
+}
+
+// normalized hash of the k-window starting at w
+__device__ __forceinline__ void window_hash(const uint32_t* w, int k, uint64_t& h1, uint64_t& h2, bool& rev) {
+    rev = true;
+    for (int j = 0; j < k / 2; j++) {
+        const uint32_t x = w[j], y = w[k - 1 - j];
+        if (x != y) { rev = x > y; break; }
+    }
+    // ONE copy of the hash for both orientations (element i of the normalized vector = w[first + i * step]): a warp
+    // whose lanes disagree on the orientation would otherwise run the ~90 instructions of Murmur twice
+    const int first = rev ? k - 1 : 0, step = rev ? -1 : 1;
+    murmur128_u32vec([&](int i) { return w[first + i * step]; }, k, h1, h2);
+}
+
+// The window starting at flat minimizer index g: does it exist (the read still holds k minimizers from g on --
+// getKminmers_complete: i in [0, n-k]), its orientation (KmerVec::normalize, Commons.hpp:886-916: the first differing
+// pair decides, a palindromic vector counts as reversed) and the hash128 of the normalized vector.  K_FIXED = 4: rem
+// and the four minimizers are loaded side by side (one memory latency instead of three; the store's buffers end in
+// >= 256 bytes of slack, so the three loads past a read's end stay inside the allocation) and every in-range lane hashes.
+template <int K_FIXED>
+__device__ __forceinline__ void window_key(const uint32_t* mins, const uint8_t* rem, uint64_t g, uint64_t g_hi, int k,
+                                           bool& active, bool& rev, uint64_t& h1, uint64_t& h2) {
+    active = false;
+    if (g >= g_hi) return;
+    if (K_FIXED == 4) {
+        const uint32_t r = rem[g];
+        const uint32_t* w = mins + g;
+        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+        active = r >= 4;
+        rev = w0 != w3 ? w0 > w3 : (w1 != w2 ? w1 > w2 : true);
+        const uint32_t x[4] = {rev ? w3 : w0, rev ? w2 : w1, rev ? w1 : w2, rev ? w0 : w3};
+        murmur128_u32vec([&](int i) { return x[i]; }, 4, h1, h2);
+    } else {
+        active = (int)rem[g] >= k;
+        if (active) window_hash(mins + g, k, h1, h2, rev);
+    }
+}
+
 // ------------------------------------------------------------------ rem[] = minimizers left in the read
 __global__ void __launch_bounds__(256) fill_rem_kernel(const uint64_t* offs, uint64_t read_lo, uint64_t read_hi,
                                                        uint8_t* rem) {
@@ -138,32 +220,52 @@ __global__ void __launch_bounds__(256) insert_kernel(const InsertArgs a) {
     block_begin(st, a.full_flag);
     const uint64_t g = a.g_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int k = K_FIXED ? K_FIXED : (int)a.k;
-    const bool active = g < a.g_hi && (int)a.rem[g] >= k;
-    int status = 1;
+    bool active = false, rev = true;
     uint64_t h1 = 0, h2 = 0;
-    bool rev = true;
-    if (active) {
-        const uint32_t* w = a.mins + g;
-        // KmerVec::normalize (Commons.hpp:886-916): first differing pair decides,
-        // a palindromic vector counts as reversed.
-        for (int j = 0; j < k / 2; j++) {
-            const uint32_t x = w[j], y = w[k - 1 - j];
-            if (x != y) { rev = x > y; break; }
-        }
-        if (rev) murmur128_u32vec([&](int i) { return w[k - 1 - i]; }, k, h1, h2);
-        else murmur128_u32vec([&](int i) { return w[i]; }, k, h1, h2);
-    }
+    window_key<K_FIXED>(a.mins, a.rem, g, a.g_hi, k, active, rev, h1, h2);
+    int status = 1;
     const bool go = block_ready(st);                                         // false: the pass is being abandoned
     if (go && active) status = table_add(a.table, a.mask, h2, h1, 1u, g | (rev ? REF_REV : 0ULL));
     block_claims(st, status, go && active, a.claims, a.claim_limit, a.full_flag);
 }
 
+// The same pass without a block barrier (see PassAux): a warp is done as soon as its own 32 probes are.
+template <int K_FIXED>
+__global__ void __launch_bounds__(128) insert_warp_kernel(const InsertArgs a) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t wid = (uint32_t)(t >> 5);
+    const uint32_t abandon = warp_abandon(a.aux, wid);                        // (in flight behind the loads below)
+    const uint64_t g = a.g_lo + t;
+    const int k = K_FIXED ? K_FIXED : (int)a.k;
+    bool active = false, rev = true;
+    uint64_t h1 = 0, h2 = 0;
+    window_key<K_FIXED>(a.mins, a.rem, g, a.g_hi, k, active, rev, h1, h2);
+    int status = 1;
+    const bool go = abandon == 0;
+    if (go && active) status = table_add(a.table, a.mask, h2, h1, 1u, g | (rev ? REF_REV : 0ULL));
+    warp_claims(a.aux, a.aux_shards, wid, status, go && active, a.claim_limit);
+}
+
+// PASS_VARIANT (MDBG_PASS_VARIANT, default 1): 0 = block form (one abandon-flag read and two barriers per 256 windows),
+// 1 = warp form (no barrier; abandon flag replicated, claim counter sharded -- PassAux)
+static int pass_variant() {
+    static const int v = [] { const char* e = getenv("MDBG_PASS_VARIANT"); return e ? atoi(e) : 1; }();
+    return v;
+}
+
 void launch_insert(const InsertArgs& a, cudaStream_t s) {
     if (a.g_hi <= a.g_lo) return;
     const uint64_t n = a.g_hi - a.g_lo;
-    const unsigned blocks = (unsigned)((n + 255) / 256);
-    if (a.k == 4) insert_kernel<4><<<blocks, 256, 0, s>>>(a);
-    else insert_kernel<0><<<blocks, 256, 0, s>>>(a);
+    if (pass_variant() == 0 || !a.aux) {
+        const unsigned blocks = (unsigned)((n + 255) / 256);
+        if (a.k == 4) insert_kernel<4><<<blocks, 256, 0, s>>>(a);
+        else insert_kernel<0><<<blocks, 256, 0, s>>>(a);
+    } else {
+        const unsigned blocks = (unsigned)((n + 127) / 128);
+        if (a.k == 4) insert_warp_kernel<4><<<blocks, 128, 0, s>>>(a);
+        else insert_warp_kernel<0><<<blocks, 128, 0, s>>>(a);
+        pass_fold_kernel<<<1, 64, 0, s>>>(a.aux, a.claims, a.full_flag);
+    }
 }
 
 // Insert-if-absent with a VALUE (next-k tables: the abundance is a function of the key -- min over the two
@@ -171,7 +273,7 @@ void launch_insert(const InsertArgs& a, cudaStream_t s) {
 // and the first writer wins).
 __device__ __forceinline__ int table_put(Slot* table, uint64_t mask, uint64_t lo, uint64_t hi, uint32_t value,
                                          uint64_t ref) {
-    uint64_t idx = lo & mask;
+    uint64_t idx = slot_of(lo, mask);
     const uint64_t max_probe = (mask + 1 < 4096) ? mask + 1 : 4096;
     for (uint64_t probe = 0; probe < max_probe; probe++) {
         Slot* s = table + idx;
@@ -188,7 +290,7 @@ __device__ __forceinline__ int table_put(Slot* table, uint64_t mask, uint64_t lo
             }
             if (olo == lo && ohi == hi) return 1;
         }
-        idx = (idx + 1) & mask;
+        idx = next_slot(idx, mask);
     }
     return 0;
 }
@@ -299,17 +401,6 @@ void launch_table_emit(const EmitArgs& a, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------ lookups, rescue, next-k
-// normalized hash of the k-window starting at w
-__device__ __forceinline__ void window_hash(const uint32_t* w, int k, uint64_t& h1, uint64_t& h2, bool& rev) {
-    rev = true;
-    for (int j = 0; j < k / 2; j++) {
-        const uint32_t x = w[j], y = w[k - 1 - j];
-        if (x != y) { rev = x > y; break; }
-    }
-    if (rev) murmur128_u32vec([&](int i) { return w[k - 1 - i]; }, k, h1, h2);
-    else murmur128_u32vec([&](int i) { return w[i]; }, k, h1, h2);
-}
-
 // RescueKminmerFunctor (CreateMdbg.hpp:4579-4637), one warp per read.  The decision only needs
 // "median * 0.1f > 1", which is unchanged when abundances are clamped at 22, so the median comes from a
 // 22-bin histogram held one bin per lane (Utils::compute_median, Commons.hpp:2973-2988).
@@ -439,7 +530,7 @@ void launch_rescue_flag(const uint32_t* vecs, uint64_t n, uint32_t k, Slot* tabl
 
 // insert-or-assign into the previous-k lookup table (value in `count`)
 __device__ __forceinline__ bool prev_put(Slot* table, uint64_t mask, uint64_t lo, uint64_t hi, uint32_t value) {
-    uint64_t idx = lo & mask;
+    uint64_t idx = slot_of(lo, mask);
     for (uint64_t probe = 0; probe <= mask && probe < 4096; probe++) {
         Slot* s = table + idx;
         uint64_t clo, chi;
@@ -452,7 +543,7 @@ __device__ __forceinline__ bool prev_put(Slot* table, uint64_t mask, uint64_t lo
             cas_key(s, lo, hi, olo, ohi);
             if ((olo == 0 && ohi == 0) || (olo == lo && ohi == hi)) { s->count = value; s->flags = SLOT_RESCUED; return true; }
         }
-        idx = (idx + 1) & mask;
+        idx = next_slot(idx, mask);
     }
     return false;
 }
@@ -493,11 +584,15 @@ void launch_prev_load(const PrevLoadArgs& a, cudaStream_t s) {
 // positions, so every lookup but one per warp is used twice -- half the hashes and random reads of one thread per
 // window.  prev_min_count filters the previous table at lookup time (an entry below it that is not rescued counts
 // as absent), which lets the previous-k table BE the table of the previous pass, unfiltered and uncopied.
-__global__ void __launch_bounds__(256) next_k_kernel(const NextKArgs a) {
+// WARP: bookkeeping per warp instead of per block (no barrier; PassAux) -- see insert_warp_kernel
+template <bool WARP>
+__global__ void __launch_bounds__(WARP ? 128 : 256) next_k_kernel(const NextKArgs a) {
     __shared__ BlockPass st;
-    block_begin(st, a.full_flag);
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t abandon = 0;
+    if (WARP) abandon = warp_abandon(a.aux, (uint32_t)warp);
+    else block_begin(st, a.full_flag);
     const uint64_t g = a.g_lo + warp * 31 + lane;
     const int k = (int)a.k;
     const uint32_t rem = g < a.g_hi ? (uint32_t)a.rem[g] : 0u;
@@ -514,7 +609,7 @@ __global__ void __launch_bounds__(256) next_k_kernel(const NextKArgs a) {
     const bool active = lane < 31 && (int)rem >= k;              // (rem >= k implies the next position has rem >= k - 1)
     int status = 1;
     uint32_t out = 1;
-    const bool go = block_ready(st);                             // false: the pass is being abandoned (it is redone as a whole)
+    const bool go = WARP ? abandon == 0 : block_ready(st);       // false: the pass is being abandoned (it is redone as a whole)
     if (active) {
         const uint32_t ab = v < v_next ? v : v_next;
         if (ab > 1) {
@@ -529,7 +624,8 @@ __global__ void __launch_bounds__(256) next_k_kernel(const NextKArgs a) {
     }
     // value of the k-min-mer starting at g, as the NEXT pass would look it up (absent => 1): see next_k_stream_kernel
     if (a.val_out && lane < 31 && g < a.g_hi) a.val_out[g] = out;
-    block_claims(st, status, go && active, a.claims, a.claim_limit, a.full_flag);
+    if (WARP) warp_claims(a.aux, a.aux_shards, (uint32_t)warp, status, go && active, a.claim_limit);
+    else block_claims(st, status, go && active, a.claims, a.claim_limit, a.full_flag);
 }
 
 // The same pass without a single lookup.  The value a pass stores for a k-min-mer is a function of the key, and
@@ -538,10 +634,14 @@ __global__ void __launch_bounds__(256) next_k_kernel(const NextKArgs a) {
 // previous-k table is nothing but the previous pass's table (no host patches, same store), pass k + 1 therefore
 // reads val[g] and val[g + 1] -- two coalesced loads -- instead of hashing and probing two (k)-min-mers; the only
 // random access left per window is the insert into the new table.  Identical tables, by induction on k.
-__global__ void __launch_bounds__(256) next_k_stream_kernel(const NextKArgs a) {
+template <bool WARP>
+__global__ void __launch_bounds__(WARP ? 128 : 256) next_k_stream_kernel(const NextKArgs a) {
     __shared__ BlockPass st;
-    block_begin(st, a.full_flag);
-    const uint64_t g = a.g_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t abandon = 0;
+    if (WARP) abandon = warp_abandon(a.aux, (uint32_t)(t >> 5));
+    else block_begin(st, a.full_flag);
+    const uint64_t g = a.g_lo + t;
     const int k = (int)a.k;
     const bool in_range = g < a.g_hi;
     const bool active = in_range && (int)a.rem[g] >= k;
@@ -559,19 +659,25 @@ __global__ void __launch_bounds__(256) next_k_stream_kernel(const NextKArgs a) {
         }
     }
     if (in_range) a.val_out[g] = out;
-    const bool go = block_ready(st);                             // false: the pass is being abandoned (it is redone as a whole)
+    const bool go = WARP ? abandon == 0 : block_ready(st);       // false: the pass is being abandoned (it is redone as a whole)
     if (go && put) status = table_put(a.table, a.mask, h2, h1, out, g | (rev ? REF_REV : 0ULL));
-    block_claims(st, status, go && active, a.claims, a.claim_limit, a.full_flag);
+    if (WARP) warp_claims(a.aux, a.aux_shards, (uint32_t)(t >> 5), status, go && active, a.claim_limit);
+    else block_claims(st, status, go && active, a.claims, a.claim_limit, a.full_flag);
 }
 
 void launch_next_k(const NextKArgs& a, cudaStream_t s) {
     if (a.g_hi <= a.g_lo) return;
+    const bool warp_form = pass_variant() != 0 && a.aux;
+    const uint64_t n = a.g_hi - a.g_lo;
     if (a.val_in) {
-        next_k_stream_kernel<<<(unsigned)((a.g_hi - a.g_lo + 255) / 256), 256, 0, s>>>(a);
-        return;
+        if (warp_form) next_k_stream_kernel<true><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(a);
+        else next_k_stream_kernel<false><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a);
+    } else {
+        const uint64_t n_warps = (n + 30) / 31;
+        if (warp_form) next_k_kernel<true><<<(unsigned)((n_warps + 3) / 4), 128, 0, s>>>(a);
+        else next_k_kernel<false><<<(unsigned)((n_warps + 7) / 8), 256, 0, s>>>(a);
     }
-    const uint64_t n_warps = (a.g_hi - a.g_lo + 30) / 31;
-    next_k_kernel<<<(unsigned)((n_warps + 7) / 8), 256, 0, s>>>(a);
+    if (warp_form) pass_fold_kernel<<<1, 64, 0, s>>>(a.aux, a.claims, a.full_flag);
 }
 
 // ------------------------------------------------------------------ edge keys of the node set (row F1)
