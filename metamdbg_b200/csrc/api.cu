@@ -1895,14 +1895,15 @@ mdbg_status mdbg_purge_palindromes(mdbg_ctx* ctx, uint32_t first_k, uint32_t las
     CK(cudaStreamSynchronize(s));
     const uint64_t new_total = ctx->h_scalar[2];
     CKS(ensure(ctx, ctx->p_newmin, (new_total + 1) * 4));
+    CKS(ensure(ctx, ctx->s_rem, ctx->s_mins + 1));                 // (sized for the old store: the new one is smaller)
     launch_purge_compact(ctx->s_min.as<uint32_t>(), ctx->s_off.as<uint64_t>(), ctx->p_newoff.as<uint64_t>(),
-                         ctx->p_keep.as<uint8_t>(), ctx->s_reads, ctx->p_newmin.as<uint32_t>(), s);
+                         ctx->p_keep.as<uint8_t>(), ctx->s_reads, ctx->p_newmin.as<uint32_t>(), s, ctx->s_rem.as<uint8_t>());
     CKS(check_launch(ctx, "purge_compact_kernel", 1));
-    CK(cudaStreamSynchronize(s));
-    std::swap(ctx->s_min, ctx->p_newmin);
+    std::swap(ctx->s_min, ctx->p_newmin);                          // (everything that follows is ordered on the same stream)
     std::swap(ctx->s_off, ctx->p_newoff);
     ctx->s_mins = new_total;
     store_rewritten(ctx);
+    ctx->rem_gen = ctx->store_gen;                                 // rem[] of the new store came out of the compaction
     return MDBG_OK;
 }
 
@@ -1935,14 +1936,15 @@ mdbg_status mdbg_store_apply_density(mdbg_ctx* ctx, float density, uint64_t* n_r
     CK(cudaStreamSynchronize(s));
     const uint64_t new_total = ctx->h_scalar[2];
     CKS(ensure(ctx, ctx->p_newmin, (new_total + 1) * 4));
+    CKS(ensure(ctx, ctx->s_rem, ctx->s_mins + 1));                 // (sized for the old store: the new one is smaller)
     launch_purge_compact(ctx->s_min.as<uint32_t>(), ctx->s_off.as<uint64_t>(), ctx->p_newoff.as<uint64_t>(),
-                         ctx->p_keep.as<uint8_t>(), ctx->s_reads, ctx->p_newmin.as<uint32_t>(), s);
+                         ctx->p_keep.as<uint8_t>(), ctx->s_reads, ctx->p_newmin.as<uint32_t>(), s, ctx->s_rem.as<uint8_t>());
     CKS(check_launch(ctx, "purge_compact_kernel", 1));
-    CK(cudaStreamSynchronize(s));
-    std::swap(ctx->s_min, ctx->p_newmin);
+    std::swap(ctx->s_min, ctx->p_newmin);                          // (everything that follows is ordered on the same stream)
     std::swap(ctx->s_off, ctx->p_newoff);
     ctx->s_mins = new_total;
     store_rewritten(ctx);
+    ctx->rem_gen = ctx->store_gen;                                 // rem[] of the new store came out of the compaction
     return MDBG_OK;
 }
 

@@ -141,8 +141,9 @@ void launch_purge_exact(const uint32_t* mins, const uint64_t* offs, uint64_t n_r
 void launch_density_filter(const uint32_t* mins, const uint64_t* offs, uint64_t n_reads, uint64_t threshold,
                            uint32_t select_none, uint8_t* keep, uint32_t* new_cnt, unsigned long long* n_changed,
                            cudaStream_t s);
+// out_rem (optional): rem[] of the compacted store (launch_fill_rem's output) as a by-product
 void launch_purge_compact(const uint32_t* mins, const uint64_t* offs, const uint64_t* new_offs, const uint8_t* keep,
-                          uint64_t n_reads, uint32_t* out_mins, cudaStream_t s);
+                          uint64_t n_reads, uint32_t* out_mins, cudaStream_t s, uint8_t* out_rem = nullptr);
 
 // ------------------------------------------------------------------ k-min-mer table
 struct __align__(32) Slot {

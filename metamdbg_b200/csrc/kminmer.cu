@@ -190,23 +190,38 @@ __device__ __forceinline__ void window_key(const uint32_t* mins, const uint8_t* 
 }
 
 // ------------------------------------------------------------------ rem[] = minimizers left in the read
-__global__ void __launch_bounds__(256) fill_rem_kernel(const uint64_t* offs, uint64_t read_lo, uint64_t read_hi,
-                                                       uint8_t* rem) {
+__global__ void __launch_bounds__(256) fill_rem_kernel(const uint64_t* __restrict__ offs, uint64_t read_lo, uint64_t read_hi,
+                                                       uint8_t* __restrict__ rem) {
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    for (uint64_t r = read_lo + warp; r < read_hi; r += n_warps) {
-        const uint64_t b = offs[r], e = offs[r + 1];
-        for (uint64_t g = b + lane; g < e; g += 32) {
-            const uint64_t left = e - g;
-            rem[g] = (uint8_t)(left > 255 ? 255 : left);
+    // 32 reads per warp and step: lane j loads the bounds of read r0 + j, then all lanes sweep the (contiguous) positions
+    // of those reads; a position finds the end of its read among the 32 ends by a binary search over shuffles
+    for (uint64_t r0 = read_lo + warp * 32; r0 < read_hi; r0 += n_warps * 32) {
+        const uint64_t rm = r0 + lane;
+        const uint64_t last = read_hi - r0 < 32 ? read_hi - r0 : 32;        // reads in this batch
+        const uint64_t e_m = offs[(rm < read_hi ? rm : read_hi - 1) + 1];      // lanes past the batch repeat the last end
+        const uint64_t b0 = offs[r0], e_last = __shfl_sync(0xffffffffu, e_m, (int)last - 1);
+        for (uint64_t g0 = b0; g0 < e_last; g0 += 32) {                        // (uniform trip count: shuffles inside)
+            const uint64_t g = g0 + lane;
+            int lo = 0;                                                        // first read of the batch whose end is > g
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const uint64_t e_probe = __shfl_sync(0xffffffffu, e_m, lo + step - 1);
+                if (e_probe <= g) lo += step;
+            }
+            const uint64_t e = __shfl_sync(0xffffffffu, e_m, lo > 31 ? 31 : lo);
+            if (g < e_last) {
+                const uint64_t left = e - g;
+                rem[g] = (uint8_t)(left > 255 ? 255 : left);
+            }
         }
     }
 }
 
 void launch_fill_rem(const uint64_t* offs, uint64_t read_lo, uint64_t read_hi, uint8_t* rem, cudaStream_t s) {
     if (read_hi <= read_lo) return;
-    uint64_t blocks = (read_hi - read_lo + 7) / 8;
+    uint64_t blocks = (read_hi - read_lo + 255) / 256;       // 32 reads per warp, 8 warps per block
     if (blocks > 148 * 16) blocks = 148 * 16;
     fill_rem_kernel<<<(unsigned)blocks, 256, 0, s>>>(offs, read_lo, read_hi, rem);
 }

@@ -20,35 +20,60 @@ __device__ __forceinline__ bool window_is_palindrome(const uint32_t* w, uint32_t
     return true;
 }
 
+// purge_flag_kernel takes 32 consecutive reads per warp at a time: lane j loads the bounds of read r0 + j (one coalesced
+// request), the warp walks the 32 reads with shuffles and votes once per batch -- a dependent pair of offset loads and
+// a warp vote per read made the first version a chain of memory latencies (0.26 ms for 1 M reads, now 0.15).  The
+// kernels that MOVE data per read (sketch.cu's compact_kernel, purge_compact_kernel) gain nothing from that form
+// (measured): they run at DRAM speed.
+//
 // A palindromic window of size k+2 contains the palindromic window of size k
 // with the same centre, and the reference scans k in ascending order
 // (Commons.hpp:1631), so the first window it ever bans has size first_k or
 // first_k+1.  A read is untouched iff it holds no palindrome of those two sizes.
-__global__ void __launch_bounds__(256) purge_flag_kernel(const uint32_t* mins, const uint64_t* offs, uint64_t n_reads,
-                                                         uint32_t first_k, uint32_t last_k, uint8_t* flags,
-                                                         unsigned long long* n_flagged) {
+__global__ void __launch_bounds__(256) purge_flag_kernel(const uint32_t* __restrict__ mins, const uint64_t* __restrict__ offs,
+                                                         uint64_t n_reads, uint32_t first_k, uint32_t last_k,
+                                                         uint8_t* __restrict__ flags, unsigned long long* n_flagged) {
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    for (uint64_t r = warp; r < n_reads; r += n_warps) {
-        const uint64_t b = offs[r], e = offs[r + 1];
-        bool hit = false;
-        for (uint64_t g = b + lane; g < e; g += 32) {
-            for (uint32_t k = first_k; k < last_k && k < first_k + 2; k++)
-                if (g + k <= e && window_is_palindrome(mins + g, k)) hit = true;
+    const bool two = first_k + 1 < last_k;               // sizes tested: first_k, and first_k + 1 when below last_k
+    for (uint64_t r0 = warp * 32; r0 < n_reads; r0 += n_warps * 32) {
+        const uint64_t rm = r0 + lane;
+        uint64_t b_m = 0, e_m = 0;
+        if (rm < n_reads) { b_m = offs[rm]; e_m = offs[rm + 1]; }
+        const int cnt = n_reads - r0 < 32 ? (int)(n_reads - r0) : 32;
+        uint32_t hits = 0;                               // bit j: this lane saw a palindrome in read r0 + j
+        if (first_k == 4) {
+#pragma unroll 2
+            for (int j = 0; j < cnt; j++) {
+                const uint64_t b = __shfl_sync(0xffffffffu, b_m, j), e = __shfl_sync(0xffffffffu, e_m, j);
+                for (uint64_t g = b + lane; g + 4 <= e; g += 32) {
+                    const bool five = two && g + 5 <= e;
+                    const uint32_t w0 = mins[g], w1 = mins[g + 1], w2 = mins[g + 2], w3 = mins[g + 3];
+                    const uint32_t w4 = five ? mins[g + 4] : 0u;
+                    const bool hit = (w0 == w3 && w1 == w2) || (five && w0 == w4 && w1 == w3);
+                    hits |= (hit ? 1u : 0u) << j;
+                }
+            }
+        } else {
+            for (int j = 0; j < cnt; j++) {
+                const uint64_t b = __shfl_sync(0xffffffffu, b_m, j), e = __shfl_sync(0xffffffffu, e_m, j);
+                for (uint64_t g = b + lane; g < e; g += 32)
+                    for (uint32_t k = first_k; k < last_k && k < first_k + 2; k++)
+                        if (g + k <= e && window_is_palindrome(mins + g, k)) hits |= 1u << j;
+            }
         }
-        hit = __any_sync(0xffffffffu, hit);
-        if (lane == 0) {
-            flags[r] = hit ? 1 : 0;
-            if (hit) atomicAdd(n_flagged, 1ULL);
-        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) hits |= __shfl_xor_sync(0xffffffffu, hits, d);
+        if (rm < n_reads) flags[rm] = (uint8_t)((hits >> lane) & 1u);
+        if (lane == 0 && hits) atomicAdd(n_flagged, (unsigned long long)__popc(hits));
     }
 }
 
 void launch_purge_flag(const uint32_t* mins, const uint64_t* offs, uint64_t n_reads, uint32_t first_k, uint32_t last_k,
                        uint8_t* flags, unsigned long long* n_flagged, cudaStream_t s) {
     if (n_reads == 0) return;
-    uint64_t blocks = (n_reads + 7) / 8;
+    uint64_t blocks = (n_reads + 255) / 256;                 // 32 reads per warp, 8 warps per block
     if (blocks > 148 * 16) blocks = 148 * 16;
     purge_flag_kernel<<<(unsigned)blocks, 256, 0, s>>>(mins, offs, n_reads, first_k, last_k, flags, n_flagged);
 }
@@ -150,31 +175,39 @@ void launch_density_filter(const uint32_t* mins, const uint64_t* offs, uint64_t 
                                                            n_changed);
 }
 
-__global__ void __launch_bounds__(256) purge_compact_kernel(const uint32_t* mins, const uint64_t* offs,
-                                                            const uint64_t* new_offs, const uint8_t* keep,
-                                                            uint64_t n_reads, uint32_t* out_mins) {
+// out_rem (optional): rem[] of the NEW store (min(#minimizers from a position to the end of its read, 255); see
+// fill_rem_kernel in kminmer.cu) as a by-product -- the table passes then need no pass of their own over the offsets.
+__global__ void __launch_bounds__(256) purge_compact_kernel(const uint32_t* __restrict__ mins, const uint64_t* __restrict__ offs,
+                                                            const uint64_t* __restrict__ new_offs,
+                                                            const uint8_t* __restrict__ keep, uint64_t n_reads,
+                                                            uint32_t* __restrict__ out_mins, uint8_t* __restrict__ out_rem) {
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     for (uint64_t r = warp; r < n_reads; r += n_warps) {
         const uint64_t b = offs[r], e = offs[r + 1];
         uint64_t dst = new_offs[r];
+        const uint64_t dst_end = new_offs[r + 1];
         for (uint64_t g0 = b; g0 < e; g0 += 32) {
             const uint64_t g = g0 + lane;
             const bool k = (g < e) && keep[g];
             const uint32_t mk = __ballot_sync(0xffffffffu, k);
-            if (k) out_mins[dst + __popc(mk & ((1u << lane) - 1u))] = mins[g];
+            if (k) {
+                const uint64_t o = dst + __popc(mk & ((1u << lane) - 1u));
+                out_mins[o] = mins[g];
+                if (out_rem) { const uint64_t left = dst_end - o; out_rem[o] = (uint8_t)(left > 255 ? 255 : left); }
+            }
             dst += __popc(mk);
         }
     }
 }
 
 void launch_purge_compact(const uint32_t* mins, const uint64_t* offs, const uint64_t* new_offs, const uint8_t* keep,
-                          uint64_t n_reads, uint32_t* out_mins, cudaStream_t s) {
+                          uint64_t n_reads, uint32_t* out_mins, cudaStream_t s, uint8_t* out_rem) {
     if (n_reads == 0) return;
     uint64_t blocks = (n_reads + 7) / 8;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    purge_compact_kernel<<<(unsigned)blocks, 256, 0, s>>>(mins, offs, new_offs, keep, n_reads, out_mins);
+    purge_compact_kernel<<<(unsigned)blocks, 256, 0, s>>>(mins, offs, new_offs, keep, n_reads, out_mins, out_rem);
 }
 
 // ------------------------------------------------------------------ synthetic reads (metamdbg_b200/synth.py)

@@ -123,7 +123,18 @@ static Store compact_with(const Store& s, const std::vector<uint8_t>& keep, cons
     out.offs.assign(s.n() + 1, 0);
     for (uint64_t r = 0; r < s.n(); r++) out.offs[r + 1] = out.offs[r] + cnt[r];
     out.mins.assign(out.offs[s.n()] + 300, 0xDEADBEEFu);
-    launch_purge_compact(s.mins.data(), s.offs.data(), out.offs.data(), keep.data(), s.n(), out.mins.data(), nullptr);
+    // rem[] of the compacted store comes out of the compaction as a by-product: it must equal fill_rem's on the new store
+    std::vector<uint8_t> rem_by(out.mins.size() + 1, 0xEE), rem_fill(out.mins.size() + 1, 0xEE);
+    launch_purge_compact(s.mins.data(), s.offs.data(), out.offs.data(), keep.data(), s.n(), out.mins.data(), nullptr, rem_by.data());
+    launch_fill_rem(out.offs.data(), 0, s.n(), rem_fill.data(), nullptr);
+    for (uint64_t g = 0; g < out.offs[s.n()]; g++) {
+        uint64_t r = 0;
+        while (out.offs[r + 1] <= g) r++;
+        const uint64_t left = out.offs[r + 1] - g;
+        CHECK(rem_fill[g] == (uint8_t)(left > 255 ? 255 : left), "fill_rem[%llu]", (unsigned long long)g);
+        CHECK(rem_by[g] == rem_fill[g], "rem by-product[%llu]", (unsigned long long)g);
+    }
+    for (uint64_t g = out.offs[s.n()]; g < rem_by.size(); g++) CHECK(rem_by[g] == 0xEE && rem_fill[g] == 0xEE, "rem written past the store end at %llu", (unsigned long long)g);
     return out;
 }
 
