@@ -238,6 +238,10 @@ mdbg_status ensure(mdbg_ctx* ctx, DevBuf& b, size_t bytes, bool keep = false) {
     void* np = nullptr;
     CK(cudaMalloc(&np, want));
     ctx->n_dev_allocs++;
+    static const bool trace = getenv("MDBG_TRACE_ALLOC") != nullptr;        // which buffer grew (offset inside the context)
+    if (trace)
+        fprintf(stderr, "[mdbg alloc] ctx %p buffer +%zu: %zu -> %zu bytes\n", (void*)ctx,
+                (size_t)(reinterpret_cast<char*>(&b) - reinterpret_cast<char*>(ctx)), b.cap, want);
     if (keep && b.p && b.cap) {
         CK(cudaMemcpyAsync(np, b.p, b.cap, cudaMemcpyDeviceToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
@@ -2049,6 +2053,22 @@ static uint64_t table_capacity_for(uint64_t expect) {
     return pow2 ? pow2ceil(want) : (want + 1023) & ~uint64_t(1023);
 }
 
+// The count table and the previous-k table swap buffers with every k of a loop (mdbg_prev_from_current), so each of
+// the two buffers has to hold the largest table of the loop sooner or later: a buffer of the pair is never allocated
+// smaller than its sibling, and a loop stops allocating after its first pass instead of after two sweeps (a
+// cudaMalloc / cudaFree pair of this size costs 5 - 10 ms on the B200 boxes, more than two next-k passes).
+static mdbg_status ensure_table_buf(mdbg_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap && b.p) return MDBG_OK;
+    // (with several ranks a third buffer, prev_src, rotates with the two: mdbg_count_add_store_next_k's lazy replication)
+    size_t sib_cap = 0;
+    for (const DevBuf* o : {&ctx->table, &ctx->prev_table, &ctx->prev_src})
+        if (o != &b && o->cap > sib_cap) sib_cap = o->cap;
+    const size_t with_slack = bytes + bytes / 8;
+    // ensure() adds its own slack of bytes / 8 + 256: ask for what makes the result at least the largest sibling's size
+    const size_t sib_payload = sib_cap > 256 ? (sib_cap - 256) - (sib_cap - 256) / 9 + 16 : 0;
+    return ensure(ctx, b, with_slack > sib_payload ? bytes : sib_payload);
+}
+
 // claim-counter shards of the warp-form passes: one per 16 k slots, at most 64 (a shard's share of the load limit must
 // be large against the 32 claims a warp can add at once and against the imbalance between shards)
 static uint32_t pass_shards(uint64_t cap) {
@@ -2070,7 +2090,7 @@ static mdbg_status table_reset(mdbg_ctx* ctx, uint64_t cap) {
         std::swap(ctx->table, ctx->prev_table);
         ctx->n_table_trades++;
     }
-    CKS(ensure(ctx, ctx->table, cap * sizeof(Slot)));
+    CKS(ensure_table_buf(ctx, ctx->table, cap * sizeof(Slot)));
     CK(cudaMemsetAsync(ctx->table.p, 0, cap * sizeof(Slot), ctx->stream));
     CK(cudaMemsetAsync(&ctx->d_small->full_flag, 0, sizeof(uint32_t), ctx->stream));
     CK(cudaMemsetAsync(&ctx->d_small->t_claims, 0, sizeof(unsigned long long), ctx->stream));
@@ -2490,7 +2510,7 @@ mdbg_status mdbg_count_rescue(mdbg_ctx* ctx, uint64_t* n_reads_rescued) {
 static mdbg_status prev_alloc(mdbg_ctx* ctx, uint64_t expect) {
     if (expect < 512) expect = 512;
     const uint64_t cap = pow2ceil(expect * 2);
-    CKS(ensure(ctx, ctx->prev_table, cap * sizeof(Slot)));
+    CKS(ensure_table_buf(ctx, ctx->prev_table, cap * sizeof(Slot)));
     CK(cudaMemsetAsync(ctx->prev_table.p, 0, cap * sizeof(Slot), ctx->stream));
     CK(cudaMemsetAsync(&ctx->d_small->full_flag, 0, sizeof(uint32_t), ctx->stream));
     ctx->prev_capacity = cap;
@@ -3251,7 +3271,7 @@ mdbg_status mdbg_count_merge(mdbg_ctx* ctx) {
     const uint64_t cap = table_capacity_for(recv_total);
     std::swap(ctx->foreign_vecs, ctx->m_recv_vecs);       // received vectors become the table's vector store
     ctx->foreign_n = recv_total;
-    CKS(ensure(ctx, ctx->table, cap * sizeof(Slot)));
+    CKS(ensure_table_buf(ctx, ctx->table, cap * sizeof(Slot)));
     CK(cudaMemsetAsync(ctx->table.p, 0, cap * sizeof(Slot), s));
     ctx->t_capacity = cap;
     InsertVecArgs iv{};
@@ -3327,7 +3347,7 @@ mdbg_status mdbg_count_merge_hashes(mdbg_ctx* ctx) {
     CKS(x.run(ctx, ctx->m_send_vecs.p, ctx->m_recv_vecs.p, 24));
     clk.lap(PH_MERGE_EXCHANGE);
     const uint64_t cap = table_capacity_for(x.recv_total);
-    CKS(ensure(ctx, ctx->table, cap * sizeof(Slot)));
+    CKS(ensure_table_buf(ctx, ctx->table, cap * sizeof(Slot)));
     CK(cudaMemsetAsync(ctx->table.p, 0, cap * sizeof(Slot), s));
     ctx->t_capacity = cap;
     launch_insert_hash_recs(ctx->m_recv_vecs.as<uint64_t>(), x.recv_total, ctx->table.as<Slot>(), cap - 1,

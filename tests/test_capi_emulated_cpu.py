@@ -57,6 +57,17 @@ def test_owner_merge_on_the_emulator(emulated, n_ranks, k, n_reads):
     assert run.returncode == 0 and run.stdout.strip().endswith("OK"), run.stdout[-2000:] + run.stderr[-3000:]
 
 
+@pytest.mark.parametrize("n_ranks,last_k", [(3, 12), (8, 9)])
+def test_multi_k_sweeps_over_several_ranks_on_the_emulator(emulated, n_ranks, last_k):
+    """Four multi-k sweeps in a row on N ranks with the keys-only owner merge after every k (tests/emu_multirank_sweeps_child.py):
+    the rotation of the three table buffers (trades, common size) leaves every table intact -- the owner-partitioned
+    tables add up to the single-context ones in every sweep -- and stops allocating within three sweeps."""
+    _, env = emulated
+    run = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu_multirank_sweeps_child.py"), str(n_ranks), str(last_k)],
+                         env=env, capture_output=True, text=True, timeout=900)
+    assert run.returncode == 0 and run.stdout.strip().endswith("OK"), run.stdout[-2000:] + run.stderr[-3000:]
+
+
 def test_gpu_parity_suites_against_the_emulated_library(emulated):
     lib, env = emulated
     run = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "tests/test_gpu_host_cpp.py", "tests/test_gpu_z_new_paths.py", "tests/test_gpu_zz_round2.py", "-m", "gpu",
