@@ -2077,6 +2077,16 @@ static uint32_t pass_shards(uint64_t cap) {
     return n;
 }
 
+// the claim accounting of a fresh table: the counter the host reads and the shards / flag copies of the warp-form passes
+// (a merged table starts from zero as well: its limit is its capacity, so only a probe sequence that runs out can still
+// raise the flag for passes added after the merge)
+static mdbg_status reset_claims(mdbg_ctx* ctx) {
+    CK(cudaMemsetAsync(&ctx->d_small->t_claims, 0, sizeof(unsigned long long), ctx->stream));
+    CKS(ensure(ctx, ctx->pass_aux, sizeof(PassAux)));
+    CK(cudaMemsetAsync(ctx->pass_aux.p, 0, sizeof(PassAux), ctx->stream));
+    return MDBG_OK;
+}
+
 static mdbg_status table_reset(mdbg_ctx* ctx, uint64_t cap) {
     PhaseClock clk(ctx);
     // mdbg_prev_from_current swaps the two table buffers, so a loop over k leaves the large first-pass buffer on either
@@ -2093,9 +2103,7 @@ static mdbg_status table_reset(mdbg_ctx* ctx, uint64_t cap) {
     CKS(ensure_table_buf(ctx, ctx->table, cap * sizeof(Slot)));
     CK(cudaMemsetAsync(ctx->table.p, 0, cap * sizeof(Slot), ctx->stream));
     CK(cudaMemsetAsync(&ctx->d_small->full_flag, 0, sizeof(uint32_t), ctx->stream));
-    CK(cudaMemsetAsync(&ctx->d_small->t_claims, 0, sizeof(unsigned long long), ctx->stream));
-    CKS(ensure(ctx, ctx->pass_aux, sizeof(PassAux)));
-    CK(cudaMemsetAsync(ctx->pass_aux.p, 0, sizeof(PassAux), ctx->stream));
+    CKS(reset_claims(ctx));
     ctx->t_capacity = cap;
     ctx->t_claim_limit = cap - cap / 5;
     clk.lap(PH_TABLE_RESET);
@@ -3273,6 +3281,7 @@ mdbg_status mdbg_count_merge(mdbg_ctx* ctx) {
     ctx->foreign_n = recv_total;
     CKS(ensure_table_buf(ctx, ctx->table, cap * sizeof(Slot)));
     CK(cudaMemsetAsync(ctx->table.p, 0, cap * sizeof(Slot), s));
+    CKS(reset_claims(ctx));
     ctx->t_capacity = cap;
     InsertVecArgs iv{};
     iv.vecs = ctx->foreign_vecs.as<uint32_t>();
@@ -3349,6 +3358,7 @@ mdbg_status mdbg_count_merge_hashes(mdbg_ctx* ctx) {
     const uint64_t cap = table_capacity_for(x.recv_total);
     CKS(ensure_table_buf(ctx, ctx->table, cap * sizeof(Slot)));
     CK(cudaMemsetAsync(ctx->table.p, 0, cap * sizeof(Slot), s));
+    CKS(reset_claims(ctx));
     ctx->t_capacity = cap;
     launch_insert_hash_recs(ctx->m_recv_vecs.as<uint64_t>(), x.recv_total, ctx->table.as<Slot>(), cap - 1,
                             ctx->t_value_mode ? 1u : 0u, &ctx->d_small->full_flag, s);
