@@ -549,10 +549,12 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     # size-independent property at full size: every k-min-mer occurrence of every read is in exactly one table
     # (after the owner merge): sum of all abundances over all ranks == sum over reads of max(0, n_minimizers - k + 1)
     occ = None
+    local_windows = 0
     if w["last_k"] == K:
         so, _ = eng.store_fetch()
         per_read = np.diff(so.astype(np.int64))
-        expect_instances = sum_over_ranks(int(np.maximum(per_read - K + 1, 0).sum()))
+        local_windows = int(np.maximum(per_read - K + 1, 0).sum())         # k-min-mer instances of this rank's insert pass
+        expect_instances = sum_over_ranks(local_windows)
         got_instances = sum_over_ranks(stats["n_instances"])
         if expect_instances != got_instances:
             raise SystemExit(f"bench.py: occurrence conservation violated: {got_instances} != {expect_instances}")
@@ -902,6 +904,19 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                                          "instruction per scheduler per cycle at the sampled SM clock",
                                  "achieved_warp_inst_per_s": ach, "peak_warp_inst_per_s": peak_issue, "frac": ach / peak_issue,
                                  "thread_instructions_per_lmer": tj.get("thread_instructions_per_lmer")}
+        # the second kernel of the step (K3, the k-min-mer insert pass): SURVEY 8d counts one 32-byte sector read and one
+        # 32-byte write per k-min-mer instance; the local (pre-merge) pass of this rank
+        table_roofline = None
+        ins_ms = float(np.mean(insert_ms)) if len(insert_ms) else 0.0
+        if ins_ms > 0 and local_windows:
+            n_windows = local_windows
+            t_ach = n_windows * 64.0 / (ins_ms * 1e-3) / 1e9
+            table_roofline = {"bound": "hbm", "kernel": "insert_warp_kernel<4>", "achieved": t_ach, "peak": peak, "unit": "GB/s",
+                              "frac": t_ach / peak, "ms_per_launch": ins_ms, "algorithmic_bytes_per_launch": n_windows * 64.0,
+                              "windows_per_launch": n_windows, "share_of_step": ins_ms / (ms_total / args.steps),
+                              "note": "every access is a random 32-byte sector of a table larger than L2: the pass is bound by "
+                                      "DRAM's random-access rate, not its byte rate (rate against table size: DESIGN.md K3, "
+                                      "profiles/r02_passes_ncu.txt)"}
         line = {
             "metric": METRIC, "value": value, "unit": "Gbp/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
@@ -916,6 +931,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                                  "int_issue and DESIGN.md",
                          "binding_pipes_ncu": ncu_pipes, "int_issue": int_issue,
                          "share_of_step": sk_ms / (ms_total / args.steps)},
+            "roofline_table_pass": table_roofline,
             "kernels_ms": {"sketch": sk_ms, "insert": float(np.mean(insert_ms))},
             "table_phase_ms_profiled_step_rank0": step_phases,
             "ascii_resident": ascii_leg, "multi_k": multi_k, "edges": edges_extra, "unitigs": unitigs_extra,
