@@ -2196,7 +2196,8 @@ static mdbg_status launch_pass(mdbg_ctx* ctx, uint64_t g_lo, uint64_t g_hi, bool
         launch_next_k(a, s);
     }
     if (timed && ctx->timing) { CK(cudaEventRecord(ctx->ev[1][1], s)); ctx->ev_valid[1] = true; }
-    return check_launch(ctx, next_k ? "next_k_kernel" : "insert_kernel", g_hi > g_lo ? 1 : 0);
+    return check_launch(ctx, next_k ? "next-k pass kernel (+ pass_fold_kernel)" : "insert pass kernel (+ pass_fold_kernel)",
+                        g_hi > g_lo ? pass_kernels_per_launch(ctx->pass_aux.p != nullptr) : 0);
 }
 
 // Runs the pass for [read_lo, read_hi); when the table proves too small (probe limit or load limit hit -- the

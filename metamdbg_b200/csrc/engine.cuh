@@ -182,6 +182,7 @@ struct InsertArgs {
     uint32_t aux_shards;    // claim-counter shards in use: a power of two <= 64
 };
 void launch_insert(const InsertArgs& a, cudaStream_t s);
+int pass_kernels_per_launch(bool have_aux);   // 1, or 2 when the warp form adds pass_fold_kernel
 
 // insert pre-normalized foreign vectors with counts (multi-GPU merge, receive side)
 struct InsertVecArgs {

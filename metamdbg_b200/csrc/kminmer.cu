@@ -268,6 +268,9 @@ static int pass_variant() {
     return v;
 }
 
+// kernels one launch_insert / launch_next_k call enqueues (the warp form adds pass_fold_kernel)
+int pass_kernels_per_launch(bool have_aux) { return pass_variant() != 0 && have_aux ? 2 : 1; }
+
 void launch_insert(const InsertArgs& a, cudaStream_t s) {
     if (a.g_hi <= a.g_lo) return;
     const uint64_t n = a.g_hi - a.g_lo;
